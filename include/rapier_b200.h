@@ -1,0 +1,206 @@
+/* rapier_b200.h -- C ABI of librapier_b200.so, the B200-native replacement for the per-step
+ * hot path of dimforge/rapier 0.35.2 (3-D, f32).
+ *
+ * The reference has no FFI layer for this path: the seam is the Rust method
+ *   PhysicsPipeline::step(gravity, &IntegrationParameters, &mut IslandManager, &mut BroadPhaseBvh,
+ *                         &mut NarrowPhase, &mut RigidBodySet, &mut ColliderSet, &mut ImpulseJointSet,
+ *                         &mut MultibodyJointSet, &mut CCDSolver, &dyn PhysicsHooks, &dyn EventHandler)
+ *   (src/pipeline/physics_pipeline/mod.rs:196-247; reached through PhysicsWorld::step,
+ *    src/pipeline/physics_world.rs:120-156).
+ * A Rust shim replacing `step_inner` (src/pipeline/physics_pipeline/substep.rs:267-581) binds the
+ * entry points below with `extern "C"`.  All pointers are caller-owned host
+ * memory; the library copies.  One RbWorld is not re-entrant (the reference takes `&mut self`).
+ * Every function returns RB_OK (0) or a negative RbStatus; rb_last_error() describes the failure.
+ * There is NO CPU fallback: without a CUDA device rb_world_create fails with RB_ERR_NO_DEVICE.
+ */
+#ifndef RAPIER_B200_H
+#define RAPIER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_ABI_VERSION 1
+
+typedef struct RbWorld RbWorld;
+
+typedef enum RbStatus {
+    RB_OK = 0,
+    RB_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product path never falls back to CPU */
+    RB_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed */
+    RB_ERR_INVALID = -3,     /* bad argument (null pointer, index out of range, unsupported shape) */
+    RB_ERR_CAPACITY = -4,    /* a device-side table overflowed (pairs, islands); state is unchanged */
+    RB_ERR_NONFINITE = -5    /* a body went non-finite (reference: Quarantine, quarantine.rs:14-47) */
+} RbStatus;
+
+/* Mirror of IntegrationParameters (src/dynamics/integration_parameters.rs:181-304), #[repr(C)]. */
+typedef struct RbIntegrationParameters {
+    float dt;                                   /* :185  default 1/60 */
+    float min_ccd_dt;                           /*       default 1/60/100 (CCD is out of scope) */
+    float contact_natural_frequency;            /* contact_softness.natural_frequency, default 30 */
+    float contact_damping_ratio;                /* contact_softness.damping_ratio,     default 10 */
+    float static_contact_natural_frequency;     /* static_contact_softness, default 60 */
+    float static_contact_damping_ratio;         /*                          default 10 */
+    float warmstart_coefficient;                /* default 1 */
+    float length_unit;                          /* default 1 */
+    float normalized_allowed_linear_error;      /* default 0.005 */
+    float normalized_max_corrective_velocity;   /* default 3 */
+    float normalized_prediction_distance;       /* default 0.02 */
+    float normalized_max_linear_velocity;       /* default 400 */
+    int32_t num_solver_iterations;              /* substeps, default 4 */
+    int32_t num_internal_pgs_iterations;        /* default 1 */
+    int32_t num_internal_stabilization_iterations; /* default 1 */
+    int32_t max_ccd_substeps;                   /* default 1 (accepted, CCD itself out of scope) */
+    int32_t contact_clustering;                 /* default 1 (no effect: single-manifold pairs only) */
+    int32_t contact_recycling;                  /* default 1 */
+    float normalized_contact_recycle_distance;  /* default 0.05 */
+    int32_t friction_in_bias_pass;              /* default 0 */
+    int32_t warmstart_joints;                   /* default 0 (1 is RB_ERR_INVALID for now) */
+    int32_t friction_model;                     /* 0 = Simplified (twist, default); 1 = Coulomb: RB_ERR_INVALID */
+} RbIntegrationParameters;
+
+/* Fills *p with IntegrationParameters::default() (integration_parameters.rs:379-407). */
+void rb_integration_parameters_default(RbIntegrationParameters* p);
+
+/* RigidBodyType (src/dynamics/rigid_body_components.rs). Kinematic bodies are not supported yet. */
+enum { RB_BODY_DYNAMIC = 0, RB_BODY_FIXED = 1 };
+
+/* Body flags */
+enum {
+    RB_BODY_GYROSCOPIC = 1,          /* forces.gyroscopic_forces_enabled (default on, rigid_body.rs:1579) */
+    RB_BODY_ALLOW_FAST_ROTATION = 2, /* ccd.allow_fast_rotation */
+    RB_BODY_LOCK_TX = 4, RB_BODY_LOCK_TY = 8, RB_BODY_LOCK_TZ = 16,   /* LockedAxes */
+    RB_BODY_LOCK_RX = 32, RB_BODY_LOCK_RY = 64, RB_BODY_LOCK_RZ = 128
+};
+
+/* One rigid body as the caller's RigidBodySet holds it (src/dynamics/rigid_body.rs:48-70).
+ * Mass properties are recomputed by the library from the attached colliders
+ * (RigidBodyMassProps::recompute_mass_properties_from_colliders, rigid_body_components.rs:421)
+ * plus `additional_mass`; pose quaternions are (x, y, z, w). */
+typedef struct RbBodyDesc {
+    int32_t body_type;            /* RB_BODY_* */
+    uint32_t flags;               /* RB_BODY_GYROSCOPIC | ... */
+    float translation[3];
+    float rotation[4];
+    float linvel[3];
+    float angvel[3];
+    float linear_damping;
+    float angular_damping;
+    float gravity_scale;
+    float additional_mass;        /* added at the body origin (MassProperties additive term); 0 = none */
+    float user_force[3];
+    float user_torque[3];
+} RbBodyDesc;
+
+enum { RB_SHAPE_BALL = 0, RB_SHAPE_CUBOID = 1 };
+
+/* CoefficientCombineRule (src/dynamics/coefficient_combine_rule.rs:8-22). */
+enum { RB_COMBINE_AVERAGE = 0, RB_COMBINE_MIN = 1, RB_COMBINE_MULTIPLY = 2, RB_COMBINE_MAX = 3,
+       RB_COMBINE_CLAMPED_SUM = 4, RB_COMBINE_GEOMETRIC_MEAN = 5 };
+
+/* One collider (src/geometry/collider.rs; ColliderBuilder defaults :688-707). */
+typedef struct RbColliderDesc {
+    int32_t shape;                /* RB_SHAPE_* */
+    float half_extents[3];        /* cuboid half extents; ball: [radius, 0, 0] */
+    int32_t parent;               /* body index, or -1 for a parentless (fixed) collider */
+    float pos_wrt_parent_t[3];    /* pose relative to the parent (world pose if parent == -1) */
+    float pos_wrt_parent_q[4];
+    float density;                /* default 1 */
+    float friction;               /* default 0.5 */
+    float restitution;            /* default 0 */
+    int32_t friction_combine_rule;     /* RB_COMBINE_* */
+    int32_t restitution_combine_rule;
+    float contact_skin;           /* default 0 */
+    uint32_t collision_memberships;    /* InteractionGroups::all() = 0xffffffff */
+    uint32_t collision_filter;
+} RbColliderDesc;
+
+/* JointAxesMask bits (src/dynamics/joint/generic_joint.rs): LIN_X=1, LIN_Y=2, LIN_Z=4,
+ * ANG_X=8, ANG_Y=16, ANG_Z=32.  Only fully locked axes are supported (spherical = 7, fixed = 63,
+ * revolute about x = 55); motors and limits are RB_ERR_INVALID. */
+typedef struct RbJointDesc {
+    int32_t body1, body2;
+    float local_frame1_t[3], local_frame1_q[4];
+    float local_frame2_t[3], local_frame2_q[4];
+    uint32_t locked_axes;
+    int32_t contacts_enabled;     /* default 1 */
+    float natural_frequency;      /* joint softness, default 1e6 (integration_parameters.rs:78-83) */
+    float damping_ratio;          /* default 1 */
+} RbJointDesc;
+
+/* Per-stage device times of the last step, named after the reference's Counters
+ * (src/counters/mod.rs:19-35).  Milliseconds, measured with CUDA events when enabled. */
+typedef struct RbCounters {
+    float step_ms;
+    float collision_detection_ms;   /* broad + narrow */
+    float broad_phase_ms;
+    float narrow_phase_ms;
+    float island_construction_ms;   /* colouring + islands + schedule */
+    float solver_ms;                /* velocity assembly + resolution + writeback */
+    float update_ms;                /* advance_to_final_positions + AABB refresh */
+    int32_t num_bodies, num_colliders, num_pairs, num_active_manifolds, num_islands, num_colors;
+    int32_t num_joints;
+    int32_t broad_phase_ran;        /* 1 if the pair set was recomputed in the last step */
+    int32_t schedule_rebuilt;       /* 1 if colours/islands/schedule were rebuilt in the last step */
+    int64_t kernels_launched;       /* cumulative count of this library's kernel launches */
+    int64_t steps;                  /* cumulative steps */
+} RbCounters;
+
+/* ---- lifetime ---- */
+int rb_abi_version(void);
+const char* rb_last_error(void);
+/* `device`: CUDA ordinal.  Fails (NULL, rb_last_error set) when no device is usable. */
+RbWorld* rb_world_create(const RbIntegrationParameters* params, int device);
+void rb_world_destroy(RbWorld* w);
+int rb_world_set_params(RbWorld* w, const RbIntegrationParameters* params);
+
+/* ---- state upload: RigidBodySet / ColliderSet / ImpulseJointSet (user changes, substep.rs:303-334) ----
+ * rb_world_set_scene replaces the whole scene (and clears pairs, contacts, warm-start state). */
+int rb_world_set_scene(RbWorld* w,
+                       int32_t num_bodies, const RbBodyDesc* bodies,
+                       int32_t num_colliders, const RbColliderDesc* colliders,
+                       int32_t num_joints, const RbJointDesc* joints);
+/* Overwrite poses/velocities of `n` bodies (indices[n]; pose7 = t(3) q(4); vel6 = lin(3) ang(3)). */
+int rb_world_set_body_states(RbWorld* w, int32_t n, const int32_t* indices,
+                             const float* pose7, const float* vel6);
+
+/* ---- the hot path: PhysicsPipeline::step ---- */
+/* Runs `nsteps` steps; host-synchronous on return only if `sync` != 0. */
+int rb_world_step(RbWorld* w, const float gravity[3], int32_t nsteps, int32_t sync);
+int rb_world_synchronize(RbWorld* w);
+
+/* ---- state download (RigidBodySet writeback) ---- */
+/* pose7 [n*7] and vel6 [n*6] may each be NULL. Synchronises the stream. */
+int rb_world_get_body_states(RbWorld* w, float* pose7, float* vel6);
+int rb_world_num_bodies(RbWorld* w);
+int rb_world_get_counters(RbWorld* w, RbCounters* out);
+int rb_world_enable_profiling(RbWorld* w, int32_t enabled);
+
+/* ---- contact graph read-back (NarrowPhase::contact_pairs; used by the parity tests) ---- */
+/* Returns the number of broad-phase pairs; fills up to `cap` entries of each non-NULL array.
+ *   pair_colliders [cap*2]   collider1, collider2 (collider1 < collider2)
+ *   num_contacts   [cap]     active solver contacts of the pair's manifold (0..4)
+ *   color          [cap]     solver colour (0..127, 128 overflow, 255 uncoloured)
+ *   normal         [cap*3]   world-space manifold normal (ContactManifoldData::normal)
+ *   impulses       [cap*4]   total normal impulse of each solver contact (ContactData::impulse) */
+int rb_world_get_contact_pairs(RbWorld* w, int32_t cap, int32_t* pair_colliders, int32_t* num_contacts,
+                               int32_t* color, float* normal, float* impulses);
+/* Raw device-table dump for debugging / parity (name-addressed; see DESIGN.md "debug tables").
+ * Returns bytes copied or a negative status. */
+int64_t rb_world_debug_read(RbWorld* w, const char* table, void* dst, int64_t cap_bytes);
+
+/* ---- multi-GPU sharding: each rank owns whole connected components ---- */
+/* Restricts this world to the bodies whose component id (as labelled by rb_world_label_components)
+ * satisfies component % world_size == rank; the other dynamic bodies become inert. */
+int rb_world_label_components(RbWorld* w, int32_t* component_of_body /* [num_bodies], host */);
+int rb_world_set_owned_bodies(RbWorld* w, const uint8_t* owned /* [num_bodies] */);
+/* Device pointers to the packed per-body state (13 floats/body: t3 q4 lin3 ang3) for NCCL
+ * all-gather of boundary body states, and the byte size. */
+int rb_world_state_buffer(RbWorld* w, void** device_ptr, int64_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAPIER_B200_H */

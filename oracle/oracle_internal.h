@@ -1,0 +1,202 @@
+// TEST INFRASTRUCTURE ONLY -- internal data model of the CPU oracle (see oracle.h header note).
+#pragma once
+#include <vector>
+#include <cstdint>
+#include "omath.h"
+#include "oracle.h"
+
+namespace orc {
+
+constexpr int MAX_MANIFOLD_POINTS = 4;     // src/lib.rs:291
+constexpr int MAX_RAW_POINTS = 8;          // two convex quads clip to <= 8 vertices
+constexpr uint8_t COLOR_UNCOLORED = 255;   // contact_pair.rs:152
+constexpr uint8_t COLOR_OVERFLOW = 128;    // contact_pair.rs:155
+constexpr int DYNAMIC_COLOR_COUNT = 120;   // contact_pair.rs:159
+constexpr int NUM_COLORS = 129;
+constexpr uint32_t NO_BODY = 0xffffffffu;  // u32::MAX solver id = world-attached
+
+struct Mask128 {
+    uint64_t lo = 0, hi = 0;
+    bool test(int c) const { return c < 64 ? ((lo >> c) & 1) : ((hi >> (c - 64)) & 1); }
+    void set(int c) { if (c < 64) lo |= (1ull << c); else hi |= (1ull << (c - 64)); }
+    void clear(int c) { if (c < 64) lo &= ~(1ull << c); else hi &= ~(1ull << (c - 64)); }
+};
+
+struct Params {
+    RbIntegrationParameters p;
+    float prediction_distance() const { return p.normalized_prediction_distance * p.length_unit; }
+    float max_corrective_velocity() const {
+        return p.normalized_max_corrective_velocity * p.length_unit;
+    }
+    float max_linear_velocity() const { return p.normalized_max_linear_velocity * p.length_unit; }
+    float contact_recycle_distance() const {
+        return p.normalized_contact_recycle_distance * p.length_unit;
+    }
+};
+
+struct Body {
+    int type;
+    uint32_t flags;
+    Pose pos;        // RigidBodyPosition::position
+    Pose next_pos;   // RigidBodyPosition::next_position
+    V3 linvel, angvel;
+    float lin_damping, ang_damping, gravity_scale;
+    V3 user_force, user_torque;
+    // local mass properties (parry MassProperties)
+    V3 local_com;
+    float inv_mass;
+    V3 principal_inertia, inv_principal_inertia;
+    Q4 principal_frame;
+    // world-space (RigidBodyMassProps)
+    V3 world_com;
+    V3 eff_inv_mass;
+    Sdp3 eff_world_inv_inertia;
+    // per-step forces
+    V3 force, torque;
+    bool is_dynamic() const { return type == RB_BODY_DYNAMIC; }
+};
+
+struct Aabb {
+    V3 mins, maxs;
+};
+
+struct Collider {
+    int shape;
+    V3 he;          // cuboid half extents, or (r,0,0)
+    int parent;     // -1 = none
+    Pose pos_wrt_parent;
+    float density, friction, restitution;
+    int friction_rule, restitution_rule;
+    float contact_skin;
+    uint32_t memberships, filter;
+    Pose pos;       // world pose
+    Aabb aabb;      // compute_broad_phase_aabb (tight + skin + prediction/2)
+    Aabb fat;       // broad-phase leaf AABB (change-detection skin)
+    bool fat_valid;
+};
+
+struct Point {  // parry TrackedContact + rapier ContactData (contact_pair.rs:54-87)
+    V3 local_p1, local_p2;
+    float dist;
+    uint32_t fid1, fid2;
+    float impulse, warmstart_impulse, warmstart_twist;
+    V3 warmstart_tangent_world;
+    V3 dp1, dp2;
+};
+
+struct SolverContact {  // contact_pair.rs:617-653 (anchors already localised)
+    V3 anchor1, anchor2;
+    int cid;
+};
+
+struct Pair {
+    int c1, c2;
+    int b1, b2;            // parent bodies (-1 none)
+    bool has_recycle;      // ContactRecycleState (contact_pair.rs:256-282)
+    Pose r_pos12;
+    Q4 r_rot1, r_rot2;
+    float r_max_extent, r_max_drift;
+    int npts;
+    V3 local_n1, local_n2;
+    Point pts[MAX_MANIFOLD_POINTS];
+    V3 normal;
+    float friction, restitution;
+    int nsc;
+    SolverContact sc[MAX_MANIFOLD_POINTS];
+    uint8_t color;
+    uint32_t color_bodies[2];
+};
+
+struct RawPoint {
+    V3 local_p1, local_p2;
+    float dist;
+    uint32_t fid1, fid2;
+};
+struct RawManifold {
+    int n;
+    RawPoint pts[MAX_RAW_POINTS];
+    V3 local_n1, local_n2;
+};
+
+// Geometry (parry restatement) -- oracle_geom.cpp
+void contact_manifold(int shape1, V3 he1, int shape2, V3 he2, const Pose& pos12, float prediction,
+                      RawManifold& out);
+Aabb shape_aabb(int shape, V3 he, const Pose& pos);
+
+struct Joint {
+    int body1, body2;
+    Pose local_frame1, local_frame2;   // as given (body space)
+    Pose sframe1, sframe2;             // solver-body space (generic_joint.rs:624-636)
+    uint32_t locked_axes;
+    int contacts_enabled;
+    float natural_frequency, damping_ratio;
+    uint32_t sid1, sid2;               // solver ids (NO_BODY = world attached)
+    int color;
+    float impulses[6];
+};
+
+struct JointRow {  // JointConstraint<Real,1> (joint_velocity_constraint.rs:68-93)
+    V3 lin_jac, ang_jac1, ang_jac2, ii_ang_jac1, ii_ang_jac2;
+    float impulse, inv_lhs, rhs, rhs_wo_bias, cfm_gain, cfm_coeff;
+    int dof;
+};
+
+// ContactWithTwistFriction + builder (contact_with_twist_friction.rs:44-55, :601-630), one lane.
+struct NormalPart {
+    V3 torque_dir1, torque_dir2, ii_torque_dir1, ii_torque_dir2;
+    float rhs, rhs_wo_bias, impulse, impulse_accumulator, r, cfm_factor;
+};
+struct Constraint {
+    int pair;
+    uint32_t id1, id2;
+    int num_contacts;
+    V3 dir1, tangent1;
+    V3 im1, im2;
+    Sdp3 ii1, ii2;
+    float limit;
+    NormalPart normal[MAX_MANIFOLD_POINTS];
+    // tangent part
+    V3 t_dp1, t_dp2, t_torque_dir1[2], t_torque_dir2[2], t_ii_torque_dir1[2], t_ii_torque_dir2[2];
+    float t_rhs[2], t_rhs_wo_bias[2], t_impulse[2], t_impulse_acc[2], t_r[3];
+    // twist part
+    float w_rhs, w_impulse, w_impulse_acc, w_r;
+    float twist_dists[MAX_MANIFOLD_POINTS];
+    int cids[MAX_MANIFOLD_POINTS];
+    // builder
+    V3 b_local_p1[MAX_MANIFOLD_POINTS], b_local_p2[MAX_MANIFOLD_POINTS];
+    float b_dist[MAX_MANIFOLD_POINTS], b_restitution_seed[MAX_MANIFOLD_POINTS];
+    V3 b_lfc1, b_lfc2, b_tangent_vel;
+    float b_restitution;
+};
+
+struct SolverBody {
+    V3 lin, ang;        // SolverVel
+    Pose pose;          // SolverPose rotation+translation (CoM centred)
+    Sdp3 ii;
+    V3 im;
+    V3 incr_lin, incr_ang;
+    bool gyro;
+    uint32_t flags;
+};
+
+struct World {
+    Params params;
+    std::vector<Body> bodies;
+    std::vector<Collider> colliders;
+    std::vector<Joint> joints;
+    std::vector<Pair> pairs;           // sorted by (c1, c2)
+    std::vector<Mask128> color_masks;  // per body (narrow_phase/mod.rs body_solver_color_masks)
+    bool bp_dirty = true;
+    // scratch
+    std::vector<SolverBody> sb;
+    std::vector<Constraint> cons;
+    std::vector<int> order;            // constraint indices in solve order
+    std::vector<int> order_color_start;  // start offset of each colour stage within `order`
+    std::vector<JointRow> jrows;
+    std::vector<int> jorder, jorder_color_start;
+    std::vector<uint64_t> nocontact_body_pairs;  // sorted keys of joints with contacts disabled
+    RbCounters counters{};
+    int last_num_colors = 0;
+};
+
+}  // namespace orc

@@ -1,0 +1,736 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle: the velocity solver + integrator (see oracle.h header note).
+//
+// Follows src/pipeline/physics_pipeline/solve.rs:159-401 (build_islands_and_solve_velocity_constraints)
+// -> src/dynamics/solver/staged_island_solver/{init.rs:30-544, worker.rs:32-898, solve.rs:12-209}
+// with the constraint arithmetic of src/dynamics/solver/contact_constraint/
+// {contact_with_twist_friction.rs, contact_constraint_element.rs} and the joint rows of
+// src/dynamics/solver/joint_constraint/{joint_constraint_builder.rs, joint_constraint_helper.rs,
+// joint_velocity_constraint.rs}.  One constraint at a time, colours in the reference's stage order.
+#include <algorithm>
+#include <cstring>
+#include "oracle_internal.h"
+#include "opool.h"
+
+namespace orc {
+
+void set_threads(int n) { Pool::get().set_threads(n); }
+int get_threads() { return Pool::get().threads(); }
+
+// integration_parameters.rs:85-149
+struct Spring {
+    float natural_frequency, damping_ratio;
+    float angular_frequency() const { return natural_frequency * 6.283185307179586f; }
+    float erp_inv_dt(float dt) const {
+        float w = angular_frequency();
+        return w / (dt * w + 2.0f * damping_ratio);
+    }
+    float erp(float dt) const { return dt * erp_inv_dt(dt); }
+    float cfm_coeff(float dt) const {
+        float e = erp(dt);
+        if (e == 0.0f) return 0.0f;
+        float inv_erp_minus_one = 1.0f / e - 1.0f;
+        return inv_erp_minus_one * inv_erp_minus_one /
+               ((1.0f + inv_erp_minus_one) * 4.0f * damping_ratio * damping_ratio);
+    }
+    float cfm_factor(float dt) const { return 1.0f / (1.0f + cfm_coeff(dt)); }
+};
+
+struct GatheredBody {  // solver_body.rs:11-33,338-350: world-attached side = identity / zero
+    V3 lin, ang;
+    Pose pose;
+    Sdp3 ii;
+    V3 im;
+};
+static inline GatheredBody gather(const World& w, uint32_t id) {
+    GatheredBody g;
+    if (id == NO_BODY) {
+        g.lin = vzero(); g.ang = vzero(); g.pose = pose_identity(); g.ii = sdp_zero(); g.im = vzero();
+    } else {
+        const SolverBody& s = w.sb[id];
+        g.lin = s.lin; g.ang = s.ang; g.pose = s.pose; g.ii = s.ii; g.im = s.im;
+    }
+    return g;
+}
+static inline void scatter_vel(World& w, uint32_t id, V3 lin, V3 ang) {
+    if (id == NO_BODY) return;
+    w.sb[id].lin = lin;
+    w.sb[id].ang = ang;
+}
+
+static inline float is_bouncy(float restitution, bool is_new) {  // contact_pair.rs:773-779
+    return is_new ? (restitution > 0.0f ? 1.0f : 0.0f) : (restitution >= 1.0f ? 1.0f : 0.0f);
+}
+
+// contact_with_twist_friction.rs:58-424 (one lane)
+static void generate(World& w, int pair_index, Constraint& c) {
+    const Pair& p = w.pairs[pair_index];
+    memset(&c, 0, sizeof(c));
+    c.pair = pair_index;
+    bool d1 = p.b1 >= 0 && w.bodies[p.b1].is_dynamic();
+    bool d2 = p.b2 >= 0 && w.bodies[p.b2].is_dynamic();
+    c.id1 = d1 ? (uint32_t)p.b1 : NO_BODY;
+    c.id2 = d2 ? (uint32_t)p.b2 : NO_BODY;
+    GatheredBody g1 = gather(w, c.id1), g2 = gather(w, c.id2);
+    V3 world_com1 = g1.pose.t, world_com2 = g2.pose.t;
+    V3 force_dir1 = -p.normal;
+    int count = p.nsc < MAX_MANIFOLD_POINTS ? p.nsc : MAX_MANIFOLD_POINTS;
+    V3 t1 = orthonormal_vector(force_dir1);   // contact_constraint/mod.rs:26-47
+    V3 t2 = cross(force_dir1, t1);
+    float inv_num_points = 1.0f / (float)count;
+    c.dir1 = force_dir1;
+    c.im1 = g1.im; c.im2 = g2.im; c.ii1 = g1.ii; c.ii2 = g2.ii;
+    c.b_restitution = p.restitution;
+    c.num_contacts = count;
+    c.tangent1 = t1;
+    c.limit = p.friction;
+
+    V3 friction_center = vzero(), friction_center2 = vzero();
+    float twist_warmstart = 0.0f;
+    float tangent_warmstart[2] = {0.0f, 0.0f};
+    V3 tangent_vel = vzero();
+    V3 points[MAX_MANIFOLD_POINTS];
+    for (int k = 0; k < count; ++k) {
+        float weight = inv_num_points;
+        const SolverContact& sc = p.sc[k];
+        const Point& pt = p.pts[sc.cid];
+        float warmstart_impulse = pt.warmstart_impulse;
+        V3 wt = pt.warmstart_tangent_world;
+        float ws_t0 = dot(wt, t1), ws_t1 = dot(wt, t2);
+        float warmstart_twist = pt.warmstart_twist;
+        bool is_new = pt.impulse == 0.0f;
+        float bouncy = is_bouncy(p.restitution, is_new);
+        V3 p1 = pose_point(g1.pose, sc.anchor1);
+        V3 p2 = pose_point(g2.pose, sc.anchor2);
+        float dist = dot(p1 - p2, force_dir1);
+        V3 dp1 = pt.dp1, dp2 = pt.dp2;
+        V3 point = world_com1 + dp1;
+        points[k] = point;
+        friction_center = friction_center + point * weight;
+        friction_center2 = friction_center2 + (world_com2 + dp2) * weight;
+        V3 vel1 = g1.lin + cross(g1.ang, dp1);
+        V3 vel2 = g2.lin + cross(g2.ang, dp2);
+        twist_warmstart = twist_warmstart + warmstart_twist * weight;
+        tangent_warmstart[0] = tangent_warmstart[0] + ws_t0 * weight;
+        tangent_warmstart[1] = tangent_warmstart[1] + ws_t1 * weight;
+        tangent_vel = tangent_vel + vzero() * weight;
+        c.cids[k] = sc.cid;
+        NormalPart& n = c.normal[k];
+        n.torque_dir1 = cross(dp1, force_dir1);
+        n.torque_dir2 = cross(dp2, -force_dir1);
+        n.ii_torque_dir1 = sdp_mul(g1.ii, n.torque_dir1);
+        n.ii_torque_dir2 = sdp_mul(g2.ii, n.torque_dir2);
+        V3 imsum = g1.im + g2.im;
+        float projected_mass = inv_or_zero(dot(force_dir1, cmul(imsum, force_dir1)) + dot(n.ii_torque_dir1, n.torque_dir1) +
+                                           dot(n.ii_torque_dir2, n.torque_dir2));
+        float projected_velocity = dot(vel1 - vel2, force_dir1);
+        float restitution_seed = bouncy * p.restitution * projected_velocity;
+        n.impulse = warmstart_impulse;
+        n.impulse_accumulator = -n.impulse;
+        n.r = projected_mass;
+        c.b_local_p1[k] = pose_inv_point(g1.pose, point);
+        c.b_local_p2[k] = pose_inv_point(g2.pose, world_com2 + dp2);
+        c.b_dist[k] = dist - dot(point - (world_com2 + dp2), force_dir1);
+        c.b_restitution_seed[k] = restitution_seed;
+    }
+    c.t_impulse[0] = tangent_warmstart[0];
+    c.t_impulse[1] = tangent_warmstart[1];
+    c.t_impulse_acc[0] = -tangent_warmstart[0];
+    c.t_impulse_acc[1] = -tangent_warmstart[1];
+    c.w_impulse = count > 1 ? twist_warmstart : 0.0f;
+    c.w_impulse_acc = -c.w_impulse;
+    c.b_lfc1 = pose_inv_point(g1.pose, friction_center);
+    c.b_lfc2 = pose_inv_point(g2.pose, friction_center2);
+    c.b_tangent_vel = tangent_vel;
+    V3 dp1 = friction_center - world_com1;
+    V3 dp2 = friction_center2 - world_com2;
+    if (count > 1) {
+        for (int k = 0; k < count; ++k) c.twist_dists[k] = length(friction_center - points[k]);
+        V3 ii_twist_dir1 = sdp_mul(g1.ii, force_dir1);
+        V3 ii_twist_dir2 = sdp_mul(g2.ii, -force_dir1);
+        c.w_rhs = 0.0f;
+        c.w_r = inv_or_zero(dot(ii_twist_dir1, force_dir1) + dot(ii_twist_dir2, -force_dir1));
+    }
+    c.t_dp1 = dp1;
+    c.t_dp2 = dp2;
+    V3 tangents[2] = {t1, t2};
+    for (int j = 0; j < 2; ++j) {
+        V3 td1 = cross(dp1, tangents[j]);
+        V3 td2 = cross(dp2, -tangents[j]);
+        V3 itd1 = sdp_mul(g1.ii, td1);
+        V3 itd2 = sdp_mul(g2.ii, td2);
+        V3 imsum = g1.im + g2.im;
+        float r = dot(tangents[j], cmul(imsum, tangents[j])) + dot(itd1, td1) + dot(itd2, td2);
+        float rhs_wo_bias = dot(tangent_vel, tangents[j]);
+        c.t_torque_dir1[j] = td1; c.t_torque_dir2[j] = td2;
+        c.t_ii_torque_dir1[j] = itd1; c.t_ii_torque_dir2[j] = itd2;
+        c.t_rhs_wo_bias[j] = rhs_wo_bias;
+        c.t_rhs[j] = rhs_wo_bias;
+        c.t_r[j] = r;
+    }
+    c.t_r[2] = 2.0f * (dot(c.t_ii_torque_dir1[0], c.t_torque_dir1[1]) + dot(c.t_ii_torque_dir2[0], c.t_torque_dir2[1]));
+}
+
+struct SubParams {
+    float dt, inv_dt;
+    float dyn_cfm, static_cfm, dyn_erp, static_erp;
+    float max_corrective_velocity, warmstart_coeff;
+};
+
+// contact_with_twist_friction.rs:426-522
+static void update(const World& w, Constraint& c, const SubParams& sp, float solved_dt) {
+    float is_static = (c.id1 == NO_BODY || c.id2 == NO_BODY) ? 1.0f : 0.0f;
+    float cfm_factor = sp.dyn_cfm + is_static * (sp.static_cfm - sp.dyn_cfm);
+    float erp_inv_dt = sp.dyn_erp + is_static * (sp.static_erp - sp.dyn_erp);
+    GatheredBody g1 = gather(w, c.id1), g2 = gather(w, c.id2);
+    V3 tangents[2] = {c.tangent1, cross(c.dir1, c.tangent1)};
+    (void)solved_dt;  // tangent_velocity is identically zero without contact-modification hooks (out of scope)
+    for (int k = 0; k < c.num_contacts; ++k) {
+        NormalPart& n = c.normal[k];
+        V3 p1 = pose_point(g1.pose, c.b_local_p1[k]);
+        V3 p2 = pose_point(g2.pose, c.b_local_p2[k]);
+        float dist = c.b_dist[k] + dot(p1 - p2, c.dir1);
+        float rhs_wo_bias = fmax2(dist, 0.0f) * sp.inv_dt;
+        float rhs_bias = fclamp(dist * erp_inv_dt, -sp.max_corrective_velocity, 0.0f);
+        n.rhs_wo_bias = rhs_wo_bias;
+        n.rhs = rhs_wo_bias + rhs_bias;
+        n.cfm_factor = dist <= 0.0f ? cfm_factor : 1.0f;
+        n.impulse_accumulator = n.impulse_accumulator + n.impulse;
+        n.impulse = n.impulse * sp.warmstart_coeff;
+    }
+    {
+        V3 p1 = pose_point(g1.pose, c.b_lfc1);
+        V3 p2 = pose_point(g2.pose, c.b_lfc2);
+        for (int j = 0; j < 2; ++j) {
+            float bias = dot(p1 - p2, tangents[j]) * sp.inv_dt;
+            c.t_rhs[j] = c.t_rhs_wo_bias[j] + bias;
+        }
+        c.t_impulse_acc[0] = c.t_impulse_acc[0] + c.t_impulse[0];
+        c.t_impulse_acc[1] = c.t_impulse_acc[1] + c.t_impulse[1];
+        c.t_impulse[0] = c.t_impulse[0] * sp.warmstart_coeff;
+        c.t_impulse[1] = c.t_impulse[1] * sp.warmstart_coeff;
+        c.w_impulse_acc = c.w_impulse_acc + c.w_impulse;
+        c.w_impulse = c.w_impulse * sp.warmstart_coeff;
+    }
+}
+
+// contact_with_twist_friction.rs:529-554
+static void refresh_rhs_wo_bias(const World& w, Constraint& c, const SubParams& sp, float solved_dt) {
+    GatheredBody g1 = gather(w, c.id1), g2 = gather(w, c.id2);
+    (void)solved_dt;  // tangent_velocity is identically zero without contact-modification hooks (out of scope)
+    for (int k = 0; k < c.num_contacts; ++k) {
+        V3 p1 = pose_point(g1.pose, c.b_local_p1[k]);
+        V3 p2 = pose_point(g2.pose, c.b_local_p2[k]);
+        float dist = c.b_dist[k] + dot(p1 - p2, c.dir1);
+        c.normal[k].rhs = fmax2(dist, 0.0f) * sp.inv_dt;
+        c.normal[k].cfm_factor = 1.0f;
+    }
+    c.t_rhs[0] = c.t_rhs_wo_bias[0];
+    c.t_rhs[1] = c.t_rhs_wo_bias[1];
+}
+
+// contact_with_twist_friction.rs:633-678 + contact_constraint_element.rs:465-478,627-647,720-732
+static void warmstart(World& w, Constraint& c) {
+    GatheredBody g1 = gather(w, c.id1), g2 = gather(w, c.id2);
+    V3 v1 = g1.lin, w1 = g1.ang, v2 = g2.lin, w2 = g2.ang;
+    for (int k = 0; k < c.num_contacts; ++k) {
+        const NormalPart& n = c.normal[k];
+        v1 = v1 + cmul(c.dir1, c.im1) * n.impulse;
+        w1 = w1 + n.ii_torque_dir1 * n.impulse;
+        v2 = v2 + cmul(c.dir1, c.im2) * (-n.impulse);
+        w2 = w2 + n.ii_torque_dir2 * n.impulse;
+    }
+    V3 t0 = c.tangent1, t1 = cross(c.dir1, c.tangent1);
+    v1 = v1 + cmul(t0 * c.t_impulse[0] + t1 * c.t_impulse[1], c.im1);
+    w1 = w1 + (c.t_ii_torque_dir1[0] * c.t_impulse[0] + c.t_ii_torque_dir1[1] * c.t_impulse[1]);
+    v2 = v2 + cmul(t0 * (-c.t_impulse[0]) + t1 * (-c.t_impulse[1]), c.im2);
+    w2 = w2 + (c.t_ii_torque_dir2[0] * c.t_impulse[0] + c.t_ii_torque_dir2[1] * c.t_impulse[1]);
+    if (c.num_contacts > 1) {
+        V3 ii_twist_dir1 = sdp_mul(c.ii1, c.dir1);
+        V3 ii_twist_dir2 = sdp_mul(c.ii2, c.dir1);
+        w1 = w1 + ii_twist_dir1 * c.w_impulse;
+        w2 = w2 - ii_twist_dir2 * c.w_impulse;
+    }
+    scatter_vel(w, c.id1, v1, w1);
+    scatter_vel(w, c.id2, v2, w2);
+}
+
+// contact_with_twist_friction.rs:680-781 + contact_constraint_element.rs:481-504,650-705,735-756
+static void solve(World& w, Constraint& c, bool solve_friction) {
+    GatheredBody g1 = gather(w, c.id1), g2 = gather(w, c.id2);
+    V3 v1 = g1.lin, w1 = g1.ang, v2 = g2.lin, w2 = g2.ang;
+    for (int k = 0; k < c.num_contacts; ++k) {
+        NormalPart& n = c.normal[k];
+        float dvel = dot(c.dir1, v1) + dot(n.torque_dir1, w1) - dot(c.dir1, v2) + dot(n.torque_dir2, w2) + n.rhs;
+        float new_impulse = n.cfm_factor * fmax2(n.impulse - n.r * dvel, 0.0f);
+        float dlambda = new_impulse - n.impulse;
+        n.impulse = new_impulse;
+        v1 = v1 + cmul(c.dir1, c.im1) * dlambda;
+        w1 = w1 + n.ii_torque_dir1 * dlambda;
+        v2 = v2 + cmul(c.dir1, c.im2) * (-dlambda);
+        w2 = w2 + n.ii_torque_dir2 * dlambda;
+    }
+    if (solve_friction) {
+        V3 t0 = c.tangent1, t1 = cross(c.dir1, c.tangent1);
+        float tangent_limit = 0.0f, twist_limit = 0.0f;
+        for (int k = 0; k < c.num_contacts; ++k) {
+            tangent_limit = tangent_limit + c.normal[k].impulse;
+            twist_limit = twist_limit + c.normal[k].impulse * c.twist_dists[k];
+        }
+        tangent_limit = tangent_limit * c.limit;
+        twist_limit = twist_limit * c.limit;
+        if (c.num_contacts > 1) {
+            V3 ii_twist_dir1 = sdp_mul(c.ii1, c.dir1);
+            V3 ii_twist_dir2 = sdp_mul(c.ii2, c.dir1);
+            float dvel = dot(c.dir1, w1 - w2) + c.w_rhs;
+            float new_impulse = fclamp(c.w_impulse - c.w_r * dvel, -twist_limit, twist_limit);
+            float dlambda = new_impulse - c.w_impulse;
+            c.w_impulse = new_impulse;
+            w1 = w1 + ii_twist_dir1 * dlambda;
+            w2 = w2 - ii_twist_dir2 * dlambda;
+        }
+        float dvel_0 = dot(t0, v1) + dot(c.t_torque_dir1[0], w1) - dot(t0, v2) + dot(c.t_torque_dir2[0], w2) + c.t_rhs[0];
+        float dvel_1 = dot(t1, v1) + dot(c.t_torque_dir1[1], w1) - dot(t1, v2) + dot(c.t_torque_dir2[1], w2) + c.t_rhs[1];
+        float k11 = c.t_r[0], k22 = c.t_r[1], k12 = c.t_r[2] * 0.5f;
+        float inv_det = inv_or_zero(k11 * k22 - k12 * k12);
+        float d0 = (k22 * dvel_0 - k12 * dvel_1) * inv_det;
+        float d1 = (k11 * dvel_1 - k12 * dvel_0) * inv_det;
+        float n0 = c.t_impulse[0] - d0, n1 = c.t_impulse[1] - d1;
+        // nalgebra simd_cap_magnitude: scale down to `limit` when longer.
+        float len = sqrtf(n0 * n0 + n1 * n1);
+        if (len > tangent_limit) {
+            float s = tangent_limit / len;
+            n0 = n0 * s;
+            n1 = n1 * s;
+        }
+        float dl0 = n0 - c.t_impulse[0], dl1 = n1 - c.t_impulse[1];
+        c.t_impulse[0] = n0;
+        c.t_impulse[1] = n1;
+        v1 = v1 + cmul(t0 * dl0 + t1 * dl1, c.im1);
+        w1 = w1 + (c.t_ii_torque_dir1[0] * dl0 + c.t_ii_torque_dir1[1] * dl1);
+        v2 = v2 + cmul(t0 * (-dl0) + t1 * (-dl1), c.im2);
+        w2 = w2 + (c.t_ii_torque_dir2[0] * dl0 + c.t_ii_torque_dir2[1] * dl1);
+    }
+    scatter_vel(w, c.id1, v1, w1);
+    scatter_vel(w, c.id2, v2, w2);
+}
+
+// contact_with_twist_friction.rs:568-597 + contact_constraint_element.rs:508-534
+static void apply_restitution(World& w, Constraint& c) {
+    bool any = false;
+    for (int k = 0; k < c.num_contacts; ++k) any = any || c.b_restitution_seed[k] < 0.0f;
+    if (!any) return;
+    GatheredBody g1 = gather(w, c.id1), g2 = gather(w, c.id2);
+    V3 v1 = g1.lin, w1 = g1.ang, v2 = g2.lin, w2 = g2.ang;
+    for (int k = 0; k < c.num_contacts; ++k) {
+        NormalPart& n = c.normal[k];
+        float seed = c.b_restitution_seed[k];
+        float dvel = dot(c.dir1, v1) + dot(n.torque_dir1, w1) - dot(c.dir1, v2) + dot(n.torque_dir2, w2) + seed;
+        bool gate = seed < 0.0f && (n.impulse_accumulator + n.impulse) > 0.0f;
+        float new_impulse = fmax2(n.impulse - n.r * dvel, 0.0f);
+        if (!gate) new_impulse = n.impulse;
+        float dlambda = new_impulse - n.impulse;
+        n.impulse = new_impulse;
+        v1 = v1 + cmul(c.dir1, c.im1) * dlambda;
+        w1 = w1 + n.ii_torque_dir1 * dlambda;
+        v2 = v2 + cmul(c.dir1, c.im2) * (-dlambda);
+        w2 = w2 + n.ii_torque_dir2 * dlambda;
+    }
+    scatter_vel(w, c.id1, v1, w1);
+    scatter_vel(w, c.id2, v2, w2);
+}
+
+static inline float canon0(float x) { return x == 0.0f ? 0.0f : x; }  // utils::canonicalize_zero
+
+// contact_with_twist_friction.rs:783-829
+static void writeback_impulses(World& w, const Constraint& c) {
+    Pair& p = w.pairs[c.pair];
+    V3 t2 = cross(c.dir1, c.tangent1);
+    float ti0 = canon0(c.t_impulse[0]), ti1 = canon0(c.t_impulse[1]);
+    V3 tw = c.tangent1 * ti0 + t2 * ti1;
+    tw = V3{canon0(tw.x), canon0(tw.y), canon0(tw.z)};
+    float twist = canon0(c.w_impulse);
+    for (int k = 0; k < c.num_contacts; ++k) {
+        Point& pt = p.pts[c.cids[k]];
+        pt.warmstart_impulse = canon0(c.normal[k].impulse);
+        pt.impulse = canon0(c.normal[k].impulse_accumulator + c.normal[k].impulse);
+        pt.warmstart_tangent_world = tw;
+        pt.warmstart_twist = twist;
+    }
+}
+
+// rigid_body.rs:2023-2046
+static V3 gyroscopic_corrected_angvel(V3 angvel, Q4 principal_axes, V3 principal_inertia, V3 inv_principal_inertia, float dt) {
+    V3 wl = qrot_inv(principal_axes, angvel);
+    V3 curr_momentum = cmul(principal_inertia, wl);
+    V3 explicit_gyro = (-cross(wl, curr_momentum)) * dt;
+    V3 total = curr_momentum + explicit_gyro;
+    float total_sq = length_sq(total);
+    if (total_sq != 0.0f) {
+        V3 capped = total * sqrtf(length_sq(curr_momentum) / total_sq);
+        return qrot(principal_axes, cmul(inv_principal_inertia, capped));
+    }
+    return angvel;
+}
+
+// ------------------------------------------------------------------------------------------
+// Joints (Appendix B of SURVEY.md): per-substep row rebuild + Gram-Schmidt + solve.
+// ------------------------------------------------------------------------------------------
+static int joint_rows_of(const Joint& j) {
+    int n = 0;
+    for (int i = 0; i < 6; ++i) n += (j.locked_axes >> i) & 1;
+    return n;
+}
+
+// joint_constraint_builder.rs:77-152 -> JointConstraint::update (joint_velocity_constraint.rs:145-357)
+// restricted to locked axes; joint_constraint_helper.rs:95-164 (new), :411-461 (lock_linear),
+// :628-675 (lock_angular), :676-722 (finalize_constraints).
+static int joint_update(const World& w, const Joint& j, float sub_dt, JointRow* out) {
+    GatheredBody g1 = gather(w, j.sid1), g2 = gather(w, j.sid2);
+    Pose frame1 = pose_mul(g1.pose, j.sframe1);
+    Pose frame2 = pose_mul(g2.pose, j.sframe2);
+    Spring soft{j.natural_frequency, j.damping_ratio};
+    float erp_inv_dt = soft.erp_inv_dt(sub_dt);
+    float cfm_coeff = soft.cfm_coeff(sub_dt);
+    M3 basis = qto_mat(frame1.q);
+    V3 bcol[3] = {basis.c0, basis.c1, basis.c2};
+    V3 lin_err = frame2.t - frame1.t;
+    V3 new_center1 = frame2.t;
+    for (int i = 0; i < 3; ++i)
+        if (j.locked_axes & (1u << i)) new_center1 = new_center1 - bcol[i] * dot(lin_err, bcol[i]);
+    frame1.t = new_center1;
+    V3 r1 = frame1.t - g1.pose.t;
+    V3 r2 = frame2.t - g2.pose.t;
+    // ang_basis = diff_conj1_2(q1, q2)^T * sgn, ang_err = q1^-1 q2 * sgn (rotation_ops.rs:121-137)
+    Q4 q1 = frame1.q, q2 = frame2.q;
+    float sgn = copysignf(1.0f, qdot(q1, q2));
+    Q4 ang_err = qmul(qconj(q1), q2);
+    ang_err = Q4{ang_err.x * sgn, ang_err.y * sgn, ang_err.z * sgn, ang_err.w * sgn};
+    V3 a = V3{q1.x, q1.y, q1.z}, b = V3{q2.x, q2.y, q2.z};
+    float w1 = q1.w, w2 = q2.w;
+    V3 cv = a * w2 + b * w1;
+    // D = 0.5 * (a b^T + w1 w2 I - [cv]x + [a]x [b]x); [a]x[b]x = b a^T - (a.b) I
+    float ab = dot(a, b);
+    float D[3][3];
+    float av[3] = {a.x, a.y, a.z}, bv[3] = {b.x, b.y, b.z}, cvv[3] = {cv.x, cv.y, cv.z};
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            float cx = 0.0f;  // [cv]x(r,c)
+            if (r == 0 && c == 1) cx = -cvv[2]; else if (r == 0 && c == 2) cx = cvv[1];
+            else if (r == 1 && c == 0) cx = cvv[2]; else if (r == 1 && c == 2) cx = -cvv[0];
+            else if (r == 2 && c == 0) cx = -cvv[1]; else if (r == 2 && c == 1) cx = cvv[0];
+            float diag = (r == c) ? (w1 * w2 - ab) : 0.0f;
+            D[r][c] = (av[r] * bv[c] + diag - cx + bv[r] * av[c]) * 0.5f;
+        }
+    // ang_basis column i = row i of D (transpose), times sgn.
+    V3 imsum = g1.im + g2.im;
+    int len = 0;
+    for (int i = 3; i < 6; ++i) {
+        if (!(j.locked_axes & (1u << i))) continue;
+        int ax = i - 3;
+        JointRow& r = out[len++];
+        V3 ang_jac = V3{D[ax][0] * sgn, D[ax][1] * sgn, D[ax][2] * sgn};
+        float imag = ax == 0 ? ang_err.x : (ax == 1 ? ang_err.y : ang_err.z);
+        r.lin_jac = vzero();
+        r.ang_jac1 = ang_jac;
+        r.ang_jac2 = ang_jac;
+        r.ii_ang_jac1 = sdp_mul(g1.ii, ang_jac);
+        r.ii_ang_jac2 = sdp_mul(g2.ii, ang_jac);
+        r.impulse = 0.0f; r.inv_lhs = 0.0f; r.cfm_coeff = cfm_coeff; r.cfm_gain = 0.0f;
+        r.rhs_wo_bias = 0.0f;
+        r.rhs = 0.0f + imag * erp_inv_dt;
+        r.dof = i;
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (!(j.locked_axes & (1u << i))) continue;
+        JointRow& r = out[len++];
+        r.lin_jac = bcol[i];
+        r.ang_jac1 = cross(r1, bcol[i]);
+        r.ang_jac2 = cross(r2, bcol[i]);
+        r.ii_ang_jac1 = sdp_mul(g1.ii, r.ang_jac1);
+        r.ii_ang_jac2 = sdp_mul(g2.ii, r.ang_jac2);
+        r.impulse = 0.0f; r.inv_lhs = 0.0f; r.cfm_coeff = cfm_coeff; r.cfm_gain = 0.0f;
+        r.rhs_wo_bias = 0.0f;
+        r.rhs = 0.0f + dot(bcol[i], lin_err) * erp_inv_dt;
+        r.dof = i;
+    }
+    // finalize_constraints: modified Gram-Schmidt in the mass metric.
+    for (int jx = 0; jx < len; ++jx) {
+        JointRow& cj = out[jx];
+        float dot_jj = dot(cj.lin_jac, cmul(imsum, cj.lin_jac)) + dot(cj.ii_ang_jac1, cj.ang_jac1) + dot(cj.ii_ang_jac2, cj.ang_jac2);
+        float cfm_gain = dot_jj * cj.cfm_coeff + cj.cfm_gain;
+        float inv_dot_jj = inv_or_zero(dot_jj);
+        cj.inv_lhs = inv_or_zero(dot_jj + cfm_gain);
+        cj.cfm_gain = cfm_gain;
+        for (int ix = jx + 1; ix < len; ++ix) {
+            JointRow& ci = out[ix];
+            float dot_ij = dot(ci.lin_jac, cmul(imsum, cj.lin_jac)) + dot(ci.ii_ang_jac1, cj.ang_jac1) + dot(ci.ii_ang_jac2, cj.ang_jac2);
+            float coeff = dot_ij * inv_dot_jj;
+            ci.lin_jac = ci.lin_jac - cj.lin_jac * coeff;
+            ci.ang_jac1 = ci.ang_jac1 - cj.ang_jac1 * coeff;
+            ci.ang_jac2 = ci.ang_jac2 - cj.ang_jac2 * coeff;
+            ci.ii_ang_jac1 = ci.ii_ang_jac1 - cj.ii_ang_jac1 * coeff;
+            ci.ii_ang_jac2 = ci.ii_ang_jac2 - cj.ii_ang_jac2 * coeff;
+            ci.rhs_wo_bias = ci.rhs_wo_bias - cj.rhs_wo_bias * coeff;
+            ci.rhs = ci.rhs - cj.rhs * coeff;
+        }
+    }
+    return len;
+}
+
+// joint_velocity_constraint.rs:97-124
+static void joint_solve(World& w, const Joint& j, JointRow* rows, int n, bool wo_bias) {
+    GatheredBody g1 = gather(w, j.sid1), g2 = gather(w, j.sid2);
+    V3 v1 = g1.lin, w1 = g1.ang, v2 = g2.lin, w2 = g2.ang;
+    for (int k = 0; k < n; ++k) {
+        JointRow& r = rows[k];
+        if (wo_bias) r.rhs = r.rhs_wo_bias;
+        float dlinvel = dot(r.lin_jac, v2 - v1);
+        float dangvel = dot(r.ang_jac2, w2) - dot(r.ang_jac1, w1);
+        float rhs = dlinvel + dangvel + r.rhs;
+        float total = r.impulse + r.inv_lhs * (rhs - r.cfm_gain * r.impulse);
+        float delta = total - r.impulse;
+        r.impulse = total;
+        V3 lin_impulse = r.lin_jac * delta;
+        v1 = v1 + cmul(lin_impulse, g1.im);
+        w1 = w1 + r.ii_ang_jac1 * delta;
+        v2 = v2 - cmul(lin_impulse, g2.im);
+        w2 = w2 - r.ii_ang_jac2 * delta;
+    }
+    scatter_vel(w, j.sid1, v1, w1);
+    scatter_vel(w, j.sid2, v2, w2);
+}
+
+// Stage order (init.rs:163-254): colours with >= `min_count` members in ascending colour, then the
+// serial tail: smaller colours ascending, then the overflow colour.
+static void build_order(const std::vector<int>& colors_of, int min_count, std::vector<int>& order,
+                        std::vector<int>& stage_start, int& num_colors) {
+    std::vector<std::vector<int>> buckets(NUM_COLORS);
+    for (int i = 0; i < (int)colors_of.size(); ++i) {
+        int c = colors_of[i];
+        if (c < 0) continue;
+        if (c > 128) c = 128;
+        buckets[c].push_back(i);
+    }
+    order.clear();
+    stage_start.clear();
+    num_colors = 0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int c = 0; c < 128; ++c) {
+            bool big = (int)buckets[c].size() >= min_count;
+            if (buckets[c].empty() || big != (pass == 0)) continue;
+            stage_start.push_back((int)order.size());
+            order.insert(order.end(), buckets[c].begin(), buckets[c].end());
+            num_colors++;
+        }
+    // overflow: sequential, one stage per element.
+    for (int i : buckets[128]) {
+        stage_start.push_back((int)order.size());
+        order.push_back(i);
+    }
+    if (!buckets[128].empty()) num_colors++;
+    stage_start.push_back((int)order.size());
+}
+
+
+static inline float inv_exact0(float x) { return x == 0.0f ? 0.0f : 1.0f / x; }
+
+void solve_island(World& w, V3 gravity) {
+    const RbIntegrationParameters& P = w.params.p;
+    const int nb = (int)w.bodies.size();
+    const int num_substeps = P.num_solver_iterations;
+    const float sub_dt = P.dt / (float)num_substeps;  // init.rs:96-101
+    const float inv_dt_full = P.dt == 0.0f ? 0.0f : 1.0f / P.dt;
+
+    SubParams sp;
+    sp.dt = sub_dt;
+    sp.inv_dt = sub_dt == 0.0f ? 0.0f : 1.0f / sub_dt;
+    Spring dyn_soft{P.contact_natural_frequency, P.contact_damping_ratio};
+    Spring static_soft{P.static_contact_natural_frequency, P.static_contact_damping_ratio};
+    sp.dyn_cfm = dyn_soft.cfm_factor(sub_dt);
+    sp.static_cfm = static_soft.cfm_factor(sub_dt);
+    sp.dyn_erp = dyn_soft.erp_inv_dt(sub_dt);
+    sp.static_erp = static_soft.erp_inv_dt(sub_dt);
+    sp.max_corrective_velocity = w.params.max_corrective_velocity();
+    sp.warmstart_coeff = P.warmstart_coefficient;
+
+    // a7 forces (solve.rs:234-291; rigid_body_components.rs:1030-1033) + S1 solver-body init
+    // (solver_body.rs:82-121; worker.rs:46-104).
+    w.sb.resize(nb);
+    for (int i = 0; i < nb; ++i) {
+        Body& b = w.bodies[i];
+        SolverBody& s = w.sb[i];
+        if (b.is_dynamic()) {
+            V3 eff_mass = V3{inv_exact0(b.eff_inv_mass.x), inv_exact0(b.eff_inv_mass.y), inv_exact0(b.eff_inv_mass.z)};
+            b.force = b.user_force + cmul(gravity, eff_mass) * b.gravity_scale;
+            b.torque = b.user_torque;
+        }
+        s.flags = b.flags;
+        s.lin = b.linvel;
+        s.ang = b.angvel;
+        s.pose = pose_prepend_translation(b.pos, b.local_com);
+        if (b.is_dynamic()) {
+            s.ii = b.eff_world_inv_inertia;
+            s.im = b.eff_inv_mass;
+        } else {
+            s.ii = sdp_zero();
+            s.im = vzero();
+        }
+        s.incr_ang = sdp_mul(b.eff_world_inv_inertia, b.torque) * sub_dt;
+        s.incr_lin = cmul(b.force, b.eff_inv_mass) * sub_dt;
+        s.gyro = (b.flags & RB_BODY_GYROSCOPIC) && b.is_dynamic();
+    }
+
+    // Solver-active manifolds, in stage order (solver_graph.rs:129-361; init.rs:163-254).
+    std::vector<int> colors_of(w.pairs.size(), -1);
+    for (int i = 0; i < (int)w.pairs.size(); ++i) {
+        const Pair& p = w.pairs[i];
+        bool d1 = p.b1 >= 0 && w.bodies[p.b1].is_dynamic();
+        bool d2 = p.b2 >= 0 && w.bodies[p.b2].is_dynamic();
+        if (p.nsc > 0 && (d1 || d2)) colors_of[i] = p.color;
+    }
+    std::vector<int> pair_order;
+    int num_colors = 0;
+    build_order(colors_of, 125, pair_order, w.order_color_start, num_colors);  // ceil(n/4) >= 32
+    w.last_num_colors = num_colors;
+    const int ncons = (int)pair_order.size();
+    w.cons.resize(ncons);
+    w.order.resize(ncons);
+    for (int i = 0; i < ncons; ++i) w.order[i] = i;
+    const std::vector<int>& cs = w.order_color_start;
+    const int nstages = (int)cs.size() - 1;
+
+    // Joints: selection (impulse_joint_set.rs:504-572) + stage order (joints.rs:318-392).
+    const int nj = (int)w.joints.size();
+    std::vector<int> jcolors(nj, -1);
+    std::vector<int> jrow_start(nj + 1, 0);
+    for (int i = 0; i < nj; ++i) {
+        Joint& j = w.joints[i];
+        jcolors[i] = j.color;
+        const Body& b1 = w.bodies[j.body1];
+        const Body& b2 = w.bodies[j.body2];
+        // generic_joint.rs:624-636 transform_to_solver_body_space
+        j.sframe1 = j.local_frame1;
+        j.sframe2 = j.local_frame2;
+        if (!b1.is_dynamic()) j.sframe1 = pose_mul(b1.pos, j.local_frame1);
+        else j.sframe1.t = j.local_frame1.t - b1.local_com;
+        if (!b2.is_dynamic()) j.sframe2 = pose_mul(b2.pos, j.local_frame2);
+        else j.sframe2.t = j.local_frame2.t - b2.local_com;
+        jrow_start[i + 1] = jrow_start[i] + joint_rows_of(j);
+    }
+    int jnum_colors = 0;
+    build_order(jcolors, 64, w.jorder, w.jorder_color_start, jnum_colors);
+    w.jrows.resize(jrow_start[nj]);
+    const std::vector<int>& js = w.jorder_color_start;
+    const int jnstages = (int)js.size() - 1;
+
+    Pool& pool = Pool::get();
+
+    // S2 constraint generation (worker.rs:109-190)
+    pool.parallel_for(0, ncons, 64, [&](int i) { generate(w, pair_order[i], w.cons[i]); });
+
+    bool has_bouncy = false;
+    for (int i = 0; i < ncons && !has_bouncy; ++i)
+        for (int k = 0; k < w.cons[i].num_contacts; ++k)
+            if (w.cons[i].b_restitution_seed[k] < 0.0f) has_bouncy = true;
+
+    const bool fused_warmstart = P.warmstart_coefficient != 0.0f;
+    const float max_lin = w.params.max_linear_velocity();
+    const float max_ang = 0.7853981633974483f * inv_dt_full;  // MAX_ROTATION * base inv_dt (worker.rs:573-580)
+
+    auto solve_pass = [&](bool wo_bias, float solved_dt) {  // staged_island_solver/solve.rs:12-209
+        bool solve_friction = wo_bias || P.friction_in_bias_pass || P.num_internal_stabilization_iterations == 0;
+        for (int s = 0; s < jnstages; ++s) {
+            pool.parallel_for(js[s], js[s + 1], 64, [&](int q) {
+                int ji = w.jorder[q];
+                joint_solve(w, w.joints[ji], &w.jrows[jrow_start[ji]], jrow_start[ji + 1] - jrow_start[ji], wo_bias);
+            });
+        }
+        for (int s = 0; s < nstages; ++s) {
+            pool.parallel_for(cs[s], cs[s + 1], 64, [&](int q) {
+                Constraint& c = w.cons[q];
+                if (wo_bias) refresh_rhs_wo_bias(w, c, sp, solved_dt);
+                solve(w, c, solve_friction);
+            });
+        }
+    };
+
+    for (int substep = 0; substep < num_substeps; ++substep) {
+        float solved_dt = (float)substep * sub_dt;
+        // S3 velocity increments + gyroscopic correction (worker.rs:235-284)
+        pool.parallel_for(0, nb, 256, [&](int i) {
+            SolverBody& s = w.sb[i];
+            if (!w.bodies[i].is_dynamic()) return;
+            s.lin = s.lin + s.incr_lin;
+            s.ang = s.ang + s.incr_ang;
+            if (s.gyro) {
+                const Body& b = w.bodies[i];
+                Q4 principal_axes = qmul(s.pose.q, b.principal_frame);
+                s.ang = gyroscopic_corrected_angvel(s.ang, principal_axes, b.principal_inertia, b.inv_principal_inertia, sub_dt);
+            }
+        });
+        // S4 joint rows rebuilt from the current poses (worker.rs:291-432); impulses restart from 0
+        // (warmstart_joints = false, joint_constraint_builder.rs:135-151).
+        pool.parallel_for(0, nj, 64, [&](int i) {
+            if (w.joints[i].color < 0) return;
+            joint_update(w, w.joints[i], sub_dt, &w.jrows[jrow_start[i]]);
+        });
+        // S5 update + warmstart, colour by colour (worker.rs:438-539)
+        if (!fused_warmstart) {
+            for (int q = 0; q < ncons; ++q) update(w, w.cons[q], sp, solved_dt);
+        } else {
+            for (int s = 0; s < nstages; ++s) {
+                pool.parallel_for(cs[s], cs[s + 1], 64, [&](int q) {
+                    update(w, w.cons[q], sp, solved_dt);
+                    warmstart(w, w.cons[q]);
+                });
+            }
+        }
+        // S6 biased solve (worker.rs:544-561)
+        for (int it = 0; it < P.num_internal_pgs_iterations; ++it) solve_pass(false, solved_dt);
+        // S7 integrate positions (worker.rs:568-631; rigid_body_components.rs:884-898)
+        pool.parallel_for(0, nb, 256, [&](int i) {
+            SolverBody& s = w.sb[i];
+            if (!w.bodies[i].is_dynamic()) return;
+            if (max_lin != 3.4028235e38f) {
+                float n = length(s.lin);
+                if (n > max_lin) s.lin = s.lin * (max_lin / n);
+            }
+            if (!(s.flags & RB_BODY_ALLOW_FAST_ROTATION)) {
+                float n = length(s.ang);
+                if (n > max_ang) s.ang = s.ang * (max_ang / n);
+            }
+            V3 hang = s.ang * (sub_dt * 0.5f);
+            Q4 id_plus_hang = Q4{hang.x, hang.y, hang.z, 1.0f};
+            s.pose.q = qnormalize(qmul(id_plus_hang, s.pose.q));
+            s.pose.t = s.pose.t + s.lin * sub_dt;
+        });
+        // S8 relax solve (worker.rs:636-649)
+        for (int it = 0; it < P.num_internal_stabilization_iterations; ++it) solve_pass(true, solved_dt + sub_dt);
+    }
+
+    // S9 restitution (worker.rs:657-734)
+    if (has_bouncy) {
+        for (int s = 0; s < nstages; ++s)
+            for (int q = cs[s]; q < cs[s + 1]; ++q) apply_restitution(w, w.cons[q]);
+    }
+    // S10 impulse writeback (worker.rs:742-802)
+    for (int q = 0; q < ncons; ++q) writeback_impulses(w, w.cons[q]);
+    for (int i = 0; i < nj; ++i) {
+        Joint& j = w.joints[i];
+        if (j.color < 0) continue;
+        for (int r = jrow_start[i]; r < jrow_start[i + 1]; ++r) j.impulses[w.jrows[r].dof] = w.jrows[r].impulse;
+    }
+    // S11 body writeback (worker.rs:809-897; rigid_body_components.rs:835-841)
+    for (int i = 0; i < nb; ++i) {
+        Body& b = w.bodies[i];
+        if (!b.is_dynamic()) continue;
+        const SolverBody& s = w.sb[i];
+        b.linvel = s.lin * (1.0f / (1.0f + P.dt * b.lin_damping));
+        b.angvel = s.ang * (1.0f / (1.0f + P.dt * b.ang_damping));
+        b.next_pos = pose_prepend_translation(s.pose, -b.local_com);
+    }
+    w.counters.num_active_manifolds = ncons;
+    w.counters.num_colors = num_colors;
+}
+
+}  // namespace orc

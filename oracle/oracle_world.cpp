@@ -1,0 +1,658 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle: scene state, collision detection bookkeeping, colouring
+// (see oracle.h header note; PARITY UNPINNED).
+//
+// Follows, in order: src/pipeline/physics_pipeline/substep.rs:267-581 (step_inner),
+// src/pipeline/physics_pipeline/solve.rs:45-157 (detect_collisions),
+// src/geometry/broad_phase_bvh/{mod.rs:170-263, update.rs:334-396,484-537} (pair-set semantics),
+// src/geometry/narrow_phase/pair_update.rs:67-680 (process_pair),
+// src/geometry/narrow_phase/{contacts.rs:300-385, mod.rs:87-172} (transitions + colouring).
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "oracle_internal.h"
+
+namespace orc {
+
+void solve_island(World& w, V3 gravity);  // oracle_solver.cpp
+
+// ---------------------------------------------------------------------------------------------
+// Mass properties: parry MassProperties::{from_cuboid, from_ball, new, world_com, world_inv_inertia}
+// as consumed by RigidBodyMassProps::recompute_mass_properties_from_colliders
+// (src/dynamics/rigid_body_components.rs:421) and update_world_mass_properties (:528-572).
+// ---------------------------------------------------------------------------------------------
+static inline float inv_exact0(float x) { return x == 0.0f ? 0.0f : 1.0f / x; }
+
+static void collider_mass(const Collider& c, float& mass, V3& principal) {
+    if (c.shape == RB_SHAPE_CUBOID) {
+        float vol = c.he.x * c.he.y * c.he.z * 8.0f;
+        V3 sq = cmul(c.he, c.he);
+        float third = 1.0f / 3.0f;
+        V3 unit = V3{(sq.y + sq.z) * third, (sq.x + sq.z) * third, (sq.x + sq.y) * third};
+        mass = vol * c.density;
+        principal = unit * mass;
+    } else {
+        float r = c.he.x;
+        float vol = 3.14159265358979323846f * r * r * r * 4.0f / 3.0f;
+        float unit = r * r * 2.0f / 5.0f;
+        mass = vol * c.density;
+        principal = V3{unit * mass, unit * mass, unit * mass};
+    }
+}
+
+static int recompute_mass_properties(World& w) {
+    int nb = (int)w.bodies.size();
+    std::vector<int> count(nb, 0), first(nb, -1);
+    for (int ci = 0; ci < (int)w.colliders.size(); ++ci) {
+        int p = w.colliders[ci].parent;
+        if (p >= 0) {
+            if (count[p] == 0) first[p] = ci;
+            count[p]++;
+        }
+    }
+    for (int bi = 0; bi < nb; ++bi) {
+        Body& b = w.bodies[bi];
+        b.local_com = vzero();
+        b.inv_mass = 0.0f;
+        b.inv_principal_inertia = vzero();
+        b.principal_inertia = vzero();
+        b.principal_frame = qidentity();
+        if (count[bi] == 1) {
+            const Collider& c = w.colliders[first[bi]];
+            float mass;
+            V3 pi;
+            collider_mass(c, mass, pi);
+            b.local_com = c.pos_wrt_parent.t;
+            b.inv_mass = inv_exact0(mass);
+            b.inv_principal_inertia = V3{inv_exact0(pi.x), inv_exact0(pi.y), inv_exact0(pi.z)};
+            b.principal_frame = c.pos_wrt_parent.q;
+        } else if (count[bi] > 1) {
+            // Sum of axis-aligned parts only (composite bodies whose summed tensor is diagonal).
+            float M = 0.0f;
+            V3 com = vzero();
+            for (const Collider& c : w.colliders) {
+                if (c.parent != bi) continue;
+                float mass; V3 pi;
+                collider_mass(c, mass, pi);
+                M = M + mass;
+                com = com + c.pos_wrt_parent.t * mass;
+            }
+            if (M == 0.0f) continue;
+            com = com * (1.0f / M);
+            V3 I = vzero();
+            for (const Collider& c : w.colliders) {
+                if (c.parent != bi) continue;
+                Q4 q = c.pos_wrt_parent.q;
+                if (!(q.x == 0.0f && q.y == 0.0f && q.z == 0.0f)) return RB_ERR_INVALID;
+                float mass; V3 pi;
+                collider_mass(c, mass, pi);
+                V3 d = c.pos_wrt_parent.t - com;
+                if ((d.x != 0.0f) + (d.y != 0.0f) + (d.z != 0.0f) > 1) return RB_ERR_INVALID;
+                float d2 = dot(d, d);
+                I = I + pi + V3{(d2 - d.x * d.x) * mass, (d2 - d.y * d.y) * mass, (d2 - d.z * d.z) * mass};
+            }
+            b.local_com = com;
+            b.inv_mass = inv_exact0(M);
+            b.inv_principal_inertia = V3{inv_exact0(I.x), inv_exact0(I.y), inv_exact0(I.z)};
+        }
+        // additional mass at the body origin is only supported for collider-less bodies.
+        (void)0;
+        b.principal_inertia = V3{inv_exact0(b.inv_principal_inertia.x), inv_exact0(b.inv_principal_inertia.y),
+                                 inv_exact0(b.inv_principal_inertia.z)};
+    }
+    return RB_OK;
+}
+
+// rigid_body_components.rs:528-572
+void update_world_mass_properties(Body& b) {
+    b.world_com = pose_point(b.pos, b.local_com);
+    bool dyn = b.is_dynamic();
+    b.eff_inv_mass = V3{b.inv_mass, b.inv_mass, b.inv_mass};
+    V3 d = b.inv_principal_inertia;
+    if (d.x != 0.0f || d.y != 0.0f || d.z != 0.0f) {
+        M3 r = qto_mat(qmul(b.pos.q, b.principal_frame));
+        float c0[3] = {r.c0.x, r.c0.y, r.c0.z}, c1[3] = {r.c1.x, r.c1.y, r.c1.z}, c2[3] = {r.c2.x, r.c2.y, r.c2.z};
+        auto e = [&](int i, int j) {
+            return (c0[i] * d.x) * c0[j] + (c1[i] * d.y) * c1[j] + (c2[i] * d.z) * c2[j];
+        };
+        b.eff_world_inv_inertia = Sdp3{e(0, 0), e(0, 1), e(0, 2), e(1, 1), e(1, 2), e(2, 2)};
+    } else {
+        b.eff_world_inv_inertia = sdp_zero();
+    }
+    if (!dyn || (b.flags & RB_BODY_LOCK_TX)) b.eff_inv_mass.x = 0.0f;
+    if (!dyn || (b.flags & RB_BODY_LOCK_TY)) b.eff_inv_mass.y = 0.0f;
+    if (!dyn || (b.flags & RB_BODY_LOCK_TZ)) b.eff_inv_mass.z = 0.0f;
+    Sdp3& m = b.eff_world_inv_inertia;
+    if (!dyn || (b.flags & RB_BODY_LOCK_RX)) { m.m11 = 0; m.m12 = 0; m.m13 = 0; }
+    if (!dyn || (b.flags & RB_BODY_LOCK_RY)) { m.m22 = 0; m.m12 = 0; m.m23 = 0; }
+    if (!dyn || (b.flags & RB_BODY_LOCK_RZ)) { m.m33 = 0; m.m13 = 0; m.m23 = 0; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Collider world pose + broad-phase AABB (collider.rs:553-599) and the fat leaf AABB with change
+// detection (broad_phase_bvh/mod.rs:170-201, :235-263; skin = 0.04 * length_unit).
+// ---------------------------------------------------------------------------------------------
+static inline Aabb loosened(const Aabb& a, float l) {
+    return Aabb{V3{a.mins.x - l, a.mins.y - l, a.mins.z - l}, V3{a.maxs.x + l, a.maxs.y + l, a.maxs.z + l}};
+}
+static inline bool aabb_contains(const Aabb& a, const Aabb& b) {
+    return a.mins.x <= b.mins.x && a.mins.y <= b.mins.y && a.mins.z <= b.mins.z && a.maxs.x >= b.maxs.x &&
+           a.maxs.y >= b.maxs.y && a.maxs.z >= b.maxs.z;
+}
+static inline bool aabb_intersects(const Aabb& a, const Aabb& b) {
+    return a.mins.x <= b.maxs.x && a.mins.y <= b.maxs.y && a.mins.z <= b.maxs.z && a.maxs.x >= b.mins.x &&
+           a.maxs.y >= b.mins.y && a.maxs.z >= b.mins.z;
+}
+
+// substep.rs:103-146 (collider pose + AABB harvest) followed by refresh_moved_collider_aabbs
+// (substep.rs:229-240) -> BroadPhaseBvh::set_aabb.
+void refresh_collider(World& w, Collider& c) {
+    if (c.parent >= 0)
+        c.pos = pose_mul(w.bodies[c.parent].pos, c.pos_wrt_parent);
+    else
+        c.pos = c.pos_wrt_parent;
+    float pred = w.params.prediction_distance();
+    c.aabb = loosened(shape_aabb(c.shape, c.he, c.pos), c.contact_skin + pred / 2.0f);
+    if (!c.fat_valid || !aabb_contains(c.fat, c.aabb)) {
+        c.fat = loosened(c.aabb, 4.0e-2f * w.params.p.length_unit);
+        c.fat_valid = true;
+        w.bp_dirty = true;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Broad phase: the pair set is exactly the set of collider pairs whose fat AABBs intersect,
+// minus same-parent / fixed-fixed / collision-group filtered pairs (update.rs:334-396); pairs
+// leave the set only when a changed leaf stops intersecting (update.rs:484-537).  Because fat
+// AABBs only change together with `changed`, the set is a pure function of the fat AABBs.
+// Realised here as a sort-and-sweep along x (the GPU build uses a device radix sort + sweep).
+// ---------------------------------------------------------------------------------------------
+static bool pair_allowed(const World& w, int c1, int c2) {
+    const Collider& a = w.colliders[c1];
+    const Collider& b = w.colliders[c2];
+    if (a.parent >= 0 && a.parent == b.parent) return false;
+    bool dyn1 = a.parent >= 0 && w.bodies[a.parent].is_dynamic();
+    bool dyn2 = b.parent >= 0 && w.bodies[b.parent].is_dynamic();
+    if (!dyn1 && !dyn2) return false;  // ActiveCollisionTypes::default(): no fixed-fixed
+    if (!((a.memberships & b.filter) != 0 && (b.memberships & a.filter) != 0)) return false;
+    if (!w.nocontact_body_pairs.empty() && a.parent >= 0 && b.parent >= 0) {
+        uint32_t lo = (uint32_t)std::min(a.parent, b.parent), hi = (uint32_t)std::max(a.parent, b.parent);
+        uint64_t key = ((uint64_t)lo << 32) | hi;
+        if (std::binary_search(w.nocontact_body_pairs.begin(), w.nocontact_body_pairs.end(), key)) return false;
+    }
+    return true;
+}
+
+static void clear_pair_color(World& w, Pair& p) {  // narrow_phase/mod.rs:154-172
+    if (p.color < COLOR_OVERFLOW) {
+        for (int k = 0; k < 2; ++k)
+            if (p.color_bodies[k] != NO_BODY) w.color_masks[p.color_bodies[k]].clear(p.color);
+    }
+    p.color = COLOR_UNCOLORED;
+    p.color_bodies[0] = p.color_bodies[1] = NO_BODY;
+}
+
+static void update_pairs(World& w) {
+    int nc = (int)w.colliders.size();
+    std::vector<int> idx(nc);
+    for (int i = 0; i < nc; ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+        return w.colliders[a].fat.mins.x < w.colliders[b].fat.mins.x;
+    });
+    std::vector<uint64_t> keys;
+    for (int ii = 0; ii < nc; ++ii) {
+        const Collider& a = w.colliders[idx[ii]];
+        for (int jj = ii + 1; jj < nc; ++jj) {
+            const Collider& b = w.colliders[idx[jj]];
+            if (b.fat.mins.x > a.fat.maxs.x) break;
+            if (!aabb_intersects(a.fat, b.fat)) continue;
+            int c1 = std::min(idx[ii], idx[jj]), c2 = std::max(idx[ii], idx[jj]);
+            if (!pair_allowed(w, c1, c2)) continue;
+            keys.push_back(((uint64_t)(uint32_t)c1 << 32) | (uint32_t)c2);
+        }
+    }
+    std::sort(keys.begin(), keys.end());
+    // Merge with the previous (sorted) pair list, carrying persistent per-pair state.
+    std::vector<Pair> np;
+    np.reserve(keys.size());
+    size_t oi = 0;
+    for (uint64_t k : keys) {
+        while (oi < w.pairs.size()) {
+            Pair& o = w.pairs[oi];
+            uint64_t ok = ((uint64_t)(uint32_t)o.c1 << 32) | (uint32_t)o.c2;
+            if (ok < k) {  // removed pair: end-touch frees its colour (contacts.rs:333-335)
+                clear_pair_color(w, o);
+                ++oi;
+            } else break;
+        }
+        if (oi < w.pairs.size()) {
+            Pair& o = w.pairs[oi];
+            uint64_t ok = ((uint64_t)(uint32_t)o.c1 << 32) | (uint32_t)o.c2;
+            if (ok == k) { np.push_back(o); ++oi; continue; }
+        }
+        Pair p;
+        memset(&p, 0, sizeof(p));
+        p.c1 = (int)(k >> 32);
+        p.c2 = (int)(k & 0xffffffffu);
+        p.b1 = w.colliders[p.c1].parent;
+        p.b2 = w.colliders[p.c2].parent;
+        p.color = COLOR_UNCOLORED;
+        p.color_bodies[0] = p.color_bodies[1] = NO_BODY;
+        np.push_back(p);
+    }
+    for (; oi < w.pairs.size(); ++oi) clear_pair_color(w, w.pairs[oi]);
+    w.pairs.swap(np);
+    w.bp_dirty = false;
+    w.counters.broad_phase_ran = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Narrow phase: process_pair (pair_update.rs:67-680).
+// ---------------------------------------------------------------------------------------------
+static float combine_coeff(float c1, float c2, int r1, int r2) {  // coefficient_combine_rule.rs:51-84
+    int rule = std::max(r1, r2);
+    switch (rule) {
+        case RB_COMBINE_AVERAGE: return (c1 + c2) / 2.0f;
+        case RB_COMBINE_MIN: return fabsf(fmin2(c1, c2));
+        case RB_COMBINE_MULTIPLY: return c1 * c2;
+        case RB_COMBINE_MAX: return fmax2(c1, c2);
+        case RB_COMBINE_CLAMPED_SUM: return fclamp(c1 + c2, 0.0f, 1.0f);
+        default: return sqrtf(fmax2(c1, 0.0f) * fmax2(c2, 0.0f));
+    }
+}
+
+static float relative_pose_drift(const Pose& base, const Pose& cur, float max_extent) {  // contact_pair.rs:299-323
+    float trans = length(cur.t - base.t);
+    Q4 d = qmul(cur.q, qconj(base.q));
+    float rot_chord = 2.0f * length(V3{d.x, d.y, d.z}) * max_extent;
+    return trans + rot_chord;
+}
+static float relative_rot_cos(Q4 base, Q4 cur) {  // contact_pair.rs:284-293
+    float c = qdot(base, cur);
+    return 2.0f * c * c - 1.0f;
+}
+
+static float shape_origin_radius(int shape, V3 he) {  // pair_update.rs:591-595 (local AABB corners)
+    if (shape == RB_SHAPE_BALL) {
+        V3 c = V3{he.x, he.x, he.x};
+        return length(c);
+    }
+    return length(he);
+}
+
+// manifold_reduction.rs:4-84
+static void reduce_manifold_naive(const RawManifold& m, int selected[4], int& num_selected, float prediction) {
+    if (m.n <= 4) return;
+    for (int i = 0; i < 4; ++i) selected[i] = -1;
+    float deepest = 3.4028235e38f;
+    for (int i = 0; i < m.n; ++i)
+        if (m.pts[i].dist < deepest) { deepest = m.pts[i].dist; selected[0] = i; }
+    if (selected[0] < 0) { num_selected = 0; return; }
+    V3 a = m.pts[selected[0]].local_p1;
+    float furthest = -3.4028235e38f;
+    for (int i = 0; i < m.n; ++i) {
+        float d = length_sq(m.pts[i].local_p1 - a);
+        if (i != selected[0] && m.pts[i].dist <= prediction && d > furthest) { furthest = d; selected[1] = i; }
+    }
+    if (selected[1] < 0) { num_selected = 1; return; }
+    V3 b = m.pts[selected[1]].local_p1;
+    if (veq(a, b)) { num_selected = 1; return; }
+    V3 ab = b - a;
+    V3 tangent = cross(ab, m.local_n1);
+    float min_dot = 3.4028235e38f, max_dot = -3.4028235e38f;
+    for (int i = 0; i < m.n; ++i) {
+        if (i == selected[0] || i == selected[1] || m.pts[i].dist > prediction) continue;
+        float d = dot(m.pts[i].local_p1 - a, tangent);
+        if (d < min_dot) { min_dot = d; selected[2] = i; }
+        if (d > max_dot) { max_dot = d; selected[3] = i; }
+    }
+    if (selected[2] < 0) num_selected = 2;
+    else if (selected[2] == selected[3]) num_selected = 3;
+    else num_selected = 4;
+}
+
+// Returns true when the pair's "has any active contact" state flipped.
+static bool process_pair(World& w, Pair& pair) {
+    const Collider& co1 = w.colliders[pair.c1];
+    const Collider& co2 = w.colliders[pair.c2];
+    const float prediction = w.params.prediction_distance();
+    const float dt = w.params.p.dt;
+    const float recycle_dist = w.params.p.contact_recycling ? w.params.contact_recycle_distance() : 0.0f;
+
+    // Contact recycling (pair_update.rs:111-171).
+    if (recycle_dist > 0.0f && pair.has_recycle) {
+        Pose pos12 = pose_inv_mul(co1.pos, co2.pos);
+        float drift = relative_pose_drift(pair.r_pos12, pos12, pair.r_max_extent);
+        float rot_cos = fmin2(relative_rot_cos(pair.r_rot1, co1.pos.q), relative_rot_cos(pair.r_rot2, co2.pos.q));
+        if (drift <= pair.r_max_drift && rot_cos > 0.98f) return false;
+    }
+
+    bool had_active = pair.nsc > 0;
+    const Body* rb1 = pair.b1 >= 0 ? &w.bodies[pair.b1] : nullptr;
+    const Body* rb2 = pair.b2 >= 0 ? &w.bodies[pair.b2] : nullptr;
+    bool dyn1 = rb1 && rb1->is_dynamic();
+    bool dyn2 = rb2 && rb2->is_dynamic();
+
+    Pose pos12 = pose_inv_mul(co1.pos, co2.pos);
+    float skin_sum = co1.contact_skin + co2.contact_skin;
+    float eff_prediction = prediction + skin_sum;  // pair_update.rs:319
+
+    RawManifold raw;
+    contact_manifold(co1.shape, co1.he, co2.shape, co2.he, pos12, eff_prediction, raw);
+
+    // parry ContactManifold::match_contacts: carry ContactData by (fid1, fid2); ball manifolds keep
+    // their single point's data (copy_geometry_from).
+    Point carried[MAX_RAW_POINTS];
+    for (int i = 0; i < raw.n; ++i) {
+        Point& p = carried[i];
+        memset(&p, 0, sizeof(p));
+        p.local_p1 = raw.pts[i].local_p1;
+        p.local_p2 = raw.pts[i].local_p2;
+        p.dist = raw.pts[i].dist;
+        p.fid1 = raw.pts[i].fid1;
+        p.fid2 = raw.pts[i].fid2;
+        bool single_ball = (co1.shape == RB_SHAPE_BALL || co2.shape == RB_SHAPE_BALL);
+        for (int j = 0; j < pair.npts; ++j) {
+            const Point& o = pair.pts[j];
+            if (single_ball || (o.fid1 == p.fid1 && o.fid2 == p.fid2)) {
+                p.impulse = o.impulse;
+                p.warmstart_impulse = o.warmstart_impulse;
+                p.warmstart_twist = o.warmstart_twist;
+                p.warmstart_tangent_world = o.warmstart_tangent_world;
+                p.dp1 = o.dp1;
+                p.dp2 = o.dp2;
+            }
+        }
+    }
+
+    pair.friction = combine_coeff(co1.friction, co2.friction, co1.friction_rule, co2.friction_rule);
+    pair.restitution = combine_coeff(co1.restitution, co2.restitution, co1.restitution_rule, co2.restitution_rule);
+    pair.local_n1 = raw.local_n1;
+    pair.local_n2 = raw.local_n2;
+    pair.normal = qrot(co1.pos.q, raw.local_n1);  // pair_update.rs:414
+
+    // Reduce to <= 4 points and sort them on the contact plane (pair_update.rs:418-457).
+    int selected[4] = {0, 1, 2, 3};
+    int num_selected = raw.n < MAX_MANIFOLD_POINTS ? raw.n : MAX_MANIFOLD_POINTS;
+    reduce_manifold_naive(raw, selected, num_selected, prediction);
+    if (num_selected > 1) {
+        V3 b0, b1;
+        orthonormal_basis(raw.local_n1, b0, b1);
+        float k0[4], k1[4];
+        int ks[4];
+        for (int i = 0; i < num_selected; ++i) {
+            V3 p = raw.pts[selected[i]].local_p1;
+            k0[i] = dot(p, b0);
+            k1[i] = dot(p, b1);
+            ks[i] = selected[i];
+        }
+        for (int i = 1; i < num_selected; ++i) {
+            float a0 = k0[i], a1 = k1[i];
+            int as = ks[i];
+            int j = i;
+            while (j > 0 && (k0[j - 1] > a0 || (k0[j - 1] == a0 && k1[j - 1] > a1))) {
+                k0[j] = k0[j - 1]; k1[j] = k1[j - 1]; ks[j] = ks[j - 1];
+                --j;
+            }
+            k0[j] = a0; k1[j] = a1; ks[j] = as;
+        }
+        for (int i = 0; i < num_selected; ++i) selected[i] = ks[i];
+    }
+    // Only the selected points persist ("manifold storage").
+    pair.npts = num_selected;
+    for (int i = 0; i < num_selected; ++i) pair.pts[i] = carried[selected[i]];
+
+    // Solver contacts (pair_update.rs:459-498) + localisation / anchor freezing (:536-577).
+    pair.nsc = 0;
+    V3 normal = pair.normal;
+    Pose com_pose1 = pose_identity(), com_pose2 = pose_identity();
+    if (dyn1) com_pose1 = pose_prepend_translation(rb1->pos, rb1->local_com);
+    if (dyn2) com_pose2 = pose_prepend_translation(rb2->pos, rb2->local_com);
+    for (int k = 0; k < pair.npts; ++k) {
+        Point& c = pair.pts[k];
+        float eff_dist = c.dist - co1.contact_skin - co2.contact_skin;
+        V3 world_pt1 = pose_point(co1.pos, c.local_p1);
+        V3 world_pt2 = pose_point(co2.pos, c.local_p2);
+        bool keep = eff_dist < prediction;
+        if (!keep) {
+            V3 vel1 = rb1 ? rb1->linvel + cross(rb1->angvel, world_pt1 - rb1->world_com) : vzero();
+            V3 vel2 = rb2 ? rb2->linvel + cross(rb2->angvel, world_pt2 - rb2->world_com) : vzero();
+            keep = eff_dist + dot(vel2 - vel1, normal) * dt < prediction;
+        }
+        if (!keep) continue;
+        SolverContact& sc = pair.sc[pair.nsc++];
+        sc.cid = k;
+        float shift = dot(world_pt2 - world_pt1, normal) - eff_dist;
+        V3 p1 = world_pt1 + normal * shift;
+        V3 point = (p1 + world_pt2) * 0.5f;
+        c.dp1 = dyn1 ? point - com_pose1.t : point;
+        c.dp2 = dyn2 ? point - com_pose2.t : point;
+        sc.anchor1 = dyn1 ? pose_inv_point(com_pose1, p1) : p1;
+        sc.anchor2 = dyn2 ? pose_inv_point(com_pose2, world_pt2) : world_pt2;
+    }
+
+    // Recycle state (pair_update.rs:582-613).
+    if (recycle_dist > 0.0f) {
+        float max_extent = pair.has_recycle
+                               ? pair.r_max_extent
+                               : fmax2(shape_origin_radius(co1.shape, co1.he), shape_origin_radius(co2.shape, co2.he));
+        float max_drift = pair.nsc > 0 ? recycle_dist : fmin2(recycle_dist, prediction);
+        pair.has_recycle = true;
+        pair.r_pos12 = pos12;
+        pair.r_rot1 = co1.pos.q;
+        pair.r_rot2 = co2.pos.q;
+        pair.r_max_extent = max_extent;
+        pair.r_max_drift = max_drift;
+    }
+    return (pair.nsc > 0) != had_active;
+}
+
+// narrow_phase/mod.rs:87-152
+static void assign_pair_color(World& w, Pair& p) {
+    if (p.color != COLOR_UNCOLORED) return;
+    bool d1 = p.b1 >= 0 && w.bodies[p.b1].is_dynamic();
+    bool d2 = p.b2 >= 0 && w.bodies[p.b2].is_dynamic();
+    if (!d1 && !d2) {
+        p.color = COLOR_OVERFLOW;
+        p.color_bodies[0] = p.color_bodies[1] = NO_BODY;
+        return;
+    }
+    int color;
+    uint32_t cb[2];
+    if (d1 && d2) {
+        Mask128 m;
+        m.lo = w.color_masks[p.b1].lo | w.color_masks[p.b2].lo;
+        m.hi = w.color_masks[p.b1].hi | w.color_masks[p.b2].hi;
+        color = 128;
+        for (int c = 0; c < DYNAMIC_COLOR_COUNT; ++c)
+            if (!m.test(c)) { color = c; break; }
+        cb[0] = (uint32_t)p.b1;
+        cb[1] = (uint32_t)p.b2;
+    } else {
+        int b = d1 ? p.b1 : p.b2;
+        const Mask128& m = w.color_masks[b];
+        color = 128;
+        for (int c = 127; c >= 0; --c)
+            if (!m.test(c)) { color = c; break; }
+        cb[0] = (uint32_t)b;
+        cb[1] = NO_BODY;
+    }
+    if (color >= 128) {
+        p.color = COLOR_OVERFLOW;
+        p.color_bodies[0] = p.color_bodies[1] = NO_BODY;
+        return;
+    }
+    for (int k = 0; k < 2; ++k)
+        if (cb[k] != NO_BODY) w.color_masks[cb[k]].set(color);
+    p.color = (uint8_t)color;
+    p.color_bodies[0] = cb[0];
+    p.color_bodies[1] = cb[1];
+}
+
+static void narrow_phase(World& w) {
+    std::vector<int> started;
+    for (int i = 0; i < (int)w.pairs.size(); ++i) {
+        Pair& p = w.pairs[i];
+        if (process_pair(w, p)) {
+            if (p.nsc > 0) started.push_back(i);
+            else clear_pair_color(w, p);  // end-touch frees the colour first (contacts.rs:333-335)
+            w.counters.schedule_rebuilt = 1;
+        }
+    }
+    // Deferred greedy colouring in canonical (min body, max body, edge) order (contacts.rs:366-385).
+    auto bid = [](int b) { return b < 0 ? 0xffffffffu : (uint32_t)b; };
+    std::stable_sort(started.begin(), started.end(), [&](int x, int y) {
+        const Pair& a = w.pairs[x];
+        const Pair& b = w.pairs[y];
+        uint32_t a1 = bid(a.b1), a2 = bid(a.b2), b1 = bid(b.b1), b2 = bid(b.b2);
+        uint64_t ka = ((uint64_t)std::min(a1, a2) << 32) | std::max(a1, a2);
+        uint64_t kb = ((uint64_t)std::min(b1, b2) << 32) | std::max(b1, b2);
+        if (ka != kb) return ka < kb;
+        return x < y;
+    });
+    for (int i : started) assign_pair_color(w, w.pairs[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One step (substep.rs:267-581).
+// ---------------------------------------------------------------------------------------------
+static inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+void step_once(World& w, V3 gravity) {
+    w.counters.broad_phase_ran = 0;
+    w.counters.schedule_rebuilt = 0;
+    double t0 = now_ms();
+    // 5. detect_collisions
+    if (w.bp_dirty) update_pairs(w);
+    double t1 = now_ms();
+    narrow_phase(w);
+    double t2 = now_ms();
+    // 7b. build_islands_and_solve_velocity_constraints
+    solve_island(w, gravity);
+    double t3 = now_ms();
+    // 7d. advance_to_final_positions (substep.rs:84-224) + 7f refresh_moved_collider_aabbs
+    for (Body& b : w.bodies) {
+        if (!b.is_dynamic()) continue;
+        b.pos = b.next_pos;
+        update_world_mass_properties(b);
+    }
+    for (Collider& c : w.colliders) {
+        if (c.parent >= 0 && w.bodies[c.parent].is_dynamic()) refresh_collider(w, c);
+    }
+    double t4 = now_ms();
+    w.counters.broad_phase_ms = (float)(t1 - t0);
+    w.counters.narrow_phase_ms = (float)(t2 - t1);
+    w.counters.collision_detection_ms = (float)(t2 - t0);
+    w.counters.solver_ms = (float)(t3 - t2);
+    w.counters.update_ms = (float)(t4 - t3);
+    w.counters.step_ms = (float)(t4 - t0);
+    w.counters.steps++;
+    w.counters.num_pairs = (int)w.pairs.size();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scene upload (RigidBodySet / ColliderSet / ImpulseJointSet user changes, substep.rs:303-334).
+// ---------------------------------------------------------------------------------------------
+static inline V3 f3(const float* p) { return V3{p[0], p[1], p[2]}; }
+static inline Q4 f4(const float* p) { return Q4{p[0], p[1], p[2], p[3]}; }
+
+int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDesc* cd, int nj,
+              const RbJointDesc* jd) {
+    w.bodies.assign(nb, Body{});
+    w.colliders.assign(nc, Collider{});
+    w.joints.assign(nj, Joint{});
+    w.pairs.clear();
+    w.color_masks.assign(nb, Mask128{});
+    w.bp_dirty = true;
+    for (int i = 0; i < nb; ++i) {
+        Body& b = w.bodies[i];
+        const RbBodyDesc& d = bd[i];
+        b.type = d.body_type;
+        b.flags = d.flags;
+        b.pos = Pose{f4(d.rotation), f3(d.translation)};
+        b.next_pos = b.pos;
+        b.linvel = f3(d.linvel);
+        b.angvel = f3(d.angvel);
+        b.lin_damping = d.linear_damping;
+        b.ang_damping = d.angular_damping;
+        b.gravity_scale = d.gravity_scale;
+        b.user_force = f3(d.user_force);
+        b.user_torque = f3(d.user_torque);
+        b.force = vzero();
+        b.torque = vzero();
+    }
+    for (int i = 0; i < nc; ++i) {
+        Collider& c = w.colliders[i];
+        const RbColliderDesc& d = cd[i];
+        if (d.shape != RB_SHAPE_BALL && d.shape != RB_SHAPE_CUBOID) return RB_ERR_INVALID;
+        if (d.parent >= nb) return RB_ERR_INVALID;
+        c.shape = d.shape;
+        c.he = f3(d.half_extents);
+        c.parent = d.parent;
+        c.pos_wrt_parent = Pose{f4(d.pos_wrt_parent_q), f3(d.pos_wrt_parent_t)};
+        c.density = d.density;
+        c.friction = d.friction;
+        c.restitution = d.restitution;
+        c.friction_rule = d.friction_combine_rule;
+        c.restitution_rule = d.restitution_combine_rule;
+        c.contact_skin = d.contact_skin;
+        c.memberships = d.collision_memberships;
+        c.filter = d.collision_filter;
+        c.fat_valid = false;
+    }
+    int rc = recompute_mass_properties(w);
+    if (rc != RB_OK) return rc;
+    for (Body& b : w.bodies) update_world_mass_properties(b);
+    for (Collider& c : w.colliders) refresh_collider(w, c);
+    w.nocontact_body_pairs.clear();
+    for (int i = 0; i < nj; ++i) {
+        Joint& j = w.joints[i];
+        const RbJointDesc& d = jd[i];
+        if (d.body1 < 0 || d.body1 >= nb || d.body2 < 0 || d.body2 >= nb) return RB_ERR_INVALID;
+        j.body1 = d.body1;
+        j.body2 = d.body2;
+        j.local_frame1 = Pose{f4(d.local_frame1_q), f3(d.local_frame1_t)};
+        j.local_frame2 = Pose{f4(d.local_frame2_q), f3(d.local_frame2_t)};
+        j.locked_axes = d.locked_axes;
+        j.contacts_enabled = d.contacts_enabled;
+        j.natural_frequency = d.natural_frequency;
+        j.damping_ratio = d.damping_ratio;
+        for (int k = 0; k < 6; ++k) j.impulses[k] = 0.0f;
+        if (!d.contacts_enabled) {
+            uint32_t lo = (uint32_t)std::min(d.body1, d.body2), hi = (uint32_t)std::max(d.body1, d.body2);
+            w.nocontact_body_pairs.push_back(((uint64_t)lo << 32) | hi);
+        }
+    }
+    std::sort(w.nocontact_body_pairs.begin(), w.nocontact_body_pairs.end());
+    // Joint colouring: greedy first fit in joint order (interaction_groups.rs:59-165), dyn-dyn from
+    // colour 0 up (< 120), dyn-fixed from 127 down.
+    std::vector<Mask128> jm(nb);
+    for (Joint& j : w.joints) {
+        bool d1 = w.bodies[j.body1].is_dynamic(), d2 = w.bodies[j.body2].is_dynamic();
+        j.sid1 = d1 ? (uint32_t)j.body1 : NO_BODY;
+        j.sid2 = d2 ? (uint32_t)j.body2 : NO_BODY;
+        j.color = 128;
+        if (d1 && d2) {
+            for (int c = 0; c < DYNAMIC_COLOR_COUNT; ++c)
+                if (!jm[j.body1].test(c) && !jm[j.body2].test(c)) { j.color = c; break; }
+            if (j.color < 128) { jm[j.body1].set(j.color); jm[j.body2].set(j.color); }
+        } else if (d1 || d2) {
+            int b = d1 ? j.body1 : j.body2;
+            for (int c = 127; c >= 0; --c)
+                if (!jm[b].test(c)) { j.color = c; break; }
+            if (j.color < 128) jm[b].set(j.color);
+        } else {
+            j.color = -1;  // both fixed: never selected (impulse_joint_set.rs:548-553)
+        }
+    }
+    w.counters = RbCounters{};
+    w.counters.num_bodies = nb;
+    w.counters.num_colliders = nc;
+    w.counters.num_joints = nj;
+    return RB_OK;
+}
+
+}  // namespace orc

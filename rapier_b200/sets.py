@@ -1,0 +1,273 @@
+"""Host-side mirror of the reference's state stores for the step hot path.
+
+Mirrors (names, argument meaning, defaults) of:
+  RigidBodyBuilder / RigidBodySet     src/dynamics/rigid_body.rs:1490-1580, rigid_body_set.rs:70-79, :150
+  ColliderBuilder / ColliderSet       src/geometry/collider.rs:688-707, :1125-1131
+  SphericalJointBuilder / FixedJointBuilder / ImpulseJointSet
+                                      src/dynamics/joint/spherical_joint.rs, impulse_joint/impulse_joint_set.rs
+Handles are plain indices (the reference's generational arena index without the generation,
+src/data/arena.rs): removal is outside the hot path and not mirrored.  The sets serialise to the
+C-ABI descriptor arrays of include/rapier_b200.h; nothing here computes physics.
+"""
+import ctypes as C
+import math
+
+from . import _abi as A
+
+
+class RigidBodyBuilder:
+    def __init__(self, body_type):
+        self.body_type = body_type
+        self._translation = (0.0, 0.0, 0.0)
+        self._rotation = (0.0, 0.0, 0.0, 1.0)
+        self._linvel = (0.0, 0.0, 0.0)
+        self._angvel = (0.0, 0.0, 0.0)
+        self._linear_damping = 0.0
+        self._angular_damping = 0.0
+        self._gravity_scale = 1.0
+        self._can_sleep = True
+        self._flags = A.RB_BODY_GYROSCOPIC  # gyroscopic forces on by default (rigid_body.rs:1579)
+        self._additional_mass = 0.0
+
+    @classmethod
+    def dynamic(cls):
+        return cls(A.RB_BODY_DYNAMIC)
+
+    @classmethod
+    def fixed(cls):
+        return cls(A.RB_BODY_FIXED)
+
+    def translation(self, v):
+        self._translation = tuple(float(x) for x in v)
+        return self
+
+    def rotation(self, axis_angle):
+        """Scaled-axis rotation, as RigidBodyBuilder::rotation(AngVector)."""
+        ax, ay, az = (float(x) for x in axis_angle)
+        ang = math.sqrt(ax * ax + ay * ay + az * az)
+        if ang == 0.0:
+            self._rotation = (0.0, 0.0, 0.0, 1.0)
+        else:
+            s = math.sin(ang / 2.0) / ang
+            self._rotation = (ax * s, ay * s, az * s, math.cos(ang / 2.0))
+        return self
+
+    def rotation_quat(self, q):
+        self._rotation = tuple(float(x) for x in q)
+        return self
+
+    def linvel(self, v):
+        self._linvel = tuple(float(x) for x in v)
+        return self
+
+    def angvel(self, v):
+        self._angvel = tuple(float(x) for x in v)
+        return self
+
+    def linear_damping(self, d):
+        self._linear_damping = float(d)
+        return self
+
+    def angular_damping(self, d):
+        self._angular_damping = float(d)
+        return self
+
+    def gravity_scale(self, s):
+        self._gravity_scale = float(s)
+        return self
+
+    def can_sleep(self, flag):
+        # Sleeping is SURVEY 8(f) "next": accepted and ignored (every benchmark scene disables it).
+        self._can_sleep = bool(flag)
+        return self
+
+    def gyroscopic_forces_enabled(self, flag):
+        if flag:
+            self._flags |= A.RB_BODY_GYROSCOPIC
+        else:
+            self._flags &= ~A.RB_BODY_GYROSCOPIC
+        return self
+
+    def locked_axes(self, bits):
+        self._flags |= int(bits) & 0xFC
+        return self
+
+    def build_desc(self):
+        d = A.RbBodyDesc()
+        d.body_type = self.body_type
+        d.flags = self._flags
+        d.translation[:] = self._translation
+        d.rotation[:] = self._rotation
+        d.linvel[:] = self._linvel
+        d.angvel[:] = self._angvel
+        d.linear_damping = self._linear_damping
+        d.angular_damping = self._angular_damping
+        d.gravity_scale = self._gravity_scale
+        d.additional_mass = self._additional_mass
+        return d
+
+
+class ColliderBuilder:
+    def __init__(self, shape, half_extents):
+        self.shape = shape
+        self.half_extents = half_extents
+        self._density = 1.0
+        self._friction = 0.5
+        self._restitution = 0.0
+        self._translation = (0.0, 0.0, 0.0)
+        self._rotation = (0.0, 0.0, 0.0, 1.0)
+        self._friction_rule = A.RB_COMBINE_AVERAGE
+        self._restitution_rule = A.RB_COMBINE_AVERAGE
+        self._contact_skin = 0.0
+        self._memberships = 0xFFFFFFFF
+        self._filter = 0xFFFFFFFF
+
+    @classmethod
+    def cuboid(cls, hx, hy, hz):
+        return cls(A.RB_SHAPE_CUBOID, (float(hx), float(hy), float(hz)))
+
+    @classmethod
+    def ball(cls, radius):
+        return cls(A.RB_SHAPE_BALL, (float(radius), 0.0, 0.0))
+
+    def density(self, d):
+        self._density = float(d)
+        return self
+
+    def friction(self, f):
+        self._friction = float(f)
+        return self
+
+    def restitution(self, r):
+        self._restitution = float(r)
+        return self
+
+    def friction_combine_rule(self, r):
+        self._friction_rule = int(r)
+        return self
+
+    def restitution_combine_rule(self, r):
+        self._restitution_rule = int(r)
+        return self
+
+    def translation(self, v):
+        self._translation = tuple(float(x) for x in v)
+        return self
+
+    def contact_skin(self, s):
+        self._contact_skin = float(s)
+        return self
+
+    def collision_groups(self, memberships, filter_):
+        self._memberships = int(memberships)
+        self._filter = int(filter_)
+        return self
+
+    def build_desc(self, parent):
+        d = A.RbColliderDesc()
+        d.shape = self.shape
+        d.half_extents[:] = self.half_extents
+        d.parent = -1 if parent is None else int(parent)
+        d.pos_wrt_parent_t[:] = self._translation
+        d.pos_wrt_parent_q[:] = self._rotation
+        d.density = self._density
+        d.friction = self._friction
+        d.restitution = self._restitution
+        d.friction_combine_rule = self._friction_rule
+        d.restitution_combine_rule = self._restitution_rule
+        d.contact_skin = self._contact_skin
+        d.collision_memberships = self._memberships
+        d.collision_filter = self._filter
+        return d
+
+
+class GenericJointBuilder:
+    """Locked-axes joints only: spherical = LIN_X|LIN_Y|LIN_Z, fixed = all six."""
+
+    def __init__(self, locked_axes):
+        self.locked_axes = locked_axes
+        self._a1 = (0.0, 0.0, 0.0)
+        self._a2 = (0.0, 0.0, 0.0)
+        self._q1 = (0.0, 0.0, 0.0, 1.0)
+        self._q2 = (0.0, 0.0, 0.0, 1.0)
+        self._contacts_enabled = True
+
+    def local_anchor1(self, v):
+        self._a1 = tuple(float(x) for x in v)
+        return self
+
+    def local_anchor2(self, v):
+        self._a2 = tuple(float(x) for x in v)
+        return self
+
+    def contacts_enabled(self, flag):
+        self._contacts_enabled = bool(flag)
+        return self
+
+    def build_desc(self, body1, body2):
+        d = A.RbJointDesc()
+        d.body1, d.body2 = int(body1), int(body2)
+        d.local_frame1_t[:] = self._a1
+        d.local_frame1_q[:] = self._q1
+        d.local_frame2_t[:] = self._a2
+        d.local_frame2_q[:] = self._q2
+        d.locked_axes = self.locked_axes
+        d.contacts_enabled = 1 if self._contacts_enabled else 0
+        d.natural_frequency = 1.0e6   # SpringCoefficients::joint_defaults (integration_parameters.rs:78-83)
+        d.damping_ratio = 1.0
+        return d
+
+
+def SphericalJointBuilder():
+    return GenericJointBuilder(0b000111)
+
+
+def FixedJointBuilder():
+    return GenericJointBuilder(0b111111)
+
+
+class RigidBodySet:
+    def __init__(self):
+        self.descs = []
+
+    def insert(self, builder):
+        self.descs.append(builder.build_desc())
+        return len(self.descs) - 1
+
+    def __len__(self):
+        return len(self.descs)
+
+
+class ColliderSet:
+    def __init__(self):
+        self.descs = []
+
+    def insert(self, builder):
+        self.descs.append(builder.build_desc(None))
+        return len(self.descs) - 1
+
+    def insert_with_parent(self, builder, parent, bodies=None):
+        self.descs.append(builder.build_desc(parent))
+        return len(self.descs) - 1
+
+    def __len__(self):
+        return len(self.descs)
+
+
+class ImpulseJointSet:
+    def __init__(self):
+        self.descs = []
+
+    def insert(self, body1, body2, builder, wake_up=True):
+        self.descs.append(builder.build_desc(body1, body2))
+        return len(self.descs) - 1
+
+    def __len__(self):
+        return len(self.descs)
+
+
+def as_array(descs, ctype):
+    arr = (ctype * max(len(descs), 1))()
+    for i, d in enumerate(descs):
+        arr[i] = d
+    return arr

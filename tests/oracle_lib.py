@@ -1,0 +1,121 @@
+"""ctypes wrapper of the CPU oracle (oracle/_build/liborc.so).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from rapier_b200 import _abi as A
+from rapier_b200.sets import as_array
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liborc.so")
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        L.orc_world_create.restype = C.c_void_p
+        L.orc_world_create.argtypes = [C.POINTER(A.RbIntegrationParameters)]
+        L.orc_world_destroy.argtypes = [C.c_void_p]
+        L.orc_world_set_scene.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_world_set_params.argtypes = [C.c_void_p, C.POINTER(A.RbIntegrationParameters)]
+        L.orc_world_step.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32]
+        L.orc_world_get_body_states.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_world_set_body_states.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_world_num_bodies.argtypes = [C.c_void_p]
+        L.orc_world_get_counters.argtypes = [C.c_void_p, C.POINTER(A.RbCounters)]
+        L.orc_world_get_contact_pairs.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_world_debug_read.restype = C.c_int64
+        L.orc_world_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_contact_manifold.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class OracleWorld:
+    """Same surface as rapier_b200.PhysicsWorld, backed by the CPU oracle."""
+
+    def __init__(self, scene, params=None, threads=1):
+        self.L = lib()
+        self.params = params or A.RbIntegrationParameters.default()
+        self.h = self.L.orc_world_create(C.byref(self.params))
+        self.gravity = scene.gravity
+        self.L.orc_set_threads(threads)
+        nb, nc, nj = len(scene.bodies), len(scene.colliders), len(scene.joints)
+        self._b = as_array(scene.bodies.descs, A.RbBodyDesc)
+        self._c = as_array(scene.colliders.descs, A.RbColliderDesc)
+        self._j = as_array(scene.joints.descs, A.RbJointDesc)
+        rc = self.L.orc_world_set_scene(self.h, nb, self._b, nc, self._c, nj, self._j)
+        if rc != 0:
+            raise RuntimeError(f"orc_world_set_scene failed: {rc}")
+        self.nb = nb
+
+    def __del__(self):
+        try:
+            self.L.orc_world_destroy(self.h)
+        except Exception:
+            pass
+
+    def step(self, n=1):
+        g = (C.c_float * 3)(*self.gravity)
+        rc = self.L.orc_world_step(self.h, g, n)
+        assert rc == 0
+
+    def body_states(self):
+        pose = np.zeros((self.nb, 7), np.float32)
+        vel = np.zeros((self.nb, 6), np.float32)
+        self.L.orc_world_get_body_states(self.h, pose.ctypes.data, vel.ctypes.data)
+        return pose, vel
+
+    def counters(self):
+        c = A.RbCounters()
+        self.L.orc_world_get_counters(self.h, C.byref(c))
+        return c.as_dict()
+
+    def contact_pairs(self):
+        n = self.L.orc_world_get_contact_pairs(self.h, 0, None, None, None, None, None)
+        pc = np.zeros((n, 2), np.int32)
+        nc = np.zeros(n, np.int32)
+        col = np.zeros(n, np.int32)
+        nrm = np.zeros((n, 3), np.float32)
+        imp = np.zeros((n, 4), np.float32)
+        self.L.orc_world_get_contact_pairs(self.h, n, pc.ctypes.data, nc.ctypes.data, col.ctypes.data, nrm.ctypes.data,
+                                           imp.ctypes.data)
+        return dict(colliders=pc, num_contacts=nc, color=col, normal=nrm, impulses=imp)
+
+    def debug_read(self, table, dtype):
+        n = self.L.orc_world_debug_read(self.h, table.encode(), None, 0)
+        if n < 0:
+            raise KeyError(table)
+        buf = np.zeros(n, np.uint8)
+        self.L.orc_world_debug_read(self.h, table.encode(), buf.ctypes.data, n)
+        return buf.view(dtype)
+
+
+def contact_manifold(shape1, he1, shape2, he2, t, q, prediction=0.02):
+    L = lib()
+    he1 = np.asarray(he1, np.float32)
+    he2 = np.asarray(he2, np.float32)
+    t = np.asarray(t, np.float32)
+    q = np.asarray(q, np.float32)
+    out = np.zeros((8, 9), np.float32)
+    n1 = np.zeros(3, np.float32)
+    n2 = np.zeros(3, np.float32)
+    n = L.orc_contact_manifold(shape1, he1.ctypes.data, shape2, he2.ctypes.data, t.ctypes.data, q.ctypes.data,
+                               C.c_float(prediction), out.ctypes.data, n1.ctypes.data, n2.ctypes.data)
+    return out[:n], n1, n2
