@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- physics steps/s on b3d_many_pyramids (3-D f32), BASELINE.json's metric.
+
+  python bench.py --gpus 1 --steps K --warmup W            our CUDA path (one JSON line)
+  python bench.py --impl reference --steps K --warmup W     CPU arm (oracle port, all host threads)
+  torchrun --nproc-per-node N bench.py --gpus N ...         weak scaling: N x the scene, sharded by island
+
+A "step" is one PhysicsPipeline::step of the whole scene.  `value` times steps with all state
+resident in HBM (CUDA events on the launching stream, max over ranks); `e2e` times the same steps
+through rb_world_step_host with HOST state buffers (H2D of every body state + D2H of the result in
+the timed region).  The reference arm is the CPU oracle (`oracle/`, a scalar restatement -- the Rust
+reference cannot be built in this image), run with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def scene_for(name, replicas=1):
+    from rapier_b200 import scenes
+    if name == "b3d_many_pyramids":
+        # reference file examples3d/b3d_many_pyramids.rs: 14 x 14 pyramids, base 10 (10 780 cubes).
+        # replicas > 1 (multi-GPU weak scaling): 14*replicas rows of the same arrangement.
+        return scenes.pyramids(14 * replicas, 14, 10, name="b3d_many_pyramids" + (f"_x{replicas}" if replicas > 1 else ""))
+    if name == "b3d_many_pyramids_80x20":
+        return scenes.pyramids(8 * replicas, 10, 20, name="b3d_many_pyramids_80x20")
+    return scenes.REGISTRY[name]()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop = False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for n, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(m, b, j):
+    """SURVEY.md 8(d) / BASELINE.md 4: streaming model, f32, twist friction, p = 4, S = 4."""
+    return 12076 * m + 1608 * b + 6576 * j
+
+
+def run_reference(args):
+    """CPU arm: the oracle (scalar port of the reference's algorithm) with all host threads."""
+    import oracle_lib
+    from rapier_b200 import scenes  # noqa: F401
+    cores = os.cpu_count() or 1
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene = scene_for(args.scene, 1)
+    w = oracle_lib.OracleWorld(scene, threads=cores)
+    # settle the first (broad-phase + full narrow-phase) steps outside the timed region, like the GPU arm
+    w.step(max(args.warmup, 3))
+    t0 = time.perf_counter()
+    w.step(args.steps)
+    dt = time.perf_counter() - t0
+    c = w.counters()
+    value = args.steps / dt
+    line = {
+        "impl": "reference", "metric": "physics steps/sec on b3d_many_pyramids (3D f32)", "value": value, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.scene, 1), "bodies": c["num_bodies"], "manifolds": c["num_active_manifolds"]},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} consecutive steps of the full scene after {max(args.warmup, 3)} warm-up steps"},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement (oracle/), not the reference binary: no Rust toolchain in this image",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(scene, replicas):
+    base = {"b3d_many_pyramids": "b3d_many_pyramids (reference file examples3d/b3d_many_pyramids.rs: 14x14 pyramids, base 10, 10780 cubes)",
+            "b3d_many_pyramids_80x20": "b3d_many_pyramids (BASELINE label: 80 pyramids x 20 levels, 16800 cubes)"}.get(scene, scene)
+    return base if replicas == 1 else f"{replicas} x {base}, one replica per GPU"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="b3d_many_pyramids")
+    ap.add_argument("--l2", default="flush", choices=["flush", "keep"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if world_size != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world_size}: launch with torchrun --nproc-per-node {args.gpus}")
+    if rank == 0:
+        ge.build()
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    torch.cuda.set_device(local_rank)
+    from rapier_b200.world import PhysicsWorld
+
+    scene = scene_for(args.scene, world_size)
+    w = PhysicsWorld(scene, device=local_rank)
+    w._flush()
+    pipe = w.physics_pipeline
+    stream = torch.cuda.current_stream()
+    pipe.set_stream(stream.cuda_stream)
+    nb = len(scene.bodies)
+    gravity = scene.gravity
+
+    # ---- multi-GPU: shard whole connected components (islands) across ranks ----
+    exchange = None
+    if world_size > 1:
+        comp = pipe.label_components()
+        roots = np.unique(comp[comp >= 0])
+        owner_of_root = {int(r): i * world_size // len(roots) for i, r in enumerate(roots)}   # contiguous blocks of islands
+        owner = np.array([owner_of_root[int(c)] if c >= 0 else -1 for c in comp], np.int32)
+        pipe.set_owned_bodies((owner == rank).astype(np.uint8))
+        counts = [int((owner == r).sum()) for r in range(world_size)]
+        maxc = max(counts)
+        idx_lists = [np.nonzero(owner == r)[0].astype(np.int32) for r in range(world_size)]
+        ptr, nbytes = pipe.state_buffer()
+
+        class _Buf:
+            def __init__(s, p, n):
+                s.__cuda_array_interface__ = {"shape": (n // 4,), "typestr": "<f4", "data": (p, False), "version": 2}
+        state = torch.as_tensor(_Buf(ptr, nbytes), device=f"cuda:{local_rank}").view(nb, 13)
+        my_idx = torch.from_numpy(idx_lists[rank]).to(state.device).long()
+        send = torch.zeros(maxc, 13, device=state.device)
+        recv = torch.zeros(world_size * maxc, 13, device=state.device)
+        others = [r for r in range(world_size) if r != rank]
+        imp_idx = torch.cat([torch.from_numpy(idx_lists[r]) for r in others]).to(state.device).int()
+        gather_rows = torch.cat([torch.arange(counts[r]) + r * maxc for r in others]).to(state.device).long()
+        imp_src = torch.zeros(len(imp_idx), 13, device=state.device)
+
+        def exchange():
+            # NCCL all-gather of every rank's owned body states over NVLink; non-owned states are imported
+            send[:counts[rank]] = state.index_select(0, my_idx)
+            dist.all_gather_into_tensor(recv, send)
+            torch.index_select(recv, 0, gather_rows, out=imp_src)
+            pipe.import_states(imp_idx.data_ptr(), imp_src.data_ptr(), len(imp_idx))
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if args.l2 == "flush" else None
+
+    def one_step():
+        pipe.step(gravity, 1, sync=False)
+        if exchange is not None:
+            exchange()
+
+    def timed_steps(k):
+        """CUDA events around each step on the launching stream; L2 flushed between steps."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        for a, b in evs:
+            if flush_buf is not None:
+                flush_buf.zero_()
+            a.record(stream)
+            one_step()
+            b.record(stream)
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    k0 = pipe.counters()["kernels_launched"]
+    with ClockSampler(local_rank) as clk:
+        ms = timed_steps(args.steps)
+        k1 = pipe.counters()["kernels_launched"]
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        # per-launch-group device times for the roofline (events inside the library, same stream)
+        pipe.enable_profiling(True)
+        pipe.step(gravity, min(args.steps, 100), sync=True)
+        prof = pipe.counters()
+        pipe.enable_profiling(False)
+        # ---- e2e: host buffers in / out every step through the public C-ABI call ----
+        e2e_steps = min(args.steps, 200)
+        pose, vel = pipe.body_states()
+        st_in = np.concatenate([pose, vel], axis=1).astype(np.float32).copy()
+        st_out = np.zeros_like(st_in)
+        for _ in range(3):
+            pipe.step_host(gravity, st_in, st_out)
+            st_in, st_out = st_out, st_in
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            pipe.step_host(gravity, st_in, st_out)
+            st_in, st_out = st_out, st_in
+            if exchange is not None:
+                exchange()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    clocks = clk.summary()
+
+    t = torch.tensor([ms, e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(t[0]), float(t[1])
+
+    c = pipe.counters()
+    per_rank_bodies = (nb - 1) // world_size
+    M = c["num_active_manifolds"]
+    # whole-job value: steps of the base scene per second (each rank advances one base-scene replica per step)
+    value = world_size * args.steps / (ms / 1000.0)
+    e2e_value = world_size * e2e_steps / e2e_s
+    solve_ms = prof["solver_ms"]
+    a_bytes = algorithmic_bytes(M, per_rank_bodies, 0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = a_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_solve_items_dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    if rank == 0:
+        cpu = None
+        try:
+            import oracle_lib
+            cores = os.cpu_count() or 1
+            ow = oracle_lib.OracleWorld(scene_for(args.scene, 1), threads=cores)
+            ow.step(3)
+            t0 = time.perf_counter()
+            n = 0
+            while time.perf_counter() - t0 < args.cpu_seconds and n < 400:
+                ow.step(5)
+                n += 5
+            cdt = time.perf_counter() - t0
+            cpu = {"value": n / cdt, "unit": "steps/s", "cores": cores, "kind": "port",
+                   "sample": f"{n} consecutive steps of the full {args.scene} scene (after 3 warm-up steps), oracle port with {cores} host threads"}
+        except Exception as e:  # the oracle is a checker, its absence must not hide the GPU number
+            cpu = {"value": None, "unit": "steps/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+        line = {
+            "metric": "physics steps/sec on b3d_many_pyramids (3D f32)", "value": value, "unit": "steps/s",
+            "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.scene, world_size), "bodies_per_gpu": per_rank_bodies,
+                       "manifolds_per_gpu": M, "substeps": 4, "sweeps_per_substep": 3,
+                       "l2": "flushed between steps (256 MiB memset)" if args.l2 == "flush" else "not flushed",
+                       "parallelism": "1 GPU" if world_size == 1 else f"islands sharded over {world_size} GPUs, NCCL all-gather of body states every step"},
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": nb * 13 * 4, "d2h_bytes_per_step": nb * 13 * 4,
+                    "steps": e2e_steps},
+            "gpu_launches": int(k1 - k0),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "kernel": "k_solve_items", "kernel_ms": solve_ms, "algorithmic_bytes_per_launch": a_bytes,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                         "note": "algorithmic bytes = streaming model of SURVEY 8(d); the working set is L2/shared-memory resident, see DESIGN.md"},
+            "cpu_baseline": cpu,
+            "stage_ms": {"collide": prof["collision_detection_ms"], "solve": prof["solver_ms"]},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -200,6 +200,15 @@ int rb_world_set_owned_bodies(RbWorld* w, const uint8_t* owned /* [num_bodies] *
  * all-gather of boundary body states, and the byte size. */
 int rb_world_state_buffer(RbWorld* w, void** device_ptr, int64_t* bytes);
 
+/* Scatter externally simulated body states (device pointers: idx[n], src[n*13]) into the world. */
+int rb_world_import_states(RbWorld* w, const int32_t* idx_dev, const float* src_dev, int32_t n);
+/* The CUDA stream all of this world's work is enqueued on / replace it by a caller-owned stream. */
+void* rb_world_stream(RbWorld* w);
+int rb_world_set_stream(RbWorld* w, void* cuda_stream);
+/* One step with HOST state buffers (13 floats per body: t3 q4 linvel3 angvel3), copies included:
+ * upload `in_state13` (may be NULL), step, download into `out_state13` (may be NULL). Synchronous. */
+int rb_world_step_host(RbWorld* w, const float gravity[3], const float* in_state13, float* out_state13);
+
 #ifdef __cplusplus
 }
 #endif

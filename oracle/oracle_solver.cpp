@@ -160,7 +160,7 @@ static void generate(World& w, int pair_index, Constraint& c) {
         V3 itd2 = sdp_mul(g2.ii, td2);
         V3 imsum = g1.im + g2.im;
         float r = dot(tangents[j], cmul(imsum, tangents[j])) + dot(itd1, td1) + dot(itd2, td2);
-        float rhs_wo_bias = dot(tangent_vel, tangents[j]);
+        float rhs_wo_bias = 0.0f;  // = tangent_vel . t with tangent_velocity identically zero (no hooks)
         c.t_torque_dir1[j] = td1; c.t_torque_dir2[j] = td2;
         c.t_ii_torque_dir1[j] = itd1; c.t_ii_torque_dir2[j] = itd2;
         c.t_rhs_wo_bias[j] = rhs_wo_bias;

@@ -1,0 +1,1086 @@
+// rb_api.cu -- kernels + the extern "C" boundary of librapier_b200.so (include/rapier_b200.h).
+//
+// Per step the host enqueues three launches on one stream, with no host synchronisation:
+//   k_collide      cooperative persistent kernel: collider refresh, [broad phase], narrow phase,
+//                  [colouring + islands + schedule]   (rb_collide.cuh)
+//   k_solve_items  one CTA per work item, bodies staged in shared memory, the whole
+//                  generate -> 4 x (warmstart, biased, integrate, relax) -> writeback chain fused
+//   k_solve_large  cooperative grid-wide solve of islands too big for a CTA (no-op otherwise)
+// All sizes that change at run time (pairs, manifolds, items) live in device memory (rb::State).
+//
+// With -DRB_EMULATE (tests/emul only) the same phase functions run single-threaded on the host with
+// malloc'd tables: a logic check for machines without a GPU, never part of the product library.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "rb_solver.cuh"
+#include "../../include/rapier_b200.h"
+
+using namespace rb;
+
+// ------------------------------------------------------------------------------------------------
+// error handling + memory backend
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static void set_err(const char* fmt, const char* a = "", int code = 0) { snprintf(g_err, sizeof(g_err), fmt, a, code); }
+
+#if RB_DEVICE_BUILD
+#define CK(call)                                                                 \
+    do {                                                                         \
+        cudaError_t e_ = (call);                                                 \
+        if (e_ != cudaSuccess) {                                                 \
+            set_err("CUDA error %s (%d) at " #call, cudaGetErrorString(e_), (int)e_); \
+            return RB_ERR_CUDA;                                                  \
+        }                                                                        \
+    } while (0)
+static cudaError_t dev_alloc(void** p, size_t n) { cudaError_t e = cudaMalloc(p, n ? n : 16); if (e == cudaSuccess) e = cudaMemset(*p, 0, n ? n : 16); return e; }
+static cudaError_t dev_free(void* p) { return cudaFree(p); }
+static cudaError_t h2d(void* d, const void* h, size_t n) { return n ? cudaMemcpy(d, h, n, cudaMemcpyHostToDevice) : cudaSuccess; }
+static cudaError_t d2h(void* h, const void* d, size_t n) { return n ? cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost) : cudaSuccess; }
+static cudaError_t dev_set(void* d, int v, size_t n) { return n ? cudaMemset(d, v, n) : cudaSuccess; }
+#else
+#define CK(call)                                 \
+    do {                                         \
+        if ((call) != 0) { set_err("emulated allocation failed%s", ""); return RB_ERR_CUDA; } \
+    } while (0)
+static cudaError_t dev_alloc(void** p, size_t n) { *p = calloc(n ? n : 16, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static cudaError_t dev_free(void* p) { free(p); return cudaSuccess; }
+static cudaError_t h2d(void* d, const void* h, size_t n) { if (n) memcpy(d, h, n); return cudaSuccess; }
+static cudaError_t d2h(void* h, const void* d, size_t n) { if (n) memcpy(h, d, n); return cudaSuccess; }
+static cudaError_t dev_set(void* d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+constexpr int COLLIDE_THREADS = 256;
+constexpr int ITEM_THREADS = 128;
+constexpr int LARGE_THREADS = 256;
+constexpr int ITEM_SMEM_BYTES = ITEM_MAX_BODIES * SB_STRIDE * 4;
+
+struct Grav { float x, y, z; };
+
+template <class Ctx>
+RB_PHASE void init_bodies_phase(const Ctx& ctx, const World& w) {
+    for (int b = ctx.gtid; b < w.nb; b += ctx.gsize) {
+        pose p = body_pose(w, b);
+        update_world_mass(w, b, p);
+        float* s = w.state13 + (size_t)b * 13;
+        vec3 l = xyz(w.b_linvel[b]), a = xyz(w.b_angvel[b]);
+        s[0] = p.t.x; s[1] = p.t.y; s[2] = p.t.z; s[3] = p.q.x; s[4] = p.q.y; s[5] = p.q.z; s[6] = p.q.w;
+        s[7] = l.x; s[8] = l.y; s[9] = l.z; s[10] = a.x; s[11] = a.y; s[12] = a.z;
+    }
+}
+
+// Scatter of externally provided body states (multi-GPU boundary all-gather): 13 floats per body.
+template <class Ctx>
+RB_PHASE void import_states_phase(const Ctx& ctx, const World& w, const int* idx, const float* src, int n) {
+    for (int k = ctx.gtid; k < n; k += ctx.gsize) {
+        int b = idx[k];
+        const float* s = src + (size_t)k * 13;
+        w.b_pos_t[b] = make_float4(s[0], s[1], s[2], 0.f);
+        w.b_pos_q[b] = make_float4(s[3], s[4], s[5], s[6]);
+        w.b_linvel[b] = make_float4(s[7], s[8], s[9], 0.f);
+        w.b_angvel[b] = make_float4(s[10], s[11], s[12], 0.f);
+        float* d = w.state13 + (size_t)b * 13;
+        for (int i = 0; i < 13; ++i) d[i] = s[i];
+        update_world_mass(w, b, body_pose(w, b));
+    }
+}
+
+#if RB_DEVICE_BUILD
+__global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w) {
+    GridCtx ctx;
+    collide_pipeline(ctx, w);
+}
+__global__ void __launch_bounds__(ITEM_THREADS) k_solve_items(World w, Grav g) {
+    extern __shared__ float smem[];
+    BlockCtx ctx;
+    SmemBodies bd;
+    bd.s = smem;
+    BlockExec ex;
+    ex.c = &ctx;
+    const int n = w.st->nitems;
+    for (int item = 1 + ctx.bid; item < n; item += ctx.nblocks) {
+        solve_item(ex, w, bd, item, mk3(g.x, g.y, g.z));
+        ex.sync();
+    }
+}
+__global__ void __launch_bounds__(LARGE_THREADS) k_solve_large(World w, Grav g) {
+    if (w.st->nlarge_bodies == 0) return;
+    GridCtx ctx;
+    GlobalBodies bd;
+    bd.w = &w;
+    GridExec ex;
+    ex.c = &ctx;
+    solve_item(ex, w, bd, 0, mk3(g.x, g.y, g.z));
+}
+__global__ void k_init_bodies(World w) {
+    GridCtx ctx;
+    init_bodies_phase(ctx, w);
+}
+__global__ void k_import_states(World w, const int* idx, const float* src, int n) {
+    GridCtx ctx;
+    import_states_phase(ctx, w, idx, src, n);
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// host-side world
+// ------------------------------------------------------------------------------------------------
+struct RbWorld {
+    World w{};
+    RbIntegrationParameters params{};
+    std::vector<RbBodyDesc> bodies;
+    std::vector<RbColliderDesc> colliders;
+    std::vector<RbJointDesc> joints;
+    std::vector<void*> allocs;
+    int device = 0;
+    int num_sms = 1;
+    int collide_blocks = 1, large_blocks = 1, item_blocks = 1;
+    long long kernels = 0, steps = 0;
+    bool profiling = false;
+    float ms_collide = 0, ms_solve = 0, ms_step = 0;
+    int njused = 0;
+    float* stage_dev = nullptr;      // [nb*13] device staging for bulk state import
+    int* ident_dev = nullptr;        // [nb] identity index list
+    float* stage_host = nullptr;     // pinned host staging (2 * nb * 13 floats: in, out)
+#if RB_DEVICE_BUILD
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::vector<cudaEvent_t> prof_ev;   // 3 events per profiled step
+    int prof_steps = 0;
+#else
+    std::vector<float> emu_smem;
+#endif
+};
+
+template <class T>
+static int alloc_arr(RbWorld* W, T** p, size_t count) {
+    void* v = nullptr;
+    if (dev_alloc(&v, count * sizeof(T)) != cudaSuccess) { set_err("device allocation failed%s", ""); return RB_ERR_CUDA; }
+    W->allocs.push_back(v);
+    *p = (T*)v;
+    return RB_OK;
+}
+#define ALLOC(ptr, count)                                   \
+    do {                                                    \
+        int rc_ = alloc_arr(W, &(ptr), (size_t)(count));    \
+        if (rc_ != RB_OK) return rc_;                       \
+    } while (0)
+
+static void free_all(RbWorld* W) {
+    for (void* p : W->allocs) dev_free(p);
+    W->allocs.clear();
+}
+
+static int next_pow2_host(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+// Derived solver coefficients (integration_parameters.rs:85-149, :305-377; init.rs:96-101).
+static void derive_params(const RbIntegrationParameters& p, Params& o) {
+    auto erp_inv_dt = [](float f, float z, float dt) { float w = f * 6.283185307179586f; return w / (dt * w + 2.0f * z); };
+    auto cfm_factor = [&](float f, float z, float dt) {
+        float e = dt * erp_inv_dt(f, z, dt);
+        float c = 0.0f;
+        if (e != 0.0f) {
+            float e1 = 1.0f / e - 1.0f;
+            c = e1 * e1 / ((1.0f + e1) * 4.0f * z * z);
+        }
+        return 1.0f / (1.0f + c);
+    };
+    o.dt = p.dt;
+    o.inv_dt_full = p.dt == 0.0f ? 0.0f : 1.0f / p.dt;
+    o.num_substeps = p.num_solver_iterations;
+    o.sub_dt = p.dt / (float)p.num_solver_iterations;
+    o.sub_inv_dt = o.sub_dt == 0.0f ? 0.0f : 1.0f / o.sub_dt;
+    o.dyn_cfm = cfm_factor(p.contact_natural_frequency, p.contact_damping_ratio, o.sub_dt);
+    o.static_cfm = cfm_factor(p.static_contact_natural_frequency, p.static_contact_damping_ratio, o.sub_dt);
+    o.dyn_erp = erp_inv_dt(p.contact_natural_frequency, p.contact_damping_ratio, o.sub_dt);
+    o.static_erp = erp_inv_dt(p.static_contact_natural_frequency, p.static_contact_damping_ratio, o.sub_dt);
+    o.max_corrective_velocity = p.normalized_max_corrective_velocity * p.length_unit;
+    o.warmstart_coeff = p.warmstart_coefficient;
+    o.prediction = p.normalized_prediction_distance * p.length_unit;
+    o.recycle_dist = p.normalized_contact_recycle_distance * p.length_unit;
+    o.length_unit = p.length_unit;
+    o.fat_skin = 4.0e-2f * p.length_unit;   // BroadPhaseBvh::CHANGE_DETECTION_FACTOR (broad_phase_bvh/mod.rs:175)
+    o.max_lin_vel = p.normalized_max_linear_velocity * p.length_unit;
+    o.max_ang_vel = 0.7853981633974483f * o.inv_dt_full;   // MAX_ROTATION * inv_dt (worker.rs:573-580)
+    o.num_pgs = p.num_internal_pgs_iterations;
+    o.num_relax = p.num_internal_stabilization_iterations;
+    o.friction_in_bias = p.friction_in_bias_pass;
+    o.contact_recycling = p.contact_recycling;
+}
+
+static int validate_params(const RbIntegrationParameters* p) {
+    if (!p) { set_err("null parameters%s", ""); return RB_ERR_INVALID; }
+    if (p->friction_model != 0) { set_err("friction_model Coulomb is not supported%s", ""); return RB_ERR_INVALID; }
+    if (p->warmstart_joints != 0) { set_err("warmstart_joints is not supported%s", ""); return RB_ERR_INVALID; }
+    if (p->num_solver_iterations < 1 || p->num_solver_iterations > 64) { set_err("num_solver_iterations out of range%s", ""); return RB_ERR_INVALID; }
+    return RB_OK;
+}
+
+// parry MassProperties::{from_cuboid, from_ball} (see oracle/oracle_world.cpp for the citation chain).
+static void collider_mass_props(const RbColliderDesc& c, float& mass, float pi[3]) {
+    if (c.shape == RB_SHAPE_CUBOID) {
+        float hx = c.half_extents[0], hy = c.half_extents[1], hz = c.half_extents[2];
+        float vol = hx * hy * hz * 8.0f;
+        float sx = hx * hx, sy = hy * hy, sz = hz * hz;
+        float third = 1.0f / 3.0f;
+        float ux = (sy + sz) * third, uy = (sx + sz) * third, uz = (sx + sy) * third;
+        mass = vol * c.density;
+        pi[0] = ux * mass; pi[1] = uy * mass; pi[2] = uz * mass;
+    } else {
+        float r = c.half_extents[0];
+        float vol = 3.14159265358979323846f * r * r * r * 4.0f / 3.0f;
+        float unit = r * r * 2.0f / 5.0f;
+        mass = vol * c.density;
+        pi[0] = pi[1] = pi[2] = unit * mass;
+    }
+}
+static inline float inv0(float x) { return x == 0.0f ? 0.0f : 1.0f / x; }
+
+struct HostMass { float lcom[3], inv_mass, ipi[3], pi[3], pframe[4]; };
+
+// RigidBodyMassProps::recompute_mass_properties_from_colliders (rigid_body_components.rs:421).
+static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out) {
+    int nb = (int)W->bodies.size();
+    out.assign(nb, HostMass{});
+    std::vector<int> count(nb, 0), first(nb, -1);
+    for (int ci = 0; ci < (int)W->colliders.size(); ++ci) {
+        int p = W->colliders[ci].parent;
+        if (p >= 0) { if (count[p] == 0) first[p] = ci; count[p]++; }
+    }
+    for (int b = 0; b < nb; ++b) {
+        HostMass& m = out[b];
+        m.pframe[3] = 1.0f;
+        if (count[b] == 1) {
+            const RbColliderDesc& c = W->colliders[first[b]];
+            float mass, pi[3];
+            collider_mass_props(c, mass, pi);
+            for (int k = 0; k < 3; ++k) { m.lcom[k] = c.pos_wrt_parent_t[k]; m.ipi[k] = inv0(pi[k]); }
+            m.inv_mass = inv0(mass);
+            for (int k = 0; k < 4; ++k) m.pframe[k] = c.pos_wrt_parent_q[k];
+        } else if (count[b] > 1) {
+            float M = 0.0f, com[3] = {0, 0, 0};
+            for (const RbColliderDesc& c : W->colliders) {
+                if (c.parent != b) continue;
+                float mass, pi[3];
+                collider_mass_props(c, mass, pi);
+                M = M + mass;
+                for (int k = 0; k < 3; ++k) com[k] = com[k] + c.pos_wrt_parent_t[k] * mass;
+            }
+            if (M != 0.0f) {
+                float invM = 1.0f / M;
+                for (int k = 0; k < 3; ++k) com[k] = com[k] * invM;
+                float I[3] = {0, 0, 0};
+                for (const RbColliderDesc& c : W->colliders) {
+                    if (c.parent != b) continue;
+                    if (!(c.pos_wrt_parent_q[0] == 0.0f && c.pos_wrt_parent_q[1] == 0.0f && c.pos_wrt_parent_q[2] == 0.0f)) {
+                        set_err("multi-collider bodies need axis-aligned colliders%s", "");
+                        return RB_ERR_INVALID;
+                    }
+                    float mass, pi[3];
+                    collider_mass_props(c, mass, pi);
+                    float d[3];
+                    for (int k = 0; k < 3; ++k) d[k] = c.pos_wrt_parent_t[k] - com[k];
+                    if ((d[0] != 0.0f) + (d[1] != 0.0f) + (d[2] != 0.0f) > 1) {
+                        set_err("multi-collider bodies need colliders offset along one axis%s", "");
+                        return RB_ERR_INVALID;
+                    }
+                    float d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                    for (int k = 0; k < 3; ++k) I[k] = I[k] + pi[k] + (d2 - d[k] * d[k]) * mass;
+                }
+                for (int k = 0; k < 3; ++k) { m.lcom[k] = com[k]; m.ipi[k] = inv0(I[k]); }
+                m.inv_mass = inv0(M);
+            }
+        }
+        for (int k = 0; k < 3; ++k) m.pi[k] = inv0(m.ipi[k]);
+    }
+    return RB_OK;
+}
+
+static int launch_init_bodies(RbWorld* W) {
+#if RB_DEVICE_BUILD
+    int blocks = (W->w.nb + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    k_init_bodies<<<blocks, 256, 0, W->stream>>>(W->w);
+    CK(cudaGetLastError());
+    W->kernels++;
+#else
+    GridCtx ctx;
+    init_bodies_phase(ctx, W->w);
+#endif
+    return RB_OK;
+}
+
+static int sync_world(RbWorld* W) {
+#if RB_DEVICE_BUILD
+    CK(cudaStreamSynchronize(W->stream));
+#endif
+    (void)W;
+    return RB_OK;
+}
+
+static int read_state(RbWorld* W, State& s) {
+    int rc = sync_world(W);
+    if (rc != RB_OK) return rc;
+    CK(d2h(&s, W->w.st, sizeof(State)));
+    return RB_OK;
+}
+
+extern "C" {
+
+int rb_abi_version(void) { return RB_ABI_VERSION; }
+const char* rb_last_error(void) { return g_err; }
+
+void rb_integration_parameters_default(RbIntegrationParameters* p) {
+    if (!p) return;
+    p->dt = 1.0f / 60.0f;
+    p->min_ccd_dt = 1.0f / 60.0f / 100.0f;
+    p->contact_natural_frequency = 30.0f;
+    p->contact_damping_ratio = 10.0f;
+    p->static_contact_natural_frequency = 60.0f;
+    p->static_contact_damping_ratio = 10.0f;
+    p->warmstart_coefficient = 1.0f;
+    p->length_unit = 1.0f;
+    p->normalized_allowed_linear_error = 0.005f;
+    p->normalized_max_corrective_velocity = 3.0f;
+    p->normalized_prediction_distance = 0.02f;
+    p->normalized_max_linear_velocity = 400.0f;
+    p->num_solver_iterations = 4;
+    p->num_internal_pgs_iterations = 1;
+    p->num_internal_stabilization_iterations = 1;
+    p->max_ccd_substeps = 1;
+    p->contact_clustering = 1;
+    p->contact_recycling = 1;
+    p->normalized_contact_recycle_distance = 0.05f;
+    p->friction_in_bias_pass = 0;
+    p->warmstart_joints = 0;
+    p->friction_model = 0;
+}
+
+RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
+    RbIntegrationParameters defp;
+    if (!params) { rb_integration_parameters_default(&defp); params = &defp; }
+    if (validate_params(params) != RB_OK) return nullptr;
+#if RB_DEVICE_BUILD
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        set_err("no usable CUDA device (%s, code %d): librapier_b200 has no CPU fallback",
+                e == cudaSuccess ? "device ordinal out of range" : cudaGetErrorString(e), (int)e);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice failed%s", ""); return nullptr; }
+#endif
+    RbWorld* W = new RbWorld();
+    W->params = *params;
+    W->device = device;
+#if RB_DEVICE_BUILD
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    W->num_sms = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) { set_err("device lacks cooperative launch%s", ""); delete W; return nullptr; }
+    cudaStreamCreateWithFlags(&W->stream, cudaStreamNonBlocking);
+    cudaFuncSetAttribute(k_solve_items, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_collide, COLLIDE_THREADS, 0);
+    if (occ < 1) { set_err("k_collide cannot be resident%s", ""); delete W; return nullptr; }
+    W->collide_blocks = W->num_sms * (occ > 2 ? 2 : occ);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_large, LARGE_THREADS, 0);
+    if (occ < 1) { set_err("k_solve_large cannot be resident%s", ""); delete W; return nullptr; }
+    W->large_blocks = W->num_sms * (occ > 2 ? 2 : occ);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_items, ITEM_THREADS, ITEM_SMEM_BYTES);
+    if (occ < 1) occ = 1;
+    W->item_blocks = W->num_sms * occ;
+#else
+    W->emu_smem.assign(ITEM_MAX_BODIES * SB_STRIDE, 0.0f);
+#endif
+    return W;
+}
+
+void rb_world_destroy(RbWorld* W) {
+    if (!W) return;
+#if RB_DEVICE_BUILD
+    cudaSetDevice(W->device);
+    cudaStreamSynchronize(W->stream);
+#endif
+    free_all(W);
+#if RB_DEVICE_BUILD
+    for (cudaEvent_t e : W->prof_ev) cudaEventDestroy(e);
+    if (W->stage_host) cudaFreeHost(W->stage_host);
+    if (W->stream && W->own_stream) cudaStreamDestroy(W->stream);
+#else
+    free(W->stage_host);
+#endif
+    delete W;
+}
+
+int rb_world_set_params(RbWorld* W, const RbIntegrationParameters* params) {
+    if (!W) { set_err("null world%s", ""); return RB_ERR_INVALID; }
+    int rc = validate_params(params);
+    if (rc != RB_OK) return rc;
+    W->params = *params;
+    derive_params(W->params, W->w.prm);
+    return RB_OK;
+}
+
+int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t nc, const RbColliderDesc* colliders,
+                       int32_t nj, const RbJointDesc* joints) {
+    if (!W || nb < 0 || nc < 0 || nj < 0 || (nb && !bodies) || (nc && !colliders) || (nj && !joints)) {
+        set_err("invalid scene arguments%s", "");
+        return RB_ERR_INVALID;
+    }
+#if RB_DEVICE_BUILD
+    CK(cudaSetDevice(W->device));
+    CK(cudaStreamSynchronize(W->stream));
+#endif
+    for (int i = 0; i < nc; ++i) {
+        const RbColliderDesc& c = colliders[i];
+        if ((c.shape != RB_SHAPE_BALL && c.shape != RB_SHAPE_CUBOID) || c.parent >= nb) {
+            set_err("collider with unsupported shape or bad parent%s", "");
+            return RB_ERR_INVALID;
+        }
+    }
+    for (int i = 0; i < nb; ++i)
+        if (bodies[i].body_type != RB_BODY_DYNAMIC && bodies[i].body_type != RB_BODY_FIXED) {
+            set_err("only dynamic and fixed bodies are supported%s", "");
+            return RB_ERR_INVALID;
+        }
+    for (int i = 0; i < nj; ++i) {
+        const RbJointDesc& j = joints[i];
+        if (j.body1 < 0 || j.body1 >= nb || j.body2 < 0 || j.body2 >= nb || (j.locked_axes & ~63u)) {
+            set_err("joint with bad body index or axes%s", "");
+            return RB_ERR_INVALID;
+        }
+    }
+    W->bodies.assign(bodies, bodies + nb);
+    W->colliders.assign(colliders, colliders + nc);
+    W->joints.assign(joints, joints + nj);
+    std::vector<HostMass> mp;
+    int rc = host_mass_props(W, mp);
+    if (rc != RB_OK) return rc;
+
+    free_all(W);
+    World& w = W->w;
+    memset(&w, 0, sizeof(w));
+    derive_params(W->params, w.prm);
+    w.nb = nb; w.nc = nc; w.nj = nj;
+    int ndyn_col = 0;
+    for (int i = 0; i < nc; ++i)
+        if (colliders[i].parent >= 0 && bodies[colliders[i].parent].body_type == RB_BODY_DYNAMIC) ndyn_col++;
+    w.pair_cap = next_pow2_host(std::max(4096, 16 * ndyn_col));
+    w.pair_cap_pow2 = w.pair_cap;
+    w.cons_cap = w.pair_cap;
+    w.joint_cap = std::max(nj, 1);
+    w.item_cap = 4 + (nb + w.pair_cap + nj) / ITEM_TARGET;
+    w.nc_pow2 = next_pow2_host(std::max(nc, 2));
+    const int NB = std::max(nb, 1), NC = std::max(nc, 1), NJ = w.joint_cap;
+
+    ALLOC(w.st, 1);
+    ALLOC(w.b_type, NB); ALLOC(w.b_flags, NB);
+    ALLOC(w.b_pos_t, NB); ALLOC(w.b_pos_q, NB); ALLOC(w.b_linvel, NB); ALLOC(w.b_angvel, NB);
+    ALLOC(w.b_lcom_im, NB); ALLOC(w.b_ipi, NB); ALLOC(w.b_pi, NB); ALLOC(w.b_pframe, NB); ALLOC(w.b_misc, NB);
+    ALLOC(w.b_uforce, NB); ALLOC(w.b_utorque, NB); ALLOC(w.b_wcom, NB); ALLOC(w.b_eim, NB);
+    ALLOC(w.b_eii0, NB); ALLOC(w.b_eii1, NB); ALLOC(w.b_owned, NB);
+    ALLOC(w.s_lin, NB); ALLOC(w.s_ang, NB); ALLOC(w.s_q, NB); ALLOC(w.s_t, NB); ALLOC(w.s_incr_lin, NB); ALLOC(w.s_incr_ang, NB);
+    ALLOC(w.state13, (size_t)NB * 13);
+    ALLOC(w.c_shape, NC); ALLOC(w.c_parent, NC); ALLOC(w.c_he, NC); ALLOC(w.c_rel_t, NC); ALLOC(w.c_rel_q, NC);
+    ALLOC(w.c_mat, NC); ALLOC(w.c_rules, NC); ALLOC(w.c_groups, NC); ALLOC(w.c_pos_t, NC); ALLOC(w.c_pos_q, NC);
+    ALLOC(w.c_aabb_min, NC); ALLOC(w.c_aabb_max, NC); ALLOC(w.c_fat_min, NC); ALLOC(w.c_fat_max, NC);
+    { unsigned long long* p = nullptr; ALLOC(p, w.nc_pow2); w.bp_sort_key = (unsigned*)p; }
+    ALLOC(w.cand_key, w.pair_cap_pow2);
+    ALLOC(w.remap_src, w.pair_cap);
+    for (int k = 0; k < 2; ++k) { ALLOC(w.pb[k].key, w.pair_cap); ALLOC(w.pb[k].rows, (size_t)PR_ROWS * w.pair_cap); }
+    ALLOC(w.todo, 16);
+    ALLOC(w.color_mask, (size_t)NB * 4); ALLOC(w.body_min, NB);
+    ALLOC(w.isl_label, NB); ALLOC(w.isl_nb, NB); ALLOC(w.isl_ncons, NB); ALLOC(w.isl_item, NB);
+    ALLOC(w.scan_tmp, (size_t)1 << 20);
+    ALLOC(w.item_body_start, w.item_cap + 2); ALLOC(w.item_cons_start, w.item_cap + 2); ALLOC(w.item_joint_start, w.item_cap + 2);
+    ALLOC(w.item_cursor, 3 * (w.item_cap + 2));
+    ALLOC(w.item_bodies, NB); ALLOC(w.body_local, NB); ALLOC(w.body_item, NB);
+    ALLOC(w.cons_pair_tmp, w.cons_cap); ALLOC(w.cons_pair, w.cons_cap);
+    ALLOC(w.item_color_off, (size_t)(w.item_cap + 1) * (NUM_COLORS + 1));
+    ALLOC(w.item_jcolor_off, (size_t)(w.item_cap + 1) * (NUM_COLORS + 1));
+    ALLOC(w.color_count, NUM_COLORS + 1); ALLOC(w.color_pos, NUM_COLORS + 1); ALLOC(w.jcolor_pos, NUM_COLORS + 1);
+    ALLOC(w.joint_tmp, NJ); ALLOC(w.joint_sched, NJ);
+    ALLOC(w.cons_hdr, w.cons_cap); ALLOC(w.cons, (size_t)CR_ROWS * w.cons_cap);
+    ALLOC(w.j_info, NJ); ALLOC(w.j_f1_t, NJ); ALLOC(w.j_f1_q, NJ); ALLOC(w.j_f2_t, NJ); ALLOC(w.j_f2_q, NJ);
+    ALLOC(w.j_soft, NJ); ALLOC(w.j_impulses, (size_t)NJ * 6);
+    ALLOC(w.j_rows, (size_t)JR_ROWS * 6 * NJ); ALLOC(w.j_sched_ids, NJ);
+
+    // ---- bodies ----
+    {
+        std::vector<int> type(NB, RB_BODY_FIXED);
+        std::vector<unsigned> flags(NB, 0);
+        std::vector<float4> pt(NB), pq(NB), lv(NB), av(NB), lc(NB), ipi(NB), pi(NB), pf(NB), misc(NB), uf(NB), ut(NB);
+        std::vector<unsigned char> owned(NB, 1);
+        std::vector<int> bmin(NB, 0x7fffffff);
+        for (int i = 0; i < nb; ++i) {
+            const RbBodyDesc& d = bodies[i];
+            type[i] = d.body_type;
+            flags[i] = d.flags;
+            pt[i] = make_float4(d.translation[0], d.translation[1], d.translation[2], 0.f);
+            pq[i] = make_float4(d.rotation[0], d.rotation[1], d.rotation[2], d.rotation[3]);
+            lv[i] = make_float4(d.linvel[0], d.linvel[1], d.linvel[2], 0.f);
+            av[i] = make_float4(d.angvel[0], d.angvel[1], d.angvel[2], 0.f);
+            lc[i] = make_float4(mp[i].lcom[0], mp[i].lcom[1], mp[i].lcom[2], mp[i].inv_mass);
+            ipi[i] = make_float4(mp[i].ipi[0], mp[i].ipi[1], mp[i].ipi[2], 0.f);
+            pi[i] = make_float4(mp[i].pi[0], mp[i].pi[1], mp[i].pi[2], 0.f);
+            pf[i] = make_float4(mp[i].pframe[0], mp[i].pframe[1], mp[i].pframe[2], mp[i].pframe[3]);
+            misc[i] = make_float4(d.linear_damping, d.angular_damping, d.gravity_scale, 0.f);
+            uf[i] = make_float4(d.user_force[0], d.user_force[1], d.user_force[2], 0.f);
+            ut[i] = make_float4(d.user_torque[0], d.user_torque[1], d.user_torque[2], 0.f);
+        }
+        CK(h2d(w.b_type, type.data(), NB * sizeof(int)));
+        CK(h2d(w.b_flags, flags.data(), NB * sizeof(unsigned)));
+        CK(h2d(w.b_pos_t, pt.data(), NB * sizeof(float4)));
+        CK(h2d(w.b_pos_q, pq.data(), NB * sizeof(float4)));
+        CK(h2d(w.b_linvel, lv.data(), NB * sizeof(float4)));
+        CK(h2d(w.b_angvel, av.data(), NB * sizeof(float4)));
+        CK(h2d(w.b_lcom_im, lc.data(), NB * sizeof(float4)));
+        CK(h2d(w.b_ipi, ipi.data(), NB * sizeof(float4)));
+        CK(h2d(w.b_pi, pi.data(), NB * sizeof(float4)));
+        CK(h2d(w.b_pframe, pf.data(), NB * sizeof(float4)));
+        CK(h2d(w.b_misc, misc.data(), NB * sizeof(float4)));
+        CK(h2d(w.b_uforce, uf.data(), NB * sizeof(float4)));
+        CK(h2d(w.b_utorque, ut.data(), NB * sizeof(float4)));
+        CK(h2d(w.b_owned, owned.data(), NB));
+        CK(h2d(w.body_min, bmin.data(), NB * sizeof(int)));
+    }
+    // ---- colliders ----
+    {
+        std::vector<int> shape(NC, 0), parent(NC, -1);
+        std::vector<float4> he(NC), rt(NC), rq(NC), mat(NC);
+        std::vector<int2> rules(NC);
+        std::vector<uint2> groups(NC);
+        for (int i = 0; i < nc; ++i) {
+            const RbColliderDesc& c = colliders[i];
+            shape[i] = c.shape;
+            parent[i] = c.parent;
+            he[i] = make_float4(c.half_extents[0], c.half_extents[1], c.half_extents[2], 0.f);
+            rt[i] = make_float4(c.pos_wrt_parent_t[0], c.pos_wrt_parent_t[1], c.pos_wrt_parent_t[2], 0.f);
+            rq[i] = make_float4(c.pos_wrt_parent_q[0], c.pos_wrt_parent_q[1], c.pos_wrt_parent_q[2], c.pos_wrt_parent_q[3]);
+            mat[i] = make_float4(c.friction, c.restitution, c.contact_skin, 0.f);
+            rules[i] = make_int2(c.friction_combine_rule, c.restitution_combine_rule);
+            groups[i] = make_uint2(c.collision_memberships, c.collision_filter);
+        }
+        CK(h2d(w.c_shape, shape.data(), NC * sizeof(int)));
+        CK(h2d(w.c_parent, parent.data(), NC * sizeof(int)));
+        CK(h2d(w.c_he, he.data(), NC * sizeof(float4)));
+        CK(h2d(w.c_rel_t, rt.data(), NC * sizeof(float4)));
+        CK(h2d(w.c_rel_q, rq.data(), NC * sizeof(float4)));
+        CK(h2d(w.c_mat, mat.data(), NC * sizeof(float4)));
+        CK(h2d(w.c_rules, rules.data(), NC * sizeof(int2)));
+        CK(h2d(w.c_groups, groups.data(), NC * sizeof(uint2)));
+    }
+    // ---- joints: static data, greedy colouring (interaction_groups.rs:59-165), stage order (joints.rs:318-392) ----
+    {
+        std::vector<int4> info(NJ, make_int4(0, 0, 0, -1));
+        std::vector<float4> f1t(NJ), f1q(NJ), f2t(NJ), f2q(NJ);
+        std::vector<float2> soft(NJ);
+        std::vector<unsigned long long> nocontact;
+        struct M128 { unsigned m[4] = {0, 0, 0, 0}; bool test(int c) const { return (m[c >> 5] >> (c & 31)) & 1u; } void set(int c) { m[c >> 5] |= 1u << (c & 31); } };
+        std::vector<M128> jm(NB);
+        std::vector<int> ccount(NUM_COLORS, 0);
+        for (int i = 0; i < nj; ++i) {
+            const RbJointDesc& j = joints[i];
+            bool d1 = bodies[j.body1].body_type == RB_BODY_DYNAMIC, d2 = bodies[j.body2].body_type == RB_BODY_DYNAMIC;
+            int color = -1;
+            if (d1 && d2) {
+                color = 128;
+                for (int c = 0; c < DYN_COLOR_COUNT; ++c)
+                    if (!jm[j.body1].test(c) && !jm[j.body2].test(c)) { color = c; break; }
+                if (color < 128) { jm[j.body1].set(color); jm[j.body2].set(color); }
+            } else if (d1 || d2) {
+                int b = d1 ? j.body1 : j.body2;
+                color = 128;
+                for (int c = 127; c >= 0; --c)
+                    if (!jm[b].test(c)) { color = c; break; }
+                if (color < 128) jm[b].set(color);
+            }
+            if (color >= 0) ccount[color]++;
+            info[i] = make_int4(j.body1, j.body2, (int)j.locked_axes, color);
+            f1t[i] = make_float4(j.local_frame1_t[0], j.local_frame1_t[1], j.local_frame1_t[2], 0.f);
+            f1q[i] = make_float4(j.local_frame1_q[0], j.local_frame1_q[1], j.local_frame1_q[2], j.local_frame1_q[3]);
+            f2t[i] = make_float4(j.local_frame2_t[0], j.local_frame2_t[1], j.local_frame2_t[2], 0.f);
+            f2q[i] = make_float4(j.local_frame2_q[0], j.local_frame2_q[1], j.local_frame2_q[2], j.local_frame2_q[3]);
+            soft[i] = make_float2(j.natural_frequency, j.damping_ratio);
+            if (!j.contacts_enabled) {
+                unsigned lo = (unsigned)std::min(j.body1, j.body2), hi = (unsigned)std::max(j.body1, j.body2);
+                nocontact.push_back(((unsigned long long)lo << 32) | hi);
+            }
+        }
+        std::sort(nocontact.begin(), nocontact.end());
+        nocontact.erase(std::unique(nocontact.begin(), nocontact.end()), nocontact.end());
+        std::vector<int> jpos(NUM_COLORS + 1, -1);
+        int pos = 0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int c = 0; c < 128; ++c) {
+                if (ccount[c] == 0 || (ccount[c] >= BIG_JCOLOR_MIN) != (pass == 0)) continue;
+                jpos[c] = pos++;
+            }
+        if (ccount[128] > 0) jpos[128] = pos++;
+        W->njused = pos;
+        CK(h2d(w.j_info, info.data(), NJ * sizeof(int4)));
+        CK(h2d(w.j_f1_t, f1t.data(), NJ * sizeof(float4)));
+        CK(h2d(w.j_f1_q, f1q.data(), NJ * sizeof(float4)));
+        CK(h2d(w.j_f2_t, f2t.data(), NJ * sizeof(float4)));
+        CK(h2d(w.j_f2_q, f2q.data(), NJ * sizeof(float4)));
+        CK(h2d(w.j_soft, soft.data(), NJ * sizeof(float2)));
+        CK(h2d(w.jcolor_pos, jpos.data(), (NUM_COLORS + 1) * sizeof(int)));
+        w.n_nocontact = (int)nocontact.size();
+        ALLOC(w.nocontact_keys, std::max<size_t>(nocontact.size(), 1));
+        CK(h2d(w.nocontact_keys, nocontact.data(), nocontact.size() * sizeof(unsigned long long)));
+    }
+    {
+        State s;
+        memset(&s, 0, sizeof(s));
+        s.bp_dirty = 1;
+        s.sched_dirty = 1;
+        s.nitems = 1;
+        s.njused_colors = W->njused;
+        CK(h2d(w.st, &s, sizeof(s)));
+        std::vector<int> cp(NUM_COLORS + 1, -1);
+        CK(h2d(w.color_pos, cp.data(), cp.size() * sizeof(int)));
+    }
+    ALLOC(W->stage_dev, (size_t)NB * 13);
+    ALLOC(W->ident_dev, NB);
+    {
+        std::vector<int> id(NB);
+        for (int i = 0; i < NB; ++i) id[i] = i;
+        CK(h2d(W->ident_dev, id.data(), NB * sizeof(int)));
+    }
+#if RB_DEVICE_BUILD
+    if (W->stage_host) { cudaFreeHost(W->stage_host); W->stage_host = nullptr; }
+    CK(cudaMallocHost((void**)&W->stage_host, (size_t)NB * 26 * sizeof(float)));
+#else
+    free(W->stage_host);
+    W->stage_host = (float*)calloc((size_t)NB * 26, sizeof(float));
+#endif
+    W->steps = 0;
+    rc = launch_init_bodies(W);
+    if (rc != RB_OK) return rc;
+    return sync_world(W);
+}
+
+int rb_world_set_body_states(RbWorld* W, int32_t n, const int32_t* indices, const float* pose7, const float* vel6) {
+    if (!W || n < 0 || (n && !indices)) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    int rc = sync_world(W);
+    if (rc != RB_OK) return rc;
+    for (int k = 0; k < n; ++k) {
+        int i = indices[k];
+        if (i < 0 || i >= W->w.nb) { set_err("body index out of range%s", ""); return RB_ERR_INVALID; }
+        if (pose7) {
+            float4 t = make_float4(pose7[k * 7], pose7[k * 7 + 1], pose7[k * 7 + 2], 0.f);
+            float4 q = make_float4(pose7[k * 7 + 3], pose7[k * 7 + 4], pose7[k * 7 + 5], pose7[k * 7 + 6]);
+            CK(h2d(W->w.b_pos_t + i, &t, sizeof(t)));
+            CK(h2d(W->w.b_pos_q + i, &q, sizeof(q)));
+        }
+        if (vel6) {
+            float4 l = make_float4(vel6[k * 6], vel6[k * 6 + 1], vel6[k * 6 + 2], 0.f);
+            float4 a = make_float4(vel6[k * 6 + 3], vel6[k * 6 + 4], vel6[k * 6 + 5], 0.f);
+            CK(h2d(W->w.b_linvel + i, &l, sizeof(l)));
+            CK(h2d(W->w.b_angvel + i, &a, sizeof(a)));
+        }
+    }
+    rc = launch_init_bodies(W);
+    if (rc != RB_OK) return rc;
+    return sync_world(W);
+}
+
+int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sync) {
+    if (!W || !gravity || nsteps < 0) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    if (W->w.nb == 0 && W->w.nc == 0) return RB_OK;
+    Grav g{gravity[0], gravity[1], gravity[2]};
+#if RB_DEVICE_BUILD
+    CK(cudaSetDevice(W->device));
+    if (W->profiling) {
+        while ((int)W->prof_ev.size() < 3 * nsteps) { cudaEvent_t e; CK(cudaEventCreate(&e)); W->prof_ev.push_back(e); }
+        W->prof_steps = nsteps;
+    }
+    for (int s = 0; s < nsteps; ++s) {
+        bool prof = W->profiling;
+        if (prof) CK(cudaEventRecord(W->prof_ev[3 * s], W->stream));
+        void* a1[] = {(void*)&W->w};
+        CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(COLLIDE_THREADS), a1, 0, W->stream));
+        if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 1], W->stream));
+        k_solve_items<<<W->item_blocks, ITEM_THREADS, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
+        CK(cudaGetLastError());
+        void* a2[] = {(void*)&W->w, (void*)&g};
+        CK(cudaLaunchCooperativeKernel((void*)k_solve_large, dim3(W->large_blocks), dim3(LARGE_THREADS), a2, 0, W->stream));
+        if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 2], W->stream));
+        W->kernels += 3;
+    }
+    W->steps += nsteps;
+    if (sync) {
+        CK(cudaStreamSynchronize(W->stream));
+        if (W->profiling && nsteps > 0) {  // mean per-step device time of each launch group over this call
+            float c = 0.f, v = 0.f;
+            for (int s = 0; s < W->prof_steps; ++s) {
+                float a = 0.f, b = 0.f;
+                cudaEventElapsedTime(&a, W->prof_ev[3 * s], W->prof_ev[3 * s + 1]);
+                cudaEventElapsedTime(&b, W->prof_ev[3 * s + 1], W->prof_ev[3 * s + 2]);
+                c += a; v += b;
+            }
+            W->ms_collide = c / W->prof_steps;
+            W->ms_solve = v / W->prof_steps;
+            W->ms_step = W->ms_collide + W->ms_solve;
+        }
+        State st;
+        CK(d2h(&st, W->w.st, sizeof(st)));
+        if (st.error) {
+            int zero = 0;
+            CK(h2d(&W->w.st->error, &zero, sizeof(int)));
+            set_err("device raised status %s%d (capacity overflow)", "", st.error);
+            return st.error;
+        }
+    }
+#else
+    (void)sync;
+    for (int s = 0; s < nsteps; ++s) {
+        GridCtx gctx;
+        collide_pipeline(gctx, W->w);
+        BlockCtx bctx;
+        SmemBodies sb;
+        sb.s = W->emu_smem.data();
+        BlockExec bex;
+        bex.c = &bctx;
+        int n = W->w.st->nitems;
+        for (int item = 1; item < n; ++item) solve_item(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
+        if (W->w.st->nlarge_bodies > 0) {
+            GlobalBodies gb;
+            gb.w = &W->w;
+            GridExec gex;
+            gex.c = &gctx;
+            solve_item(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
+        }
+        W->kernels += 3;
+    }
+    W->steps += nsteps;
+    if (W->w.st->error) { int e = W->w.st->error; W->w.st->error = 0; set_err("device raised status %s%d", "", e); return e; }
+#endif
+    return RB_OK;
+}
+
+int rb_world_synchronize(RbWorld* W) {
+    if (!W) return RB_ERR_INVALID;
+    return sync_world(W);
+}
+
+int rb_world_num_bodies(RbWorld* W) { return W ? W->w.nb : RB_ERR_INVALID; }
+
+int rb_world_get_body_states(RbWorld* W, float* pose7, float* vel6) {
+    if (!W) return RB_ERR_INVALID;
+    int rc = sync_world(W);
+    if (rc != RB_OK) return rc;
+    int nb = W->w.nb;
+    std::vector<float> s((size_t)nb * 13);
+    CK(d2h(s.data(), W->w.state13, s.size() * sizeof(float)));
+    for (int i = 0; i < nb; ++i) {
+        if (pose7) memcpy(pose7 + (size_t)i * 7, &s[(size_t)i * 13], 7 * sizeof(float));
+        if (vel6) memcpy(vel6 + (size_t)i * 6, &s[(size_t)i * 13 + 7], 6 * sizeof(float));
+    }
+    return RB_OK;
+}
+
+int rb_world_enable_profiling(RbWorld* W, int32_t enabled) {
+    if (!W) return RB_ERR_INVALID;
+    W->profiling = enabled != 0;
+    return RB_OK;
+}
+
+int rb_world_get_counters(RbWorld* W, RbCounters* out) {
+    if (!W || !out) return RB_ERR_INVALID;
+    State st;
+    int rc = read_state(W, st);
+    if (rc != RB_OK) return rc;
+    memset(out, 0, sizeof(*out));
+    out->step_ms = W->ms_step;
+    out->collision_detection_ms = W->ms_collide;
+    out->solver_ms = W->ms_solve;
+    out->num_bodies = W->w.nb;
+    out->num_colliders = W->w.nc;
+    out->num_joints = W->w.nj;
+    out->num_pairs = st.npairs;
+    out->num_active_manifolds = st.ncons;
+    out->num_islands = st.nitems;
+    out->num_colors = st.nused_colors;
+    out->broad_phase_ran = st.bp_ran;
+    out->schedule_rebuilt = st.sched_ran;
+    out->kernels_launched = W->kernels;
+    out->steps = W->steps;
+    return RB_OK;
+}
+
+static int fetch_rows(RbWorld* W, const State& st, int row, int count, std::vector<float4>& out) {
+    out.resize((size_t)count * std::max(st.npairs, 1));
+    for (int r = 0; r < count; ++r)
+        CK(d2h(out.data() + (size_t)r * st.npairs, W->w.pb[st.cur].rows + (size_t)(row + r) * W->w.pair_cap, (size_t)st.npairs * sizeof(float4)));
+    return RB_OK;
+}
+
+int rb_world_get_contact_pairs(RbWorld* W, int32_t cap, int32_t* pair_colliders, int32_t* num_contacts, int32_t* color,
+                               float* normal, float* impulses) {
+    if (!W) return RB_ERR_INVALID;
+    State st;
+    int rc = read_state(W, st);
+    if (rc != RB_OK) return rc;
+    int n = st.npairs;
+    if (cap <= 0 || n == 0) return n;
+    std::vector<unsigned long long> keys(n);
+    CK(d2h(keys.data(), W->w.pb[st.cur].key, (size_t)n * 8));
+    std::vector<float4> info, nrm, pd, a1;
+    if ((rc = fetch_rows(W, st, PR_INFO, 1, info)) != RB_OK) return rc;
+    if ((rc = fetch_rows(W, st, PR_NORMAL, 1, nrm)) != RB_OK) return rc;
+    if ((rc = fetch_rows(W, st, PR_PD, MAX_PTS, pd)) != RB_OK) return rc;
+    if ((rc = fetch_rows(W, st, PR_A1, MAX_PTS, a1)) != RB_OK) return rc;
+    for (int i = 0; i < n && i < cap; ++i) {
+        int nsc, col;
+        memcpy(&nsc, &info[i].z, 4);
+        memcpy(&col, &info[i].w, 4);
+        if (pair_colliders) { pair_colliders[2 * i] = (int)(keys[i] >> 32); pair_colliders[2 * i + 1] = (int)(keys[i] & 0xffffffffu); }
+        if (num_contacts) num_contacts[i] = nsc;
+        if (color) color[i] = col;
+        if (normal) { normal[3 * i] = nrm[i].x; normal[3 * i + 1] = nrm[i].y; normal[3 * i + 2] = nrm[i].z; }
+        if (impulses)
+            for (int k = 0; k < 4; ++k) {
+                float v = 0.0f;
+                if (k < nsc) {
+                    int cid;
+                    memcpy(&cid, &a1[(size_t)k * n + i].w, 4);
+                    v = pd[(size_t)cid * n + i].x;
+                }
+                impulses[4 * i + k] = v;
+            }
+    }
+    return n;
+}
+
+int64_t rb_world_debug_read(RbWorld* W, const char* table, void* dst, int64_t cap) {
+    if (!W || !table) return RB_ERR_INVALID;
+    State st;
+    int rc = read_state(W, st);
+    if (rc != RB_OK) return rc;
+    std::string t(table);
+    std::vector<unsigned char> out;
+    auto put = [&](const void* p, size_t n) { size_t o = out.size(); out.resize(o + n); memcpy(out.data() + o, p, n); };
+    const int n = st.npairs;
+    std::vector<float4> info;
+    if (t.rfind("pair_", 0) == 0 && n > 0) { if ((rc = fetch_rows(W, st, PR_INFO, 1, info)) != RB_OK) return rc; }
+    auto geti = [](float f) { int i; memcpy(&i, &f, 4); return i; };
+    if (t == "pair_keys") {
+        std::vector<unsigned long long> keys(std::max(n, 1));
+        CK(d2h(keys.data(), W->w.pb[st.cur].key, (size_t)n * 8));
+        put(keys.data(), (size_t)n * 8);
+    } else if (t == "pair_nsc" || t == "pair_npts" || t == "pair_color") {
+        for (int i = 0; i < n; ++i) { int v = t == "pair_nsc" ? geti(info[i].z) : (t == "pair_npts" ? geti(info[i].y) : geti(info[i].w)); put(&v, 4); }
+    } else if (t == "pair_normal") {
+        std::vector<float4> r;
+        if (n > 0 && (rc = fetch_rows(W, st, PR_NORMAL, 1, r)) != RB_OK) return rc;
+        for (int i = 0; i < n; ++i) put(&r[i], 12);
+    } else if (t == "pair_points") {
+        std::vector<float4> pa, pb, pd;
+        if (n > 0) { fetch_rows(W, st, PR_PA, MAX_PTS, pa); fetch_rows(W, st, PR_PB, MAX_PTS, pb); fetch_rows(W, st, PR_PD, MAX_PTS, pd); }
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < 4; ++k) {
+                float rec[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                if (k < geti(info[i].y)) {
+                    float4 a = pa[(size_t)k * n + i], b = pb[(size_t)k * n + i], d = pd[(size_t)k * n + i];
+                    rec[0] = a.x; rec[1] = a.y; rec[2] = a.z; rec[3] = b.x; rec[4] = b.y; rec[5] = b.z; rec[6] = a.w; rec[7] = b.w; rec[8] = d.w;
+                }
+                put(rec, 36);
+            }
+    } else if (t == "pair_data") {
+        std::vector<float4> pd, tw, d1, d2;
+        if (n > 0) { fetch_rows(W, st, PR_PD, MAX_PTS, pd); fetch_rows(W, st, PR_TW, MAX_PTS, tw); fetch_rows(W, st, PR_DP1, MAX_PTS, d1); fetch_rows(W, st, PR_DP2, MAX_PTS, d2); }
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < 4; ++k) {
+                float rec[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                if (k < geti(info[i].y)) {
+                    float4 a = pd[(size_t)k * n + i], b = tw[(size_t)k * n + i], c = d1[(size_t)k * n + i], d = d2[(size_t)k * n + i];
+                    rec[0] = a.x; rec[1] = a.y; rec[2] = a.z; rec[3] = b.x; rec[4] = b.y; rec[5] = b.z;
+                    rec[6] = c.x; rec[7] = c.y; rec[8] = c.z; rec[9] = d.x; rec[10] = d.y; rec[11] = d.z;
+                }
+                put(rec, 48);
+            }
+    } else if (t == "pair_sc") {
+        std::vector<float4> a1, a2;
+        if (n > 0) { fetch_rows(W, st, PR_A1, MAX_PTS, a1); fetch_rows(W, st, PR_A2, MAX_PTS, a2); }
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < 4; ++k) {
+                float rec[6] = {0, 0, 0, 0, 0, 0};
+                int cid = -1;
+                if (k < geti(info[i].z)) {
+                    float4 a = a1[(size_t)k * n + i], b = a2[(size_t)k * n + i];
+                    rec[0] = a.x; rec[1] = a.y; rec[2] = a.z; rec[3] = b.x; rec[4] = b.y; rec[5] = b.z;
+                    cid = geti(a.w);
+                }
+                put(rec, 24);
+                put(&cid, 4);
+            }
+    } else if (t == "collider_aabb" || t == "collider_fat") {
+        int nc = W->w.nc;
+        std::vector<float4> lo(std::max(nc, 1)), hi(std::max(nc, 1));
+        CK(d2h(lo.data(), t == "collider_aabb" ? W->w.c_aabb_min : W->w.c_fat_min, (size_t)nc * 16));
+        CK(d2h(hi.data(), t == "collider_aabb" ? W->w.c_aabb_max : W->w.c_fat_max, (size_t)nc * 16));
+        for (int i = 0; i < nc; ++i) { put(&lo[i], 12); put(&hi[i], 12); }
+    } else if (t == "body_mprops") {
+        int nb = W->w.nb;
+        std::vector<float4> lc(std::max(nb, 1)), ipi(std::max(nb, 1)), wc(std::max(nb, 1)), e0(std::max(nb, 1));
+        std::vector<float2> e1(std::max(nb, 1));
+        CK(d2h(lc.data(), W->w.b_lcom_im, (size_t)nb * 16)); CK(d2h(ipi.data(), W->w.b_ipi, (size_t)nb * 16));
+        CK(d2h(wc.data(), W->w.b_wcom, (size_t)nb * 16)); CK(d2h(e0.data(), W->w.b_eii0, (size_t)nb * 16));
+        CK(d2h(e1.data(), W->w.b_eii1, (size_t)nb * 8));
+        for (int i = 0; i < nb; ++i) { put(&lc[i], 16); put(&ipi[i], 12); put(&wc[i], 12); put(&e0[i], 16); put(&e1[i], 8); }
+    } else if (t == "joint_impulses") {
+        std::vector<float> v((size_t)std::max(W->w.nj, 1) * 6);
+        CK(d2h(v.data(), W->w.j_impulses, (size_t)W->w.nj * 24));
+        put(v.data(), (size_t)W->w.nj * 24);
+    } else if (t == "joint_color") {
+        std::vector<int4> v(std::max(W->w.nj, 1));
+        CK(d2h(v.data(), W->w.j_info, (size_t)W->w.nj * 16));
+        for (int i = 0; i < W->w.nj; ++i) put(&v[i].w, 4);
+    } else if (t == "body_item" || t == "isl_label") {
+        std::vector<int> v(std::max(W->w.nb, 1));
+        CK(d2h(v.data(), t == "body_item" ? W->w.body_item : W->w.isl_label, (size_t)W->w.nb * 4));
+        put(v.data(), (size_t)W->w.nb * 4);
+    } else if (t == "state") {
+        put(&st, sizeof(st));
+    } else {
+        set_err("unknown debug table %s", table);
+        return RB_ERR_INVALID;
+    }
+    int64_t total = (int64_t)out.size();
+    int64_t ncopy = total < cap ? total : cap;
+    if (dst && ncopy > 0) memcpy(dst, out.data(), (size_t)ncopy);
+    return total;
+}
+
+// ---- multi-GPU sharding ----
+int rb_world_label_components(RbWorld* W, int32_t* component_of_body) {
+    if (!W || !component_of_body) return RB_ERR_INVALID;
+    // Run the collision pipeline once (it leaves poses untouched) so the island labels are current.
+#if RB_DEVICE_BUILD
+    CK(cudaSetDevice(W->device));
+    int one = 1;
+    CK(cudaStreamSynchronize(W->stream));
+    CK(h2d(&W->w.st->sched_dirty, &one, sizeof(int)));
+    void* a1[] = {(void*)&W->w};
+    CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(COLLIDE_THREADS), a1, 0, W->stream));
+    W->kernels++;
+#else
+    W->w.st->sched_dirty = 1;
+    GridCtx g;
+    collide_pipeline(g, W->w);
+#endif
+    int rc = sync_world(W);
+    if (rc != RB_OK) return rc;
+    CK(d2h(component_of_body, W->w.isl_label, (size_t)W->w.nb * sizeof(int)));
+    for (int i = 0; i < W->w.nb; ++i)
+        if (W->bodies[i].body_type != RB_BODY_DYNAMIC) component_of_body[i] = -1;
+    return RB_OK;
+}
+
+int rb_world_set_owned_bodies(RbWorld* W, const uint8_t* owned) {
+    if (!W || !owned) return RB_ERR_INVALID;
+    int rc = sync_world(W);
+    if (rc != RB_OK) return rc;
+    CK(h2d(W->w.b_owned, owned, (size_t)W->w.nb));
+    // Ownership changes the pair filter: drop the pair table and every derived structure.
+    State st;
+    CK(d2h(&st, W->w.st, sizeof(st)));
+    st.npairs = 0; st.bp_dirty = 1; st.sched_dirty = 1; st.ntodo = 0; st.ncons = 0; st.nitems = 1; st.nlarge_bodies = 0;
+    CK(h2d(W->w.st, &st, sizeof(st)));
+    CK(dev_set(W->w.color_mask, 0, (size_t)std::max(W->w.nb, 1) * 16));
+    CK(dev_set(W->w.c_fat_min, 0, (size_t)std::max(W->w.nc, 1) * 16));
+    CK(dev_set(W->w.c_fat_max, 0, (size_t)std::max(W->w.nc, 1) * 16));
+    return RB_OK;
+}
+
+int rb_world_state_buffer(RbWorld* W, void** device_ptr, int64_t* bytes) {
+    if (!W || !device_ptr || !bytes) return RB_ERR_INVALID;
+    *device_ptr = W->w.state13;
+    *bytes = (int64_t)W->w.nb * 13 * 4;
+    return RB_OK;
+}
+
+// Imports externally simulated body states (device pointers): idx[n] body indices, src[n*13].
+int rb_world_import_states(RbWorld* W, const int32_t* idx_dev, const float* src_dev, int32_t n) {
+    if (!W || n < 0) return RB_ERR_INVALID;
+    if (n == 0) return RB_OK;
+#if RB_DEVICE_BUILD
+    CK(cudaSetDevice(W->device));
+    k_import_states<<<(n + 255) / 256, 256, 0, W->stream>>>(W->w, idx_dev, src_dev, n);
+    CK(cudaGetLastError());
+    W->kernels++;
+#else
+    GridCtx g;
+    import_states_phase(g, W->w, idx_dev, src_dev, n);
+#endif
+    return RB_OK;
+}
+
+// CUDA stream of the world (for callers that enqueue NCCL work behind the step).
+void* rb_world_stream(RbWorld* W) {
+#if RB_DEVICE_BUILD
+    return W ? (void*)W->stream : nullptr;
+#else
+    (void)W;
+    return nullptr;
+#endif
+}
+
+
+// Use a caller-provided CUDA stream (e.g. torch's current stream) for all of this world's work.
+int rb_world_set_stream(RbWorld* W, void* stream) {
+    if (!W) return RB_ERR_INVALID;
+#if RB_DEVICE_BUILD
+    CK(cudaStreamSynchronize(W->stream));
+    if (W->own_stream && W->stream) cudaStreamDestroy(W->stream);
+    W->stream = (cudaStream_t)stream;
+    W->own_stream = false;
+#else
+    (void)stream;
+#endif
+    return RB_OK;
+}
+
+// End-to-end step with HOST buffers (the call a host-side RigidBodySet owner makes every step):
+// uploads all body states (13 floats/body: t3 q4 lin3 ang3) from host memory, runs one step, and
+// downloads the resulting states.  Copies go through an internal pinned staging buffer.
+int rb_world_step_host(RbWorld* W, const float gravity[3], const float* in_state13, float* out_state13) {
+    if (!W || !gravity) return RB_ERR_INVALID;
+    const size_t n = (size_t)W->w.nb * 13;
+    if (in_state13) {
+        memcpy(W->stage_host, in_state13, n * sizeof(float));
+#if RB_DEVICE_BUILD
+        CK(cudaSetDevice(W->device));
+        CK(cudaMemcpyAsync(W->stage_dev, W->stage_host, n * sizeof(float), cudaMemcpyHostToDevice, W->stream));
+#else
+        memcpy(W->stage_dev, W->stage_host, n * sizeof(float));
+#endif
+        int rc = rb_world_import_states(W, W->ident_dev, W->stage_dev, W->w.nb);
+        if (rc != RB_OK) return rc;
+    }
+    int rc = rb_world_step(W, gravity, 1, 0);
+    if (rc != RB_OK) return rc;
+    if (out_state13) {
+#if RB_DEVICE_BUILD
+        CK(cudaMemcpyAsync(W->stage_host + n, W->w.state13, n * sizeof(float), cudaMemcpyDeviceToHost, W->stream));
+        CK(cudaStreamSynchronize(W->stream));
+#else
+        memcpy(W->stage_host + n, W->w.state13, n * sizeof(float));
+#endif
+        memcpy(out_state13, W->stage_host + n, n * sizeof(float));
+    } else {
+        rc = sync_world(W);
+    }
+    return rc;
+}
+
+}  // extern "C"

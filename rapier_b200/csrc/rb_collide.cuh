@@ -1,0 +1,823 @@
+// rb_collide.cuh -- collision-detection and scheduling phases of the step, executed by ONE
+// cooperative persistent kernel (k_collide): collider refresh -> [broad phase] -> narrow phase ->
+// [colouring, islands, schedule].  Bracketed sections run only when a device-side flag says the
+// fat-AABB set / touching set changed (the reference does the same work incrementally on the CPU).
+//
+// Reference path replaced:
+//   a2 Collider::compute_broad_phase_aabb           src/geometry/collider.rs:553-599
+//   a3 BroadPhaseBvh::update / set_aabb             src/geometry/broad_phase_bvh/update.rs:35-602, mod.rs:235-263
+//   a4 NarrowPhase::compute_contacts / process_pair src/geometry/narrow_phase/contacts.rs:22-293, pair_update.rs:67-680
+//   a5 apply_pair_transitions + colouring           contacts.rs:300-385, narrow_phase/mod.rs:87-172
+//   a6 maintain_solver_contact_graph                narrow_phase/solver_graph.rs:129-361 (here: islands + schedule)
+#pragma once
+#include "rb_geom.cuh"
+
+namespace rb {
+
+constexpr int ITEM_TARGET = 128;   // cost (max(bodies, constraints)) packed into one CTA work item
+constexpr int ITEM_BODY_CAP = 256; // islands above either cap go to the grid-wide "large" item 0
+constexpr int ITEM_CONS_CAP = 3072;
+constexpr int ITEM_MAX_BODIES = ITEM_BODY_CAP + ITEM_TARGET;  // shared-memory sizing of the item kernel
+constexpr int BIG_COLOR_MIN = 125;   // ceil(n/4) >= 32 chunks (init.rs:169: CHUNK_BATCH*LAYOUT_REF_WORKERS/2)
+constexpr int BIG_JCOLOR_MIN = 64;   // joints.rs:340: JOINT_BATCH*LAYOUT_REF_WORKERS/2
+
+RB_HD bool body_is_sim(const World& w, int b) {  // dynamic and simulated by this rank
+    return b >= 0 && w.b_type[b] == BODY_DYNAMIC && w.b_owned[b] != 0;
+}
+RB_HD pose body_pose(const World& w, int b) { return mkpose(mkq(w.b_pos_q[b]), xyz(w.b_pos_t[b])); }
+RB_HD pose collider_pose(const World& w, int c) { return mkpose(mkq(w.c_pos_q[c]), xyz(w.c_pos_t[c])); }
+
+// ------------------------------------------------------------------------------------------------
+// P0: collider world poses, broad-phase AABBs and fat-AABB change detection
+// (substep.rs:103-146 + refresh_moved_collider_aabbs substep.rs:229-240 -> BroadPhaseBvh::set_aabb).
+// ------------------------------------------------------------------------------------------------
+template <class Ctx>
+RB_PHASE void phase_refresh_colliders(const Ctx& ctx, const World& w) {
+    for (int c = ctx.gtid; c < w.nc; c += ctx.gsize) {
+        int parent = w.c_parent[c];
+        pose rel = mkpose(mkq(w.c_rel_q[c]), xyz(w.c_rel_t[c]));
+        pose p = parent >= 0 ? pmul(body_pose(w, parent), rel) : rel;
+        w.c_pos_t[c] = f4(p.t, 0.0f);
+        w.c_pos_q[c] = f4(p.q);
+        vec3 lo, hi;
+        shape_aabb(w.c_shape[c], xyz(w.c_he[c]), p, lo, hi);
+        float l = w.c_mat[c].z + w.prm.prediction / 2.0f;
+        lo = mk3(lo.x - l, lo.y - l, lo.z - l);
+        hi = mk3(hi.x + l, hi.y + l, hi.z + l);
+        w.c_aabb_min[c] = f4(lo, 0.0f);
+        w.c_aabb_max[c] = f4(hi, 0.0f);
+        float4 fmin = w.c_fat_min[c], fmax = w.c_fat_max[c];
+        bool valid = fmin.w != 0.0f;
+        bool contains = valid && fmin.x <= lo.x && fmin.y <= lo.y && fmin.z <= lo.z && fmax.x >= hi.x && fmax.y >= hi.y &&
+                        fmax.z >= hi.z;
+        if (!contains) {
+            float s = w.prm.fat_skin;
+            w.c_fat_min[c] = make_float4(lo.x - s, lo.y - s, lo.z - s, 1.0f);
+            w.c_fat_max[c] = make_float4(hi.x + s, hi.y + s, hi.z + s, 1.0f);
+            w.st->bp_dirty = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bitonic sort of 64-bit keys, grid-synchronised between passes (device radix sort is future work:
+// this section only runs when a fat AABB changed).
+// ------------------------------------------------------------------------------------------------
+template <class Ctx>
+RB_PHASE void grid_bitonic_sort(const Ctx& ctx, unsigned long long* a, int n) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = ctx.gtid; i < n; i += ctx.gsize) {
+                int l = i ^ j;
+                if (l > i) {
+                    unsigned long long x = a[i], y = a[l];
+                    bool asc = (i & k) == 0;
+                    if ((x > y) == asc) { a[i] = y; a[l] = x; }
+                }
+            }
+            ctx.grid_sync();
+        }
+    }
+}
+
+RB_HD int next_pow2(int n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+RB_HD unsigned sortable_float(float f) {
+    unsigned u = as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+RB_HD int bsearch_u64(const unsigned long long* a, int n, unsigned long long key) {
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        unsigned long long v = a[mid];
+        if (v == key) return mid;
+        if (v < key) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+// update.rs:334-396 filter_new
+RB_HD bool pair_allowed(const World& w, int c1, int c2) {
+    int p1 = w.c_parent[c1], p2 = w.c_parent[c2];
+    if (p1 >= 0 && p1 == p2) return false;
+    bool d1 = body_is_sim(w, p1), d2 = body_is_sim(w, p2);
+    if (!d1 && !d2) return false;
+    uint2 g1 = w.c_groups[c1], g2 = w.c_groups[c2];
+    if (!((g1.x & g2.y) != 0 && (g2.x & g1.y) != 0)) return false;
+    if (w.n_nocontact > 0 && p1 >= 0 && p2 >= 0) {
+        unsigned lo = (unsigned)(p1 < p2 ? p1 : p2), hi = (unsigned)(p1 < p2 ? p2 : p1);
+        if (bsearch_u64(w.nocontact_keys, w.n_nocontact, ((unsigned long long)lo << 32) | hi) >= 0) return false;
+    }
+    return true;
+}
+
+RB_HD void clear_color_bits(const World& w, int color, int cb0, int cb1) {
+    if (color < COLOR_OVERFLOW) {
+        unsigned bit = ~(1u << (color & 31));
+        if (cb0 >= 0) atomic_and(&w.color_mask[cb0 * 4 + (color >> 5)], bit);
+        if (cb1 >= 0) atomic_and(&w.color_mask[cb1 * 4 + (color >> 5)], bit);
+    }
+}
+
+// P1: sort-and-sweep broad phase + merge with the persistent pair table.
+template <class Ctx>
+RB_PHASE void section_broad_phase(const Ctx& ctx, const World& w) {
+    State* st = w.st;
+    unsigned long long* skey = (unsigned long long*)w.bp_sort_key;  // [nc_pow2] (min-x key << 32) | collider
+    for (int i = ctx.gtid; i < w.nc_pow2; i += ctx.gsize) {
+        skey[i] = i < w.nc ? (((unsigned long long)sortable_float(w.c_fat_min[i].x) << 32) | (unsigned)i) : ~0ull;
+    }
+    if (ctx.gtid == 0) st->ncand = 0;
+    ctx.grid_sync();
+    grid_bitonic_sort(ctx, skey, w.nc_pow2);
+    // sweep: one warp per sorted collider, lanes stride over the following colliders.
+    for (int wi = ctx.gwarp; wi < w.nc; wi += ctx.ngwarps) {
+        int ci = (int)(skey[wi] & 0xffffffffu);
+        float4 amin = w.c_fat_min[ci], amax = w.c_fat_max[ci];
+        for (int base = wi + 1; base < w.nc; base += ctx.nlanes) {
+            int j = base + ctx.lane;
+            bool stop = true;
+            if (j < w.nc) {
+                int cj = (int)(skey[j] & 0xffffffffu);
+                float4 bmin = w.c_fat_min[cj];
+                stop = bmin.x > amax.x;
+                if (!stop) {
+                    float4 bmax = w.c_fat_max[cj];
+                    bool hit = amin.x <= bmax.x && amin.y <= bmax.y && amin.z <= bmax.z && amax.x >= bmin.x && amax.y >= bmin.y &&
+                               amax.z >= bmin.z;
+                    if (hit) {
+                        int c1 = ci < cj ? ci : cj, c2 = ci < cj ? cj : ci;
+                        if (pair_allowed(w, c1, c2)) {
+                            int slot = atomic_add(&st->ncand, 1);
+                            if (slot < w.pair_cap) w.cand_key[slot] = ((unsigned long long)(unsigned)c1 << 32) | (unsigned)c2;
+                        }
+                    }
+                }
+            }
+            if (ctx.warp_any(stop)) break;
+        }
+    }
+    ctx.grid_sync();
+    int ncand = st->ncand;
+    if (ncand > w.pair_cap) {  // capacity overflow: keep the old pair set, raise the error
+        if (ctx.gtid == 0) { st->error = -4; st->bp_dirty = 0; }
+        ctx.grid_sync();
+        return;
+    }
+    int np2 = next_pow2(ncand < 2 ? 2 : ncand);
+    for (int i = ncand + ctx.gtid; i < np2; i += ctx.gsize) w.cand_key[i] = ~0ull;
+    ctx.grid_sync();
+    grid_bitonic_sort(ctx, w.cand_key, np2);
+    // merge: carry persistent per-pair state from the old sorted table to the new one.
+    int cur = st->cur, nxt = 1 - cur, nold = st->npairs;
+    const unsigned long long* okey = w.pb[cur].key;
+    for (int i = ctx.gtid; i < ncand; i += ctx.gsize) {
+        unsigned long long k = w.cand_key[i];
+        w.pb[nxt].key[i] = k;
+        w.remap_src[i] = bsearch_u64(okey, nold, k);
+    }
+    ctx.grid_sync();
+    for (long long e = ctx.gtid; e < (long long)ncand * PR_ROWS; e += ctx.gsize) {
+        int r = (int)(e / ncand), i = (int)(e % ncand);
+        int src = w.remap_src[i];
+        float4 v;
+        if (src >= 0) {
+            v = prow(w, cur, r, src);
+        } else {
+            v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r == PR_INFO) v.w = as_float_i(COLOR_UNCOLORED);
+            if (r == PR_BODIES) {
+                unsigned long long k = w.cand_key[i];
+                int c1 = (int)(k >> 32), c2 = (int)(k & 0xffffffffu);
+                v = make_float4(as_float_i(-1), as_float_i(-1), as_float_i(w.c_parent[c1]), as_float_i(w.c_parent[c2]));
+            }
+        }
+        prow(w, nxt, r, i) = v;
+    }
+    // removed pairs: end-touch frees the colour (contacts.rs:333-335).
+    for (int j = ctx.gtid; j < nold; j += ctx.gsize) {
+        if (bsearch_u64(w.cand_key, ncand, okey[j]) < 0) {
+            float4 info = prow(w, cur, PR_INFO, j), bod = prow(w, cur, PR_BODIES, j);
+            clear_color_bits(w, as_int(info.w), as_int(bod.x), as_int(bod.y));
+        }
+    }
+    ctx.grid_sync();
+    if (ctx.gtid == 0) {
+        st->cur = nxt;
+        st->npairs = ncand;
+        st->bp_dirty = 0;
+        st->bp_ran = 1;
+        st->sched_dirty = 1;
+    }
+    ctx.grid_sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// P2: narrow phase, one thread per pair (process_pair, pair_update.rs:67-680).
+// ------------------------------------------------------------------------------------------------
+RB_HD float combine_coeff(float c1, float c2, int r1, int r2) {  // coefficient_combine_rule.rs:51-84
+    int rule = r1 > r2 ? r1 : r2;
+    if (rule == 0) return (c1 + c2) / 2.0f;
+    if (rule == 1) return fabsf(min2(c1, c2));
+    if (rule == 2) return c1 * c2;
+    if (rule == 3) return max2(c1, c2);
+    if (rule == 4) return clampf(c1 + c2, 0.0f, 1.0f);
+    return sqrtf(max2(c1, 0.0f) * max2(c2, 0.0f));
+}
+
+RB_HD float pose_drift(const pose& base, const pose& cur, float max_extent) {  // contact_pair.rs:299-323
+    float trans = norm(cur.t - base.t);
+    quat d = qmul(cur.q, qconj(base.q));
+    float chord = 2.0f * norm(mk3(d.x, d.y, d.z)) * max_extent;
+    return trans + chord;
+}
+RB_HD float rot_cos(quat base, quat cur) {  // contact_pair.rs:284-293
+    float c = qdot(base, cur);
+    return 2.0f * c * c - 1.0f;
+}
+RB_HD float origin_radius(int shape, vec3 he) { return shape == SHAPE_BALL ? norm(mk3(he.x, he.x, he.x)) : norm(he); }
+
+// manifold_reduction.rs:4-84
+RB_HD void reduce_manifold(const RawManifold& m, int* sel, int& nsel, float prediction) {
+    if (m.n <= 4) return;
+    sel[0] = sel[1] = sel[2] = sel[3] = -1;
+    float deepest = FMAX32;
+    for (int i = 0; i < m.n; ++i)
+        if (m.pt[i].dist < deepest) { deepest = m.pt[i].dist; sel[0] = i; }
+    if (sel[0] < 0) { nsel = 0; return; }
+    vec3 a = m.pt[sel[0]].p1;
+    float furthest = -FMAX32;
+    for (int i = 0; i < m.n; ++i) {
+        float d = norm2(m.pt[i].p1 - a);
+        if (i != sel[0] && m.pt[i].dist <= prediction && d > furthest) { furthest = d; sel[1] = i; }
+    }
+    if (sel[1] < 0) { nsel = 1; return; }
+    vec3 b = m.pt[sel[1]].p1;
+    if (a.x == b.x && a.y == b.y && a.z == b.z) { nsel = 1; return; }
+    vec3 tangent = cross3(b - a, m.n1);
+    float mn = FMAX32, mx = -FMAX32;
+    for (int i = 0; i < m.n; ++i) {
+        if (i == sel[0] || i == sel[1] || m.pt[i].dist > prediction) continue;
+        float d = dot3(m.pt[i].p1 - a, tangent);
+        if (d < mn) { mn = d; sel[2] = i; }
+        if (d > mx) { mx = d; sel[3] = i; }
+    }
+    if (sel[2] < 0) nsel = 2;
+    else if (sel[2] == sel[3]) nsel = 3;
+    else nsel = 4;
+}
+
+template <class Ctx>
+RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
+    State* st = w.st;
+    const int buf = st->cur, np = st->npairs;
+    const float prediction = w.prm.prediction, dt = w.prm.dt;
+    const float recycle = w.prm.contact_recycling ? w.prm.recycle_dist : 0.0f;
+    for (int i = ctx.gtid; i < np; i += ctx.gsize) {
+        unsigned long long key = w.pb[buf].key[i];
+        int c1 = (int)(key >> 32), c2 = (int)(key & 0xffffffffu);
+        pose cp1 = collider_pose(w, c1), cp2 = collider_pose(w, c2);
+        float4 info = prow(w, buf, PR_INFO, i);
+        int flags = as_int(info.x), npts_old = as_int(info.y), nsc_old = as_int(info.z), color = as_int(info.w);
+        pose p12 = pinv_mul(cp1, cp2);
+        // contact recycling (pair_update.rs:111-171)
+        if (recycle > 0.0f && (flags & 1)) {
+            float4 rt = prow(w, buf, PR_RT, i);
+            pose base = mkpose(mkq(prow(w, buf, PR_RQ, i)), xyz(rt));
+            float drift = pose_drift(base, p12, rt.w);
+            float rc = min2(rot_cos(mkq(prow(w, buf, PR_ROT1, i)), cp1.q), rot_cos(mkq(prow(w, buf, PR_ROT2, i)), cp2.q));
+            if (drift <= prow(w, buf, PR_LN1, i).w && rc > 0.98f) continue;
+        }
+        float4 bod = prow(w, buf, PR_BODIES, i);
+        int b1 = as_int(bod.z), b2 = as_int(bod.w);
+        bool dyn1 = body_is_sim(w, b1), dyn2 = body_is_sim(w, b2);
+        int sh1 = w.c_shape[c1], sh2 = w.c_shape[c2];
+        vec3 he1 = xyz(w.c_he[c1]), he2 = xyz(w.c_he[c2]);
+        float4 m1 = w.c_mat[c1], m2 = w.c_mat[c2];
+        float skin1 = m1.z, skin2 = m2.z;
+        RawManifold raw;
+        contact_manifold(sh1, he1, sh2, he2, p12, prediction + (skin1 + skin2), raw);
+
+        // match_contacts: carry ContactData by feature ids (ball manifolds keep their single point).
+        float4 o_pb[MAX_PTS], o_pd[MAX_PTS], o_tw[MAX_PTS], o_d1[MAX_PTS], o_d2[MAX_PTS];
+        for (int k = 0; k < MAX_PTS; ++k) {
+            if (k < npts_old) {
+                o_pb[k] = prow(w, buf, PR_PB + k, i); o_pd[k] = prow(w, buf, PR_PD + k, i);
+                o_tw[k] = prow(w, buf, PR_TW + k, i); o_d1[k] = prow(w, buf, PR_DP1 + k, i);
+                o_d2[k] = prow(w, buf, PR_DP2 + k, i);
+            }
+        }
+        bool ball = sh1 == SHAPE_BALL || sh2 == SHAPE_BALL;
+
+        int2 rules1 = w.c_rules[c1], rules2 = w.c_rules[c2];
+        float friction = combine_coeff(m1.x, m2.x, rules1.x, rules2.x);
+        float restitution = combine_coeff(m1.y, m2.y, rules1.y, rules2.y);
+        vec3 normal = rotate(cp1.q, raw.n1);
+
+        int sel[4] = {0, 1, 2, 3};
+        int nsel = raw.n < MAX_PTS ? raw.n : MAX_PTS;
+        reduce_manifold(raw, sel, nsel, prediction);
+        if (nsel > 1) {  // planar lexicographic sort (pair_update.rs:433-457)
+            vec3 e0, e1;
+            ortho_basis(raw.n1, e0, e1);
+            float k0[4], k1[4];
+            int ks[4];
+            for (int q = 0; q < nsel; ++q) {
+                vec3 p = raw.pt[sel[q]].p1;
+                k0[q] = dot3(p, e0); k1[q] = dot3(p, e1); ks[q] = sel[q];
+            }
+            for (int q = 1; q < nsel; ++q) {
+                float a0 = k0[q], a1 = k1[q];
+                int as = ks[q];
+                int j = q;
+                while (j > 0 && (k0[j - 1] > a0 || (k0[j - 1] == a0 && k1[j - 1] > a1))) {
+                    k0[j] = k0[j - 1]; k1[j] = k1[j - 1]; ks[j] = ks[j - 1];
+                    --j;
+                }
+                k0[j] = a0; k1[j] = a1; ks[j] = as;
+            }
+            for (int q = 0; q < nsel; ++q) sel[q] = ks[q];
+        }
+
+        pose com1 = pident(), com2 = pident();
+        vec3 lv1 = zero3(), av1 = zero3(), wc1 = zero3(), lv2 = zero3(), av2 = zero3(), wc2 = zero3();
+        if (b1 >= 0) { lv1 = xyz(w.b_linvel[b1]); av1 = xyz(w.b_angvel[b1]); wc1 = xyz(w.b_wcom[b1]); }
+        if (b2 >= 0) { lv2 = xyz(w.b_linvel[b2]); av2 = xyz(w.b_angvel[b2]); wc2 = xyz(w.b_wcom[b2]); }
+        if (dyn1) com1 = prepend_translation(body_pose(w, b1), xyz(w.b_lcom_im[b1]));
+        if (dyn2) com2 = prepend_translation(body_pose(w, b2), xyz(w.b_lcom_im[b2]));
+
+        int nsc = 0;
+        for (int k = 0; k < nsel; ++k) {
+            const RawPt& rp = raw.pt[sel[k]];
+            float4 pd = make_float4(0.f, 0.f, 0.f, 0.f), tw = pd, d1 = pd, d2 = pd;
+            for (int o = 0; o < npts_old; ++o) {
+                if (ball || (as_uint(o_pb[o].w) == rp.fid1 && as_uint(o_pd[o].w) == rp.fid2)) {
+                    pd = o_pd[o]; tw = o_tw[o]; d1 = o_d1[o]; d2 = o_d2[o];
+                }
+            }
+            pd.w = as_float(rp.fid2);
+            float eff = rp.dist - skin1 - skin2;
+            vec3 wp1 = xform(cp1, rp.p1), wp2 = xform(cp2, rp.p2);
+            bool keep = eff < prediction;
+            if (!keep) {
+                vec3 v1 = b1 >= 0 ? lv1 + cross3(av1, wp1 - wc1) : zero3();
+                vec3 v2 = b2 >= 0 ? lv2 + cross3(av2, wp2 - wc2) : zero3();
+                keep = eff + dot3(v2 - v1, normal) * dt < prediction;
+            }
+            if (keep) {  // localise + freeze lever arms (pair_update.rs:536-577)
+                float shift = dot3(wp2 - wp1, normal) - eff;
+                vec3 p1 = wp1 + normal * shift;
+                vec3 point = (p1 + wp2) * 0.5f;
+                d1 = f4(dyn1 ? point - com1.t : point, 0.0f);
+                d2 = f4(dyn2 ? point - com2.t : point, 0.0f);
+                vec3 a1 = dyn1 ? xform_inv(com1, p1) : p1;
+                vec3 a2 = dyn2 ? xform_inv(com2, wp2) : wp2;
+                prow(w, buf, PR_A1 + nsc, i) = f4(a1, as_float_i(k));
+                prow(w, buf, PR_A2 + nsc, i) = f4(a2, 0.0f);
+                ++nsc;
+            }
+            prow(w, buf, PR_PA + k, i) = f4(rp.p1, rp.dist);
+            prow(w, buf, PR_PB + k, i) = f4(rp.p2, as_float(rp.fid1));
+            prow(w, buf, PR_PD + k, i) = pd;
+            prow(w, buf, PR_TW + k, i) = tw;
+            prow(w, buf, PR_DP1 + k, i) = d1;
+            prow(w, buf, PR_DP2 + k, i) = d2;
+        }
+        float max_drift = 0.0f;
+        if (recycle > 0.0f) {  // pair_update.rs:582-613
+            float max_extent = (flags & 1) ? prow(w, buf, PR_RT, i).w : max2(origin_radius(sh1, he1), origin_radius(sh2, he2));
+            max_drift = nsc > 0 ? recycle : min2(recycle, prediction);
+            flags |= 1;
+            prow(w, buf, PR_RT, i) = f4(p12.t, max_extent);
+            prow(w, buf, PR_RQ, i) = f4(p12.q);
+            prow(w, buf, PR_ROT1, i) = f4(cp1.q);
+            prow(w, buf, PR_ROT2, i) = f4(cp2.q);
+        }
+        prow(w, buf, PR_LN1, i) = f4(raw.n1, max_drift);
+        prow(w, buf, PR_LN2, i) = f4(raw.n2, restitution);
+        prow(w, buf, PR_NORMAL, i) = f4(normal, friction);
+        // transitions (pair_update.rs:622-629; contacts.rs:300-385)
+        bool had = nsc_old > 0, has = nsc > 0;
+        if (had != has) {
+            st->sched_dirty = 1;
+            if (has) {
+                flags |= 2;  // pending colour (deferred greedy pass)
+                st->ntodo = 1;
+            } else {
+                clear_color_bits(w, color, as_int(bod.x), as_int(bod.y));
+                color = COLOR_UNCOLORED;
+                prow(w, buf, PR_BODIES, i) = make_float4(as_float_i(-1), as_float_i(-1), bod.z, bod.w);
+            }
+        }
+        prow(w, buf, PR_INFO, i) = make_float4(as_float_i(flags), as_float_i(nsel), as_float_i(nsc), as_float_i(color));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// P3a: deferred greedy colouring of the pairs that began touching, in ascending pair order
+// (contacts.rs:366-385; narrow_phase/mod.rs:87-152).  Parallel formulation of the sequential
+// greedy: a pending pair is coloured in the round where it is the lowest pending pair on each of
+// its dynamic bodies, which reproduces the sequential result exactly.
+// ------------------------------------------------------------------------------------------------
+RB_HD int first_free_low(const unsigned* m) {   // lowest clear bit in 0..119, else 128
+    for (int wd = 0; wd < 4; ++wd) {
+        unsigned inv = ~m[wd];
+        if (wd == 3) inv &= 0x00ffffffu;  // colours 96..119 only
+        if (inv) {
+            int b = 0;
+            while (!((inv >> b) & 1u)) ++b;
+            return wd * 32 + b;
+        }
+    }
+    return 128;
+}
+RB_HD int first_free_high(const unsigned* m) {  // highest clear bit <= 127, else 128
+    for (int wd = 3; wd >= 0; --wd) {
+        unsigned inv = ~m[wd];
+        if (inv) {
+            int b = 31;
+            while (!((inv >> b) & 1u)) --b;
+            return wd * 32 + b;
+        }
+    }
+    return 128;
+}
+
+template <class Ctx>
+RB_PHASE void section_coloring(const Ctx& ctx, const World& w) {
+    State* st = w.st;
+    const int buf = st->cur, np = st->npairs;
+    for (;;) {
+        // A: every pending pair bids for its dynamic bodies
+        for (int i = ctx.gtid; i < np; i += ctx.gsize) {
+            int flags = as_int(prow(w, buf, PR_INFO, i).x);
+            if (!(flags & 2)) continue;
+            float4 bod = prow(w, buf, PR_BODIES, i);
+            int b1 = as_int(bod.z), b2 = as_int(bod.w);
+            if (body_is_sim(w, b1)) atomic_min(&w.body_min[b1], i);
+            if (body_is_sim(w, b2)) atomic_min(&w.body_min[b2], i);
+            atomic_add(&st->ncand, 1);  // ncand doubles as the pending counter outside the broad phase
+        }
+        ctx.grid_sync();
+        int pending = st->ncand;
+        if (pending == 0) break;
+        // B: winners take the first colour free on both bodies
+        for (int i = ctx.gtid; i < np; i += ctx.gsize) {
+            float4 info = prow(w, buf, PR_INFO, i);
+            int flags = as_int(info.x);
+            if (!(flags & 2)) continue;
+            float4 bod = prow(w, buf, PR_BODIES, i);
+            int b1 = as_int(bod.z), b2 = as_int(bod.w);
+            bool d1 = body_is_sim(w, b1), d2 = body_is_sim(w, b2);
+            if ((d1 && w.body_min[b1] != i) || (d2 && w.body_min[b2] != i)) continue;
+            int color = COLOR_OVERFLOW, cb0 = -1, cb1 = -1;
+            if (d1 && d2) {
+                unsigned m[4];
+                for (int k = 0; k < 4; ++k) m[k] = w.color_mask[b1 * 4 + k] | w.color_mask[b2 * 4 + k];
+                int c = first_free_low(m);
+                if (c < 128) { color = c; cb0 = b1; cb1 = b2; }
+            } else if (d1 || d2) {
+                int b = d1 ? b1 : b2;
+                int c = first_free_high(&w.color_mask[b * 4]);
+                if (c < 128) { color = c; cb0 = b; }
+            }
+            if (color < 128) {
+                if (cb0 >= 0) w.color_mask[cb0 * 4 + (color >> 5)] |= 1u << (color & 31);
+                if (cb1 >= 0) w.color_mask[cb1 * 4 + (color >> 5)] |= 1u << (color & 31);
+            }
+            prow(w, buf, PR_BODIES, i) = make_float4(as_float_i(cb0), as_float_i(cb1), bod.z, bod.w);
+            info.x = as_float_i((flags & ~2) | 4);  // bit2: coloured this round (scratch reset below)
+            info.w = as_float_i(color);
+            prow(w, buf, PR_INFO, i) = info;
+        }
+        ctx.grid_sync();
+        // C: reset the bidding scratch
+        for (int i = ctx.gtid; i < np; i += ctx.gsize) {
+            float4 info = prow(w, buf, PR_INFO, i);
+            int flags = as_int(info.x);
+            if (!(flags & 6)) continue;
+            float4 bod = prow(w, buf, PR_BODIES, i);
+            int b1 = as_int(bod.z), b2 = as_int(bod.w);
+            if (body_is_sim(w, b1)) w.body_min[b1] = 0x7fffffff;
+            if (body_is_sim(w, b2)) w.body_min[b2] = 0x7fffffff;
+            if (flags & 4) { info.x = as_float_i(flags & ~4); prow(w, buf, PR_INFO, i) = info; }
+        }
+        if (ctx.gtid == 0) st->ncand = 0;
+        ctx.grid_sync();
+    }
+    if (ctx.gtid == 0) st->ntodo = 0;
+    ctx.grid_sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Grid-wide exclusive scan of ints: per-thread chunks, block 0 scans the per-thread partials.
+// `tmp` needs gsize + 1 entries.  Returns the total in tmp[gsize].
+// ------------------------------------------------------------------------------------------------
+template <class Ctx>
+RB_PHASE void grid_exclusive_scan(const Ctx& ctx, const int* in, int* out, int n, int* tmp) {
+    int chunk = (n + ctx.gsize - 1) / ctx.gsize;
+    int b = ctx.gtid * chunk, e = b + chunk < n ? b + chunk : n;
+    int s = 0;
+    for (int i = b; i < e; ++i) s += in[i];
+    tmp[ctx.gtid] = s;
+    ctx.grid_sync();
+    if (ctx.bid == 0) {
+        RB_SHARED int part[1024];
+        int m = ctx.gsize;
+        int sub = (m + ctx.bsize - 1) / ctx.bsize;
+        int sb = ctx.btid * sub, se = sb + sub < m ? sb + sub : m;
+        int ps = 0;
+        for (int i = sb; i < se; ++i) ps += tmp[i];
+        part[ctx.btid] = ps;
+        ctx.block_sync();
+        if (ctx.btid == 0) {
+            int run = 0;
+            for (int t = 0; t < ctx.bsize; ++t) { int v = part[t]; part[t] = run; run += v; }
+            tmp[m] = run;
+        }
+        ctx.block_sync();
+        int run = part[ctx.btid];
+        for (int i = sb; i < se; ++i) { int v = tmp[i]; tmp[i] = run; run += v; }
+    }
+    ctx.grid_sync();
+    int run = tmp[ctx.gtid];
+    for (int i = b; i < e; ++i) { int v = in[i]; out[i] = run; run += v; }
+    ctx.grid_sync();
+}
+
+RB_HD int uf_find(int* parent, int x) {
+    int r = x;
+    while (true) {
+        int p = parent[r];
+        if (p == r) break;
+        r = p;
+    }
+    // path halving towards the root found (benign races: every store writes a valid ancestor)
+    while (true) {
+        int p = parent[x];
+        if (p == r || p == x) break;
+        parent[x] = r;
+        x = p;
+    }
+    return r;
+}
+RB_HD void uf_union(int* parent, int a, int b) {  // hook the larger root under the smaller one
+    for (;;) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        int lo = a < b ? a : b, hi = a < b ? b : a;
+        int old = atomic_cas(&parent[hi], hi, lo);
+        if (old == hi) return;
+    }
+}
+
+// P3b: connected components (persistent islands, island_manager/persistent.rs:1-3), work items,
+// colour stage order (init.rs:163-254) and the per-item constraint schedule.
+template <class Ctx>
+RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
+    State* st = w.st;
+    const int buf = st->cur, np = st->npairs, nb = w.nb, nj = w.nj;
+    // S1 reset
+    for (int b = ctx.gtid; b < nb; b += ctx.gsize) { w.isl_label[b] = b; w.isl_nb[b] = 0; w.isl_ncons[b] = 0; w.isl_item[b] = -1; }
+    for (int c = ctx.gtid; c < NUM_COLORS; c += ctx.gsize) w.color_count[c] = 0;
+    for (int i = ctx.gtid; i < 3 * (w.item_cap + 1); i += ctx.gsize) w.item_cursor[i] = 0;
+    for (int i = ctx.gtid; i <= w.item_cap; i += ctx.gsize) { w.item_body_start[i] = 0; w.item_cons_start[i] = 0; w.item_joint_start[i] = 0; }
+    ctx.grid_sync();
+    // S2 union over touching dynamic-dynamic pairs and joints
+    for (int i = ctx.gtid; i < np; i += ctx.gsize) {
+        if (as_int(prow(w, buf, PR_INFO, i).z) <= 0) continue;
+        float4 bod = prow(w, buf, PR_BODIES, i);
+        int b1 = as_int(bod.z), b2 = as_int(bod.w);
+        if (body_is_sim(w, b1) && body_is_sim(w, b2)) uf_union(w.isl_label, b1, b2);
+    }
+    for (int j = ctx.gtid; j < nj; j += ctx.gsize) {
+        int4 ji = w.j_info[j];
+        if (body_is_sim(w, ji.x) && body_is_sim(w, ji.y)) uf_union(w.isl_label, ji.x, ji.y);
+    }
+    ctx.grid_sync();
+    // S3 flatten
+    for (int b = ctx.gtid; b < nb; b += ctx.gsize) w.isl_label[b] = uf_find(w.isl_label, b);
+    ctx.grid_sync();
+    // S4 per-root counts + global colour histogram
+    for (int b = ctx.gtid; b < nb; b += ctx.gsize)
+        if (body_is_sim(w, b)) atomic_add(&w.isl_nb[w.isl_label[b]], 1);
+    for (int i = ctx.gtid; i < np; i += ctx.gsize) {
+        float4 info = prow(w, buf, PR_INFO, i);
+        if (as_int(info.z) <= 0) continue;
+        float4 bod = prow(w, buf, PR_BODIES, i);
+        int b1 = as_int(bod.z), b2 = as_int(bod.w);
+        int b = body_is_sim(w, b1) ? b1 : (body_is_sim(w, b2) ? b2 : -1);
+        if (b < 0) continue;
+        atomic_add(&w.isl_ncons[w.isl_label[b]], 1);
+        int color = as_int(info.w);
+        atomic_add(&w.color_count[color > COLOR_OVERFLOW ? COLOR_OVERFLOW : color], 1);
+    }
+    for (int j = ctx.gtid; j < nj; j += ctx.gsize) {
+        int4 ji = w.j_info[j];
+        int b = body_is_sim(w, ji.x) ? ji.x : (body_is_sim(w, ji.y) ? ji.y : -1);
+        if (b >= 0) atomic_add(&w.isl_ncons[w.isl_label[b]], 1);
+    }
+    ctx.grid_sync();
+    // S5 colour stage order: big colours ascending, then small colours ascending, then overflow.
+    if (ctx.gtid == 0) {
+        int pos = 0;
+        for (int c = 0; c < NUM_COLORS; ++c) w.color_pos[c] = -1;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int c = 0; c < 128; ++c) {
+                int n = w.color_count[c];
+                if (n == 0 || (n >= BIG_COLOR_MIN) != (pass == 0)) continue;
+                w.color_pos[c] = pos++;
+            }
+        if (w.color_count[128] > 0) w.color_pos[128] = pos++;
+        st->nused_colors = pos;
+    }
+    // S6 work items: exclusive prefix of the cost of the small islands in root order.
+    int* cost = w.isl_item;  // reuse as input, overwritten by the item id below
+    for (int b = ctx.gtid; b < nb; b += ctx.gsize) {
+        int c = 0;
+        if (body_is_sim(w, b) && w.isl_label[b] == b) {
+            int nbod = w.isl_nb[b], ncon = w.isl_ncons[b];
+            bool large = nbod > ITEM_BODY_CAP || ncon > ITEM_CONS_CAP;
+            c = large ? 0 : (nbod > ncon ? nbod : ncon);
+        }
+        cost[b] = c;
+    }
+    ctx.grid_sync();
+    grid_exclusive_scan(ctx, cost, w.body_item, nb, w.scan_tmp);  // body_item temporarily holds the prefix
+    int total_cost = w.scan_tmp[ctx.gsize];
+    int nitems = 1 + (total_cost + ITEM_TARGET - 1) / ITEM_TARGET;
+    if (nitems > w.item_cap) {
+        if (ctx.gtid == 0) st->error = -4;
+        nitems = w.item_cap;
+    }
+    for (int b = ctx.gtid; b < nb; b += ctx.gsize) {
+        int it = -1;
+        if (body_is_sim(w, b) && w.isl_label[b] == b) {
+            int nbod = w.isl_nb[b], ncon = w.isl_ncons[b];
+            bool large = nbod > ITEM_BODY_CAP || ncon > ITEM_CONS_CAP;
+            it = large ? 0 : 1 + w.body_item[b] / ITEM_TARGET;
+            if (it >= nitems) it = nitems - 1;
+        }
+        w.isl_item[b] = it;
+    }
+    ctx.grid_sync();
+    // S7 per-item counts
+    for (int b = ctx.gtid; b < nb; b += ctx.gsize) {
+        int it = body_is_sim(w, b) ? w.isl_item[w.isl_label[b]] : -1;
+        w.body_item[b] = it;
+        if (it >= 0) atomic_add(&w.item_body_start[it], 1);
+    }
+    for (int i = ctx.gtid; i < np; i += ctx.gsize) {
+        if (as_int(prow(w, buf, PR_INFO, i).z) <= 0) continue;
+        float4 bod = prow(w, buf, PR_BODIES, i);
+        int b1 = as_int(bod.z), b2 = as_int(bod.w);
+        int b = body_is_sim(w, b1) ? b1 : (body_is_sim(w, b2) ? b2 : -1);
+        if (b >= 0) atomic_add(&w.item_cons_start[w.isl_item[w.isl_label[b]]], 1);
+    }
+    for (int j = ctx.gtid; j < nj; j += ctx.gsize) {
+        int4 ji = w.j_info[j];
+        int b = body_is_sim(w, ji.x) ? ji.x : (body_is_sim(w, ji.y) ? ji.y : -1);
+        if (b >= 0) atomic_add(&w.item_joint_start[w.isl_item[w.isl_label[b]]], 1);
+    }
+    ctx.grid_sync();
+    // S8 scans (counts -> starts); entry [nitems] becomes the total.
+    grid_exclusive_scan(ctx, w.item_body_start, w.item_body_start, nitems + 1, w.scan_tmp);
+    grid_exclusive_scan(ctx, w.item_cons_start, w.item_cons_start, nitems + 1, w.scan_tmp);
+    grid_exclusive_scan(ctx, w.item_joint_start, w.item_joint_start, nitems + 1, w.scan_tmp);
+    int ncons = w.item_cons_start[nitems];
+    if (ncons > w.cons_cap) {
+        if (ctx.gtid == 0) st->error = -4;
+    }
+    // S9 scatter bodies / manifolds / joints into their item segments
+    int* cur_b = w.item_cursor;
+    int* cur_c = w.item_cursor + (w.item_cap + 1);
+    int* cur_j = w.item_cursor + 2 * (w.item_cap + 1);
+    for (int b = ctx.gtid; b < nb; b += ctx.gsize) {
+        int it = w.body_item[b];
+        if (it < 0) { w.body_local[b] = -1; continue; }
+        int l = atomic_add(&cur_b[it], 1);
+        w.item_bodies[w.item_body_start[it] + l] = b;
+        w.body_local[b] = l;
+    }
+    for (int i = ctx.gtid; i < np; i += ctx.gsize) {
+        if (as_int(prow(w, buf, PR_INFO, i).z) <= 0) continue;
+        float4 bod = prow(w, buf, PR_BODIES, i);
+        int b1 = as_int(bod.z), b2 = as_int(bod.w);
+        int b = body_is_sim(w, b1) ? b1 : (body_is_sim(w, b2) ? b2 : -1);
+        if (b < 0) continue;
+        int it = w.body_item[b];
+        int l = atomic_add(&cur_c[it], 1);
+        int pos = w.item_cons_start[it] + l;
+        if (pos < w.cons_cap) w.cons_pair_tmp[pos] = i;
+    }
+    for (int j = ctx.gtid; j < nj; j += ctx.gsize) {
+        int4 ji = w.j_info[j];
+        int b = body_is_sim(w, ji.x) ? ji.x : (body_is_sim(w, ji.y) ? ji.y : -1);
+        if (b < 0) continue;
+        int it = w.body_item[b];
+        int l = atomic_add(&cur_j[it], 1);
+        w.joint_tmp[w.item_joint_start[it] + l] = j;
+    }
+    ctx.grid_sync();
+    // S10 per-item counting sort by colour stage (one CTA per item), headers for the solver.
+    for (int it = ctx.bid; it < nitems; it += ctx.nblocks) {
+        RB_SHARED int hist[NUM_COLORS + 1];
+        RB_SHARED int curs[NUM_COLORS + 1];
+        for (int pass = 0; pass < 2; ++pass) {  // 0: contacts, 1: joints
+            const int* starts = pass == 0 ? w.item_cons_start : w.item_joint_start;
+            int s0 = starts[it], s1 = starts[it + 1];
+            if (pass == 0 && s1 > w.cons_cap) s1 = s0 > w.cons_cap ? s0 : w.cons_cap;
+            const int* src = pass == 0 ? w.cons_pair_tmp : w.joint_tmp;
+            int* dst = pass == 0 ? w.cons_pair : w.joint_sched;
+            int* offs = (pass == 0 ? w.item_color_off : w.item_jcolor_off) + (size_t)it * (NUM_COLORS + 1);
+            const int* cpos = pass == 0 ? w.color_pos : w.jcolor_pos;
+            for (int c = ctx.btid; c <= NUM_COLORS; c += ctx.bsize) { hist[c] = 0; curs[c] = 0; }
+            ctx.block_sync();
+            for (int q = s0 + ctx.btid; q < s1; q += ctx.bsize) {
+                int id = src[q];
+                int color = pass == 0 ? as_int(prow(w, buf, PR_INFO, id).w) : w.j_info[id].w;
+                if (color > COLOR_OVERFLOW) color = COLOR_OVERFLOW;
+                atomic_add(&hist[cpos[color]], 1);
+            }
+            ctx.block_sync();
+            if (ctx.btid == 0) {
+                int run = 0;
+                for (int c = 0; c <= NUM_COLORS; ++c) { int v = c < NUM_COLORS ? hist[c] : 0; hist[c] = run; offs[c] = run; run += v; }
+            }
+            ctx.block_sync();
+            for (int q = s0 + ctx.btid; q < s1; q += ctx.bsize) {
+                int id = src[q];
+                int color = pass == 0 ? as_int(prow(w, buf, PR_INFO, id).w) : w.j_info[id].w;
+                if (color > COLOR_OVERFLOW) color = COLOR_OVERFLOW;
+                int p = cpos[color];
+                int l = atomic_add(&curs[p], 1);
+                dst[s0 + hist[p] + l] = id;
+            }
+            ctx.block_sync();
+            // the overflow colour is solved sequentially: order it by index
+            if (ctx.btid == 0 && cpos[COLOR_OVERFLOW] >= 0) {
+                int p = cpos[COLOR_OVERFLOW];
+                int a = s0 + offs[p], e = s0 + offs[p + 1];
+                for (int x = a + 1; x < e; ++x) {
+                    int v = dst[x], y = x;
+                    while (y > a && dst[y - 1] > v) { dst[y] = dst[y - 1]; --y; }
+                    dst[y] = v;
+                }
+            }
+            ctx.block_sync();
+            // headers
+            for (int q = s0 + ctx.btid; q < s1; q += ctx.bsize) {
+                int id = dst[q];
+                int b1, b2;
+                if (pass == 0) {
+                    float4 bod = prow(w, buf, PR_BODIES, id);
+                    b1 = as_int(bod.z); b2 = as_int(bod.w);
+                } else {
+                    int4 ji = w.j_info[id];
+                    b1 = ji.x; b2 = ji.y;
+                }
+                int id1 = body_is_sim(w, b1) ? (it == 0 ? b1 : w.body_local[b1]) : NO_BODY;
+                int id2 = body_is_sim(w, b2) ? (it == 0 ? b2 : w.body_local[b2]) : NO_BODY;
+                if (pass == 0) w.cons_hdr[q] = make_int4(id, id1, id2, 0);
+                else w.j_sched_ids[q] = make_int4(id, id1, id2, 0);
+            }
+            ctx.block_sync();
+        }
+    }
+    ctx.grid_sync();
+    if (ctx.gtid == 0) {
+        st->nitems = nitems;
+        st->ncons = ncons < w.cons_cap ? ncons : w.cons_cap;
+        st->nlarge_bodies = w.item_body_start[1] - w.item_body_start[0];
+        st->nlarge_cons = w.item_cons_start[1] - w.item_cons_start[0];
+        st->nlarge_joints = w.item_joint_start[1] - w.item_joint_start[0];
+        int nisl = 0;
+        (void)nisl;
+        st->sched_dirty = 0;
+        st->sched_ran = 1;
+    }
+    ctx.grid_sync();
+}
+
+// The whole pre-solve pipeline of one step.
+template <class Ctx>
+RB_PHASE void collide_pipeline(const Ctx& ctx, const World& w) {
+    State* st = w.st;
+    if (ctx.gtid == 0) { st->bp_ran = 0; st->sched_ran = 0; }
+    phase_refresh_colliders(ctx, w);
+    ctx.grid_sync();
+    if (st->bp_dirty) section_broad_phase(ctx, w);
+    phase_narrow_phase(ctx, w);
+    ctx.grid_sync();
+    if (st->ntodo) section_coloring(ctx, w);
+    if (st->sched_dirty) section_schedule(ctx, w);
+}
+
+}  // namespace rb

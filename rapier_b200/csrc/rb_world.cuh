@@ -1,0 +1,201 @@
+// rb_world.cuh -- device-resident world: SoA tables in HBM (layout described in DESIGN.md §3).
+//
+// Bodies, colliders, persistent contact pairs and per-step constraint rows are structure-of-arrays
+// of float4 "rows" (16-byte aligned, coalesced across the index).  Multi-row records are stored
+// row-major: element (row r, index i) lives at table[r * cap + i], so a warp reading row r of 32
+// consecutive records issues one 512-byte coalesced request.
+#pragma once
+#include "rb_math.cuh"
+
+namespace rb {
+
+constexpr int MAX_PTS = 4;              // MAX_MANIFOLD_POINTS, src/lib.rs:291
+constexpr int MAX_RAW = 8;              // clipped quad/quad polygon
+constexpr int COLOR_UNCOLORED = 255;    // contact_pair.rs:152
+constexpr int COLOR_OVERFLOW = 128;     // contact_pair.rs:155
+constexpr int DYN_COLOR_COUNT = 120;    // contact_pair.rs:159
+constexpr int NUM_COLORS = 129;
+constexpr int NO_BODY = -1;             // world-attached side (reference: u32::MAX)
+
+constexpr int BODY_DYNAMIC = 0;
+constexpr int SHAPE_BALL = 0, SHAPE_CUBOID = 1;
+constexpr unsigned FLAG_GYRO = 1, FLAG_FAST_ROT = 2, FLAG_LTX = 4, FLAG_LTY = 8, FLAG_LTZ = 16, FLAG_LRX = 32,
+                   FLAG_LRY = 64, FLAG_LRZ = 128;
+
+// ---- persistent pair record rows (float4 each) ----
+enum PairRow {
+    PR_INFO = 0,   // int bits: x flags(bit0 has_recycle), y npts, z nsc, w colour
+    PR_BODIES,     // int bits: x colour_body0, y colour_body1, z body1, w body2 (-1 none)
+    PR_RT,         // recycle pos12.t xyz, w max_extent
+    PR_RQ,         // recycle pos12.q
+    PR_ROT1,       // recycle rot1
+    PR_ROT2,       // recycle rot2
+    PR_LN1,        // local_n1 xyz, w max_drift
+    PR_LN2,        // local_n2 xyz, w restitution
+    PR_NORMAL,     // world normal xyz, w friction
+    PR_PA,         // [4] local_p1 xyz, w dist
+    PR_PB = PR_PA + MAX_PTS,    // [4] local_p2 xyz, w fid1 bits
+    PR_PD = PR_PB + MAX_PTS,    // [4] impulse, warmstart_impulse, warmstart_twist, fid2 bits
+    PR_TW = PR_PD + MAX_PTS,    // [4] warmstart_tangent_world xyz
+    PR_DP1 = PR_TW + MAX_PTS,   // [4] solver_dp1 xyz
+    PR_DP2 = PR_DP1 + MAX_PTS,  // [4] solver_dp2 xyz
+    PR_A1 = PR_DP2 + MAX_PTS,   // [4] anchor1 xyz, w cid bits
+    PR_A2 = PR_A1 + MAX_PTS,    // [4] anchor2 xyz
+    PR_ROWS = PR_A2 + MAX_PTS
+};
+
+// ---- per-step constraint record rows (float4 each), index = slot in the schedule ----
+enum ConsRow {
+    CR_DIR = 0,                 // dir1 xyz, w friction limit
+    CR_T1,                      // tangent1 xyz, w twist r
+    CR_DP1,                     // [4] dp1 xyz, w r (projected mass)
+    CR_DP2 = CR_DP1 + MAX_PTS,  // [4] dp2 xyz, w dist0
+    CR_LP1 = CR_DP2 + MAX_PTS,  // [4] builder local_p1 xyz, w restitution seed
+    CR_LP2 = CR_LP1 + MAX_PTS,  // [4] builder local_p2 xyz
+    CR_TDP1 = CR_LP2 + MAX_PTS, // tangent dp1 xyz, w r[0]
+    CR_TDP2,                    // tangent dp2 xyz, w r[1]
+    CR_LFC1,                    // local friction centre 1 xyz, w r[2]
+    CR_LFC2,                    // local friction centre 2 xyz
+    CR_TWD,                     // twist_dists[4]
+    CR_IMP,                     // normal impulses[4]            (read-modify-write)
+    CR_ACC,                     // normal impulse accumulators[4] (read-modify-write)
+    CR_TI,                      // tangent impulse xy, accumulators zw (read-modify-write)
+    CR_WI,                      // twist impulse x, accumulator y       (read-modify-write)
+    CR_ROWS
+};
+
+struct Params {  // IntegrationParameters + derived per-substep coefficients (computed on the host)
+    float dt, inv_dt_full, sub_dt, sub_inv_dt;
+    float dyn_cfm, static_cfm, dyn_erp, static_erp;
+    float max_corrective_velocity, warmstart_coeff;
+    float prediction, recycle_dist, length_unit, fat_skin;
+    float max_lin_vel, max_ang_vel;
+    int num_substeps, num_pgs, num_relax, friction_in_bias, contact_recycling;
+};
+
+// Device-side scalars (one struct in HBM, mirrored to pinned host memory on demand).
+struct State {
+    int cur;               // which PairBuf is live (0/1)
+    int npairs;
+    int bp_dirty;          // a fat AABB changed: the pair set must be recomputed
+    int sched_dirty;       // touching set changed: colours / islands / schedule must be rebuilt
+    int ntodo;             // pairs that began touching this step
+    int ncand;             // broad-phase candidates
+    int ncons;             // solver-active manifolds
+    int nitems;            // work items (item 0 = large islands)
+    int nused_colors;      // colours in the contact stage order
+    int njused_colors;     // colours in the joint stage order
+    int nlarge_cons, nlarge_joints, nlarge_bodies;
+    int error;             // RbStatus raised on the device (capacity, non-finite)
+    int nislands;
+    int bp_ran, sched_ran; // set when the corresponding section ran in the last step
+    int any_bouncy;
+    int pad[14];
+};
+
+struct PairBuf {
+    unsigned long long* key;  // (collider1 << 32) | collider2, sorted ascending
+    float4* rows;             // [PR_ROWS][pair_cap]
+};
+
+struct World {
+    int nb, nc, nj;
+    int pair_cap, cons_cap, item_cap, joint_cap;
+    Params prm;
+    State* st;
+    // ---- bodies ----
+    int* b_type;
+    unsigned* b_flags;
+    float4 *b_pos_t, *b_pos_q;        // RigidBodyPosition::position
+    float4 *b_linvel, *b_angvel;
+    float4* b_lcom_im;                // local_com xyz, w inv_mass
+    float4 *b_ipi, *b_pi, *b_pframe;  // inverse principal inertia, principal inertia, principal frame
+    float4* b_misc;                   // linear damping, angular damping, gravity scale
+    float4 *b_uforce, *b_utorque;
+    float4* b_wcom;                   // world_com
+    float4* b_eim;                    // effective_inv_mass
+    float4* b_eii0;                   // effective_world_inv_inertia xx xy xz yy
+    float2* b_eii1;                   //                              yz zz
+    unsigned char* b_owned;           // multi-GPU sharding: 0 = body simulated by another rank
+    // solver bodies (global-memory path) + per-substep increments
+    float4 *s_lin, *s_ang, *s_q, *s_t, *s_incr_lin, *s_incr_ang;
+    float* state13;                   // packed [nb][13] t q lin ang (download / NCCL all-gather)
+    // ---- colliders ----
+    int* c_shape;
+    int* c_parent;
+    float4 *c_he, *c_rel_t, *c_rel_q;
+    float4* c_mat;                    // friction, restitution, contact_skin
+    int2* c_rules;
+    uint2* c_groups;
+    float4 *c_pos_t, *c_pos_q;
+    float4 *c_aabb_min, *c_aabb_max, *c_fat_min, *c_fat_max;
+    // ---- broad phase scratch ----
+    unsigned* bp_sort_key;            // [nc_pow2] sortable min-x
+    int* bp_sort_val;                 // [nc_pow2]
+    int nc_pow2;
+    unsigned long long* cand_key;     // [pair_cap_pow2]
+    int pair_cap_pow2;
+    unsigned long long* nocontact_keys;  // sorted body-pair keys of joints with contacts disabled
+    int n_nocontact;
+    int* remap_src;                   // [pair_cap] new pair -> old pair index or -1
+    // ---- pairs ----
+    PairBuf pb[2];
+    int* todo;                        // [pair_cap] pairs that began touching this step
+    unsigned* color_mask;             // [nb][4] 128-bit colour masks per body
+    int* body_min;                    // [nb] colouring scratch (INT_MAX when idle)
+    // ---- islands / schedule ----
+    int* isl_label;                   // [nb] union-find parent / final root
+    int* isl_nb;                      // [nb] bodies per root
+    int* isl_ncons;                   // [nb] contact manifolds + joints per root
+    int* isl_item;                    // [nb] work item of a root
+    int* scan_tmp;                    // [nb + 1025]
+    int* item_body_start;             // [item_cap + 1]
+    int* item_cons_start;             // [item_cap + 1]
+    int* item_joint_start;            // [item_cap + 1]
+    int* item_cursor;                 // [3 * (item_cap + 1)] scatter cursors
+    int* item_bodies;                 // [nb] global body ids grouped by item
+    int* body_local;                  // [nb] index of a body inside its item
+    int* body_item;                   // [nb] item of a body
+    int* cons_pair_tmp;               // [cons_cap] pair index grouped by item (unsorted)
+    int* cons_pair;                   // [cons_cap] pair index in schedule order
+    int* item_color_off;              // [item_cap][NUM_COLORS + 1] offsets relative to item_cons_start
+    int* color_count;                 // [NUM_COLORS] global histogram
+    int* color_pos;                   // [NUM_COLORS] stage position of a colour, -1 unused
+    int* joint_tmp;                   // [joint_cap]
+    int* joint_sched;                 // [joint_cap] joint index in schedule order
+    int* item_jcolor_off;             // [item_cap][NUM_COLORS + 1]
+    int* jcolor_pos;                  // [NUM_COLORS] (host computed, static per scene)
+    // ---- constraints ----
+    int4* cons_hdr;                   // [cons_cap] pair, id1, id2, num_contacts (ids item-local or global)
+    float4* cons;                     // [CR_ROWS][cons_cap]
+    // ---- joints ----
+    int4* j_info;                     // body1, body2, locked_axes, colour
+    float4 *j_f1_t, *j_f1_q, *j_f2_t, *j_f2_q;   // local frames
+    float2* j_soft;                   // natural frequency, damping ratio
+    float* j_impulses;                // [nj][6]
+    float4* j_rows;                   // [JR_ROWS][6 * joint_cap] per-substep rows
+    int4* j_sched_ids;                // [joint_cap] joint, id1, id2, nrows in schedule order
+};
+
+// joint row record (float4 rows), index = 6 * schedule slot + row
+enum JointRowRec {
+    JR_LIN = 0,   // lin_jac xyz, w impulse
+    JR_A1,        // ang_jac1 xyz, w inv_lhs
+    JR_A2,        // ang_jac2 xyz, w rhs
+    JR_IA1,       // ii_ang_jac1 xyz, w rhs_wo_bias
+    JR_IA2,       // ii_ang_jac2 xyz, w cfm_gain
+    JR_ROWS
+};
+
+RB_HD float4& prow(const World& w, int buf, int row, int i) { return w.pb[buf].rows[(size_t)row * w.pair_cap + i]; }
+RB_HD float4& crow(const World& w, int row, int i) { return w.cons[(size_t)row * w.cons_cap + i]; }
+RB_HD float4& jrow(const World& w, int row, int i) { return w.j_rows[(size_t)row * (6 * w.joint_cap) + i]; }
+
+RB_HD sym3 load_ii(const World& w, int b) {
+    float4 a = w.b_eii0[b];
+    float2 c = w.b_eii1[b];
+    sym3 m; m.xx = a.x; m.xy = a.y; m.xz = a.z; m.yy = a.w; m.yz = c.x; m.zz = c.y;
+    return m;
+}
+
+}  // namespace rb

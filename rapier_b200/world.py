@@ -1,0 +1,188 @@
+"""PhysicsWorld / PhysicsPipeline: the reference-facing call surface over the C ABI.
+
+Mirrors PhysicsWorld::{new, insert, step} (src/pipeline/physics_world.rs:120-207) and
+PhysicsPipeline::step (src/pipeline/physics_pipeline/mod.rs:196-247).  Every method is a thin
+ctypes call into librapier_b200.so; no physics is computed in Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+from ._lib import lib as _product_lib
+from .sets import ColliderSet, ImpulseJointSet, RigidBodySet, as_array
+
+
+class RapierError(RuntimeError):
+    pass
+
+
+class PhysicsPipeline:
+    """Owns the device-resident world (the reference's pipeline owns only scratch memory,
+    physics_pipeline/mod.rs:34-44; here the scratch IS the HBM mirror of the caller's sets)."""
+
+    def __init__(self, integration_parameters=None, device=0, _lib=None):
+        self.L = _lib or _product_lib()
+        self.params = integration_parameters or A.RbIntegrationParameters.default()
+        self.h = self.L.rb_world_create(C.byref(self.params), device)
+        if not self.h:
+            raise RapierError(self.L.rb_last_error().decode())
+        self.nb = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rb_world_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise RapierError(f"rapier_b200 status {rc}: {self.L.rb_last_error().decode()}")
+        return rc
+
+    def upload(self, bodies: RigidBodySet, colliders: ColliderSet, joints: ImpulseJointSet = None):
+        """handle_user_changes_to_{colliders,rigid_bodies} (substep.rs:303-334): full scene upload."""
+        joints = joints or ImpulseJointSet()
+        self._b = as_array(bodies.descs, A.RbBodyDesc)
+        self._c = as_array(colliders.descs, A.RbColliderDesc)
+        self._j = as_array(joints.descs, A.RbJointDesc)
+        self._check(self.L.rb_world_set_scene(self.h, len(bodies), self._b, len(colliders), self._c, len(joints), self._j))
+        self.nb = len(bodies)
+
+    def set_params(self, params):
+        self.params = params
+        self._check(self.L.rb_world_set_params(self.h, C.byref(params)))
+
+    def step(self, gravity, nsteps=1, sync=True):
+        g = (C.c_float * 3)(*gravity)
+        self._check(self.L.rb_world_step(self.h, g, nsteps, 1 if sync else 0))
+
+    def step_host(self, gravity, in_state13=None, out_state13=None):
+        """PhysicsPipeline::step as a host-side owner of the sets calls it: host state in, host state out."""
+        g = (C.c_float * 3)(*gravity)
+        self._check(self.L.rb_world_step_host(self.h, g,
+                                              None if in_state13 is None else in_state13.ctypes.data,
+                                              None if out_state13 is None else out_state13.ctypes.data))
+
+    def set_stream(self, cuda_stream):
+        self._check(self.L.rb_world_set_stream(self.h, cuda_stream))
+
+    def import_states(self, idx_dev_ptr, src_dev_ptr, n):
+        self._check(self.L.rb_world_import_states(self.h, idx_dev_ptr, src_dev_ptr, n))
+
+    def synchronize(self):
+        self._check(self.L.rb_world_synchronize(self.h))
+
+    def body_states(self):
+        pose = np.zeros((self.nb, 7), np.float32)
+        vel = np.zeros((self.nb, 6), np.float32)
+        self._check(self.L.rb_world_get_body_states(self.h, pose.ctypes.data, vel.ctypes.data))
+        return pose, vel
+
+    def set_body_states(self, indices, pose7=None, vel6=None):
+        idx = np.ascontiguousarray(indices, np.int32)
+        p = None if pose7 is None else np.ascontiguousarray(pose7, np.float32)
+        v = None if vel6 is None else np.ascontiguousarray(vel6, np.float32)
+        self._check(self.L.rb_world_set_body_states(self.h, len(idx), idx.ctypes.data,
+                                                    None if p is None else p.ctypes.data,
+                                                    None if v is None else v.ctypes.data))
+
+    def counters(self):
+        c = A.RbCounters()
+        self._check(self.L.rb_world_get_counters(self.h, C.byref(c)))
+        return c.as_dict()
+
+    def enable_profiling(self, flag=True):
+        self._check(self.L.rb_world_enable_profiling(self.h, 1 if flag else 0))
+
+    def contact_pairs(self):
+        n = self._check(self.L.rb_world_get_contact_pairs(self.h, 0, None, None, None, None, None))
+        pc = np.zeros((n, 2), np.int32)
+        nc = np.zeros(n, np.int32)
+        col = np.zeros(n, np.int32)
+        nrm = np.zeros((n, 3), np.float32)
+        imp = np.zeros((n, 4), np.float32)
+        if n:
+            self._check(self.L.rb_world_get_contact_pairs(self.h, n, pc.ctypes.data, nc.ctypes.data, col.ctypes.data,
+                                                          nrm.ctypes.data, imp.ctypes.data))
+        return dict(colliders=pc, num_contacts=nc, color=col, normal=nrm, impulses=imp)
+
+    def debug_read(self, table, dtype):
+        n = self.L.rb_world_debug_read(self.h, table.encode(), None, 0)
+        if n < 0:
+            raise KeyError(f"{table}: {self.L.rb_last_error().decode()}")
+        buf = np.zeros(max(int(n), 1), np.uint8)
+        self.L.rb_world_debug_read(self.h, table.encode(), buf.ctypes.data, n)
+        return buf[:n].view(dtype)
+
+    def label_components(self):
+        out = np.zeros(self.nb, np.int32)
+        self._check(self.L.rb_world_label_components(self.h, out.ctypes.data))
+        return out
+
+    def set_owned_bodies(self, owned):
+        o = np.ascontiguousarray(owned, np.uint8)
+        assert o.shape == (self.nb,)
+        self._check(self.L.rb_world_set_owned_bodies(self.h, o.ctypes.data))
+
+    def state_buffer(self):
+        p = C.c_void_p()
+        n = C.c_int64()
+        self._check(self.L.rb_world_state_buffer(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+
+class PhysicsWorld:
+    """PhysicsWorld facade (src/pipeline/physics_world.rs): sets + pipeline + gravity."""
+
+    def __init__(self, scene=None, integration_parameters=None, device=0, _lib=None):
+        self.gravity = (0.0, -9.81, 0.0)
+        self.bodies = RigidBodySet()
+        self.colliders = ColliderSet()
+        self.impulse_joints = ImpulseJointSet()
+        self.integration_parameters = integration_parameters or A.RbIntegrationParameters.default()
+        self.physics_pipeline = PhysicsPipeline(self.integration_parameters, device, _lib=_lib)
+        self._dirty = True
+        if scene is not None:
+            self.gravity = scene.gravity
+            self.bodies, self.colliders, self.impulse_joints = scene.bodies, scene.colliders, scene.joints
+
+    def insert(self, body_builder, collider_builder):
+        h = self.bodies.insert(body_builder)
+        self.colliders.insert_with_parent(collider_builder, h)
+        self._dirty = True
+        return h
+
+    def insert_impulse_joint(self, body1, body2, joint_builder):
+        self._dirty = True
+        return self.impulse_joints.insert(body1, body2, joint_builder)
+
+    def _flush(self):
+        if self._dirty:
+            self.physics_pipeline.upload(self.bodies, self.colliders, self.impulse_joints)
+            self._dirty = False
+
+    def step(self, n=1, sync=True):
+        self._flush()
+        self.physics_pipeline.step(self.gravity, n, sync)
+
+    def body_states(self):
+        self._flush()
+        return self.physics_pipeline.body_states()
+
+    def counters(self):
+        self._flush()
+        return self.physics_pipeline.counters()
+
+    def contact_pairs(self):
+        self._flush()
+        return self.physics_pipeline.contact_pairs()
+
+    def debug_read(self, table, dtype):
+        self._flush()
+        return self.physics_pipeline.debug_read(table, dtype)

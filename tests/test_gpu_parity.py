@@ -1,0 +1,121 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Bit-exact at sizes the oracle finishes in seconds; size-independent properties at BASELINE sizes."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from parity_util import compare_worlds, is_exact
+from rapier_b200 import scenes
+from rapier_b200.world import PhysicsWorld
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("pyramids_2x2x10", lambda: scenes.pyramids(2, 2, 10), 40, 10),
+    ("pile_with_joint_chain", lambda: scenes.box_pile(4, 4, 5), 200, 25),
+    ("single_pyramid_20", lambda: scenes.single_pyramid(20), 30, 10),
+    ("pyramid3_large_island", lambda: scenes.pyramid3(10), 30, 10),
+    ("joint_grid_large_island", lambda: scenes.joint_grid(20), 60, 20),
+    ("ball_on_slab", lambda: scenes.box_on_ground("ball", 2.0), 100, 25),
+    ("keva_1", lambda: scenes.keva(1), 30, 10),
+]
+
+
+@pytest.mark.parametrize("name,make,steps,every", CASES, ids=[c[0] for c in CASES])
+def test_cuda_matches_oracle_bit_for_bit(built, name, make, steps, every):
+    scene = make()
+    w = PhysicsWorld(scene)
+    o = oracle_lib.OracleWorld(scene)
+    for i in range(steps):
+        w.step()
+        o.step()
+        if i % every == every - 1 or i < 2:
+            d = compare_worlds(w, o)
+            assert is_exact(d), f"{name}: step {i}: {d}"
+
+
+def test_many_pyramids_full_size_matches_oracle(built):
+    """b3d_many_pyramids (reference file: 10 780 cubes): first steps bit-exact against the oracle."""
+    scene = scenes.many_pyramids()
+    w = PhysicsWorld(scene)
+    o = oracle_lib.OracleWorld(scene, threads=8)
+    for i in range(6):
+        w.step()
+        o.step()
+    d = compare_worlds(w, o)
+    assert is_exact(d), d
+    c = w.counters()
+    assert c["num_pairs"] == 196 * 145 and c["num_active_manifolds"] == 196 * 145
+
+
+def test_many_pyramids_full_size_properties(built):
+    """Size-independent properties after 300 steps at full size: pyramids stay standing, the ground
+    carries the whole weight (sum of ground-contact impulses = M g dt), state is finite, and a second
+    run reproduces the first bit for bit."""
+    scene = scenes.many_pyramids()
+    w = PhysicsWorld(scene)
+    p0, _ = w.body_states()
+    w.step(300)
+    p1, v1 = w.body_states()
+    assert np.isfinite(p1).all() and np.isfinite(v1).all()
+    assert np.abs(p1[:, :3] - p0[:, :3]).max() < 0.05
+    assert np.abs(v1).max() < 0.02
+    cp = w.contact_pairs()
+    ground = cp["colliders"][:, 0] == 0
+    total_weight_impulse = 10780 * 100.0 * 10.0 / 60.0   # 1 m^3 cubes, density 100, g = 10, dt = 1/60
+    got = float(cp["impulses"][ground].sum())
+    assert abs(got - total_weight_impulse) / total_weight_impulse < 0.01
+    w2 = PhysicsWorld(scene)
+    w2.step(300)
+    p2, v2 = w2.body_states()
+    assert (p1.view(np.uint32) == p2.view(np.uint32)).all() and (v1.view(np.uint32) == v2.view(np.uint32)).all()
+
+
+def test_long_run_drift_vs_oracle(built):
+    """north_star: <= 5 % pose drift vs the CPU path after 1000 steps (here the drift is exactly 0)."""
+    scene = scenes.pyramids(2, 3, 10)
+    w = PhysicsWorld(scene)
+    o = oracle_lib.OracleWorld(scene, threads=4)
+    w.step(1000)
+    o.step(1000)
+    pg, _ = w.body_states()
+    po, _ = o.body_states()
+    height = 10.0
+    drift = np.linalg.norm(pg[:, :3] - po[:, :3], axis=1).max() / height
+    assert drift <= 0.05
+    assert (pg.view(np.uint32) == po.view(np.uint32)).all()
+
+
+def test_step_host_round_trip(built):
+    """rb_world_step_host (host buffers in/out) gives the same trajectory as device-resident stepping."""
+    scene = scenes.pyramids(1, 2, 6)
+    a = PhysicsWorld(scene)
+    b = PhysicsWorld(scene)
+    b._flush()
+    nb = len(scene.bodies)
+    pose, vel = b.body_states()
+    state = np.concatenate([pose, vel], axis=1).astype(np.float32).copy()
+    out = np.zeros_like(state)
+    for _ in range(20):
+        a.step()
+        b.physics_pipeline.step_host(scene.gravity, state, out)
+        state, out = out, state
+    pa, va = a.body_states()
+    assert (state[:, :7].view(np.uint32) == pa.view(np.uint32)).all()
+    assert (state[:, 7:].view(np.uint32) == va.view(np.uint32)).all()
+    assert nb == state.shape[0]
+
+
+def test_empty_and_ragged(built):
+    from rapier_b200.sets import ColliderBuilder, RigidBodyBuilder
+    PhysicsWorld(scenes.Scene("empty")).step(3)
+    s = scenes.Scene("ragged")
+    s.bodies.insert(RigidBodyBuilder.dynamic().translation((0, 5, 0)))
+    s.insert(RigidBodyBuilder.dynamic().translation((3, 5, 0)), ColliderBuilder.ball(0.5))
+    s.colliders.insert(ColliderBuilder.cuboid(5, 0.5, 5))
+    w = PhysicsWorld(s)
+    o = oracle_lib.OracleWorld(s)
+    for _ in range(120):
+        w.step()
+        o.step()
+    assert is_exact(compare_worlds(w, o))
