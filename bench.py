@@ -83,6 +83,16 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Threads the CPU arm may use: the cores this process is allowed to run on (capped at 32: the
+    colour stages of this scene hold a few thousand constraints each)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 32))
+
+
 def algorithmic_bytes(m, b, j):
     """SURVEY.md 8(d) / BASELINE.md 4: streaming model, f32, twist friction, p = 4, S = 4."""
     return 12076 * m + 1608 * b + 6576 * j
@@ -92,7 +102,7 @@ def run_reference(args):
     """CPU arm: the oracle (scalar port of the reference's algorithm) with all host threads."""
     import oracle_lib
     from rapier_b200 import scenes  # noqa: F401
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -285,7 +295,7 @@ def main():
         cpu = None
         try:
             import oracle_lib
-            cores = os.cpu_count() or 1
+            cores = host_threads()
             ow = oracle_lib.OracleWorld(scene_for(args.scene, 1), threads=cores)
             ow.step(3)
             t0 = time.perf_counter()

@@ -40,7 +40,9 @@ public:
         pending_.store(nthreads_ - 1, std::memory_order_release);
         epoch_.fetch_add(1, std::memory_order_acq_rel);
         job(0);
+        int spins = 0;
         while (pending_.load(std::memory_order_acquire) != 0) {
+            if (++spins > 2000) { std::this_thread::yield(); spins = 1000; }
         }
     }
     ~Pool() { stop(); }
@@ -57,7 +59,7 @@ private:
                     int spins = 0;
                     while ((e = epoch_.load(std::memory_order_acquire)) == seen) {
                         if (quit_.load(std::memory_order_acquire)) return;
-                        if (++spins > 20000) { std::this_thread::yield(); spins = 0; }
+                        if (++spins > 2000) { std::this_thread::yield(); spins = 1000; }
                     }
                     seen = e;
                     (*job_)(t);

@@ -142,6 +142,7 @@ struct RbWorld {
     int device = 0;
     int num_sms = 1;
     int collide_blocks = 1, large_blocks = 1, item_blocks = 1;
+    int collide_threads = COLLIDE_THREADS, item_threads = ITEM_THREADS, large_threads = LARGE_THREADS;
     long long kernels = 0, steps = 0;
     bool profiling = false;
     float ms_collide = 0, ms_solve = 0, ms_step = 0;
@@ -397,6 +398,15 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_items, ITEM_THREADS, ITEM_SMEM_BYTES);
     if (occ < 1) occ = 1;
     W->item_blocks = W->num_sms * occ;
+    {   // debugging overrides (never needed in production): shrink the launch geometry
+        auto envi = [](const char* n, int d) { const char* v = getenv(n); return v ? atoi(v) : d; };
+        W->collide_blocks = std::min(W->collide_blocks, envi("RB_COLLIDE_BLOCKS", W->collide_blocks));
+        W->item_blocks = std::min(W->item_blocks, envi("RB_ITEM_BLOCKS", W->item_blocks));
+        W->large_blocks = std::min(W->large_blocks, envi("RB_LARGE_BLOCKS", W->large_blocks));
+        W->collide_threads = std::min(COLLIDE_THREADS, envi("RB_COLLIDE_THREADS", COLLIDE_THREADS));
+        W->item_threads = std::min(ITEM_THREADS, envi("RB_ITEM_THREADS", ITEM_THREADS));
+        W->large_threads = std::min(LARGE_THREADS, envi("RB_LARGE_THREADS", LARGE_THREADS));
+    }
 #else
     W->emu_smem.assign(ITEM_MAX_BODIES * SB_STRIDE, 0.0f);
 #endif
@@ -502,6 +512,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.scan_tmp, (size_t)1 << 20);
     ALLOC(w.item_body_start, w.item_cap + 2); ALLOC(w.item_cons_start, w.item_cap + 2); ALLOC(w.item_joint_start, w.item_cap + 2);
     ALLOC(w.item_cursor, 3 * (w.item_cap + 2));
+    ALLOC(w.item_flags, w.item_cap + 2);
     ALLOC(w.item_bodies, NB); ALLOC(w.body_local, NB); ALLOC(w.body_item, NB);
     ALLOC(w.cons_pair_tmp, w.cons_cap); ALLOC(w.cons_pair, w.cons_cap);
     ALLOC(w.item_color_off, (size_t)(w.item_cap + 1) * (NUM_COLORS + 1));
@@ -707,12 +718,12 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         bool prof = W->profiling;
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s], W->stream));
         void* a1[] = {(void*)&W->w};
-        CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(COLLIDE_THREADS), a1, 0, W->stream));
+        CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, 0, W->stream));
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 1], W->stream));
-        k_solve_items<<<W->item_blocks, ITEM_THREADS, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
+        k_solve_items<<<W->item_blocks, W->item_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
         CK(cudaGetLastError());
         void* a2[] = {(void*)&W->w, (void*)&g};
-        CK(cudaLaunchCooperativeKernel((void*)k_solve_large, dim3(W->large_blocks), dim3(LARGE_THREADS), a2, 0, W->stream));
+        CK(cudaLaunchCooperativeKernel((void*)k_solve_large, dim3(W->large_blocks), dim3(W->large_threads), a2, 0, W->stream));
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 2], W->stream));
         W->kernels += 3;
     }
@@ -971,7 +982,7 @@ int rb_world_label_components(RbWorld* W, int32_t* component_of_body) {
     CK(cudaStreamSynchronize(W->stream));
     CK(h2d(&W->w.st->sched_dirty, &one, sizeof(int)));
     void* a1[] = {(void*)&W->w};
-    CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(COLLIDE_THREADS), a1, 0, W->stream));
+    CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, 0, W->stream));
     W->kernels++;
 #else
     W->w.st->sched_dirty = 1;

@@ -551,21 +551,18 @@ RB_PHASE void grid_exclusive_scan(const Ctx& ctx, const int* in, int* out, int n
     ctx.grid_sync();
 }
 
+// Concurrent union-find (hook the larger root under the smaller one; find with path HALVING).
+// Invariant: parent[y] <= y for every y, so no cycle can form; every value a racing thread may
+// store into parent[cur] is an ancestor of cur that is smaller than cur.
 RB_HD int uf_find(int* parent, int x) {
-    int r = x;
-    while (true) {
-        int p = parent[r];
-        if (p == r) break;
-        r = p;
+    int cur = x;
+    for (;;) {
+        int next = parent[cur];
+        if (next == cur) return cur;
+        int gp = parent[next];
+        if (gp != next) parent[cur] = gp;   // gp < next < cur
+        cur = next;
     }
-    // path halving towards the root found (benign races: every store writes a valid ancestor)
-    while (true) {
-        int p = parent[x];
-        if (p == r || p == x) break;
-        parent[x] = r;
-        x = p;
-    }
-    return r;
 }
 RB_HD void uf_union(int* parent, int a, int b) {  // hook the larger root under the smaller one
     for (;;) {

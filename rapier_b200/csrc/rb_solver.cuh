@@ -98,7 +98,7 @@ RB_HD float bouncy(float restitution, bool is_new) {  // contact_pair.rs:773-779
 
 // S2: contact_with_twist_friction.rs:58-424 for the manifold scheduled at slot q.
 template <class B>
-RB_HD void cons_generate(const World& w, const B& bd, int q, int buf) {
+RB_HD void cons_generate(const World& w, const B& bd, int q, int buf, int item) {
     int4 h = w.cons_hdr[q];
     const int p = h.x, id1 = h.y, id2 = h.z;
     BodyState g1 = gather_body(bd, id1), g2 = gather_body(bd, id2);
@@ -184,7 +184,7 @@ RB_HD void cons_generate(const World& w, const B& bd, int q, int buf) {
     crow(w, CR_WI, q) = make_float4(wimp, -wimp, 0.0f, 0.0f);
     h.w = count;
     w.cons_hdr[q] = h;
-    if (any_seed) w.st->any_bouncy = 1;
+    if (any_seed) w.item_flags[item] = 1;
 }
 
 RB_HD float getk(float4 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
@@ -603,6 +603,7 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
     const int ovf = w.color_pos[COLOR_OVERFLOW], jovf = w.jcolor_pos[COLOR_OVERFLOW];
     const int tid = ex.tid(), nth = ex.nth();
 
+    if (tid == 0) w.item_flags[item] = 0;   // bit 0: some contact of this item holds a restitution seed
     // a7 + S1: forces, solver bodies, per-substep increments
     for (int l = b0 + tid; l < b1; l += nth) {
         int b = w.item_bodies[l];
@@ -621,7 +622,7 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
     }
     ex.sync();
     // S2 generate
-    for (int q = c0 + tid; q < c1; q += nth) cons_generate(w, bd, q, buf);
+    for (int q = c0 + tid; q < c1; q += nth) cons_generate(w, bd, q, buf, item);
     ex.sync();
 
     for (int sub = 0; sub < P.num_substeps; ++sub) {
@@ -723,7 +724,7 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
         }
     }
     // S9 restitution
-    if (st->any_bouncy) {
+    if (w.item_flags[item]) {
         for (int c = 0; c < ncol; ++c) {
             int a = c0 + coff[c], e = c0 + coff[c + 1];
             if (e > c1) e = c1;

@@ -153,6 +153,7 @@ struct World {
     int* item_cons_start;             // [item_cap + 1]
     int* item_joint_start;            // [item_cap + 1]
     int* item_cursor;                 // [3 * (item_cap + 1)] scatter cursors
+    int* item_flags;                  // [item_cap + 1] per-item flags of the current step
     int* item_bodies;                 // [nb] global body ids grouped by item
     int* body_local;                  // [nb] index of a body inside its item
     int* body_item;                   // [nb] item of a body
