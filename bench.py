@@ -287,7 +287,7 @@ def main():
     achieved = a_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else None
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_solve_items_dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_solve_coop_dram_bytes_per_launch")
     except Exception:
         pass
 
@@ -322,7 +322,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": "k_solve_items", "kernel_ms": solve_ms, "algorithmic_bytes_per_launch": a_bytes,
+                         "kernel": "k_solve_coop", "kernel_ms": solve_ms, "algorithmic_bytes_per_launch": a_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "note": "algorithmic bytes = streaming model of SURVEY 8(d); the working set is L2/shared-memory resident, see DESIGN.md"},
             "cpu_baseline": cpu,

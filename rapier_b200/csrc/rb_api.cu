@@ -58,9 +58,10 @@ static cudaError_t dev_set(void* d, int v, size_t n) { if (n) memset(d, v, n); r
 // kernels
 // ------------------------------------------------------------------------------------------------
 constexpr int COLLIDE_THREADS = 256;
-constexpr int ITEM_THREADS = 128;
-constexpr int LARGE_THREADS = 256;
+constexpr int COOP_THREADS = 128;
+constexpr int REST_THREADS = 256;
 constexpr int ITEM_SMEM_BYTES = ITEM_MAX_BODIES * SB_STRIDE * 4;
+constexpr int COOP_SMEM_BYTES = COOP_SMEM_FLOATS * 4;
 
 struct Grav { float x, y, z; };
 
@@ -97,27 +98,45 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w) {
     GridCtx ctx;
     collide_pipeline(ctx, w);
 }
-__global__ void __launch_bounds__(ITEM_THREADS) k_solve_items(World w, Grav g) {
+// Items that fit shared memory: one CTA per item, bodies + constraints staged in shared memory,
+// four lanes per constraint (rb_solver.cuh "lane-cooperative path").
+__global__ void __launch_bounds__(COOP_THREADS, 2) k_solve_coop(World w, Grav g) {
     extern __shared__ float smem[];
     BlockCtx ctx;
     SmemBodies bd;
     bd.s = smem;
-    BlockExec ex;
-    ex.c = &ctx;
+    CoopStore cs;
+    cs.base = smem + COOP_MAX_BODIES * SB_STRIDE;
     const int n = w.st->nitems;
     for (int item = 1 + ctx.bid; item < n; item += ctx.nblocks) {
-        solve_item(ex, w, bd, item, mk3(g.x, g.y, g.z));
-        ex.sync();
+        if (!item_is_coop(w, item)) continue;
+        solve_item_coop<4>(ctx, w, bd, cs, item, mk3(g.x, g.y, g.z));
+        ctx.block_sync();
     }
 }
-__global__ void __launch_bounds__(LARGE_THREADS) k_solve_large(World w, Grav g) {
+// Everything else: items streamed from HBM by one CTA each, then the grid-wide "large" item 0.
+__global__ void __launch_bounds__(REST_THREADS) k_solve_rest(World w, Grav g) {
+    extern __shared__ float smem[];
+    GridCtx gctx;
+    {
+        BlockCtx ctx;
+        SmemBodies bd;
+        bd.s = smem;
+        BlockExec ex;
+        ex.c = &ctx;
+        const int n = w.st->nitems;
+        for (int item = 1 + ctx.bid; item < n; item += ctx.nblocks) {
+            if (item_is_coop(w, item)) continue;
+            solve_item(ex, w, bd, item, mk3(g.x, g.y, g.z));
+            ex.sync();
+        }
+    }
     if (w.st->nlarge_bodies == 0) return;
-    GridCtx ctx;
-    GlobalBodies bd;
-    bd.w = &w;
-    GridExec ex;
-    ex.c = &ctx;
-    solve_item(ex, w, bd, 0, mk3(g.x, g.y, g.z));
+    GlobalBodies gb;
+    gb.w = &w;
+    GridExec gex;
+    gex.c = &gctx;
+    solve_item(gex, w, gb, 0, mk3(g.x, g.y, g.z));
 }
 __global__ void k_init_bodies(World w) {
     GridCtx ctx;
@@ -141,8 +160,8 @@ struct RbWorld {
     std::vector<void*> allocs;
     int device = 0;
     int num_sms = 1;
-    int collide_blocks = 1, large_blocks = 1, item_blocks = 1;
-    int collide_threads = COLLIDE_THREADS, item_threads = ITEM_THREADS, large_threads = LARGE_THREADS;
+    int collide_blocks = 1, rest_blocks = 1, coop_blocks = 1;
+    int collide_threads = COLLIDE_THREADS, coop_threads = COOP_THREADS, rest_threads = REST_THREADS;
     long long kernels = 0, steps = 0;
     bool profiling = false;
     float ms_collide = 0, ms_solve = 0, ms_step = 0;
@@ -387,28 +406,28 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
     W->num_sms = prop.multiProcessorCount;
     if (!prop.cooperativeLaunch) { set_err("device lacks cooperative launch%s", ""); delete W; return nullptr; }
     cudaStreamCreateWithFlags(&W->stream, cudaStreamNonBlocking);
-    cudaFuncSetAttribute(k_solve_items, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
+    cudaFuncSetAttribute(k_solve_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_SMEM_BYTES);
+    cudaFuncSetAttribute(k_solve_rest, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_collide, COLLIDE_THREADS, 0);
     if (occ < 1) { set_err("k_collide cannot be resident%s", ""); delete W; return nullptr; }
     W->collide_blocks = W->num_sms * (occ > 2 ? 2 : occ);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_large, LARGE_THREADS, 0);
-    if (occ < 1) { set_err("k_solve_large cannot be resident%s", ""); delete W; return nullptr; }
-    W->large_blocks = W->num_sms * (occ > 2 ? 2 : occ);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_items, ITEM_THREADS, ITEM_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_rest, REST_THREADS, ITEM_SMEM_BYTES);
+    if (occ < 1) { set_err("k_solve_rest cannot be resident%s", ""); delete W; return nullptr; }
+    W->rest_blocks = W->num_sms * (occ > 2 ? 2 : occ);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_coop, COOP_THREADS, COOP_SMEM_BYTES);
     if (occ < 1) occ = 1;
-    W->item_blocks = W->num_sms * occ;
+    W->coop_blocks = W->num_sms * occ;
     {   // debugging overrides (never needed in production): shrink the launch geometry
         auto envi = [](const char* n, int d) { const char* v = getenv(n); return v ? atoi(v) : d; };
         W->collide_blocks = std::min(W->collide_blocks, envi("RB_COLLIDE_BLOCKS", W->collide_blocks));
-        W->item_blocks = std::min(W->item_blocks, envi("RB_ITEM_BLOCKS", W->item_blocks));
-        W->large_blocks = std::min(W->large_blocks, envi("RB_LARGE_BLOCKS", W->large_blocks));
+        W->coop_blocks = std::min(W->coop_blocks, envi("RB_COOP_BLOCKS", W->coop_blocks));
+        W->rest_blocks = std::min(W->rest_blocks, envi("RB_REST_BLOCKS", W->rest_blocks));
         W->collide_threads = std::min(COLLIDE_THREADS, envi("RB_COLLIDE_THREADS", COLLIDE_THREADS));
-        W->item_threads = std::min(ITEM_THREADS, envi("RB_ITEM_THREADS", ITEM_THREADS));
-        W->large_threads = std::min(LARGE_THREADS, envi("RB_LARGE_THREADS", LARGE_THREADS));
+        W->rest_threads = std::min(REST_THREADS, envi("RB_REST_THREADS", REST_THREADS));
     }
 #else
-    W->emu_smem.assign(ITEM_MAX_BODIES * SB_STRIDE, 0.0f);
+    W->emu_smem.assign(ITEM_MAX_BODIES * SB_STRIDE + COOP_SMEM_FLOATS, 0.0f);
 #endif
     return W;
 }
@@ -720,10 +739,10 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         void* a1[] = {(void*)&W->w};
         CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, 0, W->stream));
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 1], W->stream));
-        k_solve_items<<<W->item_blocks, W->item_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
+        k_solve_coop<<<W->coop_blocks, W->coop_threads, COOP_SMEM_BYTES, W->stream>>>(W->w, g);
         CK(cudaGetLastError());
         void* a2[] = {(void*)&W->w, (void*)&g};
-        CK(cudaLaunchCooperativeKernel((void*)k_solve_large, dim3(W->large_blocks), dim3(W->large_threads), a2, 0, W->stream));
+        CK(cudaLaunchCooperativeKernel((void*)k_solve_rest, dim3(W->rest_blocks), dim3(W->rest_threads), a2, ITEM_SMEM_BYTES, W->stream));
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 2], W->stream));
         W->kernels += 3;
     }
@@ -762,7 +781,12 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         BlockExec bex;
         bex.c = &bctx;
         int n = W->w.st->nitems;
-        for (int item = 1; item < n; ++item) solve_item(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
+        CoopStore cst;
+        cst.base = W->emu_smem.data() + ITEM_MAX_BODIES * SB_STRIDE;
+        for (int item = 1; item < n; ++item) {
+            if (item_is_coop(W->w, item)) solve_item_coop<1>(bctx, W->w, sb, cst, item, mk3(g.x, g.y, g.z));
+            else solve_item(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
+        }
         if (W->w.st->nlarge_bodies > 0) {
             GlobalBodies gb;
             gb.w = &W->w;

@@ -96,9 +96,73 @@ RB_HD float bouncy(float restitution, bool is_new) {  // contact_pair.rs:773-779
     return is_new ? (restitution > 0.0f ? 1.0f : 0.0f) : (restitution >= 1.0f ? 1.0f : 0.0f);
 }
 
-// S2: contact_with_twist_friction.rs:58-424 for the manifold scheduled at slot q.
+// One contact constraint (manifold) as the sweeps see it.  In the register-resident path a thread keeps
+// its constraint in this struct for the whole step; the streaming path loads / stores it per sweep.
+struct Cons {
+    int id1, id2, nc;
+    vec3 dir; float fric;         // dir1, friction limit
+    vec3 t1; float wr;            // tangent1, twist effective mass
+    vec3 dp1[MAX_PTS]; float r[MAX_PTS];       // lever arms body 1, projected masses
+    vec3 dp2[MAX_PTS]; float dist0[MAX_PTS];   // lever arms body 2, rebased separations
+    vec3 lp1[MAX_PTS], lp2[MAX_PTS];           // builder anchors (body-local)
+    vec3 tdp1, tdp2; float tr0, tr1, tr2;      // friction-centre arms, tangent K matrix
+    float twd[MAX_PTS];
+    float imp[MAX_PTS], acc[MAX_PTS];          // normal impulses + accumulators
+    float ti0, ti1, ta0, ta1, wi, wa;          // tangent / twist impulses + accumulators
+};
+
+RB_HD void cons_store_static(const World& w, int q, const Cons& c) {
+    crow(w, CR_DIR, q) = f4(c.dir, c.fric);
+    crow(w, CR_T1, q) = f4(c.t1, c.wr);
+#pragma unroll
+    for (int k = 0; k < MAX_PTS; ++k) {
+        if (k < c.nc) {
+            crow(w, CR_DP1 + k, q) = f4(c.dp1[k], c.r[k]);
+            crow(w, CR_DP2 + k, q) = f4(c.dp2[k], c.dist0[k]);
+            float4 a = crow(w, CR_LP1 + k, q), b = crow(w, CR_LP2 + k, q);   // keep w: seed / cid
+            crow(w, CR_LP1 + k, q) = f4(c.lp1[k], a.w);
+            crow(w, CR_LP2 + k, q) = f4(c.lp2[k], b.w);
+        }
+    }
+    crow(w, CR_TDP1, q) = f4(c.tdp1, c.tr0);
+    crow(w, CR_TDP2, q) = f4(c.tdp2, c.tr1);
+    float4 l1 = crow(w, CR_LFC1, q);
+    l1.w = c.tr2;
+    crow(w, CR_LFC1, q) = l1;
+    crow(w, CR_TWD, q) = make_float4(c.twd[0], c.twd[1], c.twd[2], c.twd[3]);
+}
+RB_HD void cons_store_dyn(const World& w, int q, const Cons& c) {
+    crow(w, CR_IMP, q) = make_float4(c.imp[0], c.imp[1], c.imp[2], c.imp[3]);
+    crow(w, CR_ACC, q) = make_float4(c.acc[0], c.acc[1], c.acc[2], c.acc[3]);
+    crow(w, CR_TI, q) = make_float4(c.ti0, c.ti1, c.ta0, c.ta1);
+    crow(w, CR_WI, q) = make_float4(c.wi, c.wa, 0.0f, 0.0f);
+}
+RB_HD void cons_load(const World& w, int q, Cons& c) {
+    int4 h = w.cons_hdr[q];
+    c.id1 = h.y; c.id2 = h.z; c.nc = h.w;
+    float4 a = crow(w, CR_DIR, q), b = crow(w, CR_T1, q);
+    c.dir = xyz(a); c.fric = a.w; c.t1 = xyz(b); c.wr = b.w;
+#pragma unroll
+    for (int k = 0; k < MAX_PTS; ++k) {
+        if (k < c.nc) {
+            float4 d1 = crow(w, CR_DP1 + k, q), d2 = crow(w, CR_DP2 + k, q);
+            c.dp1[k] = xyz(d1); c.r[k] = d1.w; c.dp2[k] = xyz(d2); c.dist0[k] = d2.w;
+            c.lp1[k] = xyz(crow(w, CR_LP1 + k, q)); c.lp2[k] = xyz(crow(w, CR_LP2 + k, q));
+        }
+    }
+    float4 t1r = crow(w, CR_TDP1, q), t2r = crow(w, CR_TDP2, q), tw = crow(w, CR_TWD, q);
+    c.tdp1 = xyz(t1r); c.tr0 = t1r.w; c.tdp2 = xyz(t2r); c.tr1 = t2r.w; c.tr2 = crow(w, CR_LFC1, q).w;
+    c.twd[0] = tw.x; c.twd[1] = tw.y; c.twd[2] = tw.z; c.twd[3] = tw.w;
+    float4 im = crow(w, CR_IMP, q), ac = crow(w, CR_ACC, q), ti = crow(w, CR_TI, q), wi = crow(w, CR_WI, q);
+    c.imp[0] = im.x; c.imp[1] = im.y; c.imp[2] = im.z; c.imp[3] = im.w;
+    c.acc[0] = ac.x; c.acc[1] = ac.y; c.acc[2] = ac.z; c.acc[3] = ac.w;
+    c.ti0 = ti.x; c.ti1 = ti.y; c.ta0 = ti.z; c.ta1 = ti.w; c.wi = wi.x; c.wa = wi.y;
+}
+
+// S2: contact_with_twist_friction.rs:58-424 for the manifold scheduled at slot q.  Fills `c`; the
+// rarely used fields (restitution seeds, friction-centre anchors, contact ids) go to the HBM rows.
 template <class B>
-RB_HD void cons_generate(const World& w, const B& bd, int q, int buf, int item) {
+RB_HD void cons_generate(const World& w, const B& bd, int q, int buf, int item, Cons& c) {
     int4 h = w.cons_hdr[q];
     const int p = h.x, id1 = h.y, id2 = h.z;
     BodyState g1 = gather_body(bd, id1), g2 = gather_body(bd, id2);
@@ -114,252 +178,263 @@ RB_HD void cons_generate(const World& w, const B& bd, int q, int buf, int item) 
     vec3 fc1 = zero3(), fc2 = zero3();
     float tws = 0.0f, tgs0 = 0.0f, tgs1 = 0.0f;
     vec3 pts[MAX_PTS];
-    float imp[MAX_PTS] = {0.f, 0.f, 0.f, 0.f}, acc[MAX_PTS] = {0.f, 0.f, 0.f, 0.f};
     bool any_seed = false;
-    for (int k = 0; k < count; ++k) {
-        float4 a1 = prow(w, buf, PR_A1 + k, p), a2 = prow(w, buf, PR_A2 + k, p);
-        int cid = as_int(a1.w);
-        float4 pd = prow(w, buf, PR_PD + cid, p);
-        vec3 wt = xyz(prow(w, buf, PR_TW + cid, p));
-        vec3 dp1 = xyz(prow(w, buf, PR_DP1 + cid, p)), dp2 = xyz(prow(w, buf, PR_DP2 + cid, p));
-        float ws_imp = pd.y, ws_twist = pd.z;
-        float w0 = dot3(wt, t1), w1 = dot3(wt, t2);
-        float bz = bouncy(restitution, pd.x == 0.0f);
-        vec3 p1 = xform(g1.p, xyz(a1));
-        vec3 p2 = xform(g2.p, xyz(a2));
-        float dist = dot3(p1 - p2, dir);
-        vec3 point = com1 + dp1;
-        pts[k] = point;
-        fc1 = fc1 + point * inv_n;
-        fc2 = fc2 + (com2 + dp2) * inv_n;
-        vec3 v1 = g1.lin + cross3(g1.ang, dp1);
-        vec3 v2 = g2.lin + cross3(g2.ang, dp2);
-        tws = tws + ws_twist * inv_n;
-        tgs0 = tgs0 + w0 * inv_n;
-        tgs1 = tgs1 + w1 * inv_n;
-        vec3 td1 = cross3(dp1, dir), td2 = cross3(dp2, -dir);
-        vec3 itd1 = smul(g1.ii, td1), itd2 = smul(g2.ii, td2);
-        vec3 imsum = g1.im + g2.im;
-        float r = safe_inv(dot3(dir, had(imsum, dir)) + dot3(itd1, td1) + dot3(itd2, td2));
-        float pv = dot3(v1 - v2, dir);
-        float seed = bz * restitution * pv;
-        any_seed = any_seed || seed < 0.0f;
-        imp[k] = ws_imp;
-        acc[k] = -ws_imp;
-        crow(w, CR_DP1 + k, q) = f4(dp1, r);
-        crow(w, CR_DP2 + k, q) = f4(dp2, dist - dot3(point - (com2 + dp2), dir));
-        crow(w, CR_LP1 + k, q) = f4(xform_inv(g1.p, point), seed);
-        crow(w, CR_LP2 + k, q) = f4(xform_inv(g2.p, com2 + dp2), as_float_i(cid));
+    c.id1 = id1; c.id2 = id2; c.nc = count;
+    c.dir = dir; c.fric = nrm.w; c.t1 = t1;
+#pragma unroll
+    for (int k = 0; k < MAX_PTS; ++k) {
+        c.imp[k] = 0.0f; c.acc[k] = 0.0f; c.twd[k] = 0.0f;
+        if (k < count) {
+            float4 a1 = prow(w, buf, PR_A1 + k, p), a2 = prow(w, buf, PR_A2 + k, p);
+            int cid = as_int(a1.w);
+            float4 pd = prow(w, buf, PR_PD + cid, p);
+            vec3 wt = xyz(prow(w, buf, PR_TW + cid, p));
+            vec3 dp1 = xyz(prow(w, buf, PR_DP1 + cid, p)), dp2 = xyz(prow(w, buf, PR_DP2 + cid, p));
+            float ws_imp = pd.y, ws_twist = pd.z;
+            float w0 = dot3(wt, t1), w1 = dot3(wt, t2);
+            float bz = bouncy(restitution, pd.x == 0.0f);
+            vec3 p1 = xform(g1.p, xyz(a1));
+            vec3 p2 = xform(g2.p, xyz(a2));
+            float dist = dot3(p1 - p2, dir);
+            vec3 point = com1 + dp1;
+            pts[k] = point;
+            fc1 = fc1 + point * inv_n;
+            fc2 = fc2 + (com2 + dp2) * inv_n;
+            vec3 v1 = g1.lin + cross3(g1.ang, dp1);
+            vec3 v2 = g2.lin + cross3(g2.ang, dp2);
+            tws = tws + ws_twist * inv_n;
+            tgs0 = tgs0 + w0 * inv_n;
+            tgs1 = tgs1 + w1 * inv_n;
+            vec3 td1 = cross3(dp1, dir), td2 = cross3(dp2, -dir);
+            vec3 itd1 = smul(g1.ii, td1), itd2 = smul(g2.ii, td2);
+            vec3 imsum = g1.im + g2.im;
+            float r = safe_inv(dot3(dir, had(imsum, dir)) + dot3(itd1, td1) + dot3(itd2, td2));
+            float pv = dot3(v1 - v2, dir);
+            float seed = bz * restitution * pv;
+            any_seed = any_seed || seed < 0.0f;
+            c.imp[k] = ws_imp;
+            c.acc[k] = -ws_imp;
+            c.dp1[k] = dp1; c.r[k] = r;
+            c.dp2[k] = dp2; c.dist0[k] = dist - dot3(point - (com2 + dp2), dir);
+            c.lp1[k] = xform_inv(g1.p, point);
+            c.lp2[k] = xform_inv(g2.p, com2 + dp2);
+            crow(w, CR_LP1 + k, q).w = seed;
+            crow(w, CR_LP2 + k, q).w = as_float_i(cid);
+        }
     }
     float wimp = count > 1 ? tws : 0.0f;
     vec3 tdp1 = fc1 - com1, tdp2 = fc2 - com2;
-    float twd[MAX_PTS] = {0.f, 0.f, 0.f, 0.f};
     float wr = 0.0f;
     if (count > 1) {
-        for (int k = 0; k < count; ++k) twd[k] = norm(fc1 - pts[k]);
+#pragma unroll
+        for (int k = 0; k < MAX_PTS; ++k)
+            if (k < count) c.twd[k] = norm(fc1 - pts[k]);
         vec3 i1 = smul(g1.ii, dir), i2 = smul(g2.ii, -dir);
         wr = safe_inv(dot3(i1, dir) + dot3(i2, -dir));
     }
-    float tr[3];
-    vec3 itd1s[2], itd2s[2], td1s[2], td2s[2];
-    for (int j = 0; j < 2; ++j) {
-        vec3 tj = j == 0 ? t1 : t2;
-        vec3 td1 = cross3(tdp1, tj), td2 = cross3(tdp2, -tj);
-        vec3 itd1 = smul(g1.ii, td1), itd2 = smul(g2.ii, td2);
-        vec3 imsum = g1.im + g2.im;
-        tr[j] = dot3(tj, had(imsum, tj)) + dot3(itd1, td1) + dot3(itd2, td2);
-        td1s[j] = td1; td2s[j] = td2; itd1s[j] = itd1; itd2s[j] = itd2;
-    }
-    tr[2] = 2.0f * (dot3(itd1s[0], td1s[1]) + dot3(itd2s[0], td2s[1]));
-    crow(w, CR_DIR, q) = f4(dir, nrm.w);
-    crow(w, CR_T1, q) = f4(t1, wr);
-    crow(w, CR_TDP1, q) = f4(tdp1, tr[0]);
-    crow(w, CR_TDP2, q) = f4(tdp2, tr[1]);
-    crow(w, CR_LFC1, q) = f4(xform_inv(g1.p, fc1), tr[2]);
+    vec3 td10 = cross3(tdp1, t1), td20 = cross3(tdp2, -t1), td11 = cross3(tdp1, t2), td21 = cross3(tdp2, -t2);
+    vec3 itd10 = smul(g1.ii, td10), itd20 = smul(g2.ii, td20), itd11 = smul(g1.ii, td11), itd21 = smul(g2.ii, td21);
+    vec3 imsum = g1.im + g2.im;
+    c.tr0 = dot3(t1, had(imsum, t1)) + dot3(itd10, td10) + dot3(itd20, td20);
+    c.tr1 = dot3(t2, had(imsum, t2)) + dot3(itd11, td11) + dot3(itd21, td21);
+    c.tr2 = 2.0f * (dot3(itd10, td11) + dot3(itd20, td21));
+    c.wr = wr;
+    c.tdp1 = tdp1; c.tdp2 = tdp2;
+    c.ti0 = tgs0; c.ti1 = tgs1; c.ta0 = -tgs0; c.ta1 = -tgs1;
+    c.wi = wimp; c.wa = -wimp;
+    crow(w, CR_LFC1, q) = f4(xform_inv(g1.p, fc1), c.tr2);
     crow(w, CR_LFC2, q) = f4(xform_inv(g2.p, fc2), 0.0f);
-    crow(w, CR_TWD, q) = make_float4(twd[0], twd[1], twd[2], twd[3]);
-    crow(w, CR_IMP, q) = make_float4(imp[0], imp[1], imp[2], imp[3]);
-    crow(w, CR_ACC, q) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    crow(w, CR_TI, q) = make_float4(tgs0, tgs1, -tgs0, -tgs1);
-    crow(w, CR_WI, q) = make_float4(wimp, -wimp, 0.0f, 0.0f);
     h.w = count;
     w.cons_hdr[q] = h;
     if (any_seed) w.item_flags[item] = 1;
 }
 
-RB_HD float getk(float4 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
-RB_HD void setk(float4& v, int k, float x) { if (k == 0) v.x = x; else if (k == 1) v.y = x; else if (k == 2) v.z = x; else v.w = x; }
-
 // Sweep modes
 constexpr int MODE_WARMSTART = 0, MODE_BIASED = 1, MODE_RELAX = 2, MODE_RESTITUTION = 3;
 
-// One constraint, one sweep.  MODE_WARMSTART = builder.update + constraint.warmstart (fused,
-// worker.rs:438-539); MODE_BIASED / MODE_RELAX = (refresh_rhs_wo_bias +) solve.
+// ---- per-row primitives shared by the serial sweep and the lane-cooperative sweep -----------------
+struct PointPre { vec3 td1, td2, itd1, itd2; float rhs, cfm; };
+
+// Jacobians of one normal row + (biased / relax) its rhs and cfm from the CURRENT poses
+// (contact_with_twist_friction.rs:473-503 update, :543-550 refresh_rhs_wo_bias).
+RB_HD PointPre point_pre(const Params& P, const BodyState& g1, const BodyState& g2, vec3 dir, vec3 dp1, vec3 dp2,
+                         vec3 lp1, vec3 lp2, float dist0, int mode, float cfm_soft, float erp) {
+    PointPre o;
+    o.rhs = 0.0f;
+    o.cfm = 1.0f;
+    if (mode == MODE_BIASED || mode == MODE_RELAX) {
+        vec3 p1 = xform(g1.p, lp1);
+        vec3 p2 = xform(g2.p, lp2);
+        float dist = dist0 + dot3(p1 - p2, dir);
+        float rhs = max2(dist, 0.0f) * P.sub_inv_dt;
+        if (mode == MODE_BIASED) {
+            rhs = rhs + clampf(dist * erp, -P.max_corrective_velocity, 0.0f);
+            o.cfm = dist <= 0.0f ? cfm_soft : 1.0f;
+        }
+        o.rhs = rhs;
+    }
+    o.td1 = cross3(dp1, dir);
+    o.td2 = cross3(dp2, -dir);
+    o.itd1 = smul(g1.ii, o.td1);
+    o.itd2 = smul(g2.ii, o.td2);
+    return o;
+}
+// One projected Gauss-Seidel normal row (contact_constraint_element.rs:481-504): returns dlambda.
+RB_HD float point_solve(const PointPre& pp, float r, float imp, vec3 dir, vec3 v1, vec3 w1, vec3 v2, vec3 w2, float& new_imp) {
+    float dvel = dot3(dir, v1) + dot3(pp.td1, w1) - dot3(dir, v2) + dot3(pp.td2, w2) + pp.rhs;
+    float nl = pp.cfm * max2(imp - r * dvel, 0.0f);
+    new_imp = nl;
+    return nl - imp;
+}
+// End-of-step restitution row (contact_constraint_element.rs:508-534).
+RB_HD float point_restitution(const PointPre& pp, float r, float imp, float acc, float seed, vec3 dir, vec3 v1, vec3 w1, vec3 v2,
+                              vec3 w2, float& new_imp) {
+    float dvel = dot3(dir, v1) + dot3(pp.td1, w1) - dot3(dir, v2) + dot3(pp.td2, w2) + seed;
+    bool gate = seed < 0.0f && (acc + imp) > 0.0f;
+    float nl = max2(imp - r * dvel, 0.0f);
+    if (!gate) nl = imp;
+    new_imp = nl;
+    return nl - imp;
+}
+RB_HD void apply_normal(vec3 lin1, vec3 lin2, vec3 itd1, vec3 itd2, float dl, vec3& v1, vec3& w1, vec3& v2, vec3& w2) {
+    v1 = v1 + lin1 * dl;
+    w1 = w1 + itd1 * dl;
+    v2 = v2 + lin2 * (-dl);
+    w2 = w2 + itd2 * dl;
+}
+
+struct FrictionState { float ti0, ti1, wi; };
+// Twist then tangent (contact_with_twist_friction.rs:737-777; contact_constraint_element.rs:650-705, :735-756).
+RB_HD void friction_solve(const Params& P, const BodyState& g1, const BodyState& g2, vec3 dir, vec3 t1, vec3 t2, int nc,
+                          float tlimit, float wlimit, float wr, vec3 tdp1, vec3 tdp2, float tr0, float tr1, float tr2,
+                          bool relax, vec3 lfc1, vec3 lfc2, FrictionState& f, vec3& v1, vec3& w1, vec3& v2, vec3& w2) {
+    if (nc > 1) {
+        vec3 i1 = smul(g1.ii, dir), i2 = smul(g2.ii, dir);
+        float dvel = dot3(dir, w1 - w2) + 0.0f;
+        float nl = clampf(f.wi - wr * dvel, -wlimit, wlimit);
+        float dl = nl - f.wi;
+        f.wi = nl;
+        w1 = w1 + i1 * dl;
+        w2 = w2 - i2 * dl;
+    }
+    vec3 td10 = cross3(tdp1, t1), td11 = cross3(tdp1, t2);
+    vec3 td20 = cross3(tdp2, -t1), td21 = cross3(tdp2, -t2);
+    vec3 i10 = smul(g1.ii, td10), i11 = smul(g1.ii, td11), i20 = smul(g2.ii, td20), i21 = smul(g2.ii, td21);
+    float rhs0 = 0.0f, rhs1 = 0.0f;  // tangent rhs_wo_bias = tangent_velocity . t = 0 (no hooks)
+    if (!relax) {  // update(): bias from the friction-centre drift (contact_with_twist_friction.rs:506-514)
+        vec3 p1 = xform(g1.p, lfc1);
+        vec3 p2 = xform(g2.p, lfc2);
+        rhs0 = 0.0f + dot3(p1 - p2, t1) * P.sub_inv_dt;
+        rhs1 = 0.0f + dot3(p1 - p2, t2) * P.sub_inv_dt;
+    }
+    float dv0 = dot3(t1, v1) + dot3(td10, w1) - dot3(t1, v2) + dot3(td20, w2) + rhs0;
+    float dv1 = dot3(t2, v1) + dot3(td11, w1) - dot3(t2, v2) + dot3(td21, w2) + rhs1;
+    float k11 = tr0, k22 = tr1, k12 = tr2 * 0.5f;
+    float inv_det = safe_inv(k11 * k22 - k12 * k12);
+    float d0 = (k22 * dv0 - k12 * dv1) * inv_det;
+    float d1 = (k11 * dv1 - k12 * dv0) * inv_det;
+    float n0 = f.ti0 - d0, n1 = f.ti1 - d1;
+    float len = sqrtf(n0 * n0 + n1 * n1);
+    if (len > tlimit) {
+        float sc = tlimit / len;
+        n0 = n0 * sc;
+        n1 = n1 * sc;
+    }
+    float dl0 = n0 - f.ti0, dl1 = n1 - f.ti1;
+    f.ti0 = n0;
+    f.ti1 = n1;
+    v1 = v1 + had(t1 * dl0 + t2 * dl1, g1.im);
+    w1 = w1 + (i10 * dl0 + i11 * dl1);
+    v2 = v2 + had(t1 * (-dl0) + t2 * (-dl1), g2.im);
+    w2 = w2 + (i20 * dl0 + i21 * dl1);
+}
+// Friction + twist warm start (contact_constraint_element.rs:627-647, :720-732).
+RB_HD void friction_warmstart(const BodyState& g1, const BodyState& g2, vec3 dir, vec3 t1, vec3 t2, int nc, vec3 tdp1, vec3 tdp2,
+                              float ti0, float ti1, float wi, vec3& v1, vec3& w1, vec3& v2, vec3& w2) {
+    vec3 i10 = smul(g1.ii, cross3(tdp1, t1)), i11 = smul(g1.ii, cross3(tdp1, t2));
+    vec3 i20 = smul(g2.ii, cross3(tdp2, -t1)), i21 = smul(g2.ii, cross3(tdp2, -t2));
+    v1 = v1 + had(t1 * ti0 + t2 * ti1, g1.im);
+    w1 = w1 + (i10 * ti0 + i11 * ti1);
+    v2 = v2 + had(t1 * (-ti0) + t2 * (-ti1), g2.im);
+    w2 = w2 + (i20 * ti0 + i21 * ti1);
+    if (nc > 1) {
+        w1 = w1 + smul(g1.ii, dir) * wi;
+        w2 = w2 - smul(g2.ii, dir) * wi;
+    }
+}
+
+// One constraint, one sweep, one thread (streaming path; constraint in registers for the call).
+// MODE_WARMSTART = builder.update + constraint.warmstart (fused, worker.rs:438-539);
+// MODE_BIASED / MODE_RELAX = (refresh_rhs_wo_bias +) solve; MODE_RESTITUTION = apply_restitution.
 template <class B>
-RB_HD void cons_sweep(const World& w, const B& bd, int q, int mode, bool solve_friction) {
+RB_HD void cons_sweep(const World& w, const B& bd, int q, Cons& c, int mode, bool solve_friction) {
     const Params& P = w.prm;
-    int4 h = w.cons_hdr[q];
-    const int id1 = h.y, id2 = h.z, nc = h.w;
+    const int id1 = c.id1, id2 = c.id2, nc = c.nc;
     BodyState g1 = gather_body(bd, id1), g2 = gather_body(bd, id2);
     vec3 v1 = g1.lin, w1 = g1.ang, v2 = g2.lin, w2 = g2.ang;
-    float4 dirl = crow(w, CR_DIR, q), t1w = crow(w, CR_T1, q);
-    vec3 dir = xyz(dirl), t1 = xyz(t1w);
-    vec3 t2 = cross3(dir, t1);
-    float4 imp = crow(w, CR_IMP, q);
-    bool is_static = id1 == NO_BODY || id2 == NO_BODY;
-    float stf = is_static ? 1.0f : 0.0f;
-    float cfm_soft = P.dyn_cfm + stf * (P.static_cfm - P.dyn_cfm);
-    float erp = P.dyn_erp + stf * (P.static_erp - P.dyn_erp);
-    vec3 lin1 = had(dir, g1.im), lin2 = had(dir, g2.im);
+    const vec3 dir = c.dir, t1 = c.t1;
+    const vec3 t2 = cross3(dir, t1);
+    const bool is_static = id1 == NO_BODY || id2 == NO_BODY;
+    const float stf = is_static ? 1.0f : 0.0f;
+    const float cfm_soft = P.dyn_cfm + stf * (P.static_cfm - P.dyn_cfm);
+    const float erp = P.dyn_erp + stf * (P.static_erp - P.dyn_erp);
+    const vec3 lin1 = had(dir, g1.im), lin2 = had(dir, g2.im);
 
-    if (mode == MODE_WARMSTART) {
-        float4 acc = crow(w, CR_ACC, q);
-        for (int k = 0; k < nc; ++k) {
-            float l = getk(imp, k);
-            setk(acc, k, getk(acc, k) + l);
-            l = l * P.warmstart_coeff;
-            setk(imp, k, l);
-            vec3 dp1 = xyz(crow(w, CR_DP1 + k, q)), dp2 = xyz(crow(w, CR_DP2 + k, q));
-            vec3 itd1 = smul(g1.ii, cross3(dp1, dir)), itd2 = smul(g2.ii, cross3(dp2, -dir));
-            v1 = v1 + lin1 * l;
-            w1 = w1 + itd1 * l;
-            v2 = v2 + lin2 * (-l);
-            w2 = w2 + itd2 * l;
-        }
-        float4 ti = crow(w, CR_TI, q), wi = crow(w, CR_WI, q);
-        ti.z = ti.z + ti.x; ti.w = ti.w + ti.y;
-        ti.x = ti.x * P.warmstart_coeff; ti.y = ti.y * P.warmstart_coeff;
-        wi.y = wi.y + wi.x;
-        wi.x = wi.x * P.warmstart_coeff;
-        vec3 tdp1 = xyz(crow(w, CR_TDP1, q)), tdp2 = xyz(crow(w, CR_TDP2, q));
-        vec3 i10 = smul(g1.ii, cross3(tdp1, t1)), i11 = smul(g1.ii, cross3(tdp1, t2));
-        vec3 i20 = smul(g2.ii, cross3(tdp2, -t1)), i21 = smul(g2.ii, cross3(tdp2, -t2));
-        v1 = v1 + had(t1 * ti.x + t2 * ti.y, g1.im);
-        w1 = w1 + (i10 * ti.x + i11 * ti.y);
-        v2 = v2 + had(t1 * (-ti.x) + t2 * (-ti.y), g2.im);
-        w2 = w2 + (i20 * ti.x + i21 * ti.y);
-        if (nc > 1) {
-            w1 = w1 + smul(g1.ii, dir) * wi.x;
-            w2 = w2 - smul(g2.ii, dir) * wi.x;
-        }
-        crow(w, CR_IMP, q) = imp;
-        crow(w, CR_ACC, q) = acc;
-        crow(w, CR_TI, q) = ti;
-        crow(w, CR_WI, q) = wi;
-        scatter_vel(bd, id1, v1, w1);
-        scatter_vel(bd, id2, v2, w2);
-        return;
-    }
-
-    if (mode == MODE_RESTITUTION) {  // contact_constraint_element.rs:508-534
-        float4 acc = crow(w, CR_ACC, q);
+    if (mode == MODE_RESTITUTION) {
         bool any = false;
-        for (int k = 0; k < nc; ++k) any = any || crow(w, CR_LP1 + k, q).w < 0.0f;
+#pragma unroll
+        for (int k = 0; k < MAX_PTS; ++k)
+            if (k < nc) any = any || crow(w, CR_LP1 + k, q).w < 0.0f;
         if (!any) return;
-        for (int k = 0; k < nc; ++k) {
-            float4 d1r = crow(w, CR_DP1 + k, q);
-            vec3 dp1 = xyz(d1r), dp2 = xyz(crow(w, CR_DP2 + k, q));
-            float seed = crow(w, CR_LP1 + k, q).w;
-            vec3 td1 = cross3(dp1, dir), td2 = cross3(dp2, -dir);
-            vec3 itd1 = smul(g1.ii, td1), itd2 = smul(g2.ii, td2);
-            float l = getk(imp, k);
-            float dvel = dot3(dir, v1) + dot3(td1, w1) - dot3(dir, v2) + dot3(td2, w2) + seed;
-            bool gate = seed < 0.0f && (getk(acc, k) + l) > 0.0f;
-            float nl = max2(l - d1r.w * dvel, 0.0f);
-            if (!gate) nl = l;
-            float dl = nl - l;
-            setk(imp, k, nl);
-            v1 = v1 + lin1 * dl;
-            w1 = w1 + itd1 * dl;
-            v2 = v2 + lin2 * (-dl);
-            w2 = w2 + itd2 * dl;
-        }
-        crow(w, CR_IMP, q) = imp;
-        scatter_vel(bd, id1, v1, w1);
-        scatter_vel(bd, id2, v2, w2);
-        return;
     }
-
-    // normal rows (contact_constraint_element.rs:481-504); rhs / cfm recomputed from the current poses
-    const bool relax = mode == MODE_RELAX;
-    for (int k = 0; k < nc; ++k) {
-        float4 d1r = crow(w, CR_DP1 + k, q), d2r = crow(w, CR_DP2 + k, q);
-        vec3 dp1 = xyz(d1r), dp2 = xyz(d2r);
-        vec3 p1 = xform(g1.p, xyz(crow(w, CR_LP1 + k, q)));
-        vec3 p2 = xform(g2.p, xyz(crow(w, CR_LP2 + k, q)));
-        float dist = d2r.w + dot3(p1 - p2, dir);
-        float rhs = max2(dist, 0.0f) * P.sub_inv_dt;
-        float cfm = 1.0f;
-        if (!relax) {
-            rhs = rhs + clampf(dist * erp, -P.max_corrective_velocity, 0.0f);
-            cfm = dist <= 0.0f ? cfm_soft : 1.0f;
+#pragma unroll
+    for (int k = 0; k < MAX_PTS; ++k) {
+        if (k < nc) {
+            PointPre pp = point_pre(P, g1, g2, dir, c.dp1[k], c.dp2[k], c.lp1[k], c.lp2[k], c.dist0[k], mode, cfm_soft, erp);
+            float dl;
+            if (mode == MODE_WARMSTART) {
+                float l = c.imp[k];
+                c.acc[k] = c.acc[k] + l;
+                l = l * P.warmstart_coeff;
+                c.imp[k] = l;
+                dl = l;
+            } else if (mode == MODE_RESTITUTION) {
+                float nl;
+                dl = point_restitution(pp, c.r[k], c.imp[k], c.acc[k], crow(w, CR_LP1 + k, q).w, dir, v1, w1, v2, w2, nl);
+                c.imp[k] = nl;
+            } else {
+                float nl;
+                dl = point_solve(pp, c.r[k], c.imp[k], dir, v1, w1, v2, w2, nl);
+                c.imp[k] = nl;
+            }
+            apply_normal(lin1, lin2, pp.itd1, pp.itd2, dl, v1, w1, v2, w2);
         }
-        vec3 td1 = cross3(dp1, dir), td2 = cross3(dp2, -dir);
-        vec3 itd1 = smul(g1.ii, td1), itd2 = smul(g2.ii, td2);
-        float l = getk(imp, k);
-        float dvel = dot3(dir, v1) + dot3(td1, w1) - dot3(dir, v2) + dot3(td2, w2) + rhs;
-        float nl = cfm * max2(l - d1r.w * dvel, 0.0f);
-        float dl = nl - l;
-        setk(imp, k, nl);
-        v1 = v1 + lin1 * dl;
-        w1 = w1 + itd1 * dl;
-        v2 = v2 + lin2 * (-dl);
-        w2 = w2 + itd2 * dl;
     }
-    crow(w, CR_IMP, q) = imp;
-
-    if (solve_friction) {
-        float4 ti = crow(w, CR_TI, q), wi = crow(w, CR_WI, q), twd = crow(w, CR_TWD, q);
+    if (mode == MODE_WARMSTART) {
+        c.ta0 = c.ta0 + c.ti0; c.ta1 = c.ta1 + c.ti1;
+        c.ti0 = c.ti0 * P.warmstart_coeff; c.ti1 = c.ti1 * P.warmstart_coeff;
+        c.wa = c.wa + c.wi;
+        c.wi = c.wi * P.warmstart_coeff;
+        friction_warmstart(g1, g2, dir, t1, t2, nc, c.tdp1, c.tdp2, c.ti0, c.ti1, c.wi, v1, w1, v2, w2);
+    } else if (mode != MODE_RESTITUTION && solve_friction) {
         float tlimit = 0.0f, wlimit = 0.0f;
-        for (int k = 0; k < nc; ++k) {
-            tlimit = tlimit + getk(imp, k);
-            wlimit = wlimit + getk(imp, k) * getk(twd, k);
+#pragma unroll
+        for (int k = 0; k < MAX_PTS; ++k) {
+            if (k < nc) {
+                tlimit = tlimit + c.imp[k];
+                wlimit = wlimit + c.imp[k] * c.twd[k];
+            }
         }
-        tlimit = tlimit * dirl.w;
-        wlimit = wlimit * dirl.w;
-        if (nc > 1) {  // twist first (contact_constraint_element.rs:735-756)
-            vec3 i1 = smul(g1.ii, dir), i2 = smul(g2.ii, dir);
-            float dvel = dot3(dir, w1 - w2) + 0.0f;
-            float nl = clampf(wi.x - t1w.w * dvel, -wlimit, wlimit);
-            float dl = nl - wi.x;
-            wi.x = nl;
-            w1 = w1 + i1 * dl;
-            w2 = w2 - i2 * dl;
-        }
-        float4 tdp1r = crow(w, CR_TDP1, q), tdp2r = crow(w, CR_TDP2, q);
-        vec3 tdp1 = xyz(tdp1r), tdp2 = xyz(tdp2r);
-        vec3 td10 = cross3(tdp1, t1), td11 = cross3(tdp1, t2);
-        vec3 td20 = cross3(tdp2, -t1), td21 = cross3(tdp2, -t2);
-        vec3 i10 = smul(g1.ii, td10), i11 = smul(g1.ii, td11), i20 = smul(g2.ii, td20), i21 = smul(g2.ii, td21);
-        float rhs0 = 0.0f, rhs1 = 0.0f;  // tangent rhs_wo_bias = tangent_velocity . t = 0 (no hooks)
-        if (!relax) {  // update(): bias from the friction-centre drift (contact_with_twist_friction.rs:506-514)
-            vec3 p1 = xform(g1.p, xyz(crow(w, CR_LFC1, q)));
-            vec3 p2 = xform(g2.p, xyz(crow(w, CR_LFC2, q)));
-            rhs0 = 0.0f + dot3(p1 - p2, t1) * P.sub_inv_dt;
-            rhs1 = 0.0f + dot3(p1 - p2, t2) * P.sub_inv_dt;
-        }
-        float dv0 = dot3(t1, v1) + dot3(td10, w1) - dot3(t1, v2) + dot3(td20, w2) + rhs0;
-        float dv1 = dot3(t2, v1) + dot3(td11, w1) - dot3(t2, v2) + dot3(td21, w2) + rhs1;
-        float k11 = tdp1r.w, k22 = tdp2r.w, k12 = crow(w, CR_LFC1, q).w * 0.5f;
-        float inv_det = safe_inv(k11 * k22 - k12 * k12);
-        float d0 = (k22 * dv0 - k12 * dv1) * inv_det;
-        float d1 = (k11 * dv1 - k12 * dv0) * inv_det;
-        float n0 = ti.x - d0, n1 = ti.y - d1;
-        float len = sqrtf(n0 * n0 + n1 * n1);
-        if (len > tlimit) {
-            float s = tlimit / len;
-            n0 = n0 * s;
-            n1 = n1 * s;
-        }
-        float dl0 = n0 - ti.x, dl1 = n1 - ti.y;
-        ti.x = n0;
-        ti.y = n1;
-        v1 = v1 + had(t1 * dl0 + t2 * dl1, g1.im);
-        w1 = w1 + (i10 * dl0 + i11 * dl1);
-        v2 = v2 + had(t1 * (-dl0) + t2 * (-dl1), g2.im);
-        w2 = w2 + (i20 * dl0 + i21 * dl1);
-        crow(w, CR_TI, q) = ti;
-        crow(w, CR_WI, q) = wi;
+        tlimit = tlimit * c.fric;
+        wlimit = wlimit * c.fric;
+        const bool relax = mode == MODE_RELAX;
+        vec3 lfc1 = zero3(), lfc2 = zero3();
+        if (!relax) { lfc1 = xyz(crow(w, CR_LFC1, q)); lfc2 = xyz(crow(w, CR_LFC2, q)); }
+        FrictionState f;
+        f.ti0 = c.ti0; f.ti1 = c.ti1; f.wi = c.wi;
+        friction_solve(P, g1, g2, dir, t1, t2, nc, tlimit, wlimit, c.wr, c.tdp1, c.tdp2, c.tr0, c.tr1, c.tr2, relax, lfc1, lfc2, f,
+                       v1, w1, v2, w2);
+        c.ti0 = f.ti0; c.ti1 = f.ti1; c.wi = f.wi;
     }
     scatter_vel(bd, id1, v1, w1);
     scatter_vel(bd, id2, v2, w2);
@@ -368,25 +443,24 @@ RB_HD void cons_sweep(const World& w, const B& bd, int q, int mode, bool solve_f
 RB_HD float canon0(float x) { return x == 0.0f ? 0.0f : x; }
 
 // S10: contact_with_twist_friction.rs:783-829
-RB_HD void cons_writeback(const World& w, int q, int buf) {
-    int4 h = w.cons_hdr[q];
-    const int p = h.x, nc = h.w;
-    float4 dirl = crow(w, CR_DIR, q);
-    vec3 dir = xyz(dirl), t1 = xyz(crow(w, CR_T1, q));
-    vec3 t2 = cross3(dir, t1);
-    float4 imp = crow(w, CR_IMP, q), acc = crow(w, CR_ACC, q), ti = crow(w, CR_TI, q), wi = crow(w, CR_WI, q);
-    float a0 = canon0(ti.x), a1 = canon0(ti.y);
-    vec3 tw = t1 * a0 + t2 * a1;
+RB_HD void cons_writeback(const World& w, int q, int buf, const Cons& c) {
+    const int p = w.cons_hdr[q].x;
+    vec3 t2 = cross3(c.dir, c.t1);
+    float a0 = canon0(c.ti0), a1 = canon0(c.ti1);
+    vec3 tw = c.t1 * a0 + t2 * a1;
     tw = mk3(canon0(tw.x), canon0(tw.y), canon0(tw.z));
-    float twist = canon0(wi.x);
-    for (int k = 0; k < nc; ++k) {
-        int cid = as_int(crow(w, CR_LP2 + k, q).w);
-        float4 pd = prow(w, buf, PR_PD + cid, p);
-        pd.y = canon0(getk(imp, k));
-        pd.x = canon0(getk(acc, k) + getk(imp, k));
-        pd.z = twist;
-        prow(w, buf, PR_PD + cid, p) = pd;
-        prow(w, buf, PR_TW + cid, p) = f4(tw, 0.0f);
+    float twist = canon0(c.wi);
+#pragma unroll
+    for (int k = 0; k < MAX_PTS; ++k) {
+        if (k < c.nc) {
+            int cid = as_int(crow(w, CR_LP2 + k, q).w);
+            float4 pd = prow(w, buf, PR_PD + cid, p);
+            pd.y = canon0(c.imp[k]);
+            pd.x = canon0(c.acc[k] + c.imp[k]);
+            pd.z = twist;
+            prow(w, buf, PR_PD + cid, p) = pd;
+            prow(w, buf, PR_TW + cid, p) = f4(tw, 0.0f);
+        }
     }
 }
 
@@ -586,7 +660,75 @@ struct GridExec {
     RB_HD void sync() const { c->grid_sync(); }
 };
 
-// Solve one work item from solver-body init to the final positions of its bodies.
+// ---- body phases shared by every solve path -------------------------------------------------------
+// a7 + S1: forces, solver bodies, per-substep increments (solve.rs:234-291; solver_body.rs:82-121; worker.rs:46-104)
+template <class B>
+RB_HD void body_init(const World& w, const B& bd, int b, int id, vec3 gravity) {
+    const Params& P = w.prm;
+    float4 lc = w.b_lcom_im[b];
+    vec3 eim = xyz(w.b_eim[b]);
+    sym3 eii = load_ii(w, b);
+    float4 misc = w.b_misc[b];
+    vec3 emass = mk3(inv_exact0(eim.x), inv_exact0(eim.y), inv_exact0(eim.z));
+    vec3 force = xyz(w.b_uforce[b]) + had(gravity, emass) * misc.z;
+    vec3 torque = xyz(w.b_utorque[b]);
+    bd.set_vel(id, xyz(w.b_linvel[b]), xyz(w.b_angvel[b]));
+    bd.set_xf(id, prepend_translation(body_pose(w, b), xyz(lc)));
+    bd.set_mass(id, eii, eim);
+    bd.set_incr(id, had(force, eim) * P.sub_dt, smul(eii, torque) * P.sub_dt);
+}
+// S3: velocity increment + gyroscopic correction (worker.rs:235-284)
+template <class B>
+RB_HD void body_increment(const World& w, const B& bd, int b, int id) {
+    vec3 lin = bd.lin(id) + bd.incr_lin(id);
+    vec3 ang = bd.ang(id) + bd.incr_ang(id);
+    if (w.b_flags[b] & FLAG_GYRO) {
+        quat axes = qmul(bd.xf(id).q, mkq(w.b_pframe[b]));
+        ang = gyro_corrected(ang, axes, xyz(w.b_pi[b]), xyz(w.b_ipi[b]), w.prm.sub_dt);
+    }
+    bd.set_vel(id, lin, ang);
+}
+// S7: speed caps + linearised pose integration (worker.rs:568-631; rigid_body_components.rs:884-898)
+template <class B>
+RB_HD void body_integrate(const World& w, const B& bd, int b, int id) {
+    const Params& P = w.prm;
+    vec3 lin = bd.lin(id), ang = bd.ang(id);
+    if (P.max_lin_vel != FMAX32) {
+        float n = norm(lin);
+        if (n > P.max_lin_vel) lin = lin * (P.max_lin_vel / n);
+    }
+    if (!(w.b_flags[b] & FLAG_FAST_ROT)) {
+        float n = norm(ang);
+        if (n > P.max_ang_vel) ang = ang * (P.max_ang_vel / n);
+    }
+    bd.set_vel(id, lin, ang);
+    pose p = bd.xf(id);
+    vec3 hang = ang * (P.sub_dt * 0.5f);
+    quat dq; dq.x = hang.x; dq.y = hang.y; dq.z = hang.z; dq.w = 1.0f;
+    p.q = qnormalize(qmul(dq, p.q));
+    p.t = p.t + lin * P.sub_dt;
+    bd.set_xf(id, p);
+}
+// S11 + advance_to_final_positions (worker.rs:809-897; substep.rs:84-224)
+template <class B>
+RB_HD void body_writeback(const World& w, const B& bd, int b, int id) {
+    const Params& P = w.prm;
+    float4 misc = w.b_misc[b];
+    vec3 lin = bd.lin(id) * (1.0f / (1.0f + P.dt * misc.x));
+    vec3 ang = bd.ang(id) * (1.0f / (1.0f + P.dt * misc.y));
+    pose np = prepend_translation(bd.xf(id), -xyz(w.b_lcom_im[b]));
+    w.b_linvel[b] = f4(lin, 0.0f);
+    w.b_angvel[b] = f4(ang, 0.0f);
+    w.b_pos_t[b] = f4(np.t, 0.0f);
+    w.b_pos_q[b] = f4(np.q);
+    update_world_mass(w, b, np);
+    float* s = w.state13 + (size_t)b * 13;
+    s[0] = np.t.x; s[1] = np.t.y; s[2] = np.t.z; s[3] = np.q.x; s[4] = np.q.y; s[5] = np.q.z; s[6] = np.q.w;
+    s[7] = lin.x; s[8] = lin.y; s[9] = lin.z; s[10] = ang.x; s[11] = ang.y; s[12] = ang.z;
+}
+
+// Solve one work item from solver-body init to the final positions of its bodies, constraints
+// streaming from HBM/L2 (fallback for items too big for shared memory, items with joints, item 0).
 template <class X, class B>
 RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec3 gravity) {
     const Params& P = w.prm;
@@ -603,40 +745,34 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
     const int ovf = w.color_pos[COLOR_OVERFLOW], jovf = w.jcolor_pos[COLOR_OVERFLOW];
     const int tid = ex.tid(), nth = ex.nth();
 
+    auto stage = [&](int a, int e, bool serial, int mode, bool fric) {
+        if (serial) {
+            if (tid == 0)
+                for (int q = a; q < e; ++q) { Cons cc; cons_load(w, q, cc); cons_sweep(w, bd, q, cc, mode, fric); cons_store_dyn(w, q, cc); }
+        } else {
+            for (int q = a + tid; q < e; q += nth) { Cons cc; cons_load(w, q, cc); cons_sweep(w, bd, q, cc, mode, fric); cons_store_dyn(w, q, cc); }
+        }
+    };
+
     if (tid == 0) w.item_flags[item] = 0;   // bit 0: some contact of this item holds a restitution seed
-    // a7 + S1: forces, solver bodies, per-substep increments
     for (int l = b0 + tid; l < b1; l += nth) {
         int b = w.item_bodies[l];
-        int id = global_ids ? b : l - b0;
-        float4 lc = w.b_lcom_im[b];
-        vec3 eim = xyz(w.b_eim[b]);
-        sym3 eii = load_ii(w, b);
-        float4 misc = w.b_misc[b];
-        vec3 emass = mk3(inv_exact0(eim.x), inv_exact0(eim.y), inv_exact0(eim.z));
-        vec3 force = xyz(w.b_uforce[b]) + had(gravity, emass) * misc.z;
-        vec3 torque = xyz(w.b_utorque[b]);
-        bd.set_vel(id, xyz(w.b_linvel[b]), xyz(w.b_angvel[b]));
-        bd.set_xf(id, prepend_translation(body_pose(w, b), xyz(lc)));
-        bd.set_mass(id, eii, eim);
-        bd.set_incr(id, had(force, eim) * P.sub_dt, smul(eii, torque) * P.sub_dt);
+        body_init(w, bd, b, global_ids ? b : l - b0, gravity);
     }
     ex.sync();
     // S2 generate
-    for (int q = c0 + tid; q < c1; q += nth) cons_generate(w, bd, q, buf, item);
+    for (int q = c0 + tid; q < c1; q += nth) {
+        Cons c;
+        cons_generate(w, bd, q, buf, item, c);
+        cons_store_static(w, q, c);
+        cons_store_dyn(w, q, c);
+    }
     ex.sync();
 
     for (int sub = 0; sub < P.num_substeps; ++sub) {
-        // S3 increments + gyroscopic correction
         for (int l = b0 + tid; l < b1; l += nth) {
             int b = w.item_bodies[l];
-            int id = global_ids ? b : l - b0;
-            vec3 lin = bd.lin(id) + bd.incr_lin(id);
-            vec3 ang = bd.ang(id) + bd.incr_ang(id);
-            if (w.b_flags[b] & FLAG_GYRO) {
-                quat axes = qmul(bd.xf(id).q, mkq(w.b_pframe[b]));
-                ang = gyro_corrected(ang, axes, xyz(w.b_pi[b]), xyz(w.b_ipi[b]), P.sub_dt);
-            }
-            bd.set_vel(id, lin, ang);
+            body_increment(w, bd, b, global_ids ? b : l - b0);
         }
         ex.sync();
         // S4 joint rows from the current poses
@@ -650,22 +786,20 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
                 int a = c0 + coff[c], e = c0 + coff[c + 1];
                 if (e > c1) e = c1;
                 if (a >= e) continue;
-                if (c == ovf) {
-                    if (tid == 0) for (int q = a; q < e; ++q) cons_sweep(w, bd, q, MODE_WARMSTART, false);
-                } else {
-                    for (int q = a + tid; q < e; q += nth) cons_sweep(w, bd, q, MODE_WARMSTART, false);
-                }
+                stage(a, e, c == ovf, MODE_WARMSTART, false);
                 ex.sync();
             }
         } else {
             // warmstart_coefficient == 0: update only banks and zeroes the impulses (no velocity change)
             for (int q = c0 + tid; q < c1; q += nth) {
-                float4 imp = crow(w, CR_IMP, q), acc = crow(w, CR_ACC, q), ti = crow(w, CR_TI, q), wi = crow(w, CR_WI, q);
-                acc.x = acc.x + imp.x; acc.y = acc.y + imp.y; acc.z = acc.z + imp.z; acc.w = acc.w + imp.w;
-                imp.x = imp.x * 0.0f; imp.y = imp.y * 0.0f; imp.z = imp.z * 0.0f; imp.w = imp.w * 0.0f;
-                ti.z = ti.z + ti.x; ti.w = ti.w + ti.y; ti.x = ti.x * 0.0f; ti.y = ti.y * 0.0f;
-                wi.y = wi.y + wi.x; wi.x = wi.x * 0.0f;
-                crow(w, CR_IMP, q) = imp; crow(w, CR_ACC, q) = acc; crow(w, CR_TI, q) = ti; crow(w, CR_WI, q) = wi;
+                Cons c;
+                cons_load(w, q, c);
+#pragma unroll
+                for (int k = 0; k < MAX_PTS; ++k)
+                    if (k < c.nc) { c.acc[k] = c.acc[k] + c.imp[k]; c.imp[k] = c.imp[k] * 0.0f; }
+                c.ta0 = c.ta0 + c.ti0; c.ta1 = c.ta1 + c.ti1; c.ti0 = c.ti0 * 0.0f; c.ti1 = c.ti1 * 0.0f;
+                c.wa = c.wa + c.wi; c.wi = c.wi * 0.0f;
+                cons_store_dyn(w, q, c);
             }
             ex.sync();
         }
@@ -689,35 +823,14 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
                     int a = c0 + coff[c], e = c0 + coff[c + 1];
                     if (e > c1) e = c1;
                     if (a >= e) continue;
-                    if (c == ovf) {
-                        if (tid == 0) for (int q = a; q < e; ++q) cons_sweep(w, bd, q, relax ? MODE_RELAX : MODE_BIASED, fric);
-                    } else {
-                        for (int q = a + tid; q < e; q += nth) cons_sweep(w, bd, q, relax ? MODE_RELAX : MODE_BIASED, fric);
-                    }
+                    stage(a, e, c == ovf, relax ? MODE_RELAX : MODE_BIASED, fric);
                     ex.sync();
                 }
             }
             if (!relax) {
-                // S7 integrate (speed caps + linearised quaternion update)
                 for (int l = b0 + tid; l < b1; l += nth) {
                     int b = w.item_bodies[l];
-                    int id = global_ids ? b : l - b0;
-                    vec3 lin = bd.lin(id), ang = bd.ang(id);
-                    if (P.max_lin_vel != FMAX32) {
-                        float n = norm(lin);
-                        if (n > P.max_lin_vel) lin = lin * (P.max_lin_vel / n);
-                    }
-                    if (!(w.b_flags[b] & FLAG_FAST_ROT)) {
-                        float n = norm(ang);
-                        if (n > P.max_ang_vel) ang = ang * (P.max_ang_vel / n);
-                    }
-                    bd.set_vel(id, lin, ang);
-                    pose p = bd.xf(id);
-                    vec3 hang = ang * (P.sub_dt * 0.5f);
-                    quat dq; dq.x = hang.x; dq.y = hang.y; dq.z = hang.z; dq.w = 1.0f;
-                    p.q = qnormalize(qmul(dq, p.q));
-                    p.t = p.t + lin * P.sub_dt;
-                    bd.set_xf(id, p);
+                    body_integrate(w, bd, b, global_ids ? b : l - b0);
                 }
                 ex.sync();
             }
@@ -729,34 +842,306 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
             int a = c0 + coff[c], e = c0 + coff[c + 1];
             if (e > c1) e = c1;
             if (a >= e) continue;
-            if (c == ovf) {
-                if (tid == 0) for (int q = a; q < e; ++q) cons_sweep(w, bd, q, MODE_RESTITUTION, false);
-            } else {
-                for (int q = a + tid; q < e; q += nth) cons_sweep(w, bd, q, MODE_RESTITUTION, false);
-            }
+            stage(a, e, c == ovf, MODE_RESTITUTION, false);
             ex.sync();
         }
     }
     // S10 impulse writeback
-    for (int q = c0 + tid; q < c1; q += nth) cons_writeback(w, q, buf);
+    for (int q = c0 + tid; q < c1; q += nth) { Cons cc; cons_load(w, q, cc); cons_writeback(w, q, buf, cc); }
     for (int q = j0 + tid; q < j1; q += nth) joint_writeback(w, q);
-    // S11 body writeback + advance_to_final_positions
     for (int l = b0 + tid; l < b1; l += nth) {
         int b = w.item_bodies[l];
-        int id = global_ids ? b : l - b0;
-        float4 misc = w.b_misc[b];
-        vec3 lin = bd.lin(id) * (1.0f / (1.0f + P.dt * misc.x));
-        vec3 ang = bd.ang(id) * (1.0f / (1.0f + P.dt * misc.y));
-        pose np = prepend_translation(bd.xf(id), -xyz(w.b_lcom_im[b]));
-        w.b_linvel[b] = f4(lin, 0.0f);
-        w.b_angvel[b] = f4(ang, 0.0f);
-        w.b_pos_t[b] = f4(np.t, 0.0f);
-        w.b_pos_q[b] = f4(np.q);
-        update_world_mass(w, b, np);
-        float* s = w.state13 + (size_t)b * 13;
-        s[0] = np.t.x; s[1] = np.t.y; s[2] = np.t.z; s[3] = np.q.x; s[4] = np.q.y; s[5] = np.q.z; s[6] = np.q.w;
-        s[7] = lin.x; s[8] = lin.y; s[9] = lin.z; s[10] = ang.x; s[11] = ang.y; s[12] = ang.z;
+        body_writeback(w, bd, b, global_ids ? b : l - b0);
     }
+}
+
+// =====================================================================================================
+// Lane-cooperative shared-memory path: the island's bodies AND constraints live in shared memory for
+// the whole step; each constraint is swept by L consecutive lanes (L = 4 on the GPU: one lane per
+// manifold point), which compute the per-point jacobians / rhs in parallel and resolve the sequential
+// Gauss-Seidel dependency between the points with __shfl_sync broadcasts.  Same primitives, same
+// arithmetic, same results as the serial sweep.
+// =====================================================================================================
+constexpr int COOP_MAX_CONS = 160;     // constraints per item held in shared memory
+constexpr int COOP_CS = 168;           // slot stride (== 8 mod 32: the 4 point-lanes of 8 constraints hit 32 banks)
+constexpr int COOP_MAX_BODIES = 128;
+enum CoopPointField { PF_DP1 = 0, PF_DP2 = 3, PF_LP1 = 6, PF_LP2 = 9, PF_R = 12, PF_DIST0 = 13, PF_IMP = 14, PF_ACC = 15, PF_COUNT = 16 };
+enum CoopConsField { CF_DIR = 0, CF_FRIC = 3, CF_T1 = 4, CF_WR = 7, CF_TDP1 = 8, CF_TDP2 = 11, CF_TR = 14, CF_TWD = 17, CF_TI0 = 21,
+                     CF_TI1 = 22, CF_TA0 = 23, CF_TA1 = 24, CF_WI = 25, CF_WA = 26, CF_ID1 = 27, CF_ID2 = 28, CF_NC = 29, CF_COUNT = 30 };
+constexpr int COOP_CONS_FLOATS = (PF_COUNT * MAX_PTS + CF_COUNT) * COOP_CS;
+constexpr int COOP_SMEM_FLOATS = COOP_MAX_BODIES * SB_STRIDE + COOP_CONS_FLOATS;
+
+struct CoopStore {
+    float* base;
+    RB_HD float& pp(int f, int k, int s) const { return base[(f * MAX_PTS + k) * COOP_CS + s]; }
+    RB_HD float& pc(int f, int s) const { return base[(PF_COUNT * MAX_PTS + f) * COOP_CS + s]; }
+    RB_HD vec3 pp3(int f, int k, int s) const { return mk3(pp(f, k, s), pp(f + 1, k, s), pp(f + 2, k, s)); }
+    RB_HD vec3 pc3(int f, int s) const { return mk3(pc(f, s), pc(f + 1, s), pc(f + 2, s)); }
+    RB_HD void set_pp3(int f, int k, int s, vec3 v) const { pp(f, k, s) = v.x; pp(f + 1, k, s) = v.y; pp(f + 2, k, s) = v.z; }
+    RB_HD void set_pc3(int f, int s, vec3 v) const { pc(f, s) = v.x; pc(f + 1, s) = v.y; pc(f + 2, s) = v.z; }
+};
+
+RB_HD void coop_put(const CoopStore& cs, int s, const Cons& c) {
+#pragma unroll
+    for (int k = 0; k < MAX_PTS; ++k) {
+        if (k < c.nc) {
+            cs.set_pp3(PF_DP1, k, s, c.dp1[k]); cs.set_pp3(PF_DP2, k, s, c.dp2[k]);
+            cs.set_pp3(PF_LP1, k, s, c.lp1[k]); cs.set_pp3(PF_LP2, k, s, c.lp2[k]);
+            cs.pp(PF_R, k, s) = c.r[k]; cs.pp(PF_DIST0, k, s) = c.dist0[k];
+        }
+        cs.pp(PF_IMP, k, s) = c.imp[k]; cs.pp(PF_ACC, k, s) = c.acc[k];
+        cs.pc(CF_TWD + k, s) = c.twd[k];
+    }
+    cs.set_pc3(CF_DIR, s, c.dir); cs.pc(CF_FRIC, s) = c.fric;
+    cs.set_pc3(CF_T1, s, c.t1); cs.pc(CF_WR, s) = c.wr;
+    cs.set_pc3(CF_TDP1, s, c.tdp1); cs.set_pc3(CF_TDP2, s, c.tdp2);
+    cs.pc(CF_TR, s) = c.tr0; cs.pc(CF_TR + 1, s) = c.tr1; cs.pc(CF_TR + 2, s) = c.tr2;
+    cs.pc(CF_TI0, s) = c.ti0; cs.pc(CF_TI1, s) = c.ti1; cs.pc(CF_TA0, s) = c.ta0; cs.pc(CF_TA1, s) = c.ta1;
+    cs.pc(CF_WI, s) = c.wi; cs.pc(CF_WA, s) = c.wa;
+    cs.pc(CF_ID1, s) = as_float_i(c.id1); cs.pc(CF_ID2, s) = as_float_i(c.id2); cs.pc(CF_NC, s) = as_float_i(c.nc);
+}
+RB_HD void coop_get_for_writeback(const CoopStore& cs, int s, Cons& c) {
+    c.nc = as_int(cs.pc(CF_NC, s));
+    c.dir = cs.pc3(CF_DIR, s); c.t1 = cs.pc3(CF_T1, s);
+#pragma unroll
+    for (int k = 0; k < MAX_PTS; ++k) { c.imp[k] = cs.pp(PF_IMP, k, s); c.acc[k] = cs.pp(PF_ACC, k, s); }
+    c.ti0 = cs.pc(CF_TI0, s); c.ti1 = cs.pc(CF_TI1, s); c.wi = cs.pc(CF_WI, s);
+}
+
+// Sub-warp broadcast from lane `src` of each L-lane group.
+template <int L> RB_HD float lane_bcast(float v, int src) {
+#if RB_DEVICE_BUILD
+    if (L > 1) return __shfl_sync(0xffffffffu, v, src, L);
+#endif
+    (void)src;
+    return v;
+}
+template <int L> RB_HD vec3 lane_bcast3(vec3 v, int src) {
+    return mk3(lane_bcast<L>(v.x, src), lane_bcast<L>(v.y, src), lane_bcast<L>(v.z, src));
+}
+template <int L> RB_HD bool lane_any(bool p) {
+#if RB_DEVICE_BUILD
+    if (L > 1) {
+        int v = p ? 1 : 0;
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o, L);
+        return v != 0;
+    }
+#endif
+    return p;
+}
+
+// Sweep the constraints in slots [a, e) of the item (one colour stage) with L lanes per constraint.
+// `q0` is the global schedule slot of the item's slot 0 (rare per-constraint rows stay in HBM).
+template <int L>
+RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs, int q0, int a, int e, int tid, int nth, int mode,
+                      bool solve_friction) {
+    constexpr int PPL = MAX_PTS / L;   // points per lane
+    const Params& P = w.prm;
+    const int groups = nth / L, grp = tid / L, sub = tid % L;
+    for (int base = a; base < e; base += groups) {
+        const int s_raw = base + grp;
+        const bool active = s_raw < e && grp < groups;
+        const int s = active ? s_raw : a;   // inactive lanes shadow a valid slot (they must execute the shuffles)
+        const int id1 = as_int(cs.pc(CF_ID1, s)), id2 = as_int(cs.pc(CF_ID2, s)), nc = as_int(cs.pc(CF_NC, s));
+        BodyState g1 = gather_body(bd, id1), g2 = gather_body(bd, id2);
+        vec3 v1 = g1.lin, w1 = g1.ang, v2 = g2.lin, w2 = g2.ang;
+        const vec3 dir = cs.pc3(CF_DIR, s), t1 = cs.pc3(CF_T1, s);
+        const vec3 t2 = cross3(dir, t1);
+        const bool is_static = id1 == NO_BODY || id2 == NO_BODY;
+        const float stf = is_static ? 1.0f : 0.0f;
+        const float cfm_soft = P.dyn_cfm + stf * (P.static_cfm - P.dyn_cfm);
+        const float erp = P.dyn_erp + stf * (P.static_erp - P.dyn_erp);
+        const vec3 lin1 = had(dir, g1.im), lin2 = had(dir, g2.im);
+
+        // ---- parallel part: every lane prepares its own point(s) ----
+        PointPre pre[PPL];
+        float imp[PPL], acc[PPL], r[PPL], seed[PPL];
+        bool own_seed = false;
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) {
+            const int k = sub + j * L;
+            imp[j] = 0.0f; acc[j] = 0.0f; r[j] = 0.0f; seed[j] = 0.0f;
+            pre[j].td1 = pre[j].td2 = pre[j].itd1 = pre[j].itd2 = zero3();
+            pre[j].rhs = 0.0f; pre[j].cfm = 1.0f;
+            if (k < nc) {
+                pre[j] = point_pre(P, g1, g2, dir, cs.pp3(PF_DP1, k, s), cs.pp3(PF_DP2, k, s), cs.pp3(PF_LP1, k, s),
+                                   cs.pp3(PF_LP2, k, s), cs.pp(PF_DIST0, k, s), mode, cfm_soft, erp);
+                imp[j] = cs.pp(PF_IMP, k, s);
+                r[j] = cs.pp(PF_R, k, s);
+                if (mode == MODE_WARMSTART || mode == MODE_RESTITUTION) acc[j] = cs.pp(PF_ACC, k, s);
+                if (mode == MODE_RESTITUTION) {
+                    seed[j] = crow(w, CR_LP1 + k, q0 + s).w;
+                    own_seed = own_seed || seed[j] < 0.0f;
+                }
+                if (mode == MODE_WARMSTART) {
+                    acc[j] = acc[j] + imp[j];
+                    imp[j] = imp[j] * P.warmstart_coeff;
+                }
+            }
+        }
+        bool skip = false;
+        if (mode == MODE_RESTITUTION) skip = !lane_any<L>(own_seed);
+
+        // ---- sequential part: the points in order, owner lane computes, everyone follows ----
+#pragma unroll
+        for (int kk = 0; kk < MAX_PTS; ++kk) {
+            const int owner = kk % L, j = kk / L;
+            float dl_own = 0.0f;
+            if (sub == owner && kk < nc) {
+                if (mode == MODE_WARMSTART) {
+                    dl_own = imp[j];
+                } else if (mode == MODE_RESTITUTION) {
+                    float nl;
+                    dl_own = point_restitution(pre[j], r[j], imp[j], acc[j], seed[j], dir, v1, w1, v2, w2, nl);
+                    imp[j] = nl;
+                } else {
+                    float nl;
+                    dl_own = point_solve(pre[j], r[j], imp[j], dir, v1, w1, v2, w2, nl);
+                    imp[j] = nl;
+                }
+            }
+            const float dl = lane_bcast<L>(dl_own, owner);
+            const vec3 i1 = lane_bcast3<L>(pre[j].itd1, owner), i2 = lane_bcast3<L>(pre[j].itd2, owner);
+            if (kk < nc) apply_normal(lin1, lin2, i1, i2, dl, v1, w1, v2, w2);
+        }
+
+        float ti0 = cs.pc(CF_TI0, s), ti1 = cs.pc(CF_TI1, s), wi = cs.pc(CF_WI, s);
+        float ta0 = 0.0f, ta1 = 0.0f, wa = 0.0f;
+        if (mode == MODE_WARMSTART) {
+            ta0 = cs.pc(CF_TA0, s) + ti0; ta1 = cs.pc(CF_TA1, s) + ti1;
+            ti0 = ti0 * P.warmstart_coeff; ti1 = ti1 * P.warmstart_coeff;
+            wa = cs.pc(CF_WA, s) + wi;
+            wi = wi * P.warmstart_coeff;
+            friction_warmstart(g1, g2, dir, t1, t2, nc, cs.pc3(CF_TDP1, s), cs.pc3(CF_TDP2, s), ti0, ti1, wi, v1, w1, v2, w2);
+        } else if (mode != MODE_RESTITUTION && solve_friction) {
+            float tlimit = 0.0f, wlimit = 0.0f;
+#pragma unroll
+            for (int kk = 0; kk < MAX_PTS; ++kk) {
+                const float ik = lane_bcast<L>(imp[kk / L], kk % L);
+                if (kk < nc) {
+                    tlimit = tlimit + ik;
+                    wlimit = wlimit + ik * cs.pc(CF_TWD + kk, s);
+                }
+            }
+            const float fric = cs.pc(CF_FRIC, s);
+            tlimit = tlimit * fric;
+            wlimit = wlimit * fric;
+            const bool relax = mode == MODE_RELAX;
+            vec3 lfc1 = zero3(), lfc2 = zero3();
+            if (!relax) { lfc1 = xyz(crow(w, CR_LFC1, q0 + s)); lfc2 = xyz(crow(w, CR_LFC2, q0 + s)); }
+            FrictionState f;
+            f.ti0 = ti0; f.ti1 = ti1; f.wi = wi;
+            friction_solve(P, g1, g2, dir, t1, t2, nc, tlimit, wlimit, cs.pc(CF_WR, s), cs.pc3(CF_TDP1, s), cs.pc3(CF_TDP2, s),
+                           cs.pc(CF_TR, s), cs.pc(CF_TR + 1, s), cs.pc(CF_TR + 2, s), relax, lfc1, lfc2, f, v1, w1, v2, w2);
+            ti0 = f.ti0; ti1 = f.ti1; wi = f.wi;
+        }
+        // ---- write back: each lane its own point impulses, lane 0 the shared state ----
+        if (active && !skip) {
+#pragma unroll
+            for (int j = 0; j < PPL; ++j) {
+                const int k = sub + j * L;
+                if (k < nc) {
+                    cs.pp(PF_IMP, k, s) = imp[j];
+                    if (mode == MODE_WARMSTART) cs.pp(PF_ACC, k, s) = acc[j];
+                }
+            }
+            if (sub == 0) {
+                if (mode == MODE_WARMSTART) {
+                    cs.pc(CF_TA0, s) = ta0; cs.pc(CF_TA1, s) = ta1; cs.pc(CF_WA, s) = wa;
+                }
+                if (mode != MODE_RESTITUTION) { cs.pc(CF_TI0, s) = ti0; cs.pc(CF_TI1, s) = ti1; cs.pc(CF_WI, s) = wi; }
+                scatter_vel(bd, id1, v1, w1);
+                scatter_vel(bd, id2, v2, w2);
+            }
+        }
+    }
+}
+
+RB_HD bool item_is_coop(const World& w, int item) {
+    const int nbod = w.item_body_start[item + 1] - w.item_body_start[item];
+    const int ncons = w.item_cons_start[item + 1] - w.item_cons_start[item];
+    const int njoints = w.item_joint_start[item + 1] - w.item_joint_start[item];
+    const int ovf = w.color_pos[COLOR_OVERFLOW];
+    const int* coff = w.item_color_off + (size_t)item * (NUM_COLORS + 1);
+    const bool has_ovf = ovf >= 0 && coff[ovf + 1] > coff[ovf];
+    return item > 0 && nbod <= COOP_MAX_BODIES && ncons <= COOP_MAX_CONS && njoints == 0 && !has_ovf &&
+           w.item_cons_start[item + 1] <= w.cons_cap;
+}
+
+// One work item, start to finish, by one CTA with everything in shared memory (L lanes / constraint).
+template <int L>
+RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBodies& bd, const CoopStore& cs, int item, vec3 gravity) {
+    const Params& P = w.prm;
+    State* st = w.st;
+    const int buf = st->cur;
+    const int b0 = w.item_body_start[item], b1 = w.item_body_start[item + 1];
+    const int c0 = w.item_cons_start[item], n = w.item_cons_start[item + 1] - c0;
+    const int* coff = w.item_color_off + (size_t)item * (NUM_COLORS + 1);
+    const int ncol = st->nused_colors;
+    const int tid = ctx.btid, nth = ctx.bsize;
+
+    if (tid == 0) w.item_flags[item] = 0;
+    for (int l = b0 + tid; l < b1; l += nth) body_init(w, bd, w.item_bodies[l], l - b0, gravity);
+    ctx.block_sync();
+    for (int s = tid; s < n; s += nth) {   // S2 generate, one thread per constraint, into shared memory
+        Cons c;
+        cons_generate(w, bd, c0 + s, buf, item, c);
+        coop_put(cs, s, c);
+    }
+    ctx.block_sync();
+    for (int sub = 0; sub < P.num_substeps; ++sub) {
+        for (int l = b0 + tid; l < b1; l += nth) body_increment(w, bd, w.item_bodies[l], l - b0);
+        ctx.block_sync();
+        if (P.warmstart_coeff != 0.0f) {
+            for (int c = 0; c < ncol; ++c) {
+                if (coff[c] >= coff[c + 1]) continue;
+                coop_stage<L>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, MODE_WARMSTART, false);
+                ctx.block_sync();
+            }
+        } else {
+            for (int s = tid; s < n; s += nth) {
+#pragma unroll
+                for (int k = 0; k < MAX_PTS; ++k) {
+                    cs.pp(PF_ACC, k, s) = cs.pp(PF_ACC, k, s) + cs.pp(PF_IMP, k, s);
+                    cs.pp(PF_IMP, k, s) = cs.pp(PF_IMP, k, s) * 0.0f;
+                }
+                cs.pc(CF_TA0, s) = cs.pc(CF_TA0, s) + cs.pc(CF_TI0, s); cs.pc(CF_TA1, s) = cs.pc(CF_TA1, s) + cs.pc(CF_TI1, s);
+                cs.pc(CF_TI0, s) = cs.pc(CF_TI0, s) * 0.0f; cs.pc(CF_TI1, s) = cs.pc(CF_TI1, s) * 0.0f;
+                cs.pc(CF_WA, s) = cs.pc(CF_WA, s) + cs.pc(CF_WI, s); cs.pc(CF_WI, s) = cs.pc(CF_WI, s) * 0.0f;
+            }
+            ctx.block_sync();
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool relax = pass == 1;
+            const int iters = relax ? P.num_relax : P.num_pgs;
+            const bool fric = relax || P.friction_in_bias || P.num_relax == 0;
+            for (int it = 0; it < iters; ++it) {
+                for (int c = 0; c < ncol; ++c) {
+                    if (coff[c] >= coff[c + 1]) continue;
+                    coop_stage<L>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, relax ? MODE_RELAX : MODE_BIASED, fric);
+                    ctx.block_sync();
+                }
+            }
+            if (!relax) {
+                for (int l = b0 + tid; l < b1; l += nth) body_integrate(w, bd, w.item_bodies[l], l - b0);
+                ctx.block_sync();
+            }
+        }
+    }
+    if (w.item_flags[item]) {
+        for (int c = 0; c < ncol; ++c) {
+            if (coff[c] >= coff[c + 1]) continue;
+            coop_stage<L>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, MODE_RESTITUTION, false);
+            ctx.block_sync();
+        }
+    }
+    for (int s = tid; s < n; s += nth) {
+        Cons c;
+        coop_get_for_writeback(cs, s, c);
+        cons_writeback(w, c0 + s, buf, c);
+    }
+    for (int l = b0 + tid; l < b1; l += nth) body_writeback(w, bd, w.item_bodies[l], l - b0);
 }
 
 }  // namespace rb
