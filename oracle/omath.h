@@ -37,10 +37,16 @@ static inline V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b
 static inline V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }
 static inline V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
 static inline V3 cmul(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
-static inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// Explicit fused multiply-adds (IEEE correctly rounded, identical on CPU and GPU; the file is built
+// with -ffp-contract=off so nothing else is ever contracted).  The placement below defines the
+// arithmetic of this engine and is mirrored, expression for expression, by the CUDA kernels.
+static inline float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float dot(V3 a, V3 b) { return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x)); }
 static inline V3 cross(V3 a, V3 b) {
-    return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+    return V3{fma_(a.y, b.z, -(a.z * b.y)), fma_(a.z, b.x, -(a.x * b.z)), fma_(a.x, b.y, -(a.y * b.x))};
 }
+static inline V3 madd(V3 v, V3 a, float s) { return V3{fma_(a.x, s, v.x), fma_(a.y, s, v.y), fma_(a.z, s, v.z)}; }        // v + a*s
+static inline V3 maddv(V3 v, V3 a, V3 b) { return V3{fma_(a.x, b.x, v.x), fma_(a.y, b.y, v.y), fma_(a.z, b.z, v.z)}; }   // v + a.*b
 static inline float length_sq(V3 a) { return dot(a, a); }
 static inline float length(V3 a) { return sqrtf(dot(a, a)); }
 static inline float vget(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
@@ -56,13 +62,13 @@ static inline float inv_or_zero(float x) {
 
 static inline Q4 qidentity() { return Q4{0.f, 0.f, 0.f, 1.f}; }
 static inline Q4 qconj(Q4 q) { return Q4{-q.x, -q.y, -q.z, q.w}; }
-static inline float qdot(Q4 a, Q4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+static inline float qdot(Q4 a, Q4 b) { return fma_(a.w, b.w, fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x))); }
 // Hamilton product a*b (glam Quat::mul_quat, scalar path).
 static inline Q4 qmul(Q4 a, Q4 b) {
-    return Q4{a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
-              a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x,
-              a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w,
-              a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
+    return Q4{fma_(-a.z, b.y, fma_(a.y, b.z, fma_(a.x, b.w, a.w * b.x))),
+              fma_(a.z, b.x, fma_(a.y, b.w, fma_(-a.x, b.z, a.w * b.y))),
+              fma_(a.z, b.w, fma_(-a.y, b.x, fma_(a.x, b.y, a.w * b.z))),
+              fma_(-a.z, b.z, fma_(-a.y, b.y, fma_(-a.x, b.x, a.w * b.w)))};
 }
 static inline Q4 qnormalize(Q4 q) {
     float inv = 1.0f / sqrtf(qdot(q, q));
@@ -72,7 +78,7 @@ static inline Q4 qnormalize(Q4 q) {
 static inline V3 qrot(Q4 q, V3 v) {
     V3 b = V3{q.x, q.y, q.z};
     float b2 = dot(b, b);
-    return v * (q.w * q.w - b2) + b * (dot(v, b) * 2.0f) + cross(b, v) * (q.w * 2.0f);
+    return madd(madd(v * fma_(q.w, q.w, -b2), b, dot(v, b) * 2.0f), cross(b, v), q.w * 2.0f);
 }
 static inline V3 qrot_inv(Q4 q, V3 v) { return qrot(qconj(q), v); }
 
@@ -98,9 +104,9 @@ static inline Pose pose_prepend_translation(const Pose& p, V3 v) {
 
 static inline Sdp3 sdp_zero() { return Sdp3{0, 0, 0, 0, 0, 0}; }
 static inline V3 sdp_mul(const Sdp3& m, V3 v) {
-    return V3{m.m11 * v.x + m.m12 * v.y + m.m13 * v.z,
-              m.m12 * v.x + m.m22 * v.y + m.m23 * v.z,
-              m.m13 * v.x + m.m23 * v.y + m.m33 * v.z};
+    return V3{fma_(m.m13, v.z, fma_(m.m12, v.y, m.m11 * v.x)),
+              fma_(m.m23, v.z, fma_(m.m22, v.y, m.m12 * v.x)),
+              fma_(m.m33, v.z, fma_(m.m23, v.y, m.m13 * v.x))};
 }
 
 // Rotation matrix columns of a unit quaternion (c0,c1,c2 = images of x,y,z).

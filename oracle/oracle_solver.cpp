@@ -105,13 +105,13 @@ static void generate(World& w, int pair_index, Constraint& c) {
         V3 dp1 = pt.dp1, dp2 = pt.dp2;
         V3 point = world_com1 + dp1;
         points[k] = point;
-        friction_center = friction_center + point * weight;
-        friction_center2 = friction_center2 + (world_com2 + dp2) * weight;
+        friction_center = madd(friction_center, point, weight);
+        friction_center2 = madd(friction_center2, world_com2 + dp2, weight);
         V3 vel1 = g1.lin + cross(g1.ang, dp1);
         V3 vel2 = g2.lin + cross(g2.ang, dp2);
-        twist_warmstart = twist_warmstart + warmstart_twist * weight;
-        tangent_warmstart[0] = tangent_warmstart[0] + ws_t0 * weight;
-        tangent_warmstart[1] = tangent_warmstart[1] + ws_t1 * weight;
+        twist_warmstart = fma_(warmstart_twist, weight, twist_warmstart);
+        tangent_warmstart[0] = fma_(ws_t0, weight, tangent_warmstart[0]);
+        tangent_warmstart[1] = fma_(ws_t1, weight, tangent_warmstart[1]);
         tangent_vel = tangent_vel + vzero() * weight;
         c.cids[k] = sc.cid;
         NormalPart& n = c.normal[k];
@@ -234,21 +234,21 @@ static void warmstart(World& w, Constraint& c) {
     V3 v1 = g1.lin, w1 = g1.ang, v2 = g2.lin, w2 = g2.ang;
     for (int k = 0; k < c.num_contacts; ++k) {
         const NormalPart& n = c.normal[k];
-        v1 = v1 + cmul(c.dir1, c.im1) * n.impulse;
-        w1 = w1 + n.ii_torque_dir1 * n.impulse;
-        v2 = v2 + cmul(c.dir1, c.im2) * (-n.impulse);
-        w2 = w2 + n.ii_torque_dir2 * n.impulse;
+        v1 = madd(v1, cmul(c.dir1, c.im1), n.impulse);
+        w1 = madd(w1, n.ii_torque_dir1, n.impulse);
+        v2 = madd(v2, cmul(c.dir1, c.im2), -n.impulse);
+        w2 = madd(w2, n.ii_torque_dir2, n.impulse);
     }
     V3 t0 = c.tangent1, t1 = cross(c.dir1, c.tangent1);
-    v1 = v1 + cmul(t0 * c.t_impulse[0] + t1 * c.t_impulse[1], c.im1);
-    w1 = w1 + (c.t_ii_torque_dir1[0] * c.t_impulse[0] + c.t_ii_torque_dir1[1] * c.t_impulse[1]);
-    v2 = v2 + cmul(t0 * (-c.t_impulse[0]) + t1 * (-c.t_impulse[1]), c.im2);
-    w2 = w2 + (c.t_ii_torque_dir2[0] * c.t_impulse[0] + c.t_ii_torque_dir2[1] * c.t_impulse[1]);
+    v1 = maddv(v1, madd(t0 * c.t_impulse[0], t1, c.t_impulse[1]), c.im1);
+    w1 = madd(madd(w1, c.t_ii_torque_dir1[0], c.t_impulse[0]), c.t_ii_torque_dir1[1], c.t_impulse[1]);
+    v2 = maddv(v2, madd(t0 * (-c.t_impulse[0]), t1, -c.t_impulse[1]), c.im2);
+    w2 = madd(madd(w2, c.t_ii_torque_dir2[0], c.t_impulse[0]), c.t_ii_torque_dir2[1], c.t_impulse[1]);
     if (c.num_contacts > 1) {
         V3 ii_twist_dir1 = sdp_mul(c.ii1, c.dir1);
         V3 ii_twist_dir2 = sdp_mul(c.ii2, c.dir1);
-        w1 = w1 + ii_twist_dir1 * c.w_impulse;
-        w2 = w2 - ii_twist_dir2 * c.w_impulse;
+        w1 = madd(w1, ii_twist_dir1, c.w_impulse);
+        w2 = madd(w2, ii_twist_dir2, -c.w_impulse);
     }
     scatter_vel(w, c.id1, v1, w1);
     scatter_vel(w, c.id2, v2, w2);
@@ -261,13 +261,13 @@ static void solve(World& w, Constraint& c, bool solve_friction) {
     for (int k = 0; k < c.num_contacts; ++k) {
         NormalPart& n = c.normal[k];
         float dvel = dot(c.dir1, v1) + dot(n.torque_dir1, w1) - dot(c.dir1, v2) + dot(n.torque_dir2, w2) + n.rhs;
-        float new_impulse = n.cfm_factor * fmax2(n.impulse - n.r * dvel, 0.0f);
+        float new_impulse = n.cfm_factor * fmax2(fma_(-n.r, dvel, n.impulse), 0.0f);
         float dlambda = new_impulse - n.impulse;
         n.impulse = new_impulse;
-        v1 = v1 + cmul(c.dir1, c.im1) * dlambda;
-        w1 = w1 + n.ii_torque_dir1 * dlambda;
-        v2 = v2 + cmul(c.dir1, c.im2) * (-dlambda);
-        w2 = w2 + n.ii_torque_dir2 * dlambda;
+        v1 = madd(v1, cmul(c.dir1, c.im1), dlambda);
+        w1 = madd(w1, n.ii_torque_dir1, dlambda);
+        v2 = madd(v2, cmul(c.dir1, c.im2), -dlambda);
+        w2 = madd(w2, n.ii_torque_dir2, dlambda);
     }
     if (solve_friction) {
         V3 t0 = c.tangent1, t1 = cross(c.dir1, c.tangent1);
@@ -282,21 +282,21 @@ static void solve(World& w, Constraint& c, bool solve_friction) {
             V3 ii_twist_dir1 = sdp_mul(c.ii1, c.dir1);
             V3 ii_twist_dir2 = sdp_mul(c.ii2, c.dir1);
             float dvel = dot(c.dir1, w1 - w2) + c.w_rhs;
-            float new_impulse = fclamp(c.w_impulse - c.w_r * dvel, -twist_limit, twist_limit);
+            float new_impulse = fclamp(fma_(-c.w_r, dvel, c.w_impulse), -twist_limit, twist_limit);
             float dlambda = new_impulse - c.w_impulse;
             c.w_impulse = new_impulse;
-            w1 = w1 + ii_twist_dir1 * dlambda;
-            w2 = w2 - ii_twist_dir2 * dlambda;
+            w1 = madd(w1, ii_twist_dir1, dlambda);
+            w2 = madd(w2, ii_twist_dir2, -dlambda);
         }
         float dvel_0 = dot(t0, v1) + dot(c.t_torque_dir1[0], w1) - dot(t0, v2) + dot(c.t_torque_dir2[0], w2) + c.t_rhs[0];
         float dvel_1 = dot(t1, v1) + dot(c.t_torque_dir1[1], w1) - dot(t1, v2) + dot(c.t_torque_dir2[1], w2) + c.t_rhs[1];
         float k11 = c.t_r[0], k22 = c.t_r[1], k12 = c.t_r[2] * 0.5f;
-        float inv_det = inv_or_zero(k11 * k22 - k12 * k12);
-        float d0 = (k22 * dvel_0 - k12 * dvel_1) * inv_det;
-        float d1 = (k11 * dvel_1 - k12 * dvel_0) * inv_det;
+        float inv_det = inv_or_zero(fma_(k11, k22, -(k12 * k12)));
+        float d0 = fma_(k22, dvel_0, -(k12 * dvel_1)) * inv_det;
+        float d1 = fma_(k11, dvel_1, -(k12 * dvel_0)) * inv_det;
         float n0 = c.t_impulse[0] - d0, n1 = c.t_impulse[1] - d1;
         // nalgebra simd_cap_magnitude: scale down to `limit` when longer.
-        float len = sqrtf(n0 * n0 + n1 * n1);
+        float len = sqrtf(fma_(n1, n1, n0 * n0));
         if (len > tangent_limit) {
             float s = tangent_limit / len;
             n0 = n0 * s;
@@ -305,10 +305,10 @@ static void solve(World& w, Constraint& c, bool solve_friction) {
         float dl0 = n0 - c.t_impulse[0], dl1 = n1 - c.t_impulse[1];
         c.t_impulse[0] = n0;
         c.t_impulse[1] = n1;
-        v1 = v1 + cmul(t0 * dl0 + t1 * dl1, c.im1);
-        w1 = w1 + (c.t_ii_torque_dir1[0] * dl0 + c.t_ii_torque_dir1[1] * dl1);
-        v2 = v2 + cmul(t0 * (-dl0) + t1 * (-dl1), c.im2);
-        w2 = w2 + (c.t_ii_torque_dir2[0] * dl0 + c.t_ii_torque_dir2[1] * dl1);
+        v1 = maddv(v1, madd(t0 * dl0, t1, dl1), c.im1);
+        w1 = madd(madd(w1, c.t_ii_torque_dir1[0], dl0), c.t_ii_torque_dir1[1], dl1);
+        v2 = maddv(v2, madd(t0 * (-dl0), t1, -dl1), c.im2);
+        w2 = madd(madd(w2, c.t_ii_torque_dir2[0], dl0), c.t_ii_torque_dir2[1], dl1);
     }
     scatter_vel(w, c.id1, v1, w1);
     scatter_vel(w, c.id2, v2, w2);
@@ -326,14 +326,14 @@ static void apply_restitution(World& w, Constraint& c) {
         float seed = c.b_restitution_seed[k];
         float dvel = dot(c.dir1, v1) + dot(n.torque_dir1, w1) - dot(c.dir1, v2) + dot(n.torque_dir2, w2) + seed;
         bool gate = seed < 0.0f && (n.impulse_accumulator + n.impulse) > 0.0f;
-        float new_impulse = fmax2(n.impulse - n.r * dvel, 0.0f);
+        float new_impulse = fmax2(fma_(-n.r, dvel, n.impulse), 0.0f);
         if (!gate) new_impulse = n.impulse;
         float dlambda = new_impulse - n.impulse;
         n.impulse = new_impulse;
-        v1 = v1 + cmul(c.dir1, c.im1) * dlambda;
-        w1 = w1 + n.ii_torque_dir1 * dlambda;
-        v2 = v2 + cmul(c.dir1, c.im2) * (-dlambda);
-        w2 = w2 + n.ii_torque_dir2 * dlambda;
+        v1 = madd(v1, cmul(c.dir1, c.im1), dlambda);
+        w1 = madd(w1, n.ii_torque_dir1, dlambda);
+        v2 = madd(v2, cmul(c.dir1, c.im2), -dlambda);
+        w2 = madd(w2, n.ii_torque_dir2, dlambda);
     }
     scatter_vel(w, c.id1, v1, w1);
     scatter_vel(w, c.id2, v2, w2);
@@ -491,10 +491,10 @@ static void joint_solve(World& w, const Joint& j, JointRow* rows, int n, bool wo
         float delta = total - r.impulse;
         r.impulse = total;
         V3 lin_impulse = r.lin_jac * delta;
-        v1 = v1 + cmul(lin_impulse, g1.im);
-        w1 = w1 + r.ii_ang_jac1 * delta;
-        v2 = v2 - cmul(lin_impulse, g2.im);
-        w2 = w2 - r.ii_ang_jac2 * delta;
+        v1 = maddv(v1, lin_impulse, g1.im);
+        w1 = madd(w1, r.ii_ang_jac1, delta);
+        v2 = maddv(v2, -lin_impulse, g2.im);
+        w2 = madd(w2, r.ii_ang_jac2, -delta);
     }
     scatter_vel(w, j.sid1, v1, w1);
     scatter_vel(w, j.sid2, v2, w2);
@@ -702,7 +702,7 @@ void solve_island(World& w, V3 gravity) {
             V3 hang = s.ang * (sub_dt * 0.5f);
             Q4 id_plus_hang = Q4{hang.x, hang.y, hang.z, 1.0f};
             s.pose.q = qnormalize(qmul(id_plus_hang, s.pose.q));
-            s.pose.t = s.pose.t + s.lin * sub_dt;
+            s.pose.t = madd(s.pose.t, s.lin, sub_dt);
         });
         // S8 relax solve (worker.rs:636-649)
         for (int it = 0; it < P.num_internal_stabilization_iterations; ++it) solve_pass(true, solved_dt + sub_dt);

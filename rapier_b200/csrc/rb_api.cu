@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(COOP_THREADS, 2) k_solve_coop(World w, Grav g)
     SmemBodies bd;
     bd.s = smem;
     CoopStore cs;
-    cs.base = smem + COOP_MAX_BODIES * SB_STRIDE;
+    cs.base = smem + COOP_BODY_SLOTS * SB_STRIDE;
     const int n = w.st->nitems;
     for (int item = 1 + ctx.bid; item < n; item += ctx.nblocks) {
         if (!item_is_coop(w, item)) continue;

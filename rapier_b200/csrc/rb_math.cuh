@@ -27,8 +27,16 @@ RB_HD vec3 operator-(vec3 a, vec3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.
 RB_HD vec3 operator-(vec3 a) { return mk3(-a.x, -a.y, -a.z); }
 RB_HD vec3 operator*(vec3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 RB_HD vec3 had(vec3 a, vec3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
-RB_HD float dot3(vec3 a, vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-RB_HD vec3 cross3(vec3 a, vec3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+// Fused multiply-adds are written out explicitly (the library is compiled with -fmad=false, so the
+// compiler never contracts on its own): fmaf is correctly rounded on the GPU and on the host, which
+// keeps the kernels and the CPU oracle bit-identical while halving the FP instruction count.
+RB_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+RB_HD float dot3(vec3 a, vec3 b) { return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x)); }
+RB_HD vec3 cross3(vec3 a, vec3 b) {
+    return mk3(fma_(a.y, b.z, -(a.z * b.y)), fma_(a.z, b.x, -(a.x * b.z)), fma_(a.x, b.y, -(a.y * b.x)));
+}
+RB_HD vec3 madd3(vec3 v, vec3 a, float s) { return mk3(fma_(a.x, s, v.x), fma_(a.y, s, v.y), fma_(a.z, s, v.z)); }          // v + a*s
+RB_HD vec3 madd3v(vec3 v, vec3 a, vec3 b) { return mk3(fma_(a.x, b.x, v.x), fma_(a.y, b.y, v.y), fma_(a.z, b.z, v.z)); }    // v + a.*b
 RB_HD float norm2(vec3 a) { return dot3(a, a); }
 RB_HD float norm(vec3 a) { return sqrtf(dot3(a, a)); }
 RB_HD float comp(vec3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
@@ -43,13 +51,13 @@ RB_HD float copysign1(float s) { return copysignf(1.0f, s); }
 
 RB_HD quat qident() { quat q; q.x = 0.f; q.y = 0.f; q.z = 0.f; q.w = 1.f; return q; }
 RB_HD quat qconj(quat q) { quat r; r.x = -q.x; r.y = -q.y; r.z = -q.z; r.w = q.w; return r; }
-RB_HD float qdot(quat a, quat b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+RB_HD float qdot(quat a, quat b) { return fma_(a.w, b.w, fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x))); }
 RB_HD quat qmul(quat a, quat b) {
     quat r;
-    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
-    r.y = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
-    r.z = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w;
-    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    r.x = fma_(-a.z, b.y, fma_(a.y, b.z, fma_(a.x, b.w, a.w * b.x)));
+    r.y = fma_(a.z, b.x, fma_(a.y, b.w, fma_(-a.x, b.z, a.w * b.y)));
+    r.z = fma_(a.z, b.w, fma_(-a.y, b.x, fma_(a.x, b.y, a.w * b.z)));
+    r.w = fma_(-a.z, b.z, fma_(-a.y, b.y, fma_(-a.x, b.x, a.w * b.w)));
     return r;
 }
 RB_HD quat qnormalize(quat q) {
@@ -60,7 +68,7 @@ RB_HD quat qnormalize(quat q) {
 RB_HD vec3 rotate(quat q, vec3 v) {
     vec3 b = mk3(q.x, q.y, q.z);
     float b2 = dot3(b, b);
-    return v * (q.w * q.w - b2) + b * (dot3(v, b) * 2.0f) + cross3(b, v) * (q.w * 2.0f);
+    return madd3(madd3(v * fma_(q.w, q.w, -b2), b, dot3(v, b) * 2.0f), cross3(b, v), q.w * 2.0f);
 }
 RB_HD vec3 rotate_inv(quat q, vec3 v) { return rotate(qconj(q), v); }
 
@@ -81,8 +89,8 @@ RB_HD pose prepend_translation(const pose& p, vec3 v) { return mkpose(p.q, rotat
 
 RB_HD sym3 sym_zero() { sym3 m; m.xx = m.xy = m.xz = m.yy = m.yz = m.zz = 0.f; return m; }
 RB_HD vec3 smul(const sym3& m, vec3 v) {
-    return mk3(m.xx * v.x + m.xy * v.y + m.xz * v.z, m.xy * v.x + m.yy * v.y + m.yz * v.z,
-               m.xz * v.x + m.yz * v.y + m.zz * v.z);
+    return mk3(fma_(m.xz, v.z, fma_(m.xy, v.y, m.xx * v.x)), fma_(m.yz, v.z, fma_(m.yy, v.y, m.xy * v.x)),
+               fma_(m.zz, v.z, fma_(m.yz, v.y, m.xz * v.x)));
 }
 
 struct mat3 { vec3 c0, c1, c2; };

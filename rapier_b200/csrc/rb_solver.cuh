@@ -198,13 +198,13 @@ RB_HD void cons_generate(const World& w, const B& bd, int q, int buf, int item, 
             float dist = dot3(p1 - p2, dir);
             vec3 point = com1 + dp1;
             pts[k] = point;
-            fc1 = fc1 + point * inv_n;
-            fc2 = fc2 + (com2 + dp2) * inv_n;
+            fc1 = madd3(fc1, point, inv_n);
+            fc2 = madd3(fc2, com2 + dp2, inv_n);
             vec3 v1 = g1.lin + cross3(g1.ang, dp1);
             vec3 v2 = g2.lin + cross3(g2.ang, dp2);
-            tws = tws + ws_twist * inv_n;
-            tgs0 = tgs0 + w0 * inv_n;
-            tgs1 = tgs1 + w1 * inv_n;
+            tws = fma_(ws_twist, inv_n, tws);
+            tgs0 = fma_(w0, inv_n, tgs0);
+            tgs1 = fma_(w1, inv_n, tgs1);
             vec3 td1 = cross3(dp1, dir), td2 = cross3(dp2, -dir);
             vec3 itd1 = smul(g1.ii, td1), itd2 = smul(g2.ii, td2);
             vec3 imsum = g1.im + g2.im;
@@ -282,7 +282,7 @@ RB_HD PointPre point_pre(const Params& P, const BodyState& g1, const BodyState& 
 // One projected Gauss-Seidel normal row (contact_constraint_element.rs:481-504): returns dlambda.
 RB_HD float point_solve(const PointPre& pp, float r, float imp, vec3 dir, vec3 v1, vec3 w1, vec3 v2, vec3 w2, float& new_imp) {
     float dvel = dot3(dir, v1) + dot3(pp.td1, w1) - dot3(dir, v2) + dot3(pp.td2, w2) + pp.rhs;
-    float nl = pp.cfm * max2(imp - r * dvel, 0.0f);
+    float nl = pp.cfm * max2(fma_(-r, dvel, imp), 0.0f);
     new_imp = nl;
     return nl - imp;
 }
@@ -291,16 +291,16 @@ RB_HD float point_restitution(const PointPre& pp, float r, float imp, float acc,
                               vec3 w2, float& new_imp) {
     float dvel = dot3(dir, v1) + dot3(pp.td1, w1) - dot3(dir, v2) + dot3(pp.td2, w2) + seed;
     bool gate = seed < 0.0f && (acc + imp) > 0.0f;
-    float nl = max2(imp - r * dvel, 0.0f);
+    float nl = max2(fma_(-r, dvel, imp), 0.0f);
     if (!gate) nl = imp;
     new_imp = nl;
     return nl - imp;
 }
 RB_HD void apply_normal(vec3 lin1, vec3 lin2, vec3 itd1, vec3 itd2, float dl, vec3& v1, vec3& w1, vec3& v2, vec3& w2) {
-    v1 = v1 + lin1 * dl;
-    w1 = w1 + itd1 * dl;
-    v2 = v2 + lin2 * (-dl);
-    w2 = w2 + itd2 * dl;
+    v1 = madd3(v1, lin1, dl);
+    w1 = madd3(w1, itd1, dl);
+    v2 = madd3(v2, lin2, -dl);
+    w2 = madd3(w2, itd2, dl);
 }
 
 struct FrictionState { float ti0, ti1, wi; };
@@ -311,11 +311,11 @@ RB_HD void friction_solve(const Params& P, const BodyState& g1, const BodyState&
     if (nc > 1) {
         vec3 i1 = smul(g1.ii, dir), i2 = smul(g2.ii, dir);
         float dvel = dot3(dir, w1 - w2) + 0.0f;
-        float nl = clampf(f.wi - wr * dvel, -wlimit, wlimit);
+        float nl = clampf(fma_(-wr, dvel, f.wi), -wlimit, wlimit);
         float dl = nl - f.wi;
         f.wi = nl;
-        w1 = w1 + i1 * dl;
-        w2 = w2 - i2 * dl;
+        w1 = madd3(w1, i1, dl);
+        w2 = madd3(w2, i2, -dl);
     }
     vec3 td10 = cross3(tdp1, t1), td11 = cross3(tdp1, t2);
     vec3 td20 = cross3(tdp2, -t1), td21 = cross3(tdp2, -t2);
@@ -330,11 +330,11 @@ RB_HD void friction_solve(const Params& P, const BodyState& g1, const BodyState&
     float dv0 = dot3(t1, v1) + dot3(td10, w1) - dot3(t1, v2) + dot3(td20, w2) + rhs0;
     float dv1 = dot3(t2, v1) + dot3(td11, w1) - dot3(t2, v2) + dot3(td21, w2) + rhs1;
     float k11 = tr0, k22 = tr1, k12 = tr2 * 0.5f;
-    float inv_det = safe_inv(k11 * k22 - k12 * k12);
-    float d0 = (k22 * dv0 - k12 * dv1) * inv_det;
-    float d1 = (k11 * dv1 - k12 * dv0) * inv_det;
+    float inv_det = safe_inv(fma_(k11, k22, -(k12 * k12)));
+    float d0 = fma_(k22, dv0, -(k12 * dv1)) * inv_det;
+    float d1 = fma_(k11, dv1, -(k12 * dv0)) * inv_det;
     float n0 = f.ti0 - d0, n1 = f.ti1 - d1;
-    float len = sqrtf(n0 * n0 + n1 * n1);
+    float len = sqrtf(fma_(n1, n1, n0 * n0));
     if (len > tlimit) {
         float sc = tlimit / len;
         n0 = n0 * sc;
@@ -343,23 +343,23 @@ RB_HD void friction_solve(const Params& P, const BodyState& g1, const BodyState&
     float dl0 = n0 - f.ti0, dl1 = n1 - f.ti1;
     f.ti0 = n0;
     f.ti1 = n1;
-    v1 = v1 + had(t1 * dl0 + t2 * dl1, g1.im);
-    w1 = w1 + (i10 * dl0 + i11 * dl1);
-    v2 = v2 + had(t1 * (-dl0) + t2 * (-dl1), g2.im);
-    w2 = w2 + (i20 * dl0 + i21 * dl1);
+    v1 = madd3v(v1, madd3(t1 * dl0, t2, dl1), g1.im);
+    w1 = madd3(madd3(w1, i10, dl0), i11, dl1);
+    v2 = madd3v(v2, madd3(t1 * (-dl0), t2, -dl1), g2.im);
+    w2 = madd3(madd3(w2, i20, dl0), i21, dl1);
 }
 // Friction + twist warm start (contact_constraint_element.rs:627-647, :720-732).
 RB_HD void friction_warmstart(const BodyState& g1, const BodyState& g2, vec3 dir, vec3 t1, vec3 t2, int nc, vec3 tdp1, vec3 tdp2,
                               float ti0, float ti1, float wi, vec3& v1, vec3& w1, vec3& v2, vec3& w2) {
     vec3 i10 = smul(g1.ii, cross3(tdp1, t1)), i11 = smul(g1.ii, cross3(tdp1, t2));
     vec3 i20 = smul(g2.ii, cross3(tdp2, -t1)), i21 = smul(g2.ii, cross3(tdp2, -t2));
-    v1 = v1 + had(t1 * ti0 + t2 * ti1, g1.im);
-    w1 = w1 + (i10 * ti0 + i11 * ti1);
-    v2 = v2 + had(t1 * (-ti0) + t2 * (-ti1), g2.im);
-    w2 = w2 + (i20 * ti0 + i21 * ti1);
+    v1 = madd3v(v1, madd3(t1 * ti0, t2, ti1), g1.im);
+    w1 = madd3(madd3(w1, i10, ti0), i11, ti1);
+    v2 = madd3v(v2, madd3(t1 * (-ti0), t2, -ti1), g2.im);
+    w2 = madd3(madd3(w2, i20, ti0), i21, ti1);
     if (nc > 1) {
-        w1 = w1 + smul(g1.ii, dir) * wi;
-        w2 = w2 - smul(g2.ii, dir) * wi;
+        w1 = madd3(w1, smul(g1.ii, dir), wi);
+        w2 = madd3(w2, smul(g2.ii, dir), -wi);
     }
 }
 
@@ -597,10 +597,10 @@ RB_HD void joint_solve(const World& w, const B& bd, int q, bool wo_bias) {
         float delta = total - L.w;
         L.w = total;
         vec3 li = xyz(L) * delta;
-        v1 = v1 + had(li, g1.im);
-        w1 = w1 + xyz(I1) * delta;
-        v2 = v2 - had(li, g2.im);
-        w2 = w2 - xyz(I2) * delta;
+        v1 = madd3v(v1, li, g1.im);
+        w1 = madd3(w1, xyz(I1), delta);
+        v2 = madd3v(v2, -li, g2.im);
+        w2 = madd3(w2, xyz(I2), -delta);
         jrow(w, JR_LIN, s) = L;
         if (wo_bias) { A2.w = I1.w; jrow(w, JR_A2, s) = A2; }
     }
@@ -706,7 +706,7 @@ RB_HD void body_integrate(const World& w, const B& bd, int b, int id) {
     vec3 hang = ang * (P.sub_dt * 0.5f);
     quat dq; dq.x = hang.x; dq.y = hang.y; dq.z = hang.z; dq.w = 1.0f;
     p.q = qnormalize(qmul(dq, p.q));
-    p.t = p.t + lin * P.sub_dt;
+    p.t = madd3(p.t, lin, P.sub_dt);
     bd.set_xf(id, p);
 }
 // S11 + advance_to_final_positions (worker.rs:809-897; substep.rs:84-224)
@@ -869,7 +869,10 @@ enum CoopPointField { PF_DP1 = 0, PF_DP2 = 3, PF_LP1 = 6, PF_LP2 = 9, PF_R = 12,
 enum CoopConsField { CF_DIR = 0, CF_FRIC = 3, CF_T1 = 4, CF_WR = 7, CF_TDP1 = 8, CF_TDP2 = 11, CF_TR = 14, CF_TWD = 17, CF_TI0 = 21,
                      CF_TI1 = 22, CF_TA0 = 23, CF_TA1 = 24, CF_WI = 25, CF_WA = 26, CF_ID1 = 27, CF_ID2 = 28, CF_NC = 29, CF_COUNT = 30 };
 constexpr int COOP_CONS_FLOATS = (PF_COUNT * MAX_PTS + CF_COUNT) * COOP_CS;
-constexpr int COOP_SMEM_FLOATS = COOP_MAX_BODIES * SB_STRIDE + COOP_CONS_FLOATS;
+constexpr int COOP_WORLD_SLOT = COOP_MAX_BODIES;        // staged pseudo body: identity pose, zero velocity and mass
+constexpr int COOP_GARBAGE_SLOT = COOP_MAX_BODIES + 1;  // scatter target of world-attached sides
+constexpr int COOP_BODY_SLOTS = COOP_MAX_BODIES + 2;
+constexpr int COOP_SMEM_FLOATS = COOP_BODY_SLOTS * SB_STRIDE + COOP_CONS_FLOATS;
 
 struct CoopStore {
     float* base;
@@ -944,7 +947,8 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs,
         const bool active = s_raw < e && grp < groups;
         const int s = active ? s_raw : a;   // inactive lanes shadow a valid slot (they must execute the shuffles)
         const int id1 = as_int(cs.pc(CF_ID1, s)), id2 = as_int(cs.pc(CF_ID2, s)), nc = as_int(cs.pc(CF_NC, s));
-        BodyState g1 = gather_body(bd, id1), g2 = gather_body(bd, id2);
+        // branch-free gathers: a world-attached side reads the staged identity/zero pseudo body
+        BodyState g1 = gather_body(bd, id1 < 0 ? COOP_WORLD_SLOT : id1), g2 = gather_body(bd, id2 < 0 ? COOP_WORLD_SLOT : id2);
         vec3 v1 = g1.lin, w1 = g1.ang, v2 = g2.lin, w2 = g2.ang;
         const vec3 dir = cs.pc3(CF_DIR, s), t1 = cs.pc3(CF_T1, s);
         const vec3 t2 = cross3(dir, t1);
@@ -1051,8 +1055,8 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs,
                     cs.pc(CF_TA0, s) = ta0; cs.pc(CF_TA1, s) = ta1; cs.pc(CF_WA, s) = wa;
                 }
                 if (mode != MODE_RESTITUTION) { cs.pc(CF_TI0, s) = ti0; cs.pc(CF_TI1, s) = ti1; cs.pc(CF_WI, s) = wi; }
-                scatter_vel(bd, id1, v1, w1);
-                scatter_vel(bd, id2, v2, w2);
+                bd.set_vel(id1 < 0 ? COOP_GARBAGE_SLOT : id1, v1, w1);
+                bd.set_vel(id2 < 0 ? COOP_GARBAGE_SLOT : id2, v2, w2);
             }
         }
     }
@@ -1081,7 +1085,12 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBod
     const int ncol = st->nused_colors;
     const int tid = ctx.btid, nth = ctx.bsize;
 
-    if (tid == 0) w.item_flags[item] = 0;
+    if (tid == 0) {
+        w.item_flags[item] = 0;
+        bd.set_vel(COOP_WORLD_SLOT, zero3(), zero3());
+        bd.set_xf(COOP_WORLD_SLOT, pident());
+        bd.set_mass(COOP_WORLD_SLOT, sym_zero(), zero3());
+    }
     for (int l = b0 + tid; l < b1; l += nth) body_init(w, bd, w.item_bodies[l], l - b0, gravity);
     ctx.block_sync();
     for (int s = tid; s < n; s += nth) {   // S2 generate, one thread per constraint, into shared memory
