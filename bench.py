@@ -179,34 +179,9 @@ def main():
     # ---- multi-GPU: shard whole connected components (islands) across ranks ----
     exchange = None
     if world_size > 1:
-        comp = pipe.label_components()
-        roots = np.unique(comp[comp >= 0])
-        owner_of_root = {int(r): i * world_size // len(roots) for i, r in enumerate(roots)}   # contiguous blocks of islands
-        owner = np.array([owner_of_root[int(c)] if c >= 0 else -1 for c in comp], np.int32)
-        pipe.set_owned_bodies((owner == rank).astype(np.uint8))
-        counts = [int((owner == r).sum()) for r in range(world_size)]
-        maxc = max(counts)
-        idx_lists = [np.nonzero(owner == r)[0].astype(np.int32) for r in range(world_size)]
-        ptr, nbytes = pipe.state_buffer()
-
-        class _Buf:
-            def __init__(s, p, n):
-                s.__cuda_array_interface__ = {"shape": (n // 4,), "typestr": "<f4", "data": (p, False), "version": 2}
-        state = torch.as_tensor(_Buf(ptr, nbytes), device=f"cuda:{local_rank}").view(nb, 13)
-        my_idx = torch.from_numpy(idx_lists[rank]).to(state.device).long()
-        send = torch.zeros(maxc, 13, device=state.device)
-        recv = torch.zeros(world_size * maxc, 13, device=state.device)
-        others = [r for r in range(world_size) if r != rank]
-        imp_idx = torch.cat([torch.from_numpy(idx_lists[r]) for r in others]).to(state.device).int()
-        gather_rows = torch.cat([torch.arange(counts[r]) + r * maxc for r in others]).to(state.device).long()
-        imp_src = torch.zeros(len(imp_idx), 13, device=state.device)
-
-        def exchange():
-            # NCCL all-gather of every rank's owned body states over NVLink; non-owned states are imported
-            send[:counts[rank]] = state.index_select(0, my_idx)
-            dist.all_gather_into_tensor(recv, send)
-            torch.index_select(recv, 0, gather_rows, out=imp_src)
-            pipe.import_states(imp_idx.data_ptr(), imp_src.data_ptr(), len(imp_idx))
+        from rapier_b200.sharding import IslandShard
+        shard = IslandShard(pipe, dist, rank, world_size, torch.device("cuda", local_rank))
+        exchange = shard.exchange
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if args.l2 == "flush" else None
 

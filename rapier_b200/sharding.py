@@ -1,0 +1,67 @@
+"""Island sharding across ranks: whole connected components are assigned to ranks,
+every rank simulates only the bodies it owns, and one all-gather per step of the owned body
+states (13 floats per body: t3 q4 linvel3 angvel3) gives every rank the full world state.
+
+The reference is single-process (one awake set, src/dynamics/island_manager/manager.rs:20-25); the
+components it already tracks as persistent islands (island_manager/persistent.rs:1-3) are the unit
+of distribution here.  Works with any torch.distributed backend: NCCL over NVLink on the GPU box,
+gloo in the CPU tests (where the world is the host emulation of the kernels).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+
+def partition_components(component_of_body, world_size):
+    """Contiguous blocks of components (ascending root id) per rank, balanced by body count.
+    Returns owner[b] in [0, world_size) or -1 for non-dynamic bodies."""
+    comp = np.asarray(component_of_body)
+    roots, counts = np.unique(comp[comp >= 0], return_counts=True)
+    cum = np.cumsum(counts) - counts
+    total = max(int(counts.sum()), 1)
+    owner_of_root = np.minimum((cum * world_size) // total, world_size - 1)
+    lut = dict(zip(roots.tolist(), owner_of_root.tolist()))
+    return np.array([lut[int(c)] if c >= 0 else -1 for c in comp], np.int32)
+
+
+class _CudaBuf:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def state_tensor(pipe, device):
+    """Zero-copy torch view [nb, 13] of the library's packed body-state buffer."""
+    ptr, nbytes = pipe.state_buffer()
+    if device.type == "cuda":
+        t = torch.as_tensor(_CudaBuf(ptr, nbytes), device=device)
+    else:
+        t = torch.frombuffer((C.c_float * (nbytes // 4)).from_address(ptr), dtype=torch.float32)
+    return t.view(-1, 13)
+
+
+class IslandShard:
+    def __init__(self, pipe, dist, rank, world_size, device):
+        self.pipe, self.dist, self.rank, self.world_size = pipe, dist, rank, world_size
+        comp = pipe.label_components()
+        self.owner = partition_components(comp, world_size)
+        pipe.set_owned_bodies((self.owner == rank).astype(np.uint8))
+        self.state = state_tensor(pipe, device)
+        idx = [np.nonzero(self.owner == r)[0].astype(np.int64) for r in range(world_size)]
+        self.counts = [len(i) for i in idx]
+        self.maxc = max(max(self.counts), 1)
+        self.my_idx = torch.from_numpy(idx[rank]).to(device)
+        self.send = torch.zeros(self.maxc, 13, device=device)
+        self.recv = torch.zeros(world_size * self.maxc, 13, device=device)
+        others = [r for r in range(world_size) if r != rank]
+        self.imp_idx = torch.cat([torch.from_numpy(idx[r]) for r in others] or [torch.zeros(0, dtype=torch.int64)]).to(device).int()
+        self.rows = torch.cat([torch.arange(self.counts[r]) + r * self.maxc for r in others] or [torch.zeros(0, dtype=torch.int64)]).to(device)
+        self.imp_src = torch.zeros(len(self.imp_idx), 13, device=device)
+
+    def exchange(self):
+        """All-gather the owned body states and import the states simulated by the other ranks."""
+        self.send[:self.counts[self.rank]] = self.state.index_select(0, self.my_idx)
+        self.dist.all_gather_into_tensor(self.recv, self.send)
+        if len(self.imp_idx):
+            torch.index_select(self.recv, 0, self.rows, out=self.imp_src)
+            self.pipe.import_states(self.imp_idx.data_ptr(), self.imp_src.data_ptr(), len(self.imp_idx))
