@@ -52,3 +52,21 @@ def test_empty_and_ragged_scenes():
     assert is_exact(compare_worlds(w, o))
     pose, _ = w.body_states()
     assert abs(pose[1, 1] - 1.0) < 0.02 and np.isfinite(pose).all()
+
+
+from variant_cases import VARIANTS  # noqa: E402
+
+
+@pytest.mark.parametrize("name,make,params,steps,every", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_emulated_variants_match_oracle(name, make, params, steps, every):
+    scene = make()
+    w = PhysicsWorld(scene, integration_parameters=params, _lib=emul_lib.lib())
+    o = oracle_lib.OracleWorld(scene, params=params)
+    for i in range(steps):
+        w.step()
+        o.step()
+        if i % every == every - 1 or i < 2:
+            d = compare_worlds(w, o)
+            assert is_exact(d), f"{name}: step {i}: {d}"
+    pose, _ = w.body_states()
+    assert np.isfinite(pose).all()

@@ -1,0 +1,65 @@
+"""Scene / parameter variants shared by the emulated-kernel tests (CPU) and the CUDA parity tests (GPU):
+edge cases of the reference's own test-suite for this path (restitution, warm-start coefficients,
+friction in the bias pass, collision groups, joints with contacts disabled, multi-collider bodies,
+user forces, damping, locked axes)."""
+from rapier_b200 import _abi as A
+from rapier_b200 import scenes
+from rapier_b200.sets import ColliderBuilder, FixedJointBuilder, RigidBodyBuilder, SphericalJointBuilder
+
+
+def _params(**kw):
+    p = A.RbIntegrationParameters.default()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def bouncing_balls():
+    """issue_974_restitution.rs scene with several restitutions side by side + a bouncing cube."""
+    s = scenes.Scene("bounce")
+    s.insert(RigidBodyBuilder.fixed(), ColliderBuilder.cuboid(30.0, 0.1, 30.0).restitution(0.7))
+    for i, e in enumerate((0.0, 0.3, 0.8, 1.0)):
+        s.insert(RigidBodyBuilder.dynamic().translation((2.0 * i, 1.3 + 0.2 * i, 0.0)), ColliderBuilder.ball(0.2).restitution(e))
+    s.insert(RigidBodyBuilder.dynamic().translation((-3.0, 1.0, 0.0)).rotation((0.3, 0.2, 0.1)),
+             ColliderBuilder.cuboid(0.3, 0.2, 0.25).restitution(0.6))
+    return s
+
+
+def groups_and_joints():
+    """Collision-group filtering (interaction_groups.rs:148-154), a joint with contacts disabled
+    (pair_update.rs:193-202), a fixed joint (6 locked axes), user force/torque, damping, locked axes."""
+    s = scenes.Scene("groups")
+    s.insert(RigidBodyBuilder.fixed().translation((0, -0.5, 0)), ColliderBuilder.cuboid(20, 0.5, 20))
+    # two overlapping boxes that must NOT collide (disjoint groups) and one that collides with both
+    a = s.insert(RigidBodyBuilder.dynamic().translation((0, 1.0, 0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5).collision_groups(0b01, 0b01))
+    b = s.insert(RigidBodyBuilder.dynamic().translation((0.3, 1.2, 0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5).collision_groups(0b10, 0b10))
+    s.insert(RigidBodyBuilder.dynamic().translation((0.1, 3.0, 0.1)), ColliderBuilder.cuboid(0.4, 0.4, 0.4))
+    # overlapping balls joined by a spherical joint with contacts disabled
+    c = s.insert(RigidBodyBuilder.dynamic().translation((5, 2, 0)), ColliderBuilder.ball(0.5))
+    d = s.insert(RigidBodyBuilder.dynamic().translation((5.6, 2, 0)).linear_damping(0.5).angular_damping(1.0), ColliderBuilder.ball(0.5))
+    s.joints.insert(c, d, SphericalJointBuilder().local_anchor1((0.3, 0, 0)).local_anchor2((-0.3, 0, 0)).contacts_enabled(False))
+    # a fixed joint welding two boxes, one of them pushed by a user force / torque
+    e = s.insert(RigidBodyBuilder.dynamic().translation((-5, 2, 0)), ColliderBuilder.cuboid(0.5, 0.25, 0.25))
+    f = s.insert(RigidBodyBuilder.dynamic().translation((-4, 2, 0)), ColliderBuilder.cuboid(0.5, 0.25, 0.25))
+    s.joints.insert(e, f, FixedJointBuilder().local_anchor1((0.5, 0, 0)).local_anchor2((-0.5, 0, 0)))
+    s.bodies.descs[f].user_force[:] = (0.0, 0.0, 3.0)
+    s.bodies.descs[f].user_torque[:] = (0.2, 0.0, 0.0)
+    # a body with two colliders (composite mass properties) and a body with locked rotations
+    g = s.insert(RigidBodyBuilder.dynamic().translation((0, 2, 6)), ColliderBuilder.cuboid(0.5, 0.2, 0.2).translation((0.6, 0, 0)))
+    s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.5, 0.2, 0.2).translation((-0.6, 0, 0)), g)
+    s.insert(RigidBodyBuilder.dynamic().translation((3, 2, 6)).rotation((0.4, 0.0, 0.2)).locked_axes(A.RB_BODY_LOCK_RX | A.RB_BODY_LOCK_RZ),
+             ColliderBuilder.cuboid(0.3, 0.6, 0.3))
+    assert a >= 0 and b >= 0
+    return s
+
+
+VARIANTS = [
+    ("restitution", bouncing_balls, None, 150, 25),
+    ("groups_joints_forces", groups_and_joints, None, 150, 25),
+    ("warmstart_half", lambda: scenes.pyramids(1, 2, 6), _params(warmstart_coefficient=0.5), 40, 10),
+    ("warmstart_zero", lambda: scenes.pyramids(1, 2, 6), _params(warmstart_coefficient=0.0), 40, 10),
+    ("friction_in_bias_pass", lambda: scenes.box_pile(3, 3, 3), _params(friction_in_bias_pass=1), 120, 20),
+    ("two_pgs_no_relax", lambda: scenes.box_pile(3, 2, 3), _params(num_internal_pgs_iterations=2, num_internal_stabilization_iterations=0), 100, 20),
+    ("six_substeps_no_recycling", lambda: scenes.pyramids(1, 1, 8), _params(num_solver_iterations=6, contact_recycling=0), 40, 10),
+    ("length_unit_10", lambda: scenes.box_pile(2, 3, 2), _params(length_unit=10.0), 80, 20),
+]
