@@ -274,7 +274,7 @@ static void solve(World& w, Constraint& c, bool solve_friction) {
         float tangent_limit = 0.0f, twist_limit = 0.0f;
         for (int k = 0; k < c.num_contacts; ++k) {
             tangent_limit = tangent_limit + c.normal[k].impulse;
-            twist_limit = twist_limit + c.normal[k].impulse * c.twist_dists[k];
+            twist_limit = fma_(c.normal[k].impulse, c.twist_dists[k], twist_limit);
         }
         tangent_limit = tangent_limit * c.limit;
         twist_limit = twist_limit * c.limit;

@@ -255,13 +255,12 @@ constexpr int MODE_WARMSTART = 0, MODE_BIASED = 1, MODE_RELAX = 2, MODE_RESTITUT
 // ---- per-row primitives shared by the serial sweep and the lane-cooperative sweep -----------------
 struct PointPre { vec3 td1, td2, itd1, itd2; float rhs, cfm; };
 
-// Jacobians of one normal row + (biased / relax) its rhs and cfm from the CURRENT poses
+// rhs and cfm of one normal row from the CURRENT poses
 // (contact_with_twist_friction.rs:473-503 update, :543-550 refresh_rhs_wo_bias).
-RB_HD PointPre point_pre(const Params& P, const BodyState& g1, const BodyState& g2, vec3 dir, vec3 dp1, vec3 dp2,
-                         vec3 lp1, vec3 lp2, float dist0, int mode, float cfm_soft, float erp) {
-    PointPre o;
-    o.rhs = 0.0f;
-    o.cfm = 1.0f;
+RB_HD void point_rhs(const Params& P, const BodyState& g1, const BodyState& g2, vec3 dir, vec3 lp1, vec3 lp2, float dist0, int mode,
+                     float cfm_soft, float erp, float& rhs_out, float& cfm_out) {
+    rhs_out = 0.0f;
+    cfm_out = 1.0f;
     if (mode == MODE_BIASED || mode == MODE_RELAX) {
         vec3 p1 = xform(g1.p, lp1);
         vec3 p2 = xform(g2.p, lp2);
@@ -269,14 +268,23 @@ RB_HD PointPre point_pre(const Params& P, const BodyState& g1, const BodyState& 
         float rhs = max2(dist, 0.0f) * P.sub_inv_dt;
         if (mode == MODE_BIASED) {
             rhs = rhs + clampf(dist * erp, -P.max_corrective_velocity, 0.0f);
-            o.cfm = dist <= 0.0f ? cfm_soft : 1.0f;
+            cfm_out = dist <= 0.0f ? cfm_soft : 1.0f;
         }
-        o.rhs = rhs;
+        rhs_out = rhs;
     }
+}
+// Angular jacobians of one normal row (contact_with_twist_friction.rs:261-264); constant during a step.
+RB_HD void point_jac(const BodyState& g1, const BodyState& g2, vec3 dir, vec3 dp1, vec3 dp2, PointPre& o) {
     o.td1 = cross3(dp1, dir);
     o.td2 = cross3(dp2, -dir);
     o.itd1 = smul(g1.ii, o.td1);
     o.itd2 = smul(g2.ii, o.td2);
+}
+RB_HD PointPre point_pre(const Params& P, const BodyState& g1, const BodyState& g2, vec3 dir, vec3 dp1, vec3 dp2,
+                         vec3 lp1, vec3 lp2, float dist0, int mode, float cfm_soft, float erp) {
+    PointPre o;
+    point_rhs(P, g1, g2, dir, lp1, lp2, dist0, mode, cfm_soft, erp, o.rhs, o.cfm);
+    point_jac(g1, g2, dir, dp1, dp2, o);
     return o;
 }
 // One projected Gauss-Seidel normal row (contact_constraint_element.rs:481-504): returns dlambda.
@@ -304,22 +312,29 @@ RB_HD void apply_normal(vec3 lin1, vec3 lin2, vec3 itd1, vec3 itd2, float dl, ve
 }
 
 struct FrictionState { float ti0, ti1, wi; };
+// Jacobians of the friction rows (constant during a step): tangent torque directions and their
+// inverse-inertia images, twist directions (contact_with_twist_friction.rs:330-379).
+struct FrictionJac { vec3 td10, td11, td20, td21, i10, i11, i20, i21, tw1, tw2; };
+RB_HD FrictionJac friction_jac(const BodyState& g1, const BodyState& g2, vec3 dir, vec3 t1, vec3 t2, vec3 tdp1, vec3 tdp2) {
+    FrictionJac j;
+    j.td10 = cross3(tdp1, t1); j.td11 = cross3(tdp1, t2);
+    j.td20 = cross3(tdp2, -t1); j.td21 = cross3(tdp2, -t2);
+    j.i10 = smul(g1.ii, j.td10); j.i11 = smul(g1.ii, j.td11); j.i20 = smul(g2.ii, j.td20); j.i21 = smul(g2.ii, j.td21);
+    j.tw1 = smul(g1.ii, dir); j.tw2 = smul(g2.ii, dir);
+    return j;
+}
 // Twist then tangent (contact_with_twist_friction.rs:737-777; contact_constraint_element.rs:650-705, :735-756).
-RB_HD void friction_solve(const Params& P, const BodyState& g1, const BodyState& g2, vec3 dir, vec3 t1, vec3 t2, int nc,
-                          float tlimit, float wlimit, float wr, vec3 tdp1, vec3 tdp2, float tr0, float tr1, float tr2,
-                          bool relax, vec3 lfc1, vec3 lfc2, FrictionState& f, vec3& v1, vec3& w1, vec3& v2, vec3& w2) {
+RB_HD void friction_solve_jac(const Params& P, const BodyState& g1, const BodyState& g2, vec3 dir, vec3 t1, vec3 t2, int nc,
+                              float tlimit, float wlimit, float wr, const FrictionJac& j, float tr0, float tr1, float tr2, bool relax,
+                              vec3 lfc1, vec3 lfc2, FrictionState& f, vec3& v1, vec3& w1, vec3& v2, vec3& w2) {
     if (nc > 1) {
-        vec3 i1 = smul(g1.ii, dir), i2 = smul(g2.ii, dir);
         float dvel = dot3(dir, w1 - w2) + 0.0f;
         float nl = clampf(fma_(-wr, dvel, f.wi), -wlimit, wlimit);
         float dl = nl - f.wi;
         f.wi = nl;
-        w1 = madd3(w1, i1, dl);
-        w2 = madd3(w2, i2, -dl);
+        w1 = madd3(w1, j.tw1, dl);
+        w2 = madd3(w2, j.tw2, -dl);
     }
-    vec3 td10 = cross3(tdp1, t1), td11 = cross3(tdp1, t2);
-    vec3 td20 = cross3(tdp2, -t1), td21 = cross3(tdp2, -t2);
-    vec3 i10 = smul(g1.ii, td10), i11 = smul(g1.ii, td11), i20 = smul(g2.ii, td20), i21 = smul(g2.ii, td21);
     float rhs0 = 0.0f, rhs1 = 0.0f;  // tangent rhs_wo_bias = tangent_velocity . t = 0 (no hooks)
     if (!relax) {  // update(): bias from the friction-centre drift (contact_with_twist_friction.rs:506-514)
         vec3 p1 = xform(g1.p, lfc1);
@@ -327,8 +342,8 @@ RB_HD void friction_solve(const Params& P, const BodyState& g1, const BodyState&
         rhs0 = 0.0f + dot3(p1 - p2, t1) * P.sub_inv_dt;
         rhs1 = 0.0f + dot3(p1 - p2, t2) * P.sub_inv_dt;
     }
-    float dv0 = dot3(t1, v1) + dot3(td10, w1) - dot3(t1, v2) + dot3(td20, w2) + rhs0;
-    float dv1 = dot3(t2, v1) + dot3(td11, w1) - dot3(t2, v2) + dot3(td21, w2) + rhs1;
+    float dv0 = dot3(t1, v1) + dot3(j.td10, w1) - dot3(t1, v2) + dot3(j.td20, w2) + rhs0;
+    float dv1 = dot3(t2, v1) + dot3(j.td11, w1) - dot3(t2, v2) + dot3(j.td21, w2) + rhs1;
     float k11 = tr0, k22 = tr1, k12 = tr2 * 0.5f;
     float inv_det = safe_inv(fma_(k11, k22, -(k12 * k12)));
     float d0 = fma_(k22, dv0, -(k12 * dv1)) * inv_det;
@@ -344,23 +359,32 @@ RB_HD void friction_solve(const Params& P, const BodyState& g1, const BodyState&
     f.ti0 = n0;
     f.ti1 = n1;
     v1 = madd3v(v1, madd3(t1 * dl0, t2, dl1), g1.im);
-    w1 = madd3(madd3(w1, i10, dl0), i11, dl1);
+    w1 = madd3(madd3(w1, j.i10, dl0), j.i11, dl1);
     v2 = madd3v(v2, madd3(t1 * (-dl0), t2, -dl1), g2.im);
-    w2 = madd3(madd3(w2, i20, dl0), i21, dl1);
+    w2 = madd3(madd3(w2, j.i20, dl0), j.i21, dl1);
+}
+RB_HD void friction_solve(const Params& P, const BodyState& g1, const BodyState& g2, vec3 dir, vec3 t1, vec3 t2, int nc,
+                          float tlimit, float wlimit, float wr, vec3 tdp1, vec3 tdp2, float tr0, float tr1, float tr2,
+                          bool relax, vec3 lfc1, vec3 lfc2, FrictionState& f, vec3& v1, vec3& w1, vec3& v2, vec3& w2) {
+    FrictionJac j = friction_jac(g1, g2, dir, t1, t2, tdp1, tdp2);
+    friction_solve_jac(P, g1, g2, dir, t1, t2, nc, tlimit, wlimit, wr, j, tr0, tr1, tr2, relax, lfc1, lfc2, f, v1, w1, v2, w2);
 }
 // Friction + twist warm start (contact_constraint_element.rs:627-647, :720-732).
+RB_HD void friction_warmstart_jac(const BodyState& g1, const BodyState& g2, vec3 t1, vec3 t2, int nc, const FrictionJac& j,
+                                  float ti0, float ti1, float wi, vec3& v1, vec3& w1, vec3& v2, vec3& w2) {
+    v1 = madd3v(v1, madd3(t1 * ti0, t2, ti1), g1.im);
+    w1 = madd3(madd3(w1, j.i10, ti0), j.i11, ti1);
+    v2 = madd3v(v2, madd3(t1 * (-ti0), t2, -ti1), g2.im);
+    w2 = madd3(madd3(w2, j.i20, ti0), j.i21, ti1);
+    if (nc > 1) {
+        w1 = madd3(w1, j.tw1, wi);
+        w2 = madd3(w2, j.tw2, -wi);
+    }
+}
 RB_HD void friction_warmstart(const BodyState& g1, const BodyState& g2, vec3 dir, vec3 t1, vec3 t2, int nc, vec3 tdp1, vec3 tdp2,
                               float ti0, float ti1, float wi, vec3& v1, vec3& w1, vec3& v2, vec3& w2) {
-    vec3 i10 = smul(g1.ii, cross3(tdp1, t1)), i11 = smul(g1.ii, cross3(tdp1, t2));
-    vec3 i20 = smul(g2.ii, cross3(tdp2, -t1)), i21 = smul(g2.ii, cross3(tdp2, -t2));
-    v1 = madd3v(v1, madd3(t1 * ti0, t2, ti1), g1.im);
-    w1 = madd3(madd3(w1, i10, ti0), i11, ti1);
-    v2 = madd3v(v2, madd3(t1 * (-ti0), t2, -ti1), g2.im);
-    w2 = madd3(madd3(w2, i20, ti0), i21, ti1);
-    if (nc > 1) {
-        w1 = madd3(w1, smul(g1.ii, dir), wi);
-        w2 = madd3(w2, smul(g2.ii, dir), -wi);
-    }
+    FrictionJac j = friction_jac(g1, g2, dir, t1, t2, tdp1, tdp2);
+    friction_warmstart_jac(g1, g2, t1, t2, nc, j, ti0, ti1, wi, v1, w1, v2, w2);
 }
 
 // One constraint, one sweep, one thread (streaming path; constraint in registers for the call).
@@ -422,7 +446,7 @@ RB_HD void cons_sweep(const World& w, const B& bd, int q, Cons& c, int mode, boo
         for (int k = 0; k < MAX_PTS; ++k) {
             if (k < nc) {
                 tlimit = tlimit + c.imp[k];
-                wlimit = wlimit + c.imp[k] * c.twd[k];
+                wlimit = fma_(c.imp[k], c.twd[k], wlimit);
             }
         }
         tlimit = tlimit * c.fric;
@@ -862,12 +886,16 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
 // Gauss-Seidel dependency between the points with __shfl_sync broadcasts.  Same primitives, same
 // arithmetic, same results as the serial sweep.
 // =====================================================================================================
-constexpr int COOP_MAX_CONS = 160;     // constraints per item held in shared memory
-constexpr int COOP_CS = 168;           // slot stride (== 8 mod 32: the 4 point-lanes of 8 constraints hit 32 banks)
+constexpr int COOP_MAX_CONS = 152;     // constraints per item held in shared memory
+constexpr int COOP_CS = 152;           // slot stride (== 24 mod 32: the 4 point-lanes of 8 constraints hit 32 distinct banks)
 constexpr int COOP_MAX_BODIES = 128;
-enum CoopPointField { PF_DP1 = 0, PF_DP2 = 3, PF_LP1 = 6, PF_LP2 = 9, PF_R = 12, PF_DIST0 = 13, PF_IMP = 14, PF_ACC = 15, PF_COUNT = 16 };
-enum CoopConsField { CF_DIR = 0, CF_FRIC = 3, CF_T1 = 4, CF_WR = 7, CF_TDP1 = 8, CF_TDP2 = 11, CF_TR = 14, CF_TWD = 17, CF_TI0 = 21,
-                     CF_TI1 = 22, CF_TA0 = 23, CF_TA1 = 24, CF_WI = 25, CF_WA = 26, CF_ID1 = 27, CF_ID2 = 28, CF_NC = 29, CF_COUNT = 30 };
+// per-point fields (one copy per manifold point)
+enum CoopPointField { PF_TD1 = 0, PF_TD2 = 3, PF_ITD1 = 6, PF_ITD2 = 9, PF_LP1 = 12, PF_LP2 = 15, PF_R = 18, PF_DIST0 = 19, PF_IMP = 20,
+                      PF_ACC = 21, PF_COUNT = 22 };
+// per-constraint fields
+enum CoopConsField { CF_DIR = 0, CF_FRIC = 3, CF_T1 = 4, CF_WR = 7, CF_TR = 8, CF_TWD = 11, CF_TI0 = 15, CF_TI1 = 16, CF_TA0 = 17,
+                     CF_TA1 = 18, CF_WI = 19, CF_WA = 20, CF_ID1 = 21, CF_ID2 = 22, CF_NC = 23, CF_TD10 = 24, CF_TD11 = 27, CF_TD20 = 30,
+                     CF_TD21 = 33, CF_I10 = 36, CF_I11 = 39, CF_I20 = 42, CF_I21 = 45, CF_TW1 = 48, CF_TW2 = 51, CF_COUNT = 54 };
 constexpr int COOP_CONS_FLOATS = (PF_COUNT * MAX_PTS + CF_COUNT) * COOP_CS;
 constexpr int COOP_WORLD_SLOT = COOP_MAX_BODIES;        // staged pseudo body: identity pose, zero velocity and mass
 constexpr int COOP_GARBAGE_SLOT = COOP_MAX_BODIES + 1;  // scatter target of world-attached sides
@@ -884,20 +912,31 @@ struct CoopStore {
     RB_HD void set_pc3(int f, int s, vec3 v) const { pc(f, s) = v.x; pc(f + 1, s) = v.y; pc(f + 2, s) = v.z; }
 };
 
-RB_HD void coop_put(const CoopStore& cs, int s, const Cons& c) {
+// Stage one generated constraint in shared memory, with the jacobians that stay constant during
+// the step precomputed (the serial path recomputes the same expressions in every sweep).
+template <class B>
+RB_HD void coop_put(const CoopStore& cs, const B& bd, int s, const Cons& c) {
+    BodyState g1 = gather_body(bd, c.id1), g2 = gather_body(bd, c.id2);
 #pragma unroll
     for (int k = 0; k < MAX_PTS; ++k) {
         if (k < c.nc) {
-            cs.set_pp3(PF_DP1, k, s, c.dp1[k]); cs.set_pp3(PF_DP2, k, s, c.dp2[k]);
+            PointPre pj;
+            point_jac(g1, g2, c.dir, c.dp1[k], c.dp2[k], pj);
+            cs.set_pp3(PF_TD1, k, s, pj.td1); cs.set_pp3(PF_TD2, k, s, pj.td2);
+            cs.set_pp3(PF_ITD1, k, s, pj.itd1); cs.set_pp3(PF_ITD2, k, s, pj.itd2);
             cs.set_pp3(PF_LP1, k, s, c.lp1[k]); cs.set_pp3(PF_LP2, k, s, c.lp2[k]);
             cs.pp(PF_R, k, s) = c.r[k]; cs.pp(PF_DIST0, k, s) = c.dist0[k];
         }
         cs.pp(PF_IMP, k, s) = c.imp[k]; cs.pp(PF_ACC, k, s) = c.acc[k];
         cs.pc(CF_TWD + k, s) = c.twd[k];
     }
+    const vec3 t2 = cross3(c.dir, c.t1);
+    FrictionJac j = friction_jac(g1, g2, c.dir, c.t1, t2, c.tdp1, c.tdp2);
+    cs.set_pc3(CF_TD10, s, j.td10); cs.set_pc3(CF_TD11, s, j.td11); cs.set_pc3(CF_TD20, s, j.td20); cs.set_pc3(CF_TD21, s, j.td21);
+    cs.set_pc3(CF_I10, s, j.i10); cs.set_pc3(CF_I11, s, j.i11); cs.set_pc3(CF_I20, s, j.i20); cs.set_pc3(CF_I21, s, j.i21);
+    cs.set_pc3(CF_TW1, s, j.tw1); cs.set_pc3(CF_TW2, s, j.tw2);
     cs.set_pc3(CF_DIR, s, c.dir); cs.pc(CF_FRIC, s) = c.fric;
     cs.set_pc3(CF_T1, s, c.t1); cs.pc(CF_WR, s) = c.wr;
-    cs.set_pc3(CF_TDP1, s, c.tdp1); cs.set_pc3(CF_TDP2, s, c.tdp2);
     cs.pc(CF_TR, s) = c.tr0; cs.pc(CF_TR + 1, s) = c.tr1; cs.pc(CF_TR + 2, s) = c.tr2;
     cs.pc(CF_TI0, s) = c.ti0; cs.pc(CF_TI1, s) = c.ti1; cs.pc(CF_TA0, s) = c.ta0; cs.pc(CF_TA1, s) = c.ta1;
     cs.pc(CF_WI, s) = c.wi; cs.pc(CF_WA, s) = c.wa;
@@ -936,8 +975,9 @@ template <int L> RB_HD bool lane_any(bool p) {
 
 // Sweep the constraints in slots [a, e) of the item (one colour stage) with L lanes per constraint.
 // `q0` is the global schedule slot of the item's slot 0 (rare per-constraint rows stay in HBM).
-template <int L>
-RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs, int q0, int a, int e, int tid, int nth, int mode,
+// MODE is a compile-time constant so each sweep kind is straight-line code.
+template <int L, int MODE>
+RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs, int q0, int a, int e, int tid, int nth,
                       bool solve_friction) {
     constexpr int PPL = MAX_PTS / L;   // points per lane
     const Params& P = w.prm;
@@ -969,42 +1009,37 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs,
             pre[j].td1 = pre[j].td2 = pre[j].itd1 = pre[j].itd2 = zero3();
             pre[j].rhs = 0.0f; pre[j].cfm = 1.0f;
             if (k < nc) {
-                pre[j] = point_pre(P, g1, g2, dir, cs.pp3(PF_DP1, k, s), cs.pp3(PF_DP2, k, s), cs.pp3(PF_LP1, k, s),
-                                   cs.pp3(PF_LP2, k, s), cs.pp(PF_DIST0, k, s), mode, cfm_soft, erp);
+                pre[j].td1 = cs.pp3(PF_TD1, k, s); pre[j].td2 = cs.pp3(PF_TD2, k, s);
+                pre[j].itd1 = cs.pp3(PF_ITD1, k, s); pre[j].itd2 = cs.pp3(PF_ITD2, k, s);
+                point_rhs(P, g1, g2, dir, cs.pp3(PF_LP1, k, s), cs.pp3(PF_LP2, k, s), cs.pp(PF_DIST0, k, s), MODE, cfm_soft, erp,
+                          pre[j].rhs, pre[j].cfm);
                 imp[j] = cs.pp(PF_IMP, k, s);
                 r[j] = cs.pp(PF_R, k, s);
-                if (mode == MODE_WARMSTART || mode == MODE_RESTITUTION) acc[j] = cs.pp(PF_ACC, k, s);
-                if (mode == MODE_RESTITUTION) {
+                if (MODE == MODE_WARMSTART || MODE == MODE_RESTITUTION) acc[j] = cs.pp(PF_ACC, k, s);
+                if (MODE == MODE_RESTITUTION) {
                     seed[j] = crow(w, CR_LP1 + k, q0 + s).w;
                     own_seed = own_seed || seed[j] < 0.0f;
                 }
-                if (mode == MODE_WARMSTART) {
+                if (MODE == MODE_WARMSTART) {
                     acc[j] = acc[j] + imp[j];
                     imp[j] = imp[j] * P.warmstart_coeff;
                 }
             }
         }
         bool skip = false;
-        if (mode == MODE_RESTITUTION) skip = !lane_any<L>(own_seed);
+        if (MODE == MODE_RESTITUTION) skip = !lane_any<L>(own_seed);
 
-        // ---- sequential part: the points in order, owner lane computes, everyone follows ----
+        // ---- sequential part: the points in order; every lane evaluates its own row against the current
+        //      velocities (SIMT: same instructions), the owner's result is broadcast and applied by all ----
 #pragma unroll
         for (int kk = 0; kk < MAX_PTS; ++kk) {
             const int owner = kk % L, j = kk / L;
-            float dl_own = 0.0f;
-            if (sub == owner && kk < nc) {
-                if (mode == MODE_WARMSTART) {
-                    dl_own = imp[j];
-                } else if (mode == MODE_RESTITUTION) {
-                    float nl;
-                    dl_own = point_restitution(pre[j], r[j], imp[j], acc[j], seed[j], dir, v1, w1, v2, w2, nl);
-                    imp[j] = nl;
-                } else {
-                    float nl;
-                    dl_own = point_solve(pre[j], r[j], imp[j], dir, v1, w1, v2, w2, nl);
-                    imp[j] = nl;
-                }
-            }
+            float nl = imp[j], dl_own;
+            if (MODE == MODE_WARMSTART) dl_own = imp[j];
+            else if (MODE == MODE_RESTITUTION) dl_own = point_restitution(pre[j], r[j], imp[j], acc[j], seed[j], dir, v1, w1, v2, w2, nl);
+            else dl_own = point_solve(pre[j], r[j], imp[j], dir, v1, w1, v2, w2, nl);
+            const bool mine = sub == owner && kk < nc;
+            imp[j] = mine ? nl : imp[j];
             const float dl = lane_bcast<L>(dl_own, owner);
             const vec3 i1 = lane_bcast3<L>(pre[j].itd1, owner), i2 = lane_bcast3<L>(pre[j].itd2, owner);
             if (kk < nc) apply_normal(lin1, lin2, i1, i2, dl, v1, w1, v2, w2);
@@ -1012,33 +1047,39 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs,
 
         float ti0 = cs.pc(CF_TI0, s), ti1 = cs.pc(CF_TI1, s), wi = cs.pc(CF_WI, s);
         float ta0 = 0.0f, ta1 = 0.0f, wa = 0.0f;
-        if (mode == MODE_WARMSTART) {
-            ta0 = cs.pc(CF_TA0, s) + ti0; ta1 = cs.pc(CF_TA1, s) + ti1;
-            ti0 = ti0 * P.warmstart_coeff; ti1 = ti1 * P.warmstart_coeff;
-            wa = cs.pc(CF_WA, s) + wi;
-            wi = wi * P.warmstart_coeff;
-            friction_warmstart(g1, g2, dir, t1, t2, nc, cs.pc3(CF_TDP1, s), cs.pc3(CF_TDP2, s), ti0, ti1, wi, v1, w1, v2, w2);
-        } else if (mode != MODE_RESTITUTION && solve_friction) {
-            float tlimit = 0.0f, wlimit = 0.0f;
+        if (MODE == MODE_WARMSTART || (MODE != MODE_RESTITUTION && solve_friction)) {
+            FrictionJac fj;
+            fj.td10 = cs.pc3(CF_TD10, s); fj.td11 = cs.pc3(CF_TD11, s); fj.td20 = cs.pc3(CF_TD20, s); fj.td21 = cs.pc3(CF_TD21, s);
+            fj.i10 = cs.pc3(CF_I10, s); fj.i11 = cs.pc3(CF_I11, s); fj.i20 = cs.pc3(CF_I20, s); fj.i21 = cs.pc3(CF_I21, s);
+            fj.tw1 = cs.pc3(CF_TW1, s); fj.tw2 = cs.pc3(CF_TW2, s);
+            if (MODE == MODE_WARMSTART) {
+                ta0 = cs.pc(CF_TA0, s) + ti0; ta1 = cs.pc(CF_TA1, s) + ti1;
+                ti0 = ti0 * P.warmstart_coeff; ti1 = ti1 * P.warmstart_coeff;
+                wa = cs.pc(CF_WA, s) + wi;
+                wi = wi * P.warmstart_coeff;
+                friction_warmstart_jac(g1, g2, t1, t2, nc, fj, ti0, ti1, wi, v1, w1, v2, w2);
+            } else {
+                float tlimit = 0.0f, wlimit = 0.0f;
 #pragma unroll
-            for (int kk = 0; kk < MAX_PTS; ++kk) {
-                const float ik = lane_bcast<L>(imp[kk / L], kk % L);
-                if (kk < nc) {
-                    tlimit = tlimit + ik;
-                    wlimit = wlimit + ik * cs.pc(CF_TWD + kk, s);
+                for (int kk = 0; kk < MAX_PTS; ++kk) {
+                    const float ik = lane_bcast<L>(imp[kk / L], kk % L);
+                    if (kk < nc) {
+                        tlimit = tlimit + ik;
+                        wlimit = fma_(ik, cs.pc(CF_TWD + kk, s), wlimit);
+                    }
                 }
+                const float fric = cs.pc(CF_FRIC, s);
+                tlimit = tlimit * fric;
+                wlimit = wlimit * fric;
+                constexpr bool relax = MODE == MODE_RELAX;
+                vec3 lfc1 = zero3(), lfc2 = zero3();
+                if (!relax) { lfc1 = xyz(crow(w, CR_LFC1, q0 + s)); lfc2 = xyz(crow(w, CR_LFC2, q0 + s)); }
+                FrictionState f;
+                f.ti0 = ti0; f.ti1 = ti1; f.wi = wi;
+                friction_solve_jac(P, g1, g2, dir, t1, t2, nc, tlimit, wlimit, cs.pc(CF_WR, s), fj, cs.pc(CF_TR, s), cs.pc(CF_TR + 1, s),
+                                   cs.pc(CF_TR + 2, s), relax, lfc1, lfc2, f, v1, w1, v2, w2);
+                ti0 = f.ti0; ti1 = f.ti1; wi = f.wi;
             }
-            const float fric = cs.pc(CF_FRIC, s);
-            tlimit = tlimit * fric;
-            wlimit = wlimit * fric;
-            const bool relax = mode == MODE_RELAX;
-            vec3 lfc1 = zero3(), lfc2 = zero3();
-            if (!relax) { lfc1 = xyz(crow(w, CR_LFC1, q0 + s)); lfc2 = xyz(crow(w, CR_LFC2, q0 + s)); }
-            FrictionState f;
-            f.ti0 = ti0; f.ti1 = ti1; f.wi = wi;
-            friction_solve(P, g1, g2, dir, t1, t2, nc, tlimit, wlimit, cs.pc(CF_WR, s), cs.pc3(CF_TDP1, s), cs.pc3(CF_TDP2, s),
-                           cs.pc(CF_TR, s), cs.pc(CF_TR + 1, s), cs.pc(CF_TR + 2, s), relax, lfc1, lfc2, f, v1, w1, v2, w2);
-            ti0 = f.ti0; ti1 = f.ti1; wi = f.wi;
         }
         // ---- write back: each lane its own point impulses, lane 0 the shared state ----
         if (active && !skip) {
@@ -1047,14 +1088,14 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs,
                 const int k = sub + j * L;
                 if (k < nc) {
                     cs.pp(PF_IMP, k, s) = imp[j];
-                    if (mode == MODE_WARMSTART) cs.pp(PF_ACC, k, s) = acc[j];
+                    if (MODE == MODE_WARMSTART) cs.pp(PF_ACC, k, s) = acc[j];
                 }
             }
             if (sub == 0) {
-                if (mode == MODE_WARMSTART) {
+                if (MODE == MODE_WARMSTART) {
                     cs.pc(CF_TA0, s) = ta0; cs.pc(CF_TA1, s) = ta1; cs.pc(CF_WA, s) = wa;
                 }
-                if (mode != MODE_RESTITUTION) { cs.pc(CF_TI0, s) = ti0; cs.pc(CF_TI1, s) = ti1; cs.pc(CF_WI, s) = wi; }
+                if (MODE != MODE_RESTITUTION) { cs.pc(CF_TI0, s) = ti0; cs.pc(CF_TI1, s) = ti1; cs.pc(CF_WI, s) = wi; }
                 bd.set_vel(id1 < 0 ? COOP_GARBAGE_SLOT : id1, v1, w1);
                 bd.set_vel(id2 < 0 ? COOP_GARBAGE_SLOT : id2, v2, w2);
             }
@@ -1096,7 +1137,7 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBod
     for (int s = tid; s < n; s += nth) {   // S2 generate, one thread per constraint, into shared memory
         Cons c;
         cons_generate(w, bd, c0 + s, buf, item, c);
-        coop_put(cs, s, c);
+        coop_put(cs, bd, s, c);
     }
     ctx.block_sync();
     for (int sub = 0; sub < P.num_substeps; ++sub) {
@@ -1105,7 +1146,7 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBod
         if (P.warmstart_coeff != 0.0f) {
             for (int c = 0; c < ncol; ++c) {
                 if (coff[c] >= coff[c + 1]) continue;
-                coop_stage<L>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, MODE_WARMSTART, false);
+                coop_stage<L, MODE_WARMSTART>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, false);
                 ctx.block_sync();
             }
         } else {
@@ -1128,7 +1169,8 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBod
             for (int it = 0; it < iters; ++it) {
                 for (int c = 0; c < ncol; ++c) {
                     if (coff[c] >= coff[c + 1]) continue;
-                    coop_stage<L>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, relax ? MODE_RELAX : MODE_BIASED, fric);
+                    if (relax) coop_stage<L, MODE_RELAX>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, fric);
+                    else coop_stage<L, MODE_BIASED>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, fric);
                     ctx.block_sync();
                 }
             }
@@ -1141,7 +1183,7 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBod
     if (w.item_flags[item]) {
         for (int c = 0; c < ncol; ++c) {
             if (coff[c] >= coff[c + 1]) continue;
-            coop_stage<L>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, MODE_RESTITUTION, false);
+            coop_stage<L, MODE_RESTITUTION>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, false);
             ctx.block_sync();
         }
     }
