@@ -223,8 +223,10 @@ def main():
         # ---- e2e: host buffers in / out every step through the public C-ABI call ----
         e2e_steps = min(args.steps, 200)
         pose, vel = pipe.body_states()
-        st_in = np.concatenate([pose, vel], axis=1).astype(np.float32).copy()
-        st_out = np.zeros_like(st_in)
+        # host-side state buffers of the caller: page-locked (the library DMAs them directly)
+        st_in = torch.empty((nb, 13), dtype=torch.float32, pin_memory=True).numpy()
+        st_out = torch.empty((nb, 13), dtype=torch.float32, pin_memory=True).numpy()
+        st_in[:] = np.concatenate([pose, vel], axis=1)
         for _ in range(3):
             pipe.step_host(gravity, st_in, st_out)
             st_in, st_out = st_out, st_in

@@ -59,7 +59,6 @@ static cudaError_t dev_set(void* d, int v, size_t n) { if (n) memset(d, v, n); r
 // ------------------------------------------------------------------------------------------------
 constexpr int COLLIDE_THREADS = 256;
 constexpr int COOP_THREADS = 128;
-constexpr int REST_THREADS = 256;
 constexpr int ITEM_SMEM_BYTES = ITEM_MAX_BODIES * SB_STRIDE * 4;
 constexpr int COOP_SMEM_BYTES = COOP_SMEM_FLOATS * 4;
 
@@ -94,14 +93,40 @@ RB_PHASE void import_states_phase(const Ctx& ctx, const World& w, const int* idx
 }
 
 #if RB_DEVICE_BUILD
-__global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w) {
+// Collision pipeline, then every solve that is NOT shared-memory resident: work items streamed from
+// HBM (one CTA each) and the grid-wide "large" item 0.  Those touch bodies / constraints disjoint from
+// the items k_solve_coop handles next, so the order between the two kernels does not matter.
+// `do_collide` = 0 runs only the solve part (unused in the normal step).
+__global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, int do_solve) {
+    extern __shared__ __align__(16) float smem[];
     GridCtx ctx;
     collide_pipeline(ctx, w);
+    if (!do_solve) return;
+    ctx.grid_sync();
+    {
+        BlockCtx bctx;
+        SmemBodies bd;
+        bd.s = smem;
+        BlockExec ex;
+        ex.c = &bctx;
+        const int n = w.st->nitems;
+        for (int item = 1 + bctx.bid; item < n; item += bctx.nblocks) {
+            if (item_is_coop(w, item)) continue;
+            solve_item(ex, w, bd, item, mk3(g.x, g.y, g.z));
+            ex.sync();
+        }
+    }
+    if (w.st->nlarge_bodies == 0) return;
+    GlobalBodies gb;
+    gb.w = &w;
+    GridExec gex;
+    gex.c = &ctx;
+    solve_item(gex, w, gb, 0, mk3(g.x, g.y, g.z));
 }
 // Items that fit shared memory: one CTA per item, bodies + constraints staged in shared memory,
 // four lanes per constraint (rb_solver.cuh "lane-cooperative path").
 __global__ void __launch_bounds__(COOP_THREADS, 2) k_solve_coop(World w, Grav g) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     BlockCtx ctx;
     SmemBodies bd;
     bd.s = smem;
@@ -113,30 +138,6 @@ __global__ void __launch_bounds__(COOP_THREADS, 2) k_solve_coop(World w, Grav g)
         solve_item_coop<4>(ctx, w, bd, cs, item, mk3(g.x, g.y, g.z));
         ctx.block_sync();
     }
-}
-// Everything else: items streamed from HBM by one CTA each, then the grid-wide "large" item 0.
-__global__ void __launch_bounds__(REST_THREADS) k_solve_rest(World w, Grav g) {
-    extern __shared__ float smem[];
-    GridCtx gctx;
-    {
-        BlockCtx ctx;
-        SmemBodies bd;
-        bd.s = smem;
-        BlockExec ex;
-        ex.c = &ctx;
-        const int n = w.st->nitems;
-        for (int item = 1 + ctx.bid; item < n; item += ctx.nblocks) {
-            if (item_is_coop(w, item)) continue;
-            solve_item(ex, w, bd, item, mk3(g.x, g.y, g.z));
-            ex.sync();
-        }
-    }
-    if (w.st->nlarge_bodies == 0) return;
-    GlobalBodies gb;
-    gb.w = &w;
-    GridExec gex;
-    gex.c = &gctx;
-    solve_item(gex, w, gb, 0, mk3(g.x, g.y, g.z));
 }
 __global__ void k_init_bodies(World w) {
     GridCtx ctx;
@@ -160,8 +161,8 @@ struct RbWorld {
     std::vector<void*> allocs;
     int device = 0;
     int num_sms = 1;
-    int collide_blocks = 1, rest_blocks = 1, coop_blocks = 1;
-    int collide_threads = COLLIDE_THREADS, coop_threads = COOP_THREADS, rest_threads = REST_THREADS;
+    int collide_blocks = 1, coop_blocks = 1;
+    int collide_threads = COLLIDE_THREADS, coop_threads = COOP_THREADS;
     long long kernels = 0, steps = 0;
     bool profiling = false;
     float ms_collide = 0, ms_solve = 0, ms_step = 0;
@@ -407,14 +408,11 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
     if (!prop.cooperativeLaunch) { set_err("device lacks cooperative launch%s", ""); delete W; return nullptr; }
     cudaStreamCreateWithFlags(&W->stream, cudaStreamNonBlocking);
     cudaFuncSetAttribute(k_solve_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_SMEM_BYTES);
-    cudaFuncSetAttribute(k_solve_rest, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
+    cudaFuncSetAttribute(k_collide, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_collide, COLLIDE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_collide, COLLIDE_THREADS, ITEM_SMEM_BYTES);
     if (occ < 1) { set_err("k_collide cannot be resident%s", ""); delete W; return nullptr; }
-    W->collide_blocks = W->num_sms * (occ > 2 ? 2 : occ);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_rest, REST_THREADS, ITEM_SMEM_BYTES);
-    if (occ < 1) { set_err("k_solve_rest cannot be resident%s", ""); delete W; return nullptr; }
-    W->rest_blocks = W->num_sms * (occ > 2 ? 2 : occ);
+    W->collide_blocks = W->num_sms;   // one CTA per SM: the cheapest grid barrier that still covers the chip
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_coop, COOP_THREADS, COOP_SMEM_BYTES);
     if (occ < 1) occ = 1;
     W->coop_blocks = W->num_sms * occ;
@@ -422,9 +420,7 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
         auto envi = [](const char* n, int d) { const char* v = getenv(n); return v ? atoi(v) : d; };
         W->collide_blocks = std::min(W->collide_blocks, envi("RB_COLLIDE_BLOCKS", W->collide_blocks));
         W->coop_blocks = std::min(W->coop_blocks, envi("RB_COOP_BLOCKS", W->coop_blocks));
-        W->rest_blocks = std::min(W->rest_blocks, envi("RB_REST_BLOCKS", W->rest_blocks));
         W->collide_threads = std::min(COLLIDE_THREADS, envi("RB_COLLIDE_THREADS", COLLIDE_THREADS));
-        W->rest_threads = std::min(REST_THREADS, envi("RB_REST_THREADS", REST_THREADS));
     }
 #else
     W->emu_smem.assign(ITEM_MAX_BODIES * SB_STRIDE + COOP_SMEM_FLOATS, 0.0f);
@@ -736,15 +732,14 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
     for (int s = 0; s < nsteps; ++s) {
         bool prof = W->profiling;
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s], W->stream));
-        void* a1[] = {(void*)&W->w};
-        CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, 0, W->stream));
+        int do_solve = 1;
+        void* a1[] = {(void*)&W->w, (void*)&g, (void*)&do_solve};
+        CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, ITEM_SMEM_BYTES, W->stream));
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 1], W->stream));
         k_solve_coop<<<W->coop_blocks, W->coop_threads, COOP_SMEM_BYTES, W->stream>>>(W->w, g);
         CK(cudaGetLastError());
-        void* a2[] = {(void*)&W->w, (void*)&g};
-        CK(cudaLaunchCooperativeKernel((void*)k_solve_rest, dim3(W->rest_blocks), dim3(W->rest_threads), a2, ITEM_SMEM_BYTES, W->stream));
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 2], W->stream));
-        W->kernels += 3;
+        W->kernels += 2;
     }
     W->steps += nsteps;
     if (sync) {
@@ -794,7 +789,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
             gex.c = &gctx;
             solve_item(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
         }
-        W->kernels += 3;
+        W->kernels += 2;
     }
     W->steps += nsteps;
     if (W->w.st->error) { int e = W->w.st->error; W->w.st->error = 0; set_err("device raised status %s%d", "", e); return e; }
@@ -1005,8 +1000,10 @@ int rb_world_label_components(RbWorld* W, int32_t* component_of_body) {
     int one = 1;
     CK(cudaStreamSynchronize(W->stream));
     CK(h2d(&W->w.st->sched_dirty, &one, sizeof(int)));
-    void* a1[] = {(void*)&W->w};
-    CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, 0, W->stream));
+    Grav g0{0.f, 0.f, 0.f};
+    int do_solve = 0;
+    void* a1[] = {(void*)&W->w, (void*)&g0, (void*)&do_solve};
+    CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, ITEM_SMEM_BYTES, W->stream));
     W->kernels++;
 #else
     W->w.st->sched_dirty = 1;
@@ -1091,13 +1088,23 @@ int rb_world_set_stream(RbWorld* W, void* stream) {
 int rb_world_step_host(RbWorld* W, const float gravity[3], const float* in_state13, float* out_state13) {
     if (!W || !gravity) return RB_ERR_INVALID;
     const size_t n = (size_t)W->w.nb * 13;
-    if (in_state13) {
-        memcpy(W->stage_host, in_state13, n * sizeof(float));
 #if RB_DEVICE_BUILD
-        CK(cudaSetDevice(W->device));
-        CK(cudaMemcpyAsync(W->stage_dev, W->stage_host, n * sizeof(float), cudaMemcpyHostToDevice, W->stream));
+    CK(cudaSetDevice(W->device));
+    // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are DMA'd directly;
+    // pageable ones are staged through the library's pinned buffer.
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+#endif
+    if (in_state13) {
+#if RB_DEVICE_BUILD
+        const float* src = in_state13;
+        if (!is_pinned(in_state13)) { memcpy(W->stage_host, in_state13, n * sizeof(float)); src = W->stage_host; }
+        CK(cudaMemcpyAsync(W->stage_dev, src, n * sizeof(float), cudaMemcpyHostToDevice, W->stream));
 #else
-        memcpy(W->stage_dev, W->stage_host, n * sizeof(float));
+        memcpy(W->stage_dev, in_state13, n * sizeof(float));
 #endif
         int rc = rb_world_import_states(W, W->ident_dev, W->stage_dev, W->w.nb);
         if (rc != RB_OK) return rc;
@@ -1106,12 +1113,17 @@ int rb_world_step_host(RbWorld* W, const float gravity[3], const float* in_state
     if (rc != RB_OK) return rc;
     if (out_state13) {
 #if RB_DEVICE_BUILD
-        CK(cudaMemcpyAsync(W->stage_host + n, W->w.state13, n * sizeof(float), cudaMemcpyDeviceToHost, W->stream));
-        CK(cudaStreamSynchronize(W->stream));
+        if (is_pinned(out_state13)) {
+            CK(cudaMemcpyAsync(out_state13, W->w.state13, n * sizeof(float), cudaMemcpyDeviceToHost, W->stream));
+            CK(cudaStreamSynchronize(W->stream));
+        } else {
+            CK(cudaMemcpyAsync(W->stage_host + n, W->w.state13, n * sizeof(float), cudaMemcpyDeviceToHost, W->stream));
+            CK(cudaStreamSynchronize(W->stream));
+            memcpy(out_state13, W->stage_host + n, n * sizeof(float));
+        }
 #else
-        memcpy(W->stage_host + n, W->w.state13, n * sizeof(float));
+        memcpy(out_state13, W->w.state13, n * sizeof(float));
 #endif
-        memcpy(out_state13, W->stage_host + n, n * sizeof(float));
     } else {
         rc = sync_world(W);
     }

@@ -21,44 +21,46 @@
 
 namespace rb {
 
-constexpr int SB_STRIDE = 29;  // floats per staged body (odd: conflict-free across bodies)
-// staged body layout: lin 0-2, ang 3-5, q 6-9, t 10-12, ii 13-18, im 19-21, incr_lin 22-24, incr_ang 25-27, flags 28
+constexpr int SB_VEC = 7;              // float4 per staged body
+constexpr int SB_STRIDE = SB_VEC * 4;  // floats per staged body
+// staged body layout (float4 rows, LDS.128-friendly):
+//   0 (lin, incr_lin.x)  1 (ang, incr_lin.y)  2 q  3 (t, incr_lin.z)  4 (im, incr_ang.x)  5 (ii xx xy xz yy)  6 (ii yz zz, incr_ang.y, incr_ang.z)
 
 struct BodyState { vec3 lin, ang; pose p; sym3 ii; vec3 im; };
 
 struct SmemBodies {
     float* s;
-    RB_HD vec3 lin(int i) const { const float* b = s + i * SB_STRIDE; return mk3(b[0], b[1], b[2]); }
-    RB_HD vec3 ang(int i) const { const float* b = s + i * SB_STRIDE; return mk3(b[3], b[4], b[5]); }
+    RB_HD float4* row(int i, int r) const { return reinterpret_cast<float4*>(s) + i * SB_VEC + r; }
+    RB_HD vec3 lin(int i) const { return xyz(*row(i, 0)); }
+    RB_HD vec3 ang(int i) const { return xyz(*row(i, 1)); }
     RB_HD void set_vel(int i, vec3 l, vec3 a) const {
-        float* b = s + i * SB_STRIDE;
-        b[0] = l.x; b[1] = l.y; b[2] = l.z; b[3] = a.x; b[4] = a.y; b[5] = a.z;
+        float4* r0 = row(i, 0); float4* r1 = row(i, 1);
+        *r0 = make_float4(l.x, l.y, l.z, r0->w);
+        *r1 = make_float4(a.x, a.y, a.z, r1->w);
     }
-    RB_HD pose xf(int i) const {
-        const float* b = s + i * SB_STRIDE;
-        quat q; q.x = b[6]; q.y = b[7]; q.z = b[8]; q.w = b[9];
-        return mkpose(q, mk3(b[10], b[11], b[12]));
-    }
+    RB_HD pose xf(int i) const { return mkpose(mkq(*row(i, 2)), xyz(*row(i, 3))); }
     RB_HD void set_xf(int i, const pose& p) const {
-        float* b = s + i * SB_STRIDE;
-        b[6] = p.q.x; b[7] = p.q.y; b[8] = p.q.z; b[9] = p.q.w; b[10] = p.t.x; b[11] = p.t.y; b[12] = p.t.z;
+        *row(i, 2) = f4(p.q);
+        float4* r3 = row(i, 3);
+        *r3 = make_float4(p.t.x, p.t.y, p.t.z, r3->w);
     }
     RB_HD sym3 ii(int i) const {
-        const float* b = s + i * SB_STRIDE;
-        sym3 m; m.xx = b[13]; m.xy = b[14]; m.xz = b[15]; m.yy = b[16]; m.yz = b[17]; m.zz = b[18];
+        float4 a = *row(i, 5), b = *row(i, 6);
+        sym3 m; m.xx = a.x; m.xy = a.y; m.xz = a.z; m.yy = a.w; m.yz = b.x; m.zz = b.y;
         return m;
     }
-    RB_HD vec3 im(int i) const { const float* b = s + i * SB_STRIDE; return mk3(b[19], b[20], b[21]); }
+    RB_HD vec3 im(int i) const { return xyz(*row(i, 4)); }
     RB_HD void set_mass(int i, const sym3& m, vec3 im_) const {
-        float* b = s + i * SB_STRIDE;
-        b[13] = m.xx; b[14] = m.xy; b[15] = m.xz; b[16] = m.yy; b[17] = m.yz; b[18] = m.zz;
-        b[19] = im_.x; b[20] = im_.y; b[21] = im_.z;
+        float4* r4 = row(i, 4); float4* r6 = row(i, 6);
+        *r4 = make_float4(im_.x, im_.y, im_.z, r4->w);
+        *row(i, 5) = make_float4(m.xx, m.xy, m.xz, m.yy);
+        *r6 = make_float4(m.yz, m.zz, r6->z, r6->w);
     }
-    RB_HD vec3 incr_lin(int i) const { const float* b = s + i * SB_STRIDE; return mk3(b[22], b[23], b[24]); }
-    RB_HD vec3 incr_ang(int i) const { const float* b = s + i * SB_STRIDE; return mk3(b[25], b[26], b[27]); }
+    RB_HD vec3 incr_lin(int i) const { return mk3(row(i, 0)->w, row(i, 1)->w, row(i, 3)->w); }
+    RB_HD vec3 incr_ang(int i) const { return mk3(row(i, 4)->w, row(i, 6)->z, row(i, 6)->w); }
     RB_HD void set_incr(int i, vec3 l, vec3 a) const {
-        float* b = s + i * SB_STRIDE;
-        b[22] = l.x; b[23] = l.y; b[24] = l.z; b[25] = a.x; b[26] = a.y; b[27] = a.z;
+        row(i, 0)->w = l.x; row(i, 1)->w = l.y; row(i, 3)->w = l.z;
+        row(i, 4)->w = a.x; row(i, 6)->z = a.y; row(i, 6)->w = a.z;
     }
 };
 
@@ -886,31 +888,56 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
 // Gauss-Seidel dependency between the points with __shfl_sync broadcasts.  Same primitives, same
 // arithmetic, same results as the serial sweep.
 // =====================================================================================================
-constexpr int COOP_MAX_CONS = 152;     // constraints per item held in shared memory
-constexpr int COOP_CS = 152;           // slot stride (== 24 mod 32: the 4 point-lanes of 8 constraints hit 32 distinct banks)
+constexpr int COOP_MAX_CONS = 146;     // constraints per item held in shared memory
+constexpr int COOP_CS = 146;           // slot stride in float4 (== 2 mod 8: an LDS.128 quarter-warp = 2 constraints x 4 points, conflict-free)
 constexpr int COOP_MAX_BODIES = 128;
-// per-point fields (one copy per manifold point)
-enum CoopPointField { PF_TD1 = 0, PF_TD2 = 3, PF_ITD1 = 6, PF_ITD2 = 9, PF_LP1 = 12, PF_LP2 = 15, PF_R = 18, PF_DIST0 = 19, PF_IMP = 20,
-                      PF_ACC = 21, PF_COUNT = 22 };
-// per-constraint fields
-enum CoopConsField { CF_DIR = 0, CF_FRIC = 3, CF_T1 = 4, CF_WR = 7, CF_TR = 8, CF_TWD = 11, CF_TI0 = 15, CF_TI1 = 16, CF_TA0 = 17,
-                     CF_TA1 = 18, CF_WI = 19, CF_WA = 20, CF_ID1 = 21, CF_ID2 = 22, CF_NC = 23, CF_TD10 = 24, CF_TD11 = 27, CF_TD20 = 30,
-                     CF_TD21 = 33, CF_I10 = 36, CF_I11 = 39, CF_I20 = 42, CF_I21 = 45, CF_TW1 = 48, CF_TW2 = 51, CF_COUNT = 54 };
-constexpr int COOP_CONS_FLOATS = (PF_COUNT * MAX_PTS + CF_COUNT) * COOP_CS;
+// per-point float4 rows (one copy per manifold point)
+enum CoopPointRow { PR4_TD1R = 0,   // torque_dir1 xyz, r (projected mass)
+                    PR4_TD2D,       // torque_dir2 xyz, dist0
+                    PR4_ITD1I,      // ii1*torque_dir1 xyz, impulse
+                    PR4_ITD2A,      // ii2*torque_dir2 xyz, impulse accumulator
+                    PR4_LP1, PR4_LP2,   // builder anchors
+                    PR4_COUNT };
+// per-constraint float4 rows
+enum CoopConsRow { CR4_DIRF = 0,    // dir1 xyz, friction
+                   CR4_T1W,         // tangent1 xyz, twist effective mass
+                   CR4_TR,          // tangent K (r0 r1 r2), nc bits
+                   CR4_TWD,         // twist_dists[4]
+                   CR4_TI,          // tangent impulse xy, accumulators zw
+                   CR4_WI,          // twist impulse, accumulator, id1 bits, id2 bits
+                   CR4_J0, CR4_J1, CR4_J2, CR4_J3, CR4_J4, CR4_J5, CR4_J6, CR4_J7,   // friction jacobians, packed (see put/get)
+                   CR4_COUNT };
+constexpr int COOP_CONS_FLOATS = (PR4_COUNT * MAX_PTS + CR4_COUNT) * COOP_CS * 4;
 constexpr int COOP_WORLD_SLOT = COOP_MAX_BODIES;        // staged pseudo body: identity pose, zero velocity and mass
 constexpr int COOP_GARBAGE_SLOT = COOP_MAX_BODIES + 1;  // scatter target of world-attached sides
 constexpr int COOP_BODY_SLOTS = COOP_MAX_BODIES + 2;
 constexpr int COOP_SMEM_FLOATS = COOP_BODY_SLOTS * SB_STRIDE + COOP_CONS_FLOATS;
 
 struct CoopStore {
-    float* base;
-    RB_HD float& pp(int f, int k, int s) const { return base[(f * MAX_PTS + k) * COOP_CS + s]; }
-    RB_HD float& pc(int f, int s) const { return base[(PF_COUNT * MAX_PTS + f) * COOP_CS + s]; }
-    RB_HD vec3 pp3(int f, int k, int s) const { return mk3(pp(f, k, s), pp(f + 1, k, s), pp(f + 2, k, s)); }
-    RB_HD vec3 pc3(int f, int s) const { return mk3(pc(f, s), pc(f + 1, s), pc(f + 2, s)); }
-    RB_HD void set_pp3(int f, int k, int s, vec3 v) const { pp(f, k, s) = v.x; pp(f + 1, k, s) = v.y; pp(f + 2, k, s) = v.z; }
-    RB_HD void set_pc3(int f, int s, vec3 v) const { pc(f, s) = v.x; pc(f + 1, s) = v.y; pc(f + 2, s) = v.z; }
+    float* base;   // 16-byte aligned
+    RB_HD float4& pp(int row, int k, int s) const { return reinterpret_cast<float4*>(base)[(row * MAX_PTS + k) * COOP_CS + s]; }
+    RB_HD float4& pc(int row, int s) const { return reinterpret_cast<float4*>(base)[(PR4_COUNT * MAX_PTS + row) * COOP_CS + s]; }
 };
+
+RB_HD void coop_put_jac(const CoopStore& cs, int s, const FrictionJac& j) {
+    cs.pc(CR4_J0, s) = make_float4(j.td10.x, j.td10.y, j.td10.z, j.td11.x);
+    cs.pc(CR4_J1, s) = make_float4(j.td11.y, j.td11.z, j.td20.x, j.td20.y);
+    cs.pc(CR4_J2, s) = make_float4(j.td20.z, j.td21.x, j.td21.y, j.td21.z);
+    cs.pc(CR4_J3, s) = make_float4(j.i10.x, j.i10.y, j.i10.z, j.i11.x);
+    cs.pc(CR4_J4, s) = make_float4(j.i11.y, j.i11.z, j.i20.x, j.i20.y);
+    cs.pc(CR4_J5, s) = make_float4(j.i20.z, j.i21.x, j.i21.y, j.i21.z);
+    cs.pc(CR4_J6, s) = make_float4(j.tw1.x, j.tw1.y, j.tw1.z, j.tw2.x);
+    cs.pc(CR4_J7, s) = make_float4(j.tw2.y, j.tw2.z, 0.0f, 0.0f);
+}
+RB_HD FrictionJac coop_get_jac(const CoopStore& cs, int s) {
+    float4 a = cs.pc(CR4_J0, s), b = cs.pc(CR4_J1, s), c = cs.pc(CR4_J2, s), d = cs.pc(CR4_J3, s), e = cs.pc(CR4_J4, s),
+           f = cs.pc(CR4_J5, s), g = cs.pc(CR4_J6, s), h = cs.pc(CR4_J7, s);
+    FrictionJac j;
+    j.td10 = mk3(a.x, a.y, a.z); j.td11 = mk3(a.w, b.x, b.y); j.td20 = mk3(b.z, b.w, c.x); j.td21 = mk3(c.y, c.z, c.w);
+    j.i10 = mk3(d.x, d.y, d.z); j.i11 = mk3(d.w, e.x, e.y); j.i20 = mk3(e.z, e.w, f.x); j.i21 = mk3(f.y, f.z, f.w);
+    j.tw1 = mk3(g.x, g.y, g.z); j.tw2 = mk3(g.w, h.x, h.y);
+    return j;
+}
 
 // Stage one generated constraint in shared memory, with the jacobians that stay constant during
 // the step precomputed (the serial path recomputes the same expressions in every sweep).
@@ -919,35 +946,37 @@ RB_HD void coop_put(const CoopStore& cs, const B& bd, int s, const Cons& c) {
     BodyState g1 = gather_body(bd, c.id1), g2 = gather_body(bd, c.id2);
 #pragma unroll
     for (int k = 0; k < MAX_PTS; ++k) {
+        PointPre pj;
+        pj.td1 = pj.td2 = pj.itd1 = pj.itd2 = zero3();
+        float r = 0.0f, d0 = 0.0f;
+        vec3 l1 = zero3(), l2 = zero3();
         if (k < c.nc) {
-            PointPre pj;
             point_jac(g1, g2, c.dir, c.dp1[k], c.dp2[k], pj);
-            cs.set_pp3(PF_TD1, k, s, pj.td1); cs.set_pp3(PF_TD2, k, s, pj.td2);
-            cs.set_pp3(PF_ITD1, k, s, pj.itd1); cs.set_pp3(PF_ITD2, k, s, pj.itd2);
-            cs.set_pp3(PF_LP1, k, s, c.lp1[k]); cs.set_pp3(PF_LP2, k, s, c.lp2[k]);
-            cs.pp(PF_R, k, s) = c.r[k]; cs.pp(PF_DIST0, k, s) = c.dist0[k];
+            r = c.r[k]; d0 = c.dist0[k]; l1 = c.lp1[k]; l2 = c.lp2[k];
         }
-        cs.pp(PF_IMP, k, s) = c.imp[k]; cs.pp(PF_ACC, k, s) = c.acc[k];
-        cs.pc(CF_TWD + k, s) = c.twd[k];
+        cs.pp(PR4_TD1R, k, s) = f4(pj.td1, r);
+        cs.pp(PR4_TD2D, k, s) = f4(pj.td2, d0);
+        cs.pp(PR4_ITD1I, k, s) = f4(pj.itd1, c.imp[k]);
+        cs.pp(PR4_ITD2A, k, s) = f4(pj.itd2, c.acc[k]);
+        cs.pp(PR4_LP1, k, s) = f4(l1, 0.0f);
+        cs.pp(PR4_LP2, k, s) = f4(l2, 0.0f);
     }
     const vec3 t2 = cross3(c.dir, c.t1);
-    FrictionJac j = friction_jac(g1, g2, c.dir, c.t1, t2, c.tdp1, c.tdp2);
-    cs.set_pc3(CF_TD10, s, j.td10); cs.set_pc3(CF_TD11, s, j.td11); cs.set_pc3(CF_TD20, s, j.td20); cs.set_pc3(CF_TD21, s, j.td21);
-    cs.set_pc3(CF_I10, s, j.i10); cs.set_pc3(CF_I11, s, j.i11); cs.set_pc3(CF_I20, s, j.i20); cs.set_pc3(CF_I21, s, j.i21);
-    cs.set_pc3(CF_TW1, s, j.tw1); cs.set_pc3(CF_TW2, s, j.tw2);
-    cs.set_pc3(CF_DIR, s, c.dir); cs.pc(CF_FRIC, s) = c.fric;
-    cs.set_pc3(CF_T1, s, c.t1); cs.pc(CF_WR, s) = c.wr;
-    cs.pc(CF_TR, s) = c.tr0; cs.pc(CF_TR + 1, s) = c.tr1; cs.pc(CF_TR + 2, s) = c.tr2;
-    cs.pc(CF_TI0, s) = c.ti0; cs.pc(CF_TI1, s) = c.ti1; cs.pc(CF_TA0, s) = c.ta0; cs.pc(CF_TA1, s) = c.ta1;
-    cs.pc(CF_WI, s) = c.wi; cs.pc(CF_WA, s) = c.wa;
-    cs.pc(CF_ID1, s) = as_float_i(c.id1); cs.pc(CF_ID2, s) = as_float_i(c.id2); cs.pc(CF_NC, s) = as_float_i(c.nc);
+    coop_put_jac(cs, s, friction_jac(g1, g2, c.dir, c.t1, t2, c.tdp1, c.tdp2));
+    cs.pc(CR4_DIRF, s) = f4(c.dir, c.fric);
+    cs.pc(CR4_T1W, s) = f4(c.t1, c.wr);
+    cs.pc(CR4_TR, s) = make_float4(c.tr0, c.tr1, c.tr2, as_float_i(c.nc));
+    cs.pc(CR4_TWD, s) = make_float4(c.twd[0], c.twd[1], c.twd[2], c.twd[3]);
+    cs.pc(CR4_TI, s) = make_float4(c.ti0, c.ti1, c.ta0, c.ta1);
+    cs.pc(CR4_WI, s) = make_float4(c.wi, c.wa, as_float_i(c.id1), as_float_i(c.id2));
 }
 RB_HD void coop_get_for_writeback(const CoopStore& cs, int s, Cons& c) {
-    c.nc = as_int(cs.pc(CF_NC, s));
-    c.dir = cs.pc3(CF_DIR, s); c.t1 = cs.pc3(CF_T1, s);
+    c.nc = as_int(cs.pc(CR4_TR, s).w);
+    c.dir = xyz(cs.pc(CR4_DIRF, s)); c.t1 = xyz(cs.pc(CR4_T1W, s));
 #pragma unroll
-    for (int k = 0; k < MAX_PTS; ++k) { c.imp[k] = cs.pp(PF_IMP, k, s); c.acc[k] = cs.pp(PF_ACC, k, s); }
-    c.ti0 = cs.pc(CF_TI0, s); c.ti1 = cs.pc(CF_TI1, s); c.wi = cs.pc(CF_WI, s);
+    for (int k = 0; k < MAX_PTS; ++k) { c.imp[k] = cs.pp(PR4_ITD1I, k, s).w; c.acc[k] = cs.pp(PR4_ITD2A, k, s).w; }
+    float4 ti = cs.pc(CR4_TI, s);
+    c.ti0 = ti.x; c.ti1 = ti.y; c.wi = cs.pc(CR4_WI, s).x;
 }
 
 // Sub-warp broadcast from lane `src` of each L-lane group.
@@ -986,11 +1015,17 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs,
         const int s_raw = base + grp;
         const bool active = s_raw < e && grp < groups;
         const int s = active ? s_raw : a;   // inactive lanes shadow a valid slot (they must execute the shuffles)
-        const int id1 = as_int(cs.pc(CF_ID1, s)), id2 = as_int(cs.pc(CF_ID2, s)), nc = as_int(cs.pc(CF_NC, s));
-        // branch-free gathers: a world-attached side reads the staged identity/zero pseudo body
-        BodyState g1 = gather_body(bd, id1 < 0 ? COOP_WORLD_SLOT : id1), g2 = gather_body(bd, id2 < 0 ? COOP_WORLD_SLOT : id2);
+        const float4 dirf = cs.pc(CR4_DIRF, s), t1w = cs.pc(CR4_T1W, s), trn = cs.pc(CR4_TR, s), wi4 = cs.pc(CR4_WI, s);
+        const int id1 = as_int(wi4.z), id2 = as_int(wi4.w), nc = as_int(trn.w);
+        // branch-free gathers: a world-attached side reads the staged identity/zero pseudo body.
+        // Only what a sweep needs is loaded: velocities, inverse masses and (for the rhs) the poses.
+        const int gi1 = id1 < 0 ? COOP_WORLD_SLOT : id1, gi2 = id2 < 0 ? COOP_WORLD_SLOT : id2;
+        BodyState g1, g2;
+        g1.lin = bd.lin(gi1); g1.ang = bd.ang(gi1); g1.im = bd.im(gi1);
+        g2.lin = bd.lin(gi2); g2.ang = bd.ang(gi2); g2.im = bd.im(gi2);
+        if (MODE == MODE_BIASED || MODE == MODE_RELAX) { g1.p = bd.xf(gi1); g2.p = bd.xf(gi2); }
         vec3 v1 = g1.lin, w1 = g1.ang, v2 = g2.lin, w2 = g2.ang;
-        const vec3 dir = cs.pc3(CF_DIR, s), t1 = cs.pc3(CF_T1, s);
+        const vec3 dir = xyz(dirf), t1 = xyz(t1w);
         const vec3 t2 = cross3(dir, t1);
         const bool is_static = id1 == NO_BODY || id2 == NO_BODY;
         const float stf = is_static ? 1.0f : 0.0f;
@@ -1005,17 +1040,14 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs,
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
             const int k = sub + j * L;
-            imp[j] = 0.0f; acc[j] = 0.0f; r[j] = 0.0f; seed[j] = 0.0f;
-            pre[j].td1 = pre[j].td2 = pre[j].itd1 = pre[j].itd2 = zero3();
+            const float4 a1 = cs.pp(PR4_TD1R, k, s), a2 = cs.pp(PR4_TD2D, k, s), b1 = cs.pp(PR4_ITD1I, k, s), b2 = cs.pp(PR4_ITD2A, k, s);
+            pre[j].td1 = xyz(a1); pre[j].td2 = xyz(a2); pre[j].itd1 = xyz(b1); pre[j].itd2 = xyz(b2);
+            r[j] = a1.w; imp[j] = b1.w; acc[j] = b2.w; seed[j] = 0.0f;
             pre[j].rhs = 0.0f; pre[j].cfm = 1.0f;
             if (k < nc) {
-                pre[j].td1 = cs.pp3(PF_TD1, k, s); pre[j].td2 = cs.pp3(PF_TD2, k, s);
-                pre[j].itd1 = cs.pp3(PF_ITD1, k, s); pre[j].itd2 = cs.pp3(PF_ITD2, k, s);
-                point_rhs(P, g1, g2, dir, cs.pp3(PF_LP1, k, s), cs.pp3(PF_LP2, k, s), cs.pp(PF_DIST0, k, s), MODE, cfm_soft, erp,
-                          pre[j].rhs, pre[j].cfm);
-                imp[j] = cs.pp(PF_IMP, k, s);
-                r[j] = cs.pp(PF_R, k, s);
-                if (MODE == MODE_WARMSTART || MODE == MODE_RESTITUTION) acc[j] = cs.pp(PF_ACC, k, s);
+                if (MODE == MODE_BIASED || MODE == MODE_RELAX)
+                    point_rhs(P, g1, g2, dir, xyz(cs.pp(PR4_LP1, k, s)), xyz(cs.pp(PR4_LP2, k, s)), a2.w, MODE, cfm_soft, erp, pre[j].rhs,
+                              pre[j].cfm);
                 if (MODE == MODE_RESTITUTION) {
                     seed[j] = crow(w, CR_LP1 + k, q0 + s).w;
                     own_seed = own_seed || seed[j] < 0.0f;
@@ -1045,39 +1077,37 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs,
             if (kk < nc) apply_normal(lin1, lin2, i1, i2, dl, v1, w1, v2, w2);
         }
 
-        float ti0 = cs.pc(CF_TI0, s), ti1 = cs.pc(CF_TI1, s), wi = cs.pc(CF_WI, s);
-        float ta0 = 0.0f, ta1 = 0.0f, wa = 0.0f;
+        float4 ti4 = cs.pc(CR4_TI, s);
+        float ti0 = ti4.x, ti1 = ti4.y, wi = wi4.x;
+        float ta0 = ti4.z, ta1 = ti4.w, wa = wi4.y;
         if (MODE == MODE_WARMSTART || (MODE != MODE_RESTITUTION && solve_friction)) {
-            FrictionJac fj;
-            fj.td10 = cs.pc3(CF_TD10, s); fj.td11 = cs.pc3(CF_TD11, s); fj.td20 = cs.pc3(CF_TD20, s); fj.td21 = cs.pc3(CF_TD21, s);
-            fj.i10 = cs.pc3(CF_I10, s); fj.i11 = cs.pc3(CF_I11, s); fj.i20 = cs.pc3(CF_I20, s); fj.i21 = cs.pc3(CF_I21, s);
-            fj.tw1 = cs.pc3(CF_TW1, s); fj.tw2 = cs.pc3(CF_TW2, s);
+            const FrictionJac fj = coop_get_jac(cs, s);
             if (MODE == MODE_WARMSTART) {
-                ta0 = cs.pc(CF_TA0, s) + ti0; ta1 = cs.pc(CF_TA1, s) + ti1;
+                ta0 = ta0 + ti0; ta1 = ta1 + ti1;
                 ti0 = ti0 * P.warmstart_coeff; ti1 = ti1 * P.warmstart_coeff;
-                wa = cs.pc(CF_WA, s) + wi;
+                wa = wa + wi;
                 wi = wi * P.warmstart_coeff;
                 friction_warmstart_jac(g1, g2, t1, t2, nc, fj, ti0, ti1, wi, v1, w1, v2, w2);
             } else {
+                const float4 twd = cs.pc(CR4_TWD, s);
                 float tlimit = 0.0f, wlimit = 0.0f;
 #pragma unroll
                 for (int kk = 0; kk < MAX_PTS; ++kk) {
                     const float ik = lane_bcast<L>(imp[kk / L], kk % L);
                     if (kk < nc) {
                         tlimit = tlimit + ik;
-                        wlimit = fma_(ik, cs.pc(CF_TWD + kk, s), wlimit);
+                        wlimit = fma_(ik, kk == 0 ? twd.x : (kk == 1 ? twd.y : (kk == 2 ? twd.z : twd.w)), wlimit);
                     }
                 }
-                const float fric = cs.pc(CF_FRIC, s);
-                tlimit = tlimit * fric;
-                wlimit = wlimit * fric;
+                tlimit = tlimit * dirf.w;
+                wlimit = wlimit * dirf.w;
                 constexpr bool relax = MODE == MODE_RELAX;
                 vec3 lfc1 = zero3(), lfc2 = zero3();
                 if (!relax) { lfc1 = xyz(crow(w, CR_LFC1, q0 + s)); lfc2 = xyz(crow(w, CR_LFC2, q0 + s)); }
                 FrictionState f;
                 f.ti0 = ti0; f.ti1 = ti1; f.wi = wi;
-                friction_solve_jac(P, g1, g2, dir, t1, t2, nc, tlimit, wlimit, cs.pc(CF_WR, s), fj, cs.pc(CF_TR, s), cs.pc(CF_TR + 1, s),
-                                   cs.pc(CF_TR + 2, s), relax, lfc1, lfc2, f, v1, w1, v2, w2);
+                friction_solve_jac(P, g1, g2, dir, t1, t2, nc, tlimit, wlimit, t1w.w, fj, trn.x, trn.y, trn.z, relax, lfc1, lfc2, f, v1,
+                                   w1, v2, w2);
                 ti0 = f.ti0; ti1 = f.ti1; wi = f.wi;
             }
         }
@@ -1087,15 +1117,15 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs,
             for (int j = 0; j < PPL; ++j) {
                 const int k = sub + j * L;
                 if (k < nc) {
-                    cs.pp(PF_IMP, k, s) = imp[j];
-                    if (MODE == MODE_WARMSTART) cs.pp(PF_ACC, k, s) = acc[j];
+                    cs.pp(PR4_ITD1I, k, s).w = imp[j];
+                    if (MODE == MODE_WARMSTART) cs.pp(PR4_ITD2A, k, s).w = acc[j];
                 }
             }
             if (sub == 0) {
-                if (MODE == MODE_WARMSTART) {
-                    cs.pc(CF_TA0, s) = ta0; cs.pc(CF_TA1, s) = ta1; cs.pc(CF_WA, s) = wa;
+                if (MODE != MODE_RESTITUTION) {
+                    cs.pc(CR4_TI, s) = make_float4(ti0, ti1, ta0, ta1);
+                    cs.pc(CR4_WI, s) = make_float4(wi, wa, wi4.z, wi4.w);
                 }
-                if (MODE != MODE_RESTITUTION) { cs.pc(CF_TI0, s) = ti0; cs.pc(CF_TI1, s) = ti1; cs.pc(CF_WI, s) = wi; }
                 bd.set_vel(id1 < 0 ? COOP_GARBAGE_SLOT : id1, v1, w1);
                 bd.set_vel(id2 < 0 ? COOP_GARBAGE_SLOT : id2, v2, w2);
             }
@@ -1122,11 +1152,17 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBod
     const int buf = st->cur;
     const int b0 = w.item_body_start[item], b1 = w.item_body_start[item + 1];
     const int c0 = w.item_cons_start[item], n = w.item_cons_start[item + 1] - c0;
-    const int* coff = w.item_color_off + (size_t)item * (NUM_COLORS + 1);
-    const int ncol = st->nused_colors;
     const int tid = ctx.btid, nth = ctx.bsize;
-
+    // The non-empty colour stages of this item, staged once (no HBM/L2 reads between sweeps).
+    RB_SHARED int s_stage[NUM_COLORS + 2];
+    RB_SHARED int s_nstages;
     if (tid == 0) {
+        const int* coff = w.item_color_off + (size_t)item * (NUM_COLORS + 1);
+        const int ncol = st->nused_colors;
+        int ns = 0;
+        for (int c = 0; c < ncol; ++c)
+            if (coff[c + 1] > coff[c]) s_stage[ns++] = coff[c] | (coff[c + 1] << 16);
+        s_nstages = ns;
         w.item_flags[item] = 0;
         bd.set_vel(COOP_WORLD_SLOT, zero3(), zero3());
         bd.set_xf(COOP_WORLD_SLOT, pident());
@@ -1134,6 +1170,7 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBod
     }
     for (int l = b0 + tid; l < b1; l += nth) body_init(w, bd, w.item_bodies[l], l - b0, gravity);
     ctx.block_sync();
+    const int nstages = s_nstages;
     for (int s = tid; s < n; s += nth) {   // S2 generate, one thread per constraint, into shared memory
         Cons c;
         cons_generate(w, bd, c0 + s, buf, item, c);
@@ -1144,21 +1181,24 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBod
         for (int l = b0 + tid; l < b1; l += nth) body_increment(w, bd, w.item_bodies[l], l - b0);
         ctx.block_sync();
         if (P.warmstart_coeff != 0.0f) {
-            for (int c = 0; c < ncol; ++c) {
-                if (coff[c] >= coff[c + 1]) continue;
-                coop_stage<L, MODE_WARMSTART>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, false);
+            for (int c = 0; c < nstages; ++c) {
+                const int ae = s_stage[c];
+                coop_stage<L, MODE_WARMSTART>(w, bd, cs, c0, ae & 0xffff, ae >> 16, tid, nth, false);
                 ctx.block_sync();
             }
         } else {
             for (int s = tid; s < n; s += nth) {
 #pragma unroll
                 for (int k = 0; k < MAX_PTS; ++k) {
-                    cs.pp(PF_ACC, k, s) = cs.pp(PF_ACC, k, s) + cs.pp(PF_IMP, k, s);
-                    cs.pp(PF_IMP, k, s) = cs.pp(PF_IMP, k, s) * 0.0f;
+                    float4& i4 = cs.pp(PR4_ITD1I, k, s);
+                    float4& a4 = cs.pp(PR4_ITD2A, k, s);
+                    a4.w = a4.w + i4.w;
+                    i4.w = i4.w * 0.0f;
                 }
-                cs.pc(CF_TA0, s) = cs.pc(CF_TA0, s) + cs.pc(CF_TI0, s); cs.pc(CF_TA1, s) = cs.pc(CF_TA1, s) + cs.pc(CF_TI1, s);
-                cs.pc(CF_TI0, s) = cs.pc(CF_TI0, s) * 0.0f; cs.pc(CF_TI1, s) = cs.pc(CF_TI1, s) * 0.0f;
-                cs.pc(CF_WA, s) = cs.pc(CF_WA, s) + cs.pc(CF_WI, s); cs.pc(CF_WI, s) = cs.pc(CF_WI, s) * 0.0f;
+                float4 ti = cs.pc(CR4_TI, s), wi = cs.pc(CR4_WI, s);
+                ti.z = ti.z + ti.x; ti.w = ti.w + ti.y; ti.x = ti.x * 0.0f; ti.y = ti.y * 0.0f;
+                wi.y = wi.y + wi.x; wi.x = wi.x * 0.0f;
+                cs.pc(CR4_TI, s) = ti; cs.pc(CR4_WI, s) = wi;
             }
             ctx.block_sync();
         }
@@ -1167,10 +1207,10 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBod
             const int iters = relax ? P.num_relax : P.num_pgs;
             const bool fric = relax || P.friction_in_bias || P.num_relax == 0;
             for (int it = 0; it < iters; ++it) {
-                for (int c = 0; c < ncol; ++c) {
-                    if (coff[c] >= coff[c + 1]) continue;
-                    if (relax) coop_stage<L, MODE_RELAX>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, fric);
-                    else coop_stage<L, MODE_BIASED>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, fric);
+                for (int c = 0; c < nstages; ++c) {
+                    const int ae = s_stage[c];
+                    if (relax) coop_stage<L, MODE_RELAX>(w, bd, cs, c0, ae & 0xffff, ae >> 16, tid, nth, fric);
+                    else coop_stage<L, MODE_BIASED>(w, bd, cs, c0, ae & 0xffff, ae >> 16, tid, nth, fric);
                     ctx.block_sync();
                 }
             }
@@ -1181,9 +1221,9 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBod
         }
     }
     if (w.item_flags[item]) {
-        for (int c = 0; c < ncol; ++c) {
-            if (coff[c] >= coff[c + 1]) continue;
-            coop_stage<L, MODE_RESTITUTION>(w, bd, cs, c0, coff[c], coff[c + 1], tid, nth, false);
+        for (int c = 0; c < nstages; ++c) {
+            const int ae = s_stage[c];
+            coop_stage<L, MODE_RESTITUTION>(w, bd, cs, c0, ae & 0xffff, ae >> 16, tid, nth, false);
             ctx.block_sync();
         }
     }

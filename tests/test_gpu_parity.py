@@ -137,3 +137,23 @@ def test_cuda_variants_match_oracle(built, name, make, params, steps, every):
         if i % every == every - 1 or i < 2:
             d = compare_worlds(w, o)
             assert is_exact(d), f"{name}: step {i}: {d}"
+
+
+def test_determinism_stress(built):
+    """Race detector: the same full-size scene stepped asynchronously several times must give the
+    same bits every time (same-colour constraints commute, islands are independent, so any run-to-run
+    difference is a data race)."""
+    scene = scenes.many_pyramids()
+    ref = None
+    for rep in range(6):
+        w = PhysicsWorld(scene)
+        w.step(150, sync=False)
+        pose, vel = w.body_states()
+        tables = {name: w.debug_read(name, dt).copy() for name, dt in [("pair_keys", np.uint64), ("pair_color", np.int32), ("pair_data", np.uint32)]}
+        cur = (pose.view(np.uint32).copy(), vel.view(np.uint32).copy(), tables)
+        if ref is None:
+            ref = cur
+        else:
+            assert (cur[0] == ref[0]).all() and (cur[1] == ref[1]).all(), f"run {rep}: body state differs from run 0"
+            for k in tables:
+                assert cur[2][k].shape == ref[2][k].shape and (cur[2][k] == ref[2][k]).all(), f"run {rep}: table {k} differs"
