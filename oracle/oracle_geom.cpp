@@ -154,7 +154,7 @@ static bool closest_points_line2d(P2 e1a, P2 e1b, P2 e2a, P2 e2b, float& s, floa
 static inline void push_point(RawManifold& m, V3 p1, V3 p2, uint32_t f1, uint32_t f2, float dist) {
     if (m.n >= MAX_RAW_POINTS) return;  // two convex quads: <= 8 (cap documented in DESIGN.md)
     RawPoint& p = m.pts[m.n++];
-    p.local_p1 = p1; p.local_p2 = p2; p.fid1 = f1; p.fid2 = f2; p.dist = dist;
+    p.local_p1 = p1; p.local_p2 = p2; p.fid1 = f1; p.fid2 = f2; p.dist = dist == 0.0f ? 0.0f : dist;  // canonical zero
 }
 
 // parry PolygonalFeature::contacts_face_face (3-D, both features are 4-vertex faces).

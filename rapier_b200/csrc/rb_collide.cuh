@@ -564,6 +564,16 @@ RB_HD int uf_find(int* parent, int x) {
         cur = next;
     }
 }
+// Read-only find (no path halving): used by the flatten pass, whose in-place root writes must not be
+// overwritten by another thread's stale halving store.
+RB_HD int uf_find_ro(const int* parent, int x) {
+    int cur = x;
+    for (;;) {
+        int next = parent[cur];
+        if (next == cur) return cur;
+        cur = next;
+    }
+}
 RB_HD void uf_union(int* parent, int a, int b) {  // hook the larger root under the smaller one
     for (;;) {
         a = uf_find(parent, a);
@@ -600,7 +610,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
     }
     ctx.grid_sync();
     // S3 flatten
-    for (int b = ctx.gtid; b < nb; b += ctx.gsize) w.isl_label[b] = uf_find(w.isl_label, b);
+    for (int b = ctx.gtid; b < nb; b += ctx.gsize) w.isl_label[b] = uf_find_ro(w.isl_label, b);
     ctx.grid_sync();
     // S4 per-root counts + global colour histogram
     for (int b = ctx.gtid; b < nb; b += ctx.gsize)

@@ -128,7 +128,7 @@ RB_HD bool line_line_2d(pt2 a0, pt2 a1, pt2 b0, pt2 b1, float& s, float& t) {
 RB_HD void raw_push(RawManifold& m, vec3 p1, vec3 p2, uint32_t f1, uint32_t f2, float d) {
     if (m.n >= MAX_RAW) return;
     RawPt& q = m.pt[m.n++];
-    q.p1 = p1; q.p2 = p2; q.fid1 = f1; q.fid2 = f2; q.dist = d;
+    q.p1 = p1; q.p2 = p2; q.fid1 = f1; q.fid2 = f2; q.dist = d == 0.0f ? 0.0f : d;   // canonical zero (a signed zero carries no meaning here)
 }
 
 RB_HD void clip_faces(const pose& p12, const QuadFace& f1, vec3 axis, const QuadFace& f2, RawManifold& m) {

@@ -11,7 +11,8 @@ from rapier_b200.world import PhysicsWorld
 name = sys.argv[1] if len(sys.argv) > 1 else "pile"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 scene = {"pile": lambda: scenes.box_pile(4, 4, 5), "pyr": lambda: scenes.pyramids(2, 2, 10), "p3": lambda: scenes.pyramid3(10),
-         "jg": lambda: scenes.joint_grid(20), "keva": lambda: scenes.keva(1)}[name]()
+         "jg": lambda: scenes.joint_grid(20), "keva": lambda: scenes.keva(1), "keva5": lambda: scenes.keva(5), "jg100": lambda: scenes.joint_grid(100),
+         "keva2": lambda: scenes.keva(2), "jg40": lambda: scenes.joint_grid(40)}[name]()
 w = PhysicsWorld(scene)
 o = oracle_lib.OracleWorld(scene)
 for i in range(steps):

@@ -1,0 +1,39 @@
+"""Secondary configs of BASELINE.json (not the bench line): steps/s and first-steps parity per scene."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import oracle_lib
+from parity_util import compare_worlds, is_exact
+from rapier_b200 import scenes
+from rapier_b200.world import PhysicsWorld
+
+CONFIGS = [("b3d_many_pyramids", scenes.many_pyramids, 300), ("b3d_many_pyramids_80x20", scenes.many_pyramids_label, 300),
+           ("pyramid3_50", lambda: scenes.pyramid3(50), 100), ("b3d_joint_grid_100", lambda: scenes.joint_grid(100), 200),
+           ("keva3_5", lambda: scenes.keva(5), 200)]
+only = sys.argv[1:]
+out = []
+for name, make, steps in CONFIGS:
+    if only and name not in only:
+        continue
+    scene = make()
+    w = PhysicsWorld(scene)
+    o = oracle_lib.OracleWorld(scene, threads=16)
+    exact = True
+    for i in range(3):
+        w.step(); o.step()
+        d = compare_worlds(w, o, tables=(i == 2))
+        exact = exact and is_exact(d)
+    w.step(30)
+    w.physics_pipeline.enable_profiling(True)
+    t0 = time.perf_counter()
+    w.step(steps)
+    wall = time.perf_counter() - t0
+    c = w.counters()
+    t1 = time.perf_counter(); o.step(5); cpu = 5 / (time.perf_counter() - t1)
+    st = w.debug_read("state", np.int32)
+    rec = dict(scene=name, bodies=c["num_bodies"], pairs=c["num_pairs"], manifolds=c["num_active_manifolds"], joints=c["num_joints"],
+               items=int(st[7]), colors=c["num_colors"], large_bodies=int(st[12]), first3_steps_bit_exact=bool(exact),
+               steps_per_s=steps / wall, collide_ms=c["collision_detection_ms"], solve_ms=c["solver_ms"], cpu_port_steps_per_s_16thr=cpu)
+    print(json.dumps(rec), flush=True)
+    out.append(rec)

@@ -18,6 +18,10 @@ CASES = [
     ("joint_grid_large_island", lambda: scenes.joint_grid(20), 60, 20),
     ("ball_on_slab", lambda: scenes.box_on_ground("ball", 2.0), 100, 25),
     ("keva_1", lambda: scenes.keva(1), 30, 10),
+    ("keva_2_large_island", lambda: scenes.keva(2), 12, 4),
+    ("keva_5_full_size", lambda: scenes.keva(5), 4, 2),
+    ("joint_grid_100_full_size", lambda: scenes.joint_grid(100), 8, 4),
+    ("pyramid3_20_large_island", lambda: scenes.pyramid3(20), 30, 10),
 ]
 
 
