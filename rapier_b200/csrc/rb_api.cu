@@ -58,9 +58,12 @@ static cudaError_t dev_set(void* d, int v, size_t n) { if (n) memset(d, v, n); r
 // kernels
 // ------------------------------------------------------------------------------------------------
 constexpr int COLLIDE_THREADS = 256;
-constexpr int COOP_THREADS = 128;
 constexpr int ITEM_SMEM_BYTES = ITEM_MAX_BODIES * SB_STRIDE * 4;
-constexpr int COOP_SMEM_BYTES = COOP_SMEM_FLOATS * 4;
+// k_solve_coop launch shapes.  Small: two CTAs per SM, items resident in shared memory (many small
+// islands).  Big: one CTA per SM with all its shared memory, four times the lanes (islands whose
+// constraints are streamed from the L2 pool, or that only fit resident here).
+constexpr int COOP_SMALL_THREADS = 128, COOP_SMALL_SMEM_BYTES = 108 * 1024;
+constexpr int COOP_BIG_THREADS = 384, COOP_BIG_SMEM_BYTES = 220 * 1024;
 
 struct Grav { float x, y, z; };
 
@@ -100,6 +103,14 @@ RB_PHASE void import_states_phase(const Ctx& ctx, const World& w, const int* idx
 __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, int do_solve) {
     extern __shared__ __align__(16) float smem[];
     GridCtx ctx;
+    if (ctx.gtid == 0) {   // publish last step's launch-shape hint to the host (read without synchronising)
+        *w.host_hint = w.st->need_big;
+        w.st->need_big = 0;
+        w.st->coop_streamed = 0;
+        w.st->coop_resident = 0;
+        w.st->cursor_rest = 0;
+        w.st->cursor_coop = 0;
+    }
     collide_pipeline(ctx, w);
     if (!do_solve) return;
     ctx.grid_sync();
@@ -109,8 +120,15 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, in
         bd.s = smem;
         BlockExec ex;
         ex.c = &bctx;
-        const int n = w.st->nitems;
-        for (int item = 1 + bctx.bid; item < n; item += bctx.nblocks) {
+        __shared__ int s_next;
+        const int n = w.st->norder;
+        for (;;) {   // items that are not shared-memory items, most expensive first
+            if (bctx.btid == 0) s_next = atomicAdd(&w.st->cursor_rest, 1);
+            __syncthreads();
+            const int k = s_next;
+            __syncthreads();
+            if (k >= n) break;
+            const int item = w.item_order[k];
             if (item_is_coop(w, item)) continue;
             solve_item(ex, w, bd, item, mk3(g.x, g.y, g.z));
             ex.sync();
@@ -123,19 +141,33 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, in
     gex.c = &ctx;
     solve_item(gex, w, gb, 0, mk3(g.x, g.y, g.z));
 }
-// Items that fit shared memory: one CTA per item, bodies + constraints staged in shared memory,
+// Shared-memory items: one CTA per item, bodies (and, when they fit, constraints) staged in shared memory,
 // four lanes per constraint (rb_solver.cuh "lane-cooperative path").
-__global__ void __launch_bounds__(COOP_THREADS, 2) k_solve_coop(World w, Grav g) {
+template <int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) k_solve_coop(World w, Grav g) {
     extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
     BlockCtx ctx;
-    SmemBodies bd;
-    bd.s = smem;
-    CoopStore cs;
-    cs.base = smem + COOP_BODY_SLOTS * SB_STRIDE;
-    const int n = w.st->nitems;
-    for (int item = 1 + ctx.bid; item < n; item += ctx.nblocks) {
+    if (ctx.btid == 0) {
+        mbar_init(&s_mbar[0], 1);
+        mbar_init(&s_mbar[1], 1);
+        mbar_init_fence();
+    }
+    ctx.block_sync();
+    CoopPipe pp;
+    pp.mbar = s_mbar;
+    pp.t = 0;
+    __shared__ int s_next;
+    const int n = w.st->norder;
+    for (;;) {   // dynamic queue over the cost-ordered items
+        if (ctx.btid == 0) s_next = atomicAdd(&w.st->cursor_coop, 1);
+        __syncthreads();
+        const int k = s_next;
+        __syncthreads();
+        if (k >= n) break;
+        const int item = w.item_order[k];
         if (!item_is_coop(w, item)) continue;
-        solve_item_coop<4>(ctx, w, bd, cs, item, mk3(g.x, g.y, g.z));
+        solve_item_coop<4>(ctx, w, smem, w.coop_smem_floats, pp, item, mk3(g.x, g.y, g.z));
         ctx.block_sync();
     }
 }
@@ -162,7 +194,10 @@ struct RbWorld {
     int device = 0;
     int num_sms = 1;
     int collide_blocks = 1, coop_blocks = 1;
-    int collide_threads = COLLIDE_THREADS, coop_threads = COOP_THREADS;
+    int collide_threads = COLLIDE_THREADS;
+    int coop_blocks_big = 1;
+    int coop_shape = -1;   // RB_COOP_SHAPE debugging override: 0 small, 1 big, -1 automatic
+    int* host_hint = nullptr;
     long long kernels = 0, steps = 0;
     bool profiling = false;
     float ms_collide = 0, ms_solve = 0, ms_step = 0;
@@ -177,6 +212,7 @@ struct RbWorld {
     int prof_steps = 0;
 #else
     std::vector<float> emu_smem;
+    int emu_coop_floats = 0, emu_hint = 0;
 #endif
 };
 
@@ -407,23 +443,33 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
     W->num_sms = prop.multiProcessorCount;
     if (!prop.cooperativeLaunch) { set_err("device lacks cooperative launch%s", ""); delete W; return nullptr; }
     cudaStreamCreateWithFlags(&W->stream, cudaStreamNonBlocking);
-    cudaFuncSetAttribute(k_solve_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_SMEM_BYTES);
+    cudaFuncSetAttribute(k_solve_coop<COOP_SMALL_THREADS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_SMALL_SMEM_BYTES);
+    cudaFuncSetAttribute(k_solve_coop<COOP_BIG_THREADS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_BIG_SMEM_BYTES);
+    if (cudaHostAlloc((void**)&W->host_hint, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { set_err("cudaHostAlloc failed%s", ""); delete W; return nullptr; }
+    *W->host_hint = 0;
     cudaFuncSetAttribute(k_collide, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_collide, COLLIDE_THREADS, ITEM_SMEM_BYTES);
     if (occ < 1) { set_err("k_collide cannot be resident%s", ""); delete W; return nullptr; }
     W->collide_blocks = W->num_sms;   // one CTA per SM: the cheapest grid barrier that still covers the chip
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_coop, COOP_THREADS, COOP_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_coop<COOP_SMALL_THREADS, 2>, COOP_SMALL_THREADS, COOP_SMALL_SMEM_BYTES);
     if (occ < 1) occ = 1;
     W->coop_blocks = W->num_sms * occ;
+    W->coop_blocks_big = W->num_sms;
     {   // debugging overrides (never needed in production): shrink the launch geometry
         auto envi = [](const char* n, int d) { const char* v = getenv(n); return v ? atoi(v) : d; };
         W->collide_blocks = std::min(W->collide_blocks, envi("RB_COLLIDE_BLOCKS", W->collide_blocks));
         W->coop_blocks = std::min(W->coop_blocks, envi("RB_COOP_BLOCKS", W->coop_blocks));
         W->collide_threads = std::min(COLLIDE_THREADS, envi("RB_COLLIDE_THREADS", COLLIDE_THREADS));
+        W->coop_shape = envi("RB_COOP_SHAPE", -1);
     }
 #else
-    W->emu_smem.assign(ITEM_MAX_BODIES * SB_STRIDE + COOP_SMEM_FLOATS, 0.0f);
+    {   // emulated CTA: shared-memory size of the big launch shape, or a test override that forces streaming
+        const char* v = getenv("RB_EMU_COOP_SMEM_FLOATS");
+        W->emu_coop_floats = v ? atoi(v) : COOP_BIG_SMEM_BYTES / 4;
+        W->emu_smem.assign(ITEM_MAX_BODIES * SB_STRIDE + W->emu_coop_floats, 0.0f);
+        W->host_hint = &W->emu_hint;
+    }
 #endif
     return W;
 }
@@ -438,6 +484,7 @@ void rb_world_destroy(RbWorld* W) {
 #if RB_DEVICE_BUILD
     for (cudaEvent_t e : W->prof_ev) cudaEventDestroy(e);
     if (W->stage_host) cudaFreeHost(W->stage_host);
+    if (W->host_hint) cudaFreeHost(W->host_hint);
     if (W->stream && W->own_stream) cudaStreamDestroy(W->stream);
 #else
     free(W->stage_host);
@@ -528,6 +575,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.item_body_start, w.item_cap + 2); ALLOC(w.item_cons_start, w.item_cap + 2); ALLOC(w.item_joint_start, w.item_cap + 2);
     ALLOC(w.item_cursor, 3 * (w.item_cap + 2));
     ALLOC(w.item_flags, w.item_cap + 2);
+    ALLOC(w.item_order, w.item_cap + 2); ALLOC(w.order_hist, 2 * ORDER_BUCKETS + 2);
     ALLOC(w.item_bodies, NB); ALLOC(w.body_local, NB); ALLOC(w.body_item, NB);
     ALLOC(w.cons_pair_tmp, w.cons_cap); ALLOC(w.cons_pair, w.cons_cap);
     ALLOC(w.item_color_off, (size_t)(w.item_cap + 1) * (NUM_COLORS + 1));
@@ -535,6 +583,10 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.color_count, NUM_COLORS + 1); ALLOC(w.color_pos, NUM_COLORS + 1); ALLOC(w.jcolor_pos, NUM_COLORS + 1);
     ALLOC(w.joint_tmp, NJ); ALLOC(w.joint_sched, NJ);
     ALLOC(w.cons_hdr, w.cons_cap); ALLOC(w.cons, (size_t)CR_ROWS * w.cons_cap);
+    ALLOC(w.coop_pool, (size_t)2 * COOP_ROWS * w.cons_cap);
+    w.host_hint = W->host_hint;
+    w.coop_small_floats = COOP_SMALL_SMEM_BYTES / 4;
+    w.coop_smem_floats = w.coop_small_floats;
     ALLOC(w.j_info, NJ); ALLOC(w.j_f1_t, NJ); ALLOC(w.j_f1_q, NJ); ALLOC(w.j_f2_t, NJ); ALLOC(w.j_f2_q, NJ);
     ALLOC(w.j_soft, NJ); ALLOC(w.j_impulses, (size_t)NJ * 6);
     ALLOC(w.j_rows, (size_t)JR_ROWS * 6 * NJ); ALLOC(w.j_sched_ids, NJ);
@@ -733,10 +785,14 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         bool prof = W->profiling;
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s], W->stream));
         int do_solve = 1;
+        // launch shape of k_solve_coop for this step (both kernels must agree on it): device hint of the last step
+        const bool big = W->coop_shape >= 0 ? W->coop_shape == 1 : (*(volatile int*)W->host_hint != 0);
+        W->w.coop_smem_floats = (big ? COOP_BIG_SMEM_BYTES : COOP_SMALL_SMEM_BYTES) / 4;
         void* a1[] = {(void*)&W->w, (void*)&g, (void*)&do_solve};
         CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, ITEM_SMEM_BYTES, W->stream));
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 1], W->stream));
-        k_solve_coop<<<W->coop_blocks, W->coop_threads, COOP_SMEM_BYTES, W->stream>>>(W->w, g);
+        if (big) k_solve_coop<COOP_BIG_THREADS, 1><<<W->coop_blocks_big, COOP_BIG_THREADS, COOP_BIG_SMEM_BYTES, W->stream>>>(W->w, g);
+        else k_solve_coop<COOP_SMALL_THREADS, 2><<<W->coop_blocks, COOP_SMALL_THREADS, COOP_SMALL_SMEM_BYTES, W->stream>>>(W->w, g);
         CK(cudaGetLastError());
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 2], W->stream));
         W->kernels += 2;
@@ -769,6 +825,8 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
     (void)sync;
     for (int s = 0; s < nsteps; ++s) {
         GridCtx gctx;
+        W->emu_hint = W->w.st->need_big;
+        W->w.st->need_big = W->w.st->coop_streamed = W->w.st->coop_resident = 0;
         collide_pipeline(gctx, W->w);
         BlockCtx bctx;
         SmemBodies sb;
@@ -776,10 +834,15 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         BlockExec bex;
         bex.c = &bctx;
         int n = W->w.st->nitems;
-        CoopStore cst;
-        cst.base = W->emu_smem.data() + ITEM_MAX_BODIES * SB_STRIDE;
-        for (int item = 1; item < n; ++item) {
-            if (item_is_coop(W->w, item)) solve_item_coop<1>(bctx, W->w, sb, cst, item, mk3(g.x, g.y, g.z));
+        W->w.coop_smem_floats = W->emu_coop_floats;
+        CoopPipe pp;
+        unsigned long long mbar[2] = {0, 0};
+        pp.mbar = mbar;
+        pp.t = 0;
+        for (int k = 0; k < W->w.st->norder; ++k) {
+            const int item = W->w.item_order[k];
+            if (item_is_coop(W->w, item))
+                solve_item_coop<1>(bctx, W->w, W->emu_smem.data() + ITEM_MAX_BODIES * SB_STRIDE, W->emu_coop_floats, pp, item, mk3(g.x, g.y, g.z));
             else solve_item(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
         }
         if (W->w.st->nlarge_bodies > 0) {

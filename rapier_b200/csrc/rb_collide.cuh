@@ -799,7 +799,34 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
         }
     }
     ctx.grid_sync();
+    // S11 launch order of the items: non-empty items 1.., most expensive first (counting sort by cost class),
+    // consumed through per-kernel atomic cursors so that the long items start first and CTAs stay balanced.
+    {
+        int* hist = w.order_hist;
+        int* curs = w.order_hist + ORDER_BUCKETS + 1;
+        for (int c = ctx.gtid; c <= ORDER_BUCKETS; c += ctx.gsize) { hist[c] = 0; if (c < ORDER_BUCKETS) curs[c] = 0; }
+        ctx.grid_sync();
+        for (int it = 1 + ctx.gtid; it < nitems; it += ctx.gsize) {
+            int nbod = w.item_body_start[it + 1] - w.item_body_start[it];
+            int work = (w.item_cons_start[it + 1] - w.item_cons_start[it]) + (w.item_joint_start[it + 1] - w.item_joint_start[it]);
+            if (nbod == 0 && work == 0) continue;
+            int cost = nbod > work ? nbod : work;
+            atomic_add(&hist[ORDER_BUCKETS - 1 - (cost < ORDER_BUCKETS ? cost : ORDER_BUCKETS - 1)], 1);
+        }
+        ctx.grid_sync();
+        grid_exclusive_scan(ctx, hist, hist, ORDER_BUCKETS + 1, w.scan_tmp);
+        for (int it = 1 + ctx.gtid; it < nitems; it += ctx.gsize) {
+            int nbod = w.item_body_start[it + 1] - w.item_body_start[it];
+            int work = (w.item_cons_start[it + 1] - w.item_cons_start[it]) + (w.item_joint_start[it + 1] - w.item_joint_start[it]);
+            if (nbod == 0 && work == 0) continue;
+            int cost = nbod > work ? nbod : work;
+            int k = ORDER_BUCKETS - 1 - (cost < ORDER_BUCKETS ? cost : ORDER_BUCKETS - 1);
+            w.item_order[hist[k] + atomic_add(&curs[k], 1)] = it;
+        }
+        ctx.grid_sync();
+    }
     if (ctx.gtid == 0) {
+        st->norder = w.order_hist[ORDER_BUCKETS];
         st->nitems = nitems;
         st->ncons = ncons < w.cons_cap ? ncons : w.cons_cap;
         st->nlarge_bodies = w.item_body_start[1] - w.item_body_start[0];

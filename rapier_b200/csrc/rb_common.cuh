@@ -8,6 +8,7 @@
 // against the oracle on a machine without a GPU; that build is test infrastructure only and is never
 // loaded by the product (rapier_b200/_lib.py refuses to load anything but the CUDA library).
 #pragma once
+#include <cstring>
 #include <stdint.h>
 #include <math.h>
 #include <string.h>
@@ -95,5 +96,41 @@ RB_HD float as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 RB_HD uint32_t as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 RB_HD float as_float_i(int i) { float f; memcpy(&f, &i, 4); return f; }
 RB_HD int as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+
+
+// ---- bulk staging: 1-D TMA copies global -> shared completing on an mbarrier (emulation: memcpy) ----
+#if RB_DEVICE_BUILD
+RB_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+RB_D void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+RB_D void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+RB_D void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+RB_D void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+RB_D void mbar_wait(unsigned long long* b, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(b)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+// Orders this thread's earlier generic-proxy writes before later async-proxy (TMA) reads of them.
+RB_D void fence_async_proxy() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#else
+inline void mbar_init(unsigned long long*, int) {}
+inline void mbar_init_fence() {}
+inline void mbar_expect_tx(unsigned long long*, unsigned) {}
+inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+inline void mbar_wait(unsigned long long*, unsigned) {}
+inline void fence_async_proxy() {}
+#endif
 
 }  // namespace rb

@@ -888,14 +888,11 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
 // Gauss-Seidel dependency between the points with __shfl_sync broadcasts.  Same primitives, same
 // arithmetic, same results as the serial sweep.
 // =====================================================================================================
-constexpr int COOP_MAX_CONS = 146;     // constraints per item held in shared memory
-constexpr int COOP_CS = 146;           // slot stride in float4 (== 2 mod 8: an LDS.128 quarter-warp = 2 constraints x 4 points, conflict-free)
-constexpr int COOP_MAX_BODIES = 128;
 // per-point float4 rows (one copy per manifold point)
 enum CoopPointRow { PR4_TD1R = 0,   // torque_dir1 xyz, r (projected mass)
                     PR4_TD2D,       // torque_dir2 xyz, dist0
-                    PR4_ITD1I,      // ii1*torque_dir1 xyz, impulse
-                    PR4_ITD2A,      // ii2*torque_dir2 xyz, impulse accumulator
+                    PR4_ITD1I,      // ii1*torque_dir1 xyz, id1 bits
+                    PR4_ITD2A,      // ii2*torque_dir2 xyz, id2 bits
                     PR4_LP1, PR4_LP2,   // builder anchors
                     PR4_COUNT };
 // per-constraint float4 rows
@@ -903,23 +900,52 @@ enum CoopConsRow { CR4_DIRF = 0,    // dir1 xyz, friction
                    CR4_T1W,         // tangent1 xyz, twist effective mass
                    CR4_TR,          // tangent K (r0 r1 r2), nc bits
                    CR4_TWD,         // twist_dists[4]
-                   CR4_TI,          // tangent impulse xy, accumulators zw
-                   CR4_WI,          // twist impulse, accumulator, id1 bits, id2 bits
                    CR4_J0, CR4_J1, CR4_J2, CR4_J3, CR4_J4, CR4_J5, CR4_J6, CR4_J7,   // friction jacobians, packed (see put/get)
                    CR4_COUNT };
-constexpr int COOP_CONS_FLOATS = (PR4_COUNT * MAX_PTS + CR4_COUNT) * COOP_CS * 4;
-constexpr int COOP_WORLD_SLOT = COOP_MAX_BODIES;        // staged pseudo body: identity pose, zero velocity and mass
-constexpr int COOP_GARBAGE_SLOT = COOP_MAX_BODIES + 1;  // scatter target of world-attached sides
-constexpr int COOP_BODY_SLOTS = COOP_MAX_BODIES + 2;
-constexpr int COOP_SMEM_FLOATS = COOP_BODY_SLOTS * SB_STRIDE + COOP_CONS_FLOATS;
+constexpr int COOP_ROWS = PR4_COUNT * MAX_PTS + CR4_COUNT;   // 36 float4 = 576 B per constraint, constant during a step
+// mutable float4 rows (always resident in shared memory): the impulses
+enum CoopMutRow { MR_IMP = 0,       // normal impulses of the 4 points
+                  MR_ACC,           // their accumulators
+                  MR_TI,            // tangent impulse xy, accumulators zw
+                  MR_WI,            // twist impulse, accumulator
+                  MR_COUNT };
+constexpr int COOP_MIN_CHUNK = 8;      // smallest streaming chunk worth running (slots)
+constexpr int COOP_MAX_CHUNKS = 640;   // chunk table of a streamed item (colour stages + splits of long stages)
 
-struct CoopStore {
-    float* base;   // 16-byte aligned
-    RB_HD float4& pp(int row, int k, int s) const { return reinterpret_cast<float4*>(base)[(row * MAX_PTS + k) * COOP_CS + s]; }
-    RB_HD float4& pc(int row, int s) const { return reinterpret_cast<float4*>(base)[(PR4_COUNT * MAX_PTS + row) * COOP_CS + s]; }
+// A window of constraint slots stored row-major (row r of slot s at p[r * stride + s]): the item's
+// resident shared-memory copy, one staging buffer of the streaming pipeline, or the L2-resident pool.
+// Odd strides keep the 4 point-lanes of a constraint on distinct 16-byte bank groups.
+struct RowView {
+    float4* p;
+    int stride;
+    RB_HD float4& pp(int row, int k, int s) const { return p[(row * MAX_PTS + k) * stride + s]; }
+    RB_HD float4& pc(int row, int s) const { return p[(PR4_COUNT * MAX_PTS + row) * stride + s]; }
+    RB_HD float4& mr(int row, int s) const { return p[row * stride + s]; }                                  // mutable rows
+    RB_HD float& mf(int row, int k, int s) const { return reinterpret_cast<float*>(p + row * stride + s)[k]; }
 };
 
-RB_HD void coop_put_jac(const CoopStore& cs, int s, const FrictionJac& j) {
+// How one item maps onto the CTA's shared memory (a pure function of the item's sizes and the
+// launch's shared-memory size, so both kernels agree on it).
+struct CoopPlan {
+    int body_slots;   // nb + 2: the item's bodies, the world pseudo body, the garbage slot
+    int mstride;      // slot stride of the mutable rows
+    int resident;     // 1: every constraint lives in shared memory for the whole step
+    int stride;       // resident: slot stride of the constant rows; streaming: slots per staging buffer
+    bool ok;
+};
+RB_HD CoopPlan coop_plan(int smem_floats, int nb, int n) {
+    CoopPlan pl;
+    pl.body_slots = nb + 2;
+    pl.mstride = n | 1;
+    const int avail = (smem_floats - pl.body_slots * SB_STRIDE) / 4 - MR_COUNT * pl.mstride;   // float4 left for constant rows
+    const int R = avail > 0 ? avail / COOP_ROWS : 0;
+    pl.resident = pl.mstride <= R ? 1 : 0;
+    pl.stride = pl.resident ? pl.mstride : ((R / 2 - 1) | 1);
+    pl.ok = pl.resident || ((R / 2 - 1) >= COOP_MIN_CHUNK && n / pl.stride + NUM_COLORS + 2 <= COOP_MAX_CHUNKS);
+    return pl;
+}
+
+RB_HD void coop_put_jac(const RowView& cs, int s, const FrictionJac& j) {
     cs.pc(CR4_J0, s) = make_float4(j.td10.x, j.td10.y, j.td10.z, j.td11.x);
     cs.pc(CR4_J1, s) = make_float4(j.td11.y, j.td11.z, j.td20.x, j.td20.y);
     cs.pc(CR4_J2, s) = make_float4(j.td20.z, j.td21.x, j.td21.y, j.td21.z);
@@ -929,7 +955,7 @@ RB_HD void coop_put_jac(const CoopStore& cs, int s, const FrictionJac& j) {
     cs.pc(CR4_J6, s) = make_float4(j.tw1.x, j.tw1.y, j.tw1.z, j.tw2.x);
     cs.pc(CR4_J7, s) = make_float4(j.tw2.y, j.tw2.z, 0.0f, 0.0f);
 }
-RB_HD FrictionJac coop_get_jac(const CoopStore& cs, int s) {
+RB_HD FrictionJac coop_get_jac(const RowView& cs, int s) {
     float4 a = cs.pc(CR4_J0, s), b = cs.pc(CR4_J1, s), c = cs.pc(CR4_J2, s), d = cs.pc(CR4_J3, s), e = cs.pc(CR4_J4, s),
            f = cs.pc(CR4_J5, s), g = cs.pc(CR4_J6, s), h = cs.pc(CR4_J7, s);
     FrictionJac j;
@@ -939,10 +965,10 @@ RB_HD FrictionJac coop_get_jac(const CoopStore& cs, int s) {
     return j;
 }
 
-// Stage one generated constraint in shared memory, with the jacobians that stay constant during
+// Store one generated constraint in its row window, with the jacobians that stay constant during
 // the step precomputed (the serial path recomputes the same expressions in every sweep).
 template <class B>
-RB_HD void coop_put(const CoopStore& cs, const B& bd, int s, const Cons& c) {
+RB_HD void coop_put(const RowView& cs, const RowView& mu, const B& bd, int s, const Cons& c) {
     BodyState g1 = gather_body(bd, c.id1), g2 = gather_body(bd, c.id2);
 #pragma unroll
     for (int k = 0; k < MAX_PTS; ++k) {
@@ -956,8 +982,8 @@ RB_HD void coop_put(const CoopStore& cs, const B& bd, int s, const Cons& c) {
         }
         cs.pp(PR4_TD1R, k, s) = f4(pj.td1, r);
         cs.pp(PR4_TD2D, k, s) = f4(pj.td2, d0);
-        cs.pp(PR4_ITD1I, k, s) = f4(pj.itd1, c.imp[k]);
-        cs.pp(PR4_ITD2A, k, s) = f4(pj.itd2, c.acc[k]);
+        cs.pp(PR4_ITD1I, k, s) = f4(pj.itd1, as_float_i(c.id1));
+        cs.pp(PR4_ITD2A, k, s) = f4(pj.itd2, as_float_i(c.id2));
         cs.pp(PR4_LP1, k, s) = f4(l1, 0.0f);
         cs.pp(PR4_LP2, k, s) = f4(l2, 0.0f);
     }
@@ -967,16 +993,18 @@ RB_HD void coop_put(const CoopStore& cs, const B& bd, int s, const Cons& c) {
     cs.pc(CR4_T1W, s) = f4(c.t1, c.wr);
     cs.pc(CR4_TR, s) = make_float4(c.tr0, c.tr1, c.tr2, as_float_i(c.nc));
     cs.pc(CR4_TWD, s) = make_float4(c.twd[0], c.twd[1], c.twd[2], c.twd[3]);
-    cs.pc(CR4_TI, s) = make_float4(c.ti0, c.ti1, c.ta0, c.ta1);
-    cs.pc(CR4_WI, s) = make_float4(c.wi, c.wa, as_float_i(c.id1), as_float_i(c.id2));
+    mu.mr(MR_IMP, s) = make_float4(c.imp[0], c.imp[1], c.imp[2], c.imp[3]);
+    mu.mr(MR_ACC, s) = make_float4(c.acc[0], c.acc[1], c.acc[2], c.acc[3]);
+    mu.mr(MR_TI, s) = make_float4(c.ti0, c.ti1, c.ta0, c.ta1);
+    mu.mr(MR_WI, s) = make_float4(c.wi, c.wa, 0.0f, 0.0f);
 }
-RB_HD void coop_get_for_writeback(const CoopStore& cs, int s, Cons& c) {
+RB_HD void coop_get_for_writeback(const RowView& cs, const RowView& mu, int s, Cons& c) {
     c.nc = as_int(cs.pc(CR4_TR, s).w);
     c.dir = xyz(cs.pc(CR4_DIRF, s)); c.t1 = xyz(cs.pc(CR4_T1W, s));
-#pragma unroll
-    for (int k = 0; k < MAX_PTS; ++k) { c.imp[k] = cs.pp(PR4_ITD1I, k, s).w; c.acc[k] = cs.pp(PR4_ITD2A, k, s).w; }
-    float4 ti = cs.pc(CR4_TI, s);
-    c.ti0 = ti.x; c.ti1 = ti.y; c.wi = cs.pc(CR4_WI, s).x;
+    const float4 im = mu.mr(MR_IMP, s), ac = mu.mr(MR_ACC, s), ti = mu.mr(MR_TI, s);
+    c.imp[0] = im.x; c.imp[1] = im.y; c.imp[2] = im.z; c.imp[3] = im.w;
+    c.acc[0] = ac.x; c.acc[1] = ac.y; c.acc[2] = ac.z; c.acc[3] = ac.w;
+    c.ti0 = ti.x; c.ti1 = ti.y; c.wi = mu.mr(MR_WI, s).x;
 }
 
 // Sub-warp broadcast from lane `src` of each L-lane group.
@@ -1002,12 +1030,15 @@ template <int L> RB_HD bool lane_any(bool p) {
     return p;
 }
 
-// Sweep the constraints in slots [a, e) of the item (one colour stage) with L lanes per constraint.
+// Sweep the constraints in slots [a, e) of the item (part of one colour stage) with L lanes per constraint.
+// `cs` is the shared-memory window the constant rows are read from (the resident copy or a staging
+// buffer of the streaming pipeline), `mu` the resident window of the mutable impulses; both are
+// indexed by item slot.  `wslot` is the staged world pseudo body (wslot + 1 = garbage slot).
 // `q0` is the global schedule slot of the item's slot 0 (rare per-constraint rows stay in HBM).
 // MODE is a compile-time constant so each sweep kind is straight-line code.
 template <int L, int MODE>
-RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs, int q0, int a, int e, int tid, int nth,
-                      bool solve_friction) {
+RB_HD void coop_stage(const World& w, const SmemBodies& bd, const RowView& cs, const RowView& mu, int wslot, int q0, int a, int e,
+                      int tid, int nth, bool solve_friction) {
     constexpr int PPL = MAX_PTS / L;   // points per lane
     const Params& P = w.prm;
     const int groups = nth / L, grp = tid / L, sub = tid % L;
@@ -1015,11 +1046,11 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs,
         const int s_raw = base + grp;
         const bool active = s_raw < e && grp < groups;
         const int s = active ? s_raw : a;   // inactive lanes shadow a valid slot (they must execute the shuffles)
-        const float4 dirf = cs.pc(CR4_DIRF, s), t1w = cs.pc(CR4_T1W, s), trn = cs.pc(CR4_TR, s), wi4 = cs.pc(CR4_WI, s);
-        const int id1 = as_int(wi4.z), id2 = as_int(wi4.w), nc = as_int(trn.w);
+        const float4 dirf = cs.pc(CR4_DIRF, s), t1w = cs.pc(CR4_T1W, s), trn = cs.pc(CR4_TR, s), wi4 = mu.mr(MR_WI, s);
+        const int id1 = as_int(cs.pp(PR4_ITD1I, sub, s).w), id2 = as_int(cs.pp(PR4_ITD2A, sub, s).w), nc = as_int(trn.w);   // (replicated per point)
         // branch-free gathers: a world-attached side reads the staged identity/zero pseudo body.
         // Only what a sweep needs is loaded: velocities, inverse masses and (for the rhs) the poses.
-        const int gi1 = id1 < 0 ? COOP_WORLD_SLOT : id1, gi2 = id2 < 0 ? COOP_WORLD_SLOT : id2;
+        const int gi1 = id1 < 0 ? wslot : id1, gi2 = id2 < 0 ? wslot : id2;
         BodyState g1, g2;
         g1.lin = bd.lin(gi1); g1.ang = bd.ang(gi1); g1.im = bd.im(gi1);
         g2.lin = bd.lin(gi2); g2.ang = bd.ang(gi2); g2.im = bd.im(gi2);
@@ -1042,7 +1073,7 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs,
             const int k = sub + j * L;
             const float4 a1 = cs.pp(PR4_TD1R, k, s), a2 = cs.pp(PR4_TD2D, k, s), b1 = cs.pp(PR4_ITD1I, k, s), b2 = cs.pp(PR4_ITD2A, k, s);
             pre[j].td1 = xyz(a1); pre[j].td2 = xyz(a2); pre[j].itd1 = xyz(b1); pre[j].itd2 = xyz(b2);
-            r[j] = a1.w; imp[j] = b1.w; acc[j] = b2.w; seed[j] = 0.0f;
+            r[j] = a1.w; imp[j] = mu.mf(MR_IMP, k, s); acc[j] = mu.mf(MR_ACC, k, s); seed[j] = 0.0f;
             pre[j].rhs = 0.0f; pre[j].cfm = 1.0f;
             if (k < nc) {
                 if (MODE == MODE_BIASED || MODE == MODE_RELAX)
@@ -1077,7 +1108,7 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs,
             if (kk < nc) apply_normal(lin1, lin2, i1, i2, dl, v1, w1, v2, w2);
         }
 
-        float4 ti4 = cs.pc(CR4_TI, s);
+        float4 ti4 = mu.mr(MR_TI, s);
         float ti0 = ti4.x, ti1 = ti4.y, wi = wi4.x;
         float ta0 = ti4.z, ta1 = ti4.w, wa = wi4.y;
         if (MODE == MODE_WARMSTART || (MODE != MODE_RESTITUTION && solve_friction)) {
@@ -1117,17 +1148,17 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const CoopStore& cs,
             for (int j = 0; j < PPL; ++j) {
                 const int k = sub + j * L;
                 if (k < nc) {
-                    cs.pp(PR4_ITD1I, k, s).w = imp[j];
-                    if (MODE == MODE_WARMSTART) cs.pp(PR4_ITD2A, k, s).w = acc[j];
+                    mu.mf(MR_IMP, k, s) = imp[j];
+                    if (MODE == MODE_WARMSTART) mu.mf(MR_ACC, k, s) = acc[j];
                 }
             }
             if (sub == 0) {
                 if (MODE != MODE_RESTITUTION) {
-                    cs.pc(CR4_TI, s) = make_float4(ti0, ti1, ta0, ta1);
-                    cs.pc(CR4_WI, s) = make_float4(wi, wa, wi4.z, wi4.w);
+                    mu.mr(MR_TI, s) = make_float4(ti0, ti1, ta0, ta1);
+                    mu.mr(MR_WI, s) = make_float4(wi, wa, 0.0f, 0.0f);
                 }
-                bd.set_vel(id1 < 0 ? COOP_GARBAGE_SLOT : id1, v1, w1);
-                bd.set_vel(id2 < 0 ? COOP_GARBAGE_SLOT : id2, v2, w2);
+                bd.set_vel(id1 < 0 ? (wslot + 1) : id1, v1, w1);
+                bd.set_vel(id2 < 0 ? (wslot + 1) : id2, v2, w2);
             }
         }
     }
@@ -1140,22 +1171,108 @@ RB_HD bool item_is_coop(const World& w, int item) {
     const int ovf = w.color_pos[COLOR_OVERFLOW];
     const int* coff = w.item_color_off + (size_t)item * (NUM_COLORS + 1);
     const bool has_ovf = ovf >= 0 && coff[ovf + 1] > coff[ovf];
-    return item > 0 && nbod <= COOP_MAX_BODIES && ncons <= COOP_MAX_CONS && njoints == 0 && !has_ovf &&
-           w.item_cons_start[item + 1] <= w.cons_cap;
+    return item > 0 && njoints == 0 && !has_ovf && ncons < 65536 && w.item_cons_start[item + 1] <= w.cons_cap &&
+           coop_plan(w.coop_smem_floats, nbod, ncons).ok;
 }
 
-// One work item, start to finish, by one CTA with everything in shared memory (L lanes / constraint).
+// Streaming pipeline of one CTA: two shared-memory staging buffers filled by bulk (TMA) copies from the
+// L2-resident pool, one chunk ahead of the sweep.  A chunk is a run of at most `cap` slots of one colour
+// stage; its 36 constant rows are stored as ONE contiguous block in the pool (row stride = cnt | 1), so
+// staging a chunk is a single bulk copy.  Only rows that are constant during the step are streamed (the
+// impulses stay resident), so chunks can be prefetched at any time.  `t` counts the chunks consumed since
+// the kernel started (buffer = t & 1, mbarrier phase = (t >> 1) & 1) and lives across items.
+struct CoopPipe {
+    float4* buf[2];
+    unsigned long long* mbar;   // [2], shared memory
+    float4* pool;               // the item's region of the pool: chunk q starts at COOP_ROWS * (chunk[q] + q)
+    const int* chunk;           // [nchunks + 1] first slot of every chunk (shared memory)
+    int nchunks;
+    unsigned t;
+    bool primed;                // the chunk the next sweep starts with is already in flight
+};
+RB_HD RowView coop_chunk_rows(const CoopPipe& pp, int q) {   // pool rows of chunk q, indexed by item slot
+    const int o = pp.chunk[q], cnt = pp.chunk[q + 1] - o;
+    RowView v;
+    v.p = pp.pool + (size_t)COOP_ROWS * (o + q) - o;
+    v.stride = cnt | 1;
+    return v;
+}
+RB_HD RowView coop_slot_rows(const CoopPipe& pp, int s) {   // ... of the chunk that holds slot s
+    int lo = 0, hi = pp.nchunks - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (pp.chunk[mid] <= s) lo = mid; else hi = mid - 1;
+    }
+    return coop_chunk_rows(pp, lo);
+}
+RB_HD void coop_pipe_issue(const CoopPipe& pp, int q, int b) {   // one thread: stage chunk q into buffer b
+    const int o = pp.chunk[q], cnt = pp.chunk[q + 1] - o;
+    const unsigned bytes = (unsigned)(COOP_ROWS * (cnt | 1) * 16);
+    mbar_expect_tx(pp.mbar + b, bytes);
+    bulk_g2s(pp.buf[b], pp.pool + (size_t)COOP_ROWS * (o + q), bytes, pp.mbar + b);
+}
+
+// One sweep over all colour stages of the item.  Resident items read their shared-memory rows; streamed
+// items consume the pipeline.  `wrap`: another sweep follows, its first chunk is prefetched by the last one here.
+template <int L, int MODE>
+RB_PHASE void coop_sweep(const BlockCtx& ctx, const World& w, const SmemBodies& bd, const RowView& res, const RowView& mu, bool resident,
+                         CoopPipe& pp, const int* s_stage, int nstages, int wslot, int c0, bool fric, bool wrap) {
+    const int tid = ctx.btid, nth = ctx.bsize;
+    if (resident) {
+        for (int c = 0; c < nstages; ++c) {
+            const int ae = s_stage[c];
+            coop_stage<L, MODE>(w, bd, res, mu, wslot, c0, ae & 0xffff, ae >> 16, tid, nth, fric);
+            ctx.block_sync();
+        }
+        return;
+    }
+    if (!pp.primed && tid == 0) coop_pipe_issue(pp, 0, pp.t & 1);   // (the caller synchronised after the rows were written and fenced)
+    for (int q = 0; q < pp.nchunks; ++q) {
+        const int o = pp.chunk[q], e = pp.chunk[q + 1];
+        const int b = pp.t & 1;
+        mbar_wait(pp.mbar + b, (pp.t >> 1) & 1);
+        if (tid == 0) {   // prefetch the next chunk into the buffer the previous chunk was read from
+            if (q + 1 < pp.nchunks) coop_pipe_issue(pp, q + 1, b ^ 1);
+            else if (wrap) coop_pipe_issue(pp, 0, b ^ 1);
+        }
+        RowView rd;
+        rd.p = pp.buf[b] - o; rd.stride = (e - o) | 1;
+        coop_stage<L, MODE>(w, bd, rd, mu, wslot, c0, o, e, tid, nth, fric);
+        ctx.block_sync();
+        pp.t += 1;
+    }
+    pp.primed = wrap;
+}
+
+// One work item, start to finish, by one CTA: bodies and impulses in shared memory; the constant
+// constraint rows resident in shared memory when they fit, else streamed from the L2 pool through the
+// staging pipeline (L lanes / constraint).
 template <int L>
-RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBodies& bd, const CoopStore& cs, int item, vec3 gravity) {
+RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, int smem_floats, CoopPipe& pp, int item, vec3 gravity) {
     const Params& P = w.prm;
     State* st = w.st;
     const int buf = st->cur;
     const int b0 = w.item_body_start[item], b1 = w.item_body_start[item + 1];
     const int c0 = w.item_cons_start[item], n = w.item_cons_start[item + 1] - c0;
     const int tid = ctx.btid, nth = ctx.bsize;
-    // The non-empty colour stages of this item, staged once (no HBM/L2 reads between sweeps).
+    const CoopPlan plan = coop_plan(smem_floats, b1 - b0, n);
+    const bool resident = plan.resident != 0;
+    const int wslot = b1 - b0;
+    SmemBodies bd;
+    bd.s = smem;
+    RowView mu;     // impulses
+    mu.p = reinterpret_cast<float4*>(smem + plan.body_slots * SB_STRIDE); mu.stride = plan.mstride;
+    float4* cbase = mu.p + MR_COUNT * plan.mstride;
+    RowView res;    // the resident constant rows
+    res.p = cbase; res.stride = plan.stride;
+    // The non-empty colour stages of this item, staged once (no HBM/L2 reads between sweeps), and for
+    // streamed items the chunks they are cut into.
     RB_SHARED int s_stage[NUM_COLORS + 2];
     RB_SHARED int s_nstages;
+    RB_SHARED int s_chunk[COOP_MAX_CHUNKS + 1];
+    RB_SHARED int s_nchunks;
+    pp.buf[0] = cbase; pp.buf[1] = cbase + (size_t)COOP_ROWS * plan.stride;
+    pp.pool = w.coop_pool + (size_t)2 * COOP_ROWS * c0; pp.chunk = s_chunk; pp.primed = false;
     if (tid == 0) {
         const int* coff = w.item_color_off + (size_t)item * (NUM_COLORS + 1);
         const int ncol = st->nused_colors;
@@ -1163,42 +1280,48 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBod
         for (int c = 0; c < ncol; ++c)
             if (coff[c + 1] > coff[c]) s_stage[ns++] = coff[c] | (coff[c + 1] << 16);
         s_nstages = ns;
+        int nq = 0;
+        if (!resident)
+            for (int c = 0; c < ns; ++c)
+                for (int o = s_stage[c] & 0xffff; o < (s_stage[c] >> 16); o += plan.stride) s_chunk[nq++] = o;
+        s_chunk[nq] = n;
+        s_nchunks = nq;
         w.item_flags[item] = 0;
-        bd.set_vel(COOP_WORLD_SLOT, zero3(), zero3());
-        bd.set_xf(COOP_WORLD_SLOT, pident());
-        bd.set_mass(COOP_WORLD_SLOT, sym_zero(), zero3());
+        bd.set_vel(wslot, zero3(), zero3());
+        bd.set_xf(wslot, pident());
+        bd.set_mass(wslot, sym_zero(), zero3());
+        if (!coop_plan(w.coop_small_floats, b1 - b0, n).resident) st->need_big = 1;
+        atomic_add(resident ? &st->coop_resident : &st->coop_streamed, 1);
     }
     for (int l = b0 + tid; l < b1; l += nth) body_init(w, bd, w.item_bodies[l], l - b0, gravity);
     ctx.block_sync();
     const int nstages = s_nstages;
-    for (int s = tid; s < n; s += nth) {   // S2 generate, one thread per constraint, into shared memory
+    pp.nchunks = s_nchunks;
+    for (int s = tid; s < n; s += nth) {   // S2 generate, one thread per constraint
         Cons c;
         cons_generate(w, bd, c0 + s, buf, item, c);
-        coop_put(cs, bd, s, c);
+        coop_put(resident ? res : coop_slot_rows(pp, s), mu, bd, s, c);
     }
+    if (!resident) fence_async_proxy();   // pool rows written above are read by bulk copies from here on
     ctx.block_sync();
+    const bool bouncy_item = w.item_flags[item] != 0;
+    const bool warm = P.warmstart_coeff != 0.0f;
+    const int total_sweeps = P.num_substeps * ((warm ? 1 : 0) + P.num_pgs + P.num_relax) + (bouncy_item ? 1 : 0);
+    int done = 0;
     for (int sub = 0; sub < P.num_substeps; ++sub) {
         for (int l = b0 + tid; l < b1; l += nth) body_increment(w, bd, w.item_bodies[l], l - b0);
-        ctx.block_sync();
-        if (P.warmstart_coeff != 0.0f) {
-            for (int c = 0; c < nstages; ++c) {
-                const int ae = s_stage[c];
-                coop_stage<L, MODE_WARMSTART>(w, bd, cs, c0, ae & 0xffff, ae >> 16, tid, nth, false);
-                ctx.block_sync();
-            }
-        } else {
+        if (warm) {
+            ctx.block_sync();
+            ++done;
+            coop_sweep<L, MODE_WARMSTART>(ctx, w, bd, res, mu, resident, pp, s_stage, nstages, wslot, c0, false, done < total_sweeps);
+        } else {   // bank the impulses without applying them
             for (int s = tid; s < n; s += nth) {
-#pragma unroll
-                for (int k = 0; k < MAX_PTS; ++k) {
-                    float4& i4 = cs.pp(PR4_ITD1I, k, s);
-                    float4& a4 = cs.pp(PR4_ITD2A, k, s);
-                    a4.w = a4.w + i4.w;
-                    i4.w = i4.w * 0.0f;
-                }
-                float4 ti = cs.pc(CR4_TI, s), wi = cs.pc(CR4_WI, s);
+                float4 im = mu.mr(MR_IMP, s), ac = mu.mr(MR_ACC, s), ti = mu.mr(MR_TI, s), wi = mu.mr(MR_WI, s);
+                ac.x = ac.x + im.x; ac.y = ac.y + im.y; ac.z = ac.z + im.z; ac.w = ac.w + im.w;
+                im.x = im.x * 0.0f; im.y = im.y * 0.0f; im.z = im.z * 0.0f; im.w = im.w * 0.0f;
                 ti.z = ti.z + ti.x; ti.w = ti.w + ti.y; ti.x = ti.x * 0.0f; ti.y = ti.y * 0.0f;
                 wi.y = wi.y + wi.x; wi.x = wi.x * 0.0f;
-                cs.pc(CR4_TI, s) = ti; cs.pc(CR4_WI, s) = wi;
+                mu.mr(MR_IMP, s) = im; mu.mr(MR_ACC, s) = ac; mu.mr(MR_TI, s) = ti; mu.mr(MR_WI, s) = wi;
             }
             ctx.block_sync();
         }
@@ -1207,12 +1330,9 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBod
             const int iters = relax ? P.num_relax : P.num_pgs;
             const bool fric = relax || P.friction_in_bias || P.num_relax == 0;
             for (int it = 0; it < iters; ++it) {
-                for (int c = 0; c < nstages; ++c) {
-                    const int ae = s_stage[c];
-                    if (relax) coop_stage<L, MODE_RELAX>(w, bd, cs, c0, ae & 0xffff, ae >> 16, tid, nth, fric);
-                    else coop_stage<L, MODE_BIASED>(w, bd, cs, c0, ae & 0xffff, ae >> 16, tid, nth, fric);
-                    ctx.block_sync();
-                }
+                ++done;
+                if (relax) coop_sweep<L, MODE_RELAX>(ctx, w, bd, res, mu, resident, pp, s_stage, nstages, wslot, c0, fric, done < total_sweeps);
+                else coop_sweep<L, MODE_BIASED>(ctx, w, bd, res, mu, resident, pp, s_stage, nstages, wslot, c0, fric, done < total_sweeps);
             }
             if (!relax) {
                 for (int l = b0 + tid; l < b1; l += nth) body_integrate(w, bd, w.item_bodies[l], l - b0);
@@ -1220,16 +1340,10 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, const SmemBod
             }
         }
     }
-    if (w.item_flags[item]) {
-        for (int c = 0; c < nstages; ++c) {
-            const int ae = s_stage[c];
-            coop_stage<L, MODE_RESTITUTION>(w, bd, cs, c0, ae & 0xffff, ae >> 16, tid, nth, false);
-            ctx.block_sync();
-        }
-    }
+    if (bouncy_item) coop_sweep<L, MODE_RESTITUTION>(ctx, w, bd, res, mu, resident, pp, s_stage, nstages, wslot, c0, false, false);
     for (int s = tid; s < n; s += nth) {
         Cons c;
-        coop_get_for_writeback(cs, s, c);
+        coop_get_for_writeback(resident ? res : coop_slot_rows(pp, s), mu, s, c);
         cons_writeback(w, c0 + s, buf, c);
     }
     for (int l = b0 + tid; l < b1; l += nth) body_writeback(w, bd, w.item_bodies[l], l - b0);

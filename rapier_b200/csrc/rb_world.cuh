@@ -74,6 +74,8 @@ struct Params {  // IntegrationParameters + derived per-substep coefficients (co
 };
 
 // Device-side scalars (one struct in HBM, mirrored to pinned host memory on demand).
+constexpr int ORDER_BUCKETS = 4096;   // item cost classes of the launch-order counting sort
+
 struct State {
     int cur;               // which PairBuf is live (0/1)
     int npairs;
@@ -90,7 +92,11 @@ struct State {
     int nislands;
     int bp_ran, sched_ran; // set when the corresponding section ran in the last step
     int any_bouncy;
-    int pad[14];
+    int need_big;          // some shared-memory item does not fit resident in the small launch shape (accumulated per step)
+    int coop_streamed, coop_resident;   // shared-memory items of the last step: streamed from the pool / resident
+    int norder;            // entries of World::item_order (non-empty items 1.., by decreasing cost)
+    int cursor_rest, cursor_coop;   // dynamic work queues of the two kernels over item_order
+    int pad[8];
 };
 
 struct PairBuf {
@@ -160,6 +166,8 @@ struct World {
     int* cons_pair_tmp;               // [cons_cap] pair index grouped by item (unsorted)
     int* cons_pair;                   // [cons_cap] pair index in schedule order
     int* item_color_off;              // [item_cap][NUM_COLORS + 1] offsets relative to item_cons_start
+    int* item_order;                  // [item_cap] non-empty items 1.., most expensive first (launch order of the solve CTAs)
+    int* order_hist;                  // [2 * ORDER_BUCKETS + 1] counting-sort scratch of item_order
     int* color_count;                 // [NUM_COLORS] global histogram
     int* color_pos;                   // [NUM_COLORS] stage position of a colour, -1 unused
     int* joint_tmp;                   // [joint_cap]
@@ -169,6 +177,10 @@ struct World {
     // ---- constraints ----
     int4* cons_hdr;                   // [cons_cap] pair, id1, id2, num_contacts (ids item-local or global)
     float4* cons;                     // [CR_ROWS][cons_cap]
+    float4* coop_pool;                // [2 * COOP_ROWS * cons_cap] L2-resident constant rows of streamed items, blocked by chunk
+    int coop_smem_floats;             // dynamic shared memory of this step's k_solve_coop launch
+    int coop_small_floats;            // ... of the small launch shape (2 CTAs / SM)
+    int* host_hint;                   // pinned, host-mapped: last step's State::need_big
     // ---- joints ----
     int4* j_info;                     // body1, body2, locked_axes, colour
     float4 *j_f1_t, *j_f1_q, *j_f2_t, *j_f2_q;   // local frames

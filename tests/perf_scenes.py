@@ -33,7 +33,7 @@ for name, make, steps in CONFIGS:
     t1 = time.perf_counter(); o.step(5); cpu = 5 / (time.perf_counter() - t1)
     st = w.debug_read("state", np.int32)
     rec = dict(scene=name, bodies=c["num_bodies"], pairs=c["num_pairs"], manifolds=c["num_active_manifolds"], joints=c["num_joints"],
-               items=int(st[7]), colors=c["num_colors"], large_bodies=int(st[12]), first3_steps_bit_exact=bool(exact),
+               items=int(st[7]), streamed=int(st[19]), resident=int(st[20]), colors=c["num_colors"], large_bodies=int(st[12]), first3_steps_bit_exact=bool(exact),
                steps_per_s=steps / wall, collide_ms=c["collision_detection_ms"], solve_ms=c["solver_ms"], cpu_port_steps_per_s_16thr=cpu)
     print(json.dumps(rec), flush=True)
     out.append(rec)

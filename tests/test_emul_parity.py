@@ -34,6 +34,22 @@ def test_emulated_kernels_match_oracle_bit_for_bit(name, make, steps, every):
             assert is_exact(d), f"{name}: step {i}: {d}"
 
 
+@pytest.mark.parametrize("smem_floats", [8000, 12000])
+def test_emulated_streaming_pipeline_matches_oracle(monkeypatch, smem_floats):
+    """Items whose constraints do not fit the (here: artificially small) shared memory are streamed
+    from the pool through the two-buffer staging pipeline; results must not change."""
+    monkeypatch.setenv("RB_EMU_COOP_SMEM_FLOATS", str(smem_floats))
+    scene = scenes.pyramids(2, 2, 10)
+    w = PhysicsWorld(scene, _lib=emul_lib.lib())
+    o = oracle_lib.OracleWorld(scene)
+    for i in range(12):
+        w.step()
+        o.step()
+        assert is_exact(compare_worlds(w, o)), f"step {i}"
+    st = w.debug_read("state", np.int32)
+    assert st[19] == 4, "the four pyramids must have taken the streaming path"
+
+
 def test_empty_and_ragged_scenes():
     """Edge cases: no bodies, bodies without colliders, colliders without contacts."""
     from rapier_b200.sets import ColliderBuilder, RigidBodyBuilder
