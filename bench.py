@@ -130,7 +130,7 @@ def run_reference(args):
 
 def workload_name(scene, replicas):
     base = {"b3d_many_pyramids": "b3d_many_pyramids (reference file examples3d/b3d_many_pyramids.rs: 14x14 pyramids, base 10, 10780 cubes)",
-            "b3d_many_pyramids_80x20": "b3d_many_pyramids (BASELINE label: 80 pyramids x 20 levels, 16800 cubes)"}.get(scene, scene)
+            "b3d_many_pyramids_80x20": "b3d_many_pyramids, BASELINE.json configs[1]: 80 pyramids x 20 levels = pyramids(8, 10, 20) of examples3d/b3d_many_pyramids.rs, 16800 cubes"}.get(scene, scene)
     return base if replicas == 1 else f"{replicas} x {base}, one replica per GPU"
 
 
@@ -140,7 +140,8 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scene", default="b3d_many_pyramids")
+    ap.add_argument("--scene", default="b3d_many_pyramids_80x20",
+                    help="b3d_many_pyramids_80x20 = BASELINE.json configs[1] (headline); b3d_many_pyramids = the reference file's 14x14x10")
     ap.add_argument("--l2", default="flush", choices=["flush", "keep"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     args = ap.parse_args()
@@ -263,10 +264,29 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = a_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else None
     traffic = None
+    st = pipe.debug_read("state", np.int32)
+    kernel_name = "k_solve_coop_big" if int(st[19]) > 0 else "k_solve_coop"   # streamed items => the big launch shape ran
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_solve_coop_dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{kernel_name}_dram_bytes_per_launch:{args.scene}")
     except Exception:
         pass
+
+    # the reference file's own size of the same scene (14 x 14 pyramids of base 10), reported beside the headline
+    other = None
+    if world_size == 1 and args.scene == "b3d_many_pyramids_80x20":
+        del w
+        w2 = PhysicsWorld(scene_for("b3d_many_pyramids", 1), device=local_rank)
+        w2._flush()
+        pipe = w2.physics_pipeline
+        pipe.set_stream(stream.cuda_stream)
+        for _ in range(args.warmup):
+            one_step()
+        torch.cuda.synchronize()
+        k2 = min(args.steps, 100)
+        ms2 = timed_steps(k2)
+        c2 = pipe.counters()
+        other = {"workload": workload_name("b3d_many_pyramids", 1), "value": k2 / (ms2 / 1000.0), "unit": "steps/s",
+                 "ms_per_step": ms2 / k2, "steps": k2, "bodies": c2["num_bodies"] - 1, "manifolds": c2["num_active_manifolds"]}
 
     if rank == 0:
         cpu = None
@@ -299,11 +319,12 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": "k_solve_coop", "kernel_ms": solve_ms, "algorithmic_bytes_per_launch": a_bytes,
+                         "kernel": kernel_name, "kernel_ms": solve_ms, "algorithmic_bytes_per_launch": a_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "note": "algorithmic bytes = streaming model of SURVEY 8(d); the working set is L2/shared-memory resident, see DESIGN.md"},
             "cpu_baseline": cpu,
             "stage_ms": {"collide": prof["collision_detection_ms"], "solve": prof["solver_ms"]},
+            "other_configs": [other] if other else [],
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

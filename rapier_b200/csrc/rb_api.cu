@@ -63,7 +63,7 @@ constexpr int ITEM_SMEM_BYTES = ITEM_MAX_BODIES * SB_STRIDE * 4;
 // islands).  Big: one CTA per SM with all its shared memory, four times the lanes (islands whose
 // constraints are streamed from the L2 pool, or that only fit resident here).
 constexpr int COOP_SMALL_THREADS = 128, COOP_SMALL_SMEM_BYTES = 108 * 1024;
-constexpr int COOP_BIG_THREADS = 384, COOP_BIG_SMEM_BYTES = 220 * 1024;
+constexpr int COOP_BIG_THREADS = 256, COOP_BIG_SMEM_BYTES = 220 * 1024;
 
 struct Grav { float x, y, z; };
 
@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, in
         w.st->coop_resident = 0;
         w.st->cursor_rest = 0;
         w.st->cursor_coop = 0;
+        w.st->cursor_big = 0;
+        w.st->stamp += 1;
     }
     collide_pipeline(ctx, w);
     if (!do_solve) return;
@@ -143,8 +145,10 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, in
 }
 // Shared-memory items: one CTA per item, bodies (and, when they fit, constraints) staged in shared memory,
 // four lanes per constraint (rb_solver.cuh "lane-cooperative path").
-template <int THREADS, int MIN_CTAS>
-__global__ void __launch_bounds__(THREADS, MIN_CTAS) k_solve_coop(World w, Grav g) {
+// `big`: the optional first launch, which takes every shared-memory item; the small launch that always
+// follows takes whatever has not been claimed in this step (so correctness never depends on the hint).
+template <int L>
+__device__ __forceinline__ void solve_coop_items(const World& w, const Grav& g, int smem_floats, bool big) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) unsigned long long s_mbar[2];
     BlockCtx ctx;
@@ -157,20 +161,27 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_solve_coop(World w, Grav 
     CoopPipe pp;
     pp.mbar = s_mbar;
     pp.t = 0;
+    pp.sweep_threads = ctx.bsize;   // (set per item)
     __shared__ int s_next;
-    const int n = w.st->norder;
+    const int n = w.st->norder, stamp = w.st->stamp;
+    int* cursor = big ? &w.st->cursor_big : &w.st->cursor_coop;
     for (;;) {   // dynamic queue over the cost-ordered items
-        if (ctx.btid == 0) s_next = atomicAdd(&w.st->cursor_coop, 1);
+        if (ctx.btid == 0) s_next = atomicAdd(cursor, 1);
         __syncthreads();
         const int k = s_next;
         __syncthreads();
         if (k >= n) break;
         const int item = w.item_order[k];
-        if (!item_is_coop(w, item)) continue;
-        solve_item_coop<4>(ctx, w, smem, w.coop_smem_floats, pp, item, mk3(g.x, g.y, g.z));
+        if (!item_is_coop(w, item) || w.item_done[item] == stamp) continue;
+        solve_item_coop<L>(ctx, w, smem, smem_floats, pp, item, mk3(g.x, g.y, g.z));
+        if (ctx.btid == 0) w.item_done[item] = stamp;
         ctx.block_sync();
     }
 }
+// The two launch shapes (COOP_SMALL_* / COOP_BIG_*): same code, different register budgets.
+__global__ void __launch_bounds__(COOP_SMALL_THREADS, 2) k_solve_coop(World w, Grav g) { solve_coop_items<4>(w, g, COOP_SMALL_SMEM_BYTES / 4, false); }
+template <int THREADS, int L>
+__global__ void __launch_bounds__(THREADS, 1) k_solve_coop_big(World w, Grav g) { solve_coop_items<L>(w, g, COOP_BIG_SMEM_BYTES / 4, true); }
 __global__ void k_init_bodies(World w) {
     GridCtx ctx;
     init_bodies_phase(ctx, w);
@@ -196,6 +207,7 @@ struct RbWorld {
     int collide_blocks = 1, coop_blocks = 1;
     int collide_threads = COLLIDE_THREADS;
     int coop_blocks_big = 1;
+    int big_threads = COOP_BIG_THREADS, big_lanes = 1, sweep_threads = 0;
     int coop_shape = -1;   // RB_COOP_SHAPE debugging override: 0 small, 1 big, -1 automatic
     int* host_hint = nullptr;
     long long kernels = 0, steps = 0;
@@ -443,8 +455,10 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
     W->num_sms = prop.multiProcessorCount;
     if (!prop.cooperativeLaunch) { set_err("device lacks cooperative launch%s", ""); delete W; return nullptr; }
     cudaStreamCreateWithFlags(&W->stream, cudaStreamNonBlocking);
-    cudaFuncSetAttribute(k_solve_coop<COOP_SMALL_THREADS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_SMALL_SMEM_BYTES);
-    cudaFuncSetAttribute(k_solve_coop<COOP_BIG_THREADS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_BIG_SMEM_BYTES);
+    cudaFuncSetAttribute(k_solve_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_SMALL_SMEM_BYTES);
+#define RB_BIG_VARIANTS(X) X(256, 1) X(256, 2)
+#define RB_SET_ATTR(T, LL) cudaFuncSetAttribute(k_solve_coop_big<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_BIG_SMEM_BYTES);
+    RB_BIG_VARIANTS(RB_SET_ATTR)
     if (cudaHostAlloc((void**)&W->host_hint, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { set_err("cudaHostAlloc failed%s", ""); delete W; return nullptr; }
     *W->host_hint = 0;
     cudaFuncSetAttribute(k_collide, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
@@ -452,7 +466,7 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_collide, COLLIDE_THREADS, ITEM_SMEM_BYTES);
     if (occ < 1) { set_err("k_collide cannot be resident%s", ""); delete W; return nullptr; }
     W->collide_blocks = W->num_sms;   // one CTA per SM: the cheapest grid barrier that still covers the chip
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_coop<COOP_SMALL_THREADS, 2>, COOP_SMALL_THREADS, COOP_SMALL_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_coop, COOP_SMALL_THREADS, COOP_SMALL_SMEM_BYTES);
     if (occ < 1) occ = 1;
     W->coop_blocks = W->num_sms * occ;
     W->coop_blocks_big = W->num_sms;
@@ -462,6 +476,9 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
         W->coop_blocks = std::min(W->coop_blocks, envi("RB_COOP_BLOCKS", W->coop_blocks));
         W->collide_threads = std::min(COLLIDE_THREADS, envi("RB_COLLIDE_THREADS", COLLIDE_THREADS));
         W->coop_shape = envi("RB_COOP_SHAPE", -1);
+        W->big_threads = envi("RB_COOP_BIG_THREADS", COOP_BIG_THREADS);
+        W->big_lanes = envi("RB_COOP_BIG_LANES", 1);
+        W->sweep_threads = envi("RB_COOP_SWEEP_THREADS", 0);
     }
 #else
     {   // emulated CTA: shared-memory size of the big launch shape, or a test override that forces streaming
@@ -575,7 +592,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.item_body_start, w.item_cap + 2); ALLOC(w.item_cons_start, w.item_cap + 2); ALLOC(w.item_joint_start, w.item_cap + 2);
     ALLOC(w.item_cursor, 3 * (w.item_cap + 2));
     ALLOC(w.item_flags, w.item_cap + 2);
-    ALLOC(w.item_order, w.item_cap + 2); ALLOC(w.order_hist, 2 * ORDER_BUCKETS + 2);
+    ALLOC(w.item_order, w.item_cap + 2); ALLOC(w.item_done, w.item_cap + 2); ALLOC(w.order_hist, 2 * ORDER_BUCKETS + 2);
     ALLOC(w.item_bodies, NB); ALLOC(w.body_local, NB); ALLOC(w.body_item, NB);
     ALLOC(w.cons_pair_tmp, w.cons_cap); ALLOC(w.cons_pair, w.cons_cap);
     ALLOC(w.item_color_off, (size_t)(w.item_cap + 1) * (NUM_COLORS + 1));
@@ -586,7 +603,10 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.coop_pool, (size_t)2 * COOP_ROWS * w.cons_cap);
     w.host_hint = W->host_hint;
     w.coop_small_floats = COOP_SMALL_SMEM_BYTES / 4;
-    w.coop_smem_floats = w.coop_small_floats;
+    w.coop_sweep_threads = W->sweep_threads;
+#if !RB_DEVICE_BUILD
+    w.coop_small_floats = std::min(w.coop_small_floats, W->emu_coop_floats);   // the emulated CTA must fit what it is given
+#endif
     ALLOC(w.j_info, NJ); ALLOC(w.j_f1_t, NJ); ALLOC(w.j_f1_q, NJ); ALLOC(w.j_f2_t, NJ); ALLOC(w.j_f2_q, NJ);
     ALLOC(w.j_soft, NJ); ALLOC(w.j_impulses, (size_t)NJ * 6);
     ALLOC(w.j_rows, (size_t)JR_ROWS * 6 * NJ); ALLOC(w.j_sched_ids, NJ);
@@ -787,12 +807,15 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         int do_solve = 1;
         // launch shape of k_solve_coop for this step (both kernels must agree on it): device hint of the last step
         const bool big = W->coop_shape >= 0 ? W->coop_shape == 1 : (*(volatile int*)W->host_hint != 0);
-        W->w.coop_smem_floats = (big ? COOP_BIG_SMEM_BYTES : COOP_SMALL_SMEM_BYTES) / 4;
         void* a1[] = {(void*)&W->w, (void*)&g, (void*)&do_solve};
         CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, ITEM_SMEM_BYTES, W->stream));
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 1], W->stream));
-        if (big) k_solve_coop<COOP_BIG_THREADS, 1><<<W->coop_blocks_big, COOP_BIG_THREADS, COOP_BIG_SMEM_BYTES, W->stream>>>(W->w, g);
-        else k_solve_coop<COOP_SMALL_THREADS, 2><<<W->coop_blocks, COOP_SMALL_THREADS, COOP_SMALL_SMEM_BYTES, W->stream>>>(W->w, g);
+        if (big) {
+#define RB_LAUNCH_BIG(T, LL) if (W->big_threads == T && W->big_lanes == LL) k_solve_coop_big<T, LL><<<W->coop_blocks_big, T, COOP_BIG_SMEM_BYTES, W->stream>>>(W->w, g);
+            RB_BIG_VARIANTS(RB_LAUNCH_BIG)
+            W->kernels += 1;
+        }
+        k_solve_coop<<<W->coop_blocks, COOP_SMALL_THREADS, COOP_SMALL_SMEM_BYTES, W->stream>>>(W->w, g);
         CK(cudaGetLastError());
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 2], W->stream));
         W->kernels += 2;
@@ -834,11 +857,11 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         BlockExec bex;
         bex.c = &bctx;
         int n = W->w.st->nitems;
-        W->w.coop_smem_floats = W->emu_coop_floats;
         CoopPipe pp;
         unsigned long long mbar[2] = {0, 0};
         pp.mbar = mbar;
         pp.t = 0;
+        pp.sweep_threads = 1;
         for (int k = 0; k < W->w.st->norder; ++k) {
             const int item = W->w.item_order[k];
             if (item_is_coop(W->w, item))

@@ -46,6 +46,7 @@ RB_HD float safe_inv(float x) { return (x >= -1.0e-20f && x <= 1.0e-20f) ? 0.0f 
 RB_HD float inv_exact0(float x) { return x == 0.0f ? 0.0f : 1.0f / x; }
 RB_HD float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 RB_HD int min2i(int a, int b) { return a < b ? a : b; }
+RB_HD int max2i(int a, int b) { return a > b ? a : b; }
 RB_HD float max2(float a, float b) { return a > b ? a : b; }
 RB_HD float min2(float a, float b) { return a < b ? a : b; }
 RB_HD float copysign1(float s) { return copysignf(1.0f, s); }

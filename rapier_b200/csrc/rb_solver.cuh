@@ -102,6 +102,7 @@ RB_HD float bouncy(float restitution, bool is_new) {  // contact_pair.rs:773-779
 // its constraint in this struct for the whole step; the streaming path loads / stores it per sweep.
 struct Cons {
     int id1, id2, nc;
+    int pair, cid[MAX_PTS];       // pair-table row and per-point contact slot (writeback targets)
     vec3 dir; float fric;         // dir1, friction limit
     vec3 t1; float wr;            // tangent1, twist effective mass
     vec3 dp1[MAX_PTS]; float r[MAX_PTS];       // lever arms body 1, projected masses
@@ -181,14 +182,15 @@ RB_HD void cons_generate(const World& w, const B& bd, int q, int buf, int item, 
     float tws = 0.0f, tgs0 = 0.0f, tgs1 = 0.0f;
     vec3 pts[MAX_PTS];
     bool any_seed = false;
-    c.id1 = id1; c.id2 = id2; c.nc = count;
+    c.id1 = id1; c.id2 = id2; c.nc = count; c.pair = p;
     c.dir = dir; c.fric = nrm.w; c.t1 = t1;
 #pragma unroll
     for (int k = 0; k < MAX_PTS; ++k) {
-        c.imp[k] = 0.0f; c.acc[k] = 0.0f; c.twd[k] = 0.0f;
+        c.imp[k] = 0.0f; c.acc[k] = 0.0f; c.twd[k] = 0.0f; c.cid[k] = 0;
         if (k < count) {
             float4 a1 = prow(w, buf, PR_A1 + k, p), a2 = prow(w, buf, PR_A2 + k, p);
             int cid = as_int(a1.w);
+            c.cid[k] = cid;
             float4 pd = prow(w, buf, PR_PD + cid, p);
             vec3 wt = xyz(prow(w, buf, PR_TW + cid, p));
             vec3 dp1 = xyz(prow(w, buf, PR_DP1 + cid, p)), dp2 = xyz(prow(w, buf, PR_DP2 + cid, p));
@@ -469,8 +471,9 @@ RB_HD void cons_sweep(const World& w, const B& bd, int q, Cons& c, int mode, boo
 RB_HD float canon0(float x) { return x == 0.0f ? 0.0f : x; }
 
 // S10: contact_with_twist_friction.rs:783-829
-RB_HD void cons_writeback(const World& w, int q, int buf, const Cons& c) {
-    const int p = w.cons_hdr[q].x;
+// `ids_in_c`: c.pair / c.cid are valid (shared-memory path); otherwise they are fetched from the schedule rows.
+RB_HD void cons_writeback(const World& w, int q, int buf, const Cons& c, bool ids_in_c = false) {
+    const int p = ids_in_c ? c.pair : w.cons_hdr[q].x;
     vec3 t2 = cross3(c.dir, c.t1);
     float a0 = canon0(c.ti0), a1 = canon0(c.ti1);
     vec3 tw = c.t1 * a0 + t2 * a1;
@@ -479,12 +482,11 @@ RB_HD void cons_writeback(const World& w, int q, int buf, const Cons& c) {
 #pragma unroll
     for (int k = 0; k < MAX_PTS; ++k) {
         if (k < c.nc) {
-            int cid = as_int(crow(w, CR_LP2 + k, q).w);
-            float4 pd = prow(w, buf, PR_PD + cid, p);
-            pd.y = canon0(c.imp[k]);
-            pd.x = canon0(c.acc[k] + c.imp[k]);
-            pd.z = twist;
-            prow(w, buf, PR_PD + cid, p) = pd;
+            int cid = ids_in_c ? c.cid[k] : as_int(crow(w, CR_LP2 + k, q).w);
+            float* pd = &prow(w, buf, PR_PD + cid, p).x;   // .w (feature id) stays as it is: no read needed
+            pd[0] = canon0(c.acc[k] + c.imp[k]);
+            pd[1] = canon0(c.imp[k]);
+            pd[2] = twist;
             prow(w, buf, PR_TW + cid, p) = f4(tw, 0.0f);
         }
     }
@@ -893,7 +895,8 @@ enum CoopPointRow { PR4_TD1R = 0,   // torque_dir1 xyz, r (projected mass)
                     PR4_TD2D,       // torque_dir2 xyz, dist0
                     PR4_ITD1I,      // ii1*torque_dir1 xyz, id1 bits
                     PR4_ITD2A,      // ii2*torque_dir2 xyz, id2 bits
-                    PR4_LP1, PR4_LP2,   // builder anchors
+                    PR4_LP1,        // builder anchor on body 1 (body-local) xyz, contact slot (bits)
+                    PR4_LP2,        // builder anchor on body 2 xyz, pair-table row (bits)
                     PR4_COUNT };
 // per-constraint float4 rows
 enum CoopConsRow { CR4_DIRF = 0,    // dir1 xyz, friction
@@ -908,6 +911,7 @@ enum CoopMutRow { MR_IMP = 0,       // normal impulses of the 4 points
                   MR_ACC,           // their accumulators
                   MR_TI,            // tangent impulse xy, accumulators zw
                   MR_WI,            // twist impulse, accumulator
+                  MR_DIST,          // separation of the 4 points at the poses of the last position integration
                   MR_COUNT };
 constexpr int COOP_MIN_CHUNK = 8;      // smallest streaming chunk worth running (slots)
 constexpr int COOP_MAX_CHUNKS = 640;   // chunk table of a streamed item (colour stages + splits of long stages)
@@ -984,8 +988,8 @@ RB_HD void coop_put(const RowView& cs, const RowView& mu, const B& bd, int s, co
         cs.pp(PR4_TD2D, k, s) = f4(pj.td2, d0);
         cs.pp(PR4_ITD1I, k, s) = f4(pj.itd1, as_float_i(c.id1));
         cs.pp(PR4_ITD2A, k, s) = f4(pj.itd2, as_float_i(c.id2));
-        cs.pp(PR4_LP1, k, s) = f4(l1, 0.0f);
-        cs.pp(PR4_LP2, k, s) = f4(l2, 0.0f);
+        cs.pp(PR4_LP1, k, s) = f4(l1, as_float_i(c.cid[k]));
+        cs.pp(PR4_LP2, k, s) = f4(l2, as_float_i(c.pair));
     }
     const vec3 t2 = cross3(c.dir, c.t1);
     coop_put_jac(cs, s, friction_jac(g1, g2, c.dir, c.t1, t2, c.tdp1, c.tdp2));
@@ -997,10 +1001,21 @@ RB_HD void coop_put(const RowView& cs, const RowView& mu, const B& bd, int s, co
     mu.mr(MR_ACC, s) = make_float4(c.acc[0], c.acc[1], c.acc[2], c.acc[3]);
     mu.mr(MR_TI, s) = make_float4(c.ti0, c.ti1, c.ta0, c.ta1);
     mu.mr(MR_WI, s) = make_float4(c.wi, c.wa, 0.0f, 0.0f);
+    // separation at the initial poses: what the first biased sweep needs (later ones reuse the relax sweep's)
+    float ds[MAX_PTS];
+#pragma unroll
+    for (int k = 0; k < MAX_PTS; ++k) {
+        ds[k] = 0.0f;
+        if (k < c.nc) ds[k] = c.dist0[k] + dot3(xform(g1.p, c.lp1[k]) - xform(g2.p, c.lp2[k]), c.dir);
+    }
+    mu.mr(MR_DIST, s) = make_float4(ds[0], ds[1], ds[2], ds[3]);
 }
 RB_HD void coop_get_for_writeback(const RowView& cs, const RowView& mu, int s, Cons& c) {
     c.nc = as_int(cs.pc(CR4_TR, s).w);
     c.dir = xyz(cs.pc(CR4_DIRF, s)); c.t1 = xyz(cs.pc(CR4_T1W, s));
+    c.pair = as_int(cs.pp(PR4_LP2, 0, s).w);
+#pragma unroll
+    for (int k = 0; k < MAX_PTS; ++k) c.cid[k] = as_int(cs.pp(PR4_LP1, k, s).w);
     const float4 im = mu.mr(MR_IMP, s), ac = mu.mr(MR_ACC, s), ti = mu.mr(MR_TI, s);
     c.imp[0] = im.x; c.imp[1] = im.y; c.imp[2] = im.z; c.imp[3] = im.w;
     c.acc[0] = ac.x; c.acc[1] = ac.y; c.acc[2] = ac.z; c.acc[3] = ac.w;
@@ -1054,7 +1069,7 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const RowView& cs, c
         BodyState g1, g2;
         g1.lin = bd.lin(gi1); g1.ang = bd.ang(gi1); g1.im = bd.im(gi1);
         g2.lin = bd.lin(gi2); g2.ang = bd.ang(gi2); g2.im = bd.im(gi2);
-        if (MODE == MODE_BIASED || MODE == MODE_RELAX) { g1.p = bd.xf(gi1); g2.p = bd.xf(gi2); }
+        if (MODE == MODE_RELAX || (MODE == MODE_BIASED && solve_friction)) { g1.p = bd.xf(gi1); g2.p = bd.xf(gi2); }   // (friction in the bias pass reads the poses)
         vec3 v1 = g1.lin, w1 = g1.ang, v2 = g2.lin, w2 = g2.ang;
         const vec3 dir = xyz(dirf), t1 = xyz(t1w);
         const vec3 t2 = cross3(dir, t1);
@@ -1066,7 +1081,7 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const RowView& cs, c
 
         // ---- parallel part: every lane prepares its own point(s) ----
         PointPre pre[PPL];
-        float imp[PPL], acc[PPL], r[PPL], seed[PPL];
+        float imp[PPL], acc[PPL], r[PPL], seed[PPL], dist_new[PPL];
         bool own_seed = false;
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
@@ -1074,11 +1089,28 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const RowView& cs, c
             const float4 a1 = cs.pp(PR4_TD1R, k, s), a2 = cs.pp(PR4_TD2D, k, s), b1 = cs.pp(PR4_ITD1I, k, s), b2 = cs.pp(PR4_ITD2A, k, s);
             pre[j].td1 = xyz(a1); pre[j].td2 = xyz(a2); pre[j].itd1 = xyz(b1); pre[j].itd2 = xyz(b2);
             r[j] = a1.w; imp[j] = mu.mf(MR_IMP, k, s); acc[j] = mu.mf(MR_ACC, k, s); seed[j] = 0.0f;
-            pre[j].rhs = 0.0f; pre[j].cfm = 1.0f;
+            pre[j].rhs = 0.0f; pre[j].cfm = 1.0f; dist_new[j] = 0.0f;
             if (k < nc) {
-                if (MODE == MODE_BIASED || MODE == MODE_RELAX)
-                    point_rhs(P, g1, g2, dir, xyz(cs.pp(PR4_LP1, k, s)), xyz(cs.pp(PR4_LP2, k, s)), a2.w, MODE, cfm_soft, erp, pre[j].rhs,
-                              pre[j].cfm);
+                // point_rhs.  Poses only change in the position integration, so the separation the relax sweep
+                // evaluates is kept for the biased sweep of the next substep (the first one uses generate's).
+                if (MODE == MODE_RELAX) {
+                    vec3 p1 = xform(g1.p, xyz(cs.pp(PR4_LP1, k, s)));
+                    vec3 p2 = xform(g2.p, xyz(cs.pp(PR4_LP2, k, s)));
+                    const float dist = a2.w + dot3(p1 - p2, dir);
+                    dist_new[j] = dist;
+                    pre[j].rhs = max2(dist, 0.0f) * P.sub_inv_dt;
+                }
+                if (MODE == MODE_BIASED) {
+                    float dist = mu.mf(MR_DIST, k, s);
+                    if (P.num_relax == 0) {   // no relax sweep refreshes the cache: evaluate here
+                        const pose x1 = bd.xf(gi1), x2 = bd.xf(gi2);
+                        dist = a2.w + dot3(xform(x1, xyz(cs.pp(PR4_LP1, k, s))) - xform(x2, xyz(cs.pp(PR4_LP2, k, s))), dir);
+                    }
+                    float rhs = max2(dist, 0.0f) * P.sub_inv_dt;
+                    rhs = rhs + clampf(dist * erp, -P.max_corrective_velocity, 0.0f);
+                    pre[j].cfm = dist <= 0.0f ? cfm_soft : 1.0f;
+                    pre[j].rhs = rhs;
+                }
                 if (MODE == MODE_RESTITUTION) {
                     seed[j] = crow(w, CR_LP1 + k, q0 + s).w;
                     own_seed = own_seed || seed[j] < 0.0f;
@@ -1150,6 +1182,7 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const RowView& cs, c
                 if (k < nc) {
                     mu.mf(MR_IMP, k, s) = imp[j];
                     if (MODE == MODE_WARMSTART) mu.mf(MR_ACC, k, s) = acc[j];
+                    if (MODE == MODE_RELAX) mu.mf(MR_DIST, k, s) = dist_new[j];
                 }
             }
             if (sub == 0) {
@@ -1172,7 +1205,7 @@ RB_HD bool item_is_coop(const World& w, int item) {
     const int* coff = w.item_color_off + (size_t)item * (NUM_COLORS + 1);
     const bool has_ovf = ovf >= 0 && coff[ovf + 1] > coff[ovf];
     return item > 0 && njoints == 0 && !has_ovf && ncons < 65536 && w.item_cons_start[item + 1] <= w.cons_cap &&
-           coop_plan(w.coop_smem_floats, nbod, ncons).ok;
+           coop_plan(w.coop_small_floats, nbod, ncons).ok;
 }
 
 // Streaming pipeline of one CTA: two shared-memory staging buffers filled by bulk (TMA) copies from the
@@ -1188,6 +1221,7 @@ struct CoopPipe {
     const int* chunk;           // [nchunks + 1] first slot of every chunk (shared memory)
     int nchunks;
     unsigned t;
+    int sweep_threads;          // threads that take part in the sweeps (a multiple of the warp size, <= block size)
     bool primed;                // the chunk the next sweep starts with is already in flight
 };
 RB_HD RowView coop_chunk_rows(const CoopPipe& pp, int q) {   // pool rows of chunk q, indexed by item slot
@@ -1217,11 +1251,11 @@ RB_HD void coop_pipe_issue(const CoopPipe& pp, int q, int b) {   // one thread: 
 template <int L, int MODE>
 RB_PHASE void coop_sweep(const BlockCtx& ctx, const World& w, const SmemBodies& bd, const RowView& res, const RowView& mu, bool resident,
                          CoopPipe& pp, const int* s_stage, int nstages, int wslot, int c0, bool fric, bool wrap) {
-    const int tid = ctx.btid, nth = ctx.bsize;
+    const int tid = ctx.btid, nth = pp.sweep_threads;   // warps beyond the sweep width only take part in the barriers
     if (resident) {
         for (int c = 0; c < nstages; ++c) {
             const int ae = s_stage[c];
-            coop_stage<L, MODE>(w, bd, res, mu, wslot, c0, ae & 0xffff, ae >> 16, tid, nth, fric);
+            if (tid < nth) coop_stage<L, MODE>(w, bd, res, mu, wslot, c0, ae & 0xffff, ae >> 16, tid, nth, fric);
             ctx.block_sync();
         }
         return;
@@ -1237,7 +1271,7 @@ RB_PHASE void coop_sweep(const BlockCtx& ctx, const World& w, const SmemBodies& 
         }
         RowView rd;
         rd.p = pp.buf[b] - o; rd.stride = (e - o) | 1;
-        coop_stage<L, MODE>(w, bd, rd, mu, wslot, c0, o, e, tid, nth, fric);
+        if (tid < nth) coop_stage<L, MODE>(w, bd, rd, mu, wslot, c0, o, e, tid, nth, fric);
         ctx.block_sync();
         pp.t += 1;
     }
@@ -1271,6 +1305,7 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, 
     RB_SHARED int s_nstages;
     RB_SHARED int s_chunk[COOP_MAX_CHUNKS + 1];
     RB_SHARED int s_nchunks;
+    RB_SHARED int s_width;
     pp.buf[0] = cbase; pp.buf[1] = cbase + (size_t)COOP_ROWS * plan.stride;
     pp.pool = w.coop_pool + (size_t)2 * COOP_ROWS * c0; pp.chunk = s_chunk; pp.primed = false;
     if (tid == 0) {
@@ -1280,6 +1315,13 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, 
         for (int c = 0; c < ncol; ++c)
             if (coff[c + 1] > coff[c]) s_stage[ns++] = coff[c] | (coff[c + 1] << 16);
         s_nstages = ns;
+        // sweep width: enough lanes for the longest colour stage in one pass, at least 4 warps; the other warps
+        // of the CTA only help with generation, integration and writeback (fewer warps = shorter issue queues)
+        int longest = 0;
+        for (int c = 0; c < ns; ++c) longest = max2i(longest, (s_stage[c] >> 16) - (s_stage[c] & 0xffff));
+        int width = (longest * L + 31) & ~31;
+        if (w.coop_sweep_threads > 0) width = w.coop_sweep_threads;
+        s_width = min2i(nth, max2i(width, 128));
         int nq = 0;
         if (!resident)
             for (int c = 0; c < ns; ++c)
@@ -1297,6 +1339,7 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, 
     ctx.block_sync();
     const int nstages = s_nstages;
     pp.nchunks = s_nchunks;
+    pp.sweep_threads = s_width;
     for (int s = tid; s < n; s += nth) {   // S2 generate, one thread per constraint
         Cons c;
         cons_generate(w, bd, c0 + s, buf, item, c);
@@ -1344,7 +1387,7 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, 
     for (int s = tid; s < n; s += nth) {
         Cons c;
         coop_get_for_writeback(resident ? res : coop_slot_rows(pp, s), mu, s, c);
-        cons_writeback(w, c0 + s, buf, c);
+        cons_writeback(w, c0 + s, buf, c, true);
     }
     for (int l = b0 + tid; l < b1; l += nth) body_writeback(w, bd, w.item_bodies[l], l - b0);
 }

@@ -95,8 +95,9 @@ struct State {
     int need_big;          // some shared-memory item does not fit resident in the small launch shape (accumulated per step)
     int coop_streamed, coop_resident;   // shared-memory items of the last step: streamed from the pool / resident
     int norder;            // entries of World::item_order (non-empty items 1.., by decreasing cost)
-    int cursor_rest, cursor_coop;   // dynamic work queues of the two kernels over item_order
-    int pad[8];
+    int cursor_rest, cursor_coop, cursor_big;   // dynamic work queues of the kernels over item_order
+    int stamp;             // step counter (claims in World::item_done)
+    int pad[6];
 };
 
 struct PairBuf {
@@ -166,6 +167,7 @@ struct World {
     int* cons_pair_tmp;               // [cons_cap] pair index grouped by item (unsorted)
     int* cons_pair;                   // [cons_cap] pair index in schedule order
     int* item_color_off;              // [item_cap][NUM_COLORS + 1] offsets relative to item_cons_start
+    int* item_done;                   // [item_cap] stamp of the step in which a shared-memory kernel claimed the item
     int* item_order;                  // [item_cap] non-empty items 1.., most expensive first (launch order of the solve CTAs)
     int* order_hist;                  // [2 * ORDER_BUCKETS + 1] counting-sort scratch of item_order
     int* color_count;                 // [NUM_COLORS] global histogram
@@ -178,8 +180,8 @@ struct World {
     int4* cons_hdr;                   // [cons_cap] pair, id1, id2, num_contacts (ids item-local or global)
     float4* cons;                     // [CR_ROWS][cons_cap]
     float4* coop_pool;                // [2 * COOP_ROWS * cons_cap] L2-resident constant rows of streamed items, blocked by chunk
-    int coop_smem_floats;             // dynamic shared memory of this step's k_solve_coop launch
-    int coop_small_floats;            // ... of the small launch shape (2 CTAs / SM)
+    int coop_small_floats;            // dynamic shared memory of the small launch shape (2 CTAs / SM), which must fit every shared-memory item
+    int coop_sweep_threads;           // sweep width of the big launch shape (0 = whole block)
     int* host_hint;                   // pinned, host-mapped: last step's State::need_big
     // ---- joints ----
     int4* j_info;                     // body1, body2, locked_axes, colour
