@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, in
 }
 // Shared-memory items: one CTA per item, bodies (and, when they fit, constraints) staged in shared memory,
 // four lanes per constraint (rb_solver.cuh "lane-cooperative path").
-// `big`: the optional first launch, which takes every shared-memory item; the small launch that always
-// follows takes whatever has not been claimed in this step (so correctness never depends on the hint).
+// Either launch shape takes every shared-memory item (the small one streams what does not fit), so the
+// host's choice between them -- a hint read without synchronising -- only affects speed.
 template <int L>
 __device__ __forceinline__ void solve_coop_items(const World& w, const Grav& g, int smem_floats, bool big) {
     extern __shared__ __align__(16) float smem[];
@@ -592,7 +592,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.item_body_start, w.item_cap + 2); ALLOC(w.item_cons_start, w.item_cap + 2); ALLOC(w.item_joint_start, w.item_cap + 2);
     ALLOC(w.item_cursor, 3 * (w.item_cap + 2));
     ALLOC(w.item_flags, w.item_cap + 2);
-    ALLOC(w.item_order, w.item_cap + 2); ALLOC(w.item_done, w.item_cap + 2); ALLOC(w.order_hist, 2 * ORDER_BUCKETS + 2);
+    ALLOC(w.item_order, w.item_cap + 2); ALLOC(w.item_done, w.item_cap + 2); ALLOC(w.dbg_times, 32); ALLOC(w.order_hist, 2 * ORDER_BUCKETS + 2);
     ALLOC(w.item_bodies, NB); ALLOC(w.body_local, NB); ALLOC(w.body_item, NB);
     ALLOC(w.cons_pair_tmp, w.cons_cap); ALLOC(w.cons_pair, w.cons_cap);
     ALLOC(w.item_color_off, (size_t)(w.item_cap + 1) * (NUM_COLORS + 1));
@@ -604,6 +604,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     w.host_hint = W->host_hint;
     w.coop_small_floats = COOP_SMALL_SMEM_BYTES / 4;
     w.coop_sweep_threads = W->sweep_threads;
+    { const char* v = getenv("RB_DEBUG_FLAGS"); w.debug_flags = v ? atoi(v) : 0; }
 #if !RB_DEVICE_BUILD
     w.coop_small_floats = std::min(w.coop_small_floats, W->emu_coop_floats);   // the emulated CTA must fit what it is given
 #endif
@@ -813,9 +814,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         if (big) {
 #define RB_LAUNCH_BIG(T, LL) if (W->big_threads == T && W->big_lanes == LL) k_solve_coop_big<T, LL><<<W->coop_blocks_big, T, COOP_BIG_SMEM_BYTES, W->stream>>>(W->w, g);
             RB_BIG_VARIANTS(RB_LAUNCH_BIG)
-            W->kernels += 1;
-        }
-        k_solve_coop<<<W->coop_blocks, COOP_SMALL_THREADS, COOP_SMALL_SMEM_BYTES, W->stream>>>(W->w, g);
+        } else k_solve_coop<<<W->coop_blocks, COOP_SMALL_THREADS, COOP_SMALL_SMEM_BYTES, W->stream>>>(W->w, g);
         CK(cudaGetLastError());
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 2], W->stream));
         W->kernels += 2;
@@ -1065,6 +1064,10 @@ int64_t rb_world_debug_read(RbWorld* W, const char* table, void* dst, int64_t ca
         std::vector<int> v(std::max(W->w.nb, 1));
         CK(d2h(v.data(), t == "body_item" ? W->w.body_item : W->w.isl_label, (size_t)W->w.nb * 4));
         put(v.data(), (size_t)W->w.nb * 4);
+    } else if (t == "dbg_times") {
+        long long v[32];
+        CK(d2h(v, W->w.dbg_times, sizeof(v)));
+        put(v, sizeof(v));
     } else if (t == "state") {
         put(&st, sizeof(st));
     } else {

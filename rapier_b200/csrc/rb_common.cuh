@@ -98,6 +98,12 @@ RB_HD float as_float_i(int i) { float f; memcpy(&f, &i, 4); return f; }
 RB_HD int as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 
 
+#if RB_DEVICE_BUILD
+RB_D long long rb_clock() { return clock64(); }
+#else
+inline long long rb_clock() { return 0; }
+#endif
+
 // ---- bulk staging: 1-D TMA copies global -> shared completing on an mbarrier (emulation: memcpy) ----
 #if RB_DEVICE_BUILD
 RB_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

@@ -1252,6 +1252,7 @@ template <int L, int MODE>
 RB_PHASE void coop_sweep(const BlockCtx& ctx, const World& w, const SmemBodies& bd, const RowView& res, const RowView& mu, bool resident,
                          CoopPipe& pp, const int* s_stage, int nstages, int wslot, int c0, bool fric, bool wrap) {
     const int tid = ctx.btid, nth = pp.sweep_threads;   // warps beyond the sweep width only take part in the barriers
+    if (w.debug_flags & 1) return;
     if (resident) {
         for (int c = 0; c < nstages; ++c) {
             const int ae = s_stage[c];
@@ -1335,8 +1336,13 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, 
         if (!coop_plan(w.coop_small_floats, b1 - b0, n).resident) st->need_big = 1;
         atomic_add(resident ? &st->coop_resident : &st->coop_streamed, 1);
     }
+    const bool trace = (w.debug_flags & 2) && ctx.bid == 0 && tid == 0;
+    int tr = 0;
+#define RB_TRACE() if (trace && tr < 32) w.dbg_times[tr++] = rb_clock()
+    RB_TRACE();
     for (int l = b0 + tid; l < b1; l += nth) body_init(w, bd, w.item_bodies[l], l - b0, gravity);
     ctx.block_sync();
+    RB_TRACE();
     const int nstages = s_nstages;
     pp.nchunks = s_nchunks;
     pp.sweep_threads = s_width;
@@ -1347,6 +1353,7 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, 
     }
     if (!resident) fence_async_proxy();   // pool rows written above are read by bulk copies from here on
     ctx.block_sync();
+    RB_TRACE();
     const bool bouncy_item = w.item_flags[item] != 0;
     const bool warm = P.warmstart_coeff != 0.0f;
     const int total_sweeps = P.num_substeps * ((warm ? 1 : 0) + P.num_pgs + P.num_relax) + (bouncy_item ? 1 : 0);
@@ -1356,7 +1363,9 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, 
         if (warm) {
             ctx.block_sync();
             ++done;
+            if (sub == 0) RB_TRACE();
             coop_sweep<L, MODE_WARMSTART>(ctx, w, bd, res, mu, resident, pp, s_stage, nstages, wslot, c0, false, done < total_sweeps);
+            if (sub == 0) RB_TRACE();
         } else {   // bank the impulses without applying them
             for (int s = tid; s < n; s += nth) {
                 float4 im = mu.mr(MR_IMP, s), ac = mu.mr(MR_ACC, s), ti = mu.mr(MR_TI, s), wi = mu.mr(MR_WI, s);
@@ -1376,20 +1385,27 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, 
                 ++done;
                 if (relax) coop_sweep<L, MODE_RELAX>(ctx, w, bd, res, mu, resident, pp, s_stage, nstages, wslot, c0, fric, done < total_sweeps);
                 else coop_sweep<L, MODE_BIASED>(ctx, w, bd, res, mu, resident, pp, s_stage, nstages, wslot, c0, fric, done < total_sweeps);
+                if (sub == 0) RB_TRACE();
             }
             if (!relax) {
                 for (int l = b0 + tid; l < b1; l += nth) body_integrate(w, bd, w.item_bodies[l], l - b0);
                 ctx.block_sync();
+                if (sub == 0) RB_TRACE();
             }
         }
     }
     if (bouncy_item) coop_sweep<L, MODE_RESTITUTION>(ctx, w, bd, res, mu, resident, pp, s_stage, nstages, wslot, c0, false, false);
+    RB_TRACE();
     for (int s = tid; s < n; s += nth) {
         Cons c;
         coop_get_for_writeback(resident ? res : coop_slot_rows(pp, s), mu, s, c);
         cons_writeback(w, c0 + s, buf, c, true);
     }
+    if (trace) { ctx.block_sync(); }
+    RB_TRACE();
     for (int l = b0 + tid; l < b1; l += nth) body_writeback(w, bd, w.item_bodies[l], l - b0);
+    RB_TRACE();
+#undef RB_TRACE
 }
 
 }  // namespace rb

@@ -181,6 +181,8 @@ struct World {
     float4* cons;                     // [CR_ROWS][cons_cap]
     float4* coop_pool;                // [2 * COOP_ROWS * cons_cap] L2-resident constant rows of streamed items, blocked by chunk
     int coop_small_floats;            // dynamic shared memory of the small launch shape (2 CTAs / SM), which must fit every shared-memory item
+    long long* dbg_times;             // [32] phase timestamps of one item (debug_flags & 2)
+    int debug_flags;                  // RB_DEBUG_FLAGS (profiling experiments only): 1 = skip the sweeps, 2 = record dbg_times
     int coop_sweep_threads;           // sweep width of the big launch shape (0 = whole block)
     int* host_hint;                   // pinned, host-mapped: last step's State::need_big
     // ---- joints ----
