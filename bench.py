@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""bench.py -- physics steps/s on b3d_many_pyramids (3-D f32), BASELINE.json's metric.
+"""bench.py -- physics steps/s on b3d_many_pyramids (3-D f32), BASELINE.json's metric, on BASELINE.json's
+configs[1] (80 pyramids x 20 levels); the reference file's own 14 x 14 x 10 size is reported in `other_configs`.
 
   python bench.py --gpus 1 --steps K --warmup W            our CUDA path (one JSON line)
   python bench.py --impl reference --steps K --warmup W     CPU arm (oracle port, all host threads)

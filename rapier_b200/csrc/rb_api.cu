@@ -1,11 +1,12 @@
 // rb_api.cu -- kernels + the extern "C" boundary of librapier_b200.so (include/rapier_b200.h).
 //
-// Per step the host enqueues three launches on one stream, with no host synchronisation:
-//   k_collide      cooperative persistent kernel: collider refresh, [broad phase], narrow phase,
-//                  [colouring + islands + schedule]   (rb_collide.cuh)
-//   k_solve_items  one CTA per work item, bodies staged in shared memory, the whole
-//                  generate -> 4 x (warmstart, biased, integrate, relax) -> writeback chain fused
-//   k_solve_large  cooperative grid-wide solve of islands too big for a CTA (no-op otherwise)
+// Per step the host enqueues two launches on one stream, with no host synchronisation:
+//   k_collide       cooperative persistent kernel: collider refresh, [broad phase], narrow phase,
+//                   [colouring + islands + schedule]   (rb_collide.cuh); then the solves that are not
+//                   shared-memory items (items with joints, the grid-wide "large" item 0)
+//   k_solve_coop /  one CTA per shared-memory item from a cost-ordered queue: bodies + impulses in shared
+//   k_solve_coop_big  memory, the whole generate -> 4 x (warmstart, biased, integrate, relax) -> writeback
+//                   chain fused; constant constraint rows resident or streamed from L2 by bulk (TMA) copies
 // All sizes that change at run time (pairs, manifolds, items) live in device memory (rb::State).
 //
 // With -DRB_EMULATE (tests/emul only) the same phase functions run single-threaded on the host with

@@ -1401,7 +1401,7 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, 
         coop_get_for_writeback(resident ? res : coop_slot_rows(pp, s), mu, s, c);
         cons_writeback(w, c0 + s, buf, c, true);
     }
-    if (trace) { ctx.block_sync(); }
+    if (w.debug_flags & 2) ctx.block_sync();   // (uniform: only to attribute the two writebacks separately)
     RB_TRACE();
     for (int l = b0 + tid; l < b1; l += nth) body_writeback(w, bd, w.item_bodies[l], l - b0);
     RB_TRACE();
