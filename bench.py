@@ -182,7 +182,8 @@ def main():
     exchange = None
     if world_size > 1:
         from rapier_b200.sharding import IslandShard
-        shard = IslandShard(pipe, dist, rank, world_size, torch.device("cuda", local_rank))
+        shard = IslandShard(pipe, dist, rank, world_size, torch.device("cuda", local_rank),
+                            overlap=os.environ.get("RB_SHARD_OVERLAP", "0") == "1")   # measured slower at N=2 (host-bound), see DESIGN.md 6
         exchange = shard.exchange
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if args.l2 == "flush" else None
@@ -243,6 +244,17 @@ def main():
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
     clocks = clk.summary()
+    shard_check = None
+    if dist is not None:   # after draining the exchange every rank must hold bit-identical states of ALL bodies
+        shard.finish()
+        torch.cuda.synchronize()
+        from rapier_b200.sharding import state_tensor
+        mine = state_tensor(pipe, torch.device("cuda", local_rank)).clone()
+        ref0 = mine.clone()
+        dist.broadcast(ref0, src=0)
+        diff = (mine.view(torch.int32) != ref0.view(torch.int32)).sum().to(torch.float64)
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        shard_check = {"state_words_differing_from_rank0_max_over_ranks": int(diff.item()), "finite": bool(torch.isfinite(mine).all().item())}
 
     t = torch.tensor([ms, e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
     if dist is not None:
@@ -313,7 +325,7 @@ def main():
             "config": {"workload": workload_name(args.scene, world_size), "bodies_per_gpu": per_rank_bodies,
                        "manifolds_per_gpu": M, "substeps": 4, "sweeps_per_substep": 3,
                        "l2": "flushed between steps (256 MiB memset)" if args.l2 == "flush" else "not flushed",
-                       "parallelism": "1 GPU" if world_size == 1 else f"islands sharded over {world_size} GPUs, NCCL all-gather of body states every step"},
+                       "parallelism": "1 GPU" if world_size == 1 else f"islands sharded over {world_size} GPUs, NCCL all-gather of body states every step" + (" (asynchronous: overlapped with the next step, imported one step late, drained at the end)" if os.environ.get("RB_SHARD_OVERLAP", "0") == "1" else " (in place on the state buffer)")},
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": nb * 13 * 4, "d2h_bytes_per_step": nb * 13 * 4,
                     "steps": e2e_steps},
             "gpu_launches": int(k1 - k0),
@@ -326,6 +338,7 @@ def main():
             "cpu_baseline": cpu,
             "stage_ms": {"collide": prof["collision_detection_ms"], "solve": prof["solver_ms"]},
             "other_configs": [other] if other else [],
+            "shard_check": shard_check,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

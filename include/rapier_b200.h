@@ -200,7 +200,9 @@ int rb_world_set_owned_bodies(RbWorld* w, const uint8_t* owned /* [num_bodies] *
  * all-gather of boundary body states, and the byte size. */
 int rb_world_state_buffer(RbWorld* w, void** device_ptr, int64_t* bytes);
 
-/* Scatter externally simulated body states (device pointers: idx[n], src[n*13]) into the world. */
+/* Scatter externally simulated body states (device pointers: idx[n], src[n*13]) into the world.
+ * src_dev == NULL: the rows were all-gathered in place into rb_world_state_buffer; body idx[k] is
+ * imported from its own row. */
 int rb_world_import_states(RbWorld* w, const int32_t* idx_dev, const float* src_dev, int32_t n);
 /* The CUDA stream all of this world's work is enqueued on / replace it by a caller-owned stream. */
 void* rb_world_stream(RbWorld* w);

@@ -85,13 +85,14 @@ template <class Ctx>
 RB_PHASE void import_states_phase(const Ctx& ctx, const World& w, const int* idx, const float* src, int n) {
     for (int k = ctx.gtid; k < n; k += ctx.gsize) {
         int b = idx[k];
-        const float* s = src + (size_t)k * 13;
+        float* d = w.state13 + (size_t)b * 13;
+        const float* s = src ? src + (size_t)k * 13 : d;   // src == NULL: the rows were gathered in place into the state buffer
         w.b_pos_t[b] = make_float4(s[0], s[1], s[2], 0.f);
         w.b_pos_q[b] = make_float4(s[3], s[4], s[5], s[6]);
         w.b_linvel[b] = make_float4(s[7], s[8], s[9], 0.f);
         w.b_angvel[b] = make_float4(s[10], s[11], s[12], 0.f);
-        float* d = w.state13 + (size_t)b * 13;
-        for (int i = 0; i < 13; ++i) d[i] = s[i];
+        if (src)
+            for (int i = 0; i < 13; ++i) d[i] = s[i];
         update_world_mass(w, b, body_pose(w, b));
     }
 }
@@ -111,8 +112,6 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, in
         w.st->coop_resident = 0;
         w.st->cursor_rest = 0;
         w.st->cursor_coop = 0;
-        w.st->cursor_big = 0;
-        w.st->stamp += 1;
     }
     collide_pipeline(ctx, w);
     if (!do_solve) return;
@@ -164,8 +163,9 @@ __device__ __forceinline__ void solve_coop_items(const World& w, const Grav& g, 
     pp.t = 0;
     pp.sweep_threads = ctx.bsize;   // (set per item)
     __shared__ int s_next;
-    const int n = w.st->norder, stamp = w.st->stamp;
-    int* cursor = big ? &w.st->cursor_big : &w.st->cursor_coop;
+    const int n = w.st->norder;
+    int* cursor = &w.st->cursor_coop;
+    (void)big;
     for (;;) {   // dynamic queue over the cost-ordered items
         if (ctx.btid == 0) s_next = atomicAdd(cursor, 1);
         __syncthreads();
@@ -173,9 +173,8 @@ __device__ __forceinline__ void solve_coop_items(const World& w, const Grav& g, 
         __syncthreads();
         if (k >= n) break;
         const int item = w.item_order[k];
-        if (!item_is_coop(w, item) || w.item_done[item] == stamp) continue;
+        if (!item_is_coop(w, item)) continue;
         solve_item_coop<L>(ctx, w, smem, smem_floats, pp, item, mk3(g.x, g.y, g.z));
-        if (ctx.btid == 0) w.item_done[item] = stamp;
         ctx.block_sync();
     }
 }
@@ -208,7 +207,7 @@ struct RbWorld {
     int collide_blocks = 1, coop_blocks = 1;
     int collide_threads = COLLIDE_THREADS;
     int coop_blocks_big = 1;
-    int big_threads = COOP_BIG_THREADS, big_lanes = 1, sweep_threads = 0;
+    int big_threads = COOP_BIG_THREADS, sweep_threads = 0;
     int coop_shape = -1;   // RB_COOP_SHAPE debugging override: 0 small, 1 big, -1 automatic
     int* host_hint = nullptr;
     long long kernels = 0, steps = 0;
@@ -457,7 +456,7 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
     if (!prop.cooperativeLaunch) { set_err("device lacks cooperative launch%s", ""); delete W; return nullptr; }
     cudaStreamCreateWithFlags(&W->stream, cudaStreamNonBlocking);
     cudaFuncSetAttribute(k_solve_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_SMALL_SMEM_BYTES);
-#define RB_BIG_VARIANTS(X) X(256, 1) X(256, 2)
+#define RB_BIG_VARIANTS(X) X(256, 1)
 #define RB_SET_ATTR(T, LL) cudaFuncSetAttribute(k_solve_coop_big<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_BIG_SMEM_BYTES);
     RB_BIG_VARIANTS(RB_SET_ATTR)
     if (cudaHostAlloc((void**)&W->host_hint, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { set_err("cudaHostAlloc failed%s", ""); delete W; return nullptr; }
@@ -477,8 +476,6 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
         W->coop_blocks = std::min(W->coop_blocks, envi("RB_COOP_BLOCKS", W->coop_blocks));
         W->collide_threads = std::min(COLLIDE_THREADS, envi("RB_COLLIDE_THREADS", COLLIDE_THREADS));
         W->coop_shape = envi("RB_COOP_SHAPE", -1);
-        W->big_threads = envi("RB_COOP_BIG_THREADS", COOP_BIG_THREADS);
-        W->big_lanes = envi("RB_COOP_BIG_LANES", 1);
         W->sweep_threads = envi("RB_COOP_SWEEP_THREADS", 0);
     }
 #else
@@ -593,7 +590,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.item_body_start, w.item_cap + 2); ALLOC(w.item_cons_start, w.item_cap + 2); ALLOC(w.item_joint_start, w.item_cap + 2);
     ALLOC(w.item_cursor, 3 * (w.item_cap + 2));
     ALLOC(w.item_flags, w.item_cap + 2);
-    ALLOC(w.item_order, w.item_cap + 2); ALLOC(w.item_done, w.item_cap + 2); ALLOC(w.dbg_times, 32); ALLOC(w.order_hist, 2 * ORDER_BUCKETS + 2);
+    ALLOC(w.item_order, w.item_cap + 2); ALLOC(w.dbg_times, 32); ALLOC(w.order_hist, 2 * ORDER_BUCKETS + 2);
     ALLOC(w.item_bodies, NB); ALLOC(w.body_local, NB); ALLOC(w.body_item, NB);
     ALLOC(w.cons_pair_tmp, w.cons_cap); ALLOC(w.cons_pair, w.cons_cap);
     ALLOC(w.item_color_off, (size_t)(w.item_cap + 1) * (NUM_COLORS + 1));
@@ -813,7 +810,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, ITEM_SMEM_BYTES, W->stream));
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 1], W->stream));
         if (big) {
-#define RB_LAUNCH_BIG(T, LL) if (W->big_threads == T && W->big_lanes == LL) k_solve_coop_big<T, LL><<<W->coop_blocks_big, T, COOP_BIG_SMEM_BYTES, W->stream>>>(W->w, g);
+#define RB_LAUNCH_BIG(T, LL) if (W->big_threads == T) k_solve_coop_big<T, LL><<<W->coop_blocks_big, T, COOP_BIG_SMEM_BYTES, W->stream>>>(W->w, g);
             RB_BIG_VARIANTS(RB_LAUNCH_BIG)
         } else k_solve_coop<<<W->coop_blocks, COOP_SMALL_THREADS, COOP_SMALL_SMEM_BYTES, W->stream>>>(W->w, g);
         CK(cudaGetLastError());

@@ -282,6 +282,10 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
     for (int i = ctx.gtid; i < np; i += ctx.gsize) {
         unsigned long long key = w.pb[buf].key[i];
         int c1 = (int)(key >> 32), c2 = (int)(key & 0xffffffffu);
+        {   // pairs without a body simulated by this rank (multi-GPU sharding) belong to another rank
+            float4 bod0 = prow(w, buf, PR_BODIES, i);
+            if (!body_is_sim(w, as_int(bod0.z)) && !body_is_sim(w, as_int(bod0.w))) continue;
+        }
         pose cp1 = collider_pose(w, c1), cp2 = collider_pose(w, c2);
         float4 info = prow(w, buf, PR_INFO, i);
         int flags = as_int(info.x), npts_old = as_int(info.y), nsc_old = as_int(info.z), color = as_int(info.w);

@@ -95,9 +95,8 @@ struct State {
     int need_big;          // some shared-memory item does not fit resident in the small launch shape (accumulated per step)
     int coop_streamed, coop_resident;   // shared-memory items of the last step: streamed from the pool / resident
     int norder;            // entries of World::item_order (non-empty items 1.., by decreasing cost)
-    int cursor_rest, cursor_coop, cursor_big;   // dynamic work queues of the kernels over item_order
-    int stamp;             // step counter (claims in World::item_done)
-    int pad[6];
+    int cursor_rest, cursor_coop;   // dynamic work queues of the two kernels over item_order
+    int pad[8];
 };
 
 struct PairBuf {
@@ -167,7 +166,6 @@ struct World {
     int* cons_pair_tmp;               // [cons_cap] pair index grouped by item (unsorted)
     int* cons_pair;                   // [cons_cap] pair index in schedule order
     int* item_color_off;              // [item_cap][NUM_COLORS + 1] offsets relative to item_cons_start
-    int* item_done;                   // [item_cap] stamp of the step in which a shared-memory kernel claimed the item
     int* item_order;                  // [item_cap] non-empty items 1.., most expensive first (launch order of the solve CTAs)
     int* order_hist;                  // [2 * ORDER_BUCKETS + 1] counting-sort scratch of item_order
     int* color_count;                 // [NUM_COLORS] global histogram

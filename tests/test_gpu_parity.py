@@ -52,6 +52,41 @@ def test_many_pyramids_full_size_matches_oracle(built):
     assert c["num_pairs"] == 196 * 145 and c["num_active_manifolds"] == 196 * 145
 
 
+def test_headline_workload_80x20_matches_oracle(built):
+    """BASELINE.json configs[1] (80 pyramids x 20 levels, 16 800 cubes): islands of 590 manifolds do not fit
+    shared memory, so their constraint rows are streamed from the L2 pool by bulk copies.  The first steps
+    run in the small launch shape (4 lanes / constraint), later ones in the big shape (1 lane / constraint)
+    once the device hint has reached the host: all of them must match the oracle bit for bit."""
+    scene = scenes.many_pyramids_label()
+    w = PhysicsWorld(scene)
+    o = oracle_lib.OracleWorld(scene, threads=8)
+    for i in range(7):
+        w.step()
+        o.step()
+        if i in (0, 1, 6):
+            d = compare_worlds(w, o, tables=(i == 6))
+            assert is_exact(d), (i, d)
+    st = w.debug_read("state", np.int32)
+    assert st[19] == 80, "the 80 pyramids must have been streamed"
+    c = w.counters()
+    assert c["num_active_manifolds"] == 80 * 590
+
+
+@pytest.mark.parametrize("shape", ["0", "1"])
+def test_streamed_item_in_both_launch_shapes(built, monkeypatch, shape):
+    """A 20-level pyramid (streamed item) forced through the small (4 lanes) or the big (1 lane) launch shape."""
+    monkeypatch.setenv("RB_COOP_SHAPE", shape)
+    scene = scenes.single_pyramid(20)
+    w = PhysicsWorld(scene)
+    o = oracle_lib.OracleWorld(scene)
+    for i in range(25):
+        w.step()
+        o.step()
+        if i % 8 == 7 or i < 2:
+            assert is_exact(compare_worlds(w, o)), i
+    assert w.debug_read("state", np.int32)[19] == 1
+
+
 def test_many_pyramids_full_size_properties(built):
     """Size-independent properties after 300 steps at full size: pyramids stay standing, the ground
     carries the whole weight (sum of ground-contact impulses = M g dt), state is finite, and a second
