@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, in
     gb.w = &w;
     GridExec gex;
     gex.c = &ctx;
-    solve_item(gex, w, gb, 0, mk3(g.x, g.y, g.z));
+    solve_item_lanes<4>(gex, w, gb, mk3(g.x, g.y, g.z));
 }
 // Shared-memory items: one CTA per item, bodies (and, when they fit, constraints) staged in shared memory,
 // four lanes per constraint (rb_solver.cuh "lane-cooperative path").
@@ -572,9 +572,10 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.b_type, NB); ALLOC(w.b_flags, NB);
     ALLOC(w.b_pos_t, NB); ALLOC(w.b_pos_q, NB); ALLOC(w.b_linvel, NB); ALLOC(w.b_angvel, NB);
     ALLOC(w.b_lcom_im, NB); ALLOC(w.b_ipi, NB); ALLOC(w.b_pi, NB); ALLOC(w.b_pframe, NB); ALLOC(w.b_misc, NB);
-    ALLOC(w.b_uforce, NB); ALLOC(w.b_utorque, NB); ALLOC(w.b_wcom, NB); ALLOC(w.b_eim, NB);
+    ALLOC(w.b_uforce, NB); ALLOC(w.b_utorque, NB); ALLOC(w.b_wcom, NB); ALLOC(w.b_eim, NB + 2);
     ALLOC(w.b_eii0, NB); ALLOC(w.b_eii1, NB); ALLOC(w.b_owned, NB);
-    ALLOC(w.s_lin, NB); ALLOC(w.s_ang, NB); ALLOC(w.s_q, NB); ALLOC(w.s_t, NB); ALLOC(w.s_incr_lin, NB); ALLOC(w.s_incr_ang, NB);
+    ALLOC(w.s_lin, NB + 2); ALLOC(w.s_ang, NB + 2); ALLOC(w.s_q, NB + 2); ALLOC(w.s_t, NB + 2);   // + world pseudo body, garbage slot
+    ALLOC(w.s_incr_lin, NB); ALLOC(w.s_incr_ang, NB);
     ALLOC(w.state13, (size_t)NB * 13);
     ALLOC(w.c_shape, NC); ALLOC(w.c_parent, NC); ALLOC(w.c_he, NC); ALLOC(w.c_rel_t, NC); ALLOC(w.c_rel_q, NC);
     ALLOC(w.c_mat, NC); ALLOC(w.c_rules, NC); ALLOC(w.c_groups, NC); ALLOC(w.c_pos_t, NC); ALLOC(w.c_pos_q, NC);
@@ -599,6 +600,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.joint_tmp, NJ); ALLOC(w.joint_sched, NJ);
     ALLOC(w.cons_hdr, w.cons_cap); ALLOC(w.cons, (size_t)CR_ROWS * w.cons_cap);
     ALLOC(w.coop_pool, (size_t)2 * COOP_ROWS * w.cons_cap);
+    ALLOC(w.large_pool, (size_t)COOP_ROWS * w.cons_cap); ALLOC(w.large_mut, (size_t)MR_COUNT * w.cons_cap);
     w.host_hint = W->host_hint;
     w.coop_small_floats = COOP_SMALL_SMEM_BYTES / 4;
     w.coop_sweep_threads = W->sweep_threads;
@@ -870,7 +872,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
             gb.w = &W->w;
             GridExec gex;
             gex.c = &gctx;
-            solve_item(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
+            solve_item_lanes<1>(gex, W->w, gb, mk3(g.x, g.y, g.z));
         }
         W->kernels += 2;
     }

@@ -1051,8 +1051,8 @@ template <int L> RB_HD bool lane_any(bool p) {
 // indexed by item slot.  `wslot` is the staged world pseudo body (wslot + 1 = garbage slot).
 // `q0` is the global schedule slot of the item's slot 0 (rare per-constraint rows stay in HBM).
 // MODE is a compile-time constant so each sweep kind is straight-line code.
-template <int L, int MODE>
-RB_HD void coop_stage(const World& w, const SmemBodies& bd, const RowView& cs, const RowView& mu, int wslot, int q0, int a, int e,
+template <int L, int MODE, class B>
+RB_HD void coop_stage(const World& w, const B& bd, const RowView& cs, const RowView& mu, int wslot, int q0, int a, int e,
                       int tid, int nth, bool solve_friction) {
     constexpr int PPL = MAX_PTS / L;   // points per lane
     const Params& P = w.prm;
@@ -1194,6 +1194,147 @@ RB_HD void coop_stage(const World& w, const SmemBodies& bd, const RowView& cs, c
                 bd.set_vel(id2 < 0 ? (wslot + 1) : id2, v2, w2);
             }
         }
+    }
+}
+
+// The grid-wide "large" item 0 (islands too big for a CTA), lane-cooperative form: the same coop_stage as the
+// shared-memory items, with the constraint rows in the L2-resident World::large_pool / large_mut (row stride
+// cons_cap, indexed by schedule slot), the solver bodies in the global s_* tables (ids are body indices; the
+// world pseudo body is entry nb, the garbage slot nb + 1), and a grid barrier between colour stages.
+template <int L, class X, class B>
+RB_PHASE void solve_item_lanes(const X& ex, const World& w, const B& bd, vec3 gravity) {
+    const Params& P = w.prm;
+    State* st = w.st;
+    const int item = 0, buf = st->cur;
+    const int b0 = w.item_body_start[0], b1 = w.item_body_start[1];
+    const int c0 = w.item_cons_start[0];
+    const int c1 = w.item_cons_start[1] < w.cons_cap ? w.item_cons_start[1] : w.cons_cap;
+    const int j0 = w.item_joint_start[0], j1 = w.item_joint_start[1];
+    const int* coff = w.item_color_off;
+    const int* joff = w.item_jcolor_off;
+    const int ncol = st->nused_colors, njcol = st->njused_colors;
+    const int ovf = w.color_pos[COLOR_OVERFLOW], jovf = w.jcolor_pos[COLOR_OVERFLOW];
+    const int tid = ex.tid(), nth = ex.nth();
+    const int wslot = w.nb;
+    RowView rows, mu;
+    rows.p = w.large_pool; rows.stride = w.cons_cap;
+    mu.p = w.large_mut; mu.stride = w.cons_cap;
+
+    auto stage = [&](int a, int e, bool serial, int mode, bool fric) {
+        // the overflow colour is solved one constraint after the other by the first L lanes
+        const int t = tid, n = serial ? L : nth;
+        if (serial && tid >= L) return;
+        // stages with more constraints than lane groups are throughput-bound: one lane per constraint
+        // executes fewer instructions in total than L lanes sharing it
+        if (L > 1 && !serial && (e - a) * L > nth) {
+            if (mode == MODE_WARMSTART) coop_stage<1, MODE_WARMSTART>(w, bd, rows, mu, wslot, 0, a, e, t, n, fric);
+            else if (mode == MODE_BIASED) coop_stage<1, MODE_BIASED>(w, bd, rows, mu, wslot, 0, a, e, t, n, fric);
+            else if (mode == MODE_RELAX) coop_stage<1, MODE_RELAX>(w, bd, rows, mu, wslot, 0, a, e, t, n, fric);
+            else coop_stage<1, MODE_RESTITUTION>(w, bd, rows, mu, wslot, 0, a, e, t, n, fric);
+            return;
+        }
+        if (mode == MODE_WARMSTART) coop_stage<L, MODE_WARMSTART>(w, bd, rows, mu, wslot, 0, a, e, t, n, fric);
+        else if (mode == MODE_BIASED) coop_stage<L, MODE_BIASED>(w, bd, rows, mu, wslot, 0, a, e, t, n, fric);
+        else if (mode == MODE_RELAX) coop_stage<L, MODE_RELAX>(w, bd, rows, mu, wslot, 0, a, e, t, n, fric);
+        else coop_stage<L, MODE_RESTITUTION>(w, bd, rows, mu, wslot, 0, a, e, t, n, fric);
+    };
+
+    if (tid == 0) {
+        w.item_flags[item] = 0;
+        bd.set_vel(wslot, zero3(), zero3());
+        bd.set_xf(wslot, pident());
+        w.b_eim[wslot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int l = b0 + tid; l < b1; l += nth) {
+        int b = w.item_bodies[l];
+        body_init(w, bd, b, b, gravity);
+    }
+    ex.sync();
+    for (int q = c0 + tid; q < c1; q += nth) {   // S2 generate
+        Cons c;
+        cons_generate(w, bd, q, buf, item, c);
+        coop_put(rows, mu, bd, q, c);
+    }
+    ex.sync();
+    for (int sub = 0; sub < P.num_substeps; ++sub) {
+        for (int l = b0 + tid; l < b1; l += nth) {
+            int b = w.item_bodies[l];
+            body_increment(w, bd, b, b);
+        }
+        ex.sync();
+        if (j1 > j0) {   // S4 joint rows from the current poses
+            for (int q = j0 + tid; q < j1; q += nth) joint_update(w, bd, q);
+            ex.sync();
+        }
+        if (P.warmstart_coeff != 0.0f) {   // S5 update + warmstart, colour by colour
+            for (int c = 0; c < ncol; ++c) {
+                int a = c0 + coff[c], e = c0 + coff[c + 1];
+                if (e > c1) e = c1;
+                if (a >= e) continue;
+                stage(a, e, c == ovf, MODE_WARMSTART, false);
+                ex.sync();
+            }
+        } else {   // warmstart_coefficient == 0: update only banks and zeroes the impulses
+            for (int s = c0 + tid; s < c1; s += nth) {
+                float4 im = mu.mr(MR_IMP, s), ac = mu.mr(MR_ACC, s), ti = mu.mr(MR_TI, s), wi = mu.mr(MR_WI, s);
+                ac.x = ac.x + im.x; ac.y = ac.y + im.y; ac.z = ac.z + im.z; ac.w = ac.w + im.w;
+                im.x = im.x * 0.0f; im.y = im.y * 0.0f; im.z = im.z * 0.0f; im.w = im.w * 0.0f;
+                ti.z = ti.z + ti.x; ti.w = ti.w + ti.y; ti.x = ti.x * 0.0f; ti.y = ti.y * 0.0f;
+                wi.y = wi.y + wi.x; wi.x = wi.x * 0.0f;
+                mu.mr(MR_IMP, s) = im; mu.mr(MR_ACC, s) = ac; mu.mr(MR_TI, s) = ti; mu.mr(MR_WI, s) = wi;
+            }
+            ex.sync();
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool relax = pass == 1;
+            const int iters = relax ? P.num_relax : P.num_pgs;
+            const bool fric = relax || P.friction_in_bias || P.num_relax == 0;
+            for (int it = 0; it < iters; ++it) {
+                for (int c = 0; c < njcol; ++c) {   // joints first (solve.rs:89-92), then contacts
+                    int a = j0 + joff[c], e = j0 + joff[c + 1];
+                    if (a >= e) continue;
+                    if (c == jovf) {
+                        if (tid == 0) for (int q = a; q < e; ++q) joint_solve(w, bd, q, relax);
+                    } else {
+                        for (int q = a + tid; q < e; q += nth) joint_solve(w, bd, q, relax);
+                    }
+                    ex.sync();
+                }
+                for (int c = 0; c < ncol; ++c) {
+                    int a = c0 + coff[c], e = c0 + coff[c + 1];
+                    if (e > c1) e = c1;
+                    if (a >= e) continue;
+                    stage(a, e, c == ovf, relax ? MODE_RELAX : MODE_BIASED, fric);
+                    ex.sync();
+                }
+            }
+            if (!relax) {
+                for (int l = b0 + tid; l < b1; l += nth) {
+                    int b = w.item_bodies[l];
+                    body_integrate(w, bd, b, b);
+                }
+                ex.sync();
+            }
+        }
+    }
+    if (w.item_flags[item]) {   // S9 restitution
+        for (int c = 0; c < ncol; ++c) {
+            int a = c0 + coff[c], e = c0 + coff[c + 1];
+            if (e > c1) e = c1;
+            if (a >= e) continue;
+            stage(a, e, c == ovf, MODE_RESTITUTION, false);
+            ex.sync();
+        }
+    }
+    for (int q = c0 + tid; q < c1; q += nth) {   // S10 impulse writeback
+        Cons c;
+        coop_get_for_writeback(rows, mu, q, c);
+        cons_writeback(w, q, buf, c, true);
+    }
+    for (int q = j0 + tid; q < j1; q += nth) joint_writeback(w, q);
+    for (int l = b0 + tid; l < b1; l += nth) {
+        int b = w.item_bodies[l];
+        body_writeback(w, bd, b, b);
     }
 }
 

@@ -177,6 +177,8 @@ struct World {
     // ---- constraints ----
     int4* cons_hdr;                   // [cons_cap] pair, id1, id2, num_contacts (ids item-local or global)
     float4* cons;                     // [CR_ROWS][cons_cap]
+    float4* large_pool;               // [COOP_ROWS][cons_cap] constant rows of the grid-wide item 0 (lane-cooperative form)
+    float4* large_mut;                // [MR_COUNT][cons_cap] its impulses
     float4* coop_pool;                // [2 * COOP_ROWS * cons_cap] L2-resident constant rows of streamed items, blocked by chunk
     int coop_small_floats;            // dynamic shared memory of the small launch shape (2 CTAs / SM), which must fit every shared-memory item
     long long* dbg_times;             // [32] phase timestamps of one item (debug_flags & 2)
