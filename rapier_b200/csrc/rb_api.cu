@@ -208,6 +208,7 @@ struct RbWorld {
     int collide_threads = COLLIDE_THREADS;
     int coop_blocks_big = 1;
     int big_threads = COOP_BIG_THREADS, sweep_threads = 0;
+    int steps_since_scene = 0;   // the launch-shape hint of a new scene is awaited once (see rb_world_step)
     int coop_shape = -1;   // RB_COOP_SHAPE debugging override: 0 small, 1 big, -1 automatic
     int* host_hint = nullptr;
     long long kernels = 0, steps = 0;
@@ -545,6 +546,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
             return RB_ERR_INVALID;
         }
     }
+    W->steps_since_scene = 0;
     W->bodies.assign(bodies, bodies + nb);
     W->colliders.assign(colliders, colliders + nc);
     W->joints.assign(joints, joints + nj);
@@ -591,6 +593,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.item_body_start, w.item_cap + 2); ALLOC(w.item_cons_start, w.item_cap + 2); ALLOC(w.item_joint_start, w.item_cap + 2);
     ALLOC(w.item_cursor, 3 * (w.item_cap + 2));
     ALLOC(w.item_flags, w.item_cap + 2);
+    ALLOC(w.adj_off, NB + 2); ALLOC(w.adj_cnt, NB + 2); ALLOC(w.adj_list, (size_t)2 * w.cons_cap + 2);
     ALLOC(w.item_order, w.item_cap + 2); ALLOC(w.dbg_times, 32); ALLOC(w.order_hist, 2 * ORDER_BUCKETS + 2);
     ALLOC(w.item_bodies, NB); ALLOC(w.body_local, NB); ALLOC(w.body_item, NB);
     ALLOC(w.cons_pair_tmp, w.cons_cap); ALLOC(w.cons_pair, w.cons_cap);
@@ -806,6 +809,11 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         bool prof = W->profiling;
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s], W->stream));
         int do_solve = 1;
+        // A new scene's islands are only known after its first schedule.  A caller that enqueues many steps in
+        // one asynchronous call would otherwise run all of them in the launch shape chosen before that, so the
+        // first call after a scene upload waits ONCE, after its second step, for the device hint.
+        if (W->steps_since_scene == 2 && nsteps > 3) CK(cudaStreamSynchronize(W->stream));
+        W->steps_since_scene++;
         // launch shape of k_solve_coop for this step (both kernels must agree on it): device hint of the last step
         const bool big = W->coop_shape >= 0 ? W->coop_shape == 1 : (*(volatile int*)W->host_hint != 0);
         void* a1[] = {(void*)&W->w, (void*)&g, (void*)&do_solve};

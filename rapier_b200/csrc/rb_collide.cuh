@@ -800,6 +800,40 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
                 else w.j_sched_ids[q] = make_int4(id, id1, id2, 0);
             }
             ctx.block_sync();
+            // per-body adjacency of the contact constraints, in stage (= slot) order: entry = slot * 2 + side.
+            // The body-centric warm start of the shared-memory items walks it (rb_solver.cuh).
+            if (pass == 0 && it > 0) {
+                const int lb0 = w.item_body_start[it], lb1 = w.item_body_start[it + 1];
+                for (int l = lb0 + ctx.btid; l < lb1; l += ctx.bsize) w.adj_cnt[l] = 0;
+                ctx.block_sync();
+                for (int q = s0 + ctx.btid; q < s1; q += ctx.bsize) {
+                    int4 h = w.cons_hdr[q];
+                    if (h.y >= 0) atomic_add(&w.adj_cnt[lb0 + h.y], 1);
+                    if (h.z >= 0) atomic_add(&w.adj_cnt[lb0 + h.z], 1);
+                }
+                ctx.block_sync();
+                if (ctx.btid == 0) {
+                    int run = 2 * s0;
+                    for (int l = lb0; l < lb1; ++l) { w.adj_off[l] = run; run += w.adj_cnt[l]; w.adj_cnt[l] = 0; }
+                }
+                ctx.block_sync();
+                for (int q = s0 + ctx.btid; q < s1; q += ctx.bsize) {
+                    int4 h = w.cons_hdr[q];
+                    if (h.y >= 0) w.adj_list[w.adj_off[lb0 + h.y] + atomic_add(&w.adj_cnt[lb0 + h.y], 1)] = (q - s0) * 2;
+                    if (h.z >= 0) w.adj_list[w.adj_off[lb0 + h.z] + atomic_add(&w.adj_cnt[lb0 + h.z], 1)] = (q - s0) * 2 + 1;
+                }
+                ctx.block_sync();
+                for (int l = lb0 + ctx.btid; l < lb1; l += ctx.bsize) {   // order every short list by slot
+                    int* a = w.adj_list + w.adj_off[l];
+                    const int n = w.adj_cnt[l];
+                    for (int x = 1; x < n; ++x) {
+                        int v = a[x], y = x;
+                        while (y > 0 && a[y - 1] > v) { a[y] = a[y - 1]; --y; }
+                        a[y] = v;
+                    }
+                }
+                ctx.block_sync();
+            }
         }
     }
     ctx.grid_sync();

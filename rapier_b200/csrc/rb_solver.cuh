@@ -1420,6 +1420,50 @@ RB_PHASE void coop_sweep(const BlockCtx& ctx, const World& w, const SmemBodies& 
     pp.primed = wrap;
 }
 
+// ---- warm start of a shared-memory item, body-centric ------------------------------------------------
+// The reference applies the banked impulses constraint by constraint, colour by colour (update + warmstart,
+// contact_with_twist_friction.rs:426-522, :633-678).  A warm start only ADDS to the two bodies of its
+// constraint, so what a body ends up with is the sequence of additions of ITS constraints in colour order.
+// Walking each body's adjacency list (slot order = colour order, built by the schedule) reproduces exactly
+// that sequence -- same operands, same order, same bits -- with one barrier instead of one per colour.
+RB_HD void coop_warmstart_bank(const Params& P, const RowView& mu, int s) {   // the per-constraint half: bank and scale
+    float4 im = mu.mr(MR_IMP, s), ac = mu.mr(MR_ACC, s), ti = mu.mr(MR_TI, s), wi = mu.mr(MR_WI, s);
+    ac.x = ac.x + im.x; ac.y = ac.y + im.y; ac.z = ac.z + im.z; ac.w = ac.w + im.w;
+    im.x = im.x * P.warmstart_coeff; im.y = im.y * P.warmstart_coeff; im.z = im.z * P.warmstart_coeff; im.w = im.w * P.warmstart_coeff;
+    ti.z = ti.z + ti.x; ti.w = ti.w + ti.y; ti.x = ti.x * P.warmstart_coeff; ti.y = ti.y * P.warmstart_coeff;
+    wi.y = wi.y + wi.x; wi.x = wi.x * P.warmstart_coeff;
+    mu.mr(MR_IMP, s) = im; mu.mr(MR_ACC, s) = ac; mu.mr(MR_TI, s) = ti; mu.mr(MR_WI, s) = wi;
+}
+// One side of one constraint applied to its body (v, wv): the operations coop_stage<MODE_WARMSTART> performs on that side.
+RB_HD void coop_warmstart_side(const RowView& cs, const RowView& mu, int s, int side, vec3 im, vec3& v, vec3& wv) {
+    const float4 dirf = cs.pc(CR4_DIRF, s), t1w = cs.pc(CR4_T1W, s), trn = cs.pc(CR4_TR, s);
+    const float4 imp4 = mu.mr(MR_IMP, s), ti4 = mu.mr(MR_TI, s), wi4 = mu.mr(MR_WI, s);
+    const int nc = as_int(trn.w);
+    const vec3 dir = xyz(dirf), t1 = xyz(t1w);
+    const vec3 t2 = cross3(dir, t1);
+    const vec3 lin = had(dir, im);
+    const float imp[MAX_PTS] = {imp4.x, imp4.y, imp4.z, imp4.w};
+#pragma unroll
+    for (int k = 0; k < MAX_PTS; ++k) {
+        if (k < nc) {
+            const vec3 itd = xyz(cs.pp(side == 0 ? PR4_ITD1I : PR4_ITD2A, k, s));
+            v = madd3(v, lin, side == 0 ? imp[k] : -imp[k]);
+            wv = madd3(wv, itd, imp[k]);
+        }
+    }
+    const FrictionJac j = coop_get_jac(cs, s);
+    const float ti0 = ti4.x, ti1 = ti4.y, wi = wi4.x;
+    if (side == 0) {
+        v = madd3v(v, madd3(t1 * ti0, t2, ti1), im);
+        wv = madd3(madd3(wv, j.i10, ti0), j.i11, ti1);
+        if (nc > 1) wv = madd3(wv, j.tw1, wi);
+    } else {
+        v = madd3v(v, madd3(t1 * (-ti0), t2, -ti1), im);
+        wv = madd3(madd3(wv, j.i20, ti0), j.i21, ti1);
+        if (nc > 1) wv = madd3(wv, j.tw2, -wi);
+    }
+}
+
 // One work item, start to finish, by one CTA: bodies and impulses in shared memory; the constant
 // constraint rows resident in shared memory when they fit, else streamed from the L2 pool through the
 // staging pipeline (L lanes / constraint).
@@ -1497,15 +1541,33 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, 
     RB_TRACE();
     const bool bouncy_item = w.item_flags[item] != 0;
     const bool warm = P.warmstart_coeff != 0.0f;
-    const int total_sweeps = P.num_substeps * ((warm ? 1 : 0) + P.num_pgs + P.num_relax) + (bouncy_item ? 1 : 0);
+    const int total_sweeps = P.num_substeps * ((warm ? 1 : 0) + P.num_pgs + P.num_relax) + (bouncy_item ? 1 : 0);   // (pipeline sweeps of a streamed item)
     int done = 0;
     for (int sub = 0; sub < P.num_substeps; ++sub) {
         for (int l = b0 + tid; l < b1; l += nth) body_increment(w, bd, w.item_bodies[l], l - b0);
-        if (warm) {
+        if (warm && !resident) {   // streamed rows: warm start colour by colour through the staging pipeline
             ctx.block_sync();
             ++done;
             if (sub == 0) RB_TRACE();
             coop_sweep<L, MODE_WARMSTART>(ctx, w, bd, res, mu, resident, pp, s_stage, nstages, wslot, c0, false, done < total_sweeps);
+            if (sub == 0) RB_TRACE();
+        } else if (warm) {         // resident rows: body-centric (one barrier instead of one per colour)
+            if (sub == 0) RB_TRACE();
+            for (int s = tid; s < n; s += nth) coop_warmstart_bank(P, mu, s);
+            ctx.block_sync();   // (also orders the increments above before the gathers below)
+            if (!(w.debug_flags & 1))
+                for (int l = tid; l < b1 - b0; l += nth) {
+                    const int* adj = w.adj_list + w.adj_off[b0 + l];
+                    const int cnt = w.adj_cnt[b0 + l];
+                    vec3 v = bd.lin(l), wv = bd.ang(l);
+                    const vec3 im = bd.im(l);
+                    for (int i = 0; i < cnt; ++i) {
+                        const int e = adj[i];
+                        coop_warmstart_side(res, mu, e >> 1, e & 1, im, v, wv);
+                    }
+                    bd.set_vel(l, v, wv);
+                }
+            ctx.block_sync();
             if (sub == 0) RB_TRACE();
         } else {   // bank the impulses without applying them
             for (int s = tid; s < n; s += nth) {

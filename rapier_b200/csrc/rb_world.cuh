@@ -166,6 +166,9 @@ struct World {
     int* cons_pair_tmp;               // [cons_cap] pair index grouped by item (unsorted)
     int* cons_pair;                   // [cons_cap] pair index in schedule order
     int* item_color_off;              // [item_cap][NUM_COLORS + 1] offsets relative to item_cons_start
+    int* adj_off;                     // [nb] per item body slot: start of its contact adjacency in adj_list
+    int* adj_cnt;                     // [nb] ... and its length
+    int* adj_list;                    // [2 * cons_cap] item-local slot * 2 + side, ascending (= colour stage order)
     int* item_order;                  // [item_cap] non-empty items 1.., most expensive first (launch order of the solve CTAs)
     int* order_hist;                  // [2 * ORDER_BUCKETS + 1] counting-sort scratch of item_order
     int* color_count;                 // [NUM_COLORS] global histogram
