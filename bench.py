@@ -183,7 +183,7 @@ def main():
     if world_size > 1:
         from rapier_b200.sharding import IslandShard
         shard = IslandShard(pipe, dist, rank, world_size, torch.device("cuda", local_rank),
-                            overlap=os.environ.get("RB_SHARD_OVERLAP", "0") == "1")   # measured slower at N=2 (host-bound), see DESIGN.md 6
+                            overlap=os.environ.get("RB_SHARD_OVERLAP", "1") == "1")   # asynchronous in-place gather of the double-buffered state
         exchange = shard.exchange
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if args.l2 == "flush" else None
@@ -224,6 +224,9 @@ def main():
         prof = pipe.counters()
         pipe.enable_profiling(False)
         # ---- e2e: host buffers in / out every step through the public C-ABI call ----
+        if exchange is not None:   # host-fed steps overwrite every body's state: exchange synchronously here
+            shard.finish()
+            shard.overlap = False
         e2e_steps = min(args.steps, 200)
         pose, vel = pipe.body_states()
         # host-side state buffers of the caller: page-locked (the library DMAs them directly)
@@ -325,7 +328,7 @@ def main():
             "config": {"workload": workload_name(args.scene, world_size), "bodies_per_gpu": per_rank_bodies,
                        "manifolds_per_gpu": M, "substeps": 4, "sweeps_per_substep": 3,
                        "l2": "flushed between steps (256 MiB memset)" if args.l2 == "flush" else "not flushed",
-                       "parallelism": "1 GPU" if world_size == 1 else f"islands sharded over {world_size} GPUs, NCCL all-gather of body states every step" + (" (asynchronous: overlapped with the next step, imported one step late, drained at the end)" if os.environ.get("RB_SHARD_OVERLAP", "0") == "1" else " (in place on the state buffer)")},
+                       "parallelism": "1 GPU" if world_size == 1 else f"islands sharded over {world_size} GPUs, NCCL all-gather of body states every step" + (" (asynchronous: overlapped with the next step, imported one step late, drained at the end)" if os.environ.get("RB_SHARD_OVERLAP", "1") == "1" else " (in place on the state buffer)")},
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": nb * 13 * 4, "d2h_bytes_per_step": nb * 13 * 4,
                     "steps": e2e_steps},
             "gpu_launches": int(k1 - k0),

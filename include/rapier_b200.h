@@ -204,6 +204,12 @@ int rb_world_state_buffer(RbWorld* w, void** device_ptr, int64_t* bytes);
  * src_dev == NULL: the rows were all-gathered in place into rb_world_state_buffer; body idx[k] is
  * imported from its own row. */
 int rb_world_import_states(RbWorld* w, const int32_t* idx_dev, const float* src_dev, int32_t n);
+/* ... from a whole [num_bodies][13] state table (device pointer; typically one of the two buffers below). */
+int rb_world_import_states_from(RbWorld* w, const int32_t* idx_dev, const float* table_dev, int32_t n);
+/* Double-buffers the packed state: counted from this call, step k writes buffer (k & 1), so the buffer just
+ * written can be all-gathered in place, asynchronously, under the next step.  rb_world_get_body_states and
+ * rb_world_step_host keep reading / writing the most recent buffer. */
+int rb_world_state_buffers(RbWorld* w, void** device_ptr0, void** device_ptr1, int64_t* bytes);
 /* The CUDA stream all of this world's work is enqueued on / replace it by a caller-owned stream. */
 void* rb_world_stream(RbWorld* w);
 int rb_world_set_stream(RbWorld* w, void* cuda_stream);

@@ -18,7 +18,7 @@ EXPORTS = [
     "rb_world_step", "rb_world_synchronize", "rb_world_get_body_states", "rb_world_num_bodies",
     "rb_world_get_counters", "rb_world_enable_profiling", "rb_world_get_contact_pairs",
     "rb_world_debug_read", "rb_world_label_components", "rb_world_set_owned_bodies",
-    "rb_world_state_buffer", "rb_world_import_states", "rb_world_stream", "rb_world_set_stream",
+    "rb_world_state_buffer", "rb_world_import_states", "rb_world_import_states_from", "rb_world_state_buffers", "rb_world_stream", "rb_world_set_stream",
     "rb_world_step_host",
 ]
 
@@ -48,6 +48,8 @@ def declare(L):
     L.rb_world_set_owned_bodies.argtypes = [vp, vp]
     L.rb_world_state_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
     L.rb_world_import_states.argtypes = [vp, vp, vp, i32]
+    L.rb_world_import_states_from.argtypes = [vp, vp, vp, i32]
+    L.rb_world_state_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64)]
     L.rb_world_stream.restype = vp
     L.rb_world_stream.argtypes = [vp]
     L.rb_world_set_stream.argtypes = [vp, vp]

@@ -82,16 +82,17 @@ RB_PHASE void init_bodies_phase(const Ctx& ctx, const World& w) {
 
 // Scatter of externally provided body states (multi-GPU boundary all-gather): 13 floats per body.
 template <class Ctx>
-RB_PHASE void import_states_phase(const Ctx& ctx, const World& w, const int* idx, const float* src, int n) {
+RB_PHASE void import_states_phase(const Ctx& ctx, const World& w, const int* idx, const float* src, int n, int table) {
     for (int k = ctx.gtid; k < n; k += ctx.gsize) {
         int b = idx[k];
         float* d = w.state13 + (size_t)b * 13;
-        const float* s = src ? src + (size_t)k * 13 : d;   // src == NULL: the rows were gathered in place into the state buffer
+        // src == NULL: the rows were gathered in place into the state buffer; table: src is a whole [nb][13] table
+        const float* s = src ? src + (size_t)(table ? b : k) * 13 : d;
         w.b_pos_t[b] = make_float4(s[0], s[1], s[2], 0.f);
         w.b_pos_q[b] = make_float4(s[3], s[4], s[5], s[6]);
         w.b_linvel[b] = make_float4(s[7], s[8], s[9], 0.f);
         w.b_angvel[b] = make_float4(s[10], s[11], s[12], 0.f);
-        if (src)
+        if (s != d && !table)   // (table mode: the current buffer's rows of these bodies belong to an in-flight gather)
             for (int i = 0; i < 13; ++i) d[i] = s[i];
         update_world_mass(w, b, body_pose(w, b));
     }
@@ -186,9 +187,9 @@ __global__ void k_init_bodies(World w) {
     GridCtx ctx;
     init_bodies_phase(ctx, w);
 }
-__global__ void k_import_states(World w, const int* idx, const float* src, int n) {
+__global__ void k_import_states(World w, const int* idx, const float* src, int n, int table) {
     GridCtx ctx;
-    import_states_phase(ctx, w, idx, src, n);
+    import_states_phase(ctx, w, idx, src, n, table);
 }
 #endif
 
@@ -208,6 +209,8 @@ struct RbWorld {
     int collide_threads = COLLIDE_THREADS;
     int coop_blocks_big = 1;
     int big_threads = COOP_BIG_THREADS, sweep_threads = 0;
+    float* state_buf[2] = {nullptr, nullptr};   // double-buffered packed state (rb_world_state_buffers), else unused
+    int state_next = 0;
     int steps_since_scene = 0;   // the launch-shape hint of a new scene is awaited once (see rb_world_step)
     int coop_shape = -1;   // RB_COOP_SHAPE debugging override: 0 small, 1 big, -1 automatic
     int* host_hint = nullptr;
@@ -547,6 +550,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
         }
     }
     W->steps_since_scene = 0;
+    W->state_buf[0] = W->state_buf[1] = nullptr;
     W->bodies.assign(bodies, bodies + nb);
     W->colliders.assign(colliders, colliders + nc);
     W->joints.assign(joints, joints + nj);
@@ -809,6 +813,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         bool prof = W->profiling;
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s], W->stream));
         int do_solve = 1;
+        if (W->state_buf[1]) { W->w.state13 = W->state_buf[W->state_next]; W->state_next ^= 1; }
         // A new scene's islands are only known after its first schedule.  A caller that enqueues many steps in
         // one asynchronous call would otherwise run all of them in the launch shape chosen before that, so the
         // first call after a scene upload waits ONCE, after its second step, for the device hint.
@@ -855,6 +860,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
     (void)sync;
     for (int s = 0; s < nsteps; ++s) {
         GridCtx gctx;
+        if (W->state_buf[1]) { W->w.state13 = W->state_buf[W->state_next]; W->state_next ^= 1; }
         W->emu_hint = W->w.st->need_big;
         W->w.st->need_big = W->w.st->coop_streamed = W->w.st->coop_resident = 0;
         collide_pipeline(gctx, W->w);
@@ -1138,19 +1144,51 @@ int rb_world_state_buffer(RbWorld* W, void** device_ptr, int64_t* bytes) {
     return RB_OK;
 }
 
-// Imports externally simulated body states (device pointers): idx[n] body indices, src[n*13].
-int rb_world_import_states(RbWorld* W, const int32_t* idx_dev, const float* src_dev, int32_t n) {
+static int import_states_impl(RbWorld* W, const int32_t* idx_dev, const float* src_dev, int32_t n, int table) {
     if (!W || n < 0) return RB_ERR_INVALID;
     if (n == 0) return RB_OK;
 #if RB_DEVICE_BUILD
     CK(cudaSetDevice(W->device));
-    k_import_states<<<(n + 255) / 256, 256, 0, W->stream>>>(W->w, idx_dev, src_dev, n);
+    k_import_states<<<(n + 255) / 256, 256, 0, W->stream>>>(W->w, idx_dev, src_dev, n, table);
     CK(cudaGetLastError());
     W->kernels++;
 #else
     GridCtx g;
-    import_states_phase(g, W->w, idx_dev, src_dev, n);
+    import_states_phase(g, W->w, idx_dev, src_dev, n, table);
 #endif
+    return RB_OK;
+}
+// Imports externally simulated body states (device pointers): idx[n] body indices, src[n*13].
+int rb_world_import_states(RbWorld* W, const int32_t* idx_dev, const float* src_dev, int32_t n) {
+    return import_states_impl(W, idx_dev, src_dev, n, 0);
+}
+// ... from a whole [num_bodies][13] state table (one of the two buffers of rb_world_state_buffers).
+int rb_world_import_states_from(RbWorld* W, const int32_t* idx_dev, const float* table_dev, int32_t n) {
+    if (!table_dev) return RB_ERR_INVALID;
+    return import_states_impl(W, idx_dev, table_dev, n, 1);
+}
+// Turns on double buffering of the packed state: step k writes buffer (k & 1) counted from this call, so an
+// asynchronous in-place all-gather of the buffer just written can run under the next step.
+int rb_world_state_buffers(RbWorld* W, void** ptr0, void** ptr1, int64_t* bytes) {
+    if (!W || !ptr0 || !ptr1 || !bytes) return RB_ERR_INVALID;
+    const size_t n = (size_t)std::max(W->w.nb, 1) * 13;
+    if (!W->state_buf[1]) {
+        float* second = nullptr;
+        int rc = alloc_arr(W, &second, n);
+        if (rc != RB_OK) return rc;
+        W->state_buf[0] = W->w.state13;
+        W->state_buf[1] = second;
+#if RB_DEVICE_BUILD
+        CK(cudaSetDevice(W->device));
+        CK(cudaMemcpyAsync(second, W->w.state13, n * sizeof(float), cudaMemcpyDeviceToDevice, W->stream));
+        CK(cudaStreamSynchronize(W->stream));
+#else
+        memcpy(second, W->w.state13, n * sizeof(float));
+#endif
+        W->state_next = 0;
+    }
+    *ptr0 = W->state_buf[0]; *ptr1 = W->state_buf[1];
+    *bytes = (int64_t)W->w.nb * 13 * 4;
     return RB_OK;
 }
 

@@ -30,6 +30,14 @@ class _CudaBuf:
         self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
+def _view(ptr, nbytes, device):
+    if device.type == "cuda":
+        t = torch.as_tensor(_CudaBuf(ptr, nbytes), device=device)
+    else:
+        t = torch.frombuffer((C.c_float * (nbytes // 4)).from_address(ptr), dtype=torch.float32)
+    return t.view(-1, 13)
+
+
 def state_tensor(pipe, device):
     """Zero-copy torch view [nb, 13] of the library's packed body-state buffer."""
     ptr, nbytes = pipe.state_buffer()
@@ -41,15 +49,18 @@ def state_tensor(pipe, device):
 
 
 class IslandShard:
-    """`overlap=True` (CUDA only): the all-gather of step n runs asynchronously on NCCL's stream while
-    step n+1 is computed, and its result is imported before step n+2.  Bodies simulated by other ranks
-    are then seen one step late -- they never touch this rank's components, the states only feed
-    proximity detection and download -- and `finish()` drains the pipeline so every rank ends with the
-    exact state of every body."""
+    """`overlap=True`: the all-gather of step n runs asynchronously (on NCCL's stream) while step n+1 is
+    computed, and its result is imported before step n+2.  Bodies simulated by other ranks are then seen
+    one step late -- they never touch this rank's components, the states only feed proximity detection
+    and download -- and `finish()` drains the pipeline so every rank ends with the exact state of every
+    body.  With contiguous equal shards the library double-buffers its packed state (step k writes buffer
+    k & 1) and the gather runs IN PLACE on the buffer just written: per step one collective and one
+    import kernel, no packing, nothing on the critical path but the import."""
 
     def __init__(self, pipe, dist, rank, world_size, device, overlap=False):
         self.pipe, self.dist, self.rank, self.world_size = pipe, dist, rank, world_size
-        self.overlap = bool(overlap) and device.type == "cuda"
+        self.overlap = bool(overlap)
+        self.device = device
         self.pending = None
         self.tick = 0
         comp = pipe.label_components()
@@ -77,7 +88,13 @@ class IslandShard:
             n = self.counts[0]
             self.block = self.state[lo[0]:lo[0] + world_size * n].view(world_size, n * 13)
             self.block_flat = self.block.view(-1)
-        if self.overlap:   # double-buffered snapshots / receive buffers of the asynchronous all-gather
+        if self.overlap and self.inplace:   # double-buffered library state: gather the buffer the step just wrote
+            p0, p1, nbytes = pipe.state_buffers()
+            self.tables = [_view(p0, nbytes, device), _view(p1, nbytes, device)]
+            self.table_ptr = [p0, p1]
+            n = self.counts[0]
+            self.blocks = [t[lo[0]:lo[0] + world_size * n].view(world_size, n * 13) for t in self.tables]
+        elif self.overlap:                  # packed: double-buffered snapshots / receive buffers
             self.send2 = [torch.zeros(self.maxc, 13, device=device) for _ in range(2)]
             self.recv2 = [torch.zeros(world_size * self.maxc, 13, device=device) for _ in range(2)]
 
@@ -91,11 +108,30 @@ class IslandShard:
         if self.pending is not None:
             work, recv = self.pending
             work.wait()
-            self._import_from(recv)
+            if isinstance(recv, int):
+                if len(self.imp_idx):
+                    self.pipe.import_states_from(self.imp_idx.data_ptr(), self.table_ptr[recv], len(self.imp_idx))
+            else:
+                self._import_from(recv)
             self.pending = None
 
     def exchange(self):
         """All-gather the owned body states and import the states simulated by the other ranks."""
+        if self.inplace and hasattr(self, "tables"):
+            k = self.table_ptr.index(self.pipe.state_buffer()[0])   # the buffer the step that was just enqueued writes
+            if not self.overlap:   # (overlap switched off at run time: same buffers, synchronous)
+                self.finish()
+                self.dist.all_gather_into_tensor(self.blocks[k].view(-1), self.blocks[k][self.rank])
+                if len(self.imp_idx):
+                    self.pipe.import_states_from(self.imp_idx.data_ptr(), self.table_ptr[k], len(self.imp_idx))
+                return
+            work = self.dist.all_gather_into_tensor(self.blocks[k].view(-1), self.blocks[k][self.rank], async_op=True)
+            previous, self.pending = self.pending, (work, k)
+            if previous is not None:   # the previous step's gather: import it before the next step
+                previous[0].wait()
+                if len(self.imp_idx):
+                    self.pipe.import_states_from(self.imp_idx.data_ptr(), self.table_ptr[previous[1]], len(self.imp_idx))
+            return
         if self.overlap:
             send, recv = self.send2[self.tick & 1], self.recv2[self.tick & 1]
             self.tick += 1

@@ -136,6 +136,15 @@ class PhysicsPipeline:
         self._check(self.L.rb_world_state_buffer(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def state_buffers(self):
+        """Turns on double buffering of the packed state (see include/rapier_b200.h); returns (ptr0, ptr1, bytes)."""
+        p0, p1, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._check(self.L.rb_world_state_buffers(self.h, C.byref(p0), C.byref(p1), C.byref(n)))
+        return p0.value, p1.value, n.value
+
+    def import_states_from(self, idx_dev_ptr, table_dev_ptr, n):
+        self._check(self.L.rb_world_import_states_from(self.h, idx_dev_ptr, table_dev_ptr, n))
+
 
 class PhysicsWorld:
     """PhysicsWorld facade (src/pipeline/physics_world.rs): sets + pipeline + gravity."""

@@ -21,12 +21,13 @@ dist.init_process_group("gloo")
 rank, ws = dist.get_rank(), dist.get_world_size()
 scene = scenes.pyramids(*{shape!r})
 w = PhysicsWorld(scene, _lib=emul_lib.lib()); w._flush()
-shard = IslandShard(w.physics_pipeline, dist, rank, ws, torch.device("cpu"))
+shard = IslandShard(w.physics_pipeline, dist, rank, ws, torch.device("cpu"), overlap={overlap!r})
 assert sorted(set(shard.owner.tolist())) == [-1, 0, 1], set(shard.owner.tolist())
 assert shard.inplace == {inplace!r}, shard.inplace
 for _ in range(25):
     w.physics_pipeline.step(scene.gravity, 1)
     shard.exchange()
+shard.finish()
 pose, vel = w.body_states()
 np.save({out!r} + f"_{{rank}}.npy", np.concatenate([pose, vel], axis=1))
 dist.destroy_process_group()
@@ -36,15 +37,16 @@ dist.destroy_process_group()
 import pytest
 
 
-@pytest.mark.parametrize("shape,inplace", [((2, 2, 6), True), ((1, 3, 6), False)], ids=["equal_contiguous_shards_in_place", "unequal_shards_packed"])
-def test_sharded_run_matches_single_process(tmp_path, shape, inplace):
+@pytest.mark.parametrize("shape,inplace,overlap", [((2, 2, 6), True, False), ((1, 3, 6), False, False), ((2, 2, 6), True, True), ((1, 3, 6), False, True)],
+                         ids=["equal_contiguous_shards_in_place", "unequal_shards_packed", "in_place_double_buffered_async", "packed_async"])
+def test_sharded_run_matches_single_process(tmp_path, shape, inplace, overlap):
     import emul_lib
     from rapier_b200 import scenes
     from rapier_b200.world import PhysicsWorld
     emul_lib.lib()
     out = str(tmp_path / "state")
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, out=out, shape=shape, inplace=inplace))
+    script.write_text(WORKER.format(root=ROOT, out=out, shape=shape, inplace=inplace, overlap=overlap))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
     subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                            "--master-port", "29533", str(script)], env=env, timeout=600)
