@@ -124,7 +124,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} consecutive steps of the full scene after {max(args.warmup, 3)} warm-up steps"},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU restatement (oracle/), not the reference binary: no Rust toolchain in this image",
+        "note": "CPU restatement (oracle/), not the reference binary: no Rust toolchain in this image. value = steps/s of ONE replica of the workload on all host threads; under weak scaling (N replicas) a CPU's replica-steps/s stay the same, so it is the comparable whole-job figure for every N",
     }
     print(json.dumps(line), flush=True)
 
