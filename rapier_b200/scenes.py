@@ -5,7 +5,7 @@ no RNG).  Each builder returns a `Scene` (bodies, colliders, joi
 """
 import numpy as np
 
-from .sets import (ColliderBuilder, ColliderSet, ImpulseJointSet, RigidBodyBuilder, RigidBodySet,
+from .sets import (ColliderBuilder, ColliderSet, ImpulseJointSet, RevoluteJointBuilder, RigidBodyBuilder, RigidBodySet,
                    SphericalJointBuilder)
 
 F = np.float32
@@ -195,3 +195,43 @@ REGISTRY = {
     "b3d_joint_grid": joint_grid,
     "keva3": keva,
 }
+
+
+def offset_com_pendulums(n=128, spacing=20.0, com_offset=1.0):
+    """crates/rapier3d/tests/issue_952_simd_joint_offset_com.rs:20-44: n independent pendulums, each a dynamic
+    body whose collider (and so its centre of mass) is offset from the body origin, pinned at its ORIGIN to a
+    fixed base by a revolute joint about Z.  (The reference uses a capsule; a cuboid of the same extent stands
+    in for it -- only the offset centre of mass matters.)"""
+    s = Scene(f"offset_com_pendulums_{n}")
+    s.pendulums = []
+    for i in range(n):
+        base_pos = (float(i) * spacing, 0.0, 0.0)
+        base = s.bodies.insert(RigidBodyBuilder.fixed().translation(base_pos))
+        body = s.bodies.insert(RigidBodyBuilder.dynamic().translation(base_pos))
+        s.colliders.insert_with_parent(ColliderBuilder.cuboid(com_offset, 0.2, 0.2).translation((com_offset, 0.0, 0.0)), body)
+        s.joints.insert(base, body, RevoluteJointBuilder((0.0, 0.0, 1.0)).contacts_enabled(False))
+        s.pendulums.append((body, base_pos))
+    return s
+
+
+def heavy_end_chain(num=17, rad=0.2):
+    """crates/rapier3d/tests/substep_chain_high_mass_ratio.rs:17-55: a chain of balls on spherical joints hanging
+    from a fixed ball, the last ball 10x the radius (1000:1 mass ratio).  Gravity is the default (0, -9.81, 0);
+    the chain is laid out along z, so it swings."""
+    s = Scene(f"heavy_end_chain_{num}")
+    s.chain_joints = []
+    prev = None
+    shift1 = rad * 1.1
+    for i in range(num):
+        ball_rad = rad * 10.0 if i == num - 1 else rad
+        shift2 = ball_rad + rad * 0.1
+        z = 0.0 if i == 0 else (float(i) - 1.0) * 2.0 * shift1 + shift1 + shift2
+        bb = (RigidBodyBuilder.fixed() if i == 0 else RigidBodyBuilder.dynamic()).translation((0.0, 0.0, z))
+        h = s.insert(bb, ColliderBuilder.ball(ball_rad))
+        if prev is not None:
+            a1 = (0.0, 0.0, 0.0) if i == 1 else (0.0, 0.0, shift1)
+            a2 = (0.0, 0.0, -shift1 * 2.0) if i == 1 else (0.0, 0.0, -shift2)
+            s.joints.insert(prev, h, SphericalJointBuilder().local_anchor1(a1).local_anchor2(a2))
+            s.chain_joints.append((prev, h, a1, a2))
+        prev = h
+    return s

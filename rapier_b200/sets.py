@@ -226,6 +226,30 @@ def FixedJointBuilder():
     return GenericJointBuilder(0b111111)
 
 
+def _rotation_arc_from_x(axis):
+    """Minimal rotation taking +X to `axis` (GenericJoint::complete_ang_frame, generic_joint.rs:374-389), xyzw."""
+    import math
+    a = [float(x) for x in axis]
+    n = math.sqrt(sum(x * x for x in a))
+    a = [x / n for x in a]
+    d = a[0]                       # dot(X, axis)
+    if d > 1.0 - 1e-7:
+        return (0.0, 0.0, 0.0, 1.0)
+    if d < -1.0 + 1e-7:
+        return (0.0, 0.0, 1.0, 0.0)   # half turn about Z
+    c = (0.0, -a[2], a[1])         # cross(X, axis)
+    s = math.sqrt((1.0 + d) * 2.0)
+    return (c[0] / s, c[1] / s, c[2] / s, s * 0.5)
+
+
+def RevoluteJointBuilder(axis):
+    """RevoluteJointBuilder::new(axis) (revolute_joint.rs): every axis locked except the rotation about `axis`,
+    which is the X axis of both joint frames."""
+    b = GenericJointBuilder(0b110111)   # LIN_X | LIN_Y | LIN_Z | ANG_Y | ANG_Z
+    b._q1 = b._q2 = _rotation_arc_from_x(axis)
+    return b
+
+
 class RigidBodySet:
     def __init__(self):
         self.descs = []

@@ -139,3 +139,53 @@ def test_manifold_rotated_box_eight_points():
                                              (0.0, 1.0, 0.0), (0, s, 0, c))
     assert len(pts) == 8
     assert np.allclose(np.abs(pts[:, 6]), 0.0, atol=1e-5)
+
+
+def _rotate(q, v):
+    x, y, z, w = q
+    u = np.array([x, y, z])
+    return v + 2.0 * np.cross(u, np.cross(u, v) + w * v)
+
+
+@pytest.mark.parametrize("n", [8, 128])
+def test_joint_anchor_with_offset_centre_of_mass(n):
+    """crates/rapier3d/tests/issue_952_simd_joint_offset_com.rs:48-83: a joint anchored at the ORIGIN of a body whose
+    centre of mass is offset must pin the origin (error < 1e-2 over 120 steps), for few and for many joints."""
+    scene = scenes.offset_com_pendulums(n)
+    w = oracle_lib.OracleWorld(scene)
+    max_err = 0.0
+    for _ in range(120):
+        w.step()
+        pose, _ = w.body_states()
+        for body, base in scene.pendulums:
+            max_err = max(max_err, float(np.linalg.norm(pose[body, :3] - np.array(base))))
+    assert max_err < 1.0e-2, max_err
+    # and it really is a pendulum: the body swung down about the joint
+    pose, _ = w.body_states()
+    assert pose[scene.pendulums[0][0], 3:].tolist() != [0.0, 0.0, 0.0, 1.0]
+
+
+def _peak_stretch(world, scene, steps):
+    peak = 0.0
+    for _ in range(steps):
+        world.step()
+        pose, _ = world.body_states()
+        for b1, b2, a1, a2 in scene.chain_joints:
+            p1 = pose[b1, :3] + _rotate(pose[b1, 3:], np.array(a1))
+            p2 = pose[b2, :3] + _rotate(pose[b2, 3:], np.array(a2))
+            peak = max(peak, float(np.linalg.norm(p1 - p2)))
+    return peak
+
+
+def test_heavy_end_chain_stiffens_with_more_substeps():
+    """crates/rapier3d/tests/substep_chain_high_mass_ratio.rs:147-161: 1000:1 chain over 300 steps; 16 additional
+    solver iterations (= 20 substeps for the chain's group, the whole scene here) must cut the peak joint stretch
+    at least 4x compared to the default 4."""
+    scene = scenes.heavy_end_chain()
+    baseline = _peak_stretch(oracle_lib.OracleWorld(scene), scene, 300)
+    from rapier_b200._abi import RbIntegrationParameters
+    params = RbIntegrationParameters.default()
+    params.num_solver_iterations = 20
+    elevated = _peak_stretch(oracle_lib.OracleWorld(scene, params=params), scene, 300)
+    assert np.isfinite(baseline) and np.isfinite(elevated)
+    assert elevated < baseline / 4.0, (baseline, elevated)

@@ -62,4 +62,8 @@ VARIANTS = [
     ("two_pgs_no_relax", lambda: scenes.box_pile(3, 2, 3), _params(num_internal_pgs_iterations=2, num_internal_stabilization_iterations=0), 100, 20),
     ("six_substeps_no_recycling", lambda: scenes.pyramids(1, 1, 8), _params(num_solver_iterations=6, contact_recycling=0), 40, 10),
     ("length_unit_10", lambda: scenes.box_pile(2, 3, 2), _params(length_unit=10.0), 80, 20),
+    # scenes of the reference's joint known-answer tests (tests/test_oracle_kat.py): revolute joints on bodies with an
+    # offset centre of mass (issue_952), and the 1000:1 chain with 20 substeps (substep_chain_high_mass_ratio)
+    ("revolute_offset_com", lambda: scenes.offset_com_pendulums(16), None, 80, 20),
+    ("heavy_chain_20_substeps", scenes.heavy_end_chain, _params(num_solver_iterations=20), 60, 20),
 ]
