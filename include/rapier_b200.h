@@ -89,7 +89,8 @@ typedef struct RbBodyDesc {
     float linear_damping;
     float angular_damping;
     float gravity_scale;
-    float additional_mass;        /* added at the body origin (MassProperties additive term); 0 = none */
+    float additional_mass;        /* RigidBodyAdditionalMassProps::Mass: added to the colliders' mass, angular inertia rescaled
+                                   * (derived from the shape at unit density when the colliders are massless); 0 = none */
     float user_force[3];
     float user_torque[3];
 } RbBodyDesc;

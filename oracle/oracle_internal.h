@@ -41,6 +41,7 @@ struct Body {
     Pose next_pos;   // RigidBodyPosition::next_position
     V3 linvel, angvel;
     float lin_damping, ang_damping, gravity_scale;
+    float additional_mass;   // RigidBodyAdditionalMassProps::Mass (0 = none)
     V3 user_force, user_torque;
     // local mass properties (parry MassProperties)
     V3 local_com;

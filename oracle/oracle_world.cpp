@@ -96,8 +96,32 @@ static int recompute_mass_properties(World& w) {
             b.inv_mass = inv_exact0(M);
             b.inv_principal_inertia = V3{inv_exact0(I.x), inv_exact0(I.y), inv_exact0(I.z)};
         }
-        // additional mass at the body origin is only supported for collider-less bodies.
-        (void)0;
+        // RigidBodyAdditionalMassProps::Mass (rigid_body_components.rs:454-486); MassProperties::set_mass(m, true)
+        // [parry] rescales the angular inertia by new_mass / old_mass, i.e. its inverse by inv(new) * old.
+        if (b.additional_mass > 0.0f) {
+            const float add = b.additional_mass;
+            const float prev = inv_exact0(b.inv_mass);
+            if (prev > 0.0f) {
+                const float inv_new = inv_exact0(prev + add);
+                b.inv_principal_inertia = b.inv_principal_inertia * (inv_new * prev);
+                b.inv_mass = inv_new;
+            } else if (count[bi] == 1) {
+                // massless collider: inertia and centre of mass of the shape at unit density, rescaled to the mass
+                Collider u = w.colliders[first[bi]];
+                u.density = 1.0f;
+                float um; V3 upi;
+                collider_mass(u, um, upi);
+                const float inv_new = inv_exact0(add);
+                b.local_com = u.pos_wrt_parent.t;
+                b.principal_frame = u.pos_wrt_parent.q;
+                b.inv_principal_inertia = V3{inv_exact0(upi.x), inv_exact0(upi.y), inv_exact0(upi.z)} * (inv_new * um);
+                b.inv_mass = inv_new;
+            } else if (count[bi] == 0) {
+                b.inv_mass = inv_exact0(add);   // no shape to derive an inertia from: just the mass
+            } else {
+                return RB_ERR_INVALID;          // massless multi-collider bodies with additional mass: not supported
+            }
+        }
         b.principal_inertia = V3{inv_exact0(b.inv_principal_inertia.x), inv_exact0(b.inv_principal_inertia.y),
                                  inv_exact0(b.inv_principal_inertia.z)};
     }
@@ -579,6 +603,7 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
         b.lin_damping = d.linear_damping;
         b.ang_damping = d.angular_damping;
         b.gravity_scale = d.gravity_scale;
+        b.additional_mass = d.additional_mass;
         b.user_force = f3(d.user_force);
         b.user_torque = f3(d.user_torque);
         b.force = vzero();

@@ -371,6 +371,32 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out) {
                 m.inv_mass = inv0(M);
             }
         }
+        // RigidBodyAdditionalMassProps::Mass (rigid_body_components.rs:454-486); MassProperties::set_mass(m, true)
+        // [parry] rescales the angular inertia by new_mass / old_mass, i.e. its inverse by inv(new) * old.
+        const float add = W->bodies[b].additional_mass;
+        if (add > 0.0f) {
+            const float prev = inv0(m.inv_mass);
+            if (prev > 0.0f) {
+                const float inv_new = inv0(prev + add);
+                for (int k = 0; k < 3; ++k) m.ipi[k] = m.ipi[k] * (inv_new * prev);
+                m.inv_mass = inv_new;
+            } else if (count[b] == 1) {
+                // massless collider: inertia and centre of mass of the shape at unit density, rescaled to the mass
+                RbColliderDesc u = W->colliders[first[b]];
+                u.density = 1.0f;
+                float um, upi[3];
+                collider_mass_props(u, um, upi);
+                const float inv_new = inv0(add);
+                for (int k = 0; k < 3; ++k) { m.lcom[k] = u.pos_wrt_parent_t[k]; m.ipi[k] = inv0(upi[k]) * (inv_new * um); }
+                for (int k = 0; k < 4; ++k) m.pframe[k] = u.pos_wrt_parent_q[k];
+                m.inv_mass = inv_new;
+            } else if (count[b] == 0) {
+                m.inv_mass = inv0(add);   // no shape to derive an inertia from: just the mass
+            } else {
+                set_err("additional mass on a massless multi-collider body is not supported%s", "");
+                return RB_ERR_INVALID;
+            }
+        }
         for (int k = 0; k < 3; ++k) m.pi[k] = inv0(m.ipi[k]);
     }
     return RB_OK;

@@ -64,6 +64,11 @@ class RigidBodyBuilder:
         self._angvel = tuple(float(x) for x in v)
         return self
 
+    def additional_mass(self, m):
+        """RigidBodyBuilder::additional_mass (RigidBodyAdditionalMassProps::Mass)."""
+        self._additional_mass = float(m)
+        return self
+
     def linear_damping(self, d):
         self._linear_damping = float(d)
         return self

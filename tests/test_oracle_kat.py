@@ -189,3 +189,67 @@ def test_heavy_end_chain_stiffens_with_more_substeps():
     elevated = _peak_stretch(oracle_lib.OracleWorld(scene, params=params), scene, 300)
     assert np.isfinite(baseline) and np.isfinite(elevated)
     assert elevated < baseline / 4.0, (baseline, elevated)
+
+
+def _mass_twin_world(additional, tall):
+    """Scenes of issue_78_additional_mass_rest.rs:9-40 (tilted cube dropped on a slab) and
+    issue_666_additional_mass_inertia.rs:12-39 (fast tall cuboid on rough ground): the body's mass comes either from
+    its collider's density or from RigidBody::additional_mass with a massless collider."""
+    from rapier_b200.sets import ColliderBuilder, RigidBodyBuilder
+    s = scenes.Scene("mass_twin")
+    if tall:
+        s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.1, 0.0)), ColliderBuilder.cuboid(100.1, 0.1, 100.1).friction(0.5))
+        body = RigidBodyBuilder.dynamic().translation((-10.0, 6.0, 0.0)).linvel((20.0, 0.0, 0.0))
+        he, mass = (0.2, 5.0, 1.5), 0.5
+    else:
+        s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(5.0, 0.5, 5.0).friction(0.5))
+        body = RigidBodyBuilder.dynamic().translation((0.0, 1.0, 0.0)).rotation((0.0, 0.0, np.pi / 4 * 0.9))
+        he, mass = (0.5, 0.5, 0.5), 100.0
+    volume = 8.0 * he[0] * he[1] * he[2]
+    col = ColliderBuilder.cuboid(*he).friction(0.5).restitution(0.0)
+    if additional:
+        body = body.additional_mass(mass)
+        col = col.density(0.0)
+    else:
+        col = col.density(mass / volume)    # ColliderBuilder::mass(m)
+    h = s.insert(body, col)
+    return s, h
+
+
+def test_additional_mass_body_rests_like_density_twin():
+    """crates/rapier3d/tests/issue_78_additional_mass_rest.rs:58-78 (sleeping is out of scope: "at rest" = slow)."""
+    rest_y, rest_step = [], []
+    for additional in (False, True):
+        scene, h = _mass_twin_world(additional, tall=False)
+        w = oracle_lib.OracleWorld(scene)
+        at = None
+        for step in range(600):
+            w.step()
+            pose, vel = w.body_states()
+            assert pose[h, 1] > -0.5, f"tunnelled at step {step}"
+            if at is None and step > 10 and np.abs(vel[h]).max() < 1e-2:
+                at = step
+        assert at is not None, "never came to rest"
+        rest_y.append(float(pose[h, 1])); rest_step.append(at)
+    assert abs(rest_y[0] - rest_y[1]) < 0.1, rest_y
+    assert rest_step[1] < max(rest_step[0], 1) * 4, rest_step
+
+
+def test_additional_mass_body_topples_like_density_twin():
+    """crates/rapier3d/tests/issue_666_additional_mass_inertia.rs:53-83: additional mass on a massless collider must
+    get an angular inertia from the shape, so the fast tall cuboid topples (rotation > 0.5 rad within 200 steps)."""
+    angles = []
+    for additional in (False, True):
+        scene, h = _mass_twin_world(additional, tall=True)
+        w = oracle_lib.OracleWorld(scene)
+        w.step()
+        if additional:
+            mp = w.debug_read("body_mprops", np.float32).reshape(-1, 16)
+            assert np.abs(mp[h, 4:7]).max() > 0.0, "additional_mass must produce a non-zero angular inertia"
+        mx = 0.0
+        for _ in range(200):
+            w.step()
+            pose, _ = w.body_states()
+            mx = max(mx, 2.0 * float(np.arccos(min(1.0, abs(pose[h, 6])))))
+        angles.append(mx)
+    assert angles[0] > 0.5 and angles[1] > 0.5, angles

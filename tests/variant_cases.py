@@ -53,6 +53,25 @@ def groups_and_joints():
     return s
 
 
+def additional_mass_twins():
+    """issue_78 / issue_666 scenes side by side: mass from collider density vs RigidBody::additional_mass on a
+    massless collider (host-side mass properties; tests/test_oracle_kat.py holds the known-answer checks)."""
+    from rapier_b200.sets import ColliderBuilder, RigidBodyBuilder
+    s = scenes.Scene("additional_mass_twins")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(30.0, 0.5, 30.0).friction(0.5))
+    for i, additional in enumerate((False, True, True)):
+        body = RigidBodyBuilder.dynamic().translation((-6.0 + 6.0 * i, 1.0, 0.0)).rotation((0.0, 0.0, 0.7))
+        col = ColliderBuilder.cuboid(0.5, 0.5, 0.5).friction(0.5)
+        if additional:
+            body = body.additional_mass(100.0)
+            col = col.density(0.0 if i == 1 else 50.0)   # massless collider / extra mass on top of a dense one
+        else:
+            col = col.density(100.0)
+        s.insert(body, col)
+    s.insert(RigidBodyBuilder.dynamic().translation((12.0, 3.0, 0.0)).additional_mass(2.0).linvel((0.0, 0.0, 1.0)), ColliderBuilder.ball(0.4).density(0.0))
+    return s
+
+
 VARIANTS = [
     ("restitution", bouncing_balls, None, 150, 25),
     ("groups_joints_forces", groups_and_joints, None, 150, 25),
@@ -66,4 +85,5 @@ VARIANTS = [
     # offset centre of mass (issue_952), and the 1000:1 chain with 20 substeps (substep_chain_high_mass_ratio)
     ("revolute_offset_com", lambda: scenes.offset_com_pendulums(16), None, 80, 20),
     ("heavy_chain_20_substeps", scenes.heavy_end_chain, _params(num_solver_iterations=20), 60, 20),
+    ("additional_mass_twins", additional_mass_twins, None, 120, 20),
 ]
