@@ -253,3 +253,26 @@ def test_additional_mass_body_topples_like_density_twin():
             mx = max(mx, 2.0 * float(np.arccos(min(1.0, abs(pose[h, 6])))))
         angles.append(mx)
     assert angles[0] > 0.5 and angles[1] > 0.5, angles
+
+
+def test_no_fixed_fixed_pairs():
+    """crates/rapier3d/tests/broad_phase_pair_filter.rs:9-29: two overlapping parentless (fixed) colliders never form
+    a pair; the same colliders form one as soon as one of them hangs on a dynamic body."""
+    from rapier_b200.sets import ColliderBuilder, RigidBodyBuilder
+    import emul_lib
+    from rapier_b200.world import PhysicsWorld
+    s = scenes.Scene("fixed_fixed")
+    s.colliders.insert(ColliderBuilder.cuboid(1.0, 1.0, 1.0))
+    s.colliders.insert(ColliderBuilder.cuboid(1.0, 1.0, 1.0).translation((0.5, 0.5, 0.0)))
+    w = oracle_lib.OracleWorld(s)
+    w.step(3)
+    assert w.counters()["num_pairs"] == 0
+    k = PhysicsWorld(s, _lib=emul_lib.lib())   # the kernels' logic (host emulation) applies the same filter
+    k.step(3)
+    assert k.counters()["num_pairs"] == 0
+    s2 = scenes.Scene("fixed_dynamic")
+    s2.colliders.insert(ColliderBuilder.cuboid(1.0, 1.0, 1.0))
+    s2.insert(RigidBodyBuilder.dynamic().translation((0.5, 0.5, 0.0)), ColliderBuilder.cuboid(1.0, 1.0, 1.0))
+    w2 = oracle_lib.OracleWorld(s2)
+    w2.step(3)
+    assert w2.counters()["num_pairs"] == 1
