@@ -235,3 +235,31 @@ def heavy_end_chain(num=17, rad=0.2):
             s.chain_joints.append((prev, h, a1, a2))
         prev = h
     return s
+
+
+def large_world(grid=1000, spheres=100, cell=10.0):
+    """examples3d/b3d_large_world.rs:14-77: a grid x grid floor of parentless (fixed) cuboid colliders and `spheres`
+    dynamic balls dropped over the inner 80 % of it.  The reference inserts one ball every 5 steps; here they are
+    all present from the start (scene uploads replace the whole scene), staggered in height instead."""
+    s = Scene(f"large_world_{grid}_{spheres}", gravity=(0.0, -10.0, 0.0))
+    cell = F(cell)
+    half_span = F(0.5) * cell * F(grid)
+    for i in range(grid):
+        x = -half_span + (F(i) + F(0.5)) * cell
+        for j in range(grid):
+            z = -half_span + (F(j) + F(0.5)) * cell
+            s.colliders.insert(ColliderBuilder.cuboid(F(0.5) * cell, 0.25, F(0.5) * cell).translation((x, 0.0, z)))
+    side = 1
+    while side * side < spheres:
+        side += 1
+    inset = F(0.1) * F(2.0) * half_span
+    usable = F(2.0) * half_span - F(2.0) * inset
+    for idx in range(spheres):
+        gi, gj = idx % side, idx // side
+        x = -half_span + inset + (F(gi) + F(0.5)) * (usable / F(side))
+        z = -half_span + inset + (F(gj) + F(0.5)) * (usable / F(side))
+        s.insert(RigidBodyBuilder.dynamic().translation((x, F(1.5) + F(0.25) * F(idx % 7), z)), ColliderBuilder.ball(0.5))
+    return s
+
+
+REGISTRY["large_world"] = large_world

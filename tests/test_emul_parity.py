@@ -18,6 +18,7 @@ CASES = [
     ("joint_grid_large_island", lambda: scenes.joint_grid(18), 40, 10),
     ("ball_on_slab", lambda: scenes.box_on_ground("ball", 2.0), 80, 20),
     ("keva_small", lambda: scenes.keva(1), 20, 5),
+    ("large_world_reduced", lambda: scenes.large_world(grid=60, spheres=16), 150, 30),   # parentless static floor tiles
 ]
 
 

