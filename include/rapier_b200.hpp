@@ -76,6 +76,12 @@ public:
     static ColliderBuilder cuboid(float hx, float hy, float hz) { return ColliderBuilder(RB_SHAPE_CUBOID, hx, hy, hz); }
     static ColliderBuilder ball(float r) { return ColliderBuilder(RB_SHAPE_BALL, r, 0.0f, 0.0f); }
     ColliderBuilder& density(float x) { d_.density = x; return *this; }
+    ColliderBuilder& mass(float m) {   // ColliderMassProps::Mass: the density that gives the shape this mass
+        const float* h = d_.half_extents;
+        float vol = d_.shape == RB_SHAPE_CUBOID ? 8.0f * h[0] * h[1] * h[2] : 4.18879020478639f * h[0] * h[0] * h[0];
+        d_.density = vol > 0.0f ? m / vol : 0.0f;
+        return *this;
+    }
     ColliderBuilder& friction(float x) { d_.friction = x; return *this; }
     ColliderBuilder& restitution(float x) { d_.restitution = x; return *this; }
     ColliderBuilder& friction_combine_rule(int r) { d_.friction_combine_rule = r; return *this; }

@@ -139,6 +139,26 @@ class ColliderBuilder:
         self._density = float(d)
         return self
 
+    def mass(self, m):
+        """ColliderBuilder::mass (ColliderMassProps::Mass): the density that gives the shape this mass."""
+        import math
+        hx, hy, hz = self.half_extents
+        volume = 8.0 * hx * hy * hz if self.shape == A.RB_SHAPE_CUBOID else 4.0 / 3.0 * math.pi * hx ** 3
+        self._density = float(m) / volume if volume > 0.0 else 0.0
+        return self
+
+    def rotation(self, axis_angle):
+        """ColliderBuilder::rotation: orientation relative to the parent body, as a scaled axis."""
+        import math
+        ax = [float(x) for x in axis_angle]
+        a = math.sqrt(sum(x * x for x in ax))
+        if a == 0.0:
+            self._rotation = (0.0, 0.0, 0.0, 1.0)
+        else:
+            k = math.sin(a / 2.0) / a
+            self._rotation = (ax[0] * k, ax[1] * k, ax[2] * k, math.cos(a / 2.0))
+        return self
+
     def friction(self, f):
         self._friction = float(f)
         return self
