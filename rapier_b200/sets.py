@@ -97,6 +97,14 @@ class RigidBodyBuilder:
         self._flags |= int(bits) & 0xFC
         return self
 
+    def lock_rotations(self):
+        """RigidBodyBuilder::lock_rotations (LockedAxes::ROTATION_LOCKED)."""
+        return self.locked_axes(A.RB_BODY_LOCK_RX | A.RB_BODY_LOCK_RY | A.RB_BODY_LOCK_RZ)
+
+    def lock_translations(self):
+        """RigidBodyBuilder::lock_translations (LockedAxes::TRANSLATION_LOCKED)."""
+        return self.locked_axes(A.RB_BODY_LOCK_TX | A.RB_BODY_LOCK_TY | A.RB_BODY_LOCK_TZ)
+
     def build_desc(self):
         d = A.RbBodyDesc()
         d.body_type = self.body_type

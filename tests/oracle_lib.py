@@ -82,6 +82,14 @@ class OracleWorld:
         self.L.orc_world_get_body_states(self.h, pose.ctypes.data, vel.ctypes.data)
         return pose, vel
 
+    def set_body_states(self, indices, pose7=None, vel6=None):
+        idx = np.ascontiguousarray(indices, np.int32)
+        p = None if pose7 is None else np.ascontiguousarray(pose7, np.float32)
+        v = None if vel6 is None else np.ascontiguousarray(vel6, np.float32)
+        rc = self.L.orc_world_set_body_states(self.h, len(idx), idx.ctypes.data, None if p is None else p.ctypes.data,
+                                              None if v is None else v.ctypes.data)
+        assert rc == 0
+
     def counters(self):
         c = A.RbCounters()
         self.L.orc_world_get_counters(self.h, C.byref(c))

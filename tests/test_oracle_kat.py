@@ -276,3 +276,58 @@ def test_no_fixed_fixed_pairs():
     w2 = oracle_lib.OracleWorld(s2)
     w2.step(3)
     assert w2.counters()["num_pairs"] == 1
+
+
+def _offset_com_locked_body():
+    from rapier_b200.sets import ColliderBuilder, RigidBodyBuilder
+    s = scenes.Scene("locked_rotations_offset_com", gravity=(0.0, 0.0, 0.0))
+    b = s.bodies.insert(RigidBodyBuilder.dynamic().lock_rotations())
+    s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.5, 0.5, 0.5).translation((1.0, 0.0, 0.0)), b)
+    return s, b
+
+
+def _world_com(pose, local_com):
+    return pose[:3] + _rotate(pose[3:], np.array(local_com))
+
+
+@pytest.mark.parametrize("which", ["oracle", "emulated_kernels"])
+def test_locked_rotations_pivot_about_centre_of_mass(which):
+    """crates/rapier3d/tests/issue_309_locked_rotations_offset_com.rs:8-38: a rotation-locked body whose collider is
+    offset from its origin, spun by a manually set angular velocity every step, must rotate about its centre of mass
+    (the world-space centre of mass moves < 1e-3 over 100 steps)."""
+    scene, b = _offset_com_locked_body()
+    if which == "oracle":
+        w = oracle_lib.OracleWorld(scene)
+    else:
+        import emul_lib
+        from rapier_b200.world import PhysicsWorld
+        w = PhysicsWorld(scene, _lib=emul_lib.lib())
+    w.step()
+    pose, _ = w.body_states()
+    com0 = _world_com(pose[b], (1.0, 0.0, 0.0))
+    for i in range(100):
+        vel = np.array([[0.0, 0.0, 0.0, 0.0, 0.0, 3.0]], np.float32)
+        if which == "oracle":
+            w.set_body_states([b], vel6=vel)
+        else:
+            w.physics_pipeline.set_body_states([b], vel6=vel)
+        w.step()
+        pose, _ = w.body_states()
+        assert np.linalg.norm(_world_com(pose[b], (1.0, 0.0, 0.0)) - com0) < 1.0e-3, i
+    assert abs(pose[b, 6]) < 0.999, "the body must actually have rotated"
+
+
+def test_set_rotation_does_not_inject_motion():
+    """issue_309_locked_rotations_offset_com.rs:40-72: teleporting the orientation about the body origin every step
+    must not make the body drift or acquire velocity."""
+    scene, b = _offset_com_locked_body()
+    w = oracle_lib.OracleWorld(scene)
+    for i in range(100):
+        a = 0.05 * i
+        pose = np.array([[0.0, 0.0, 0.0, 0.0, 0.0, np.sin(a / 2), np.cos(a / 2)]], np.float32)
+        p_now, _ = w.body_states()
+        pose[0, :3] = p_now[b, :3]
+        w.set_body_states([b], pose7=pose)
+        w.step()
+        p, v = w.body_states()
+        assert np.linalg.norm(p[b, :3]) < 1.0e-4 and np.linalg.norm(v[b, :3]) < 1.0e-4, (i, p[b], v[b])
