@@ -51,9 +51,12 @@ private:
     Pool() {}
     void start() {
         quit_.store(false);
+        // The epoch a worker starts from is fixed HERE, not when its thread first runs: a worker that came up
+        // after the first parallel_for had already bumped the epoch would otherwise skip that job for ever.
+        const uint64_t seen0 = epoch_.load(std::memory_order_acquire);
         for (int t = 1; t < nthreads_; ++t)
-            workers_.emplace_back([this, t] {
-                uint64_t seen = epoch_.load(std::memory_order_acquire);
+            workers_.emplace_back([this, t, seen0] {
+                uint64_t seen = seen0;
                 for (;;) {
                     uint64_t e;
                     int spins = 0;

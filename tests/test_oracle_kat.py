@@ -331,3 +331,18 @@ def test_set_rotation_does_not_inject_motion():
         w.step()
         p, v = w.body_states()
         assert np.linalg.norm(p[b, :3]) < 1.0e-4 and np.linalg.norm(v[b, :3]) < 1.0e-4, (i, p[b], v[b])
+
+
+def test_thread_count_determinism():
+    """crates/rapier3d/tests/thread_count_determinism.rs:94-150 (scene: jittered 12x3x12 pile + a swinging joint
+    chain; the golden hash itself needs the reference binary): every thread count must give the same bits."""
+    ref = None
+    for threads in (1, 3, 8):
+        w = oracle_lib.OracleWorld(scenes.box_pile(12, 3, 12), threads=threads)
+        w.step(60)
+        pose, vel = w.body_states()
+        bits = (pose.view(np.uint32).copy(), vel.view(np.uint32).copy())
+        if ref is None:
+            ref = bits
+        else:
+            assert (bits[0] == ref[0]).all() and (bits[1] == ref[1]).all(), threads
