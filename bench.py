@@ -219,6 +219,8 @@ def main():
         if dist is not None:
             dist.barrier()
         # per-launch-group device times for the roofline (events inside the library, same stream)
+        if exchange is not None:
+            shard.finish()   # no gather may be in flight while steps run without exchange() in between
         pipe.enable_profiling(True)
         pipe.step(gravity, min(args.steps, 100), sync=True)
         prof = pipe.counters()
