@@ -1384,7 +1384,7 @@ RB_HD void coop_pipe_issue(const CoopPipe& pp, int q, int b) {   // one thread: 
     const int o = pp.chunk[q], cnt = pp.chunk[q + 1] - o;
     const unsigned bytes = (unsigned)(COOP_ROWS * (cnt | 1) * 16);
     mbar_expect_tx(pp.mbar + b, bytes);
-    bulk_g2s(pp.buf[b], pp.pool + (size_t)COOP_ROWS * (o + q), bytes, pp.mbar + b);
+    bulk_g2s(b ? pp.buf[1] : pp.buf[0], pp.pool + (size_t)COOP_ROWS * (o + q), bytes, pp.mbar + b);
 }
 
 // One sweep over all colour stages of the item.  Resident items read their shared-memory rows; streamed
@@ -1412,7 +1412,8 @@ RB_PHASE void coop_sweep(const BlockCtx& ctx, const World& w, const SmemBodies& 
             else if (wrap) coop_pipe_issue(pp, 0, b ^ 1);
         }
         RowView rd;
-        rd.p = pp.buf[b] - o; rd.stride = (e - o) | 1;
+        rd.p = (b ? pp.buf[1] : pp.buf[0]) - o;   // (a select, not a dynamically indexed array: keeps the pointers in registers and the loads LDS)
+        rd.stride = (e - o) | 1;
         if (tid < nth) coop_stage<L, MODE>(w, bd, rd, mu, wslot, c0, o, e, tid, nth, fric);
         ctx.block_sync();
         pp.t += 1;
