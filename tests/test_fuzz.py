@@ -1,0 +1,12 @@
+"""A few seeds of the differential fuzzer (tests/fuzz_emul_vs_oracle.py) in the default CPU suite: random scenes
+through the host emulation of the kernels and through the oracle must agree bit for bit (every third seed with a
+shared-memory size that forces the streaming pipeline)."""
+import pytest
+
+import fuzz_emul_vs_oracle as fuzz
+
+
+@pytest.mark.parametrize("seed", [3, 7, 12, 21, 34, 55, 89, 144])
+def test_random_scene_emulated_kernels_match_oracle(seed):
+    ok, msg = fuzz.run(seed, smem_floats=(9000 if seed % 3 == 0 else None))
+    assert ok, msg

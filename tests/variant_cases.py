@@ -72,6 +72,19 @@ def additional_mass_twins():
     return s
 
 
+def plate_with_overflow_colour():
+    """A dynamic plate carrying 156 small cubes: the plate has more contacts than the 120 dyn-dyn colours, so 36 of
+    them land in the overflow colour 128 (contact_pair.rs:155), which is solved serially after the parallel colours."""
+    from rapier_b200.sets import ColliderBuilder, RigidBodyBuilder
+    s = scenes.Scene("plate_overflow")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(20.0, 0.5, 20.0))
+    s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.3, 0.0)), ColliderBuilder.cuboid(7.0, 0.25, 7.0).density(5.0))
+    for i in range(13):
+        for k in range(12):
+            s.insert(RigidBodyBuilder.dynamic().translation((-6.0 + i * 1.0, 0.86, -5.5 + k * 1.0)), ColliderBuilder.cuboid(0.3, 0.3, 0.3))
+    return s
+
+
 VARIANTS = [
     ("restitution", bouncing_balls, None, 150, 25),
     ("groups_joints_forces", groups_and_joints, None, 150, 25),
@@ -86,4 +99,5 @@ VARIANTS = [
     ("revolute_offset_com", lambda: scenes.offset_com_pendulums(16), None, 80, 20),
     ("heavy_chain_20_substeps", scenes.heavy_end_chain, _params(num_solver_iterations=20), 60, 20),
     ("additional_mass_twins", additional_mass_twins, None, 120, 20),
+    ("overflow_colour", plate_with_overflow_colour, None, 60, 15),
 ]
