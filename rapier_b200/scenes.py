@@ -263,3 +263,5 @@ def large_world(grid=1000, spheres=100, cell=10.0):
 
 
 REGISTRY["large_world"] = large_world
+REGISTRY["falling_pile_2000"] = lambda: box_pile(10, 10, 20)
+REGISTRY["pyramid3_20"] = lambda: pyramid3(20)

@@ -22,6 +22,8 @@ CASES = [
     ("keva_5_full_size", lambda: scenes.keva(5), 4, 2),
     ("joint_grid_100_full_size", lambda: scenes.joint_grid(100), 8, 4),
     ("pyramid3_20_large_island", lambda: scenes.pyramid3(20), 30, 10),
+    ("large_world_reduced", lambda: scenes.large_world(grid=60, spheres=16), 150, 30),
+    ("large_world_300", lambda: scenes.large_world(grid=300, spheres=100), 40, 20),
 ]
 
 
@@ -125,6 +127,39 @@ def test_long_run_drift_vs_oracle(built):
     assert (pg.view(np.uint32) == po.view(np.uint32)).all()
 
 
+def test_full_size_dynamic_scene_1000_steps(built):
+    """north_star drift contract on a full-size DYNAMIC scene: a falling, collapsing pile of 2 000 tilted cubes
+    plus a jointed chain (broad phase, full narrow phase, colouring and schedule rebuilt on most steps),
+    1 000 steps, GPU vs oracle: <= 5 % of the scene height, and in fact identical bits."""
+    scene = scenes.box_pile(10, 10, 20)
+    w = PhysicsWorld(scene)
+    o = oracle_lib.OracleWorld(scene, threads=8)
+    for _ in range(10):
+        w.step(100)
+        o.step(100)
+        pg, vg = w.body_states()
+        po, vo = o.body_states()
+        assert np.isfinite(pg).all()
+        height = float(po[:, 1].max() - po[:, 1].min()) or 1.0
+        assert np.linalg.norm(pg[:, :3] - po[:, :3], axis=1).max() / height <= 0.05
+    assert (pg.view(np.uint32) == po.view(np.uint32)).all() and (vg.view(np.uint32) == vo.view(np.uint32)).all()
+    assert is_exact(compare_worlds(w, o))
+
+
+def test_headline_1000_steps_drift(built):
+    """north_star drift contract at the headline size (80 pyramids x 20 levels, 16 800 cubes), 1 000 steps."""
+    scene = scenes.many_pyramids_label()
+    w = PhysicsWorld(scene)
+    o = oracle_lib.OracleWorld(scene, threads=16)
+    w.step(1000)
+    o.step(1000)
+    pg, _ = w.body_states()
+    po, _ = o.body_states()
+    drift = np.linalg.norm(pg[:, :3] - po[:, :3], axis=1).max() / 20.0
+    assert drift <= 0.05
+    assert (pg.view(np.uint32) == po.view(np.uint32)).all()
+
+
 def test_step_host_round_trip(built):
     """rb_world_step_host (host buffers in/out) gives the same trajectory as device-resident stepping."""
     scene = scenes.pyramids(1, 2, 6)
@@ -163,10 +198,7 @@ def test_empty_and_ragged(built):
 from variant_cases import VARIANTS  # noqa: E402
 
 
-# Variants added after the round's GPU budget was spent run on the CPU only (emulated kernels) until they have
-# been through the hardware once; a first-time failure here would hide the tests that follow under `-x`.
-NOT_YET_ON_HARDWARE = {"additional_mass_twins", "overflow_colour"}
-GPU_VARIANTS = [v for v in VARIANTS if v[0] not in NOT_YET_ON_HARDWARE]
+GPU_VARIANTS = list(VARIANTS)
 
 
 @pytest.mark.parametrize("name,make,params,steps,every", GPU_VARIANTS, ids=[v[0] for v in GPU_VARIANTS])
