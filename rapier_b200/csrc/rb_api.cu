@@ -617,7 +617,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.remap_src, w.pair_cap);
     for (int k = 0; k < 2; ++k) { ALLOC(w.pb[k].key, w.pair_cap); ALLOC(w.pb[k].rows, (size_t)PR_ROWS * w.pair_cap); }
     ALLOC(w.todo, 16);
-    ALLOC(w.color_mask, (size_t)NB * 4); ALLOC(w.body_min, NB);
+    ALLOC(w.color_mask, (size_t)NB * 4); ALLOC(w.body_min, NB); ALLOC(w.body_minkey, NB);
     ALLOC(w.isl_label, NB); ALLOC(w.isl_nb, NB); ALLOC(w.isl_ncons, NB); ALLOC(w.isl_item, NB);
     ALLOC(w.scan_tmp, (size_t)1 << 20);
     ALLOC(w.item_body_start, w.item_cap + 2); ALLOC(w.item_cons_start, w.item_cap + 2); ALLOC(w.item_joint_start, w.item_cap + 2);
@@ -683,6 +683,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
         CK(h2d(w.b_utorque, ut.data(), NB * sizeof(float4)));
         CK(h2d(w.b_owned, owned.data(), NB));
         CK(h2d(w.body_min, bmin.data(), NB * sizeof(int)));
+        CK(dev_set(w.body_minkey, 0xff, NB * sizeof(unsigned long long)));
     }
     // ---- colliders ----
     {

@@ -424,10 +424,13 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// P3a: deferred greedy colouring of the pairs that began touching, in ascending pair order
-// (contacts.rs:366-385; narrow_phase/mod.rs:87-152).  Parallel formulation of the sequential
-// greedy: a pending pair is coloured in the round where it is the lowest pending pair on each of
-// its dynamic bodies, which reproduces the sequential result exactly.
+// P3a: deferred greedy colouring of the pairs that began touching, in the reference's canonical order
+// (min body, max body, edge) (contacts.rs:366-385; narrow_phase/mod.rs:87-152) -- body = arena index of the
+// collider's parent (fixed bodies included), u32::MAX for a parentless collider; the edge index, which only
+// orders pairs between the SAME two bodies, is replaced by the pair-table index (ascending collider pair).
+// Parallel formulation of the sequential greedy: a pending pair is coloured in the round where it is the
+// first pending pair, in that order, on each of its dynamic bodies -- which reproduces the sequential result
+// exactly.  Two-level minimum per body: the smallest order key, then the smallest pair index with that key.
 // ------------------------------------------------------------------------------------------------
 RB_HD int first_free_low(const unsigned* m) {   // lowest clear bit in 0..119, else 128
     for (int wd = 0; wd < 4; ++wd) {
@@ -452,25 +455,41 @@ RB_HD int first_free_high(const unsigned* m) {  // highest clear bit <= 127, els
     }
     return 128;
 }
+RB_HD unsigned long long color_order_key(int b1, int b2) {
+    const unsigned a = b1 < 0 ? 0xffffffffu : (unsigned)b1, b = b2 < 0 ? 0xffffffffu : (unsigned)b2;
+    return ((unsigned long long)(a < b ? a : b) << 32) | (a < b ? b : a);
+}
 
 template <class Ctx>
 RB_PHASE void section_coloring(const Ctx& ctx, const World& w) {
     State* st = w.st;
     const int buf = st->cur, np = st->npairs;
     for (;;) {
-        // A: every pending pair bids for its dynamic bodies
+        // A1: every pending pair bids its order key for its dynamic bodies
         for (int i = ctx.gtid; i < np; i += ctx.gsize) {
             int flags = as_int(prow(w, buf, PR_INFO, i).x);
             if (!(flags & 2)) continue;
             float4 bod = prow(w, buf, PR_BODIES, i);
             int b1 = as_int(bod.z), b2 = as_int(bod.w);
-            if (body_is_sim(w, b1)) atomic_min(&w.body_min[b1], i);
-            if (body_is_sim(w, b2)) atomic_min(&w.body_min[b2], i);
+            const unsigned long long key = color_order_key(b1, b2);
+            if (body_is_sim(w, b1)) atomic_min64(&w.body_minkey[b1], key);
+            if (body_is_sim(w, b2)) atomic_min64(&w.body_minkey[b2], key);
             atomic_add(&st->ncand, 1);  // ncand doubles as the pending counter outside the broad phase
         }
         ctx.grid_sync();
         int pending = st->ncand;
         if (pending == 0) break;
+        // A2: among the pairs holding a body's smallest key, the lowest pair index
+        for (int i = ctx.gtid; i < np; i += ctx.gsize) {
+            int flags = as_int(prow(w, buf, PR_INFO, i).x);
+            if (!(flags & 2)) continue;
+            float4 bod = prow(w, buf, PR_BODIES, i);
+            int b1 = as_int(bod.z), b2 = as_int(bod.w);
+            const unsigned long long key = color_order_key(b1, b2);
+            if (body_is_sim(w, b1) && w.body_minkey[b1] == key) atomic_min(&w.body_min[b1], i);
+            if (body_is_sim(w, b2) && w.body_minkey[b2] == key) atomic_min(&w.body_min[b2], i);
+        }
+        ctx.grid_sync();
         // B: winners take the first colour free on both bodies
         for (int i = ctx.gtid; i < np; i += ctx.gsize) {
             float4 info = prow(w, buf, PR_INFO, i);
@@ -508,8 +527,8 @@ RB_PHASE void section_coloring(const Ctx& ctx, const World& w) {
             if (!(flags & 6)) continue;
             float4 bod = prow(w, buf, PR_BODIES, i);
             int b1 = as_int(bod.z), b2 = as_int(bod.w);
-            if (body_is_sim(w, b1)) w.body_min[b1] = 0x7fffffff;
-            if (body_is_sim(w, b2)) w.body_min[b2] = 0x7fffffff;
+            if (body_is_sim(w, b1)) { w.body_min[b1] = 0x7fffffff; w.body_minkey[b1] = ~0ull; }
+            if (body_is_sim(w, b2)) { w.body_min[b2] = 0x7fffffff; w.body_minkey[b2] = ~0ull; }
             if (flags & 4) { info.x = as_float_i(flags & ~4); prow(w, buf, PR_INFO, i) = info; }
         }
         if (ctx.gtid == 0) st->ncand = 0;

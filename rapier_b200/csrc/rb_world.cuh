@@ -149,6 +149,7 @@ struct World {
     int* todo;                        // [pair_cap] pairs that began touching this step
     unsigned* color_mask;             // [nb][4] 128-bit colour masks per body
     int* body_min;                    // [nb] colouring scratch (INT_MAX when idle)
+    unsigned long long* body_minkey;  // [nb] colouring scratch: smallest pending order key (~0 when idle)
     // ---- islands / schedule ----
     int* isl_label;                   // [nb] union-find parent / final root
     int* isl_nb;                      // [nb] bodies per root

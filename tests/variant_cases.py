@@ -85,6 +85,25 @@ def plate_with_overflow_colour():
     return s
 
 
+def shuffled_collider_order():
+    """Bodies inserted first, colliders attached afterwards in REVERSE body order, so the pair table's
+    (collider1, collider2) order is the opposite of the reference's colouring order (min body, max body)
+    (contacts.rs:366-385): a stack of boxes next to a column of balls, all touching from step 0."""
+    s = scenes.Scene("shuffled_colliders")
+    ground = s.bodies.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)))
+    hs = []
+    for k in range(3):
+        for i in range(4):
+            for j in range(4 - i):
+                hs.append((s.bodies.insert(RigidBodyBuilder.dynamic().translation((i * 0.5 + j * 1.0, 0.5 + i * 1.0, k * 1.0))), "box"))
+    for i in range(5):
+        hs.append((s.bodies.insert(RigidBodyBuilder.dynamic().translation((8.0, 0.4 + 0.8 * i, 0.0))), "ball"))
+    for h, kind in reversed(hs):
+        s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.5, 0.5, 0.5) if kind == "box" else ColliderBuilder.ball(0.4), h)
+    s.colliders.insert_with_parent(ColliderBuilder.cuboid(20.0, 0.5, 20.0), ground)
+    return s
+
+
 VARIANTS = [
     ("restitution", bouncing_balls, None, 150, 25),
     ("groups_joints_forces", groups_and_joints, None, 150, 25),
@@ -100,4 +119,5 @@ VARIANTS = [
     ("heavy_chain_20_substeps", scenes.heavy_end_chain, _params(num_solver_iterations=20), 60, 20),
     ("additional_mass_twins", additional_mass_twins, None, 120, 20),
     ("overflow_colour", plate_with_overflow_colour, None, 60, 15),
+    ("shuffled_collider_order", shuffled_collider_order, None, 60, 15),
 ]
