@@ -192,6 +192,12 @@ int rb_world_get_contact_pairs(RbWorld* w, int32_t cap, int32_t* pair_colliders,
  * Returns bytes copied or a negative status. */
 int64_t rb_world_debug_read(RbWorld* w, const char* table, void* dst, int64_t cap_bytes);
 
+/* Unit-level known-answer evaluation for parity tests: runs ONE device function of the path (named: "pose_drift"
+ * contact_pair.rs:299-323, "reduce_manifold" manifold_reduction.rs:4-84, "normal_solve" / "tangent_solve"
+ * contact_constraint_element.rs:481-504 / :650-705, "generate" contact_with_twist_friction.rs:58-424) on literal
+ * inputs and returns its outputs (float layouts: tests/golden/make_ref_vectors.py). Needs a CUDA device. */
+int rb_debug_kat(const char* name, const float* in, int32_t n_in, float* out, int32_t n_out);
+
 /* ---- multi-GPU sharding: each rank owns whole connected components ---- */
 /* Restricts this world to the bodies whose component id (as labelled by rb_world_label_components)
  * satisfies component % world_size == rank; the other dynamic bodies become inert. */

@@ -44,6 +44,9 @@ int orc_contact_manifold(int shape1, const float he1[3], int shape2, const float
                          const float pos12_t[3], const float pos12_q[4], float prediction,
                          float* out_points, float out_n1[3], float out_n2[3]);
 
+// One function of the path on literal inputs (see oracle_capi.cpp).
+int orc_kat(const char* name, const float* in, int32_t n_in, float* out, int32_t n_out);
+
 #ifdef __cplusplus
 }
 #endif

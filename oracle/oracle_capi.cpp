@@ -227,4 +227,13 @@ int orc_contact_manifold(int shape1, const float he1[3], int shape2, const float
     return m.n;
 }
 
+// Unit-level known-answer entry point: evaluates ONE function of the restated path on literal inputs
+// (names and float layouts: tests/golden/make_ref_vectors.py; mirrored by rb_debug_kat).
+int orc_kat(const char* name, const float* in, int32_t n_in, float* out, int32_t n_out) {
+    if (!name || !in || !out) return RB_ERR_INVALID;
+    int rc = kat_solver(name, in, n_in, out, n_out);
+    if (rc == -100) rc = kat_world(name, in, n_in, out, n_out);
+    return rc == -100 ? RB_ERR_INVALID : rc;
+}
+
 }  // extern "C"

@@ -200,4 +200,7 @@ struct World {
     int last_num_colors = 0;
 };
 
+int kat_solver(const char* name, const float* in, int n_in, float* out, int n_out);   // oracle_solver.cpp
+int kat_world(const char* name, const float* in, int n_in, float* out, int n_out);    // oracle_world.cpp
+
 }  // namespace orc

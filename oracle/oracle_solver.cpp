@@ -8,6 +8,7 @@
 // joint_velocity_constraint.rs}.  One constraint at a time, colours in the reference's stage order.
 #include <algorithm>
 #include <cstring>
+#include <string>
 #include "oracle_internal.h"
 #include "opool.h"
 
@@ -731,6 +732,93 @@ void solve_island(World& w, V3 gravity) {
     }
     w.counters.num_active_manifolds = ncons;
     w.counters.num_colors = num_colors;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Unit-level known-answer entry points (tests/test_ref_vectors.py; layouts documented in
+// tests/golden/make_ref_vectors.py, shared with rb_debug_kat of the CUDA library).
+// ---------------------------------------------------------------------------------------------
+int kat_solver(const char* name_c, const float* in, int n_in, float* out, int n_out) {
+    const std::string name(name_c);
+    auto v3at = [&](int o) { return V3{in[o], in[o + 1], in[o + 2]}; };
+    auto put3 = [&](int o, V3 v) { out[o] = v.x; out[o + 1] = v.y; out[o + 2] = v.z; };
+    if (name == "generate") {   // contact_with_twist_friction.rs:58-424 on a synthetic, world-attached manifold
+        if (n_in < 6 || n_out < 39) return -3;
+        World w;
+        Pair p{};
+        p.c1 = 0; p.c2 = 1; p.b1 = -1; p.b2 = -1;
+        p.normal = v3at(0); p.friction = in[3]; p.restitution = in[4];
+        const int n = (int)in[5];
+        if (n < 1 || n > MAX_MANIFOLD_POINTS || n_in < 6 + 19 * n) return -3;
+        p.nsc = n; p.npts = n;
+        for (int k = 0; k < n; ++k) {
+            const int o = 6 + 19 * k;
+            p.sc[k].anchor1 = v3at(o); p.sc[k].anchor2 = v3at(o + 3); p.sc[k].cid = (int)in[o + 6];
+            Point& pt = p.pts[p.sc[k].cid];
+            pt.impulse = in[o + 7]; pt.warmstart_impulse = in[o + 8]; pt.warmstart_twist = in[o + 9];
+            pt.warmstart_tangent_world = v3at(o + 10); pt.dp1 = v3at(o + 13); pt.dp2 = v3at(o + 16);
+        }
+        w.pairs.push_back(p);
+        Constraint c;
+        generate(w, 0, c);
+        for (int i = 0; i < 39; ++i) out[i] = 0.0f;
+        out[0] = (float)c.num_contacts; put3(1, c.dir1); put3(4, c.tangent1); out[7] = c.limit;
+        for (int k = 0; k < MAX_MANIFOLD_POINTS; ++k) {
+            out[8 + k] = c.normal[k].impulse; out[12 + k] = c.normal[k].impulse_accumulator; out[16 + k] = c.normal[k].r;
+            out[20 + k] = c.b_dist[k]; out[24 + k] = c.twist_dists[k];
+            out[35 + k] = k < c.num_contacts ? (float)c.cids[k] : 255.0f;   // u8::MAX marks an inactive slot
+        }
+        out[28] = c.t_impulse[0]; out[29] = c.t_impulse[1]; out[30] = c.t_impulse_acc[0]; out[31] = c.t_impulse_acc[1];
+        out[32] = c.w_impulse; out[33] = c.w_impulse_acc; out[34] = c.w_r;
+        return 0;
+    }
+    if (name == "normal_solve" || name == "tangent_solve") {
+        World w;
+        w.sb.resize(2);
+        Constraint c;
+        memset(&c, 0, sizeof(c));
+        c.id1 = 0; c.id2 = 1; c.num_contacts = 1;
+        int o;
+        if (name == "normal_solve") {   // contact_constraint_element.rs:481-504
+            if (n_in < 37 || n_out < 13) return -3;
+            c.dir1 = v3at(0); c.im1 = v3at(3); c.im2 = v3at(6);
+            NormalPart& n = c.normal[0];
+            n.torque_dir1 = v3at(9); n.torque_dir2 = v3at(12); n.ii_torque_dir1 = v3at(15); n.ii_torque_dir2 = v3at(18);
+            n.r = in[21]; n.rhs = in[22]; n.impulse = in[23]; n.cfm_factor = in[24];
+            o = 25;
+        } else {                        // contact_constraint_element.rs:650-705 (coupled 2x2 tangent solve, no twist: one point)
+            if (n_in < 59 || n_out < 14) return -3;
+            c.dir1 = v3at(0); c.tangent1 = v3at(3);   // t2 = dir x t1 must equal the fixture's second tangent
+            c.im1 = v3at(9); c.im2 = v3at(12);
+            c.t_torque_dir1[0] = v3at(15); c.t_torque_dir1[1] = v3at(18); c.t_torque_dir2[0] = v3at(21); c.t_torque_dir2[1] = v3at(24);
+            c.t_ii_torque_dir1[0] = v3at(27); c.t_ii_torque_dir1[1] = v3at(30); c.t_ii_torque_dir2[0] = v3at(33); c.t_ii_torque_dir2[1] = v3at(36);
+            c.t_r[0] = in[39]; c.t_r[1] = in[40]; c.t_r[2] = in[41];
+            const V3 lfc1 = v3at(42);   // rhs_j = lfc1 . t_j (unit sub-step inverse dt)
+            c.t_rhs[0] = dot(lfc1, v3at(3)); c.t_rhs[1] = dot(lfc1, v3at(6));
+            c.t_impulse[0] = in[45]; c.t_impulse[1] = in[46];
+            c.limit = 0.0f;   // tangent limit = limit * sum(normal impulses); the fixture's limit rides on the normal impulse
+            c.normal[0].impulse = in[47]; c.limit = 1.0f;
+            c.normal[0].r = 0.0f; c.normal[0].cfm_factor = 1.0f; c.normal[0].rhs = 0.0f;   // normal row inert: r = 0 keeps its impulse
+            o = 48;
+        }
+        w.sb[0].lin = v3at(o); w.sb[0].ang = v3at(o + 3); w.sb[1].lin = v3at(o + 6); w.sb[1].ang = v3at(o + 9);
+        w.sb[0].im = c.im1; w.sb[1].im = c.im2;
+        w.sb[0].pose = pose_identity(); w.sb[1].pose = pose_identity();
+        w.sb[0].ii = sdp_zero(); w.sb[1].ii = sdp_zero();
+        if (name == "normal_solve") {
+            solve(w, c, false);
+            out[0] = c.normal[0].impulse;
+            put3(1, w.sb[0].lin); put3(4, w.sb[0].ang); put3(7, w.sb[1].lin); put3(10, w.sb[1].ang);
+        } else {
+            // the normal row must not move anything: impulse kept by max(impulse - 0 * dvel, 0) * 1
+            solve(w, c, true);
+            out[0] = c.t_impulse[0]; out[1] = c.t_impulse[1];
+            put3(2, w.sb[0].lin); put3(5, w.sb[0].ang); put3(8, w.sb[1].lin); put3(11, w.sb[1].ang);
+        }
+        return 0;
+    }
+    return -100;   // not one of this file's
 }
 
 }  // namespace orc

@@ -680,4 +680,32 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
     return RB_OK;
 }
 
+
+// Unit-level known-answer entry points of this file (see kat_solver in oracle_solver.cpp).
+int kat_world(const char* name_c, const float* in, int n_in, float* out, int n_out) {
+    const std::string name(name_c);
+    if (name == "pose_drift") {   // contact_pair.rs:299-323
+        if (n_in < 15 || n_out < 1) return -3;
+        Pose base{Q4{in[3], in[4], in[5], in[6]}, V3{in[0], in[1], in[2]}};
+        Pose cur{Q4{in[10], in[11], in[12], in[13]}, V3{in[7], in[8], in[9]}};
+        out[0] = relative_pose_drift(base, cur, in[14]);
+        return 0;
+    }
+    if (name == "reduce_manifold") {   // manifold_reduction.rs:4-84
+        if (n_in < 5 || n_out < 5) return -3;
+        RawManifold m{};
+        m.n = (int)in[0];
+        if (m.n < 0 || m.n > MAX_RAW_POINTS || n_in < 5 + 4 * m.n) return -3;
+        m.local_n1 = V3{in[2], in[3], in[4]};
+        for (int i = 0; i < m.n; ++i) { m.pts[i].local_p1 = V3{in[5 + 4 * i], in[6 + 4 * i], in[7 + 4 * i]}; m.pts[i].dist = in[8 + 4 * i]; }
+        int sel[4] = {0, 1, 2, 3};
+        int nsel = m.n < MAX_MANIFOLD_POINTS ? m.n : MAX_MANIFOLD_POINTS;
+        reduce_manifold_naive(m, sel, nsel, in[1]);
+        out[0] = (float)nsel;
+        for (int i = 0; i < 4; ++i) out[1 + i] = i < nsel ? (float)sel[i] : -1.0f;
+        return 0;
+    }
+    return -100;
+}
+
 }  // namespace orc

@@ -98,6 +98,88 @@ RB_PHASE void import_states_phase(const Ctx& ctx, const World& w, const int* idx
     }
 }
 
+// Unit-level known-answer evaluation: ONE device function of the path on literal inputs (rb_debug_kat;
+// float layouts in tests/golden/make_ref_vectors.py).  Runs as a single thread; `w` is a one-pair, one-slot
+// scratch world for the functions that read the pair / constraint tables.
+enum { KAT_POSE_DRIFT = 0, KAT_REDUCE, KAT_NORMAL_SOLVE, KAT_TANGENT_SOLVE, KAT_GENERATE };
+RB_PHASE void kat_phase(const World& w, int which, const float* in, float* out) {
+    auto v3at = [&](int o) { return mk3(in[o], in[o + 1], in[o + 2]); };
+    auto put3 = [&](int o, vec3 v) { out[o] = v.x; out[o + 1] = v.y; out[o + 2] = v.z; };
+    if (which == KAT_POSE_DRIFT) {
+        quat qb, qc;
+        qb.x = in[3]; qb.y = in[4]; qb.z = in[5]; qb.w = in[6];
+        qc.x = in[10]; qc.y = in[11]; qc.z = in[12]; qc.w = in[13];
+        out[0] = pose_drift(mkpose(qb, v3at(0)), mkpose(qc, v3at(7)), in[14]);
+    } else if (which == KAT_REDUCE) {
+        RawManifold m;
+        m.n = (int)in[0];
+        m.n1 = v3at(2);
+        for (int i = 0; i < m.n; ++i) { m.pt[i].p1 = v3at(5 + 4 * i); m.pt[i].dist = in[8 + 4 * i]; }
+        int sel[4] = {0, 1, 2, 3};
+        int nsel = m.n < MAX_PTS ? m.n : MAX_PTS;
+        reduce_manifold(m, sel, nsel, in[1]);
+        out[0] = (float)nsel;
+        for (int i = 0; i < 4; ++i) out[1 + i] = i < nsel ? (float)sel[i] : -1.0f;
+    } else if (which == KAT_NORMAL_SOLVE) {
+        const vec3 dir = v3at(0), im1 = v3at(3), im2 = v3at(6);
+        PointPre pp;
+        pp.td1 = v3at(9); pp.td2 = v3at(12); pp.itd1 = v3at(15); pp.itd2 = v3at(18);
+        pp.rhs = in[22]; pp.cfm = in[24];
+        vec3 v1 = v3at(25), w1 = v3at(28), v2 = v3at(31), w2 = v3at(34);
+        float nl;
+        const float dl = point_solve(pp, in[21], in[23], dir, v1, w1, v2, w2, nl);
+        apply_normal(had(dir, im1), had(dir, im2), pp.itd1, pp.itd2, dl, v1, w1, v2, w2);
+        out[0] = nl;
+        put3(1, v1); put3(4, w1); put3(7, v2); put3(10, w2);
+    } else if (which == KAT_TANGENT_SOLVE) {
+        Params P = w.prm;
+        P.sub_inv_dt = 1.0f;
+        BodyState g1, g2;
+        g1.p = pident(); g2.p = pident(); g1.ii = sym_zero(); g2.ii = sym_zero();
+        g1.im = v3at(9); g2.im = v3at(12);
+        FrictionJac j;
+        j.td10 = v3at(15); j.td11 = v3at(18); j.td20 = v3at(21); j.td21 = v3at(24);
+        j.i10 = v3at(27); j.i11 = v3at(30); j.i20 = v3at(33); j.i21 = v3at(36);
+        j.tw1 = zero3(); j.tw2 = zero3();
+        FrictionState f;
+        f.ti0 = in[45]; f.ti1 = in[46]; f.wi = 0.0f;
+        vec3 v1 = v3at(48), w1 = v3at(51), v2 = v3at(54), w2 = v3at(57);
+        g1.lin = v1; g1.ang = w1; g2.lin = v2; g2.ang = w2;
+        friction_solve_jac(P, g1, g2, v3at(0), v3at(3), v3at(6), 1, in[47], 0.0f, 0.0f, j, in[39], in[40], in[41], false, v3at(42),
+                           zero3(), f, v1, w1, v2, w2);
+        out[0] = f.ti0; out[1] = f.ti1;
+        put3(2, v1); put3(5, w1); put3(8, v2); put3(11, w2);
+    } else if (which == KAT_GENERATE) {
+        const int n = (int)in[5];
+        for (int r = 0; r < PR_ROWS; ++r) prow(w, 0, r, 0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        prow(w, 0, PR_INFO, 0) = make_float4(as_float_i(0), as_float_i(n), as_float_i(n), as_float_i(0));
+        prow(w, 0, PR_NORMAL, 0) = make_float4(in[0], in[1], in[2], in[3]);
+        prow(w, 0, PR_LN2, 0) = make_float4(0.f, 0.f, 0.f, in[4]);
+        for (int k = 0; k < n; ++k) {
+            const int o = 6 + 19 * k, cid = (int)in[o + 6];
+            prow(w, 0, PR_A1 + k, 0) = make_float4(in[o], in[o + 1], in[o + 2], as_float_i(cid));
+            prow(w, 0, PR_A2 + k, 0) = make_float4(in[o + 3], in[o + 4], in[o + 5], 0.f);
+            prow(w, 0, PR_PD + cid, 0) = make_float4(in[o + 7], in[o + 8], in[o + 9], 0.f);
+            prow(w, 0, PR_TW + cid, 0) = make_float4(in[o + 10], in[o + 11], in[o + 12], 0.f);
+            prow(w, 0, PR_DP1 + cid, 0) = make_float4(in[o + 13], in[o + 14], in[o + 15], 0.f);
+            prow(w, 0, PR_DP2 + cid, 0) = make_float4(in[o + 16], in[o + 17], in[o + 18], 0.f);
+        }
+        w.cons_hdr[0] = make_int4(0, NO_BODY, NO_BODY, 0);
+        GlobalBodies gb;
+        gb.w = &w;
+        Cons c;
+        cons_generate(w, gb, 0, 0, 0, c);
+        for (int i = 0; i < 39; ++i) out[i] = 0.0f;
+        out[0] = (float)c.nc; put3(1, c.dir); put3(4, c.t1); out[7] = c.fric;
+        for (int k = 0; k < MAX_PTS; ++k) {
+            out[8 + k] = c.imp[k]; out[12 + k] = c.acc[k]; out[16 + k] = k < c.nc ? c.r[k] : 0.0f;
+            out[20 + k] = k < c.nc ? c.dist0[k] : 0.0f; out[24 + k] = c.twd[k];
+            out[35 + k] = k < c.nc ? (float)c.cid[k] : 255.0f;
+        }
+        out[28] = c.ti0; out[29] = c.ti1; out[30] = c.ta0; out[31] = c.ta1; out[32] = c.wi; out[33] = c.wa; out[34] = c.wr;
+    }
+}
+
 #if RB_DEVICE_BUILD
 // Collision pipeline, then every solve that is NOT shared-memory resident: work items streamed from
 // HBM (one CTA each) and the grid-wide "large" item 0.  Those touch bodies / constraints disjoint from
@@ -183,6 +265,7 @@ __device__ __forceinline__ void solve_coop_items(const World& w, const Grav& g, 
 __global__ void __launch_bounds__(COOP_SMALL_THREADS, 2) k_solve_coop(World w, Grav g) { solve_coop_items<4>(w, g, COOP_SMALL_SMEM_BYTES / 4, false); }
 template <int THREADS, int L>
 __global__ void __launch_bounds__(THREADS, 1) k_solve_coop_big(World w, Grav g) { solve_coop_items<L>(w, g, COOP_BIG_SMEM_BYTES / 4, true); }
+__global__ void k_kat(World w, int which, const float* in, float* out) { kat_phase(w, which, in, out); }
 __global__ void k_init_bodies(World w) {
     GridCtx ctx;
     init_bodies_phase(ctx, w);
@@ -1105,6 +1188,15 @@ int64_t rb_world_debug_read(RbWorld* W, const char* table, void* dst, int64_t ca
         std::vector<int> v(std::max(W->w.nb, 1));
         CK(d2h(v.data(), t == "body_item" ? W->w.body_item : W->w.isl_label, (size_t)W->w.nb * 4));
         put(v.data(), (size_t)W->w.nb * 4);
+    } else if (t == "sched_cons_pair" || t == "sched_item_cons_start" || t == "sched_item_color_off" || t == "sched_color_pos" || t == "sched_cons_hdr") {
+        // the constraint schedule (solver_contact_graph.rs analogue): pair index per schedule slot, slot range per item,
+        // colour-stage offsets per item, stage position of each colour, (pair, id1, id2, n) headers
+        const int ni = st.nitems;
+        if (t == "sched_cons_pair") { std::vector<int> v(std::max(st.ncons, 1)); CK(d2h(v.data(), W->w.cons_pair, (size_t)st.ncons * 4)); put(v.data(), (size_t)st.ncons * 4); }
+        else if (t == "sched_cons_hdr") { std::vector<int4> v(std::max(st.ncons, 1)); CK(d2h(v.data(), W->w.cons_hdr, (size_t)st.ncons * 16)); put(v.data(), (size_t)st.ncons * 16); }
+        else if (t == "sched_item_cons_start") { std::vector<int> v(ni + 1); CK(d2h(v.data(), W->w.item_cons_start, (size_t)(ni + 1) * 4)); put(v.data(), (size_t)(ni + 1) * 4); }
+        else if (t == "sched_item_color_off") { std::vector<int> v((size_t)ni * (NUM_COLORS + 1)); CK(d2h(v.data(), W->w.item_color_off, v.size() * 4)); put(v.data(), v.size() * 4); }
+        else { std::vector<int> v(NUM_COLORS + 1); CK(d2h(v.data(), W->w.color_pos, v.size() * 4)); put(v.data(), v.size() * 4); }
     } else if (t == "dbg_times") {
         long long v[32];
         CK(d2h(v, W->w.dbg_times, sizeof(v)));
@@ -1119,6 +1211,49 @@ int64_t rb_world_debug_read(RbWorld* W, const char* table, void* dst, int64_t ca
     int64_t ncopy = total < cap ? total : cap;
     if (dst && ncopy > 0) memcpy(dst, out.data(), (size_t)ncopy);
     return total;
+}
+
+// Unit-level known-answer entry point (parity tests): evaluates one device function on literal inputs.
+int rb_debug_kat(const char* name, const float* in, int32_t n_in, float* out, int32_t n_out) {
+    if (!name || !in || !out || n_in <= 0 || n_out <= 0) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    static const struct { const char* n; int id, nin, nout; } T[] = {
+        {"pose_drift", KAT_POSE_DRIFT, 15, 1}, {"reduce_manifold", KAT_REDUCE, 5, 5}, {"normal_solve", KAT_NORMAL_SOLVE, 37, 13},
+        {"tangent_solve", KAT_TANGENT_SOLVE, 59, 14}, {"generate", KAT_GENERATE, 25, 39}};
+    int which = -1, nout = 0;
+    for (auto& t : T)
+        if (!strcmp(t.n, name)) {
+            if (n_in < t.nin || n_out < t.nout) { set_err("buffer too small for %s", name); return RB_ERR_INVALID; }
+            which = t.id; nout = t.nout;
+        }
+    if (which < 0) { set_err("unknown function %s", name); return RB_ERR_INVALID; }
+    if (which == KAT_REDUCE && ((int)in[0] < 0 || (int)in[0] > MAX_RAW || n_in < 5 + 4 * (int)in[0])) return RB_ERR_INVALID;
+    if (which == KAT_GENERATE && ((int)in[5] < 1 || (int)in[5] > MAX_PTS || n_in < 6 + 19 * (int)in[5])) return RB_ERR_INVALID;
+    RbWorld tmp;
+    RbWorld* W = &tmp;
+    World& w = W->w;
+    w.pair_cap = 1; w.cons_cap = 1;
+    RbIntegrationParameters dp;
+    rb_integration_parameters_default(&dp);
+    derive_params(dp, w.prm);
+    float *din = nullptr, *dout = nullptr;
+    int rc = RB_OK;
+    auto body = [&]() -> int {
+        ALLOC(w.pb[0].rows, PR_ROWS); ALLOC(w.cons_hdr, 1); ALLOC(w.cons, CR_ROWS); ALLOC(w.item_flags, 2);
+        ALLOC(din, n_in); ALLOC(dout, nout);
+        CK(h2d(din, in, (size_t)n_in * sizeof(float)));
+#if RB_DEVICE_BUILD
+        k_kat<<<1, 1>>>(w, which, din, dout);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+#else
+        kat_phase(w, which, din, dout);
+#endif
+        CK(d2h(out, dout, (size_t)nout * sizeof(float)));
+        return RB_OK;
+    };
+    rc = body();
+    free_all(W);
+    return rc;
 }
 
 // ---- multi-GPU sharding ----

@@ -43,6 +43,7 @@ def lib():
         L.orc_set_threads.argtypes = [C.c_int]
         L.orc_contact_manifold.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_kat.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
         _lib = L
     return _lib
 
