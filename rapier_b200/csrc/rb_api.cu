@@ -311,7 +311,7 @@ struct RbWorld {
     int prof_steps = 0;
 #else
     std::vector<float> emu_smem;
-    int emu_coop_floats = 0, emu_hint = 0;
+    int emu_coop_floats = 0, emu_hint[4] = {0, 0, 0, 0};
 #endif
 };
 
@@ -499,16 +499,28 @@ static int launch_init_bodies(RbWorld* W) {
     return RB_OK;
 }
 
-static int sync_world(RbWorld* W) {
+// Waits for the world's stream.  `check`: also report (and clear) a status the device raised since the last check --
+// capacity overflow or non-finite state -- so asynchronous stepping (sync = 0, rb_world_step_host) cannot hide it.
+static int sync_world(RbWorld* W, bool check = true) {
 #if RB_DEVICE_BUILD
     CK(cudaStreamSynchronize(W->stream));
 #endif
-    (void)W;
+    if (check && W->host_hint && W->w.st) {
+        const int code = *(volatile int*)(W->host_hint + 1);
+        if (code != 0) {
+            W->host_hint[1] = 0;
+            int zero = 0;
+            CK(h2d(&W->w.st->error, &zero, sizeof(int)));
+            set_err(code == RB_ERR_NONFINITE ? "device raised status %s%d (non-finite body state: see rb_world_get_quarantine)"
+                                             : "device raised status %s%d (capacity overflow: the step kept the previous pair set / truncated the schedule)", "", code);
+            return code;
+        }
+    }
     return RB_OK;
 }
 
 static int read_state(RbWorld* W, State& s) {
-    int rc = sync_world(W);
+    int rc = sync_world(W, false);   // (counters / debug reads must stay readable after an overflow; they do not consume the status)
     if (rc != RB_OK) return rc;
     CK(d2h(&s, W->w.st, sizeof(State)));
     return RB_OK;
@@ -572,8 +584,8 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
 #define RB_BIG_VARIANTS(X) X(256, 1)
 #define RB_SET_ATTR(T, LL) cudaFuncSetAttribute(k_solve_coop_big<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_BIG_SMEM_BYTES);
     RB_BIG_VARIANTS(RB_SET_ATTR)
-    if (cudaHostAlloc((void**)&W->host_hint, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { set_err("cudaHostAlloc failed%s", ""); delete W; return nullptr; }
-    *W->host_hint = 0;
+    if (cudaHostAlloc((void**)&W->host_hint, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) { set_err("cudaHostAlloc failed%s", ""); delete W; return nullptr; }
+    for (int i = 0; i < 4; ++i) W->host_hint[i] = 0;
     cudaFuncSetAttribute(k_collide, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_collide, COLLIDE_THREADS, ITEM_SMEM_BYTES);
@@ -596,7 +608,7 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
         const char* v = getenv("RB_EMU_COOP_SMEM_FLOATS");
         W->emu_coop_floats = v ? atoi(v) : COOP_BIG_SMEM_BYTES / 4;
         W->emu_smem.assign(ITEM_MAX_BODIES * SB_STRIDE + W->emu_coop_floats, 0.0f);
-        W->host_hint = &W->emu_hint;
+        W->host_hint = W->emu_hint;
     }
 #endif
     return W;
@@ -659,6 +671,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
         }
     }
     W->steps_since_scene = 0;
+    if (W->host_hint) W->host_hint[1] = 0;
     W->state_buf[0] = W->state_buf[1] = nullptr;
     W->bodies.assign(bodies, bodies + nb);
     W->colliders.assign(colliders, colliders + nc);
@@ -720,7 +733,9 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     w.host_hint = W->host_hint;
     w.coop_small_floats = COOP_SMALL_SMEM_BYTES / 4;
     w.coop_sweep_threads = W->sweep_threads;
+#ifdef RB_DEBUG
     { const char* v = getenv("RB_DEBUG_FLAGS"); w.debug_flags = v ? atoi(v) : 0; }
+#endif
 #if !RB_DEVICE_BUILD
     w.coop_small_floats = std::min(w.coop_small_floats, W->emu_coop_floats);   // the emulated CTA must fit what it is given
 #endif
@@ -957,21 +972,13 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
             W->ms_solve = v / W->prof_steps;
             W->ms_step = W->ms_collide + W->ms_solve;
         }
-        State st;
-        CK(d2h(&st, W->w.st, sizeof(st)));
-        if (st.error) {
-            int zero = 0;
-            CK(h2d(&W->w.st->error, &zero, sizeof(int)));
-            set_err("device raised status %s%d (capacity overflow)", "", st.error);
-            return st.error;
-        }
+        return sync_world(W);
     }
 #else
-    (void)sync;
     for (int s = 0; s < nsteps; ++s) {
         GridCtx gctx;
         if (W->state_buf[1]) { W->w.state13 = W->state_buf[W->state_next]; W->state_next ^= 1; }
-        W->emu_hint = W->w.st->need_big;
+        W->emu_hint[0] = W->w.st->need_big;
         W->w.st->need_big = W->w.st->coop_streamed = W->w.st->coop_resident = 0;
         collide_pipeline(gctx, W->w);
         BlockCtx bctx;
@@ -1001,7 +1008,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         W->kernels += 2;
     }
     W->steps += nsteps;
-    if (W->w.st->error) { int e = W->w.st->error; W->w.st->error = 0; set_err("device raised status %s%d", "", e); return e; }
+    if (sync) return sync_world(W);
 #endif
     return RB_OK;
 }
@@ -1421,10 +1428,8 @@ int rb_world_step_host(RbWorld* W, const float gravity[3], const float* in_state
 #else
         memcpy(out_state13, W->w.state13, n * sizeof(float));
 #endif
-    } else {
-        rc = sync_world(W);
     }
-    return rc;
+    return sync_world(W);   // (the stream is idle by now: this only reports a status the device raised)
 }
 
 }  // extern "C"

@@ -165,8 +165,9 @@ RB_PHASE void section_broad_phase(const Ctx& ctx, const World& w) {
     }
     ctx.grid_sync();
     int ncand = st->ncand;
-    if (ncand > w.pair_cap) {  // capacity overflow: keep the old pair set, raise the error
-        if (ctx.gtid == 0) { st->error = -4; st->bp_dirty = 0; }
+    if (ncand > w.pair_cap) {  // capacity overflow: keep the old pair set and raise the status; the pair set stays dirty,
+                               // so every step raises it again until the world fits (no silently stale physics)
+        if (ctx.gtid == 0) RB_RAISE(w, -4);
         ctx.grid_sync();
         return;
     }
@@ -684,7 +685,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
     int total_cost = w.scan_tmp[ctx.gsize];
     int nitems = 1 + (total_cost + ITEM_TARGET - 1) / ITEM_TARGET;
     if (nitems > w.item_cap) {
-        if (ctx.gtid == 0) st->error = -4;
+        if (ctx.gtid == 0) RB_RAISE(w, -4);
         nitems = w.item_cap;
     }
     for (int b = ctx.gtid; b < nb; b += ctx.gsize) {
@@ -723,7 +724,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
     grid_exclusive_scan(ctx, w.item_joint_start, w.item_joint_start, nitems + 1, w.scan_tmp);
     int ncons = w.item_cons_start[nitems];
     if (ncons > w.cons_cap) {
-        if (ctx.gtid == 0) st->error = -4;
+        if (ctx.gtid == 0) RB_RAISE(w, -4);
     }
     // S9 scatter bodies / manifolds / joints into their item segments
     int* cur_b = w.item_cursor;

@@ -94,6 +94,10 @@ inline void thread_fence() {}
 
 #endif
 
+// Raise a device-side status (capacity overflow, non-finite state): sticky in State::error and mirrored into the
+// host-mapped status word so that every synchronising call of the C ABI sees it, also after asynchronous steps.
+#define RB_RAISE(w, code) do { (w).st->error = (code); if ((w).host_hint[1] == 0) (w).host_hint[1] = (code); } while (0)
+
 RB_HD float as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 RB_HD uint32_t as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 RB_HD float as_float_i(int i) { float f; memcpy(&f, &i, 4); return f; }

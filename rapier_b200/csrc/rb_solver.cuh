@@ -1393,7 +1393,9 @@ template <int L, int MODE>
 RB_PHASE void coop_sweep(const BlockCtx& ctx, const World& w, const SmemBodies& bd, const RowView& res, const RowView& mu, bool resident,
                          CoopPipe& pp, const int* s_stage, int nstages, int wslot, int c0, bool fric, bool wrap) {
     const int tid = ctx.btid, nth = pp.sweep_threads;   // warps beyond the sweep width only take part in the barriers
-    if (w.debug_flags & 1) return;
+#ifdef RB_DEBUG
+    if (w.debug_flags & 1) return;   // profiling experiment (debug build only): skip the sweeps
+#endif
     if (resident) {
         for (int c = 0; c < nstages; ++c) {
             const int ae = s_stage[c];
@@ -1522,9 +1524,13 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, 
         if (!coop_plan(w.coop_small_floats, b1 - b0, n).resident) st->need_big = 1;
         atomic_add(resident ? &st->coop_resident : &st->coop_streamed, 1);
     }
+#ifdef RB_DEBUG   // phase timeline of one item (debug build only: librapier_b200_dbg.so, tests/prof_phases.py)
     const bool trace = (w.debug_flags & 2) && ctx.bid == 0 && tid == 0;
     int tr = 0;
 #define RB_TRACE() if (trace && tr < 32) w.dbg_times[tr++] = rb_clock()
+#else
+#define RB_TRACE() do {} while (0)
+#endif
     RB_TRACE();
     for (int l = b0 + tid; l < b1; l += nth) body_init(w, bd, w.item_bodies[l], l - b0, gravity);
     ctx.block_sync();
@@ -1556,7 +1562,9 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, 
             if (sub == 0) RB_TRACE();
             for (int s = tid; s < n; s += nth) coop_warmstart_bank(P, mu, s);
             ctx.block_sync();   // (also orders the increments above before the gathers below)
+#ifdef RB_DEBUG
             if (!(w.debug_flags & 1))
+#endif
                 for (int l = tid; l < b1 - b0; l += nth) {
                     const int* adj = w.adj_list + w.adj_off[b0 + l];
                     const int cnt = w.adj_cnt[b0 + l];
@@ -1605,7 +1613,9 @@ RB_PHASE void solve_item_coop(const BlockCtx& ctx, const World& w, float* smem, 
         coop_get_for_writeback(resident ? res : coop_slot_rows(pp, s), mu, s, c);
         cons_writeback(w, c0 + s, buf, c, true);
     }
+#ifdef RB_DEBUG
     if (w.debug_flags & 2) ctx.block_sync();   // (uniform: only to attribute the two writebacks separately)
+#endif
     RB_TRACE();
     for (int l = b0 + tid; l < b1; l += nth) body_writeback(w, bd, w.item_bodies[l], l - b0);
     RB_TRACE();

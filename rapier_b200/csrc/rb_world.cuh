@@ -186,9 +186,10 @@ struct World {
     float4* coop_pool;                // [2 * COOP_ROWS * cons_cap] L2-resident constant rows of streamed items, blocked by chunk
     int coop_small_floats;            // dynamic shared memory of the small launch shape (2 CTAs / SM), which must fit every shared-memory item
     long long* dbg_times;             // [32] phase timestamps of one item (debug_flags & 2)
-    int debug_flags;                  // RB_DEBUG_FLAGS (profiling experiments only): 1 = skip the sweeps, 2 = record dbg_times
+    int debug_flags;                  // RB_DEBUG_FLAGS, honoured only by the -DRB_DEBUG build: 1 = skip the sweeps, 2 = record dbg_times
     int coop_sweep_threads;           // sweep width of the big launch shape (0 = whole block)
-    int* host_hint;                   // pinned, host-mapped: last step's State::need_big
+    int* host_hint;                   // pinned, host-mapped words read by the host without synchronising: [0] last step's State::need_big,
+                                      // [1] first status raised on the device since the host last cleared it (RbStatus; 0 = none)
     // ---- joints ----
     int4* j_info;                     // body1, body2, locked_axes, colour
     float4 *j_f1_t, *j_f1_q, *j_f2_t, *j_f2_q;   // local frames

@@ -18,15 +18,35 @@ def build():
     subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def _cpu_tag():
+    """Hash of this host's CPU feature flags: the -march=native baseline build is only valid where it was built."""
+    import hashlib
+    flags = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                flags = line
+                break
+    except OSError:
+        pass
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+def lib(fast=False):
+    """fast=False: the bit-exact oracle (the parity checker).  fast=True: the CPU-baseline build of the same sources
+    (-O3 -march=native, built on this host; bench.py's cpu_baseline / --impl reference legs only)."""
+    if fast not in _libs:
+        path = LIB_PATH
+        if fast:
+            tag = _cpu_tag()
+            path = os.path.join(ORACLE_DIR, "_build", f"liborc_fast_{tag}.so")
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "fast", f"FAST_TAG={tag}"])
+        elif not os.path.exists(LIB_PATH):
             build()
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         L.orc_world_create.restype = C.c_void_p
         L.orc_world_create.argtypes = [C.POINTER(A.RbIntegrationParameters)]
         L.orc_world_destroy.argtypes = [C.c_void_p]
@@ -44,15 +64,15 @@ def lib():
         L.orc_contact_manifold.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_kat.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
-        _lib = L
-    return _lib
+        _libs[fast] = L
+    return _libs[fast]
 
 
 class OracleWorld:
     """Same surface as rapier_b200.PhysicsWorld, backed by the CPU oracle."""
 
-    def __init__(self, scene, params=None, threads=1):
-        self.L = lib()
+    def __init__(self, scene, params=None, threads=1, fast=False):
+        self.L = lib(fast)
         self.params = params or A.RbIntegrationParameters.default()
         self.h = self.L.orc_world_create(C.byref(self.params))
         self.gravity = scene.gravity

@@ -1,5 +1,6 @@
 """Helper (not a test): phase timeline of one shared-memory item (RB_DEBUG_FLAGS=2) and solve time with the sweeps skipped (=1)."""
 import sys, os
+os.environ["RAPIER_B200_DEBUG_LIB"] = "1"   # the -DRB_DEBUG build (python -c "import __graft_entry__ as g; g.build_cuda(debug=True)")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from rapier_b200 import scenes

@@ -87,3 +87,20 @@ def test_emulated_variants_match_oracle(name, make, params, steps, every):
             assert is_exact(d), f"{name}: step {i}: {d}"
     pose, _ = w.body_states()
     assert np.isfinite(pose).all()
+
+
+def test_capacity_overflow_is_reported_after_asynchronous_steps():
+    """A status raised on the device (here: more broad-phase pairs than the pair table holds) must reach the caller
+    at the next synchronising call even when the steps were enqueued asynchronously (sync = 0 / step_host)."""
+    from rapier_b200.sets import ColliderBuilder, RigidBodyBuilder
+    from rapier_b200.world import RapierError
+    s = scenes.Scene("crowd", gravity=(0.0, 0.0, 0.0))
+    for i in range(330):   # 330 balls within one ball radius of each other: 54 285 pairs > 16 per dynamic collider
+        s.insert(RigidBodyBuilder.dynamic().translation((0.001 * i, 0.0, 0.0)), ColliderBuilder.ball(0.5))
+    w = PhysicsWorld(s, _lib=emul_lib.lib())
+    w.step(1, sync=False)
+    with pytest.raises(RapierError, match="-4"):
+        w.physics_pipeline.synchronize()
+    w.physics_pipeline.synchronize()   # reported once, then cleared
+    with pytest.raises(RapierError, match="-4"):
+        w.physics_pipeline.step_host(s.gravity, None, None)

@@ -346,3 +346,16 @@ def test_thread_count_determinism():
             ref = bits
         else:
             assert (bits[0] == ref[0]).all() and (bits[1] == ref[1]).all(), threads
+
+
+def test_cpu_baseline_build_tracks_the_bit_exact_oracle():
+    """bench.py's CPU arm uses the oracle sources rebuilt -O3 -march=native with FMA contraction (oracle/Makefile
+    `fast`): a BASELINE, never a checker.  It must stay within 1e-4 of the bit-exact oracle after 10 steps."""
+    scene = scenes.box_pile(4, 4, 5)
+    a = oracle_lib.OracleWorld(scene)
+    b = oracle_lib.OracleWorld(scene, fast=True, threads=2)
+    a.step(10)
+    b.step(10)
+    pa, va = a.body_states()
+    pb, vb = b.body_states()
+    assert np.abs(pa - pb).max() <= 1e-4 and np.abs(va - vb).max() <= 1e-3
