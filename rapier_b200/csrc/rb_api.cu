@@ -688,12 +688,10 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     int ndyn_col = 0;
     for (int i = 0; i < nc; ++i)
         if (colliders[i].parent >= 0 && bodies[colliders[i].parent].body_type == RB_BODY_DYNAMIC) ndyn_col++;
-    w.pair_cap = next_pow2_host(std::max(4096, 16 * ndyn_col));
-    w.pair_cap_pow2 = w.pair_cap;
+    w.pair_cap = next_pow2_host(std::max(4096, 16 * ndyn_col)) + 160;   // (+160: row strides that are no power of two spread the rows of a record over the L2 slices)
     w.cons_cap = w.pair_cap;
     w.joint_cap = std::max(nj, 1);
     w.item_cap = 4 + (nb + w.pair_cap + nj) / ITEM_TARGET;
-    w.nc_pow2 = next_pow2_host(std::max(nc, 2));
     const int NB = std::max(nb, 1), NC = std::max(nc, 1), NJ = w.joint_cap;
 
     ALLOC(w.st, 1);
@@ -708,8 +706,10 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.c_shape, NC); ALLOC(w.c_parent, NC); ALLOC(w.c_he, NC); ALLOC(w.c_rel_t, NC); ALLOC(w.c_rel_q, NC);
     ALLOC(w.c_mat, NC); ALLOC(w.c_rules, NC); ALLOC(w.c_groups, NC); ALLOC(w.c_pos_t, NC); ALLOC(w.c_pos_q, NC);
     ALLOC(w.c_aabb_min, NC); ALLOC(w.c_aabb_max, NC); ALLOC(w.c_fat_min, NC); ALLOC(w.c_fat_max, NC);
-    { unsigned long long* p = nullptr; ALLOC(p, w.nc_pow2); w.bp_sort_key = (unsigned*)p; }
-    ALLOC(w.cand_key, w.pair_cap_pow2);
+    ALLOC(w.dyn_list, NC); ALLOC(w.wide_list, WIDE_CAP);
+    for (int k = 0; k < 2; ++k) { ALLOC(w.dyn_key[k], NC); ALLOC(w.stat_key[k], NC); }
+    ALLOC(w.radix_hist, (size_t)9 * 1024 * RADIX);   // (grids of up to 1024 CTAs; the collide grid is one CTA per SM)
+    ALLOC(w.cand_key, w.pair_cap); ALLOC(w.cand_key2, w.pair_cap);
     ALLOC(w.remap_src, w.pair_cap);
     for (int k = 0; k < 2; ++k) { ALLOC(w.pb[k].key, w.pair_cap); ALLOC(w.pb[k].rows, (size_t)PR_ROWS * w.pair_cap); }
     ALLOC(w.todo, 16);
@@ -872,6 +872,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
         State s;
         memset(&s, 0, sizeof(s));
         s.bp_dirty = 1;
+        s.lists_dirty = 1;
         s.sched_dirty = 1;
         s.nitems = 1;
         s.njused_colors = W->njused;
@@ -917,6 +918,16 @@ int rb_world_set_body_states(RbWorld* W, int32_t n, const int32_t* indices, cons
             float4 a = make_float4(vel6[k * 6 + 3], vel6[k * 6 + 4], vel6[k * 6 + 5], 0.f);
             CK(h2d(W->w.b_linvel + i, &l, sizeof(l)));
             CK(h2d(W->w.b_angvel + i, &a, sizeof(a)));
+        }
+    }
+    {   // a teleported FIXED body moves static colliders: rebuild the broad-phase lists (and re-sort the static ones)
+        bool moved_static = false;
+        if (pose7)
+            for (int k = 0; k < n; ++k) moved_static = moved_static || W->bodies[indices[k]].body_type != RB_BODY_DYNAMIC;
+        if (moved_static) {
+            int one = 1;
+            CK(h2d(&W->w.st->lists_dirty, &one, sizeof(int)));
+            CK(h2d(&W->w.st->bp_dirty, &one, sizeof(int)));
         }
     }
     rc = launch_init_bodies(W);
@@ -1298,7 +1309,7 @@ int rb_world_set_owned_bodies(RbWorld* W, const uint8_t* owned) {
     // Ownership changes the pair filter: drop the pair table and every derived structure.
     State st;
     CK(d2h(&st, W->w.st, sizeof(st)));
-    st.npairs = 0; st.bp_dirty = 1; st.sched_dirty = 1; st.ntodo = 0; st.ncons = 0; st.nitems = 1; st.nlarge_bodies = 0;
+    st.npairs = 0; st.bp_dirty = 1; st.lists_dirty = 1; st.sched_dirty = 1; st.ntodo = 0; st.ncons = 0; st.nitems = 1; st.nlarge_bodies = 0;
     CK(h2d(W->w.st, &st, sizeof(st)));
     CK(dev_set(W->w.color_mask, 0, (size_t)std::max(W->w.nb, 1) * 16));
     CK(dev_set(W->w.c_fat_min, 0, (size_t)std::max(W->w.nc, 1) * 16));

@@ -30,53 +30,40 @@ RB_HD pose collider_pose(const World& w, int c) { return mkpose(mkq(w.c_pos_q[c]
 // ------------------------------------------------------------------------------------------------
 // P0: collider world poses, broad-phase AABBs and fat-AABB change detection
 // (substep.rs:103-146 + refresh_moved_collider_aabbs substep.rs:229-240 -> BroadPhaseBvh::set_aabb).
+// Static colliders (no parent, or a parent that is not dynamic) never move: once the static / dynamic lists
+// exist only the dynamic list is refreshed (a 10^6-tile floor costs nothing per step).
 // ------------------------------------------------------------------------------------------------
-template <class Ctx>
-RB_PHASE void phase_refresh_colliders(const Ctx& ctx, const World& w) {
-    for (int c = ctx.gtid; c < w.nc; c += ctx.gsize) {
-        int parent = w.c_parent[c];
-        pose rel = mkpose(mkq(w.c_rel_q[c]), xyz(w.c_rel_t[c]));
-        pose p = parent >= 0 ? pmul(body_pose(w, parent), rel) : rel;
-        w.c_pos_t[c] = f4(p.t, 0.0f);
-        w.c_pos_q[c] = f4(p.q);
-        vec3 lo, hi;
-        shape_aabb(w.c_shape[c], xyz(w.c_he[c]), p, lo, hi);
-        float l = w.c_mat[c].z + w.prm.prediction / 2.0f;
-        lo = mk3(lo.x - l, lo.y - l, lo.z - l);
-        hi = mk3(hi.x + l, hi.y + l, hi.z + l);
-        w.c_aabb_min[c] = f4(lo, 0.0f);
-        w.c_aabb_max[c] = f4(hi, 0.0f);
-        float4 fmin = w.c_fat_min[c], fmax = w.c_fat_max[c];
-        bool valid = fmin.w != 0.0f;
-        bool contains = valid && fmin.x <= lo.x && fmin.y <= lo.y && fmin.z <= lo.z && fmax.x >= hi.x && fmax.y >= hi.y &&
-                        fmax.z >= hi.z;
-        if (!contains) {
-            float s = w.prm.fat_skin;
-            w.c_fat_min[c] = make_float4(lo.x - s, lo.y - s, lo.z - s, 1.0f);
-            w.c_fat_max[c] = make_float4(hi.x + s, hi.y + s, hi.z + s, 1.0f);
-            w.st->bp_dirty = 1;
-        }
+RB_HD void refresh_collider(const World& w, int c) {
+    int parent = w.c_parent[c];
+    pose rel = mkpose(mkq(w.c_rel_q[c]), xyz(w.c_rel_t[c]));
+    pose p = parent >= 0 ? pmul(body_pose(w, parent), rel) : rel;
+    w.c_pos_t[c] = f4(p.t, 0.0f);
+    w.c_pos_q[c] = f4(p.q);
+    vec3 lo, hi;
+    shape_aabb(w.c_shape[c], xyz(w.c_he[c]), p, lo, hi);
+    float l = w.c_mat[c].z + w.prm.prediction / 2.0f;
+    lo = mk3(lo.x - l, lo.y - l, lo.z - l);
+    hi = mk3(hi.x + l, hi.y + l, hi.z + l);
+    w.c_aabb_min[c] = f4(lo, 0.0f);
+    w.c_aabb_max[c] = f4(hi, 0.0f);
+    float4 fmin = w.c_fat_min[c], fmax = w.c_fat_max[c];
+    bool valid = fmin.w != 0.0f;
+    bool contains = valid && fmin.x <= lo.x && fmin.y <= lo.y && fmin.z <= lo.z && fmax.x >= hi.x && fmax.y >= hi.y &&
+                    fmax.z >= hi.z;
+    if (!contains) {
+        float s = w.prm.fat_skin;
+        w.c_fat_min[c] = make_float4(lo.x - s, lo.y - s, lo.z - s, 1.0f);
+        w.c_fat_max[c] = make_float4(hi.x + s, hi.y + s, hi.z + s, 1.0f);
+        w.st->bp_dirty = 1;
     }
 }
-
-// ------------------------------------------------------------------------------------------------
-// Bitonic sort of 64-bit keys, grid-synchronised between passes (device radix sort is future work:
-// this section only runs when a fat AABB changed).
-// ------------------------------------------------------------------------------------------------
 template <class Ctx>
-RB_PHASE void grid_bitonic_sort(const Ctx& ctx, unsigned long long* a, int n) {
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = ctx.gtid; i < n; i += ctx.gsize) {
-                int l = i ^ j;
-                if (l > i) {
-                    unsigned long long x = a[i], y = a[l];
-                    bool asc = (i & k) == 0;
-                    if ((x > y) == asc) { a[i] = y; a[l] = x; }
-                }
-            }
-            ctx.grid_sync();
-        }
+RB_PHASE void phase_refresh_colliders(const Ctx& ctx, const World& w) {
+    if (w.st->lists_dirty) {
+        for (int c = ctx.gtid; c < w.nc; c += ctx.gsize) refresh_collider(w, c);
+    } else {
+        const int nd = w.st->ndyn;
+        for (int i = ctx.gtid; i < nd; i += ctx.gsize) refresh_collider(w, w.dyn_list[i]);
     }
 }
 
@@ -100,6 +87,119 @@ RB_HD int bsearch_u64(const unsigned long long* a, int n, unsigned long long key
         if (v < key) lo = mid + 1; else hi = mid - 1;
     }
     return -1;
+}
+RB_HD int lower_bound_u64(const unsigned long long* a, int n, unsigned long long key) {   // first index with a[i] >= key
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Grid-wide stable LSD radix sort of 64-bit keys on the bits [lo, hi), 8 bits per pass, ONE grid barrier per
+// pass (the north star's "device radix sort"; it replaced a bitonic network with log^2 n barriers).
+//   * every CTA owns a contiguous chunk of the array, every warp a contiguous part of that chunk, so "block,
+//     warp, position" order is index order and the scatter is stable;
+//   * the per-(block, digit) counts of pass p+1 are accumulated with global atomics WHILE pass p scatters
+//     (the destination block of a key is known then), so a pass needs no counting sweep of its own;
+//   * offsets: each CTA sums the small [blocks][256] count table itself (no grid-wide scan).
+// `hist` holds (passes + 1) tables of nblocks x 256 ints and must be ZERO on entry, the keys must be in `a`,
+// and a grid barrier must separate both from this call.  Returns the buffer that holds the result.
+// ------------------------------------------------------------------------------------------------
+constexpr int RADIX = 256;
+constexpr int RADIX_MAX_WARPS = 8;
+RB_HD int radix_passes(int lo, int hi) { return (hi - lo + 7) / 8; }
+RB_HD int bits_for(int n) { int b = 1; while ((1 << b) < n && b < 31) ++b; return b; }
+
+#if RB_DEVICE_BUILD
+RB_D unsigned warp_match_any(int v) { return __match_any_sync(0xffffffffu, v); }
+RB_D void warp_sync() { __syncwarp(); }
+RB_D int popc(unsigned x) { return __popc(x); }
+#else
+inline unsigned warp_match_any(int) { return 1u; }
+inline void warp_sync() {}
+inline int popc(unsigned x) { return __builtin_popcount(x); }
+#endif
+
+template <class Ctx>
+RB_PHASE void grid_radix_zero(const Ctx& ctx, int* hist, int passes) {
+    const int n = (passes + 1) * ctx.nblocks * RADIX;
+    for (int i = ctx.gtid; i < n; i += ctx.gsize) hist[i] = 0;
+}
+
+template <class Ctx>
+RB_PHASE unsigned long long* grid_radix_sort(const Ctx& ctx, unsigned long long* a, unsigned long long* b, int n, int lo, int hi,
+                                             int* hist) {
+    RB_SHARED int s_warp[RADIX_MAX_WARPS][RADIX];   // per-warp digit counts, then running scatter offsets
+    RB_SHARED int s_tot[RADIX];
+    const int passes = radix_passes(lo, hi);
+    const int nblocks = ctx.nblocks;
+    const int chunk = (n + nblocks - 1) / nblocks > 0 ? (n + nblocks - 1) / nblocks : 1;
+    const int nwarps = ctx.bsize / ctx.nlanes < RADIX_MAX_WARPS ? ctx.bsize / ctx.nlanes : RADIX_MAX_WARPS;
+    const int wchunk = (chunk + nwarps - 1) / nwarps;
+    const int warp = ctx.btid / ctx.nlanes;
+    const int b0 = ctx.bid * chunk, b1 = b0 + chunk < n ? b0 + chunk : n;
+    // counts of the first pass
+    for (int i = b0 + ctx.btid; i < b1; i += ctx.bsize) atomic_add(&hist[ctx.bid * RADIX + (int)((a[i] >> lo) & 255)], 1);
+    ctx.grid_sync();
+    for (int p = 0; p < passes; ++p) {
+        const int shift = lo + 8 * p;
+        const int* h = hist + (size_t)p * nblocks * RADIX;
+        int* hn = hist + (size_t)(p + 1) * nblocks * RADIX;
+        // per digit: total over all blocks, and the part of it that precedes this block
+        for (int d = ctx.btid; d < RADIX; d += ctx.bsize) {
+            int tot = 0, before = 0;
+            for (int k = 0; k < nblocks; ++k) {
+                int v = h[k * RADIX + d];
+                tot += v;
+                if (k < ctx.bid) before += v;
+            }
+            s_tot[d] = tot;
+            s_warp[0][d] = before;   // (parked here until the exclusive scan below)
+        }
+        ctx.block_sync();
+        if (ctx.btid == 0) {
+            int run = 0;
+            for (int d = 0; d < RADIX; ++d) { int v = s_tot[d]; s_tot[d] = run + s_warp[0][d]; run += v; }   // s_tot = first slot of (digit, this block)
+        }
+        ctx.block_sync();
+        for (int i = ctx.btid; i < nwarps * RADIX; i += ctx.bsize) s_warp[i / RADIX][i % RADIX] = 0;
+        ctx.block_sync();
+        // per-warp counts over the warp's own part of the chunk
+        const int w0 = b0 + warp * wchunk, w1 = (w0 + wchunk < b1 ? w0 + wchunk : b1);
+        if (warp < nwarps)
+            for (int i = w0 + ctx.lane; i < w1; i += ctx.nlanes) atomic_add(&s_warp[warp][(int)((a[i] >> shift) & 255)], 1);
+        ctx.block_sync();
+        for (int d = ctx.btid; d < RADIX; d += ctx.bsize) {   // counts -> first slot of (digit, this warp)
+            int run = s_tot[d];
+            for (int k = 0; k < nwarps; ++k) { int v = s_warp[k][d]; s_warp[k][d] = run; run += v; }
+        }
+        ctx.block_sync();
+        // stable scatter, a warp-load at a time in index order
+        if (warp < nwarps)
+            for (int base = w0; base < w1; base += ctx.nlanes) {
+                const int i = base + ctx.lane;
+                const bool valid = i < w1;
+                unsigned long long key = valid ? a[i] : 0ull;
+                const int d = valid ? (int)((key >> shift) & 255) : 0x1000 + ctx.lane;
+                const unsigned peers = warp_match_any(d);
+                const int rank = popc(peers & ((1u << ctx.lane) - 1u));
+                int dest = 0;
+                if (valid) {
+                    dest = s_warp[warp][d] + rank;
+                    b[dest] = key;
+                    if (p + 1 < passes) atomic_add(&hn[(dest / chunk) * RADIX + (int)((key >> (shift + 8)) & 255)], 1);
+                }
+                warp_sync();
+                if (valid && rank == 0) s_warp[warp][d] += popc(peers);
+                warp_sync();
+            }
+        ctx.grid_sync();
+        unsigned long long* t = a; a = b; b = t;
+    }
+    return a;
 }
 
 // update.rs:334-396 filter_new
@@ -125,61 +225,150 @@ RB_HD void clear_color_bits(const World& w, int color, int cb0, int cb1) {
     }
 }
 
-// P1: sort-and-sweep broad phase + merge with the persistent pair table.
+RB_HD bool collider_is_static(const World& w, int c) {   // never moves: no parent, or a parent that is not a dynamic body
+    const int p = w.c_parent[c];
+    return p < 0 || w.b_type[p] != BODY_DYNAMIC;
+}
+RB_HD bool fat_overlap(float4 amin, float4 amax, float4 bmin, float4 bmax) {
+    return amin.x <= bmax.x && amin.y <= bmax.y && amin.z <= bmax.z && amax.x >= bmin.x && amax.y >= bmin.y && amax.z >= bmin.z;
+}
+RB_HD void emit_candidate(const World& w, int ci, int cj) {
+    const int c1 = ci < cj ? ci : cj, c2 = ci < cj ? cj : ci;
+    if (!pair_allowed(w, c1, c2)) return;
+    const int slot = atomic_add(&w.st->ncand, 1);
+    if (slot < w.pair_cap) w.cand_key[slot] = ((unsigned long long)(unsigned)c1 << 32) | (unsigned)c2;
+}
+
+constexpr int WIDE_CAP = 1024;   // static colliders much wider than the rest (a ground slab under a tiled floor): tested by every mover
+
+// P1 (lists): split the colliders into the movers (sorted every time an AABB changes) and the static ones (sorted
+// here, once): the reference keeps all leaves in one tree and only re-tests CHANGED leaves (broad_phase_bvh/
+// update.rs:441-601), which static leaves never are.  Static colliders much wider along x than the average go to a
+// short list every mover tests, so that one big slab does not defeat the interval search over the narrow ones.
+template <class Ctx>
+RB_PHASE void section_build_lists(const Ctx& ctx, const World& w) {
+    State* st = w.st;
+    if (ctx.gtid == 0) { st->ndyn = 0; st->nstat = 0; st->nwide = 0; st->stat_count = 0; st->stat_wsum = 0.0f; st->stat_wn_bits = 0u; }
+    grid_radix_zero(ctx, w.radix_hist, 4);
+    ctx.grid_sync();
+    for (int c = ctx.gtid; c < w.nc; c += ctx.gsize)
+        if (collider_is_static(w, c)) {
+            atomic_add(&st->stat_count, 1);
+            atomic_add(&st->stat_wsum, w.c_fat_max[c].x - w.c_fat_min[c].x);
+        }
+    ctx.grid_sync();
+    const float wide_thr = st->stat_count > 0 ? 4.0f * (st->stat_wsum / (float)st->stat_count) : 0.0f;
+    for (int c = ctx.gtid; c < w.nc; c += ctx.gsize) {
+        if (!collider_is_static(w, c)) { w.dyn_list[atomic_add(&st->ndyn, 1)] = c; continue; }
+        const float4 lo = w.c_fat_min[c], hi = w.c_fat_max[c];
+        const float width = hi.x - lo.x;
+        bool wide = width > wide_thr;
+        if (wide) {
+            const int k = atomic_add(&st->nwide, 1);
+            if (k < WIDE_CAP) w.wide_list[k] = c; else wide = false;   // (the count is clamped where it is read)
+        }
+        if (!wide) {
+            w.stat_key[0][atomic_add(&st->nstat, 1)] = ((unsigned long long)sortable_float(lo.x) << 32) | (unsigned)c;
+            atomic_max_u(&st->stat_wn_bits, as_uint(width > 0.0f ? width : 0.0f));   // (non-negative floats order like their bits)
+        }
+    }
+    ctx.grid_sync();
+    unsigned long long* sorted = grid_radix_sort(ctx, w.stat_key[0], w.stat_key[1], st->nstat, 32, 64, w.radix_hist);
+    if (ctx.gtid == 0) { st->stat_sorted = sorted == w.stat_key[0] ? 0 : 1; st->lists_dirty = 0; st->bp_dirty = 1; }
+    ctx.grid_sync();
+}
+
+// P1: sort-and-sweep broad phase over the movers + interval search into the sorted static colliders, then the
+// merge with the persistent pair table (skipped when the pair set did not change).
 template <class Ctx>
 RB_PHASE void section_broad_phase(const Ctx& ctx, const World& w) {
     State* st = w.st;
-    unsigned long long* skey = (unsigned long long*)w.bp_sort_key;  // [nc_pow2] (min-x key << 32) | collider
-    for (int i = ctx.gtid; i < w.nc_pow2; i += ctx.gsize) {
-        skey[i] = i < w.nc ? (((unsigned long long)sortable_float(w.c_fat_min[i].x) << 32) | (unsigned)i) : ~0ull;
+    if (st->lists_dirty) section_build_lists(ctx, w);
+    const int nd = st->ndyn, ns = st->nstat;
+    const int nwide = st->nwide < WIDE_CAP ? st->nwide : WIDE_CAP;
+    const unsigned long long* skey = w.stat_key[st->stat_sorted];
+    for (int i = ctx.gtid; i < nd; i += ctx.gsize) {
+        const int c = w.dyn_list[i];
+        w.dyn_key[0][i] = ((unsigned long long)sortable_float(w.c_fat_min[c].x) << 32) | (unsigned)c;
     }
+    grid_radix_zero(ctx, w.radix_hist, 4);
     if (ctx.gtid == 0) st->ncand = 0;
     ctx.grid_sync();
-    grid_bitonic_sort(ctx, skey, w.nc_pow2);
-    // sweep: one warp per sorted collider, lanes stride over the following colliders.
-    for (int wi = ctx.gwarp; wi < w.nc; wi += ctx.ngwarps) {
-        int ci = (int)(skey[wi] & 0xffffffffu);
-        float4 amin = w.c_fat_min[ci], amax = w.c_fat_max[ci];
-        for (int base = wi + 1; base < w.nc; base += ctx.nlanes) {
-            int j = base + ctx.lane;
+    const unsigned long long* dkey = grid_radix_sort(ctx, w.dyn_key[0], w.dyn_key[1], nd, 32, 64, w.radix_hist);
+    // sweep: one warp per mover, lanes stride over what follows it in x
+    const float wn = as_float(st->stat_wn_bits) * 1.0001f + 1.0e-6f;   // widest narrow static collider (with rounding slack)
+    for (int wi = ctx.gwarp; wi < nd; wi += ctx.ngwarps) {
+        const int ci = (int)(dkey[wi] & 0xffffffffu);
+        const float4 amin = w.c_fat_min[ci], amax = w.c_fat_max[ci];
+        const unsigned amax_key = sortable_float(amax.x);
+        for (int base = wi + 1; base < nd; base += ctx.nlanes) {   // movers with a larger (or equal) min-x
+            const int j = base + ctx.lane;
             bool stop = true;
-            if (j < w.nc) {
-                int cj = (int)(skey[j] & 0xffffffffu);
-                float4 bmin = w.c_fat_min[cj];
-                stop = bmin.x > amax.x;
+            if (j < nd) {
+                const unsigned long long kj = dkey[j];
+                stop = (unsigned)(kj >> 32) > amax_key;
                 if (!stop) {
-                    float4 bmax = w.c_fat_max[cj];
-                    bool hit = amin.x <= bmax.x && amin.y <= bmax.y && amin.z <= bmax.z && amax.x >= bmin.x && amax.y >= bmin.y &&
-                               amax.z >= bmin.z;
-                    if (hit) {
-                        int c1 = ci < cj ? ci : cj, c2 = ci < cj ? cj : ci;
-                        if (pair_allowed(w, c1, c2)) {
-                            int slot = atomic_add(&st->ncand, 1);
-                            if (slot < w.pair_cap) w.cand_key[slot] = ((unsigned long long)(unsigned)c1 << 32) | (unsigned)c2;
-                        }
-                    }
+                    const int cj = (int)(kj & 0xffffffffu);
+                    if (fat_overlap(amin, amax, w.c_fat_min[cj], w.c_fat_max[cj])) emit_candidate(w, ci, cj);
                 }
             }
             if (ctx.warp_any(stop)) break;
         }
+        // narrow static colliders whose x interval can reach [amin.x, amax.x]: min-x in [amin.x - wn, amax.x]
+        const int first = lower_bound_u64(skey, ns, (unsigned long long)sortable_float(amin.x - wn) << 32);
+        for (int base = first; base < ns; base += ctx.nlanes) {
+            const int j = base + ctx.lane;
+            bool stop = true;
+            if (j < ns) {
+                const unsigned long long kj = skey[j];
+                stop = (unsigned)(kj >> 32) > amax_key;
+                if (!stop) {
+                    const int cj = (int)(kj & 0xffffffffu);
+                    if (fat_overlap(amin, amax, w.c_fat_min[cj], w.c_fat_max[cj])) emit_candidate(w, ci, cj);
+                }
+            }
+            if (ctx.warp_any(stop)) break;
+        }
+        for (int k = ctx.lane; k < nwide; k += ctx.nlanes) {       // the few wide ones
+            const int cj = w.wide_list[k];
+            if (fat_overlap(amin, amax, w.c_fat_min[cj], w.c_fat_max[cj])) emit_candidate(w, ci, cj);
+        }
     }
+    const int cbits = bits_for(w.nc > 2 ? w.nc : 2);
+    const int p_lo = radix_passes(0, cbits), p_hi = radix_passes(32, 32 + cbits);
+    grid_radix_zero(ctx, w.radix_hist, p_lo > p_hi ? p_lo : p_hi);
     ctx.grid_sync();
-    int ncand = st->ncand;
+    const int ncand = st->ncand;
     if (ncand > w.pair_cap) {  // capacity overflow: keep the old pair set and raise the status; the pair set stays dirty,
                                // so every step raises it again until the world fits (no silently stale physics)
         if (ctx.gtid == 0) RB_RAISE(w, -4);
         ctx.grid_sync();
         return;
     }
-    int np2 = next_pow2(ncand < 2 ? 2 : ncand);
-    for (int i = ncand + ctx.gtid; i < np2; i += ctx.gsize) w.cand_key[i] = ~0ull;
+    // order the candidates by (collider1, collider2): LSD over the low word's used bits, then the high word's
+    unsigned long long* ck = grid_radix_sort(ctx, w.cand_key, w.cand_key2, ncand, 0, cbits, w.radix_hist);
+    unsigned long long* other = ck == w.cand_key ? w.cand_key2 : w.cand_key;
+    grid_radix_zero(ctx, w.radix_hist, p_hi);
     ctx.grid_sync();
-    grid_bitonic_sort(ctx, w.cand_key, np2);
-    // merge: carry persistent per-pair state from the old sorted table to the new one.
+    ck = grid_radix_sort(ctx, ck, other, ncand, 32, 32 + cbits, w.radix_hist);
+    // unchanged pair set (the usual case while AABBs merely move): nothing to merge, the schedule stays valid
     int cur = st->cur, nxt = 1 - cur, nold = st->npairs;
     const unsigned long long* okey = w.pb[cur].key;
+    if (ctx.gtid == 0) st->bp_diff = ncand != nold ? 1 : 0;
+    ctx.grid_sync();
+    if (ncand == nold) {
+        int diff = 0;
+        for (int i = ctx.gtid; i < ncand; i += ctx.gsize) diff |= ck[i] != okey[i];
+        if (diff) st->bp_diff = 1;
+        ctx.grid_sync();
+    }
+    if (!st->bp_diff) {   // (bp_dirty / bp_ran are not read again during this step)
+        if (ctx.gtid == 0) { st->bp_dirty = 0; st->bp_ran = 1; st->ncand = 0; }
+        return;
+    }
+    // merge: carry persistent per-pair state from the old sorted table to the new one.
     for (int i = ctx.gtid; i < ncand; i += ctx.gsize) {
-        unsigned long long k = w.cand_key[i];
+        unsigned long long k = ck[i];
         w.pb[nxt].key[i] = k;
         w.remap_src[i] = bsearch_u64(okey, nold, k);
     }
@@ -194,7 +383,7 @@ RB_PHASE void section_broad_phase(const Ctx& ctx, const World& w) {
             v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r == PR_INFO) v.w = as_float_i(COLOR_UNCOLORED);
             if (r == PR_BODIES) {
-                unsigned long long k = w.cand_key[i];
+                unsigned long long k = ck[i];
                 int c1 = (int)(k >> 32), c2 = (int)(k & 0xffffffffu);
                 v = make_float4(as_float_i(-1), as_float_i(-1), as_float_i(w.c_parent[c1]), as_float_i(w.c_parent[c2]));
             }
@@ -203,7 +392,7 @@ RB_PHASE void section_broad_phase(const Ctx& ctx, const World& w) {
     }
     // removed pairs: end-touch frees the colour (contacts.rs:333-335).
     for (int j = ctx.gtid; j < nold; j += ctx.gsize) {
-        if (bsearch_u64(w.cand_key, ncand, okey[j]) < 0) {
+        if (bsearch_u64(ck, ncand, okey[j]) < 0) {
             float4 info = prow(w, cur, PR_INFO, j), bod = prow(w, cur, PR_BODIES, j);
             clear_color_bits(w, as_int(info.w), as_int(bod.x), as_int(bod.y));
         }
@@ -215,6 +404,7 @@ RB_PHASE void section_broad_phase(const Ctx& ctx, const World& w) {
         st->bp_dirty = 0;
         st->bp_ran = 1;
         st->sched_dirty = 1;
+        st->ncand = 0;   // (doubles as the colouring's pending counter)
     }
     ctx.grid_sync();
 }
@@ -905,7 +1095,7 @@ RB_PHASE void collide_pipeline(const Ctx& ctx, const World& w) {
     if (ctx.gtid == 0) { st->bp_ran = 0; st->sched_ran = 0; }
     phase_refresh_colliders(ctx, w);
     ctx.grid_sync();
-    if (st->bp_dirty) section_broad_phase(ctx, w);
+    if (st->bp_dirty || st->lists_dirty) section_broad_phase(ctx, w);
     phase_narrow_phase(ctx, w);
     ctx.grid_sync();
     if (st->ntodo) section_coloring(ctx, w);

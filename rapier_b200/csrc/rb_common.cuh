@@ -66,6 +66,7 @@ template <class T> RB_D T atomic_add(T* p, T v) { return atomicAdd(p, v); }
 RB_D int atomic_min(int* p, int v) { return atomicMin(p, v); }
 RB_D unsigned long long atomic_min64(unsigned long long* p, unsigned long long v) { return atomicMin(p, v); }
 RB_D unsigned atomic_and(unsigned* p, unsigned v) { return atomicAnd(p, v); }
+RB_D unsigned atomic_max_u(unsigned* p, unsigned v) { return atomicMax(p, v); }
 RB_D unsigned atomic_or(unsigned* p, unsigned v) { return atomicOr(p, v); }
 RB_D int atomic_cas(int* p, int cmp, int v) { return atomicCAS(p, cmp, v); }
 RB_D void thread_fence() { __threadfence(); }
@@ -87,6 +88,7 @@ template <class T> inline T atomic_add(T* p, T v) { T o = *p; *p = o + v; return
 inline int atomic_min(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
 inline unsigned long long atomic_min64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; if (v < o) *p = v; return o; }
 inline unsigned atomic_and(unsigned* p, unsigned v) { unsigned o = *p; *p = o & v; return o; }
+inline unsigned atomic_max_u(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
 inline unsigned atomic_or(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 inline int atomic_cas(int* p, int cmp, int v) { int o = *p; if (o == cmp) *p = v; return o; }
 inline void thread_fence() {}

@@ -96,7 +96,15 @@ struct State {
     int coop_streamed, coop_resident;   // shared-memory items of the last step: streamed from the pool / resident
     int norder;            // entries of World::item_order (non-empty items 1.., by decreasing cost)
     int cursor_rest, cursor_coop;   // dynamic work queues of the two kernels over item_order
-    int pad[8];
+    // broad phase: collider lists (rebuilt when lists_dirty) and scratch of the last run
+    int lists_dirty;       // the static / dynamic collider lists must be rebuilt (scene upload, insertion, teleported fixed body)
+    int ndyn, nstat, nwide; // movers, narrow static colliders (sorted by min-x), wide static colliders
+    int stat_sorted;       // which of World::stat_key holds the sorted static keys
+    int stat_count;        // all static colliders
+    float stat_wsum;       // sum of their widths along x (classification threshold)
+    unsigned stat_wn_bits; // widest narrow static collider along x (float bits)
+    int bp_diff;           // the candidate pair set differs from the pair table
+    int pad[7];
 };
 
 struct PairBuf {
@@ -136,11 +144,13 @@ struct World {
     float4 *c_pos_t, *c_pos_q;
     float4 *c_aabb_min, *c_aabb_max, *c_fat_min, *c_fat_max;
     // ---- broad phase scratch ----
-    unsigned* bp_sort_key;            // [nc_pow2] sortable min-x
-    int* bp_sort_val;                 // [nc_pow2]
-    int nc_pow2;
-    unsigned long long* cand_key;     // [pair_cap_pow2]
-    int pair_cap_pow2;
+    int* dyn_list;                    // [nc] colliders that can move
+    int* wide_list;                   // [WIDE_CAP] static colliders much wider than the rest
+    unsigned long long* dyn_key[2];   // [nc] (sortable min-x << 32) | collider of the movers, radix-sort ping-pong
+    unsigned long long* stat_key[2];  // [nc] ... of the narrow static colliders, sorted once
+    int* radix_hist;                  // [9][grid blocks][256] digit counts of the radix sorts
+    unsigned long long* cand_key;     // [pair_cap] candidate pairs (collider1 << 32) | collider2
+    unsigned long long* cand_key2;    // [pair_cap] radix-sort ping-pong
     unsigned long long* nocontact_keys;  // sorted body-pair keys of joints with contacts disabled
     int n_nocontact;
     int* remap_src;                   // [pair_cap] new pair -> old pair index or -1
