@@ -188,8 +188,9 @@ RB_PHASE void kat_phase(const World& w, int which, const float* in, float* out) 
 __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, int do_solve) {
     extern __shared__ __align__(16) float smem[];
     GridCtx ctx;
-    if (ctx.gtid == 0) {   // publish last step's launch-shape hint to the host (read without synchronising)
-        *w.host_hint = w.st->need_big;
+    if (ctx.gtid == 0) {   // publish last step's launch hints to the host (read without synchronising)
+        w.host_hint[0] = w.st->need_big;
+        w.host_hint[2] = w.st->nlarge_bodies > 0 ? 1 : 0;   // a grid-wide island exists: launch k_solve_large
         w.st->need_big = 0;
         w.st->coop_streamed = 0;
         w.st->coop_resident = 0;
@@ -219,10 +220,25 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, in
             ex.sync();
         }
     }
+    // The grid-wide "large" item 0 normally has its own launch (k_solve_large, register budget and work placement of
+    // its own).  The host decides that launch from a hint that is one step old, so the step in which a large island
+    // first appears is solved here instead (do_solve bit 1 clear = no k_solve_large follows).
+    if (w.st->nlarge_bodies == 0 || (do_solve & 2)) return;
+    GlobalBodies gb;
+    gb.w = &w;
+    GridSpreadExec gex;
+    gex.c = &ctx;
+    solve_item_lanes<4>(gex, w, gb, mk3(g.x, g.y, g.z));
+}
+// The grid-wide item 0: islands too large for one CTA (pyramid3, keva3, joint grids).  Cooperative, one CTA per SM;
+// bodies in the global solver-body tables, constant rows in the L2-resident large pool, one grid barrier per colour
+// stage; consecutive warps of a stage's constraints go to different SMs (GridSpreadExec).
+__global__ void __launch_bounds__(COLLIDE_THREADS, 1) k_solve_large(World w, Grav g) {
+    GridCtx ctx;
     if (w.st->nlarge_bodies == 0) return;
     GlobalBodies gb;
     gb.w = &w;
-    GridExec gex;
+    GridSpreadExec gex;
     gex.c = &ctx;
     solve_item_lanes<4>(gex, w, gb, mk3(g.x, g.y, g.z));
 }
@@ -671,7 +687,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
         }
     }
     W->steps_since_scene = 0;
-    if (W->host_hint) W->host_hint[1] = 0;
+    if (W->host_hint) W->host_hint[0] = W->host_hint[1] = W->host_hint[2] = 0;
     W->state_buf[0] = W->state_buf[1] = nullptr;
     W->bodies.assign(bodies, bodies + nb);
     W->colliders.assign(colliders, colliders + nc);
@@ -948,7 +964,9 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
     for (int s = 0; s < nsteps; ++s) {
         bool prof = W->profiling;
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s], W->stream));
-        int do_solve = 1;
+        // a grid-wide island existed after the last schedule the host knows of: it gets its own launch
+        const bool large = *(volatile int*)(W->host_hint + 2) != 0;
+        int do_solve = large ? 3 : 1;
         if (W->state_buf[1]) { W->w.state13 = W->state_buf[W->state_next]; W->state_next ^= 1; }
         // A new scene's islands are only known after its first schedule.  A caller that enqueues many steps in
         // one asynchronous call would otherwise run all of them in the launch shape chosen before that, so the
@@ -960,6 +978,11 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         void* a1[] = {(void*)&W->w, (void*)&g, (void*)&do_solve};
         CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, ITEM_SMEM_BYTES, W->stream));
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 1], W->stream));
+        if (large) {
+            void* a2[] = {(void*)&W->w, (void*)&g};
+            CK(cudaLaunchCooperativeKernel((void*)k_solve_large, dim3(W->collide_blocks), dim3(W->collide_threads), a2, 0, W->stream));
+            W->kernels++;
+        }
         if (big) {
 #define RB_LAUNCH_BIG(T, LL) if (W->big_threads == T) k_solve_coop_big<T, LL><<<W->coop_blocks_big, T, COOP_BIG_SMEM_BYTES, W->stream>>>(W->w, g);
             RB_BIG_VARIANTS(RB_LAUNCH_BIG)

@@ -509,12 +509,14 @@ RB_HD vec3 gyro_corrected(vec3 angvel, quat axes, vec3 pin, vec3 ipin, float dt)
 // ------------------------------------------------------------------------------------------------
 // Joints (locked axes): per-substep rows (joint_constraint_helper.rs:95-164, :411-461, :628-722).
 // ------------------------------------------------------------------------------------------------
-template <class B>
-RB_HD void joint_update(const World& w, const B& bd, int q) {
+// MASK: the joint's locked axes when known at compile time (0 = read them from the joint): the unrolled row loops
+// then only keep the locked slots, which is what keeps a spherical joint's three rows in registers.
+template <unsigned MASK, class B>
+RB_HD void joint_update_t(const World& w, const B& bd, int q) {
     int4 h = w.j_sched_ids[q];
     const int j = h.x, id1 = h.y, id2 = h.z;
     int4 ji = w.j_info[j];
-    unsigned locked = (unsigned)ji.z;
+    const unsigned locked = MASK ? MASK : (unsigned)ji.z;
     BodyState g1 = gather_body(bd, id1), g2 = gather_body(bd, id2);
     // transform_to_solver_body_space (generic_joint.rs:624-636)
     pose lf1 = mkpose(mkq(w.j_f1_q[j]), xyz(w.j_f1_t[j]));
@@ -536,6 +538,7 @@ RB_HD void joint_update(const World& w, const B& bd, int q) {
     vec3 bc[3] = {basis.c0, basis.c1, basis.c2};
     vec3 lin_err = f2.t - f1.t;
     vec3 nc1 = f2.t;
+#pragma unroll
     for (int i = 0; i < 3; ++i)
         if (locked & (1u << i)) nc1 = nc1 - bc[i] * dot3(lin_err, bc[i]);
     f1.t = nc1;
@@ -548,40 +551,51 @@ RB_HD void joint_update(const World& w, const B& bd, int q) {
     vec3 cv = a * wb + b * wa;
     float ab = dot3(a, b);
     vec3 imsum = g1.im + g2.im;
+    // Row slots are FIXED (0..2 = locked angular x y z, 3..5 = locked linear x y z: the reference's row order,
+    // joint_constraint_helper.rs) and every loop below is fully unrolled with the slot's lock bit as a predicate, so
+    // the rows stay in registers (a compacted, dynamically indexed array would live in local memory).  Unlocked
+    // slots are skipped, so the locked rows see exactly the operations of the compacted form.
     vec3 lin[6], aj1[6], aj2[6], ia1[6], ia2[6];
     float rhs[6], rwb[6], cg[6], il[6];
-    int dof[6] = {0, 0, 0, 0, 0, 0};
-    int len = 0;
-    for (int i = 3; i < 6; ++i) {
-        if (!(locked & (1u << i))) continue;
-        int ax = i - 3;
-        // row `ax` of D = 0.5 (a b^T + (wa wb - a.b) I - [cv]x + b a^T)  (rotation_ops.rs:121-137), times sgn
-        float av = comp(a, ax), bv = comp(b, ax);
-        float dg = wa * wb - ab;
-        vec3 cx = ax == 0 ? mk3(0.0f, -cv.z, cv.y) : (ax == 1 ? mk3(cv.z, 0.0f, -cv.x) : mk3(-cv.y, cv.x, 0.0f));
-        vec3 row = mk3((av * b.x + (ax == 0 ? dg : 0.0f) - cx.x + bv * a.x) * 0.5f,
-                       (av * b.y + (ax == 1 ? dg : 0.0f) - cx.y + bv * a.y) * 0.5f,
-                       (av * b.z + (ax == 2 ? dg : 0.0f) - cx.z + bv * a.z) * 0.5f);
-        vec3 aj = row * sgn;
-        lin[len] = zero3(); aj1[len] = aj; aj2[len] = aj;
-        ia1[len] = smul(g1.ii, aj); ia2[len] = smul(g2.ii, aj);
-        rwb[len] = 0.0f; rhs[len] = 0.0f + comp(aerr, ax) * erp_inv_dt; cg[len] = 0.0f; il[len] = 0.0f; dof[len] = i;
-        ++len;
+    bool on[6];
+#pragma unroll
+    for (int sl = 0; sl < 6; ++sl) {
+        const int dofi = sl < 3 ? sl + 3 : sl - 3;   // slot -> degree of freedom (3..5 angular, 0..2 linear)
+        on[sl] = (locked & (1u << dofi)) != 0;
+        lin[sl] = aj1[sl] = aj2[sl] = ia1[sl] = ia2[sl] = zero3();
+        rhs[sl] = rwb[sl] = cg[sl] = il[sl] = 0.0f;
+        if (!on[sl]) continue;
+        if (sl < 3) {
+            const int ax = sl;
+            // row `ax` of D = 0.5 (a b^T + (wa wb - a.b) I - [cv]x + b a^T)  (rotation_ops.rs:121-137), times sgn
+            float av = comp(a, ax), bv = comp(b, ax);
+            float dg = wa * wb - ab;
+            vec3 cx = ax == 0 ? mk3(0.0f, -cv.z, cv.y) : (ax == 1 ? mk3(cv.z, 0.0f, -cv.x) : mk3(-cv.y, cv.x, 0.0f));
+            vec3 row = mk3((av * b.x + (ax == 0 ? dg : 0.0f) - cx.x + bv * a.x) * 0.5f,
+                           (av * b.y + (ax == 1 ? dg : 0.0f) - cx.y + bv * a.y) * 0.5f,
+                           (av * b.z + (ax == 2 ? dg : 0.0f) - cx.z + bv * a.z) * 0.5f);
+            vec3 aj = row * sgn;
+            aj1[sl] = aj; aj2[sl] = aj;
+            ia1[sl] = smul(g1.ii, aj); ia2[sl] = smul(g2.ii, aj);
+            rhs[sl] = 0.0f + comp(aerr, ax) * erp_inv_dt;
+        } else {
+            const int i = sl - 3;
+            lin[sl] = bc[i]; aj1[sl] = cross3(r1, bc[i]); aj2[sl] = cross3(r2, bc[i]);
+            ia1[sl] = smul(g1.ii, aj1[sl]); ia2[sl] = smul(g2.ii, aj2[sl]);
+            rhs[sl] = 0.0f + dot3(bc[i], lin_err) * erp_inv_dt;
+        }
     }
-    for (int i = 0; i < 3; ++i) {
-        if (!(locked & (1u << i))) continue;
-        lin[len] = bc[i]; aj1[len] = cross3(r1, bc[i]); aj2[len] = cross3(r2, bc[i]);
-        ia1[len] = smul(g1.ii, aj1[len]); ia2[len] = smul(g2.ii, aj2[len]);
-        rwb[len] = 0.0f; rhs[len] = 0.0f + dot3(bc[i], lin_err) * erp_inv_dt; cg[len] = 0.0f; il[len] = 0.0f; dof[len] = i;
-        ++len;
-    }
-    for (int jx = 0; jx < len; ++jx) {  // finalize_constraints: Gram-Schmidt in the mass metric
+#pragma unroll
+    for (int jx = 0; jx < 6; ++jx) {  // finalize_constraints: Gram-Schmidt in the mass metric
+        if (!on[jx]) continue;
         float djj = dot3(lin[jx], had(imsum, lin[jx])) + dot3(ia1[jx], aj1[jx]) + dot3(ia2[jx], aj2[jx]);
         float gain = djj * cfm_coeff + cg[jx];
         float inv_djj = safe_inv(djj);
         il[jx] = safe_inv(djj + gain);
         cg[jx] = gain;
-        for (int ix = jx + 1; ix < len; ++ix) {
+#pragma unroll
+        for (int ix = jx + 1; ix < 6; ++ix) {
+            if (!on[ix]) continue;
             float dij = dot3(lin[ix], had(imsum, lin[jx])) + dot3(ia1[ix], aj1[jx]) + dot3(ia2[ix], aj2[jx]);
             float coeff = dij * inv_djj;
             lin[ix] = lin[ix] - lin[jx] * coeff;
@@ -593,44 +607,69 @@ RB_HD void joint_update(const World& w, const B& bd, int q) {
             rhs[ix] = rhs[ix] - rhs[jx] * coeff;
         }
     }
-    for (int r = 0; r < len; ++r) {
-        int s = 6 * q + r;
-        jrow(w, JR_LIN, s) = f4(lin[r], 0.0f);   // impulse restarts from 0 (warmstart_joints = false)
-        jrow(w, JR_A1, s) = f4(aj1[r], il[r]);
-        jrow(w, JR_A2, s) = f4(aj2[r], rhs[r]);
-        jrow(w, JR_IA1, s) = f4(ia1[r], rwb[r]);
-        jrow(w, JR_IA2, s) = f4(ia2[r], cg[r]);
+    int len = 0, packed = 0;
+#pragma unroll
+    for (int sl = 0; sl < 6; ++sl) {
+        if (!on[sl]) continue;
+        const int dofi = sl < 3 ? sl + 3 : sl - 3;
+        const int s = 6 * q + len;
+        jrow(w, JR_LIN, s) = f4(lin[sl], 0.0f);   // impulse restarts from 0 (warmstart_joints = false)
+        jrow(w, JR_A1, s) = f4(aj1[sl], il[sl]);
+        jrow(w, JR_A2, s) = f4(aj2[sl], rhs[sl]);
+        jrow(w, JR_IA1, s) = f4(ia1[sl], rwb[sl]);
+        jrow(w, JR_IA2, s) = f4(ia2[sl], cg[sl]);
+        packed |= dofi << (8 + 4 * len);
+        ++len;
     }
-    h.w = len | (dof[0] << 8) | (len > 1 ? dof[1] << 12 : 0) | (len > 2 ? dof[2] << 16 : 0) | (len > 3 ? dof[3] << 20 : 0) |
-          (len > 4 ? dof[4] << 24 : 0) | (len > 5 ? dof[5] << 28 : 0);
+    h.w = len | packed;
     w.j_sched_ids[q] = h;
 }
+template <class B>
+RB_HD void joint_update(const World& w, const B& bd, int q) {
+    const unsigned locked = (unsigned)w.j_info[w.j_sched_ids[q].x].z;
+    if (locked == 7u) joint_update_t<7u>(w, bd, q);          // spherical: linear x y z
+    else if (locked == 63u) joint_update_t<63u>(w, bd, q);   // fixed
+    else joint_update_t<0u>(w, bd, q);
+}
 
-// joint_velocity_constraint.rs:97-124
+// joint_velocity_constraint.rs:97-124.  The rows are loaded three at a time before the first of them is solved
+// (their addresses do not depend on the sweep, and the stores of one row must not delay the loads of the next);
+// three rows = a spherical joint, the common case, in one batch.
 template <class B>
 RB_HD void joint_solve(const World& w, const B& bd, int q, bool wo_bias) {
     int4 h = w.j_sched_ids[q];
     const int id1 = h.y, id2 = h.z, len = h.w & 0xff;
     BodyState g1 = gather_body(bd, id1), g2 = gather_body(bd, id2);
     vec3 v1 = g1.lin, w1 = g1.ang, v2 = g2.lin, w2 = g2.ang;
-    for (int r = 0; r < len; ++r) {
-        int s = 6 * q + r;
-        float4 L = jrow(w, JR_LIN, s), A1 = jrow(w, JR_A1, s), A2 = jrow(w, JR_A2, s), I1 = jrow(w, JR_IA1, s),
-               I2 = jrow(w, JR_IA2, s);
-        float rhs_c = wo_bias ? I1.w : A2.w;
-        float dlin = dot3(xyz(L), v2 - v1);
-        float dang = dot3(xyz(A2), w2) - dot3(xyz(A1), w1);
-        float rhs = dlin + dang + rhs_c;
-        float total = L.w + A1.w * (rhs - I2.w * L.w);
-        float delta = total - L.w;
-        L.w = total;
-        vec3 li = xyz(L) * delta;
-        v1 = madd3v(v1, li, g1.im);
-        w1 = madd3(w1, xyz(I1), delta);
-        v2 = madd3v(v2, -li, g2.im);
-        w2 = madd3(w2, xyz(I2), -delta);
-        jrow(w, JR_LIN, s) = L;
-        if (wo_bias) { A2.w = I1.w; jrow(w, JR_A2, s) = A2; }
+    for (int r0 = 0; r0 < len; r0 += 3) {
+        float4 L[3], A1[3], A2[3], I1[3], I2[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (r0 + k < len) {
+                const int s = 6 * q + r0 + k;
+                L[k] = jrow(w, JR_LIN, s); A1[k] = jrow(w, JR_A1, s); A2[k] = jrow(w, JR_A2, s); I1[k] = jrow(w, JR_IA1, s);
+                I2[k] = jrow(w, JR_IA2, s);
+            }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (r0 + k < len) {
+                const int s = 6 * q + r0 + k;
+                float rhs_c = wo_bias ? I1[k].w : A2[k].w;
+                float dlin = dot3(xyz(L[k]), v2 - v1);
+                float dang = dot3(xyz(A2[k]), w2) - dot3(xyz(A1[k]), w1);
+                float rhs = dlin + dang + rhs_c;
+                float total = L[k].w + A1[k].w * (rhs - I2[k].w * L[k].w);
+                float delta = total - L[k].w;
+                L[k].w = total;
+                vec3 li = xyz(L[k]) * delta;
+                v1 = madd3v(v1, li, g1.im);
+                w1 = madd3(w1, xyz(I1[k]), delta);
+                v2 = madd3v(v2, -li, g2.im);
+                w2 = madd3(w2, xyz(I2[k]), -delta);
+                jrow(w, JR_LIN, s) = L[k];
+                if (wo_bias) { A2[k].w = I1[k].w; jrow(w, JR_A2, s) = A2[k]; }
+            }
+        }
     }
     scatter_vel(bd, id1, v1, w1);
     scatter_vel(bd, id2, v2, w2);
@@ -684,6 +723,15 @@ struct BlockExec {
 struct GridExec {
     const GridCtx* c;
     RB_HD int tid() const { return c->gtid; }
+    RB_HD int nth() const { return c->gsize; }
+    RB_HD void sync() const { c->grid_sync(); }
+};
+
+// Grid-wide executor that deals consecutive WARPS of work to different CTAs: a colour stage with a few hundred
+// constraints then runs on a few warps of EVERY SM instead of filling the first SMs and leaving the rest idle.
+struct GridSpreadExec {
+    const GridCtx* c;
+    RB_HD int tid() const { return ((c->btid / c->nlanes) * c->nblocks + c->bid) * c->nlanes + c->lane; }
     RB_HD int nth() const { return c->gsize; }
     RB_HD void sync() const { c->grid_sync(); }
 };
