@@ -192,6 +192,19 @@ int rb_world_get_contact_pairs(RbWorld* w, int32_t cap, int32_t* pair_colliders,
  * Returns bytes copied or a negative status. */
 int64_t rb_world_debug_read(RbWorld* w, const char* table, void* dst, int64_t cap_bytes);
 
+/* ---- incremental changes of the sets (src/pipeline/user_changes.rs:11-46; substep.rs:303-334) ----
+ * rb_world_set_scene replaces the whole world and forgets every contact; these keep it.
+ * rb_world_reserve: room for later insertions, applied by the NEXT rb_world_set_scene.
+ * rb_world_insert: appends bodies and colliders (RigidBodySet::insert, ColliderSet::insert_with_parent); existing
+ *   indices, contact pairs, warm-start impulses, colours and islands are untouched.  collider.parent is the FINAL body
+ *   index; new colliders may only be attached to the new bodies (or have no parent).  Returns the first new indices.
+ * rb_world_remove_bodies: RigidBodySet::remove(handle, .., remove_attached_colliders = true); slots stay allocated
+ *   (tombstones), the colliders leave the broad phase and their contact pairs end at the next step. */
+int rb_world_reserve(RbWorld* w, int32_t max_bodies, int32_t max_colliders);
+int rb_world_insert(RbWorld* w, int32_t num_bodies, const RbBodyDesc* bodies, int32_t num_colliders,
+                    const RbColliderDesc* colliders, int32_t* first_body_index, int32_t* first_collider_index);
+int rb_world_remove_bodies(RbWorld* w, int32_t n, const int32_t* body_indices);
+
 /* Unit-level known-answer evaluation for parity tests: runs ONE device function of the path (named: "pose_drift"
  * contact_pair.rs:299-323, "reduce_manifold" manifold_reduction.rs:4-84, "normal_solve" / "tangent_solve"
  * contact_constraint_element.rs:481-504 / :650-705, "generate" contact_with_twist_friction.rs:58-424) on literal

@@ -7,6 +7,8 @@
 namespace orc {
 void step_once(World& w, V3 gravity);
 int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDesc* cd, int nj, const RbJointDesc* jd);
+int insert(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDesc* cd);
+int remove_bodies(World& w, int n, const int* indices);
 void update_world_mass_properties(Body& b);
 void refresh_collider(World& w, Collider& c);
 void set_threads(int n);
@@ -76,6 +78,14 @@ int orc_world_set_scene(OrcWorld* w, int32_t nb, const RbBodyDesc* bodies, int32
     if (!w) return RB_ERR_INVALID;
     return set_scene(w->w, nb, bodies, nc, colliders, nj, joints);
 }
+int orc_world_insert(OrcWorld* w, int32_t nb, const RbBodyDesc* bodies, int32_t nc, const RbColliderDesc* colliders) {
+    if (!w || nb < 0 || nc < 0) return RB_ERR_INVALID;
+    return insert(w->w, nb, bodies, nc, colliders);
+}
+int orc_world_remove_bodies(OrcWorld* w, int32_t n, const int32_t* indices) {
+    if (!w || n < 0) return RB_ERR_INVALID;
+    return remove_bodies(w->w, n, indices);
+}
 int orc_world_set_body_states(OrcWorld* o, int32_t n, const int32_t* indices, const float* pose7, const float* vel6) {
     if (!o) return RB_ERR_INVALID;
     World& w = o->w;
@@ -87,6 +97,7 @@ int orc_world_set_body_states(OrcWorld* o, int32_t n, const int32_t* indices, co
             b.pos.t = V3{pose7[k * 7 + 0], pose7[k * 7 + 1], pose7[k * 7 + 2]};
             b.pos.q = Q4{pose7[k * 7 + 3], pose7[k * 7 + 4], pose7[k * 7 + 5], pose7[k * 7 + 6]};
             b.next_pos = b.pos;
+            if (!b.is_dynamic()) w.static_dirty = true;   // a teleported fixed body moves static colliders
             update_world_mass_properties(b);
             for (Collider& c : w.colliders)
                 if (c.parent == i) refresh_collider(w, c);

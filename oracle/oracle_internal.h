@@ -188,6 +188,9 @@ struct World {
     std::vector<Pair> pairs;           // sorted by (c1, c2)
     std::vector<Mask128> color_masks;  // per body (narrow_phase/mod.rs body_solver_color_masks)
     bool bp_dirty = true;
+    bool static_dirty = true;          // the sorted list of static colliders must be rebuilt
+    std::vector<int> static_sorted;    // static colliders by fat min-x
+    float static_max_width = 0.0f;     // widest of them along x
     // scratch
     std::vector<SolverBody> sb;
     std::vector<Constraint> cons;

@@ -41,17 +41,19 @@ static void collider_mass(const Collider& c, float& mass, V3& principal) {
     }
 }
 
-static int recompute_mass_properties(World& w) {
+// `first_body` / `first_collider`: only the bodies from first_body on, from the colliders from first_collider on
+// (insertion appends bodies that carry appended colliders only).
+static int recompute_mass_properties(World& w, int first_body = 0, int first_collider = 0) {
     int nb = (int)w.bodies.size();
     std::vector<int> count(nb, 0), first(nb, -1);
-    for (int ci = 0; ci < (int)w.colliders.size(); ++ci) {
+    for (int ci = first_collider; ci < (int)w.colliders.size(); ++ci) {
         int p = w.colliders[ci].parent;
         if (p >= 0) {
             if (count[p] == 0) first[p] = ci;
             count[p]++;
         }
     }
-    for (int bi = 0; bi < nb; ++bi) {
+    for (int bi = first_body; bi < nb; ++bi) {
         Body& b = w.bodies[bi];
         b.local_com = vzero();
         b.inv_mass = 0.0f;
@@ -71,7 +73,8 @@ static int recompute_mass_properties(World& w) {
             // Sum of axis-aligned parts only (composite bodies whose summed tensor is diagonal).
             float M = 0.0f;
             V3 com = vzero();
-            for (const Collider& c : w.colliders) {
+            for (size_t ci = (size_t)first_collider; ci < w.colliders.size(); ++ci) {
+                const Collider& c = w.colliders[ci];
                 if (c.parent != bi) continue;
                 float mass; V3 pi;
                 collider_mass(c, mass, pi);
@@ -81,7 +84,8 @@ static int recompute_mass_properties(World& w) {
             if (M == 0.0f) continue;
             com = com * (1.0f / M);
             V3 I = vzero();
-            for (const Collider& c : w.colliders) {
+            for (size_t ci = (size_t)first_collider; ci < w.colliders.size(); ++ci) {
+                const Collider& c = w.colliders[ci];
                 if (c.parent != bi) continue;
                 Q4 q = c.pos_wrt_parent.q;
                 if (!(q.x == 0.0f && q.y == 0.0f && q.z == 0.0f)) return RB_ERR_INVALID;
@@ -219,21 +223,54 @@ static void clear_pair_color(World& w, Pair& p) {  // narrow_phase/mod.rs:154-17
 
 static void update_pairs(World& w) {
     int nc = (int)w.colliders.size();
-    std::vector<int> idx(nc);
-    for (int i = 0; i < nc; ++i) idx[i] = i;
+    // Only pairs with a collider that can move matter (static-static pairs are filtered anyway), so the sweep runs
+    // over the movers, and each mover searches the static colliders, which are sorted once (they never move).
+    auto is_static = [&](const Collider& c) { return c.parent < 0 || !w.bodies[c.parent].is_dynamic(); };
+    if (w.static_dirty) {
+        w.static_sorted.clear();
+        w.static_max_width = 0.0f;
+        for (int i = 0; i < nc; ++i) {
+            const Collider& c = w.colliders[i];
+            if (c.shape < 0 || !is_static(c)) continue;
+            w.static_sorted.push_back(i);
+            w.static_max_width = fmax2(w.static_max_width, c.fat.maxs.x - c.fat.mins.x);
+        }
+        std::stable_sort(w.static_sorted.begin(), w.static_sorted.end(), [&](int a, int b) {
+            return w.colliders[a].fat.mins.x < w.colliders[b].fat.mins.x;
+        });
+        w.static_dirty = false;
+    }
+    std::vector<int> idx;
+    for (int i = 0; i < nc; ++i)
+        if (w.colliders[i].shape >= 0 && !is_static(w.colliders[i])) idx.push_back(i);
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
         return w.colliders[a].fat.mins.x < w.colliders[b].fat.mins.x;
     });
     std::vector<uint64_t> keys;
-    for (int ii = 0; ii < nc; ++ii) {
+    auto emit = [&](int i, int j) {
+        int c1 = std::min(i, j), c2 = std::max(i, j);
+        if (!pair_allowed(w, c1, c2)) return;
+        keys.push_back(((uint64_t)(uint32_t)c1 << 32) | (uint32_t)c2);
+    };
+    const int nd = (int)idx.size(), ns = (int)w.static_sorted.size();
+    const float wn = w.static_max_width * 1.0001f + 1.0e-6f;
+    for (int ii = 0; ii < nd; ++ii) {
         const Collider& a = w.colliders[idx[ii]];
-        for (int jj = ii + 1; jj < nc; ++jj) {
+        for (int jj = ii + 1; jj < nd; ++jj) {
             const Collider& b = w.colliders[idx[jj]];
             if (b.fat.mins.x > a.fat.maxs.x) break;
-            if (!aabb_intersects(a.fat, b.fat)) continue;
-            int c1 = std::min(idx[ii], idx[jj]), c2 = std::max(idx[ii], idx[jj]);
-            if (!pair_allowed(w, c1, c2)) continue;
-            keys.push_back(((uint64_t)(uint32_t)c1 << 32) | (uint32_t)c2);
+            if (aabb_intersects(a.fat, b.fat)) emit(idx[ii], idx[jj]);
+        }
+        const float x0 = a.fat.mins.x - wn;
+        int lo = 0, hi = ns;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (w.colliders[w.static_sorted[mid]].fat.mins.x < x0) lo = mid + 1; else hi = mid;
+        }
+        for (int jj = lo; jj < ns; ++jj) {
+            const Collider& b = w.colliders[w.static_sorted[jj]];
+            if (b.fat.mins.x > a.fat.maxs.x) break;
+            if (aabb_intersects(a.fat, b.fat)) emit(idx[ii], w.static_sorted[jj]);
         }
     }
     std::sort(keys.begin(), keys.end());
@@ -564,7 +601,7 @@ void step_once(World& w, V3 gravity) {
         update_world_mass_properties(b);
     }
     for (Collider& c : w.colliders) {
-        if (c.parent >= 0 && w.bodies[c.parent].is_dynamic()) refresh_collider(w, c);
+        if (c.shape >= 0 && c.parent >= 0 && w.bodies[c.parent].is_dynamic()) refresh_collider(w, c);
     }
     double t4 = now_ms();
     w.counters.broad_phase_ms = (float)(t1 - t0);
@@ -591,6 +628,7 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
     w.pairs.clear();
     w.color_masks.assign(nb, Mask128{});
     w.bp_dirty = true;
+    w.static_dirty = true;
     for (int i = 0; i < nb; ++i) {
         Body& b = w.bodies[i];
         const RbBodyDesc& d = bd[i];
@@ -680,6 +718,73 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
     return RB_OK;
 }
 
+
+// Incremental changes of the sets (src/pipeline/user_changes.rs:11-46): appended bodies / colliders keep every
+// existing index, so the persistent pair list (merged by collider key), colours and warm-start data survive.
+static void fill_body(Body& b, const RbBodyDesc& d) {
+    b.type = d.body_type;
+    b.flags = d.flags;
+    b.pos = Pose{f4(d.rotation), f3(d.translation)};
+    b.next_pos = b.pos;
+    b.linvel = f3(d.linvel);
+    b.angvel = f3(d.angvel);
+    b.lin_damping = d.linear_damping;
+    b.ang_damping = d.angular_damping;
+    b.gravity_scale = d.gravity_scale;
+    b.additional_mass = d.additional_mass;
+    b.user_force = f3(d.user_force);
+    b.user_torque = f3(d.user_torque);
+    b.force = vzero();
+    b.torque = vzero();
+}
+static void fill_collider(Collider& c, const RbColliderDesc& d) {
+    c.shape = d.shape;
+    c.he = f3(d.half_extents);
+    c.parent = d.parent;
+    c.pos_wrt_parent = Pose{f4(d.pos_wrt_parent_q), f3(d.pos_wrt_parent_t)};
+    c.density = d.density;
+    c.friction = d.friction;
+    c.restitution = d.restitution;
+    c.friction_rule = d.friction_combine_rule;
+    c.restitution_rule = d.restitution_combine_rule;
+    c.contact_skin = d.contact_skin;
+    c.memberships = d.collision_memberships;
+    c.filter = d.collision_filter;
+    c.fat_valid = false;
+}
+int insert(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDesc* cd) {
+    const int nb0 = (int)w.bodies.size(), nc0 = (int)w.colliders.size();
+    for (int i = 0; i < nc; ++i) {
+        if (cd[i].shape != RB_SHAPE_BALL && cd[i].shape != RB_SHAPE_CUBOID) return RB_ERR_INVALID;
+        if (cd[i].parent >= nb0 + nb || (cd[i].parent >= 0 && cd[i].parent < nb0)) return RB_ERR_INVALID;
+    }
+    w.bodies.resize(nb0 + nb);
+    w.colliders.resize(nc0 + nc);
+    w.color_masks.resize(nb0 + nb, Mask128{});
+    for (int i = 0; i < nb; ++i) { w.bodies[nb0 + i] = Body{}; fill_body(w.bodies[nb0 + i], bd[i]); }
+    for (int i = 0; i < nc; ++i) { w.colliders[nc0 + i] = Collider{}; fill_collider(w.colliders[nc0 + i], cd[i]); }
+    int rc = recompute_mass_properties(w, nb0, nc0);
+    if (rc != RB_OK) return rc;
+    for (int i = nb0; i < nb0 + nb; ++i) update_world_mass_properties(w.bodies[i]);
+    for (int i = nc0; i < nc0 + nc; ++i) refresh_collider(w, w.colliders[i]);
+    w.bp_dirty = true;
+    w.static_dirty = true;
+    w.counters.num_bodies = nb0 + nb;
+    w.counters.num_colliders = nc0 + nc;
+    return RB_OK;
+}
+int remove_bodies(World& w, int n, const int* indices) {
+    for (int k = 0; k < n; ++k)
+        if (indices[k] < 0 || indices[k] >= (int)w.bodies.size()) return RB_ERR_INVALID;
+    for (int k = 0; k < n; ++k) {
+        w.bodies[indices[k]].type = 3;   // removed: not dynamic, never simulated again
+        for (Collider& c : w.colliders)
+            if (c.parent == indices[k]) c.shape = -1;   // leaves the broad phase: its pairs end at the next step
+    }
+    w.bp_dirty = true;
+    w.static_dirty = true;
+    return RB_OK;
+}
 
 // Unit-level known-answer entry points of this file (see kat_solver in oracle_solver.cpp).
 int kat_world(const char* name_c, const float* in, int n_in, float* out, int n_out) {

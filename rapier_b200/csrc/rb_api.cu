@@ -69,8 +69,8 @@ constexpr int COOP_BIG_THREADS = 256, COOP_BIG_SMEM_BYTES = 220 * 1024;
 struct Grav { float x, y, z; };
 
 template <class Ctx>
-RB_PHASE void init_bodies_phase(const Ctx& ctx, const World& w) {
-    for (int b = ctx.gtid; b < w.nb; b += ctx.gsize) {
+RB_PHASE void init_bodies_phase(const Ctx& ctx, const World& w, int first) {
+    for (int b = first + ctx.gtid; b < w.nb; b += ctx.gsize) {
         pose p = body_pose(w, b);
         update_world_mass(w, b, p);
         float* s = w.state13 + (size_t)b * 13;
@@ -282,9 +282,9 @@ __global__ void __launch_bounds__(COOP_SMALL_THREADS, 2) k_solve_coop(World w, G
 template <int THREADS, int L>
 __global__ void __launch_bounds__(THREADS, 1) k_solve_coop_big(World w, Grav g) { solve_coop_items<L>(w, g, COOP_BIG_SMEM_BYTES / 4, true); }
 __global__ void k_kat(World w, int which, const float* in, float* out) { kat_phase(w, which, in, out); }
-__global__ void k_init_bodies(World w) {
+__global__ void k_init_bodies(World w, int first) {
     GridCtx ctx;
-    init_bodies_phase(ctx, w);
+    init_bodies_phase(ctx, w, first);
 }
 __global__ void k_import_states(World w, const int* idx, const float* src, int n, int table) {
     GridCtx ctx;
@@ -302,6 +302,8 @@ struct RbWorld {
     std::vector<RbColliderDesc> colliders;
     std::vector<RbJointDesc> joints;
     std::vector<void*> allocs;
+    int reserve_bodies = 0, reserve_colliders = 0;   // rb_world_reserve: room for later insertions
+    int body_cap = 0, collider_cap = 0;               // allocated table lengths of the current scene
     int device = 0;
     int num_sms = 1;
     int collide_blocks = 1, coop_blocks = 1;
@@ -418,15 +420,17 @@ static inline float inv0(float x) { return x == 0.0f ? 0.0f : 1.0f / x; }
 struct HostMass { float lcom[3], inv_mass, ipi[3], pi[3], pframe[4]; };
 
 // RigidBodyMassProps::recompute_mass_properties_from_colliders (rigid_body_components.rs:421).
-static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out) {
+// `first_body` / `first_collider`: only the bodies from first_body on are computed, from the colliders from
+// first_collider on (rb_world_insert: appended bodies carry appended colliders only).
+static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out, int first_body = 0, int first_collider = 0) {
     int nb = (int)W->bodies.size();
     out.assign(nb, HostMass{});
     std::vector<int> count(nb, 0), first(nb, -1);
-    for (int ci = 0; ci < (int)W->colliders.size(); ++ci) {
+    for (int ci = first_collider; ci < (int)W->colliders.size(); ++ci) {
         int p = W->colliders[ci].parent;
         if (p >= 0) { if (count[p] == 0) first[p] = ci; count[p]++; }
     }
-    for (int b = 0; b < nb; ++b) {
+    for (int b = first_body; b < nb; ++b) {
         HostMass& m = out[b];
         m.pframe[3] = 1.0f;
         if (count[b] == 1) {
@@ -438,7 +442,8 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out) {
             for (int k = 0; k < 4; ++k) m.pframe[k] = c.pos_wrt_parent_q[k];
         } else if (count[b] > 1) {
             float M = 0.0f, com[3] = {0, 0, 0};
-            for (const RbColliderDesc& c : W->colliders) {
+            for (size_t ci = (size_t)first_collider; ci < W->colliders.size(); ++ci) {
+                const RbColliderDesc& c = W->colliders[ci];
                 if (c.parent != b) continue;
                 float mass, pi[3];
                 collider_mass_props(c, mass, pi);
@@ -449,7 +454,8 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out) {
                 float invM = 1.0f / M;
                 for (int k = 0; k < 3; ++k) com[k] = com[k] * invM;
                 float I[3] = {0, 0, 0};
-                for (const RbColliderDesc& c : W->colliders) {
+                for (size_t ci = (size_t)first_collider; ci < W->colliders.size(); ++ci) {
+                    const RbColliderDesc& c = W->colliders[ci];
                     if (c.parent != b) continue;
                     if (!(c.pos_wrt_parent_q[0] == 0.0f && c.pos_wrt_parent_q[1] == 0.0f && c.pos_wrt_parent_q[2] == 0.0f)) {
                         set_err("multi-collider bodies need axis-aligned colliders%s", "");
@@ -501,16 +507,16 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out) {
     return RB_OK;
 }
 
-static int launch_init_bodies(RbWorld* W) {
+static int launch_init_bodies(RbWorld* W, int first = 0) {
 #if RB_DEVICE_BUILD
-    int blocks = (W->w.nb + 255) / 256;
+    int blocks = (W->w.nb - first + 255) / 256;
     if (blocks < 1) blocks = 1;
-    k_init_bodies<<<blocks, 256, 0, W->stream>>>(W->w);
+    k_init_bodies<<<blocks, 256, 0, W->stream>>>(W->w, first);
     CK(cudaGetLastError());
     W->kernels++;
 #else
     GridCtx ctx;
-    init_bodies_phase(ctx, W->w);
+    init_bodies_phase(ctx, W->w, first);
 #endif
     return RB_OK;
 }
@@ -539,6 +545,91 @@ static int read_state(RbWorld* W, State& s) {
     int rc = sync_world(W, false);   // (counters / debug reads must stay readable after an overflow; they do not consume the status)
     if (rc != RB_OK) return rc;
     CK(d2h(&s, W->w.st, sizeof(State)));
+    return RB_OK;
+}
+
+// Upload the static data of bodies [first, first + count) / colliders [first, first + count) from the host copies.
+static int upload_bodies(RbWorld* W, const std::vector<HostMass>& mp, int first, int count) {
+    World& w = W->w;
+    if (count <= 0) return RB_OK;
+    std::vector<int> type(count);
+    std::vector<unsigned> flags(count);
+    std::vector<float4> pt(count), pq(count), lv(count), av(count), lc(count), ipi(count), pi(count), pf(count), misc(count), uf(count), ut(count);
+    for (int k = 0; k < count; ++k) {
+        const int i = first + k;
+        const RbBodyDesc& d = W->bodies[i];
+        type[k] = d.body_type;
+        flags[k] = d.flags;
+        pt[k] = make_float4(d.translation[0], d.translation[1], d.translation[2], 0.f);
+        pq[k] = make_float4(d.rotation[0], d.rotation[1], d.rotation[2], d.rotation[3]);
+        lv[k] = make_float4(d.linvel[0], d.linvel[1], d.linvel[2], 0.f);
+        av[k] = make_float4(d.angvel[0], d.angvel[1], d.angvel[2], 0.f);
+        lc[k] = make_float4(mp[i].lcom[0], mp[i].lcom[1], mp[i].lcom[2], mp[i].inv_mass);
+        ipi[k] = make_float4(mp[i].ipi[0], mp[i].ipi[1], mp[i].ipi[2], 0.f);
+        pi[k] = make_float4(mp[i].pi[0], mp[i].pi[1], mp[i].pi[2], 0.f);
+        pf[k] = make_float4(mp[i].pframe[0], mp[i].pframe[1], mp[i].pframe[2], mp[i].pframe[3]);
+        misc[k] = make_float4(d.linear_damping, d.angular_damping, d.gravity_scale, 0.f);
+        uf[k] = make_float4(d.user_force[0], d.user_force[1], d.user_force[2], 0.f);
+        ut[k] = make_float4(d.user_torque[0], d.user_torque[1], d.user_torque[2], 0.f);
+    }
+    const size_t n = (size_t)count;
+    CK(h2d(w.b_type + first, type.data(), n * sizeof(int)));
+    CK(h2d(w.b_flags + first, flags.data(), n * sizeof(unsigned)));
+    CK(h2d(w.b_pos_t + first, pt.data(), n * sizeof(float4)));
+    CK(h2d(w.b_pos_q + first, pq.data(), n * sizeof(float4)));
+    CK(h2d(w.b_linvel + first, lv.data(), n * sizeof(float4)));
+    CK(h2d(w.b_angvel + first, av.data(), n * sizeof(float4)));
+    CK(h2d(w.b_lcom_im + first, lc.data(), n * sizeof(float4)));
+    CK(h2d(w.b_ipi + first, ipi.data(), n * sizeof(float4)));
+    CK(h2d(w.b_pi + first, pi.data(), n * sizeof(float4)));
+    CK(h2d(w.b_pframe + first, pf.data(), n * sizeof(float4)));
+    CK(h2d(w.b_misc + first, misc.data(), n * sizeof(float4)));
+    CK(h2d(w.b_uforce + first, uf.data(), n * sizeof(float4)));
+    CK(h2d(w.b_utorque + first, ut.data(), n * sizeof(float4)));
+    return RB_OK;
+}
+static int upload_colliders(RbWorld* W, int first, int count) {
+    World& w = W->w;
+    if (count <= 0) return RB_OK;
+    std::vector<int> shape(count), parent(count);
+    std::vector<float4> he(count), rt(count), rq(count), mat(count);
+    std::vector<int2> rules(count);
+    std::vector<uint2> groups(count);
+    for (int k = 0; k < count; ++k) {
+        const RbColliderDesc& c = W->colliders[first + k];
+        shape[k] = c.shape;
+        parent[k] = c.parent;
+        he[k] = make_float4(c.half_extents[0], c.half_extents[1], c.half_extents[2], 0.f);
+        rt[k] = make_float4(c.pos_wrt_parent_t[0], c.pos_wrt_parent_t[1], c.pos_wrt_parent_t[2], 0.f);
+        rq[k] = make_float4(c.pos_wrt_parent_q[0], c.pos_wrt_parent_q[1], c.pos_wrt_parent_q[2], c.pos_wrt_parent_q[3]);
+        mat[k] = make_float4(c.friction, c.restitution, c.contact_skin, 0.f);
+        rules[k] = make_int2(c.friction_combine_rule, c.restitution_combine_rule);
+        groups[k] = make_uint2(c.collision_memberships, c.collision_filter);
+    }
+    const size_t n = (size_t)count;
+    CK(h2d(w.c_shape + first, shape.data(), n * sizeof(int)));
+    CK(h2d(w.c_parent + first, parent.data(), n * sizeof(int)));
+    CK(h2d(w.c_he + first, he.data(), n * sizeof(float4)));
+    CK(h2d(w.c_rel_t + first, rt.data(), n * sizeof(float4)));
+    CK(h2d(w.c_rel_q + first, rq.data(), n * sizeof(float4)));
+    CK(h2d(w.c_mat + first, mat.data(), n * sizeof(float4)));
+    CK(h2d(w.c_rules + first, rules.data(), n * sizeof(int2)));
+    CK(h2d(w.c_groups + first, groups.data(), n * sizeof(uint2)));
+    return RB_OK;
+}
+static int validate_descs(int nb_total, int nb, const RbBodyDesc* bodies, int nc, const RbColliderDesc* colliders) {
+    for (int i = 0; i < nc; ++i) {
+        const RbColliderDesc& c = colliders[i];
+        if ((c.shape != RB_SHAPE_BALL && c.shape != RB_SHAPE_CUBOID) || c.parent >= nb_total) {
+            set_err("collider with unsupported shape or bad parent%s", "");
+            return RB_ERR_INVALID;
+        }
+    }
+    for (int i = 0; i < nb; ++i)
+        if (bodies[i].body_type != RB_BODY_DYNAMIC && bodies[i].body_type != RB_BODY_FIXED) {
+            set_err("only dynamic and fixed bodies are supported%s", "");
+            return RB_ERR_INVALID;
+        }
     return RB_OK;
 }
 
@@ -667,18 +758,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     CK(cudaSetDevice(W->device));
     CK(cudaStreamSynchronize(W->stream));
 #endif
-    for (int i = 0; i < nc; ++i) {
-        const RbColliderDesc& c = colliders[i];
-        if ((c.shape != RB_SHAPE_BALL && c.shape != RB_SHAPE_CUBOID) || c.parent >= nb) {
-            set_err("collider with unsupported shape or bad parent%s", "");
-            return RB_ERR_INVALID;
-        }
-    }
-    for (int i = 0; i < nb; ++i)
-        if (bodies[i].body_type != RB_BODY_DYNAMIC && bodies[i].body_type != RB_BODY_FIXED) {
-            set_err("only dynamic and fixed bodies are supported%s", "");
-            return RB_ERR_INVALID;
-        }
+    { int vrc = validate_descs(nb, nb, bodies, nc, colliders); if (vrc != RB_OK) return vrc; }
     for (int i = 0; i < nj; ++i) {
         const RbJointDesc& j = joints[i];
         if (j.body1 < 0 || j.body1 >= nb || j.body2 < 0 || j.body2 >= nb || (j.locked_axes & ~63u)) {
@@ -704,11 +784,15 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     int ndyn_col = 0;
     for (int i = 0; i < nc; ++i)
         if (colliders[i].parent >= 0 && bodies[colliders[i].parent].body_type == RB_BODY_DYNAMIC) ndyn_col++;
+    // capacities: the scene plus what rb_world_reserve asked for (reserved colliders are assumed to be movers)
+    const int NB = std::max(std::max(nb, W->reserve_bodies), 1), NC = std::max(std::max(nc, W->reserve_colliders), 1);
+    W->body_cap = NB; W->collider_cap = NC;
+    ndyn_col += NC - std::max(nc, 1);
     w.pair_cap = next_pow2_host(std::max(4096, 16 * ndyn_col)) + 160;   // (+160: row strides that are no power of two spread the rows of a record over the L2 slices)
     w.cons_cap = w.pair_cap;
     w.joint_cap = std::max(nj, 1);
-    w.item_cap = 4 + (nb + w.pair_cap + nj) / ITEM_TARGET;
-    const int NB = std::max(nb, 1), NC = std::max(nc, 1), NJ = w.joint_cap;
+    w.item_cap = 4 + (NB + w.pair_cap + nj) / ITEM_TARGET;
+    const int NJ = w.joint_cap;
 
     ALLOC(w.st, 1);
     ALLOC(w.b_type, NB); ALLOC(w.b_flags, NB);
@@ -759,71 +843,20 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.j_soft, NJ); ALLOC(w.j_impulses, (size_t)NJ * 6);
     ALLOC(w.j_rows, (size_t)JR_ROWS * 6 * NJ); ALLOC(w.j_sched_ids, NJ);
 
-    // ---- bodies ----
+    // ---- bodies + colliders (unused capacity: fixed bodies / parentless nothing, never listed) ----
     {
         std::vector<int> type(NB, RB_BODY_FIXED);
-        std::vector<unsigned> flags(NB, 0);
-        std::vector<float4> pt(NB), pq(NB), lv(NB), av(NB), lc(NB), ipi(NB), pi(NB), pf(NB), misc(NB), uf(NB), ut(NB);
         std::vector<unsigned char> owned(NB, 1);
-        std::vector<int> bmin(NB, 0x7fffffff);
-        for (int i = 0; i < nb; ++i) {
-            const RbBodyDesc& d = bodies[i];
-            type[i] = d.body_type;
-            flags[i] = d.flags;
-            pt[i] = make_float4(d.translation[0], d.translation[1], d.translation[2], 0.f);
-            pq[i] = make_float4(d.rotation[0], d.rotation[1], d.rotation[2], d.rotation[3]);
-            lv[i] = make_float4(d.linvel[0], d.linvel[1], d.linvel[2], 0.f);
-            av[i] = make_float4(d.angvel[0], d.angvel[1], d.angvel[2], 0.f);
-            lc[i] = make_float4(mp[i].lcom[0], mp[i].lcom[1], mp[i].lcom[2], mp[i].inv_mass);
-            ipi[i] = make_float4(mp[i].ipi[0], mp[i].ipi[1], mp[i].ipi[2], 0.f);
-            pi[i] = make_float4(mp[i].pi[0], mp[i].pi[1], mp[i].pi[2], 0.f);
-            pf[i] = make_float4(mp[i].pframe[0], mp[i].pframe[1], mp[i].pframe[2], mp[i].pframe[3]);
-            misc[i] = make_float4(d.linear_damping, d.angular_damping, d.gravity_scale, 0.f);
-            uf[i] = make_float4(d.user_force[0], d.user_force[1], d.user_force[2], 0.f);
-            ut[i] = make_float4(d.user_torque[0], d.user_torque[1], d.user_torque[2], 0.f);
-        }
+        std::vector<int> bmin(NB, 0x7fffffff), parent(NC, -1);
         CK(h2d(w.b_type, type.data(), NB * sizeof(int)));
-        CK(h2d(w.b_flags, flags.data(), NB * sizeof(unsigned)));
-        CK(h2d(w.b_pos_t, pt.data(), NB * sizeof(float4)));
-        CK(h2d(w.b_pos_q, pq.data(), NB * sizeof(float4)));
-        CK(h2d(w.b_linvel, lv.data(), NB * sizeof(float4)));
-        CK(h2d(w.b_angvel, av.data(), NB * sizeof(float4)));
-        CK(h2d(w.b_lcom_im, lc.data(), NB * sizeof(float4)));
-        CK(h2d(w.b_ipi, ipi.data(), NB * sizeof(float4)));
-        CK(h2d(w.b_pi, pi.data(), NB * sizeof(float4)));
-        CK(h2d(w.b_pframe, pf.data(), NB * sizeof(float4)));
-        CK(h2d(w.b_misc, misc.data(), NB * sizeof(float4)));
-        CK(h2d(w.b_uforce, uf.data(), NB * sizeof(float4)));
-        CK(h2d(w.b_utorque, ut.data(), NB * sizeof(float4)));
         CK(h2d(w.b_owned, owned.data(), NB));
         CK(h2d(w.body_min, bmin.data(), NB * sizeof(int)));
         CK(dev_set(w.body_minkey, 0xff, NB * sizeof(unsigned long long)));
-    }
-    // ---- colliders ----
-    {
-        std::vector<int> shape(NC, 0), parent(NC, -1);
-        std::vector<float4> he(NC), rt(NC), rq(NC), mat(NC);
-        std::vector<int2> rules(NC);
-        std::vector<uint2> groups(NC);
-        for (int i = 0; i < nc; ++i) {
-            const RbColliderDesc& c = colliders[i];
-            shape[i] = c.shape;
-            parent[i] = c.parent;
-            he[i] = make_float4(c.half_extents[0], c.half_extents[1], c.half_extents[2], 0.f);
-            rt[i] = make_float4(c.pos_wrt_parent_t[0], c.pos_wrt_parent_t[1], c.pos_wrt_parent_t[2], 0.f);
-            rq[i] = make_float4(c.pos_wrt_parent_q[0], c.pos_wrt_parent_q[1], c.pos_wrt_parent_q[2], c.pos_wrt_parent_q[3]);
-            mat[i] = make_float4(c.friction, c.restitution, c.contact_skin, 0.f);
-            rules[i] = make_int2(c.friction_combine_rule, c.restitution_combine_rule);
-            groups[i] = make_uint2(c.collision_memberships, c.collision_filter);
-        }
-        CK(h2d(w.c_shape, shape.data(), NC * sizeof(int)));
         CK(h2d(w.c_parent, parent.data(), NC * sizeof(int)));
-        CK(h2d(w.c_he, he.data(), NC * sizeof(float4)));
-        CK(h2d(w.c_rel_t, rt.data(), NC * sizeof(float4)));
-        CK(h2d(w.c_rel_q, rq.data(), NC * sizeof(float4)));
-        CK(h2d(w.c_mat, mat.data(), NC * sizeof(float4)));
-        CK(h2d(w.c_rules, rules.data(), NC * sizeof(int2)));
-        CK(h2d(w.c_groups, groups.data(), NC * sizeof(uint2)));
+        rc = upload_bodies(W, mp, 0, nb);
+        if (rc != RB_OK) return rc;
+        rc = upload_colliders(W, 0, nc);
+        if (rc != RB_OK) return rc;
     }
     // ---- joints: static data, greedy colouring (interaction_groups.rs:59-165), stage order (joints.rs:318-392) ----
     {
@@ -888,7 +921,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
         State s;
         memset(&s, 0, sizeof(s));
         s.bp_dirty = 1;
-        s.lists_dirty = 1;
+        s.lists_dirty = 3;
         s.sched_dirty = 1;
         s.nitems = 1;
         s.njused_colors = W->njused;
@@ -916,6 +949,78 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     return sync_world(W);
 }
 
+// ---- incremental changes of the sets (src/pipeline/user_changes.rs:11-46, substep.rs:303-334) ----
+// Room for later rb_world_insert calls; takes effect at the next rb_world_set_scene.
+int rb_world_reserve(RbWorld* W, int32_t max_bodies, int32_t max_colliders) {
+    if (!W || max_bodies < 0 || max_colliders < 0) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    W->reserve_bodies = max_bodies;
+    W->reserve_colliders = max_colliders;
+    return RB_OK;
+}
+
+// Appends bodies and colliders to the world (RigidBodySet::insert / ColliderSet::insert_with_parent): indices of
+// existing bodies, colliders and contact pairs do not change, so warm-start data, colours and islands persist.
+// New colliders may only be attached to the new bodies (or to none).  Joints cannot be inserted this way.
+int rb_world_insert(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t nc, const RbColliderDesc* colliders,
+                    int32_t* first_body, int32_t* first_collider) {
+    if (!W || nb < 0 || nc < 0 || (nb && !bodies) || (nc && !colliders) || !W->w.st) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    const int nb0 = W->w.nb, nc0 = W->w.nc;
+    if (nb0 + nb > W->body_cap || nc0 + nc > W->collider_cap) {
+        set_err("rb_world_insert exceeds the reserved capacity (rb_world_reserve before rb_world_set_scene)%s", "");
+        return RB_ERR_CAPACITY;
+    }
+    int rc = validate_descs(nb0 + nb, nb, bodies, nc, colliders);
+    if (rc != RB_OK) return rc;
+    for (int i = 0; i < nc; ++i)
+        if (colliders[i].parent >= 0 && colliders[i].parent < nb0) { set_err("new colliders may only be attached to new bodies%s", ""); return RB_ERR_INVALID; }
+    rc = sync_world(W);
+    if (rc != RB_OK) return rc;
+    W->bodies.insert(W->bodies.end(), bodies, bodies + nb);
+    W->colliders.insert(W->colliders.end(), colliders, colliders + nc);
+    std::vector<HostMass> mp;
+    rc = host_mass_props(W, mp, nb0, nc0);
+    if (rc != RB_OK) { W->bodies.resize(nb0); W->colliders.resize(nc0); return rc; }
+    W->w.nb = nb0 + nb;
+    W->w.nc = nc0 + nc;
+    if ((rc = upload_bodies(W, mp, nb0, nb)) != RB_OK) return rc;
+    if ((rc = upload_colliders(W, nc0, nc)) != RB_OK) return rc;
+    int one = 1, lists = 1;   // lists: 1 = only movers were added, 3 = static colliders too (re-sort them)
+    for (int i = 0; i < nc; ++i)
+        if (colliders[i].parent < 0 || W->bodies[colliders[i].parent].body_type != RB_BODY_DYNAMIC) lists = 3;
+    CK(h2d(&W->w.st->lists_dirty, &lists, sizeof(int)));
+    CK(h2d(&W->w.st->bp_dirty, &one, sizeof(int)));
+    CK(h2d(&W->w.st->sched_dirty, &one, sizeof(int)));
+    if (first_body) *first_body = nb0;
+    if (first_collider) *first_collider = nc0;
+    rc = launch_init_bodies(W, nb0);
+    if (rc != RB_OK) return rc;
+    return sync_world(W);
+}
+
+// Removes bodies with their colliders (RigidBodySet::remove with remove_attached_colliders): the slots stay
+// allocated (indices of everything else are unchanged), the colliders leave the broad phase, so their contact
+// pairs end at the next step.
+int rb_world_remove_bodies(RbWorld* W, int32_t n, const int32_t* indices) {
+    if (!W || n < 0 || (n && !indices) || !W->w.st) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    int rc = sync_world(W);
+    if (rc != RB_OK) return rc;
+    for (int k = 0; k < n; ++k)
+        if (indices[k] < 0 || indices[k] >= W->w.nb) { set_err("body index out of range%s", ""); return RB_ERR_INVALID; }
+    const int removed_type = BODY_REMOVED, removed_shape = SHAPE_REMOVED;
+    for (int k = 0; k < n; ++k) {
+        const int b = indices[k];
+        W->bodies[b].body_type = BODY_REMOVED;
+        CK(h2d(W->w.b_type + b, &removed_type, sizeof(int)));
+        for (int c = 0; c < (int)W->colliders.size(); ++c)
+            if (W->colliders[c].parent == b) CK(h2d(W->w.c_shape + c, &removed_shape, sizeof(int)));
+    }
+    int one = 1, lists = 3;
+    CK(h2d(&W->w.st->lists_dirty, &lists, sizeof(int)));
+    CK(h2d(&W->w.st->bp_dirty, &one, sizeof(int)));
+    CK(h2d(&W->w.st->sched_dirty, &one, sizeof(int)));
+    return RB_OK;
+}
+
 int rb_world_set_body_states(RbWorld* W, int32_t n, const int32_t* indices, const float* pose7, const float* vel6) {
     if (!W || n < 0 || (n && !indices)) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
     int rc = sync_world(W);
@@ -941,8 +1046,8 @@ int rb_world_set_body_states(RbWorld* W, int32_t n, const int32_t* indices, cons
         if (pose7)
             for (int k = 0; k < n; ++k) moved_static = moved_static || W->bodies[indices[k]].body_type != RB_BODY_DYNAMIC;
         if (moved_static) {
-            int one = 1;
-            CK(h2d(&W->w.st->lists_dirty, &one, sizeof(int)));
+            int one = 1, lists = 3;
+            CK(h2d(&W->w.st->lists_dirty, &lists, sizeof(int)));
             CK(h2d(&W->w.st->bp_dirty, &one, sizeof(int)));
         }
     }
@@ -1332,7 +1437,7 @@ int rb_world_set_owned_bodies(RbWorld* W, const uint8_t* owned) {
     // Ownership changes the pair filter: drop the pair table and every derived structure.
     State st;
     CK(d2h(&st, W->w.st, sizeof(st)));
-    st.npairs = 0; st.bp_dirty = 1; st.lists_dirty = 1; st.sched_dirty = 1; st.ntodo = 0; st.ncons = 0; st.nitems = 1; st.nlarge_bodies = 0;
+    st.npairs = 0; st.bp_dirty = 1; st.lists_dirty = 3; st.sched_dirty = 1; st.ntodo = 0; st.ncons = 0; st.nitems = 1; st.nlarge_bodies = 0;
     CK(h2d(W->w.st, &st, sizeof(st)));
     CK(dev_set(W->w.color_mask, 0, (size_t)std::max(W->w.nb, 1) * 16));
     CK(dev_set(W->w.c_fat_min, 0, (size_t)std::max(W->w.nc, 1) * 16));

@@ -60,7 +60,8 @@ RB_HD void refresh_collider(const World& w, int c) {
 template <class Ctx>
 RB_PHASE void phase_refresh_colliders(const Ctx& ctx, const World& w) {
     if (w.st->lists_dirty) {
-        for (int c = ctx.gtid; c < w.nc; c += ctx.gsize) refresh_collider(w, c);
+        for (int c = ctx.gtid; c < w.nc; c += ctx.gsize)
+            if (w.c_shape[c] != SHAPE_REMOVED) refresh_collider(w, c);
     } else {
         const int nd = w.st->ndyn;
         for (int i = ctx.gtid; i < nd; i += ctx.gsize) refresh_collider(w, w.dyn_list[i]);
@@ -248,18 +249,26 @@ constexpr int WIDE_CAP = 1024;   // static colliders much wider than the rest (a
 template <class Ctx>
 RB_PHASE void section_build_lists(const Ctx& ctx, const World& w) {
     State* st = w.st;
-    if (ctx.gtid == 0) { st->ndyn = 0; st->nstat = 0; st->nwide = 0; st->stat_count = 0; st->stat_wsum = 0.0f; st->stat_wn_bits = 0u; }
-    grid_radix_zero(ctx, w.radix_hist, 4);
+    const bool statics = (st->lists_dirty & 2) != 0;   // bit 1: the static colliders changed too (else only movers were added)
+    if (ctx.gtid == 0) {
+        st->ndyn = 0;
+        if (statics) { st->nstat = 0; st->nwide = 0; st->stat_count = 0; st->stat_wsum = 0.0f; st->stat_wn_bits = 0u; }
+    }
+    if (statics) grid_radix_zero(ctx, w.radix_hist, 4);
     ctx.grid_sync();
-    for (int c = ctx.gtid; c < w.nc; c += ctx.gsize)
-        if (collider_is_static(w, c)) {
-            atomic_add(&st->stat_count, 1);
-            atomic_add(&st->stat_wsum, w.c_fat_max[c].x - w.c_fat_min[c].x);
-        }
-    ctx.grid_sync();
+    if (statics) {
+        for (int c = ctx.gtid; c < w.nc; c += ctx.gsize)
+            if (w.c_shape[c] != SHAPE_REMOVED && collider_is_static(w, c)) {
+                atomic_add(&st->stat_count, 1);
+                atomic_add(&st->stat_wsum, w.c_fat_max[c].x - w.c_fat_min[c].x);
+            }
+        ctx.grid_sync();
+    }
     const float wide_thr = st->stat_count > 0 ? 4.0f * (st->stat_wsum / (float)st->stat_count) : 0.0f;
     for (int c = ctx.gtid; c < w.nc; c += ctx.gsize) {
+        if (w.c_shape[c] == SHAPE_REMOVED) continue;   // collider of a removed body: in no list, so its pairs end
         if (!collider_is_static(w, c)) { w.dyn_list[atomic_add(&st->ndyn, 1)] = c; continue; }
+        if (!statics) continue;
         const float4 lo = w.c_fat_min[c], hi = w.c_fat_max[c];
         const float width = hi.x - lo.x;
         bool wide = width > wide_thr;
@@ -273,8 +282,11 @@ RB_PHASE void section_build_lists(const Ctx& ctx, const World& w) {
         }
     }
     ctx.grid_sync();
-    unsigned long long* sorted = grid_radix_sort(ctx, w.stat_key[0], w.stat_key[1], st->nstat, 32, 64, w.radix_hist);
-    if (ctx.gtid == 0) { st->stat_sorted = sorted == w.stat_key[0] ? 0 : 1; st->lists_dirty = 0; st->bp_dirty = 1; }
+    if (statics) {
+        unsigned long long* sorted = grid_radix_sort(ctx, w.stat_key[0], w.stat_key[1], st->nstat, 32, 64, w.radix_hist);
+        if (ctx.gtid == 0) st->stat_sorted = sorted == w.stat_key[0] ? 0 : 1;
+    }
+    if (ctx.gtid == 0) { st->lists_dirty = 0; st->bp_dirty = 1; }
     ctx.grid_sync();
 }
 

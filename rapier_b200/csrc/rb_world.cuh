@@ -18,7 +18,9 @@ constexpr int NUM_COLORS = 129;
 constexpr int NO_BODY = -1;             // world-attached side (reference: u32::MAX)
 
 constexpr int BODY_DYNAMIC = 0;
+constexpr int BODY_REMOVED = 3;          // removed (rb_world_remove_bodies) or quarantined: not simulated, its colliders are gone
 constexpr int SHAPE_BALL = 0, SHAPE_CUBOID = 1;
+constexpr int SHAPE_REMOVED = -1;        // collider of a removed body: in neither broad-phase list, in no pair
 constexpr unsigned FLAG_GYRO = 1, FLAG_FAST_ROT = 2, FLAG_LTX = 4, FLAG_LTY = 8, FLAG_LTZ = 16, FLAG_LRX = 32,
                    FLAG_LRY = 64, FLAG_LRZ = 128;
 

@@ -262,6 +262,50 @@ def large_world(grid=1000, spheres=100, cell=10.0):
     return s
 
 
+def large_world_floor(grid=1000, cell=10.0, name=None):
+    """The static part of examples3d/b3d_large_world.rs:27-41: grid x grid parentless cuboid colliders."""
+    s = Scene(name or f"large_world_floor_{grid}", gravity=(0.0, -10.0, 0.0))
+    cell = F(cell)
+    half_span = F(0.5) * cell * F(grid)
+    for i in range(grid):
+        x = -half_span + (F(i) + F(0.5)) * cell
+        for j in range(grid):
+            z = -half_span + (F(j) + F(0.5)) * cell
+            s.colliders.insert(ColliderBuilder.cuboid(F(0.5) * cell, 0.25, F(0.5) * cell).translation((x, 0.0, z)))
+    return s
+
+
+def large_world_sphere(idx, grid=1000, spheres=100, cell=10.0):
+    """The idx-th sphere of b3d_large_world.rs:55-70 (dropped every 5 steps at y = 1.5 over the inner 80 % of the floor)."""
+    cell = F(cell)
+    half_span = F(0.5) * cell * F(grid)
+    side = 1
+    while side * side < spheres:
+        side += 1
+    gi, gj = idx % side, idx // side
+    inset = F(0.1) * F(2.0) * half_span
+    usable = F(2.0) * half_span - F(2.0) * inset
+    x = -half_span + inset + (F(gi) + F(0.5)) * (usable / F(side))
+    z = -half_span + inset + (F(gj) + F(0.5)) * (usable / F(side))
+    return RigidBodyBuilder.dynamic().translation((x, 1.5, z)), ColliderBuilder.ball(0.5)
+
+
+def run_large_world_protocol(world, steps, grid=1000, spheres=100, drop_interval=5, on_step=None):
+    """StepLargeWorld (b3d_large_world.rs:55-77): one sphere inserted every `drop_interval` steps (from step
+    `drop_interval` on) up to `spheres`, each followed by a step.  `world` needs insert(body_builder,
+    collider_builder) and step()."""
+    dropped = 0
+    for step_count in range(steps):
+        if dropped < spheres and step_count > 0 and step_count % drop_interval == 0:
+            bb, cb = large_world_sphere(dropped, grid, spheres)
+            world.insert(bb, cb)
+            dropped += 1
+        world.step()
+        if on_step is not None:
+            on_step(step_count)
+    return dropped
+
+
 REGISTRY["large_world"] = large_world
 REGISTRY["falling_pile_2000"] = lambda: box_pile(10, 10, 20)
 REGISTRY["pyramid3_20"] = lambda: pyramid3(20)

@@ -54,6 +54,24 @@ class PhysicsPipeline:
         self._check(self.L.rb_world_set_scene(self.h, len(bodies), self._b, len(colliders), self._c, len(joints), self._j))
         self.nb = len(bodies)
 
+    def reserve(self, max_bodies, max_colliders):
+        """Room for later insert() calls (applied by the next upload)."""
+        self._check(self.L.rb_world_reserve(self.h, max_bodies, max_colliders))
+
+    def insert(self, body_descs, collider_descs):
+        """handle_user_changes_to_{rigid_bodies,colliders} for INSERTED bodies / colliders (user_changes.rs:11-46):
+        appended without disturbing any contact state.  Returns (first body index, first collider index)."""
+        b = as_array(body_descs, A.RbBodyDesc)
+        c = as_array(collider_descs, A.RbColliderDesc)
+        fb, fc = C.c_int32(-1), C.c_int32(-1)
+        self._check(self.L.rb_world_insert(self.h, len(body_descs), b, len(collider_descs), c, C.byref(fb), C.byref(fc)))
+        self.nb += len(body_descs)
+        return fb.value, fc.value
+
+    def remove_bodies(self, indices):
+        idx = np.ascontiguousarray(indices, np.int32)
+        self._check(self.L.rb_world_remove_bodies(self.h, len(idx), idx.ctypes.data))
+
     def set_params(self, params):
         self.params = params
         self._check(self.L.rb_world_set_params(self.h, C.byref(params)))
@@ -157,15 +175,33 @@ class PhysicsWorld:
         self.integration_parameters = integration_parameters or A.RbIntegrationParameters.default()
         self.physics_pipeline = PhysicsPipeline(self.integration_parameters, device, _lib=_lib)
         self._dirty = True
+        self._uploaded = (0, 0, 0)   # bodies, colliders, joints the device already has
         if scene is not None:
             self.gravity = scene.gravity
             self.bodies, self.colliders, self.impulse_joints = scene.bodies, scene.colliders, scene.joints
 
+    def reserve(self, max_bodies, max_colliders):
+        """Capacity for bodies / colliders inserted after the first step (RigidBodySet / ColliderSet grow on demand in the
+        reference; the device tables are sized once)."""
+        self.physics_pipeline.reserve(max_bodies, max_colliders)
+
     def insert(self, body_builder, collider_builder):
+        """PhysicsWorld::insert (physics_world.rs:184-207).  After the world has been stepped, the new body and collider
+        are appended on the device (contacts, warm-start data and islands of everything else persist)."""
         h = self.bodies.insert(body_builder)
         self.colliders.insert_with_parent(collider_builder, h)
         self._dirty = True
         return h
+
+    def insert_collider(self, collider_builder, parent=None):
+        """PhysicsWorld::insert_collider (parentless = static geometry)."""
+        self._dirty = True
+        return self.colliders.insert(collider_builder) if parent is None else self.colliders.insert_with_parent(collider_builder, parent)
+
+    def remove(self, body_handle):
+        """RigidBodySet::remove with its attached colliders; the handle's slot stays allocated."""
+        self._flush()
+        self.physics_pipeline.remove_bodies([body_handle])
 
     def insert_impulse_joint(self, body1, body2, joint_builder):
         self._dirty = True
@@ -173,7 +209,13 @@ class PhysicsWorld:
 
     def _flush(self):
         if self._dirty:
-            self.physics_pipeline.upload(self.bodies, self.colliders, self.impulse_joints)
+            nb0, nc0, nj0 = self._uploaded
+            nb, nc, nj = len(self.bodies), len(self.colliders), len(self.impulse_joints)
+            if nb0 + nc0 > 0 and nj == nj0 and nb >= nb0 and nc >= nc0:   # only appended since the last upload: incremental
+                self.physics_pipeline.insert(self.bodies.descs[nb0:], self.colliders.descs[nc0:])
+            else:
+                self.physics_pipeline.upload(self.bodies, self.colliders, self.impulse_joints)
+            self._uploaded = (nb, nc, nj)
             self._dirty = False
 
     def step(self, n=1, sync=True):

@@ -63,6 +63,8 @@ def lib(fast=False):
         L.orc_set_threads.argtypes = [C.c_int]
         L.orc_contact_manifold.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_world_insert.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_world_remove_bodies.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_kat.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
         _libs[fast] = L
     return _libs[fast]
@@ -96,6 +98,19 @@ class OracleWorld:
         g = (C.c_float * 3)(*self.gravity)
         rc = self.L.orc_world_step(self.h, g, n)
         assert rc == 0
+
+    def insert(self, body_descs, collider_descs):
+        """Mirror of PhysicsPipeline.insert (appended bodies / colliders)."""
+        b = as_array(body_descs, A.RbBodyDesc)
+        c = as_array(collider_descs, A.RbColliderDesc)
+        rc = self.L.orc_world_insert(self.h, len(body_descs), b, len(collider_descs), c)
+        assert rc == 0, rc
+        self.nb += len(body_descs)
+
+    def remove_bodies(self, indices):
+        idx = np.ascontiguousarray(indices, np.int32)
+        rc = self.L.orc_world_remove_bodies(self.h, len(idx), idx.ctypes.data)
+        assert rc == 0, rc
 
     def body_states(self):
         pose = np.zeros((self.nb, 7), np.float32)

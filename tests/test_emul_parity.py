@@ -104,3 +104,15 @@ def test_capacity_overflow_is_reported_after_asynchronous_steps():
     w.physics_pipeline.synchronize()   # reported once, then cleared
     with pytest.raises(RapierError, match="-4"):
         w.physics_pipeline.step_host(s.gravity, None, None)
+
+
+def test_large_world_insertion_protocol_emulated():
+    """b3d_large_world.rs:55-77 as written: a static tiled floor, one sphere INSERTED every 5 steps (the pair table,
+    colours and warm-start data of the spheres already resting must survive every insertion)."""
+    from incremental_cases import large_world_protocol_case
+    large_world_protocol_case(lib=emul_lib.lib())
+
+
+def test_body_removal_and_insertion_emulated():
+    from incremental_cases import removal_case
+    removal_case(lib=emul_lib.lib())

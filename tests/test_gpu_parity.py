@@ -234,3 +234,38 @@ def test_determinism_stress(built):
             assert (cur[0] == ref[0]).all() and (cur[1] == ref[1]).all(), f"run {rep}: body state differs from run 0"
             for k in tables:
                 assert cur[2][k].shape == ref[2][k].shape and (cur[2][k] == ref[2][k]).all(), f"run {rep}: table {k} differs"
+
+
+def test_large_world_insertion_protocol(built):
+    """b3d_large_world.rs:55-77 as written (reduced floor): one sphere inserted every 5 steps through rb_world_insert."""
+    from incremental_cases import large_world_protocol_case
+    large_world_protocol_case(grid=20, spheres=12, steps=100, every=10)
+
+
+def test_large_world_full_size_insertion_protocol(built):
+    """BASELINE configs[4] at the reference size: 10^6 static colliders (radix-sorted once), spheres inserted every
+    5 steps, the first 60 steps bit for bit against the oracle."""
+    from incremental_cases import large_world_protocol_case
+    w, o = large_world_protocol_case(grid=1000, spheres=100, steps=60, every=20, threads=4)
+    c = w.counters()
+    assert c["num_colliders"] == 1000 * 1000 + 11 and c["num_bodies"] == 11
+
+
+def test_body_removal_and_insertion(built):
+    from incremental_cases import removal_case
+    removal_case()
+
+
+def test_capacity_overflow_is_reported_after_asynchronous_steps(built):
+    from rapier_b200.sets import ColliderBuilder, RigidBodyBuilder
+    from rapier_b200.world import RapierError
+    s = scenes.Scene("crowd", gravity=(0.0, 0.0, 0.0))
+    for i in range(330):
+        s.insert(RigidBodyBuilder.dynamic().translation((0.001 * i, 0.0, 0.0)), ColliderBuilder.ball(0.5))
+    w = PhysicsWorld(s)
+    w.step(1, sync=False)
+    with pytest.raises(RapierError, match="-4"):
+        w.physics_pipeline.synchronize()
+    w.physics_pipeline.synchronize()
+    with pytest.raises(RapierError, match="-4"):
+        w.physics_pipeline.step_host(s.gravity, None, None)
