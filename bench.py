@@ -123,6 +123,17 @@ def best_cpu_world(scene, budget_s=8.0):
     return w, best[0], sweep
 
 
+def csrc_sha1():
+    """Hash of the kernel sources: ties profiles/traffic.json to the build it was measured on."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "rapier_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
+
+
 def algorithmic_bytes(m, b, j):
     """SURVEY.md 8(d) / BASELINE.md 4: streaming model, f32, twist friction, p = 4, S = 4."""
     return 12076 * m + 1608 * b + 6576 * j
@@ -211,7 +222,7 @@ def main():
     if world_size > 1:
         from rapier_b200.sharding import IslandShard
         shard = IslandShard(pipe, dist, rank, world_size, torch.device("cuda", local_rank),
-                            overlap=os.environ.get("RB_SHARD_OVERLAP", "1") == "1")   # asynchronous in-place gather of the double-buffered state
+                            refresh_every=int(os.environ.get("RB_SHARD_REFRESH", "32")))   # halo states every step, everything every 32 steps
         exchange = shard.exchange
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if args.l2 == "flush" else None
@@ -250,13 +261,19 @@ def main():
         if exchange is not None:
             shard.finish()   # no gather may be in flight while steps run without exchange() in between
         pipe.enable_profiling(True)
-        pipe.step(gravity, min(args.steps, 100), sync=True)
-        prof = pipe.counters()
+        prof = {"collision_detection_ms": 0.0, "solver_ms": 0.0}
+        nprof = min(args.steps, 100)
+        for _ in range(nprof):   # same conditions as the timed region: L2 flushed before every step
+            if flush_buf is not None:
+                flush_buf.zero_()
+            pipe.step(gravity, 1, sync=True)
+            c1 = pipe.counters()
+            prof["collision_detection_ms"] += c1["collision_detection_ms"] / nprof
+            prof["solver_ms"] += c1["solver_ms"] / nprof
         pipe.enable_profiling(False)
         # ---- e2e: host buffers in / out every step through the public C-ABI call ----
-        if exchange is not None:   # host-fed steps overwrite every body's state: exchange synchronously here
+        if exchange is not None:
             shard.finish()
-            shard.overlap = False
         e2e_steps = min(args.steps, 200)
         pose, vel = pipe.body_states()
         # host-side state buffers of the caller: page-locked (the library DMAs them directly)
@@ -312,8 +329,10 @@ def main():
     traffic = None
     st = pipe.debug_read("state", np.int32)
     kernel_name = "k_solve_coop_big" if int(st[19]) > 0 else "k_solve_coop"   # streamed items => the big launch shape ran
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{kernel_name}_dram_bytes_per_launch:{args.scene}")
+    try:   # ncu dram bytes of THIS build (profiles/traffic.json carries the hash of the kernel sources it was captured from), else null
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("csrc_sha1") == csrc_sha1():
+            traffic = tj.get(f"{kernel_name}_dram_bytes_per_launch:{args.scene}")
     except Exception:
         pass
 
@@ -356,7 +375,7 @@ def main():
             "config": {"workload": workload_name(args.scene, world_size), "bodies_per_gpu": per_rank_bodies,
                        "manifolds_per_gpu": M, "substeps": 4, "sweeps_per_substep": 3,
                        "l2": "flushed between steps (256 MiB memset)" if args.l2 == "flush" else "not flushed",
-                       "parallelism": "1 GPU" if world_size == 1 else f"islands sharded over {world_size} GPUs, NCCL all-gather of body states every step" + (" (asynchronous: overlapped with the next step, imported one step late, drained at the end)" if os.environ.get("RB_SHARD_OVERLAP", "1") == "1" else " (in place on the state buffer)")},
+                       "parallelism": "1 GPU" if world_size == 1 else f"islands sharded over {world_size} GPUs; NCCL all-gather of the boundary (halo) body states every step -- none in this scene: {shard.halo_steps} steps needed it --, of all body states every {shard.refresh_every} steps and at the end"},
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": nb * 13 * 4, "d2h_bytes_per_step": nb * 13 * 4,
                     "steps": e2e_steps},
             "gpu_launches": int(k1 - k0),

@@ -32,7 +32,7 @@ typedef enum RbStatus {
     RB_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed */
     RB_ERR_INVALID = -3,     /* bad argument (null pointer, index out of range, unsupported shape) */
     RB_ERR_CAPACITY = -4,    /* a device-side table overflowed (pairs, islands); state is unchanged */
-    RB_ERR_NONFINITE = -5    /* a body went non-finite (reference: Quarantine, quarantine.rs:14-47) */
+    RB_ERR_NONFINITE = -5, RB_ERR_SHARD = -6    /* a body went non-finite (reference: Quarantine, quarantine.rs:14-47) */
 } RbStatus;
 
 /* Mirror of IntegrationParameters (src/dynamics/integration_parameters.rs:181-304), #[repr(C)]. */
@@ -215,7 +215,12 @@ int rb_debug_kat(const char* name, const float* in, int32_t n_in, float* out, in
 /* Restricts this world to the bodies whose component id (as labelled by rb_world_label_components)
  * satisfies component % world_size == rank; the other dynamic bodies become inert. */
 int rb_world_label_components(RbWorld* w, int32_t* component_of_body /* [num_bodies], host */);
-int rb_world_set_owned_bodies(RbWorld* w, const uint8_t* owned /* [num_bodies] */);
+int rb_world_set_owned_bodies(RbWorld* w, const uint8_t* owned /* [num_bodies]: 1 = simulated here, 0 = elsewhere; before the first step */);
+/* Halo bodies: bodies of other ranks close enough to be tracked here (proximity detection only; a CONTACT with one
+ * raises RB_ERR_SHARD: the islands of two shards merged).  flags_dev: DEVICE array [num_bodies], non-zero = track;
+ * stream-ordered, keeps all contact state.  rb_world_import_halo copies their states out of the packed state table. */
+int rb_world_set_halo_bodies(RbWorld* w, const uint8_t* flags_dev);
+int rb_world_import_halo(RbWorld* w);
 /* Device pointers to the packed per-body state (13 floats/body: t3 q4 lin3 ang3) for NCCL
  * all-gather of boundary body states, and the byte size. */
 int rb_world_state_buffer(RbWorld* w, void** device_ptr, int64_t* bytes);

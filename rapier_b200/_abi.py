@@ -11,6 +11,7 @@ RB_ERR_CUDA = -2
 RB_ERR_INVALID = -3
 RB_ERR_CAPACITY = -4
 RB_ERR_NONFINITE = -5
+RB_ERR_SHARD = -6
 
 RB_BODY_DYNAMIC = 0
 RB_BODY_FIXED = 1

@@ -180,6 +180,29 @@ RB_PHASE void kat_phase(const World& w, int which, const float* in, float* out) 
     }
 }
 
+// Halo bodies (b_owned == 2): take their state from the packed state table (filled by the exchange).
+template <class Ctx>
+RB_PHASE void import_halo_phase(const Ctx& ctx, const World& w) {
+    for (int b = ctx.gtid; b < w.nb; b += ctx.gsize) {
+        if (w.b_owned[b] != 2) continue;
+        const float* s = w.state13 + (size_t)b * 13;
+        w.b_pos_t[b] = make_float4(s[0], s[1], s[2], 0.f);
+        w.b_pos_q[b] = make_float4(s[3], s[4], s[5], s[6]);
+        w.b_linvel[b] = make_float4(s[7], s[8], s[9], 0.f);
+        w.b_angvel[b] = make_float4(s[10], s[11], s[12], 0.f);
+        update_world_mass(w, b, body_pose(w, b));
+    }
+}
+// New halo flags (device array, 0 / 2 for foreign bodies; entries of owned bodies are ignored).
+template <class Ctx>
+RB_PHASE void set_halo_phase(const Ctx& ctx, const World& w, const unsigned char* flags) {
+    for (int b = ctx.gtid; b < w.nb; b += ctx.gsize) {
+        if (w.b_owned[b] == 1) continue;
+        const unsigned char f = flags[b] ? 2 : 0;
+        if (w.b_owned[b] != f) { w.b_owned[b] = f; w.st->lists_dirty |= 1; w.st->bp_dirty = 1; }
+    }
+}
+
 #if RB_DEVICE_BUILD
 // Collision pipeline, then every solve that is NOT shared-memory resident: work items streamed from
 // HBM (one CTA each) and the grid-wide "large" item 0.  Those touch bodies / constraints disjoint from
@@ -285,6 +308,14 @@ __global__ void k_kat(World w, int which, const float* in, float* out) { kat_pha
 __global__ void k_init_bodies(World w, int first) {
     GridCtx ctx;
     init_bodies_phase(ctx, w, first);
+}
+__global__ void k_import_halo(World w) {
+    GridCtx ctx;
+    import_halo_phase(ctx, w);
+}
+__global__ void k_set_halo(World w, const unsigned char* flags) {
+    GridCtx ctx;
+    set_halo_phase(ctx, w, flags);
 }
 __global__ void k_import_states(World w, const int* idx, const float* src, int n, int table) {
     GridCtx ctx;
@@ -533,7 +564,7 @@ static int sync_world(RbWorld* W, bool check = true) {
             W->host_hint[1] = 0;
             int zero = 0;
             CK(h2d(&W->w.st->error, &zero, sizeof(int)));
-            set_err(code == RB_ERR_NONFINITE ? "device raised status %s%d (non-finite body state: see rb_world_get_quarantine)"
+            set_err(code == -6 ? "device raised status %s%d (a contact formed between bodies simulated by different ranks: the shards' islands merged, repartition)" : code == RB_ERR_NONFINITE ? "device raised status %s%d (non-finite body state: see rb_world_get_quarantine)"
                                              : "device raised status %s%d (capacity overflow: the step kept the previous pair set / truncated the schedule)", "", code);
             return code;
         }
@@ -1431,6 +1462,10 @@ int rb_world_label_components(RbWorld* W, int32_t* component_of_body) {
 
 int rb_world_set_owned_bodies(RbWorld* W, const uint8_t* owned) {
     if (!W || !owned) return RB_ERR_INVALID;
+    if (W->steps > 0) {   // the partition drops the pair table (warm start, colours): only before the first step
+        set_err("rb_world_set_owned_bodies must be called before the world is stepped%s", "");
+        return RB_ERR_INVALID;
+    }
     int rc = sync_world(W);
     if (rc != RB_OK) return rc;
     CK(h2d(W->w.b_owned, owned, (size_t)W->w.nb));
@@ -1442,6 +1477,36 @@ int rb_world_set_owned_bodies(RbWorld* W, const uint8_t* owned) {
     CK(dev_set(W->w.color_mask, 0, (size_t)std::max(W->w.nb, 1) * 16));
     CK(dev_set(W->w.c_fat_min, 0, (size_t)std::max(W->w.nc, 1) * 16));
     CK(dev_set(W->w.c_fat_max, 0, (size_t)std::max(W->w.nc, 1) * 16));
+    return RB_OK;
+}
+
+// Halo bodies: which bodies of OTHER ranks this rank tracks (flags_dev: device array [num_bodies], non-zero = track).
+// Stream-ordered, no host synchronisation; contact state of everything else is untouched.
+int rb_world_set_halo_bodies(RbWorld* W, const uint8_t* flags_dev) {
+    if (!W || !flags_dev) return RB_ERR_INVALID;
+#if RB_DEVICE_BUILD
+    CK(cudaSetDevice(W->device));
+    k_set_halo<<<(W->w.nb + 255) / 256, 256, 0, W->stream>>>(W->w, flags_dev);
+    CK(cudaGetLastError());
+    W->kernels++;
+#else
+    GridCtx g;
+    set_halo_phase(g, W->w, flags_dev);
+#endif
+    return RB_OK;
+}
+// Imports the states of the halo bodies from the packed state table (after an exchange wrote their rows).
+int rb_world_import_halo(RbWorld* W) {
+    if (!W) return RB_ERR_INVALID;
+#if RB_DEVICE_BUILD
+    CK(cudaSetDevice(W->device));
+    k_import_halo<<<(W->w.nb + 255) / 256, 256, 0, W->stream>>>(W->w);
+    CK(cudaGetLastError());
+    W->kernels++;
+#else
+    GridCtx g;
+    import_halo_phase(g, W->w);
+#endif
     return RB_OK;
 }
 

@@ -21,8 +21,11 @@ constexpr int ITEM_MAX_BODIES = ITEM_BODY_CAP + ITEM_TARGET;  // shared-memory s
 constexpr int BIG_COLOR_MIN = 125;   // ceil(n/4) >= 32 chunks (init.rs:169: CHUNK_BATCH*LAYOUT_REF_WORKERS/2)
 constexpr int BIG_JCOLOR_MIN = 64;   // joints.rs:340: JOINT_BATCH*LAYOUT_REF_WORKERS/2
 
+// Multi-GPU sharding (b_owned): 1 = simulated by this rank, 2 = "halo": simulated by another rank but close enough to
+// be tracked here (its state is imported every step, its colliders take part in proximity detection), 0 = simulated
+// by another rank and far away (ignored until the next halo refresh).
 RB_HD bool body_is_sim(const World& w, int b) {  // dynamic and simulated by this rank
-    return b >= 0 && w.b_type[b] == BODY_DYNAMIC && w.b_owned[b] != 0;
+    return b >= 0 && w.b_type[b] == BODY_DYNAMIC && w.b_owned[b] == 1;
 }
 RB_HD pose body_pose(const World& w, int b) { return mkpose(mkq(w.b_pos_q[b]), xyz(w.b_pos_t[b])); }
 RB_HD pose collider_pose(const World& w, int c) { return mkpose(mkq(w.c_pos_q[c]), xyz(w.c_pos_t[c])); }
@@ -267,7 +270,10 @@ RB_PHASE void section_build_lists(const Ctx& ctx, const World& w) {
     const float wide_thr = st->stat_count > 0 ? 4.0f * (st->stat_wsum / (float)st->stat_count) : 0.0f;
     for (int c = ctx.gtid; c < w.nc; c += ctx.gsize) {
         if (w.c_shape[c] == SHAPE_REMOVED) continue;   // collider of a removed body: in no list, so its pairs end
-        if (!collider_is_static(w, c)) { w.dyn_list[atomic_add(&st->ndyn, 1)] = c; continue; }
+        if (!collider_is_static(w, c)) {
+            if (w.b_owned[w.c_parent[c]] != 0) w.dyn_list[atomic_add(&st->ndyn, 1)] = c;   // (far foreign bodies are not tracked)
+            continue;
+        }
         if (!statics) continue;
         const float4 lo = w.c_fat_min[c], hi = w.c_fat_max[c];
         const float width = hi.x - lo.x;
@@ -611,6 +617,10 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
         prow(w, buf, PR_NORMAL, i) = f4(normal, friction);
         // transitions (pair_update.rs:622-629; contacts.rs:300-385)
         bool had = nsc_old > 0, has = nsc > 0;
+        if (has && dyn1 != dyn2) {   // sharding: a contact with a body simulated by ANOTHER rank means two shards' islands merged
+            const int bo = dyn1 ? b2 : b1;
+            if (bo >= 0 && w.b_type[bo] == BODY_DYNAMIC && w.b_owned[bo] != 1) RB_RAISE(w, -6);
+        }
         if (had != has) {
             st->sched_dirty = 1;
             if (has) {

@@ -1,11 +1,19 @@
-"""Island sharding across ranks: whole connected components are assigned to ranks,
-every rank simulates only the bodies it owns, and one all-gather per step of the owned body
-states (13 floats per body: t3 q4 linvel3 angvel3) gives every rank the full world state.
+"""Island sharding across ranks: whole connected components are assigned to ranks and every rank
+simulates only the bodies it owns.  What crosses NVLink is the north star's "all-gather of boundary body states":
 
-The reference is single-process (one awake set, src/dynamics/island_manager/manager.rs:20-25); the
-components it already tracks as persistent islands (island_manager/persistent.rs:1-3) are the unit
-of distribution here.  Works with any torch.distributed backend: NCCL over NVLink on the GPU box,
-gloo in the CPU tests (where the world is the host emulation of the kernels).
+  * HALO bodies -- bodies of other ranks inside (or near) the bounding box of this rank's bodies -- are tracked here
+    for proximity detection only; their states (13 floats: t3 q4 linvel3 angvel3) are all-gathered EVERY step and
+    imported before the next one.  A rank with no halo takes part in no per-step collective at all.
+  * every `refresh_every` steps the owned states of ALL bodies are all-gathered, every rank re-derives its halo set
+    from them (bounding box of its own bodies, inflated by a margin that covers `refresh_every` steps at the fastest
+    body's current speed) and tells the others which of their bodies it now tracks.
+  * a CONTACT between an owned and a halo body means two shards' islands merged: the device raises RB_ERR_SHARD
+    (reported by the next synchronising call); nothing is silently simulated wrong.
+  * `finish()` gathers everything once more, so all ranks end with the exact state of every body.
+
+The reference is single-process (one awake set, src/dynamics/island_manager/manager.rs:20-25); the components it
+tracks as persistent islands (island_manager/persistent.rs:1-3) are the unit of distribution.  Works with any
+torch.distributed backend: NCCL over NVLink on the GPU box, gloo in the CPU tests (host emulation of the kernels).
 """
 import ctypes as C
 
@@ -30,14 +38,6 @@ class _CudaBuf:
         self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
-def _view(ptr, nbytes, device):
-    if device.type == "cuda":
-        t = torch.as_tensor(_CudaBuf(ptr, nbytes), device=device)
-    else:
-        t = torch.frombuffer((C.c_float * (nbytes // 4)).from_address(ptr), dtype=torch.float32)
-    return t.view(-1, 13)
-
-
 def state_tensor(pipe, device):
     """Zero-copy torch view [nb, 13] of the library's packed body-state buffer."""
     ptr, nbytes = pipe.state_buffer()
@@ -48,107 +48,114 @@ def state_tensor(pipe, device):
     return t.view(-1, 13)
 
 
-class IslandShard:
-    """`overlap=True`: the all-gather of step n runs asynchronously (on NCCL's stream) while step n+1 is
-    computed, and its result is imported before step n+2.  Bodies simulated by other ranks are then seen
-    one step late -- they never touch this rank's components, the states only feed proximity detection
-    and download -- and `finish()` drains the pipeline so every rank ends with the exact state of every
-    body.  With contiguous equal shards the library double-buffers its packed state (step k writes buffer
-    k & 1) and the gather runs IN PLACE on the buffer just written: per step one collective and one
-    import kernel, no packing, nothing on the critical path but the import."""
+def body_radii(pipe):
+    """Bounding radius of each body about its origin (from the collider descriptors the pipeline uploaded)."""
+    r = np.zeros(pipe.nb, np.float32)
+    for c in pipe._c:
+        if c.parent < 0:
+            continue
+        he = np.array(c.half_extents[:], np.float64)
+        ext = float(he[0]) if c.shape == 0 else float(np.linalg.norm(he))
+        off = float(np.linalg.norm(np.array(c.pos_wrt_parent_t[:], np.float64)))
+        r[c.parent] = max(r[c.parent], off + ext)
+    return r
 
-    def __init__(self, pipe, dist, rank, world_size, device, overlap=False):
-        self.pipe, self.dist, self.rank, self.world_size = pipe, dist, rank, world_size
-        self.overlap = bool(overlap)
-        self.device = device
-        self.pending = None
+
+class IslandShard:
+    def __init__(self, pipe, dist, rank, world_size, device, refresh_every=32, min_margin=0.5, overlap=None):
+        self.pipe, self.dist, self.rank, self.world_size, self.device = pipe, dist, rank, world_size, device
+        self.refresh_every = int(refresh_every)
+        self.min_margin = float(min_margin)
+        self.dt = float(pipe.params.dt)
         self.tick = 0
         comp = pipe.label_components()
         self.owner = partition_components(comp, world_size)
         pipe.set_owned_bodies((self.owner == rank).astype(np.uint8))
+        nb = pipe.nb
         self.state = state_tensor(pipe, device)
+        owner_t = torch.from_numpy(self.owner.astype(np.int64)).to(device)
+        self.mine = owner_t == rank
+        self.foreign = (owner_t >= 0) & ~self.mine
+        self.radius = torch.from_numpy(body_radii(pipe)).to(device)
         idx = [np.nonzero(self.owner == r)[0].astype(np.int64) for r in range(world_size)]
         self.counts = [len(i) for i in idx]
         self.maxc = max(max(self.counts), 1)
         self.my_idx = torch.from_numpy(idx[rank]).to(device)
-        self.send = torch.zeros(self.maxc, 13, device=device)
-        self.recv = torch.zeros(world_size * self.maxc, 13, device=device)
+        # full exchange: packed owned rows of every rank -> rows of the state table
+        self.full_send = torch.zeros(self.maxc, 13, device=device)
+        self.full_recv = torch.zeros(world_size * self.maxc, 13, device=device)
         others = [r for r in range(world_size) if r != rank]
-        self.imp_idx = torch.cat([torch.from_numpy(idx[r]) for r in others] or [torch.zeros(0, dtype=torch.int64)]).to(device).int()
-        self.rows = torch.cat([torch.arange(self.counts[r]) + r * self.maxc for r in others] or [torch.zeros(0, dtype=torch.int64)]).to(device)
-        self.imp_src = torch.zeros(len(self.imp_idx), 13, device=device)
-        # Fast path: every rank owns one contiguous, equally long range of body indices, in rank order
-        # (what weak-scaling replicas of a scene give).  The all-gather then runs IN PLACE on the library's
-        # state buffer -- one collective and one import kernel per step, no packing.
-        lo = [int(i[0]) if len(i) else -1 for i in idx]
-        self.inplace = (len(set(self.counts)) == 1 and self.counts[0] > 0 and
-                        all(np.array_equal(i, np.arange(l, l + len(i))) for i, l in zip(idx, lo)) and
-                        all(lo[r + 1] == lo[r] + self.counts[r] for r in range(world_size - 1)))
-        if self.inplace:
-            n = self.counts[0]
-            self.block = self.state[lo[0]:lo[0] + world_size * n].view(world_size, n * 13)
-            self.block_flat = self.block.view(-1)
-        if self.overlap and self.inplace:   # double-buffered library state: gather the buffer the step just wrote
-            p0, p1, nbytes = pipe.state_buffers()
-            self.tables = [_view(p0, nbytes, device), _view(p1, nbytes, device)]
-            self.table_ptr = [p0, p1]
-            n = self.counts[0]
-            self.blocks = [t[lo[0]:lo[0] + world_size * n].view(world_size, n * 13) for t in self.tables]
-        elif self.overlap:                  # packed: double-buffered snapshots / receive buffers
-            self.send2 = [torch.zeros(self.maxc, 13, device=device) for _ in range(2)]
-            self.recv2 = [torch.zeros(world_size * self.maxc, 13, device=device) for _ in range(2)]
+        self.other_idx = torch.cat([torch.from_numpy(idx[r]) for r in others] or [torch.zeros(0, dtype=torch.int64)]).to(device)
+        self.other_rows = torch.cat([torch.arange(self.counts[r]) + r * self.maxc for r in others] or [torch.zeros(0, dtype=torch.int64)]).to(device)
+        self.halo = torch.zeros(nb, dtype=torch.uint8, device=device)   # foreign bodies tracked here
+        self.export_max = 0          # per-step halo exchange: rows per rank (0 = no per-step collective)
+        self.halo_steps = 0          # steps that needed the per-step halo exchange (diagnostic)
+        self.refresh(classify=True)
 
-    def _import_from(self, recv):
-        if len(self.imp_idx):
-            torch.index_select(recv, 0, self.rows, out=self.imp_src)
-            self.pipe.import_states(self.imp_idx.data_ptr(), self.imp_src.data_ptr(), len(self.imp_idx))
+    # ---- full exchange (every refresh_every steps, at start-up and in finish) ----
+    def _gather_all(self):
+        n = self.counts[self.rank]
+        self.full_send[:n] = self.state.index_select(0, self.my_idx)
+        self.dist.all_gather_into_tensor(self.full_recv, self.full_send)
+        if len(self.other_idx):
+            self.state.index_copy_(0, self.other_idx, self.full_recv.index_select(0, self.other_rows))
+
+    def refresh(self, classify=True):
+        """All ranks get all states; each re-derives the bodies of other ranks it has to track (its halo) and learns which
+        of its own bodies the others track (its exports)."""
+        self._gather_all()
+        if not classify:
+            return
+        pos, lin = self.state[:, 0:3], self.state[:, 7:10]
+        speed = lin.norm(dim=1).max() if lin.numel() else torch.zeros((), device=self.device)
+        margin = self.min_margin + 2.0 * self.refresh_every * self.dt * speed
+        r = self.radius.unsqueeze(1)
+        if bool(self.mine.any()):
+            lo = (pos - r)[self.mine].min(dim=0).values - margin
+            hi = (pos + r)[self.mine].max(dim=0).values + margin
+            near = ((pos + r) >= lo).all(dim=1) & ((pos - r) <= hi).all(dim=1)
+            self.halo = (near & self.foreign).to(torch.uint8)
+        else:
+            self.halo = torch.zeros_like(self.halo)
+        self.pipe.set_halo_bodies(self.halo.data_ptr())
+        self.pipe.import_halo()
+        # who tracks whom: all halo masks -> my export list and everybody's (for unpacking)
+        masks = torch.zeros(self.world_size, self.halo.numel(), dtype=torch.uint8, device=self.device)
+        self.dist.all_gather_into_tensor(masks.view(-1), self.halo)
+        tracked = masks.any(dim=0)                      # bodies tracked by a rank other than their owner
+        owner_t = torch.from_numpy(self.owner.astype(np.int64)).to(self.device)
+        self.export_idx = []
+        counts = []
+        for rk in range(self.world_size):
+            e = torch.nonzero(tracked & (owner_t == rk)).flatten()
+            self.export_idx.append(e)
+            counts.append(int(e.numel()))               # (one host synchronisation per refresh)
+        self.export_max = max(counts) if counts else 0
+        if self.export_max > 0:
+            self.halo_send = torch.zeros(self.export_max, 13, device=self.device)
+            self.halo_recv = torch.zeros(self.world_size * self.export_max, 13, device=self.device)
+            self.halo_dst = torch.cat([e for rk, e in enumerate(self.export_idx) if rk != self.rank] or [torch.zeros(0, dtype=torch.int64, device=self.device)])
+            self.halo_rows = torch.cat([torch.arange(int(e.numel()), device=self.device) + rk * self.export_max
+                                        for rk, e in enumerate(self.export_idx) if rk != self.rank] or [torch.zeros(0, dtype=torch.int64, device=self.device)])
+
+    # ---- per step ----
+    def exchange(self):
+        """Call after every step: boundary (halo) states every step, everything every `refresh_every` steps."""
+        self.tick += 1
+        if self.tick % self.refresh_every == 0:
+            self.refresh(classify=True)
+            return
+        if self.export_max == 0:
+            return
+        self.halo_steps += 1
+        mine = self.export_idx[self.rank]
+        if mine.numel():
+            self.halo_send[:mine.numel()] = self.state.index_select(0, mine)
+        self.dist.all_gather_into_tensor(self.halo_recv, self.halo_send)
+        if self.halo_dst.numel():
+            self.state.index_copy_(0, self.halo_dst, self.halo_recv.index_select(0, self.halo_rows))
+        self.pipe.import_halo()
 
     def finish(self):
-        """Drain the asynchronous exchange: afterwards every rank holds the current state of every body."""
-        if self.pending is not None:
-            work, recv = self.pending
-            work.wait()
-            if isinstance(recv, int):
-                if len(self.imp_idx):
-                    self.pipe.import_states_from(self.imp_idx.data_ptr(), self.table_ptr[recv], len(self.imp_idx))
-            else:
-                self._import_from(recv)
-            self.pending = None
-
-    def exchange(self):
-        """All-gather the owned body states and import the states simulated by the other ranks."""
-        if self.inplace and hasattr(self, "tables"):
-            k = self.table_ptr.index(self.pipe.state_buffer()[0])   # the buffer the step that was just enqueued writes
-            if not self.overlap:   # (overlap switched off at run time: same buffers, synchronous)
-                self.finish()
-                self.dist.all_gather_into_tensor(self.blocks[k].view(-1), self.blocks[k][self.rank])
-                if len(self.imp_idx):
-                    self.pipe.import_states_from(self.imp_idx.data_ptr(), self.table_ptr[k], len(self.imp_idx))
-                return
-            work = self.dist.all_gather_into_tensor(self.blocks[k].view(-1), self.blocks[k][self.rank], async_op=True)
-            previous, self.pending = self.pending, (work, k)
-            if previous is not None:   # the previous step's gather: import it before the next step
-                previous[0].wait()
-                if len(self.imp_idx):
-                    self.pipe.import_states_from(self.imp_idx.data_ptr(), self.table_ptr[previous[1]], len(self.imp_idx))
-            return
-        if self.overlap:
-            send, recv = self.send2[self.tick & 1], self.recv2[self.tick & 1]
-            self.tick += 1
-            send[:self.counts[self.rank]] = self.state.index_select(0, self.my_idx)   # snapshot: the next step overwrites the rows
-            work = self.dist.all_gather_into_tensor(recv, send, async_op=True)
-            previous, self.pending = self.pending, (work, recv)
-            if previous is not None:   # import what the previous step's gather brought, before the next step
-                previous[0].wait()
-                self._import_from(previous[1])
-            return
-        if self.inplace:
-            self.dist.all_gather_into_tensor(self.block_flat, self.block[self.rank])
-            if len(self.imp_idx):
-                self.pipe.import_states(self.imp_idx.data_ptr(), 0, len(self.imp_idx))
-            return
-        self.send[:self.counts[self.rank]] = self.state.index_select(0, self.my_idx)
-        self.dist.all_gather_into_tensor(self.recv, self.send)
-        if len(self.imp_idx):
-            torch.index_select(self.recv, 0, self.rows, out=self.imp_src)
-            self.pipe.import_states(self.imp_idx.data_ptr(), self.imp_src.data_ptr(), len(self.imp_idx))
+        """Afterwards every rank holds the current state of every body."""
+        self.refresh(classify=False)

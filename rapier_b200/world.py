@@ -148,6 +148,13 @@ class PhysicsPipeline:
         assert o.shape == (self.nb,)
         self._check(self.L.rb_world_set_owned_bodies(self.h, o.ctypes.data))
 
+    def set_halo_bodies(self, flags_dev_ptr):
+        """Which bodies of other ranks are tracked here (device array of num_bodies bytes; see sharding.py)."""
+        self._check(self.L.rb_world_set_halo_bodies(self.h, flags_dev_ptr))
+
+    def import_halo(self):
+        self._check(self.L.rb_world_import_halo(self.h))
+
     def state_buffer(self):
         p = C.c_void_p()
         n = C.c_int64()

@@ -21,12 +21,13 @@ dist.init_process_group("gloo")
 rank, ws = dist.get_rank(), dist.get_world_size()
 scene = scenes.pyramids(*{shape!r})
 w = PhysicsWorld(scene, _lib=emul_lib.lib()); w._flush()
-shard = IslandShard(w.physics_pipeline, dist, rank, ws, torch.device("cpu"), overlap={overlap!r})
+shard = IslandShard(w.physics_pipeline, dist, rank, ws, torch.device("cpu"), refresh_every={refresh!r})
 assert sorted(set(shard.owner.tolist())) == [-1, 0, 1], set(shard.owner.tolist())
-assert shard.inplace == {inplace!r}, shard.inplace
 for _ in range(25):
     w.physics_pipeline.step(scene.gravity, 1)
     shard.exchange()
+assert (shard.halo_steps > 0) == {halo!r}, (shard.halo_steps, shard.export_max)
+mid_pose, _ = w.body_states()     # before finish(): the rows of far foreign bodies are at most `refresh` steps old
 shard.finish()
 pose, vel = w.body_states()
 np.save({out!r} + f"_{{rank}}.npy", np.concatenate([pose, vel], axis=1))
@@ -37,19 +38,27 @@ dist.destroy_process_group()
 import pytest
 
 
-@pytest.mark.parametrize("shape,inplace,overlap", [((2, 2, 6), True, False), ((1, 3, 6), False, False), ((2, 2, 6), True, True), ((1, 3, 6), False, True)],
-                         ids=["equal_contiguous_shards_in_place", "unequal_shards_packed", "in_place_double_buffered_async", "packed_async"])
-def test_sharded_run_matches_single_process(tmp_path, shape, inplace, overlap):
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("shape,halo,refresh", [((2, 2, 6), False, 8), ((1, 3, 6), True, 8), ((1, 3, 6), True, 1000)],
+                         ids=["far_shards_no_per_step_collective", "neighbouring_pyramids_halo_exchange", "halo_exchange_without_refresh"])
+def test_sharded_run_matches_single_process(tmp_path, shape, halo, refresh):
     import emul_lib
     from rapier_b200 import scenes
     from rapier_b200.world import PhysicsWorld
     emul_lib.lib()
     out = str(tmp_path / "state")
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, out=out, shape=shape, inplace=inplace, overlap=overlap))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    script.write_text(WORKER.format(root=ROOT, out=out, shape=shape, halo=halo, refresh=refresh))
+    port = str(_free_port())
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
     subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                           "--master-port", "29533", str(script)], env=env, timeout=600)
+                           "--master-port", port, str(script)], env=env, timeout=600)
     scene = scenes.pyramids(*shape)
     ref = PhysicsWorld(scene, _lib=emul_lib.lib())
     ref.step(25)
@@ -58,6 +67,29 @@ def test_sharded_run_matches_single_process(tmp_path, shape, inplace, overlap):
     for r in range(2):
         got = np.load(out + f"_{r}.npy")
         assert (got.view(np.uint32) == expect.view(np.uint32)).all(), f"rank {r} differs from the single-process run"
+
+
+def test_contact_across_shards_is_reported():
+    """A body simulated here that comes to TOUCH a body simulated by another rank (here: a tracked halo body that is
+    never updated) must raise RB_ERR_SHARD instead of being solved against a frozen neighbour."""
+    import emul_lib
+    from rapier_b200 import scenes
+    from rapier_b200.sets import ColliderBuilder, RigidBodyBuilder
+    from rapier_b200.world import PhysicsWorld, RapierError
+    s = scenes.Scene("two_shards", gravity=(0.0, -9.81, 0.0))
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(20.0, 0.5, 20.0))
+    a = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.5, 0.0)).linvel((8.0, 0.0, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5).friction(0.0))
+    b = s.insert(RigidBodyBuilder.dynamic().translation((3.0, 0.5, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    w = PhysicsWorld(s, _lib=emul_lib.lib())
+    w._flush()
+    pipe = w.physics_pipeline
+    owned = np.zeros(3, np.uint8); owned[a] = 1
+    pipe.set_owned_bodies(owned)
+    halo = np.zeros(3, np.uint8); halo[b] = 1
+    pipe.set_halo_bodies(halo.ctypes.data)
+    with pytest.raises(RapierError, match="-6"):
+        for _ in range(120):
+            pipe.step(s.gravity, 1)
 
 
 def test_partition_is_balanced_and_whole_components():
