@@ -222,7 +222,7 @@ def main():
     if world_size > 1:
         from rapier_b200.sharding import IslandShard
         shard = IslandShard(pipe, dist, rank, world_size, torch.device("cuda", local_rank),
-                            refresh_every=int(os.environ.get("RB_SHARD_REFRESH", "32")))   # halo states every step, everything every 32 steps
+                            refresh_every=int(os.environ.get("RB_SHARD_REFRESH", "128")))   # halo states every step, everything every 128 steps
         exchange = shard.exchange
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if args.l2 == "flush" else None

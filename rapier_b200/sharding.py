@@ -4,7 +4,7 @@ simulates only the bodies it owns.  What crosses NVLink is the north star's "all
   * HALO bodies -- bodies of other ranks inside (or near) the bounding box of this rank's bodies -- are tracked here
     for proximity detection only; their states (13 floats: t3 q4 linvel3 angvel3) are all-gathered EVERY step and
     imported before the next one.  A rank with no halo takes part in no per-step collective at all.
-  * every `refresh_every` steps the owned states of ALL bodies are all-gathered, every rank re-derives its halo set
+  * every `refresh_every` (128) steps the owned states of ALL bodies are all-gathered, every rank re-derives its halo set
     from them (bounding box of its own bodies, inflated by a margin that covers `refresh_every` steps at the fastest
     body's current speed) and tells the others which of their bodies it now tracks.
   * a CONTACT between an owned and a halo body means two shards' islands merged: the device raises RB_ERR_SHARD
@@ -62,7 +62,7 @@ def body_radii(pipe):
 
 
 class IslandShard:
-    def __init__(self, pipe, dist, rank, world_size, device, refresh_every=32, min_margin=0.5, overlap=None):
+    def __init__(self, pipe, dist, rank, world_size, device, refresh_every=128, min_margin=0.5, overlap=None):
         self.pipe, self.dist, self.rank, self.world_size, self.device = pipe, dist, rank, world_size, device
         self.refresh_every = int(refresh_every)
         self.min_margin = float(min_margin)
@@ -88,9 +88,11 @@ class IslandShard:
         self.other_idx = torch.cat([torch.from_numpy(idx[r]) for r in others] or [torch.zeros(0, dtype=torch.int64)]).to(device)
         self.other_rows = torch.cat([torch.arange(self.counts[r]) + r * self.maxc for r in others] or [torch.zeros(0, dtype=torch.int64)]).to(device)
         self.halo = torch.zeros(nb, dtype=torch.uint8, device=device)   # foreign bodies tracked here
+        self.owner_t = owner_t
         self.export_max = 0          # per-step halo exchange: rows per rank (0 = no per-step collective)
         self.halo_steps = 0          # steps that needed the per-step halo exchange (diagnostic)
-        self.refresh(classify=True)
+        self.refreshes = 0
+        self.refresh(classify=True, force=True)
 
     # ---- full exchange (every refresh_every steps, at start-up and in finish) ----
     def _gather_all(self):
@@ -100,36 +102,41 @@ class IslandShard:
         if len(self.other_idx):
             self.state.index_copy_(0, self.other_idx, self.full_recv.index_select(0, self.other_rows))
 
-    def refresh(self, classify=True):
-        """All ranks get all states; each re-derives the bodies of other ranks it has to track (its halo) and learns which
-        of its own bodies the others track (its exports)."""
+    def refresh(self, classify=True, force=False):
+        """All ranks get all states; each re-derives the bodies of other ranks it has to track (its halo) and, when any
+        rank's halo changed, learns which of its own bodies the others track (its exports).  One host synchronisation."""
         self._gather_all()
         if not classify:
             return
+        self.refreshes += 1
         pos, lin = self.state[:, 0:3], self.state[:, 7:10]
         speed = lin.norm(dim=1).max() if lin.numel() else torch.zeros((), device=self.device)
         margin = self.min_margin + 2.0 * self.refresh_every * self.dt * speed
         r = self.radius.unsqueeze(1)
-        if bool(self.mine.any()):
-            lo = (pos - r)[self.mine].min(dim=0).values - margin
-            hi = (pos + r)[self.mine].max(dim=0).values + margin
-            near = ((pos + r) >= lo).all(dim=1) & ((pos - r) <= hi).all(dim=1)
-            self.halo = (near & self.foreign).to(torch.uint8)
+        lo_all, hi_all = pos - r, pos + r
+        if bool(self.counts[self.rank]):
+            lo = lo_all[self.my_idx].min(dim=0).values - margin
+            hi = hi_all[self.my_idx].max(dim=0).values + margin
+            halo = ((hi_all >= lo).all(dim=1) & (lo_all <= hi).all(dim=1) & self.foreign).to(torch.uint8)
         else:
-            self.halo = torch.zeros_like(self.halo)
+            halo = torch.zeros_like(self.halo)
+        changed = (halo != self.halo).any().to(torch.int32).reshape(1)
+        self.dist.all_reduce(changed, op=self.dist.ReduceOp.MAX)
+        if not force and int(changed.item()) == 0:     # (the host synchronisation of a refresh)
+            return
+        self.halo = halo
         self.pipe.set_halo_bodies(self.halo.data_ptr())
         self.pipe.import_halo()
         # who tracks whom: all halo masks -> my export list and everybody's (for unpacking)
         masks = torch.zeros(self.world_size, self.halo.numel(), dtype=torch.uint8, device=self.device)
         self.dist.all_gather_into_tensor(masks.view(-1), self.halo)
         tracked = masks.any(dim=0)                      # bodies tracked by a rank other than their owner
-        owner_t = torch.from_numpy(self.owner.astype(np.int64)).to(self.device)
         self.export_idx = []
         counts = []
         for rk in range(self.world_size):
-            e = torch.nonzero(tracked & (owner_t == rk)).flatten()
+            e = torch.nonzero(tracked & (self.owner_t == rk)).flatten()
             self.export_idx.append(e)
-            counts.append(int(e.numel()))               # (one host synchronisation per refresh)
+            counts.append(int(e.numel()))
         self.export_max = max(counts) if counts else 0
         if self.export_max > 0:
             self.halo_send = torch.zeros(self.export_max, 13, device=self.device)
