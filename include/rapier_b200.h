@@ -72,7 +72,8 @@ enum {
     RB_BODY_GYROSCOPIC = 1,          /* forces.gyroscopic_forces_enabled (default on, rigid_body.rs:1579) */
     RB_BODY_ALLOW_FAST_ROTATION = 2, /* ccd.allow_fast_rotation */
     RB_BODY_LOCK_TX = 4, RB_BODY_LOCK_TY = 8, RB_BODY_LOCK_TZ = 16,   /* LockedAxes */
-    RB_BODY_LOCK_RX = 32, RB_BODY_LOCK_RY = 64, RB_BODY_LOCK_RZ = 128
+    RB_BODY_LOCK_RX = 32, RB_BODY_LOCK_RY = 64, RB_BODY_LOCK_RZ = 128,
+    RB_BODY_NO_SLEEP = 256           /* RigidBodyActivation::cannot_sleep() (RigidBodyBuilder::can_sleep(false)); default: may sleep */
 };
 
 /* One rigid body as the caller's RigidBodySet holds it (src/dynamics/rigid_body.rs:48-70).
@@ -204,6 +205,15 @@ int rb_world_reserve(RbWorld* w, int32_t max_bodies, int32_t max_colliders);
 int rb_world_insert(RbWorld* w, int32_t num_bodies, const RbBodyDesc* bodies, int32_t num_colliders,
                     const RbColliderDesc* colliders, int32_t* first_body_index, int32_t* first_collider_index);
 int rb_world_remove_bodies(RbWorld* w, int32_t n, const int32_t* body_indices);
+
+/* ---- sleeping (src/dynamics/island_manager/sleep.rs, manager.rs:320-425; rigid_body_components.rs:1417-1470) ----
+ * A connected component of touching contacts / joints falls asleep as a whole once EVERY body in it has moved less
+ * than 0.05 length units / s for 0.5 s (and may sleep at all: RB_BODY_NO_SLEEP); it wakes as a whole when a contact
+ * with one of its bodies begins, when one of its bodies is changed through rb_world_set_body_states / rb_world_wake_up,
+ * or when a body is removed.  Sleeping bodies keep their contact pairs and warm-start data but are neither solved nor
+ * integrated.  sleeping[num_bodies]: 1 = asleep. */
+int rb_world_get_sleeping(RbWorld* w, uint8_t* sleeping);
+int rb_world_wake_up(RbWorld* w, int32_t n, const int32_t* body_indices);
 
 /* Unit-level known-answer evaluation for parity tests: runs ONE device function of the path (named: "pose_drift"
  * contact_pair.rs:299-323, "reduce_manifold" manifold_reduction.rs:4-84, "normal_solve" / "tangent_solve"

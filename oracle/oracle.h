@@ -23,6 +23,9 @@ void orc_world_destroy(OrcWorld* w);
 int orc_world_set_params(OrcWorld* w, const RbIntegrationParameters* params);
 int orc_world_set_scene(OrcWorld* w, int32_t nb, const RbBodyDesc* bodies, int32_t nc,
                         const RbColliderDesc* colliders, int32_t nj, const RbJointDesc* joints);
+// Mirrors of rb_world_get_sleeping / rb_world_wake_up.
+int orc_world_get_sleeping(OrcWorld* w, uint8_t* sleeping);
+int orc_world_wake_up(OrcWorld* w, int32_t n, const int32_t* indices);
 // Mirrors of rb_world_insert / rb_world_remove_bodies (appended bodies and colliders; tombstoned removals).
 int orc_world_insert(OrcWorld* w, int32_t nb, const RbBodyDesc* bodies, int32_t nc, const RbColliderDesc* colliders);
 int orc_world_remove_bodies(OrcWorld* w, int32_t n, const int32_t* indices);

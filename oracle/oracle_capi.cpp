@@ -78,6 +78,26 @@ int orc_world_set_scene(OrcWorld* w, int32_t nb, const RbBodyDesc* bodies, int32
     if (!w) return RB_ERR_INVALID;
     return set_scene(w->w, nb, bodies, nc, colliders, nj, joints);
 }
+int orc_world_wake_up(OrcWorld* o, int32_t n, const int32_t* indices) {
+    if (!o || n < 0) return RB_ERR_INVALID;
+    World& w = o->w;
+    for (int k = 0; k < n; ++k) {
+        const int i = indices[k];
+        if (i < 0 || i >= (int)w.bodies.size()) return RB_ERR_INVALID;
+        if (!w.bodies[i].is_dynamic()) continue;
+        const int root = i < (int)w.island_of.size() ? w.island_of[i] : -1;
+        for (int b = 0; b < (int)w.bodies.size(); ++b) {
+            const bool same = b == i || (root >= 0 && b < (int)w.island_of.size() && w.island_of[b] == root);
+            if (same && w.bodies[b].sleeping) { w.bodies[b].sleeping = false; w.bodies[b].sleep_time = 0.0f; }
+        }
+    }
+    return RB_OK;
+}
+int orc_world_get_sleeping(OrcWorld* o, uint8_t* out) {
+    if (!o || !out) return RB_ERR_INVALID;
+    for (size_t i = 0; i < o->w.bodies.size(); ++i) out[i] = o->w.bodies[i].sleeping ? 1 : 0;
+    return RB_OK;
+}
 int orc_world_insert(OrcWorld* w, int32_t nb, const RbBodyDesc* bodies, int32_t nc, const RbColliderDesc* colliders) {
     if (!w || nb < 0 || nc < 0) return RB_ERR_INVALID;
     return insert(w->w, nb, bodies, nc, colliders);
@@ -107,7 +127,7 @@ int orc_world_set_body_states(OrcWorld* o, int32_t n, const int32_t* indices, co
             b.angvel = V3{vel6[k * 6 + 3], vel6[k * 6 + 4], vel6[k * 6 + 5]};
         }
     }
-    return RB_OK;
+    return orc_world_wake_up(o, n, indices);   // a user change wakes the body's island (user_changes.rs)
 }
 int orc_world_step(OrcWorld* w, const float gravity[3], int32_t nsteps) {
     if (!w || !gravity) return RB_ERR_INVALID;

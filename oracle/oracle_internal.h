@@ -54,7 +54,13 @@ struct Body {
     Sdp3 eff_world_inv_inertia;
     // per-step forces
     V3 force, torque;
+    // RigidBodyActivation (rigid_body_components.rs:1296-1326) + mprops.max_extent (:491-515)
+    bool sleeping = false;
+    float sleep_time = 0.0f;          // time_since_can_sleep
+    Pose sleep_prev_pose{Q4{0.f, 0.f, 0.f, 1.f}, V3{0.f, 0.f, 0.f}};
+    float max_extent = 0.0f;
     bool is_dynamic() const { return type == RB_BODY_DYNAMIC; }
+    bool is_awake() const { return type == RB_BODY_DYNAMIC && !sleeping; }   // member of the active set
 };
 
 struct Aabb {
@@ -188,6 +194,8 @@ struct World {
     std::vector<Pair> pairs;           // sorted by (c1, c2)
     std::vector<Mask128> color_masks;  // per body (narrow_phase/mod.rs body_solver_color_masks)
     bool bp_dirty = true;
+    std::vector<int> island_of;        // connected component (root body) of every dynamic body, -1 otherwise
+    bool islands_dirty = true;         // the touching set or the joints changed: relabel
     bool static_dirty = true;          // the sorted list of static colliders must be rebuilt
     std::vector<int> static_sorted;    // static colliders by fat min-x
     float static_max_width = 0.0f;     // widest of them along x

@@ -67,8 +67,8 @@ static void generate(World& w, int pair_index, Constraint& c) {
     const Pair& p = w.pairs[pair_index];
     memset(&c, 0, sizeof(c));
     c.pair = pair_index;
-    bool d1 = p.b1 >= 0 && w.bodies[p.b1].is_dynamic();
-    bool d2 = p.b2 >= 0 && w.bodies[p.b2].is_dynamic();
+    bool d1 = p.b1 >= 0 && w.bodies[p.b1].is_awake();
+    bool d2 = p.b2 >= 0 && w.bodies[p.b2].is_awake();
     c.id1 = d1 ? (uint32_t)p.b1 : NO_BODY;
     c.id2 = d2 ? (uint32_t)p.b2 : NO_BODY;
     GatheredBody g1 = gather(w, c.id1), g2 = gather(w, c.id2);
@@ -560,7 +560,7 @@ void solve_island(World& w, V3 gravity) {
     for (int i = 0; i < nb; ++i) {
         Body& b = w.bodies[i];
         SolverBody& s = w.sb[i];
-        if (b.is_dynamic()) {
+        if (b.is_awake()) {
             V3 eff_mass = V3{inv_exact0(b.eff_inv_mass.x), inv_exact0(b.eff_inv_mass.y), inv_exact0(b.eff_inv_mass.z)};
             b.force = b.user_force + cmul(gravity, eff_mass) * b.gravity_scale;
             b.torque = b.user_torque;
@@ -569,7 +569,7 @@ void solve_island(World& w, V3 gravity) {
         s.lin = b.linvel;
         s.ang = b.angvel;
         s.pose = pose_prepend_translation(b.pos, b.local_com);
-        if (b.is_dynamic()) {
+        if (b.is_awake()) {
             s.ii = b.eff_world_inv_inertia;
             s.im = b.eff_inv_mass;
         } else {
@@ -578,15 +578,15 @@ void solve_island(World& w, V3 gravity) {
         }
         s.incr_ang = sdp_mul(b.eff_world_inv_inertia, b.torque) * sub_dt;
         s.incr_lin = cmul(b.force, b.eff_inv_mass) * sub_dt;
-        s.gyro = (b.flags & RB_BODY_GYROSCOPIC) && b.is_dynamic();
+        s.gyro = (b.flags & RB_BODY_GYROSCOPIC) && b.is_awake();
     }
 
     // Solver-active manifolds, in stage order (solver_graph.rs:129-361; init.rs:163-254).
     std::vector<int> colors_of(w.pairs.size(), -1);
     for (int i = 0; i < (int)w.pairs.size(); ++i) {
         const Pair& p = w.pairs[i];
-        bool d1 = p.b1 >= 0 && w.bodies[p.b1].is_dynamic();
-        bool d2 = p.b2 >= 0 && w.bodies[p.b2].is_dynamic();
+        bool d1 = p.b1 >= 0 && w.bodies[p.b1].is_awake();
+        bool d2 = p.b2 >= 0 && w.bodies[p.b2].is_awake();
         if (p.nsc > 0 && (d1 || d2)) colors_of[i] = p.color;
     }
     std::vector<int> pair_order;
@@ -606,15 +606,18 @@ void solve_island(World& w, V3 gravity) {
     std::vector<int> jrow_start(nj + 1, 0);
     for (int i = 0; i < nj; ++i) {
         Joint& j = w.joints[i];
-        jcolors[i] = j.color;
         const Body& b1 = w.bodies[j.body1];
         const Body& b2 = w.bodies[j.body2];
+        const bool active = b1.is_awake() || b2.is_awake();   // joints of a sleeping island are not solved
+        jcolors[i] = active ? j.color : -1;
+        j.sid1 = b1.is_awake() ? (uint32_t)j.body1 : NO_BODY;
+        j.sid2 = b2.is_awake() ? (uint32_t)j.body2 : NO_BODY;
         // generic_joint.rs:624-636 transform_to_solver_body_space
         j.sframe1 = j.local_frame1;
         j.sframe2 = j.local_frame2;
-        if (!b1.is_dynamic()) j.sframe1 = pose_mul(b1.pos, j.local_frame1);
+        if (!b1.is_awake()) j.sframe1 = pose_mul(b1.pos, j.local_frame1);
         else j.sframe1.t = j.local_frame1.t - b1.local_com;
-        if (!b2.is_dynamic()) j.sframe2 = pose_mul(b2.pos, j.local_frame2);
+        if (!b2.is_awake()) j.sframe2 = pose_mul(b2.pos, j.local_frame2);
         else j.sframe2.t = j.local_frame2.t - b2.local_com;
         jrow_start[i + 1] = jrow_start[i] + joint_rows_of(j);
     }
@@ -660,7 +663,7 @@ void solve_island(World& w, V3 gravity) {
         // S3 velocity increments + gyroscopic correction (worker.rs:235-284)
         pool.parallel_for(0, nb, 256, [&](int i) {
             SolverBody& s = w.sb[i];
-            if (!w.bodies[i].is_dynamic()) return;
+            if (!w.bodies[i].is_awake()) return;
             s.lin = s.lin + s.incr_lin;
             s.ang = s.ang + s.incr_ang;
             if (s.gyro) {
@@ -672,7 +675,7 @@ void solve_island(World& w, V3 gravity) {
         // S4 joint rows rebuilt from the current poses (worker.rs:291-432); impulses restart from 0
         // (warmstart_joints = false, joint_constraint_builder.rs:135-151).
         pool.parallel_for(0, nj, 64, [&](int i) {
-            if (w.joints[i].color < 0) return;
+            if (jcolors[i] < 0) return;
             joint_update(w, w.joints[i], sub_dt, &w.jrows[jrow_start[i]]);
         });
         // S5 update + warmstart, colour by colour (worker.rs:438-539)
@@ -691,7 +694,7 @@ void solve_island(World& w, V3 gravity) {
         // S7 integrate positions (worker.rs:568-631; rigid_body_components.rs:884-898)
         pool.parallel_for(0, nb, 256, [&](int i) {
             SolverBody& s = w.sb[i];
-            if (!w.bodies[i].is_dynamic()) return;
+            if (!w.bodies[i].is_awake()) return;
             if (max_lin != 3.4028235e38f) {
                 float n = length(s.lin);
                 if (n > max_lin) s.lin = s.lin * (max_lin / n);
@@ -718,13 +721,13 @@ void solve_island(World& w, V3 gravity) {
     for (int q = 0; q < ncons; ++q) writeback_impulses(w, w.cons[q]);
     for (int i = 0; i < nj; ++i) {
         Joint& j = w.joints[i];
-        if (j.color < 0) continue;
+        if (jcolors[i] < 0) continue;
         for (int r = jrow_start[i]; r < jrow_start[i + 1]; ++r) j.impulses[w.jrows[r].dof] = w.jrows[r].impulse;
     }
     // S11 body writeback (worker.rs:809-897; rigid_body_components.rs:835-841)
     for (int i = 0; i < nb; ++i) {
         Body& b = w.bodies[i];
-        if (!b.is_dynamic()) continue;
+        if (!b.is_awake()) continue;
         const SolverBody& s = w.sb[i];
         b.linvel = s.lin * (1.0f / (1.0f + P.dt * b.lin_damping));
         b.angvel = s.ang * (1.0f / (1.0f + P.dt * b.ang_damping));

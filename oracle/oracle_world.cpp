@@ -128,6 +128,14 @@ static int recompute_mass_properties(World& w, int first_body = 0, int first_col
         }
         b.principal_inertia = V3{inv_exact0(b.inv_principal_inertia.x), inv_exact0(b.inv_principal_inertia.y),
                                  inv_exact0(b.inv_principal_inertia.z)};
+        // recompute_max_extent (rigid_body_components.rs:491-515): bounding spheres about the local centre of mass
+        b.max_extent = 0.0f;
+        for (size_t ci = (size_t)first_collider; ci < w.colliders.size(); ++ci) {
+            const Collider& c = w.colliders[ci];
+            if (c.parent != bi) continue;
+            const float radius = c.shape == RB_SHAPE_BALL ? c.he.x : length(c.he);
+            b.max_extent = fmax2(b.max_extent, length(c.pos_wrt_parent.t - b.local_com) + radius);
+        }
     }
     return RB_OK;
 }
@@ -551,16 +559,35 @@ static void assign_pair_color(World& w, Pair& p) {
     p.color_bodies[1] = cb[1];
 }
 
+// Whole-island wake (island_manager/sleep.rs:8-80): every body of the component, timers reset ("strong").
+static void wake_island_of(World& w, int body) {
+    if (body < 0 || body >= (int)w.island_of.size()) return;
+    const int root = w.island_of[body];
+    if (root < 0) { w.bodies[body].sleeping = false; w.bodies[body].sleep_time = 0.0f; return; }
+    for (int i = 0; i < (int)w.bodies.size(); ++i)
+        if (w.island_of[i] == root && w.bodies[i].sleeping) { w.bodies[i].sleeping = false; w.bodies[i].sleep_time = 0.0f; }
+}
+
 static void narrow_phase(World& w) {
     std::vector<int> started;
+    std::vector<int> to_wake;
     for (int i = 0; i < (int)w.pairs.size(); ++i) {
         Pair& p = w.pairs[i];
+        // pairs without an awake body are not updated (their bodies do not move)
+        const bool a1 = p.b1 >= 0 && w.bodies[p.b1].is_awake(), a2 = p.b2 >= 0 && w.bodies[p.b2].is_awake();
+        if (!a1 && !a2) continue;
         if (process_pair(w, p)) {
-            if (p.nsc > 0) started.push_back(i);
-            else clear_pair_color(w, p);  // end-touch frees the colour first (contacts.rs:333-335)
+            if (p.nsc > 0) {
+                started.push_back(i);
+                // a contact that begins wakes the sleeping side's whole island (narrow_phase/mod.rs:53-67)
+                if (p.b1 >= 0 && w.bodies[p.b1].is_dynamic() && w.bodies[p.b1].sleeping) to_wake.push_back(p.b1);
+                if (p.b2 >= 0 && w.bodies[p.b2].is_dynamic() && w.bodies[p.b2].sleeping) to_wake.push_back(p.b2);
+            } else clear_pair_color(w, p);  // end-touch frees the colour first (contacts.rs:333-335)
             w.counters.schedule_rebuilt = 1;
+            w.islands_dirty = true;
         }
     }
+    for (int b : to_wake) wake_island_of(w, b);
     // Deferred greedy colouring in canonical (min body, max body, edge) order (contacts.rs:366-385).
     auto bid = [](int b) { return b < 0 ? 0xffffffffu : (uint32_t)b; };
     std::stable_sort(started.begin(), started.end(), [&](int x, int y) {
@@ -573,6 +600,68 @@ static void narrow_phase(World& w) {
         return x < y;
     });
     for (int i : started) assign_pair_color(w, w.pairs[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Islands and sleeping.
+// ---------------------------------------------------------------------------------------------
+static int dsu_find(std::vector<int>& p, int x) {
+    while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; }
+    return x;
+}
+static void label_islands(World& w) {
+    const int nb = (int)w.bodies.size();
+    std::vector<int> parent(nb);
+    for (int i = 0; i < nb; ++i) parent[i] = i;
+    auto unite = [&](int a, int b) {
+        a = dsu_find(parent, a); b = dsu_find(parent, b);
+        if (a != b) parent[std::max(a, b)] = std::min(a, b);   // the smaller index is the root (as on the device)
+    };
+    for (const Pair& p : w.pairs)
+        if (p.nsc > 0 && p.b1 >= 0 && p.b2 >= 0 && w.bodies[p.b1].is_dynamic() && w.bodies[p.b2].is_dynamic()) unite(p.b1, p.b2);
+    for (const Joint& j : w.joints)
+        if (w.bodies[j.body1].is_dynamic() && w.bodies[j.body2].is_dynamic()) unite(j.body1, j.body2);
+    w.island_of.assign(nb, -1);
+    for (int i = 0; i < nb; ++i)
+        if (w.bodies[i].is_dynamic()) w.island_of[i] = dsu_find(parent, i);
+    w.islands_dirty = false;
+}
+
+// RigidBodyActivation::update_energy (rigid_body_components.rs:1417-1470) for every awake body, then the
+// whole-island decision (island_manager/manager.rs:367-392): an island sleeps when all of its bodies are eligible.
+static void update_sleep(World& w) {
+    const float dt = w.params.p.dt;
+    const float linear_threshold = 0.05f * w.params.p.length_unit;   // default_normalized_linear_threshold
+    const float angular_threshold = 0.5f, time_until_sleep = 0.5f;
+    const int nb = (int)w.bodies.size();
+    std::vector<char> blocked(nb, 0);
+    bool any = false;
+    for (int i = 0; i < nb; ++i) {
+        Body& b = w.bodies[i];
+        if (!b.is_awake()) continue;
+        const bool may = !(b.flags & RB_BODY_NO_SLEEP);
+        const Pose prev = b.sleep_prev_pose;
+        b.sleep_prev_pose = b.pos;
+        const float sq_angvel = dot(b.angvel, b.angvel);
+        bool angular_ok;
+        if (b.max_extent > 0.0f) angular_ok = may && sq_angvel < 1.5707963267948966f * 1.5707963267948966f;
+        else angular_ok = may && sq_angvel < angular_threshold * angular_threshold;
+        const float drift = relative_pose_drift(prev, b.pos, b.max_extent);
+        const bool can = may && angular_ok && drift * 0.5f < linear_threshold * dt;
+        b.sleep_time = can ? b.sleep_time + dt : 0.0f;
+        if (!(b.sleep_time >= time_until_sleep)) blocked[w.island_of[i]] = 1;
+        any = true;
+    }
+    if (!any) return;
+    for (int i = 0; i < nb; ++i) {
+        Body& b = w.bodies[i];
+        if (!b.is_awake() || blocked[w.island_of[i]]) continue;
+        b.sleeping = true;                 // RigidBody::sleep (rigid_body.rs:804-807)
+        b.sleep_time = time_until_sleep;
+        b.linvel = vzero();
+        b.angvel = vzero();
+        w.counters.schedule_rebuilt = 1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -591,17 +680,21 @@ void step_once(World& w, V3 gravity) {
     double t1 = now_ms();
     narrow_phase(w);
     double t2 = now_ms();
+    // 7a. islands (connected components of touching contacts and joints between dynamic bodies; the reference keeps
+    //     them incrementally, island_manager/persistent.rs) and the whole-island sleep decision (solve.rs:234-306).
+    if (w.islands_dirty) label_islands(w);
+    update_sleep(w);
     // 7b. build_islands_and_solve_velocity_constraints
     solve_island(w, gravity);
     double t3 = now_ms();
     // 7d. advance_to_final_positions (substep.rs:84-224) + 7f refresh_moved_collider_aabbs
     for (Body& b : w.bodies) {
-        if (!b.is_dynamic()) continue;
+        if (!b.is_awake()) continue;
         b.pos = b.next_pos;
         update_world_mass_properties(b);
     }
     for (Collider& c : w.colliders) {
-        if (c.shape >= 0 && c.parent >= 0 && w.bodies[c.parent].is_dynamic()) refresh_collider(w, c);
+        if (c.shape >= 0 && c.parent >= 0 && w.bodies[c.parent].is_awake()) refresh_collider(w, c);
     }
     double t4 = now_ms();
     w.counters.broad_phase_ms = (float)(t1 - t0);
@@ -629,6 +722,8 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
     w.color_masks.assign(nb, Mask128{});
     w.bp_dirty = true;
     w.static_dirty = true;
+    w.islands_dirty = true;
+    w.island_of.clear();
     for (int i = 0; i < nb; ++i) {
         Body& b = w.bodies[i];
         const RbBodyDesc& d = bd[i];
@@ -769,6 +864,7 @@ int insert(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDesc*
     for (int i = nc0; i < nc0 + nc; ++i) refresh_collider(w, w.colliders[i]);
     w.bp_dirty = true;
     w.static_dirty = true;
+    w.islands_dirty = true;
     w.counters.num_bodies = nb0 + nb;
     w.counters.num_colliders = nc0 + nc;
     return RB_OK;
@@ -781,8 +877,11 @@ int remove_bodies(World& w, int n, const int* indices) {
         for (Collider& c : w.colliders)
             if (c.parent == indices[k]) c.shape = -1;   // leaves the broad phase: its pairs end at the next step
     }
+    for (Body& b : w.bodies)
+        if (b.sleeping) { b.sleeping = false; b.sleep_time = 0.0f; }   // (the reference wakes what touched the removed body; here: everything)
     w.bp_dirty = true;
     w.static_dirty = true;
+    w.islands_dirty = true;
     return RB_OK;
 }
 

@@ -193,6 +193,32 @@ RB_PHASE void import_halo_phase(const Ctx& ctx, const World& w) {
         update_world_mass(w, b, body_pose(w, b));
     }
 }
+// Wake the islands of the listed bodies (idx == NULL: every sleeping body), timers reset.
+template <class Ctx>
+RB_PHASE void wake_phase(const Ctx& ctx, const World& w, const int* idx, int n) {
+    if (!idx) {
+        for (int b = ctx.gtid; b < w.nb; b += ctx.gsize)
+            if (w.b_sleeping[b]) { w.b_sleeping[b] = 0; w.b_sleep_time[b] = 0.0f; w.st->sched_dirty = 1; }
+        return;
+    }
+    for (int k = ctx.gtid; k < n; k += ctx.gsize) {
+        const int b = idx[k];
+        if (b < 0 || b >= w.nb || w.b_type[b] != BODY_DYNAMIC) continue;
+        w.wake_req[w.isl_label[b]] = 1;   // (labels are roots; wake_apply_phase wakes the whole island right away, the
+        w.st->wake_any = 1;               //  next step's wake pass clears the requests)
+        if (w.b_sleeping[b]) { w.b_sleeping[b] = 0; w.b_sleep_time[b] = 0.0f; w.st->sched_dirty = 1; }
+    }
+}
+template <class Ctx>
+RB_PHASE void wake_apply_phase(const Ctx& ctx, const World& w) {
+    for (int b = ctx.gtid; b < w.nb; b += ctx.gsize)
+        if (w.b_type[b] == BODY_DYNAMIC && w.b_sleeping[b] && w.wake_req[w.isl_label[b]]) {
+            w.b_sleeping[b] = 0;
+            w.b_sleep_time[b] = 0.0f;
+            w.st->sched_dirty = 1;
+        }
+}
+
 // New halo flags (device array, 0 / 2 for foreign bodies; entries of owned bodies are ignored).
 template <class Ctx>
 RB_PHASE void set_halo_phase(const Ctx& ctx, const World& w, const unsigned char* flags) {
@@ -308,6 +334,14 @@ __global__ void k_kat(World w, int which, const float* in, float* out) { kat_pha
 __global__ void k_init_bodies(World w, int first) {
     GridCtx ctx;
     init_bodies_phase(ctx, w, first);
+}
+__global__ void k_wake(World w, const int* idx, int n) {
+    GridCtx ctx;
+    wake_phase(ctx, w, idx, n);
+}
+__global__ void k_wake_apply(World w) {
+    GridCtx ctx;
+    wake_apply_phase(ctx, w);
 }
 __global__ void k_import_halo(World w) {
     GridCtx ctx;
@@ -448,7 +482,7 @@ static void collider_mass_props(const RbColliderDesc& c, float& mass, float pi[3
 }
 static inline float inv0(float x) { return x == 0.0f ? 0.0f : 1.0f / x; }
 
-struct HostMass { float lcom[3], inv_mass, ipi[3], pi[3], pframe[4]; };
+struct HostMass { float lcom[3], inv_mass, ipi[3], pi[3], pframe[4], max_extent; };
 
 // RigidBodyMassProps::recompute_mass_properties_from_colliders (rigid_body_components.rs:421).
 // `first_body` / `first_collider`: only the bodies from first_body on are computed, from the colliders from
@@ -534,6 +568,16 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out, int fir
             }
         }
         for (int k = 0; k < 3; ++k) m.pi[k] = inv0(m.ipi[k]);
+        // recompute_max_extent (rigid_body_components.rs:491-515): bounding spheres about the local centre of mass
+        m.max_extent = 0.0f;
+        for (size_t ci = (size_t)first_collider; ci < W->colliders.size(); ++ci) {
+            const RbColliderDesc& c = W->colliders[ci];
+            if (c.parent != b) continue;
+            const float hx = c.half_extents[0], hy = c.half_extents[1], hz = c.half_extents[2];
+            const float radius = c.shape == RB_SHAPE_BALL ? hx : sqrtf(fmaf(hz, hz, fmaf(hy, hy, hx * hx)));
+            const float dx = c.pos_wrt_parent_t[0] - m.lcom[0], dy = c.pos_wrt_parent_t[1] - m.lcom[1], dz = c.pos_wrt_parent_t[2] - m.lcom[2];
+            m.max_extent = std::max(m.max_extent, sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) + radius);
+        }
     }
     return RB_OK;
 }
@@ -572,6 +616,8 @@ static int sync_world(RbWorld* W, bool check = true) {
     return RB_OK;
 }
 
+extern "C" { static int wake_impl(RbWorld* W, const int32_t* indices_host, int n); }
+
 static int read_state(RbWorld* W, State& s) {
     int rc = sync_world(W, false);   // (counters / debug reads must stay readable after an overflow; they do not consume the status)
     if (rc != RB_OK) return rc;
@@ -586,8 +632,11 @@ static int upload_bodies(RbWorld* W, const std::vector<HostMass>& mp, int first,
     std::vector<int> type(count);
     std::vector<unsigned> flags(count);
     std::vector<float4> pt(count), pq(count), lv(count), av(count), lc(count), ipi(count), pi(count), pf(count), misc(count), uf(count), ut(count);
+    std::vector<float> ext(count);
+    std::vector<float4> prev_t(count, make_float4(0.f, 0.f, 0.f, 0.f)), prev_q(count, make_float4(0.f, 0.f, 0.f, 1.f));   // sleep_prev_pose = identity
     for (int k = 0; k < count; ++k) {
         const int i = first + k;
+        ext[k] = mp[i].max_extent;
         const RbBodyDesc& d = W->bodies[i];
         type[k] = d.body_type;
         flags[k] = d.flags;
@@ -617,6 +666,13 @@ static int upload_bodies(RbWorld* W, const std::vector<HostMass>& mp, int first,
     CK(h2d(w.b_misc + first, misc.data(), n * sizeof(float4)));
     CK(h2d(w.b_uforce + first, uf.data(), n * sizeof(float4)));
     CK(h2d(w.b_utorque + first, ut.data(), n * sizeof(float4)));
+    CK(h2d(w.b_max_extent + first, ext.data(), n * sizeof(float)));
+    CK(h2d(w.b_sleep_prev_t + first, prev_t.data(), n * sizeof(float4)));
+    CK(h2d(w.b_sleep_prev_q + first, prev_q.data(), n * sizeof(float4)));
+    CK(dev_set(w.b_sleeping + first, 0, n));
+    CK(dev_set(w.b_sleep_time + first, 0, n * sizeof(float)));
+    for (int k = 0; k < count; ++k)
+        if (type[k] == RB_BODY_DYNAMIC && !(flags[k] & RB_BODY_NO_SLEEP)) w.sleep_enabled = 1;
     return RB_OK;
 }
 static int upload_colliders(RbWorld* W, int first, int count) {
@@ -831,6 +887,8 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.b_lcom_im, NB); ALLOC(w.b_ipi, NB); ALLOC(w.b_pi, NB); ALLOC(w.b_pframe, NB); ALLOC(w.b_misc, NB);
     ALLOC(w.b_uforce, NB); ALLOC(w.b_utorque, NB); ALLOC(w.b_wcom, NB); ALLOC(w.b_eim, NB + 2);
     ALLOC(w.b_eii0, NB); ALLOC(w.b_eii1, NB); ALLOC(w.b_owned, NB);
+    ALLOC(w.b_sleeping, NB); ALLOC(w.b_sleep_time, NB); ALLOC(w.b_sleep_prev_t, NB); ALLOC(w.b_sleep_prev_q, NB); ALLOC(w.b_max_extent, NB);
+    ALLOC(w.wake_req, NB); ALLOC(w.isl_block, NB);
     ALLOC(w.s_lin, NB + 2); ALLOC(w.s_ang, NB + 2); ALLOC(w.s_q, NB + 2); ALLOC(w.s_t, NB + 2);   // + world pseudo body, garbage slot
     ALLOC(w.s_incr_lin, NB); ALLOC(w.s_incr_ang, NB);
     ALLOC(w.state13, (size_t)NB * 13);
@@ -1049,7 +1107,44 @@ int rb_world_remove_bodies(RbWorld* W, int32_t n, const int32_t* indices) {
     CK(h2d(&W->w.st->lists_dirty, &lists, sizeof(int)));
     CK(h2d(&W->w.st->bp_dirty, &one, sizeof(int)));
     CK(h2d(&W->w.st->sched_dirty, &one, sizeof(int)));
+    return wake_impl(W, nullptr, 0);   // (the reference wakes what touched the removed body; here: everything asleep)
+}
+
+int rb_world_get_sleeping(RbWorld* W, uint8_t* sleeping) {
+    if (!W || !sleeping || !W->w.st) return RB_ERR_INVALID;
+    int rc = sync_world(W, false);
+    if (rc != RB_OK) return rc;
+    CK(d2h(sleeping, W->w.b_sleeping, (size_t)W->w.nb));
     return RB_OK;
+}
+
+static int wake_impl(RbWorld* W, const int32_t* indices_host, int n) {
+    int* idx_dev = nullptr;
+    if (indices_host) {
+        if (dev_alloc((void**)&idx_dev, (size_t)std::max(n, 1) * sizeof(int)) != cudaSuccess) { set_err("device allocation failed%s", ""); return RB_ERR_CUDA; }
+        CK(h2d(idx_dev, indices_host, (size_t)n * sizeof(int)));
+    }
+#if RB_DEVICE_BUILD
+    CK(cudaSetDevice(W->device));
+    const int work = indices_host ? n : W->w.nb;
+    k_wake<<<(std::max(work, 1) + 255) / 256, 256, 0, W->stream>>>(W->w, idx_dev, n);
+    if (indices_host) k_wake_apply<<<(std::max(W->w.nb, 1) + 255) / 256, 256, 0, W->stream>>>(W->w);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(W->stream));
+    W->kernels += 2;
+#else
+    GridCtx g;
+    wake_phase(g, W->w, idx_dev, n);
+    if (indices_host) wake_apply_phase(g, W->w);
+#endif
+    if (idx_dev) dev_free(idx_dev);
+    return RB_OK;
+}
+// RigidBody::wake_up(strong = true) through IslandManager::wake_up: the bodies' whole islands.
+int rb_world_wake_up(RbWorld* W, int32_t n, const int32_t* indices) {
+    if (!W || n < 0 || (n && !indices) || !W->w.st) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    if (n == 0) return RB_OK;
+    return wake_impl(W, indices, n);
 }
 
 int rb_world_set_body_states(RbWorld* W, int32_t n, const int32_t* indices, const float* pose7, const float* vel6) {
@@ -1084,6 +1179,7 @@ int rb_world_set_body_states(RbWorld* W, int32_t n, const int32_t* indices, cons
     }
     rc = launch_init_bodies(W);
     if (rc != RB_OK) return rc;
+    if (n > 0 && (rc = wake_impl(W, indices, n)) != RB_OK) return rc;   // a user change wakes the body's island (user_changes.rs)
     return sync_world(W);
 }
 

@@ -24,9 +24,11 @@ constexpr int BIG_JCOLOR_MIN = 64;   // joints.rs:340: JOINT_BATCH*LAYOUT_REF_WO
 // Multi-GPU sharding (b_owned): 1 = simulated by this rank, 2 = "halo": simulated by another rank but close enough to
 // be tracked here (its state is imported every step, its colliders take part in proximity detection), 0 = simulated
 // by another rank and far away (ignored until the next halo refresh).
-RB_HD bool body_is_sim(const World& w, int b) {  // dynamic and simulated by this rank
+RB_HD bool body_is_dyn(const World& w, int b) {  // dynamic and simulated by this rank (awake or asleep)
     return b >= 0 && w.b_type[b] == BODY_DYNAMIC && w.b_owned[b] == 1;
 }
+// ... and awake: a member of the active set (island_manager: sleeping bodies are neither solved nor integrated)
+RB_HD bool body_is_sim(const World& w, int b) { return body_is_dyn(w, b) && !w.b_sleeping[b]; }
 RB_HD pose body_pose(const World& w, int b) { return mkpose(mkq(w.b_pos_q[b]), xyz(w.b_pos_t[b])); }
 RB_HD pose collider_pose(const World& w, int c) { return mkpose(mkq(w.c_pos_q[c]), xyz(w.c_pos_t[c])); }
 
@@ -210,7 +212,7 @@ RB_PHASE unsigned long long* grid_radix_sort(const Ctx& ctx, unsigned long long*
 RB_HD bool pair_allowed(const World& w, int c1, int c2) {
     int p1 = w.c_parent[c1], p2 = w.c_parent[c2];
     if (p1 >= 0 && p1 == p2) return false;
-    bool d1 = body_is_sim(w, p1), d2 = body_is_sim(w, p2);
+    bool d1 = body_is_dyn(w, p1), d2 = body_is_dyn(w, p2);   // (sleeping bodies keep their pairs)
     if (!d1 && !d2) return false;
     uint2 g1 = w.c_groups[c1], g2 = w.c_groups[c2];
     if (!((g1.x & g2.y) != 0 && (g2.x & g1.y) != 0)) return false;
@@ -491,7 +493,8 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
     for (int i = ctx.gtid; i < np; i += ctx.gsize) {
         unsigned long long key = w.pb[buf].key[i];
         int c1 = (int)(key >> 32), c2 = (int)(key & 0xffffffffu);
-        {   // pairs without a body simulated by this rank (multi-GPU sharding) belong to another rank
+        {   // pairs without an AWAKE body simulated by this rank are not updated: they belong to another rank
+            // (multi-GPU sharding) or to a sleeping island, whose bodies do not move
             float4 bod0 = prow(w, buf, PR_BODIES, i);
             if (!body_is_sim(w, as_int(bod0.z)) && !body_is_sim(w, as_int(bod0.w))) continue;
         }
@@ -509,7 +512,7 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
         }
         float4 bod = prow(w, buf, PR_BODIES, i);
         int b1 = as_int(bod.z), b2 = as_int(bod.w);
-        bool dyn1 = body_is_sim(w, b1), dyn2 = body_is_sim(w, b2);
+        bool dyn1 = body_is_dyn(w, b1), dyn2 = body_is_dyn(w, b2);
         int sh1 = w.c_shape[c1], sh2 = w.c_shape[c2];
         vec3 he1 = xyz(w.c_he[c1]), he2 = xyz(w.c_he[c2]);
         float4 m1 = w.c_mat[c1], m2 = w.c_mat[c2];
@@ -626,6 +629,9 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
             if (has) {
                 flags |= 2;  // pending colour (deferred greedy pass)
                 st->ntodo = 1;
+                // a contact that begins wakes the sleeping side's whole island (narrow_phase/mod.rs:53-67)
+                if (dyn1 && w.b_sleeping[b1]) { w.wake_req[w.isl_label[b1]] = 1; st->wake_any = 1; }
+                if (dyn2 && w.b_sleeping[b2]) { w.wake_req[w.isl_label[b2]] = 1; st->wake_any = 1; }
             } else {
                 clear_color_bits(w, color, as_int(bod.x), as_int(bod.y));
                 color = COLOR_UNCOLORED;
@@ -685,8 +691,8 @@ RB_PHASE void section_coloring(const Ctx& ctx, const World& w) {
             float4 bod = prow(w, buf, PR_BODIES, i);
             int b1 = as_int(bod.z), b2 = as_int(bod.w);
             const unsigned long long key = color_order_key(b1, b2);
-            if (body_is_sim(w, b1)) atomic_min64(&w.body_minkey[b1], key);
-            if (body_is_sim(w, b2)) atomic_min64(&w.body_minkey[b2], key);
+            if (body_is_dyn(w, b1)) atomic_min64(&w.body_minkey[b1], key);
+            if (body_is_dyn(w, b2)) atomic_min64(&w.body_minkey[b2], key);
             atomic_add(&st->ncand, 1);  // ncand doubles as the pending counter outside the broad phase
         }
         ctx.grid_sync();
@@ -699,8 +705,8 @@ RB_PHASE void section_coloring(const Ctx& ctx, const World& w) {
             float4 bod = prow(w, buf, PR_BODIES, i);
             int b1 = as_int(bod.z), b2 = as_int(bod.w);
             const unsigned long long key = color_order_key(b1, b2);
-            if (body_is_sim(w, b1) && w.body_minkey[b1] == key) atomic_min(&w.body_min[b1], i);
-            if (body_is_sim(w, b2) && w.body_minkey[b2] == key) atomic_min(&w.body_min[b2], i);
+            if (body_is_dyn(w, b1) && w.body_minkey[b1] == key) atomic_min(&w.body_min[b1], i);
+            if (body_is_dyn(w, b2) && w.body_minkey[b2] == key) atomic_min(&w.body_min[b2], i);
         }
         ctx.grid_sync();
         // B: winners take the first colour free on both bodies
@@ -710,7 +716,7 @@ RB_PHASE void section_coloring(const Ctx& ctx, const World& w) {
             if (!(flags & 2)) continue;
             float4 bod = prow(w, buf, PR_BODIES, i);
             int b1 = as_int(bod.z), b2 = as_int(bod.w);
-            bool d1 = body_is_sim(w, b1), d2 = body_is_sim(w, b2);
+            bool d1 = body_is_dyn(w, b1), d2 = body_is_dyn(w, b2);
             if ((d1 && w.body_min[b1] != i) || (d2 && w.body_min[b2] != i)) continue;
             int color = COLOR_OVERFLOW, cb0 = -1, cb1 = -1;
             if (d1 && d2) {
@@ -740,8 +746,8 @@ RB_PHASE void section_coloring(const Ctx& ctx, const World& w) {
             if (!(flags & 6)) continue;
             float4 bod = prow(w, buf, PR_BODIES, i);
             int b1 = as_int(bod.z), b2 = as_int(bod.w);
-            if (body_is_sim(w, b1)) { w.body_min[b1] = 0x7fffffff; w.body_minkey[b1] = ~0ull; }
-            if (body_is_sim(w, b2)) { w.body_min[b2] = 0x7fffffff; w.body_minkey[b2] = ~0ull; }
+            if (body_is_dyn(w, b1)) { w.body_min[b1] = 0x7fffffff; w.body_minkey[b1] = ~0ull; }
+            if (body_is_dyn(w, b2)) { w.body_min[b2] = 0x7fffffff; w.body_minkey[b2] = ~0ull; }
             if (flags & 4) { info.x = as_float_i(flags & ~4); prow(w, buf, PR_INFO, i) = info; }
         }
         if (ctx.gtid == 0) st->ncand = 0;
@@ -823,30 +829,99 @@ RB_HD void uf_union(int* parent, int a, int b) {  // hook the larger root under 
 
 // P3b: connected components (persistent islands, island_manager/persistent.rs:1-3), work items,
 // colour stage order (init.rs:163-254) and the per-item constraint schedule.
+// Connected components over ALL dynamic bodies of this rank, awake or asleep (a sleeping island keeps its label, so
+// that a contact with any of its bodies can wake all of them).
+template <class Ctx>
+RB_PHASE void section_components(const Ctx& ctx, const World& w) {
+    State* st = w.st;
+    const int buf = st->cur, np = st->npairs, nb = w.nb, nj = w.nj;
+    for (int b = ctx.gtid; b < nb; b += ctx.gsize) w.isl_label[b] = b;
+    ctx.grid_sync();
+    // union over touching dynamic-dynamic pairs and joints
+    for (int i = ctx.gtid; i < np; i += ctx.gsize) {
+        if (as_int(prow(w, buf, PR_INFO, i).z) <= 0) continue;
+        float4 bod = prow(w, buf, PR_BODIES, i);
+        int b1 = as_int(bod.z), b2 = as_int(bod.w);
+        if (body_is_dyn(w, b1) && body_is_dyn(w, b2)) uf_union(w.isl_label, b1, b2);
+    }
+    for (int j = ctx.gtid; j < nj; j += ctx.gsize) {
+        int4 ji = w.j_info[j];
+        if (body_is_dyn(w, ji.x) && body_is_dyn(w, ji.y)) uf_union(w.isl_label, ji.x, ji.y);
+    }
+    ctx.grid_sync();
+    // flatten
+    for (int b = ctx.gtid; b < nb; b += ctx.gsize) w.isl_label[b] = uf_find_ro(w.isl_label, b);
+    ctx.grid_sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sleeping (island_manager/sleep.rs, manager.rs:320-392; RigidBodyActivation::update_energy,
+// rigid_body_components.rs:1417-1470).  Whole islands only: an island falls asleep when EVERY body in it has been
+// below the motion threshold for time_until_sleep, and a contact that begins with one of its bodies wakes all of them.
+// ------------------------------------------------------------------------------------------------
+constexpr float SLEEP_LINEAR_THRESHOLD = 0.05f, SLEEP_ANGULAR_THRESHOLD = 0.5f, SLEEP_TIME_UNTIL = 0.5f;
+
+template <class Ctx>
+RB_PHASE void section_wake(const Ctx& ctx, const World& w) {
+    State* st = w.st;
+    for (int b = ctx.gtid; b < w.nb; b += ctx.gsize)
+        if (body_is_dyn(w, b) && w.b_sleeping[b] && w.wake_req[w.isl_label[b]]) {
+            w.b_sleeping[b] = 0;
+            w.b_sleep_time[b] = 0.0f;   // "strong" wake-up: the timer restarts
+            st->sched_dirty = 1;
+        }
+    ctx.grid_sync();
+    for (int b = ctx.gtid; b < w.nb; b += ctx.gsize) w.wake_req[b] = 0;
+    if (ctx.gtid == 0) st->wake_any = 0;
+    ctx.grid_sync();
+}
+
+template <class Ctx>
+RB_PHASE void section_sleep(const Ctx& ctx, const World& w) {
+    State* st = w.st;
+    const int stamp = st->sleep_stamp;
+    const float dt = w.prm.dt, linear_threshold = SLEEP_LINEAR_THRESHOLD * w.prm.length_unit;
+    for (int b = ctx.gtid; b < w.nb; b += ctx.gsize) {
+        if (!body_is_sim(w, b)) continue;
+        const bool may = !(w.b_flags[b] & FLAG_NO_SLEEP);
+        const pose cur = body_pose(w, b);
+        const pose prev = mkpose(mkq(w.b_sleep_prev_q[b]), xyz(w.b_sleep_prev_t[b]));
+        w.b_sleep_prev_t[b] = f4(cur.t, 0.0f);
+        w.b_sleep_prev_q[b] = f4(cur.q);
+        const vec3 av = xyz(w.b_angvel[b]);
+        const float sq_angvel = dot3(av, av), ext = w.b_max_extent[b];
+        const bool angular_ok = ext > 0.0f ? (may && sq_angvel < 1.5707963267948966f * 1.5707963267948966f)
+                                           : (may && sq_angvel < SLEEP_ANGULAR_THRESHOLD * SLEEP_ANGULAR_THRESHOLD);
+        const float drift = pose_drift(prev, cur, ext);
+        const bool can = may && angular_ok && drift * 0.5f < linear_threshold * dt;
+        const float t = can ? w.b_sleep_time[b] + dt : 0.0f;
+        w.b_sleep_time[b] = t;
+        if (!(t >= SLEEP_TIME_UNTIL)) w.isl_block[w.isl_label[b]] = stamp;   // one restless body keeps its island awake
+    }
+    ctx.grid_sync();
+    for (int b = ctx.gtid; b < w.nb; b += ctx.gsize) {
+        if (!body_is_sim(w, b) || w.isl_block[w.isl_label[b]] == stamp) continue;
+        w.b_sleeping[b] = 1;                  // RigidBody::sleep (rigid_body.rs:804-807)
+        w.b_sleep_time[b] = SLEEP_TIME_UNTIL;
+        w.b_linvel[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w.b_angvel[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* s13 = w.state13 + (size_t)b * 13;
+        for (int k = 7; k < 13; ++k) s13[k] = 0.0f;
+        st->sched_dirty = 1;
+    }
+    ctx.grid_sync();
+}
+
+// P3b: work items, colour stage order (init.rs:163-254) and the per-item constraint schedule of the AWAKE islands.
 template <class Ctx>
 RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
     State* st = w.st;
     const int buf = st->cur, np = st->npairs, nb = w.nb, nj = w.nj;
     // S1 reset
-    for (int b = ctx.gtid; b < nb; b += ctx.gsize) { w.isl_label[b] = b; w.isl_nb[b] = 0; w.isl_ncons[b] = 0; w.isl_item[b] = -1; }
+    for (int b = ctx.gtid; b < nb; b += ctx.gsize) { w.isl_nb[b] = 0; w.isl_ncons[b] = 0; w.isl_item[b] = -1; }
     for (int c = ctx.gtid; c < NUM_COLORS; c += ctx.gsize) w.color_count[c] = 0;
     for (int i = ctx.gtid; i < 3 * (w.item_cap + 1); i += ctx.gsize) w.item_cursor[i] = 0;
     for (int i = ctx.gtid; i <= w.item_cap; i += ctx.gsize) { w.item_body_start[i] = 0; w.item_cons_start[i] = 0; w.item_joint_start[i] = 0; }
-    ctx.grid_sync();
-    // S2 union over touching dynamic-dynamic pairs and joints
-    for (int i = ctx.gtid; i < np; i += ctx.gsize) {
-        if (as_int(prow(w, buf, PR_INFO, i).z) <= 0) continue;
-        float4 bod = prow(w, buf, PR_BODIES, i);
-        int b1 = as_int(bod.z), b2 = as_int(bod.w);
-        if (body_is_sim(w, b1) && body_is_sim(w, b2)) uf_union(w.isl_label, b1, b2);
-    }
-    for (int j = ctx.gtid; j < nj; j += ctx.gsize) {
-        int4 ji = w.j_info[j];
-        if (body_is_sim(w, ji.x) && body_is_sim(w, ji.y)) uf_union(w.isl_label, ji.x, ji.y);
-    }
-    ctx.grid_sync();
-    // S3 flatten
-    for (int b = ctx.gtid; b < nb; b += ctx.gsize) w.isl_label[b] = uf_find_ro(w.isl_label, b);
     ctx.grid_sync();
     // S4 per-root counts + global colour histogram
     for (int b = ctx.gtid; b < nb; b += ctx.gsize)
@@ -1114,13 +1189,16 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
 template <class Ctx>
 RB_PHASE void collide_pipeline(const Ctx& ctx, const World& w) {
     State* st = w.st;
-    if (ctx.gtid == 0) { st->bp_ran = 0; st->sched_ran = 0; }
+    if (ctx.gtid == 0) { st->bp_ran = 0; st->sched_ran = 0; st->sleep_stamp += 1; }
     phase_refresh_colliders(ctx, w);
     ctx.grid_sync();
     if (st->bp_dirty || st->lists_dirty) section_broad_phase(ctx, w);
     phase_narrow_phase(ctx, w);
     ctx.grid_sync();
+    if (st->wake_any) section_wake(ctx, w);
     if (st->ntodo) section_coloring(ctx, w);
+    if (st->sched_dirty) section_components(ctx, w);
+    if (w.sleep_enabled) section_sleep(ctx, w);
     if (st->sched_dirty) section_schedule(ctx, w);
 }
 

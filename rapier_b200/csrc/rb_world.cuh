@@ -22,7 +22,7 @@ constexpr int BODY_REMOVED = 3;          // removed (rb_world_remove_bodies) or 
 constexpr int SHAPE_BALL = 0, SHAPE_CUBOID = 1;
 constexpr int SHAPE_REMOVED = -1;        // collider of a removed body: in neither broad-phase list, in no pair
 constexpr unsigned FLAG_GYRO = 1, FLAG_FAST_ROT = 2, FLAG_LTX = 4, FLAG_LTY = 8, FLAG_LTZ = 16, FLAG_LRX = 32,
-                   FLAG_LRY = 64, FLAG_LRZ = 128;
+                   FLAG_LRY = 64, FLAG_LRZ = 128, FLAG_NO_SLEEP = 256;
 
 // ---- persistent pair record rows (float4 each) ----
 enum PairRow {
@@ -106,7 +106,9 @@ struct State {
     float stat_wsum;       // sum of their widths along x (classification threshold)
     unsigned stat_wn_bits; // widest narrow static collider along x (float bits)
     int bp_diff;           // the candidate pair set differs from the pair table
-    int pad[7];
+    int wake_any;          // a contact began with a sleeping body this step: run the wake pass
+    int sleep_stamp;       // step counter of the sleep decision (isl_block holds the stamp of the last veto)
+    int pad[5];
 };
 
 struct PairBuf {
@@ -132,7 +134,15 @@ struct World {
     float4* b_eim;                    // effective_inv_mass
     float4* b_eii0;                   // effective_world_inv_inertia xx xy xz yy
     float2* b_eii1;                   //                              yz zz
-    unsigned char* b_owned;           // multi-GPU sharding: 0 = body simulated by another rank
+    unsigned char* b_owned;           // multi-GPU sharding: 1 = simulated here, 2 = tracked halo, 0 = far foreign body
+    // sleeping (RigidBodyActivation, rigid_body_components.rs:1296-1326)
+    unsigned char* b_sleeping;        // 1 = asleep: not in the active set
+    float* b_sleep_time;              // time_since_can_sleep
+    float4 *b_sleep_prev_t, *b_sleep_prev_q;   // pose at the previous sleep check
+    float* b_max_extent;              // mprops.max_extent: farthest shape point from the local centre of mass
+    int* wake_req;                    // [nb] by island root: wake this island (a contact began)
+    int* isl_block;                   // [nb] by island root: stamp of the last step a body of the island was not sleep-eligible
+    int sleep_enabled;                // some body may sleep: run the sleep decision
     // solver bodies (global-memory path) + per-substep increments
     float4 *s_lin, *s_ang, *s_q, *s_t, *s_incr_lin, *s_incr_ang;
     float* state13;                   // packed [nb][13] t q lin ang (download / NCCL all-gather)

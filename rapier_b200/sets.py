@@ -82,8 +82,12 @@ class RigidBodyBuilder:
         return self
 
     def can_sleep(self, flag):
-        # Sleeping is SURVEY 8(f) "next": accepted and ignored (every benchmark scene disables it).
+        """RigidBodyBuilder::can_sleep (rigid_body.rs; false = RigidBodyActivation::cannot_sleep())."""
         self._can_sleep = bool(flag)
+        if flag:
+            self._flags &= ~A.RB_BODY_NO_SLEEP
+        else:
+            self._flags |= A.RB_BODY_NO_SLEEP
         return self
 
     def gyroscopic_forces_enabled(self, flag):

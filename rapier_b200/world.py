@@ -148,6 +148,17 @@ class PhysicsPipeline:
         assert o.shape == (self.nb,)
         self._check(self.L.rb_world_set_owned_bodies(self.h, o.ctypes.data))
 
+    def sleeping(self):
+        """RigidBody::is_sleeping of every body."""
+        out = np.zeros(self.nb, np.uint8)
+        self._check(self.L.rb_world_get_sleeping(self.h, out.ctypes.data))
+        return out
+
+    def wake_up(self, indices):
+        """IslandManager::wake_up(handle, strong = true): wakes the bodies' whole islands."""
+        idx = np.ascontiguousarray(indices, np.int32)
+        self._check(self.L.rb_world_wake_up(self.h, len(idx), idx.ctypes.data))
+
     def set_halo_bodies(self, flags_dev_ptr):
         """Which bodies of other ranks are tracked here (device array of num_bodies bytes; see sharding.py)."""
         self._check(self.L.rb_world_set_halo_bodies(self.h, flags_dev_ptr))
@@ -236,6 +247,14 @@ class PhysicsWorld:
     def counters(self):
         self._flush()
         return self.physics_pipeline.counters()
+
+    def sleeping(self):
+        self._flush()
+        return self.physics_pipeline.sleeping()
+
+    def wake_up(self, handles):
+        self._flush()
+        self.physics_pipeline.wake_up(handles)
 
     def contact_pairs(self):
         self._flush()

@@ -65,6 +65,8 @@ def lib(fast=False):
                                            C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_world_insert.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_world_remove_bodies.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_world_get_sleeping.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_world_wake_up.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_kat.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
         _libs[fast] = L
     return _libs[fast]
@@ -106,6 +108,15 @@ class OracleWorld:
         rc = self.L.orc_world_insert(self.h, len(body_descs), b, len(collider_descs), c)
         assert rc == 0, rc
         self.nb += len(body_descs)
+
+    def sleeping(self):
+        out = np.zeros(self.nb, np.uint8)
+        self.L.orc_world_get_sleeping(self.h, out.ctypes.data)
+        return out
+
+    def wake_up(self, indices):
+        idx = np.ascontiguousarray(indices, np.int32)
+        assert self.L.orc_world_wake_up(self.h, len(idx), idx.ctypes.data) == 0
 
     def remove_bodies(self, indices):
         idx = np.ascontiguousarray(indices, np.int32)

@@ -116,3 +116,31 @@ def test_large_world_insertion_protocol_emulated():
 def test_body_removal_and_insertion_emulated():
     from incremental_cases import removal_case
     removal_case(lib=emul_lib.lib())
+
+
+def test_whole_island_sleep_emulated_kernels():
+    from test_oracle_kat import sleeping_stack_is_woken_by_an_impact, whole_island_blocks_partial_sleep
+    whole_island_blocks_partial_sleep(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()))
+    sleeping_stack_is_woken_by_an_impact(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()))
+
+
+def test_sleep_and_wake_match_oracle_bit_for_bit():
+    """A pile that settles, falls asleep island by island, and is woken by a late projectile: every step of it."""
+    from rapier_b200.sets import ColliderBuilder, RigidBodyBuilder
+    scene = scenes.box_pile(3, 3, 3)
+    scene.insert(RigidBodyBuilder.dynamic().translation((0.0, 60.0, 0.3)).linvel((0.0, -2.0, 0.0)), ColliderBuilder.ball(0.5).density(5.0))
+    w = PhysicsWorld(scene, _lib=emul_lib.lib())
+    o = oracle_lib.OracleWorld(scene)
+    seen_sleep = seen_wake = False
+    prev = 0
+    for i in range(330):
+        w.step(); o.step()
+        sw, so = w.sleeping(), o.sleeping()
+        assert (sw == so).all(), i
+        n = int(sw.sum())
+        seen_sleep = seen_sleep or n > 5
+        seen_wake = seen_wake or (prev > 5 and n < prev)
+        prev = n
+        if i % 15 == 14:
+            assert is_exact(compare_worlds(w, o)), i
+    assert seen_sleep and seen_wake

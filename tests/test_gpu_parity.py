@@ -269,3 +269,32 @@ def test_capacity_overflow_is_reported_after_asynchronous_steps(built):
     w.physics_pipeline.synchronize()
     with pytest.raises(RapierError, match="-4"):
         w.physics_pipeline.step_host(s.gravity, None, None)
+
+
+def test_whole_island_sleep(built):
+    """crates/rapier3d/tests/whole_island_sleep.rs:40-83 on the CUDA path + wake by impact."""
+    from test_oracle_kat import sleeping_stack_is_woken_by_an_impact, whole_island_blocks_partial_sleep
+    whole_island_blocks_partial_sleep(lambda s: PhysicsWorld(s))
+    sleeping_stack_is_woken_by_an_impact(lambda s: PhysicsWorld(s))
+
+
+def test_sleep_and_wake_match_oracle_bit_for_bit(built):
+    from rapier_b200.sets import ColliderBuilder, RigidBodyBuilder
+    scene = scenes.box_pile(5, 5, 6)
+    scene.insert(RigidBodyBuilder.dynamic().translation((0.0, 70.0, 0.3)).linvel((0.0, -2.0, 0.0)), ColliderBuilder.ball(0.5).density(5.0))
+    w = PhysicsWorld(scene)
+    o = oracle_lib.OracleWorld(scene, threads=4)
+    seen_sleep = seen_wake = False
+    prev = 0
+    for i in range(400):
+        w.step(); o.step()
+        if i % 5 == 4:
+            sw, so = w.sleeping(), o.sleeping()
+            assert (sw == so).all(), i
+            n = int(sw.sum())
+            seen_sleep = seen_sleep or n > 20
+            seen_wake = seen_wake or (prev > 20 and n < prev)
+            prev = n
+        if i % 40 == 39:
+            assert is_exact(compare_worlds(w, o)), i
+    assert seen_sleep and seen_wake

@@ -359,3 +359,51 @@ def test_cpu_baseline_build_tracks_the_bit_exact_oracle():
     pa, va = a.body_states()
     pb, vb = b.body_states()
     assert np.abs(pa - pb).max() <= 1e-4 and np.abs(va - vb).max() <= 1e-3
+
+
+# ---- sleeping: crates/rapier3d/tests/whole_island_sleep.rs ----
+def _stack_world(n, restless=False):
+    s = scenes.Scene("stack")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(100.0, 0.5, 100.0))
+    stack = [s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.5 + i, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5)) for i in range(n)]
+    r = None
+    if restless:
+        r = s.insert(RigidBodyBuilder.dynamic().translation((0.0, n + 0.5, 0.0)).can_sleep(False), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    return s, stack, r
+
+
+def whole_island_blocks_partial_sleep(make_world):
+    """whole_island_sleep.rs:40-83: a can_sleep(false) body atop a stack keeps the WHOLE stack awake; once removed the
+    stack sleeps; waking one body wakes the island as a unit."""
+    s, stack, restless = _stack_world(6, restless=True)
+    w = make_world(s)
+    w.step(240)
+    assert w.sleeping().sum() == 0
+    w.remove_bodies([restless]) if hasattr(w, "remove_bodies") else w.remove(restless)
+    w.step(240)
+    sl = w.sleeping()
+    assert all(sl[b] == 1 for b in stack)
+    w.wake_up([stack[0]])
+    assert w.sleeping().sum() == 0
+
+
+def sleeping_stack_is_woken_by_an_impact(make_world):
+    """A resting stack falls asleep (no constraint is solved any more); a ball dropped on it wakes every body."""
+    s, stack, _ = _stack_world(4)
+    ball = s.insert(RigidBodyBuilder.dynamic().translation((0.2, 40.0, 0.0)).can_sleep(False), ColliderBuilder.ball(0.4))
+    w = make_world(s)
+    w.step(100)
+    sl = w.sleeping()
+    assert all(sl[b] == 1 for b in stack) and sl[ball] == 0
+    assert w.counters()["num_active_manifolds"] == 0
+    for _ in range(120):
+        w.step(1)
+        if w.sleeping()[stack[0]] == 0:
+            break
+    sl = w.sleeping()
+    assert all(sl[b] == 0 for b in stack), "the impact must wake the whole island"
+
+
+def test_whole_island_sleep_oracle():
+    whole_island_blocks_partial_sleep(lambda s: oracle_lib.OracleWorld(s))
+    sleeping_stack_is_woken_by_an_impact(lambda s: oracle_lib.OracleWorld(s))
