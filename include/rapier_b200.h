@@ -213,6 +213,11 @@ int rb_world_remove_bodies(RbWorld* w, int32_t n, const int32_t* body_indices);
  * or when a body is removed.  Sleeping bodies keep their contact pairs and warm-start data but are neither solved nor
  * integrated.  sleeping[num_bodies]: 1 = asleep. */
 int rb_world_get_sleeping(RbWorld* w, uint8_t* sleeping);
+/* Quarantine (src/pipeline/physics_pipeline/quarantine.rs:14-47): a body whose state goes non-finite during a step keeps
+ * its last valid pose, loses its velocities and forces and is disabled like a removed body; the step reports
+ * RB_ERR_NONFINITE at the next synchronising call.  Returns the number of bodies quarantined since the last call and
+ * writes up to `cap` indices (ascending); the list is cleared by a call that reads it. */
+int rb_world_get_quarantine(RbWorld* w, int32_t* bodies, int32_t cap);
 int rb_world_wake_up(RbWorld* w, int32_t n, const int32_t* body_indices);
 
 /* Unit-level known-answer evaluation for parity tests: runs ONE device function of the path (named: "pose_drift"

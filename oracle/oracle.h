@@ -25,6 +25,7 @@ int orc_world_set_scene(OrcWorld* w, int32_t nb, const RbBodyDesc* bodies, int32
                         const RbColliderDesc* colliders, int32_t nj, const RbJointDesc* joints);
 // Mirrors of rb_world_get_sleeping / rb_world_wake_up.
 int orc_world_get_sleeping(OrcWorld* w, uint8_t* sleeping);
+int orc_world_get_quarantine(OrcWorld* w, int32_t* bodies, int32_t cap);
 int orc_world_wake_up(OrcWorld* w, int32_t n, const int32_t* indices);
 // Mirrors of rb_world_insert / rb_world_remove_bodies (appended bodies and colliders; tombstoned removals).
 int orc_world_insert(OrcWorld* w, int32_t nb, const RbBodyDesc* bodies, int32_t nc, const RbColliderDesc* colliders);

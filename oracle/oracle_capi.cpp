@@ -2,6 +2,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include "oracle_internal.h"
 
 namespace orc {
@@ -92,6 +93,17 @@ int orc_world_wake_up(OrcWorld* o, int32_t n, const int32_t* indices) {
         }
     }
     return RB_OK;
+}
+int orc_world_get_quarantine(OrcWorld* o, int32_t* bodies, int32_t cap) {
+    if (!o) return RB_ERR_INVALID;
+    std::vector<int>& q = o->w.quarantine;
+    const int n = (int)q.size();
+    if (bodies && cap > 0 && n > 0) {
+        std::sort(q.begin(), q.end());
+        for (int i = 0; i < n && i < cap; ++i) bodies[i] = q[i];
+        q.clear();
+    }
+    return n;
 }
 int orc_world_get_sleeping(OrcWorld* o, uint8_t* out) {
     if (!o || !out) return RB_ERR_INVALID;

@@ -196,6 +196,7 @@ struct World {
     bool bp_dirty = true;
     std::vector<int> island_of;        // connected component (root body) of every dynamic body, -1 otherwise
     bool islands_dirty = true;         // the touching set or the joints changed: relabel
+    std::vector<int> quarantine;       // bodies disabled because their state went non-finite (since last read)
     bool static_dirty = true;          // the sorted list of static colliders must be rebuilt
     std::vector<int> static_sorted;    // static colliders by fat min-x
     float static_max_width = 0.0f;     // widest of them along x

@@ -729,9 +729,24 @@ void solve_island(World& w, V3 gravity) {
         Body& b = w.bodies[i];
         if (!b.is_awake()) continue;
         const SolverBody& s = w.sb[i];
-        b.linvel = s.lin * (1.0f / (1.0f + P.dt * b.lin_damping));
-        b.angvel = s.ang * (1.0f / (1.0f + P.dt * b.ang_damping));
-        b.next_pos = pose_prepend_translation(s.pose, -b.local_com);
+        V3 lin = s.lin * (1.0f / (1.0f + P.dt * b.lin_damping));
+        V3 ang = s.ang * (1.0f / (1.0f + P.dt * b.ang_damping));
+        Pose np = pose_prepend_translation(s.pose, -b.local_com);
+        auto fin3 = [](V3 v) { return std::isfinite(v.x) && std::isfinite(v.y) && std::isfinite(v.z); };
+        if (!(fin3(lin) && fin3(ang) && fin3(np.t) && std::isfinite(np.q.x) && std::isfinite(np.q.y) && std::isfinite(np.q.z) && std::isfinite(np.q.w))) {
+            // quarantine.rs:126-178: roll back to the last valid pose, zero the dynamics, disable, report
+            b.linvel = vzero(); b.angvel = vzero(); b.user_force = vzero(); b.user_torque = vzero();
+            b.next_pos = b.pos;
+            b.type = 3;
+            for (Collider& c : w.colliders)
+                if (c.parent == i) c.shape = -1;
+            w.quarantine.push_back(i);
+            w.bp_dirty = true; w.static_dirty = true; w.islands_dirty = true;
+            continue;
+        }
+        b.linvel = lin;
+        b.angvel = ang;
+        b.next_pos = np;
     }
     w.counters.num_active_manifolds = ncons;
     w.counters.num_colors = num_colors;

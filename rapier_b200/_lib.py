@@ -21,7 +21,7 @@ EXPORTS = [
     "rb_world_get_counters", "rb_world_enable_profiling", "rb_world_get_contact_pairs",
     "rb_world_debug_read", "rb_world_label_components", "rb_world_set_owned_bodies",
     "rb_world_state_buffer", "rb_world_import_states", "rb_world_import_states_from", "rb_world_state_buffers", "rb_world_stream", "rb_world_set_stream",
-    "rb_world_step_host", "rb_debug_kat", "rb_world_get_sleeping", "rb_world_wake_up", "rb_world_set_halo_bodies", "rb_world_import_halo", "rb_world_reserve", "rb_world_insert", "rb_world_remove_bodies",
+    "rb_world_step_host", "rb_debug_kat", "rb_world_get_quarantine", "rb_world_get_sleeping", "rb_world_wake_up", "rb_world_set_halo_bodies", "rb_world_import_halo", "rb_world_reserve", "rb_world_insert", "rb_world_remove_bodies",
 ]
 
 
@@ -56,6 +56,7 @@ def declare(L):
     L.rb_world_stream.argtypes = [vp]
     L.rb_world_set_stream.argtypes = [vp, vp]
     L.rb_world_step_host.argtypes = [vp, C.POINTER(C.c_float), vp, vp]
+    L.rb_world_get_quarantine.argtypes = [vp, vp, i32]
     L.rb_world_get_sleeping.argtypes = [vp, vp]
     L.rb_world_wake_up.argtypes = [vp, i32, vp]
     L.rb_world_set_halo_bodies.argtypes = [vp, vp]

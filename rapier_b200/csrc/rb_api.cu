@@ -888,7 +888,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.b_uforce, NB); ALLOC(w.b_utorque, NB); ALLOC(w.b_wcom, NB); ALLOC(w.b_eim, NB + 2);
     ALLOC(w.b_eii0, NB); ALLOC(w.b_eii1, NB); ALLOC(w.b_owned, NB);
     ALLOC(w.b_sleeping, NB); ALLOC(w.b_sleep_time, NB); ALLOC(w.b_sleep_prev_t, NB); ALLOC(w.b_sleep_prev_q, NB); ALLOC(w.b_max_extent, NB);
-    ALLOC(w.wake_req, NB); ALLOC(w.isl_block, NB);
+    ALLOC(w.wake_req, NB); ALLOC(w.isl_block, NB); ALLOC(w.quarantine, NB);
     ALLOC(w.s_lin, NB + 2); ALLOC(w.s_ang, NB + 2); ALLOC(w.s_q, NB + 2); ALLOC(w.s_t, NB + 2);   // + world pseudo body, garbage slot
     ALLOC(w.s_incr_lin, NB); ALLOC(w.s_incr_ang, NB);
     ALLOC(w.state13, (size_t)NB * 13);
@@ -1108,6 +1108,27 @@ int rb_world_remove_bodies(RbWorld* W, int32_t n, const int32_t* indices) {
     CK(h2d(&W->w.st->bp_dirty, &one, sizeof(int)));
     CK(h2d(&W->w.st->sched_dirty, &one, sizeof(int)));
     return wake_impl(W, nullptr, 0);   // (the reference wakes what touched the removed body; here: everything asleep)
+}
+
+// Quarantine::bodies (quarantine.rs:34-37): bodies disabled because their state went non-finite since the last call.
+int rb_world_get_quarantine(RbWorld* W, int32_t* bodies, int32_t cap) {
+    if (!W || !W->w.st) return RB_ERR_INVALID;
+    State st;
+    int rc = read_state(W, st);
+    if (rc != RB_OK) return rc;
+    const int n = std::min(st.nquarantine, W->w.nb);
+    if (bodies && cap > 0 && n > 0) {
+        std::vector<int> q(n);
+        CK(d2h(q.data(), W->w.quarantine, (size_t)n * sizeof(int)));
+        std::sort(q.begin(), q.end());
+        for (int i = 0; i < n && i < cap; ++i) {
+            bodies[i] = q[i];
+            if (q[i] >= 0 && q[i] < (int)W->bodies.size()) W->bodies[q[i]].body_type = BODY_REMOVED;
+        }
+        int zero = 0;
+        CK(h2d(&W->w.st->nquarantine, &zero, sizeof(int)));
+    }
+    return n;
 }
 
 int rb_world_get_sleeping(RbWorld* W, uint8_t* sleeping) {

@@ -65,8 +65,11 @@ RB_HD void refresh_collider(const World& w, int c) {
 template <class Ctx>
 RB_PHASE void phase_refresh_colliders(const Ctx& ctx, const World& w) {
     if (w.st->lists_dirty) {
-        for (int c = ctx.gtid; c < w.nc; c += ctx.gsize)
+        for (int c = ctx.gtid; c < w.nc; c += ctx.gsize) {
+            const int parent = w.c_parent[c];
+            if (parent >= 0 && w.b_type[parent] == BODY_REMOVED) w.c_shape[c] = SHAPE_REMOVED;   // (removed or quarantined body)
             if (w.c_shape[c] != SHAPE_REMOVED) refresh_collider(w, c);
+        }
     } else {
         const int nd = w.st->ndyn;
         for (int i = ctx.gtid; i < nd; i += ctx.gsize) refresh_collider(w, w.dyn_list[i]);

@@ -42,6 +42,7 @@ RB_HD float norm(vec3 a) { return sqrtf(dot3(a, a)); }
 RB_HD float comp(vec3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 RB_HD vec3 with_comp(vec3 a, int i, float v) { if (i == 0) a.x = v; else if (i == 1) a.y = v; else a.z = v; return a; }
 
+RB_HD bool finite3(vec3 a) { return isfinite(a.x) && isfinite(a.y) && isfinite(a.z); }
 RB_HD float safe_inv(float x) { return (x >= -1.0e-20f && x <= 1.0e-20f) ? 0.0f : 1.0f / x; }
 RB_HD float inv_exact0(float x) { return x == 0.0f ? 0.0f : 1.0f / x; }
 RB_HD float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }

@@ -793,6 +793,23 @@ RB_HD void body_writeback(const World& w, const B& bd, int b, int id) {
     vec3 lin = bd.lin(id) * (1.0f / (1.0f + P.dt * misc.x));
     vec3 ang = bd.ang(id) * (1.0f / (1.0f + P.dt * misc.y));
     pose np = prepend_translation(bd.xf(id), -xyz(w.b_lcom_im[b]));
+    if (!(finite3(lin) && finite3(ang) && finite3(np.t) && isfinite(np.q.x) && isfinite(np.q.y) && isfinite(np.q.z) && isfinite(np.q.w))) {
+        // Containment of non-finite state at the end-of-step chokepoint (physics_pipeline/quarantine.rs:14-47, :126-178):
+        // the body keeps its last valid pose, loses its velocities and forces, is disabled (its colliders leave the
+        // broad phase at the next step) and is reported through rb_world_get_quarantine; the step raises RB_ERR_NONFINITE.
+        w.b_linvel[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w.b_angvel[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w.b_uforce[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w.b_utorque[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w.b_type[b] = BODY_REMOVED;
+        float* s = w.state13 + (size_t)b * 13;
+        for (int k = 7; k < 13; ++k) s[k] = 0.0f;
+        const int slot = atomic_add(&w.st->nquarantine, 1);
+        if (slot < w.nb) w.quarantine[slot] = b;
+        w.st->lists_dirty = 3; w.st->bp_dirty = 1; w.st->sched_dirty = 1;
+        RB_RAISE(w, -5);
+        return;
+    }
     w.b_linvel[b] = f4(lin, 0.0f);
     w.b_angvel[b] = f4(ang, 0.0f);
     w.b_pos_t[b] = f4(np.t, 0.0f);

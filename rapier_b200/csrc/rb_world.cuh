@@ -108,7 +108,8 @@ struct State {
     int bp_diff;           // the candidate pair set differs from the pair table
     int wake_any;          // a contact began with a sleeping body this step: run the wake pass
     int sleep_stamp;       // step counter of the sleep decision (isl_block holds the stamp of the last veto)
-    int pad[5];
+    int nquarantine;       // bodies quarantined since the host last read the list (non-finite state)
+    int pad[4];
 };
 
 struct PairBuf {
@@ -143,6 +144,7 @@ struct World {
     int* wake_req;                    // [nb] by island root: wake this island (a contact began)
     int* isl_block;                   // [nb] by island root: stamp of the last step a body of the island was not sleep-eligible
     int sleep_enabled;                // some body may sleep: run the sleep decision
+    int* quarantine;                  // [nb] bodies disabled because their state went non-finite (Quarantine::bodies)
     // solver bodies (global-memory path) + per-substep increments
     float4 *s_lin, *s_ang, *s_q, *s_t, *s_incr_lin, *s_incr_ang;
     float* state13;                   // packed [nb][13] t q lin ang (download / NCCL all-gather)

@@ -148,6 +148,14 @@ class PhysicsPipeline:
         assert o.shape == (self.nb,)
         self._check(self.L.rb_world_set_owned_bodies(self.h, o.ctypes.data))
 
+    def quarantine(self):
+        """PhysicsPipeline::quarantine().bodies(): bodies disabled since the last call because their state went non-finite."""
+        n = self._check(self.L.rb_world_get_quarantine(self.h, None, 0))
+        out = np.zeros(max(n, 1), np.int32)
+        if n:
+            self._check(self.L.rb_world_get_quarantine(self.h, out.ctypes.data, n))
+        return out[:n]
+
     def sleeping(self):
         """RigidBody::is_sleeping of every body."""
         out = np.zeros(self.nb, np.uint8)
@@ -247,6 +255,10 @@ class PhysicsWorld:
     def counters(self):
         self._flush()
         return self.physics_pipeline.counters()
+
+    def quarantine(self):
+        self._flush()
+        return self.physics_pipeline.quarantine()
 
     def sleeping(self):
         self._flush()

@@ -65,6 +65,7 @@ def lib(fast=False):
                                            C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_world_insert.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_world_remove_bodies.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_world_get_quarantine.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.orc_world_get_sleeping.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_world_wake_up.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_kat.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
@@ -108,6 +109,13 @@ class OracleWorld:
         rc = self.L.orc_world_insert(self.h, len(body_descs), b, len(collider_descs), c)
         assert rc == 0, rc
         self.nb += len(body_descs)
+
+    def quarantine(self):
+        n = self.L.orc_world_get_quarantine(self.h, None, 0)
+        out = np.zeros(max(n, 1), np.int32)
+        if n:
+            self.L.orc_world_get_quarantine(self.h, out.ctypes.data, n)
+        return out[:n]
 
     def sleeping(self):
         out = np.zeros(self.nb, np.uint8)

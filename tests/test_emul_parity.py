@@ -144,3 +144,8 @@ def test_sleep_and_wake_match_oracle_bit_for_bit():
         if i % 15 == 14:
             assert is_exact(compare_worlds(w, o)), i
     assert seen_sleep and seen_wake
+
+
+def test_quarantine_emulated_kernels():
+    from test_oracle_kat import nan_force_is_quarantined
+    nan_force_is_quarantined(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), expect_error=True)

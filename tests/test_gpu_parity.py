@@ -298,3 +298,8 @@ def test_sleep_and_wake_match_oracle_bit_for_bit(built):
         if i % 40 == 39:
             assert is_exact(compare_worlds(w, o)), i
     assert seen_sleep and seen_wake
+
+
+def test_quarantine(built):
+    from test_oracle_kat import nan_force_is_quarantined
+    nan_force_is_quarantined(lambda s: PhysicsWorld(s), expect_error=True)

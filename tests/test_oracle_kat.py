@@ -407,3 +407,38 @@ def sleeping_stack_is_woken_by_an_impact(make_world):
 def test_whole_island_sleep_oracle():
     whole_island_blocks_partial_sleep(lambda s: oracle_lib.OracleWorld(s))
     sleeping_stack_is_woken_by_an_impact(lambda s: oracle_lib.OracleWorld(s))
+
+
+# ---- quarantine: src/pipeline/physics_pipeline/quarantine.rs:295-352 ----
+def nan_force_is_quarantined(make_world, expect_error):
+    """`nan_force_is_quarantined_at_end_of_step` + `nan_spread_through_contacts_is_contained`: a NaN force becomes a NaN
+    velocity mid-step; the end-of-step chokepoint rolls the body back to its last valid pose, zeroes its velocity,
+    disables it and reports it; whatever it infected through contacts is quarantined too, nothing else is corrupted."""
+    s = scenes.Scene("nan")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(50.0, 0.5, 50.0))
+    poisoned = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 3.0, 0.0)), ColliderBuilder.ball(0.5))
+    s.bodies.descs[poisoned].user_force[:] = (float("nan"), 0.0, 0.0)
+    bottom = s.insert(RigidBodyBuilder.dynamic().translation((5.0, 0.5, 0.0)), ColliderBuilder.ball(0.5))
+    s.bodies.descs[bottom].user_torque[:] = (0.0, float("nan"), 0.0)
+    top = s.insert(RigidBodyBuilder.dynamic().translation((5.0, 1.5, 0.0)), ColliderBuilder.ball(0.5))
+    healthy = s.insert(RigidBodyBuilder.dynamic().translation((-6.0, 0.5, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    w = make_world(s)
+    if expect_error:
+        with pytest.raises(Exception, match="-5"):
+            w.step()
+    else:
+        w.step()
+    q = w.quarantine().tolist()
+    assert poisoned in q and bottom in q and healthy not in q
+    pose, vel = w.body_states()
+    assert np.allclose(pose[poisoned], [0.0, 3.0, 0.0, 0.0, 0.0, 0.0, 1.0]) and (vel[poisoned] == 0).all()
+    for _ in range(10):
+        w.step()
+        assert len(w.quarantine()) == 0 or set(w.quarantine().tolist()) <= {top}
+        pose, vel = w.body_states()
+        alive = [b for b in (top, healthy) if b not in q]
+        assert np.isfinite(pose[alive]).all() and np.isfinite(vel[alive]).all()
+
+
+def test_quarantine_oracle():
+    nan_force_is_quarantined(lambda s: oracle_lib.OracleWorld(s), expect_error=False)
