@@ -2,7 +2,7 @@
 set -x
 O=gpurun_out/r02d; mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()"
-timeout 1500 python -m pytest tests -m gpu -q -x > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
 tail -15 $O/pytest_gpu.log
 timeout 900 python tests/perf_scenes.py > $O/perf_scenes.jsonl 2> $O/perf_scenes.err
 cat $O/perf_scenes.jsonl | cut -c1-520
