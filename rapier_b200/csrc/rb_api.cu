@@ -237,7 +237,6 @@ RB_PHASE void set_halo_phase(const Ctx& ctx, const World& w, const unsigned char
 __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, int do_solve) {
     extern __shared__ __align__(16) float smem[];
     GridCtx ctx;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel of the stream may be set up now (it waits for our completion itself)
     if (ctx.gtid == 0) {   // publish last step's launch hints to the host (read without synchronising)
         w.host_hint[0] = w.st->need_big;
         w.host_hint[2] = w.st->nlarge_bodies > 0 ? 1 : 0;   // a grid-wide island exists: launch k_solve_large
@@ -298,7 +297,6 @@ __global__ void __launch_bounds__(COLLIDE_THREADS, 1) k_solve_large(World w, Gra
 template <int L>
 __device__ __forceinline__ void solve_coop_items(const World& w, const Grav& g, int smem_floats, bool big) {
     extern __shared__ __align__(16) float smem[];
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // (programmatic dependent launch: k_collide's results are visible from here)
     __shared__ __align__(8) unsigned long long s_mbar[2];
     BlockCtx ctx;
     if (ctx.btid == 0) {
@@ -376,8 +374,6 @@ struct RbWorld {
     int collide_threads = COLLIDE_THREADS;
     int coop_blocks_big = 1;
     int big_threads = COOP_BIG_THREADS, sweep_threads = 0;
-    int big_lanes = 1;     // lanes per constraint of the big launch shape (RB_BIG_LANES experiment: 1 or 2)
-    int use_pdl = 1;       // programmatic dependent launch of the big solve kernel (RB_PDL=0 disables)
     float* state_buf[2] = {nullptr, nullptr};   // double-buffered packed state (rb_world_state_buffers), else unused
     int state_next = 0;
     int steps_since_scene = 0;   // the launch-shape hint of a new scene is awaited once (see rb_world_step)
@@ -778,7 +774,7 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
     if (!prop.cooperativeLaunch) { set_err("device lacks cooperative launch%s", ""); delete W; return nullptr; }
     cudaStreamCreateWithFlags(&W->stream, cudaStreamNonBlocking);
     cudaFuncSetAttribute(k_solve_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_SMALL_SMEM_BYTES);
-#define RB_BIG_VARIANTS(X) X(256, 1) X(256, 2)
+#define RB_BIG_VARIANTS(X) X(256, 1)
 #define RB_SET_ATTR(T, LL) cudaFuncSetAttribute(k_solve_coop_big<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, COOP_BIG_SMEM_BYTES);
     RB_BIG_VARIANTS(RB_SET_ATTR)
     if (cudaHostAlloc((void**)&W->host_hint, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) { set_err("cudaHostAlloc failed%s", ""); delete W; return nullptr; }
@@ -799,8 +795,6 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
         W->collide_threads = std::min(COLLIDE_THREADS, envi("RB_COLLIDE_THREADS", COLLIDE_THREADS));
         W->coop_shape = envi("RB_COOP_SHAPE", -1);
         W->sweep_threads = envi("RB_COOP_SWEEP_THREADS", 0);
-        W->big_lanes = envi("RB_BIG_LANES", 1) == 2 ? 2 : 1;
-        W->use_pdl = envi("RB_PDL", 1);
     }
 #else
     {   // emulated CTA: shared-memory size of the big launch shape, or a test override that forces streaming
@@ -900,7 +894,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.c_shape, NC); ALLOC(w.c_parent, NC); ALLOC(w.c_he, NC); ALLOC(w.c_rel_t, NC); ALLOC(w.c_rel_q, NC);
     ALLOC(w.c_mat, NC); ALLOC(w.c_rules, NC); ALLOC(w.c_groups, NC); ALLOC(w.c_pos_t, NC); ALLOC(w.c_pos_q, NC);
     ALLOC(w.c_aabb_min, NC); ALLOC(w.c_aabb_max, NC); ALLOC(w.c_fat_min, NC); ALLOC(w.c_fat_max, NC);
-    ALLOC(w.dyn_list, NC); ALLOC(w.wide_list, WIDE_CAP);
+    ALLOC(w.dyn_list, NC); ALLOC(w.wide_list, WIDE_CAP); ALLOC(w.dyn_smin, NC); ALLOC(w.dyn_smax, NC);
     for (int k = 0; k < 2; ++k) { ALLOC(w.dyn_key[k], NC); ALLOC(w.stat_key[k], NC); }
     ALLOC(w.radix_hist, (size_t)9 * 1024 * RADIX);   // (grids of up to 1024 CTAs; the collide grid is one CTA per SM)
     ALLOC(w.cand_key, w.pair_cap); ALLOC(w.cand_key2, w.pair_cap);
@@ -1242,15 +1236,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
             W->kernels++;
         }
         if (big) {
-            // programmatic dependent launch: the solve kernel's launch is set up while k_collide still runs; it
-            // waits (griddepcontrol.wait) for k_collide's results before it reads anything
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(W->coop_blocks_big); cfg.blockDim = dim3(W->big_threads); cfg.dynamicSmemBytes = COOP_BIG_SMEM_BYTES; cfg.stream = W->stream;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = at; cfg.numAttrs = (W->use_pdl && !large) ? 1 : 0;
-#define RB_LAUNCH_BIG(T, LL) if (W->big_threads == T && W->big_lanes == LL) CK(cudaLaunchKernelEx(&cfg, k_solve_coop_big<T, LL>, W->w, g));
+#define RB_LAUNCH_BIG(T, LL) if (W->big_threads == T) k_solve_coop_big<T, LL><<<W->coop_blocks_big, T, COOP_BIG_SMEM_BYTES, W->stream>>>(W->w, g);
             RB_BIG_VARIANTS(RB_LAUNCH_BIG)
         } else k_solve_coop<<<W->coop_blocks, COOP_SMALL_THREADS, COOP_SMALL_SMEM_BYTES, W->stream>>>(W->w, g);
         CK(cudaGetLastError());

@@ -303,6 +303,16 @@ RB_PHASE void section_build_lists(const Ctx& ctx, const World& w) {
 
 // P1: sort-and-sweep broad phase over the movers + interval search into the sorted static colliders, then the
 // merge with the persistent pair table (skipped when the pair set did not change).
+// The movers are binned into STRIPS along z as wide as the widest mover, and sorted by (strip, quantised min-x): a
+// mover can only touch movers of its own strip and the next one, so a dense 3-D pile costs its neighbours in x of
+// two strips, not of the whole x column (a plain 1-axis sweep of a 50 x 50 x 50 brick pyramid tests 2 500 candidates
+// per brick).  The sorted AABBs are gathered into contiguous arrays, so the sweep reads coalesced rows.
+constexpr int STRIP_BITS = 12, STRIP_COUNT = 1 << STRIP_BITS, XQ_BITS = 32 - STRIP_BITS;
+RB_HD unsigned strip_key(float minz, float minx, float inv_wz) {
+    float f = floorf(minz * inv_wz) + (float)(STRIP_COUNT / 2);
+    f = f < 0.0f ? 0.0f : (f > (float)(STRIP_COUNT - 1) ? (float)(STRIP_COUNT - 1) : f);   // (far strips merge: more tests, never fewer)
+    return ((unsigned)f << XQ_BITS) | (sortable_float(minx) >> STRIP_BITS);
+}
 template <class Ctx>
 RB_PHASE void section_broad_phase(const Ctx& ctx, const World& w) {
     State* st = w.st;
@@ -310,34 +320,66 @@ RB_PHASE void section_broad_phase(const Ctx& ctx, const World& w) {
     const int nd = st->ndyn, ns = st->nstat;
     const int nwide = st->nwide < WIDE_CAP ? st->nwide : WIDE_CAP;
     const unsigned long long* skey = w.stat_key[st->stat_sorted];
+    if (ctx.gtid == 0) { st->mov_wz_bits = 0u; st->mov_wx_bits = 0u; st->ncand = 0; }
+    grid_radix_zero(ctx, w.radix_hist, 4);
+    ctx.grid_sync();
+    for (int i = ctx.gtid; i < nd; i += ctx.gsize) {   // widest mover along z (strip width) and x (search reach)
+        const int c = w.dyn_list[i];
+        const float4 lo = w.c_fat_min[c], hi = w.c_fat_max[c];
+        atomic_max_u(&st->mov_wz_bits, as_uint(hi.z - lo.z > 0.0f ? hi.z - lo.z : 0.0f));
+        atomic_max_u(&st->mov_wx_bits, as_uint(hi.x - lo.x > 0.0f ? hi.x - lo.x : 0.0f));
+    }
+    ctx.grid_sync();
+    const float wz = as_float(st->mov_wz_bits) * 1.01f + 1.0e-3f, wx = as_float(st->mov_wx_bits) * 1.0001f + 1.0e-6f;   // (1 %: strips of overlapping movers differ by at most one, also after rounding)
+    const float inv_wz = 1.0f / wz;
     for (int i = ctx.gtid; i < nd; i += ctx.gsize) {
         const int c = w.dyn_list[i];
-        w.dyn_key[0][i] = ((unsigned long long)sortable_float(w.c_fat_min[c].x) << 32) | (unsigned)c;
+        const float4 lo = w.c_fat_min[c];
+        w.dyn_key[0][i] = ((unsigned long long)strip_key(lo.z, lo.x, inv_wz) << 32) | (unsigned)c;
     }
-    grid_radix_zero(ctx, w.radix_hist, 4);
-    if (ctx.gtid == 0) st->ncand = 0;
     ctx.grid_sync();
     const unsigned long long* dkey = grid_radix_sort(ctx, w.dyn_key[0], w.dyn_key[1], nd, 32, 64, w.radix_hist);
-    // sweep: one warp per mover, lanes stride over what follows it in x
+    for (int i = ctx.gtid; i < nd; i += ctx.gsize) {   // the sorted movers' AABBs, contiguous
+        const int c = (int)(dkey[i] & 0xffffffffu);
+        w.dyn_smin[i] = w.c_fat_min[c];
+        w.dyn_smax[i] = w.c_fat_max[c];
+    }
+    ctx.grid_sync();
+    // sweep: one warp per mover, lanes stride over what follows it
     const float wn = as_float(st->stat_wn_bits) * 1.0001f + 1.0e-6f;   // widest narrow static collider (with rounding slack)
     for (int wi = ctx.gwarp; wi < nd; wi += ctx.ngwarps) {
-        const int ci = (int)(dkey[wi] & 0xffffffffu);
-        const float4 amin = w.c_fat_min[ci], amax = w.c_fat_max[ci];
-        const unsigned amax_key = sortable_float(amax.x);
-        for (int base = wi + 1; base < nd; base += ctx.nlanes) {   // movers with a larger (or equal) min-x
+        const unsigned long long ki = dkey[wi];
+        const int ci = (int)(ki & 0xffffffffu);
+        const float4 amin = w.dyn_smin[wi], amax = w.dyn_smax[wi];
+        const unsigned strip = (unsigned)(ki >> 32) >> XQ_BITS;
+        const unsigned own_end = (strip << XQ_BITS) | (sortable_float(amax.x) >> STRIP_BITS);   // last key of the own strip that can overlap in x
+        for (int base = wi + 1; base < nd; base += ctx.nlanes) {   // own strip: movers that follow in (quantised) x
             const int j = base + ctx.lane;
             bool stop = true;
             if (j < nd) {
                 const unsigned long long kj = dkey[j];
-                stop = (unsigned)(kj >> 32) > amax_key;
-                if (!stop) {
-                    const int cj = (int)(kj & 0xffffffffu);
-                    if (fat_overlap(amin, amax, w.c_fat_min[cj], w.c_fat_max[cj])) emit_candidate(w, ci, cj);
-                }
+                stop = (unsigned)(kj >> 32) > own_end;
+                if (!stop && fat_overlap(amin, amax, w.dyn_smin[j], w.dyn_smax[j])) emit_candidate(w, ci, (int)(kj & 0xffffffffu));
             }
             if (ctx.warp_any(stop)) break;
         }
+        if (strip + 1 < (unsigned)STRIP_COUNT) {   // next strip: movers whose x interval can reach ours
+            const unsigned nlo = ((strip + 1) << XQ_BITS) | (sortable_float(amin.x - wx) >> STRIP_BITS);
+            const unsigned nhi = ((strip + 1) << XQ_BITS) | (sortable_float(amax.x) >> STRIP_BITS);
+            const int first = lower_bound_u64(dkey, nd, (unsigned long long)nlo << 32);
+            for (int base = first; base < nd; base += ctx.nlanes) {
+                const int j = base + ctx.lane;
+                bool stop = true;
+                if (j < nd) {
+                    const unsigned long long kj = dkey[j];
+                    stop = (unsigned)(kj >> 32) > nhi;
+                    if (!stop && fat_overlap(amin, amax, w.dyn_smin[j], w.dyn_smax[j])) emit_candidate(w, ci, (int)(kj & 0xffffffffu));
+                }
+                if (ctx.warp_any(stop)) break;
+            }
+        }
         // narrow static colliders whose x interval can reach [amin.x, amax.x]: min-x in [amin.x - wn, amax.x]
+        const unsigned amax_key = sortable_float(amax.x);
         const int first = lower_bound_u64(skey, ns, (unsigned long long)sortable_float(amin.x - wn) << 32);
         for (int base = first; base < ns; base += ctx.nlanes) {
             const int j = base + ctx.lane;

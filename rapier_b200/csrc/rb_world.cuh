@@ -108,8 +108,9 @@ struct State {
     int bp_diff;           // the candidate pair set differs from the pair table
     int wake_any;          // a contact began with a sleeping body this step: run the wake pass
     int sleep_stamp;       // step counter of the sleep decision (isl_block holds the stamp of the last veto)
+    unsigned mov_wz_bits, mov_wx_bits;   // widest mover along z / x of the last broad-phase run (float bits)
     int nquarantine;       // bodies quarantined since the host last read the list (non-finite state)
-    int pad[4];
+    int pad[2];
 };
 
 struct PairBuf {
@@ -162,6 +163,7 @@ struct World {
     int* wide_list;                   // [WIDE_CAP] static colliders much wider than the rest
     unsigned long long* dyn_key[2];   // [nc] (sortable min-x << 32) | collider of the movers, radix-sort ping-pong
     unsigned long long* stat_key[2];  // [nc] ... of the narrow static colliders, sorted once
+    float4 *dyn_smin, *dyn_smax;      // [nc] fat AABBs of the movers in sorted order (coalesced sweep)
     int* radix_hist;                  // [9][grid blocks][256] digit counts of the radix sorts
     unsigned long long* cand_key;     // [pair_cap] candidate pairs (collider1 << 32) | collider2
     unsigned long long* cand_key2;    // [pair_cap] radix-sort ping-pong
