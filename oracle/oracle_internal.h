@@ -153,8 +153,14 @@ struct NormalPart {
     V3 torque_dir1, torque_dir2, ii_torque_dir1, ii_torque_dir2;
     float rhs, rhs_wo_bias, impulse, impulse_accumulator, r, cfm_factor;
 };
+// ContactConstraintTangentPart (contact_constraint_element.rs:14-36), one per point: FrictionModel::Coulomb only.
+struct TangentPart {
+    V3 torque_dir1[2], torque_dir2[2], ii_torque_dir1[2], ii_torque_dir2[2];
+    float rhs[2], rhs_wo_bias[2], impulse[2], impulse_acc[2], r[3];
+};
 struct Constraint {
     int pair;
+    bool coulomb;          // ContactWithCoulombFriction (contact_with_coulomb_friction.rs:532-549) instead of the twist form
     uint32_t id1, id2;
     int num_contacts;
     V3 dir1, tangent1;
@@ -168,6 +174,7 @@ struct Constraint {
     // twist part
     float w_rhs, w_impulse, w_impulse_acc, w_r;
     float twist_dists[MAX_MANIFOLD_POINTS];
+    TangentPart tangent[MAX_MANIFOLD_POINTS];   // Coulomb: one coupled 2x2 tangent part per point
     int cids[MAX_MANIFOLD_POINTS];
     // builder
     V3 b_local_p1[MAX_MANIFOLD_POINTS], b_local_p2[MAX_MANIFOLD_POINTS];

@@ -67,6 +67,7 @@ static void generate(World& w, int pair_index, Constraint& c) {
     const Pair& p = w.pairs[pair_index];
     memset(&c, 0, sizeof(c));
     c.pair = pair_index;
+    c.coulomb = w.params.p.friction_model == 1;   // FrictionModel::Coulomb (init.rs:419)
     bool d1 = p.b1 >= 0 && w.bodies[p.b1].is_awake();
     bool d2 = p.b2 >= 0 && w.bodies[p.b2].is_awake();
     c.id1 = d1 ? (uint32_t)p.b1 : NO_BODY;
@@ -132,7 +133,24 @@ static void generate(World& w, int pair_index, Constraint& c) {
         c.b_local_p2[k] = pose_inv_point(g2.pose, world_com2 + dp2);
         c.b_dist[k] = dist - dot(point - (world_com2 + dp2), force_dir1);
         c.b_restitution_seed[k] = restitution_seed;
+        if (c.coulomb) {   // contact_with_coulomb_friction.rs:255-302: one tangent part per point, arms = the point's own
+            TangentPart& tp = c.tangent[k];
+            tp.impulse[0] = ws_t0; tp.impulse[1] = ws_t1;
+            tp.impulse_acc[0] = -ws_t0; tp.impulse_acc[1] = -ws_t1;
+            const V3 tj[2] = {t1, t2};
+            for (int j = 0; j < 2; ++j) {
+                tp.torque_dir1[j] = cross(dp1, tj[j]);
+                tp.torque_dir2[j] = cross(dp2, -tj[j]);
+                tp.ii_torque_dir1[j] = sdp_mul(g1.ii, tp.torque_dir1[j]);
+                tp.ii_torque_dir2[j] = sdp_mul(g2.ii, tp.torque_dir2[j]);
+                tp.r[j] = dot(tj[j], cmul(imsum, tj[j])) + dot(tp.ii_torque_dir1[j], tp.torque_dir1[j]) + dot(tp.ii_torque_dir2[j], tp.torque_dir2[j]);
+                tp.rhs_wo_bias[j] = 0.0f;   // tangent_velocity . t_j, identically zero without contact-modification hooks
+                tp.rhs[j] = 0.0f;
+            }
+            tp.r[2] = 2.0f * (dot(tp.ii_torque_dir1[0], tp.torque_dir1[1]) + dot(tp.ii_torque_dir2[0], tp.torque_dir2[1]));
+        }
     }
+    if (c.coulomb) return;   // no friction centre, no twist row (contact_with_coulomb_friction.rs:41-49)
     c.t_impulse[0] = tangent_warmstart[0];
     c.t_impulse[1] = tangent_warmstart[1];
     c.t_impulse_acc[0] = -tangent_warmstart[0];
@@ -197,8 +215,17 @@ static void update(const World& w, Constraint& c, const SubParams& sp, float sol
         n.cfm_factor = dist <= 0.0f ? cfm_factor : 1.0f;
         n.impulse_accumulator = n.impulse_accumulator + n.impulse;
         n.impulse = n.impulse * sp.warmstart_coeff;
+        if (c.coulomb) {   // contact_with_coulomb_friction.rs:438-447
+            TangentPart& tp = c.tangent[k];
+            for (int j = 0; j < 2; ++j) {
+                tp.impulse_acc[j] = tp.impulse_acc[j] + tp.impulse[j];
+                tp.impulse[j] = tp.impulse[j] * sp.warmstart_coeff;
+                float bias = dot(p1 - p2, tangents[j]) * sp.inv_dt;
+                tp.rhs[j] = tp.rhs_wo_bias[j] + bias;
+            }
+        }
     }
-    {
+    if (!c.coulomb) {
         V3 p1 = pose_point(g1.pose, c.b_lfc1);
         V3 p2 = pose_point(g2.pose, c.b_lfc2);
         for (int j = 0; j < 2; ++j) {
@@ -224,6 +251,7 @@ static void refresh_rhs_wo_bias(const World& w, Constraint& c, const SubParams& 
         float dist = c.b_dist[k] + dot(p1 - p2, c.dir1);
         c.normal[k].rhs = fmax2(dist, 0.0f) * sp.inv_dt;
         c.normal[k].cfm_factor = 1.0f;
+        if (c.coulomb) { c.tangent[k].rhs[0] = c.tangent[k].rhs_wo_bias[0]; c.tangent[k].rhs[1] = c.tangent[k].rhs_wo_bias[1]; }
     }
     c.t_rhs[0] = c.t_rhs_wo_bias[0];
     c.t_rhs[1] = c.t_rhs_wo_bias[1];
@@ -241,6 +269,18 @@ static void warmstart(World& w, Constraint& c) {
         w2 = madd(w2, n.ii_torque_dir2, n.impulse);
     }
     V3 t0 = c.tangent1, t1 = cross(c.dir1, c.tangent1);
+    if (c.coulomb) {   // contact_with_coulomb_friction.rs:584-592 + contact_constraint_element.rs:64-98, point by point
+        for (int k = 0; k < c.num_contacts; ++k) {
+            const TangentPart& tp = c.tangent[k];
+            v1 = maddv(v1, madd(t0 * tp.impulse[0], t1, tp.impulse[1]), c.im1);
+            w1 = madd(madd(w1, tp.ii_torque_dir1[0], tp.impulse[0]), tp.ii_torque_dir1[1], tp.impulse[1]);
+            v2 = maddv(v2, madd(t0 * (-tp.impulse[0]), t1, -tp.impulse[1]), c.im2);
+            w2 = madd(madd(w2, tp.ii_torque_dir2[0], tp.impulse[0]), tp.ii_torque_dir2[1], tp.impulse[1]);
+        }
+        scatter_vel(w, c.id1, v1, w1);
+        scatter_vel(w, c.id2, v2, w2);
+        return;
+    }
     v1 = maddv(v1, madd(t0 * c.t_impulse[0], t1, c.t_impulse[1]), c.im1);
     w1 = madd(madd(w1, c.t_ii_torque_dir1[0], c.t_impulse[0]), c.t_ii_torque_dir1[1], c.t_impulse[1]);
     v2 = maddv(v2, madd(t0 * (-c.t_impulse[0]), t1, -c.t_impulse[1]), c.im2);
@@ -270,7 +310,33 @@ static void solve(World& w, Constraint& c, bool solve_friction) {
         v2 = madd(v2, cmul(c.dir1, c.im2), -dlambda);
         w2 = madd(w2, n.ii_torque_dir2, dlambda);
     }
-    if (solve_friction) {
+    if (solve_friction && c.coulomb) {   // contact_with_coulomb_friction.rs:659-676 + contact_constraint_element.rs:124-176
+        V3 t0 = c.tangent1, t1 = cross(c.dir1, c.tangent1);
+        for (int k = 0; k < c.num_contacts; ++k) {
+            TangentPart& tp = c.tangent[k];
+            const float limit = (0.0f + c.normal[k].impulse) * c.limit;
+            float dvel_0 = dot(t0, v1) + dot(tp.torque_dir1[0], w1) - dot(t0, v2) + dot(tp.torque_dir2[0], w2) + tp.rhs[0];
+            float dvel_1 = dot(t1, v1) + dot(tp.torque_dir1[1], w1) - dot(t1, v2) + dot(tp.torque_dir2[1], w2) + tp.rhs[1];
+            float k11 = tp.r[0], k22 = tp.r[1], k12 = tp.r[2] * 0.5f;
+            float inv_det = inv_or_zero(fma_(k11, k22, -(k12 * k12)));
+            float d0 = fma_(k22, dvel_0, -(k12 * dvel_1)) * inv_det;
+            float d1 = fma_(k11, dvel_1, -(k12 * dvel_0)) * inv_det;
+            float n0 = tp.impulse[0] - d0, n1 = tp.impulse[1] - d1;
+            float len = sqrtf(fma_(n1, n1, n0 * n0));
+            if (len > limit) {
+                float s = limit / len;
+                n0 = n0 * s;
+                n1 = n1 * s;
+            }
+            float dl0 = n0 - tp.impulse[0], dl1 = n1 - tp.impulse[1];
+            tp.impulse[0] = n0;
+            tp.impulse[1] = n1;
+            v1 = maddv(v1, madd(t0 * dl0, t1, dl1), c.im1);
+            w1 = madd(madd(w1, tp.ii_torque_dir1[0], dl0), tp.ii_torque_dir1[1], dl1);
+            v2 = maddv(v2, madd(t0 * (-dl0), t1, -dl1), c.im2);
+            w2 = madd(madd(w2, tp.ii_torque_dir2[0], dl0), tp.ii_torque_dir2[1], dl1);
+        }
+    } else if (solve_friction) {
         V3 t0 = c.tangent1, t1 = cross(c.dir1, c.tangent1);
         float tangent_limit = 0.0f, twist_limit = 0.0f;
         for (int k = 0; k < c.num_contacts; ++k) {
@@ -346,6 +412,17 @@ static inline float canon0(float x) { return x == 0.0f ? 0.0f : x; }  // utils::
 static void writeback_impulses(World& w, const Constraint& c) {
     Pair& p = w.pairs[c.pair];
     V3 t2 = cross(c.dir1, c.tangent1);
+    if (c.coulomb) {   // contact_with_coulomb_friction.rs:683-740: per-point world tangent impulse, the twist slot is left alone
+        for (int k = 0; k < c.num_contacts; ++k) {
+            Point& pt = p.pts[c.cids[k]];
+            float a0 = canon0(c.tangent[k].impulse[0]), a1 = canon0(c.tangent[k].impulse[1]);
+            V3 tw = c.tangent1 * a0 + t2 * a1;
+            pt.warmstart_impulse = canon0(c.normal[k].impulse);
+            pt.impulse = canon0(c.normal[k].impulse_accumulator + c.normal[k].impulse);
+            pt.warmstart_tangent_world = V3{canon0(tw.x), canon0(tw.y), canon0(tw.z)};
+        }
+        return;
+    }
     float ti0 = canon0(c.t_impulse[0]), ti1 = canon0(c.t_impulse[1]);
     V3 tw = c.tangent1 * ti0 + t2 * ti1;
     tw = V3{canon0(tw.x), canon0(tw.y), canon0(tw.z)};
