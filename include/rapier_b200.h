@@ -58,7 +58,7 @@ typedef struct RbIntegrationParameters {
     float normalized_contact_recycle_distance;  /* default 0.05 */
     int32_t friction_in_bias_pass;              /* default 0 */
     int32_t warmstart_joints;                   /* default 0 (1 is RB_ERR_INVALID for now) */
-    int32_t friction_model;                     /* 0 = Simplified (twist, default); 1 = Coulomb: RB_ERR_INVALID */
+    int32_t friction_model;                     /* 0 = Simplified (twist, default); 1 = Coulomb (one friction part per point) */
 } RbIntegrationParameters;
 
 /* Fills *p with IntegrationParameters::default() (integration_parameters.rs:379-407). */

@@ -290,6 +290,37 @@ __global__ void __launch_bounds__(COLLIDE_THREADS, 1) k_solve_large(World w, Gra
     gex.c = &ctx;
     solve_item_lanes<4>(gex, w, gb, mk3(g.x, g.y, g.z));
 }
+// FrictionModel::Coulomb (integration_parameters.rs:26-29): one coupled tangent part per contact point instead of the
+// twist model's one per manifold.  Every work item takes the streaming solve (solve_item<1>: bodies in shared memory,
+// rows in HBM/L2), the grid-wide item 0 the same code with grid barriers; the twist kernels carry none of this code.
+__global__ void __launch_bounds__(COLLIDE_THREADS) k_solve_items_coulomb(World w, Grav g) {
+    extern __shared__ __align__(16) float smem[];
+    BlockCtx bctx;
+    SmemBodies bd;
+    bd.s = smem;
+    BlockExec ex;
+    ex.c = &bctx;
+    __shared__ int s_next;
+    const int n = w.st->norder;
+    for (;;) {
+        if (bctx.btid == 0) s_next = atomicAdd(&w.st->cursor_rest, 1);
+        __syncthreads();
+        const int k = s_next;
+        __syncthreads();
+        if (k >= n) break;
+        solve_item<1>(ex, w, bd, w.item_order[k], mk3(g.x, g.y, g.z));
+        ex.sync();
+    }
+}
+__global__ void __launch_bounds__(COLLIDE_THREADS, 1) k_solve_large_coulomb(World w, Grav g) {
+    GridCtx ctx;
+    if (w.st->nlarge_bodies == 0) return;
+    GlobalBodies gb;
+    gb.w = &w;
+    GridExec gex;
+    gex.c = &ctx;
+    solve_item<1>(gex, w, gb, 0, mk3(g.x, g.y, g.z));
+}
 // Shared-memory items: one CTA per item, bodies (and, when they fit, constraints) staged in shared memory,
 // four lanes per constraint (rb_solver.cuh "lane-cooperative path").
 // Either launch shape takes every shared-memory item (the small one streams what does not fit), so the
@@ -451,11 +482,12 @@ static void derive_params(const RbIntegrationParameters& p, Params& o) {
     o.num_relax = p.num_internal_stabilization_iterations;
     o.friction_in_bias = p.friction_in_bias_pass;
     o.contact_recycling = p.contact_recycling;
+    o.friction_model = p.friction_model;
 }
 
 static int validate_params(const RbIntegrationParameters* p) {
     if (!p) { set_err("null parameters%s", ""); return RB_ERR_INVALID; }
-    if (p->friction_model != 0) { set_err("friction_model Coulomb is not supported%s", ""); return RB_ERR_INVALID; }
+    if (p->friction_model != 0 && p->friction_model != 1) { set_err("friction_model must be 0 (Simplified) or 1 (Coulomb)%s", ""); return RB_ERR_INVALID; }
     if (p->warmstart_joints != 0) { set_err("warmstart_joints is not supported%s", ""); return RB_ERR_INVALID; }
     if (p->num_solver_iterations < 1 || p->num_solver_iterations > 64) { set_err("num_solver_iterations out of range%s", ""); return RB_ERR_INVALID; }
     return RB_OK;
@@ -780,6 +812,7 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
     if (cudaHostAlloc((void**)&W->host_hint, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) { set_err("cudaHostAlloc failed%s", ""); delete W; return nullptr; }
     for (int i = 0; i < 4; ++i) W->host_hint[i] = 0;
     cudaFuncSetAttribute(k_collide, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
+    cudaFuncSetAttribute(k_solve_items_coulomb, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_collide, COLLIDE_THREADS, ITEM_SMEM_BYTES);
     if (occ < 1) { set_err("k_collide cannot be resident%s", ""); delete W; return nullptr; }
@@ -1217,8 +1250,9 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         bool prof = W->profiling;
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s], W->stream));
         // a grid-wide island existed after the last schedule the host knows of: it gets its own launch
+        const bool coulomb = W->w.prm.friction_model == 1;
         const bool large = *(volatile int*)(W->host_hint + 2) != 0;
-        int do_solve = large ? 3 : 1;
+        int do_solve = coulomb ? 0 : (large ? 3 : 1);
         if (W->state_buf[1]) { W->w.state13 = W->state_buf[W->state_next]; W->state_next ^= 1; }
         // A new scene's islands are only known after its first schedule.  A caller that enqueues many steps in
         // one asynchronous call would otherwise run all of them in the launch shape chosen before that, so the
@@ -1230,6 +1264,14 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         void* a1[] = {(void*)&W->w, (void*)&g, (void*)&do_solve};
         CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, ITEM_SMEM_BYTES, W->stream));
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 1], W->stream));
+        if (coulomb) {   // every item through the streaming solve; the grid-wide item's kernel returns at once when there is none
+            void* a2[] = {(void*)&W->w, (void*)&g};
+            k_solve_items_coulomb<<<W->collide_blocks, W->collide_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
+            CK(cudaLaunchCooperativeKernel((void*)k_solve_large_coulomb, dim3(W->collide_blocks), dim3(W->collide_threads), a2, 0, W->stream));
+            if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 2], W->stream));
+            W->kernels += 3;
+            continue;
+        }
         if (large) {
             void* a2[] = {(void*)&W->w, (void*)&g};
             CK(cudaLaunchCooperativeKernel((void*)k_solve_large, dim3(W->collide_blocks), dim3(W->collide_threads), a2, 0, W->stream));
@@ -1280,7 +1322,8 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         pp.sweep_threads = 1;
         for (int k = 0; k < W->w.st->norder; ++k) {
             const int item = W->w.item_order[k];
-            if (item_is_coop(W->w, item))
+            if (W->w.prm.friction_model == 1) solve_item<1>(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
+            else if (item_is_coop(W->w, item))
                 solve_item_coop<1>(bctx, W->w, W->emu_smem.data() + ITEM_MAX_BODIES * SB_STRIDE, W->emu_coop_floats, pp, item, mk3(g.x, g.y, g.z));
             else solve_item(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
         }
@@ -1289,7 +1332,8 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
             gb.w = &W->w;
             GridExec gex;
             gex.c = &gctx;
-            solve_item_lanes<1>(gex, W->w, gb, mk3(g.x, g.y, g.z));
+            if (W->w.prm.friction_model == 1) solve_item<1>(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
+            else solve_item_lanes<1>(gex, W->w, gb, mk3(g.x, g.y, g.z));
         }
         W->kernels += 2;
     }

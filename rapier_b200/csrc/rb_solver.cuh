@@ -112,8 +112,12 @@ struct Cons {
     float twd[MAX_PTS];
     float imp[MAX_PTS], acc[MAX_PTS];          // normal impulses + accumulators
     float ti0, ti1, ta0, ta1, wi, wa;          // tangent / twist impulses + accumulators
+    // FrictionModel::Coulomb: per-point tangent impulses + accumulators and tangent K (the jacobians are
+    // recomputed from dp1 / dp2 in every sweep, like the twist model's friction-centre jacobians)
+    float pti0[MAX_PTS], pti1[MAX_PTS], pta0[MAX_PTS], pta1[MAX_PTS], pk0[MAX_PTS], pk1[MAX_PTS], pk2[MAX_PTS];
 };
 
+template <int FM = 0>
 RB_HD void cons_store_static(const World& w, int q, const Cons& c) {
     crow(w, CR_DIR, q) = f4(c.dir, c.fric);
     crow(w, CR_T1, q) = f4(c.t1, c.wr);
@@ -125,6 +129,7 @@ RB_HD void cons_store_static(const World& w, int q, const Cons& c) {
             float4 a = crow(w, CR_LP1 + k, q), b = crow(w, CR_LP2 + k, q);   // keep w: seed / cid
             crow(w, CR_LP1 + k, q) = f4(c.lp1[k], a.w);
             crow(w, CR_LP2 + k, q) = f4(c.lp2[k], b.w);
+            if (FM) crow(w, CR_PTK + k, q) = make_float4(c.pk0[k], c.pk1[k], c.pk2[k], 0.0f);
         }
     }
     crow(w, CR_TDP1, q) = f4(c.tdp1, c.tr0);
@@ -134,12 +139,19 @@ RB_HD void cons_store_static(const World& w, int q, const Cons& c) {
     crow(w, CR_LFC1, q) = l1;
     crow(w, CR_TWD, q) = make_float4(c.twd[0], c.twd[1], c.twd[2], c.twd[3]);
 }
+template <int FM = 0>
 RB_HD void cons_store_dyn(const World& w, int q, const Cons& c) {
     crow(w, CR_IMP, q) = make_float4(c.imp[0], c.imp[1], c.imp[2], c.imp[3]);
     crow(w, CR_ACC, q) = make_float4(c.acc[0], c.acc[1], c.acc[2], c.acc[3]);
     crow(w, CR_TI, q) = make_float4(c.ti0, c.ti1, c.ta0, c.ta1);
     crow(w, CR_WI, q) = make_float4(c.wi, c.wa, 0.0f, 0.0f);
+    if (FM) {
+#pragma unroll
+        for (int k = 0; k < MAX_PTS; ++k)
+            if (k < c.nc) crow(w, CR_PTI + k, q) = make_float4(c.pti0[k], c.pti1[k], c.pta0[k], c.pta1[k]);
+    }
 }
+template <int FM = 0>
 RB_HD void cons_load(const World& w, int q, Cons& c) {
     int4 h = w.cons_hdr[q];
     c.id1 = h.y; c.id2 = h.z; c.nc = h.w;
@@ -160,11 +172,21 @@ RB_HD void cons_load(const World& w, int q, Cons& c) {
     c.imp[0] = im.x; c.imp[1] = im.y; c.imp[2] = im.z; c.imp[3] = im.w;
     c.acc[0] = ac.x; c.acc[1] = ac.y; c.acc[2] = ac.z; c.acc[3] = ac.w;
     c.ti0 = ti.x; c.ti1 = ti.y; c.ta0 = ti.z; c.ta1 = ti.w; c.wi = wi.x; c.wa = wi.y;
+    if (FM) {
+#pragma unroll
+        for (int k = 0; k < MAX_PTS; ++k)
+            if (k < c.nc) {
+                float4 pi = crow(w, CR_PTI + k, q), pk = crow(w, CR_PTK + k, q);
+                c.pti0[k] = pi.x; c.pti1[k] = pi.y; c.pta0[k] = pi.z; c.pta1[k] = pi.w;
+                c.pk0[k] = pk.x; c.pk1[k] = pk.y; c.pk2[k] = pk.z;
+            }
+    }
 }
 
 // S2: contact_with_twist_friction.rs:58-424 for the manifold scheduled at slot q.  Fills `c`; the
 // rarely used fields (restitution seeds, friction-centre anchors, contact ids) go to the HBM rows.
-template <class B>
+// FM: friction model (compile time, so the twist kernels carry none of the Coulomb code): 0 = Simplified (twist), 1 = Coulomb.
+template <int FM = 0, class B>
 RB_HD void cons_generate(const World& w, const B& bd, int q, int buf, int item, Cons& c) {
     int4 h = w.cons_hdr[q];
     const int p = h.x, id1 = h.y, id2 = h.z;
@@ -224,6 +246,14 @@ RB_HD void cons_generate(const World& w, const B& bd, int q, int buf, int item, 
             c.lp2[k] = xform_inv(g2.p, com2 + dp2);
             crow(w, CR_LP1 + k, q).w = seed;
             crow(w, CR_LP2 + k, q).w = as_float_i(cid);
+            if (FM) {   // contact_with_coulomb_friction.rs:255-302: one tangent part per point, arms = the point's own
+                const vec3 a10 = cross3(dp1, t1), a20 = cross3(dp2, -t1), a11 = cross3(dp1, t2), a21 = cross3(dp2, -t2);
+                const vec3 i10 = smul(g1.ii, a10), i20 = smul(g2.ii, a20), i11 = smul(g1.ii, a11), i21 = smul(g2.ii, a21);
+                c.pti0[k] = w0; c.pti1[k] = w1; c.pta0[k] = -w0; c.pta1[k] = -w1;
+                c.pk0[k] = dot3(t1, had(imsum, t1)) + dot3(i10, a10) + dot3(i20, a20);
+                c.pk1[k] = dot3(t2, had(imsum, t2)) + dot3(i11, a11) + dot3(i21, a21);
+                c.pk2[k] = 2.0f * (dot3(i10, a11) + dot3(i20, a21));
+            }
         }
     }
     float wimp = count > 1 ? tws : 0.0f;
@@ -394,7 +424,7 @@ RB_HD void friction_warmstart(const BodyState& g1, const BodyState& g2, vec3 dir
 // One constraint, one sweep, one thread (streaming path; constraint in registers for the call).
 // MODE_WARMSTART = builder.update + constraint.warmstart (fused, worker.rs:438-539);
 // MODE_BIASED / MODE_RELAX = (refresh_rhs_wo_bias +) solve; MODE_RESTITUTION = apply_restitution.
-template <class B>
+template <int FM = 0, class B>
 RB_HD void cons_sweep(const World& w, const B& bd, int q, Cons& c, int mode, bool solve_friction) {
     const Params& P = w.prm;
     const int id1 = c.id1, id2 = c.id2, nc = c.nc;
@@ -438,7 +468,29 @@ RB_HD void cons_sweep(const World& w, const B& bd, int q, Cons& c, int mode, boo
             apply_normal(lin1, lin2, pp.itd1, pp.itd2, dl, v1, w1, v2, w2);
         }
     }
-    if (mode == MODE_WARMSTART) {
+    if (FM && mode == MODE_WARMSTART) {   // contact_with_coulomb_friction.rs:438-447, :584-592
+#pragma unroll
+        for (int k = 0; k < MAX_PTS; ++k) {
+            if (k < nc) {
+                c.pta0[k] = c.pta0[k] + c.pti0[k]; c.pta1[k] = c.pta1[k] + c.pti1[k];
+                c.pti0[k] = c.pti0[k] * P.warmstart_coeff; c.pti1[k] = c.pti1[k] * P.warmstart_coeff;
+                friction_warmstart(g1, g2, dir, t1, t2, 1, c.dp1[k], c.dp2[k], c.pti0[k], c.pti1[k], 0.0f, v1, w1, v2, w2);
+            }
+        }
+    } else if (FM && mode != MODE_RESTITUTION && solve_friction) {   // :659-676, limit = mu * lambda_k per point
+        const bool relax = mode == MODE_RELAX;
+#pragma unroll
+        for (int k = 0; k < MAX_PTS; ++k) {
+            if (k < nc) {
+                const float tlimit = (0.0f + c.imp[k]) * c.fric;
+                FrictionState f;
+                f.ti0 = c.pti0[k]; f.ti1 = c.pti1[k]; f.wi = 0.0f;
+                friction_solve(P, g1, g2, dir, t1, t2, 1, tlimit, 0.0f, 0.0f, c.dp1[k], c.dp2[k], c.pk0[k], c.pk1[k], c.pk2[k], relax,
+                               c.lp1[k], c.lp2[k], f, v1, w1, v2, w2);
+                c.pti0[k] = f.ti0; c.pti1[k] = f.ti1;
+            }
+        }
+    } else if (mode == MODE_WARMSTART) {
         c.ta0 = c.ta0 + c.ti0; c.ta1 = c.ta1 + c.ti1;
         c.ti0 = c.ti0 * P.warmstart_coeff; c.ti1 = c.ti1 * P.warmstart_coeff;
         c.wa = c.wa + c.wi;
@@ -472,9 +524,25 @@ RB_HD float canon0(float x) { return x == 0.0f ? 0.0f : x; }
 
 // S10: contact_with_twist_friction.rs:783-829
 // `ids_in_c`: c.pair / c.cid are valid (shared-memory path); otherwise they are fetched from the schedule rows.
+template <int FM = 0>
 RB_HD void cons_writeback(const World& w, int q, int buf, const Cons& c, bool ids_in_c = false) {
     const int p = ids_in_c ? c.pair : w.cons_hdr[q].x;
     vec3 t2 = cross3(c.dir, c.t1);
+    if (FM) {   // contact_with_coulomb_friction.rs:683-740: per-point world tangent impulse; the twist slot is left alone
+#pragma unroll
+        for (int k = 0; k < MAX_PTS; ++k) {
+            if (k < c.nc) {
+                const int cid = ids_in_c ? c.cid[k] : as_int(crow(w, CR_LP2 + k, q).w);
+                const float b0 = canon0(c.pti0[k]), b1 = canon0(c.pti1[k]);
+                vec3 twk = c.t1 * b0 + t2 * b1;
+                float* pd = &prow(w, buf, PR_PD + cid, p).x;
+                pd[0] = canon0(c.acc[k] + c.imp[k]);
+                pd[1] = canon0(c.imp[k]);
+                prow(w, buf, PR_TW + cid, p) = f4(mk3(canon0(twk.x), canon0(twk.y), canon0(twk.z)), 0.0f);
+            }
+        }
+        return;
+    }
     float a0 = canon0(c.ti0), a1 = canon0(c.ti1);
     vec3 tw = c.t1 * a0 + t2 * a1;
     tw = mk3(canon0(tw.x), canon0(tw.y), canon0(tw.z));
@@ -822,7 +890,7 @@ RB_HD void body_writeback(const World& w, const B& bd, int b, int id) {
 
 // Solve one work item from solver-body init to the final positions of its bodies, constraints
 // streaming from HBM/L2 (fallback for items too big for shared memory, items with joints, item 0).
-template <class X, class B>
+template <int FM = 0, class X, class B>
 RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec3 gravity) {
     const Params& P = w.prm;
     State* st = w.st;
@@ -841,9 +909,9 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
     auto stage = [&](int a, int e, bool serial, int mode, bool fric) {
         if (serial) {
             if (tid == 0)
-                for (int q = a; q < e; ++q) { Cons cc; cons_load(w, q, cc); cons_sweep(w, bd, q, cc, mode, fric); cons_store_dyn(w, q, cc); }
+                for (int q = a; q < e; ++q) { Cons cc; cons_load<FM>(w, q, cc); cons_sweep<FM>(w, bd, q, cc, mode, fric); cons_store_dyn<FM>(w, q, cc); }
         } else {
-            for (int q = a + tid; q < e; q += nth) { Cons cc; cons_load(w, q, cc); cons_sweep(w, bd, q, cc, mode, fric); cons_store_dyn(w, q, cc); }
+            for (int q = a + tid; q < e; q += nth) { Cons cc; cons_load<FM>(w, q, cc); cons_sweep<FM>(w, bd, q, cc, mode, fric); cons_store_dyn<FM>(w, q, cc); }
         }
     };
 
@@ -856,9 +924,9 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
     // S2 generate
     for (int q = c0 + tid; q < c1; q += nth) {
         Cons c;
-        cons_generate(w, bd, q, buf, item, c);
-        cons_store_static(w, q, c);
-        cons_store_dyn(w, q, c);
+        cons_generate<FM>(w, bd, q, buf, item, c);
+        cons_store_static<FM>(w, q, c);
+        cons_store_dyn<FM>(w, q, c);
     }
     ex.sync();
 
@@ -886,13 +954,21 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
             // warmstart_coefficient == 0: update only banks and zeroes the impulses (no velocity change)
             for (int q = c0 + tid; q < c1; q += nth) {
                 Cons c;
-                cons_load(w, q, c);
+                cons_load<FM>(w, q, c);
 #pragma unroll
                 for (int k = 0; k < MAX_PTS; ++k)
                     if (k < c.nc) { c.acc[k] = c.acc[k] + c.imp[k]; c.imp[k] = c.imp[k] * 0.0f; }
                 c.ta0 = c.ta0 + c.ti0; c.ta1 = c.ta1 + c.ti1; c.ti0 = c.ti0 * 0.0f; c.ti1 = c.ti1 * 0.0f;
                 c.wa = c.wa + c.wi; c.wi = c.wi * 0.0f;
-                cons_store_dyn(w, q, c);
+                if (FM) {
+#pragma unroll
+                    for (int k = 0; k < MAX_PTS; ++k)
+                        if (k < c.nc) {
+                            c.pta0[k] = c.pta0[k] + c.pti0[k]; c.pta1[k] = c.pta1[k] + c.pti1[k];
+                            c.pti0[k] = c.pti0[k] * 0.0f; c.pti1[k] = c.pti1[k] * 0.0f;
+                        }
+                }
+                cons_store_dyn<FM>(w, q, c);
             }
             ex.sync();
         }
@@ -940,7 +1016,7 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
         }
     }
     // S10 impulse writeback
-    for (int q = c0 + tid; q < c1; q += nth) { Cons cc; cons_load(w, q, cc); cons_writeback(w, q, buf, cc); }
+    for (int q = c0 + tid; q < c1; q += nth) { Cons cc; cons_load<FM>(w, q, cc); cons_writeback<FM>(w, q, buf, cc); }
     for (int q = j0 + tid; q < j1; q += nth) joint_writeback(w, q);
     for (int l = b0 + tid; l < b1; l += nth) {
         int b = w.item_bodies[l];
@@ -1410,7 +1486,7 @@ RB_HD bool item_is_coop(const World& w, int item) {
     const int ovf = w.color_pos[COLOR_OVERFLOW];
     const int* coff = w.item_color_off + (size_t)item * (NUM_COLORS + 1);
     const bool has_ovf = ovf >= 0 && coff[ovf + 1] > coff[ovf];
-    return item > 0 && njoints == 0 && !has_ovf && ncons < 65536 && w.item_cons_start[item + 1] <= w.cons_cap &&
+    return item > 0 && njoints == 0 && !has_ovf && !w.prm.friction_model && ncons < 65536 && w.item_cons_start[item + 1] <= w.cons_cap &&
            coop_plan(w.coop_small_floats, nbod, ncons).ok;
 }
 

@@ -63,7 +63,10 @@ enum ConsRow {
     CR_ACC,                     // normal impulse accumulators[4] (read-modify-write)
     CR_TI,                      // tangent impulse xy, accumulators zw (read-modify-write)
     CR_WI,                      // twist impulse x, accumulator y       (read-modify-write)
-    CR_ROWS
+    // FrictionModel::Coulomb only (one coupled tangent part per point, contact_constraint_element.rs:14-36)
+    CR_PTI,                     // [4] tangent impulse xy, accumulators zw of point k   (read-modify-write)
+    CR_PTK = CR_PTI + MAX_PTS,  // [4] tangent K of point k: r0 r1 r2
+    CR_ROWS = CR_PTK + MAX_PTS
 };
 
 struct Params {  // IntegrationParameters + derived per-substep coefficients (computed on the host)
@@ -73,6 +76,7 @@ struct Params {  // IntegrationParameters + derived per-substep coefficients (co
     float prediction, recycle_dist, length_unit, fat_skin;
     float max_lin_vel, max_ang_vel;
     int num_substeps, num_pgs, num_relax, friction_in_bias, contact_recycling;
+    int friction_model;   // 0 = Simplified (twist), 1 = Coulomb (integration_parameters.rs:16-30)
 };
 
 // Device-side scalars (one struct in HBM, mirrored to pinned host memory on demand).

@@ -146,6 +146,11 @@ def test_sleep_and_wake_match_oracle_bit_for_bit():
     assert seen_sleep and seen_wake
 
 
+def test_coulomb_friction_cone_emulated_kernels():
+    from test_oracle_kat import _coulomb_params, coulomb_friction_cone
+    coulomb_friction_cone(lambda s: PhysicsWorld(s, integration_parameters=_coulomb_params(), _lib=emul_lib.lib()))
+
+
 def test_quarantine_emulated_kernels():
     from test_oracle_kat import nan_force_is_quarantined
     nan_force_is_quarantined(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), expect_error=True)

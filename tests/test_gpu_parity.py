@@ -303,3 +303,18 @@ def test_sleep_and_wake_match_oracle_bit_for_bit(built):
 def test_quarantine(built):
     from test_oracle_kat import nan_force_is_quarantined
     nan_force_is_quarantined(lambda s: PhysicsWorld(s), expect_error=True)
+
+
+def test_coulomb_friction_model(built):
+    """FrictionModel::Coulomb on hardware: the friction-cone known answers through the C ABI, and the reference
+    file's b3d_many_pyramids (10 780 cubes, every island through the streaming solve) bit-exact against the oracle."""
+    from test_oracle_kat import _coulomb_params, coulomb_friction_cone
+    coulomb_friction_cone(lambda s: PhysicsWorld(s, integration_parameters=_coulomb_params()))
+    scene = scenes.many_pyramids()
+    w = PhysicsWorld(scene, integration_parameters=_coulomb_params())
+    o = oracle_lib.OracleWorld(scene, params=_coulomb_params(), threads=8)
+    for i in range(4):
+        w.step()
+        o.step()
+    d = compare_worlds(w, o)
+    assert is_exact(d), d

@@ -442,3 +442,57 @@ def nan_force_is_quarantined(make_world, expect_error):
 
 def test_quarantine_oracle():
     nan_force_is_quarantined(lambda s: oracle_lib.OracleWorld(s), expect_error=False)
+
+
+# ---- FrictionModel::Coulomb (contact_with_coulomb_friction.rs; integration_parameters.rs:16-30) --------------------
+def _coulomb_params():
+    p = A.RbIntegrationParameters.default()
+    p.friction_model = 1
+    return p
+
+
+def coulomb_friction_cone(make_world):
+    """Coulomb's law per contact point (contact_with_coulomb_friction.rs:659-671: tangent impulse capped at mu * lambda_k):
+    a unit cube (mu = 0.5, m = 1) pushed sideways on a slab stays put for F < mu m g and accelerates at (F - mu m g) / m
+    above it.  The total contact impulse is m g dt as under the twist model (total_contact_impulse.rs:58-75)."""
+    for force, slides in ((3.0, False), (8.0, True)):
+        s = scenes.box_on_ground("cuboid")
+        s.bodies.descs[1].user_force[:] = (force, 0.0, 0.0)
+        w = make_world(s)
+        w.step(30)
+        pose0, vel0 = w.body_states()
+        w.step(30)
+        pose1, vel1 = w.body_states()
+        if not slides:
+            assert abs(vel1[1, 0]) < 1e-3 and abs(pose1[1, 0] - pose0[1, 0]) < 1e-3
+        else:
+            acc = (vel1[1, 0] - vel0[1, 0]) / 0.5
+            assert abs(acc - (force - 0.5 * 9.81)) < 0.5, acc   # friction force within 10 % of mu m g
+        if hasattr(w, "contact_pairs") and not slides:
+            total = float(w.contact_pairs()["impulses"].sum())
+            assert abs(total - 9.81 / 60.0) / (9.81 / 60.0) < 0.01
+
+
+def test_coulomb_friction_cone_oracle():
+    coulomb_friction_cone(lambda s: oracle_lib.OracleWorld(s, params=_coulomb_params()))
+
+
+def test_coulomb_differs_from_twist_only_in_friction():
+    """Both models share the normal rows: a resting pyramid stays put under either; a spinning box on the ground is
+    braked by per-point friction under Coulomb and by the twist row under the simplified model (different trajectories)."""
+    s = scenes.Scene("spin")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(10.0, 0.5, 10.0))
+    s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.5, 0.0)).angvel((0.0, 6.0, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    wc = oracle_lib.OracleWorld(s, params=_coulomb_params())
+    wt = oracle_lib.OracleWorld(s)
+    wc.step(8); wt.step(8)
+    (_, vc), (_, vt) = wc.body_states(), wt.body_states()
+    assert 0.0 < vc[1, 4] < 6.0 and 0.0 < vt[1, 4] < 6.0 and vc[1, 4] != vt[1, 4]   # both brake the spin, differently
+    wc.step(200); wt.step(200)
+    assert abs(wc.body_states()[1][1, 4]) < 1e-2 and abs(wt.body_states()[1][1, 4]) < 1e-2
+    p = scenes.pyramids(1, 1, 8)
+    w = oracle_lib.OracleWorld(p, params=_coulomb_params())
+    start, _ = w.body_states()
+    w.step(200)
+    end, _ = w.body_states()
+    assert np.abs(end[:, :3] - start[:, :3]).max() < 0.02

@@ -120,4 +120,12 @@ VARIANTS = [
     ("additional_mass_twins", additional_mass_twins, None, 120, 20),
     ("overflow_colour", plate_with_overflow_colour, None, 60, 15),
     ("shuffled_collider_order", shuffled_collider_order, None, 60, 15),
+    # FrictionModel::Coulomb (contact_with_coulomb_friction.rs): one coupled tangent part per contact point
+    ("coulomb_pile_with_joints", lambda: scenes.box_pile(3, 3, 3), _params(friction_model=1), 120, 20),
+    ("coulomb_restitution", bouncing_balls, _params(friction_model=1), 120, 20),
+    ("coulomb_groups_joints_forces", groups_and_joints, _params(friction_model=1), 120, 20),
+    ("coulomb_pyramids_warmstart_half", lambda: scenes.pyramids(1, 2, 6), _params(friction_model=1, warmstart_coefficient=0.5), 40, 10),
+    ("coulomb_warmstart_zero_friction_in_bias", lambda: scenes.box_pile(2, 3, 2), _params(friction_model=1, warmstart_coefficient=0.0, friction_in_bias_pass=1), 60, 15),
+    ("coulomb_large_island", lambda: scenes.pyramid3(9), _params(friction_model=1), 25, 5),
+    ("coulomb_overflow_colour", plate_with_overflow_colour, _params(friction_model=1), 40, 10),
 ]
