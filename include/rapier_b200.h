@@ -38,7 +38,7 @@ typedef enum RbStatus {
 /* Mirror of IntegrationParameters (src/dynamics/integration_parameters.rs:181-304), #[repr(C)]. */
 typedef struct RbIntegrationParameters {
     float dt;                                   /* :185  default 1/60 */
-    float min_ccd_dt;                           /*       default 1/60/100 (CCD is out of scope) */
+    float min_ccd_dt;                           /*       default 1/60/100 (only read by the multi-substep CCD splitter, which is not supported) */
     float contact_natural_frequency;            /* contact_softness.natural_frequency, default 30 */
     float contact_damping_ratio;                /* contact_softness.damping_ratio,     default 10 */
     float static_contact_natural_frequency;     /* static_contact_softness, default 60 */
@@ -52,7 +52,7 @@ typedef struct RbIntegrationParameters {
     int32_t num_solver_iterations;              /* substeps, default 4 */
     int32_t num_internal_pgs_iterations;        /* default 1 */
     int32_t num_internal_stabilization_iterations; /* default 1 */
-    int32_t max_ccd_substeps;                   /* default 1 (accepted, CCD itself out of scope) */
+    int32_t max_ccd_substeps;                   /* default 1: CCD motion clamping of fast bodies vs fixed colliders; 0 = off; > 1: RB_ERR_INVALID */
     int32_t contact_clustering;                 /* default 1 (no effect: single-manifold pairs only) */
     int32_t contact_recycling;                  /* default 1 */
     float normalized_contact_recycle_distance;  /* default 0.05 */

@@ -59,6 +59,7 @@ struct Body {
     float sleep_time = 0.0f;          // time_since_can_sleep
     Pose sleep_prev_pose{Q4{0.f, 0.f, 0.f, 1.f}, V3{0.f, 0.f, 0.f}};
     float max_extent = 0.0f;
+    float ccd_thickness = 3.4028235e38f;   // RigidBodyCcd::ccd_thickness
     bool is_dynamic() const { return type == RB_BODY_DYNAMIC; }
     bool is_awake() const { return type == RB_BODY_DYNAMIC && !sleeping; }   // member of the active set
 };

@@ -16,6 +16,7 @@
 namespace orc {
 
 void solve_island(World& w, V3 gravity);  // oracle_solver.cpp
+void ccd_motion_clamping(World& w);       // oracle_ccd.cpp
 
 // ---------------------------------------------------------------------------------------------
 // Mass properties: parry MassProperties::{from_cuboid, from_ball, new, world_com, world_inv_inertia}
@@ -130,9 +131,11 @@ static int recompute_mass_properties(World& w, int first_body = 0, int first_col
                                  inv_exact0(b.inv_principal_inertia.z)};
         // recompute_max_extent (rigid_body_components.rs:491-515): bounding spheres about the local centre of mass
         b.max_extent = 0.0f;
+        b.ccd_thickness = 3.4028235e38f;   // RigidBodyCcd::default (:1076); min over the colliders' Shape::ccd_thickness (:1224-1228)
         for (size_t ci = (size_t)first_collider; ci < w.colliders.size(); ++ci) {
             const Collider& c = w.colliders[ci];
             if (c.parent != bi) continue;
+            b.ccd_thickness = fmin2(b.ccd_thickness, c.shape == RB_SHAPE_BALL ? c.he.x : fmin2(c.he.x, fmin2(c.he.y, c.he.z)));
             const float radius = c.shape == RB_SHAPE_BALL ? c.he.x : length(c.he);
             b.max_extent = fmax2(b.max_extent, length(c.pos_wrt_parent.t - b.local_com) + radius);
         }
@@ -686,6 +689,8 @@ void step_once(World& w, V3 gravity) {
     update_sleep(w);
     // 7b. build_islands_and_solve_velocity_constraints
     solve_island(w, gravity);
+    // 7c. CCD motion clamping of the fast bodies' next_position (substep.rs:492-520)
+    ccd_motion_clamping(w);
     double t3 = now_ms();
     // 7d. advance_to_final_positions (substep.rs:84-224) + 7f refresh_moved_collider_aabbs
     for (Body& b : w.bodies) {

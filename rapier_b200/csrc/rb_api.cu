@@ -483,12 +483,15 @@ static void derive_params(const RbIntegrationParameters& p, Params& o) {
     o.friction_in_bias = p.friction_in_bias_pass;
     o.contact_recycling = p.contact_recycling;
     o.friction_model = p.friction_model;
+    o.ccd = p.max_ccd_substeps != 0 ? 1 : 0;
+    o.linear_slop = p.normalized_allowed_linear_error * p.length_unit;
 }
 
 static int validate_params(const RbIntegrationParameters* p) {
     if (!p) { set_err("null parameters%s", ""); return RB_ERR_INVALID; }
     if (p->friction_model != 0 && p->friction_model != 1) { set_err("friction_model must be 0 (Simplified) or 1 (Coulomb)%s", ""); return RB_ERR_INVALID; }
     if (p->warmstart_joints != 0) { set_err("warmstart_joints is not supported%s", ""); return RB_ERR_INVALID; }
+    if (p->max_ccd_substeps < 0 || p->max_ccd_substeps > 1) { set_err("max_ccd_substeps must be 0 (CCD off) or 1 (motion clamping); the multi-substep splitter is not supported%s", ""); return RB_ERR_INVALID; }
     if (p->num_solver_iterations < 1 || p->num_solver_iterations > 64) { set_err("num_solver_iterations out of range%s", ""); return RB_ERR_INVALID; }
     return RB_OK;
 }
@@ -513,7 +516,7 @@ static void collider_mass_props(const RbColliderDesc& c, float& mass, float pi[3
 }
 static inline float inv0(float x) { return x == 0.0f ? 0.0f : 1.0f / x; }
 
-struct HostMass { float lcom[3], inv_mass, ipi[3], pi[3], pframe[4], max_extent; };
+struct HostMass { float lcom[3], inv_mass, ipi[3], pi[3], pframe[4], max_extent, ccd_thickness; };
 
 // RigidBodyMassProps::recompute_mass_properties_from_colliders (rigid_body_components.rs:421).
 // `first_body` / `first_collider`: only the bodies from first_body on are computed, from the colliders from
@@ -601,10 +604,12 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out, int fir
         for (int k = 0; k < 3; ++k) m.pi[k] = inv0(m.ipi[k]);
         // recompute_max_extent (rigid_body_components.rs:491-515): bounding spheres about the local centre of mass
         m.max_extent = 0.0f;
+        m.ccd_thickness = 3.4028235e38f;   // RigidBodyCcd::default (rigid_body_components.rs:1076), min over the colliders (:1224-1228)
         for (size_t ci = (size_t)first_collider; ci < W->colliders.size(); ++ci) {
             const RbColliderDesc& c = W->colliders[ci];
             if (c.parent != b) continue;
             const float hx = c.half_extents[0], hy = c.half_extents[1], hz = c.half_extents[2];
+            m.ccd_thickness = std::min(m.ccd_thickness, c.shape == RB_SHAPE_BALL ? hx : std::min(hx, std::min(hy, hz)));   // parry Shape::ccd_thickness
             const float radius = c.shape == RB_SHAPE_BALL ? hx : sqrtf(fmaf(hz, hz, fmaf(hy, hy, hx * hx)));
             const float dx = c.pos_wrt_parent_t[0] - m.lcom[0], dy = c.pos_wrt_parent_t[1] - m.lcom[1], dz = c.pos_wrt_parent_t[2] - m.lcom[2];
             m.max_extent = std::max(m.max_extent, sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) + radius);
@@ -663,11 +668,12 @@ static int upload_bodies(RbWorld* W, const std::vector<HostMass>& mp, int first,
     std::vector<int> type(count);
     std::vector<unsigned> flags(count);
     std::vector<float4> pt(count), pq(count), lv(count), av(count), lc(count), ipi(count), pi(count), pf(count), misc(count), uf(count), ut(count);
-    std::vector<float> ext(count);
+    std::vector<float> ext(count), thick(count);
     std::vector<float4> prev_t(count, make_float4(0.f, 0.f, 0.f, 0.f)), prev_q(count, make_float4(0.f, 0.f, 0.f, 1.f));   // sleep_prev_pose = identity
     for (int k = 0; k < count; ++k) {
         const int i = first + k;
         ext[k] = mp[i].max_extent;
+        thick[k] = mp[i].ccd_thickness;
         const RbBodyDesc& d = W->bodies[i];
         type[k] = d.body_type;
         flags[k] = d.flags;
@@ -698,6 +704,7 @@ static int upload_bodies(RbWorld* W, const std::vector<HostMass>& mp, int first,
     CK(h2d(w.b_uforce + first, uf.data(), n * sizeof(float4)));
     CK(h2d(w.b_utorque + first, ut.data(), n * sizeof(float4)));
     CK(h2d(w.b_max_extent + first, ext.data(), n * sizeof(float)));
+    CK(h2d(w.b_ccd_thick + first, thick.data(), n * sizeof(float)));
     CK(h2d(w.b_sleep_prev_t + first, prev_t.data(), n * sizeof(float4)));
     CK(h2d(w.b_sleep_prev_q + first, prev_q.data(), n * sizeof(float4)));
     CK(dev_set(w.b_sleeping + first, 0, n));
@@ -706,9 +713,13 @@ static int upload_bodies(RbWorld* W, const std::vector<HostMass>& mp, int first,
         if (type[k] == RB_BODY_DYNAMIC && !(flags[k] & RB_BODY_NO_SLEEP)) w.sleep_enabled = 1;
     return RB_OK;
 }
-static int upload_colliders(RbWorld* W, int first, int count) {
+static int upload_colliders(RbWorld* W, int first, int count, int first_body = 0) {
     World& w = W->w;
-    if (count <= 0) return RB_OK;
+    if (count <= 0) {
+        const int nbn = (int)W->bodies.size() - first_body;
+        if (nbn > 0) { std::vector<int> head(nbn, -1); CK(h2d(w.b_col_head + first_body, head.data(), (size_t)nbn * sizeof(int))); }
+        return RB_OK;
+    }
     std::vector<int> shape(count), parent(count);
     std::vector<float4> he(count), rt(count), rq(count), mat(count);
     std::vector<int2> rules(count);
@@ -733,6 +744,16 @@ static int upload_colliders(RbWorld* W, int first, int count) {
     CK(h2d(w.c_mat + first, mat.data(), n * sizeof(float4)));
     CK(h2d(w.c_rules + first, rules.data(), n * sizeof(int2)));
     CK(h2d(w.c_groups + first, groups.data(), n * sizeof(uint2)));
+    // per-body collider chains (RigidBodyColliders): appended colliders only ever belong to appended bodies
+    // (rb_world_insert), so the chains of the bodies from `first_body` on are rebuilt from the colliders from `first` on
+    const int nb_all = (int)W->bodies.size();
+    std::vector<int> head(std::max(nb_all - first_body, 0), -1), next(count, -1);
+    for (int k = count - 1; k >= 0; --k) {
+        const int p = parent[k];
+        if (p >= first_body) { next[k] = head[p - first_body]; head[p - first_body] = first + k; }
+    }
+    CK(h2d(w.c_next + first, next.data(), n * sizeof(int)));
+    if (!head.empty()) CK(h2d(w.b_col_head + first_body, head.data(), head.size() * sizeof(int)));
     return RB_OK;
 }
 static int validate_descs(int nb_total, int nb, const RbBodyDesc* bodies, int nc, const RbColliderDesc* colliders) {
@@ -919,7 +940,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.b_lcom_im, NB); ALLOC(w.b_ipi, NB); ALLOC(w.b_pi, NB); ALLOC(w.b_pframe, NB); ALLOC(w.b_misc, NB);
     ALLOC(w.b_uforce, NB); ALLOC(w.b_utorque, NB); ALLOC(w.b_wcom, NB); ALLOC(w.b_eim, NB + 2);
     ALLOC(w.b_eii0, NB); ALLOC(w.b_eii1, NB); ALLOC(w.b_owned, NB);
-    ALLOC(w.b_sleeping, NB); ALLOC(w.b_sleep_time, NB); ALLOC(w.b_sleep_prev_t, NB); ALLOC(w.b_sleep_prev_q, NB); ALLOC(w.b_max_extent, NB);
+    ALLOC(w.b_sleeping, NB); ALLOC(w.b_sleep_time, NB); ALLOC(w.b_sleep_prev_t, NB); ALLOC(w.b_sleep_prev_q, NB); ALLOC(w.b_max_extent, NB); ALLOC(w.b_ccd_thick, NB); ALLOC(w.b_col_head, NB); ALLOC(w.c_next, NC);
     ALLOC(w.wake_req, NB); ALLOC(w.isl_block, NB); ALLOC(w.quarantine, NB);
     ALLOC(w.s_lin, NB + 2); ALLOC(w.s_ang, NB + 2); ALLOC(w.s_q, NB + 2); ALLOC(w.s_t, NB + 2);   // + world pseudo body, garbage slot
     ALLOC(w.s_incr_lin, NB); ALLOC(w.s_incr_ang, NB);
@@ -1104,7 +1125,7 @@ int rb_world_insert(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t nc
     W->w.nb = nb0 + nb;
     W->w.nc = nc0 + nc;
     if ((rc = upload_bodies(W, mp, nb0, nb)) != RB_OK) return rc;
-    if ((rc = upload_colliders(W, nc0, nc)) != RB_OK) return rc;
+    if ((rc = upload_colliders(W, nc0, nc, nb0)) != RB_OK) return rc;
     int one = 1, lists = 1;   // lists: 1 = only movers were added, 3 = static colliders too (re-sort them)
     for (int i = 0; i < nc; ++i)
         if (colliders[i].parent < 0 || W->bodies[colliders[i].parent].body_type != RB_BODY_DYNAMIC) lists = 3;

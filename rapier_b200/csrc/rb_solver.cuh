@@ -18,6 +18,7 @@
 // staged body state in every sweep (same expressions, hence the same bits, as storing them).
 #pragma once
 #include "rb_collide.cuh"
+#include "rb_ccd.cuh"
 
 namespace rb {
 
@@ -861,6 +862,10 @@ RB_HD void body_writeback(const World& w, const B& bd, int b, int id) {
     vec3 lin = bd.lin(id) * (1.0f / (1.0f + P.dt * misc.x));
     vec3 ang = bd.ang(id) * (1.0f / (1.0f + P.dt * misc.y));
     pose np = prepend_translation(bd.xf(id), -xyz(w.b_lcom_im[b]));
+    if (P.ccd) {   // CCD motion clamping of fast bodies against fixed colliders (substep.rs:492-520; rb_ccd.cuh): pose only
+        const pose op = body_pose(w, b);
+        if (finite3(np.t) && ccd_is_moving_fast(w, b, op, np)) np = ccd_clamp_body(w, b, op, np);
+    }
     if (!(finite3(lin) && finite3(ang) && finite3(np.t) && isfinite(np.q.x) && isfinite(np.q.y) && isfinite(np.q.z) && isfinite(np.q.w))) {
         // Containment of non-finite state at the end-of-step chokepoint (physics_pipeline/quarantine.rs:14-47, :126-178):
         // the body keeps its last valid pose, loses its velocities and forces, is disabled (its colliders leave the

@@ -18,6 +18,7 @@ constexpr int NUM_COLORS = 129;
 constexpr int NO_BODY = -1;             // world-attached side (reference: u32::MAX)
 
 constexpr int BODY_DYNAMIC = 0;
+constexpr int BODY_FIXED = 1;
 constexpr int BODY_REMOVED = 3;          // removed (rb_world_remove_bodies) or quarantined: not simulated, its colliders are gone
 constexpr int SHAPE_BALL = 0, SHAPE_CUBOID = 1;
 constexpr int SHAPE_REMOVED = -1;        // collider of a removed body: in neither broad-phase list, in no pair
@@ -76,6 +77,8 @@ struct Params {  // IntegrationParameters + derived per-substep coefficients (co
     float prediction, recycle_dist, length_unit, fat_skin;
     float max_lin_vel, max_ang_vel;
     int num_substeps, num_pgs, num_relax, friction_in_bias, contact_recycling;
+    int ccd;              // max_ccd_substeps != 0: motion clamping of fast bodies (substep.rs:404-409, :492-520)
+    float linear_slop;    // allowed_linear_error(): target distance of the time of impact (ccd_solver.rs:184)
     int friction_model;   // 0 = Simplified (twist), 1 = Coulomb (integration_parameters.rs:16-30)
 };
 
@@ -146,6 +149,9 @@ struct World {
     float* b_sleep_time;              // time_since_can_sleep
     float4 *b_sleep_prev_t, *b_sleep_prev_q;   // pose at the previous sleep check
     float* b_max_extent;              // mprops.max_extent: farthest shape point from the local centre of mass
+    float* b_ccd_thick;               // RigidBodyCcd::ccd_thickness: thinnest extent over the body's colliders (FLT_MAX without colliders)
+    int* b_col_head;                  // [nb] first collider of the body (-1 none); the chain continues through c_next
+    int* c_next;                      // [nc] next collider of the same body (-1 end)
     int* wake_req;                    // [nb] by island root: wake this island (a contact began)
     int* isl_block;                   // [nb] by island root: stamp of the last step a body of the island was not sleep-eligible
     int sleep_enabled;                // some body may sleep: run the sleep decision

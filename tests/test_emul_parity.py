@@ -151,6 +151,13 @@ def test_coulomb_friction_cone_emulated_kernels():
     coulomb_friction_cone(lambda s: PhysicsWorld(s, integration_parameters=_coulomb_params(), _lib=emul_lib.lib()))
 
 
+def test_ccd_emulated_kernels():
+    from test_oracle_kat import ccd_default_tier, ccd_large_dt_no_mid_air_hitch
+    mk = lambda s, p: PhysicsWorld(s, integration_parameters=p, _lib=emul_lib.lib())
+    ccd_default_tier(mk)
+    ccd_large_dt_no_mid_air_hitch(mk)
+
+
 def test_quarantine_emulated_kernels():
     from test_oracle_kat import nan_force_is_quarantined
     nan_force_is_quarantined(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), expect_error=True)

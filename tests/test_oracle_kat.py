@@ -496,3 +496,62 @@ def test_coulomb_differs_from_twist_only_in_friction():
     w.step(200)
     end, _ = w.body_states()
     assert np.abs(end[:, :3] - start[:, :3]).max() < 0.02
+
+
+# ---- CCD motion clamping (src/dynamics/ccd; crates/rapier3d/tests/ccd_default_vs_fixed.rs, issue_217_ccd_large_dt_hitch.rs) ----
+def _thin_wall_scene(with_second_body=False):
+    s = scenes.Scene("ccd_wall", gravity=(0.0, 0.0, 0.0))
+    if not with_second_body:
+        s.insert(RigidBodyBuilder.fixed(), ColliderBuilder.cuboid(0.05, 5.0, 5.0))                      # insert_thin_fixed_wall
+    s.insert(RigidBodyBuilder.dynamic().translation((-3.0, 0.0, 0.0)).linvel((200.0, 0.0, 0.0)), ColliderBuilder.cuboid(0.1, 0.1, 0.1))
+    if with_second_body:
+        s.insert(RigidBodyBuilder.dynamic().translation((3.0, 0.0, 0.0)).linvel((-200.0, 0.0, 0.0)), ColliderBuilder.cuboid(0.1, 0.1, 0.1))
+    return s
+
+
+def ccd_default_tier(make_world):
+    """ccd_default_vs_fixed.rs: default_ccd_vs_fixed_no_tunnel (a 0.2 m cube at 200 m/s is stopped on the near side of a
+    0.1 m fixed wall, :98-113), global_ccd_off_tunnels (max_ccd_substeps = 0: it tunnels, :190-205),
+    default_tier_ignores_dynamic (two fast dynamic bodies pass through each other, :118-152)."""
+    w = make_world(_thin_wall_scene(), None)
+    w.step(120)
+    assert w.body_states()[0][1, 0] < 0.0
+    p = A.RbIntegrationParameters.default()
+    p.max_ccd_substeps = 0
+    w = make_world(_thin_wall_scene(), p)
+    w.step(60)
+    assert w.body_states()[0][1, 0] > 1.0
+    w = make_world(_thin_wall_scene(with_second_body=True), None)
+    w.step(5)
+    pose, _ = w.body_states()
+    assert pose[0, 0] > 0.0 and pose[1, 0] < 0.0
+
+
+def ccd_large_dt_no_mid_air_hitch(make_world):
+    """issue_217_ccd_large_dt_hitch.rs:62-121: ball (r = 0.5, 20 m/s, dt = 0.25: 5 m per step) against a thin wall whose
+    near face is at x = 12.2: full-speed advance while far, then adjacent to the wall (never through, never frozen short
+    of it), at rest from the fifth step on."""
+    p = A.RbIntegrationParameters.default()
+    p.dt = 0.25
+    s = scenes.Scene("ccd_hitch", gravity=(0.0, 0.0, 0.0))
+    s.insert(RigidBodyBuilder.fixed(), ColliderBuilder.cuboid(0.05, 5.0, 5.0).translation((12.25, 0.0, 0.0)))
+    s.insert(RigidBodyBuilder.dynamic().linvel((20.0, 0.0, 0.0)), ColliderBuilder.ball(0.5))
+    w = make_world(s, p)
+    contact_x, travel, prev_x = 12.2 - 0.5, 5.0, 0.0
+    for i in range(10):
+        w.step()
+        pose, vel = w.body_states()
+        x, vx = float(pose[1, 0]), float(vel[1, 0])
+        if prev_x + travel < contact_x - 0.5:
+            assert abs(x - (prev_x + travel)) < 1.0e-3, (i, x)
+        else:
+            assert contact_x - 0.35 < x < contact_x + 0.01, (i, x)
+            if i >= 4:
+                assert abs(vx) < 0.1, (i, vx)
+        prev_x = x
+
+
+def test_ccd_oracle():
+    mk = lambda s, p: oracle_lib.OracleWorld(s, params=p)
+    ccd_default_tier(mk)
+    ccd_large_dt_no_mid_air_hitch(mk)

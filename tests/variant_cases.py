@@ -104,6 +104,28 @@ def shuffled_collider_order():
     return s
 
 
+def ccd_barrage():
+    """Fast spinning cubes and balls fired at thin fixed walls, a tiled floor (many narrow static colliders + one wide
+    slab: both static lists of the broad phase) and each other: CCD motion clamping (src/dynamics/ccd) of several
+    bodies per step, single- and multi-collider bodies, impacts from the first step on."""
+    s = scenes.Scene("ccd_barrage", gravity=(0.0, -9.81, 0.0))
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.55, 0.0)), ColliderBuilder.cuboid(40.0, 0.05, 40.0))
+    for i in range(12):
+        for k in range(12):
+            s.colliders.insert(ColliderBuilder.cuboid(0.5, 0.04, 0.5).translation((-6.0 + i * 1.0, -0.46, -6.0 + k * 1.0)))
+    s.insert(RigidBodyBuilder.fixed().translation((8.0, 2.0, 0.0)), ColliderBuilder.cuboid(0.04, 3.0, 8.0))
+    s.insert(RigidBodyBuilder.fixed().translation((-8.0, 2.0, 0.0)).rotation((0.0, 0.0, 0.3)), ColliderBuilder.cuboid(0.04, 3.0, 8.0))
+    for i in range(6):
+        s.insert(RigidBodyBuilder.dynamic().translation((-2.0 + 0.7 * i, 1.0 + 0.5 * i, -2.0 + i)).linvel((150.0 - 40.0 * i, -30.0 * i, 10.0))
+                 .angvel((3.0, 1.0 * i, -2.0)), ColliderBuilder.cuboid(0.1, 0.15, 0.2))
+        s.insert(RigidBodyBuilder.dynamic().translation((1.0 - 0.7 * i, 3.0 + 0.5 * i, 2.0 - i)).linvel((-120.0 + 30.0 * i, -60.0, -5.0 * i)),
+                 ColliderBuilder.ball(0.12 + 0.02 * i))
+    g = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 6.0, 4.0)).linvel((90.0, -90.0, 0.0)).angvel((0.0, 0.0, 8.0)),
+                 ColliderBuilder.cuboid(0.3, 0.05, 0.05).translation((0.3, 0.0, 0.0)))
+    s.colliders.insert_with_parent(ColliderBuilder.ball(0.08).translation((-0.3, 0.0, 0.0)), g)
+    return s
+
+
 VARIANTS = [
     ("restitution", bouncing_balls, None, 150, 25),
     ("groups_joints_forces", groups_and_joints, None, 150, 25),
@@ -128,4 +150,8 @@ VARIANTS = [
     ("coulomb_warmstart_zero_friction_in_bias", lambda: scenes.box_pile(2, 3, 2), _params(friction_model=1, warmstart_coefficient=0.0, friction_in_bias_pass=1), 60, 15),
     ("coulomb_large_island", lambda: scenes.pyramid3(9), _params(friction_model=1), 25, 5),
     ("coulomb_overflow_colour", plate_with_overflow_colour, _params(friction_model=1), 40, 10),
+    # CCD motion clamping (src/dynamics/ccd): fast bodies against thin fixed walls / a tiled floor; and switched off
+    ("ccd_barrage", ccd_barrage, None, 90, 10),
+    ("ccd_barrage_ccd_off", ccd_barrage, _params(max_ccd_substeps=0), 30, 10),
+    ("ccd_barrage_coulomb_dt_large", ccd_barrage, _params(friction_model=1, dt=1.0 / 30.0), 40, 10),
 ]
