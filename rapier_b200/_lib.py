@@ -13,6 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "librapier_b200.so")
 if os.environ.get("RAPIER_B200_DEBUG_LIB") == "1":   # profiling experiments only (-DRB_DEBUG build of the same sources)
     LIB_PATH = os.path.join(HERE, "csrc", "librapier_b200_dbg.so")
+elif os.environ.get("RAPIER_B200_DEBUG_LIB"):        # ... or another CUDA build of the same sources, by file name (A/B timing of kernels)
+    LIB_PATH = os.path.join(HERE, "csrc", os.path.basename(os.environ["RAPIER_B200_DEBUG_LIB"]))
 
 EXPORTS = [
     "rb_abi_version", "rb_last_error", "rb_integration_parameters_default", "rb_world_create",

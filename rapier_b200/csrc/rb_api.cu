@@ -246,6 +246,15 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, in
         w.st->cursor_rest = 0;
         w.st->cursor_coop = 0;
     }
+    {   // CCD clamps queued by the last step's body writeback (rb_solver.cuh): applied before anything reads the poses.
+        // Every CTA reads the count before the barrier, thread 0 resets it after it.
+        const int nccd = w.st->nccd;
+        if (nccd > 0) {
+            phase_ccd_pending(ctx, w, nccd);
+            ctx.grid_sync();
+            if (ctx.gtid == 0) { w.st->nccd = 0; w.host_hint[3] = 0; }
+        }
+    }
     collide_pipeline(ctx, w);   // (ends with a grid barrier: after the narrow phase, or after the last optional section)
     if (!do_solve) return;
     {
@@ -361,6 +370,16 @@ __global__ void __launch_bounds__(COOP_SMALL_THREADS, 2) k_solve_coop(World w, G
 template <int THREADS, int L>
 __global__ void __launch_bounds__(THREADS, 1) k_solve_coop_big(World w, Grav g) { solve_coop_items<L>(w, g, COOP_BIG_SMEM_BYTES / 4, true); }
 __global__ void k_kat(World w, int which, const float* in, float* out) { kat_phase(w, which, in, out); }
+// The CCD clamps queued by the last step's body writeback (rb_solver.cuh) when NO further step follows: a synchronising
+// call launches this (one CTA: fast bodies are rare) if the device flagged any; otherwise the next k_collide applies them.
+__global__ void k_ccd_pending(World w) {
+    GridCtx ctx;
+    const int n = w.st->nccd;
+    if (n == 0) return;
+    phase_ccd_pending(ctx, w, n);
+    __syncthreads();
+    if (ctx.gtid == 0) { w.st->nccd = 0; w.host_hint[3] = 0; }
+}
 __global__ void k_init_bodies(World w, int first) {
     GridCtx ctx;
     init_bodies_phase(ctx, w, first);
@@ -637,6 +656,12 @@ static int launch_init_bodies(RbWorld* W, int first = 0) {
 static int sync_world(RbWorld* W, bool check = true) {
 #if RB_DEVICE_BUILD
     CK(cudaStreamSynchronize(W->stream));
+    if (W->host_hint && W->w.st && *(volatile int*)(W->host_hint + 3) != 0) {   // CCD clamps queued by the last step: apply them now
+        k_ccd_pending<<<1, 256, 0, W->stream>>>(W->w);
+        CK(cudaGetLastError());
+        W->kernels++;
+        CK(cudaStreamSynchronize(W->stream));
+    }
 #endif
     if (check && W->host_hint && W->w.st) {
         const int code = *(volatile int*)(W->host_hint + 1);
@@ -907,7 +932,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
         }
     }
     W->steps_since_scene = 0;
-    if (W->host_hint) W->host_hint[0] = W->host_hint[1] = W->host_hint[2] = 0;
+    if (W->host_hint) W->host_hint[0] = W->host_hint[1] = W->host_hint[2] = W->host_hint[3] = 0;
     W->state_buf[0] = W->state_buf[1] = nullptr;
     W->bodies.assign(bodies, bodies + nb);
     W->colliders.assign(colliders, colliders + nc);
@@ -941,6 +966,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.b_uforce, NB); ALLOC(w.b_utorque, NB); ALLOC(w.b_wcom, NB); ALLOC(w.b_eim, NB + 2);
     ALLOC(w.b_eii0, NB); ALLOC(w.b_eii1, NB); ALLOC(w.b_owned, NB);
     ALLOC(w.b_sleeping, NB); ALLOC(w.b_sleep_time, NB); ALLOC(w.b_sleep_prev_t, NB); ALLOC(w.b_sleep_prev_q, NB); ALLOC(w.b_max_extent, NB); ALLOC(w.b_ccd_thick, NB); ALLOC(w.b_col_head, NB); ALLOC(w.c_next, NC);
+    ALLOC(w.ccd_list, NB); ALLOC(w.ccd_start_t, NB); ALLOC(w.ccd_start_q, NB);
     ALLOC(w.wake_req, NB); ALLOC(w.isl_block, NB); ALLOC(w.quarantine, NB);
     ALLOC(w.s_lin, NB + 2); ALLOC(w.s_ang, NB + 2); ALLOC(w.s_q, NB + 2); ALLOC(w.s_t, NB + 2);   // + world pseudo body, garbage slot
     ALLOC(w.s_incr_lin, NB); ALLOC(w.s_incr_ang, NB);
@@ -1355,6 +1381,11 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
             gex.c = &gctx;
             if (W->w.prm.friction_model == 1) solve_item<1>(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
             else solve_item_lanes<1>(gex, W->w, gb, mk3(g.x, g.y, g.z));
+        }
+        if (W->w.st->nccd > 0) {   // the queued CCD clamps (the device applies them at the next k_collide / synchronising call)
+            phase_ccd_pending(gctx, W->w, W->w.st->nccd);
+            W->w.st->nccd = 0;
+            W->w.host_hint[3] = 0;
         }
         W->kernels += 2;
     }
@@ -1805,9 +1836,21 @@ int rb_world_step_host(RbWorld* W, const float gravity[3], const float* in_state
         if (is_pinned(out_state13)) {
             CK(cudaMemcpyAsync(out_state13, W->w.state13, n * sizeof(float), cudaMemcpyDeviceToHost, W->stream));
             CK(cudaStreamSynchronize(W->stream));
+            if (*(volatile int*)(W->host_hint + 3) != 0) {   // CCD clamps were queued by this step: apply them and fetch the state again
+                int rc2 = sync_world(W, false);
+                if (rc2 != RB_OK) return rc2;
+                CK(cudaMemcpyAsync(out_state13, W->w.state13, n * sizeof(float), cudaMemcpyDeviceToHost, W->stream));
+                CK(cudaStreamSynchronize(W->stream));
+            }
         } else {
             CK(cudaMemcpyAsync(W->stage_host + n, W->w.state13, n * sizeof(float), cudaMemcpyDeviceToHost, W->stream));
             CK(cudaStreamSynchronize(W->stream));
+            if (*(volatile int*)(W->host_hint + 3) != 0) {
+                int rc2 = sync_world(W, false);
+                if (rc2 != RB_OK) return rc2;
+                CK(cudaMemcpyAsync(W->stage_host + n, W->w.state13, n * sizeof(float), cudaMemcpyDeviceToHost, W->stream));
+                CK(cudaStreamSynchronize(W->stream));
+            }
             memcpy(out_state13, W->stage_host + n, n * sizeof(float));
         }
 #else

@@ -152,26 +152,20 @@ RB_HD float ccd_toi(int shA, vec3 heA, const pose& pA, int shB, vec3 heB, const 
 // rigid_body_components.rs:1125-1156 is_moving_fast_with_next_position on the solved motion of body b (`op` = position,
 // `np` = next_position): the larger of the pose delta and the interpolated-velocity estimate (pose_errors, :178-196;
 // the scaled-axis angle through ccd_quat_angle) against half the thinnest extent.
-RB_HD bool ccd_is_moving_fast(const World& w, int b, const pose& op, const pose& np) {
-    const Params& P = w.prm;
-    const vec3 lcom = xyz(w.b_lcom_im[b]);
+RB_HD bool ccd_is_moving_fast(const Params& P, vec3 lcom, const pose& op, const pose& np, float ext, float thickness) {
     const vec3 dcom = xform(np, lcom) - xform(op, lcom);
     const quat dq = qmul(np.q, qconj(op.q));
     const float x = norm(mk3(dq.x, dq.y, dq.z));
-    const float ext = w.b_max_extent[b];
     const float max_delta_position = norm(dcom) + 2.0f * x * ext;
     const float max_velocity = norm(dcom * P.inv_dt_full) + (ccd_quat_angle(x, dq.w) * P.inv_dt_full) * ext;
-    return max2(max_delta_position, max_velocity * P.dt) > 0.5f * w.b_ccd_thick[b];
+    return max2(max_delta_position, max_velocity * P.dt) > 0.5f * thickness;
 }
 
 // sweep_fast_body + apply_clamps for one fast, non-bullet body: the earliest impact of any of its colliders against
 // the fixed colliders, and the pose at that fraction of the body's own sweep.  One thread; fast bodies are rare.
-#if RB_DEVICE_BUILD
-__device__ __noinline__
-#else
-inline
-#endif
-pose ccd_clamp_body(const World& w, int b, pose op, pose np) {
+// (Always inlined: as an out-of-line call inside k_collide -- ABI call, 900 B more stack -- it cost 7 us per step on the headline
+//  workload without ever being executed; inlined it costs 0.4 us: profiles/bench_r02m_ccd_placement.txt.)
+RB_HD pose ccd_clamp_body(const World& w, int b, pose op, pose np) {
     const State* st = w.st;
     const vec3 lcom = xyz(w.b_lcom_im[b]);
     const float slop = w.prm.linear_slop;

@@ -782,6 +782,23 @@ RB_HD void update_world_mass(const World& w, int b, const pose& p) {
     w.b_eii1[b] = make_float2(m.yz, m.zz);
 }
 
+// The queued CCD clamps (see body_writeback): sweep_fast_body + apply_clamps (ccd_solver.rs:162-238, :325-340), then
+// advance_to_final_positions for the clamped bodies.  `n` = State::nccd read before the call; the caller resets it.
+template <class Ctx>
+RB_PHASE void phase_ccd_pending(const Ctx& ctx, const World& w, int n) {
+    for (int k = ctx.gtid; k < n; k += ctx.gsize) {
+        const int b = w.ccd_list[k];
+        if (w.b_type[b] != BODY_DYNAMIC) continue;
+        const pose op = mkpose(mkq(w.ccd_start_q[b]), xyz(w.ccd_start_t[b])), np = body_pose(w, b);
+        const pose cl = ccd_clamp_body(w, b, op, np);
+        w.b_pos_t[b] = f4(cl.t, 0.0f);
+        w.b_pos_q[b] = f4(cl.q);
+        update_world_mass(w, b, cl);
+        float* s = w.state13 + (size_t)b * 13;
+        s[0] = cl.t.x; s[1] = cl.t.y; s[2] = cl.t.z; s[3] = cl.q.x; s[4] = cl.q.y; s[5] = cl.q.z; s[6] = cl.q.w;
+    }
+}
+
 // Executors: how the threads of an item iterate and synchronise.
 struct BlockExec {
     const BlockCtx* c;
@@ -859,13 +876,13 @@ template <class B>
 RB_HD void body_writeback(const World& w, const B& bd, int b, int id) {
     const Params& P = w.prm;
     float4 misc = w.b_misc[b];
+    // (what the CCD test below reads is fetched here, with the other loads, so that it adds no round trip of its own)
+    pose ccd_op = pident();
+    float ccd_ext = 0.0f, ccd_thick = 0.0f;
+    if (P.ccd) { ccd_op = body_pose(w, b); ccd_ext = w.b_max_extent[b]; ccd_thick = w.b_ccd_thick[b]; }
     vec3 lin = bd.lin(id) * (1.0f / (1.0f + P.dt * misc.x));
     vec3 ang = bd.ang(id) * (1.0f / (1.0f + P.dt * misc.y));
     pose np = prepend_translation(bd.xf(id), -xyz(w.b_lcom_im[b]));
-    if (P.ccd) {   // CCD motion clamping of fast bodies against fixed colliders (substep.rs:492-520; rb_ccd.cuh): pose only
-        const pose op = body_pose(w, b);
-        if (finite3(np.t) && ccd_is_moving_fast(w, b, op, np)) np = ccd_clamp_body(w, b, op, np);
-    }
     if (!(finite3(lin) && finite3(ang) && finite3(np.t) && isfinite(np.q.x) && isfinite(np.q.y) && isfinite(np.q.z) && isfinite(np.q.w))) {
         // Containment of non-finite state at the end-of-step chokepoint (physics_pipeline/quarantine.rs:14-47, :126-178):
         // the body keeps its last valid pose, loses its velocities and forces, is disabled (its colliders leave the
@@ -882,6 +899,16 @@ RB_HD void body_writeback(const World& w, const B& bd, int b, int id) {
         w.st->lists_dirty = 3; w.st->bp_dirty = 1; w.st->sched_dirty = 1;
         RB_RAISE(w, -5);
         return;
+    }
+    if (P.ccd && ccd_is_moving_fast(P, xyz(w.b_lcom_im[b]), ccd_op, np, ccd_ext, ccd_thick)) {
+        // CCD (substep.rs:492-520): a body whose solved motion exceeds half its thinnest extent is queued for motion clamping
+        // with its start pose; the sweep itself (rb_ccd.cuh) runs at the start of the next step's
+        // k_collide or at the next synchronising call (k_ccd_pending), so the solve kernels carry only this test.
+        w.ccd_start_t[b] = f4(ccd_op.t, 0.0f);
+        w.ccd_start_q[b] = f4(ccd_op.q);
+        w.ccd_list[atomic_add(&w.st->nccd, 1)] = b;
+        atomic_add(&w.st->ccd_total, 1);
+        w.host_hint[3] = 1;
     }
     w.b_linvel[b] = f4(lin, 0.0f);
     w.b_angvel[b] = f4(ang, 0.0f);

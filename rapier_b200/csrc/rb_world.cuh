@@ -117,7 +117,8 @@ struct State {
     int sleep_stamp;       // step counter of the sleep decision (isl_block holds the stamp of the last veto)
     unsigned mov_wz_bits, mov_wx_bits;   // widest mover along z / x of the last broad-phase run (float bits)
     int nquarantine;       // bodies quarantined since the host last read the list (non-finite state)
-    int pad[2];
+    int nccd;              // fast bodies queued for CCD motion clamping by the last solve (World::ccd_list)
+    int ccd_total;         // fast bodies queued since the scene was uploaded (diagnostic)
 };
 
 struct PairBuf {
@@ -152,6 +153,8 @@ struct World {
     float* b_ccd_thick;               // RigidBodyCcd::ccd_thickness: thinnest extent over the body's colliders (FLT_MAX without colliders)
     int* b_col_head;                  // [nb] first collider of the body (-1 none); the chain continues through c_next
     int* c_next;                      // [nc] next collider of the same body (-1 end)
+    int* ccd_list;                    // [nb] bodies queued for motion clamping (State::nccd entries)
+    float4 *ccd_start_t, *ccd_start_q;   // [nb] their pose at the start of the step (RigidBodyPosition::position)
     int* wake_req;                    // [nb] by island root: wake this island (a contact began)
     int* isl_block;                   // [nb] by island root: stamp of the last step a body of the island was not sleep-eligible
     int sleep_enabled;                // some body may sleep: run the sleep decision
@@ -226,6 +229,7 @@ struct World {
     int coop_sweep_threads;           // sweep width of the big launch shape (0 = whole block)
     int* host_hint;                   // pinned, host-mapped words read by the host without synchronising: [0] last step's State::need_big,
                                       // [1] first status raised on the device since the host last cleared it (RbStatus; 0 = none)
+                                      // [2] a grid-wide island exists, [3] CCD clamps are queued (applied by the next k_collide or synchronising call)
     // ---- joints ----
     int4* j_info;                     // body1, body2, locked_axes, colour
     float4 *j_f1_t, *j_f1_q, *j_f2_t, *j_f2_q;   // local frames
