@@ -707,10 +707,10 @@ static int upload_bodies(RbWorld* W, const std::vector<HostMass>& mp, int first,
         lv[k] = make_float4(d.linvel[0], d.linvel[1], d.linvel[2], 0.f);
         av[k] = make_float4(d.angvel[0], d.angvel[1], d.angvel[2], 0.f);
         lc[k] = make_float4(mp[i].lcom[0], mp[i].lcom[1], mp[i].lcom[2], mp[i].inv_mass);
-        ipi[k] = make_float4(mp[i].ipi[0], mp[i].ipi[1], mp[i].ipi[2], 0.f);
+        ipi[k] = make_float4(mp[i].ipi[0], mp[i].ipi[1], mp[i].ipi[2], mp[i].max_extent);       // .w: copy of b_max_extent for the CCD test
         pi[k] = make_float4(mp[i].pi[0], mp[i].pi[1], mp[i].pi[2], 0.f);
         pf[k] = make_float4(mp[i].pframe[0], mp[i].pframe[1], mp[i].pframe[2], mp[i].pframe[3]);
-        misc[k] = make_float4(d.linear_damping, d.angular_damping, d.gravity_scale, 0.f);
+        misc[k] = make_float4(d.linear_damping, d.angular_damping, d.gravity_scale, mp[i].ccd_thickness);   // .w: copy of b_ccd_thick
         uf[k] = make_float4(d.user_force[0], d.user_force[1], d.user_force[2], 0.f);
         ut[k] = make_float4(d.user_torque[0], d.user_torque[1], d.user_torque[2], 0.f);
     }

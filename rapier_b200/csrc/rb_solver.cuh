@@ -879,7 +879,7 @@ RB_HD void body_writeback(const World& w, const B& bd, int b, int id) {
     // (what the CCD test below reads is fetched here, with the other loads, so that it adds no round trip of its own)
     pose ccd_op = pident();
     float ccd_ext = 0.0f, ccd_thick = 0.0f;
-    if (P.ccd) { ccd_op = body_pose(w, b); ccd_ext = w.b_max_extent[b]; ccd_thick = w.b_ccd_thick[b]; }
+    if (P.ccd) { ccd_op = body_pose(w, b); ccd_ext = w.b_ipi[b].w; ccd_thick = misc.w; }   // (copies of b_max_extent / b_ccd_thick in rows this function reads anyway)
     vec3 lin = bd.lin(id) * (1.0f / (1.0f + P.dt * misc.x));
     vec3 ang = bd.ang(id) * (1.0f / (1.0f + P.dt * misc.y));
     pose np = prepend_translation(bd.xf(id), -xyz(w.b_lcom_im[b]));

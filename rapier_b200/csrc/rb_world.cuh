@@ -137,8 +137,8 @@ struct World {
     float4 *b_pos_t, *b_pos_q;        // RigidBodyPosition::position
     float4 *b_linvel, *b_angvel;
     float4* b_lcom_im;                // local_com xyz, w inv_mass
-    float4 *b_ipi, *b_pi, *b_pframe;  // inverse principal inertia, principal inertia, principal frame
-    float4* b_misc;                   // linear damping, angular damping, gravity scale
+    float4 *b_ipi, *b_pi, *b_pframe;  // inverse principal inertia (w: max_extent), principal inertia, principal frame
+    float4* b_misc;                   // linear damping, angular damping, gravity scale, ccd_thickness
     float4 *b_uforce, *b_utorque;
     float4* b_wcom;                   // world_com
     float4* b_eim;                    // effective_inv_mass
