@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 1
+#define RB_ABI_VERSION 2
 
 typedef struct RbWorld RbWorld;
 
@@ -117,7 +117,26 @@ typedef struct RbColliderDesc {
     float contact_skin;           /* default 0 */
     uint32_t collision_memberships;    /* InteractionGroups::all() = 0xffffffff */
     uint32_t collision_filter;
+    uint32_t active_events;            /* RB_EVENT_* (ActiveEvents, collider.rs); default 0 */
+    float contact_force_event_threshold;   /* default 0; only read with RB_EVENT_CONTACT_FORCE */
 } RbColliderDesc;
+
+/* ActiveEvents (src/pipeline/event_handler.rs). */
+enum { RB_EVENT_COLLISION = 1, RB_EVENT_CONTACT_FORCE = 2 };
+
+/* CollisionEvent::{Started, Stopped} (src/geometry/mod.rs; emitted by apply_pair_transitions, narrow_phase/contacts.rs:312-324,
+ * and when a touching pair leaves the broad phase).  `step` = index of the step that emitted it (1 = first step). */
+typedef struct RbCollisionEvent { int32_t collider1, collider2, started, step; } RbCollisionEvent;
+/* ContactForceEvent (src/geometry/mod.rs:191-258; NarrowPhase::emit_contact_force_events, solver_graph.rs:462-498). */
+typedef struct RbContactForceEvent {
+    int32_t collider1, collider2;
+    float total_force[3];
+    float total_force_magnitude;
+    float max_force_direction[3];
+    float max_force_magnitude;
+    int32_t started;               /* first step above the pair's threshold (coming from below or from separation) */
+    int32_t step;
+} RbContactForceEvent;
 
 /* JointAxesMask bits (src/dynamics/joint/generic_joint.rs): LIN_X=1, LIN_Y=2, LIN_Z=4,
  * ANG_X=8, ANG_Y=16, ANG_Z=32.  Only fully locked axes are supported (spherical = 7, fixed = 63,
@@ -178,6 +197,16 @@ int rb_world_synchronize(RbWorld* w);
 int rb_world_get_body_states(RbWorld* w, float* pose7, float* vel6);
 int rb_world_num_bodies(RbWorld* w);
 int rb_world_get_counters(RbWorld* w, RbCounters* out);
+
+/* ---- events (EventHandler, src/pipeline/event_handler.rs).  The reference calls the handler during the step; here the
+ * step appends to device buffers (only for colliders with the matching RB_EVENT_* bit) that these calls drain: they
+ * synchronise, copy out up to `cap` events ordered by (step, collider1, collider2), and empty the buffer.  Return
+ * value: the number of events that were buffered (may exceed cap), or a negative status. */
+int rb_world_drain_collision_events(RbWorld* w, int32_t cap, RbCollisionEvent* out);
+int rb_world_drain_contact_force_events(RbWorld* w, int32_t cap, RbContactForceEvent* out);
+/* RigidBody::reset_forces + add_force / add_torque between steps: replaces the user force / torque of the listed bodies
+ * (either array may be NULL). */
+int rb_world_set_body_forces(RbWorld* w, int32_t n, const int32_t* indices, const float* force3, const float* torque3);
 int rb_world_enable_profiling(RbWorld* w, int32_t enabled);
 
 /* ---- contact graph read-back (NarrowPhase::contact_pairs; used by the parity tests) ---- */

@@ -94,6 +94,8 @@ public:
     ColliderBuilder& collision_groups(unsigned memberships, unsigned filter) {
         d_.collision_memberships = memberships; d_.collision_filter = filter; return *this;
     }
+    ColliderBuilder& active_events(unsigned events) { d_.active_events = events; return *this; }   // RB_EVENT_*
+    ColliderBuilder& contact_force_event_threshold(float t) { d_.contact_force_event_threshold = t; return *this; }
     RbColliderDesc desc(int parent) const { RbColliderDesc d = d_; d.parent = parent; return d; }
 
 private:

@@ -141,6 +141,33 @@ int orc_world_set_body_states(OrcWorld* o, int32_t n, const int32_t* indices, co
     }
     return orc_world_wake_up(o, n, indices);   // a user change wakes the body's island (user_changes.rs)
 }
+int orc_world_set_body_forces(OrcWorld* o, int32_t n, const int32_t* indices, const float* force3, const float* torque3) {
+    if (!o) return RB_ERR_INVALID;
+    World& w = o->w;
+    for (int k = 0; k < n; ++k) {
+        int i = indices[k];
+        if (i < 0 || i >= (int)w.bodies.size()) return RB_ERR_INVALID;
+        if (force3) w.bodies[i].user_force = V3{force3[k * 3], force3[k * 3 + 1], force3[k * 3 + 2]};
+        if (torque3) w.bodies[i].user_torque = V3{torque3[k * 3], torque3[k * 3 + 1], torque3[k * 3 + 2]};
+    }
+    return orc_world_wake_up(o, n, indices);
+}
+int orc_world_drain_collision_events(OrcWorld* o, int32_t cap, RbCollisionEvent* out) {
+    if (!o) return RB_ERR_INVALID;
+    std::vector<RbCollisionEvent>& ev = o->w.collision_events;
+    const int n = (int)ev.size();
+    for (int i = 0; i < n && i < cap && out; ++i) out[i] = ev[i];
+    ev.clear();
+    return n;
+}
+int orc_world_drain_contact_force_events(OrcWorld* o, int32_t cap, RbContactForceEvent* out) {
+    if (!o) return RB_ERR_INVALID;
+    std::vector<RbContactForceEvent>& ev = o->w.force_events;
+    const int n = (int)ev.size();
+    for (int i = 0; i < n && i < cap && out; ++i) out[i] = ev[i];
+    ev.clear();
+    return n;
+}
 int orc_world_step(OrcWorld* w, const float gravity[3], int32_t nsteps) {
     if (!w || !gravity) return RB_ERR_INVALID;
     for (int i = 0; i < nsteps; ++i) step_once(w->w, V3{gravity[0], gravity[1], gravity[2]});

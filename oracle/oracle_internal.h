@@ -77,6 +77,8 @@ struct Collider {
     int friction_rule, restitution_rule;
     float contact_skin;
     uint32_t memberships, filter;
+    uint32_t active_events;         // ActiveEvents
+    float force_event_threshold;    // contact_force_event_threshold
     Pose pos;       // world pose
     Aabb aabb;      // compute_broad_phase_aabb (tight + skin + prediction/2)
     Aabb fat;       // broad-phase leaf AABB (change-detection skin)
@@ -113,6 +115,7 @@ struct Pair {
     SolverContact sc[MAX_MANIFOLD_POINTS];
     uint8_t color;
     uint32_t color_bodies[2];
+    bool force_event_emitted;   // PairEventStatus::INITIAL_FORCE_THRESHOLD_EVENT_EMITTED
 };
 
 struct RawPoint {
@@ -204,6 +207,8 @@ struct World {
     bool bp_dirty = true;
     std::vector<int> island_of;        // connected component (root body) of every dynamic body, -1 otherwise
     bool islands_dirty = true;         // the touching set or the joints changed: relabel
+    std::vector<RbCollisionEvent> collision_events;      // since the last drain (EventHandler::handle_collision_event)
+    std::vector<RbContactForceEvent> force_events;       // (EventHandler::handle_contact_force_event)
     std::vector<int> quarantine;       // bodies disabled because their state went non-finite (since last read)
     bool static_dirty = true;          // the sorted list of static colliders must be rebuilt
     std::vector<int> static_sorted;    // static colliders by fat min-x

@@ -232,6 +232,12 @@ static void clear_pair_color(World& w, Pair& p) {  // narrow_phase/mod.rs:154-17
     p.color_bodies[0] = p.color_bodies[1] = NO_BODY;
 }
 
+// A pair that leaves the broad phase while touching stops (pair_management.rs: emit_stop_event) and frees its colour.
+static void removed_pair(World& w, Pair& o) {
+    if (o.nsc > 0 && ((w.colliders[o.c1].active_events | w.colliders[o.c2].active_events) & RB_EVENT_COLLISION))
+        w.collision_events.push_back(RbCollisionEvent{o.c1, o.c2, 0, (int)w.counters.steps + 1});
+    clear_pair_color(w, o);
+}
 static void update_pairs(World& w) {
     int nc = (int)w.colliders.size();
     // Only pairs with a collider that can move matter (static-static pairs are filtered anyway), so the sweep runs
@@ -294,7 +300,7 @@ static void update_pairs(World& w) {
             Pair& o = w.pairs[oi];
             uint64_t ok = ((uint64_t)(uint32_t)o.c1 << 32) | (uint32_t)o.c2;
             if (ok < k) {  // removed pair: end-touch frees its colour (contacts.rs:333-335)
-                clear_pair_color(w, o);
+                removed_pair(w, o);
                 ++oi;
             } else break;
         }
@@ -313,7 +319,7 @@ static void update_pairs(World& w) {
         p.color_bodies[0] = p.color_bodies[1] = NO_BODY;
         np.push_back(p);
     }
-    for (; oi < w.pairs.size(); ++oi) clear_pair_color(w, w.pairs[oi]);
+    for (; oi < w.pairs.size(); ++oi) removed_pair(w, w.pairs[oi]);
     w.pairs.swap(np);
     w.bp_dirty = false;
     w.counters.broad_phase_ran = 1;
@@ -580,6 +586,10 @@ static void narrow_phase(World& w) {
         const bool a1 = p.b1 >= 0 && w.bodies[p.b1].is_awake(), a2 = p.b2 >= 0 && w.bodies[p.b2].is_awake();
         if (!a1 && !a2) continue;
         if (process_pair(w, p)) {
+            // contacts.rs:312-324: start / stop events for colliders that ask for them
+            if ((w.colliders[p.c1].active_events | w.colliders[p.c2].active_events) & RB_EVENT_COLLISION)
+                w.collision_events.push_back(RbCollisionEvent{p.c1, p.c2, p.nsc > 0 ? 1 : 0, (int)w.counters.steps + 1});
+            if (p.nsc == 0) p.force_event_emitted = false;
             if (p.nsc > 0) {
                 started.push_back(i);
                 // a contact that begins wakes the sleeping side's whole island (narrow_phase/mod.rs:53-67)
@@ -701,6 +711,40 @@ void step_once(World& w, V3 gravity) {
     for (Collider& c : w.colliders) {
         if (c.shape >= 0 && c.parent >= 0 && w.bodies[c.parent].is_awake()) refresh_collider(w, c);
     }
+    // NarrowPhase::emit_contact_force_events (solver_graph.rs:462-498; ContactForceEvent::from_contact_pair, geometry/mod.rs:223-258)
+    {
+        const float inv_dt = w.params.p.dt == 0.0f ? 0.0f : 1.0f / w.params.p.dt;
+        for (Pair& p : w.pairs) {
+            if (p.nsc <= 0) continue;
+            const bool a1 = p.b1 >= 0 && w.bodies[p.b1].is_awake(), a2 = p.b2 >= 0 && w.bodies[p.b2].is_awake();
+            if (!a1 && !a2) continue;   // solver-active pairs only
+            const Collider &c1 = w.colliders[p.c1], &c2 = w.colliders[p.c2];
+            const float t1 = (c1.active_events & RB_EVENT_CONTACT_FORCE) ? c1.force_event_threshold : 3.4028235e38f;
+            const float t2 = (c2.active_events & RB_EVENT_CONTACT_FORCE) ? c2.force_event_threshold : 3.4028235e38f;
+            const float threshold = fmin2(t1, t2);
+            if (!(threshold < 3.4028235e38f)) continue;
+            float total = 0.0f, maxi = 0.0f;
+            for (int k = 0; k < p.nsc; ++k) {
+                const float imp = p.pts[p.sc[k].cid].impulse;
+                total = total + imp;
+                if (imp > maxi) maxi = imp;
+            }
+            const float magnitude = total * inv_dt;
+            if (magnitude > threshold) {
+                RbContactForceEvent e{};
+                e.collider1 = p.c1; e.collider2 = p.c2;
+                const V3 tf = (p.normal * total) * inv_dt;
+                e.total_force[0] = tf.x; e.total_force[1] = tf.y; e.total_force[2] = tf.z;
+                e.total_force_magnitude = magnitude;
+                if (maxi > 0.0f) { e.max_force_direction[0] = p.normal.x; e.max_force_direction[1] = p.normal.y; e.max_force_direction[2] = p.normal.z; }
+                e.max_force_magnitude = maxi * inv_dt;
+                e.started = p.force_event_emitted ? 0 : 1;
+                e.step = (int)w.counters.steps + 1;
+                w.force_events.push_back(e);
+                p.force_event_emitted = true;
+            } else p.force_event_emitted = false;
+        }
+    }
     double t4 = now_ms();
     w.counters.broad_phase_ms = (float)(t1 - t0);
     w.counters.narrow_phase_ms = (float)(t2 - t1);
@@ -762,7 +806,9 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
         c.friction_rule = d.friction_combine_rule;
         c.restitution_rule = d.restitution_combine_rule;
         c.contact_skin = d.contact_skin;
-        c.memberships = d.collision_memberships;
+        c.active_events = d.active_events;
+    c.force_event_threshold = d.contact_force_event_threshold;
+    c.memberships = d.collision_memberships;
         c.filter = d.collision_filter;
         c.fat_valid = false;
     }
@@ -848,6 +894,8 @@ static void fill_collider(Collider& c, const RbColliderDesc& d) {
     c.friction_rule = d.friction_combine_rule;
     c.restitution_rule = d.restitution_combine_rule;
     c.contact_skin = d.contact_skin;
+    c.active_events = d.active_events;
+    c.force_event_threshold = d.contact_force_event_threshold;
     c.memberships = d.collision_memberships;
     c.filter = d.collision_filter;
     c.fat_valid = false;

@@ -79,7 +79,20 @@ class RbColliderDesc(C.Structure):
         ("friction_combine_rule", i32), ("restitution_combine_rule", i32),
         ("contact_skin", f32),
         ("collision_memberships", u32), ("collision_filter", u32),
+        ("active_events", u32), ("contact_force_event_threshold", f32),
     ]
+
+
+class RbCollisionEvent(C.Structure):
+    _fields_ = [("collider1", i32), ("collider2", i32), ("started", i32), ("step", i32)]
+
+
+class RbContactForceEvent(C.Structure):
+    _fields_ = [("collider1", i32), ("collider2", i32), ("total_force", f32 * 3), ("total_force_magnitude", f32),
+                ("max_force_direction", f32 * 3), ("max_force_magnitude", f32), ("started", i32), ("step", i32)]
+
+
+RB_EVENT_COLLISION, RB_EVENT_CONTACT_FORCE = 1, 2
 
 
 class RbJointDesc(C.Structure):

@@ -370,6 +370,11 @@ __global__ void __launch_bounds__(COOP_SMALL_THREADS, 2) k_solve_coop(World w, G
 template <int THREADS, int L>
 __global__ void __launch_bounds__(THREADS, 1) k_solve_coop_big(World w, Grav g) { solve_coop_items<L>(w, g, COOP_BIG_SMEM_BYTES / 4, true); }
 __global__ void k_kat(World w, int which, const float* in, float* out) { kat_phase(w, which, in, out); }
+// Contact force events of the step just solved (launched only for worlds in which a collider asks for them).
+__global__ void k_force_events(World w) {
+    GridCtx ctx;
+    phase_force_events(ctx, w);
+}
 // The CCD clamps queued by the last step's body writeback (rb_solver.cuh) when NO further step follows: a synchronising
 // call launches this (one CTA: fast bodies are rare) if the device flagged any; otherwise the next k_collide applies them.
 __global__ void k_ccd_pending(World w) {
@@ -426,6 +431,7 @@ struct RbWorld {
     int big_threads = COOP_BIG_THREADS, sweep_threads = 0;
     float* state_buf[2] = {nullptr, nullptr};   // double-buffered packed state (rb_world_state_buffers), else unused
     int state_next = 0;
+    bool force_events = false;   // some collider has RB_EVENT_CONTACT_FORCE: run k_force_events after every step
     int steps_since_scene = 0;   // the launch-shape hint of a new scene is awaited once (see rb_world_step)
     int coop_shape = -1;   // RB_COOP_SHAPE debugging override: 0 small, 1 big, -1 automatic
     int* host_hint = nullptr;
@@ -749,8 +755,13 @@ static int upload_colliders(RbWorld* W, int first, int count, int first_body = 0
     std::vector<float4> he(count), rt(count), rq(count), mat(count);
     std::vector<int2> rules(count);
     std::vector<uint2> groups(count);
+    std::vector<int> events(count);
+    std::vector<float> thr(count);
     for (int k = 0; k < count; ++k) {
         const RbColliderDesc& c = W->colliders[first + k];
+        events[k] = (int)c.active_events;
+        thr[k] = c.contact_force_event_threshold;
+        if (c.active_events & RB_EVENT_CONTACT_FORCE) W->force_events = true;
         shape[k] = c.shape;
         parent[k] = c.parent;
         he[k] = make_float4(c.half_extents[0], c.half_extents[1], c.half_extents[2], 0.f);
@@ -769,6 +780,8 @@ static int upload_colliders(RbWorld* W, int first, int count, int first_body = 0
     CK(h2d(w.c_mat + first, mat.data(), n * sizeof(float4)));
     CK(h2d(w.c_rules + first, rules.data(), n * sizeof(int2)));
     CK(h2d(w.c_groups + first, groups.data(), n * sizeof(uint2)));
+    CK(h2d(w.c_events + first, events.data(), n * sizeof(int)));
+    CK(h2d(w.c_force_thr + first, thr.data(), n * sizeof(float)));
     // per-body collider chains (RigidBodyColliders): appended colliders only ever belong to appended bodies
     // (rb_world_insert), so the chains of the bodies from `first_body` on are rebuilt from the colliders from `first` on
     const int nb_all = (int)W->bodies.size();
@@ -943,6 +956,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
 
     free_all(W);
     World& w = W->w;
+    W->force_events = false;
     memset(&w, 0, sizeof(w));
     derive_params(W->params, w.prm);
     w.nb = nb; w.nc = nc; w.nj = nj;
@@ -972,13 +986,15 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.s_incr_lin, NB); ALLOC(w.s_incr_ang, NB);
     ALLOC(w.state13, (size_t)NB * 13);
     ALLOC(w.c_shape, NC); ALLOC(w.c_parent, NC); ALLOC(w.c_he, NC); ALLOC(w.c_rel_t, NC); ALLOC(w.c_rel_q, NC);
-    ALLOC(w.c_mat, NC); ALLOC(w.c_rules, NC); ALLOC(w.c_groups, NC); ALLOC(w.c_pos_t, NC); ALLOC(w.c_pos_q, NC);
+    ALLOC(w.c_mat, NC); ALLOC(w.c_rules, NC); ALLOC(w.c_groups, NC); ALLOC(w.c_events, NC); ALLOC(w.c_force_thr, NC); ALLOC(w.c_pos_t, NC); ALLOC(w.c_pos_q, NC);
     ALLOC(w.c_aabb_min, NC); ALLOC(w.c_aabb_max, NC); ALLOC(w.c_fat_min, NC); ALLOC(w.c_fat_max, NC);
     ALLOC(w.dyn_list, NC); ALLOC(w.wide_list, WIDE_CAP); ALLOC(w.dyn_smin, NC); ALLOC(w.dyn_smax, NC);
     for (int k = 0; k < 2; ++k) { ALLOC(w.dyn_key[k], NC); ALLOC(w.stat_key[k], NC); }
     ALLOC(w.radix_hist, (size_t)9 * 1024 * RADIX);   // (grids of up to 1024 CTAs; the collide grid is one CTA per SM)
     ALLOC(w.cand_key, w.pair_cap); ALLOC(w.cand_key2, w.pair_cap);
     ALLOC(w.remap_src, w.pair_cap);
+    w.ev_cap = w.pair_cap;
+    ALLOC(w.ev_coll, w.ev_cap); ALLOC(w.ev_force, (size_t)3 * w.ev_cap);
     for (int k = 0; k < 2; ++k) { ALLOC(w.pb[k].key, w.pair_cap); ALLOC(w.pb[k].rows, (size_t)PR_ROWS * w.pair_cap); }
     ALLOC(w.todo, 16);
     ALLOC(w.color_mask, (size_t)NB * 4); ALLOC(w.body_min, NB); ALLOC(w.body_minkey, NB);
@@ -1283,6 +1299,76 @@ int rb_world_set_body_states(RbWorld* W, int32_t n, const int32_t* indices, cons
     return sync_world(W);
 }
 
+int rb_world_set_body_forces(RbWorld* W, int32_t n, const int32_t* indices, const float* force3, const float* torque3) {
+    if (!W || n < 0 || (n && !indices)) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    int rc = sync_world(W);
+    if (rc != RB_OK) return rc;
+    for (int k = 0; k < n; ++k) {
+        const int i = indices[k];
+        if (i < 0 || i >= W->w.nb) { set_err("body index out of range%s", ""); return RB_ERR_INVALID; }
+        if (force3) {
+            float4 f = make_float4(force3[k * 3], force3[k * 3 + 1], force3[k * 3 + 2], 0.f);
+            CK(h2d(W->w.b_uforce + i, &f, sizeof(f)));
+            for (int a = 0; a < 3; ++a) W->bodies[i].user_force[a] = force3[k * 3 + a];
+        }
+        if (torque3) {
+            float4 t = make_float4(torque3[k * 3], torque3[k * 3 + 1], torque3[k * 3 + 2], 0.f);
+            CK(h2d(W->w.b_utorque + i, &t, sizeof(t)));
+            for (int a = 0; a < 3; ++a) W->bodies[i].user_torque[a] = torque3[k * 3 + a];
+        }
+    }
+    if (n > 0 && (rc = wake_impl(W, indices, n)) != RB_OK) return rc;   // add_force(.., wake_up = true)
+    return sync_world(W);
+}
+
+int rb_world_drain_collision_events(RbWorld* W, int32_t cap, RbCollisionEvent* out) {
+    if (!W || cap < 0 || !W->w.st) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    State st;
+    int rc = read_state(W, st);
+    if (rc != RB_OK) return rc;
+    const int n = std::min(st.nev_coll, W->w.ev_cap);
+    std::vector<int4> ev(std::max(n, 1));
+    CK(d2h(ev.data(), W->w.ev_coll, (size_t)n * sizeof(int4)));
+    std::sort(ev.begin(), ev.begin() + n, [](const int4& a, const int4& b) {
+        if (a.w != b.w) return a.w < b.w;
+        if (a.x != b.x) return a.x < b.x;
+        if (a.y != b.y) return a.y < b.y;
+        return a.z < b.z;
+    });
+    for (int i = 0; i < n && i < cap && out; ++i) out[i] = RbCollisionEvent{ev[i].x, ev[i].y, ev[i].z, ev[i].w};
+    int zero = 0;
+    CK(h2d(&W->w.st->nev_coll, &zero, sizeof(int)));
+    return n;
+}
+
+int rb_world_drain_contact_force_events(RbWorld* W, int32_t cap, RbContactForceEvent* out) {
+    if (!W || cap < 0 || !W->w.st) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    State st;
+    int rc = read_state(W, st);
+    if (rc != RB_OK) return rc;
+    const int n = std::min(st.nev_force, W->w.ev_cap), ec = W->w.ev_cap;
+    std::vector<float4> r0(std::max(n, 1)), r1(std::max(n, 1)), r2(std::max(n, 1));
+    CK(d2h(r0.data(), W->w.ev_force, (size_t)n * sizeof(float4)));
+    CK(d2h(r1.data(), W->w.ev_force + ec, (size_t)n * sizeof(float4)));
+    CK(d2h(r2.data(), W->w.ev_force + 2 * (size_t)ec, (size_t)n * sizeof(float4)));
+    std::vector<RbContactForceEvent> ev(n);
+    for (int i = 0; i < n; ++i) {
+        RbContactForceEvent& e = ev[i];
+        memcpy(&e.collider1, &r0[i].x, 4); memcpy(&e.collider2, &r0[i].y, 4); memcpy(&e.started, &r0[i].z, 4); memcpy(&e.step, &r0[i].w, 4);
+        e.total_force[0] = r1[i].x; e.total_force[1] = r1[i].y; e.total_force[2] = r1[i].z; e.total_force_magnitude = r1[i].w;
+        e.max_force_direction[0] = r2[i].x; e.max_force_direction[1] = r2[i].y; e.max_force_direction[2] = r2[i].z; e.max_force_magnitude = r2[i].w;
+    }
+    std::sort(ev.begin(), ev.end(), [](const RbContactForceEvent& a, const RbContactForceEvent& b) {
+        if (a.step != b.step) return a.step < b.step;
+        if (a.collider1 != b.collider1) return a.collider1 < b.collider1;
+        return a.collider2 < b.collider2;
+    });
+    for (int i = 0; i < n && i < cap && out; ++i) out[i] = ev[i];
+    int zero = 0;
+    CK(h2d(&W->w.st->nev_force, &zero, sizeof(int)));
+    return n;
+}
+
 int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sync) {
     if (!W || !gravity || nsteps < 0) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
     if (W->w.nb == 0 && W->w.nc == 0) return RB_OK;
@@ -1308,6 +1394,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         W->steps_since_scene++;
         // launch shape of k_solve_coop for this step (both kernels must agree on it): device hint of the last step
         const bool big = W->coop_shape >= 0 ? W->coop_shape == 1 : (*(volatile int*)W->host_hint != 0);
+        W->w.step_index = (int)(W->steps + s + 1);
         void* a1[] = {(void*)&W->w, (void*)&g, (void*)&do_solve};
         CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, ITEM_SMEM_BYTES, W->stream));
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 1], W->stream));
@@ -1315,6 +1402,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
             void* a2[] = {(void*)&W->w, (void*)&g};
             k_solve_items_coulomb<<<W->collide_blocks, W->collide_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
             CK(cudaLaunchCooperativeKernel((void*)k_solve_large_coulomb, dim3(W->collide_blocks), dim3(W->collide_threads), a2, 0, W->stream));
+            if (W->force_events) { k_force_events<<<W->collide_blocks, 256, 0, W->stream>>>(W->w); W->kernels++; }
             if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 2], W->stream));
             W->kernels += 3;
             continue;
@@ -1328,6 +1416,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
 #define RB_LAUNCH_BIG(T, LL) if (W->big_threads == T) k_solve_coop_big<T, LL><<<W->coop_blocks_big, T, COOP_BIG_SMEM_BYTES, W->stream>>>(W->w, g);
             RB_BIG_VARIANTS(RB_LAUNCH_BIG)
         } else k_solve_coop<<<W->coop_blocks, COOP_SMALL_THREADS, COOP_SMALL_SMEM_BYTES, W->stream>>>(W->w, g);
+        if (W->force_events) { k_force_events<<<W->collide_blocks, 256, 0, W->stream>>>(W->w); W->kernels++; }
         CK(cudaGetLastError());
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 2], W->stream));
         W->kernels += 2;
@@ -1352,6 +1441,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
 #else
     for (int s = 0; s < nsteps; ++s) {
         GridCtx gctx;
+        W->w.step_index = (int)(W->steps + s + 1);
         if (W->state_buf[1]) { W->w.state13 = W->state_buf[W->state_next]; W->state_next ^= 1; }
         W->emu_hint[0] = W->w.st->need_big;
         W->w.st->need_big = W->w.st->coop_streamed = W->w.st->coop_resident = 0;
@@ -1382,6 +1472,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
             if (W->w.prm.friction_model == 1) solve_item<1>(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
             else solve_item_lanes<1>(gex, W->w, gb, mk3(g.x, g.y, g.z));
         }
+        if (W->force_events) phase_force_events(gctx, W->w);
         if (W->w.st->nccd > 0) {   // the queued CCD clamps (the device applies them at the next k_collide / synchronising call)
             phase_ccd_pending(gctx, W->w, W->w.st->nccd);
             W->w.st->nccd = 0;

@@ -234,6 +234,14 @@ RB_HD void clear_color_bits(const World& w, int color, int cb0, int cb1) {
     }
 }
 
+// EventHandler::handle_collision_event (contacts.rs:312-324): buffered for the host when either collider asks for it.
+RB_HD void emit_collision_event(const World& w, int c1, int c2, bool started) {
+    if (!((w.c_events[c1] | w.c_events[c2]) & 1)) return;
+    const int slot = atomic_add(&w.st->nev_coll, 1);
+    if (slot < w.ev_cap) w.ev_coll[slot] = make_int4(c1, c2, started ? 1 : 0, w.step_index);
+    else RB_RAISE(w, -4);
+}
+
 RB_HD bool collider_is_static(const World& w, int c) {   // never moves: no parent, or a parent that is not a dynamic body
     const int p = w.c_parent[c];
     return p < 0 || w.b_type[p] != BODY_DYNAMIC;
@@ -459,6 +467,7 @@ RB_PHASE void section_broad_phase(const Ctx& ctx, const World& w) {
     for (int j = ctx.gtid; j < nold; j += ctx.gsize) {
         if (bsearch_u64(ck, ncand, okey[j]) < 0) {
             float4 info = prow(w, cur, PR_INFO, j), bod = prow(w, cur, PR_BODIES, j);
+            if (as_int(info.z) > 0) emit_collision_event(w, (int)(okey[j] >> 32), (int)(okey[j] & 0xffffffffu), false);   // a touching pair that leaves the broad phase stops
             clear_color_bits(w, as_int(info.w), as_int(bod.x), as_int(bod.y));
         }
     }
@@ -671,6 +680,8 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
         }
         if (had != has) {
             st->sched_dirty = 1;
+            emit_collision_event(w, c1, c2, has);
+            if (!has) flags &= ~8;   // the force-event status resets when the colliders separate (geometry/mod.rs:208-217)
             if (has) {
                 flags |= 2;  // pending colour (deferred greedy pass)
                 st->ntodo = 1;

@@ -799,6 +799,48 @@ RB_PHASE void phase_ccd_pending(const Ctx& ctx, const World& w, int n) {
     }
 }
 
+// NarrowPhase::emit_contact_force_events (solver_graph.rs:462-498) + ContactForceEvent::from_contact_pair (geometry/mod.rs:
+// 223-258), after the impulse writeback: solver-active pairs whose colliders ask for force events and whose total
+// normal impulse / dt exceeds the smaller threshold.  `started` = the pair was not above its threshold last step.
+template <class Ctx>
+RB_PHASE void phase_force_events(const Ctx& ctx, const World& w) {
+    State* st = w.st;
+    const int buf = st->cur, np = st->npairs;
+    for (int i = ctx.gtid; i < np; i += ctx.gsize) {
+        float4 info = prow(w, buf, PR_INFO, i);
+        const int nsc = as_int(info.z);
+        if (nsc <= 0) continue;
+        const unsigned long long key = w.pb[buf].key[i];
+        const int c1 = (int)(key >> 32), c2 = (int)(key & 0xffffffffu);
+        const float t1 = (w.c_events[c1] & 2) ? w.c_force_thr[c1] : FMAX32, t2 = (w.c_events[c2] & 2) ? w.c_force_thr[c2] : FMAX32;
+        const float threshold = min2(t1, t2);
+        if (!(threshold < FMAX32)) continue;
+        const float4 bod = prow(w, buf, PR_BODIES, i);
+        if (!body_is_sim(w, as_int(bod.z)) && !body_is_sim(w, as_int(bod.w))) continue;
+        float total = 0.0f, maxi = 0.0f;
+        for (int k = 0; k < nsc && k < MAX_PTS; ++k) {
+            const int cid = as_int(prow(w, buf, PR_A1 + k, i).w);
+            const float imp = prow(w, buf, PR_PD + cid, i).x;
+            total = total + imp;
+            if (imp > maxi) maxi = imp;
+        }
+        const float magnitude = total * w.prm.inv_dt_full;
+        int flags = as_int(info.x);
+        if (magnitude > threshold) {
+            const vec3 n = xyz(prow(w, buf, PR_NORMAL, i));
+            const vec3 tf = (n * total) * w.prm.inv_dt_full;
+            const int slot = atomic_add(&st->nev_force, 1);
+            if (slot < w.ev_cap) {
+                w.ev_force[slot] = make_float4(as_float_i(c1), as_float_i(c2), as_float_i((flags & 8) ? 0 : 1), as_float_i(w.step_index));
+                w.ev_force[w.ev_cap + slot] = f4(tf, magnitude);
+                w.ev_force[2 * w.ev_cap + slot] = f4(maxi > 0.0f ? n : zero3(), maxi * w.prm.inv_dt_full);
+            } else RB_RAISE(w, -4);
+            flags |= 8;
+        } else flags &= ~8;
+        if (flags != as_int(info.x)) { info.x = as_float_i(flags); prow(w, buf, PR_INFO, i) = info; }
+    }
+}
+
 // Executors: how the threads of an item iterate and synchronise.
 struct BlockExec {
     const BlockCtx* c;

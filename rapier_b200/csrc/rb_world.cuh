@@ -27,7 +27,7 @@ constexpr unsigned FLAG_GYRO = 1, FLAG_FAST_ROT = 2, FLAG_LTX = 4, FLAG_LTY = 8,
 
 // ---- persistent pair record rows (float4 each) ----
 enum PairRow {
-    PR_INFO = 0,   // int bits: x flags(bit0 has_recycle), y npts, z nsc, w colour
+    PR_INFO = 0,   // int bits: x flags(bit0 has_recycle, bit1 pending colour, bit2 colouring scratch, bit3 force event emitted last step), y npts, z nsc, w colour
     PR_BODIES,     // int bits: x colour_body0, y colour_body1, z body1, w body2 (-1 none)
     PR_RT,         // recycle pos12.t xyz, w max_extent
     PR_RQ,         // recycle pos12.q
@@ -119,6 +119,7 @@ struct State {
     int nquarantine;       // bodies quarantined since the host last read the list (non-finite state)
     int nccd;              // fast bodies queued for CCD motion clamping by the last solve (World::ccd_list)
     int ccd_total;         // fast bodies queued since the scene was uploaded (diagnostic)
+    int nev_coll, nev_force;   // buffered collision / contact-force events since the host last drained them
 };
 
 struct PairBuf {
@@ -169,6 +170,8 @@ struct World {
     float4* c_mat;                    // friction, restitution, contact_skin
     int2* c_rules;
     uint2* c_groups;
+    int* c_events;                    // ActiveEvents bits (1 = collision events, 2 = contact force events)
+    float* c_force_thr;               // contact_force_event_threshold
     float4 *c_pos_t, *c_pos_q;
     float4 *c_aabb_min, *c_aabb_max, *c_fat_min, *c_fat_max;
     // ---- broad phase scratch ----
@@ -183,6 +186,11 @@ struct World {
     unsigned long long* nocontact_keys;  // sorted body-pair keys of joints with contacts disabled
     int n_nocontact;
     int* remap_src;                   // [pair_cap] new pair -> old pair index or -1
+    // ---- events (EventHandler): appended by the step, drained by the host ----
+    int4* ev_coll;                    // [ev_cap] collider1, collider2, started, step
+    float4* ev_force;                 // [3][ev_cap] (c1, c2, started, step as int bits) | total force xyz, magnitude | max direction xyz, max magnitude
+    int ev_cap;
+    int step_index;                   // index of the step being enqueued (1 = first step after the scene upload)
     // ---- pairs ----
     PairBuf pb[2];
     int* todo;                        // [pair_cap] pairs that began touching this step

@@ -200,6 +200,15 @@ class ColliderBuilder:
         self._filter = int(filter_)
         return self
 
+    def active_events(self, events):
+        """ColliderBuilder::active_events (ActiveEvents: RB_EVENT_COLLISION | RB_EVENT_CONTACT_FORCE)."""
+        self._active_events = int(events)
+        return self
+
+    def contact_force_event_threshold(self, threshold):
+        self._force_threshold = float(threshold)
+        return self
+
     def build_desc(self, parent):
         d = A.RbColliderDesc()
         d.shape = self.shape
@@ -215,6 +224,8 @@ class ColliderBuilder:
         d.contact_skin = self._contact_skin
         d.collision_memberships = self._memberships
         d.collision_filter = self._filter
+        d.active_events = getattr(self, "_active_events", 0)
+        d.contact_force_event_threshold = getattr(self, "_force_threshold", 0.0)
         return d
 
 

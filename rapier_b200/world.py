@@ -110,6 +110,30 @@ class PhysicsPipeline:
                                                     None if p is None else p.ctypes.data,
                                                     None if v is None else v.ctypes.data))
 
+    def set_body_forces(self, indices, force3=None, torque3=None):
+        """RigidBody::reset_forces + add_force / add_torque: replaces the user force / torque of the listed bodies."""
+        idx = np.ascontiguousarray(indices, np.int32)
+        f = None if force3 is None else np.ascontiguousarray(force3, np.float32)
+        t = None if torque3 is None else np.ascontiguousarray(torque3, np.float32)
+        self._check(self.L.rb_world_set_body_forces(self.h, len(idx), idx.ctypes.data, None if f is None else f.ctypes.data,
+                                                    None if t is None else t.ctypes.data))
+
+    def collision_events(self):
+        """Drains the buffered CollisionEvents (EventHandler::handle_collision_event): [(collider1, collider2, started, step)]."""
+        buf = (A.RbCollisionEvent * 65536)()
+        n = self.L.rb_world_drain_collision_events(self.h, 65536, buf)
+        self._check(min(n, 0))
+        return [(e.collider1, e.collider2, e.started, e.step) for e in buf[:min(n, 65536)]]
+
+    def contact_force_events(self):
+        """Drains the buffered ContactForceEvents (EventHandler::handle_contact_force_event)."""
+        buf = (A.RbContactForceEvent * 65536)()
+        n = self.L.rb_world_drain_contact_force_events(self.h, 65536, buf)
+        self._check(min(n, 0))
+        return [dict(collider1=e.collider1, collider2=e.collider2, total_force=tuple(e.total_force), total_force_magnitude=e.total_force_magnitude,
+                     max_force_direction=tuple(e.max_force_direction), max_force_magnitude=e.max_force_magnitude, started=e.started, step=e.step)
+                for e in buf[:min(n, 65536)]]
+
     def counters(self):
         c = A.RbCounters()
         self._check(self.L.rb_world_get_counters(self.h, C.byref(c)))
@@ -271,6 +295,18 @@ class PhysicsWorld:
     def contact_pairs(self):
         self._flush()
         return self.physics_pipeline.contact_pairs()
+
+    def set_body_forces(self, handles, force3=None, torque3=None):
+        self._flush()
+        self.physics_pipeline.set_body_forces(handles, force3, torque3)
+
+    def collision_events(self):
+        self._flush()
+        return self.physics_pipeline.collision_events()
+
+    def contact_force_events(self):
+        self._flush()
+        return self.physics_pipeline.contact_force_events()
 
     def debug_read(self, table, dtype):
         self._flush()

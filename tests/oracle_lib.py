@@ -68,6 +68,9 @@ def lib(fast=False):
         L.orc_world_get_quarantine.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.orc_world_get_sleeping.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_world_wake_up.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_world_set_body_forces.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_world_drain_collision_events.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_world_drain_contact_force_events.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_kat.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
         _libs[fast] = L
     return _libs[fast]
@@ -149,6 +152,27 @@ class OracleWorld:
         c = A.RbCounters()
         self.L.orc_world_get_counters(self.h, C.byref(c))
         return c.as_dict()
+
+    def set_body_forces(self, indices, force3=None, torque3=None):
+        idx = np.ascontiguousarray(indices, np.int32)
+        f = None if force3 is None else np.ascontiguousarray(force3, np.float32)
+        t = None if torque3 is None else np.ascontiguousarray(torque3, np.float32)
+        rc = self.L.orc_world_set_body_forces(self.h, len(idx), idx.ctypes.data, None if f is None else f.ctypes.data,
+                                              None if t is None else t.ctypes.data)
+        assert rc == 0
+
+    def collision_events(self):
+        """Drains the buffered CollisionEvents: list of (collider1, collider2, started, step)."""
+        buf = (A.RbCollisionEvent * 65536)()
+        n = self.L.orc_world_drain_collision_events(self.h, 65536, buf)
+        return [(e.collider1, e.collider2, e.started, e.step) for e in buf[:n]]
+
+    def contact_force_events(self):
+        buf = (A.RbContactForceEvent * 65536)()
+        n = self.L.orc_world_drain_contact_force_events(self.h, 65536, buf)
+        return [dict(collider1=e.collider1, collider2=e.collider2, total_force=tuple(e.total_force), total_force_magnitude=e.total_force_magnitude,
+                     max_force_direction=tuple(e.max_force_direction), max_force_magnitude=e.max_force_magnitude, started=e.started, step=e.step)
+                for e in buf[:n]]
 
     def contact_pairs(self):
         n = self.L.orc_world_get_contact_pairs(self.h, 0, None, None, None, None, None)

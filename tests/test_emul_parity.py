@@ -158,6 +158,16 @@ def test_ccd_emulated_kernels():
     ccd_large_dt_no_mid_air_hitch(mk)
 
 
+def test_contact_force_events_emulated_kernels():
+    from test_oracle_kat import contact_force_event_started_marks_threshold_crossings
+    contact_force_event_started_marks_threshold_crossings(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()))
+
+
+def test_event_lists_match_oracle():
+    from variant_cases import events_parity_case
+    events_parity_case(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), lambda s: oracle_lib.OracleWorld(s))
+
+
 def test_quarantine_emulated_kernels():
     from test_oracle_kat import nan_force_is_quarantined
     nan_force_is_quarantined(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), expect_error=True)

@@ -326,3 +326,12 @@ def test_ccd_motion_clamping(built):
     mk = lambda s, p: PhysicsWorld(s, integration_parameters=p)
     ccd_default_tier(mk)
     ccd_large_dt_no_mid_air_hitch(mk)
+
+
+def test_events(built):
+    """Collision / contact-force events through the C ABI: the reference's threshold-crossing known answer
+    (contact_force_event_first_tick.rs) and event lists identical to the oracle's on a collapsing pile."""
+    from test_oracle_kat import contact_force_event_started_marks_threshold_crossings
+    from variant_cases import events_parity_case
+    contact_force_event_started_marks_threshold_crossings(lambda s: PhysicsWorld(s))
+    events_parity_case(lambda s: PhysicsWorld(s), lambda s: oracle_lib.OracleWorld(s))

@@ -555,3 +555,42 @@ def test_ccd_oracle():
     mk = lambda s, p: oracle_lib.OracleWorld(s, params=p)
     ccd_default_tier(mk)
     ccd_large_dt_no_mid_air_hitch(mk)
+
+
+# ---- events (EventHandler; crates/rapier3d/tests/contact_force_event_first_tick.rs) -------------------------------------
+def contact_force_event_started_marks_threshold_crossings(make_world):
+    """contact_force_event_first_tick.rs:53-170: a 1 kg ball resting on a slab (threshold 30 N) emits one
+    CollisionEvent::Started and no force event; pressed with 100 N it emits force events whose FIRST has started = true
+    and the following ones false; released, the events stop; pressed again, a new episode starts with started = true."""
+    s = scenes.Scene("force_events", gravity=(0.0, -9.81, 0.0))
+    s.colliders.insert(ColliderBuilder.cuboid(10.0, 0.5, 10.0).translation((0.0, -0.5, 0.0)))
+    ball = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.5, 0.0)).additional_mass(1.0).can_sleep(False),
+                    ColliderBuilder.ball(0.5).density(0.0).active_events(A.RB_EVENT_COLLISION | A.RB_EVENT_CONTACT_FORCE)
+                    .contact_force_event_threshold(30.0))
+    w = make_world(s)
+    started_steps, force_events = [], []
+
+    def run(rng, press):
+        for i in rng:
+            w.set_body_forces([ball], force3=[(0.0, -100.0 if press else 0.0, 0.0)])
+            w.step()
+            started_steps.extend(i for (_, _, st, _) in w.collision_events() if st)
+            force_events.extend((i, bool(e["started"])) for e in w.contact_force_events())
+
+    run(range(0, 100), False)
+    assert len(started_steps) == 1 and not force_events
+    run(range(100, 160), True)
+    assert force_events and force_events[0][1] and force_events[0][0] >= 100 and force_events[0][0] > started_steps[0] + 50
+    assert all(not first for _, first in force_events[1:]) and len(force_events) > 10
+    run(range(160, 165), False)
+    assert all(not first for _, first in force_events[1:])
+    n_after = len(force_events)
+    run(range(165, 220), False)
+    assert len(force_events) == n_after
+    run(range(220, 280), True)
+    episode = force_events[n_after:]
+    assert episode and episode[0][1] and all(not first for _, first in episode[1:])
+
+
+def test_contact_force_events_oracle():
+    contact_force_event_started_marks_threshold_crossings(lambda s: oracle_lib.OracleWorld(s))

@@ -126,6 +126,41 @@ def ccd_barrage():
     return s
 
 
+def events_scene():
+    """A pile collapsing onto a slab, a bouncing ball and a body that leaves the scene: every collider asks for collision
+    and contact-force events (thresholds from 0 to 40 N), so starts, stops, pairs that leave the broad phase while
+    touching and force-threshold crossings all occur."""
+    ev = A.RB_EVENT_COLLISION | A.RB_EVENT_CONTACT_FORCE
+    s = scenes.Scene("events")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(6.0, 0.5, 6.0).active_events(ev).contact_force_event_threshold(5.0))
+    for i in range(4):
+        for k in range(3):
+            s.insert(RigidBodyBuilder.dynamic().translation((0.3 * i - 0.4, 0.6 + 1.05 * i, 0.35 * k)).rotation((0.1 * k, 0.2, 0.05 * i)),
+                     ColliderBuilder.cuboid(0.5, 0.5, 0.5).active_events(ev).contact_force_event_threshold(10.0 * (i % 3)))
+    s.insert(RigidBodyBuilder.dynamic().translation((3.0, 2.0, 0.0)), ColliderBuilder.ball(0.3).restitution(0.8).active_events(A.RB_EVENT_COLLISION))
+    s.insert(RigidBodyBuilder.dynamic().translation((5.5, 0.5, 0.0)).linvel((6.0, 0.0, 0.0)), ColliderBuilder.cuboid(0.4, 0.4, 0.4).active_events(ev))
+    return s
+
+
+def events_parity_case(make_world, make_oracle, steps=150):
+    """The drained event lists of both worlds must be identical (ids, started flags, step, and every float bit)."""
+    s = events_scene()
+    w, o = make_world(s), make_oracle(s)
+    nc = nf = 0
+    for i in range(steps):
+        w.step(); o.step()
+        if i % 7 == 6 or i == steps - 1:   # (drained every few steps: the buffers accumulate across steps)
+            cw, co = w.collision_events(), o.collision_events()
+            assert cw == co, (i, cw[:4], co[:4])
+            fw, fo = w.contact_force_events(), o.contact_force_events()
+            assert len(fw) == len(fo), (i, len(fw), len(fo))
+            for a, b in zip(fw, fo):
+                assert a == b, (i, a, b)
+            nc += len(cw); nf += len(fw)
+    assert nc > 20 and nf > 50, (nc, nf)
+    return nc, nf
+
+
 VARIANTS = [
     ("restitution", bouncing_balls, None, 150, 25),
     ("groups_joints_forces", groups_and_joints, None, 150, 25),
