@@ -65,7 +65,7 @@ typedef struct RbIntegrationParameters {
 void rb_integration_parameters_default(RbIntegrationParameters* p);
 
 /* RigidBodyType (src/dynamics/rigid_body_components.rs). Kinematic bodies are not supported yet. */
-enum { RB_BODY_DYNAMIC = 0, RB_BODY_FIXED = 1 };
+enum { RB_BODY_DYNAMIC = 0, RB_BODY_FIXED = 1, RB_BODY_KINEMATIC_POSITION_BASED = 2, RB_BODY_KINEMATIC_VELOCITY_BASED = 3 };   /* RigidBodyType */
 
 /* Body flags */
 enum {
@@ -207,6 +207,9 @@ int rb_world_drain_contact_force_events(RbWorld* w, int32_t cap, RbContactForceE
 /* RigidBody::reset_forces + add_force / add_torque between steps: replaces the user force / torque of the listed bodies
  * (either array may be NULL). */
 int rb_world_set_body_forces(RbWorld* w, int32_t n, const int32_t* indices, const float* force3, const float* torque3);
+/* RigidBody::set_next_kinematic_position (rigid_body.rs:1085-1090) of position-based kinematic bodies: the pose they
+ * reach at the end of the next step; their velocity during that step is interpolated from it.  Other bodies: RB_ERR_INVALID. */
+int rb_world_set_next_kinematic_positions(RbWorld* w, int32_t n, const int32_t* indices, const float* pose7);
 int rb_world_enable_profiling(RbWorld* w, int32_t enabled);
 
 /* ---- contact graph read-back (NarrowPhase::contact_pairs; used by the parity tests) ---- */

@@ -39,6 +39,8 @@ class RigidBodyBuilder {
 public:
     static RigidBodyBuilder dynamic() { return RigidBodyBuilder(RB_BODY_DYNAMIC); }
     static RigidBodyBuilder fixed() { return RigidBodyBuilder(RB_BODY_FIXED); }
+    static RigidBodyBuilder kinematic_position_based() { return RigidBodyBuilder(RB_BODY_KINEMATIC_POSITION_BASED); }
+    static RigidBodyBuilder kinematic_velocity_based() { return RigidBodyBuilder(RB_BODY_KINEMATIC_VELOCITY_BASED); }
     RigidBodyBuilder& translation(Vector v) { for (int i = 0; i < 3; ++i) d_.translation[i] = v[i]; return *this; }
     RigidBodyBuilder& rotation(Vector axis_angle) {   // scaled axis, like RigidBodyBuilder::rotation
         float a = std::sqrt(axis_angle[0] * axis_angle[0] + axis_angle[1] * axis_angle[1] + axis_angle[2] * axis_angle[2]);

@@ -34,6 +34,7 @@ int orc_world_set_body_states(OrcWorld* w, int32_t n, const int32_t* indices, co
                               const float* vel6);
 int orc_world_step(OrcWorld* w, const float gravity[3], int32_t nsteps);
 int orc_world_set_body_forces(OrcWorld* w, int32_t n, const int32_t* indices, const float* force3, const float* torque3);
+int orc_world_set_next_kinematic_positions(OrcWorld* w, int32_t n, const int32_t* indices, const float* pose7);
 int orc_world_drain_collision_events(OrcWorld* w, int32_t cap, RbCollisionEvent* out);
 int orc_world_drain_contact_force_events(OrcWorld* w, int32_t cap, RbContactForceEvent* out);
 int orc_world_get_body_states(OrcWorld* w, float* pose7, float* vel6);

@@ -129,6 +129,7 @@ int orc_world_set_body_states(OrcWorld* o, int32_t n, const int32_t* indices, co
             b.pos.t = V3{pose7[k * 7 + 0], pose7[k * 7 + 1], pose7[k * 7 + 2]};
             b.pos.q = Q4{pose7[k * 7 + 3], pose7[k * 7 + 4], pose7[k * 7 + 5], pose7[k * 7 + 6]};
             b.next_pos = b.pos;
+            b.kin_target = b.pos;
             if (!b.is_dynamic()) w.static_dirty = true;   // a teleported fixed body moves static colliders
             update_world_mass_properties(b);
             for (Collider& c : w.colliders)
@@ -149,6 +150,16 @@ int orc_world_set_body_forces(OrcWorld* o, int32_t n, const int32_t* indices, co
         if (i < 0 || i >= (int)w.bodies.size()) return RB_ERR_INVALID;
         if (force3) w.bodies[i].user_force = V3{force3[k * 3], force3[k * 3 + 1], force3[k * 3 + 2]};
         if (torque3) w.bodies[i].user_torque = V3{torque3[k * 3], torque3[k * 3 + 1], torque3[k * 3 + 2]};
+    }
+    return orc_world_wake_up(o, n, indices);
+}
+int orc_world_set_next_kinematic_positions(OrcWorld* o, int32_t n, const int32_t* indices, const float* pose7) {
+    if (!o || !pose7) return RB_ERR_INVALID;
+    World& w = o->w;
+    for (int k = 0; k < n; ++k) {
+        int i = indices[k];
+        if (i < 0 || i >= (int)w.bodies.size() || w.bodies[i].type != RB_BODY_KINEMATIC_POSITION_BASED) return RB_ERR_INVALID;
+        w.bodies[i].kin_target = Pose{Q4{pose7[k * 7 + 3], pose7[k * 7 + 4], pose7[k * 7 + 5], pose7[k * 7 + 6]}, V3{pose7[k * 7], pose7[k * 7 + 1], pose7[k * 7 + 2]}};
     }
     return orc_world_wake_up(o, n, indices);
 }

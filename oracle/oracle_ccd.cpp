@@ -27,7 +27,7 @@ static inline float ccd_atan01(float z) {   // atan on [0, 1], explicit arithmet
     p = fma_(p, s, 0.99997726f);
     return p * z;
 }
-static inline float ccd_quat_angle(float vlen, float w) {
+float ccd_quat_angle(float vlen, float w) {
     const float aw = w < 0.0f ? -w : w;
     if (vlen == 0.0f) return 0.0f;
     const float half = vlen <= aw ? ccd_atan01(vlen / aw) : 1.5707964f - ccd_atan01(aw / vlen);
@@ -143,7 +143,7 @@ void ccd_motion_clamping(World& w) {
     const float slop = P.normalized_allowed_linear_error * P.length_unit;
     for (int bi = 0; bi < (int)w.bodies.size(); ++bi) {
         Body& b = w.bodies[bi];
-        if (!b.is_awake()) continue;
+        if (!b.is_awake() || !b.is_strict_dynamic()) continue;
         const V3& nt = b.next_pos.t;
         if (!(std::isfinite(nt.x) && std::isfinite(nt.y) && std::isfinite(nt.z))) continue;   // (left to the quarantine chokepoint)
         if (!is_moving_fast_with_next_position(w, b)) continue;

@@ -39,6 +39,7 @@ struct Body {
     uint32_t flags;
     Pose pos;        // RigidBodyPosition::position
     Pose next_pos;   // RigidBodyPosition::next_position
+    Pose kin_target; // ... as set by set_next_kinematic_position (position-based kinematic bodies)
     V3 linvel, angvel;
     float lin_damping, ang_damping, gravity_scale;
     float additional_mass;   // RigidBodyAdditionalMassProps::Mass (0 = none)
@@ -60,8 +61,11 @@ struct Body {
     Pose sleep_prev_pose{Q4{0.f, 0.f, 0.f, 1.f}, V3{0.f, 0.f, 0.f}};
     float max_extent = 0.0f;
     float ccd_thickness = 3.4028235e38f;   // RigidBodyCcd::ccd_thickness
-    bool is_dynamic() const { return type == RB_BODY_DYNAMIC; }
-    bool is_awake() const { return type == RB_BODY_DYNAMIC && !sleeping; }   // member of the active set
+    // Kinematic bodies are solver bodies like dynamic ones (zero effective inverse mass; solver_body.rs:112-120) and are
+    // coloured like them (narrow_phase/mod.rs:105-106).  DEVIATION shared with the kernels: they are island members too.
+    bool is_dynamic() const { return type == RB_BODY_DYNAMIC || type == RB_BODY_KINEMATIC_POSITION_BASED || type == RB_BODY_KINEMATIC_VELOCITY_BASED; }
+    bool is_strict_dynamic() const { return type == RB_BODY_DYNAMIC; }
+    bool is_awake() const { return is_dynamic() && !sleeping; }   // member of the active set
 };
 
 struct Aabb {

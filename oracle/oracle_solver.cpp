@@ -612,8 +612,27 @@ static void build_order(const std::vector<int>& colors_of, int min_count, std::v
 
 static inline float inv_exact0(float x) { return x == 0.0f ? 0.0f : 1.0f / x; }
 
+float ccd_quat_angle(float vlen, float w);   // oracle_ccd.cpp
+
 void solve_island(World& w, V3 gravity) {
     const RbIntegrationParameters& P = w.params.p;
+    // interpolate_kinematic_velocities (substep.rs:242-265; rigid_body_components.rs:147-196)
+    for (Body& b : w.bodies) {
+        if (b.type != RB_BODY_KINEMATIC_POSITION_BASED || !b.is_awake()) continue;
+        const float inv_dt = P.dt == 0.0f ? 0.0f : 1.0f / P.dt;
+        const V3 dl = pose_point(b.kin_target, b.local_com) - pose_point(b.pos, b.local_com);
+        const Q4 dq = qmul(b.kin_target.q, qconj(b.pos.q));
+        const V3 dv = V3{dq.x, dq.y, dq.z};
+        const float len = length(dv);
+        V3 sa = vzero();
+        if (len > 1.0e-12f) {
+            float angle = ccd_quat_angle(len, dq.w);
+            if (dq.w < 0.0f) angle = 6.2831855f - angle;
+            sa = dv * (angle / len);
+        }
+        b.linvel = dl * inv_dt;
+        b.angvel = sa * inv_dt;
+    }
     const int nb = (int)w.bodies.size();
     const int num_substeps = P.num_solver_iterations;
     const float sub_dt = P.dt / (float)num_substeps;  // init.rs:96-101
@@ -655,7 +674,7 @@ void solve_island(World& w, V3 gravity) {
         }
         s.incr_ang = sdp_mul(b.eff_world_inv_inertia, b.torque) * sub_dt;
         s.incr_lin = cmul(b.force, b.eff_inv_mass) * sub_dt;
-        s.gyro = (b.flags & RB_BODY_GYROSCOPIC) && b.is_awake();
+        s.gyro = (b.flags & RB_BODY_GYROSCOPIC) && b.is_strict_dynamic() && b.is_awake();   // worker.rs:86
     }
 
     // Solver-active manifolds, in stage order (solver_graph.rs:129-361; init.rs:163-254).
@@ -814,7 +833,7 @@ void solve_island(World& w, V3 gravity) {
             // quarantine.rs:126-178: roll back to the last valid pose, zero the dynamics, disable, report
             b.linvel = vzero(); b.angvel = vzero(); b.user_force = vzero(); b.user_torque = vzero();
             b.next_pos = b.pos;
-            b.type = 3;
+            b.type = 7;
             for (Collider& c : w.colliders)
                 if (c.parent == i) c.shape = -1;
             w.quarantine.push_back(i);
@@ -823,7 +842,7 @@ void solve_island(World& w, V3 gravity) {
         }
         b.linvel = lin;
         b.angvel = ang;
-        b.next_pos = np;
+        b.next_pos = b.type == RB_BODY_KINEMATIC_POSITION_BASED ? b.kin_target : np;   // worker.rs:836-842
     }
     w.counters.num_active_manifolds = ncons;
     w.counters.num_colors = num_colors;

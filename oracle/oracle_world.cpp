@@ -146,7 +146,7 @@ static int recompute_mass_properties(World& w, int first_body = 0, int first_col
 // rigid_body_components.rs:528-572
 void update_world_mass_properties(Body& b) {
     b.world_com = pose_point(b.pos, b.local_com);
-    bool dyn = b.is_dynamic();
+    bool dyn = b.is_strict_dynamic();
     b.eff_inv_mass = V3{b.inv_mass, b.inv_mass, b.inv_mass};
     V3 d = b.inv_principal_inertia;
     if (d.x != 0.0f || d.y != 0.0f || d.z != 0.0f) {
@@ -211,9 +211,9 @@ static bool pair_allowed(const World& w, int c1, int c2) {
     const Collider& a = w.colliders[c1];
     const Collider& b = w.colliders[c2];
     if (a.parent >= 0 && a.parent == b.parent) return false;
-    bool dyn1 = a.parent >= 0 && w.bodies[a.parent].is_dynamic();
-    bool dyn2 = b.parent >= 0 && w.bodies[b.parent].is_dynamic();
-    if (!dyn1 && !dyn2) return false;  // ActiveCollisionTypes::default(): no fixed-fixed
+    bool dyn1 = a.parent >= 0 && w.bodies[a.parent].is_strict_dynamic();
+    bool dyn2 = b.parent >= 0 && w.bodies[b.parent].is_strict_dynamic();
+    if (!dyn1 && !dyn2) return false;  // ActiveCollisionTypes::default(): DYNAMIC_DYNAMIC | DYNAMIC_KINEMATIC | DYNAMIC_FIXED
     if (!((a.memberships & b.filter) != 0 && (b.memberships & a.filter) != 0)) return false;
     if (!w.nocontact_body_pairs.empty() && a.parent >= 0 && b.parent >= 0) {
         uint32_t lo = (uint32_t)std::min(a.parent, b.parent), hi = (uint32_t)std::max(a.parent, b.parent);
@@ -660,7 +660,8 @@ static void update_sleep(World& w) {
         if (b.max_extent > 0.0f) angular_ok = may && sq_angvel < 1.5707963267948966f * 1.5707963267948966f;
         else angular_ok = may && sq_angvel < angular_threshold * angular_threshold;
         const float drift = relative_pose_drift(prev, b.pos, b.max_extent);
-        const bool can = may && angular_ok && drift * 0.5f < linear_threshold * dt;
+        bool can = may && angular_ok && drift * 0.5f < linear_threshold * dt;
+        if (!b.is_strict_dynamic()) can = may && dot(b.linvel, b.linvel) == 0.0f && sq_angvel == 0.0f;   // platforms: exactly zero (:1457-1461)
         b.sleep_time = can ? b.sleep_time + dt : 0.0f;
         if (!(b.sleep_time >= time_until_sleep)) blocked[w.island_of[i]] = 1;
         any = true;
@@ -780,6 +781,7 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
         b.flags = d.flags;
         b.pos = Pose{f4(d.rotation), f3(d.translation)};
         b.next_pos = b.pos;
+        b.kin_target = b.pos;
         b.linvel = f3(d.linvel);
         b.angvel = f3(d.angvel);
         b.lin_damping = d.linear_damping;
@@ -872,6 +874,7 @@ static void fill_body(Body& b, const RbBodyDesc& d) {
     b.flags = d.flags;
     b.pos = Pose{f4(d.rotation), f3(d.translation)};
     b.next_pos = b.pos;
+    b.kin_target = b.pos;
     b.linvel = f3(d.linvel);
     b.angvel = f3(d.angvel);
     b.lin_damping = d.linear_damping;
@@ -926,7 +929,7 @@ int remove_bodies(World& w, int n, const int* indices) {
     for (int k = 0; k < n; ++k)
         if (indices[k] < 0 || indices[k] >= (int)w.bodies.size()) return RB_ERR_INVALID;
     for (int k = 0; k < n; ++k) {
-        w.bodies[indices[k]].type = 3;   // removed: not dynamic, never simulated again
+        w.bodies[indices[k]].type = 7;   // removed: not dynamic, never simulated again
         for (Collider& c : w.colliders)
             if (c.parent == indices[k]) c.shape = -1;   // leaves the broad phase: its pairs end at the next step
     }

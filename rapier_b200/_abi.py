@@ -15,6 +15,8 @@ RB_ERR_SHARD = -6
 
 RB_BODY_DYNAMIC = 0
 RB_BODY_FIXED = 1
+RB_BODY_KINEMATIC_POSITION_BASED = 2
+RB_BODY_KINEMATIC_VELOCITY_BASED = 3
 RB_BODY_GYROSCOPIC = 1
 RB_BODY_ALLOW_FAST_ROTATION = 2
 RB_BODY_LOCK_TX, RB_BODY_LOCK_TY, RB_BODY_LOCK_TZ = 4, 8, 16

@@ -203,7 +203,7 @@ RB_PHASE void wake_phase(const Ctx& ctx, const World& w, const int* idx, int n) 
     }
     for (int k = ctx.gtid; k < n; k += ctx.gsize) {
         const int b = idx[k];
-        if (b < 0 || b >= w.nb || w.b_type[b] != BODY_DYNAMIC) continue;
+        if (b < 0 || b >= w.nb || !type_is_solver(w.b_type[b])) continue;
         w.wake_req[w.isl_label[b]] = 1;   // (labels are roots; wake_apply_phase wakes the whole island right away, the
         w.st->wake_any = 1;               //  next step's wake pass clears the requests)
         if (w.b_sleeping[b]) { w.b_sleeping[b] = 0; w.b_sleep_time[b] = 0.0f; w.st->sched_dirty = 1; }
@@ -212,7 +212,7 @@ RB_PHASE void wake_phase(const Ctx& ctx, const World& w, const int* idx, int n) 
 template <class Ctx>
 RB_PHASE void wake_apply_phase(const Ctx& ctx, const World& w) {
     for (int b = ctx.gtid; b < w.nb; b += ctx.gsize)
-        if (w.b_type[b] == BODY_DYNAMIC && w.b_sleeping[b] && w.wake_req[w.isl_label[b]]) {
+        if (type_is_solver(w.b_type[b]) && w.b_sleeping[b] && w.wake_req[w.isl_label[b]]) {
             w.b_sleeping[b] = 0;
             w.b_sleep_time[b] = 0.0f;
             w.st->sched_dirty = 1;
@@ -540,6 +540,7 @@ static void collider_mass_props(const RbColliderDesc& c, float& mass, float pi[3
     }
 }
 static inline float inv0(float x) { return x == 0.0f ? 0.0f : 1.0f / x; }
+static inline bool type_moves(int t) { return t == RB_BODY_DYNAMIC || t == RB_BODY_KINEMATIC_POSITION_BASED || t == RB_BODY_KINEMATIC_VELOCITY_BASED; }
 
 struct HostMass { float lcom[3], inv_mass, ipi[3], pi[3], pframe[4], max_extent, ccd_thickness; };
 
@@ -707,7 +708,7 @@ static int upload_bodies(RbWorld* W, const std::vector<HostMass>& mp, int first,
         thick[k] = mp[i].ccd_thickness;
         const RbBodyDesc& d = W->bodies[i];
         type[k] = d.body_type;
-        flags[k] = d.flags;
+        flags[k] = d.body_type == RB_BODY_DYNAMIC ? d.flags : (d.flags & ~(unsigned)RB_BODY_GYROSCOPIC);   // gyroscopic term: dynamic bodies only (worker.rs:86)
         pt[k] = make_float4(d.translation[0], d.translation[1], d.translation[2], 0.f);
         pq[k] = make_float4(d.rotation[0], d.rotation[1], d.rotation[2], d.rotation[3]);
         lv[k] = make_float4(d.linvel[0], d.linvel[1], d.linvel[2], 0.f);
@@ -725,6 +726,8 @@ static int upload_bodies(RbWorld* W, const std::vector<HostMass>& mp, int first,
     CK(h2d(w.b_flags + first, flags.data(), n * sizeof(unsigned)));
     CK(h2d(w.b_pos_t + first, pt.data(), n * sizeof(float4)));
     CK(h2d(w.b_pos_q + first, pq.data(), n * sizeof(float4)));
+    CK(h2d(w.b_next_t + first, pt.data(), n * sizeof(float4)));   // next_position = position until the user sets a target
+    CK(h2d(w.b_next_q + first, pq.data(), n * sizeof(float4)));
     CK(h2d(w.b_linvel + first, lv.data(), n * sizeof(float4)));
     CK(h2d(w.b_angvel + first, av.data(), n * sizeof(float4)));
     CK(h2d(w.b_lcom_im + first, lc.data(), n * sizeof(float4)));
@@ -741,7 +744,14 @@ static int upload_bodies(RbWorld* W, const std::vector<HostMass>& mp, int first,
     CK(dev_set(w.b_sleeping + first, 0, n));
     CK(dev_set(w.b_sleep_time + first, 0, n * sizeof(float)));
     for (int k = 0; k < count; ++k)
-        if (type[k] == RB_BODY_DYNAMIC && !(flags[k] & RB_BODY_NO_SLEEP)) w.sleep_enabled = 1;
+        if (type_moves(type[k]) && !(flags[k] & RB_BODY_NO_SLEEP)) w.sleep_enabled = 1;
+    {   // the position-based kinematic bodies, for the velocity interpolation at the start of the solve
+        std::vector<int> kin;
+        for (int i = 0; i < (int)W->bodies.size(); ++i)
+            if (W->bodies[i].body_type == RB_BODY_KINEMATIC_POSITION_BASED) kin.push_back(i);
+        w.nkinpos = (int)kin.size();
+        if (!kin.empty()) CK(h2d(w.kinpos_list, kin.data(), kin.size() * sizeof(int)));
+    }
     return RB_OK;
 }
 static int upload_colliders(RbWorld* W, int first, int count, int first_body = 0) {
@@ -803,8 +813,8 @@ static int validate_descs(int nb_total, int nb, const RbBodyDesc* bodies, int nc
         }
     }
     for (int i = 0; i < nb; ++i)
-        if (bodies[i].body_type != RB_BODY_DYNAMIC && bodies[i].body_type != RB_BODY_FIXED) {
-            set_err("only dynamic and fixed bodies are supported%s", "");
+        if (bodies[i].body_type < RB_BODY_DYNAMIC || bodies[i].body_type > RB_BODY_KINEMATIC_VELOCITY_BASED) {
+            set_err("unknown body type%s", "");
             return RB_ERR_INVALID;
         }
     return RB_OK;
@@ -962,7 +972,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     w.nb = nb; w.nc = nc; w.nj = nj;
     int ndyn_col = 0;
     for (int i = 0; i < nc; ++i)
-        if (colliders[i].parent >= 0 && bodies[colliders[i].parent].body_type == RB_BODY_DYNAMIC) ndyn_col++;
+        if (colliders[i].parent >= 0 && type_moves(bodies[colliders[i].parent].body_type)) ndyn_col++;
     // capacities: the scene plus what rb_world_reserve asked for (reserved colliders are assumed to be movers)
     const int NB = std::max(std::max(nb, W->reserve_bodies), 1), NC = std::max(std::max(nc, W->reserve_colliders), 1);
     W->body_cap = NB; W->collider_cap = NC;
@@ -975,7 +985,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
 
     ALLOC(w.st, 1);
     ALLOC(w.b_type, NB); ALLOC(w.b_flags, NB);
-    ALLOC(w.b_pos_t, NB); ALLOC(w.b_pos_q, NB); ALLOC(w.b_linvel, NB); ALLOC(w.b_angvel, NB);
+    ALLOC(w.b_pos_t, NB); ALLOC(w.b_pos_q, NB); ALLOC(w.b_next_t, NB); ALLOC(w.b_next_q, NB); ALLOC(w.kinpos_list, NB); ALLOC(w.b_linvel, NB); ALLOC(w.b_angvel, NB);
     ALLOC(w.b_lcom_im, NB); ALLOC(w.b_ipi, NB); ALLOC(w.b_pi, NB); ALLOC(w.b_pframe, NB); ALLOC(w.b_misc, NB);
     ALLOC(w.b_uforce, NB); ALLOC(w.b_utorque, NB); ALLOC(w.b_wcom, NB); ALLOC(w.b_eim, NB + 2);
     ALLOC(w.b_eii0, NB); ALLOC(w.b_eii1, NB); ALLOC(w.b_owned, NB);
@@ -1053,7 +1063,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
         std::vector<int> ccount(NUM_COLORS, 0);
         for (int i = 0; i < nj; ++i) {
             const RbJointDesc& j = joints[i];
-            bool d1 = bodies[j.body1].body_type == RB_BODY_DYNAMIC, d2 = bodies[j.body2].body_type == RB_BODY_DYNAMIC;
+            bool d1 = type_moves(bodies[j.body1].body_type), d2 = type_moves(bodies[j.body2].body_type);   // (kinematic bodies conflict like dynamic ones)
             int color = -1;
             if (d1 && d2) {
                 color = 128;
@@ -1170,7 +1180,7 @@ int rb_world_insert(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t nc
     if ((rc = upload_colliders(W, nc0, nc, nb0)) != RB_OK) return rc;
     int one = 1, lists = 1;   // lists: 1 = only movers were added, 3 = static colliders too (re-sort them)
     for (int i = 0; i < nc; ++i)
-        if (colliders[i].parent < 0 || W->bodies[colliders[i].parent].body_type != RB_BODY_DYNAMIC) lists = 3;
+        if (colliders[i].parent < 0 || !type_moves(W->bodies[colliders[i].parent].body_type)) lists = 3;
     CK(h2d(&W->w.st->lists_dirty, &lists, sizeof(int)));
     CK(h2d(&W->w.st->bp_dirty, &one, sizeof(int)));
     CK(h2d(&W->w.st->sched_dirty, &one, sizeof(int)));
@@ -1275,6 +1285,8 @@ int rb_world_set_body_states(RbWorld* W, int32_t n, const int32_t* indices, cons
             float4 q = make_float4(pose7[k * 7 + 3], pose7[k * 7 + 4], pose7[k * 7 + 5], pose7[k * 7 + 6]);
             CK(h2d(W->w.b_pos_t + i, &t, sizeof(t)));
             CK(h2d(W->w.b_pos_q + i, &q, sizeof(q)));
+            CK(h2d(W->w.b_next_t + i, &t, sizeof(t)));
+            CK(h2d(W->w.b_next_q + i, &q, sizeof(q)));
         }
         if (vel6) {
             float4 l = make_float4(vel6[k * 6], vel6[k * 6 + 1], vel6[k * 6 + 2], 0.f);
@@ -1286,7 +1298,7 @@ int rb_world_set_body_states(RbWorld* W, int32_t n, const int32_t* indices, cons
     {   // a teleported FIXED body moves static colliders: rebuild the broad-phase lists (and re-sort the static ones)
         bool moved_static = false;
         if (pose7)
-            for (int k = 0; k < n; ++k) moved_static = moved_static || W->bodies[indices[k]].body_type != RB_BODY_DYNAMIC;
+            for (int k = 0; k < n; ++k) moved_static = moved_static || !type_moves(W->bodies[indices[k]].body_type);
         if (moved_static) {
             int one = 1, lists = 3;
             CK(h2d(&W->w.st->lists_dirty, &lists, sizeof(int)));
@@ -1318,6 +1330,25 @@ int rb_world_set_body_forces(RbWorld* W, int32_t n, const int32_t* indices, cons
         }
     }
     if (n > 0 && (rc = wake_impl(W, indices, n)) != RB_OK) return rc;   // add_force(.., wake_up = true)
+    return sync_world(W);
+}
+
+int rb_world_set_next_kinematic_positions(RbWorld* W, int32_t n, const int32_t* indices, const float* pose7) {
+    if (!W || n < 0 || (n && (!indices || !pose7))) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    int rc = sync_world(W);
+    if (rc != RB_OK) return rc;
+    for (int k = 0; k < n; ++k) {
+        const int i = indices[k];
+        if (i < 0 || i >= W->w.nb || W->bodies[i].body_type != RB_BODY_KINEMATIC_POSITION_BASED) {
+            set_err("rb_world_set_next_kinematic_positions: not a position-based kinematic body%s", "");
+            return RB_ERR_INVALID;
+        }
+        float4 t = make_float4(pose7[k * 7], pose7[k * 7 + 1], pose7[k * 7 + 2], 0.f);
+        float4 q = make_float4(pose7[k * 7 + 3], pose7[k * 7 + 4], pose7[k * 7 + 5], pose7[k * 7 + 6]);
+        CK(h2d(W->w.b_next_t + i, &t, sizeof(t)));
+        CK(h2d(W->w.b_next_q + i, &q, sizeof(q)));
+    }
+    if (n > 0 && (rc = wake_impl(W, indices, n)) != RB_OK) return rc;
     return sync_world(W);
 }
 
@@ -1759,7 +1790,7 @@ int rb_world_label_components(RbWorld* W, int32_t* component_of_body) {
     if (rc != RB_OK) return rc;
     CK(d2h(component_of_body, W->w.isl_label, (size_t)W->w.nb * sizeof(int)));
     for (int i = 0; i < W->w.nb; ++i)
-        if (W->bodies[i].body_type != RB_BODY_DYNAMIC) component_of_body[i] = -1;
+        if (!type_moves(W->bodies[i].body_type)) component_of_body[i] = -1;
     return RB_OK;
 }
 

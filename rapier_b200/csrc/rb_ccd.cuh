@@ -24,25 +24,7 @@ namespace rb {
 
 constexpr int CCD_MAX_ITERS = 32;
 
-// atan(z) for z in [0, 1]: odd minimax polynomial evaluated with explicit fused multiply-adds, so the kernels and the
-// oracle agree bit for bit (libm's atan2f differs between the host and the device in the last place).
-RB_HD float ccd_atan01(float z) {
-    const float s = z * z;
-    float p = -0.0117212f;
-    p = fma_(p, s, 0.05265332f);
-    p = fma_(p, s, -0.11643287f);
-    p = fma_(p, s, 0.19354346f);
-    p = fma_(p, s, -0.33262347f);
-    p = fma_(p, s, 0.99997726f);
-    return p * z;
-}
-// Rotation angle (0..pi) of a unit quaternion with vector-part length `vlen` and scalar part `w`: 2 atan2(vlen, |w|).
-RB_HD float ccd_quat_angle(float vlen, float w) {
-    const float aw = w < 0.0f ? -w : w;
-    if (vlen == 0.0f) return 0.0f;
-    const float half = vlen <= aw ? ccd_atan01(vlen / aw) : 1.5707964f - ccd_atan01(aw / vlen);
-    return half * 2.0f;
-}
+// (ccd_atan01 / ccd_quat_angle: rb_collide.cuh, shared with the kinematic velocity interpolation)
 
 // Sweep::from_poses / Sweep::transform_at (Box2D b2Sweep): the centre of mass moves on a straight line, the rotation is
 // the normalised linear interpolation of the two quaternions, the frame origin follows from the local centre.

@@ -24,9 +24,16 @@ constexpr int BIG_JCOLOR_MIN = 64;   // joints.rs:340: JOINT_BATCH*LAYOUT_REF_WO
 // Multi-GPU sharding (b_owned): 1 = simulated by this rank, 2 = "halo": simulated by another rank but close enough to
 // be tracked here (its state is imported every step, its colliders take part in proximity detection), 0 = simulated
 // by another rank and far away (ignored until the next halo refresh).
-RB_HD bool body_is_dyn(const World& w, int b) {  // dynamic and simulated by this rank (awake or asleep)
-    return b >= 0 && w.b_type[b] == BODY_DYNAMIC && w.b_owned[b] == 1;
+// Kinematic bodies are solver bodies like dynamic ones -- zero effective inverse mass, velocities read by their
+// contacts, poses integrated by the substeps (solver_body.rs:112-120; is_dynamic_or_kinematic) -- and are coloured
+// like them (narrow_phase/mod.rs:105-106: "conflicting" = not fixed).  DEVIATION: here they are also island members
+// (the reference keeps them as singleton islands, substep_groups.rs:64-66), so what a platform carries shares its
+// island: same solve, coarser sleeping and scheduling granularity.
+RB_HD bool type_is_solver(int t) { return t == BODY_DYNAMIC || t == BODY_KIN_POS || t == BODY_KIN_VEL; }
+RB_HD bool body_is_dyn(const World& w, int b) {  // dynamic or kinematic, and simulated by this rank (awake or asleep)
+    return b >= 0 && type_is_solver(w.b_type[b]) && w.b_owned[b] == 1;
 }
+RB_HD bool body_is_strict_dyn(const World& w, int b) { return b >= 0 && w.b_type[b] == BODY_DYNAMIC && w.b_owned[b] == 1; }
 // ... and awake: a member of the active set (island_manager: sleeping bodies are neither solved nor integrated)
 RB_HD bool body_is_sim(const World& w, int b) { return body_is_dyn(w, b) && !w.b_sleeping[b]; }
 RB_HD pose body_pose(const World& w, int b) { return mkpose(mkq(w.b_pos_q[b]), xyz(w.b_pos_t[b])); }
@@ -215,8 +222,8 @@ RB_PHASE unsigned long long* grid_radix_sort(const Ctx& ctx, unsigned long long*
 RB_HD bool pair_allowed(const World& w, int c1, int c2) {
     int p1 = w.c_parent[c1], p2 = w.c_parent[c2];
     if (p1 >= 0 && p1 == p2) return false;
-    bool d1 = body_is_dyn(w, p1), d2 = body_is_dyn(w, p2);   // (sleeping bodies keep their pairs)
-    if (!d1 && !d2) return false;
+    bool d1 = body_is_strict_dyn(w, p1), d2 = body_is_strict_dyn(w, p2);   // (sleeping bodies keep their pairs)
+    if (!d1 && !d2) return false;   // ActiveCollisionTypes::default(): DYNAMIC_DYNAMIC | DYNAMIC_KINEMATIC | DYNAMIC_FIXED
     uint2 g1 = w.c_groups[c1], g2 = w.c_groups[c2];
     if (!((g1.x & g2.y) != 0 && (g2.x & g1.y) != 0)) return false;
     if (w.n_nocontact > 0 && p1 >= 0 && p2 >= 0) {
@@ -242,9 +249,9 @@ RB_HD void emit_collision_event(const World& w, int c1, int c2, bool started) {
     else RB_RAISE(w, -4);
 }
 
-RB_HD bool collider_is_static(const World& w, int c) {   // never moves: no parent, or a parent that is not a dynamic body
+RB_HD bool collider_is_static(const World& w, int c) {   // never moves: no parent, or a parent that is neither dynamic nor kinematic
     const int p = w.c_parent[c];
-    return p < 0 || w.b_type[p] != BODY_DYNAMIC;
+    return p < 0 || !type_is_solver(w.b_type[p]);
 }
 RB_HD bool fat_overlap(float4 amin, float4 amax, float4 bmin, float4 bmax) {
     return amin.x <= bmax.x && amin.y <= bmax.y && amin.z <= bmax.z && amax.x >= bmin.x && amax.y >= bmin.y && amax.z >= bmin.z;
@@ -949,7 +956,11 @@ RB_PHASE void section_sleep(const Ctx& ctx, const World& w) {
         const bool angular_ok = ext > 0.0f ? (may && sq_angvel < 1.5707963267948966f * 1.5707963267948966f)
                                            : (may && sq_angvel < SLEEP_ANGULAR_THRESHOLD * SLEEP_ANGULAR_THRESHOLD);
         const float drift = pose_drift(prev, cur, ext);
-        const bool can = may && angular_ok && drift * 0.5f < linear_threshold * dt;
+        bool can = may && angular_ok && drift * 0.5f < linear_threshold * dt;
+        if (w.b_type[b] != BODY_DYNAMIC) {   // platforms only sleep while both velocities are exactly zero (:1457-1461)
+            const vec3 lv = xyz(w.b_linvel[b]);
+            can = may && dot3(lv, lv) == 0.0f && sq_angvel == 0.0f;
+        }
         const float t = can ? w.b_sleep_time[b] + dt : 0.0f;
         w.b_sleep_time[b] = t;
         if (!(t >= SLEEP_TIME_UNTIL)) w.isl_block[w.isl_label[b]] = stamp;   // one restless body keeps its island awake
@@ -1242,6 +1253,51 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
 }
 
 // The whole pre-solve pipeline of one step.
+// atan(z) for z in [0, 1]: odd minimax polynomial evaluated with explicit fused multiply-adds, so the kernels and the
+// oracle agree bit for bit (libm's atan2f differs between the host and the device in the last place).
+RB_HD float ccd_atan01(float z) {
+    const float s = z * z;
+    float p = -0.0117212f;
+    p = fma_(p, s, 0.05265332f);
+    p = fma_(p, s, -0.11643287f);
+    p = fma_(p, s, 0.19354346f);
+    p = fma_(p, s, -0.33262347f);
+    p = fma_(p, s, 0.99997726f);
+    return p * z;
+}
+// Rotation angle (0..pi) of a unit quaternion with vector-part length `vlen` and scalar part `w`: 2 atan2(vlen, |w|).
+RB_HD float ccd_quat_angle(float vlen, float w) {
+    const float aw = w < 0.0f ? -w : w;
+    if (vlen == 0.0f) return 0.0f;
+    const float half = vlen <= aw ? ccd_atan01(vlen / aw) : 1.5707964f - ccd_atan01(aw / vlen);
+    return half * 2.0f;
+}
+
+// interpolate_kinematic_velocities (substep.rs:242-265; RigidBodyPosition::interpolate_velocity, rigid_body_components.rs:
+// 147-196): a position-based kinematic body gets the velocity that reaches its next_position in one step (the
+// rotation's scaled axis through ccd_quat_angle).  After collision detection, before the solve, like the reference.
+template <class Ctx>
+RB_PHASE void phase_kinematic_velocities(const Ctx& ctx, const World& w) {
+    for (int k = ctx.gtid; k < w.nkinpos; k += ctx.gsize) {
+        const int b = w.kinpos_list[k];
+        if (w.b_type[b] != BODY_KIN_POS) continue;
+        const vec3 lc = xyz(w.b_lcom_im[b]);
+        const pose cur = body_pose(w, b), nxt = mkpose(mkq(w.b_next_q[b]), xyz(w.b_next_t[b]));
+        const vec3 dl = xform(nxt, lc) - xform(cur, lc);
+        const quat dq = qmul(nxt.q, qconj(cur.q));
+        const vec3 dv = mk3(dq.x, dq.y, dq.z);
+        const float len = norm(dv);
+        vec3 sa = zero3();
+        if (len > 1.0e-12f) {
+            float angle = ccd_quat_angle(len, dq.w);
+            if (dq.w < 0.0f) angle = 6.2831855f - angle;   // 2 atan2(len, w) for w < 0
+            sa = dv * (angle / len);
+        }
+        w.b_linvel[b] = f4(dl * w.prm.inv_dt_full, 0.0f);
+        w.b_angvel[b] = f4(sa * w.prm.inv_dt_full, 0.0f);
+    }
+}
+
 template <class Ctx>
 RB_PHASE void collide_pipeline(const Ctx& ctx, const World& w) {
     State* st = w.st;
@@ -1251,6 +1307,7 @@ RB_PHASE void collide_pipeline(const Ctx& ctx, const World& w) {
     if (st->bp_dirty || st->lists_dirty) section_broad_phase(ctx, w);
     phase_narrow_phase(ctx, w);
     ctx.grid_sync();
+    if (w.nkinpos > 0) { phase_kinematic_velocities(ctx, w); ctx.grid_sync(); }   // (a kernel parameter: uniform)
     if (st->wake_any) section_wake(ctx, w);
     if (st->ntodo) section_coloring(ctx, w);
     if (st->sched_dirty) section_components(ctx, w);

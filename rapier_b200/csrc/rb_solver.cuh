@@ -925,6 +925,8 @@ RB_HD void body_writeback(const World& w, const B& bd, int b, int id) {
     vec3 lin = bd.lin(id) * (1.0f / (1.0f + P.dt * misc.x));
     vec3 ang = bd.ang(id) * (1.0f / (1.0f + P.dt * misc.y));
     pose np = prepend_translation(bd.xf(id), -xyz(w.b_lcom_im[b]));
+    // (a position-based kinematic body keeps exactly the pose its user asked for: worker.rs:836-842)
+    if (w.b_type[b] == BODY_KIN_POS) np = mkpose(mkq(w.b_next_q[b]), xyz(w.b_next_t[b]));
     if (!(finite3(lin) && finite3(ang) && finite3(np.t) && isfinite(np.q.x) && isfinite(np.q.y) && isfinite(np.q.z) && isfinite(np.q.w))) {
         // Containment of non-finite state at the end-of-step chokepoint (physics_pipeline/quarantine.rs:14-47, :126-178):
         // the body keeps its last valid pose, loses its velocities and forces, is disabled (its colliders leave the
@@ -942,7 +944,7 @@ RB_HD void body_writeback(const World& w, const B& bd, int b, int id) {
         RB_RAISE(w, -5);
         return;
     }
-    if (P.ccd && ccd_is_moving_fast(P, xyz(w.b_lcom_im[b]), ccd_op, np, ccd_ext, ccd_thick)) {
+    if (P.ccd && w.b_type[b] == BODY_DYNAMIC && ccd_is_moving_fast(P, xyz(w.b_lcom_im[b]), ccd_op, np, ccd_ext, ccd_thick)) {
         // CCD (substep.rs:492-520): a body whose solved motion exceeds half its thinnest extent is queued for motion clamping
         // with its start pose; the sweep itself (rb_ccd.cuh) runs at the start of the next step's
         // k_collide or at the next synchronising call (k_ccd_pending), so the solve kernels carry only this test.

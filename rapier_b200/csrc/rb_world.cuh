@@ -19,7 +19,8 @@ constexpr int NO_BODY = -1;             // world-attached side (reference: u32::
 
 constexpr int BODY_DYNAMIC = 0;
 constexpr int BODY_FIXED = 1;
-constexpr int BODY_REMOVED = 3;          // removed (rb_world_remove_bodies) or quarantined: not simulated, its colliders are gone
+constexpr int BODY_KIN_POS = 2, BODY_KIN_VEL = 3;   // RigidBodyType::{KinematicPositionBased, KinematicVelocityBased} (rigid_body_components.rs:20-46)
+constexpr int BODY_REMOVED = 7;          // removed (rb_world_remove_bodies) or quarantined: not simulated, its colliders are gone
 constexpr int SHAPE_BALL = 0, SHAPE_CUBOID = 1;
 constexpr int SHAPE_REMOVED = -1;        // collider of a removed body: in neither broad-phase list, in no pair
 constexpr unsigned FLAG_GYRO = 1, FLAG_FAST_ROT = 2, FLAG_LTX = 4, FLAG_LTY = 8, FLAG_LTZ = 16, FLAG_LRX = 32,
@@ -137,6 +138,9 @@ struct World {
     unsigned* b_flags;
     float4 *b_pos_t, *b_pos_q;        // RigidBodyPosition::position
     float4 *b_linvel, *b_angvel;
+    float4 *b_next_t, *b_next_q;      // RigidBodyPosition::next_position of position-based kinematic bodies (the user's target)
+    int* kinpos_list;                 // [nkinpos] the position-based kinematic bodies
+    int nkinpos;
     float4* b_lcom_im;                // local_com xyz, w inv_mass
     float4 *b_ipi, *b_pi, *b_pframe;  // inverse principal inertia (w: max_extent), principal inertia, principal frame
     float4* b_misc;                   // linear damping, angular damping, gravity scale, ccd_thickness

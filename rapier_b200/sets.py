@@ -37,6 +37,14 @@ class RigidBodyBuilder:
     def fixed(cls):
         return cls(A.RB_BODY_FIXED)
 
+    @classmethod
+    def kinematic_position_based(cls):
+        return cls(A.RB_BODY_KINEMATIC_POSITION_BASED)
+
+    @classmethod
+    def kinematic_velocity_based(cls):
+        return cls(A.RB_BODY_KINEMATIC_VELOCITY_BASED)
+
     def translation(self, v):
         self._translation = tuple(float(x) for x in v)
         return self

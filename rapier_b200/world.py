@@ -118,6 +118,12 @@ class PhysicsPipeline:
         self._check(self.L.rb_world_set_body_forces(self.h, len(idx), idx.ctypes.data, None if f is None else f.ctypes.data,
                                                     None if t is None else t.ctypes.data))
 
+    def set_next_kinematic_positions(self, indices, pose7):
+        """RigidBody::set_next_kinematic_position of position-based kinematic bodies ([n, 7]: translation, quaternion xyzw)."""
+        idx = np.ascontiguousarray(indices, np.int32)
+        p = np.ascontiguousarray(pose7, np.float32)
+        self._check(self.L.rb_world_set_next_kinematic_positions(self.h, len(idx), idx.ctypes.data, p.ctypes.data))
+
     def collision_events(self):
         """Drains the buffered CollisionEvents (EventHandler::handle_collision_event): [(collider1, collider2, started, step)]."""
         buf = (A.RbCollisionEvent * 65536)()
@@ -299,6 +305,10 @@ class PhysicsWorld:
     def set_body_forces(self, handles, force3=None, torque3=None):
         self._flush()
         self.physics_pipeline.set_body_forces(handles, force3, torque3)
+
+    def set_next_kinematic_positions(self, handles, pose7):
+        self._flush()
+        self.physics_pipeline.set_next_kinematic_positions(handles, pose7)
 
     def collision_events(self):
         self._flush()

@@ -69,6 +69,7 @@ def lib(fast=False):
         L.orc_world_get_sleeping.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_world_wake_up.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_world_set_body_forces.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_world_set_next_kinematic_positions.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.orc_world_drain_collision_events.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_world_drain_contact_force_events.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_kat.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
@@ -160,6 +161,11 @@ class OracleWorld:
         rc = self.L.orc_world_set_body_forces(self.h, len(idx), idx.ctypes.data, None if f is None else f.ctypes.data,
                                               None if t is None else t.ctypes.data)
         assert rc == 0
+
+    def set_next_kinematic_positions(self, indices, pose7):
+        idx = np.ascontiguousarray(indices, np.int32)
+        p = np.ascontiguousarray(pose7, np.float32)
+        assert self.L.orc_world_set_next_kinematic_positions(self.h, len(idx), idx.ctypes.data, p.ctypes.data) == 0
 
     def collision_events(self):
         """Drains the buffered CollisionEvents: list of (collider1, collider2, started, step)."""

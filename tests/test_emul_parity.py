@@ -168,6 +168,14 @@ def test_event_lists_match_oracle():
     events_parity_case(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), lambda s: oracle_lib.OracleWorld(s))
 
 
+def test_kinematic_bodies_emulated_kernels():
+    from test_oracle_kat import kinematic_bodies, moving_kinematic_wakes_jointed_dynamic
+    from variant_cases import kinematic_parity_case
+    kinematic_bodies(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()))
+    moving_kinematic_wakes_jointed_dynamic(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()))
+    kinematic_parity_case(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), lambda s: oracle_lib.OracleWorld(s))
+
+
 def test_quarantine_emulated_kernels():
     from test_oracle_kat import nan_force_is_quarantined
     nan_force_is_quarantined(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), expect_error=True)

@@ -335,3 +335,13 @@ def test_events(built):
     from variant_cases import events_parity_case
     contact_force_event_started_marks_threshold_crossings(lambda s: PhysicsWorld(s))
     events_parity_case(lambda s: PhysicsWorld(s), lambda s: oracle_lib.OracleWorld(s))
+
+
+def test_kinematic_bodies(built):
+    """Kinematic bodies through the C ABI: the behavioural known answers (platform / lift / pair filter, issue_287) and a
+    bit-exact run of a turntable, a conveyor and a position-driven lift against the oracle."""
+    from test_oracle_kat import kinematic_bodies, moving_kinematic_wakes_jointed_dynamic
+    from variant_cases import kinematic_parity_case
+    kinematic_bodies(lambda s: PhysicsWorld(s))
+    moving_kinematic_wakes_jointed_dynamic(lambda s: PhysicsWorld(s))
+    kinematic_parity_case(lambda s: PhysicsWorld(s), lambda s: oracle_lib.OracleWorld(s))

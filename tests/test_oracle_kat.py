@@ -594,3 +594,73 @@ def contact_force_event_started_marks_threshold_crossings(make_world):
 
 def test_contact_force_events_oracle():
     contact_force_event_started_marks_threshold_crossings(lambda s: oracle_lib.OracleWorld(s))
+
+
+# ---- kinematic bodies (RigidBodyType::Kinematic*; rigid_body_components.rs:20-46) ----------------------------------------
+def kinematic_bodies(make_world):
+    """A velocity-based kinematic platform carries a box riding on it at its own speed (its velocity enters the contact rows: a
+    platform read as static would brake the box to rest) and is not slowed by it; a
+    position-based one lifts a box to the targets it is given and ends exactly on them (worker.rs:836-842); kinematic
+    bodies collide with neither fixed nor other kinematic bodies (ActiveCollisionTypes::default()); a kinematic wall is
+    not a CCD target of the default tier (ccd_default_vs_fixed.rs: kinematic_not_a_default_target)."""
+    s = scenes.Scene("kinematic")
+    plat = s.insert(RigidBodyBuilder.kinematic_velocity_based().translation((0.0, 0.0, 0.0)).linvel((1.5, 0.0, 0.0)), ColliderBuilder.cuboid(4.0, 0.25, 2.0).friction(1.0))
+    box = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.76, 0.0)).linvel((1.5, 0.0, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5).friction(1.0))
+    lift = s.insert(RigidBodyBuilder.kinematic_position_based().translation((10.0, 0.0, 0.0)), ColliderBuilder.cuboid(1.0, 0.25, 1.0))
+    cargo = s.insert(RigidBodyBuilder.dynamic().translation((10.0, 0.76, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    s.insert(RigidBodyBuilder.fixed().translation((10.0, 0.3, 0.0)), ColliderBuilder.cuboid(0.3, 0.3, 0.3))        # inside the lift: no pair
+    s.insert(RigidBodyBuilder.kinematic_velocity_based().translation((0.5, -0.1, 0.0)).linvel((1.5, 0.0, 0.0)), ColliderBuilder.ball(0.3))   # inside the platform: no pair
+    w = make_world(s)
+    for i in range(120):
+        w.set_next_kinematic_positions([lift], [(10.0, 0.01 * (i + 1), 0.0, 0.0, 0.0, 0.0, 1.0)])
+        w.step()
+    pose, vel = w.body_states()
+    assert abs(pose[plat, 0] - 1.5 * 2.0) < 1e-3 and abs(vel[plat, 0] - 1.5) < 1e-6 and abs(pose[plat, 1]) < 1e-6   # unperturbed
+    assert abs(vel[box, 0] - 1.5) < 0.05 and abs(pose[box, 0] - pose[plat, 0]) < 0.2 and abs(pose[box, 1] - 0.75) < 0.02   # carried along
+    assert pose[lift, 1] == np.float32(0.01 * 120) and abs(vel[lift, 1] - 0.6) < 1e-3                              # exactly on its target
+    assert abs(pose[cargo, 1] - (1.2 + 0.75)) < 0.03 and abs(vel[cargo, 1] - 0.6) < 0.05                            # lifted
+    pairs = w.contact_pairs()["colliders"]
+    got = set(map(tuple, pairs.tolist()))
+    assert (0, 1) in got and (2, 3) in got and (0, 5) not in got and (2, 4) not in got, pairs   # no kinematic-kinematic / kinematic-fixed pair
+    w.step(30)                                           # no new target: the lift stops (next_position == position)
+    pose2, vel2 = w.body_states()
+    assert pose2[lift, 1] == pose[lift, 1] and vel2[lift, 1] == 0.0
+
+
+def test_kinematic_bodies_oracle():
+    kinematic_bodies(lambda s: oracle_lib.OracleWorld(s))
+
+
+def moving_kinematic_wakes_jointed_dynamic(make_world):
+    """issue_287_kinematic_wakes_jointed_dynamic.rs: a ball hanging from a position-based kinematic body by a revolute
+    joint falls asleep; driving the kinematic body sideways wakes it and drags it along."""
+    from rapier_b200.sets import RevoluteJointBuilder
+    s = scenes.Scene("issue_287")
+    kin = s.bodies.insert(RigidBodyBuilder.kinematic_position_based())
+    dyn = s.insert(RigidBodyBuilder.dynamic().translation((0.0, -2.0, 0.0)), ColliderBuilder.ball(0.5))
+    s.joints.insert(kin, dyn, RevoluteJointBuilder((1.0, 0.0, 0.0)).local_anchor1((0.0, 0.0, 0.0)).local_anchor2((0.0, 2.0, 0.0)))
+    w = make_world(s)
+    steps = 0
+    while not w.sleeping()[dyn]:
+        w.step()
+        steps += 1
+        assert steps < 2000, "dynamic body never fell asleep"
+    woke, x = False, 0.0
+    for _ in range(200):
+        x += 0.05
+        w.set_next_kinematic_positions([kin], [(x, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0)])
+        w.step()
+        woke = woke or not w.sleeping()[dyn]
+    assert woke
+    assert abs(float(w.body_states()[0][dyn, 0]) - x) < 2.0
+
+
+def test_kinematic_wakes_jointed_dynamic_oracle():
+    moving_kinematic_wakes_jointed_dynamic(lambda s: oracle_lib.OracleWorld(s))
+    # ccd_default_vs_fixed.rs: kinematic_not_a_default_target -- a default-tier fast body tunnels through a kinematic wall
+    s = scenes.Scene("ccd_kinematic_wall", gravity=(0.0, 0.0, 0.0))
+    s.insert(RigidBodyBuilder.kinematic_position_based(), ColliderBuilder.cuboid(0.05, 5.0, 5.0))
+    s.insert(RigidBodyBuilder.dynamic().translation((-3.0, 0.0, 0.0)).linvel((200.0, 0.0, 0.0)), ColliderBuilder.cuboid(0.1, 0.1, 0.1))
+    w = oracle_lib.OracleWorld(s)
+    w.step(60)
+    assert w.body_states()[0][1, 0] > 1.0

@@ -161,6 +161,34 @@ def events_parity_case(make_world, make_oracle, steps=150):
     return nc, nf
 
 
+def kinematic_parity_case(make_world, make_oracle, steps=150, every=15):
+    """A velocity-based kinematic turntable and conveyor carrying boxes and balls, and a position-based lift driven
+    along a curve with a new target every step: bit-exact against the oracle."""
+    import math
+    from parity_util import compare_worlds, is_exact
+    s = scenes.Scene("kinematic_parity")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -1.0, 0.0)), ColliderBuilder.cuboid(30.0, 0.5, 30.0))
+    s.insert(RigidBodyBuilder.kinematic_velocity_based().translation((0.0, 0.0, 0.0)).angvel((0.0, 0.8, 0.0)), ColliderBuilder.cuboid(3.0, 0.2, 3.0).friction(0.9))
+    s.insert(RigidBodyBuilder.kinematic_velocity_based().translation((8.0, 0.0, 0.0)).linvel((0.0, 0.0, 1.0)), ColliderBuilder.cuboid(1.5, 0.2, 6.0))
+    lift = s.insert(RigidBodyBuilder.kinematic_position_based().translation((-8.0, 0.0, 0.0)), ColliderBuilder.cuboid(1.5, 0.2, 1.5))
+    for i in range(4):
+        s.insert(RigidBodyBuilder.dynamic().translation((1.2 * math.cos(i * 1.6), 0.75 + 0.05 * i, 1.2 * math.sin(i * 1.6))), ColliderBuilder.cuboid(0.4, 0.5, 0.3))
+        s.insert(RigidBodyBuilder.dynamic().translation((8.0 + 0.3 * i, 0.7 + 0.9 * i, -2.0 + 0.2 * i)), ColliderBuilder.ball(0.35) if i % 2 else ColliderBuilder.cuboid(0.3, 0.4, 0.3))
+        s.insert(RigidBodyBuilder.dynamic().translation((-8.0 + 0.1 * i, 0.65 + 0.85 * i, 0.1 * i)), ColliderBuilder.cuboid(0.4, 0.4, 0.4))
+    w, o = make_world(s), make_oracle(s)
+    for i in range(steps):
+        t = (i + 1) / 60.0
+        h = 0.5 * math.sin(0.5 * t)
+        target = [(-8.0 + 0.5 * math.sin(t), 1.0 - math.cos(1.5 * t), 0.3 * t, 0.0, math.sin(h), 0.0, math.cos(h))]
+        for world in (w, o):
+            world.set_next_kinematic_positions([lift], target)
+            world.step()
+        if i % every == every - 1 or i < 2:
+            d = compare_worlds(w, o)
+            assert is_exact(d), (i, d)
+    return w
+
+
 VARIANTS = [
     ("restitution", bouncing_balls, None, 150, 25),
     ("groups_joints_forces", groups_and_joints, None, 150, 25),
