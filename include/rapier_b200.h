@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 2
+#define RB_ABI_VERSION 3
 
 typedef struct RbWorld RbWorld;
 
@@ -139,8 +139,14 @@ typedef struct RbContactForceEvent {
 } RbContactForceEvent;
 
 /* JointAxesMask bits (src/dynamics/joint/generic_joint.rs): LIN_X=1, LIN_Y=2, LIN_Z=4,
- * ANG_X=8, ANG_Y=16, ANG_Z=32.  Only fully locked axes are supported (spherical = 7, fixed = 63,
- * revolute about x = 55); motors and limits are RB_ERR_INVALID. */
+ * ANG_X=8, ANG_Y=16, ANG_Z=32 (spherical = 7 locked, fixed = 63, revolute about x = 55, prismatic along x = 62).
+ * Free axes may carry limits (JointLimits, generic_joint.rs:142-160) and motors (JointMotor, :203-232); coupled
+ * axes are not supported. */
+typedef struct RbJointMotor {
+    float target_vel, target_pos, stiffness, damping;
+    float max_force;              /* default FLT_MAX */
+    int32_t model;                /* 0 = AccelerationBased (default), 1 = ForceBased (motor_model.rs) */
+} RbJointMotor;
 typedef struct RbJointDesc {
     int32_t body1, body2;
     float local_frame1_t[3], local_frame1_q[4];
@@ -149,6 +155,10 @@ typedef struct RbJointDesc {
     int32_t contacts_enabled;     /* default 1 */
     float natural_frequency;      /* joint softness, default 1e6 (integration_parameters.rs:78-83) */
     float damping_ratio;          /* default 1 */
+    uint32_t limit_axes;          /* JointAxesMask of the limited free axes */
+    uint32_t motor_axes;          /* JointAxesMask of the motorised free axes */
+    float limits[6][2];           /* [axis] min, max (distance along a linear axis, angle about an angular one) */
+    RbJointMotor motors[6];
 } RbJointDesc;
 
 /* Per-stage device times of the last step, named after the reference's Counters

@@ -17,7 +17,7 @@ namespace orc {
 
 static const int CCD_MAX_ITERS = 32;
 
-static inline float ccd_atan01(float z) {   // atan on [0, 1], explicit arithmetic (the kernels evaluate the same polynomial)
+float ccd_atan01(float z) {   // atan on [0, 1], explicit arithmetic (the kernels evaluate the same polynomial)
     const float s = z * z;
     float p = -0.0117212f;
     p = fma_(p, s, 0.05265332f);

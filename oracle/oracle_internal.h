@@ -148,12 +148,20 @@ struct Joint {
     uint32_t sid1, sid2;               // solver ids (NO_BODY = world attached)
     int color;
     float impulses[6];
+    // limits and motors of the free axes (generic_joint.rs:142-232, :268-300)
+    uint32_t limit_axes, motor_axes;
+    float limits[6][2];
+    RbJointMotor motors[6];
+    float ang_limit_center[3][2], ang_limit_half_range[3];   // AngularLimitParams (joint_constraint_helper.rs:34-73)
+    float limit_impulses[6], motor_impulses[6];
 };
 
 struct JointRow {  // JointConstraint<Real,1> (joint_velocity_constraint.rs:68-93)
     V3 lin_jac, ang_jac1, ang_jac2, ii_ang_jac1, ii_ang_jac2;
     float impulse, inv_lhs, rhs, rhs_wo_bias, cfm_gain, cfm_coeff;
+    float lo, hi;   // impulse_bounds
     int dof;
+    int kind;       // WritebackId: 0 = Dof, 1 = Limit, 2 = Motor
 };
 
 // ContactWithTwistFriction + builder (contact_with_twist_friction.rs:44-55, :601-630), one lane.

@@ -455,8 +455,44 @@ static V3 gyroscopic_corrected_angvel(V3 angvel, Q4 principal_axes, V3 principal
 // ------------------------------------------------------------------------------------------
 static int joint_rows_of(const Joint& j) {
     int n = 0;
-    for (int i = 0; i < 6; ++i) n += (j.locked_axes >> i) & 1;
+    const uint32_t free_axes = ~j.locked_axes & 63u;
+    for (int i = 0; i < 6; ++i) n += ((j.locked_axes >> i) & 1) + (((j.limit_axes & free_axes) >> i) & 1) + (((j.motor_axes & free_axes) >> i) & 1);
     return n;
+}
+
+float ccd_atan01(float z);   // oracle_ccd.cpp (explicit-arithmetic arctangent shared with the kernels)
+static float atan2_poly(float y, float x) {   // atan2 in (-pi, pi] from the [0, 1] polynomial
+    const float ax = x < 0.0f ? -x : x, ay = y < 0.0f ? -y : y;
+    if (ax == 0.0f && ay == 0.0f) return 0.0f;
+    float a = ay <= ax ? ccd_atan01(ay / ax) : 1.5707964f - ccd_atan01(ax / ay);
+    if (x < 0.0f) a = 3.1415927f - a;
+    return y < 0.0f ? -a : a;
+}
+static const float FMAX = 3.4028234663852886e38f, FINF = __builtin_inff();
+
+// JointConstraintHelper::finalize_constraints (joint_constraint_helper.rs:676-722) on rows [a, b)
+static void finalize_rows(JointRow* out, int a, int b, V3 imsum) {
+    for (int jx = a; jx < b; ++jx) {
+        JointRow& cj = out[jx];
+        float dot_jj = dot(cj.lin_jac, cmul(imsum, cj.lin_jac)) + dot(cj.ii_ang_jac1, cj.ang_jac1) + dot(cj.ii_ang_jac2, cj.ang_jac2);
+        float cfm_gain = dot_jj * cj.cfm_coeff + cj.cfm_gain;
+        float inv_dot_jj = inv_or_zero(dot_jj);
+        cj.inv_lhs = inv_or_zero(dot_jj + cfm_gain);
+        cj.cfm_gain = cfm_gain;
+        if (!(cj.lo == -FMAX && cj.hi == FMAX)) continue;   // rows with limited forces are not removed from the others
+        for (int ix = jx + 1; ix < b; ++ix) {
+            JointRow& ci = out[ix];
+            float dot_ij = dot(ci.lin_jac, cmul(imsum, cj.lin_jac)) + dot(ci.ii_ang_jac1, cj.ang_jac1) + dot(ci.ii_ang_jac2, cj.ang_jac2);
+            float coeff = dot_ij * inv_dot_jj;
+            ci.lin_jac = ci.lin_jac - cj.lin_jac * coeff;
+            ci.ang_jac1 = ci.ang_jac1 - cj.ang_jac1 * coeff;
+            ci.ang_jac2 = ci.ang_jac2 - cj.ang_jac2 * coeff;
+            ci.ii_ang_jac1 = ci.ii_ang_jac1 - cj.ii_ang_jac1 * coeff;
+            ci.ii_ang_jac2 = ci.ii_ang_jac2 - cj.ii_ang_jac2 * coeff;
+            ci.rhs_wo_bias = ci.rhs_wo_bias - cj.rhs_wo_bias * coeff;
+            ci.rhs = ci.rhs - cj.rhs * coeff;
+        }
+    }
 }
 
 // joint_constraint_builder.rs:77-152 -> JointConstraint::update (joint_velocity_constraint.rs:145-357)
@@ -501,7 +537,80 @@ static int joint_update(const World& w, const Joint& j, float sub_dt, JointRow* 
         }
     // ang_basis column i = row i of D (transpose), times sgn.
     V3 imsum = g1.im + g2.im;
+    const uint32_t free_axes = ~j.locked_axes & 63u;
+    const uint32_t motor_axes = j.motor_axes & free_axes, limit_axes = j.limit_axes & free_axes;
+    const float inv_dt = sub_dt == 0.0f ? 0.0f : 1.0f / sub_dt;
+    const float max_bias = w.params.max_corrective_velocity();
+    const float aerr[3] = {ang_err.x, ang_err.y, ang_err.z};
+    auto lock_linear_row = [&](int i, float erp, float cfm, int dof, int kind) {   // lock_linear (joint_constraint_helper.rs:411-461)
+        JointRow r;
+        r.lin_jac = bcol[i];
+        r.ang_jac1 = cross(r1, bcol[i]);
+        r.ang_jac2 = cross(r2, bcol[i]);
+        r.ii_ang_jac1 = sdp_mul(g1.ii, r.ang_jac1);
+        r.ii_ang_jac2 = sdp_mul(g2.ii, r.ang_jac2);
+        r.impulse = 0.0f; r.inv_lhs = 0.0f; r.cfm_coeff = cfm; r.cfm_gain = 0.0f;
+        r.rhs_wo_bias = 0.0f;
+        r.rhs = 0.0f + dot(bcol[i], lin_err) * erp;
+        r.lo = -FMAX; r.hi = FMAX;
+        r.dof = dof; r.kind = kind;
+        return r;
+    };
+    auto motor_coeffs = [&](const RbJointMotor& m, float& m_erp, float& m_cfm_coeff, float& m_cfm_gain) {   // MotorModel::combine_coefficients
+        m_erp = m.stiffness * inv_or_zero(sub_dt * m.stiffness + m.damping);
+        const float c = inv_or_zero(sub_dt * sub_dt * m.stiffness + sub_dt * m.damping);
+        m_cfm_coeff = m.model == 0 ? c : 0.0f;
+        m_cfm_gain = m.model == 0 ? 0.0f : c;
+    };
     int len = 0;
+    // ---- motors (joint_velocity_constraint.rs:191-223): angular then linear, orthogonalised among themselves
+    for (int i = 3; i < 6; ++i) {
+        if (!(motor_axes & (1u << i))) continue;
+        const RbJointMotor& m = j.motors[i];
+        float m_erp, m_cc, m_cg;
+        motor_coeffs(m, m_erp, m_cc, m_cg);
+        JointRow& r = out[len++];   // motor_angular (joint_constraint_helper.rs:566-626)
+        const V3 ang_jac = bcol[i - 3];
+        float rhs_wo_bias = 0.0f;
+        if (m_erp != 0.0f) {
+            const float ce = fclamp(aerr[i - 3], -1.0f, 1.0f);
+            const float ang_dist = atan2_poly(ce, sqrtf(fmax2(1.0f - ce * ce, 0.0f))) * 2.0f;   // asin(clamped) * 2
+            float s_err = ang_dist - m.target_pos;   // utils::smallest_abs_diff_between_angles
+            const float sg = s_err > 0.0f ? 1.0f : (s_err < 0.0f ? -1.0f : 0.0f);
+            const float comp = s_err - sg * 6.2831855f;
+            if (!(fabsf(s_err) < fabsf(comp))) s_err = comp;
+            rhs_wo_bias = rhs_wo_bias + s_err * m_erp;
+        }
+        rhs_wo_bias = rhs_wo_bias + -m.target_vel;
+        r.lin_jac = vzero(); r.ang_jac1 = ang_jac; r.ang_jac2 = ang_jac;
+        r.ii_ang_jac1 = sdp_mul(g1.ii, ang_jac); r.ii_ang_jac2 = sdp_mul(g2.ii, ang_jac);
+        r.impulse = 0.0f; r.inv_lhs = 0.0f; r.cfm_coeff = m_cc; r.cfm_gain = m_cg;
+        r.rhs = rhs_wo_bias; r.rhs_wo_bias = rhs_wo_bias;
+        r.lo = -(m.max_force * sub_dt); r.hi = m.max_force * sub_dt;
+        r.dof = i; r.kind = 2;
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (!(motor_axes & (1u << i))) continue;
+        const RbJointMotor& m = j.motors[i];
+        float m_erp, m_cc, m_cg;
+        motor_coeffs(m, m_erp, m_cc, m_cg);
+        JointRow r = lock_linear_row(i, 0.0f, 0.0f, i, 2);   // motor_linear (joint_constraint_helper.rs:285-330)
+        float rhs_wo_bias = 0.0f;
+        if (m_erp != 0.0f) rhs_wo_bias = rhs_wo_bias + (dot(lin_err, r.lin_jac) - m.target_pos) * m_erp;
+        float target_vel = m.target_vel;
+        if (limit_axes & (1u << i)) {
+            const float dist = dot(lin_err, r.lin_jac);
+            target_vel = fclamp(target_vel, (j.limits[i][0] - dist) * inv_dt, (j.limits[i][1] - dist) * inv_dt);
+        }
+        rhs_wo_bias = rhs_wo_bias + -target_vel;
+        r.cfm_coeff = m_cc; r.cfm_gain = m_cg;
+        r.lo = -(m.max_force * sub_dt); r.hi = m.max_force * sub_dt;
+        r.rhs = rhs_wo_bias; r.rhs_wo_bias = rhs_wo_bias;
+        out[len++] = r;
+    }
+    finalize_rows(out, 0, len, imsum);
+    const int start = len;
+    // ---- locked axes, then limits (joint_velocity_constraint.rs:259-355), orthogonalised together
     for (int i = 3; i < 6; ++i) {
         if (!(j.locked_axes & (1u << i))) continue;
         int ax = i - 3;
@@ -516,42 +625,47 @@ static int joint_update(const World& w, const Joint& j, float sub_dt, JointRow* 
         r.impulse = 0.0f; r.inv_lhs = 0.0f; r.cfm_coeff = cfm_coeff; r.cfm_gain = 0.0f;
         r.rhs_wo_bias = 0.0f;
         r.rhs = 0.0f + imag * erp_inv_dt;
-        r.dof = i;
+        r.lo = -FMAX; r.hi = FMAX;
+        r.dof = i; r.kind = 0;
     }
     for (int i = 0; i < 3; ++i) {
         if (!(j.locked_axes & (1u << i))) continue;
+        out[len++] = lock_linear_row(i, erp_inv_dt, cfm_coeff, i, 0);
+    }
+    for (int i = 3; i < 6; ++i) {
+        if (!(limit_axes & (1u << i))) continue;
+        const int ax = i - 3;
+        // recentered_angle (joint_constraint_helper.rs:468-499) + limit_angular (:503-564)
+        const float c_cos = j.ang_limit_center[ax][0], c_sin = j.ang_limit_center[ax][1], half_range = j.ang_limit_half_range[ax];
+        const float x = aerr[ax], wq = ang_err.w;
+        const float sin_half = c_cos * x - c_sin * wq, cos_half = c_cos * wq + c_sin * x;
+        float half = atan2_poly(sin_half, cos_half);
+        if (fabsf(half) > 1.5707964f) half = half - copysignf(3.1415927f, half);
+        const float ang = half * 2.0f;
+        const bool min_enabled = ang <= -half_range, max_enabled = half_range <= ang;
         JointRow& r = out[len++];
-        r.lin_jac = bcol[i];
-        r.ang_jac1 = cross(r1, bcol[i]);
-        r.ang_jac2 = cross(r2, bcol[i]);
-        r.ii_ang_jac1 = sdp_mul(g1.ii, r.ang_jac1);
-        r.ii_ang_jac2 = sdp_mul(g2.ii, r.ang_jac2);
+        const V3 ang_jac = bcol[ax];
+        const float rhs_bias = fclamp((fmax2(ang - half_range, 0.0f) - fmax2(-half_range - ang, 0.0f)) * erp_inv_dt, -max_bias, max_bias);
+        r.lin_jac = vzero(); r.ang_jac1 = ang_jac; r.ang_jac2 = ang_jac;
+        r.ii_ang_jac1 = sdp_mul(g1.ii, ang_jac); r.ii_ang_jac2 = sdp_mul(g2.ii, ang_jac);
         r.impulse = 0.0f; r.inv_lhs = 0.0f; r.cfm_coeff = cfm_coeff; r.cfm_gain = 0.0f;
         r.rhs_wo_bias = 0.0f;
-        r.rhs = 0.0f + dot(bcol[i], lin_err) * erp_inv_dt;
-        r.dof = i;
+        r.rhs = 0.0f + rhs_bias;
+        r.lo = min_enabled ? -FINF : 0.0f; r.hi = max_enabled ? FINF : 0.0f;
+        r.dof = i; r.kind = 1;
     }
-    // finalize_constraints: modified Gram-Schmidt in the mass metric.
-    for (int jx = 0; jx < len; ++jx) {
-        JointRow& cj = out[jx];
-        float dot_jj = dot(cj.lin_jac, cmul(imsum, cj.lin_jac)) + dot(cj.ii_ang_jac1, cj.ang_jac1) + dot(cj.ii_ang_jac2, cj.ang_jac2);
-        float cfm_gain = dot_jj * cj.cfm_coeff + cj.cfm_gain;
-        float inv_dot_jj = inv_or_zero(dot_jj);
-        cj.inv_lhs = inv_or_zero(dot_jj + cfm_gain);
-        cj.cfm_gain = cfm_gain;
-        for (int ix = jx + 1; ix < len; ++ix) {
-            JointRow& ci = out[ix];
-            float dot_ij = dot(ci.lin_jac, cmul(imsum, cj.lin_jac)) + dot(ci.ii_ang_jac1, cj.ang_jac1) + dot(ci.ii_ang_jac2, cj.ang_jac2);
-            float coeff = dot_ij * inv_dot_jj;
-            ci.lin_jac = ci.lin_jac - cj.lin_jac * coeff;
-            ci.ang_jac1 = ci.ang_jac1 - cj.ang_jac1 * coeff;
-            ci.ang_jac2 = ci.ang_jac2 - cj.ang_jac2 * coeff;
-            ci.ii_ang_jac1 = ci.ii_ang_jac1 - cj.ii_ang_jac1 * coeff;
-            ci.ii_ang_jac2 = ci.ii_ang_jac2 - cj.ii_ang_jac2 * coeff;
-            ci.rhs_wo_bias = ci.rhs_wo_bias - cj.rhs_wo_bias * coeff;
-            ci.rhs = ci.rhs - cj.rhs * coeff;
-        }
+    for (int i = 0; i < 3; ++i) {
+        if (!(limit_axes & (1u << i))) continue;
+        JointRow r = lock_linear_row(i, erp_inv_dt, cfm_coeff, i, 1);   // limit_linear (joint_constraint_helper.rs:166-207)
+        const float dist = dot(lin_err, r.lin_jac);
+        const bool min_enabled = dist <= j.limits[i][0], max_enabled = j.limits[i][1] <= dist;
+        const float rhs_bias = fclamp((fmax2(dist - j.limits[i][1], 0.0f) - fmax2(j.limits[i][0] - dist, 0.0f)) * erp_inv_dt, -max_bias, max_bias);
+        r.rhs = r.rhs_wo_bias + rhs_bias;
+        r.cfm_coeff = cfm_coeff;
+        r.lo = min_enabled ? -FINF : 0.0f; r.hi = max_enabled ? FINF : 0.0f;
+        out[len++] = r;
     }
+    finalize_rows(out, start, len, imsum);
     return len;
 }
 
@@ -565,7 +679,7 @@ static void joint_solve(World& w, const Joint& j, JointRow* rows, int n, bool wo
         float dlinvel = dot(r.lin_jac, v2 - v1);
         float dangvel = dot(r.ang_jac2, w2) - dot(r.ang_jac1, w1);
         float rhs = dlinvel + dangvel + r.rhs;
-        float total = r.impulse + r.inv_lhs * (rhs - r.cfm_gain * r.impulse);
+        float total = fclamp(r.impulse + r.inv_lhs * (rhs - r.cfm_gain * r.impulse), r.lo, r.hi);   // impulse_bounds
         float delta = total - r.impulse;
         r.impulse = total;
         V3 lin_impulse = r.lin_jac * delta;
@@ -818,7 +932,10 @@ void solve_island(World& w, V3 gravity) {
     for (int i = 0; i < nj; ++i) {
         Joint& j = w.joints[i];
         if (jcolors[i] < 0) continue;
-        for (int r = jrow_start[i]; r < jrow_start[i + 1]; ++r) j.impulses[w.jrows[r].dof] = w.jrows[r].impulse;
+        for (int r = jrow_start[i]; r < jrow_start[i + 1]; ++r) {
+            const JointRow& row = w.jrows[r];
+            (row.kind == 0 ? j.impulses : (row.kind == 1 ? j.limit_impulses : j.motor_impulses))[row.dof] = row.impulse;
+        }
     }
     // S11 body writeback (worker.rs:809-897; rigid_body_components.rs:835-841)
     for (int i = 0; i < nb; ++i) {

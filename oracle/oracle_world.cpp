@@ -831,7 +831,23 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
         j.contacts_enabled = d.contacts_enabled;
         j.natural_frequency = d.natural_frequency;
         j.damping_ratio = d.damping_ratio;
-        for (int k = 0; k < 6; ++k) j.impulses[k] = 0.0f;
+        j.limit_axes = d.limit_axes; j.motor_axes = d.motor_axes;
+        for (int k = 0; k < 6; ++k) {
+            j.impulses[k] = 0.0f; j.limit_impulses[k] = 0.0f; j.motor_impulses[k] = 0.0f;
+            j.limits[k][0] = d.limits[k][0]; j.limits[k][1] = d.limits[k][1];
+            j.motors[k] = d.motors[k];
+        }
+        for (int k = 0; k < 3; ++k) {   // AngularLimitParams::new (joint_constraint_helper.rs:44-73)
+            const float lo = d.limits[3 + k][0], hi = d.limits[3 + k][1];
+            const float half_range = (hi - lo) * 0.5f;
+            if (half_range >= 3.14159265358979323846f || half_range != half_range) {
+                j.ang_limit_center[k][0] = 1.0f; j.ang_limit_center[k][1] = 0.0f; j.ang_limit_half_range[k] = 10.0f;
+            } else {
+                const float center = (lo + hi) * 0.5f;
+                j.ang_limit_center[k][0] = cosf(center * 0.5f); j.ang_limit_center[k][1] = sinf(center * 0.5f);
+                j.ang_limit_half_range[k] = half_range;
+            }
+        }
         if (!d.contacts_enabled) {
             uint32_t lo = (uint32_t)std::min(d.body1, d.body2), hi = (uint32_t)std::max(d.body1, d.body2);
             w.nocontact_body_pairs.push_back(((uint64_t)lo << 32) | hi);

@@ -97,6 +97,10 @@ class RbContactForceEvent(C.Structure):
 RB_EVENT_COLLISION, RB_EVENT_CONTACT_FORCE = 1, 2
 
 
+class RbJointMotor(C.Structure):
+    _fields_ = [("target_vel", f32), ("target_pos", f32), ("stiffness", f32), ("damping", f32), ("max_force", f32), ("model", i32)]
+
+
 class RbJointDesc(C.Structure):
     _fields_ = [
         ("body1", i32), ("body2", i32),
@@ -104,6 +108,7 @@ class RbJointDesc(C.Structure):
         ("local_frame2_t", f32 * 3), ("local_frame2_q", f32 * 4),
         ("locked_axes", u32), ("contacts_enabled", i32),
         ("natural_frequency", f32), ("damping_ratio", f32),
+        ("limit_axes", u32), ("motor_axes", u32), ("limits", (f32 * 2) * 6), ("motors", RbJointMotor * 6),
     ]
 
 

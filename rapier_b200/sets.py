@@ -238,7 +238,7 @@ class ColliderBuilder:
 
 
 class GenericJointBuilder:
-    """Locked-axes joints only: spherical = LIN_X|LIN_Y|LIN_Z, fixed = all six."""
+    """GenericJoint: locked axes (spherical = LIN_X|LIN_Y|LIN_Z, fixed = all six), limits and motors on the free ones."""
 
     def __init__(self, locked_axes):
         self.locked_axes = locked_axes
@@ -247,6 +247,8 @@ class GenericJointBuilder:
         self._q1 = (0.0, 0.0, 0.0, 1.0)
         self._q2 = (0.0, 0.0, 0.0, 1.0)
         self._contacts_enabled = True
+        self._limits = {}
+        self._motors = {}
 
     def local_anchor1(self, v):
         self._a1 = tuple(float(x) for x in v)
@@ -260,6 +262,36 @@ class GenericJointBuilder:
         self._contacts_enabled = bool(flag)
         return self
 
+    # GenericJoint::{set_limits, set_motor_velocity, set_motor_position, set_motor, set_motor_max_force, set_motor_model}
+    # (generic_joint.rs:470-560); `axis` = 0..5 (LinX LinY LinZ AngX AngY AngZ)
+    def limits(self, axis, lo, hi):
+        self._limits[axis] = (float(lo), float(hi))
+        return self
+
+    def _motor(self, axis):
+        return self._motors.setdefault(axis, dict(target_vel=0.0, target_pos=0.0, stiffness=0.0, damping=0.0, max_force=3.4028234663852886e38, model=0))
+
+    def motor_velocity(self, axis, target_vel, factor):
+        m = self._motor(axis)
+        m.update(target_vel=float(target_vel), target_pos=0.0, stiffness=0.0, damping=float(factor))   # set_motor(axis, 0, vel, 0, factor)
+        return self
+
+    def motor_position(self, axis, target_pos, stiffness, damping):
+        self._motor(axis).update(target_vel=0.0, target_pos=float(target_pos), stiffness=float(stiffness), damping=float(damping))
+        return self
+
+    def motor(self, axis, target_pos, target_vel, stiffness, damping):
+        self._motor(axis).update(target_vel=float(target_vel), target_pos=float(target_pos), stiffness=float(stiffness), damping=float(damping))
+        return self
+
+    def motor_max_force(self, axis, max_force):
+        self._motor(axis)["max_force"] = float(max_force)
+        return self
+
+    def motor_model(self, axis, model):
+        self._motor(axis)["model"] = int(model)
+        return self
+
     def build_desc(self, body1, body2):
         d = A.RbJointDesc()
         d.body1, d.body2 = int(body1), int(body2)
@@ -271,6 +303,16 @@ class GenericJointBuilder:
         d.contacts_enabled = 1 if self._contacts_enabled else 0
         d.natural_frequency = 1.0e6   # SpringCoefficients::joint_defaults (integration_parameters.rs:78-83)
         d.damping_ratio = 1.0
+        for ax in range(6):
+            d.limits[ax][0], d.limits[ax][1] = -3.4028234663852886e38, 3.4028234663852886e38   # JointLimits::default
+            d.motors[ax].max_force = 3.4028234663852886e38                                        # JointMotor::default
+        for ax, (lo, hi) in self._limits.items():
+            d.limit_axes |= 1 << ax
+            d.limits[ax][0], d.limits[ax][1] = lo, hi
+        for ax, m in self._motors.items():
+            d.motor_axes |= 1 << ax
+            for k, v in m.items():
+                setattr(d.motors[ax], k, v)
         return d
 
 
@@ -302,6 +344,14 @@ def RevoluteJointBuilder(axis):
     """RevoluteJointBuilder::new(axis) (revolute_joint.rs): every axis locked except the rotation about `axis`,
     which is the X axis of both joint frames."""
     b = GenericJointBuilder(0b110111)   # LIN_X | LIN_Y | LIN_Z | ANG_Y | ANG_Z
+    b._q1 = b._q2 = _rotation_arc_from_x(axis)
+    return b
+
+
+def PrismaticJointBuilder(axis):
+    """PrismaticJointBuilder::new(axis) (prismatic_joint.rs): every axis locked except the translation along `axis`,
+    which is the X axis of both joint frames."""
+    b = GenericJointBuilder(0b111110)   # LIN_Y | LIN_Z | ANG_X | ANG_Y | ANG_Z
     b._q1 = b._q2 = _rotation_arc_from_x(axis)
     return b
 
