@@ -299,10 +299,13 @@ __global__ void __launch_bounds__(COLLIDE_THREADS, 1) k_solve_large(World w, Gra
     gex.c = &ctx;
     solve_item_lanes<4>(gex, w, gb, mk3(g.x, g.y, g.z));
 }
-// FrictionModel::Coulomb (integration_parameters.rs:26-29): one coupled tangent part per contact point instead of the
-// twist model's one per manifold.  Every work item takes the streaming solve (solve_item<1>: bodies in shared memory,
-// rows in HBM/L2), the grid-wide item 0 the same code with grid barriers; the twist kernels carry none of this code.
-__global__ void __launch_bounds__(COLLIDE_THREADS) k_solve_items_coulomb(World w, Grav g) {
+// The general solve path, compiled per (friction model FM, joint model JM):
+//   FM = 1  FrictionModel::Coulomb (integration_parameters.rs:26-29): one coupled tangent part per contact point
+//   JM = 1  some joint has limits or motors (joint_velocity_constraint.rs:145-357): generic joint rows
+// Every work item takes the streaming solve (solve_item<FM, JM>: bodies in shared memory, rows in HBM/L2), the
+// grid-wide item 0 the same code with grid barriers.  The twist / locked-axes kernels carry none of this code.
+template <int FM, int JM>
+__global__ void __launch_bounds__(COLLIDE_THREADS) k_solve_items_x(World w, Grav g) {
     extern __shared__ __align__(16) float smem[];
     BlockCtx bctx;
     SmemBodies bd;
@@ -317,18 +320,19 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_solve_items_coulomb(World w
         const int k = s_next;
         __syncthreads();
         if (k >= n) break;
-        solve_item<1>(ex, w, bd, w.item_order[k], mk3(g.x, g.y, g.z));
+        solve_item<FM, JM>(ex, w, bd, w.item_order[k], mk3(g.x, g.y, g.z));
         ex.sync();
     }
 }
-__global__ void __launch_bounds__(COLLIDE_THREADS, 1) k_solve_large_coulomb(World w, Grav g) {
+template <int FM, int JM>
+__global__ void __launch_bounds__(COLLIDE_THREADS, 1) k_solve_large_x(World w, Grav g) {
     GridCtx ctx;
     if (w.st->nlarge_bodies == 0) return;
     GlobalBodies gb;
     gb.w = &w;
     GridExec gex;
     gex.c = &ctx;
-    solve_item<1>(gex, w, gb, 0, mk3(g.x, g.y, g.z));
+    solve_item<FM, JM>(gex, w, gb, 0, mk3(g.x, g.y, g.z));
 }
 // Shared-memory items: one CTA per item, bodies (and, when they fit, constraints) staged in shared memory,
 // four lanes per constraint (rb_solver.cuh "lane-cooperative path").
@@ -881,7 +885,9 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
     if (cudaHostAlloc((void**)&W->host_hint, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) { set_err("cudaHostAlloc failed%s", ""); delete W; return nullptr; }
     for (int i = 0; i < 4; ++i) W->host_hint[i] = 0;
     cudaFuncSetAttribute(k_collide, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
-    cudaFuncSetAttribute(k_solve_items_coulomb, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
+    cudaFuncSetAttribute(k_solve_items_x<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
+    cudaFuncSetAttribute(k_solve_items_x<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
+    cudaFuncSetAttribute(k_solve_items_x<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_collide, COLLIDE_THREADS, ITEM_SMEM_BYTES);
     if (occ < 1) { set_err("k_collide cannot be resident%s", ""); delete W; return nullptr; }
@@ -982,6 +988,11 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     w.joint_cap = std::max(nj, 1);
     w.item_cap = 4 + (NB + w.pair_cap + nj) / ITEM_TARGET;
     const int NJ = w.joint_cap;
+    w.generic_joints = 0;
+    for (int i = 0; i < nj; ++i) {   // any limit or motor on a free axis: the generic joint path (12 row slots per joint)
+        const unsigned free_axes = ~joints[i].locked_axes & 63u;
+        if ((joints[i].limit_axes | joints[i].motor_axes) & free_axes) w.generic_joints = 1;
+    }
 
     ALLOC(w.st, 1);
     ALLOC(w.b_type, NB); ALLOC(w.b_flags, NB);
@@ -1035,7 +1046,12 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
 #endif
     ALLOC(w.j_info, NJ); ALLOC(w.j_f1_t, NJ); ALLOC(w.j_f1_q, NJ); ALLOC(w.j_f2_t, NJ); ALLOC(w.j_f2_q, NJ);
     ALLOC(w.j_soft, NJ); ALLOC(w.j_impulses, (size_t)NJ * 6);
-    ALLOC(w.j_rows, (size_t)JR_ROWS * 6 * NJ); ALLOC(w.j_sched_ids, NJ);
+    ALLOC(w.j_rows, (size_t)JR_ROWS * (w.generic_joints ? JROWS_GENERIC : 6) * NJ); ALLOC(w.j_sched_ids, NJ);
+    if (w.generic_joints) {
+        ALLOC(w.j_axes, NJ); ALLOC(w.j_limits, (size_t)NJ * 6); ALLOC(w.j_motor_a, (size_t)NJ * 6); ALLOC(w.j_motor_b, (size_t)NJ * 6);
+        ALLOC(w.j_anglim, (size_t)NJ * 3); ALLOC(w.j_bnd, (size_t)JROWS_GENERIC * NJ);
+        ALLOC(w.j_limit_impulses, (size_t)NJ * 6); ALLOC(w.j_motor_impulses, (size_t)NJ * 6);
+    }
 
     // ---- bodies + colliders (unused capacity: fixed bodies / parentless nothing, never listed) ----
     {
@@ -1106,6 +1122,36 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
         CK(h2d(w.j_f2_t, f2t.data(), NJ * sizeof(float4)));
         CK(h2d(w.j_f2_q, f2q.data(), NJ * sizeof(float4)));
         CK(h2d(w.j_soft, soft.data(), NJ * sizeof(float2)));
+        if (w.generic_joints) {
+            std::vector<uint2> axes(NJ);
+            std::vector<float2> lim((size_t)NJ * 6), mb((size_t)NJ * 6);
+            std::vector<float4> ma((size_t)NJ * 6), al((size_t)NJ * 3);
+            for (int i = 0; i < nj; ++i) {
+                const RbJointDesc& j = joints[i];
+                axes[i] = make_uint2(j.limit_axes, j.motor_axes);
+                for (int k = 0; k < 6; ++k) {
+                    lim[(size_t)i * 6 + k] = make_float2(j.limits[k][0], j.limits[k][1]);
+                    ma[(size_t)i * 6 + k] = make_float4(j.motors[k].target_vel, j.motors[k].target_pos, j.motors[k].stiffness, j.motors[k].damping);
+                    float model_bits;
+                    memcpy(&model_bits, &j.motors[k].model, 4);
+                    mb[(size_t)i * 6 + k] = make_float2(j.motors[k].max_force, model_bits);
+                }
+                for (int k = 0; k < 3; ++k) {   // AngularLimitParams::new (joint_constraint_helper.rs:44-73)
+                    const float lo = j.limits[3 + k][0], hi = j.limits[3 + k][1];
+                    const float half_range = (hi - lo) * 0.5f;
+                    if (half_range >= 3.14159265358979323846f || half_range != half_range) al[(size_t)i * 3 + k] = make_float4(1.0f, 0.0f, 10.0f, 0.0f);
+                    else {
+                        const float center = (lo + hi) * 0.5f;
+                        al[(size_t)i * 3 + k] = make_float4(cosf(center * 0.5f), sinf(center * 0.5f), half_range, 0.0f);
+                    }
+                }
+            }
+            CK(h2d(w.j_axes, axes.data(), NJ * sizeof(uint2)));
+            CK(h2d(w.j_limits, lim.data(), lim.size() * sizeof(float2)));
+            CK(h2d(w.j_motor_a, ma.data(), ma.size() * sizeof(float4)));
+            CK(h2d(w.j_motor_b, mb.data(), mb.size() * sizeof(float2)));
+            CK(h2d(w.j_anglim, al.data(), al.size() * sizeof(float4)));
+        }
         CK(h2d(w.jcolor_pos, jpos.data(), (NUM_COLORS + 1) * sizeof(int)));
         w.n_nocontact = (int)nocontact.size();
         ALLOC(w.nocontact_keys, std::max<size_t>(nocontact.size(), 1));
@@ -1414,7 +1460,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         bool prof = W->profiling;
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s], W->stream));
         // a grid-wide island existed after the last schedule the host knows of: it gets its own launch
-        const bool coulomb = W->w.prm.friction_model == 1;
+        const bool coulomb = W->w.prm.friction_model == 1 || W->w.generic_joints != 0;   // (the general solve path)
         const bool large = *(volatile int*)(W->host_hint + 2) != 0;
         int do_solve = coulomb ? 0 : (large ? 3 : 1);
         if (W->state_buf[1]) { W->w.state13 = W->state_buf[W->state_next]; W->state_next ^= 1; }
@@ -1431,8 +1477,12 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 1], W->stream));
         if (coulomb) {   // every item through the streaming solve; the grid-wide item's kernel returns at once when there is none
             void* a2[] = {(void*)&W->w, (void*)&g};
-            k_solve_items_coulomb<<<W->collide_blocks, W->collide_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
-            CK(cudaLaunchCooperativeKernel((void*)k_solve_large_coulomb, dim3(W->collide_blocks), dim3(W->collide_threads), a2, 0, W->stream));
+            const int fm = W->w.prm.friction_model == 1 ? 1 : 0, jm = W->w.generic_joints ? 1 : 0;
+            void* large = fm ? (jm ? (void*)k_solve_large_x<1, 1> : (void*)k_solve_large_x<1, 0>) : (void*)k_solve_large_x<0, 1>;
+            if (fm && jm) k_solve_items_x<1, 1><<<W->collide_blocks, W->collide_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
+            else if (fm) k_solve_items_x<1, 0><<<W->collide_blocks, W->collide_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
+            else k_solve_items_x<0, 1><<<W->collide_blocks, W->collide_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
+            CK(cudaLaunchCooperativeKernel(large, dim3(W->collide_blocks), dim3(W->collide_threads), a2, 0, W->stream));
             if (W->force_events) { k_force_events<<<W->collide_blocks, 256, 0, W->stream>>>(W->w); W->kernels++; }
             if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 2], W->stream));
             W->kernels += 3;
@@ -1490,7 +1540,10 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         pp.sweep_threads = 1;
         for (int k = 0; k < W->w.st->norder; ++k) {
             const int item = W->w.item_order[k];
-            if (W->w.prm.friction_model == 1) solve_item<1>(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
+            const bool fm1 = W->w.prm.friction_model == 1, jm1 = W->w.generic_joints != 0;
+            if (fm1 && jm1) solve_item<1, 1>(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
+            else if (fm1) solve_item<1, 0>(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
+            else if (jm1) solve_item<0, 1>(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
             else if (item_is_coop(W->w, item))
                 solve_item_coop<1>(bctx, W->w, W->emu_smem.data() + ITEM_MAX_BODIES * SB_STRIDE, W->emu_coop_floats, pp, item, mk3(g.x, g.y, g.z));
             else solve_item(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
@@ -1500,7 +1553,10 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
             gb.w = &W->w;
             GridExec gex;
             gex.c = &gctx;
-            if (W->w.prm.friction_model == 1) solve_item<1>(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
+            const bool fm1 = W->w.prm.friction_model == 1, jm1 = W->w.generic_joints != 0;
+            if (fm1 && jm1) solve_item<1, 1>(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
+            else if (fm1) solve_item<1, 0>(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
+            else if (jm1) solve_item<0, 1>(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
             else solve_item_lanes<1>(gex, W->w, gb, mk3(g.x, g.y, g.z));
         }
         if (W->force_events) phase_force_events(gctx, W->w);

@@ -16,6 +16,7 @@ struct RawManifold { int n; RawPt pt[MAX_RAW]; vec3 n1, n2; };
 
 constexpr float EPS32 = 1.1920929e-7f;
 constexpr float FMAX32 = 3.4028235e38f;
+#define RB_INF (as_float(0x7f800000u))
 constexpr uint32_t FID_VERTEX = 0x10000000u, FID_FACE = 0x20000000u, FID_EDGE = 0x30000000u;
 
 RB_HD vec3 box_support(vec3 he, vec3 d) { return mk3(copysignf(he.x, d.x), copysignf(he.y, d.y), copysignf(he.z, d.z)); }

@@ -753,6 +753,255 @@ RB_HD void joint_writeback(const World& w, int q) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Generic joint path (JM = 1): locked axes + limits + motors, rows in the reference's order
+// (JointConstraint::update, joint_velocity_constraint.rs:145-357): motors (angular, linear) orthogonalised among
+// themselves, then locked axes and limits orthogonalised together; rows with bounded impulses are never pivots
+// (finalize_constraints, joint_constraint_helper.rs:676-722).  12 row slots per joint; one thread builds a joint's rows
+// in local memory (these joints are rare next to contacts; the locked-only path above keeps its register-resident form).
+// ------------------------------------------------------------------------------------------------
+constexpr int JROWS_GENERIC = 12;
+struct GRow { vec3 lin, a1, a2, ia1, ia2; float inv_lhs, rhs, rwb, cg, cc, lo, hi; int dof, kind; };
+
+RB_HD float atan2_poly(float y, float x) {   // atan2 in (-pi, pi] from ccd_atan01 (explicit arithmetic, equal to the oracle's bit for bit)
+    const float ax = x < 0.0f ? -x : x, ay = y < 0.0f ? -y : y;
+    if (ax == 0.0f && ay == 0.0f) return 0.0f;
+    float a = ay <= ax ? ccd_atan01(ay / ax) : 1.5707964f - ccd_atan01(ax / ay);
+    if (x < 0.0f) a = 3.1415927f - a;
+    return y < 0.0f ? -a : a;
+}
+RB_HD float fabs1(float x) { return x < 0.0f ? -x : x; }
+RB_HD void grows_finalize(GRow* r, int a, int b, vec3 imsum) {
+    for (int jx = a; jx < b; ++jx) {
+        GRow& cj = r[jx];
+        const float djj = dot3(cj.lin, had(imsum, cj.lin)) + dot3(cj.ia1, cj.a1) + dot3(cj.ia2, cj.a2);
+        const float gain = djj * cj.cc + cj.cg;
+        const float inv_djj = safe_inv(djj);
+        cj.inv_lhs = safe_inv(djj + gain);
+        cj.cg = gain;
+        if (!(cj.lo == -FMAX32 && cj.hi == FMAX32)) continue;
+        for (int ix = jx + 1; ix < b; ++ix) {
+            GRow& ci = r[ix];
+            const float dij = dot3(ci.lin, had(imsum, cj.lin)) + dot3(ci.ia1, cj.a1) + dot3(ci.ia2, cj.a2);
+            const float coeff = dij * inv_djj;
+            ci.lin = ci.lin - cj.lin * coeff;
+            ci.a1 = ci.a1 - cj.a1 * coeff;
+            ci.a2 = ci.a2 - cj.a2 * coeff;
+            ci.ia1 = ci.ia1 - cj.ia1 * coeff;
+            ci.ia2 = ci.ia2 - cj.ia2 * coeff;
+            ci.rwb = ci.rwb - cj.rwb * coeff;
+            ci.rhs = ci.rhs - cj.rhs * coeff;
+        }
+    }
+}
+template <class B>
+RB_HD void joint_update_generic(const World& w, const B& bd, int q) {
+    int4 h = w.j_sched_ids[q];
+    const int j = h.x, id1 = h.y, id2 = h.z;
+    const int4 ji = w.j_info[j];
+    const unsigned locked = (unsigned)ji.z;
+    BodyState g1 = gather_body(bd, id1), g2 = gather_body(bd, id2);
+    pose lf1 = mkpose(mkq(w.j_f1_q[j]), xyz(w.j_f1_t[j]));
+    pose lf2 = mkpose(mkq(w.j_f2_q[j]), xyz(w.j_f2_t[j]));
+    if (id1 == NO_BODY) lf1 = pmul(body_pose(w, ji.x), lf1); else lf1.t = lf1.t - xyz(w.b_lcom_im[ji.x]);
+    if (id2 == NO_BODY) lf2 = pmul(body_pose(w, ji.y), lf2); else lf2.t = lf2.t - xyz(w.b_lcom_im[ji.y]);
+    pose f1 = pmul(g1.p, lf1), f2 = pmul(g2.p, lf2);
+    const float2 soft = w.j_soft[j];
+    const float omega = soft.x * 6.283185307179586f;
+    const float sdt = w.prm.sub_dt;
+    const float erp_inv_dt = omega / (sdt * omega + 2.0f * soft.y);
+    const float erpv = sdt * erp_inv_dt;
+    float cfm_coeff = 0.0f;
+    if (erpv != 0.0f) {
+        const float e1 = 1.0f / erpv - 1.0f;
+        cfm_coeff = e1 * e1 / ((1.0f + e1) * 4.0f * soft.y * soft.y);
+    }
+    const mat3 basis = rotmat(f1.q);
+    const vec3 bc[3] = {basis.c0, basis.c1, basis.c2};
+    const vec3 lin_err = f2.t - f1.t;
+    vec3 nc1 = f2.t;
+    for (int i = 0; i < 3; ++i)
+        if (locked & (1u << i)) nc1 = nc1 - bc[i] * dot3(lin_err, bc[i]);
+    f1.t = nc1;
+    const vec3 r1 = f1.t - g1.p.t, r2 = f2.t - g2.p.t;
+    const float sgn = copysign1(qdot(f1.q, f2.q));
+    const quat ae = qmul(qconj(f1.q), f2.q);
+    const float aerr[3] = {ae.x * sgn, ae.y * sgn, ae.z * sgn};
+    const float aew = ae.w * sgn;
+    const vec3 a = mk3(f1.q.x, f1.q.y, f1.q.z), b = mk3(f2.q.x, f2.q.y, f2.q.z);
+    const float wa = f1.q.w, wb = f2.q.w;
+    const vec3 cv = a * wb + b * wa;
+    const float ab = dot3(a, b);
+    const vec3 imsum = g1.im + g2.im;
+    const unsigned free_axes = ~locked & 63u;
+    const uint2 axes = w.j_axes[j];
+    const unsigned limit_axes = axes.x & free_axes, motor_axes = axes.y & free_axes;
+    const float inv_dt = w.prm.sub_inv_dt, max_bias = w.prm.max_corrective_velocity;
+    GRow rows[JROWS_GENERIC];
+    auto lock_linear_row = [&](int i, float erp, float cfm, int dof, int kind) {
+        GRow r;
+        r.lin = bc[i]; r.a1 = cross3(r1, bc[i]); r.a2 = cross3(r2, bc[i]);
+        r.ia1 = smul(g1.ii, r.a1); r.ia2 = smul(g2.ii, r.a2);
+        r.inv_lhs = 0.0f; r.cc = cfm; r.cg = 0.0f; r.rwb = 0.0f;
+        r.rhs = 0.0f + dot3(bc[i], lin_err) * erp;
+        r.lo = -FMAX32; r.hi = FMAX32; r.dof = dof; r.kind = kind;
+        return r;
+    };
+    auto motor_coeffs = [&](int i, float4& ma, float& m_erp, float& m_cc, float& m_cg, float& max_imp) {
+        ma = w.j_motor_a[j * 6 + i];
+        const float2 mb = w.j_motor_b[j * 6 + i];
+        m_erp = ma.z * safe_inv(sdt * ma.z + ma.w);
+        const float c = safe_inv(sdt * sdt * ma.z + sdt * ma.w);
+        const bool acc = as_int(mb.y) == 0;
+        m_cc = acc ? c : 0.0f;
+        m_cg = acc ? 0.0f : c;
+        max_imp = mb.x * sdt;
+    };
+    int len = 0;
+    for (int i = 3; i < 6; ++i) {   // motor_angular
+        if (!(motor_axes & (1u << i))) continue;
+        float4 ma; float m_erp, m_cc, m_cg, max_imp;
+        motor_coeffs(i, ma, m_erp, m_cc, m_cg, max_imp);
+        GRow& r = rows[len++];
+        const vec3 aj = bc[i - 3];
+        float rwb = 0.0f;
+        if (m_erp != 0.0f) {
+            const float ce = clampf(aerr[i - 3], -1.0f, 1.0f);
+            const float ang_dist = atan2_poly(ce, sqrtf(max2(1.0f - ce * ce, 0.0f))) * 2.0f;
+            float s_err = ang_dist - ma.y;
+            const float sg = s_err > 0.0f ? 1.0f : (s_err < 0.0f ? -1.0f : 0.0f);
+            const float comp = s_err - sg * 6.2831855f;
+            if (!(fabs1(s_err) < fabs1(comp))) s_err = comp;
+            rwb = rwb + s_err * m_erp;
+        }
+        rwb = rwb + -ma.x;
+        r.lin = zero3(); r.a1 = aj; r.a2 = aj; r.ia1 = smul(g1.ii, aj); r.ia2 = smul(g2.ii, aj);
+        r.inv_lhs = 0.0f; r.cc = m_cc; r.cg = m_cg; r.rhs = rwb; r.rwb = rwb;
+        r.lo = -max_imp; r.hi = max_imp; r.dof = i; r.kind = 2;
+    }
+    for (int i = 0; i < 3; ++i) {   // motor_linear
+        if (!(motor_axes & (1u << i))) continue;
+        float4 ma; float m_erp, m_cc, m_cg, max_imp;
+        motor_coeffs(i, ma, m_erp, m_cc, m_cg, max_imp);
+        GRow r = lock_linear_row(i, 0.0f, 0.0f, i, 2);
+        float rwb = 0.0f;
+        if (m_erp != 0.0f) rwb = rwb + (dot3(lin_err, r.lin) - ma.y) * m_erp;
+        float target_vel = ma.x;
+        if (limit_axes & (1u << i)) {
+            const float dist = dot3(lin_err, r.lin);
+            const float2 lim = w.j_limits[j * 6 + i];
+            target_vel = clampf(target_vel, (lim.x - dist) * inv_dt, (lim.y - dist) * inv_dt);
+        }
+        rwb = rwb + -target_vel;
+        r.cc = m_cc; r.cg = m_cg; r.lo = -max_imp; r.hi = max_imp; r.rhs = rwb; r.rwb = rwb;
+        rows[len++] = r;
+    }
+    grows_finalize(rows, 0, len, imsum);
+    const int start = len;
+    for (int i = 3; i < 6; ++i) {   // lock_angular
+        if (!(locked & (1u << i))) continue;
+        const int ax = i - 3;
+        const float av = comp(a, ax), bv = comp(b, ax);
+        const float dg = wa * wb - ab;
+        const vec3 cx = ax == 0 ? mk3(0.0f, -cv.z, cv.y) : (ax == 1 ? mk3(cv.z, 0.0f, -cv.x) : mk3(-cv.y, cv.x, 0.0f));
+        const vec3 row = mk3((av * b.x + (ax == 0 ? dg : 0.0f) - cx.x + bv * a.x) * 0.5f,
+                             (av * b.y + (ax == 1 ? dg : 0.0f) - cx.y + bv * a.y) * 0.5f,
+                             (av * b.z + (ax == 2 ? dg : 0.0f) - cx.z + bv * a.z) * 0.5f);
+        const vec3 aj = row * sgn;
+        GRow& r = rows[len++];
+        r.lin = zero3(); r.a1 = aj; r.a2 = aj; r.ia1 = smul(g1.ii, aj); r.ia2 = smul(g2.ii, aj);
+        r.inv_lhs = 0.0f; r.cc = cfm_coeff; r.cg = 0.0f; r.rwb = 0.0f;
+        r.rhs = 0.0f + aerr[ax] * erp_inv_dt;
+        r.lo = -FMAX32; r.hi = FMAX32; r.dof = i; r.kind = 0;
+    }
+    for (int i = 0; i < 3; ++i)
+        if (locked & (1u << i)) rows[len++] = lock_linear_row(i, erp_inv_dt, cfm_coeff, i, 0);
+    for (int i = 3; i < 6; ++i) {   // limit_angular on the re-centred angle
+        if (!(limit_axes & (1u << i))) continue;
+        const int ax = i - 3;
+        const float4 al = w.j_anglim[j * 3 + ax];
+        const float x = aerr[ax];
+        const float sin_half = al.x * x - al.y * aew, cos_half = al.x * aew + al.y * x;
+        float half = atan2_poly(sin_half, cos_half);
+        if (fabs1(half) > 1.5707964f) half = half - copysignf(3.1415927f, half);
+        const float ang = half * 2.0f;
+        const bool min_enabled = ang <= -al.z, max_enabled = al.z <= ang;
+        const vec3 aj = bc[ax];
+        const float rhs_bias = clampf((max2(ang - al.z, 0.0f) - max2(-al.z - ang, 0.0f)) * erp_inv_dt, -max_bias, max_bias);
+        GRow& r = rows[len++];
+        r.lin = zero3(); r.a1 = aj; r.a2 = aj; r.ia1 = smul(g1.ii, aj); r.ia2 = smul(g2.ii, aj);
+        r.inv_lhs = 0.0f; r.cc = cfm_coeff; r.cg = 0.0f; r.rwb = 0.0f;
+        r.rhs = 0.0f + rhs_bias;
+        r.lo = min_enabled ? -RB_INF : 0.0f; r.hi = max_enabled ? RB_INF : 0.0f; r.dof = i; r.kind = 1;
+    }
+    for (int i = 0; i < 3; ++i) {   // limit_linear
+        if (!(limit_axes & (1u << i))) continue;
+        GRow r = lock_linear_row(i, erp_inv_dt, cfm_coeff, i, 1);
+        const float dist = dot3(lin_err, r.lin);
+        const float2 lim = w.j_limits[j * 6 + i];
+        const bool min_enabled = dist <= lim.x, max_enabled = lim.y <= dist;
+        const float rhs_bias = clampf((max2(dist - lim.y, 0.0f) - max2(lim.x - dist, 0.0f)) * erp_inv_dt, -max_bias, max_bias);
+        r.rhs = r.rwb + rhs_bias;
+        r.cc = cfm_coeff;
+        r.lo = min_enabled ? -RB_INF : 0.0f; r.hi = max_enabled ? RB_INF : 0.0f;
+        rows[len++] = r;
+    }
+    grows_finalize(rows, start, len, imsum);
+    const size_t rs = (size_t)JROWS_GENERIC * w.joint_cap;   // row stride of the generic row tables
+    for (int k = 0; k < len; ++k) {
+        const size_t s = (size_t)JROWS_GENERIC * q + k;
+        const GRow& r = rows[k];
+        w.j_rows[JR_LIN * rs + s] = f4(r.lin, 0.0f);   // impulse restarts from 0 (warmstart_joints = false)
+        w.j_rows[JR_A1 * rs + s] = f4(r.a1, r.inv_lhs);
+        w.j_rows[JR_A2 * rs + s] = f4(r.a2, r.rhs);
+        w.j_rows[JR_IA1 * rs + s] = f4(r.ia1, r.rwb);
+        w.j_rows[JR_IA2 * rs + s] = f4(r.ia2, r.cg);
+        w.j_bnd[s] = make_float4(r.lo, r.hi, as_float_i(r.dof), as_float_i(r.kind));
+    }
+    h.w = len;
+    w.j_sched_ids[q] = h;
+}
+template <class B>
+RB_HD void joint_solve_generic(const World& w, const B& bd, int q, bool wo_bias) {   // solve_generic with impulse_bounds (joint_velocity_constraint.rs:97-120)
+    const int4 h = w.j_sched_ids[q];
+    const int id1 = h.y, id2 = h.z, len = h.w;
+    BodyState g1 = gather_body(bd, id1), g2 = gather_body(bd, id2);
+    vec3 v1 = g1.lin, w1 = g1.ang, v2 = g2.lin, w2 = g2.ang;
+    const size_t rs = (size_t)JROWS_GENERIC * w.joint_cap;
+    for (int k = 0; k < len; ++k) {
+        const size_t s = (size_t)JROWS_GENERIC * q + k;
+        float4 L = w.j_rows[JR_LIN * rs + s], A1 = w.j_rows[JR_A1 * rs + s], A2 = w.j_rows[JR_A2 * rs + s];
+        const float4 I1 = w.j_rows[JR_IA1 * rs + s], I2 = w.j_rows[JR_IA2 * rs + s], bnd = w.j_bnd[s];
+        const float rhs_c = wo_bias ? I1.w : A2.w;
+        const float dlin = dot3(xyz(L), v2 - v1);
+        const float dang = dot3(xyz(A2), w2) - dot3(xyz(A1), w1);
+        const float rhs = dlin + dang + rhs_c;
+        const float total = clampf(L.w + A1.w * (rhs - I2.w * L.w), bnd.x, bnd.y);
+        const float delta = total - L.w;
+        L.w = total;
+        const vec3 li = xyz(L) * delta;
+        v1 = madd3v(v1, li, g1.im);
+        w1 = madd3(w1, xyz(I1), delta);
+        v2 = madd3v(v2, -li, g2.im);
+        w2 = madd3(w2, xyz(I2), -delta);
+        w.j_rows[JR_LIN * rs + s] = L;
+        if (wo_bias) { A2.w = I1.w; w.j_rows[JR_A2 * rs + s] = A2; }
+    }
+    scatter_vel(bd, id1, v1, w1);
+    scatter_vel(bd, id2, v2, w2);
+}
+RB_HD void joint_writeback_generic(const World& w, int q) {
+    const int4 h = w.j_sched_ids[q];
+    const size_t rs = (size_t)JROWS_GENERIC * w.joint_cap;
+    for (int k = 0; k < h.w; ++k) {
+        const size_t s = (size_t)JROWS_GENERIC * q + k;
+        const float4 bnd = w.j_bnd[s];
+        const int dof = as_int(bnd.z), kind = as_int(bnd.w);
+        float* dst = kind == 0 ? w.j_impulses : (kind == 1 ? w.j_limit_impulses : w.j_motor_impulses);
+        dst[h.x * 6 + dof] = w.j_rows[JR_LIN * rs + s].w;
+    }
+}
+
 // rigid_body_components.rs:528-572 for body b at pose p; writes world_com / effective masses.
 RB_HD void update_world_mass(const World& w, int b, const pose& p) {
     float4 lc = w.b_lcom_im[b];
@@ -966,7 +1215,7 @@ RB_HD void body_writeback(const World& w, const B& bd, int b, int id) {
 
 // Solve one work item from solver-body init to the final positions of its bodies, constraints
 // streaming from HBM/L2 (fallback for items too big for shared memory, items with joints, item 0).
-template <int FM = 0, class X, class B>
+template <int FM = 0, int JM = 0, class X, class B>
 RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec3 gravity) {
     const Params& P = w.prm;
     State* st = w.st;
@@ -1014,7 +1263,7 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
         ex.sync();
         // S4 joint rows from the current poses
         if (j1 > j0) {
-            for (int q = j0 + tid; q < j1; q += nth) joint_update(w, bd, q);
+            for (int q = j0 + tid; q < j1; q += nth) { if (JM) joint_update_generic(w, bd, q); else joint_update(w, bd, q); }
             ex.sync();
         }
         // S5 update + warmstart, colour by colour
@@ -1058,9 +1307,9 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
                     int a = j0 + joff[c], e = j0 + joff[c + 1];
                     if (a >= e) continue;
                     if (c == jovf) {
-                        if (tid == 0) for (int q = a; q < e; ++q) joint_solve(w, bd, q, relax);
+                        if (tid == 0) for (int q = a; q < e; ++q) { if (JM) joint_solve_generic(w, bd, q, relax); else joint_solve(w, bd, q, relax); }
                     } else {
-                        for (int q = a + tid; q < e; q += nth) joint_solve(w, bd, q, relax);
+                        for (int q = a + tid; q < e; q += nth) { if (JM) joint_solve_generic(w, bd, q, relax); else joint_solve(w, bd, q, relax); }
                     }
                     ex.sync();
                 }
@@ -1093,7 +1342,7 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
     }
     // S10 impulse writeback
     for (int q = c0 + tid; q < c1; q += nth) { Cons cc; cons_load<FM>(w, q, cc); cons_writeback<FM>(w, q, buf, cc); }
-    for (int q = j0 + tid; q < j1; q += nth) joint_writeback(w, q);
+    for (int q = j0 + tid; q < j1; q += nth) { if (JM) joint_writeback_generic(w, q); else joint_writeback(w, q); }
     for (int l = b0 + tid; l < b1; l += nth) {
         int b = w.item_bodies[l];
         body_writeback(w, bd, b, global_ids ? b : l - b0);

@@ -249,6 +249,16 @@ struct World {
     float* j_impulses;                // [nj][6]
     float4* j_rows;                   // [JR_ROWS][6 * joint_cap] per-substep rows
     int4* j_sched_ids;                // [joint_cap] joint, id1, id2, nrows in schedule order
+    // limits and motors of the free axes (JointLimits / JointMotor, generic_joint.rs:142-232): only worlds in which some joint
+    // has any take the generic joint path (solve_item<FM, 1>, 12 row slots per joint instead of 6)
+    int generic_joints;
+    uint2* j_axes;                    // limit_axes, motor_axes
+    float2* j_limits;                 // [nj][6] min, max
+    float4* j_motor_a;                // [nj][6] target_vel, target_pos, stiffness, damping
+    float2* j_motor_b;                // [nj][6] max_force, model (int bits)
+    float4* j_anglim;                 // [nj][3] AngularLimitParams: cos, sin of half the centre angle, half range
+    float4* j_bnd;                    // [12 * joint_cap] per generic row: impulse bounds lo hi, dof (int bits), WritebackId kind (int bits)
+    float *j_limit_impulses, *j_motor_impulses;   // [nj][6]
 };
 
 // joint row record (float4 rows), index = 6 * schedule slot + row

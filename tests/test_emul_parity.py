@@ -176,6 +176,17 @@ def test_kinematic_bodies_emulated_kernels():
     kinematic_parity_case(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), lambda s: oracle_lib.OracleWorld(s))
 
 
+def test_joint_limits_and_motors_emulated_kernels():
+    from test_oracle_kat import angular_limits_are_reached, prismatic_limits_and_position_motor
+    from variant_cases import joint_limits_parity_case
+    mk = lambda s: PhysicsWorld(s, _lib=emul_lib.lib())
+    angular_limits_are_reached(mk, cases=((-45.0, 45.0), (45.0, 315.0)))
+    prismatic_limits_and_position_motor(mk)
+    joint_limits_parity_case(mk, lambda s, p=None: oracle_lib.OracleWorld(s, params=p))
+    joint_limits_parity_case(lambda s, p=None: PhysicsWorld(s, integration_parameters=p, _lib=emul_lib.lib()),
+                             lambda s, p=None: oracle_lib.OracleWorld(s, params=p), coulomb=True)
+
+
 def test_quarantine_emulated_kernels():
     from test_oracle_kat import nan_force_is_quarantined
     nan_force_is_quarantined(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), expect_error=True)

@@ -345,3 +345,16 @@ def test_kinematic_bodies(built):
     kinematic_bodies(lambda s: PhysicsWorld(s))
     moving_kinematic_wakes_jointed_dynamic(lambda s: PhysicsWorld(s))
     kinematic_parity_case(lambda s: PhysicsWorld(s), lambda s: oracle_lib.OracleWorld(s))
+
+
+def test_joint_limits_and_motors(built):
+    """Joint limits and motors through the C ABI: issue_499_angular_limits.rs cases, prismatic limits / position spring /
+    bounded motor, and the generic-row scene bit-exact against the oracle under both friction models."""
+    from test_oracle_kat import angular_limits_are_reached, prismatic_limits_and_position_motor
+    from variant_cases import joint_limits_parity_case
+    angular_limits_are_reached(lambda s: PhysicsWorld(s), cases=((-45.0, 45.0), (0.0, 270.0), (45.0, 315.0)))
+    prismatic_limits_and_position_motor(lambda s: PhysicsWorld(s))
+    mk = lambda s, p=None: PhysicsWorld(s, integration_parameters=p)
+    mo = lambda s, p=None: oracle_lib.OracleWorld(s, params=p)
+    joint_limits_parity_case(mk, mo)
+    joint_limits_parity_case(mk, mo, coulomb=True)

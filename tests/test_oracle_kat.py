@@ -664,3 +664,71 @@ def test_kinematic_wakes_jointed_dynamic_oracle():
     w = oracle_lib.OracleWorld(s)
     w.step(60)
     assert w.body_states()[0][1, 0] > 1.0
+
+
+# ---- joint limits and motors (joint_constraint_helper.rs:166-626; crates/rapier3d/tests/issue_499_angular_limits.rs) -----------
+def _settled_angle(make_world, drive, limits_deg, direction):
+    """issue_499_angular_limits.rs:32-100: a bar on a revolute joint about Z with angular limits, driven into a limit
+    by a velocity motor (5 rad/s, factor 20) or by a constant torque; the unwrapped angle after 600 steps, degrees."""
+    import math
+    from rapier_b200.sets import RevoluteJointBuilder
+    s = scenes.Scene("issue_499", gravity=(0.0, 0.0, 0.0))
+    b1 = s.bodies.insert(RigidBodyBuilder.fixed())
+    b2 = s.insert(RigidBodyBuilder.dynamic().translation((1.0, 0.0, 0.0)).angular_damping(3.0).can_sleep(False), ColliderBuilder.cuboid(0.5, 0.1, 0.1))
+    j = RevoluteJointBuilder((0.0, 0.0, 1.0)).local_anchor1((0.0, 0.0, 0.0)).local_anchor2((-1.0, 0.0, 0.0))
+    j = j.limits(3, math.radians(limits_deg[0]), math.radians(limits_deg[1]))
+    if drive == "motor":
+        j = j.motor_velocity(3, direction * 5.0, 20.0)
+    s.joints.insert(b1, b2, j)
+    w = make_world(s)
+    if drive == "torque":
+        w.set_body_forces([b2], torque3=[(0.0, 0.0, direction * 0.1)])
+    unwrapped = prev = 0.0
+    for _ in range(600):
+        w.step()
+        q = w.body_states()[0][b2, 3:7]
+        ang = 2.0 * math.atan2(float(q[2]), float(q[3]))
+        delta = ang - prev
+        if delta > math.pi:
+            delta -= 2.0 * math.pi
+        elif delta < -math.pi:
+            delta += 2.0 * math.pi
+        unwrapped += delta
+        prev = ang
+    return math.degrees(unwrapped)
+
+
+def angular_limits_are_reached(make_world, cases=((-45.0, 45.0), (0.0, 90.0), (0.0, 270.0), (45.0, 315.0), (-170.0, -10.0))):
+    for lim in cases:
+        for drive in ("motor", "torque"):
+            hi = _settled_angle(make_world, drive, lim, 1.0)
+            lo = _settled_angle(make_world, drive, lim, -1.0)
+            assert abs(hi - lim[1]) < 2.0 and abs(lo - lim[0]) < 2.0, (lim, drive, lo, hi)
+    assert _settled_angle(make_world, "motor", (-200.0, 200.0), 1.0) > 360.0   # wider than a turn: free
+
+
+def prismatic_limits_and_position_motor(make_world):
+    """A body on a prismatic joint along X under gravity along +X stops at its upper limit (limit_linear, :166-207); a
+    position motor (spring, motor_linear :285-330) holds another one near its target against gravity; a velocity motor
+    with a small max force cannot lift a third one (impulse bounds)."""
+    from rapier_b200.sets import PrismaticJointBuilder
+    s = scenes.Scene("prismatic", gravity=(3.0, 0.0, 0.0))
+    base = s.bodies.insert(RigidBodyBuilder.fixed())
+    a = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.0, 0.0)).can_sleep(False), ColliderBuilder.cuboid(0.2, 0.2, 0.2))
+    s.joints.insert(base, a, PrismaticJointBuilder((1.0, 0.0, 0.0)).limits(0, -0.5, 1.5))
+    b = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 2.0, 0.0)).can_sleep(False), ColliderBuilder.cuboid(0.2, 0.2, 0.2))
+    s.joints.insert(base, b, PrismaticJointBuilder((1.0, 0.0, 0.0)).local_anchor1((0.0, 2.0, 0.0)).motor_position(0, -0.7, 400.0, 40.0))
+    c = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 4.0, 0.0)).can_sleep(False), ColliderBuilder.cuboid(0.2, 0.2, 0.2))
+    s.joints.insert(base, c, PrismaticJointBuilder((1.0, 0.0, 0.0)).local_anchor1((0.0, 4.0, 0.0)).motor_velocity(0, -2.0, 50.0).motor_max_force(0, 0.05).limits(0, -3.0, 0.8))
+    w = make_world(s)
+    w.step(400)
+    pose, vel = w.body_states()
+    assert abs(pose[a, 0] - 1.5) < 0.02 and abs(vel[a, 0]) < 0.02 and abs(pose[a, 1]) < 1e-3
+    assert abs(pose[b, 0] - (-0.7)) < 0.05 and abs(vel[b, 0]) < 0.02     # acceleration-based spring: offset g / k = 3 / 400
+    assert abs(pose[c, 0] - 0.8) < 0.02                                     # the weak motor loses against gravity: upper limit
+
+
+def test_joint_limits_and_motors_oracle():
+    mk = lambda s: oracle_lib.OracleWorld(s)
+    angular_limits_are_reached(mk)
+    prismatic_limits_and_position_motor(mk)

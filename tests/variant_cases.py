@@ -4,6 +4,7 @@ friction in the bias pass, collision groups, joints with contacts disabled, mult
 user forces, damping, locked axes)."""
 from rapier_b200 import _abi as A
 from rapier_b200 import scenes
+import numpy as np
 from rapier_b200.sets import ColliderBuilder, FixedJointBuilder, RigidBodyBuilder, SphericalJointBuilder
 
 
@@ -187,6 +188,61 @@ def kinematic_parity_case(make_world, make_oracle, steps=150, every=15):
             d = compare_worlds(w, o)
             assert is_exact(d), (i, d)
     return w
+
+
+def joint_limits_scene():
+    """Every generic joint row kind next to contacts: revolute joints with angular limits and velocity / position motors
+    (force- and acceleration-based), prismatic joints with linear limits and motors, a spherical joint with angular motors on
+    all three axes, locked-only joints (fixed, spherical) in the same world, a jointed chain resting on the ground."""
+    from rapier_b200.sets import PrismaticJointBuilder, RevoluteJointBuilder
+    s = scenes.Scene("joint_limits")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(30.0, 0.5, 30.0))
+    base = s.bodies.insert(RigidBodyBuilder.fixed().translation((0.0, 4.0, 0.0)))
+    prev = base
+    for i in range(5):   # a chain of bars on limited revolute joints, the last ones motorised
+        b = s.insert(RigidBodyBuilder.dynamic().translation((1.0 + 1.0 * i, 4.0, 0.0)), ColliderBuilder.cuboid(0.45, 0.1, 0.1))
+        j = RevoluteJointBuilder((0.0, 0.0, 1.0)).local_anchor1((0.5 if i else 0.0, 0.0, 0.0)).local_anchor2((-0.5, 0.0, 0.0)).limits(3, -0.6 - 0.1 * i, 0.3 + 0.2 * i)
+        if i == 3:
+            j = j.motor_velocity(3, 2.0, 5.0).motor_max_force(3, 40.0)
+        if i == 4:
+            j = j.motor_position(3, 0.4, 30.0, 3.0).motor_model(3, 1)
+        s.joints.insert(prev, b, j)
+        prev = b
+    for k in range(3):   # sliders: limits, a position spring, a velocity motor against a limit
+        b = s.insert(RigidBodyBuilder.dynamic().translation((-4.0, 1.0 + 1.5 * k, 2.0 * k)), ColliderBuilder.cuboid(0.3, 0.3, 0.3))
+        j = PrismaticJointBuilder((0.3, 1.0, 0.1)).local_anchor1((-4.0, 1.5 + 1.5 * k, 2.0 * k)).limits(0, -0.8, 0.6)
+        if k == 1:
+            j = j.motor_position(0, 0.3, 60.0, 6.0)
+        if k == 2:
+            j = j.motor_velocity(0, 1.5, 10.0)
+        s.joints.insert(base, b, j)
+    ball = s.insert(RigidBodyBuilder.dynamic().translation((5.0, 3.0, 0.0)), ColliderBuilder.cuboid(0.4, 0.2, 0.3))
+    j = SphericalJointBuilder().local_anchor1((5.0, -0.5, 0.0)).local_anchor2((0.0, 0.5, 0.0))
+    for ax in (3, 4, 5):
+        j = j.motor(ax, 0.2 * (ax - 3), 0.5, 20.0, 2.0).limits(ax, -1.0, 1.2) if ax != 4 else j.motor_velocity(ax, 1.0, 4.0)
+    s.joints.insert(base, ball, j)
+    a = s.insert(RigidBodyBuilder.dynamic().translation((8.0, 0.5, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    b = s.insert(RigidBodyBuilder.dynamic().translation((9.0, 0.5, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    s.joints.insert(a, b, FixedJointBuilder().local_anchor1((0.5, 0.0, 0.0)).local_anchor2((-0.5, 0.0, 0.0)))
+    c = s.insert(RigidBodyBuilder.dynamic().translation((9.0, 1.6, 0.0)), ColliderBuilder.ball(0.5))
+    s.joints.insert(b, c, SphericalJointBuilder().local_anchor1((0.0, 0.55, 0.0)).local_anchor2((0.0, -0.55, 0.0)))
+    return s
+
+
+def joint_limits_parity_case(make_world, make_oracle, steps=150, every=15, coulomb=False):
+    from parity_util import compare_worlds, is_exact
+    s = joint_limits_scene()
+    p = _params(friction_model=1) if coulomb else None
+    w, o = (make_world(s, p), make_oracle(s, p)) if coulomb else (make_world(s), make_oracle(s))
+    for i in range(steps):
+        w.step(); o.step()
+        if i % every == every - 1 or i < 2:
+            d = compare_worlds(w, o)
+            assert is_exact(d), (i, d)
+            ji_w, ji_o = w.debug_read("joint_impulses", np.float32), o.debug_read("joint_impulses", np.float32)
+            assert (ji_w.view(np.uint32) == ji_o.view(np.uint32)).all(), i
+    pose, _ = w.body_states()
+    assert np.isfinite(pose).all()
 
 
 VARIANTS = [
