@@ -167,6 +167,12 @@ int orc_world_drain_collision_events(OrcWorld* o, int32_t cap, RbCollisionEvent*
     if (!o) return RB_ERR_INVALID;
     std::vector<RbCollisionEvent>& ev = o->w.collision_events;
     const int n = (int)ev.size();
+    std::sort(ev.begin(), ev.end(), [](const RbCollisionEvent& a, const RbCollisionEvent& b) {   // the drain order of the C ABI: (step, collider1, collider2, started)
+        if (a.step != b.step) return a.step < b.step;
+        if (a.collider1 != b.collider1) return a.collider1 < b.collider1;
+        if (a.collider2 != b.collider2) return a.collider2 < b.collider2;
+        return a.started < b.started;
+    });
     for (int i = 0; i < n && i < cap && out; ++i) out[i] = ev[i];
     ev.clear();
     return n;

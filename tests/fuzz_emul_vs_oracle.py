@@ -1,7 +1,9 @@
 """Differential fuzzing on the CPU (helper, also driven by tests/test_fuzz.py with a few seeds): random small
 scenes -- cuboids and balls of random sizes, poses, velocities, materials, collision groups, locked axes,
-additional mass, spherical / fixed / revolute joints -- stepped through the host emulation of the kernels and
-through the oracle; every pose, velocity and persistent contact table must agree bit for bit.
+additional mass, spherical / fixed / revolute / prismatic joints with random limits and motors, kinematic bodies
+(velocity- and position-based), fast bodies (CCD), either friction model, collision / contact-force events --
+stepped through the host emulation of the kernels and through the oracle; every pose, velocity, persistent
+contact table, joint impulse and event must agree bit for bit.
 
     python tests/fuzz_emul_vs_oracle.py [first_seed] [count]
 """
@@ -18,8 +20,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def random_scene(seed):
     from rapier_b200 import _abi as A
     from rapier_b200 import scenes
-    from rapier_b200.sets import (ColliderBuilder, FixedJointBuilder, RevoluteJointBuilder, RigidBodyBuilder,
-                                  SphericalJointBuilder)
+    from rapier_b200.sets import (ColliderBuilder, FixedJointBuilder, PrismaticJointBuilder, RevoluteJointBuilder,
+                                  RigidBodyBuilder, SphericalJointBuilder)
     r = np.random.default_rng(seed)
     s = scenes.Scene(f"fuzz_{seed}", gravity=(0.0, float(r.choice([-9.81, -10.0, -3.0])), 0.0))
     s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)),
@@ -29,11 +31,16 @@ def random_scene(seed):
             s.colliders.insert(ColliderBuilder.cuboid(0.3, 1.5, 3.0).translation((4.0 + i * 0.7, 1.5, 0.0)))
     n = int(r.integers(2, 40))
     handles = []
+    kinematic = []
     dense = r.random() < 0.5    # dense: bodies start close together (many contacts); sparse: mostly free fall
     span = 1.5 if dense else 5.0
     for i in range(n):
         pos = (float(r.uniform(-span, span)), float(r.uniform(0.4, 3.0 if dense else 8.0)), float(r.uniform(-span, span)))
-        b = RigidBodyBuilder.dynamic().translation(pos)
+        kin = r.random() < 0.08
+        b = (RigidBodyBuilder.kinematic_velocity_based() if r.random() < 0.5 else RigidBodyBuilder.kinematic_position_based()) if kin else RigidBodyBuilder.dynamic()
+        b = b.translation(pos)
+        if r.random() < 0.06:   # a fast body: CCD motion clamping against the ground / the walls
+            b = b.linvel((float(r.uniform(-150.0, 150.0)), float(r.uniform(-200.0, 20.0)), float(r.uniform(-150.0, 150.0))))
         if r.random() < 0.7:
             b = b.rotation(tuple(float(x) for x in r.uniform(-1.0, 1.0, 3)))
         if r.random() < 0.5:
@@ -56,13 +63,33 @@ def random_scene(seed):
             c = c.collision_groups(int(r.choice([1, 2, 3])), int(r.choice([1, 2, 3])))
         if r.random() < 0.1:
             c = c.translation(tuple(float(x) for x in r.uniform(-0.3, 0.3, 3)))
+        if r.random() < 0.3:
+            c = c.active_events(int(r.integers(1, 4))).contact_force_event_threshold(float(r.choice([0.0, 5.0, 50.0])))
         handles.append(s.insert(b, c))
+        if kin:
+            kinematic.append(handles[-1])
+    generic = r.random() < 0.4
     for _ in range(int(r.integers(0, max(1, n // 4)))):
         a, b = (int(x) for x in r.choice(handles, 2, replace=False)) if n >= 2 else (handles[0], handles[0])
         if a == b:
             continue
-        kind = r.integers(0, 3)
-        j = SphericalJointBuilder() if kind == 0 else (FixedJointBuilder() if kind == 1 else RevoluteJointBuilder(tuple(float(x) for x in r.choice([(1, 0, 0), (0, 0, 1), (0.6, 0.0, 0.8)]))))
+        kind = r.integers(0, 4)
+        axis = tuple(float(x) for x in r.choice([(1, 0, 0), (0, 0, 1), (0.6, 0.0, 0.8)]))
+        j = SphericalJointBuilder() if kind == 0 else (FixedJointBuilder() if kind == 1 else (RevoluteJointBuilder(axis) if kind == 2 else PrismaticJointBuilder(axis)))
+        if generic and kind != 1:   # limits / motors on the free axes
+            for ax in ((3, 4, 5) if kind == 0 else ((3,) if kind == 2 else (0,))):
+                if r.random() < 0.6:
+                    lo = float(r.uniform(-1.5, 0.2))
+                    j = j.limits(ax, lo, lo + float(r.uniform(0.1, 2.5)))
+                m = r.random()
+                if m < 0.3:
+                    j = j.motor_velocity(ax, float(r.uniform(-3.0, 3.0)), float(r.uniform(0.5, 30.0)))
+                elif m < 0.5:
+                    j = j.motor_position(ax, float(r.uniform(-1.0, 1.0)), float(r.uniform(5.0, 200.0)), float(r.uniform(0.5, 20.0)))
+                if m < 0.5 and r.random() < 0.4:
+                    j = j.motor_max_force(ax, float(r.uniform(0.5, 50.0)))
+                if m < 0.5 and r.random() < 0.3:
+                    j = j.motor_model(ax, 1)
         j = j.local_anchor1(tuple(float(x) for x in r.uniform(-0.5, 0.5, 3))).local_anchor2(tuple(float(x) for x in r.uniform(-0.5, 0.5, 3)))
         if r.random() < 0.3:
             j = j.contacts_enabled(False)
@@ -75,6 +102,11 @@ def random_scene(seed):
         params.warmstart_coefficient = float(r.choice([0.0, 0.5, 1.0]))
         params.friction_in_bias_pass = int(r.choice([0, 1]))
         params.contact_recycling = int(r.choice([0, 1]))
+    if r.random() < 0.3:
+        params.friction_model = 1
+    if r.random() < 0.15:
+        params.max_ccd_substeps = 0
+    s.kinematic_position_based = [h for h in kinematic if s.bodies.descs[h].body_type == A.RB_BODY_KINEMATIC_POSITION_BASED]
     return s, params
 
 
@@ -90,13 +122,25 @@ def run(seed, steps=90, smem_floats=None):
     scene, params = random_scene(seed)
     w = PhysicsWorld(scene, integration_parameters=params, _lib=emul_lib.lib())
     o = oracle_lib.OracleWorld(scene, params=params)
+    import math
     for i in range(steps):
+        if scene.kinematic_position_based and i % 2 == 0:   # drive the position-based kinematic bodies along a curve
+            t = 0.02 * (i + 1)
+            poses = [(scene.bodies.descs[h].translation[0] + math.sin(t + h), scene.bodies.descs[h].translation[1] + 0.5 * t,
+                      scene.bodies.descs[h].translation[2], 0.0, math.sin(0.3 * t), 0.0, math.cos(0.3 * t)) for h in scene.kinematic_position_based]
+            w.set_next_kinematic_positions(scene.kinematic_position_based, poses)
+            o.set_next_kinematic_positions(scene.kinematic_position_based, poses)
         w.step()
         o.step()
         if i % 15 == 14 or i < 2:
             d = compare_worlds(w, o)
             if not is_exact(d):
                 return False, f"seed {seed} step {i}: {d}"
+            if w.collision_events() != o.collision_events() or w.contact_force_events() != o.contact_force_events():
+                return False, f"seed {seed} step {i}: event lists differ"
+            ji_w, ji_o = w.debug_read("joint_impulses", np.float32), o.debug_read("joint_impulses", np.float32)
+            if not (ji_w.view(np.uint32) == ji_o.view(np.uint32)).all():
+                return False, f"seed {seed} step {i}: joint impulses differ"
     pose, vel = w.body_states()
     if not (np.isfinite(pose).all() and np.isfinite(vel).all()):
         return False, f"seed {seed}: non-finite state"
