@@ -96,7 +96,7 @@ typedef struct RbBodyDesc {
     float user_torque[3];
 } RbBodyDesc;
 
-enum { RB_SHAPE_BALL = 0, RB_SHAPE_CUBOID = 1 };
+enum { RB_SHAPE_BALL = 0, RB_SHAPE_CUBOID = 1, RB_SHAPE_CAPSULE = 2 };
 
 /* CoefficientCombineRule (src/dynamics/coefficient_combine_rule.rs:8-22). */
 enum { RB_COMBINE_AVERAGE = 0, RB_COMBINE_MIN = 1, RB_COMBINE_MULTIPLY = 2, RB_COMBINE_MAX = 3,
@@ -105,7 +105,7 @@ enum { RB_COMBINE_AVERAGE = 0, RB_COMBINE_MIN = 1, RB_COMBINE_MULTIPLY = 2, RB_C
 /* One collider (src/geometry/collider.rs; ColliderBuilder defaults :688-707). */
 typedef struct RbColliderDesc {
     int32_t shape;                /* RB_SHAPE_* */
-    float half_extents[3];        /* cuboid half extents; ball: [radius, 0, 0] */
+    float half_extents[3];        /* cuboid half extents; ball: [radius, 0, 0]; capsule: [half height, radius, axis 0 | 1 | 2] */
     int32_t parent;               /* body index, or -1 for a parentless (fixed) collider */
     float pos_wrt_parent_t[3];    /* pose relative to the parent (world pose if parent == -1) */
     float pos_wrt_parent_q[4];

@@ -80,6 +80,7 @@ class ColliderBuilder {
 public:
     static ColliderBuilder cuboid(float hx, float hy, float hz) { return ColliderBuilder(RB_SHAPE_CUBOID, hx, hy, hz); }
     static ColliderBuilder ball(float r) { return ColliderBuilder(RB_SHAPE_BALL, r, 0.0f, 0.0f); }
+    static ColliderBuilder capsule_y(float half_height, float radius) { return ColliderBuilder(RB_SHAPE_CAPSULE, half_height, radius, 1.0f); }
     ColliderBuilder& density(float x) { d_.density = x; return *this; }
     ColliderBuilder& mass(float m) {   // ColliderMassProps::Mass: the density that gives the shape this mass
         const float* h = d_.half_extents;

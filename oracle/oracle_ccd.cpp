@@ -150,7 +150,7 @@ void ccd_motion_clamping(World& w) {
         float frac = 1.0f;
         for (int ci = 0; ci < (int)w.colliders.size(); ++ci) {
             const Collider& c1 = w.colliders[ci];
-            if (c1.parent != bi || c1.shape < 0) continue;
+            if (c1.parent != bi || c1.shape < 0 || c1.shape == RB_SHAPE_CAPSULE) continue;   // (capsules are not swept)
             const Pose cs = pose_mul(b.pos, c1.pos_wrt_parent), ce = pose_mul(b.next_pos, c1.pos_wrt_parent);
             const Sweep sw = sweep_from_poses(cs, ce, pose_inv_point(c1.pos_wrt_parent, b.local_com));
             const Aabb a1 = shape_aabb(c1.shape, c1.he, cs), a2 = shape_aabb(c1.shape, c1.he, ce);
@@ -158,7 +158,7 @@ void ccd_motion_clamping(World& w) {
             swept.mins = V3{fmin2(a1.mins.x, a2.mins.x), fmin2(a1.mins.y, a2.mins.y), fmin2(a1.mins.z, a2.mins.z)};
             swept.maxs = V3{fmax2(a1.maxs.x, a2.maxs.x), fmax2(a1.maxs.y, a2.maxs.y), fmax2(a1.maxs.z, a2.maxs.z)};
             for (const Collider& c2 : w.colliders) {
-                if (c2.shape < 0) continue;
+                if (c2.shape < 0 || c2.shape == RB_SHAPE_CAPSULE) continue;
                 if (c2.parent >= 0 && w.bodies[c2.parent].type != RB_BODY_FIXED) continue;   // tier_allows: fixed targets only
                 const Aabb& f = c2.fat;   // (any superset of the colliders within the prediction distance gives the same minimum)
                 if (!(swept.mins.x <= f.maxs.x && swept.mins.y <= f.maxs.y && swept.mins.z <= f.maxs.z && swept.maxs.x >= f.mins.x &&

@@ -324,11 +324,202 @@ static bool cuboid_ball(V3 he, float r, const Pose& posb_c, float prediction, V3
     return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Capsules (parry Capsule: segment + radius; he = (half height, radius, axis)).  PARITY UNPINNED like the cuboid
+// manifolds: parry's contact_manifold_capsule_capsule / _cuboid_capsule / _ball_convex are not in the tree, so the
+// manifolds are written from first principles (closest features of the segment cores, points on the surfaces).
+// ---------------------------------------------------------------------------------------------
+static inline V3 capsule_dir(V3 he) { return he.z == 0.0f ? V3{1.f, 0.f, 0.f} : (he.z == 1.0f ? V3{0.f, 1.f, 0.f} : V3{0.f, 0.f, 1.f}); }
+static inline V3 vwith(V3 v, int i, float x) { vset(v, i, x); return v; }
+
+// closest points of two segments (Ericson, Real-Time Collision Detection, 5.1.9)
+static void seg_seg_params(V3 p1, V3 d1, V3 p2, V3 d2, float& s, float& t) {
+    const V3 r = p1 - p2;
+    const float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r);
+    if (a <= F32_EPS && e <= F32_EPS) { s = 0.0f; t = 0.0f; return; }
+    if (a <= F32_EPS) { s = 0.0f; t = fclamp(f / e, 0.0f, 1.0f); return; }
+    const float c = dot(d1, r);
+    if (e <= F32_EPS) { t = 0.0f; s = fclamp(-c / a, 0.0f, 1.0f); return; }
+    const float b = dot(d1, d2);
+    const float denom = a * e - b * b;
+    s = denom > 1.0e-6f * a * e ? fclamp((b * f - c * e) / denom, 0.0f, 1.0f) : 0.0f;
+    t = (b * s + f) / e;
+    if (t < 0.0f) { t = 0.0f; s = fclamp(-c / a, 0.0f, 1.0f); }
+    else if (t > 1.0f) { t = 1.0f; s = fclamp((b - c) / a, 0.0f, 1.0f); }
+}
+
+static void manifold_capsule_capsule(V3 he1, V3 he2, const Pose& p12, float prediction, RawManifold& m) {
+    m.n = 0; m.local_n1 = vzero(); m.local_n2 = vzero();
+    const float hh1 = he1.x, r1 = he1.y, hh2 = he2.x, r2 = he2.y;
+    const V3 u1 = capsule_dir(he1), u2 = qrot(p12.q, capsule_dir(he2));
+    const V3 a1 = u1 * (-hh1), d1 = u1 * (2.0f * hh1);
+    const V3 a2 = p12.t - u2 * hh2, d2 = u2 * (2.0f * hh2);
+    const V3 cr = cross(d1, d2);
+    const float l1 = length_sq(d1), l2 = length_sq(d2);
+    if (l1 > F32_EPS && l2 > F32_EPS && length_sq(cr) <= 1.0e-6f * l1 * l2) {
+        const float inv = 1.0f / l1;
+        const float ta = dot(a2 - a1, d1) * inv, tb = dot((a2 + d2) - a1, d1) * inv;
+        const float lo = fmax2(fmin2(ta, tb), 0.0f), hi = fmin2(fmax2(ta, tb), 1.0f);
+        if (hi > lo) {
+            const V3 w0 = a2 - a1;
+            const V3 wv = w0 - d1 * (dot(w0, d1) * inv);
+            const float wl = length(wv);
+            const V3 n1 = wl > F32_EPS ? wv * (1.0f / wl) : orthonormal_vector(u1);
+            const float dist = wl - r1 - r2;
+            if (!(dist < prediction)) return;
+            const float ts[2] = {lo, hi};
+            for (int k = 0; k < 2; ++k) {
+                const V3 q1 = a1 + d1 * ts[k];
+                const V3 q2 = q1 + n1 * wl;
+                push_point(m, q1 + n1 * r1, pose_inv_point(p12, q2 - n1 * r2), 0x10000000u | (uint32_t)k, 0x10000000u | (uint32_t)k, dist);
+            }
+            m.local_n1 = n1;
+            m.local_n2 = qrot_inv(p12.q, -n1);
+            return;
+        }
+    }
+    float s, t;
+    seg_seg_params(a1, d1, a2, d2, s, t);
+    const V3 q1 = a1 + d1 * s, q2 = a2 + d2 * t;
+    const V3 dl = q2 - q1;
+    const float len = length(dl);
+    V3 n1;
+    if (len > F32_EPS) n1 = dl * (1.0f / len);
+    else { const float cl = length(cr); n1 = cl > F32_EPS ? cr * (1.0f / cl) : orthonormal_vector(u1); }
+    const float dist = len - r1 - r2;
+    if (!(dist < prediction)) return;
+    push_point(m, q1 + n1 * r1, pose_inv_point(p12, q2 - n1 * r2), 0x30000000u | 2u, 0x30000000u | 2u, dist);
+    m.local_n1 = n1;
+    m.local_n2 = qrot_inv(p12.q, -n1);
+}
+
+static bool capsule_ball(V3 hec, float rb, const Pose& pb, float prediction, V3& p_cap, V3& p_ball, V3& n_cap, V3& n_ball, float& dist) {
+    const float hh = hec.x, rc = hec.y;
+    const V3 u = capsule_dir(hec);
+    const V3 a = u * (-hh), d = u * (2.0f * hh);
+    const float l2 = length_sq(d);
+    const float t = l2 > F32_EPS ? fclamp(dot(pb.t - a, d) / l2, 0.0f, 1.0f) : 0.0f;
+    const V3 q = a + d * t;
+    const V3 dl = pb.t - q;
+    const float len = length(dl);
+    const V3 n = len > F32_EPS ? dl * (1.0f / len) : orthonormal_vector(u);
+    dist = len - rc - rb;
+    if (!(dist < prediction)) return false;
+    n_cap = n; n_ball = qrot_inv(pb.q, -n);
+    p_cap = q + n * rc; p_ball = n_ball * rb;
+    return true;
+}
+
+static void cuboid_capsule(V3 he, V3 hec, const Pose& pc, float prediction, RawManifold& m) {
+    m.n = 0; m.local_n1 = vzero(); m.local_n2 = vzero();
+    const float hh = hec.x, r = hec.y;
+    const V3 u = qrot(pc.q, capsule_dir(hec));
+    const V3 A = pc.t - u * hh, B = pc.t + u * hh;
+    float best = -3.4028235e38f;
+    V3 n = V3{0.f, 1.f, 0.f};
+    int kind = 0, bi = 0;
+    for (int i = 0; i < 3; ++i) {
+        const float ai = vget(A, i), bb = vget(B, i), h = vget(he, i);
+        const float sp = fmin2(ai, bb) - h, sm = -fmax2(ai, bb) - h;
+        if (sp > best) { best = sp; n = vwith(vzero(), i, 1.0f); kind = 0; bi = i; }
+        if (sm > best) { best = sm; n = vwith(vzero(), i, -1.0f); kind = 0; bi = i; }
+    }
+    for (int i = 0; i < 3; ++i) {
+        const V3 c = cross(vwith(vzero(), i, 1.0f), u);
+        const float l2 = length_sq(c);
+        if (!(l2 > 1.0e-6f)) continue;
+        V3 nn = c * (1.0f / sqrtf(l2));
+        float s0 = dot(nn, A);
+        if (s0 < 0.0f) { nn = -nn; s0 = -s0; }
+        const float sep = s0 - fma_(he.z, fabsf(nn.z), fma_(he.y, fabsf(nn.y), he.x * fabsf(nn.x)));
+        if (sep > best) { best = sep; n = nn; kind = 1; bi = i; }
+    }
+    if (!(best - r < prediction)) return;
+    const V3 D = B - A;
+    if (kind == 0) {
+        const float sg = vget(n, bi);
+        float t0 = 0.0f, t1 = 1.0f;
+        bool miss = false;
+        for (int j = 0; j < 3; ++j) {
+            if (j == bi) continue;
+            const float aj = vget(A, j), dj = vget(D, j), h = vget(he, j);
+            if (fabsf(dj) <= F32_EPS) { if (fabsf(aj) > h) miss = true; continue; }
+            float ta = (-h - aj) / dj, tb = (h - aj) / dj;
+            if (ta > tb) { const float tmp = ta; ta = tb; tb = tmp; }
+            t0 = fmax2(t0, ta); t1 = fmin2(t1, tb);
+        }
+        if (!miss && t0 <= t1) {
+            const float ts[2] = {t0, t1};
+            const int np = (t1 - t0 > 1.0e-5f) ? 2 : 1;
+            for (int k = 0; k < np; ++k) {
+                const V3 q = A + D * ts[k];
+                const float dp = sg * vget(q, bi) - vget(he, bi);
+                const float dist = dp - r;
+                if (!(dist < prediction)) continue;
+                push_point(m, q - n * dp, pose_inv_point(pc, q - n * r), 0x20000000u | (uint32_t)(bi + (sg < 0.0f ? 3 : 0)), 0x10000000u | (uint32_t)k, dist);
+            }
+            m.local_n1 = n;
+            m.local_n2 = qrot_inv(pc.q, -n);
+            return;
+        }
+        const V3 q = (sg * vget(A, bi) <= sg * vget(B, bi)) ? A : B;
+        const V3 pb = V3{fclamp(q.x, -he.x, he.x), fclamp(q.y, -he.y, he.y), fclamp(q.z, -he.z, he.z)};
+        const V3 dl = q - pb;
+        const float len = length(dl);
+        const V3 nn = len > F32_EPS ? dl * (1.0f / len) : n;
+        const float dist = len - r;
+        if (!(dist < prediction)) return;
+        push_point(m, pb, pose_inv_point(pc, q - nn * r), vertex_id(pb), 0x10000000u | 3u, dist);
+        m.local_n1 = nn;
+        m.local_n2 = qrot_inv(pc.q, -nn);
+        return;
+    }
+    V3 e0 = support_point(he, n), ed = vzero();
+    vset(e0, bi, -vget(he, bi));
+    vset(ed, bi, 2.0f * vget(he, bi));
+    float s, t;
+    seg_seg_params(e0, ed, A, D, s, t);
+    const V3 pe = e0 + ed * s, q = A + D * t;
+    const float dist = dot(q - pe, n) - r;
+    if (!(dist < prediction)) return;
+    push_point(m, pe, pose_inv_point(pc, q - n * r), 0x30000000u | ((uint32_t)bi << 4) | (vertex_id(e0) & 7u), 0x30000000u | 2u, dist);
+    m.local_n1 = n;
+    m.local_n2 = qrot_inv(pc.q, -n);
+}
+
+static void manifold_flip(const RawManifold& a, RawManifold& m) {
+    m.n = a.n; m.local_n1 = a.local_n2; m.local_n2 = a.local_n1;
+    for (int i = 0; i < a.n; ++i) {
+        m.pts[i].local_p1 = a.pts[i].local_p2; m.pts[i].local_p2 = a.pts[i].local_p1; m.pts[i].dist = a.pts[i].dist;
+        m.pts[i].fid1 = a.pts[i].fid2; m.pts[i].fid2 = a.pts[i].fid1;
+    }
+}
+static void contact_manifold_capsules(int sh1, V3 he1, int sh2, V3 he2, const Pose& p12, float prediction, RawManifold& m) {
+    m.n = 0; m.local_n1 = vzero(); m.local_n2 = vzero();
+    if (sh1 == RB_SHAPE_CAPSULE && sh2 == RB_SHAPE_CAPSULE) { manifold_capsule_capsule(he1, he2, p12, prediction, m); return; }
+    if (sh1 == RB_SHAPE_CUBOID) { cuboid_capsule(he1, he2, p12, prediction, m); return; }
+    if (sh2 == RB_SHAPE_CUBOID) {
+        RawManifold t;
+        cuboid_capsule(he2, he1, pose_inverse(p12), prediction, t);
+        manifold_flip(t, m);
+        return;
+    }
+    V3 pc, pb, nc, nb;
+    float d;
+    if (sh1 == RB_SHAPE_CAPSULE) {
+        if (capsule_ball(he1, he2.x, p12, prediction, pc, pb, nc, nb, d)) { push_point(m, pc, pb, 0x30000000u | 2u, 0x20000000u, d); m.local_n1 = nc; m.local_n2 = nb; }
+    } else {
+        if (capsule_ball(he2, he1.x, pose_inverse(p12), prediction, pc, pb, nc, nb, d)) { push_point(m, pb, pc, 0x20000000u, 0x30000000u | 2u, d); m.local_n1 = nb; m.local_n2 = nc; }
+    }
+}
+
 void contact_manifold(int shape1, V3 he1, int shape2, V3 he2, const Pose& pos12, float prediction,
                       RawManifold& m) {
     m.n = 0;
     m.local_n1 = vzero();
     m.local_n2 = vzero();
+    if (shape1 == RB_SHAPE_CAPSULE || shape2 == RB_SHAPE_CAPSULE) { contact_manifold_capsules(shape1, he1, shape2, he2, pos12, prediction, m); return; }
     if (shape1 == RB_SHAPE_CUBOID && shape2 == RB_SHAPE_CUBOID) {
         manifold_cuboid_cuboid(he1, he2, pos12, prediction, m);
     } else if (shape1 == RB_SHAPE_BALL && shape2 == RB_SHAPE_BALL) {
@@ -360,6 +551,9 @@ Aabb shape_aabb(int shape, V3 he, const Pose& pos) {
     V3 ws;
     if (shape == RB_SHAPE_BALL) {
         ws = V3{he.x, he.x, he.x};
+    } else if (shape == RB_SHAPE_CAPSULE) {
+        const V3 u = qrot(pos.q, capsule_dir(he));
+        ws = V3{fabsf(u.x) * he.x + he.y, fabsf(u.y) * he.x + he.y, fabsf(u.z) * he.x + he.y};
     } else {
         M3 r = qto_mat(pos.q);
         ws = V3{fabsf(r.c0.x) * he.x + fabsf(r.c1.x) * he.y + fabsf(r.c2.x) * he.z,

@@ -33,6 +33,20 @@ static void collider_mass(const Collider& c, float& mass, V3& principal) {
         V3 unit = V3{(sq.y + sq.z) * third, (sq.x + sq.z) * third, (sq.x + sq.y) * third};
         mass = vol * c.density;
         principal = unit * mass;
+    } else if (c.shape == RB_SHAPE_CAPSULE) {   // parry MassProperties::from_capsule (restated: cylinder + two half balls)
+        const float hh = c.he.x, r = c.he.y;
+        const int ax = (int)c.he.z;
+        const float pi_ = 3.14159265358979323846f;
+        const float cyl_vol = hh * r * r * pi_ * 2.0f, ball_vol = pi_ * r * r * r * 4.0f / 3.0f;
+        const float sq_r = r * r, sq_h = hh * hh * 4.0f;
+        const float cyl_off = (sq_r * 3.0f + sq_h) / 12.0f, cyl_axis = sq_r / 2.0f, ball_unit = sq_r * 2.0f / 5.0f;
+        const float h = hh * 2.0f;
+        const float extra = (h * h * 0.25f + h * r * 3.0f / 8.0f) * ball_vol * c.density;
+        const float i_off = (cyl_off * cyl_vol + ball_unit * ball_vol) * c.density + extra;
+        const float i_axis = (cyl_axis * cyl_vol + ball_unit * ball_vol) * c.density;
+        mass = (cyl_vol + ball_vol) * c.density;
+        principal = V3{i_off, i_off, i_off};
+        vset(principal, ax, i_axis);
     } else {
         float r = c.he.x;
         float vol = 3.14159265358979323846f * r * r * r * 4.0f / 3.0f;
@@ -135,8 +149,9 @@ static int recompute_mass_properties(World& w, int first_body = 0, int first_col
         for (size_t ci = (size_t)first_collider; ci < w.colliders.size(); ++ci) {
             const Collider& c = w.colliders[ci];
             if (c.parent != bi) continue;
-            b.ccd_thickness = fmin2(b.ccd_thickness, c.shape == RB_SHAPE_BALL ? c.he.x : fmin2(c.he.x, fmin2(c.he.y, c.he.z)));
-            const float radius = c.shape == RB_SHAPE_BALL ? c.he.x : length(c.he);
+            if (c.shape != RB_SHAPE_CAPSULE)   // (capsules are never swept here: they do not count)
+                b.ccd_thickness = fmin2(b.ccd_thickness, c.shape == RB_SHAPE_BALL ? c.he.x : fmin2(c.he.x, fmin2(c.he.y, c.he.z)));
+            const float radius = c.shape == RB_SHAPE_BALL ? c.he.x : (c.shape == RB_SHAPE_CAPSULE ? c.he.x + c.he.y : length(c.he));
             b.max_extent = fmax2(b.max_extent, length(c.pos_wrt_parent.t - b.local_com) + radius);
         }
     }
@@ -356,6 +371,7 @@ static float shape_origin_radius(int shape, V3 he) {  // pair_update.rs:591-595 
         V3 c = V3{he.x, he.x, he.x};
         return length(c);
     }
+    if (shape == RB_SHAPE_CAPSULE) return length(V3{he.y, he.x + he.y, he.y});
     return length(he);
 }
 
@@ -796,7 +812,7 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
     for (int i = 0; i < nc; ++i) {
         Collider& c = w.colliders[i];
         const RbColliderDesc& d = cd[i];
-        if (d.shape != RB_SHAPE_BALL && d.shape != RB_SHAPE_CUBOID) return RB_ERR_INVALID;
+        if (d.shape != RB_SHAPE_BALL && d.shape != RB_SHAPE_CUBOID && d.shape != RB_SHAPE_CAPSULE) return RB_ERR_INVALID;
         if (d.parent >= nb) return RB_ERR_INVALID;
         c.shape = d.shape;
         c.he = f3(d.half_extents);
@@ -922,7 +938,7 @@ static void fill_collider(Collider& c, const RbColliderDesc& d) {
 int insert(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDesc* cd) {
     const int nb0 = (int)w.bodies.size(), nc0 = (int)w.colliders.size();
     for (int i = 0; i < nc; ++i) {
-        if (cd[i].shape != RB_SHAPE_BALL && cd[i].shape != RB_SHAPE_CUBOID) return RB_ERR_INVALID;
+        if (cd[i].shape != RB_SHAPE_BALL && cd[i].shape != RB_SHAPE_CUBOID && cd[i].shape != RB_SHAPE_CAPSULE) return RB_ERR_INVALID;
         if (cd[i].parent >= nb0 + nb || (cd[i].parent >= 0 && cd[i].parent < nb0)) return RB_ERR_INVALID;
     }
     w.bodies.resize(nb0 + nb);

@@ -24,6 +24,7 @@ RB_BODY_LOCK_RX, RB_BODY_LOCK_RY, RB_BODY_LOCK_RZ = 32, 64, 128
 RB_BODY_NO_SLEEP = 256
 RB_SHAPE_BALL = 0
 RB_SHAPE_CUBOID = 1
+RB_SHAPE_CAPSULE = 2
 (RB_COMBINE_AVERAGE, RB_COMBINE_MIN, RB_COMBINE_MULTIPLY, RB_COMBINE_MAX, RB_COMBINE_CLAMPED_SUM,
  RB_COMBINE_GEOMETRIC_MEAN) = range(6)
 

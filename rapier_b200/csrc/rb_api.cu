@@ -234,6 +234,8 @@ RB_PHASE void set_halo_phase(const Ctx& ctx, const World& w, const unsigned char
 // HBM (one CTA each) and the grid-wide "large" item 0.  Those touch bodies / constraints disjoint from
 // the items k_solve_coop handles next, so the order between the two kernels does not matter.
 // `do_collide` = 0 runs only the solve part (unused in the normal step).
+// SHAPES = 1: the variant for worlds with capsules (rb_geom.cuh); the ball / cuboid kernel is SHAPES = 0.
+template <int SHAPES>
 __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, int do_solve) {
     extern __shared__ __align__(16) float smem[];
     GridCtx ctx;
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, in
             if (ctx.gtid == 0) { w.st->nccd = 0; w.host_hint[3] = 0; }
         }
     }
-    collide_pipeline(ctx, w);   // (ends with a grid barrier: after the narrow phase, or after the last optional section)
+    collide_pipeline<SHAPES>(ctx, w);   // (ends with a grid barrier: after the narrow phase, or after the last optional section)
     if (!do_solve) return;
     {
         BlockCtx bctx;
@@ -435,6 +437,7 @@ struct RbWorld {
     int big_threads = COOP_BIG_THREADS, sweep_threads = 0;
     float* state_buf[2] = {nullptr, nullptr};   // double-buffered packed state (rb_world_state_buffers), else unused
     int state_next = 0;
+    bool ext_shapes = false;     // some collider is a capsule: the SHAPES = 1 collision kernel
     bool force_events = false;   // some collider has RB_EVENT_CONTACT_FORCE: run k_force_events after every step
     int steps_since_scene = 0;   // the launch-shape hint of a new scene is awaited once (see rb_world_step)
     int coop_shape = -1;   // RB_COOP_SHAPE debugging override: 0 small, 1 big, -1 automatic
@@ -535,6 +538,21 @@ static void collider_mass_props(const RbColliderDesc& c, float& mass, float pi[3
         float ux = (sy + sz) * third, uy = (sx + sz) * third, uz = (sx + sy) * third;
         mass = vol * c.density;
         pi[0] = ux * mass; pi[1] = uy * mass; pi[2] = uz * mass;
+    } else if (c.shape == RB_SHAPE_CAPSULE) {
+        // parry MassProperties::from_capsule: a cylinder plus the two half balls (restated from the published formulas)
+        const float hh = c.half_extents[0], r = c.half_extents[1];
+        const int ax = (int)c.half_extents[2];
+        const float pi_ = 3.14159265358979323846f;
+        const float cyl_vol = hh * r * r * pi_ * 2.0f, ball_vol = pi_ * r * r * r * 4.0f / 3.0f;
+        const float sq_r = r * r, sq_h = hh * hh * 4.0f;
+        const float cyl_off = (sq_r * 3.0f + sq_h) / 12.0f, cyl_axis = sq_r / 2.0f, ball_unit = sq_r * 2.0f / 5.0f;
+        const float h = hh * 2.0f;
+        const float extra = (h * h * 0.25f + h * r * 3.0f / 8.0f) * ball_vol * c.density;
+        const float i_off = (cyl_off * cyl_vol + ball_unit * ball_vol) * c.density + extra;
+        const float i_axis = (cyl_axis * cyl_vol + ball_unit * ball_vol) * c.density;
+        mass = (cyl_vol + ball_vol) * c.density;
+        pi[0] = pi[1] = pi[2] = i_off;
+        pi[ax] = i_axis;
     } else {
         float r = c.half_extents[0];
         float vol = 3.14159265358979323846f * r * r * r * 4.0f / 3.0f;
@@ -639,8 +657,9 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out, int fir
             const RbColliderDesc& c = W->colliders[ci];
             if (c.parent != b) continue;
             const float hx = c.half_extents[0], hy = c.half_extents[1], hz = c.half_extents[2];
-            m.ccd_thickness = std::min(m.ccd_thickness, c.shape == RB_SHAPE_BALL ? hx : std::min(hx, std::min(hy, hz)));   // parry Shape::ccd_thickness
-            const float radius = c.shape == RB_SHAPE_BALL ? hx : sqrtf(fmaf(hz, hz, fmaf(hy, hy, hx * hx)));
+            if (c.shape != RB_SHAPE_CAPSULE)   // (capsules are never swept here, like the reference's never-swept shapes: they do not count, rigid_body_components.rs:1224-1228)
+                m.ccd_thickness = std::min(m.ccd_thickness, c.shape == RB_SHAPE_BALL ? hx : std::min(hx, std::min(hy, hz)));   // parry Shape::ccd_thickness
+            const float radius = c.shape == RB_SHAPE_BALL ? hx : (c.shape == RB_SHAPE_CAPSULE ? hx + hy : sqrtf(fmaf(hz, hz, fmaf(hy, hy, hx * hx))));
             const float dx = c.pos_wrt_parent_t[0] - m.lcom[0], dy = c.pos_wrt_parent_t[1] - m.lcom[1], dz = c.pos_wrt_parent_t[2] - m.lcom[2];
             m.max_extent = std::max(m.max_extent, sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) + radius);
         }
@@ -776,6 +795,7 @@ static int upload_colliders(RbWorld* W, int first, int count, int first_body = 0
         events[k] = (int)c.active_events;
         thr[k] = c.contact_force_event_threshold;
         if (c.active_events & RB_EVENT_CONTACT_FORCE) W->force_events = true;
+        if (c.shape == RB_SHAPE_CAPSULE) W->ext_shapes = true;
         shape[k] = c.shape;
         parent[k] = c.parent;
         he[k] = make_float4(c.half_extents[0], c.half_extents[1], c.half_extents[2], 0.f);
@@ -811,7 +831,8 @@ static int upload_colliders(RbWorld* W, int first, int count, int first_body = 0
 static int validate_descs(int nb_total, int nb, const RbBodyDesc* bodies, int nc, const RbColliderDesc* colliders) {
     for (int i = 0; i < nc; ++i) {
         const RbColliderDesc& c = colliders[i];
-        if ((c.shape != RB_SHAPE_BALL && c.shape != RB_SHAPE_CUBOID) || c.parent >= nb_total) {
+        const bool capsule_ok = c.shape == RB_SHAPE_CAPSULE && (c.half_extents[2] == 0.0f || c.half_extents[2] == 1.0f || c.half_extents[2] == 2.0f);
+        if ((c.shape != RB_SHAPE_BALL && c.shape != RB_SHAPE_CUBOID && !capsule_ok) || c.parent >= nb_total) {
             set_err("collider with unsupported shape or bad parent%s", "");
             return RB_ERR_INVALID;
         }
@@ -884,12 +905,13 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
     RB_BIG_VARIANTS(RB_SET_ATTR)
     if (cudaHostAlloc((void**)&W->host_hint, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) { set_err("cudaHostAlloc failed%s", ""); delete W; return nullptr; }
     for (int i = 0; i < 4; ++i) W->host_hint[i] = 0;
-    cudaFuncSetAttribute(k_collide, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
+    cudaFuncSetAttribute(k_collide<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
+    cudaFuncSetAttribute(k_collide<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
     cudaFuncSetAttribute(k_solve_items_x<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
     cudaFuncSetAttribute(k_solve_items_x<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
     cudaFuncSetAttribute(k_solve_items_x<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_collide, COLLIDE_THREADS, ITEM_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_collide<1>, COLLIDE_THREADS, ITEM_SMEM_BYTES);
     if (occ < 1) { set_err("k_collide cannot be resident%s", ""); delete W; return nullptr; }
     W->collide_blocks = W->num_sms;   // one CTA per SM: the cheapest grid barrier that still covers the chip
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_coop, COOP_SMALL_THREADS, COOP_SMALL_SMEM_BYTES);
@@ -973,6 +995,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     free_all(W);
     World& w = W->w;
     W->force_events = false;
+    W->ext_shapes = false;
     memset(&w, 0, sizeof(w));
     derive_params(W->params, w.prm);
     w.nb = nb; w.nc = nc; w.nj = nj;
@@ -1473,7 +1496,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         const bool big = W->coop_shape >= 0 ? W->coop_shape == 1 : (*(volatile int*)W->host_hint != 0);
         W->w.step_index = (int)(W->steps + s + 1);
         void* a1[] = {(void*)&W->w, (void*)&g, (void*)&do_solve};
-        CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, ITEM_SMEM_BYTES, W->stream));
+        CK(cudaLaunchCooperativeKernel(W->ext_shapes ? (void*)k_collide<1> : (void*)k_collide<0>, dim3(W->collide_blocks), dim3(W->collide_threads), a1, ITEM_SMEM_BYTES, W->stream));
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 1], W->stream));
         if (coulomb) {   // every item through the streaming solve; the grid-wide item's kernel returns at once when there is none
             void* a2[] = {(void*)&W->w, (void*)&g};
@@ -1526,7 +1549,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         if (W->state_buf[1]) { W->w.state13 = W->state_buf[W->state_next]; W->state_next ^= 1; }
         W->emu_hint[0] = W->w.st->need_big;
         W->w.st->need_big = W->w.st->coop_streamed = W->w.st->coop_resident = 0;
-        collide_pipeline(gctx, W->w);
+        collide_pipeline<1>(gctx, W->w);   // (the emulation always carries the capsule code)
         BlockCtx bctx;
         SmemBodies sb;
         sb.s = W->emu_smem.data();
@@ -1835,12 +1858,12 @@ int rb_world_label_components(RbWorld* W, int32_t* component_of_body) {
     Grav g0{0.f, 0.f, 0.f};
     int do_solve = 0;
     void* a1[] = {(void*)&W->w, (void*)&g0, (void*)&do_solve};
-    CK(cudaLaunchCooperativeKernel((void*)k_collide, dim3(W->collide_blocks), dim3(W->collide_threads), a1, ITEM_SMEM_BYTES, W->stream));
+    CK(cudaLaunchCooperativeKernel(W->ext_shapes ? (void*)k_collide<1> : (void*)k_collide<0>, dim3(W->collide_blocks), dim3(W->collide_threads), a1, ITEM_SMEM_BYTES, W->stream));
     W->kernels++;
 #else
     W->w.st->sched_dirty = 1;
     GridCtx g;
-    collide_pipeline(g, W->w);
+    collide_pipeline<1>(g, W->w);
 #endif
     int rc = sync_world(W);
     if (rc != RB_OK) return rc;

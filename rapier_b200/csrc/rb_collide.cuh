@@ -513,7 +513,10 @@ RB_HD float rot_cos(quat base, quat cur) {  // contact_pair.rs:284-293
     float c = qdot(base, cur);
     return 2.0f * c * c - 1.0f;
 }
-RB_HD float origin_radius(int shape, vec3 he) { return shape == SHAPE_BALL ? norm(mk3(he.x, he.x, he.x)) : norm(he); }
+RB_HD float origin_radius(int shape, vec3 he) {
+    if (shape == SHAPE_CAPSULE) return norm(mk3(he.y, he.x + he.y, he.y));   // corner of the local AABB (the axis only permutes it)
+    return shape == SHAPE_BALL ? norm(mk3(he.x, he.x, he.x)) : norm(he);
+}
 
 // manifold_reduction.rs:4-84
 RB_HD void reduce_manifold(const RawManifold& m, int* sel, int& nsel, float prediction) {
@@ -545,7 +548,7 @@ RB_HD void reduce_manifold(const RawManifold& m, int* sel, int& nsel, float pred
     else nsel = 4;
 }
 
-template <class Ctx>
+template <int SHAPES = 0, class Ctx>
 RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
     State* st = w.st;
     const int buf = st->cur, np = st->npairs;
@@ -579,7 +582,7 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
         float4 m1 = w.c_mat[c1], m2 = w.c_mat[c2];
         float skin1 = m1.z, skin2 = m2.z;
         RawManifold raw;
-        contact_manifold(sh1, he1, sh2, he2, p12, prediction + (skin1 + skin2), raw);
+        contact_manifold<SHAPES>(sh1, he1, sh2, he2, p12, prediction + (skin1 + skin2), raw);
 
         // match_contacts: carry ContactData by feature ids (ball manifolds keep their single point).
         float4 o_pb[MAX_PTS], o_pd[MAX_PTS], o_tw[MAX_PTS], o_d1[MAX_PTS], o_d2[MAX_PTS];
@@ -1298,14 +1301,14 @@ RB_PHASE void phase_kinematic_velocities(const Ctx& ctx, const World& w) {
     }
 }
 
-template <class Ctx>
+template <int SHAPES = 0, class Ctx>
 RB_PHASE void collide_pipeline(const Ctx& ctx, const World& w) {
     State* st = w.st;
     if (ctx.gtid == 0) { st->bp_ran = 0; st->sched_ran = 0; st->sleep_stamp += 1; }
     phase_refresh_colliders(ctx, w);
     ctx.grid_sync();
     if (st->bp_dirty || st->lists_dirty) section_broad_phase(ctx, w);
-    phase_narrow_phase(ctx, w);
+    phase_narrow_phase<SHAPES>(ctx, w);
     ctx.grid_sync();
     if (w.nkinpos > 0) { phase_kinematic_velocities(ctx, w); ctx.grid_sync(); }   // (a kernel parameter: uniform)
     if (st->wake_any) section_wake(ctx, w);

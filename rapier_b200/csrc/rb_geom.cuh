@@ -270,8 +270,207 @@ RB_HD bool box_ball(vec3 he, float r, const pose& pb, float prediction, vec3& p_
     return true;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Capsules (parry Capsule: a segment + a radius; ColliderBuilder::capsule_{x,y,z}).  he = (half height, radius, axis).
+// Restated from first principles like the cuboid manifolds (parry's contact_manifold_capsule_capsule /
+// _cuboid_capsule / _ball_convex are not in the tree): closest features of the segment cores, contact points on the
+// surfaces, `dist` = surface distance.  Capsule-capsule: two points when the axes are parallel and overlap, else one;
+// cuboid-capsule: the segment clipped against the reference face (up to two points), or the closest points of the
+// segment and the supporting box edge; ball-capsule: one point.
+// ------------------------------------------------------------------------------------------------
+RB_HD vec3 capsule_dir(vec3 he) { return he.z == 0.0f ? mk3(1.f, 0.f, 0.f) : (he.z == 1.0f ? mk3(0.f, 1.f, 0.f) : mk3(0.f, 0.f, 1.f)); }
+
+// closest points of two segments p1 + s d1, p2 + t d2 (s, t in [0, 1]); Ericson, Real-Time Collision Detection, 5.1.9
+RB_HD void seg_seg_params(vec3 p1, vec3 d1, vec3 p2, vec3 d2, float& s, float& t) {
+    const vec3 r = p1 - p2;
+    const float a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r);
+    if (a <= EPS32 && e <= EPS32) { s = 0.0f; t = 0.0f; return; }
+    if (a <= EPS32) { s = 0.0f; t = clampf(f / e, 0.0f, 1.0f); return; }
+    const float c = dot3(d1, r);
+    if (e <= EPS32) { t = 0.0f; s = clampf(-c / a, 0.0f, 1.0f); return; }
+    const float b = dot3(d1, d2);
+    const float denom = a * e - b * b;
+    s = denom > 1.0e-6f * a * e ? clampf((b * f - c * e) / denom, 0.0f, 1.0f) : 0.0f;
+    t = (b * s + f) / e;
+    if (t < 0.0f) { t = 0.0f; s = clampf(-c / a, 0.0f, 1.0f); }
+    else if (t > 1.0f) { t = 1.0f; s = clampf((b - c) / a, 0.0f, 1.0f); }
+}
+
+RB_HD void manifold_capsule_capsule(vec3 he1, vec3 he2, const pose& p12, float prediction, RawManifold& m) {
+    m.n = 0; m.n1 = zero3(); m.n2 = zero3();
+    const float hh1 = he1.x, r1 = he1.y, hh2 = he2.x, r2 = he2.y;
+    const vec3 u1 = capsule_dir(he1), u2 = rotate(p12.q, capsule_dir(he2));
+    const vec3 a1 = u1 * (-hh1), d1 = u1 * (2.0f * hh1);
+    const vec3 a2 = p12.t - u2 * hh2, d2 = u2 * (2.0f * hh2);
+    const vec3 cr = cross3(d1, d2);
+    const float l1 = norm2(d1), l2 = norm2(d2);
+    if (l1 > EPS32 && l2 > EPS32 && norm2(cr) <= 1.0e-6f * l1 * l2) {   // parallel axes: the shared interval, if any, gives two contacts
+        const float inv = 1.0f / l1;
+        const float ta = dot3(a2 - a1, d1) * inv, tb = dot3((a2 + d2) - a1, d1) * inv;
+        const float lo = max2(min2(ta, tb), 0.0f), hi = min2(max2(ta, tb), 1.0f);
+        if (hi > lo) {
+            const vec3 w0 = a2 - a1;
+            const vec3 wv = w0 - d1 * (dot3(w0, d1) * inv);   // offset between the two lines
+            const float wl = norm(wv);
+            const vec3 n1 = wl > EPS32 ? wv * (1.0f / wl) : ortho_vector(u1);
+            const float dist = wl - r1 - r2;
+            if (!(dist < prediction)) return;
+            const float ts[2] = {lo, hi};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const vec3 q1 = a1 + d1 * ts[k];
+                const vec3 q2 = q1 + n1 * wl;
+                raw_push(m, q1 + n1 * r1, xform_inv(p12, q2 - n1 * r2), FID_VERTEX | (uint32_t)k, FID_VERTEX | (uint32_t)k, dist);
+            }
+            m.n1 = n1;
+            m.n2 = rotate_inv(p12.q, -n1);
+            return;
+        }
+    }
+    float s, t;
+    seg_seg_params(a1, d1, a2, d2, s, t);
+    const vec3 q1 = a1 + d1 * s, q2 = a2 + d2 * t;
+    const vec3 dl = q2 - q1;
+    const float len = norm(dl);
+    vec3 n1;
+    if (len > EPS32) n1 = dl * (1.0f / len);
+    else { const float cl = norm(cr); n1 = cl > EPS32 ? cr * (1.0f / cl) : ortho_vector(u1); }
+    const float dist = len - r1 - r2;
+    if (!(dist < prediction)) return;
+    raw_push(m, q1 + n1 * r1, xform_inv(p12, q2 - n1 * r2), FID_EDGE | 2u, FID_EDGE | 2u, dist);
+    m.n1 = n1;
+    m.n2 = rotate_inv(p12.q, -n1);
+}
+
+// Ball (pose `pb` in the capsule's frame) against a capsule.
+RB_HD bool capsule_ball(vec3 hec, float rb, const pose& pb, float prediction, vec3& p_cap, vec3& p_ball, vec3& n_cap, vec3& n_ball, float& dist) {
+    const float hh = hec.x, rc = hec.y;
+    const vec3 u = capsule_dir(hec);
+    const vec3 a = u * (-hh), d = u * (2.0f * hh);
+    const float l2 = norm2(d);
+    const float t = l2 > EPS32 ? clampf(dot3(pb.t - a, d) / l2, 0.0f, 1.0f) : 0.0f;
+    const vec3 q = a + d * t;
+    const vec3 dl = pb.t - q;
+    const float len = norm(dl);
+    const vec3 n = len > EPS32 ? dl * (1.0f / len) : ortho_vector(u);
+    dist = len - rc - rb;
+    if (!(dist < prediction)) return false;
+    n_cap = n; n_ball = rotate_inv(pb.q, -n);
+    p_cap = q + n * rc; p_ball = n_ball * rb;
+    return true;
+}
+
+// Capsule (pose `pc` in the box's frame) against a box: points in the box's / the capsule's frame, normal from the box.
+RB_HD void box_capsule(vec3 he, vec3 hec, const pose& pc, float prediction, RawManifold& m) {
+    m.n = 0; m.n1 = zero3(); m.n2 = zero3();
+    const float hh = hec.x, r = hec.y;
+    const vec3 u = rotate(pc.q, capsule_dir(hec));
+    const vec3 A = pc.t - u * hh, B = pc.t + u * hh;
+    float best = -FMAX32;
+    vec3 n = mk3(0.f, 1.f, 0.f);
+    int kind = 0, bi = 0;   // kind 0 = box face bi (sign in n), 1 = box edge parallel to axis bi
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float ai = comp(A, i), bb = comp(B, i), h = comp(he, i);
+        const float sp = min2(ai, bb) - h, sm = -max2(ai, bb) - h;
+        if (sp > best) { best = sp; n = with_comp(zero3(), i, 1.0f); kind = 0; bi = i; }
+        if (sm > best) { best = sm; n = with_comp(zero3(), i, -1.0f); kind = 0; bi = i; }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const vec3 c = cross3(with_comp(zero3(), i, 1.0f), u);
+        const float l2 = norm2(c);
+        if (!(l2 > 1.0e-6f)) continue;
+        vec3 nn = c * (1.0f / sqrtf(l2));
+        float s0 = dot3(nn, A);
+        if (s0 < 0.0f) { nn = -nn; s0 = -s0; }
+        const float sep = s0 - fma_(he.z, fabsf(nn.z), fma_(he.y, fabsf(nn.y), he.x * fabsf(nn.x)));
+        if (sep > best) { best = sep; n = nn; kind = 1; bi = i; }
+    }
+    if (!(best - r < prediction)) return;
+    const vec3 D = B - A;
+    if (kind == 0) {
+        const float sg = comp(n, bi);
+        float t0 = 0.0f, t1 = 1.0f;
+        bool miss = false;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {   // Liang-Barsky against the side planes of the face
+            if (j == bi) continue;
+            const float aj = comp(A, j), dj = comp(D, j), h = comp(he, j);
+            if (fabsf(dj) <= EPS32) { if (fabsf(aj) > h) miss = true; continue; }
+            float ta = (-h - aj) / dj, tb = (h - aj) / dj;
+            if (ta > tb) { const float tmp = ta; ta = tb; tb = tmp; }
+            t0 = max2(t0, ta); t1 = min2(t1, tb);
+        }
+        if (!miss && t0 <= t1) {
+            const float ts[2] = {t0, t1};
+            const int np = (t1 - t0 > 1.0e-5f) ? 2 : 1;
+            for (int k = 0; k < np; ++k) {
+                const vec3 q = A + D * ts[k];
+                const float dp = sg * comp(q, bi) - comp(he, bi);
+                const float dist = dp - r;
+                if (!(dist < prediction)) continue;
+                raw_push(m, q - n * dp, xform_inv(pc, q - n * r), FID_FACE | (uint32_t)(bi + (sg < 0.0f ? 3 : 0)), FID_VERTEX | (uint32_t)k, dist);
+            }
+            m.n1 = n;
+            m.n2 = rotate_inv(pc.q, -n);
+            return;
+        }
+        // the segment passes beside the face: closest point of the box to the nearer end of the segment
+        const vec3 q = (sg * comp(A, bi) <= sg * comp(B, bi)) ? A : B;
+        const vec3 pb = mk3(clampf(q.x, -he.x, he.x), clampf(q.y, -he.y, he.y), clampf(q.z, -he.z, he.z));
+        const vec3 dl = q - pb;
+        const float len = norm(dl);
+        const vec3 nn = len > EPS32 ? dl * (1.0f / len) : n;
+        const float dist = len - r;
+        if (!(dist < prediction)) return;
+        raw_push(m, pb, xform_inv(pc, q - nn * r), box_vertex_id(pb), FID_VERTEX | 3u, dist);
+        m.n1 = nn;
+        m.n2 = rotate_inv(pc.q, -nn);
+        return;
+    }
+    // box edge parallel to axis bi at the corner the normal points to, against the capsule's axis
+    vec3 e0 = box_support(he, n), ed = zero3();
+    e0 = with_comp(e0, bi, -comp(he, bi));
+    ed = with_comp(ed, bi, 2.0f * comp(he, bi));
+    float s, t;
+    seg_seg_params(e0, ed, A, D, s, t);
+    const vec3 pe = e0 + ed * s, q = A + D * t;
+    const float dist = dot3(q - pe, n) - r;
+    if (!(dist < prediction)) return;
+    raw_push(m, pe, xform_inv(pc, q - n * r), FID_EDGE | ((uint32_t)bi << 4) | (box_vertex_id(e0) & 7u), FID_EDGE | 2u, dist);
+    m.n1 = n;
+    m.n2 = rotate_inv(pc.q, -n);
+}
+
+RB_HD void manifold_flip(const RawManifold& a, RawManifold& m) {   // the same contacts seen from the other shape
+    m.n = a.n; m.n1 = a.n2; m.n2 = a.n1;
+    for (int i = 0; i < a.n; ++i) { m.pt[i].p1 = a.pt[i].p2; m.pt[i].p2 = a.pt[i].p1; m.pt[i].dist = a.pt[i].dist; m.pt[i].fid1 = a.pt[i].fid2; m.pt[i].fid2 = a.pt[i].fid1; }
+}
+RB_HD void contact_manifold_capsules(int sh1, vec3 he1, int sh2, vec3 he2, const pose& p12, float prediction, RawManifold& m) {
+    m.n = 0; m.n1 = zero3(); m.n2 = zero3();
+    if (sh1 == SHAPE_CAPSULE && sh2 == SHAPE_CAPSULE) { manifold_capsule_capsule(he1, he2, p12, prediction, m); return; }
+    if (sh1 == SHAPE_CUBOID) { box_capsule(he1, he2, p12, prediction, m); return; }
+    if (sh2 == SHAPE_CUBOID) {
+        RawManifold t;
+        box_capsule(he2, he1, pinverse(p12), prediction, t);
+        manifold_flip(t, m);
+        return;
+    }
+    vec3 pc, pb, nc, nb; float d;
+    if (sh1 == SHAPE_CAPSULE) {   // capsule - ball
+        if (capsule_ball(he1, he2.x, p12, prediction, pc, pb, nc, nb, d)) { raw_push(m, pc, pb, FID_EDGE | 2u, FID_FACE, d); m.n1 = nc; m.n2 = nb; }
+    } else {                      // ball - capsule
+        if (capsule_ball(he2, he1.x, pinverse(p12), prediction, pc, pb, nc, nb, d)) { raw_push(m, pb, pc, FID_FACE, FID_EDGE | 2u, d); m.n1 = nb; m.n2 = nc; }
+    }
+}
+
+// SHAPES = 1: worlds with capsules (a compile-time variant of the collision kernel, so the ball / cuboid one is unchanged)
+template <int SHAPES = 0>
 RB_HD void contact_manifold(int sh1, vec3 he1, int sh2, vec3 he2, const pose& p12, float prediction, RawManifold& m) {
     m.n = 0; m.n1 = zero3(); m.n2 = zero3();
+    if (SHAPES && (sh1 == SHAPE_CAPSULE || sh2 == SHAPE_CAPSULE)) { contact_manifold_capsules(sh1, he1, sh2, he2, p12, prediction, m); return; }
     if (sh1 == SHAPE_CUBOID && sh2 == SHAPE_CUBOID) {
         manifold_box_box(he1, he2, p12, prediction, m);
     } else if (sh1 == SHAPE_BALL && sh2 == SHAPE_BALL) {
@@ -296,6 +495,9 @@ RB_HD void shape_aabb(int shape, vec3 he, const pose& p, vec3& lo, vec3& hi) {
     vec3 ws;
     if (shape == SHAPE_BALL) {
         ws = mk3(he.x, he.x, he.x);
+    } else if (shape == SHAPE_CAPSULE) {   // the segment's box loosened by the radius
+        const vec3 u = rotate(p.q, capsule_dir(he));
+        ws = mk3(fabsf(u.x) * he.x + he.y, fabsf(u.y) * he.x + he.y, fabsf(u.z) * he.x + he.y);
     } else {
         mat3 r = rotmat(p.q);
         ws = mk3(fabsf(r.c0.x) * he.x + fabsf(r.c1.x) * he.y + fabsf(r.c2.x) * he.z,

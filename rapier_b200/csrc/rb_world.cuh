@@ -22,6 +22,7 @@ constexpr int BODY_FIXED = 1;
 constexpr int BODY_KIN_POS = 2, BODY_KIN_VEL = 3;   // RigidBodyType::{KinematicPositionBased, KinematicVelocityBased} (rigid_body_components.rs:20-46)
 constexpr int BODY_REMOVED = 7;          // removed (rb_world_remove_bodies) or quarantined: not simulated, its colliders are gone
 constexpr int SHAPE_BALL = 0, SHAPE_CUBOID = 1;
+constexpr int SHAPE_CAPSULE = 2;         // half extents = (half height of the segment, radius, axis 0 | 1 | 2)
 constexpr int SHAPE_REMOVED = -1;        // collider of a removed body: in neither broad-phase list, in no pair
 constexpr unsigned FLAG_GYRO = 1, FLAG_FAST_ROT = 2, FLAG_LTX = 4, FLAG_LTY = 8, FLAG_LTZ = 16, FLAG_LRX = 32,
                    FLAG_LRY = 64, FLAG_LRZ = 128, FLAG_NO_SLEEP = 256;

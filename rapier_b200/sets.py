@@ -155,6 +155,19 @@ class ColliderBuilder:
     def ball(cls, radius):
         return cls(A.RB_SHAPE_BALL, (float(radius), 0.0, 0.0))
 
+    @classmethod
+    def capsule_x(cls, half_height, radius):
+        return cls(A.RB_SHAPE_CAPSULE, (float(half_height), float(radius), 0.0))
+
+    @classmethod
+    def capsule_y(cls, half_height, radius):
+        """ColliderBuilder::capsule_y (collider.rs): a segment of 2 * half_height along Y, inflated by `radius`."""
+        return cls(A.RB_SHAPE_CAPSULE, (float(half_height), float(radius), 1.0))
+
+    @classmethod
+    def capsule_z(cls, half_height, radius):
+        return cls(A.RB_SHAPE_CAPSULE, (float(half_height), float(radius), 2.0))
+
     def density(self, d):
         self._density = float(d)
         return self
@@ -164,6 +177,8 @@ class ColliderBuilder:
         import math
         hx, hy, hz = self.half_extents
         volume = 8.0 * hx * hy * hz if self.shape == A.RB_SHAPE_CUBOID else 4.0 / 3.0 * math.pi * hx ** 3
+        if self.shape == A.RB_SHAPE_CAPSULE:
+            volume = 2.0 * hx * math.pi * hy ** 2 + 4.0 / 3.0 * math.pi * hy ** 3
         self._density = float(m) / volume if volume > 0.0 else 0.0
         return self
 

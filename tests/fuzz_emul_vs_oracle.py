@@ -1,5 +1,5 @@
 """Differential fuzzing on the CPU (helper, also driven by tests/test_fuzz.py with a few seeds): random small
-scenes -- cuboids and balls of random sizes, poses, velocities, materials, collision groups, locked axes,
+scenes -- cuboids, balls and capsules of random sizes, poses, velocities, materials, collision groups, locked axes,
 additional mass, spherical / fixed / revolute / prismatic joints with random limits and motors, kinematic bodies
 (velocity- and position-based), fast bodies (CCD), either friction model, collision / contact-force events --
 stepped through the host emulation of the kernels and through the oracle; every pose, velocity, persistent
@@ -32,6 +32,7 @@ def random_scene(seed):
     n = int(r.integers(2, 40))
     handles = []
     kinematic = []
+    capsules = r.random() < 0.5
     dense = r.random() < 0.5    # dense: bodies start close together (many contacts); sparse: mostly free fall
     span = 1.5 if dense else 5.0
     for i in range(n):
@@ -53,10 +54,13 @@ def random_scene(seed):
             b = b.additional_mass(float(r.uniform(0.5, 20.0)))
         if r.random() < 0.1:
             b = b.gyroscopic_forces_enabled(False)
-        if r.random() < 0.6:
+        sh = r.random()
+        if sh < 0.5:
             c = ColliderBuilder.cuboid(*[float(x) for x in r.uniform(0.15, 0.7, 3)])
-        else:
+        elif sh < 0.8 or not capsules:
             c = ColliderBuilder.ball(float(r.uniform(0.15, 0.6)))
+        else:
+            c = [ColliderBuilder.capsule_x, ColliderBuilder.capsule_y, ColliderBuilder.capsule_z][int(r.integers(0, 3))](float(r.uniform(0.1, 0.7)), float(r.uniform(0.12, 0.4)))
         c = c.density(float(r.choice([0.0, 0.5, 1.0, 10.0, 100.0]) if r.random() < 0.9 else 1.0))
         c = c.friction(float(r.uniform(0.0, 1.2))).restitution(float(r.choice([0.0, 0.0, 0.0, 0.3, 0.9, 1.0])))
         if r.random() < 0.1:

@@ -187,6 +187,11 @@ def test_joint_limits_and_motors_emulated_kernels():
                              lambda s, p=None: oracle_lib.OracleWorld(s, params=p), coulomb=True)
 
 
+def test_capsules_emulated_kernels():
+    from test_oracle_kat import capsules_rest
+    capsules_rest(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()))
+
+
 def test_quarantine_emulated_kernels():
     from test_oracle_kat import nan_force_is_quarantined
     nan_force_is_quarantined(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), expect_error=True)

@@ -358,3 +358,9 @@ def test_joint_limits_and_motors(built):
     mo = lambda s, p=None: oracle_lib.OracleWorld(s, params=p)
     joint_limits_parity_case(mk, mo)
     joint_limits_parity_case(mk, mo, coulomb=True)
+
+
+def test_capsules(built):
+    """Capsules through the C ABI (SHAPES = 1 variant of the collision kernel): rest heights / two-point manifolds / total impulse."""
+    from test_oracle_kat import capsules_rest
+    capsules_rest(lambda s: PhysicsWorld(s))

@@ -732,3 +732,32 @@ def test_joint_limits_and_motors_oracle():
     mk = lambda s: oracle_lib.OracleWorld(s)
     angular_limits_are_reached(mk)
     prismatic_limits_and_position_motor(mk)
+
+
+# ---- capsules (parry Capsule; ColliderBuilder::capsule_{x,y,z}) ------------------------------------------------------------------
+def capsules_rest(make_world):
+    """Capsules of unit mass on a slab: lying (two-point manifold, rest height = radius), standing (rest height = half height +
+    radius), a capsule lying along another one (two contacts on the shared interval), a ball on a capsule; the total contact
+    impulse of each resting body on its support is m g dt within 1 % (total_contact_impulse.rs:58-75 with capsules)."""
+    s = scenes.Scene("capsules", gravity=(0.0, -9.81, 0.0))
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(20.0, 0.5, 20.0))
+    lying = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.3, 0.0)), ColliderBuilder.capsule_x(0.5, 0.3).mass(1.0))
+    standing = s.insert(RigidBodyBuilder.dynamic().translation((4.0, 0.8, 0.0)), ColliderBuilder.capsule_y(0.5, 0.3).mass(1.0))
+    lower = s.insert(RigidBodyBuilder.dynamic().translation((8.0, 0.5, 0.0)), ColliderBuilder.cuboid(1.0, 0.5, 0.5).mass(5.0))
+    upper = s.insert(RigidBodyBuilder.dynamic().translation((8.0, 1.3, 0.0)), ColliderBuilder.capsule_x(0.6, 0.3).mass(1.0))
+    w = make_world(s)
+    w.step(300)
+    pose, vel = w.body_states()
+    assert abs(pose[lying, 1] - 0.3) < 0.01 and abs(pose[standing, 1] - 0.8) < 0.01 and abs(pose[upper, 1] - 1.3) < 0.015
+    assert np.abs(vel).max() < 0.05
+    cp = w.contact_pairs()
+    by_pair = {tuple(k): (n, imp.sum()) for k, n, imp in zip(cp["colliders"].tolist(), cp["num_contacts"].tolist(), cp["impulses"])}
+    mg_dt = 9.81 / 60.0
+    assert by_pair[(0, lying + 0)][0] == 2 and abs(by_pair[(0, 1)][1] - mg_dt) / mg_dt < 0.01          # lying: two points
+    assert abs(by_pair[(0, 2)][1] - mg_dt) / mg_dt < 0.01                                               # standing
+    assert by_pair[(3, 4)][0] == 2 and abs(by_pair[(3, 4)][1] - mg_dt) / mg_dt < 0.01                   # capsule along a box: two points
+    assert abs(by_pair[(0, 3)][1] - 6.0 * mg_dt) / (6.0 * mg_dt) < 0.01                                 # the box carries both
+
+
+def test_capsules_oracle():
+    capsules_rest(lambda s: oracle_lib.OracleWorld(s))

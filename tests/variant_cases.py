@@ -245,6 +245,30 @@ def joint_limits_parity_case(make_world, make_oracle, steps=150, every=15, coulo
     assert np.isfinite(pose).all()
 
 
+def capsule_pile():
+    """Capsules of all three axes, cuboids and balls dropped together: capsule-capsule (crossed and parallel), capsule-cuboid
+    (face clipping, edges, ends) and capsule-ball manifolds, recycling and warm start across them, a two-collider body
+    (capsule + box), parentless capsules as static geometry."""
+    s = scenes.Scene("capsule_pile")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(15.0, 0.5, 15.0))
+    s.colliders.insert(ColliderBuilder.capsule_z(4.0, 0.4).translation((-2.5, 0.4, 0.0)))
+    s.colliders.insert(ColliderBuilder.capsule_z(4.0, 0.4).translation((2.5, 0.4, 0.0)))
+    k = 0
+    for layer in range(4):
+        for i in range(3):
+            for j in range(2):
+                pos = (-1.2 + 1.2 * i + 0.07 * layer, 0.8 + 1.1 * layer, -0.7 + 1.4 * j + 0.05 * i)
+                b = RigidBodyBuilder.dynamic().translation(pos).rotation((0.3 * ((k * 7) % 5 - 2), 0.2 * ((k * 3) % 7 - 3), 0.25 * ((k * 5) % 3 - 1)))
+                kind = k % 5
+                c = (ColliderBuilder.capsule_y(0.35, 0.2) if kind == 0 else ColliderBuilder.capsule_x(0.5, 0.25) if kind == 1 else
+                     ColliderBuilder.cuboid(0.4, 0.3, 0.35) if kind == 2 else ColliderBuilder.ball(0.3) if kind == 3 else ColliderBuilder.capsule_z(0.3, 0.3))
+                s.insert(b, c.restitution(0.2 if k % 4 == 0 else 0.0))
+                k += 1
+    g = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 6.0, 0.0)), ColliderBuilder.capsule_x(0.6, 0.2).translation((0.0, 0.3, 0.0)))
+    s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.3, 0.15, 0.3).translation((0.0, -0.1, 0.0)), g)
+    return s
+
+
 VARIANTS = [
     ("restitution", bouncing_balls, None, 150, 25),
     ("groups_joints_forces", groups_and_joints, None, 150, 25),
@@ -269,6 +293,9 @@ VARIANTS = [
     ("coulomb_warmstart_zero_friction_in_bias", lambda: scenes.box_pile(2, 3, 2), _params(friction_model=1, warmstart_coefficient=0.0, friction_in_bias_pass=1), 60, 15),
     ("coulomb_large_island", lambda: scenes.pyramid3(9), _params(friction_model=1), 25, 5),
     ("coulomb_overflow_colour", plate_with_overflow_colour, _params(friction_model=1), 40, 10),
+    # capsules (SHAPES = 1 variant of the collision kernel)
+    ("capsule_pile", capsule_pile, None, 180, 20),
+    ("capsule_pile_coulomb_no_recycling", capsule_pile, _params(friction_model=1, contact_recycling=0), 60, 15),
     # CCD motion clamping (src/dynamics/ccd): fast bodies against thin fixed walls / a tiled floor; and switched off
     ("ccd_barrage", ccd_barrage, None, 90, 10),
     ("ccd_barrage_ccd_off", ccd_barrage, _params(max_ccd_substeps=0), 30, 10),
