@@ -73,6 +73,7 @@ enum {
     RB_BODY_ALLOW_FAST_ROTATION = 2, /* ccd.allow_fast_rotation */
     RB_BODY_LOCK_TX = 4, RB_BODY_LOCK_TY = 8, RB_BODY_LOCK_TZ = 16,   /* LockedAxes */
     RB_BODY_LOCK_RX = 32, RB_BODY_LOCK_RY = 64, RB_BODY_LOCK_RZ = 128,
+    RB_BODY_CCD_ENABLED = 512,       /* RigidBodyCcd::ccd_enabled: a "bullet" also sweeps against kinematic / dynamic bodies (never other bullets) */
     RB_BODY_NO_SLEEP = 256           /* RigidBodyActivation::cannot_sleep() (RigidBodyBuilder::can_sleep(false)); default: may sleep */
 };
 

@@ -56,6 +56,7 @@ public:
     RigidBodyBuilder& angular_damping(float x) { d_.angular_damping = x; return *this; }
     RigidBodyBuilder& gravity_scale(float x) { d_.gravity_scale = x; return *this; }
     RigidBodyBuilder& additional_mass(float m) { d_.additional_mass = m; return *this; }
+    RigidBodyBuilder& ccd_enabled(bool on) { if (on) d_.flags |= RB_BODY_CCD_ENABLED; else d_.flags &= ~RB_BODY_CCD_ENABLED; return *this; }
     RigidBodyBuilder& can_sleep(bool on) {   // RigidBodyActivation::cannot_sleep() when false
         if (on) d_.flags &= ~RB_BODY_NO_SLEEP; else d_.flags |= RB_BODY_NO_SLEEP;
         return *this;

@@ -141,12 +141,15 @@ void ccd_motion_clamping(World& w) {
     const RbIntegrationParameters& P = w.params.p;
     if (P.max_ccd_substeps == 0) return;
     const float slop = P.normalized_allowed_linear_error * P.length_unit;
+  for (int pass = 0; pass < 2; ++pass) {   // pass 0: non-bullets vs fixed targets; pass 1: bullets vs everything but bullets (ccd_solver.rs:190-263)
     for (int bi = 0; bi < (int)w.bodies.size(); ++bi) {
         Body& b = w.bodies[bi];
         if (!b.is_awake() || !b.is_strict_dynamic()) continue;
         const V3& nt = b.next_pos.t;
         if (!(std::isfinite(nt.x) && std::isfinite(nt.y) && std::isfinite(nt.z))) continue;   // (left to the quarantine chokepoint)
         if (!is_moving_fast_with_next_position(w, b)) continue;
+        const bool bullet = (b.flags & RB_BODY_CCD_ENABLED) != 0;   // is_bullet (sweeps.rs:31-33)
+        if (bullet != (pass == 1)) continue;
         float frac = 1.0f;
         for (int ci = 0; ci < (int)w.colliders.size(); ++ci) {
             const Collider& c1 = w.colliders[ci];
@@ -159,17 +162,23 @@ void ccd_motion_clamping(World& w) {
             swept.maxs = V3{fmax2(a1.maxs.x, a2.maxs.x), fmax2(a1.maxs.y, a2.maxs.y), fmax2(a1.maxs.z, a2.maxs.z)};
             for (const Collider& c2 : w.colliders) {
                 if (c2.shape < 0 || c2.shape == RB_SHAPE_CAPSULE) continue;
-                if (c2.parent >= 0 && w.bodies[c2.parent].type != RB_BODY_FIXED) continue;   // tier_allows: fixed targets only
+                Pose target_pose = c2.pos;
+                if (c2.parent >= 0 && w.bodies[c2.parent].type != RB_BODY_FIXED) {   // tier_allows (sweeps.rs:36-42)
+                    const Body& t = w.bodies[c2.parent];
+                    if (!bullet || c2.parent == bi || !t.is_dynamic() || (t.is_strict_dynamic() && (t.flags & RB_BODY_CCD_ENABLED))) continue;
+                    target_pose = pose_mul(t.is_awake() ? t.next_pos : t.pos, c2.pos_wrt_parent);   // target_collider_pose (:101-109)
+                }
                 const Aabb& f = c2.fat;   // (any superset of the colliders within the prediction distance gives the same minimum)
                 if (!(swept.mins.x <= f.maxs.x && swept.mins.y <= f.maxs.y && swept.mins.z <= f.maxs.z && swept.maxs.x >= f.mins.x &&
                       swept.maxs.y >= f.mins.y && swept.maxs.z >= f.mins.z)) continue;
                 if (!((c1.memberships & c2.filter) != 0 && (c2.memberships & c1.filter) != 0)) continue;
-                const float fr = toi(c2.shape, c2.he, c2.pos, c1.shape, c1.he, sw, slop);
+                const float fr = toi(c2.shape, c2.he, target_pose, c1.shape, c1.he, sw, slop);
                 if (fr > 0.0f && fr < frac) frac = fr;
             }
         }
         if (frac < 1.0f) b.next_pos = sweep_transform_at(sweep_from_poses(b.pos, b.next_pos, b.local_com), frac);
     }
+  }
 }
 
 }  // namespace orc

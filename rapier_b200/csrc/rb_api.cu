@@ -252,9 +252,11 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, in
         // Every CTA reads the count before the barrier, thread 0 resets it after it.
         const int nccd = w.st->nccd;
         if (nccd > 0) {
-            phase_ccd_pending(ctx, w, nccd);
+            const int nbullets = w.st->nccd_bullets;
+            phase_ccd_pending(ctx, w, nccd, false);
             ctx.grid_sync();
-            if (ctx.gtid == 0) { w.st->nccd = 0; w.host_hint[3] = 0; }
+            if (nbullets > 0) { phase_ccd_pending(ctx, w, nccd, true); ctx.grid_sync(); }
+            if (ctx.gtid == 0) { w.st->nccd = 0; w.st->nccd_bullets = 0; w.host_hint[3] = 0; }
         }
     }
     collide_pipeline<SHAPES>(ctx, w);   // (ends with a grid barrier: after the narrow phase, or after the last optional section)
@@ -387,9 +389,10 @@ __global__ void k_ccd_pending(World w) {
     GridCtx ctx;
     const int n = w.st->nccd;
     if (n == 0) return;
-    phase_ccd_pending(ctx, w, n);
+    phase_ccd_pending(ctx, w, n, false);
     __syncthreads();
-    if (ctx.gtid == 0) { w.st->nccd = 0; w.host_hint[3] = 0; }
+    if (w.st->nccd_bullets > 0) { phase_ccd_pending(ctx, w, n, true); __syncthreads(); }
+    if (ctx.gtid == 0) { w.st->nccd = 0; w.st->nccd_bullets = 0; w.host_hint[3] = 0; }
 }
 __global__ void k_init_bodies(World w, int first) {
     GridCtx ctx;
@@ -1584,8 +1587,10 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         }
         if (W->force_events) phase_force_events(gctx, W->w);
         if (W->w.st->nccd > 0) {   // the queued CCD clamps (the device applies them at the next k_collide / synchronising call)
-            phase_ccd_pending(gctx, W->w, W->w.st->nccd);
+            phase_ccd_pending(gctx, W->w, W->w.st->nccd, false);
+            if (W->w.st->nccd_bullets > 0) phase_ccd_pending(gctx, W->w, W->w.st->nccd, true);
             W->w.st->nccd = 0;
+            W->w.st->nccd_bullets = 0;
             W->w.host_hint[3] = 0;
         }
         W->kernels += 2;

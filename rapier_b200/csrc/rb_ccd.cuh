@@ -147,7 +147,7 @@ RB_HD bool ccd_is_moving_fast(const Params& P, vec3 lcom, const pose& op, const 
 // the fixed colliders, and the pose at that fraction of the body's own sweep.  One thread; fast bodies are rare.
 // (Always inlined: as an out-of-line call inside k_collide -- ABI call, 900 B more stack -- it cost 7 us per step on the headline
 //  workload without ever being executed; inlined it costs 0.4 us: profiles/bench_r02m_ccd_placement.txt.)
-RB_HD pose ccd_clamp_body(const World& w, int b, pose op, pose np) {
+RB_HD pose ccd_clamp_body(const World& w, int b, pose op, pose np, bool bullet = false) {
     const State* st = w.st;
     const vec3 lcom = xyz(w.b_lcom_im[b]);
     const float slop = w.prm.linear_slop;
@@ -178,6 +178,25 @@ RB_HD pose ccd_clamp_body(const World& w, int b, pose op, pose np) {
             const float f = ccd_toi(w.c_shape[cj], xyz(w.c_he[cj]), collider_pose(w, cj), sh, he, sw, slop);
             if (f > 0.0f && f < frac) frac = f;
         };
+        if (bullet) {
+            // a bullet also sweeps the colliders of kinematic / dynamic bodies -- never of other bullets -- standing still at their
+            // end-of-step pose (already clamped by the first pass): sweeps.rs:36-42, :101-109; candidates by their broad-phase
+            // (fat) AABBs of this step, like the reference's BVH query (:111-127)
+            const int nd = st->ndyn;
+            for (int i = 0; i < nd; ++i) {
+                const int cj = w.dyn_list[i];
+                const int pj = w.c_parent[cj], shj = w.c_shape[cj];
+                if (pj == b || pj < 0 || shj == SHAPE_REMOVED || shj == SHAPE_CAPSULE) continue;
+                if (!type_is_solver(w.b_type[pj])) continue;
+                if (w.b_type[pj] == BODY_DYNAMIC && (w.b_flags[pj] & FLAG_CCD)) continue;
+                if (!fat_overlap(amin, amax, w.c_fat_min[cj], w.c_fat_max[cj])) continue;
+                const uint2 g2 = w.c_groups[cj];
+                if (!((g1.x & g2.y) != 0 && (g2.x & g1.y) != 0)) continue;
+                const pose tp = pmul(body_pose(w, pj), mkpose(mkq(w.c_rel_q[cj]), xyz(w.c_rel_t[cj])));
+                const float f = ccd_toi(shj, xyz(w.c_he[cj]), tp, sh, he, sw, slop);
+                if (f > 0.0f && f < frac) frac = f;
+            }
+        }
         const unsigned amax_key = sortable_float(amax.x);
         for (int j = lower_bound_u64(skey, ns, (unsigned long long)sortable_float(amin.x - wn) << 32); j < ns; ++j) {
             const unsigned long long kj = skey[j];

@@ -1033,13 +1033,16 @@ RB_HD void update_world_mass(const World& w, int b, const pose& p) {
 
 // The queued CCD clamps (see body_writeback): sweep_fast_body + apply_clamps (ccd_solver.rs:162-238, :325-340), then
 // advance_to_final_positions for the clamped bodies.  `n` = State::nccd read before the call; the caller resets it.
+// `bullets`: false = the first pass (fast non-bullets against the fixed colliders), true = the second one (bullets against
+// everything but bullets, at the poses the first pass left); the caller puts a barrier between the two.
 template <class Ctx>
-RB_PHASE void phase_ccd_pending(const Ctx& ctx, const World& w, int n) {
+RB_PHASE void phase_ccd_pending(const Ctx& ctx, const World& w, int n, bool bullets) {
     for (int k = ctx.gtid; k < n; k += ctx.gsize) {
         const int b = w.ccd_list[k];
         if (w.b_type[b] != BODY_DYNAMIC) continue;
+        if (((w.b_flags[b] & FLAG_CCD) != 0) != bullets) continue;
         const pose op = mkpose(mkq(w.ccd_start_q[b]), xyz(w.ccd_start_t[b])), np = body_pose(w, b);
-        const pose cl = ccd_clamp_body(w, b, op, np);
+        const pose cl = ccd_clamp_body(w, b, op, np, bullets);
         w.b_pos_t[b] = f4(cl.t, 0.0f);
         w.b_pos_q[b] = f4(cl.q);
         update_world_mass(w, b, cl);
@@ -1200,6 +1203,7 @@ RB_HD void body_writeback(const World& w, const B& bd, int b, int id) {
         w.ccd_start_t[b] = f4(ccd_op.t, 0.0f);
         w.ccd_start_q[b] = f4(ccd_op.q);
         w.ccd_list[atomic_add(&w.st->nccd, 1)] = b;
+        if (w.b_flags[b] & FLAG_CCD) atomic_add(&w.st->nccd_bullets, 1);
         atomic_add(&w.st->ccd_total, 1);
         w.host_hint[3] = 1;
     }

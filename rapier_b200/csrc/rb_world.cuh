@@ -25,7 +25,7 @@ constexpr int SHAPE_BALL = 0, SHAPE_CUBOID = 1;
 constexpr int SHAPE_CAPSULE = 2;         // half extents = (half height of the segment, radius, axis 0 | 1 | 2)
 constexpr int SHAPE_REMOVED = -1;        // collider of a removed body: in neither broad-phase list, in no pair
 constexpr unsigned FLAG_GYRO = 1, FLAG_FAST_ROT = 2, FLAG_LTX = 4, FLAG_LTY = 8, FLAG_LTZ = 16, FLAG_LRX = 32,
-                   FLAG_LRY = 64, FLAG_LRZ = 128, FLAG_NO_SLEEP = 256;
+                   FLAG_LRY = 64, FLAG_LRZ = 128, FLAG_NO_SLEEP = 256, FLAG_CCD = 512;
 
 // ---- persistent pair record rows (float4 each) ----
 enum PairRow {
@@ -121,6 +121,7 @@ struct State {
     int nquarantine;       // bodies quarantined since the host last read the list (non-finite state)
     int nccd;              // fast bodies queued for CCD motion clamping by the last solve (World::ccd_list)
     int ccd_total;         // fast bodies queued since the scene was uploaded (diagnostic)
+    int nccd_bullets;      // ... of which bullets (ccd_enabled): they sweep in a second pass, against the already clamped poses
     int nev_coll, nev_force;   // buffered collision / contact-force events since the host last drained them
 };
 

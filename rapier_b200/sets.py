@@ -89,6 +89,14 @@ class RigidBodyBuilder:
         self._gravity_scale = float(s)
         return self
 
+    def ccd_enabled(self, flag):
+        """RigidBodyBuilder::ccd_enabled: upgrade to a bullet (sweeps against moving bodies too)."""
+        if flag:
+            self._flags |= A.RB_BODY_CCD_ENABLED
+        else:
+            self._flags &= ~A.RB_BODY_CCD_ENABLED
+        return self
+
     def can_sleep(self, flag):
         """RigidBodyBuilder::can_sleep (rigid_body.rs; false = RigidBodyActivation::cannot_sleep())."""
         self._can_sleep = bool(flag)

@@ -41,7 +41,7 @@ def random_scene(seed):
         b = (RigidBodyBuilder.kinematic_velocity_based() if r.random() < 0.5 else RigidBodyBuilder.kinematic_position_based()) if kin else RigidBodyBuilder.dynamic()
         b = b.translation(pos)
         if r.random() < 0.06:   # a fast body: CCD motion clamping against the ground / the walls
-            b = b.linvel((float(r.uniform(-150.0, 150.0)), float(r.uniform(-200.0, 20.0)), float(r.uniform(-150.0, 150.0))))
+            b = b.linvel((float(r.uniform(-150.0, 150.0)), float(r.uniform(-200.0, 20.0)), float(r.uniform(-150.0, 150.0)))).ccd_enabled(bool(r.random() < 0.5))
         if r.random() < 0.7:
             b = b.rotation(tuple(float(x) for x in r.uniform(-1.0, 1.0, 3)))
         if r.random() < 0.5:
@@ -118,7 +118,7 @@ def run(seed, steps=90, smem_floats=None):
     import emul_lib
     import oracle_lib
     from parity_util import compare_worlds, is_exact
-    from rapier_b200.world import PhysicsWorld
+    from rapier_b200.world import PhysicsWorld, RapierError
     if smem_floats is not None:
         os.environ["RB_EMU_COOP_SMEM_FLOATS"] = str(smem_floats)
     else:
@@ -134,8 +134,18 @@ def run(seed, steps=90, smem_floats=None):
                       scene.bodies.descs[h].translation[2], 0.0, math.sin(0.3 * t), 0.0, math.cos(0.3 * t)) for h in scene.kinematic_position_based]
             w.set_next_kinematic_positions(scene.kinematic_position_based, poses)
             o.set_next_kinematic_positions(scene.kinematic_position_based, poses)
-        w.step()
+        try:
+            w.step()
+        except RapierError as e:   # a blow-up (random motors can be that violent) must quarantine the same bodies on both sides
+            if "-5" not in str(e):
+                raise
+            o.step()
+            if sorted(w.quarantine().tolist()) != sorted(o.quarantine().tolist()):
+                return False, f"seed {seed} step {i}: quarantine lists differ"
+            continue
         o.step()
+        if len(o.quarantine()):
+            return False, f"seed {seed} step {i}: only the oracle quarantined"
         if i % 15 == 14 or i < 2:
             d = compare_worlds(w, o)
             if not is_exact(d):
@@ -143,7 +153,7 @@ def run(seed, steps=90, smem_floats=None):
             if w.collision_events() != o.collision_events() or w.contact_force_events() != o.contact_force_events():
                 return False, f"seed {seed} step {i}: event lists differ"
             ji_w, ji_o = w.debug_read("joint_impulses", np.float32), o.debug_read("joint_impulses", np.float32)
-            if not (ji_w.view(np.uint32) == ji_o.view(np.uint32)).all():
+            if not ((ji_w.view(np.uint32) == ji_o.view(np.uint32)) | (np.isnan(ji_w) & np.isnan(ji_o))).all():   # (NaN payloads of a blown-up joint carry no meaning)
                 return False, f"seed {seed} step {i}: joint impulses differ"
     pose, vel = w.body_states()
     if not (np.isfinite(pose).all() and np.isfinite(vel).all()):

@@ -152,10 +152,11 @@ def test_coulomb_friction_cone_emulated_kernels():
 
 
 def test_ccd_emulated_kernels():
-    from test_oracle_kat import ccd_default_tier, ccd_large_dt_no_mid_air_hitch
+    from test_oracle_kat import ccd_bullet_still_hits_dynamic, ccd_default_tier, ccd_large_dt_no_mid_air_hitch
     mk = lambda s, p: PhysicsWorld(s, integration_parameters=p, _lib=emul_lib.lib())
     ccd_default_tier(mk)
     ccd_large_dt_no_mid_air_hitch(mk)
+    ccd_bullet_still_hits_dynamic(mk)
 
 
 def test_contact_force_events_emulated_kernels():

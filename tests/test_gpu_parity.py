@@ -322,10 +322,11 @@ def test_coulomb_friction_model(built):
 
 def test_ccd_motion_clamping(built):
     """CCD known answers of the reference's test-suite (ccd_default_vs_fixed.rs, issue_217_ccd_large_dt_hitch.rs) through the C ABI."""
-    from test_oracle_kat import ccd_default_tier, ccd_large_dt_no_mid_air_hitch
+    from test_oracle_kat import ccd_bullet_still_hits_dynamic, ccd_default_tier, ccd_large_dt_no_mid_air_hitch
     mk = lambda s, p: PhysicsWorld(s, integration_parameters=p)
     ccd_default_tier(mk)
     ccd_large_dt_no_mid_air_hitch(mk)
+    ccd_bullet_still_hits_dynamic(mk)
 
 
 def test_events(built):

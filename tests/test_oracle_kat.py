@@ -527,6 +527,18 @@ def ccd_default_tier(make_world):
     assert pose[0, 0] > 0.0 and pose[1, 0] < 0.0
 
 
+def ccd_bullet_still_hits_dynamic(make_world):
+    """ccd_default_vs_fixed.rs:157-186: a ccd_enabled body (a bullet) sweeps against a dynamic target: after 60 steps the
+    target has been pushed along +X and the bullet is still behind it."""
+    s = scenes.Scene("ccd_bullet", gravity=(0.0, 0.0, 0.0))
+    bullet = s.insert(RigidBodyBuilder.dynamic().translation((-3.0, 0.0, 0.0)).linvel((200.0, 0.0, 0.0)).ccd_enabled(True), ColliderBuilder.cuboid(0.1, 0.1, 0.1))
+    target = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.0, 0.0)), ColliderBuilder.cuboid(0.2, 0.2, 0.2))
+    w = make_world(s, None)
+    w.step(60)
+    pose, _ = w.body_states()
+    assert pose[target, 0] > 0.05 and pose[bullet, 0] < pose[target, 0], pose[:, 0]
+
+
 def ccd_large_dt_no_mid_air_hitch(make_world):
     """issue_217_ccd_large_dt_hitch.rs:62-121: ball (r = 0.5, 20 m/s, dt = 0.25: 5 m per step) against a thin wall whose
     near face is at x = 12.2: full-speed advance while far, then adjacent to the wall (never through, never frozen short
@@ -555,6 +567,7 @@ def test_ccd_oracle():
     mk = lambda s, p: oracle_lib.OracleWorld(s, params=p)
     ccd_default_tier(mk)
     ccd_large_dt_no_mid_air_hitch(mk)
+    ccd_bullet_still_hits_dynamic(mk)
 
 
 # ---- events (EventHandler; crates/rapier3d/tests/contact_force_event_first_tick.rs) -------------------------------------

@@ -119,11 +119,14 @@ def ccd_barrage():
     for i in range(6):
         s.insert(RigidBodyBuilder.dynamic().translation((-2.0 + 0.7 * i, 1.0 + 0.5 * i, -2.0 + i)).linvel((150.0 - 40.0 * i, -30.0 * i, 10.0))
                  .angvel((3.0, 1.0 * i, -2.0)), ColliderBuilder.cuboid(0.1, 0.15, 0.2))
-        s.insert(RigidBodyBuilder.dynamic().translation((1.0 - 0.7 * i, 3.0 + 0.5 * i, 2.0 - i)).linvel((-120.0 + 30.0 * i, -60.0, -5.0 * i)),
-                 ColliderBuilder.ball(0.12 + 0.02 * i))
+        s.insert(RigidBodyBuilder.dynamic().translation((1.0 - 0.7 * i, 3.0 + 0.5 * i, 2.0 - i)).linvel((-120.0 + 30.0 * i, -60.0, -5.0 * i)).ccd_enabled(i % 2 == 0),
+                 ColliderBuilder.ball(0.12 + 0.02 * i))   # (every other ball is a bullet: it also sweeps against the moving bodies)
     g = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 6.0, 4.0)).linvel((90.0, -90.0, 0.0)).angvel((0.0, 0.0, 8.0)),
                  ColliderBuilder.cuboid(0.3, 0.05, 0.05).translation((0.3, 0.0, 0.0)))
     s.colliders.insert_with_parent(ColliderBuilder.ball(0.08).translation((-0.3, 0.0, 0.0)), g)
+    for i in range(4):   # slow targets in the line of fire, and a bullet cube aimed at them
+        s.insert(RigidBodyBuilder.dynamic().translation((3.0 + 0.9 * i, 0.0, 5.0)), ColliderBuilder.cuboid(0.3, 0.45, 0.3))
+    s.insert(RigidBodyBuilder.dynamic().translation((-5.0, 0.1, 5.0)).linvel((180.0, 0.0, 0.0)).angvel((0.0, 0.0, 5.0)).ccd_enabled(True), ColliderBuilder.cuboid(0.1, 0.12, 0.08))
     return s
 
 
