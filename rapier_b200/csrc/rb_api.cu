@@ -252,10 +252,12 @@ __global__ void __launch_bounds__(COLLIDE_THREADS) k_collide(World w, Grav g, in
         // Every CTA reads the count before the barrier, thread 0 resets it after it.
         const int nccd = w.st->nccd;
         if (nccd > 0) {
-            const int nbullets = w.st->nccd_bullets;
-            phase_ccd_pending(ctx, w, nccd, false);
-            ctx.grid_sync();
-            if (nbullets > 0) { phase_ccd_pending(ctx, w, nccd, true); ctx.grid_sync(); }
+            const int npass = w.st->nccd_bullets > 0 ? 2 : 1;
+#pragma unroll 1
+            for (int pass = 0; pass < npass; ++pass) {   // (one inlined copy of the sweep: the kernel's stack frame stays small)
+                phase_ccd_pending(ctx, w, nccd, pass == 1);
+                ctx.grid_sync();
+            }
             if (ctx.gtid == 0) { w.st->nccd = 0; w.st->nccd_bullets = 0; w.host_hint[3] = 0; }
         }
     }
@@ -389,9 +391,12 @@ __global__ void k_ccd_pending(World w) {
     GridCtx ctx;
     const int n = w.st->nccd;
     if (n == 0) return;
-    phase_ccd_pending(ctx, w, n, false);
-    __syncthreads();
-    if (w.st->nccd_bullets > 0) { phase_ccd_pending(ctx, w, n, true); __syncthreads(); }
+    const int npass = w.st->nccd_bullets > 0 ? 2 : 1;
+#pragma unroll 1
+    for (int pass = 0; pass < npass; ++pass) {
+        phase_ccd_pending(ctx, w, n, pass == 1);
+        __syncthreads();
+    }
     if (ctx.gtid == 0) { w.st->nccd = 0; w.st->nccd_bullets = 0; w.host_hint[3] = 0; }
 }
 __global__ void k_init_bodies(World w, int first) {
