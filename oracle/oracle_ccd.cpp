@@ -9,7 +9,7 @@
 // ToiProxy, sweep_time_of_impact, a Box2D-v3-style b2TimeOfImpact over point-cloud proxies), which is not under
 // /root/reference.  Restated from the published algorithm's contract (target = max(slop, r1 + r2 - slop), tolerance
 // 0.25 slop, pairs that start within the target report fraction 0 and are ignored) as conservative advancement on a
-// separating-axis lower bound of the core distance.  Bullets (ccd_enabled) and max_ccd_substeps > 1 are not restated.
+// separating-axis lower bound of the core distance.  max_ccd_substeps > 1 is not restated.
 #include <algorithm>
 #include "oracle_internal.h"
 

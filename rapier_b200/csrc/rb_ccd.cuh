@@ -15,8 +15,8 @@
 // within `0.25 * slop`; a pair that starts within that distance reports fraction 0 and is ignored (3-D: "advances",
 // sweeps.rs:287-289).  The advance is conservative advancement on a separating-axis lower bound of the distance
 // (exact for face / edge / edge-edge features), so the clamp is never later than the true impact: parity with the
-// fork is within the tolerance band, not bit-level ("parity unpinned").  Bullets (`ccd_enabled`, sweeps
-// against moving bodies) and the multi-substep splitter (max_ccd_substeps > 1) are not implemented.
+// fork is within the tolerance band, not bit-level ("parity unpinned").  The multi-substep splitter
+// (max_ccd_substeps > 1) and sensor-crossing events are not implemented.
 #pragma once
 #include "rb_collide.cuh"
 

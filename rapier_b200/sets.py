@@ -285,6 +285,15 @@ class GenericJointBuilder:
         self._contacts_enabled = bool(flag)
         return self
 
+    def local_axis1(self, axis):
+        """GenericJoint::set_local_axis1: the joint's X axis in the first body's frame (generic_joint.rs:374-389)."""
+        self._q1 = _rotation_arc_from_x(axis)
+        return self
+
+    def local_axis2(self, axis):
+        self._q2 = _rotation_arc_from_x(axis)
+        return self
+
     # GenericJoint::{set_limits, set_motor_velocity, set_motor_position, set_motor, set_motor_max_force, set_motor_model}
     # (generic_joint.rs:470-560); `axis` = 0..5 (LinX LinY LinZ AngX AngY AngZ)
     def limits(self, axis, lo, hi):

@@ -302,6 +302,11 @@ class PhysicsWorld:
         self._flush()
         return self.physics_pipeline.contact_pairs()
 
+    def set_body_states(self, handles, pose7=None, vel6=None):
+        """RigidBody::set_position / set_linvel / set_angvel (wakes the bodies' islands)."""
+        self._flush()
+        self.physics_pipeline.set_body_states(handles, pose7, vel6)
+
     def set_body_forces(self, handles, force3=None, torque3=None):
         self._flush()
         self.physics_pipeline.set_body_forces(handles, force3, torque3)

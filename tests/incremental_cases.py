@@ -34,6 +34,12 @@ class OracleSets:
     def debug_read(self, table, dtype):
         return self.o.debug_read(table, dtype)
 
+    def sleeping(self):
+        return self.o.sleeping()
+
+    def set_body_states(self, handles, pose7=None, vel6=None):
+        self.o.set_body_states(handles, pose7, vel6)
+
 
 def large_world_protocol_case(lib=None, grid=20, spheres=12, steps=100, every=10, threads=1):
     floor = scenes.large_world_floor(grid)

@@ -193,6 +193,22 @@ def test_capsules_emulated_kernels():
     capsules_rest(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()))
 
 
+def test_more_joint_known_answers_emulated_kernels():
+    from test_oracle_kat import motor_position_with_rotating_base_stays_finite, prismatic_joint_stays_bounded_for_all_axis_rotations
+    mk = lambda s, p: PhysicsWorld(s, integration_parameters=p, _lib=emul_lib.lib())
+    prismatic_joint_stays_bounded_for_all_axis_rotations(mk)
+    motor_position_with_rotating_base_stays_finite(mk)
+
+
+def test_sleep_wake_scenarios_emulated_kernels():
+    from test_oracle_kat import sleep_wake_scenarios
+    def mk(s):
+        w = PhysicsWorld(s, _lib=emul_lib.lib())
+        w.reserve(32, 32)   # (totals: room for the body the impact scenario inserts)
+        return w
+    sleep_wake_scenarios(mk)
+
+
 def test_quarantine_emulated_kernels():
     from test_oracle_kat import nan_force_is_quarantined
     nan_force_is_quarantined(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), expect_error=True)

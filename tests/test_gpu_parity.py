@@ -365,3 +365,19 @@ def test_capsules(built):
     """Capsules through the C ABI (SHAPES = 1 variant of the collision kernel): rest heights / two-point manifolds / total impulse."""
     from test_oracle_kat import capsules_rest
     capsules_rest(lambda s: PhysicsWorld(s))
+
+
+def test_more_reference_known_answers(built):
+    """sleep_wake.rs scenarios, issue_746 (prismatic axis frames) and issue_856 (stiff position motor on a re-oriented base)
+    through the C ABI."""
+    from test_oracle_kat import (motor_position_with_rotating_base_stays_finite, prismatic_joint_stays_bounded_for_all_axis_rotations,
+                                 sleep_wake_scenarios)
+
+    def mk(s):
+        w = PhysicsWorld(s)
+        w.reserve(32, 32)
+        return w
+    sleep_wake_scenarios(mk)
+    mkp = lambda s, p: PhysicsWorld(s, integration_parameters=p)
+    prismatic_joint_stays_bounded_for_all_axis_rotations(mkp)
+    motor_position_with_rotating_base_stays_finite(mkp)
