@@ -57,14 +57,14 @@ typedef struct RbIntegrationParameters {
     int32_t contact_recycling;                  /* default 1 */
     float normalized_contact_recycle_distance;  /* default 0.05 */
     int32_t friction_in_bias_pass;              /* default 0 */
-    int32_t warmstart_joints;                   /* default 0 (1 is RB_ERR_INVALID for now) */
+    int32_t warmstart_joints;                   /* default 0; 1: joint rows are seeded with last step's impulses (joint_constraint_builder.rs:116-150) */
     int32_t friction_model;                     /* 0 = Simplified (twist, default); 1 = Coulomb (one friction part per point) */
 } RbIntegrationParameters;
 
 /* Fills *p with IntegrationParameters::default() (integration_parameters.rs:379-407). */
 void rb_integration_parameters_default(RbIntegrationParameters* p);
 
-/* RigidBodyType (src/dynamics/rigid_body_components.rs). Kinematic bodies are not supported yet. */
+/* RigidBodyType (src/dynamics/rigid_body_components.rs:20-46). */
 enum { RB_BODY_DYNAMIC = 0, RB_BODY_FIXED = 1, RB_BODY_KINEMATIC_POSITION_BASED = 2, RB_BODY_KINEMATIC_VELOCITY_BASED = 3 };   /* RigidBodyType */
 
 /* Body flags */
@@ -76,6 +76,12 @@ enum {
     RB_BODY_CCD_ENABLED = 512,       /* RigidBodyCcd::ccd_enabled: a "bullet" also sweeps against kinematic / dynamic bodies (never other bullets) */
     RB_BODY_NO_SLEEP = 256           /* RigidBodyActivation::cannot_sleep() (RigidBodyBuilder::can_sleep(false)); default: may sleep */
 };
+/* RigidBodyDominance (rigid_body_components.rs:1255-1276): a signed 8-bit group carried in bits 16..23 of `flags`
+ * (default 0).  In a contact between bodies of different groups the body of the HIGHER group is seen as world-attached
+ * (infinite mass, zero velocity: contact_with_twist_friction.rs:71-84); fixed bodies dominate every group. */
+#define RB_BODY_DOMINANCE_SHIFT 16
+#define RB_BODY_DOMINANCE(group) (((uint32_t)(uint8_t)(int8_t)(group)) << RB_BODY_DOMINANCE_SHIFT)
+#define RB_BODY_DOMINANCE_OF(flags) ((int)(int8_t)(uint8_t)(((flags) >> RB_BODY_DOMINANCE_SHIFT) & 0xffu))
 
 /* One rigid body as the caller's RigidBodySet holds it (src/dynamics/rigid_body.rs:48-70).
  * Mass properties are recomputed by the library from the attached colliders

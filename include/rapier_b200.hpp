@@ -8,6 +8,7 @@
 // Every method is a thin call into librapier_b200.so; no physics is computed here.
 #pragma once
 #include <array>
+#include <cfloat>
 #include <cmath>
 #include <stdexcept>
 #include <string>
@@ -56,6 +57,9 @@ public:
     RigidBodyBuilder& angular_damping(float x) { d_.angular_damping = x; return *this; }
     RigidBodyBuilder& gravity_scale(float x) { d_.gravity_scale = x; return *this; }
     RigidBodyBuilder& additional_mass(float m) { d_.additional_mass = m; return *this; }
+    RigidBodyBuilder& dominance_group(int group) {   // RigidBodyBuilder::dominance_group (i8)
+        d_.flags = (d_.flags & ~(0xffu << RB_BODY_DOMINANCE_SHIFT)) | RB_BODY_DOMINANCE(group); return *this;
+    }
     RigidBodyBuilder& ccd_enabled(bool on) { if (on) d_.flags |= RB_BODY_CCD_ENABLED; else d_.flags &= ~RB_BODY_CCD_ENABLED; return *this; }
     RigidBodyBuilder& can_sleep(bool on) {   // RigidBodyActivation::cannot_sleep() when false
         if (on) d_.flags &= ~RB_BODY_NO_SLEEP; else d_.flags |= RB_BODY_NO_SLEEP;
@@ -115,20 +119,63 @@ private:
     RbColliderDesc d_;
 };
 
-class SphericalJointBuilder {
+// GenericJoint / GenericJointBuilder (src/dynamics/joint/generic_joint.rs): locked axes, limits and motors on the free
+// ones.  `axis` arguments are JointAxis indices 0..5 (LinX LinY LinZ AngX AngY AngZ).
+class GenericJointBuilder {
 public:
-    SphericalJointBuilder() : d_{} {
+    explicit GenericJointBuilder(unsigned locked_axes) : d_{} {
         d_.local_frame1_q[3] = 1.0f; d_.local_frame2_q[3] = 1.0f;
-        d_.locked_axes = 7u; d_.contacts_enabled = 1;
+        d_.locked_axes = locked_axes; d_.contacts_enabled = 1;
         d_.natural_frequency = 1.0e6f; d_.damping_ratio = 1.0f;                 // integration_parameters.rs:78-83
+        for (int ax = 0; ax < 6; ++ax) {
+            d_.limits[ax][0] = -FLT_MAX; d_.limits[ax][1] = FLT_MAX;            // JointLimits::default
+            d_.motors[ax].max_force = FLT_MAX;                                  // JointMotor::default
+        }
     }
-    SphericalJointBuilder& local_anchor1(Vector v) { for (int i = 0; i < 3; ++i) d_.local_frame1_t[i] = v[i]; return *this; }
-    SphericalJointBuilder& local_anchor2(Vector v) { for (int i = 0; i < 3; ++i) d_.local_frame2_t[i] = v[i]; return *this; }
-    SphericalJointBuilder& contacts_enabled(bool on) { d_.contacts_enabled = on ? 1 : 0; return *this; }
+    GenericJointBuilder& local_anchor1(Vector v) { for (int i = 0; i < 3; ++i) d_.local_frame1_t[i] = v[i]; return *this; }
+    GenericJointBuilder& local_anchor2(Vector v) { for (int i = 0; i < 3; ++i) d_.local_frame2_t[i] = v[i]; return *this; }
+    // GenericJoint::set_local_axis{1,2}: the joint's X axis in the body's frame (generic_joint.rs:374-389)
+    GenericJointBuilder& local_axis1(Vector axis) { arc_from_x(axis, d_.local_frame1_q); return *this; }
+    GenericJointBuilder& local_axis2(Vector axis) { arc_from_x(axis, d_.local_frame2_q); return *this; }
+    GenericJointBuilder& contacts_enabled(bool on) { d_.contacts_enabled = on ? 1 : 0; return *this; }
+    // generic_joint.rs:470-560
+    GenericJointBuilder& limits(int axis, float lo, float hi) {
+        d_.limit_axes |= 1u << axis; d_.limits[axis][0] = lo; d_.limits[axis][1] = hi; return *this;
+    }
+    GenericJointBuilder& motor(int axis, float target_pos, float target_vel, float stiffness, float damping) {
+        d_.motor_axes |= 1u << axis;
+        RbJointMotor& m = d_.motors[axis];
+        m.target_pos = target_pos; m.target_vel = target_vel; m.stiffness = stiffness; m.damping = damping;
+        return *this;
+    }
+    GenericJointBuilder& motor_velocity(int axis, float target_vel, float factor) { return motor(axis, 0.0f, target_vel, 0.0f, factor); }
+    GenericJointBuilder& motor_position(int axis, float target_pos, float stiffness, float damping) {
+        return motor(axis, target_pos, 0.0f, stiffness, damping);
+    }
+    GenericJointBuilder& motor_max_force(int axis, float max_force) { d_.motor_axes |= 1u << axis; d_.motors[axis].max_force = max_force; return *this; }
+    GenericJointBuilder& motor_model(int axis, int model) { d_.motor_axes |= 1u << axis; d_.motors[axis].model = model; return *this; }   // 0 acceleration-, 1 force-based
     RbJointDesc desc(int b1, int b2) const { RbJointDesc d = d_; d.body1 = b1; d.body2 = b2; return d; }
 
 private:
+    // minimal rotation taking +X to `axis`, written as (x, y, z, w)
+    static void arc_from_x(Vector axis, float q[4]) {
+        const float n = std::sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+        const float ax = axis[0] / n, ay = axis[1] / n, az = axis[2] / n;
+        if (ax > 1.0f - 1e-7f) { q[0] = q[1] = q[2] = 0.0f; q[3] = 1.0f; return; }
+        if (ax < -1.0f + 1e-7f) { q[0] = q[1] = 0.0f; q[2] = 1.0f; q[3] = 0.0f; return; }   // half turn about Z
+        const float s = std::sqrt((1.0f + ax) * 2.0f);
+        q[0] = 0.0f; q[1] = -az / s; q[2] = ay / s; q[3] = s * 0.5f;
+    }
     RbJointDesc d_;
+};
+// SphericalJointBuilder / FixedJointBuilder / RevoluteJointBuilder / PrismaticJointBuilder (src/dynamics/joint/*.rs)
+struct SphericalJointBuilder : GenericJointBuilder { SphericalJointBuilder() : GenericJointBuilder(0x07u) {} };
+struct FixedJointBuilder : GenericJointBuilder { FixedJointBuilder() : GenericJointBuilder(0x3fu) {} };
+struct RevoluteJointBuilder : GenericJointBuilder {   // free: the rotation about `axis` (the X axis of both joint frames)
+    explicit RevoluteJointBuilder(Vector axis) : GenericJointBuilder(0x37u) { local_axis1(axis); local_axis2(axis); }
+};
+struct PrismaticJointBuilder : GenericJointBuilder {  // free: the translation along `axis`
+    explicit PrismaticJointBuilder(Vector axis) : GenericJointBuilder(0x3eu) { local_axis1(axis); local_axis2(axis); }
 };
 
 struct RigidBodySet {
@@ -149,7 +196,7 @@ struct ColliderSet {
 struct ImpulseJointSet {
     std::vector<RbJointDesc> joints;
     bool modified = true;
-    ImpulseJointHandle insert(RigidBodyHandle b1, RigidBodyHandle b2, const SphericalJointBuilder& j, bool = true) {
+    ImpulseJointHandle insert(RigidBodyHandle b1, RigidBodyHandle b2, const GenericJointBuilder& j, bool = true) {
         joints.push_back(j.desc(b1.index, b2.index)); modified = true; return {int(joints.size()) - 1};
     }
 };

@@ -65,6 +65,8 @@ struct Body {
     // coloured like them (narrow_phase/mod.rs:105-106).  DEVIATION shared with the kernels: they are island members too.
     bool is_dynamic() const { return type == RB_BODY_DYNAMIC || type == RB_BODY_KINEMATIC_POSITION_BASED || type == RB_BODY_KINEMATIC_VELOCITY_BASED; }
     bool is_strict_dynamic() const { return type == RB_BODY_DYNAMIC; }
+    // RigidBodyDominance::effective_group (rigid_body_components.rs:1267-1275)
+    int effective_dominance() const { return is_dynamic() ? RB_BODY_DOMINANCE_OF(flags) : 128; }
     bool is_awake() const { return is_dynamic() && !sleeping; }   // member of the active set
 };
 
@@ -121,6 +123,11 @@ struct Pair {
     uint32_t color_bodies[2];
     bool force_event_emitted;   // PairEventStatus::INITIAL_FORCE_THRESHOLD_EVENT_EMITTED
 };
+
+// ContactManifoldData::relative_dominance (pair_update.rs:381-382): > 0 = body 1 dominates (world-attached in this contact).
+inline int relative_dominance(const Body* rb1, const Body* rb2) {
+    return (rb1 ? rb1->effective_dominance() : 128) - (rb2 ? rb2->effective_dominance() : 128);
+}
 
 struct RawPoint {
     V3 local_p1, local_p2;

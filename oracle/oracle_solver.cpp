@@ -68,8 +68,9 @@ static void generate(World& w, int pair_index, Constraint& c) {
     memset(&c, 0, sizeof(c));
     c.pair = pair_index;
     c.coulomb = w.params.p.friction_model == 1;   // FrictionModel::Coulomb (init.rs:419)
-    bool d1 = p.b1 >= 0 && w.bodies[p.b1].is_awake();
-    bool d2 = p.b2 >= 0 && w.bodies[p.b2].is_awake();
+    const int rel_dom = relative_dominance(p.b1 >= 0 ? &w.bodies[p.b1] : nullptr, p.b2 >= 0 ? &w.bodies[p.b2] : nullptr);
+    bool d1 = p.b1 >= 0 && w.bodies[p.b1].is_awake() && rel_dom <= 0;   // contact_with_twist_friction.rs:71-84
+    bool d2 = p.b2 >= 0 && w.bodies[p.b2].is_awake() && rel_dom >= 0;
     c.id1 = d1 ? (uint32_t)p.b1 : NO_BODY;
     c.id2 = d2 ? (uint32_t)p.b2 : NO_BODY;
     GatheredBody g1 = gather(w, c.id1), g2 = gather(w, c.id2);
@@ -670,12 +671,19 @@ static int joint_update(const World& w, const Joint& j, float sub_dt, JointRow* 
 }
 
 // joint_velocity_constraint.rs:97-124
-static void joint_solve(World& w, const Joint& j, JointRow* rows, int n, bool wo_bias) {
+static void joint_solve(World& w, const Joint& j, JointRow* rows, int n, bool wo_bias, bool warm = false) {
     GatheredBody g1 = gather(w, j.sid1), g2 = gather(w, j.sid2);
     V3 v1 = g1.lin, w1 = g1.ang, v2 = g2.lin, w2 = g2.ang;
     for (int k = 0; k < n; ++k) {
         JointRow& r = rows[k];
         if (wo_bias) r.rhs = r.rhs_wo_bias;
+        if (warm) {   // warmstart_generic (joint_velocity_constraint.rs:129-141), row by row right before its solve (solve.rs:41)
+            V3 li = r.lin_jac * r.impulse;
+            v1 = maddv(v1, li, g1.im);
+            w1 = madd(w1, r.ii_ang_jac1, r.impulse);
+            v2 = maddv(v2, -li, g2.im);
+            w2 = madd(w2, r.ii_ang_jac2, -r.impulse);
+        }
         float dlinvel = dot(r.lin_jac, v2 - v1);
         float dangvel = dot(r.ang_jac2, w2) - dot(r.ang_jac1, w1);
         float rhs = dlinvel + dangvel + r.rhs;
@@ -851,12 +859,12 @@ void solve_island(World& w, V3 gravity) {
     const float max_lin = w.params.max_linear_velocity();
     const float max_ang = 0.7853981633974483f * inv_dt_full;  // MAX_ROTATION * base inv_dt (worker.rs:573-580)
 
-    auto solve_pass = [&](bool wo_bias, float solved_dt) {  // staged_island_solver/solve.rs:12-209
+    auto solve_pass = [&](bool wo_bias, float solved_dt, bool warm_joints = false) {  // staged_island_solver/solve.rs:12-209
         bool solve_friction = wo_bias || P.friction_in_bias_pass || P.num_internal_stabilization_iterations == 0;
         for (int s = 0; s < jnstages; ++s) {
             pool.parallel_for(js[s], js[s + 1], 64, [&](int q) {
                 int ji = w.jorder[q];
-                joint_solve(w, w.joints[ji], &w.jrows[jrow_start[ji]], jrow_start[ji + 1] - jrow_start[ji], wo_bias);
+                joint_solve(w, w.joints[ji], &w.jrows[jrow_start[ji]], jrow_start[ji + 1] - jrow_start[ji], wo_bias, warm_joints);
             });
         }
         for (int s = 0; s < nstages; ++s) {
@@ -882,11 +890,26 @@ void solve_island(World& w, V3 gravity) {
                 s.ang = gyroscopic_corrected_angvel(s.ang, principal_axes, b.principal_inertia, b.inv_principal_inertia, sub_dt);
             }
         });
-        // S4 joint rows rebuilt from the current poses (worker.rs:291-432); impulses restart from 0
-        // (warmstart_joints = false, joint_constraint_builder.rs:135-151).
+        // S4 joint rows rebuilt from the current poses (worker.rs:291-432); impulses restart from 0, or with
+        // warmstart_joints from last step's written-back impulses (first substep) / the previous substep's rows, times
+        // warmstart_coefficient (joint_constraint_builder.rs:116-150).
         pool.parallel_for(0, nj, 64, [&](int i) {
             if (jcolors[i] < 0) return;
-            joint_update(w, w.joints[i], sub_dt, &w.jrows[jrow_start[i]]);
+            JointRow* rows = &w.jrows[jrow_start[i]];
+            const Joint& j = w.joints[i];
+            float prev[24];
+            const int nprev = jrow_start[i + 1] - jrow_start[i];
+            if (P.warmstart_joints && substep > 0)
+                for (int k = 0; k < nprev && k < 24; ++k) prev[k] = rows[k].impulse;
+            const int len = joint_update(w, j, sub_dt, rows);
+            if (P.warmstart_joints) {
+                for (int k = 0; k < len && k < 24; ++k) {
+                    JointRow& r = rows[k];
+                    float seed = substep > 0 ? prev[k]
+                                             : (r.kind == 0 ? j.impulses[r.dof] : r.kind == 1 ? j.limit_impulses[r.dof] : j.motor_impulses[r.dof]);
+                    r.impulse = seed * P.warmstart_coefficient;
+                }
+            }
         });
         // S5 update + warmstart, colour by colour (worker.rs:438-539)
         if (!fused_warmstart) {
@@ -900,7 +923,7 @@ void solve_island(World& w, V3 gravity) {
             }
         }
         // S6 biased solve (worker.rs:544-561)
-        for (int it = 0; it < P.num_internal_pgs_iterations; ++it) solve_pass(false, solved_dt);
+        for (int it = 0; it < P.num_internal_pgs_iterations; ++it) solve_pass(false, solved_dt, P.warmstart_joints != 0 && it == 0);   // worker.rs:548
         // S7 integrate positions (worker.rs:568-631; rigid_body_components.rs:884-898)
         pool.parallel_for(0, nb, 256, [&](int i) {
             SolverBody& s = w.sb[i];

@@ -425,8 +425,9 @@ static bool process_pair(World& w, Pair& pair) {
     bool had_active = pair.nsc > 0;
     const Body* rb1 = pair.b1 >= 0 ? &w.bodies[pair.b1] : nullptr;
     const Body* rb2 = pair.b2 >= 0 ? &w.bodies[pair.b2] : nullptr;
-    bool dyn1 = rb1 && rb1->is_dynamic();
-    bool dyn2 = rb2 && rb2->is_dynamic();
+    const int rel_dom = relative_dominance(rb1, rb2);
+    bool dyn1 = rb1 && rb1->is_dynamic() && rel_dom <= 0;   // pair_update.rs:538-545: dominance-superior sides keep world anchors
+    bool dyn2 = rb2 && rb2->is_dynamic() && rel_dom >= 0;
 
     Pose pos12 = pose_inv_mul(co1.pos, co2.pos);
     float skin_sum = co1.contact_skin + co2.contact_skin;

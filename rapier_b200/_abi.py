@@ -23,6 +23,7 @@ RB_BODY_LOCK_TX, RB_BODY_LOCK_TY, RB_BODY_LOCK_TZ = 4, 8, 16
 RB_BODY_LOCK_RX, RB_BODY_LOCK_RY, RB_BODY_LOCK_RZ = 32, 64, 128
 RB_BODY_NO_SLEEP = 256
 RB_BODY_CCD_ENABLED = 512
+RB_BODY_DOMINANCE_SHIFT = 16   # RB_BODY_DOMINANCE(group): signed 8-bit dominance group in bits 16..23 of flags
 RB_SHAPE_BALL = 0
 RB_SHAPE_CUBOID = 1
 RB_SHAPE_CAPSULE = 2

@@ -523,6 +523,7 @@ static void derive_params(const RbIntegrationParameters& p, Params& o) {
     o.friction_in_bias = p.friction_in_bias_pass;
     o.contact_recycling = p.contact_recycling;
     o.friction_model = p.friction_model;
+    o.warmstart_joints = p.warmstart_joints != 0 ? 1 : 0;
     o.ccd = p.max_ccd_substeps != 0 ? 1 : 0;
     o.linear_slop = p.normalized_allowed_linear_error * p.length_unit;
 }
@@ -530,7 +531,7 @@ static void derive_params(const RbIntegrationParameters& p, Params& o) {
 static int validate_params(const RbIntegrationParameters* p) {
     if (!p) { set_err("null parameters%s", ""); return RB_ERR_INVALID; }
     if (p->friction_model != 0 && p->friction_model != 1) { set_err("friction_model must be 0 (Simplified) or 1 (Coulomb)%s", ""); return RB_ERR_INVALID; }
-    if (p->warmstart_joints != 0) { set_err("warmstart_joints is not supported%s", ""); return RB_ERR_INVALID; }
+    if (p->warmstart_joints != 0 && p->warmstart_joints != 1) { set_err("warmstart_joints must be 0 or 1%s", ""); return RB_ERR_INVALID; }
     if (p->max_ccd_substeps < 0 || p->max_ccd_substeps > 1) { set_err("max_ccd_substeps must be 0 (CCD off) or 1 (motion clamping); the multi-substep splitter is not supported%s", ""); return RB_ERR_INVALID; }
     if (p->num_solver_iterations < 1 || p->num_solver_iterations > 64) { set_err("num_solver_iterations out of range%s", ""); return RB_ERR_INVALID; }
     return RB_OK;
@@ -967,6 +968,11 @@ int rb_world_set_params(RbWorld* W, const RbIntegrationParameters* params) {
     if (!W) { set_err("null world%s", ""); return RB_ERR_INVALID; }
     int rc = validate_params(params);
     if (rc != RB_OK) return rc;
+    // joint warm starting runs on the generic joint path, whose row tables are sized when the scene is set
+    if (params->warmstart_joints && !W->w.generic_joints && !W->joints.empty()) {
+        set_err("warmstart_joints must be enabled before the scene is set%s", "");
+        return RB_ERR_INVALID;
+    }
     W->params = *params;
     derive_params(W->params, W->w.prm);
     return RB_OK;
@@ -1019,7 +1025,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     w.joint_cap = std::max(nj, 1);
     w.item_cap = 4 + (NB + w.pair_cap + nj) / ITEM_TARGET;
     const int NJ = w.joint_cap;
-    w.generic_joints = 0;
+    w.generic_joints = (nj > 0 && W->params.warmstart_joints) ? 1 : 0;   // joint warm starting: generic path too
     for (int i = 0; i < nj; ++i) {   // any limit or motor on a free axis: the generic joint path (12 row slots per joint)
         const unsigned free_axes = ~joints[i].locked_axes & 63u;
         if ((joints[i].limit_axes | joints[i].motor_axes) & free_axes) w.generic_joints = 1;

@@ -36,6 +36,12 @@ RB_HD bool body_is_dyn(const World& w, int b) {  // dynamic or kinematic, and si
 RB_HD bool body_is_strict_dyn(const World& w, int b) { return b >= 0 && w.b_type[b] == BODY_DYNAMIC && w.b_owned[b] == 1; }
 // ... and awake: a member of the active set (island_manager: sleeping bodies are neither solved nor integrated)
 RB_HD bool body_is_sim(const World& w, int b) { return body_is_dyn(w, b) && !w.b_sleeping[b]; }
+// ContactManifoldData::relative_dominance (pair_update.rs:381-382; effective_group rigid_body_components.rs:1267-1275):
+// > 0 = body 1 dominates and is world-attached in this contact, < 0 = body 2.  The group is a signed byte in b_flags.
+RB_HD int body_dominance(const World& w, int b) {
+    return (b >= 0 && type_is_solver(w.b_type[b])) ? (int)(signed char)((w.b_flags[b] >> 16) & 0xffu) : 128;
+}
+RB_HD int relative_dominance(const World& w, int b1, int b2) { return body_dominance(w, b1) - body_dominance(w, b2); }
 RB_HD pose body_pose(const World& w, int b) { return mkpose(mkq(w.b_pos_q[b]), xyz(w.b_pos_t[b])); }
 RB_HD pose collider_pose(const World& w, int c) { return mkpose(mkq(w.c_pos_q[c]), xyz(w.c_pos_t[c])); }
 
@@ -629,8 +635,10 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
         vec3 lv1 = zero3(), av1 = zero3(), wc1 = zero3(), lv2 = zero3(), av2 = zero3(), wc2 = zero3();
         if (b1 >= 0) { lv1 = xyz(w.b_linvel[b1]); av1 = xyz(w.b_angvel[b1]); wc1 = xyz(w.b_wcom[b1]); }
         if (b2 >= 0) { lv2 = xyz(w.b_linvel[b2]); av2 = xyz(w.b_angvel[b2]); wc2 = xyz(w.b_wcom[b2]); }
-        if (dyn1) com1 = prepend_translation(body_pose(w, b1), xyz(w.b_lcom_im[b1]));
-        if (dyn2) com2 = prepend_translation(body_pose(w, b2), xyz(w.b_lcom_im[b2]));
+        const int rel_dom = relative_dominance(w, b1, b2);
+        const bool loc1 = dyn1 && rel_dom <= 0, loc2 = dyn2 && rel_dom >= 0;   // dominance-superior sides keep world anchors (pair_update.rs:538-545)
+        if (loc1) com1 = prepend_translation(body_pose(w, b1), xyz(w.b_lcom_im[b1]));
+        if (loc2) com2 = prepend_translation(body_pose(w, b2), xyz(w.b_lcom_im[b2]));
 
         int nsc = 0;
         for (int k = 0; k < nsel; ++k) {
@@ -654,10 +662,10 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
                 float shift = dot3(wp2 - wp1, normal) - eff;
                 vec3 p1 = wp1 + normal * shift;
                 vec3 point = (p1 + wp2) * 0.5f;
-                d1 = f4(dyn1 ? point - com1.t : point, 0.0f);
-                d2 = f4(dyn2 ? point - com2.t : point, 0.0f);
-                vec3 a1 = dyn1 ? xform_inv(com1, p1) : p1;
-                vec3 a2 = dyn2 ? xform_inv(com2, wp2) : wp2;
+                d1 = f4(loc1 ? point - com1.t : point, 0.0f);
+                d2 = f4(loc2 ? point - com2.t : point, 0.0f);
+                vec3 a1 = loc1 ? xform_inv(com1, p1) : p1;
+                vec3 a2 = loc2 ? xform_inv(com2, wp2) : wp2;
                 prow(w, buf, PR_A1 + nsc, i) = f4(a1, as_float_i(k));
                 prow(w, buf, PR_A2 + nsc, i) = f4(a2, 0.0f);
                 ++nsc;
@@ -1173,6 +1181,11 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
                 }
                 int id1 = body_is_sim(w, b1) ? (it == 0 ? b1 : w.body_local[b1]) : NO_BODY;
                 int id2 = body_is_sim(w, b2) ? (it == 0 ? b2 : w.body_local[b2]) : NO_BODY;
+                if (pass == 0) {   // contact_with_twist_friction.rs:71-84
+                    const int rel_dom = relative_dominance(w, b1, b2);
+                    if (rel_dom > 0) id1 = NO_BODY;
+                    if (rel_dom < 0) id2 = NO_BODY;
+                }
                 if (pass == 0) w.cons_hdr[q] = make_int4(id, id1, id2, 0);
                 else w.j_sched_ids[q] = make_int4(id, id1, id2, 0);
             }

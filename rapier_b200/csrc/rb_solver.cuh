@@ -795,7 +795,7 @@ RB_HD void grows_finalize(GRow* r, int a, int b, vec3 imsum) {
     }
 }
 template <class B>
-RB_HD void joint_update_generic(const World& w, const B& bd, int q) {
+RB_HD void joint_update_generic(const World& w, const B& bd, int q, int sub) {
     int4 h = w.j_sched_ids[q];
     const int j = h.x, id1 = h.y, id2 = h.z;
     const int4 ji = w.j_info[j];
@@ -951,7 +951,15 @@ RB_HD void joint_update_generic(const World& w, const B& bd, int q) {
     for (int k = 0; k < len; ++k) {
         const size_t s = (size_t)JROWS_GENERIC * q + k;
         const GRow& r = rows[k];
-        w.j_rows[JR_LIN * rs + s] = f4(r.lin, 0.0f);   // impulse restarts from 0 (warmstart_joints = false)
+        // the impulse restarts from 0, or with warmstart_joints from last step's written-back impulse (first substep) /
+        // the same row of the previous substep, scaled by warmstart_coefficient (joint_constraint_builder.rs:116-150)
+        float imp = 0.0f;
+        if (w.prm.warmstart_joints) {
+            const float* src = r.kind == 0 ? w.j_impulses : (r.kind == 1 ? w.j_limit_impulses : w.j_motor_impulses);
+            const float seed = sub > 0 ? w.j_rows[JR_LIN * rs + s].w : src[j * 6 + r.dof];
+            imp = seed * w.prm.warmstart_coeff;
+        }
+        w.j_rows[JR_LIN * rs + s] = f4(r.lin, imp);
         w.j_rows[JR_A1 * rs + s] = f4(r.a1, r.inv_lhs);
         w.j_rows[JR_A2 * rs + s] = f4(r.a2, r.rhs);
         w.j_rows[JR_IA1 * rs + s] = f4(r.ia1, r.rwb);
@@ -962,7 +970,7 @@ RB_HD void joint_update_generic(const World& w, const B& bd, int q) {
     w.j_sched_ids[q] = h;
 }
 template <class B>
-RB_HD void joint_solve_generic(const World& w, const B& bd, int q, bool wo_bias) {   // solve_generic with impulse_bounds (joint_velocity_constraint.rs:97-120)
+RB_HD void joint_solve_generic(const World& w, const B& bd, int q, bool wo_bias, bool warm) {   // solve_generic with impulse_bounds (joint_velocity_constraint.rs:97-120)
     const int4 h = w.j_sched_ids[q];
     const int id1 = h.y, id2 = h.z, len = h.w;
     BodyState g1 = gather_body(bd, id1), g2 = gather_body(bd, id2);
@@ -972,6 +980,13 @@ RB_HD void joint_solve_generic(const World& w, const B& bd, int q, bool wo_bias)
         const size_t s = (size_t)JROWS_GENERIC * q + k;
         float4 L = w.j_rows[JR_LIN * rs + s], A1 = w.j_rows[JR_A1 * rs + s], A2 = w.j_rows[JR_A2 * rs + s];
         const float4 I1 = w.j_rows[JR_IA1 * rs + s], I2 = w.j_rows[JR_IA2 * rs + s], bnd = w.j_bnd[s];
+        if (warm) {   // warmstart_generic (joint_velocity_constraint.rs:129-141): the carried impulse, right before the row's solve
+            const vec3 wl = xyz(L) * L.w;
+            v1 = madd3v(v1, wl, g1.im);
+            w1 = madd3(w1, xyz(I1), L.w);
+            v2 = madd3v(v2, -wl, g2.im);
+            w2 = madd3(w2, xyz(I2), -L.w);
+        }
         const float rhs_c = wo_bias ? I1.w : A2.w;
         const float dlin = dot3(xyz(L), v2 - v1);
         const float dang = dot3(xyz(A2), w2) - dot3(xyz(A1), w1);
@@ -1267,7 +1282,7 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
         ex.sync();
         // S4 joint rows from the current poses
         if (j1 > j0) {
-            for (int q = j0 + tid; q < j1; q += nth) { if (JM) joint_update_generic(w, bd, q); else joint_update(w, bd, q); }
+            for (int q = j0 + tid; q < j1; q += nth) { if (JM) joint_update_generic(w, bd, q, sub); else joint_update(w, bd, q); }
             ex.sync();
         }
         // S5 update + warmstart, colour by colour
@@ -1306,14 +1321,15 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
             const int iters = relax ? P.num_relax : P.num_pgs;
             const bool fric = relax || P.friction_in_bias || P.num_relax == 0;
             for (int it = 0; it < iters; ++it) {
+                const bool jwarm = JM && P.warmstart_joints && !relax && it == 0;   // fused into the first biased pass (worker.rs:548)
                 // joints first (solve.rs:89-92), then contacts
                 for (int c = 0; c < njcol; ++c) {
                     int a = j0 + joff[c], e = j0 + joff[c + 1];
                     if (a >= e) continue;
                     if (c == jovf) {
-                        if (tid == 0) for (int q = a; q < e; ++q) { if (JM) joint_solve_generic(w, bd, q, relax); else joint_solve(w, bd, q, relax); }
+                        if (tid == 0) for (int q = a; q < e; ++q) { if (JM) joint_solve_generic(w, bd, q, relax, jwarm); else joint_solve(w, bd, q, relax); }
                     } else {
-                        for (int q = a + tid; q < e; q += nth) { if (JM) joint_solve_generic(w, bd, q, relax); else joint_solve(w, bd, q, relax); }
+                        for (int q = a + tid; q < e; q += nth) { if (JM) joint_solve_generic(w, bd, q, relax, jwarm); else joint_solve(w, bd, q, relax); }
                     }
                     ex.sync();
                 }

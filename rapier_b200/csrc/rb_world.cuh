@@ -82,6 +82,7 @@ struct Params {  // IntegrationParameters + derived per-substep coefficients (co
     int ccd;              // max_ccd_substeps != 0: motion clamping of fast bodies (substep.rs:404-409, :492-520)
     float linear_slop;    // allowed_linear_error(): target distance of the time of impact (ccd_solver.rs:184)
     int friction_model;   // 0 = Simplified (twist), 1 = Coulomb (integration_parameters.rs:16-30)
+    int warmstart_joints; // joint rows carry their impulses (integration_parameters.rs:300); served by the generic joint path
 };
 
 // Device-side scalars (one struct in HBM, mirrored to pinned host memory on demand).

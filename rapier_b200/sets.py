@@ -97,6 +97,15 @@ class RigidBodyBuilder:
             self._flags &= ~A.RB_BODY_CCD_ENABLED
         return self
 
+    def dominance_group(self, group):
+        """RigidBodyBuilder::dominance_group (rigid_body.rs): signed 8-bit group; in a contact the body of the higher group
+        is seen as immovable by the other one (RigidBodyDominance, rigid_body_components.rs:1255-1276)."""
+        g = int(group)
+        if not -128 <= g <= 127:
+            raise ValueError("dominance group must fit an i8")
+        self._flags = (self._flags & ~(0xFF << A.RB_BODY_DOMINANCE_SHIFT)) | ((g & 0xFF) << A.RB_BODY_DOMINANCE_SHIFT)
+        return self
+
     def can_sleep(self, flag):
         """RigidBodyBuilder::can_sleep (rigid_body.rs; false = RigidBodyActivation::cannot_sleep())."""
         self._can_sleep = bool(flag)

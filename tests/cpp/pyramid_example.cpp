@@ -25,7 +25,15 @@ int main(int argc, char** argv) {
         world.insert(RigidBodyBuilder::fixed().translation({0.0f, -1.0f, 0.0f}), ColliderBuilder::cuboid(30.0f, 1.0f, 30.0f));
         create_small_pyramid(world, 10, 0.5f, 0.0f, 0.0f);
         create_small_pyramid(world, 10, 0.5f, 12.0f, 0.0f);
+        // a bar on a limited revolute joint (revolute_joint.rs + generic_joint.rs limits), far from the pyramids
+        RigidBodyHandle anchor = world.bodies.insert(RigidBodyBuilder::fixed().translation({-40.0f, 20.0f, 0.0f}));
+        RigidBodyHandle bar = world.insert(RigidBodyBuilder::dynamic().translation({-39.0f, 20.0f, 0.0f}).can_sleep(false).dominance_group(3),
+                                           ColliderBuilder::cuboid(1.0f, 0.1f, 0.1f));
+        world.impulse_joints.insert(anchor, bar, RevoluteJointBuilder({0.0f, 0.0f, 1.0f}).local_anchor2({-1.0f, 0.0f, 0.0f}).limits(3, -0.5f, 0.25f));
         world.step(steps);
+        const RbBodyDesc& bd = world.bodies.bodies[bar.index];
+        const float bar_angle = 2.0f * std::atan2(bd.rotation[2], bd.rotation[3]);   // rotation about Z
+        if (steps >= 100 && !(bar_angle > -0.55f && bar_angle < -0.45f)) { fprintf(stderr, "bar angle %f outside its limit\n", bar_angle); return 4; }
         RbCounters c = world.physics_pipeline.counters();
         float top_y = world.bodies.bodies[55].translation[1];   // apex cube of the first pyramid
         printf("steps=%d bodies=%d pairs=%d manifolds=%d apex_y=%.4f\n", steps, c.num_bodies, c.num_pairs, c.num_active_manifolds, top_y);

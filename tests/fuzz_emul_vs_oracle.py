@@ -23,6 +23,8 @@ def random_scene(seed):
     from rapier_b200.sets import (ColliderBuilder, FixedJointBuilder, PrismaticJointBuilder, RevoluteJointBuilder,
                                   RigidBodyBuilder, SphericalJointBuilder)
     r = np.random.default_rng(seed)
+    r2 = np.random.default_rng(seed + 1000003)   # later options draw from a second stream: the scenes of old seeds keep their shape
+    dominance = r2.random() < 0.35
     s = scenes.Scene(f"fuzz_{seed}", gravity=(0.0, float(r.choice([-9.81, -10.0, -3.0])), 0.0))
     s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)),
              ColliderBuilder.cuboid(12.0, 0.5, 12.0).friction(float(r.uniform(0.0, 1.0))).restitution(float(r.choice([0.0, 0.0, 0.5]))))
@@ -54,6 +56,8 @@ def random_scene(seed):
             b = b.additional_mass(float(r.uniform(0.5, 20.0)))
         if r.random() < 0.1:
             b = b.gyroscopic_forces_enabled(False)
+        if dominance and r2.random() < 0.4:
+            b = b.dominance_group(int(r2.choice([-128, -2, -1, 1, 3, 127])))
         sh = r.random()
         if sh < 0.5:
             c = ColliderBuilder.cuboid(*[float(x) for x in r.uniform(0.15, 0.7, 3)])
@@ -110,6 +114,8 @@ def random_scene(seed):
         params.friction_model = 1
     if r.random() < 0.15:
         params.max_ccd_substeps = 0
+    if r2.random() < 0.3:
+        params.warmstart_joints = 1
     s.kinematic_position_based = [h for h in kinematic if s.bodies.descs[h].body_type == A.RB_BODY_KINEMATIC_POSITION_BASED]
     return s, params
 

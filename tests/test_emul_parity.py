@@ -188,6 +188,25 @@ def test_joint_limits_and_motors_emulated_kernels():
                              lambda s, p=None: oracle_lib.OracleWorld(s, params=p), coulomb=True)
 
 
+def test_dominance_groups_emulated_kernels():
+    from test_oracle_kat import dominance_groups
+    from variant_cases import dominance_parity_case
+    dominance_groups(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()))
+    dominance_parity_case(lambda s, p=None: PhysicsWorld(s, integration_parameters=p, _lib=emul_lib.lib()),
+                          lambda s, p=None: oracle_lib.OracleWorld(s, params=p))
+
+
+def test_joint_warmstart_emulated_kernels():
+    from test_oracle_kat import joint_warmstart
+    from variant_cases import joint_limits_parity_case
+    mk = lambda s, p=None: PhysicsWorld(s, integration_parameters=p, _lib=emul_lib.lib())
+    mo = lambda s, p=None: oracle_lib.OracleWorld(s, params=p)
+    joint_warmstart(mk)
+    joint_limits_parity_case(mk, mo, warmstart_joints=True)
+    joint_limits_parity_case(mk, mo, warmstart_joints=True, coulomb=True, steps=60)
+    joint_limits_parity_case(mk, mo, warmstart_joints=True, scene=scenes.joint_grid(6), steps=60)   # locked-only joints on the generic path
+
+
 def test_capsules_emulated_kernels():
     from test_oracle_kat import capsules_rest
     capsules_rest(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()))

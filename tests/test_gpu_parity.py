@@ -381,3 +381,18 @@ def test_more_reference_known_answers(built):
     mkp = lambda s, p: PhysicsWorld(s, integration_parameters=p)
     prismatic_joint_stays_bounded_for_all_axis_rotations(mkp)
     motor_position_with_rotating_base_stays_finite(mkp)
+
+
+def test_dominance_groups_and_joint_warmstart(built):
+    """RigidBodyDominance and IntegrationParameters::warmstart_joints: known answers through the C ABI and bit-exact parity
+    with the oracle (twist and Coulomb friction; limits / motors and a locked-only joint grid on the generic joint path)."""
+    from test_oracle_kat import dominance_groups, joint_warmstart
+    from variant_cases import dominance_parity_case, joint_limits_parity_case
+    mk = lambda s, p=None: PhysicsWorld(s, integration_parameters=p)
+    mo = lambda s, p=None: oracle_lib.OracleWorld(s, params=p)
+    dominance_groups(mk)
+    dominance_parity_case(mk, mo)
+    joint_warmstart(mk)
+    joint_limits_parity_case(mk, mo, warmstart_joints=True)
+    joint_limits_parity_case(mk, mo, warmstart_joints=True, coulomb=True, steps=60)
+    joint_limits_parity_case(mk, mo, warmstart_joints=True, scene=scenes.joint_grid(20), steps=60)

@@ -898,3 +898,96 @@ def sleep_wake_scenarios(make_world):
 def test_sleep_wake_oracle():
     from incremental_cases import OracleSets
     sleep_wake_scenarios(lambda s: OracleSets(s))
+
+
+def dominance_groups(make_world):
+    """RigidBodyDominance (rigid_body_components.rs:1255-1276; contact_with_twist_friction.rs:71-84): in a contact between
+    two groups the higher one is world-attached.  No test of the reference pins this; the scenarios follow its documented
+    behaviour: (1) a light dominating box carries a dominated box 320 times its mass without sinking, while the same pair
+    with equal groups sinks measurably deeper into the ground contact; (2) a dominating dynamic box is not pushed by a
+    kinematic wall sweeping through it, an ordinary one is; (3) a dominated ball bounces off a dominating free-floating
+    box without moving it."""
+    def crush(groups):
+        s = scenes.Scene("crush", gravity=(0.0, -9.81, 0.0))
+        s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(10.0, 0.5, 10.0))
+        light = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.25, 0.0)).dominance_group(groups[0]), ColliderBuilder.cuboid(0.25, 0.25, 0.25).density(0.5))
+        heavy = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 1.0, 0.0)).dominance_group(groups[1]), ColliderBuilder.cuboid(0.5, 0.5, 0.5).density(20.0))
+        w = make_world(s)
+        w.step(240)
+        pose, vel = w.body_states()
+        assert np.abs(vel[[light, heavy]]).max() < 0.05
+        return float(pose[light, 1]), float(pose[heavy, 1])
+    y_dom, top_dom = crush((4, 0))
+    y_eq, _ = crush((0, 0))
+    assert abs(y_dom - 0.25) < 0.003 and abs(top_dom - 1.0) < 0.01, (y_dom, top_dom)   # as if nothing lay on it
+    assert y_eq < y_dom - 1e-4, (y_eq, y_dom)                                             # the load shows without dominance
+    s = scenes.Scene("wall", gravity=(0.0, 0.0, 0.0))
+    s.insert(RigidBodyBuilder.kinematic_velocity_based().translation((-2.0, 0.0, 0.0)).linvel((2.0, 0.0, 0.0)), ColliderBuilder.cuboid(0.2, 1.0, 1.0))
+    proud = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.0, 0.0)).dominance_group(1), ColliderBuilder.cuboid(0.3, 0.3, 0.3))
+    s.insert(RigidBodyBuilder.kinematic_velocity_based().translation((-2.0, 0.0, 10.0)).linvel((2.0, 0.0, 0.0)), ColliderBuilder.cuboid(0.2, 1.0, 1.0))
+    meek = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.0, 10.0)), ColliderBuilder.cuboid(0.3, 0.3, 0.3))
+    w = make_world(s)
+    w.step(90)
+    pose, vel = w.body_states()
+    assert abs(pose[proud, 0]) < 1e-6 and np.abs(vel[proud]).max() < 1e-6     # the wall passed through it
+    assert pose[meek, 0] > 0.4 and vel[meek, 0] > 1.5                          # the ordinary box is shoved along
+    s = scenes.Scene("bounce_off", gravity=(0.0, 0.0, 0.0))
+    rock = s.insert(RigidBodyBuilder.dynamic().dominance_group(7), ColliderBuilder.cuboid(0.5, 0.5, 0.5).restitution(1.0))
+    ball = s.insert(RigidBodyBuilder.dynamic().translation((-3.0, 0.0, 0.0)).linvel((5.0, 0.0, 0.0)).dominance_group(-7), ColliderBuilder.ball(0.3).restitution(1.0))
+    w = make_world(s)
+    w.step(90)
+    pose, vel = w.body_states()
+    assert np.abs(pose[rock, :3]).max() < 1e-6 and np.abs(vel[rock]).max() < 1e-6
+    assert vel[ball, 0] < -4.0                                                  # full elastic return: the rock took no momentum
+
+
+def test_dominance_groups_oracle():
+    dominance_groups(lambda s: oracle_lib.OracleWorld(s))
+
+
+def joint_warmstart(make_world):
+    """IntegrationParameters::warmstart_joints (integration_parameters.rs:300; joint_constraint_builder.rs:116-150;
+    worker.rs:548).  The carried impulse is applied row by row right before that row's exact solve, so for rigid
+    (unbounded, cfm ~ 0) rows the body velocities after the solve are those of a cold solve: the option only shows through
+    the cfm term of soft rows.  No reference test pins it; checked here: a hanging chain of rigid joints moves as without
+    the option (to rounding), its top joint reports the same impulse (the chain's weight x substep length), a spring
+    (position) motor DOES respond differently, and with a warm-start coefficient of 0 the option is a no-op bit for bit."""
+    from rapier_b200.sets import RevoluteJointBuilder, SphericalJointBuilder
+    def chain(warm, coeff=1.0, spring=False):
+        s = scenes.Scene("chain", gravity=(0.0, -9.81, 0.0))
+        prev = s.bodies.insert(RigidBodyBuilder.fixed().translation((0.0, 10.0, 0.0)))
+        ids = []
+        for i in range(12):
+            b = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 9.5 - 1.0 * i, 0.0)).can_sleep(False), ColliderBuilder.ball(0.2).density(30.0))
+            s.joints.insert(prev, b, SphericalJointBuilder().local_anchor1((0.0, -0.5, 0.0) if i else (0.0, 0.0, 0.0)).local_anchor2((0.0, 0.5, 0.0)))
+            ids.append(b)
+            prev = b
+        if spring:
+            arm = s.insert(RigidBodyBuilder.dynamic().translation((5.5, 10.0, 0.0)).can_sleep(False), ColliderBuilder.cuboid(0.5, 0.1, 0.1))
+            s.joints.insert(0, arm, RevoluteJointBuilder((0.0, 0.0, 1.0)).local_anchor1((5.0, 0.0, 0.0)).local_anchor2((-0.5, 0.0, 0.0)).motor_position(3, 0.5, 40.0, 2.0))
+            ids.append(arm)
+        p = A.RbIntegrationParameters.default()
+        p.warmstart_joints = 1 if warm else 0
+        p.warmstart_coefficient = coeff
+        w = make_world(s, p)
+        w.step(240)
+        pose, vel = w.body_states()
+        assert np.isfinite(pose).all()
+        return pose[ids], w
+    cold, wc = chain(False)
+    warm, ww = chain(True)
+    assert np.abs(cold - warm).max() < 1e-3 and abs(float(warm[-1, 1]) + 1.5) < 0.05
+    mass = 12 * 30.0 * 4.0 / 3.0 * np.pi * 0.2 ** 3
+    for w in (wc, ww):
+        ji = w.debug_read("joint_impulses", np.float32).reshape(-1, 6)
+        assert abs(np.abs(ji[0, :3]).max() - mass * 9.81 / 240.0) < 0.05 * mass * 9.81 / 240.0, (ji[0], mass * 9.81 / 240.0)
+    cold_s, _ = chain(False, spring=True)
+    warm_s, _ = chain(True, spring=True)
+    assert (cold_s[-1].view(np.uint32) != warm_s[-1].view(np.uint32)).any() and np.abs(cold_s[-1] - warm_s[-1]).max() < 0.2
+    off, _ = chain(True, coeff=0.0, spring=True)
+    ref, _ = chain(False, coeff=0.0, spring=True)
+    assert (off.view(np.uint32) == ref.view(np.uint32)).all()
+
+
+def test_joint_warmstart_oracle():
+    joint_warmstart(lambda s, p: oracle_lib.OracleWorld(s, params=p))

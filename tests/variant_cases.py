@@ -232,11 +232,16 @@ def joint_limits_scene():
     return s
 
 
-def joint_limits_parity_case(make_world, make_oracle, steps=150, every=15, coulomb=False):
+def joint_limits_parity_case(make_world, make_oracle, steps=150, every=15, coulomb=False, warmstart_joints=False, scene=None):
     from parity_util import compare_worlds, is_exact
-    s = joint_limits_scene()
-    p = _params(friction_model=1) if coulomb else None
-    w, o = (make_world(s, p), make_oracle(s, p)) if coulomb else (make_world(s), make_oracle(s))
+    s = scene if scene is not None else joint_limits_scene()
+    kw = {}
+    if coulomb:
+        kw["friction_model"] = 1
+    if warmstart_joints:
+        kw["warmstart_joints"] = 1
+    p = _params(**kw) if kw else None
+    w, o = (make_world(s, p), make_oracle(s, p)) if kw else (make_world(s), make_oracle(s))
     for i in range(steps):
         w.step(); o.step()
         if i % every == every - 1 or i < 2:
@@ -304,3 +309,53 @@ VARIANTS = [
     ("ccd_barrage_ccd_off", ccd_barrage, _params(max_ccd_substeps=0), 30, 10),
     ("ccd_barrage_coulomb_dt_large", ccd_barrage, _params(friction_model=1, dt=1.0 / 30.0), 40, 10),
 ]
+
+
+def dominance_scene():
+    """RigidBodyDominance next to ordinary contacts: a stack whose middle box dominates (its neighbours see it as immovable,
+    it still rests on the one below), a heavy dominated box dropped on a light dominating one, a dynamic box dominating the
+    kinematic platform that sweeps into it, dominated balls rolling against a dominating box, two jointed boxes of
+    different groups, and a small pile of mixed groups (a group changes the constraint's world-attached side, not the
+    colouring)."""
+    s = scenes.Scene("dominance")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(30.0, 0.5, 30.0))
+    for k, g in enumerate((0, 5, 0)):
+        s.insert(RigidBodyBuilder.dynamic().translation((0.02 * k, 0.5 + 1.0 * k, 0.0)).dominance_group(g), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    s.insert(RigidBodyBuilder.dynamic().translation((4.0, 0.3, 0.0)).dominance_group(10), ColliderBuilder.cuboid(0.3, 0.3, 0.3).density(0.5))
+    s.insert(RigidBodyBuilder.dynamic().translation((4.1, 2.0, 0.05)).dominance_group(-3), ColliderBuilder.cuboid(0.6, 0.6, 0.6).density(20.0))
+    s.insert(RigidBodyBuilder.kinematic_velocity_based().translation((-6.0, 0.5, 0.0)).linvel((1.5, 0.0, 0.0)).dominance_group(-1),
+             ColliderBuilder.cuboid(0.4, 0.5, 1.0))
+    s.insert(RigidBodyBuilder.dynamic().translation((-4.0, 0.4, 0.0)).dominance_group(2), ColliderBuilder.cuboid(0.4, 0.4, 0.4))
+    s.insert(RigidBodyBuilder.dynamic().translation((-2.5, 0.4, 0.2)), ColliderBuilder.cuboid(0.4, 0.4, 0.4))
+    s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.6, 5.0)).dominance_group(127), ColliderBuilder.cuboid(0.6, 0.6, 0.6))
+    for i in range(3):
+        s.insert(RigidBodyBuilder.dynamic().translation((-3.0 - 1.2 * i, 0.4, 5.0 + 0.1 * i)).linvel((4.0, 0.0, 0.0)).dominance_group(-128 + i),
+                 ColliderBuilder.ball(0.4))
+    a = s.insert(RigidBodyBuilder.dynamic().translation((8.0, 0.5, 0.0)).dominance_group(1), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    b = s.insert(RigidBodyBuilder.dynamic().translation((9.1, 0.5, 0.0)).dominance_group(-1), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    s.joints.insert(a, b, SphericalJointBuilder().local_anchor1((0.55, 0.5, 0.0)).local_anchor2((-0.55, 0.5, 0.0)))
+    s.insert(RigidBodyBuilder.dynamic().translation((8.5, 1.6, 0.0)), ColliderBuilder.cuboid(0.45, 0.45, 0.45))
+    k = 0
+    for layer in range(3):
+        for i in range(3):
+            for j in range(2):
+                pos = (-1.0 + 1.05 * i + 0.06 * layer, 0.5 + 1.02 * layer, -10.0 + 1.05 * j + 0.04 * i)
+                s.insert(RigidBodyBuilder.dynamic().translation(pos).dominance_group((k * 5) % 4 - 1),
+                         ColliderBuilder.cuboid(0.5, 0.5, 0.5) if k % 3 else ColliderBuilder.ball(0.5))
+                k += 1
+    return s
+
+
+def dominance_parity_case(make_world, make_oracle, steps=180, every=12):
+    from parity_util import compare_worlds, is_exact
+    s = dominance_scene()
+    for coulomb in (False, True):
+        p = _params(friction_model=1) if coulomb else None
+        w, o = (make_world(s, p), make_oracle(s, p)) if coulomb else (make_world(s), make_oracle(s))
+        for i in range(steps):
+            w.step(); o.step()
+            if i % every == every - 1 or i < 2:
+                d = compare_worlds(w, o)
+                assert is_exact(d), (coulomb, i, d)
+        pose, _ = w.body_states()
+        assert np.isfinite(pose).all()
