@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 3
+#define RB_ABI_VERSION 4
 
 typedef struct RbWorld RbWorld;
 
@@ -103,7 +103,7 @@ typedef struct RbBodyDesc {
     float user_torque[3];
 } RbBodyDesc;
 
-enum { RB_SHAPE_BALL = 0, RB_SHAPE_CUBOID = 1, RB_SHAPE_CAPSULE = 2 };
+enum { RB_SHAPE_BALL = 0, RB_SHAPE_CUBOID = 1, RB_SHAPE_CAPSULE = 2, RB_SHAPE_CONVEX = 3 };
 
 /* CoefficientCombineRule (src/dynamics/coefficient_combine_rule.rs:8-22). */
 enum { RB_COMBINE_AVERAGE = 0, RB_COMBINE_MIN = 1, RB_COMBINE_MULTIPLY = 2, RB_COMBINE_MAX = 3,
@@ -112,7 +112,8 @@ enum { RB_COMBINE_AVERAGE = 0, RB_COMBINE_MIN = 1, RB_COMBINE_MULTIPLY = 2, RB_C
 /* One collider (src/geometry/collider.rs; ColliderBuilder defaults :688-707). */
 typedef struct RbColliderDesc {
     int32_t shape;                /* RB_SHAPE_* */
-    float half_extents[3];        /* cuboid half extents; ball: [radius, 0, 0]; capsule: [half height, radius, axis 0 | 1 | 2] */
+    float half_extents[3];        /* cuboid half extents; ball: [radius, 0, 0]; capsule: [half height, radius, axis 0 | 1 | 2];
+                                   * convex polyhedron: [hull id of rb_world_add_hull, border radius (round_convex_hull), 0] */
     int32_t parent;               /* body index, or -1 for a parentless (fixed) collider */
     float pos_wrt_parent_t[3];    /* pose relative to the parent (world pose if parent == -1) */
     float pos_wrt_parent_q[4];
@@ -254,6 +255,19 @@ int rb_world_reserve(RbWorld* w, int32_t max_bodies, int32_t max_colliders);
 int rb_world_insert(RbWorld* w, int32_t num_bodies, const RbBodyDesc* bodies, int32_t num_colliders,
                     const RbColliderDesc* colliders, int32_t* first_body_index, int32_t* first_collider_index);
 int rb_world_remove_bodies(RbWorld* w, int32_t n, const int32_t* body_indices);
+
+/* ---- convex polyhedra (ColliderBuilder::{convex_hull, convex_mesh, round_convex_hull}, src/geometry/collider.rs:1039-1090;
+ *      parry ConvexPolyhedron) ----
+ * rb_world_add_hull registers a closed convex mesh -- at most 32 vertices, 32 polygonal faces of 3..8 vertices (either
+ * winding), 64 edges -- and returns the hull id (>= 1; hull 0 is the unit cube) that RB_SHAPE_CONVEX colliders carry in
+ * half_extents[0]; half_extents[1] is the border radius of a "round" polyhedron (0 = sharp).  Planes, edges, volume,
+ * centre of mass and principal inertia are derived here.  Hulls persist across rb_world_set_scene; ids are per world.
+ * rb_convex_hull (host only, no world needed) computes the hull mesh of 4..32 points: buffers need room for 32 vertices
+ * (96 floats), 32 face sizes and 256 face indices. */
+int32_t rb_world_add_hull(RbWorld* w, int32_t num_vertices, const float* vertices3, int32_t num_faces,
+                          const int32_t* face_sizes, const int32_t* face_indices);
+int32_t rb_convex_hull(int32_t num_points, const float* points3, int32_t* num_vertices, float* vertices3,
+                       int32_t* num_faces, int32_t* face_sizes, int32_t* face_indices);
 
 /* ---- sleeping (src/dynamics/island_manager/sleep.rs, manager.rs:320-425; rigid_body_components.rs:1417-1470) ----
  * A connected component of touching contacts / joints falls asleep as a whole once EVERY body in it has moved less

@@ -28,6 +28,8 @@ int orc_world_get_sleeping(OrcWorld* w, uint8_t* sleeping);
 int orc_world_get_quarantine(OrcWorld* w, int32_t* bodies, int32_t cap);
 int orc_world_wake_up(OrcWorld* w, int32_t n, const int32_t* indices);
 // Mirrors of rb_world_insert / rb_world_remove_bodies (appended bodies and colliders; tombstoned removals).
+int32_t orc_world_add_hull(OrcWorld* w, int32_t num_vertices, const float* vertices3, int32_t num_faces,
+                           const int32_t* face_sizes, const int32_t* face_indices);   /* rb_world_add_hull */
 int orc_world_insert(OrcWorld* w, int32_t nb, const RbBodyDesc* bodies, int32_t nc, const RbColliderDesc* colliders);
 int orc_world_remove_bodies(OrcWorld* w, int32_t n, const int32_t* indices);
 int orc_world_set_body_states(OrcWorld* w, int32_t n, const int32_t* indices, const float* pose7,

@@ -66,7 +66,16 @@ OrcWorld* orc_world_create(const RbIntegrationParameters* params) {
     OrcWorld* o = new OrcWorld();
     if (params) o->w.params.p = *params;
     else default_params(&o->w.params.p);
+    o->w.hulls.emplace_back();
+    hull_unit_cube(o->w.hulls[0]);
     return o;
+}
+int32_t orc_world_add_hull(OrcWorld* o, int32_t nv, const float* verts, int32_t nf, const int32_t* face_sizes, const int32_t* face_indices) {
+    if (!o || !verts || !face_sizes || !face_indices) return RB_ERR_INVALID;
+    Hull h;
+    if (!hull_from_mesh(nv, verts, nf, face_sizes, face_indices, h)) return RB_ERR_INVALID;
+    o->w.hulls.push_back(h);
+    return (int32_t)o->w.hulls.size() - 1;
 }
 void orc_world_destroy(OrcWorld* w) { delete w; }
 int orc_world_set_params(OrcWorld* w, const RbIntegrationParameters* params) {

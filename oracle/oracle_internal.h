@@ -70,6 +70,24 @@ struct Body {
     bool is_awake() const { return is_dynamic() && !sleeping; }   // member of the active set
 };
 
+// Convex polyhedra (parry ConvexPolyhedron as used by ColliderBuilder::convex_hull / convex_mesh); oracle_hull.cpp
+constexpr int HULL_MAX_VERTS = 32, HULL_MAX_FACES = 32, HULL_MAX_FACE_VERTS = 8, HULL_MAX_EDGES = 64;
+struct HullEdge { int v0, v1, f0, f1; };   // f0: the face on which the edge runs v0 -> v1
+struct Hull {
+    std::vector<V3> verts;
+    std::vector<int> face_start, face_count, loops;   // counter-clockwise loops seen from outside
+    std::vector<V3> normals;
+    std::vector<float> offsets;
+    std::vector<HullEdge> edges;
+    float volume = 0.0f;                               // unit-density mass properties about the centre of mass
+    V3 com{0.f, 0.f, 0.f}, principal_inertia{0.f, 0.f, 0.f};
+    Q4 principal_frame{0.f, 0.f, 0.f, 1.f};
+    V3 aabb{0.f, 0.f, 0.f};                            // max |coordinate| per axis
+    float radius = 0.0f;                               // max |vertex|
+};
+bool hull_from_mesh(int nv, const float* verts, int nf, const int32_t* face_sizes, const int32_t* face_indices, Hull& h);
+void hull_unit_cube(Hull& h);
+
 struct Aabb {
     V3 mins, maxs;
 };
@@ -144,6 +162,10 @@ struct RawManifold {
 void contact_manifold(int shape1, V3 he1, int shape2, V3 he2, const Pose& pos12, float prediction,
                       RawManifold& out);
 Aabb shape_aabb(int shape, V3 he, const Pose& pos);
+// pairs with a convex polyhedron, and its AABB -- oracle_poly.cpp
+void contact_manifold_convex(const std::vector<Hull>& hulls, int sh1, V3 he1, int sh2, V3 he2, const Pose& p12, float prediction,
+                             RawManifold& out);
+Aabb convex_aabb(const std::vector<Hull>& hulls, V3 he, const Pose& pos);
 
 struct Joint {
     int body1, body2;
@@ -220,6 +242,7 @@ struct World {
     Params params;
     std::vector<Body> bodies;
     std::vector<Collider> colliders;
+    std::vector<Hull> hulls;           // [0] = the unit cube; ids of RB_SHAPE_CONVEX colliders (he.x)
     std::vector<Joint> joints;
     std::vector<Pair> pairs;           // sorted by (c1, c2)
     std::vector<Mask128> color_masks;  // per body (narrow_phase/mod.rs body_solver_color_masks)

@@ -75,7 +75,29 @@ static int recompute_mass_properties(World& w, int first_body = 0, int first_col
         b.inv_principal_inertia = vzero();
         b.principal_inertia = vzero();
         b.principal_frame = qidentity();
-        if (count[bi] == 1) {
+        if (count[bi] == 1 && w.colliders[first[bi]].shape == RB_SHAPE_CONVEX) {
+            // MassProperties::from_convex_polyhedron [parry]: unit-density properties of the hull times the density; its centre
+            // of mass and principal frame go through the collider's pose (in double, rounded once)
+            const Collider& c = w.colliders[first[bi]];
+            const Hull& h = w.hulls[(int)c.he.x];
+            const float mass = h.volume * c.density;
+            const V3 pi = h.principal_inertia * c.density;
+            const double q[4] = {c.pos_wrt_parent.q.x, c.pos_wrt_parent.q.y, c.pos_wrt_parent.q.z, c.pos_wrt_parent.q.w};
+            const double v[3] = {h.com.x, h.com.y, h.com.z};
+            double t[3] = {q[1] * v[2] - q[2] * v[1], q[2] * v[0] - q[0] * v[2], q[0] * v[1] - q[1] * v[0]};
+            for (int k = 0; k < 3; ++k) t[k] *= 2.0;
+            const double u[3] = {q[1] * t[2] - q[2] * t[1], q[2] * t[0] - q[0] * t[2], q[0] * t[1] - q[1] * t[0]};
+            b.local_com = V3{(float)((double)c.pos_wrt_parent.t.x + (v[0] + q[3] * t[0] + u[0])),
+                             (float)((double)c.pos_wrt_parent.t.y + (v[1] + q[3] * t[1] + u[1])),
+                             (float)((double)c.pos_wrt_parent.t.z + (v[2] + q[3] * t[2] + u[2]))};
+            const double g[4] = {h.principal_frame.x, h.principal_frame.y, h.principal_frame.z, h.principal_frame.w};
+            b.principal_frame = Q4{(float)(q[3] * g[0] + q[0] * g[3] + q[1] * g[2] - q[2] * g[1]),
+                                   (float)(q[3] * g[1] - q[0] * g[2] + q[1] * g[3] + q[2] * g[0]),
+                                   (float)(q[3] * g[2] + q[0] * g[1] - q[1] * g[0] + q[2] * g[3]),
+                                   (float)(q[3] * g[3] - q[0] * g[0] - q[1] * g[1] - q[2] * g[2])};
+            b.inv_mass = inv_exact0(mass);
+            b.inv_principal_inertia = V3{inv_exact0(pi.x), inv_exact0(pi.y), inv_exact0(pi.z)};
+        } else if (count[bi] == 1) {
             const Collider& c = w.colliders[first[bi]];
             float mass;
             V3 pi;
@@ -91,6 +113,7 @@ static int recompute_mass_properties(World& w, int first_body = 0, int first_col
             for (size_t ci = (size_t)first_collider; ci < w.colliders.size(); ++ci) {
                 const Collider& c = w.colliders[ci];
                 if (c.parent != bi) continue;
+                if (c.shape == RB_SHAPE_CONVEX) return RB_ERR_INVALID;   // polyhedra in multi-collider bodies: not supported
                 float mass; V3 pi;
                 collider_mass(c, mass, pi);
                 M = M + mass;
@@ -124,6 +147,8 @@ static int recompute_mass_properties(World& w, int first_body = 0, int first_col
                 const float inv_new = inv_exact0(prev + add);
                 b.inv_principal_inertia = b.inv_principal_inertia * (inv_new * prev);
                 b.inv_mass = inv_new;
+            } else if (count[bi] == 1 && w.colliders[first[bi]].shape == RB_SHAPE_CONVEX) {
+                return RB_ERR_INVALID;          // additional mass on a massless polyhedron: not supported
             } else if (count[bi] == 1) {
                 // massless collider: inertia and centre of mass of the shape at unit density, rescaled to the mass
                 Collider u = w.colliders[first[bi]];
@@ -149,9 +174,10 @@ static int recompute_mass_properties(World& w, int first_body = 0, int first_col
         for (size_t ci = (size_t)first_collider; ci < w.colliders.size(); ++ci) {
             const Collider& c = w.colliders[ci];
             if (c.parent != bi) continue;
-            if (c.shape != RB_SHAPE_CAPSULE)   // (capsules are never swept here: they do not count)
+            if (c.shape != RB_SHAPE_CAPSULE && c.shape != RB_SHAPE_CONVEX)   // (capsules and polyhedra are never swept here: they do not count)
                 b.ccd_thickness = fmin2(b.ccd_thickness, c.shape == RB_SHAPE_BALL ? c.he.x : fmin2(c.he.x, fmin2(c.he.y, c.he.z)));
-            const float radius = c.shape == RB_SHAPE_BALL ? c.he.x : (c.shape == RB_SHAPE_CAPSULE ? c.he.x + c.he.y : length(c.he));
+            const float radius = c.shape == RB_SHAPE_CONVEX ? w.hulls[(int)c.he.x].radius + c.he.y
+                               : c.shape == RB_SHAPE_BALL ? c.he.x : (c.shape == RB_SHAPE_CAPSULE ? c.he.x + c.he.y : length(c.he));
             b.max_extent = fmax2(b.max_extent, length(c.pos_wrt_parent.t - b.local_com) + radius);
         }
     }
@@ -207,7 +233,7 @@ void refresh_collider(World& w, Collider& c) {
     else
         c.pos = c.pos_wrt_parent;
     float pred = w.params.prediction_distance();
-    c.aabb = loosened(shape_aabb(c.shape, c.he, c.pos), c.contact_skin + pred / 2.0f);
+    c.aabb = loosened(c.shape == RB_SHAPE_CONVEX ? convex_aabb(w.hulls, c.he, c.pos) : shape_aabb(c.shape, c.he, c.pos), c.contact_skin + pred / 2.0f);
     if (!c.fat_valid || !aabb_contains(c.fat, c.aabb)) {
         c.fat = loosened(c.aabb, 4.0e-2f * w.params.p.length_unit);
         c.fat_valid = true;
@@ -366,7 +392,8 @@ static float relative_rot_cos(Q4 base, Q4 cur) {  // contact_pair.rs:284-293
     return 2.0f * c * c - 1.0f;
 }
 
-static float shape_origin_radius(int shape, V3 he) {  // pair_update.rs:591-595 (local AABB corners)
+static float shape_origin_radius(const World& w, int shape, V3 he) {  // pair_update.rs:591-595 (local AABB corners)
+    if (shape == RB_SHAPE_CONVEX) { const V3 a = w.hulls[(int)he.x].aabb; return length(V3{a.x + he.y, a.y + he.y, a.z + he.y}); }
     if (shape == RB_SHAPE_BALL) {
         V3 c = V3{he.x, he.x, he.x};
         return length(c);
@@ -434,7 +461,8 @@ static bool process_pair(World& w, Pair& pair) {
     float eff_prediction = prediction + skin_sum;  // pair_update.rs:319
 
     RawManifold raw;
-    contact_manifold(co1.shape, co1.he, co2.shape, co2.he, pos12, eff_prediction, raw);
+    if (co1.shape == RB_SHAPE_CONVEX || co2.shape == RB_SHAPE_CONVEX) contact_manifold_convex(w.hulls, co1.shape, co1.he, co2.shape, co2.he, pos12, eff_prediction, raw);
+    else contact_manifold(co1.shape, co1.he, co2.shape, co2.he, pos12, eff_prediction, raw);
 
     // parry ContactManifold::match_contacts: carry ContactData by (fid1, fid2); ball manifolds keep
     // their single point's data (copy_geometry_from).
@@ -531,7 +559,7 @@ static bool process_pair(World& w, Pair& pair) {
     if (recycle_dist > 0.0f) {
         float max_extent = pair.has_recycle
                                ? pair.r_max_extent
-                               : fmax2(shape_origin_radius(co1.shape, co1.he), shape_origin_radius(co2.shape, co2.he));
+                               : fmax2(shape_origin_radius(w, co1.shape, co1.he), shape_origin_radius(w, co2.shape, co2.he));
         float max_drift = pair.nsc > 0 ? recycle_dist : fmin2(recycle_dist, prediction);
         pair.has_recycle = true;
         pair.r_pos12 = pos12;
@@ -813,7 +841,8 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
     for (int i = 0; i < nc; ++i) {
         Collider& c = w.colliders[i];
         const RbColliderDesc& d = cd[i];
-        if (d.shape != RB_SHAPE_BALL && d.shape != RB_SHAPE_CUBOID && d.shape != RB_SHAPE_CAPSULE) return RB_ERR_INVALID;
+        if (d.shape != RB_SHAPE_BALL && d.shape != RB_SHAPE_CUBOID && d.shape != RB_SHAPE_CAPSULE && d.shape != RB_SHAPE_CONVEX) return RB_ERR_INVALID;
+        if (d.shape == RB_SHAPE_CONVEX && !(d.half_extents[0] >= 0.0f && d.half_extents[0] < (float)w.hulls.size())) return RB_ERR_INVALID;
         if (d.parent >= nb) return RB_ERR_INVALID;
         c.shape = d.shape;
         c.he = f3(d.half_extents);
@@ -939,7 +968,8 @@ static void fill_collider(Collider& c, const RbColliderDesc& d) {
 int insert(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDesc* cd) {
     const int nb0 = (int)w.bodies.size(), nc0 = (int)w.colliders.size();
     for (int i = 0; i < nc; ++i) {
-        if (cd[i].shape != RB_SHAPE_BALL && cd[i].shape != RB_SHAPE_CUBOID && cd[i].shape != RB_SHAPE_CAPSULE) return RB_ERR_INVALID;
+        if (cd[i].shape != RB_SHAPE_BALL && cd[i].shape != RB_SHAPE_CUBOID && cd[i].shape != RB_SHAPE_CAPSULE && cd[i].shape != RB_SHAPE_CONVEX) return RB_ERR_INVALID;
+        if (cd[i].shape == RB_SHAPE_CONVEX && !(cd[i].half_extents[0] >= 0.0f && cd[i].half_extents[0] < (float)w.hulls.size())) return RB_ERR_INVALID;
         if (cd[i].parent >= nb0 + nb || (cd[i].parent >= 0 && cd[i].parent < nb0)) return RB_ERR_INVALID;
     }
     w.bodies.resize(nb0 + nb);

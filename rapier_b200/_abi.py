@@ -27,6 +27,7 @@ RB_BODY_DOMINANCE_SHIFT = 16   # RB_BODY_DOMINANCE(group): signed 8-bit dominanc
 RB_SHAPE_BALL = 0
 RB_SHAPE_CUBOID = 1
 RB_SHAPE_CAPSULE = 2
+RB_SHAPE_CONVEX = 3
 (RB_COMBINE_AVERAGE, RB_COMBINE_MIN, RB_COMBINE_MULTIPLY, RB_COMBINE_MAX, RB_COMBINE_CLAMPED_SUM,
  RB_COMBINE_GEOMETRIC_MEAN) = range(6)
 

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "rb_solver.cuh"
+#include "rb_hull.h"
 #include "../../include/rapier_b200.h"
 
 using namespace rb;
@@ -445,7 +446,9 @@ struct RbWorld {
     int big_threads = COOP_BIG_THREADS, sweep_threads = 0;
     float* state_buf[2] = {nullptr, nullptr};   // double-buffered packed state (rb_world_state_buffers), else unused
     int state_next = 0;
-    bool ext_shapes = false;     // some collider is a capsule: the SHAPES = 1 collision kernel
+    bool ext_shapes = false;     // some collider is a capsule or a convex polyhedron: the SHAPES = 1 collision kernel
+    std::vector<rbhull::Hull> hulls;   // convex polyhedra (rb_world_add_hull); hull 0 = the unit cube
+    int hulls_uploaded = 0;            // how many of them the device tables hold
     bool force_events = false;   // some collider has RB_EVENT_CONTACT_FORCE: run k_force_events after every step
     int steps_since_scene = 0;   // the launch-shape hint of a new scene is awaited once (see rb_world_step)
     int coop_shape = -1;   // RB_COOP_SHAPE debugging override: 0 small, 1 big, -1 automatic
@@ -592,15 +595,38 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out, int fir
         if (count[b] == 1) {
             const RbColliderDesc& c = W->colliders[first[b]];
             float mass, pi[3];
+            if (c.shape == RB_SHAPE_CONVEX) {
+                // MassProperties::from_convex_polyhedron [parry]: the hull's unit-density properties scaled by the density,
+                // centre of mass and principal frame carried through the collider's pose (double arithmetic, rounded once)
+                const rbhull::Hull& h = W->hulls[(int)c.half_extents[0]];
+                mass = h.volume * c.density;
+                for (int k = 0; k < 3; ++k) pi[k] = h.principal_inertia[k] * c.density;
+                const double q[4] = {c.pos_wrt_parent_q[0], c.pos_wrt_parent_q[1], c.pos_wrt_parent_q[2], c.pos_wrt_parent_q[3]};
+                const double v[3] = {h.com[0], h.com[1], h.com[2]};
+                double t[3], u[3];
+                rbhull::cross3d(q, v, t);
+                for (int k = 0; k < 3; ++k) t[k] *= 2.0;
+                rbhull::cross3d(q, t, u);
+                for (int k = 0; k < 3; ++k) m.lcom[k] = (float)((double)c.pos_wrt_parent_t[k] + (v[k] + q[3] * t[k] + u[k]));
+                const double g[4] = {h.principal_frame[0], h.principal_frame[1], h.principal_frame[2], h.principal_frame[3]};
+                m.pframe[0] = (float)(q[3] * g[0] + q[0] * g[3] + q[1] * g[2] - q[2] * g[1]);
+                m.pframe[1] = (float)(q[3] * g[1] - q[0] * g[2] + q[1] * g[3] + q[2] * g[0]);
+                m.pframe[2] = (float)(q[3] * g[2] + q[0] * g[1] - q[1] * g[0] + q[2] * g[3]);
+                m.pframe[3] = (float)(q[3] * g[3] - q[0] * g[0] - q[1] * g[1] - q[2] * g[2]);
+                for (int k = 0; k < 3; ++k) m.ipi[k] = inv0(pi[k]);
+                m.inv_mass = inv0(mass);
+            } else {
             collider_mass_props(c, mass, pi);
             for (int k = 0; k < 3; ++k) { m.lcom[k] = c.pos_wrt_parent_t[k]; m.ipi[k] = inv0(pi[k]); }
             m.inv_mass = inv0(mass);
             for (int k = 0; k < 4; ++k) m.pframe[k] = c.pos_wrt_parent_q[k];
+            }
         } else if (count[b] > 1) {
             float M = 0.0f, com[3] = {0, 0, 0};
             for (size_t ci = (size_t)first_collider; ci < W->colliders.size(); ++ci) {
                 const RbColliderDesc& c = W->colliders[ci];
                 if (c.parent != b) continue;
+                if (c.shape == RB_SHAPE_CONVEX) { set_err("multi-collider bodies with convex polyhedra are not supported%s", ""); return RB_ERR_INVALID; }
                 float mass, pi[3];
                 collider_mass_props(c, mass, pi);
                 M = M + mass;
@@ -641,6 +667,9 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out, int fir
                 const float inv_new = inv0(prev + add);
                 for (int k = 0; k < 3; ++k) m.ipi[k] = m.ipi[k] * (inv_new * prev);
                 m.inv_mass = inv_new;
+            } else if (count[b] == 1 && W->colliders[first[b]].shape == RB_SHAPE_CONVEX) {
+                set_err("additional mass on a massless convex polyhedron is not supported%s", "");
+                return RB_ERR_INVALID;
             } else if (count[b] == 1) {
                 // massless collider: inertia and centre of mass of the shape at unit density, rescaled to the mass
                 RbColliderDesc u = W->colliders[first[b]];
@@ -666,9 +695,10 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out, int fir
             const RbColliderDesc& c = W->colliders[ci];
             if (c.parent != b) continue;
             const float hx = c.half_extents[0], hy = c.half_extents[1], hz = c.half_extents[2];
-            if (c.shape != RB_SHAPE_CAPSULE)   // (capsules are never swept here, like the reference's never-swept shapes: they do not count, rigid_body_components.rs:1224-1228)
+            if (c.shape != RB_SHAPE_CAPSULE && c.shape != RB_SHAPE_CONVEX)   // (capsules and polyhedra are never swept here, like the reference's never-swept shapes: they do not count, rigid_body_components.rs:1224-1228)
                 m.ccd_thickness = std::min(m.ccd_thickness, c.shape == RB_SHAPE_BALL ? hx : std::min(hx, std::min(hy, hz)));   // parry Shape::ccd_thickness
-            const float radius = c.shape == RB_SHAPE_BALL ? hx : (c.shape == RB_SHAPE_CAPSULE ? hx + hy : sqrtf(fmaf(hz, hz, fmaf(hy, hy, hx * hx))));
+            const float radius = c.shape == RB_SHAPE_CONVEX ? W->hulls[(int)hx].radius + hy
+                               : c.shape == RB_SHAPE_BALL ? hx : (c.shape == RB_SHAPE_CAPSULE ? hx + hy : sqrtf(fmaf(hz, hz, fmaf(hy, hy, hx * hx))));
             const float dx = c.pos_wrt_parent_t[0] - m.lcom[0], dy = c.pos_wrt_parent_t[1] - m.lcom[1], dz = c.pos_wrt_parent_t[2] - m.lcom[2];
             m.max_extent = std::max(m.max_extent, sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) + radius);
         }
@@ -804,7 +834,7 @@ static int upload_colliders(RbWorld* W, int first, int count, int first_body = 0
         events[k] = (int)c.active_events;
         thr[k] = c.contact_force_event_threshold;
         if (c.active_events & RB_EVENT_CONTACT_FORCE) W->force_events = true;
-        if (c.shape == RB_SHAPE_CAPSULE) W->ext_shapes = true;
+        if (c.shape == RB_SHAPE_CAPSULE || c.shape == RB_SHAPE_CONVEX) W->ext_shapes = true;
         shape[k] = c.shape;
         parent[k] = c.parent;
         he[k] = make_float4(c.half_extents[0], c.half_extents[1], c.half_extents[2], 0.f);
@@ -837,12 +867,55 @@ static int upload_colliders(RbWorld* W, int first, int count, int first_body = 0
     if (!head.empty()) CK(h2d(w.b_col_head + first_body, head.data(), head.size() * sizeof(int)));
     return RB_OK;
 }
-static int validate_descs(int nb_total, int nb, const RbBodyDesc* bodies, int nc, const RbColliderDesc* colliders) {
+// Device tables of the convex polyhedra (rb_poly.cuh): rebuilt whenever hulls were added since the last upload.
+// Only worlds that hold a convex collider carry them.
+static int upload_hulls(RbWorld* W) {
+    bool any = false;
+    for (const RbColliderDesc& c : W->colliders) any = any || c.shape == RB_SHAPE_CONVEX;
+    if (!any || (W->w.hulls.desc && W->hulls_uploaded == (int)W->hulls.size())) return RB_OK;
+    const int nh = (int)W->hulls.size();
+    std::vector<int4> desc(nh), desc2(nh), edges;
+    std::vector<float4> info(nh), verts, planes;
+    std::vector<int2> faces;
+    std::vector<int> loops;
+    for (int h = 0; h < nh; ++h) {
+        const rbhull::Hull& H = W->hulls[h];
+        desc[h] = make_int4((int)verts.size(), H.nv(), (int)faces.size(), H.nf());
+        desc2[h] = make_int4((int)edges.size(), H.ne(), (int)loops.size(), 0);
+        info[h] = make_float4(H.aabb[0], H.aabb[1], H.aabb[2], H.radius);
+        for (int i = 0; i < H.nv(); ++i) verts.push_back(make_float4(H.verts[3 * i], H.verts[3 * i + 1], H.verts[3 * i + 2], 0.0f));
+        for (int f = 0; f < H.nf(); ++f) {
+            planes.push_back(make_float4(H.planes[4 * f], H.planes[4 * f + 1], H.planes[4 * f + 2], H.planes[4 * f + 3]));
+            faces.push_back(make_int2(H.face_start[f], H.face_count[f]));
+        }
+        for (int e = 0; e < H.ne(); ++e) edges.push_back(make_int4(H.edges[4 * e], H.edges[4 * e + 1], H.edges[4 * e + 2], H.edges[4 * e + 3]));
+        loops.insert(loops.end(), H.loops.begin(), H.loops.end());
+    }
+    World& w = W->w;
+    int4 *d_desc, *d_desc2, *d_edges;
+    float4 *d_info, *d_verts, *d_planes;
+    int2* d_faces;
+    int* d_loops;
+    ALLOC(d_desc, nh); ALLOC(d_desc2, nh); ALLOC(d_info, nh); ALLOC(d_verts, verts.size()); ALLOC(d_planes, planes.size());
+    ALLOC(d_faces, faces.size()); ALLOC(d_loops, loops.size()); ALLOC(d_edges, edges.size());
+    CK(h2d(d_desc, desc.data(), nh * sizeof(int4))); CK(h2d(d_desc2, desc2.data(), nh * sizeof(int4)));
+    CK(h2d(d_info, info.data(), nh * sizeof(float4))); CK(h2d(d_verts, verts.data(), verts.size() * sizeof(float4)));
+    CK(h2d(d_planes, planes.data(), planes.size() * sizeof(float4))); CK(h2d(d_faces, faces.data(), faces.size() * sizeof(int2)));
+    CK(h2d(d_loops, loops.data(), loops.size() * sizeof(int))); CK(h2d(d_edges, edges.data(), edges.size() * sizeof(int4)));
+    w.hulls.desc = d_desc; w.hulls.desc2 = d_desc2; w.hulls.info = d_info; w.hulls.verts = d_verts; w.hulls.planes = d_planes;
+    w.hulls.faces = d_faces; w.hulls.loops = d_loops; w.hulls.edges = d_edges;
+    W->hulls_uploaded = nh;
+    return RB_OK;
+}
+
+static int validate_descs(int nb_total, int nb, const RbBodyDesc* bodies, int nc, const RbColliderDesc* colliders, int nhulls) {
     for (int i = 0; i < nc; ++i) {
         const RbColliderDesc& c = colliders[i];
         const bool capsule_ok = c.shape == RB_SHAPE_CAPSULE && (c.half_extents[2] == 0.0f || c.half_extents[2] == 1.0f || c.half_extents[2] == 2.0f);
-        if ((c.shape != RB_SHAPE_BALL && c.shape != RB_SHAPE_CUBOID && !capsule_ok) || c.parent >= nb_total) {
-            set_err("collider with unsupported shape or bad parent%s", "");
+        const bool convex_ok = c.shape == RB_SHAPE_CONVEX && c.half_extents[0] >= 0.0f && c.half_extents[0] < (float)nhulls &&
+                               c.half_extents[0] == (float)(int)c.half_extents[0] && c.half_extents[1] >= 0.0f;
+        if ((c.shape != RB_SHAPE_BALL && c.shape != RB_SHAPE_CUBOID && !capsule_ok && !convex_ok) || c.parent >= nb_total) {
+            set_err("collider with unsupported shape, unknown hull or bad parent%s", "");
             return RB_ERR_INVALID;
         }
     }
@@ -902,6 +975,8 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
     RbWorld* W = new RbWorld();
     W->params = *params;
     W->device = device;
+    W->hulls.emplace_back();
+    rbhull::unit_cube(W->hulls[0]);
 #if RB_DEVICE_BUILD
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
@@ -988,7 +1063,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     CK(cudaSetDevice(W->device));
     CK(cudaStreamSynchronize(W->stream));
 #endif
-    { int vrc = validate_descs(nb, nb, bodies, nc, colliders); if (vrc != RB_OK) return vrc; }
+    { int vrc = validate_descs(nb, nb, bodies, nc, colliders, (int)W->hulls.size()); if (vrc != RB_OK) return vrc; }
     for (int i = 0; i < nj; ++i) {
         const RbJointDesc& j = joints[i];
         if (j.body1 < 0 || j.body1 >= nb || j.body2 < 0 || j.body2 >= nb || (j.locked_axes & ~63u)) {
@@ -1010,6 +1085,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     World& w = W->w;
     W->force_events = false;
     W->ext_shapes = false;
+    W->hulls_uploaded = 0;
     memset(&w, 0, sizeof(w));
     derive_params(W->params, w.prm);
     w.nb = nb; w.nc = nc; w.nj = nj;
@@ -1101,6 +1177,8 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
         CK(dev_set(w.body_minkey, 0xff, NB * sizeof(unsigned long long)));
         CK(h2d(w.c_parent, parent.data(), NC * sizeof(int)));
         rc = upload_bodies(W, mp, 0, nb);
+        if (rc != RB_OK) return rc;
+        rc = upload_hulls(W);
         if (rc != RB_OK) return rc;
         rc = upload_colliders(W, 0, nc);
         if (rc != RB_OK) return rc;
@@ -1235,6 +1313,32 @@ int rb_world_reserve(RbWorld* W, int32_t max_bodies, int32_t max_colliders) {
     return RB_OK;
 }
 
+// Registers a convex polyhedron (closed convex mesh: vertices + polygonal faces) that RB_SHAPE_CONVEX colliders refer to
+// by the id returned (>= 1; 0 is the unit cube).  Negative = RB_ERR_*.  Hulls persist across rb_world_set_scene.
+int32_t rb_world_add_hull(RbWorld* W, int32_t nv, const float* verts, int32_t nf, const int32_t* face_sizes, const int32_t* face_indices) {
+    if (!W || !verts || !face_sizes || !face_indices) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    rbhull::Hull h;
+    const char* why = rbhull::from_mesh(nv, verts, nf, face_sizes, face_indices, h);
+    if (why) { set_err("convex mesh rejected: %s", why); return RB_ERR_INVALID; }
+    W->hulls.push_back(h);
+    return (int32_t)W->hulls.size() - 1;
+}
+
+// ColliderBuilder::convex_hull's hull computation (parry transformation::convex_hull) for at most 32 points: writes the
+// hull's vertices (a subset of the points, in input order), face sizes and face vertex indices.  Host code only.
+int32_t rb_convex_hull(int32_t npoints, const float* points, int32_t* nv, float* verts, int32_t* nf, int32_t* face_sizes, int32_t* face_indices) {
+    if (!points || !nv || !verts || !nf || !face_sizes || !face_indices) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    std::vector<float> v;
+    std::vector<int32_t> sizes, idx;
+    const char* why = rbhull::convex_hull(npoints, points, v, sizes, idx);
+    if (why) { set_err("convex hull failed: %s", why); return RB_ERR_INVALID; }
+    *nv = (int32_t)v.size() / 3; *nf = (int32_t)sizes.size();
+    memcpy(verts, v.data(), v.size() * sizeof(float));
+    memcpy(face_sizes, sizes.data(), sizes.size() * sizeof(int32_t));
+    memcpy(face_indices, idx.data(), idx.size() * sizeof(int32_t));
+    return RB_OK;
+}
+
 // Appends bodies and colliders to the world (RigidBodySet::insert / ColliderSet::insert_with_parent): indices of
 // existing bodies, colliders and contact pairs do not change, so warm-start data, colours and islands persist.
 // New colliders may only be attached to the new bodies (or to none).  Joints cannot be inserted this way.
@@ -1246,7 +1350,7 @@ int rb_world_insert(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t nc
         set_err("rb_world_insert exceeds the reserved capacity (rb_world_reserve before rb_world_set_scene)%s", "");
         return RB_ERR_CAPACITY;
     }
-    int rc = validate_descs(nb0 + nb, nb, bodies, nc, colliders);
+    int rc = validate_descs(nb0 + nb, nb, bodies, nc, colliders, (int)W->hulls.size());
     if (rc != RB_OK) return rc;
     for (int i = 0; i < nc; ++i)
         if (colliders[i].parent >= 0 && colliders[i].parent < nb0) { set_err("new colliders may only be attached to new bodies%s", ""); return RB_ERR_INVALID; }
@@ -1259,6 +1363,7 @@ int rb_world_insert(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t nc
     if (rc != RB_OK) { W->bodies.resize(nb0); W->colliders.resize(nc0); return rc; }
     W->w.nb = nb0 + nb;
     W->w.nc = nc0 + nc;
+    if ((rc = upload_hulls(W)) != RB_OK) return rc;
     if ((rc = upload_bodies(W, mp, nb0, nb)) != RB_OK) return rc;
     if ((rc = upload_colliders(W, nc0, nc, nb0)) != RB_OK) return rc;
     int one = 1, lists = 1;   // lists: 1 = only movers were added, 3 = static colliders too (re-sort them)

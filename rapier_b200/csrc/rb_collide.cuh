@@ -51,6 +51,7 @@ RB_HD pose collider_pose(const World& w, int c) { return mkpose(mkq(w.c_pos_q[c]
 // Static colliders (no parent, or a parent that is not dynamic) never move: once the static / dynamic lists
 // exist only the dynamic list is refreshed (a 10^6-tile floor costs nothing per step).
 // ------------------------------------------------------------------------------------------------
+template <int SHAPES = 0>
 RB_HD void refresh_collider(const World& w, int c) {
     int parent = w.c_parent[c];
     pose rel = mkpose(mkq(w.c_rel_q[c]), xyz(w.c_rel_t[c]));
@@ -58,7 +59,8 @@ RB_HD void refresh_collider(const World& w, int c) {
     w.c_pos_t[c] = f4(p.t, 0.0f);
     w.c_pos_q[c] = f4(p.q);
     vec3 lo, hi;
-    shape_aabb(w.c_shape[c], xyz(w.c_he[c]), p, lo, hi);
+    if (SHAPES && w.c_shape[c] == SHAPE_CONVEX) convex_aabb(w.hulls, xyz(w.c_he[c]), p, lo, hi);
+    else shape_aabb(w.c_shape[c], xyz(w.c_he[c]), p, lo, hi);
     float l = w.c_mat[c].z + w.prm.prediction / 2.0f;
     lo = mk3(lo.x - l, lo.y - l, lo.z - l);
     hi = mk3(hi.x + l, hi.y + l, hi.z + l);
@@ -75,17 +77,17 @@ RB_HD void refresh_collider(const World& w, int c) {
         w.st->bp_dirty = 1;
     }
 }
-template <class Ctx>
+template <int SHAPES = 0, class Ctx>
 RB_PHASE void phase_refresh_colliders(const Ctx& ctx, const World& w) {
     if (w.st->lists_dirty) {
         for (int c = ctx.gtid; c < w.nc; c += ctx.gsize) {
             const int parent = w.c_parent[c];
             if (parent >= 0 && w.b_type[parent] == BODY_REMOVED) w.c_shape[c] = SHAPE_REMOVED;   // (removed or quarantined body)
-            if (w.c_shape[c] != SHAPE_REMOVED) refresh_collider(w, c);
+            if (w.c_shape[c] != SHAPE_REMOVED) refresh_collider<SHAPES>(w, c);
         }
     } else {
         const int nd = w.st->ndyn;
-        for (int i = ctx.gtid; i < nd; i += ctx.gsize) refresh_collider(w, w.dyn_list[i]);
+        for (int i = ctx.gtid; i < nd; i += ctx.gsize) refresh_collider<SHAPES>(w, w.dyn_list[i]);
     }
 }
 
@@ -519,7 +521,8 @@ RB_HD float rot_cos(quat base, quat cur) {  // contact_pair.rs:284-293
     float c = qdot(base, cur);
     return 2.0f * c * c - 1.0f;
 }
-RB_HD float origin_radius(int shape, vec3 he) {
+RB_HD float origin_radius(const World& w, int shape, vec3 he) {
+    if (shape == SHAPE_CONVEX) { const float4 i = w.hulls.info[(int)he.x]; return norm(mk3(i.x + he.y, i.y + he.y, i.z + he.y)); }
     if (shape == SHAPE_CAPSULE) return norm(mk3(he.y, he.x + he.y, he.y));   // corner of the local AABB (the axis only permutes it)
     return shape == SHAPE_BALL ? norm(mk3(he.x, he.x, he.x)) : norm(he);
 }
@@ -588,7 +591,7 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
         float4 m1 = w.c_mat[c1], m2 = w.c_mat[c2];
         float skin1 = m1.z, skin2 = m2.z;
         RawManifold raw;
-        contact_manifold<SHAPES>(sh1, he1, sh2, he2, p12, prediction + (skin1 + skin2), raw);
+        contact_manifold<SHAPES>(w.hulls, sh1, he1, sh2, he2, p12, prediction + (skin1 + skin2), raw);
 
         // match_contacts: carry ContactData by feature ids (ball manifolds keep their single point).
         float4 o_pb[MAX_PTS], o_pd[MAX_PTS], o_tw[MAX_PTS], o_d1[MAX_PTS], o_d2[MAX_PTS];
@@ -679,7 +682,7 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
         }
         float max_drift = 0.0f;
         if (recycle > 0.0f) {  // pair_update.rs:582-613
-            float max_extent = (flags & 1) ? prow(w, buf, PR_RT, i).w : max2(origin_radius(sh1, he1), origin_radius(sh2, he2));
+            float max_extent = (flags & 1) ? prow(w, buf, PR_RT, i).w : max2(origin_radius(w, sh1, he1), origin_radius(w, sh2, he2));
             max_drift = nsc > 0 ? recycle : min2(recycle, prediction);
             flags |= 1;
             prow(w, buf, PR_RT, i) = f4(p12.t, max_extent);
@@ -1318,7 +1321,7 @@ template <int SHAPES = 0, class Ctx>
 RB_PHASE void collide_pipeline(const Ctx& ctx, const World& w) {
     State* st = w.st;
     if (ctx.gtid == 0) { st->bp_ran = 0; st->sched_ran = 0; st->sleep_stamp += 1; }
-    phase_refresh_colliders(ctx, w);
+    phase_refresh_colliders<SHAPES>(ctx, w);
     ctx.grid_sync();
     if (st->bp_dirty || st->lists_dirty) section_broad_phase(ctx, w);
     phase_narrow_phase<SHAPES>(ctx, w);

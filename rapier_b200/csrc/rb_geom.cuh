@@ -466,10 +466,15 @@ RB_HD void contact_manifold_capsules(int sh1, vec3 he1, int sh2, vec3 he2, const
     }
 }
 
-// SHAPES = 1: worlds with capsules (a compile-time variant of the collision kernel, so the ball / cuboid one is unchanged)
+}  // namespace rb
+#include "rb_poly.cuh"
+namespace rb {
+
+// SHAPES = 1: worlds with capsules or convex polyhedra (a compile-time variant of the collision kernel, so the ball / cuboid one is unchanged)
 template <int SHAPES = 0>
-RB_HD void contact_manifold(int sh1, vec3 he1, int sh2, vec3 he2, const pose& p12, float prediction, RawManifold& m) {
+RB_HD void contact_manifold(const HullTables& hulls, int sh1, vec3 he1, int sh2, vec3 he2, const pose& p12, float prediction, RawManifold& m) {
     m.n = 0; m.n1 = zero3(); m.n2 = zero3();
+    if (SHAPES && (sh1 == SHAPE_CONVEX || sh2 == SHAPE_CONVEX)) { contact_manifold_convex(hulls, sh1, he1, sh2, he2, p12, prediction, m); return; }
     if (SHAPES && (sh1 == SHAPE_CAPSULE || sh2 == SHAPE_CAPSULE)) { contact_manifold_capsules(sh1, he1, sh2, he2, p12, prediction, m); return; }
     if (sh1 == SHAPE_CUBOID && sh2 == SHAPE_CUBOID) {
         manifold_box_box(he1, he2, p12, prediction, m);

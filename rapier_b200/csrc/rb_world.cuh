@@ -23,9 +23,24 @@ constexpr int BODY_KIN_POS = 2, BODY_KIN_VEL = 3;   // RigidBodyType::{Kinematic
 constexpr int BODY_REMOVED = 7;          // removed (rb_world_remove_bodies) or quarantined: not simulated, its colliders are gone
 constexpr int SHAPE_BALL = 0, SHAPE_CUBOID = 1;
 constexpr int SHAPE_CAPSULE = 2;         // half extents = (half height of the segment, radius, axis 0 | 1 | 2)
+constexpr int SHAPE_CONVEX = 3;          // convex polyhedron: half extents = (hull id, border radius, 0)
+constexpr int HULL_MAX_VERTS = 32, HULL_MAX_FACES = 32, HULL_MAX_FACE_VERTS = 8, HULL_MAX_EDGES = 64;
 constexpr int SHAPE_REMOVED = -1;        // collider of a removed body: in neither broad-phase list, in no pair
 constexpr unsigned FLAG_GYRO = 1, FLAG_FAST_ROT = 2, FLAG_LTX = 4, FLAG_LTY = 8, FLAG_LTZ = 16, FLAG_LRX = 32,
                    FLAG_LRY = 64, FLAG_LRZ = 128, FLAG_NO_SLEEP = 256, FLAG_CCD = 512;
+
+// Convex polyhedra shared by colliders (rb_world_add_hull); hull 0 is the unit cube, whose topology a cuboid borrows
+// when it meets a polyhedron (rb_poly.cuh).  Read-only on the device.
+struct HullTables {
+    const int4* desc;      // per hull: first vertex, vertex count, first face, face count
+    const int4* desc2;     // per hull: first edge, edge count, first loop entry, 0
+    const float4* info;    // per hull: max |x|, |y|, |z| over the vertices (local AABB about the origin), bounding radius about the origin
+    const float4* verts;   // xyz
+    const float4* planes;  // outward unit normal, offset
+    const int2* faces;     // start in the hull's loop entries, vertex count (counter-clockwise seen from outside)
+    const int* loops;      // vertex indices (hull-local)
+    const int4* edges;     // v0, v1, the face on which the edge runs v0 -> v1, the other face
+};
 
 // ---- persistent pair record rows (float4 each) ----
 enum PairRow {
@@ -255,6 +270,7 @@ struct World {
     // limits and motors of the free axes (JointLimits / JointMotor, generic_joint.rs:142-232): only worlds in which some joint
     // has any take the generic joint path (solve_item<FM, 1>, 12 row slots per joint instead of 6)
     int generic_joints;
+    HullTables hulls;                 // convex polyhedra (worlds with SHAPE_CONVEX colliders only; else null)
     uint2* j_axes;                    // limit_axes, motor_axes
     float2* j_limits;                 // [nj][6] min, max
     float4* j_motor_a;                // [nj][6] target_vel, target_pos, stiffness, damping

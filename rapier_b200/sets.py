@@ -12,6 +12,8 @@ C-ABI descriptor arrays of include/rapier_b200.h; nothing here computes physics.
 import ctypes as C
 import math
 
+import numpy as np
+
 from . import _abi as A
 
 
@@ -184,6 +186,26 @@ class ColliderBuilder:
     @classmethod
     def capsule_z(cls, half_height, radius):
         return cls(A.RB_SHAPE_CAPSULE, (float(half_height), float(radius), 2.0))
+
+    @classmethod
+    def convex_mesh(cls, points, faces, border_radius=0.0):
+        """ColliderBuilder::convex_mesh / round_convex_mesh (collider.rs:1070-1090): a closed convex mesh given by its
+        vertices and polygonal faces (vertex index loops, either winding).  The ColliderSet registers the polyhedron
+        (rb_world_add_hull) when the collider is inserted."""
+        b = cls(A.RB_SHAPE_CONVEX, (0.0, float(border_radius), 0.0))
+        b._hull = (np.ascontiguousarray(points, np.float32).reshape(-1, 3), [[int(i) for i in f] for f in faces])
+        return b
+
+    @classmethod
+    def convex_hull(cls, points, border_radius=0.0):
+        """ColliderBuilder::convex_hull (collider.rs:1039-1044): the convex hull of at most 32 points."""
+        verts, faces = convex_hull_mesh(points)
+        return cls.convex_mesh(verts, faces, border_radius)
+
+    @classmethod
+    def round_convex_hull(cls, points, border_radius):
+        """ColliderBuilder::round_convex_hull (collider.rs:1046-1060): the hull dilated by `border_radius`."""
+        return cls.convex_hull(points, border_radius)
 
     def density(self, d):
         self._density = float(d)
@@ -412,13 +434,26 @@ class RigidBodySet:
 class ColliderSet:
     def __init__(self):
         self.descs = []
+        self.hulls = []        # convex polyhedra referred to by RB_SHAPE_CONVEX colliders: (vertices [n, 3] f32, faces); id = index + 1
+        self._hull_ids = {}
+
+    def _desc(self, builder, parent):
+        d = builder.build_desc(parent)
+        hull = getattr(builder, "_hull", None)
+        if hull is not None:
+            key = (hull[0].tobytes(), tuple(tuple(f) for f in hull[1]))
+            if key not in self._hull_ids:
+                self.hulls.append(hull)
+                self._hull_ids[key] = len(self.hulls)
+            d.half_extents[0] = float(self._hull_ids[key])
+        return d
 
     def insert(self, builder):
-        self.descs.append(builder.build_desc(None))
+        self.descs.append(self._desc(builder, None))
         return len(self.descs) - 1
 
     def insert_with_parent(self, builder, parent, bodies=None):
-        self.descs.append(builder.build_desc(parent))
+        self.descs.append(self._desc(builder, parent))
         return len(self.descs) - 1
 
     def __len__(self):
@@ -435,6 +470,34 @@ class ImpulseJointSet:
 
     def __len__(self):
         return len(self.descs)
+
+
+def convex_hull_mesh(points):
+    """Hull mesh (vertices, faces) of 4..32 points, computed by the library's host routine rb_convex_hull."""
+    import ctypes as C
+    from ._lib import lib
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    L = lib()
+    nv, nf = C.c_int32(0), C.c_int32(0)
+    verts = np.zeros((32, 3), np.float32)
+    sizes = np.zeros(32, np.int32)
+    idx = np.zeros(256, np.int32)
+    rc = L.rb_convex_hull(len(pts), pts.ctypes.data, C.byref(nv), verts.ctypes.data, C.byref(nf), sizes.ctypes.data, idx.ctypes.data)
+    if rc < 0:
+        raise ValueError(L.rb_last_error().decode())
+    faces, at = [], 0
+    for f in range(nf.value):
+        faces.append([int(i) for i in idx[at:at + sizes[f]]])
+        at += int(sizes[f])
+    return verts[:nv.value].copy(), faces
+
+
+def hull_arrays(hull):
+    """(vertices, face sizes, face indices) of a registered hull as contiguous arrays for rb_world_add_hull."""
+    verts, faces = hull
+    sizes = np.array([len(f) for f in faces], np.int32)
+    idx = np.array([i for f in faces for i in f], np.int32)
+    return np.ascontiguousarray(verts, np.float32), sizes, idx
 
 
 def as_array(descs, ctype):

@@ -28,6 +28,16 @@ class PhysicsPipeline:
         if not self.h:
             raise RapierError(self.L.rb_last_error().decode())
         self.nb = 0
+        self._nhulls = 0
+
+    def sync_hulls(self, colliders):
+        """Registers the convex polyhedra the collider set has collected since the last call (rb_world_add_hull)."""
+        from .sets import hull_arrays
+        for k in range(self._nhulls, len(getattr(colliders, "hulls", []))):
+            verts, sizes, idx = hull_arrays(colliders.hulls[k])
+            hid = self._check(self.L.rb_world_add_hull(self.h, len(verts), verts.ctypes.data, len(sizes), sizes.ctypes.data, idx.ctypes.data))
+            assert hid == k + 1, (hid, k)
+            self._nhulls = k + 1
 
     def close(self):
         if getattr(self, "h", None):
@@ -48,6 +58,7 @@ class PhysicsPipeline:
     def upload(self, bodies: RigidBodySet, colliders: ColliderSet, joints: ImpulseJointSet = None):
         """handle_user_changes_to_{colliders,rigid_bodies} (substep.rs:303-334): full scene upload."""
         joints = joints or ImpulseJointSet()
+        self.sync_hulls(colliders)
         self._b = as_array(bodies.descs, A.RbBodyDesc)
         self._c = as_array(colliders.descs, A.RbColliderDesc)
         self._j = as_array(joints.descs, A.RbJointDesc)
@@ -268,6 +279,7 @@ class PhysicsWorld:
             nb0, nc0, nj0 = self._uploaded
             nb, nc, nj = len(self.bodies), len(self.colliders), len(self.impulse_joints)
             if nb0 + nc0 > 0 and nj == nj0 and nb >= nb0 and nc >= nc0:   # only appended since the last upload: incremental
+                self.physics_pipeline.sync_hulls(self.colliders)
                 self.physics_pipeline.insert(self.bodies.descs[nb0:], self.colliders.descs[nc0:])
             else:
                 self.physics_pipeline.upload(self.bodies, self.colliders, self.impulse_joints)

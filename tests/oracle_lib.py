@@ -73,6 +73,8 @@ def lib(fast=False):
         L.orc_world_drain_collision_events.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_world_drain_contact_force_events.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_kat.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+        L.orc_world_add_hull.restype = C.c_int32
+        L.orc_world_add_hull.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _libs[fast] = L
     return _libs[fast]
 
@@ -87,6 +89,8 @@ class OracleWorld:
         self.gravity = scene.gravity
         self.L.orc_set_threads(threads)
         nb, nc, nj = len(scene.bodies), len(scene.colliders), len(scene.joints)
+        self._nhulls = 0
+        self.sync_hulls(scene.colliders)
         self._b = as_array(scene.bodies.descs, A.RbBodyDesc)
         self._c = as_array(scene.colliders.descs, A.RbColliderDesc)
         self._j = as_array(scene.joints.descs, A.RbJointDesc)
@@ -100,6 +104,14 @@ class OracleWorld:
             self.L.orc_world_destroy(self.h)
         except Exception:
             pass
+
+    def sync_hulls(self, colliders):
+        from rapier_b200.sets import hull_arrays
+        for k in range(self._nhulls, len(getattr(colliders, "hulls", []))):
+            verts, sizes, idx = hull_arrays(colliders.hulls[k])
+            hid = self.L.orc_world_add_hull(self.h, len(verts), verts.ctypes.data, len(sizes), sizes.ctypes.data, idx.ctypes.data)
+            assert hid == k + 1, (hid, k)
+            self._nhulls = k + 1
 
     def step(self, n=1):
         g = (C.c_float * 3)(*self.gravity)
