@@ -309,3 +309,25 @@ def run_large_world_protocol(world, steps, grid=1000, spheres=100, drop_interval
 REGISTRY["large_world"] = large_world
 REGISTRY["falling_pile_2000"] = lambda: box_pile(10, 10, 20)
 REGISTRY["pyramid3_20"] = lambda: pyramid3(20)
+
+
+def convex_polyhedra(layers=25, num=5, scale=2.0, border_rad=0.1, seed=0):
+    """examples3d/convex_polyhedron3.rs:15-58: `layers` x num x num round convex hulls of 10 random points in
+    [0, scale)^3 dropped on a 40 x 0.1 x 40 ground slab.  The reference draws the points from rand's StdRng(0), which
+    cannot be reproduced here: numpy's default_rng(seed) instead (same distribution, other points)."""
+    s = Scene(f"convex_polyhedra_{layers}")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.1, 0.0)), ColliderBuilder.cuboid(40.0, 0.1, 40.0))
+    shift = F(border_rad) * F(2.0) + F(scale)
+    centerx = shift * F(num // 2)
+    centery = shift / F(2.0)
+    centerz = shift * F(num // 2)
+    rng = np.random.default_rng(seed)
+    for j in range(layers):
+        for i in range(num):
+            for k in range(num):
+                x = F(i) * shift - centerx
+                y = F(j) * shift + centery + F(3.0)
+                z = F(k) * shift - centerz
+                pts = rng.random((10, 3), dtype=np.float32) * F(scale)
+                s.insert(RigidBodyBuilder.dynamic().translation((x, y, z)), ColliderBuilder.round_convex_hull(pts, border_rad))
+    return s

@@ -25,6 +25,7 @@ def random_scene(seed):
     r = np.random.default_rng(seed)
     r2 = np.random.default_rng(seed + 1000003)   # later options draw from a second stream: the scenes of old seeds keep their shape
     dominance = r2.random() < 0.35
+    convex = r2.random() < 0.4
     s = scenes.Scene(f"fuzz_{seed}", gravity=(0.0, float(r.choice([-9.81, -10.0, -3.0])), 0.0))
     s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)),
              ColliderBuilder.cuboid(12.0, 0.5, 12.0).friction(float(r.uniform(0.0, 1.0))).restitution(float(r.choice([0.0, 0.0, 0.5]))))
@@ -65,7 +66,12 @@ def random_scene(seed):
             c = ColliderBuilder.ball(float(r.uniform(0.15, 0.6)))
         else:
             c = [ColliderBuilder.capsule_x, ColliderBuilder.capsule_y, ColliderBuilder.capsule_z][int(r.integers(0, 3))](float(r.uniform(0.1, 0.7)), float(r.uniform(0.12, 0.4)))
+        hull = convex and r2.random() < 0.4
+        if hull:   # a random convex polyhedron (sharp or round) instead
+            c = ColliderBuilder.round_convex_hull(r2.uniform(-0.6, 0.6, (int(r2.integers(4, 14)), 3)), float(r2.choice([0.0, 0.0, 0.05, 0.15])))
         c = c.density(float(r.choice([0.0, 0.5, 1.0, 10.0, 100.0]) if r.random() < 0.9 else 1.0))
+        if hull and c._density == 0.0:
+            c = c.density(1.0)
         c = c.friction(float(r.uniform(0.0, 1.2))).restitution(float(r.choice([0.0, 0.0, 0.0, 0.3, 0.9, 1.0])))
         if r.random() < 0.1:
             c = c.collision_groups(int(r.choice([1, 2, 3])), int(r.choice([1, 2, 3])))

@@ -11,7 +11,8 @@ from rapier_b200.world import PhysicsWorld
 CONFIGS = [("b3d_many_pyramids", scenes.many_pyramids, 300), ("b3d_many_pyramids_80x20", scenes.many_pyramids_label, 300),
            ("pyramid3_50", lambda: scenes.pyramid3(50), 100), ("b3d_joint_grid_100", lambda: scenes.joint_grid(100), 200),
            ("keva3_5", lambda: scenes.keva(5), 200),
-           ("large_world_300", lambda: scenes.large_world(grid=300, spheres=100), 200)]   # (1000 = the reference size; opt-in by name)
+           ("large_world_300", lambda: scenes.large_world(grid=300, spheres=100), 200),
+           ("convex_polyhedron3", lambda: scenes.convex_polyhedra(25), 200)]   # examples3d/convex_polyhedron3.rs (625 round hulls)   # (1000 = the reference size; opt-in by name)
 only = sys.argv[1:]
 out = []
 

@@ -207,6 +207,11 @@ def test_joint_warmstart_emulated_kernels():
     joint_limits_parity_case(mk, mo, warmstart_joints=True, scene=scenes.joint_grid(6), steps=60)   # locked-only joints on the generic path
 
 
+def test_convex_polyhedra_emulated_kernels():
+    from test_oracle_kat import convex_polyhedra
+    convex_polyhedra(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()))
+
+
 def test_capsules_emulated_kernels():
     from test_oracle_kat import capsules_rest
     capsules_rest(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()))

@@ -6,7 +6,8 @@ import pytest
 import fuzz_emul_vs_oracle as fuzz
 
 
-@pytest.mark.parametrize("seed", [3, 7, 12, 21, 34, 55, 89, 144, 232, 269, 284, 291, 377, 610, 987])
+@pytest.mark.parametrize("seed", [3, 7, 12, 21, 34, 55, 89, 144, 232, 269, 284, 291, 377, 610, 987,
+                                  9001, 9004, 9009, 9011, 9013, 9015])   # (9000+: convex polyhedra, dominance groups, warmstart_joints in the mix)
 def test_random_scene_emulated_kernels_match_oracle(seed):
     ok, msg = fuzz.run(seed, smem_floats=(9000 if seed % 3 == 0 else None))
     assert ok, msg

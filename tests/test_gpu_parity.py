@@ -396,3 +396,18 @@ def test_dominance_groups_and_joint_warmstart(built):
     joint_limits_parity_case(mk, mo, warmstart_joints=True)
     joint_limits_parity_case(mk, mo, warmstart_joints=True, coulomb=True, steps=60)
     joint_limits_parity_case(mk, mo, warmstart_joints=True, scene=scenes.joint_grid(20), steps=60)
+
+
+def test_convex_polyhedra(built):
+    """ColliderBuilder::{convex_hull, round_convex_hull}: known answers through the C ABI (the convex_pile parity variants
+    run with the other variants) and the reference's examples3d/convex_polyhedron3.rs drop (reduced: 5 x 5 x 4 round hulls of
+    10 random points) bit-exact against the oracle."""
+    from test_oracle_kat import convex_polyhedra
+    convex_polyhedra(lambda s: PhysicsWorld(s))
+    s = scenes.convex_polyhedra(4)
+    w, o = PhysicsWorld(s), oracle_lib.OracleWorld(s, threads=8)
+    for i in range(150):
+        w.step(); o.step()
+        if i % 15 == 14 or i < 2:
+            d = compare_worlds(w, o)
+            assert is_exact(d), (i, d)

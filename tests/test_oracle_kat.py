@@ -991,3 +991,97 @@ def joint_warmstart(make_world):
 
 def test_joint_warmstart_oracle():
     joint_warmstart(lambda s, p: oracle_lib.OracleWorld(s, params=p))
+
+
+def convex_polyhedra(make_world):
+    """ColliderBuilder::{convex_hull, round_convex_hull} (collider.rs:1039-1060) against everything else.  parry's manifolds
+    are not in the tree, so the answers are physical: (1) a tetrahedron of mass 1 (volume 1/6, density 6) rests on its
+    base and is carried by exactly its weight (total_contact_impulse.rs's criterion: sum of impulses = m g dt +- 1 %);
+    (2) a cube given as a hull moves like the cuboid twin dropped beside it; (3) hull-on-hull, ball-on-hull, hull-on-
+    cuboid and capsule-on-hull stacks rest at the analytic heights; a round hull rests higher by its border radius;
+    (4) a spinning free tetrahedron keeps its angular momentum direction (principal axes and centre of mass are right:
+    no wobble of the centre of mass); (5) a heap of random hulls settles on the ground without sinking in."""
+    tet = [(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0)]
+    cube = [(x, y, z) for x in (-0.5, 0.5) for y in (-0.5, 0.5) for z in (-0.5, 0.5)]
+    s = scenes.Scene("convex", gravity=(0.0, -9.81, 0.0))
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(30.0, 0.5, 30.0))
+    t = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.3, 0.0)).can_sleep(False), ColliderBuilder.convex_hull(tet).density(6.0))
+    hc = s.insert(RigidBodyBuilder.dynamic().translation((4.0, 2.0, 0.0)).rotation((0.3, 0.2, 0.1)).can_sleep(False), ColliderBuilder.convex_hull(cube))
+    cc = s.insert(RigidBodyBuilder.dynamic().translation((8.0, 2.0, 0.0)).rotation((0.3, 0.2, 0.1)).can_sleep(False), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    a0 = s.insert(RigidBodyBuilder.dynamic().translation((12.0, 0.55, 0.0)), ColliderBuilder.convex_hull(cube))
+    a1 = s.insert(RigidBodyBuilder.dynamic().translation((12.05, 1.6, 0.05)), ColliderBuilder.convex_hull(cube))
+    a2 = s.insert(RigidBodyBuilder.dynamic().translation((12.0, 2.5, 0.0)), ColliderBuilder.ball(0.4))
+    b0 = s.insert(RigidBodyBuilder.dynamic().translation((16.0, 0.55, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    b1 = s.insert(RigidBodyBuilder.dynamic().translation((16.0, 1.6, 0.0)).rotation((0.0, 0.4, 0.0)), ColliderBuilder.convex_hull(cube))
+    b2 = s.insert(RigidBodyBuilder.dynamic().translation((16.0, 2.4, 0.0)), ColliderBuilder.capsule_x(0.3, 0.2))
+    rd = s.insert(RigidBodyBuilder.dynamic().translation((20.0, 0.7, 0.0)), ColliderBuilder.round_convex_hull(cube, 0.1))
+    w = make_world(s)
+    w.step(300)
+    pose, vel = w.body_states()
+    assert np.abs(vel).max() < 0.05
+    assert abs(pose[t, 1]) < 0.01                                               # on its base (the body origin is the corner)
+    cp = w.contact_pairs()
+    tet_impulse = sum(float(imp.sum()) for k, imp in zip(cp["colliders"].tolist(), cp["impulses"]) if 1 in k)
+    assert abs(tet_impulse - 9.81 / 60.0) < 0.01 * 9.81 / 60.0, tet_impulse
+    assert abs(pose[hc, 1] - 0.5) < 0.01 and abs(pose[cc, 1] - 0.5) < 0.01
+    assert np.abs((pose[hc, :3] - pose[cc, :3]) - (-4.0, 0.0, 0.0)).max() < 0.05     # same tumble as the cuboid twin
+    assert abs(pose[a0, 1] - 0.5) < 0.01 and abs(pose[a1, 1] - 1.5) < 0.015 and abs(pose[a2, 1] - 2.4) < 0.02
+    assert abs(pose[b0, 1] - 0.5) < 0.01 and abs(pose[b1, 1] - 1.5) < 0.015 and abs(pose[b2, 1] - 2.2) < 0.02
+    assert abs(pose[rd, 1] - 0.6) < 0.01
+    s = scenes.Scene("spin", gravity=(0.0, 0.0, 0.0))
+    sp = s.insert(RigidBodyBuilder.dynamic().angvel((0.0, 3.0, 0.0)).linvel((0.5, 0.0, 0.0)), ColliderBuilder.convex_hull(tet))
+    w = make_world(s)
+    w.step(1)
+    p0, _ = w.body_states()
+    w.step(239)
+    p1, v1 = w.body_states()
+
+    def com(p):   # centre of mass (1/4, 1/4, 1/4) of the tetrahedron carried by the pose
+        x, y, z, qw = p[3], p[4], p[5], p[6]
+        v = np.array([0.25, 0.25, 0.25])
+        q = np.array([x, y, z])
+        tt = 2.0 * np.cross(q, v)
+        return p[:3] + v + qw * tt + np.cross(q, tt)
+    travelled = com(p1[sp]) - com(p0[sp])
+    assert np.abs(travelled - (0.5 * 239 / 60.0, 0.0, 0.0)).max() < 2e-3, travelled   # the centre of mass moves straight
+    assert abs(np.linalg.norm(v1[sp, 3:]) - 3.0) < 0.2
+    s = scenes.Scene("heap", gravity=(0.0, -9.81, 0.0))
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(30.0, 0.5, 30.0))
+    r = np.random.default_rng(7)
+    ids = []
+    for i in range(30):
+        pts = r.uniform(-0.5, 0.5, (10, 3))
+        ids.append(s.insert(RigidBodyBuilder.dynamic().translation((0.4 * (i % 3), 1.0 + 1.2 * i, 0.3 * (i % 2))).rotation(tuple(r.uniform(-1, 1, 3))),
+                            ColliderBuilder.round_convex_hull(pts, 0.03 * (i % 3))))
+    w = make_world(s)
+    w.step(700)
+    pose, vel = w.body_states()
+    assert np.isfinite(pose).all() and pose[ids, 1].min() > 0.0 and pose[ids, 1].max() < 6.0, (pose[ids, 1].min(), pose[ids, 1].max())
+    assert np.abs(vel[ids]).max() < 1.0
+
+
+def test_convex_polyhedra_oracle():
+    convex_polyhedra(lambda s: oracle_lib.OracleWorld(s))
+
+
+def test_convex_hull_builder_and_mesh_validation():
+    """rb_convex_hull (host routine of the product library): hulls of random point sets are closed convex meshes (Euler's
+    formula, every point behind every face), interior points are dropped, a cube's coplanar corners merge into 6 quads;
+    rb_world_add_hull's checks are mirrored by the oracle's."""
+    from rapier_b200.sets import convex_hull_mesh
+    cube = [(x, y, z) for x in (-1.0, 1.0) for y in (-1.0, 1.0) for z in (-1.0, 1.0)]
+    v, f = convex_hull_mesh(cube + [(0.0, 0.0, 0.0), (0.3, -0.2, 0.9)])
+    assert len(v) == 8 and sorted(len(x) for x in f) == [4] * 6
+    r = np.random.default_rng(3)
+    for _ in range(20):
+        pts = r.uniform(-1.0, 1.0, (int(r.integers(4, 20)), 3)).astype(np.float32)
+        v, f = convex_hull_mesh(pts)
+        e = sum(len(x) for x in f) // 2
+        assert len(v) - e + len(f) == 2
+        for loop in f:
+            a, b, c = v[loop[0]], v[loop[1]], v[loop[2]]
+            n = np.cross(b - a, c - a).astype(np.float64)
+            n /= np.linalg.norm(n)
+            assert ((pts - a) @ n).max() < 1e-4          # counter-clockwise seen from outside: everything behind
+    with pytest.raises(ValueError):
+        convex_hull_mesh([(0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0)])   # coplanar

@@ -2,6 +2,8 @@
 edge cases of the reference's own test-suite for this path (restitution, warm-start coefficients,
 friction in the bias pass, collision groups, joints with contacts disabled, multi-collider bodies,
 user forces, damping, locked axes)."""
+import math
+
 from rapier_b200 import _abi as A
 from rapier_b200 import scenes
 import numpy as np
@@ -277,6 +279,48 @@ def capsule_pile():
     return s
 
 
+def convex_pile():
+    """Convex polyhedra against everything: random hulls (sharp and round) tumbling into a heap on a floor of a cuboid plus
+    a static prism, hull-cubes stacked on hull-cubes / cuboids, a ball and capsules of all axes dropped among them,
+    a tetrahedron, a hexagonal prism (6-vertex faces: clipped polygons beyond eight points), a kinematic hull sweeping
+    through, a hull on a spherical joint."""
+    s = scenes.Scene("convex_pile")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(15.0, 0.5, 15.0))
+    hexagon = [(math.cos(k * math.pi / 3.0), y, math.sin(k * math.pi / 3.0)) for k in range(6) for y in (-0.3, 0.3)]
+    s.colliders.insert(ColliderBuilder.convex_hull([(2.0 * x, 1.5 * y + 0.45, 2.0 * z) for x, y, z in hexagon]).translation((0.0, 0.0, 4.0)))
+    cube = [(x, y, z) for x in (-0.5, 0.5) for y in (-0.5, 0.5) for z in (-0.5, 0.5)]
+    tet = [(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0)]
+    r = np.random.default_rng(11)
+    k = 0
+    for layer in range(5):
+        for i in range(3):
+            for j in range(2):
+                pos = (-1.3 + 1.3 * i + 0.07 * layer, 0.9 + 1.25 * layer, -0.7 + 1.4 * j + 0.05 * i)
+                b = RigidBodyBuilder.dynamic().translation(pos).rotation(tuple(float(x) for x in r.uniform(-1.0, 1.0, 3)))
+                kind = k % 6
+                if kind == 0:
+                    c = ColliderBuilder.convex_hull(r.uniform(-0.55, 0.55, (10, 3)))
+                elif kind == 1:
+                    c = ColliderBuilder.round_convex_hull(r.uniform(-0.45, 0.45, (8, 3)), 0.08)
+                elif kind == 2:
+                    c = ColliderBuilder.convex_hull([(0.6 * x, 0.5 * y, 0.6 * z) for x, y, z in hexagon])
+                elif kind == 3:
+                    c = ColliderBuilder.cuboid(0.4, 0.3, 0.5) if layer % 2 else ColliderBuilder.ball(0.45)
+                elif kind == 4:
+                    c = [ColliderBuilder.capsule_x, ColliderBuilder.capsule_y, ColliderBuilder.capsule_z][layer % 3](0.4, 0.25)
+                else:
+                    c = ColliderBuilder.convex_hull(tet).density(3.0)
+                s.insert(b, c.friction(0.3 + 0.1 * (k % 5)).restitution(0.2 if k % 7 == 0 else 0.0))
+                k += 1
+    for i in range(3):   # stacks: hull cube on hull cube on cuboid
+        s.insert(RigidBodyBuilder.dynamic().translation((6.0, 0.5 + 1.0 * i, 0.0)), ColliderBuilder.convex_hull(cube) if i else ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    s.insert(RigidBodyBuilder.kinematic_velocity_based().translation((-8.0, 0.6, 0.0)).linvel((1.5, 0.0, 0.0)), ColliderBuilder.convex_hull([(0.4 * x, 1.2 * y, 3.0 * z) for x, y, z in cube]))
+    anchor = s.bodies.insert(RigidBodyBuilder.fixed().translation((-4.0, 5.0, -5.0)))
+    swing = s.insert(RigidBodyBuilder.dynamic().translation((-2.5, 5.0, -5.0)), ColliderBuilder.convex_hull(r.uniform(-0.5, 0.5, (12, 3))))
+    s.joints.insert(anchor, swing, SphericalJointBuilder().local_anchor2((-1.5, 0.0, 0.0)))
+    return s
+
+
 VARIANTS = [
     ("restitution", bouncing_balls, None, 150, 25),
     ("groups_joints_forces", groups_and_joints, None, 150, 25),
@@ -304,6 +348,9 @@ VARIANTS = [
     # capsules (SHAPES = 1 variant of the collision kernel)
     ("capsule_pile", capsule_pile, None, 180, 20),
     ("capsule_pile_coulomb_no_recycling", capsule_pile, _params(friction_model=1, contact_recycling=0), 60, 15),
+    # convex polyhedra (rb_poly.cuh)
+    ("convex_pile", convex_pile, None, 200, 20),
+    ("convex_pile_coulomb_no_recycling", convex_pile, _params(friction_model=1, contact_recycling=0), 60, 15),
     # CCD motion clamping (src/dynamics/ccd): fast bodies against thin fixed walls / a tiled floor; and switched off
     ("ccd_barrage", ccd_barrage, None, 90, 10),
     ("ccd_barrage_ccd_off", ccd_barrage, _params(max_ccd_substeps=0), 30, 10),
