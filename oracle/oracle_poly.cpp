@@ -2,7 +2,8 @@
 //
 // Stands in for parry3d 0.30.2's contact_manifolds on pairs with a ConvexPolyhedron (pair_update.rs:323-330); parry is
 // not in the tree.  Contract kept from the cuboid routine: the manifold normal is the axis of largest
-// separation among the face normals of both shapes and the cross products of SUPPORTING edge pairs; a face axis gives
+// separation among the face normals of both shapes and the cross products of the edge pairs that form a face of the
+// Minkowski difference (Gauss-map test; supporting edge pairs when one shape is a capsule's segment); a face axis gives
 // the incident face of the other shape clipped (Sutherland-Hodgman) against the side planes of the reference face, an
 // edge axis the closest points of the two edges; points closer than `prediction`; `dist` along the normal.  Cuboids
 // enter as the scaled unit cube (hull 0), capsules as their segment with a radius; round polyhedra carry a radius too.
@@ -169,25 +170,41 @@ void solid_solid(const Solid& A, const Solid& B, const Pose& p12, float predicti
     float ebest = -F32_MAX;
     V3 en = bn;
     int ei = 0, ej = 0;
+    const bool gauss = A.nfaces() > 0 && B.nfaces() > 0;   // Gauss-map pruning of the edge pairs (Gregorius, GDC 2013)
+    V3 ca = vzero();
+    for (const V3& x : va) ca = ca + x;
+    ca = ca * (1.0f / (float)va.size());
     for (int ea = 0; ea < A.nedges(); ++ea) {
         HullEdge e1 = A.edge(ea);
         V3 da = va[e1.v1] - va[e1.v0];
         float la = length_sq(da);
+        V3 u1 = vzero(), v1 = vzero();
+        if (gauss) { u1 = A.n[e1.f0]; v1 = A.n[e1.f1]; }
         for (int eb = 0; eb < B.nedges(); ++eb) {
             HullEdge e2 = B.edge(eb);
             V3 db = vb[e2.v1] - vb[e2.v0];
+            if (gauss) {
+                float du2 = dot(nb[e2.f0], da), dv2 = dot(nb[e2.f1], da), du1 = dot(u1, db), dv1 = dot(v1, db);
+                if (!(du2 * dv2 < 0.0f && du1 * dv1 < 0.0f && du2 * dv1 < 0.0f)) continue;
+            }
             V3 c = cross(da, db);
             float l2 = length_sq(c);
             if (!(l2 > 1.0e-8f * la * length_sq(db))) continue;
             V3 n = c * (1.0f / sqrtf(l2));
-            float pa = dot(n, va[e1.v0]), pb = dot(n, vb[e2.v0]);
-            if (pb < pa) { n = -n; pa = -pa; pb = -pb; }
-            float tol = 1.0e-5f * (1.0f + fabsf(pa) + fabsf(pb));
-            bool support = true;
-            for (size_t i = 0; i < va.size() && support; ++i) support = dot(n, va[i]) <= pa + tol;
-            for (size_t i = 0; i < vb.size() && support; ++i) support = dot(n, vb[i]) >= pb - tol;
-            if (!support) continue;
-            float s = pb - pa;
+            float s;
+            if (gauss) {
+                if (dot(n, va[e1.v0] - ca) < 0.0f) n = -n;
+                s = dot(n, vb[e2.v0] - va[e1.v0]);
+            } else {
+                float pa = dot(n, va[e1.v0]), pb = dot(n, vb[e2.v0]);
+                if (pb < pa) { n = -n; pa = -pa; pb = -pb; }
+                float tol = 1.0e-5f * (1.0f + fabsf(pa) + fabsf(pb));
+                bool support = true;
+                for (size_t i = 0; i < va.size() && support; ++i) support = dot(n, va[i]) <= pa + tol;
+                for (size_t i = 0; i < vb.size() && support; ++i) support = dot(n, vb[i]) >= pb - tol;
+                if (!support) continue;
+                s = pb - pa;
+            }
             if (s > eff) return;
             if (s > ebest) { ebest = s; en = n; ei = ea; ej = eb; }
         }

@@ -904,6 +904,7 @@ static int upload_hulls(RbWorld* W) {
     CK(h2d(d_loops, loops.data(), loops.size() * sizeof(int))); CK(h2d(d_edges, edges.data(), edges.size() * sizeof(int4)));
     w.hulls.desc = d_desc; w.hulls.desc2 = d_desc2; w.hulls.info = d_info; w.hulls.verts = d_verts; w.hulls.planes = d_planes;
     w.hulls.faces = d_faces; w.hulls.loops = d_loops; w.hulls.edges = d_edges;
+    if (!w.convex_work) { ALLOC(w.convex_work, w.pair_cap); ALLOC(w.convex_raw, (size_t)w.pair_cap * POLY_RAW_STRIDE); }
     W->hulls_uploaded = nh;
     return RB_OK;
 }

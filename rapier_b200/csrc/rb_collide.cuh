@@ -557,6 +557,62 @@ RB_HD void reduce_manifold(const RawManifold& m, int* sel, int& nsel, float pred
     else nsel = 4;
 }
 
+// Polyhedron manifolds (SHAPES = 1 only).  A separating-axis search over two polyhedra is hundreds of candidate axes: one
+// thread per pair takes ~0.7 ms of dependent local-memory traffic however few pairs there are.  So the pairs that will get
+// a full manifold this step (same tests as the per-pair loop below: an awake owned body, not recycled) are listed first,
+// then each is handed to a whole WARP (consecutive list entries to different CTAs), whose lanes share the candidate axes
+// (rb_poly.cuh) with the polyhedra staged in shared memory; the raw manifold goes to a scratch table the per-pair pass reads.
+template <class Ctx>
+RB_PHASE void phase_convex_manifolds(const Ctx& ctx, const World& w) {
+    State* st = w.st;
+    const int buf = st->cur, np = st->npairs;
+    const float prediction = w.prm.prediction;
+    const float recycle = w.prm.contact_recycling ? w.prm.recycle_dist : 0.0f;
+    for (int i = ctx.gtid; i < np; i += ctx.gsize) {
+        const unsigned long long key = w.pb[buf].key[i];
+        const int c1 = (int)(key >> 32), c2 = (int)(key & 0xffffffffu);
+        if (!pair_is_poly_poly(w.c_shape[c1], w.c_shape[c2])) continue;
+        const float4 bod0 = prow(w, buf, PR_BODIES, i);
+        if (!body_is_sim(w, as_int(bod0.z)) && !body_is_sim(w, as_int(bod0.w))) continue;
+        const int flags = as_int(prow(w, buf, PR_INFO, i).x);
+        if (recycle > 0.0f && (flags & 1)) {
+            const pose cp1 = collider_pose(w, c1), cp2 = collider_pose(w, c2);
+            const pose p12 = pinv_mul(cp1, cp2);
+            const float4 rt = prow(w, buf, PR_RT, i);
+            const pose base = mkpose(mkq(prow(w, buf, PR_RQ, i)), xyz(rt));
+            const float drift = pose_drift(base, p12, rt.w);
+            const float rc = min2(rot_cos(mkq(prow(w, buf, PR_ROT1, i)), cp1.q), rot_cos(mkq(prow(w, buf, PR_ROT2, i)), cp2.q));
+            if (drift <= prow(w, buf, PR_LN1, i).w && rc > 0.98f) continue;
+        }
+        w.convex_work[atomic_add(&st->nconvex, 1)] = i;
+    }
+    ctx.grid_sync();
+    RB_SHARED float s_poly[RADIX_MAX_WARPS][3 * 3 * HULL_MAX_VERTS];   // per warp: va, vb, nb
+    const int nwork = st->nconvex;
+    const int warps_per_block = ctx.bsize / ctx.nlanes < RADIX_MAX_WARPS ? ctx.bsize / ctx.nlanes : RADIX_MAX_WARPS;
+    const int warp = ctx.btid / ctx.nlanes;
+    if (warp < warps_per_block) {
+        vec3* va = reinterpret_cast<vec3*>(s_poly[warp]);
+        vec3* vb = va + HULL_MAX_VERTS;
+        vec3* nb = vb + HULL_MAX_VERTS;
+        for (int k = warp * ctx.nblocks + ctx.bid; k < nwork; k += warps_per_block * ctx.nblocks) {
+            const int i = w.convex_work[k];
+            const unsigned long long key = w.pb[buf].key[i];
+            const int c1 = (int)(key >> 32), c2 = (int)(key & 0xffffffffu);
+            const pose p12 = pinv_mul(collider_pose(w, c1), collider_pose(w, c2));
+            PolyLocal l1, l2;
+            float r1, r2;
+            const Poly A = poly_of_shape(w.hulls, w.c_shape[c1], xyz(w.c_he[c1]), l1, r1);
+            const Poly B = poly_of_shape(w.hulls, w.c_shape[c2], xyz(w.c_he[c2]), l2, r2);
+            RawManifold raw;
+            manifold_poly_poly(ctx.lane, ctx.nlanes, A, r1, B, r2, p12, prediction + (w.c_mat[c1].z + w.c_mat[c2].z), va, vb, nb, raw);
+            if (ctx.lane == 0) poly_raw_store(w.convex_raw + (size_t)i * POLY_RAW_STRIDE, raw);
+        }
+    }
+    ctx.grid_sync();
+    if (ctx.gtid == 0) st->nconvex = 0;
+}
+
 template <int SHAPES = 0, class Ctx>
 RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
     State* st = w.st;
@@ -591,7 +647,8 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
         float4 m1 = w.c_mat[c1], m2 = w.c_mat[c2];
         float skin1 = m1.z, skin2 = m2.z;
         RawManifold raw;
-        contact_manifold<SHAPES>(w.hulls, sh1, he1, sh2, he2, p12, prediction + (skin1 + skin2), raw);
+        if (SHAPES && pair_is_poly_poly(sh1, sh2)) poly_raw_load(w.convex_raw + (size_t)i * POLY_RAW_STRIDE, raw);   // (phase_convex_manifolds)
+        else contact_manifold<SHAPES>(w.hulls, sh1, he1, sh2, he2, p12, prediction + (skin1 + skin2), raw);
 
         // match_contacts: carry ContactData by feature ids (ball manifolds keep their single point).
         float4 o_pb[MAX_PTS], o_pd[MAX_PTS], o_tw[MAX_PTS], o_d1[MAX_PTS], o_d2[MAX_PTS];
@@ -1024,18 +1081,31 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
         if (b >= 0) atomic_add(&w.isl_ncons[w.isl_label[b]], 1);
     }
     ctx.grid_sync();
-    // S5 colour stage order: big colours ascending, then small colours ascending, then overflow.
-    if (ctx.gtid == 0) {
-        int pos = 0;
-        for (int c = 0; c < NUM_COLORS; ++c) w.color_pos[c] = -1;
-        for (int pass = 0; pass < 2; ++pass)
-            for (int c = 0; c < 128; ++c) {
-                int n = w.color_count[c];
-                if (n == 0 || (n >= BIG_COLOR_MIN) != (pass == 0)) continue;
-                w.color_pos[c] = pos++;
+    // S5 colour stage order: big colours ascending, then small colours ascending, then overflow.  One CTA, a thread per
+    // colour ranking itself against a shared copy of the counts (a single thread walking global memory cost ~150 us).
+    if (ctx.bid == 0) {
+        RB_SHARED int s_cnt[NUM_COLORS];
+        for (int c = ctx.btid; c < NUM_COLORS; c += ctx.bsize) s_cnt[c] = w.color_count[c];
+        ctx.block_sync();
+        for (int c = ctx.btid; c < NUM_COLORS; c += ctx.bsize) {
+            const int n = s_cnt[c];
+            int nbig = 0, nsmall = 0, before = 0;
+            const bool big = n >= BIG_COLOR_MIN;
+            for (int k = 0; k < 128; ++k) {
+                const int nk = s_cnt[k];
+                if (nk == 0) continue;
+                const bool kb = nk >= BIG_COLOR_MIN;
+                if (kb) ++nbig; else ++nsmall;
+                if (k < c && kb == big) ++before;
             }
-        if (w.color_count[128] > 0) w.color_pos[128] = pos++;
-        st->nused_colors = pos;
+            int p = -1;
+            if (c < 128) { if (n > 0) p = big ? before : nbig + before; }
+            else {
+                if (n > 0) p = nbig + nsmall;
+                st->nused_colors = nbig + nsmall + (n > 0 ? 1 : 0);
+            }
+            w.color_pos[c] = p;
+        }
     }
     // S6 work items: exclusive prefix of the cost of the small islands in root order.
     int* cost = w.isl_item;  // reuse as input, overwritten by the item id below
@@ -1317,21 +1387,36 @@ RB_PHASE void phase_kinematic_velocities(const Ctx& ctx, const World& w) {
     }
 }
 
+// -DRB_DEBUG build with RB_DEBUG_FLAGS & 4: thread 0 stamps the end of every section (tests/prof_collide_phases.py)
+#ifdef RB_DEBUG
+#define RB_CSTAMP(k) do { if ((w.debug_flags & 4) && ctx.gtid == 0) w.dbg_times[16 + (k)] = rb_clock(); } while (0)
+#else
+#define RB_CSTAMP(k) do { } while (0)
+#endif
+
 template <int SHAPES = 0, class Ctx>
 RB_PHASE void collide_pipeline(const Ctx& ctx, const World& w) {
     State* st = w.st;
     if (ctx.gtid == 0) { st->bp_ran = 0; st->sched_ran = 0; st->sleep_stamp += 1; }
+    RB_CSTAMP(0);
     phase_refresh_colliders<SHAPES>(ctx, w);
     ctx.grid_sync();
+    RB_CSTAMP(1);
     if (st->bp_dirty || st->lists_dirty) section_broad_phase(ctx, w);
+    RB_CSTAMP(2);
+    if constexpr (SHAPES != 0) { if (w.convex_work) phase_convex_manifolds(ctx, w); }   // (a kernel parameter: uniform)
     phase_narrow_phase<SHAPES>(ctx, w);
     ctx.grid_sync();
+    RB_CSTAMP(3);
     if (w.nkinpos > 0) { phase_kinematic_velocities(ctx, w); ctx.grid_sync(); }   // (a kernel parameter: uniform)
     if (st->wake_any) section_wake(ctx, w);
     if (st->ntodo) section_coloring(ctx, w);
+    RB_CSTAMP(4);
     if (st->sched_dirty) section_components(ctx, w);
     if (w.sleep_enabled) section_sleep(ctx, w);
+    RB_CSTAMP(5);
     if (st->sched_dirty) section_schedule(ctx, w);
+    RB_CSTAMP(6);
 }
 
 }  // namespace rb

@@ -3,7 +3,8 @@
 // Replaces the reference's call into parry3d 0.30.2 (`query_dispatcher.contact_manifolds`,
 // src/geometry/narrow_phase/pair_update.rs:323-330) for pairs that involve a ConvexPolyhedron.  parry's own routine
 // (GJK/EPA + PolygonalFeatureMap clipping) is not in the tree; this is a first-principles restatement with the same
-// contract as the cuboid path: separating-axis search (face normals of both shapes, then SUPPORTING edge pairs),
+// contract as the cuboid path: separating-axis search (face normals of both shapes, then the edge pairs that form a face of the Minkowski
+// difference -- pruned on the Gauss map; for a capsule's segment: supporting edge pairs),
 // reference / incident feature selection, Sutherland-Hodgman clipping of the incident face against the side planes of
 // the reference face, points within `prediction` kept, `dist` measured along the manifold normal, stable feature ids.
 // A cuboid meets a polyhedron as the unit-cube topology (hull 0) scaled by its half extents, a capsule as a segment
@@ -86,7 +87,7 @@ RB_HD int poly_clip_plane(const ClipPt* in, int n, bool closed, vec3 sn, float s
 
 // Face `rf` of the reference shape (vertices rv, outward normal n, offset d, all in ONE frame) against the incident
 // feature of the other shape (vertices iv in the same frame): its face most opposed to n, or the segment itself.
-// Emits the clipped points: q on the incident feature and its signed distance to the reference plane.
+// `inormals`: the incident shape's face normals in that frame, or null = its own planes.  Emits the clipped points.
 RB_HD int poly_clip_incident(const Poly& R, const vec3* rv, int rf, vec3 n, const Poly& I, const vec3* iv, const vec3* inormals,
                              ClipPt* out) {
     ClipPt a[POLY_CLIP_MAX], b[POLY_CLIP_MAX];
@@ -100,16 +101,15 @@ RB_HD int poly_clip_incident(const Poly& R, const vec3* rv, int rf, vec3 n, cons
         int inc = 0;
         float most = FMAX32;
         for (int f = 0; f < I.nf; ++f) {
-            const float c = dot3(inormals[f], n);
+            const float c = dot3(inormals ? inormals[f] : xyz(I.pl[f]), n);
             if (c < most) { most = c; inc = f; }
         }
         const int2 fc = I.fc[inc];
         for (int k = 0; k < fc.y; ++k) {
             const int vi = I.lp[fc.x + k];
-            a[k].p = iv[vi]; a[k].id = PID_VERT | (uint32_t)vi; a[k].eout = k;
+            a[k].p = iv[vi]; a[k].id = (PID_VERT | (uint32_t)vi) | ((uint32_t)inc << 16); a[k].eout = k;   // (the incident face is part of the feature id)
         }
         cnt = fc.y;
-        for (int k = 0; k < cnt; ++k) a[k].id |= (uint32_t)inc << 16;   // (the incident face is part of the feature id)
     }
     const int2 rfc = R.fc[rf];
     ClipPt* src = a;
@@ -125,63 +125,117 @@ RB_HD int poly_clip_incident(const Poly& R, const vec3* rv, int rf, vec3 n, cons
     return cnt;
 }
 
-// Polyhedron A (radius ra, own frame) against polyhedron B (radius rb, pose p12 in A's frame).
-RB_HD void manifold_poly_poly(const Poly& A, float ra, const Poly& B, float rb, const pose& p12, float prediction, RawManifold& m) {
+// Warp helpers of the cooperative search (one lane, no-ops, in the host emulation).
+#if RB_DEVICE_BUILD
+RB_D void poly_warp_sync() { __syncwarp(); }
+RB_D bool poly_warp_any(bool p) { return __any_sync(0xffffffffu, p); }
+RB_D void poly_warp_argmax(float& s, int& idx) {   // largest s, the SMALLEST index among equals (= the first one a serial scan meets)
+    for (int o = 16; o > 0; o >>= 1) {
+        const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (s2 > s || (s2 == s && i2 < idx)) { s = s2; idx = i2; }
+    }
+}
+#else
+inline void poly_warp_sync() {}
+inline bool poly_warp_any(bool p) { return p; }
+inline void poly_warp_argmax(float&, int&) {}
+#endif
+
+// Separation of the edge pair (ea of A, eb of B) along the normalised cross product of the edges, or false when the
+// pair is no candidate: with faces on both sides it must be a face of the Minkowski difference (the arcs of the two
+// edges cross on the Gauss map; Gregorius, GDC 2013), else -- a capsule's segment -- a SUPPORTING pair along the axis.
+RB_HD bool poly_edge_axis(bool gauss, const Poly& A, const Poly& B, const vec3* va, const vec3* vb, const vec3* nb, vec3 ca, int ea, int eb,
+                          vec3& n, float& s) {
+    const int4 e1 = A.ed[ea], e2 = B.ed[eb];
+    const vec3 da = va[e1.y] - va[e1.x], db = vb[e2.y] - vb[e2.x];
+    if (gauss) {
+        const vec3 u1 = xyz(A.pl[e1.z]), v1 = xyz(A.pl[e1.w]);
+        const float du2 = dot3(nb[e2.z], da), dv2 = dot3(nb[e2.w], da), du1 = dot3(u1, db), dv1 = dot3(v1, db);
+        if (!(du2 * dv2 < 0.0f && du1 * dv1 < 0.0f && du2 * dv1 < 0.0f)) return false;
+    }
+    const vec3 c = cross3(da, db);
+    const float l2 = norm2(c);
+    if (!(l2 > 1.0e-8f * norm2(da) * norm2(db))) return false;
+    n = c * (1.0f / sqrtf(l2));
+    if (gauss) {
+        if (dot3(n, va[e1.x] - ca) < 0.0f) n = -n;   // away from A
+        s = dot3(n, vb[e2.x] - va[e1.x]);
+        return true;
+    }
+    float pa = dot3(n, va[e1.x]), pb = dot3(n, vb[e2.x]);
+    if (pb < pa) { n = -n; pa = -pa; pb = -pb; }   // from A to B
+    const float tol = 1.0e-5f * (1.0f + fabsf(pa) + fabsf(pb));
+    bool support = true;
+    for (int i = 0; i < A.nv && support; ++i) support = dot3(n, va[i]) <= pa + tol;
+    for (int i = 0; i < B.nv && support; ++i) support = dot3(n, vb[i]) >= pb - tol;
+    if (!support) return false;
+    s = pb - pa;
+    return true;
+}
+
+// Polyhedron A (radius ra, own frame) against polyhedron B (radius rb, pose p12 in A's frame), by the `nl` lanes of a
+// warp together (lane = this one; nl = 1: one thread alone): the lanes share the candidate axes and agree on the best
+// one -- largest separation, lowest candidate index among equals, which is what a serial scan in index order finds --
+// then every lane derives the (small) manifold from it redundantly.  sva / svb / snb: 3 x 32 vec3 of scratch shared by
+// the lanes (shared memory on the device).
+RB_HD void manifold_poly_poly(int lane, int nl, const Poly& A, float ra, const Poly& B, float rb, const pose& p12, float prediction,
+                              vec3* va, vec3* vb, vec3* nb, RawManifold& m) {
     m.n = 0; m.n1 = zero3(); m.n2 = zero3();
     const float eff = prediction + ra + rb;
-    vec3 va[HULL_MAX_VERTS], vb[HULL_MAX_VERTS], nb[HULL_MAX_FACES];
-    for (int i = 0; i < A.nv; ++i) va[i] = xyz(A.v[i]);
-    for (int i = 0; i < B.nv; ++i) vb[i] = xform(p12, xyz(B.v[i]));
+    poly_warp_sync();   // (the scratch may still be read by a lane finishing the previous pair)
+    for (int i = lane; i < A.nv; i += nl) va[i] = xyz(A.v[i]);
+    for (int i = lane; i < B.nv; i += nl) vb[i] = xform(p12, xyz(B.v[i]));
+    for (int f = lane; f < B.nf; f += nl) nb[f] = rotate(p12.q, xyz(B.pl[f]));
+    poly_warp_sync();
+    bool separated = false;
     float best = -FMAX32;
-    vec3 bn = mk3(0.f, 1.f, 0.f);
-    int kind = -1, bi = 0, bj = 0;
-    for (int f = 0; f < A.nf; ++f) {   // face normals of A
-        const vec3 n = xyz(A.pl[f]);
+    int bidx = 0x7fffffff;
+    for (int c = lane; c < A.nf + B.nf; c += nl) {   // face normals of A, then of B (in A's frame)
         float s = FMAX32;
-        for (int i = 0; i < B.nv; ++i) s = min2(s, dot3(n, vb[i]));
-        s = s - A.pl[f].w;
-        if (s > eff) return;
-        if (s > best) { best = s; bn = n; kind = 0; bi = f; }
-    }
-    for (int f = 0; f < B.nf; ++f) {   // face normals of B, in A's frame
-        const vec3 n = rotate(p12.q, xyz(B.pl[f]));
-        nb[f] = n;
-        const float d = B.pl[f].w + dot3(n, p12.t);
-        float s = FMAX32;
-        for (int i = 0; i < A.nv; ++i) s = min2(s, dot3(n, va[i]));
-        s = s - d;
-        if (s > eff) return;
-        if (s > best) { best = s; bn = -n; kind = 1; bi = f; }
-    }
-    float ebest = -FMAX32;
-    vec3 en = bn;
-    int ei = 0, ej = 0;
-    for (int ea = 0; ea < A.ne; ++ea) {   // supporting edge pairs
-        const int4 e1 = A.ed[ea];
-        const vec3 da = va[e1.y] - va[e1.x];
-        const float la = norm2(da);
-        for (int eb = 0; eb < B.ne; ++eb) {
-            const int4 e2 = B.ed[eb];
-            const vec3 db = vb[e2.y] - vb[e2.x];
-            const vec3 c = cross3(da, db);
-            const float l2 = norm2(c);
-            if (!(l2 > 1.0e-8f * la * norm2(db))) continue;
-            vec3 n = c * (1.0f / sqrtf(l2));
-            float pa = dot3(n, va[e1.x]), pb = dot3(n, vb[e2.x]);
-            if (pb < pa) { n = -n; pa = -pa; pb = -pb; }   // from A to B
-            const float tol = 1.0e-5f * (1.0f + fabsf(pa) + fabsf(pb));
-            bool support = true;
-            for (int i = 0; i < A.nv && support; ++i) support = dot3(n, va[i]) <= pa + tol;
-            for (int i = 0; i < B.nv && support; ++i) support = dot3(n, vb[i]) >= pb - tol;
-            if (!support) continue;
-            const float s = pb - pa;
-            if (s > eff) return;
-            if (s > ebest) { ebest = s; en = n; ei = ea; ej = eb; }
+        if (c < A.nf) {
+            const vec3 n = xyz(A.pl[c]);
+            for (int i = 0; i < B.nv; ++i) s = min2(s, dot3(n, vb[i]));
+            s = s - A.pl[c].w;
+        } else {
+            const int f = c - A.nf;
+            const vec3 n = nb[f];
+            const float d = B.pl[f].w + dot3(n, p12.t);
+            for (int i = 0; i < A.nv; ++i) s = min2(s, dot3(n, va[i]));
+            s = s - d;
         }
+        if (s > eff) separated = true;
+        if (s > best) { best = s; bidx = c; }
     }
-    if (kind < 0 || ebest > best + 1.0e-4f) {
-        if (ebest == -FMAX32) return;
-        best = ebest; bn = en; kind = 2; bi = ei; bj = ej;
+    if (poly_warp_any(separated)) return;
+    poly_warp_argmax(best, bidx);
+    const bool gauss = A.nf > 0 && B.nf > 0;
+    vec3 ca = zero3();
+    for (int i = 0; i < A.nv; ++i) ca = ca + va[i];
+    ca = ca * (1.0f / (float)A.nv);
+    float ebest = -FMAX32;
+    int eidx = 0x7fffffff;
+    const int npairs = A.ne * B.ne;
+    for (int c = lane; c < npairs; c += nl) {
+        vec3 n;
+        float s;
+        if (!poly_edge_axis(gauss, A, B, va, vb, nb, ca, c / B.ne, c % B.ne, n, s)) continue;
+        if (s > eff) separated = true;
+        if (s > ebest) { ebest = s; eidx = c; }
+    }
+    if (poly_warp_any(separated)) return;
+    poly_warp_argmax(ebest, eidx);
+    int kind, bi, bj = 0;
+    vec3 bn;
+    if (bidx == 0x7fffffff || ebest > best + 1.0e-4f) {
+        if (eidx == 0x7fffffff) return;
+        kind = 2; bi = eidx / B.ne; bj = eidx % B.ne;
+        float s;
+        poly_edge_axis(gauss, A, B, va, vb, nb, ca, bi, bj, bn, s);
+    } else if (bidx < A.nf) {
+        kind = 0; bi = bidx; bn = xyz(A.pl[bi]);
+    } else {
+        kind = 1; bi = bidx - A.nf; bn = -nb[bi];
     }
     const vec3 n2 = rotate_inv(p12.q, -bn);
     if (kind == 2) {
@@ -200,14 +254,11 @@ RB_HD void manifold_poly_poly(const Poly& A, float ra, const Poly& B, float rb, 
     vec3 rn;   // outward normal of the reference face, in A's frame
     float rd;
     if (kind == 0) {
-        vec3 an[1];
         rn = bn; rd = A.pl[bi].w;
-        cnt = poly_clip_incident(A, va, bi, rn, B, vb, B.nf ? nb : an, pts);
+        cnt = poly_clip_incident(A, va, bi, rn, B, vb, nb, pts);
     } else {
-        vec3 na[HULL_MAX_FACES];
-        for (int f = 0; f < A.nf; ++f) na[f] = xyz(A.pl[f]);
         rn = -bn; rd = B.pl[bi].w + dot3(rn, p12.t);
-        cnt = poly_clip_incident(B, vb, bi, rn, A, va, na, pts);
+        cnt = poly_clip_incident(B, vb, bi, rn, A, va, nullptr, pts);
     }
     int keep[POLY_CLIP_MAX], nk = 0;
     for (int k = 0; k < cnt; ++k)
@@ -222,6 +273,29 @@ RB_HD void manifold_poly_poly(const Poly& A, float ra, const Poly& B, float rb, 
     }
     m.n1 = bn; m.n2 = n2;
 }
+
+// Raw manifolds of polyhedron pairs travel from the cooperative pass to the per-pair pass through a global scratch table.
+constexpr int POLY_RAW_STRIDE = 8 + MAX_RAW * 9;   // n, n1, n2, pad, then p1 p2 dist fid1 fid2 per point
+RB_HD void poly_raw_store(float* d, const RawManifold& m) {
+    d[0] = as_float_i(m.n); d[1] = m.n1.x; d[2] = m.n1.y; d[3] = m.n1.z; d[4] = m.n2.x; d[5] = m.n2.y; d[6] = m.n2.z;
+    for (int k = 0; k < m.n; ++k) {
+        float* q = d + 8 + 9 * k;
+        const RawPt& p = m.pt[k];
+        q[0] = p.p1.x; q[1] = p.p1.y; q[2] = p.p1.z; q[3] = p.p2.x; q[4] = p.p2.y; q[5] = p.p2.z; q[6] = p.dist;
+        q[7] = as_float(p.fid1); q[8] = as_float(p.fid2);
+    }
+}
+RB_HD void poly_raw_load(const float* d, RawManifold& m) {
+    m.n = as_int(d[0]); m.n1 = mk3(d[1], d[2], d[3]); m.n2 = mk3(d[4], d[5], d[6]);
+    for (int k = 0; k < m.n; ++k) {
+        const float* q = d + 8 + 9 * k;
+        RawPt& p = m.pt[k];
+        p.p1 = mk3(q[0], q[1], q[2]); p.p2 = mk3(q[3], q[4], q[5]); p.dist = q[6]; p.fid1 = as_uint(q[7]); p.fid2 = as_uint(q[8]);
+    }
+}
+RB_HD bool shape_is_poly(int sh) { return sh == SHAPE_CONVEX || sh == SHAPE_CUBOID || sh == SHAPE_CAPSULE; }
+// pairs the cooperative pass computes: a convex polyhedron against a polyhedron, a cuboid or a capsule
+RB_HD bool pair_is_poly_poly(int sh1, int sh2) { return (sh1 == SHAPE_CONVEX || sh2 == SHAPE_CONVEX) && shape_is_poly(sh1) && shape_is_poly(sh2); }
 
 // Ball (centre c in the polyhedron's frame, radius r) against polyhedron P (border radius rp).
 RB_HD bool poly_ball(const Poly& P, float rp, vec3 c, float r, float prediction, vec3& p_poly, vec3& n_poly, float& dist, uint32_t& fid) {
@@ -273,7 +347,7 @@ RB_HD bool poly_ball(const Poly& P, float rp, vec3 c, float r, float prediction,
     return true;
 }
 
-// Dispatch for pairs with at least one convex polyhedron.
+// Dispatch for a ball against a convex polyhedron (the other pairs with a polyhedron: phase_convex_manifolds, rb_collide.cuh).
 RB_HD void contact_manifold_convex(const HullTables& h, int sh1, vec3 he1, int sh2, vec3 he2, const pose& p12, float prediction, RawManifold& m) {
     m.n = 0; m.n1 = zero3(); m.n2 = zero3();
     PolyLocal s1, s2;
@@ -299,8 +373,7 @@ RB_HD void contact_manifold_convex(const HullTables& h, int sh1, vec3 he1, int s
         }
         return;
     }
-    const Poly A = poly_of_shape(h, sh1, he1, s1, r1), B = poly_of_shape(h, sh2, he2, s2, r2);
-    manifold_poly_poly(A, r1, B, r2, p12, prediction, m);
+    // (polyhedron against polyhedron / cuboid / capsule: phase_convex_manifolds computed it, the caller reads the scratch table)
 }
 
 RB_HD void convex_aabb(const HullTables& h, vec3 he, const pose& p, vec3& lo, vec3& hi) {

@@ -139,6 +139,7 @@ struct State {
     int ccd_total;         // fast bodies queued since the scene was uploaded (diagnostic)
     int nccd_bullets;      // ... of which bullets (ccd_enabled): they sweep in a second pass, against the already clamped poses
     int nev_coll, nev_force;   // buffered collision / contact-force events since the host last drained them
+    int nconvex;           // polyhedron pairs whose manifold the warps compute together this step (World::convex_work)
 };
 
 struct PairBuf {
@@ -271,6 +272,8 @@ struct World {
     // has any take the generic joint path (solve_item<FM, 1>, 12 row slots per joint instead of 6)
     int generic_joints;
     HullTables hulls;                 // convex polyhedra (worlds with SHAPE_CONVEX colliders only; else null)
+    int* convex_work;                 // [pair_cap] pairs of this step that need a polyhedron manifold (phase_convex_manifolds)
+    float* convex_raw;                // [pair_cap][POLY_RAW_STRIDE] their raw manifolds, read back by the per-pair narrow phase
     uint2* j_axes;                    // limit_axes, motor_axes
     float2* j_limits;                 // [nj][6] min, max
     float4* j_motor_a;                // [nj][6] target_vel, target_pos, stiffness, damping
