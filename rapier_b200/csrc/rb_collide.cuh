@@ -14,6 +14,14 @@
 
 namespace rb {
 
+// -DRB_DEBUG build with RB_DEBUG_FLAGS & 4: thread 0 stamps the end of every section (tests/prof_collide_phases.py)
+#ifdef RB_DEBUG
+#define RB_CSTAMP(k) do { if ((w.debug_flags & 4) && ctx.gtid == 0) w.dbg_times[16 + (k)] = rb_clock(); } while (0)
+#else
+#define RB_CSTAMP(k) do { } while (0)
+#endif
+
+
 constexpr int ITEM_TARGET = 128;   // cost (max(bodies, constraints)) packed into one CTA work item
 constexpr int ITEM_BODY_CAP = 256; // islands above either cap go to the grid-wide "large" item 0
 constexpr int ITEM_CONS_CAP = 3072;
@@ -159,7 +167,9 @@ RB_PHASE unsigned long long* grid_radix_sort(const Ctx& ctx, unsigned long long*
     RB_SHARED int s_warp[RADIX_MAX_WARPS][RADIX];   // per-warp digit counts, then running scatter offsets
     RB_SHARED int s_tot[RADIX];
     const int passes = radix_passes(lo, hi);
-    const int nblocks = ctx.nblocks;
+    // CTAs that take part: at least 1024 keys each (a handful of keys spread over every CTA only lengthens the
+    // per-digit walk over the CTAs' histograms below: 148 dependent L2 reads per pass); the others hold empty chunks
+    const int nblocks = ctx.nblocks < (n + 1023) / 1024 ? ctx.nblocks : ((n + 1023) / 1024 > 0 ? (n + 1023) / 1024 : 1);
     const int chunk = (n + nblocks - 1) / nblocks > 0 ? (n + nblocks - 1) / nblocks : 1;
     const int nwarps = ctx.bsize / ctx.nlanes < RADIX_MAX_WARPS ? ctx.bsize / ctx.nlanes : RADIX_MAX_WARPS;
     const int wchunk = (chunk + nwarps - 1) / nwarps;
@@ -170,8 +180,8 @@ RB_PHASE unsigned long long* grid_radix_sort(const Ctx& ctx, unsigned long long*
     ctx.grid_sync();
     for (int p = 0; p < passes; ++p) {
         const int shift = lo + 8 * p;
-        const int* h = hist + (size_t)p * nblocks * RADIX;
-        int* hn = hist + (size_t)(p + 1) * nblocks * RADIX;
+        const int* h = hist + (size_t)p * ctx.nblocks * RADIX;
+        int* hn = hist + (size_t)(p + 1) * ctx.nblocks * RADIX;
         // per digit: total over all blocks, and the part of it that precedes this block
         for (int d = ctx.btid; d < RADIX; d += ctx.bsize) {
             int tot = 0, before = 0;
@@ -892,37 +902,46 @@ RB_PHASE void section_coloring(const Ctx& ctx, const World& w) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Grid-wide exclusive scan of ints: per-thread chunks, block 0 scans the per-thread partials.
-// `tmp` needs gsize + 1 entries.  Returns the total in tmp[gsize].
+// Grid-wide exclusive scan of ints: per-thread chunks, a shared-memory scan of the partial sums inside every CTA, then
+// every CTA adds up the totals of the CTAs before it (no serial pass of one CTA over all the partials: that cost ~45 us
+// per scan).  `tmp` needs gsize + 1 entries.  Returns the total in tmp[gsize].
 // ------------------------------------------------------------------------------------------------
 template <class Ctx>
 RB_PHASE void grid_exclusive_scan(const Ctx& ctx, const int* in, int* out, int n, int* tmp) {
+    RB_SHARED int s_part[1024];
+    RB_SHARED int s_base;
     int chunk = (n + ctx.gsize - 1) / ctx.gsize;
     int b = ctx.gtid * chunk, e = b + chunk < n ? b + chunk : n;
     int s = 0;
     for (int i = b; i < e; ++i) s += in[i];
-    tmp[ctx.gtid] = s;
-    ctx.grid_sync();
-    if (ctx.bid == 0) {
-        RB_SHARED int part[1024];
-        int m = ctx.gsize;
-        int sub = (m + ctx.bsize - 1) / ctx.bsize;
-        int sb = ctx.btid * sub, se = sb + sub < m ? sb + sub : m;
-        int ps = 0;
-        for (int i = sb; i < se; ++i) ps += tmp[i];
-        part[ctx.btid] = ps;
+    // inclusive scan of the per-thread sums within the CTA (Hillis-Steele)
+    s_part[ctx.btid] = s;
+    ctx.block_sync();
+    for (int off = 1; off < ctx.bsize; off <<= 1) {
+        const int v = ctx.btid >= off ? s_part[ctx.btid - off] : 0;
         ctx.block_sync();
-        if (ctx.btid == 0) {
-            int run = 0;
-            for (int t = 0; t < ctx.bsize; ++t) { int v = part[t]; part[t] = run; run += v; }
-            tmp[m] = run;
-        }
+        s_part[ctx.btid] += v;
         ctx.block_sync();
-        int run = part[ctx.btid];
-        for (int i = sb; i < se; ++i) { int v = tmp[i]; tmp[i] = run; run += v; }
     }
+    const int excl = s_part[ctx.btid] - s;
+    if (ctx.btid == ctx.bsize - 1) tmp[ctx.bid] = s_part[ctx.btid];   // the CTA's total
     ctx.grid_sync();
-    int run = tmp[ctx.gtid];
+    // what the CTAs before this one hold (and, by the last CTA, the grand total)
+    int before = 0;
+    for (int k = ctx.btid; k < ctx.bid; k += ctx.bsize) before += tmp[k];
+    ctx.block_sync();   // (s_part is reused)
+    s_part[ctx.btid] = before;
+    ctx.block_sync();
+    for (int off = ctx.bsize >> 1; off > 0; off >>= 1) {
+        if (ctx.btid < off) s_part[ctx.btid] += s_part[ctx.btid + off];
+        ctx.block_sync();
+    }
+    if (ctx.btid == 0) {
+        s_base = s_part[0];
+        if (ctx.bid == ctx.nblocks - 1) tmp[ctx.gsize] = s_part[0] + tmp[ctx.bid];
+    }
+    ctx.block_sync();
+    int run = s_base + excl;
     for (int i = b; i < e; ++i) { int v = in[i]; out[i] = run; run += v; }
     ctx.grid_sync();
 }
@@ -1061,6 +1080,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
     for (int i = ctx.gtid; i < 3 * (w.item_cap + 1); i += ctx.gsize) w.item_cursor[i] = 0;
     for (int i = ctx.gtid; i <= w.item_cap; i += ctx.gsize) { w.item_body_start[i] = 0; w.item_cons_start[i] = 0; w.item_joint_start[i] = 0; }
     ctx.grid_sync();
+    RB_CSTAMP(7);
     // S4 per-root counts + global colour histogram
     for (int b = ctx.gtid; b < nb; b += ctx.gsize)
         if (body_is_sim(w, b)) atomic_add(&w.isl_nb[w.isl_label[b]], 1);
@@ -1081,6 +1101,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
         if (b >= 0) atomic_add(&w.isl_ncons[w.isl_label[b]], 1);
     }
     ctx.grid_sync();
+    RB_CSTAMP(8);
     // S5 colour stage order: big colours ascending, then small colours ascending, then overflow.  One CTA, a thread per
     // colour ranking itself against a shared copy of the counts (a single thread walking global memory cost ~150 us).
     if (ctx.bid == 0) {
@@ -1107,6 +1128,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
             w.color_pos[c] = p;
         }
     }
+    RB_CSTAMP(9);
     // S6 work items: exclusive prefix of the cost of the small islands in root order.
     int* cost = w.isl_item;  // reuse as input, overwritten by the item id below
     for (int b = ctx.gtid; b < nb; b += ctx.gsize) {
@@ -1137,6 +1159,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
         w.isl_item[b] = it;
     }
     ctx.grid_sync();
+    RB_CSTAMP(10);
     // S7 per-item counts
     for (int b = ctx.gtid; b < nb; b += ctx.gsize) {
         int it = body_is_sim(w, b) ? w.isl_item[w.isl_label[b]] : -1;
@@ -1156,6 +1179,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
         if (b >= 0) atomic_add(&w.item_joint_start[w.isl_item[w.isl_label[b]]], 1);
     }
     ctx.grid_sync();
+    RB_CSTAMP(11);
     // S8 scans (counts -> starts); entry [nitems] becomes the total.
     grid_exclusive_scan(ctx, w.item_body_start, w.item_body_start, nitems + 1, w.scan_tmp);
     grid_exclusive_scan(ctx, w.item_cons_start, w.item_cons_start, nitems + 1, w.scan_tmp);
@@ -1164,6 +1188,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
     if (ncons > w.cons_cap) {
         if (ctx.gtid == 0) RB_RAISE(w, -4);
     }
+    RB_CSTAMP(12);
     // S9 scatter bodies / manifolds / joints into their item segments
     int* cur_b = w.item_cursor;
     int* cur_c = w.item_cursor + (w.item_cap + 1);
@@ -1195,6 +1220,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
         w.joint_tmp[w.item_joint_start[it] + l] = j;
     }
     ctx.grid_sync();
+    RB_CSTAMP(13);
     // S10 per-item counting sort by colour stage (one CTA per item), headers for the solver.
     for (int it = ctx.bid; it < nitems; it += ctx.nblocks) {
         RB_SHARED int hist[NUM_COLORS + 1];
@@ -1300,6 +1326,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
         }
     }
     ctx.grid_sync();
+    RB_CSTAMP(14);
     // S11 launch order of the items: non-empty items 1.., most expensive first (counting sort by cost class),
     // consumed through per-kernel atomic cursors so that the long items start first and CTAs stay balanced.
     {
@@ -1386,13 +1413,6 @@ RB_PHASE void phase_kinematic_velocities(const Ctx& ctx, const World& w) {
         w.b_angvel[b] = f4(sa * w.prm.inv_dt_full, 0.0f);
     }
 }
-
-// -DRB_DEBUG build with RB_DEBUG_FLAGS & 4: thread 0 stamps the end of every section (tests/prof_collide_phases.py)
-#ifdef RB_DEBUG
-#define RB_CSTAMP(k) do { if ((w.debug_flags & 4) && ctx.gtid == 0) w.dbg_times[16 + (k)] = rb_clock(); } while (0)
-#else
-#define RB_CSTAMP(k) do { } while (0)
-#endif
 
 template <int SHAPES = 0, class Ctx>
 RB_PHASE void collide_pipeline(const Ctx& ctx, const World& w) {
