@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 4
+#define RB_ABI_VERSION 5
 
 typedef struct RbWorld RbWorld;
 
@@ -82,6 +82,12 @@ enum {
 #define RB_BODY_DOMINANCE_SHIFT 16
 #define RB_BODY_DOMINANCE(group) (((uint32_t)(uint8_t)(int8_t)(group)) << RB_BODY_DOMINANCE_SHIFT)
 #define RB_BODY_DOMINANCE_OF(flags) ((int)(int8_t)(uint8_t)(((flags) >> RB_BODY_DOMINANCE_SHIFT) & 0xffu))
+/* RigidBody::additional_solver_iterations (rigid_body.rs; island_manager/substep_groups.rs): 0..255 in bits 24..31 of
+ * `flags` (default 0; ABI 5).  The body's whole connected component of awake dynamic bodies (touching contacts + joints)
+ * runs num_solver_iterations + max-over-members substeps of dt / that count; other components keep the base cadence. */
+#define RB_BODY_EXTRA_ITERS_SHIFT 24
+#define RB_BODY_EXTRA_ITERS(n) (((uint32_t)(n) & 0xffu) << RB_BODY_EXTRA_ITERS_SHIFT)
+#define RB_BODY_EXTRA_ITERS_OF(flags) ((int)(((flags) >> RB_BODY_EXTRA_ITERS_SHIFT) & 0xffu))
 
 /* One rigid body as the caller's RigidBodySet holds it (src/dynamics/rigid_body.rs:48-70).
  * Mass properties are recomputed by the library from the attached colliders
@@ -167,6 +173,11 @@ typedef struct RbJointDesc {
     uint32_t motor_axes;          /* JointAxesMask of the motorised free axes */
     float limits[6][2];           /* [axis] min, max (distance along a linear axis, angle about an angular one) */
     RbJointMotor motors[6];
+    uint32_t coupled_axes;        /* JointAxesMask of the coupled axes (GenericJoint::coupled_axes; ABI 5).  Coupled LINEAR axes share one
+                                   * row on the DISTANCE between the anchors, driven by the limit (max only) and the motor of the first
+                                   * coupled axis -- SpringJoint / RopeJoint (spring_joint.rs:32-38, rope_joint.rs:32-38).  Exactly two
+                                   * coupled ANGULAR axes share one limit row on the angle between the third axes of the two frames; their
+                                   * motors produce no row, as in the reference (joint_velocity_constraint.rs:224-226).  Default 0. */
 } RbJointDesc;
 
 /* Per-stage device times of the last step, named after the reference's Counters

@@ -60,6 +60,9 @@ public:
     RigidBodyBuilder& dominance_group(int group) {   // RigidBodyBuilder::dominance_group (i8)
         d_.flags = (d_.flags & ~(0xffu << RB_BODY_DOMINANCE_SHIFT)) | RB_BODY_DOMINANCE(group); return *this;
     }
+    RigidBodyBuilder& additional_solver_iterations(unsigned n) {   // RigidBodyBuilder::additional_solver_iterations (0..255)
+        d_.flags = (d_.flags & ~(0xffu << RB_BODY_EXTRA_ITERS_SHIFT)) | RB_BODY_EXTRA_ITERS(n); return *this;
+    }
     RigidBodyBuilder& ccd_enabled(bool on) { if (on) d_.flags |= RB_BODY_CCD_ENABLED; else d_.flags &= ~RB_BODY_CCD_ENABLED; return *this; }
     RigidBodyBuilder& can_sleep(bool on) {   // RigidBodyActivation::cannot_sleep() when false
         if (on) d_.flags &= ~RB_BODY_NO_SLEEP; else d_.flags |= RB_BODY_NO_SLEEP;
@@ -154,6 +157,7 @@ public:
     }
     GenericJointBuilder& motor_max_force(int axis, float max_force) { d_.motor_axes |= 1u << axis; d_.motors[axis].max_force = max_force; return *this; }
     GenericJointBuilder& motor_model(int axis, int model) { d_.motor_axes |= 1u << axis; d_.motors[axis].model = model; return *this; }   // 0 acceleration-, 1 force-based
+    GenericJointBuilder& coupled_axes(unsigned mask) { d_.coupled_axes = mask & 63u; return *this; }   // GenericJointBuilder::coupled_axes
     RbJointDesc desc(int b1, int b2) const { RbJointDesc d = d_; d.body1 = b1; d.body2 = b2; return d; }
 
 private:
@@ -171,6 +175,14 @@ private:
 // SphericalJointBuilder / FixedJointBuilder / RevoluteJointBuilder / PrismaticJointBuilder (src/dynamics/joint/*.rs)
 struct SphericalJointBuilder : GenericJointBuilder { SphericalJointBuilder() : GenericJointBuilder(0x07u) {} };
 struct FixedJointBuilder : GenericJointBuilder { FixedJointBuilder() : GenericJointBuilder(0x3fu) {} };
+struct SpringJointBuilder : GenericJointBuilder {      // spring_joint.rs:32-38: LIN_AXES coupled, force-based position motor on the distance
+    SpringJointBuilder(float rest_length, float stiffness, float damping) : GenericJointBuilder(0u) {
+        coupled_axes(0x07u); motor_position(0, rest_length, stiffness, damping); motor_model(0, 1);
+    }
+};
+struct RopeJointBuilder : GenericJointBuilder {        // rope_joint.rs:32-38, :153-156: LIN_AXES coupled, distance <= max_dist
+    explicit RopeJointBuilder(float max_dist) : GenericJointBuilder(0u) { coupled_axes(0x07u); limits(0, 0.0f, max_dist); }
+};
 struct RevoluteJointBuilder : GenericJointBuilder {   // free: the rotation about `axis` (the X axis of both joint frames)
     explicit RevoluteJointBuilder(Vector axis) : GenericJointBuilder(0x37u) { local_axis1(axis); local_axis2(axis); }
 };

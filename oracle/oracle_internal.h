@@ -179,6 +179,7 @@ struct Joint {
     float impulses[6];
     // limits and motors of the free axes (generic_joint.rs:142-232, :268-300)
     uint32_t limit_axes, motor_axes;
+    uint32_t coupled_axes;             // JointAxesMask of the coupled axes (generic_joint.rs: spring / rope joints couple LIN_AXES)
     float limits[6][2];
     RbJointMotor motors[6];
     float ang_limit_center[3][2], ang_limit_half_range[3];   // AngularLimitParams (joint_constraint_helper.rs:34-73)

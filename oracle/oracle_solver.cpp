@@ -457,7 +457,12 @@ static V3 gyroscopic_corrected_angvel(V3 angvel, Q4 principal_axes, V3 principal
 static int joint_rows_of(const Joint& j) {
     int n = 0;
     const uint32_t free_axes = ~j.locked_axes & 63u;
-    for (int i = 0; i < 6; ++i) n += ((j.locked_axes >> i) & 1) + (((j.limit_axes & free_axes) >> i) & 1) + (((j.motor_axes & free_axes) >> i) & 1);
+    const uint32_t coupled = j.coupled_axes, lim = j.limit_axes & free_axes, mot = j.motor_axes & free_axes;
+    for (int i = 0; i < 6; ++i) n += ((j.locked_axes >> i) & 1) + (((lim & ~coupled) >> i) & 1) + (((mot & ~coupled) >> i) & 1);
+    // coupled axes (joint_velocity_constraint.rs:224-250, :319-355): one motor row for the linear ones, one limit row per kind
+    if (mot & coupled & 7u) n++;
+    if ((coupled & 7u) && (lim & (1u << __builtin_ctz(coupled & 7u)))) n++;
+    if ((coupled & 56u) && (lim & (1u << __builtin_ctz(coupled & 56u))) && __builtin_popcount(coupled & 56u) == 2) n++;
     return n;
 }
 
@@ -540,6 +545,9 @@ static int joint_update(const World& w, const Joint& j, float sub_dt, JointRow* 
     V3 imsum = g1.im + g2.im;
     const uint32_t free_axes = ~j.locked_axes & 63u;
     const uint32_t motor_axes = j.motor_axes & free_axes, limit_axes = j.limit_axes & free_axes;
+    const uint32_t coupled = j.coupled_axes;   // joint_velocity_constraint.rs:163-178
+    const bool has_lin_coupling = (coupled & 7u) != 0, has_ang_coupling = (coupled & 56u) != 0;
+    const int first_lin = has_lin_coupling ? __builtin_ctz(coupled & 7u) : 0, first_ang = has_ang_coupling ? __builtin_ctz(coupled & 56u) : 0;
     const float inv_dt = sub_dt == 0.0f ? 0.0f : 1.0f / sub_dt;
     const float max_bias = w.params.max_corrective_velocity();
     const float aerr[3] = {ang_err.x, ang_err.y, ang_err.z};
@@ -566,7 +574,7 @@ static int joint_update(const World& w, const Joint& j, float sub_dt, JointRow* 
     int len = 0;
     // ---- motors (joint_velocity_constraint.rs:191-223): angular then linear, orthogonalised among themselves
     for (int i = 3; i < 6; ++i) {
-        if (!(motor_axes & (1u << i))) continue;
+        if (!((motor_axes & ~coupled) & (1u << i))) continue;
         const RbJointMotor& m = j.motors[i];
         float m_erp, m_cc, m_cg;
         motor_coeffs(m, m_erp, m_cc, m_cg);
@@ -591,7 +599,7 @@ static int joint_update(const World& w, const Joint& j, float sub_dt, JointRow* 
         r.dof = i; r.kind = 2;
     }
     for (int i = 0; i < 3; ++i) {
-        if (!(motor_axes & (1u << i))) continue;
+        if (!((motor_axes & ~coupled) & (1u << i))) continue;
         const RbJointMotor& m = j.motors[i];
         float m_erp, m_cc, m_cg;
         motor_coeffs(m, m_erp, m_cc, m_cg);
@@ -607,6 +615,42 @@ static int joint_update(const World& w, const Joint& j, float sub_dt, JointRow* 
         r.cfm_coeff = m_cc; r.cfm_gain = m_cg;
         r.lo = -(m.max_force * sub_dt); r.hi = m.max_force * sub_dt;
         r.rhs = rhs_wo_bias; r.rhs_wo_bias = rhs_wo_bias;
+        out[len++] = r;
+    }
+    // the distance row of the coupled linear axes (limit_linear_coupled / motor_linear_coupled, joint_constraint_helper.rs:210-283, :333-409)
+    auto coupled_linear_row = [&](float& dist) {
+        JointRow r;
+        V3 lin_jac = vzero(), ang_jac1 = vzero(), ang_jac2 = vzero();
+        for (int i = 0; i < 3; ++i) {
+            if (!(coupled & (1u << i))) continue;
+            const float coeff = dot(bcol[i], lin_err);
+            lin_jac = lin_jac + bcol[i] * coeff;
+            ang_jac1 = ang_jac1 + cross(r1, bcol[i]) * coeff;
+            ang_jac2 = ang_jac2 + cross(r2, bcol[i]) * coeff;
+        }
+        dist = sqrtf(dot(lin_jac, lin_jac));
+        const float inv_dist = inv_or_zero(dist);
+        r.lin_jac = lin_jac * inv_dist; r.ang_jac1 = ang_jac1 * inv_dist; r.ang_jac2 = ang_jac2 * inv_dist;
+        r.ii_ang_jac1 = sdp_mul(g1.ii, r.ang_jac1); r.ii_ang_jac2 = sdp_mul(g2.ii, r.ang_jac2);
+        r.impulse = 0.0f; r.inv_lhs = 0.0f;
+        return r;
+    };
+    // (motor_axes & coupled_axes) & ANG_AXES: "TODO: coupled angular motor constraint" in the reference -- no row (:224-226)
+    if ((motor_axes & coupled) & 7u) {   // motor_linear_coupled (:228-250): the motor of the first coupled linear axis acts on the distance
+        const RbJointMotor& m = j.motors[first_lin];
+        float m_erp, m_cc, m_cg;
+        motor_coeffs(m, m_erp, m_cc, m_cg);
+        float dist;
+        JointRow r = coupled_linear_row(dist);
+        float rhs_wo_bias = 0.0f;
+        if (m_erp != 0.0f) rhs_wo_bias = rhs_wo_bias + (dist - m.target_pos) * m_erp;
+        float target_vel = m.target_vel;
+        if (limit_axes & (1u << first_lin)) target_vel = fclamp(target_vel, (j.limits[first_lin][0] - dist) * inv_dt, (j.limits[first_lin][1] - dist) * inv_dt);
+        rhs_wo_bias = rhs_wo_bias + -target_vel;
+        r.cfm_coeff = m_cc; r.cfm_gain = m_cg;
+        r.lo = -(m.max_force * sub_dt); r.hi = m.max_force * sub_dt;
+        r.rhs = rhs_wo_bias; r.rhs_wo_bias = rhs_wo_bias;
+        r.dof = first_lin; r.kind = 2;
         out[len++] = r;
     }
     finalize_rows(out, 0, len, imsum);
@@ -634,7 +678,7 @@ static int joint_update(const World& w, const Joint& j, float sub_dt, JointRow* 
         out[len++] = lock_linear_row(i, erp_inv_dt, cfm_coeff, i, 0);
     }
     for (int i = 3; i < 6; ++i) {
-        if (!(limit_axes & (1u << i))) continue;
+        if (!((limit_axes & ~coupled) & (1u << i))) continue;
         const int ax = i - 3;
         // recentered_angle (joint_constraint_helper.rs:468-499) + limit_angular (:503-564)
         const float c_cos = j.ang_limit_center[ax][0], c_sin = j.ang_limit_center[ax][1], half_range = j.ang_limit_half_range[ax];
@@ -656,7 +700,7 @@ static int joint_update(const World& w, const Joint& j, float sub_dt, JointRow* 
         r.dof = i; r.kind = 1;
     }
     for (int i = 0; i < 3; ++i) {
-        if (!(limit_axes & (1u << i))) continue;
+        if (!((limit_axes & ~coupled) & (1u << i))) continue;
         JointRow r = lock_linear_row(i, erp_inv_dt, cfm_coeff, i, 1);   // limit_linear (joint_constraint_helper.rs:166-207)
         const float dist = dot(lin_err, r.lin_jac);
         const bool min_enabled = dist <= j.limits[i][0], max_enabled = j.limits[i][1] <= dist;
@@ -664,6 +708,61 @@ static int joint_update(const World& w, const Joint& j, float sub_dt, JointRow* 
         r.rhs = r.rhs_wo_bias + rhs_bias;
         r.cfm_coeff = cfm_coeff;
         r.lo = min_enabled ? -FINF : 0.0f; r.hi = max_enabled ? FINF : 0.0f;
+        out[len++] = r;
+    }
+    if (has_ang_coupling && (limit_axes & (1u << first_ang))) {   // limit_angular_coupled (joint_constraint_helper.rs:725-798): exactly two coupled angular axes
+        const uint32_t ac = coupled >> 3;
+        const int not_coupled = (ac & 1u) == 0 ? 0 : ((ac & 2u) == 0 ? 1 : ((ac & 4u) == 0 ? 2 : 3));   // trailing_ones
+        if (not_coupled < 3) {
+            const M3 basis2 = qto_mat(frame2.q);
+            const V3 b2col[3] = {basis2.c0, basis2.c1, basis2.c2};
+            const V3 axis1 = bcol[not_coupled], axis2 = b2col[not_coupled];
+            // Rot3::from_rotation_arc(axis1, axis2).to_axis_angle() (glam; third-party arithmetic restated, atan2 by the shared polynomial)
+            const float d = dot(axis1, axis2);
+            const float one_minus_eps = 1.0f - 2.0f * 1.1920929e-7f;
+            Q4 rot;
+            if (d > one_minus_eps) rot = Q4{0.0f, 0.0f, 0.0f, 1.0f};
+            else if (d < -one_minus_eps) {   // half turn about any orthonormal vector
+                const float sg = copysignf(1.0f, axis1.z), a = -1.0f / (sg + axis1.z), b = axis1.x * axis1.y * a;
+                rot = Q4{b, sg + axis1.y * axis1.y * a, -axis1.y, -4.371139e-8f};
+            } else {
+                const V3 c = cross(axis1, axis2);
+                const float ww = 1.0f + d;
+                const float inv = 1.0f / sqrtf(c.x * c.x + c.y * c.y + c.z * c.z + ww * ww);
+                rot = Q4{c.x * inv, c.y * inv, c.z * inv, ww * inv};
+            }
+            V3 ang_jac = V3{1.0f, 0.0f, 0.0f};
+            float angle = 0.0f;
+            const V3 v = V3{rot.x, rot.y, rot.z};
+            const float vl = sqrtf(dot(v, v));
+            if (vl >= 1.0e-8f) { angle = 2.0f * atan2_poly(vl, rot.w); ang_jac = v * (1.0f / vl); }
+            if (angle == 0.0f) {   // axis1.orthonormal_basis()[0] (utils/orthonormal_basis.rs:76-86)
+                const float sg = copysignf(1.0f, axis1.z), a = -1.0f / (sg + axis1.z), b = axis1.x * axis1.y * a;
+                ang_jac = V3{1.0f + sg * axis1.x * axis1.x * a, sg * b, -sg * axis1.x};
+            }
+            const float lo = j.limits[first_ang][0], hi = j.limits[first_ang][1];
+            const bool min_enabled = angle <= lo, max_enabled = hi <= angle;
+            const float rhs_bias = fclamp((fmax2(angle - hi, 0.0f) - fmax2(lo - angle, 0.0f)) * erp_inv_dt, -max_bias, max_bias);
+            JointRow& r = out[len++];
+            r.lin_jac = vzero(); r.ang_jac1 = ang_jac; r.ang_jac2 = ang_jac;
+            r.ii_ang_jac1 = sdp_mul(g1.ii, ang_jac); r.ii_ang_jac2 = sdp_mul(g2.ii, ang_jac);
+            r.impulse = 0.0f; r.inv_lhs = 0.0f; r.cfm_coeff = cfm_coeff; r.cfm_gain = 0.0f;
+            r.rhs_wo_bias = 0.0f;
+            r.rhs = 0.0f + rhs_bias;
+            r.lo = min_enabled ? -FINF : 0.0f; r.hi = max_enabled ? FINF : 0.0f;
+            r.dof = first_ang; r.kind = 1;
+        }
+    }
+    if (has_lin_coupling && (limit_axes & (1u << first_lin))) {   // limit_linear_coupled (:210-283): max distance only ("FIXME: handle min limit too")
+        float dist;
+        JointRow r = coupled_linear_row(dist);
+        const float hi = j.limits[first_lin][1];
+        r.rhs_wo_bias = fmin2(dist - hi, 0.0f) * inv_dt;
+        const float rhs_bias = fclamp(fmax2(dist - hi, 0.0f) * erp_inv_dt, -max_bias, max_bias);
+        r.rhs = r.rhs_wo_bias + rhs_bias;
+        r.cfm_coeff = cfm_coeff; r.cfm_gain = 0.0f;
+        r.lo = 0.0f; r.hi = FINF;
+        r.dof = first_lin; r.kind = 1;
         out[len++] = r;
     }
     finalize_rows(out, start, len, imsum);

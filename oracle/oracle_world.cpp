@@ -877,7 +877,7 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
         j.contacts_enabled = d.contacts_enabled;
         j.natural_frequency = d.natural_frequency;
         j.damping_ratio = d.damping_ratio;
-        j.limit_axes = d.limit_axes; j.motor_axes = d.motor_axes;
+        j.limit_axes = d.limit_axes; j.motor_axes = d.motor_axes; j.coupled_axes = d.coupled_axes & 63u;
         for (int k = 0; k < 6; ++k) {
             j.impulses[k] = 0.0f; j.limit_impulses[k] = 0.0f; j.motor_impulses[k] = 0.0f;
             j.limits[k][0] = d.limits[k][0]; j.limits[k][1] = d.limits[k][1];

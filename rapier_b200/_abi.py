@@ -24,6 +24,7 @@ RB_BODY_LOCK_RX, RB_BODY_LOCK_RY, RB_BODY_LOCK_RZ = 32, 64, 128
 RB_BODY_NO_SLEEP = 256
 RB_BODY_CCD_ENABLED = 512
 RB_BODY_DOMINANCE_SHIFT = 16   # RB_BODY_DOMINANCE(group): signed 8-bit dominance group in bits 16..23 of flags
+RB_BODY_EXTRA_ITERS_SHIFT = 24  # RB_BODY_EXTRA_ITERS(n): additional_solver_iterations (0..255) in bits 24..31 of flags
 RB_SHAPE_BALL = 0
 RB_SHAPE_CUBOID = 1
 RB_SHAPE_CAPSULE = 2
@@ -113,6 +114,7 @@ class RbJointDesc(C.Structure):
         ("locked_axes", u32), ("contacts_enabled", i32),
         ("natural_frequency", f32), ("damping_ratio", f32),
         ("limit_axes", u32), ("motor_axes", u32), ("limits", (f32 * 2) * 6), ("motors", RbJointMotor * 6),
+        ("coupled_axes", u32),
     ]
 
 

@@ -1071,6 +1071,11 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
             set_err("joint with bad body index or axes%s", "");
             return RB_ERR_INVALID;
         }
+        const unsigned ac = (j.coupled_axes >> 3) & 7u;   // limit_angular_coupled asserts exactly two coupled angular axes (joint_constraint_helper.rs:737-739)
+        if ((j.coupled_axes & ~63u) || (ac != 0 && ac != 3u && ac != 5u && ac != 6u)) {
+            set_err("joint %s%d: coupled_axes must couple exactly two angular axes (or none)", "", i);
+            return RB_ERR_INVALID;
+        }
     }
     W->steps_since_scene = 0;
     if (W->host_hint) W->host_hint[0] = W->host_hint[1] = W->host_hint[2] = W->host_hint[3] = 0;
@@ -1105,7 +1110,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     w.generic_joints = (nj > 0 && W->params.warmstart_joints) ? 1 : 0;   // joint warm starting: generic path too
     for (int i = 0; i < nj; ++i) {   // any limit or motor on a free axis: the generic joint path (12 row slots per joint)
         const unsigned free_axes = ~joints[i].locked_axes & 63u;
-        if ((joints[i].limit_axes | joints[i].motor_axes) & free_axes) w.generic_joints = 1;
+        if ((joints[i].limit_axes | joints[i].motor_axes) & free_axes) w.generic_joints = 1;   // (coupled axes only act through a limit or a motor)
     }
 
     ALLOC(w.st, 1);
@@ -1244,7 +1249,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
             std::vector<float4> ma((size_t)NJ * 6), al((size_t)NJ * 3);
             for (int i = 0; i < nj; ++i) {
                 const RbJointDesc& j = joints[i];
-                axes[i] = make_uint2(j.limit_axes, j.motor_axes);
+                axes[i] = make_uint2((j.limit_axes & 63u) | ((j.coupled_axes & 63u) << 8), j.motor_axes);
                 for (int k = 0; k < 6; ++k) {
                     lim[(size_t)i * 6 + k] = make_float2(j.limits[k][0], j.limits[k][1]);
                     ma[(size_t)i * 6 + k] = make_float4(j.motors[k].target_vel, j.motors[k].target_pos, j.motors[k].stiffness, j.motors[k].damping);

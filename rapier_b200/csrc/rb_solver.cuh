@@ -836,6 +836,10 @@ RB_HD void joint_update_generic(const World& w, const B& bd, int q, int sub) {
     const unsigned free_axes = ~locked & 63u;
     const uint2 axes = w.j_axes[j];
     const unsigned limit_axes = axes.x & free_axes, motor_axes = axes.y & free_axes;
+    const unsigned coupled = (axes.x >> 8) & 63u;   // coupled_axes (joint_velocity_constraint.rs:163-178)
+    const bool has_lin_coupling = (coupled & 7u) != 0, has_ang_coupling = (coupled & 56u) != 0;
+    const int first_lin = (coupled & 1u) ? 0 : ((coupled & 2u) ? 1 : 2);
+    const int first_ang = (coupled & 8u) ? 3 : ((coupled & 16u) ? 4 : 5);
     const float inv_dt = w.prm.sub_inv_dt, max_bias = w.prm.max_corrective_velocity;
     GRow rows[JROWS_GENERIC];
     auto lock_linear_row = [&](int i, float erp, float cfm, int dof, int kind) {
@@ -859,7 +863,7 @@ RB_HD void joint_update_generic(const World& w, const B& bd, int q, int sub) {
     };
     int len = 0;
     for (int i = 3; i < 6; ++i) {   // motor_angular
-        if (!(motor_axes & (1u << i))) continue;
+        if (!((motor_axes & ~coupled) & (1u << i))) continue;
         float4 ma; float m_erp, m_cc, m_cg, max_imp;
         motor_coeffs(i, ma, m_erp, m_cc, m_cg, max_imp);
         GRow& r = rows[len++];
@@ -880,7 +884,7 @@ RB_HD void joint_update_generic(const World& w, const B& bd, int q, int sub) {
         r.lo = -max_imp; r.hi = max_imp; r.dof = i; r.kind = 2;
     }
     for (int i = 0; i < 3; ++i) {   // motor_linear
-        if (!(motor_axes & (1u << i))) continue;
+        if (!((motor_axes & ~coupled) & (1u << i))) continue;
         float4 ma; float m_erp, m_cc, m_cg, max_imp;
         motor_coeffs(i, ma, m_erp, m_cc, m_cg, max_imp);
         GRow r = lock_linear_row(i, 0.0f, 0.0f, i, 2);
@@ -894,6 +898,41 @@ RB_HD void joint_update_generic(const World& w, const B& bd, int q, int sub) {
         }
         rwb = rwb + -target_vel;
         r.cc = m_cc; r.cg = m_cg; r.lo = -max_imp; r.hi = max_imp; r.rhs = rwb; r.rwb = rwb;
+        rows[len++] = r;
+    }
+    // the distance row of the coupled linear axes (limit_linear_coupled / motor_linear_coupled, joint_constraint_helper.rs:210-283, :333-409)
+    auto coupled_linear_row = [&](float& dist) {
+        GRow r;
+        vec3 lj = zero3(), a1 = zero3(), a2 = zero3();
+        for (int i = 0; i < 3; ++i) {
+            if (!(coupled & (1u << i))) continue;
+            const float coeff = dot3(bc[i], lin_err);
+            lj = lj + bc[i] * coeff;
+            a1 = a1 + cross3(r1, bc[i]) * coeff;
+            a2 = a2 + cross3(r2, bc[i]) * coeff;
+        }
+        dist = sqrtf(dot3(lj, lj));
+        const float inv_dist = safe_inv(dist);
+        r.lin = lj * inv_dist; r.a1 = a1 * inv_dist; r.a2 = a2 * inv_dist;
+        r.ia1 = smul(g1.ii, r.a1); r.ia2 = smul(g2.ii, r.a2);
+        r.inv_lhs = 0.0f;
+        return r;
+    };
+    if ((motor_axes & coupled) & 7u) {   // motor_linear_coupled (:228-250); coupled angular motors build no row (:224-226)
+        float4 ma; float m_erp, m_cc, m_cg, max_imp;
+        motor_coeffs(first_lin, ma, m_erp, m_cc, m_cg, max_imp);
+        float dist;
+        GRow r = coupled_linear_row(dist);
+        float rwb = 0.0f;
+        if (m_erp != 0.0f) rwb = rwb + (dist - ma.y) * m_erp;
+        float target_vel = ma.x;
+        if (limit_axes & (1u << first_lin)) {
+            const float2 lim = w.j_limits[j * 6 + first_lin];
+            target_vel = clampf(target_vel, (lim.x - dist) * inv_dt, (lim.y - dist) * inv_dt);
+        }
+        rwb = rwb + -target_vel;
+        r.cc = m_cc; r.cg = m_cg; r.lo = -max_imp; r.hi = max_imp; r.rhs = rwb; r.rwb = rwb;
+        r.dof = first_lin; r.kind = 2;
         rows[len++] = r;
     }
     grows_finalize(rows, 0, len, imsum);
@@ -917,7 +956,7 @@ RB_HD void joint_update_generic(const World& w, const B& bd, int q, int sub) {
     for (int i = 0; i < 3; ++i)
         if (locked & (1u << i)) rows[len++] = lock_linear_row(i, erp_inv_dt, cfm_coeff, i, 0);
     for (int i = 3; i < 6; ++i) {   // limit_angular on the re-centred angle
-        if (!(limit_axes & (1u << i))) continue;
+        if (!((limit_axes & ~coupled) & (1u << i))) continue;
         const int ax = i - 3;
         const float4 al = w.j_anglim[j * 3 + ax];
         const float x = aerr[ax];
@@ -935,7 +974,7 @@ RB_HD void joint_update_generic(const World& w, const B& bd, int q, int sub) {
         r.lo = min_enabled ? -RB_INF : 0.0f; r.hi = max_enabled ? RB_INF : 0.0f; r.dof = i; r.kind = 1;
     }
     for (int i = 0; i < 3; ++i) {   // limit_linear
-        if (!(limit_axes & (1u << i))) continue;
+        if (!((limit_axes & ~coupled) & (1u << i))) continue;
         GRow r = lock_linear_row(i, erp_inv_dt, cfm_coeff, i, 1);
         const float dist = dot3(lin_err, r.lin);
         const float2 lim = w.j_limits[j * 6 + i];
@@ -944,6 +983,56 @@ RB_HD void joint_update_generic(const World& w, const B& bd, int q, int sub) {
         r.rhs = r.rwb + rhs_bias;
         r.cc = cfm_coeff;
         r.lo = min_enabled ? -RB_INF : 0.0f; r.hi = max_enabled ? RB_INF : 0.0f;
+        rows[len++] = r;
+    }
+    if (has_ang_coupling && (limit_axes & (1u << first_ang))) {   // limit_angular_coupled (joint_constraint_helper.rs:725-798): two coupled angular axes
+        const unsigned ac = coupled >> 3;
+        const int not_coupled = (ac & 1u) == 0 ? 0 : ((ac & 2u) == 0 ? 1 : ((ac & 4u) == 0 ? 2 : 3));
+        if (not_coupled < 3) {
+            const mat3 basis2 = rotmat(f2.q);
+            const vec3 axis1 = bc[not_coupled], axis2 = not_coupled == 0 ? basis2.c0 : (not_coupled == 1 ? basis2.c1 : basis2.c2);
+            // Rot3::from_rotation_arc(axis1, axis2).to_axis_angle() (glam, restated; atan2 by the shared polynomial)
+            const float d = dot3(axis1, axis2);
+            const float one_minus_eps = 1.0f - 2.0f * 1.1920929e-7f;
+            float qx, qy, qz, qw;
+            if (d > one_minus_eps) { qx = 0.0f; qy = 0.0f; qz = 0.0f; qw = 1.0f; }
+            else if (d < -one_minus_eps) {
+                const float sg = copysign1(axis1.z), aa = -1.0f / (sg + axis1.z), bb = axis1.x * axis1.y * aa;
+                qx = bb; qy = sg + axis1.y * axis1.y * aa; qz = -axis1.y; qw = -4.371139e-8f;
+            } else {
+                const vec3 c = cross3(axis1, axis2);
+                const float ww = 1.0f + d;
+                const float inv = 1.0f / sqrtf(c.x * c.x + c.y * c.y + c.z * c.z + ww * ww);
+                qx = c.x * inv; qy = c.y * inv; qz = c.z * inv; qw = ww * inv;
+            }
+            vec3 aj = mk3(1.0f, 0.0f, 0.0f);
+            float angle = 0.0f;
+            const vec3 v = mk3(qx, qy, qz);
+            const float vl = sqrtf(dot3(v, v));
+            if (vl >= 1.0e-8f) { angle = 2.0f * atan2_poly(vl, qw); aj = v * (1.0f / vl); }
+            if (angle == 0.0f) {   // axis1.orthonormal_basis()[0]
+                const float sg = copysign1(axis1.z), aa = -1.0f / (sg + axis1.z), bb = axis1.x * axis1.y * aa;
+                aj = mk3(1.0f + sg * axis1.x * axis1.x * aa, sg * bb, -sg * axis1.x);
+            }
+            const float2 lim = w.j_limits[j * 6 + first_ang];
+            const bool min_enabled = angle <= lim.x, max_enabled = lim.y <= angle;
+            const float rhs_bias = clampf((max2(angle - lim.y, 0.0f) - max2(lim.x - angle, 0.0f)) * erp_inv_dt, -max_bias, max_bias);
+            GRow& r = rows[len++];
+            r.lin = zero3(); r.a1 = aj; r.a2 = aj; r.ia1 = smul(g1.ii, aj); r.ia2 = smul(g2.ii, aj);
+            r.inv_lhs = 0.0f; r.cc = cfm_coeff; r.cg = 0.0f; r.rwb = 0.0f;
+            r.rhs = 0.0f + rhs_bias;
+            r.lo = min_enabled ? -RB_INF : 0.0f; r.hi = max_enabled ? RB_INF : 0.0f; r.dof = first_ang; r.kind = 1;
+        }
+    }
+    if (has_lin_coupling && (limit_axes & (1u << first_lin))) {   // limit_linear_coupled (:210-283): the maximum distance only
+        float dist;
+        GRow r = coupled_linear_row(dist);
+        const float hi = w.j_limits[j * 6 + first_lin].y;
+        r.rwb = min2(dist - hi, 0.0f) * inv_dt;
+        const float rhs_bias = clampf(max2(dist - hi, 0.0f) * erp_inv_dt, -max_bias, max_bias);
+        r.rhs = r.rwb + rhs_bias;
+        r.cc = cfm_coeff; r.cg = 0.0f;
+        r.lo = 0.0f; r.hi = RB_INF; r.dof = first_lin; r.kind = 1;
         rows[len++] = r;
     }
     grows_finalize(rows, start, len, imsum);

@@ -108,6 +108,15 @@ class RigidBodyBuilder:
         self._flags = (self._flags & ~(0xFF << A.RB_BODY_DOMINANCE_SHIFT)) | ((g & 0xFF) << A.RB_BODY_DOMINANCE_SHIFT)
         return self
 
+    def additional_solver_iterations(self, n):
+        """RigidBodyBuilder::additional_solver_iterations (rigid_body.rs): the body's whole connected component runs that many
+        extra substeps at a smaller dt (island_manager/substep_groups.rs)."""
+        n = int(n)
+        if not 0 <= n <= 255:
+            raise ValueError("additional_solver_iterations must be in 0..255")
+        self._flags = (self._flags & ~(0xFF << A.RB_BODY_EXTRA_ITERS_SHIFT)) | (n << A.RB_BODY_EXTRA_ITERS_SHIFT)
+        return self
+
     def can_sleep(self, flag):
         """RigidBodyBuilder::can_sleep (rigid_body.rs; false = RigidBodyActivation::cannot_sleep())."""
         self._can_sleep = bool(flag)
@@ -303,6 +312,13 @@ class GenericJointBuilder:
         self._contacts_enabled = True
         self._limits = {}
         self._motors = {}
+        self._coupled_axes = 0
+
+    def coupled_axes(self, mask):
+        """GenericJointBuilder::coupled_axes (generic_joint.rs): coupled linear axes share one distance row (spring / rope
+        joints), two coupled angular axes one cone-like limit row."""
+        self._coupled_axes = int(mask) & 63
+        return self
 
     def local_anchor1(self, v):
         self._a1 = tuple(float(x) for x in v)
@@ -376,6 +392,7 @@ class GenericJointBuilder:
             d.motor_axes |= 1 << ax
             for k, v in m.items():
                 setattr(d.motors[ax], k, v)
+        d.coupled_axes = self._coupled_axes
         return d
 
 
@@ -385,6 +402,18 @@ def SphericalJointBuilder():
 
 def FixedJointBuilder():
     return GenericJointBuilder(0b111111)
+
+
+def SpringJointBuilder(rest_length, stiffness, damping):
+    """SpringJointBuilder::new (spring_joint.rs:32-38): no locked axis, LIN_AXES coupled, a force-based position motor on
+    LinX acting on the distance between the anchors."""
+    return GenericJointBuilder(0).coupled_axes(0b000111).motor_position(0, rest_length, stiffness, damping).motor_model(0, 1)
+
+
+def RopeJointBuilder(max_dist):
+    """RopeJointBuilder::new (rope_joint.rs:32-38, :153-156): LIN_AXES coupled, limits [0, max_dist] on LinX = an upper bound on
+    the distance between the anchors."""
+    return GenericJointBuilder(0).coupled_axes(0b000111).limits(0, 0.0, max_dist)
 
 
 def _rotation_arc_from_x(axis):

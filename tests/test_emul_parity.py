@@ -188,6 +188,18 @@ def test_joint_limits_and_motors_emulated_kernels():
                              lambda s, p=None: oracle_lib.OracleWorld(s, params=p), coulomb=True)
 
 
+def test_coupled_joint_axes_emulated_kernels():
+    from test_oracle_kat import coupled_angular_spring_joint_stays_finite, heavy_cubes_rest_on_spring_jointed_balls, spring_and_rope_joints
+    from variant_cases import coupled_axes_parity_case
+    mk = lambda s, p=None: PhysicsWorld(s, integration_parameters=p, _lib=emul_lib.lib())
+    mo = lambda s, p=None: oracle_lib.OracleWorld(s, params=p)
+    spring_and_rope_joints(mk)
+    heavy_cubes_rest_on_spring_jointed_balls(mk, num=12)
+    coupled_angular_spring_joint_stays_finite(mk)
+    coupled_axes_parity_case(mk, mo)
+    coupled_axes_parity_case(mk, mo, coulomb=True, warmstart_joints=True, steps=60)
+
+
 def test_dominance_groups_emulated_kernels():
     from test_oracle_kat import dominance_groups
     from variant_cases import dominance_parity_case

@@ -398,6 +398,21 @@ def test_dominance_groups_and_joint_warmstart(built):
     joint_limits_parity_case(mk, mo, warmstart_joints=True, scene=scenes.joint_grid(20), steps=60)
 
 
+def test_coupled_joint_axes(built):
+    """GenericJoint::coupled_axes -- SpringJoint / RopeJoint (one row on the distance between the anchors) and the cone limit of
+    two coupled angular axes: the reference's joint_contact_solve_order.rs and issue_792 scenarios plus closed-form answers
+    through the C ABI, and a scene mixing them with contacts bit-exact against the oracle (twist and Coulomb + warmstart_joints)."""
+    from test_oracle_kat import coupled_angular_spring_joint_stays_finite, heavy_cubes_rest_on_spring_jointed_balls, spring_and_rope_joints
+    from variant_cases import coupled_axes_parity_case
+    mk = lambda s, p=None: PhysicsWorld(s, integration_parameters=p)
+    mo = lambda s, p=None: oracle_lib.OracleWorld(s, params=p)
+    spring_and_rope_joints(mk)
+    heavy_cubes_rest_on_spring_jointed_balls(mk)
+    coupled_angular_spring_joint_stays_finite(mk)
+    coupled_axes_parity_case(mk, mo)
+    coupled_axes_parity_case(mk, mo, coulomb=True, warmstart_joints=True, steps=60)
+
+
 def test_convex_polyhedra(built):
     """ColliderBuilder::{convex_hull, round_convex_hull}: known answers through the C ABI (the convex_pile parity variants
     run with the other variants) and the reference's examples3d/convex_polyhedron3.rs drop (reduced: 5 x 5 x 4 round hulls of

@@ -747,6 +747,118 @@ def test_joint_limits_and_motors_oracle():
     prismatic_limits_and_position_motor(mk)
 
 
+# ---- coupled joint axes: SpringJoint / RopeJoint / coupled angular limit (joint_constraint_helper.rs:210-283, :333-409, :725-798) ----
+def spring_and_rope_joints(make_world):
+    """A ball hanging from a SpringJoint rests where k * extension = m g (force-based motor on the distance between the anchors,
+    spring_joint.rs:32-38); a ball on a RopeJoint released sideways never gets farther than max_dist from its anchor and ends
+    up hanging at max_dist (rope_joint.rs); a rope shorter than needed leaves a resting ball alone (limit row inactive)."""
+    import math
+    from rapier_b200.sets import SpringJointBuilder, RopeJointBuilder
+    s = scenes.Scene("spring_rope", gravity=(0.0, -9.81, 0.0))
+    base = s.bodies.insert(RigidBodyBuilder.fixed())
+    m = 4.0 / 3.0 * math.pi * 0.5 ** 3
+    a = s.insert(RigidBodyBuilder.dynamic().translation((0.0, -2.0, 0.0)).can_sleep(False), ColliderBuilder.ball(0.5))
+    s.joints.insert(base, a, SpringJointBuilder(1.5, 50.0, 5.0))
+    b = s.insert(RigidBodyBuilder.dynamic().translation((11.0, 0.0, 0.0)).linear_damping(0.8).can_sleep(False), ColliderBuilder.ball(0.5))
+    s.joints.insert(base, b, RopeJointBuilder(2.0).local_anchor1((10.0, 0.0, 0.0)))
+    s.insert(RigidBodyBuilder.fixed().translation((20.0, -0.5, 0.0)), ColliderBuilder.cuboid(2.0, 0.5, 2.0))
+    c = s.insert(RigidBodyBuilder.dynamic().translation((20.0, 0.5, 0.0)).can_sleep(False), ColliderBuilder.ball(0.5))
+    s.joints.insert(base, c, RopeJointBuilder(5.0).local_anchor1((20.0, 3.0, 0.0)))
+    w = make_world(s)
+    far = 0.0
+    for _ in range(600):
+        w.step()
+        pb = w.body_states()[0][b, :3]
+        far = max(far, math.dist(pb, (10.0, 0.0, 0.0)))
+    pose, vel = w.body_states()
+    assert abs(pose[a, 1] - (-(1.5 + m * 9.81 / 50.0))) < 0.02 and abs(pose[a, 0]) < 1e-3 and abs(vel[a, 1]) < 0.02, pose[a]
+    assert far < 2.06, far
+    assert abs(math.dist(pose[b, :3], (10.0, 0.0, 0.0)) - 2.0) < 0.03 and abs(pose[b, 0] - 10.0) < 0.2, pose[b]
+    assert abs(pose[c, 1] - 0.5) < 0.01 and abs(pose[c, 0] - 20.0) < 1e-3
+
+
+def heavy_cubes_rest_on_spring_jointed_balls(make_world, num=30):
+    """crates/rapier3d/tests/joint_contact_solve_order.rs: heavy cubes (200 x the ball mass) dropped onto light balls hanging
+    from spring joints of increasing damping; joints are solved before contacts in every pass, so no cube tunnels through."""
+    import math
+    from rapier_b200.sets import SpringJointBuilder
+    s = scenes.Scene("spring_balls", gravity=(0.0, -9.81, 0.0))
+    ground = s.bodies.insert(RigidBodyBuilder.fixed())
+    radius, stiffness = 0.5, 1.0e3
+    mass = 4.0 / 3.0 * math.pi * radius ** 3
+    critical = 2.0 * math.sqrt(stiffness * mass)
+    pairs = []
+    for i in range(num + 1):
+        bp = (-6.0 + 1.5 * i, 4.5, 0.0)
+        ball = s.insert(RigidBodyBuilder.dynamic().translation(bp).can_sleep(False), ColliderBuilder.ball(radius))
+        damping = (i / (num / 2.0)) * critical
+        s.joints.insert(ground, ball, SpringJointBuilder(0.0, stiffness, damping).local_anchor1((bp[0], bp[1] - 3.0, bp[2])))
+        cube = s.insert(RigidBodyBuilder.dynamic().translation((bp[0], bp[1] + 5.0, bp[2])), ColliderBuilder.cuboid(radius, radius, radius).density(100.0))
+        pairs.append((ball, cube))
+    w = make_world(s)
+    w.step(300)
+    pose, _ = w.body_states()
+    assert np.isfinite(pose).all()
+    for i, (ball, cube) in enumerate(pairs):
+        assert pose[cube, 1] > pose[ball, 1], (i, pose[cube, 1], pose[ball, 1])
+
+
+def coupled_angular_spring_joint_stays_finite(make_world):
+    """crates/rapier3d/tests/issue_792_coupled_angular_spring.rs: coupled ANG_X | ANG_Z axes with spring-like motors and
+    limits [0, 0.5], first body kinematic; the coupled angular motor is a solver no-op, the coupled limit keeps the angle
+    between the two frames' Y axes inside the cone."""
+    import math
+    from rapier_b200.sets import GenericJointBuilder
+    s = scenes.Scene("issue_792", gravity=(0.0, -9.81, 0.0))
+    kin = s.insert(RigidBodyBuilder.kinematic_position_based(), ColliderBuilder.ball(1.0))
+    dyn = s.insert(RigidBodyBuilder.dynamic().translation((0.0, -5.0, 0.0)).linvel((0.1, 0.0, 0.1)).can_sleep(False), ColliderBuilder.ball(1.0))
+    j = (GenericJointBuilder(0b000111).local_anchor2((0.0, 5.0, 0.0)).motor(3, 0.0, 0.0, 0.0, 0.5).motor(5, 0.0, 0.0, 0.0, 0.5)
+         .limits(3, 0.0, 0.5).limits(5, 0.0, 0.5).coupled_axes(0b101000))
+    s.joints.insert(kin, dyn, j)
+    w = make_world(s)
+    m = 4.0 / 3.0 * math.pi
+    worst = 0.0
+    for i in range(200):
+        if i == 50:   # apply_impulse((5, 0, 0))
+            pose, vel = w.body_states()
+            v = vel[dyn].copy()
+            v[0] += 5.0 / m
+            w.set_body_states([dyn], vel6=[v])
+        w.step()
+        pose, _ = w.body_states()
+        q = pose[dyn, 3:7]
+        ycol_y = 1.0 - 2.0 * (float(q[0]) ** 2 + float(q[2]) ** 2)          # (R e_y) . e_y
+        worst = max(worst, math.acos(max(-1.0, min(1.0, ycol_y))))
+    pose, vel = w.body_states()
+    assert np.isfinite(pose).all() and np.isfinite(vel).all()
+    assert abs(math.dist(pose[dyn, :3], (0.0, 0.0, 0.0)) - 5.0) < 0.05      # the spherical part holds
+    assert worst < 0.5 + 0.08, worst                                         # the cone limit holds (soft: a few degrees of overshoot)
+    # the cone itself: two bodies pinned at their centres, no gravity; one tumbles about X and is stopped when its Y axis has
+    # tilted by the limit, the other spins about Y (the axis that is not coupled) and is not limited at all
+    s = scenes.Scene("cone_limit", gravity=(0.0, 0.0, 0.0))
+    base = s.bodies.insert(RigidBodyBuilder.fixed())
+    tilt = s.insert(RigidBodyBuilder.dynamic().angvel((1.5, 0.0, 0.0)).can_sleep(False), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    spin = s.insert(RigidBodyBuilder.dynamic().translation((5.0, 0.0, 0.0)).angvel((0.0, 2.0, 0.0)).can_sleep(False), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    s.joints.insert(base, tilt, GenericJointBuilder(0b000111).limits(3, 0.0, 0.5).limits(5, 0.0, 0.5).coupled_axes(0b101000))
+    s.joints.insert(base, spin, GenericJointBuilder(0b000111).local_anchor1((5.0, 0.0, 0.0)).limits(3, 0.0, 0.5).limits(5, 0.0, 0.5).coupled_axes(0b101000))
+    w = make_world(s)
+    worst = 0.0
+    for i in range(240):
+        w.step()
+        q = w.body_states()[0][tilt, 3:7]
+        worst = max(worst, math.acos(max(-1.0, min(1.0, 1.0 - 2.0 * (float(q[0]) ** 2 + float(q[2]) ** 2)))))
+    pose, vel = w.body_states()
+    assert 0.45 < worst < 0.56, worst
+    assert abs(vel[spin, 4] - 2.0) < 1e-3 and abs(vel[tilt, 3]) < 1.5        # the spin is untouched, the tumble was stopped / reversed
+
+
+def test_coupled_joint_axes_oracle():
+    mk = lambda s: oracle_lib.OracleWorld(s)
+    spring_and_rope_joints(mk)
+    heavy_cubes_rest_on_spring_jointed_balls(mk)
+    coupled_angular_spring_joint_stays_finite(mk)
+
+
 # ---- capsules (parry Capsule; ColliderBuilder::capsule_{x,y,z}) ------------------------------------------------------------------
 def capsules_rest(make_world):
     """Capsules of unit mass on a slab: lying (two-point manifold, rest height = radius), standing (rest height = half height +

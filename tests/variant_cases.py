@@ -234,6 +234,51 @@ def joint_limits_scene():
     return s
 
 
+def coupled_axes_scene():
+    """Coupled joint axes next to contacts and the other generic rows: spring joints (force- and acceleration-based, with and
+    without a distance limit), rope joints between dynamic bodies and to the world, a net of springs carrying a plate that boxes
+    fall on, cone limits (two coupled angular axes, all three pairings) on bodies that tumble, a spring with only two coupled
+    linear axes next to a limited third one."""
+    from rapier_b200.sets import GenericJointBuilder, RopeJointBuilder, SpringJointBuilder
+    s = scenes.Scene("coupled_axes")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(30.0, 0.5, 30.0))
+    base = s.bodies.insert(RigidBodyBuilder.fixed().translation((0.0, 6.0, 0.0)))
+    prev = base
+    for i in range(5):   # a rope of rope joints released sideways, then a chain of springs under it
+        b = s.insert(RigidBodyBuilder.dynamic().translation((0.9 * (i + 1), 6.0, 0.0)).can_sleep(False), ColliderBuilder.ball(0.2))
+        s.joints.insert(prev, b, RopeJointBuilder(1.0))
+        prev = b
+    for i in range(3):
+        b = s.insert(RigidBodyBuilder.dynamic().translation((0.9 * 5 + 0.3, 5.0 - i, 0.0)).can_sleep(False), ColliderBuilder.cuboid(0.2, 0.2, 0.2))
+        j = SpringJointBuilder(0.8, 120.0, 4.0 + i)
+        if i == 1:
+            j = j.motor_model(0, 0)
+        if i == 2:
+            j = j.limits(0, 0.0, 1.1)   # spring with a hard maximum length (motor_linear_coupled clamps its target velocity too)
+        s.joints.insert(prev, b, j)
+        prev = b
+    plate = s.insert(RigidBodyBuilder.dynamic().translation((-6.0, 2.0, 0.0)).can_sleep(False), ColliderBuilder.cuboid(1.5, 0.1, 1.5))
+    for k, (dx, dz) in enumerate(((-1.4, -1.4), (1.4, -1.4), (-1.4, 1.4), (1.4, 1.4))):
+        s.joints.insert(base, plate, SpringJointBuilder(1.0, 300.0, 10.0 + k).local_anchor1((-6.0 + 1.3 * dx, -2.5, 1.3 * dz)).local_anchor2((dx, 0.0, dz)))
+    for k in range(3):
+        s.insert(RigidBodyBuilder.dynamic().translation((-6.3 + 0.3 * k, 3.0 + 0.9 * k, 0.1 * k)), ColliderBuilder.cuboid(0.3, 0.3, 0.3))
+    for k, mask in enumerate((0b101000, 0b011000, 0b110000)):   # cone limits about Y, Z, X
+        b = s.insert(RigidBodyBuilder.dynamic().translation((6.0 + 2.5 * k, 3.0, 4.0)).angvel((1.5 - k, 0.4 * k, 1.0 + 0.3 * k)).can_sleep(False),
+                     ColliderBuilder.cuboid(0.5, 0.3, 0.4))
+        first = 3 if mask & 0b001000 else 4
+        j = GenericJointBuilder(0b000111).local_anchor1((6.0 + 2.5 * k, -2.0, 4.0)).local_anchor2((0.0, 1.0, 0.0)).coupled_axes(mask).limits(first, 0.0 if k else -0.1, 0.4 + 0.1 * k)
+        if k == 2:
+            j = j.motor(4, 0.0, 0.0, 5.0, 0.5)   # coupled angular motor: no row
+        s.joints.insert(base, b, j)
+    b = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 3.0, -5.0)).can_sleep(False), ColliderBuilder.ball(0.4))
+    s.joints.insert(base, b, GenericJointBuilder(0).local_anchor1((0.0, -1.5, -5.0)).coupled_axes(0b000101).motor_position(0, 1.0, 80.0, 5.0).limits(1, -0.3, 0.6))
+    return s
+
+
+def coupled_axes_parity_case(make_world, make_oracle, steps=150, every=15, **kw):
+    joint_limits_parity_case(make_world, make_oracle, steps=steps, every=every, scene=coupled_axes_scene(), **kw)
+
+
 def joint_limits_parity_case(make_world, make_oracle, steps=150, every=15, coulomb=False, warmstart_joints=False, scene=None):
     from parity_util import compare_worlds, is_exact
     s = scene if scene is not None else joint_limits_scene()
