@@ -855,21 +855,32 @@ void solve_island(World& w, V3 gravity) {
         b.angvel = sa * inv_dt;
     }
     const int nb = (int)w.bodies.size();
-    const int num_substeps = P.num_solver_iterations;
-    const float sub_dt = P.dt / (float)num_substeps;  // init.rs:96-101
     const float inv_dt_full = P.dt == 0.0f ? 0.0f : 1.0f / P.dt;
 
-    SubParams sp;
-    sp.dt = sub_dt;
-    sp.inv_dt = sub_dt == 0.0f ? 0.0f : 1.0f / sub_dt;
-    Spring dyn_soft{P.contact_natural_frequency, P.contact_damping_ratio};
-    Spring static_soft{P.static_contact_natural_frequency, P.static_contact_damping_ratio};
-    sp.dyn_cfm = dyn_soft.cfm_factor(sub_dt);
-    sp.static_cfm = static_soft.cfm_factor(sub_dt);
-    sp.dyn_erp = dyn_soft.erp_inv_dt(sub_dt);
-    sp.static_erp = static_soft.erp_inv_dt(sub_dt);
-    sp.max_corrective_velocity = w.params.max_corrective_velocity();
-    sp.warmstart_coeff = P.warmstart_coefficient;
+    // Substep solve-groups (island_manager/substep_groups.rs; staged_island_solver/init.rs:52-91): every island runs
+    // num_solver_iterations + key substeps of dt / that count, key = the largest additional_solver_iterations among its
+    // awake members.  Islands share no solver body (kinematic bodies are island members here, oracle_internal.h), so the
+    // groups are independent; they run in the reference's order, highest cadence first.
+    std::vector<int> bkey(nb, 0);
+    std::vector<int> group_keys;
+    if ((int)w.island_of.size() == nb) {
+        std::vector<int> ikey(nb, 0);
+        for (int i = 0; i < nb; ++i) {
+            const Body& b = w.bodies[i];
+            const int extra = RB_BODY_EXTRA_ITERS_OF(b.flags);
+            if (extra > 0 && b.is_awake() && w.island_of[i] >= 0) ikey[w.island_of[i]] = std::max(ikey[w.island_of[i]], extra);
+        }
+        bool seen[256] = {false};
+        for (int i = 0; i < nb; ++i) {
+            if (!w.bodies[i].is_awake() || w.island_of[i] < 0) continue;
+            bkey[i] = ikey[w.island_of[i]];
+            seen[bkey[i]] = true;
+        }
+        for (int k = 255; k >= 0; --k)
+            if (seen[k]) group_keys.push_back(k);
+    }
+    if (group_keys.empty()) group_keys.push_back(0);
+    const bool multi = group_keys.size() > 1 || group_keys[0] != 0;
 
     // a7 forces (solve.rs:234-291; rigid_body_components.rs:1030-1033) + S1 solver-body init
     // (solver_body.rs:82-121; worker.rs:46-104).
@@ -893,8 +904,9 @@ void solve_island(World& w, V3 gravity) {
             s.ii = sdp_zero();
             s.im = vzero();
         }
-        s.incr_ang = sdp_mul(b.eff_world_inv_inertia, b.torque) * sub_dt;
-        s.incr_lin = cmul(b.force, b.eff_inv_mass) * sub_dt;
+        const float body_sub_dt = P.dt / (float)(P.num_solver_iterations + bkey[i]);   // the slot's group substep dt (worker.rs:66-77)
+        s.incr_ang = sdp_mul(b.eff_world_inv_inertia, b.torque) * body_sub_dt;
+        s.incr_lin = cmul(b.force, b.eff_inv_mass) * body_sub_dt;
         s.gyro = (b.flags & RB_BODY_GYROSCOPIC) && b.is_strict_dynamic() && b.is_awake();   // worker.rs:86
     }
 
@@ -958,16 +970,45 @@ void solve_island(World& w, V3 gravity) {
     const float max_lin = w.params.max_linear_velocity();
     const float max_ang = 0.7853981633974483f * inv_dt_full;  // MAX_ROTATION * base inv_dt (worker.rs:573-580)
 
+    // group of every scheduled constraint / joint = the group of its awake body
+    std::vector<int> ckey(ncons, 0), jkey(nj, 0);
+    if (multi) {
+        for (int q = 0; q < ncons; ++q) {
+            const Pair& p = w.pairs[pair_order[q]];
+            ckey[q] = bkey[(p.b1 >= 0 && w.bodies[p.b1].is_awake()) ? p.b1 : p.b2];
+        }
+        for (int i = 0; i < nj; ++i) {
+            const Joint& j = w.joints[i];
+            if (jcolors[i] >= 0) jkey[i] = bkey[w.bodies[j.body1].is_awake() ? j.body1 : j.body2];
+        }
+    }
+    for (const int key : group_keys) {   // the group ring (worker.rs:193-207)
+    const int num_substeps = P.num_solver_iterations + key;
+    const float sub_dt = P.dt / (float)num_substeps;  // init.rs:64-77, :96-101
+    SubParams sp;
+    sp.dt = sub_dt;
+    sp.inv_dt = sub_dt == 0.0f ? 0.0f : 1.0f / sub_dt;
+    Spring dyn_soft{P.contact_natural_frequency, P.contact_damping_ratio};
+    Spring static_soft{P.static_contact_natural_frequency, P.static_contact_damping_ratio};
+    sp.dyn_cfm = dyn_soft.cfm_factor(sub_dt);
+    sp.static_cfm = static_soft.cfm_factor(sub_dt);
+    sp.dyn_erp = dyn_soft.erp_inv_dt(sub_dt);
+    sp.static_erp = static_soft.erp_inv_dt(sub_dt);
+    sp.max_corrective_velocity = w.params.max_corrective_velocity();
+    sp.warmstart_coeff = P.warmstart_coefficient;
+
     auto solve_pass = [&](bool wo_bias, float solved_dt, bool warm_joints = false) {  // staged_island_solver/solve.rs:12-209
         bool solve_friction = wo_bias || P.friction_in_bias_pass || P.num_internal_stabilization_iterations == 0;
         for (int s = 0; s < jnstages; ++s) {
             pool.parallel_for(js[s], js[s + 1], 64, [&](int q) {
                 int ji = w.jorder[q];
+                if (multi && jkey[ji] != key) return;
                 joint_solve(w, w.joints[ji], &w.jrows[jrow_start[ji]], jrow_start[ji + 1] - jrow_start[ji], wo_bias, warm_joints);
             });
         }
         for (int s = 0; s < nstages; ++s) {
             pool.parallel_for(cs[s], cs[s + 1], 64, [&](int q) {
+                if (multi && ckey[q] != key) return;
                 Constraint& c = w.cons[q];
                 if (wo_bias) refresh_rhs_wo_bias(w, c, sp, solved_dt);
                 solve(w, c, solve_friction);
@@ -980,7 +1021,7 @@ void solve_island(World& w, V3 gravity) {
         // S3 velocity increments + gyroscopic correction (worker.rs:235-284)
         pool.parallel_for(0, nb, 256, [&](int i) {
             SolverBody& s = w.sb[i];
-            if (!w.bodies[i].is_awake()) return;
+            if (!w.bodies[i].is_awake() || (multi && bkey[i] != key)) return;
             s.lin = s.lin + s.incr_lin;
             s.ang = s.ang + s.incr_ang;
             if (s.gyro) {
@@ -993,7 +1034,7 @@ void solve_island(World& w, V3 gravity) {
         // warmstart_joints from last step's written-back impulses (first substep) / the previous substep's rows, times
         // warmstart_coefficient (joint_constraint_builder.rs:116-150).
         pool.parallel_for(0, nj, 64, [&](int i) {
-            if (jcolors[i] < 0) return;
+            if (jcolors[i] < 0 || (multi && jkey[i] != key)) return;
             JointRow* rows = &w.jrows[jrow_start[i]];
             const Joint& j = w.joints[i];
             float prev[24];
@@ -1012,10 +1053,11 @@ void solve_island(World& w, V3 gravity) {
         });
         // S5 update + warmstart, colour by colour (worker.rs:438-539)
         if (!fused_warmstart) {
-            for (int q = 0; q < ncons; ++q) update(w, w.cons[q], sp, solved_dt);
+            for (int q = 0; q < ncons; ++q) { if (multi && ckey[q] != key) continue; update(w, w.cons[q], sp, solved_dt); }
         } else {
             for (int s = 0; s < nstages; ++s) {
                 pool.parallel_for(cs[s], cs[s + 1], 64, [&](int q) {
+                    if (multi && ckey[q] != key) return;
                     update(w, w.cons[q], sp, solved_dt);
                     warmstart(w, w.cons[q]);
                 });
@@ -1026,7 +1068,7 @@ void solve_island(World& w, V3 gravity) {
         // S7 integrate positions (worker.rs:568-631; rigid_body_components.rs:884-898)
         pool.parallel_for(0, nb, 256, [&](int i) {
             SolverBody& s = w.sb[i];
-            if (!w.bodies[i].is_awake()) return;
+            if (!w.bodies[i].is_awake() || (multi && bkey[i] != key)) return;
             if (max_lin != 3.4028235e38f) {
                 float n = length(s.lin);
                 if (n > max_lin) s.lin = s.lin * (max_lin / n);
@@ -1043,6 +1085,7 @@ void solve_island(World& w, V3 gravity) {
         // S8 relax solve (worker.rs:636-649)
         for (int it = 0; it < P.num_internal_stabilization_iterations; ++it) solve_pass(true, solved_dt + sub_dt);
     }
+    }   // (groups)
 
     // S9 restitution (worker.rs:657-734)
     if (has_bouncy) {

@@ -278,6 +278,7 @@ static void removed_pair(World& w, Pair& o) {
     if (o.nsc > 0 && ((w.colliders[o.c1].active_events | w.colliders[o.c2].active_events) & RB_EVENT_COLLISION))
         w.collision_events.push_back(RbCollisionEvent{o.c1, o.c2, 0, (int)w.counters.steps + 1});
     clear_pair_color(w, o);
+    if (o.nsc > 0) w.islands_dirty = true;   // a touching pair that leaves the broad phase may split its island (persistent.rs; the kernels relabel whenever the pair table changes)
 }
 static void update_pairs(World& w) {
     int nc = (int)w.colliders.size();

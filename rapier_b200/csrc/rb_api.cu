@@ -450,6 +450,7 @@ struct RbWorld {
     std::vector<rbhull::Hull> hulls;   // convex polyhedra (rb_world_add_hull); hull 0 = the unit cube
     int hulls_uploaded = 0;            // how many of them the device tables hold
     bool force_events = false;   // some collider has RB_EVENT_CONTACT_FORCE: run k_force_events after every step
+    std::vector<int> extra_keys; // distinct additional_solver_iterations of the bodies, descending (substep solve-groups); {0} = none
     int steps_since_scene = 0;   // the launch-shape hint of a new scene is awaited once (see rb_world_step)
     int coop_shape = -1;   // RB_COOP_SHAPE debugging override: 0 small, 1 big, -1 automatic
     int* host_hint = nullptr;
@@ -493,7 +494,9 @@ static void free_all(RbWorld* W) {
 static int next_pow2_host(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 // Derived solver coefficients (integration_parameters.rs:85-149, :305-377; init.rs:96-101).
-static void derive_params(const RbIntegrationParameters& p, Params& o) {
+static void derive_params(const RbIntegrationParameters& p_in, Params& o, int extra_substeps = 0) {
+    RbIntegrationParameters p = p_in;   // a substep solve-group: num_solver_iterations + extra at dt / that count (init.rs:64-66)
+    p.num_solver_iterations += extra_substeps;
     auto erp_inv_dt = [](float f, float z, float dt) { float w = f * 6.283185307179586f; return w / (dt * w + 2.0f * z); };
     auto cfm_factor = [&](float f, float z, float dt) {
         float e = dt * erp_inv_dt(f, z, dt);
@@ -529,6 +532,19 @@ static void derive_params(const RbIntegrationParameters& p, Params& o) {
     o.warmstart_joints = p.warmstart_joints != 0 ? 1 : 0;
     o.ccd = p.max_ccd_substeps != 0 ? 1 : 0;
     o.linear_slop = p.normalized_allowed_linear_error * p.length_unit;
+}
+
+// Substep solve-groups: the distinct additional_solver_iterations among the bodies (an island's key is the max over its
+// members, so it is always one of these), descending as the reference orders its groups (substep_groups.rs:18-20).
+static void refresh_extra_keys(RbWorld* W) {
+    bool seen[256] = {false};
+    seen[0] = true;
+    for (const RbBodyDesc& d : W->bodies) seen[RB_BODY_EXTRA_ITERS_OF(d.flags)] = true;
+    W->extra_keys.clear();
+    for (int k = 255; k >= 0; --k)
+        if (seen[k]) W->extra_keys.push_back(k);
+    W->w.any_extra = W->extra_keys.size() > 1 ? 1 : 0;
+    W->w.pass_key = 0;
 }
 
 static int validate_params(const RbIntegrationParameters* p) {
@@ -995,6 +1011,7 @@ RbWorld* rb_world_create(const RbIntegrationParameters* params, int device) {
     cudaFuncSetAttribute(k_solve_items_x<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
     cudaFuncSetAttribute(k_solve_items_x<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
     cudaFuncSetAttribute(k_solve_items_x<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
+    cudaFuncSetAttribute(k_solve_items_x<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ITEM_SMEM_BYTES);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_collide<1>, COLLIDE_THREADS, ITEM_SMEM_BYTES);
     if (occ < 1) { set_err("k_collide cannot be resident%s", ""); delete W; return nullptr; }
@@ -1095,6 +1112,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     memset(&w, 0, sizeof(w));
     derive_params(W->params, w.prm);
     w.nb = nb; w.nc = nc; w.nj = nj;
+    refresh_extra_keys(W);
     int ndyn_col = 0;
     for (int i = 0; i < nc; ++i)
         if (colliders[i].parent >= 0 && type_moves(bodies[colliders[i].parent].body_type)) ndyn_col++;
@@ -1152,6 +1170,7 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ALLOC(w.color_count, NUM_COLORS + 1); ALLOC(w.color_pos, NUM_COLORS + 1); ALLOC(w.jcolor_pos, NUM_COLORS + 1);
     ALLOC(w.joint_tmp, NJ); ALLOC(w.joint_sched, NJ);
     ALLOC(w.cons_hdr, w.cons_cap); ALLOC(w.cons, (size_t)CR_ROWS * w.cons_cap);
+    ALLOC(w.isl_key, NB); ALLOC(w.b_key, NB); ALLOC(w.cons_key, w.cons_cap); ALLOC(w.j_key, NJ);
     ALLOC(w.coop_pool, (size_t)2 * COOP_ROWS * w.cons_cap);
     ALLOC(w.large_pool, (size_t)COOP_ROWS * w.cons_cap); ALLOC(w.large_mut, (size_t)MR_COUNT * w.cons_cap);
     w.host_hint = W->host_hint;
@@ -1369,6 +1388,7 @@ int rb_world_insert(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t nc
     if (rc != RB_OK) { W->bodies.resize(nb0); W->colliders.resize(nc0); return rc; }
     W->w.nb = nb0 + nb;
     W->w.nc = nc0 + nc;
+    refresh_extra_keys(W);
     if ((rc = upload_hulls(W)) != RB_OK) return rc;
     if ((rc = upload_bodies(W, mp, nb0, nb)) != RB_OK) return rc;
     if ((rc = upload_colliders(W, nc0, nc, nb0)) != RB_OK) return rc;
@@ -1608,7 +1628,7 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         bool prof = W->profiling;
         if (prof) CK(cudaEventRecord(W->prof_ev[3 * s], W->stream));
         // a grid-wide island existed after the last schedule the host knows of: it gets its own launch
-        const bool coulomb = W->w.prm.friction_model == 1 || W->w.generic_joints != 0;   // (the general solve path)
+        const bool coulomb = W->w.prm.friction_model == 1 || W->w.generic_joints != 0 || W->w.any_extra != 0;   // (the general solve path)
         const bool large = *(volatile int*)(W->host_hint + 2) != 0;
         int do_solve = coulomb ? 0 : (large ? 3 : 1);
         if (W->state_buf[1]) { W->w.state13 = W->state_buf[W->state_next]; W->state_next ^= 1; }
@@ -1626,14 +1646,26 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         if (coulomb) {   // every item through the streaming solve; the grid-wide item's kernel returns at once when there is none
             void* a2[] = {(void*)&W->w, (void*)&g};
             const int fm = W->w.prm.friction_model == 1 ? 1 : 0, jm = W->w.generic_joints ? 1 : 0;
-            void* large = fm ? (jm ? (void*)k_solve_large_x<1, 1> : (void*)k_solve_large_x<1, 0>) : (void*)k_solve_large_x<0, 1>;
-            if (fm && jm) k_solve_items_x<1, 1><<<W->collide_blocks, W->collide_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
-            else if (fm) k_solve_items_x<1, 0><<<W->collide_blocks, W->collide_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
-            else k_solve_items_x<0, 1><<<W->collide_blocks, W->collide_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
-            CK(cudaLaunchCooperativeKernel(large, dim3(W->collide_blocks), dim3(W->collide_threads), a2, 0, W->stream));
+            void* large = fm ? (jm ? (void*)k_solve_large_x<1, 1> : (void*)k_solve_large_x<1, 0>) : (jm ? (void*)k_solve_large_x<0, 1> : (void*)k_solve_large_x<0, 0>);
+            // substep solve-groups: one pass of both kernels per distinct key, each with the parameters of its cadence
+            const size_t npass = W->w.any_extra ? W->extra_keys.size() : 1;
+            for (size_t ki = 0; ki < npass; ++ki) {
+                if (W->w.any_extra) {
+                    W->w.pass_key = W->extra_keys[ki];
+                    derive_params(W->params, W->w.prm, W->w.pass_key);
+                    if (ki > 0) CK(cudaMemsetAsync(&W->w.st->cursor_rest, 0, sizeof(int), W->stream));
+                }
+                if (fm && jm) k_solve_items_x<1, 1><<<W->collide_blocks, W->collide_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
+                else if (fm) k_solve_items_x<1, 0><<<W->collide_blocks, W->collide_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
+                else if (jm) k_solve_items_x<0, 1><<<W->collide_blocks, W->collide_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
+                else k_solve_items_x<0, 0><<<W->collide_blocks, W->collide_threads, ITEM_SMEM_BYTES, W->stream>>>(W->w, g);
+                CK(cudaLaunchCooperativeKernel(large, dim3(W->collide_blocks), dim3(W->collide_threads), a2, 0, W->stream));
+                W->kernels += 2;
+            }
+            if (W->w.any_extra) { W->w.pass_key = 0; derive_params(W->params, W->w.prm); }
             if (W->force_events) { k_force_events<<<W->collide_blocks, 256, 0, W->stream>>>(W->w); W->kernels++; }
             if (prof) CK(cudaEventRecord(W->prof_ev[3 * s + 2], W->stream));
-            W->kernels += 3;
+            W->kernels += 1;
             continue;
         }
         if (large) {
@@ -1686,12 +1718,17 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
         pp.mbar = mbar;
         pp.t = 0;
         pp.sweep_threads = 1;
+        const size_t npass = W->w.any_extra ? W->extra_keys.size() : 1;   // substep solve-groups: one pass per distinct key
+        for (size_t ki = 0; ki < npass; ++ki) {
+        if (W->w.any_extra) { W->w.pass_key = W->extra_keys[ki]; derive_params(W->params, W->w.prm, W->w.pass_key); }
+        const bool grp = W->w.any_extra != 0;
         for (int k = 0; k < W->w.st->norder; ++k) {
             const int item = W->w.item_order[k];
             const bool fm1 = W->w.prm.friction_model == 1, jm1 = W->w.generic_joints != 0;
             if (fm1 && jm1) solve_item<1, 1>(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
             else if (fm1) solve_item<1, 0>(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
             else if (jm1) solve_item<0, 1>(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
+            else if (grp) solve_item<0, 0>(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
             else if (item_is_coop(W->w, item))
                 solve_item_coop<1>(bctx, W->w, W->emu_smem.data() + ITEM_MAX_BODIES * SB_STRIDE, W->emu_coop_floats, pp, item, mk3(g.x, g.y, g.z));
             else solve_item(bex, W->w, sb, item, mk3(g.x, g.y, g.z));
@@ -1705,8 +1742,11 @@ int rb_world_step(RbWorld* W, const float gravity[3], int32_t nsteps, int32_t sy
             if (fm1 && jm1) solve_item<1, 1>(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
             else if (fm1) solve_item<1, 0>(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
             else if (jm1) solve_item<0, 1>(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
+            else if (grp) solve_item<0, 0>(gex, W->w, gb, 0, mk3(g.x, g.y, g.z));
             else solve_item_lanes<1>(gex, W->w, gb, mk3(g.x, g.y, g.z));
         }
+        }
+        if (W->w.any_extra) { W->w.pass_key = 0; derive_params(W->params, W->w.prm); }
         if (W->force_events) phase_force_events(gctx, W->w);
         if (W->w.st->nccd > 0) {   // the queued CCD clamps (the device applies them at the next k_collide / synchronising call)
             phase_ccd_pending(gctx, W->w, W->w.st->nccd, false);

@@ -1090,6 +1090,8 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
     const int buf = st->cur, np = st->npairs, nb = w.nb, nj = w.nj;
     // S1 reset
     for (int b = ctx.gtid; b < nb; b += ctx.gsize) { w.isl_nb[b] = 0; w.isl_ncons[b] = 0; w.isl_item[b] = -1; }
+    if (w.any_extra)
+        for (int b = ctx.gtid; b < nb; b += ctx.gsize) w.isl_key[b] = 0u;
     for (int c = ctx.gtid; c < NUM_COLORS; c += ctx.gsize) w.color_count[c] = 0;
     for (int i = ctx.gtid; i < 3 * (w.item_cap + 1); i += ctx.gsize) w.item_cursor[i] = 0;
     for (int i = ctx.gtid; i <= w.item_cap; i += ctx.gsize) { w.item_body_start[i] = 0; w.item_cons_start[i] = 0; w.item_joint_start[i] = 0; }
@@ -1098,6 +1100,13 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
     // S4 per-root counts + global colour histogram
     for (int b = ctx.gtid; b < nb; b += ctx.gsize)
         if (body_is_sim(w, b)) atomic_add(&w.isl_nb[w.isl_label[b]], 1);
+    // substep solve-groups (island_manager/substep_groups.rs:107-123): an island's key = the largest
+    // additional_solver_iterations among its members (bits 24..31 of the body flags)
+    if (w.any_extra)
+        for (int b = ctx.gtid; b < nb; b += ctx.gsize) {
+            const unsigned extra = w.b_flags[b] >> 24;
+            if (extra != 0u && body_is_sim(w, b)) atomic_max_u(&w.isl_key[w.isl_label[b]], extra);
+        }
     for (int i = ctx.gtid; i < np; i += ctx.gsize) {
         float4 info = prow(w, buf, PR_INFO, i);
         if (as_int(info.z) <= 0) continue;
@@ -1179,6 +1188,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
         int it = body_is_sim(w, b) ? w.isl_item[w.isl_label[b]] : -1;
         w.body_item[b] = it;
         if (it >= 0) atomic_add(&w.item_body_start[it], 1);
+        if (w.any_extra) w.b_key[b] = (unsigned char)(it >= 0 ? w.isl_key[w.isl_label[b]] : 0u);
     }
     for (int i = ctx.gtid; i < np; i += ctx.gsize) {
         if (as_int(prow(w, buf, PR_INFO, i).z) <= 0) continue;
@@ -1316,6 +1326,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
             }
             int id1 = body_is_sim(w, b1) ? b1 : NO_BODY;
             int id2 = body_is_sim(w, b2) ? b2 : NO_BODY;
+            if (w.any_extra) (pass == 0 ? w.cons_key : w.j_key)[q] = w.b_key[id1 != NO_BODY ? b1 : b2];   // (both ends share the island)
             if (pass == 0) {   // contact_with_twist_friction.rs:71-84
                 const int rel_dom = relative_dominance(w, b1, b2);
                 if (rel_dom > 0) id1 = NO_BODY;
@@ -1386,6 +1397,7 @@ RB_PHASE void section_schedule(const Ctx& ctx, const World& w) {
                 }
                 int id1 = body_is_sim(w, b1) ? (it == 0 ? b1 : w.body_local[b1]) : NO_BODY;
                 int id2 = body_is_sim(w, b2) ? (it == 0 ? b2 : w.body_local[b2]) : NO_BODY;
+                if (w.any_extra) (pass == 0 ? w.cons_key : w.j_key)[q] = w.b_key[id1 != NO_BODY ? b1 : b2];
                 if (pass == 0) {   // contact_with_twist_friction.rs:71-84
                     const int rel_dom = relative_dominance(w, b1, b2);
                     if (rel_dom > 0) id1 = NO_BODY;

@@ -1338,24 +1338,29 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
     const int ncol = st->nused_colors, njcol = st->njused_colors;
     const int ovf = w.color_pos[COLOR_OVERFLOW], jovf = w.jcolor_pos[COLOR_OVERFLOW];
     const int tid = ex.tid(), nth = ex.nth();
+    // substep solve-groups: this launch solves the islands whose key is pass_key, at the cadence w.prm was derived for
+    const bool grp = w.any_extra != 0;
+    const unsigned char gk = (unsigned char)w.pass_key;
 
     auto stage = [&](int a, int e, bool serial, int mode, bool fric) {
         if (serial) {
             if (tid == 0)
-                for (int q = a; q < e; ++q) { Cons cc; cons_load<FM>(w, q, cc); cons_sweep<FM>(w, bd, q, cc, mode, fric); cons_store_dyn<FM>(w, q, cc); }
+                for (int q = a; q < e; ++q) { if (grp && w.cons_key[q] != gk) continue; Cons cc; cons_load<FM>(w, q, cc); cons_sweep<FM>(w, bd, q, cc, mode, fric); cons_store_dyn<FM>(w, q, cc); }
         } else {
-            for (int q = a + tid; q < e; q += nth) { Cons cc; cons_load<FM>(w, q, cc); cons_sweep<FM>(w, bd, q, cc, mode, fric); cons_store_dyn<FM>(w, q, cc); }
+            for (int q = a + tid; q < e; q += nth) { if (grp && w.cons_key[q] != gk) continue; Cons cc; cons_load<FM>(w, q, cc); cons_sweep<FM>(w, bd, q, cc, mode, fric); cons_store_dyn<FM>(w, q, cc); }
         }
     };
 
     if (tid == 0) w.item_flags[item] = 0;   // bit 0: some contact of this item holds a restitution seed
     for (int l = b0 + tid; l < b1; l += nth) {
         int b = w.item_bodies[l];
+        if (grp && w.b_key[b] != gk) continue;
         body_init(w, bd, b, global_ids ? b : l - b0, gravity);
     }
     ex.sync();
     // S2 generate
     for (int q = c0 + tid; q < c1; q += nth) {
+        if (grp && w.cons_key[q] != gk) continue;
         Cons c;
         cons_generate<FM>(w, bd, q, buf, item, c);
         cons_store_static<FM>(w, q, c);
@@ -1366,12 +1371,13 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
     for (int sub = 0; sub < P.num_substeps; ++sub) {
         for (int l = b0 + tid; l < b1; l += nth) {
             int b = w.item_bodies[l];
+            if (grp && w.b_key[b] != gk) continue;
             body_increment(w, bd, b, global_ids ? b : l - b0);
         }
         ex.sync();
         // S4 joint rows from the current poses
         if (j1 > j0) {
-            for (int q = j0 + tid; q < j1; q += nth) { if (JM) joint_update_generic(w, bd, q, sub); else joint_update(w, bd, q); }
+            for (int q = j0 + tid; q < j1; q += nth) { if (grp && w.j_key[q] != gk) continue; if (JM) joint_update_generic(w, bd, q, sub); else joint_update(w, bd, q); }
             ex.sync();
         }
         // S5 update + warmstart, colour by colour
@@ -1386,6 +1392,7 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
         } else {
             // warmstart_coefficient == 0: update only banks and zeroes the impulses (no velocity change)
             for (int q = c0 + tid; q < c1; q += nth) {
+                if (grp && w.cons_key[q] != gk) continue;
                 Cons c;
                 cons_load<FM>(w, q, c);
 #pragma unroll
@@ -1416,9 +1423,9 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
                     int a = j0 + joff[c], e = j0 + joff[c + 1];
                     if (a >= e) continue;
                     if (c == jovf) {
-                        if (tid == 0) for (int q = a; q < e; ++q) { if (JM) joint_solve_generic(w, bd, q, relax, jwarm); else joint_solve(w, bd, q, relax); }
+                        if (tid == 0) for (int q = a; q < e; ++q) { if (grp && w.j_key[q] != gk) continue; if (JM) joint_solve_generic(w, bd, q, relax, jwarm); else joint_solve(w, bd, q, relax); }
                     } else {
-                        for (int q = a + tid; q < e; q += nth) { if (JM) joint_solve_generic(w, bd, q, relax, jwarm); else joint_solve(w, bd, q, relax); }
+                        for (int q = a + tid; q < e; q += nth) { if (grp && w.j_key[q] != gk) continue; if (JM) joint_solve_generic(w, bd, q, relax, jwarm); else joint_solve(w, bd, q, relax); }
                     }
                     ex.sync();
                 }
@@ -1433,6 +1440,7 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
             if (!relax) {
                 for (int l = b0 + tid; l < b1; l += nth) {
                     int b = w.item_bodies[l];
+                    if (grp && w.b_key[b] != gk) continue;
                     body_integrate(w, bd, b, global_ids ? b : l - b0);
                 }
                 ex.sync();
@@ -1450,10 +1458,11 @@ RB_PHASE void solve_item(const X& ex, const World& w, const B& bd, int item, vec
         }
     }
     // S10 impulse writeback
-    for (int q = c0 + tid; q < c1; q += nth) { Cons cc; cons_load<FM>(w, q, cc); cons_writeback<FM>(w, q, buf, cc); }
-    for (int q = j0 + tid; q < j1; q += nth) { if (JM) joint_writeback_generic(w, q); else joint_writeback(w, q); }
+    for (int q = c0 + tid; q < c1; q += nth) { if (grp && w.cons_key[q] != gk) continue; Cons cc; cons_load<FM>(w, q, cc); cons_writeback<FM>(w, q, buf, cc); }
+    for (int q = j0 + tid; q < j1; q += nth) { if (grp && w.j_key[q] != gk) continue; if (JM) joint_writeback_generic(w, q); else joint_writeback(w, q); }
     for (int l = b0 + tid; l < b1; l += nth) {
         int b = w.item_bodies[l];
+        if (grp && w.b_key[b] != gk) continue;
         body_writeback(w, bd, b, global_ids ? b : l - b0);
     }
 }

@@ -271,6 +271,13 @@ struct World {
     // limits and motors of the free axes (JointLimits / JointMotor, generic_joint.rs:142-232): only worlds in which some joint
     // has any take the generic joint path (solve_item<FM, 1>, 12 row slots per joint instead of 6)
     int generic_joints;
+    // Substep solve-groups (RigidBody::additional_solver_iterations; island_manager/substep_groups.rs): any_extra = some
+    // body asks for extra substeps.  Then every island carries a key (max over its members, isl_key), the general solve
+    // path is launched once per distinct key -- pass_key, with prm derived for num_solver_iterations + pass_key -- and each
+    // launch takes the bodies / constraints / joints of the islands with that key (b_key, cons_key, j_key).
+    int any_extra, pass_key;
+    unsigned* isl_key;                // [nb] key of a root
+    unsigned char *b_key, *cons_key, *j_key;   // [nb] [cons_cap] [joint_cap] key per body / scheduled constraint / scheduled joint
     HullTables hulls;                 // convex polyhedra (worlds with SHAPE_CONVEX colliders only; else null)
     int* convex_work;                 // [pair_cap] pairs of this step that need a polyhedron manifold (phase_convex_manifolds)
     float* convex_raw;                // [pair_cap][POLY_RAW_STRIDE] their raw manifolds, read back by the per-pair narrow phase

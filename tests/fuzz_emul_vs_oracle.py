@@ -133,6 +133,9 @@ def random_scene(seed):
                     j = j.limits(1, -0.5, 0.5)
             j = j.local_anchor1(tuple(float(x) for x in r3.uniform(-0.5, 0.5, 3))).local_anchor2(tuple(float(x) for x in r3.uniform(-0.5, 0.5, 3)))
             s.joints.insert(a, b, j)
+    if r3.random() < 0.3:   # substep solve-groups: extra substeps for the islands of a few bodies
+        for h in r3.choice(handles, min(len(handles), int(r3.integers(1, 4))), replace=False):
+            s.bodies.descs[int(h)].flags |= int(r3.choice([1, 2, 5])) << A.RB_BODY_EXTRA_ITERS_SHIFT
     params = A.RbIntegrationParameters.default()
     if r.random() < 0.4:
         params.num_solver_iterations = int(r.choice([1, 2, 6]))

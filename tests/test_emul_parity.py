@@ -200,6 +200,16 @@ def test_coupled_joint_axes_emulated_kernels():
     coupled_axes_parity_case(mk, mo, coulomb=True, warmstart_joints=True, steps=60)
 
 
+def test_additional_solver_iterations_emulated_kernels():
+    from test_oracle_kat import additional_solver_iterations
+    from variant_cases import substep_groups_parity_case
+    mk = lambda s, p=None: PhysicsWorld(s, integration_parameters=p, _lib=emul_lib.lib())
+    mo = lambda s, p=None: oracle_lib.OracleWorld(s, params=p)
+    additional_solver_iterations(mk)
+    substep_groups_parity_case(mk, mo, steps=40)
+    substep_groups_parity_case(mk, mo, steps=30, big=False, coulomb=True, warmstart_joints=True)
+
+
 def test_dominance_groups_emulated_kernels():
     from test_oracle_kat import dominance_groups
     from variant_cases import dominance_parity_case

@@ -413,6 +413,19 @@ def test_coupled_joint_axes(built):
     coupled_axes_parity_case(mk, mo, coulomb=True, warmstart_joints=True, steps=60)
 
 
+def test_additional_solver_iterations(built):
+    """RigidBody::additional_solver_iterations (substep solve-groups, island_manager/substep_groups.rs): the scenarios of
+    crates/rapier3d/tests/additional_solver_iterations.rs through the C ABI, and islands of three cadences (jointed, on a kinematic
+    platform, bouncing, a grid-wide one) bit-exact against the oracle -- one pass of the general solve kernels per cadence."""
+    from test_oracle_kat import additional_solver_iterations
+    from variant_cases import substep_groups_parity_case
+    mk = lambda s, p=None: PhysicsWorld(s, integration_parameters=p)
+    mo = lambda s, p=None: oracle_lib.OracleWorld(s, params=p)
+    additional_solver_iterations(mk)
+    substep_groups_parity_case(mk, mo, steps=60)
+    substep_groups_parity_case(mk, mo, steps=40, big=False, coulomb=True, warmstart_joints=True)
+
+
 def test_convex_polyhedra(built):
     """ColliderBuilder::{convex_hull, round_convex_hull}: known answers through the C ABI (the convex_pile parity variants
     run with the other variants) and the reference's examples3d/convex_polyhedron3.rs drop (reduced: 5 x 5 x 4 round hulls of

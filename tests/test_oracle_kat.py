@@ -859,6 +859,75 @@ def test_coupled_joint_axes_oracle():
     coupled_angular_spring_joint_stays_finite(mk)
 
 
+# ---- substep solve-groups: RigidBody::additional_solver_iterations (island_manager/substep_groups.rs; crates/rapier3d/tests/additional_solver_iterations.rs) ----
+def _heavy_stack(extra, drop=False):
+    s = scenes.Scene("heavy_stack", gravity=(0.0, -9.81, 0.0))
+    s.insert(RigidBodyBuilder.fixed(), ColliderBuilder.cuboid(10.0, 0.5, 10.0).translation((0.0, -0.5, 0.0)))
+    light = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.5, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5).density(1.0))
+    heavy = s.insert(RigidBodyBuilder.dynamic().translation((0.1, 3.0, 0.0) if drop else (0.0, 1.5, 0.0)).additional_solver_iterations(extra),
+                     ColliderBuilder.cuboid(0.5, 0.5, 0.5).density(200.0))
+    return s, light, heavy
+
+
+def additional_solver_iterations(make_world):
+    """additional_solver_iterations.rs: a heavy cube (200 x) on a light one with 16 extra substeps on the heavy body stays put;
+    a rope of spherical joints with a 100 x heavier end and 16 extra substeps keeps its length; the extra substeps change the
+    trajectory of a stack that is still settling and are deterministic; a second, unrelated stack in the same world keeps the
+    base cadence: it moves exactly as it does alone (the groups are per connected component)."""
+    s, light, heavy = _heavy_stack(16)
+    w = make_world(s)
+    w.step(300)
+    pose, vel = w.body_states()
+    assert 0.3 < pose[light, 1] < 0.7 and 1.2 < pose[heavy, 1] < 1.8, (pose[light], pose[heavy])
+    assert np.linalg.norm(vel[heavy, :3]) < 0.1
+
+    from rapier_b200.sets import SphericalJointBuilder
+    s = scenes.Scene("heavy_chain", gravity=(0.0, -9.81, 0.0))
+    prev = s.bodies.insert(RigidBodyBuilder.fixed())
+    for i in range(6):
+        last = i == 5
+        b = RigidBodyBuilder.dynamic().translation((0.0, -(i + 1.0), 0.0))
+        if last:
+            b = b.additional_solver_iterations(16)
+        link = s.insert(b, ColliderBuilder.ball(0.4).density(100.0 if last else 1.0))
+        s.joints.insert(prev, link, SphericalJointBuilder().local_anchor1((0.0, -0.5, 0.0)).local_anchor2((0.0, 0.5, 0.0)))
+        prev = link
+    w = make_world(s)
+    w.step(300)
+    end = w.body_states()[0][prev, :3]
+    assert np.isfinite(end).all() and np.linalg.norm(end) < 20.0 and -7.5 < end[1] < -4.5, end
+    assert -6.1 < end[1] < -5.9, end   # (with 20 substeps the joints barely stretch)
+
+    def run(extra):
+        s, light, heavy = _heavy_stack(extra, drop=True)
+        w = make_world(s)
+        w.step(60)
+        pose, _ = w.body_states()
+        return pose[[light, heavy]].copy()
+    plain, extra1, extra2 = run(0), run(8), run(8)
+    assert (extra1.view(np.uint32) == extra2.view(np.uint32)).all()
+    assert not (plain.view(np.uint32) == extra1.view(np.uint32)).all()
+
+    # per-component cadence: a base-cadence stack next to an elevated one moves as it does on its own, bit for bit
+    def twin(with_elevated):
+        s = scenes.Scene("twin", gravity=(0.0, -9.81, 0.0))
+        s.insert(RigidBodyBuilder.fixed(), ColliderBuilder.cuboid(30.0, 0.5, 30.0).translation((0.0, -0.5, 0.0)))
+        a = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.6, 0.0)).rotation((0.0, 0.3, 0.1)), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+        b = s.insert(RigidBodyBuilder.dynamic().translation((0.2, 1.9, 0.1)), ColliderBuilder.cuboid(0.4, 0.4, 0.4).density(3.0))
+        if with_elevated:
+            s.insert(RigidBodyBuilder.dynamic().translation((8.0, 0.5, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5).density(1.0))
+            s.insert(RigidBodyBuilder.dynamic().translation((8.1, 2.5, 0.0)).additional_solver_iterations(5), ColliderBuilder.cuboid(0.5, 0.5, 0.5).density(200.0))
+        w = make_world(s)
+        w.step(90)
+        return w.body_states()[0][[a, b]].copy()
+    alone, beside = twin(False), twin(True)
+    assert (alone.view(np.uint32) == beside.view(np.uint32)).all()
+
+
+def test_additional_solver_iterations_oracle():
+    additional_solver_iterations(lambda s: oracle_lib.OracleWorld(s))
+
+
 # ---- capsules (parry Capsule; ColliderBuilder::capsule_{x,y,z}) ------------------------------------------------------------------
 def capsules_rest(make_world):
     """Capsules of unit mass on a slab: lying (two-point manifold, rest height = radius), standing (rest height = half height +

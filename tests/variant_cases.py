@@ -279,6 +279,44 @@ def coupled_axes_parity_case(make_world, make_oracle, steps=150, every=15, **kw)
     joint_limits_parity_case(make_world, make_oracle, steps=steps, every=every, scene=coupled_axes_scene(), **kw)
 
 
+def substep_groups_scene(big=True):
+    """Substep solve-groups: islands of three cadences side by side (0, 3 and 8 extra substeps; the key of an island is the
+    largest additional_solver_iterations among its members), one of them jointed, one riding a kinematic platform, one with
+    restitution, a wall of bricks large enough for the grid-wide item with 2 extra substeps on a single brick, and plain stacks."""
+    s = scenes.Scene("substep_groups", gravity=(0.0, -9.81, 0.0))
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(60.0, 0.5, 60.0))
+    for k, extra in enumerate((0, 3, 8, 0, 3)):   # heavy-on-light stacks
+        x = -12.0 + 4.0 * k
+        s.insert(RigidBodyBuilder.dynamic().translation((x, 0.5, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+        s.insert(RigidBodyBuilder.dynamic().translation((x + 0.05, 1.6, 0.02)), ColliderBuilder.cuboid(0.45, 0.5, 0.45).restitution(0.4 if k == 1 else 0.0))
+        s.insert(RigidBodyBuilder.dynamic().translation((x, 3.0, 0.0)).additional_solver_iterations(extra), ColliderBuilder.cuboid(0.5, 0.5, 0.5).density(50.0))
+    base = s.bodies.insert(RigidBodyBuilder.fixed().translation((0.0, 8.0, 6.0)))
+    prev = base
+    for i in range(6):   # rope with a heavy end: 8 extra substeps for the whole chain, a box resting against it joins the island
+        last = i == 5
+        b = RigidBodyBuilder.dynamic().translation((0.6 * (i + 1), 8.0, 6.0))
+        if last:
+            b = b.additional_solver_iterations(8)
+        link = s.insert(b, ColliderBuilder.ball(0.25).density(60.0 if last else 1.0))
+        s.joints.insert(prev, link, SphericalJointBuilder().local_anchor1((0.3 if i else 0.0, 0.0, 0.0)).local_anchor2((-0.3, 0.0, 0.0)))
+        prev = link
+    s.kin = s.insert(RigidBodyBuilder.kinematic_velocity_based().translation((10.0, 1.0, 6.0)).linvel((0.4, 0.0, 0.0)), ColliderBuilder.cuboid(2.0, 0.2, 2.0))
+    s.insert(RigidBodyBuilder.dynamic().translation((10.0, 1.7, 6.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    s.insert(RigidBodyBuilder.dynamic().translation((10.0, 2.75, 6.0)).additional_solver_iterations(3), ColliderBuilder.cuboid(0.5, 0.5, 0.5).density(40.0))
+    if big:   # a brick wall: one island above the item caps
+        for i in range(14):
+            for j in range(24):
+                b = RigidBodyBuilder.dynamic().translation((-20.0 + 1.0 * j + (0.5 if i % 2 else 0.0), 0.25 + 0.5 * i, -8.0))
+                if i == 3 and j == 5:
+                    b = b.additional_solver_iterations(2)
+                s.insert(b, ColliderBuilder.cuboid(0.5, 0.25, 0.3))
+    return s
+
+
+def substep_groups_parity_case(make_world, make_oracle, steps=60, every=10, big=True, **kw):
+    joint_limits_parity_case(make_world, make_oracle, steps=steps, every=every, scene=substep_groups_scene(big), **kw)
+
+
 def joint_limits_parity_case(make_world, make_oracle, steps=150, every=15, coulomb=False, warmstart_joints=False, scene=None):
     from parity_util import compare_worlds, is_exact
     s = scene if scene is not None else joint_limits_scene()
