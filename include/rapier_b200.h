@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 5
+#define RB_ABI_VERSION 6
 
 typedef struct RbWorld RbWorld;
 
@@ -133,6 +133,9 @@ typedef struct RbColliderDesc {
     uint32_t collision_filter;
     uint32_t active_events;            /* RB_EVENT_* (ActiveEvents, collider.rs); default 0 */
     float contact_force_event_threshold;   /* default 0; only read with RB_EVENT_CONTACT_FORCE */
+    int32_t sensor;                    /* ColliderBuilder::sensor (collider.rs; ABI 6): a sensor takes no part in contacts -- its pairs
+                                        * are tested for intersection only (narrow_phase/intersections.rs) and report CollisionEvents
+                                        * carrying RB_COLLISION_EVENT_SENSOR; it still counts for the mass of its body.  Default 0. */
 } RbColliderDesc;
 
 /* ActiveEvents (src/pipeline/event_handler.rs). */
@@ -140,7 +143,8 @@ enum { RB_EVENT_COLLISION = 1, RB_EVENT_CONTACT_FORCE = 2 };
 
 /* CollisionEvent::{Started, Stopped} (src/geometry/mod.rs; emitted by apply_pair_transitions, narrow_phase/contacts.rs:312-324,
  * and when a touching pair leaves the broad phase).  `step` = index of the step that emitted it (1 = first step). */
-typedef struct RbCollisionEvent { int32_t collider1, collider2, started, step; } RbCollisionEvent;
+enum { RB_COLLISION_EVENT_SENSOR = 1 };   /* CollisionEventFlags::SENSOR: at least one of the two colliders is a sensor */
+typedef struct RbCollisionEvent { int32_t collider1, collider2, started, step, flags; } RbCollisionEvent;
 /* ContactForceEvent (src/geometry/mod.rs:191-258; NarrowPhase::emit_contact_force_events, solver_graph.rs:462-498). */
 typedef struct RbContactForceEvent {
     int32_t collider1, collider2;

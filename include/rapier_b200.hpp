@@ -107,6 +107,7 @@ public:
     }
     ColliderBuilder& active_events(unsigned events) { d_.active_events = events; return *this; }   // RB_EVENT_*
     ColliderBuilder& contact_force_event_threshold(float t) { d_.contact_force_event_threshold = t; return *this; }
+    ColliderBuilder& sensor(bool on = true) { d_.sensor = on ? 1 : 0; return *this; }   // ColliderBuilder::sensor
     RbColliderDesc desc(int parent) const { RbColliderDesc d = d_; d.parent = parent; return d; }
 
 private:

@@ -182,7 +182,11 @@ int orc_world_drain_collision_events(OrcWorld* o, int32_t cap, RbCollisionEvent*
         if (a.collider2 != b.collider2) return a.collider2 < b.collider2;
         return a.started < b.started;
     });
-    for (int i = 0; i < n && i < cap && out; ++i) out[i] = ev[i];
+    auto is_sensor = [&](int c) { return c >= 0 && c < (int)o->w.colliders.size() && o->w.colliders[c].sensor != 0; };
+    for (int i = 0; i < n && i < cap && out; ++i) {
+        out[i] = ev[i];
+        out[i].flags = (is_sensor(ev[i].collider1) || is_sensor(ev[i].collider2)) ? RB_COLLISION_EVENT_SENSOR : 0;
+    }
     ev.clear();
     return n;
 }

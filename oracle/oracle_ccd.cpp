@@ -153,7 +153,7 @@ void ccd_motion_clamping(World& w) {
         float frac = 1.0f;
         for (int ci = 0; ci < (int)w.colliders.size(); ++ci) {
             const Collider& c1 = w.colliders[ci];
-            if (c1.parent != bi || c1.shape < 0 || c1.shape >= RB_SHAPE_CAPSULE) continue;   // (capsules and polyhedra are not swept)
+            if (c1.parent != bi || c1.shape < 0 || c1.shape >= RB_SHAPE_CAPSULE || c1.sensor) continue;   // (capsules and polyhedra are not swept; sensors never: ccd_solver.rs:92-93)
             const Pose cs = pose_mul(b.pos, c1.pos_wrt_parent), ce = pose_mul(b.next_pos, c1.pos_wrt_parent);
             const Sweep sw = sweep_from_poses(cs, ce, pose_inv_point(c1.pos_wrt_parent, b.local_com));
             const Aabb a1 = shape_aabb(c1.shape, c1.he, cs), a2 = shape_aabb(c1.shape, c1.he, ce);
@@ -161,7 +161,7 @@ void ccd_motion_clamping(World& w) {
             swept.mins = V3{fmin2(a1.mins.x, a2.mins.x), fmin2(a1.mins.y, a2.mins.y), fmin2(a1.mins.z, a2.mins.z)};
             swept.maxs = V3{fmax2(a1.maxs.x, a2.maxs.x), fmax2(a1.maxs.y, a2.maxs.y), fmax2(a1.maxs.z, a2.maxs.z)};
             for (const Collider& c2 : w.colliders) {
-                if (c2.shape < 0 || c2.shape >= RB_SHAPE_CAPSULE) continue;
+                if (c2.shape < 0 || c2.shape >= RB_SHAPE_CAPSULE || c2.sensor) continue;
                 Pose target_pose = c2.pos;
                 if (c2.parent >= 0 && w.bodies[c2.parent].type != RB_BODY_FIXED) {   // tier_allows (sweeps.rs:36-42)
                     const Body& t = w.bodies[c2.parent];

@@ -102,6 +102,7 @@ struct Collider {
     float contact_skin;
     uint32_t memberships, filter;
     uint32_t active_events;         // ActiveEvents
+    int sensor;                     // Collider::is_sensor: intersection events only (narrow_phase/intersections.rs)
     float force_event_threshold;    // contact_force_event_threshold
     Pose pos;       // world pose
     Aabb aabb;      // compute_broad_phase_aabb (tight + skin + prediction/2)
@@ -140,6 +141,7 @@ struct Pair {
     uint8_t color;
     uint32_t color_bodies[2];
     bool force_event_emitted;   // PairEventStatus::INITIAL_FORCE_THRESHOLD_EVENT_EMITTED
+    bool intersecting;          // IntersectionPair::intersecting of a pair with a sensor
 };
 
 // ContactManifoldData::relative_dominance (pair_update.rs:381-382): > 0 = body 1 dominates (world-attached in this contact).

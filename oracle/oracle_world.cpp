@@ -63,6 +63,7 @@ static int recompute_mass_properties(World& w, int first_body = 0, int first_col
     std::vector<int> count(nb, 0), first(nb, -1);
     for (int ci = first_collider; ci < (int)w.colliders.size(); ++ci) {
         int p = w.colliders[ci].parent;
+        if (w.colliders[ci].sensor && w.colliders[ci].density == 0.0f) continue;   // a massless sensor adds nothing
         if (p >= 0) {
             if (count[p] == 0) first[p] = ci;
             count[p]++;
@@ -112,7 +113,7 @@ static int recompute_mass_properties(World& w, int first_body = 0, int first_col
             V3 com = vzero();
             for (size_t ci = (size_t)first_collider; ci < w.colliders.size(); ++ci) {
                 const Collider& c = w.colliders[ci];
-                if (c.parent != bi) continue;
+                if (c.parent != bi || (c.sensor && c.density == 0.0f)) continue;
                 if (c.shape == RB_SHAPE_CONVEX) return RB_ERR_INVALID;   // polyhedra in multi-collider bodies: not supported
                 float mass; V3 pi;
                 collider_mass(c, mass, pi);
@@ -124,7 +125,7 @@ static int recompute_mass_properties(World& w, int first_body = 0, int first_col
             V3 I = vzero();
             for (size_t ci = (size_t)first_collider; ci < w.colliders.size(); ++ci) {
                 const Collider& c = w.colliders[ci];
-                if (c.parent != bi) continue;
+                if (c.parent != bi || (c.sensor && c.density == 0.0f)) continue;
                 Q4 q = c.pos_wrt_parent.q;
                 if (!(q.x == 0.0f && q.y == 0.0f && q.z == 0.0f)) return RB_ERR_INVALID;
                 float mass; V3 pi;
@@ -275,7 +276,7 @@ static void clear_pair_color(World& w, Pair& p) {  // narrow_phase/mod.rs:154-17
 
 // A pair that leaves the broad phase while touching stops (pair_management.rs: emit_stop_event) and frees its colour.
 static void removed_pair(World& w, Pair& o) {
-    if (o.nsc > 0 && ((w.colliders[o.c1].active_events | w.colliders[o.c2].active_events) & RB_EVENT_COLLISION))
+    if ((o.nsc > 0 || o.intersecting) && ((w.colliders[o.c1].active_events | w.colliders[o.c2].active_events) & RB_EVENT_COLLISION))
         w.collision_events.push_back(RbCollisionEvent{o.c1, o.c2, 0, (int)w.counters.steps + 1});
     clear_pair_color(w, o);
     if (o.nsc > 0) w.islands_dirty = true;   // a touching pair that leaves the broad phase may split its island (persistent.rs; the kernels relabel whenever the pair table changes)
@@ -631,6 +632,23 @@ static void narrow_phase(World& w) {
         // pairs without an awake body are not updated (their bodies do not move)
         const bool a1 = p.b1 >= 0 && w.bodies[p.b1].is_awake(), a2 = p.b2 >= 0 && w.bodies[p.b2].is_awake();
         if (!a1 && !a2) continue;
+        if (w.colliders[p.c1].sensor || w.colliders[p.c2].sensor) {
+            // a pair with a sensor (narrow_phase/intersections.rs:17-221): no contacts, no colour, no island edge -- only whether
+            // the shapes intersect (the deepest manifold point is not positive), with a CollisionEvent when that changes
+            const Collider& co1 = w.colliders[p.c1];
+            const Collider& co2 = w.colliders[p.c2];
+            const Pose pos12 = pose_inv_mul(co1.pos, co2.pos);
+            const float eff_prediction = w.params.prediction_distance() + (co1.contact_skin + co2.contact_skin);
+            RawManifold raw;
+            if (co1.shape == RB_SHAPE_CONVEX || co2.shape == RB_SHAPE_CONVEX) contact_manifold_convex(w.hulls, co1.shape, co1.he, co2.shape, co2.he, pos12, eff_prediction, raw);
+            else contact_manifold(co1.shape, co1.he, co2.shape, co2.he, pos12, eff_prediction, raw);
+            bool inter = false;
+            for (int k = 0; k < raw.n; ++k) inter = inter || raw.pts[k].dist <= 0.0f;
+            if (inter != p.intersecting && ((co1.active_events | co2.active_events) & RB_EVENT_COLLISION))
+                w.collision_events.push_back(RbCollisionEvent{p.c1, p.c2, inter ? 1 : 0, (int)w.counters.steps + 1, RB_COLLISION_EVENT_SENSOR});
+            p.intersecting = inter;
+            continue;
+        }
         if (process_pair(w, p)) {
             // contacts.rs:312-324: start / stop events for colliders that ask for them
             if ((w.colliders[p.c1].active_events | w.colliders[p.c2].active_events) & RB_EVENT_COLLISION)
@@ -856,6 +874,8 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
         c.restitution_rule = d.restitution_combine_rule;
         c.contact_skin = d.contact_skin;
         c.active_events = d.active_events;
+    c.sensor = d.sensor;
+        c.sensor = d.sensor;
     c.force_event_threshold = d.contact_force_event_threshold;
     c.memberships = d.collision_memberships;
         c.filter = d.collision_filter;

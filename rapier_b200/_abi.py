@@ -86,12 +86,12 @@ class RbColliderDesc(C.Structure):
         ("friction_combine_rule", i32), ("restitution_combine_rule", i32),
         ("contact_skin", f32),
         ("collision_memberships", u32), ("collision_filter", u32),
-        ("active_events", u32), ("contact_force_event_threshold", f32),
+        ("active_events", u32), ("contact_force_event_threshold", f32), ("sensor", i32),
     ]
 
 
 class RbCollisionEvent(C.Structure):
-    _fields_ = [("collider1", i32), ("collider2", i32), ("started", i32), ("step", i32)]
+    _fields_ = [("collider1", i32), ("collider2", i32), ("started", i32), ("step", i32), ("flags", i32)]
 
 
 class RbContactForceEvent(C.Structure):
@@ -100,6 +100,7 @@ class RbContactForceEvent(C.Structure):
 
 
 RB_EVENT_COLLISION, RB_EVENT_CONTACT_FORCE = 1, 2
+RB_COLLISION_EVENT_SENSOR = 1   # CollisionEventFlags::SENSOR
 
 
 class RbJointMotor(C.Structure):

@@ -603,6 +603,7 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out, int fir
     std::vector<int> count(nb, 0), first(nb, -1);
     for (int ci = first_collider; ci < (int)W->colliders.size(); ++ci) {
         int p = W->colliders[ci].parent;
+        if (W->colliders[ci].sensor && W->colliders[ci].density == 0.0f) continue;   // a massless sensor adds nothing (and must not force the composite path)
         if (p >= 0) { if (count[p] == 0) first[p] = ci; count[p]++; }
     }
     for (int b = first_body; b < nb; ++b) {
@@ -641,7 +642,7 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out, int fir
             float M = 0.0f, com[3] = {0, 0, 0};
             for (size_t ci = (size_t)first_collider; ci < W->colliders.size(); ++ci) {
                 const RbColliderDesc& c = W->colliders[ci];
-                if (c.parent != b) continue;
+                if (c.parent != b || (c.sensor && c.density == 0.0f)) continue;
                 if (c.shape == RB_SHAPE_CONVEX) { set_err("multi-collider bodies with convex polyhedra are not supported%s", ""); return RB_ERR_INVALID; }
                 float mass, pi[3];
                 collider_mass_props(c, mass, pi);
@@ -654,7 +655,7 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out, int fir
                 float I[3] = {0, 0, 0};
                 for (size_t ci = (size_t)first_collider; ci < W->colliders.size(); ++ci) {
                     const RbColliderDesc& c = W->colliders[ci];
-                    if (c.parent != b) continue;
+                    if (c.parent != b || (c.sensor && c.density == 0.0f)) continue;
                     if (!(c.pos_wrt_parent_q[0] == 0.0f && c.pos_wrt_parent_q[1] == 0.0f && c.pos_wrt_parent_q[2] == 0.0f)) {
                         set_err("multi-collider bodies need axis-aligned colliders%s", "");
                         return RB_ERR_INVALID;
@@ -847,7 +848,8 @@ static int upload_colliders(RbWorld* W, int first, int count, int first_body = 0
     std::vector<float> thr(count);
     for (int k = 0; k < count; ++k) {
         const RbColliderDesc& c = W->colliders[first + k];
-        events[k] = (int)c.active_events;
+        events[k] = (int)(c.active_events & 3u) | (c.sensor ? 4 : 0);
+        if (c.sensor) w.has_sensors = 1;
         thr[k] = c.contact_force_event_threshold;
         if (c.active_events & RB_EVENT_CONTACT_FORCE) W->force_events = true;
         if (c.shape == RB_SHAPE_CAPSULE || c.shape == RB_SHAPE_CONVEX) W->ext_shapes = true;
@@ -1580,7 +1582,9 @@ int rb_world_drain_collision_events(RbWorld* W, int32_t cap, RbCollisionEvent* o
         if (a.y != b.y) return a.y < b.y;
         return a.z < b.z;
     });
-    for (int i = 0; i < n && i < cap && out; ++i) out[i] = RbCollisionEvent{ev[i].x, ev[i].y, ev[i].z, ev[i].w};
+    auto is_sensor = [&](int c) { return c >= 0 && c < (int)W->colliders.size() && W->colliders[c].sensor != 0; };
+    for (int i = 0; i < n && i < cap && out; ++i)
+        out[i] = RbCollisionEvent{ev[i].x, ev[i].y, ev[i].z, ev[i].w, (is_sensor(ev[i].x) || is_sensor(ev[i].y)) ? RB_COLLISION_EVENT_SENSOR : 0};
     int zero = 0;
     CK(h2d(&W->w.st->nev_coll, &zero, sizeof(int)));
     return n;

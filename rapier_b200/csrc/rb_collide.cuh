@@ -492,7 +492,7 @@ RB_PHASE void section_broad_phase(const Ctx& ctx, const World& w) {
     for (int j = ctx.gtid; j < nold; j += ctx.gsize) {
         if (bsearch_u64(ck, ncand, okey[j]) < 0) {
             float4 info = prow(w, cur, PR_INFO, j), bod = prow(w, cur, PR_BODIES, j);
-            if (as_int(info.z) > 0) emit_collision_event(w, (int)(okey[j] >> 32), (int)(okey[j] & 0xffffffffu), false);   // a touching pair that leaves the broad phase stops
+            if (as_int(info.z) > 0 || (as_int(info.x) & 16)) emit_collision_event(w, (int)(okey[j] >> 32), (int)(okey[j] & 0xffffffffu), false);   // a touching (or intersecting sensor) pair that leaves the broad phase stops
             clear_color_bits(w, as_int(info.w), as_int(bod.x), as_int(bod.y));
         }
     }
@@ -659,6 +659,16 @@ RB_PHASE void phase_narrow_phase(const Ctx& ctx, const World& w) {
         RawManifold raw;
         if (SHAPES && pair_is_poly_poly(sh1, sh2)) poly_raw_load(w.convex_raw + (size_t)i * POLY_RAW_STRIDE, raw);   // (phase_convex_manifolds)
         else contact_manifold<SHAPES>(w.hulls, sh1, he1, sh2, he2, p12, prediction + (skin1 + skin2), raw);
+
+        if (w.has_sensors && ((w.c_events[c1] | w.c_events[c2]) & 4)) {   // (a kernel parameter guards the loads)
+            // a pair with a sensor (narrow_phase/intersections.rs:17-221): no contacts, no colour, no island edge -- only whether
+            // the shapes intersect (the deepest manifold point is not positive), with a CollisionEvent when that changes
+            bool inter = false;
+            for (int k = 0; k < raw.n; ++k) inter = inter || raw.pt[k].dist <= 0.0f;
+            if (inter != ((flags & 16) != 0)) emit_collision_event(w, c1, c2, inter);
+            prow(w, buf, PR_INFO, i) = make_float4(as_float_i(inter ? 16 : 0), as_float_i(0), as_float_i(0), as_float_i(color));
+            continue;
+        }
 
         // match_contacts: carry ContactData by feature ids (ball manifolds keep their single point).
         float4 o_pb[MAX_PTS], o_pd[MAX_PTS], o_tw[MAX_PTS], o_d1[MAX_PTS], o_d2[MAX_PTS];

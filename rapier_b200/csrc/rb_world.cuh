@@ -44,7 +44,7 @@ struct HullTables {
 
 // ---- persistent pair record rows (float4 each) ----
 enum PairRow {
-    PR_INFO = 0,   // int bits: x flags(bit0 has_recycle, bit1 pending colour, bit2 colouring scratch, bit3 force event emitted last step), y npts, z nsc, w colour
+    PR_INFO = 0,   // int bits: x flags(bit0 has_recycle, bit1 pending colour, bit2 colouring scratch, bit3 force event emitted last step, bit4 sensor pair intersecting), y npts, z nsc, w colour
     PR_BODIES,     // int bits: x colour_body0, y colour_body1, z body1, w body2 (-1 none)
     PR_RT,         // recycle pos12.t xyz, w max_extent
     PR_RQ,         // recycle pos12.q
@@ -193,7 +193,8 @@ struct World {
     float4* c_mat;                    // friction, restitution, contact_skin
     int2* c_rules;
     uint2* c_groups;
-    int* c_events;                    // ActiveEvents bits (1 = collision events, 2 = contact force events)
+    int* c_events;                    // ActiveEvents bits (1 = collision events, 2 = contact force events) | 4 = the collider is a sensor
+    int has_sensors;                  // some collider is a sensor (Collider::is_sensor): intersection-only pairs exist
     float* c_force_thr;               // contact_force_event_threshold
     float4 *c_pos_t, *c_pos_q;
     float4 *c_aabb_min, *c_aabb_max, *c_fat_min, *c_fat_max;

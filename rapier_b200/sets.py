@@ -276,6 +276,11 @@ class ColliderBuilder:
         self._active_events = int(events)
         return self
 
+    def sensor(self, flag=True):
+        """ColliderBuilder::sensor (collider.rs): intersection events only, no contacts."""
+        self._sensor = bool(flag)
+        return self
+
     def contact_force_event_threshold(self, threshold):
         self._force_threshold = float(threshold)
         return self
@@ -297,6 +302,7 @@ class ColliderBuilder:
         d.collision_filter = self._filter
         d.active_events = getattr(self, "_active_events", 0)
         d.contact_force_event_threshold = getattr(self, "_force_threshold", 0.0)
+        d.sensor = 1 if getattr(self, "_sensor", False) else 0
         return d
 
 

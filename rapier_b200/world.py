@@ -135,11 +135,14 @@ class PhysicsPipeline:
         p = np.ascontiguousarray(pose7, np.float32)
         self._check(self.L.rb_world_set_next_kinematic_positions(self.h, len(idx), idx.ctypes.data, p.ctypes.data))
 
-    def collision_events(self):
-        """Drains the buffered CollisionEvents (EventHandler::handle_collision_event): [(collider1, collider2, started, step)]."""
+    def collision_events(self, with_flags=False):
+        """Drains the buffered CollisionEvents (EventHandler::handle_collision_event): [(collider1, collider2, started, step)],
+        with_flags: [(..., flags)] (RB_COLLISION_EVENT_SENSOR)."""
         buf = (A.RbCollisionEvent * 65536)()
         n = self.L.rb_world_drain_collision_events(self.h, 65536, buf)
         self._check(min(n, 0))
+        if with_flags:
+            return [(e.collider1, e.collider2, e.started, e.step, e.flags) for e in buf[:min(n, 65536)]]
         return [(e.collider1, e.collider2, e.started, e.step) for e in buf[:min(n, 65536)]]
 
     def contact_force_events(self):
@@ -327,9 +330,9 @@ class PhysicsWorld:
         self._flush()
         self.physics_pipeline.set_next_kinematic_positions(handles, pose7)
 
-    def collision_events(self):
+    def collision_events(self, with_flags=False):
         self._flush()
-        return self.physics_pipeline.collision_events()
+        return self.physics_pipeline.collision_events(with_flags)
 
     def contact_force_events(self):
         self._flush()

@@ -133,6 +133,14 @@ def random_scene(seed):
                     j = j.limits(1, -0.5, 0.5)
             j = j.local_anchor1(tuple(float(x) for x in r3.uniform(-0.5, 0.5, 3))).local_anchor2(tuple(float(x) for x in r3.uniform(-0.5, 0.5, 3)))
             s.joints.insert(a, b, j)
+    if r3.random() < 0.3:   # sensors: fixed zones and auras on bodies (intersection events only)
+        for _ in range(int(r3.integers(1, 4))):
+            c = (ColliderBuilder.ball(float(r3.uniform(0.3, 1.5))) if r3.random() < 0.5 else
+                 ColliderBuilder.cuboid(*(float(x) for x in r3.uniform(0.3, 2.0, 3)))).sensor(True).active_events(int(r3.integers(0, 2)))
+            if r3.random() < 0.5:
+                s.colliders.insert(c.translation(tuple(float(x) for x in r3.uniform(-3.0, 3.0, 3))))
+            else:
+                s.colliders.insert_with_parent(c.density(0.0), int(r3.choice(handles)))   # (massless: the body keeps its mass properties)
     if r3.random() < 0.3:   # substep solve-groups: extra substeps for the islands of a few bodies
         for h in r3.choice(handles, min(len(handles), int(r3.integers(1, 4))), replace=False):
             s.bodies.descs[int(h)].flags |= int(r3.choice([1, 2, 5])) << A.RB_BODY_EXTRA_ITERS_SHIFT

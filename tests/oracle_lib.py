@@ -179,10 +179,12 @@ class OracleWorld:
         p = np.ascontiguousarray(pose7, np.float32)
         assert self.L.orc_world_set_next_kinematic_positions(self.h, len(idx), idx.ctypes.data, p.ctypes.data) == 0
 
-    def collision_events(self):
-        """Drains the buffered CollisionEvents: list of (collider1, collider2, started, step)."""
+    def collision_events(self, with_flags=False):
+        """Drains the buffered CollisionEvents: list of (collider1, collider2, started, step[, flags])."""
         buf = (A.RbCollisionEvent * 65536)()
         n = self.L.orc_world_drain_collision_events(self.h, 65536, buf)
+        if with_flags:
+            return [(e.collider1, e.collider2, e.started, e.step, e.flags) for e in buf[:n]]
         return [(e.collider1, e.collider2, e.started, e.step) for e in buf[:n]]
 
     def contact_force_events(self):

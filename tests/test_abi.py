@@ -23,7 +23,7 @@ def test_exports_every_declared_symbol(built):
     assert len(names) >= 18
     for n in names:
         assert hasattr(L, n), f"librapier_b200.so does not export {n}"
-    assert L.rb_abi_version() == 5   # (2: RbColliderDesc events fields; 3: RbJointDesc limits + motors; 4: convex polyhedra; 5: coupled_axes, additional_solver_iterations)
+    assert L.rb_abi_version() == 6   # (2: RbColliderDesc events fields; 3: RbJointDesc limits + motors; 4: convex polyhedra; 5: coupled_axes, additional_solver_iterations; 6: sensors, RbCollisionEvent.flags)
 
 
 def test_default_parameters_match_reference_defaults(built):

@@ -210,6 +210,13 @@ def test_additional_solver_iterations_emulated_kernels():
     substep_groups_parity_case(mk, mo, steps=30, big=False, coulomb=True, warmstart_joints=True)
 
 
+def test_sensors_emulated_kernels():
+    from test_oracle_kat import sensors
+    from variant_cases import sensors_parity_case
+    sensors(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()))
+    sensors_parity_case(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), lambda s: oracle_lib.OracleWorld(s))
+
+
 def test_dominance_groups_emulated_kernels():
     from test_oracle_kat import dominance_groups
     from variant_cases import dominance_parity_case

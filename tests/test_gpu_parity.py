@@ -426,6 +426,16 @@ def test_additional_solver_iterations(built):
     substep_groups_parity_case(mk, mo, steps=40, big=False, coulomb=True, warmstart_joints=True)
 
 
+def test_sensors(built):
+    """Collider::is_sensor: intersection-only pairs with CollisionEventFlags::SENSOR events -- free fall through a zone bit-exact
+    with the zone-less twin, an aura that reports the ground early, a thin sensor wall a fast body ignores -- through the C ABI, and a
+    pile falling through zones of every shape family bit-exact against the oracle (states, pair tables, flagged event lists)."""
+    from test_oracle_kat import sensors
+    from variant_cases import sensors_parity_case
+    sensors(lambda s: PhysicsWorld(s))
+    sensors_parity_case(lambda s: PhysicsWorld(s), lambda s: oracle_lib.OracleWorld(s))
+
+
 def test_convex_polyhedra(built):
     """ColliderBuilder::{convex_hull, round_convex_hull}: known answers through the C ABI (the convex_pile parity variants
     run with the other variants) and the reference's examples3d/convex_polyhedron3.rs drop (reduced: 5 x 5 x 4 round hulls of

@@ -928,6 +928,71 @@ def test_additional_solver_iterations_oracle():
     additional_solver_iterations(lambda s: oracle_lib.OracleWorld(s))
 
 
+# ---- sensors (Collider::is_sensor; narrow_phase/intersections.rs; CollisionEventFlags::SENSOR) ---------------------------------
+def sensors(make_world):
+    """A ball falls through a fixed sensor zone: Started then Stopped with the SENSOR flag, and its fall is the free fall of the
+    same scene without the zone, bit for bit; a massless sensor aura on a dynamic body reports the ground before the body
+    touches it and does not hold the body up; a fast body is not stopped by a thin sensor wall (a solid twin of the wall stops it)."""
+    def scene(with_zone):
+        s = scenes.Scene("sensor_zone", gravity=(0.0, -9.81, 0.0))
+        s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(10.0, 0.5, 10.0))
+        ball = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 6.0, 0.0)).can_sleep(False), ColliderBuilder.ball(0.3).active_events(1))
+        zone = s.colliders.insert(ColliderBuilder.cuboid(2.0, 0.5, 2.0).translation((0.0, 3.0, 0.0)).sensor(True)) if with_zone else -1
+        return s, ball, zone
+    s, ball, zone = scene(True)
+    w = make_world(s)
+    s0, ball0, _ = scene(False)
+    w0 = make_world(s0)
+    events = []
+    for i in range(70):
+        w.step(); w0.step()
+        events += w.collision_events(with_flags=True)
+        if i < 60:
+            assert (w.body_states()[0][ball].view(np.uint32) == w0.body_states()[0][ball0].view(np.uint32)).all(), i
+    zone_events = [e for e in events if zone in (e[0], e[1])]
+    assert [e[2] for e in zone_events] == [1, 0] and all(e[4] == 1 for e in zone_events), zone_events
+    assert zone_events[0][3] < zone_events[1][3]
+    # the narrow phase of step k sees the pose after k - 1 steps of 4 substeps of semi-implicit Euler; the ball (radius 0.3) and
+    # the zone (y in [2.5, 3.5]) intersect while 2.2 <= y <= 3.8
+    g, h = 9.81, 1.0 / 240.0
+    y_after = lambda n: 6.0 - g * h * h * (4 * n) * (4 * n + 1) / 2.0
+    k_in, k_out = zone_events[0][3], zone_events[1][3]
+    assert y_after(k_in - 1) <= 3.8 < y_after(k_in - 2), (k_in, y_after(k_in - 1))
+    assert y_after(k_out - 1) < 2.2 <= y_after(k_out - 2), (k_out, y_after(k_out - 1))
+    ground_events = [e for e in events if zone not in (e[0], e[1])]
+    assert ground_events and all(e[4] == 0 for e in ground_events)
+
+    s = scenes.Scene("sensor_aura", gravity=(0.0, -9.81, 0.0))
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(10.0, 0.5, 10.0))
+    body = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 3.0, 0.0)).can_sleep(False), ColliderBuilder.cuboid(0.3, 0.3, 0.3))
+    aura = s.colliders.insert_with_parent(ColliderBuilder.ball(1.0).density(0.0).sensor(True).active_events(1), body)
+    w = make_world(s)
+    first = None
+    for i in range(120):
+        w.step()
+        for e in w.collision_events(with_flags=True):
+            if aura in (e[0], e[1]) and e[2] == 1 and first is None:
+                first = (i, float(w.body_states()[0][body, 1]))
+                assert e[4] == 1
+    pose, vel = w.body_states()
+    assert first is not None and 0.75 < first[1] < 1.0, first         # reported in the step whose narrow phase saw the aura (radius 1) reach the ground
+    assert abs(pose[body, 1] - 0.3) < 0.01 and abs(vel[body, 1]) < 0.02   # the box rests on the ground: the aura carries nothing
+
+    def wall(sensor):
+        s = scenes.Scene("sensor_wall", gravity=(0.0, 0.0, 0.0))
+        c = ColliderBuilder.cuboid(0.02, 2.0, 2.0).translation((3.0, 0.0, 0.0))
+        s.colliders.insert(c.sensor(True) if sensor else c)
+        b = s.insert(RigidBodyBuilder.dynamic().linvel((300.0, 0.0, 0.0)).can_sleep(False), ColliderBuilder.ball(0.2))
+        w = make_world(s)
+        w.step(3)
+        return float(w.body_states()[0][b, 0])
+    assert wall(True) > 10.0 and wall(False) < 3.0
+
+
+def test_sensors_oracle():
+    sensors(lambda s: oracle_lib.OracleWorld(s))
+
+
 # ---- capsules (parry Capsule; ColliderBuilder::capsule_{x,y,z}) ------------------------------------------------------------------
 def capsules_rest(make_world):
     """Capsules of unit mass on a slab: lying (two-point manifold, rest height = radius), standing (rest height = half height +

@@ -167,6 +167,52 @@ def events_parity_case(make_world, make_oracle, steps=150):
     return nc, nf
 
 
+def sensors_scene():
+    """Sensor colliders of every shape family among a falling pile: fixed zones (cuboid, ball, capsule, round hull), a zone that
+    leaves the scene with its kinematic carrier, massless and massive sensor auras on dynamic bodies (sensor-sensor pairs too), a
+    sensor floor tile next to solid ones, bodies that sleep inside a zone."""
+    ev = A.RB_EVENT_COLLISION
+    s = scenes.Scene("sensors")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(12.0, 0.5, 12.0))
+    s.colliders.insert(ColliderBuilder.cuboid(3.0, 0.6, 3.0).translation((0.0, 2.0, 0.0)).sensor(True).active_events(ev))
+    s.colliders.insert(ColliderBuilder.ball(1.2).translation((2.5, 1.0, 0.5)).sensor(True).active_events(ev))
+    s.colliders.insert(ColliderBuilder.capsule_x(1.5, 0.4).translation((-2.0, 0.8, 1.0)).sensor(True))
+    s.colliders.insert(ColliderBuilder.round_convex_hull([(-1, 0, -1), (1, 0, -1), (1, 0, 1), (-1, 0, 1), (0, 1.5, 0)], 0.05).translation((0.0, 0.2, -3.0)).sensor(True).active_events(ev))
+    s.insert(RigidBodyBuilder.kinematic_velocity_based().translation((-5.0, 1.5, 0.0)).linvel((1.5, 0.0, 0.0)), ColliderBuilder.cuboid(0.5, 1.5, 4.0).sensor(True).active_events(ev))
+    k = 0
+    for layer in range(4):
+        for i in range(3):
+            for j in range(3):
+                pos = (-1.5 + 1.5 * i + 0.11 * layer, 3.5 + 1.2 * layer, -1.5 + 1.5 * j + 0.07 * i)
+                b = RigidBodyBuilder.dynamic().translation(pos).rotation((0.2 * (k % 3), 0.1 * (k % 5), 0.15 * (k % 4)))
+                kind = k % 4
+                c = (ColliderBuilder.cuboid(0.4, 0.3, 0.35) if kind == 0 else ColliderBuilder.ball(0.35) if kind == 1 else
+                     ColliderBuilder.capsule_y(0.3, 0.2) if kind == 2 else ColliderBuilder.cuboid(0.3, 0.3, 0.3))
+                h = s.insert(b, c.active_events(ev if k % 2 else 0))
+                if k % 5 == 0:
+                    s.colliders.insert_with_parent(ColliderBuilder.ball(0.8).density(0.0 if k % 10 else 0.5).sensor(True).active_events(ev), h)
+                k += 1
+    return s
+
+
+def sensors_parity_case(make_world, make_oracle, steps=200, every=20):
+    """Body states, pair tables and the drained event lists (with their SENSOR flags) of both worlds must be identical."""
+    from parity_util import compare_worlds, is_exact
+    s = sensors_scene()
+    w, o = make_world(s), make_oracle(s)
+    nsens = 0
+    for i in range(steps):
+        w.step(); o.step()
+        if i % 7 == 6 or i == steps - 1:
+            cw, co = w.collision_events(with_flags=True), o.collision_events(with_flags=True)
+            assert cw == co, (i, cw[:4], co[:4])
+            nsens += sum(1 for e in cw if e[4])
+        if i % every == every - 1 or i < 2:
+            d = compare_worlds(w, o)
+            assert is_exact(d), (i, d)
+    assert nsens > 30, nsens
+
+
 def kinematic_parity_case(make_world, make_oracle, steps=150, every=15):
     """A velocity-based kinematic turntable and conveyor carrying boxes and balls, and a position-based lift driven
     along a curve with a new target every step: bit-exact against the oracle."""
