@@ -7,7 +7,10 @@
 // src/geometry/narrow_phase/pair_update.rs:67-680 (process_pair),
 // src/geometry/narrow_phase/{contacts.rs:300-385, mod.rs:87-172} (transitions + colouring).
 #include <algorithm>
+#include <array>
 #include <chrono>
+#include <cmath>
+#include <vector>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -54,6 +57,89 @@ static void collider_mass(const Collider& c, float& mass, V3& principal) {
         mass = vol * c.density;
         principal = V3{unit * mass, unit * mass, unit * mass};
     }
+}
+
+// General composite mass properties (MassProperties sum + from_inertia_tensor / symmetric eigen-decomposition [parry],
+// restated): parts with mass m_i, principal inertia pi_i in their own frame (rotation q_i, centre t_i).  Sums the world
+// tensors about the common centre of mass (parallel-axis theorem) in double precision and diagonalises the sum with cyclic
+// Jacobi rotations.  Outputs the centre of mass, the principal inertia and the principal frame (x, y, z, w).
+static void composite_inertia(int n, const float* mass, const float (*pi)[3], const float (*q)[4], const float (*t)[3],
+                              float com_out[3], float pi_out[3], float frame_out[4]) {
+    double M = 0.0, com[3] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < n; ++i) {
+        M += (double)mass[i];
+        for (int k = 0; k < 3; ++k) com[k] += (double)t[i][k] * (double)mass[i];
+    }
+    for (int k = 0; k < 3; ++k) com[k] /= M;
+    double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int i = 0; i < n; ++i) {
+        const double x = q[i][0], y = q[i][1], z = q[i][2], w = q[i][3];
+        const double R[3][3] = {{1.0 - 2.0 * (y * y + z * z), 2.0 * (x * y - z * w), 2.0 * (x * z + y * w)},
+                                {2.0 * (x * y + z * w), 1.0 - 2.0 * (x * x + z * z), 2.0 * (y * z - x * w)},
+                                {2.0 * (x * z - y * w), 2.0 * (y * z + x * w), 1.0 - 2.0 * (x * x + y * y)}};
+        double d[3];
+        for (int k = 0; k < 3; ++k) d[k] = (double)t[i][k] - com[k];
+        const double d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                double v = 0.0;
+                for (int k = 0; k < 3; ++k) v += R[r][k] * (double)pi[i][k] * R[c][k];
+                v += (double)mass[i] * ((r == c ? d2 : 0.0) - d[r] * d[c]);
+                A[r][c] += v;
+            }
+    }
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+        const double diag = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+        if (off <= 1.0e-30 * diag || off == 0.0) break;
+        for (int p = 0; p < 2; ++p)
+            for (int r = p + 1; r < 3; ++r) {
+                if (A[p][r] == 0.0) continue;
+                const double theta = (A[r][r] - A[p][p]) / (2.0 * A[p][r]);
+                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+                for (int k = 0; k < 3; ++k) {   // A <- A J
+                    const double akp = A[k][p], akr = A[k][r];
+                    A[k][p] = c * akp - s * akr;
+                    A[k][r] = s * akp + c * akr;
+                }
+                for (int k = 0; k < 3; ++k) {   // A <- J^T A
+                    const double apk = A[p][k], ark = A[r][k];
+                    A[p][k] = c * apk - s * ark;
+                    A[r][k] = s * apk + c * ark;
+                }
+                for (int k = 0; k < 3; ++k) {   // V <- V J
+                    const double vkp = V[k][p], vkr = V[k][r];
+                    V[k][p] = c * vkp - s * vkr;
+                    V[k][r] = s * vkp + c * vkr;
+                }
+            }
+    }
+    // a proper rotation: flip the third axis if the eigenvectors came out left-handed
+    const double det = V[0][0] * (V[1][1] * V[2][2] - V[1][2] * V[2][1]) - V[0][1] * (V[1][0] * V[2][2] - V[1][2] * V[2][0]) +
+                       V[0][2] * (V[1][0] * V[2][1] - V[1][1] * V[2][0]);
+    if (det < 0.0)
+        for (int k = 0; k < 3; ++k) V[k][2] = -V[k][2];
+    // rotation matrix -> quaternion (largest-component branch)
+    double qw, qx, qy, qz;
+    const double tr = V[0][0] + V[1][1] + V[2][2];
+    if (tr > 0.0) {
+        const double s = sqrt(tr + 1.0) * 2.0;
+        qw = 0.25 * s; qx = (V[2][1] - V[1][2]) / s; qy = (V[0][2] - V[2][0]) / s; qz = (V[1][0] - V[0][1]) / s;
+    } else if (V[0][0] > V[1][1] && V[0][0] > V[2][2]) {
+        const double s = sqrt(1.0 + V[0][0] - V[1][1] - V[2][2]) * 2.0;
+        qw = (V[2][1] - V[1][2]) / s; qx = 0.25 * s; qy = (V[0][1] + V[1][0]) / s; qz = (V[0][2] + V[2][0]) / s;
+    } else if (V[1][1] > V[2][2]) {
+        const double s = sqrt(1.0 + V[1][1] - V[0][0] - V[2][2]) * 2.0;
+        qw = (V[0][2] - V[2][0]) / s; qx = (V[0][1] + V[1][0]) / s; qy = 0.25 * s; qz = (V[1][2] + V[2][1]) / s;
+    } else {
+        const double s = sqrt(1.0 + V[2][2] - V[0][0] - V[1][1]) * 2.0;
+        qw = (V[1][0] - V[0][1]) / s; qx = (V[0][2] + V[2][0]) / s; qy = (V[1][2] + V[2][1]) / s; qz = 0.25 * s;
+    }
+    const double qn = sqrt(qx * qx + qy * qy + qz * qz + qw * qw);
+    frame_out[0] = (float)(qx / qn); frame_out[1] = (float)(qy / qn); frame_out[2] = (float)(qz / qn); frame_out[3] = (float)(qw / qn);
+    for (int k = 0; k < 3; ++k) { com_out[k] = (float)com[k]; pi_out[k] = (float)A[k][k]; }
 }
 
 // `first_body` / `first_collider`: only the bodies from first_body on, from the colliders from first_collider on
@@ -122,22 +208,50 @@ static int recompute_mass_properties(World& w, int first_body = 0, int first_col
             }
             if (M == 0.0f) continue;
             com = com * (1.0f / M);
-            V3 I = vzero();
+            bool simple = true;   // axis-aligned parts offset from the centre of mass along one axis: the summed tensor is diagonal
             for (size_t ci = (size_t)first_collider; ci < w.colliders.size(); ++ci) {
                 const Collider& c = w.colliders[ci];
                 if (c.parent != bi || (c.sensor && c.density == 0.0f)) continue;
                 Q4 q = c.pos_wrt_parent.q;
-                if (!(q.x == 0.0f && q.y == 0.0f && q.z == 0.0f)) return RB_ERR_INVALID;
-                float mass; V3 pi;
-                collider_mass(c, mass, pi);
+                if (!(q.x == 0.0f && q.y == 0.0f && q.z == 0.0f)) simple = false;
                 V3 d = c.pos_wrt_parent.t - com;
-                if ((d.x != 0.0f) + (d.y != 0.0f) + (d.z != 0.0f) > 1) return RB_ERR_INVALID;
-                float d2 = dot(d, d);
-                I = I + pi + V3{(d2 - d.x * d.x) * mass, (d2 - d.y * d.y) * mass, (d2 - d.z * d.z) * mass};
+                if ((d.x != 0.0f) + (d.y != 0.0f) + (d.z != 0.0f) > 1) simple = false;
             }
-            b.local_com = com;
+            if (simple) {
+                V3 I = vzero();
+                for (size_t ci = (size_t)first_collider; ci < w.colliders.size(); ++ci) {
+                    const Collider& c = w.colliders[ci];
+                    if (c.parent != bi || (c.sensor && c.density == 0.0f)) continue;
+                    float mass; V3 pi;
+                    collider_mass(c, mass, pi);
+                    V3 d = c.pos_wrt_parent.t - com;
+                    float d2 = dot(d, d);
+                    I = I + pi + V3{(d2 - d.x * d.x) * mass, (d2 - d.y * d.y) * mass, (d2 - d.z * d.z) * mass};
+                }
+                b.local_com = com;
+                b.inv_principal_inertia = V3{inv_exact0(I.x), inv_exact0(I.y), inv_exact0(I.z)};
+            } else {   // compound bodies in general: full tensor, principal axes by eigen-decomposition
+                std::vector<float> pm;
+                std::vector<std::array<float, 3>> ppi, pt;
+                std::vector<std::array<float, 4>> pq;
+                for (size_t ci = (size_t)first_collider; ci < w.colliders.size(); ++ci) {
+                    const Collider& c = w.colliders[ci];
+                    if (c.parent != bi || (c.sensor && c.density == 0.0f)) continue;
+                    float mass; V3 pi;
+                    collider_mass(c, mass, pi);
+                    pm.push_back(mass);
+                    ppi.push_back({pi.x, pi.y, pi.z});
+                    pt.push_back({c.pos_wrt_parent.t.x, c.pos_wrt_parent.t.y, c.pos_wrt_parent.t.z});
+                    pq.push_back({c.pos_wrt_parent.q.x, c.pos_wrt_parent.q.y, c.pos_wrt_parent.q.z, c.pos_wrt_parent.q.w});
+                }
+                float lc[3], I[3], fr[4];
+                composite_inertia((int)pm.size(), pm.data(), reinterpret_cast<const float(*)[3]>(ppi.data()), reinterpret_cast<const float(*)[4]>(pq.data()),
+                                  reinterpret_cast<const float(*)[3]>(pt.data()), lc, I, fr);
+                b.local_com = V3{lc[0], lc[1], lc[2]};
+                b.principal_frame = Q4{fr[0], fr[1], fr[2], fr[3]};
+                b.inv_principal_inertia = V3{inv_exact0(I[0]), inv_exact0(I[1]), inv_exact0(I[2])};
+            }
             b.inv_mass = inv_exact0(M);
-            b.inv_principal_inertia = V3{inv_exact0(I.x), inv_exact0(I.y), inv_exact0(I.z)};
         }
         // RigidBodyAdditionalMassProps::Mass (rigid_body_components.rs:454-486); MassProperties::set_mass(m, true)
         // [parry] rescales the angular inertia by new_mass / old_mass, i.e. its inverse by inv(new) * old.

@@ -16,6 +16,7 @@
 #include <string.h>
 #include <algorithm>
 #include <string>
+#include <array>
 #include <vector>
 
 #include "rb_solver.cuh"
@@ -594,6 +595,90 @@ static inline bool type_moves(int t) { return t == RB_BODY_DYNAMIC || t == RB_BO
 
 struct HostMass { float lcom[3], inv_mass, ipi[3], pi[3], pframe[4], max_extent, ccd_thickness; };
 
+// General composite mass properties (MassProperties sum + from_inertia_tensor / symmetric eigen-decomposition [parry],
+// restated): parts with mass m_i, principal inertia pi_i in their own frame (rotation q_i, centre t_i).  Sums the world
+// tensors about the common centre of mass (parallel-axis theorem) in double precision and diagonalises the sum with cyclic
+// Jacobi rotations.  Outputs the centre of mass, the principal inertia and the principal frame (x, y, z, w).
+static void composite_inertia(int n, const float* mass, const float (*pi)[3], const float (*q)[4], const float (*t)[3],
+                              float com_out[3], float pi_out[3], float frame_out[4]) {
+    double M = 0.0, com[3] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < n; ++i) {
+        M += (double)mass[i];
+        for (int k = 0; k < 3; ++k) com[k] += (double)t[i][k] * (double)mass[i];
+    }
+    for (int k = 0; k < 3; ++k) com[k] /= M;
+    double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int i = 0; i < n; ++i) {
+        const double x = q[i][0], y = q[i][1], z = q[i][2], w = q[i][3];
+        const double R[3][3] = {{1.0 - 2.0 * (y * y + z * z), 2.0 * (x * y - z * w), 2.0 * (x * z + y * w)},
+                                {2.0 * (x * y + z * w), 1.0 - 2.0 * (x * x + z * z), 2.0 * (y * z - x * w)},
+                                {2.0 * (x * z - y * w), 2.0 * (y * z + x * w), 1.0 - 2.0 * (x * x + y * y)}};
+        double d[3];
+        for (int k = 0; k < 3; ++k) d[k] = (double)t[i][k] - com[k];
+        const double d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                double v = 0.0;
+                for (int k = 0; k < 3; ++k) v += R[r][k] * (double)pi[i][k] * R[c][k];
+                v += (double)mass[i] * ((r == c ? d2 : 0.0) - d[r] * d[c]);
+                A[r][c] += v;
+            }
+    }
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+        const double diag = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+        if (off <= 1.0e-30 * diag || off == 0.0) break;
+        for (int p = 0; p < 2; ++p)
+            for (int r = p + 1; r < 3; ++r) {
+                if (A[p][r] == 0.0) continue;
+                const double theta = (A[r][r] - A[p][p]) / (2.0 * A[p][r]);
+                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+                for (int k = 0; k < 3; ++k) {   // A <- A J
+                    const double akp = A[k][p], akr = A[k][r];
+                    A[k][p] = c * akp - s * akr;
+                    A[k][r] = s * akp + c * akr;
+                }
+                for (int k = 0; k < 3; ++k) {   // A <- J^T A
+                    const double apk = A[p][k], ark = A[r][k];
+                    A[p][k] = c * apk - s * ark;
+                    A[r][k] = s * apk + c * ark;
+                }
+                for (int k = 0; k < 3; ++k) {   // V <- V J
+                    const double vkp = V[k][p], vkr = V[k][r];
+                    V[k][p] = c * vkp - s * vkr;
+                    V[k][r] = s * vkp + c * vkr;
+                }
+            }
+    }
+    // a proper rotation: flip the third axis if the eigenvectors came out left-handed
+    const double det = V[0][0] * (V[1][1] * V[2][2] - V[1][2] * V[2][1]) - V[0][1] * (V[1][0] * V[2][2] - V[1][2] * V[2][0]) +
+                       V[0][2] * (V[1][0] * V[2][1] - V[1][1] * V[2][0]);
+    if (det < 0.0)
+        for (int k = 0; k < 3; ++k) V[k][2] = -V[k][2];
+    // rotation matrix -> quaternion (largest-component branch)
+    double qw, qx, qy, qz;
+    const double tr = V[0][0] + V[1][1] + V[2][2];
+    if (tr > 0.0) {
+        const double s = sqrt(tr + 1.0) * 2.0;
+        qw = 0.25 * s; qx = (V[2][1] - V[1][2]) / s; qy = (V[0][2] - V[2][0]) / s; qz = (V[1][0] - V[0][1]) / s;
+    } else if (V[0][0] > V[1][1] && V[0][0] > V[2][2]) {
+        const double s = sqrt(1.0 + V[0][0] - V[1][1] - V[2][2]) * 2.0;
+        qw = (V[2][1] - V[1][2]) / s; qx = 0.25 * s; qy = (V[0][1] + V[1][0]) / s; qz = (V[0][2] + V[2][0]) / s;
+    } else if (V[1][1] > V[2][2]) {
+        const double s = sqrt(1.0 + V[1][1] - V[0][0] - V[2][2]) * 2.0;
+        qw = (V[0][2] - V[2][0]) / s; qx = (V[0][1] + V[1][0]) / s; qy = 0.25 * s; qz = (V[1][2] + V[2][1]) / s;
+    } else {
+        const double s = sqrt(1.0 + V[2][2] - V[0][0] - V[1][1]) * 2.0;
+        qw = (V[1][0] - V[0][1]) / s; qx = (V[0][2] + V[2][0]) / s; qy = (V[1][2] + V[2][1]) / s; qz = 0.25 * s;
+    }
+    const double qn = sqrt(qx * qx + qy * qy + qz * qz + qw * qw);
+    frame_out[0] = (float)(qx / qn); frame_out[1] = (float)(qy / qn); frame_out[2] = (float)(qz / qn); frame_out[3] = (float)(qw / qn);
+    for (int k = 0; k < 3; ++k) { com_out[k] = (float)com[k]; pi_out[k] = (float)A[k][k]; }
+}
+
+
 // RigidBodyMassProps::recompute_mass_properties_from_colliders (rigid_body_components.rs:421).
 // `first_body` / `first_collider`: only the bodies from first_body on are computed, from the colliders from
 // first_collider on (rb_world_insert: appended bodies carry appended colliders only).
@@ -640,6 +725,7 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out, int fir
             }
         } else if (count[b] > 1) {
             float M = 0.0f, com[3] = {0, 0, 0};
+            bool simple = true;   // axis-aligned parts whose offsets from the centre of mass lie along one axis: the summed tensor is diagonal
             for (size_t ci = (size_t)first_collider; ci < W->colliders.size(); ++ci) {
                 const RbColliderDesc& c = W->colliders[ci];
                 if (c.parent != b || (c.sensor && c.density == 0.0f)) continue;
@@ -652,26 +738,46 @@ static int host_mass_props(const RbWorld* W, std::vector<HostMass>& out, int fir
             if (M != 0.0f) {
                 float invM = 1.0f / M;
                 for (int k = 0; k < 3; ++k) com[k] = com[k] * invM;
-                float I[3] = {0, 0, 0};
                 for (size_t ci = (size_t)first_collider; ci < W->colliders.size(); ++ci) {
                     const RbColliderDesc& c = W->colliders[ci];
                     if (c.parent != b || (c.sensor && c.density == 0.0f)) continue;
-                    if (!(c.pos_wrt_parent_q[0] == 0.0f && c.pos_wrt_parent_q[1] == 0.0f && c.pos_wrt_parent_q[2] == 0.0f)) {
-                        set_err("multi-collider bodies need axis-aligned colliders%s", "");
-                        return RB_ERR_INVALID;
-                    }
-                    float mass, pi[3];
-                    collider_mass_props(c, mass, pi);
+                    if (!(c.pos_wrt_parent_q[0] == 0.0f && c.pos_wrt_parent_q[1] == 0.0f && c.pos_wrt_parent_q[2] == 0.0f)) simple = false;
                     float d[3];
                     for (int k = 0; k < 3; ++k) d[k] = c.pos_wrt_parent_t[k] - com[k];
-                    if ((d[0] != 0.0f) + (d[1] != 0.0f) + (d[2] != 0.0f) > 1) {
-                        set_err("multi-collider bodies need colliders offset along one axis%s", "");
-                        return RB_ERR_INVALID;
-                    }
-                    float d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-                    for (int k = 0; k < 3; ++k) I[k] = I[k] + pi[k] + (d2 - d[k] * d[k]) * mass;
+                    if ((d[0] != 0.0f) + (d[1] != 0.0f) + (d[2] != 0.0f) > 1) simple = false;
                 }
-                for (int k = 0; k < 3; ++k) { m.lcom[k] = com[k]; m.ipi[k] = inv0(I[k]); }
+                if (simple) {
+                    float I[3] = {0, 0, 0};
+                    for (size_t ci = (size_t)first_collider; ci < W->colliders.size(); ++ci) {
+                        const RbColliderDesc& c = W->colliders[ci];
+                        if (c.parent != b || (c.sensor && c.density == 0.0f)) continue;
+                        float mass, pi[3];
+                        collider_mass_props(c, mass, pi);
+                        float d[3];
+                        for (int k = 0; k < 3; ++k) d[k] = c.pos_wrt_parent_t[k] - com[k];
+                        float d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                        for (int k = 0; k < 3; ++k) I[k] = I[k] + pi[k] + (d2 - d[k] * d[k]) * mass;
+                    }
+                    for (int k = 0; k < 3; ++k) { m.lcom[k] = com[k]; m.ipi[k] = inv0(I[k]); }
+                } else {   // compound bodies in general (e.g. stress_tests/compound3.rs): full tensor, principal axes by eigen-decomposition
+                    std::vector<float> pm;
+                    std::vector<std::array<float, 3>> ppi, pt;
+                    std::vector<std::array<float, 4>> pq;
+                    for (size_t ci = (size_t)first_collider; ci < W->colliders.size(); ++ci) {
+                        const RbColliderDesc& c = W->colliders[ci];
+                        if (c.parent != b || (c.sensor && c.density == 0.0f)) continue;
+                        float mass, pi[3];
+                        collider_mass_props(c, mass, pi);
+                        pm.push_back(mass);
+                        ppi.push_back({pi[0], pi[1], pi[2]});
+                        pt.push_back({c.pos_wrt_parent_t[0], c.pos_wrt_parent_t[1], c.pos_wrt_parent_t[2]});
+                        pq.push_back({c.pos_wrt_parent_q[0], c.pos_wrt_parent_q[1], c.pos_wrt_parent_q[2], c.pos_wrt_parent_q[3]});
+                    }
+                    float I[3];
+                    composite_inertia((int)pm.size(), pm.data(), reinterpret_cast<const float(*)[3]>(ppi.data()), reinterpret_cast<const float(*)[4]>(pq.data()),
+                                      reinterpret_cast<const float(*)[3]>(pt.data()), m.lcom, I, m.pframe);
+                    for (int k = 0; k < 3; ++k) m.ipi[k] = inv0(I[k]);
+                }
                 m.inv_mass = inv0(M);
             }
         }

@@ -141,6 +141,17 @@ def random_scene(seed):
                 s.colliders.insert(c.translation(tuple(float(x) for x in r3.uniform(-3.0, 3.0, 3))))
             else:
                 s.colliders.insert_with_parent(c.density(0.0), int(r3.choice(handles)))   # (massless: the body keeps its mass properties)
+    if r3.random() < 0.3:   # compound bodies: extra massive parts at arbitrary offsets and orientations (general composite inertia)
+        for _ in range(int(r3.integers(1, 4))):
+            h = int(r3.choice(handles))
+            if any(d.parent == h and d.shape == A.RB_SHAPE_CONVEX for d in s.colliders.descs):   # (no multi-collider bodies with hulls)
+                continue
+            c = (ColliderBuilder.ball(float(r3.uniform(0.15, 0.4))) if r3.random() < 0.3 else
+                 ColliderBuilder.cuboid(*(float(x) for x in r3.uniform(0.1, 0.6, 3))))
+            c = c.translation(tuple(float(x) for x in r3.uniform(-0.7, 0.7, 3))).density(float(r3.uniform(0.5, 3.0)))
+            if r3.random() < 0.6:
+                c = c.rotation(tuple(float(x) for x in r3.uniform(-1.0, 1.0, 3)))
+            s.colliders.insert_with_parent(c, h)
     if r3.random() < 0.3:   # substep solve-groups: extra substeps for the islands of a few bodies
         for h in r3.choice(handles, min(len(handles), int(r3.integers(1, 4))), replace=False):
             s.bodies.descs[int(h)].flags |= int(r3.choice([1, 2, 5])) << A.RB_BODY_EXTRA_ITERS_SHIFT

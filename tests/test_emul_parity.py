@@ -217,6 +217,20 @@ def test_sensors_emulated_kernels():
     sensors_parity_case(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), lambda s: oracle_lib.OracleWorld(s))
 
 
+def test_compound_bodies_emulated_kernels():
+    from parity_util import compare_worlds, is_exact
+    from test_oracle_kat import compound_bodies
+    from variant_cases import compound_pile
+    compound_bodies(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), n=4)
+    s = compound_pile()
+    w, o = PhysicsWorld(s, _lib=emul_lib.lib()), oracle_lib.OracleWorld(s)
+    for i in range(200):
+        w.step(); o.step()
+        if i % 20 == 19 or i < 2:
+            d = compare_worlds(w, o)
+            assert is_exact(d), (i, d)
+
+
 def test_dominance_groups_emulated_kernels():
     from test_oracle_kat import dominance_groups
     from variant_cases import dominance_parity_case

@@ -436,6 +436,23 @@ def test_sensors(built):
     sensors_parity_case(lambda s: PhysicsWorld(s), lambda s: oracle_lib.OracleWorld(s))
 
 
+def test_compound_bodies(built):
+    """Multi-collider bodies with general mass properties (full tensor diagonalised by the host): sleep_wide_bodies.rs (64 U-shaped
+    compounds all asleep after 300 steps, a still far-reaching body neither moves nor stays awake), a diagonal dumbbell spinning
+    about its principal axis / conserving angular momentum, an L shape at rest -- through the C ABI; a pile of U / L / dumbbell /
+    three-shape compounds bit-exact against the oracle."""
+    from test_oracle_kat import compound_bodies
+    from variant_cases import compound_pile
+    compound_bodies(lambda s: PhysicsWorld(s))
+    s = compound_pile()
+    w, o = PhysicsWorld(s), oracle_lib.OracleWorld(s)
+    for i in range(200):
+        w.step(); o.step()
+        if i % 20 == 19 or i < 2:
+            d = compare_worlds(w, o)
+            assert is_exact(d), (i, d)
+
+
 def test_convex_polyhedra(built):
     """ColliderBuilder::{convex_hull, round_convex_hull}: known answers through the C ABI (the convex_pile parity variants
     run with the other variants) and the reference's examples3d/convex_polyhedron3.rs drop (reduced: 5 x 5 x 4 round hulls of

@@ -993,6 +993,92 @@ def test_sensors_oracle():
     sensors(lambda s: oracle_lib.OracleWorld(s))
 
 
+# ---- compound bodies: general composite mass properties, wide bodies asleep (crates/rapier3d/tests/sleep_wide_bodies.rs) ----------
+def _wide_compound_scene(n=8):
+    """sleep_wide_bodies.rs:10-48: U-shaped compounds (a wide bar plus two uprights, max_extent ~ 4) at varied yaws."""
+    s = scenes.Scene("wide_compounds", gravity=(0.0, -9.81, 0.0))
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.1, 0.0)), ColliderBuilder.cuboid(50.0, 0.1, 50.0))
+    rad = 0.2
+    handles = []
+    for i in range(n):
+        for k in range(n):
+            h = s.insert(RigidBodyBuilder.dynamic().translation((i * 6.0, rad + 0.01, k * 6.0)).rotation((0.0, i * 0.11 + k * 0.037, 0.0)),
+                         ColliderBuilder.cuboid(rad * 10.0, rad, rad))
+            s.colliders.insert_with_parent(ColliderBuilder.cuboid(rad, rad * 10.0, rad).translation((rad * 10.0, rad * 10.0, 0.0)), h)
+            s.colliders.insert_with_parent(ColliderBuilder.cuboid(rad, rad * 10.0, rad).translation((-rad * 10.0, rad * 10.0, 0.0)), h)
+            handles.append(h)
+    return s, handles
+
+
+def compound_bodies(make_world, n=8):
+    """sleep_wide_bodies.rs: wide compounds at rest fall asleep (all of them), a still far-reaching body does not move at all and
+    sleeps.  The composite mass properties behind them: a dumbbell of two boxes rotated by 45 degrees about Z spins about its long
+    axis at constant rate (a principal axis found by the eigen-decomposition) and its angular momentum is conserved when it tumbles;
+    an L-shaped body (products of inertia non-zero in the body frame) dropped flat comes to rest flat."""
+    import math
+    s, handles = _wide_compound_scene(n)
+    w = make_world(s)
+    w.step(300)
+    asleep = w.sleeping()
+    assert all(asleep[h] for h in handles), int(sum(1 for h in handles if not asleep[h]))
+
+    s = scenes.Scene("still_wide", gravity=(0.0, 0.0, 0.0))
+    h = s.insert(RigidBodyBuilder.dynamic().rotation((0.3, -0.7, 0.15)), ColliderBuilder.cuboid(0.2, 8.0, 0.2))
+    w = make_world(s)
+    p0 = w.body_states()[0][h].copy()
+    w.step(200)
+    assert (w.body_states()[0][h].view(np.uint32) == p0.view(np.uint32)).all() and w.sleeping()[h]
+
+    # dumbbell along the (1, 1, 0) diagonal: two cubes offset by +-(1, 1, 0), each rotated 45 degrees about Z
+    q45 = (0.0, 0.0, math.pi / 4.0)
+    def dumbbell(angvel):
+        s = scenes.Scene("dumbbell", gravity=(0.0, 0.0, 0.0))
+        b = s.insert(RigidBodyBuilder.dynamic().angvel(angvel).can_sleep(False), ColliderBuilder.cuboid(0.5, 0.2, 0.2).translation((1.0, 1.0, 0.0)).rotation(q45))
+        s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.5, 0.2, 0.2).translation((-1.0, -1.0, 0.0)).rotation(q45), b)
+        return s, b
+    s, b = dumbbell((2.0 / math.sqrt(2.0), 2.0 / math.sqrt(2.0), 0.0))   # spin about the long (principal) axis
+    w = make_world(s)
+    w.step(120)
+    pose, vel = w.body_states()
+    assert np.allclose(vel[b, 3:], (math.sqrt(2.0), math.sqrt(2.0), 0.0), atol=2e-3), vel[b]
+    assert np.allclose(pose[b, :3], 0.0, atol=1e-4)
+    # tumbling about a non-principal axis: |L| = |I w| is conserved by the gyroscopic term; analytic principal moments
+    m = 0.5 * 0.2 * 0.2 * 8.0
+    i_long = 2.0 * (m * (0.2 ** 2 + 0.2 ** 2) / 3.0)
+    i_cross = 2.0 * (m * (0.5 ** 2 + 0.2 ** 2) / 3.0 + m * 2.0)
+    s, b = dumbbell((1.0, 0.0, 0.5))
+    w = make_world(s)
+    def ang_momentum():
+        pose, vel = w.body_states()
+        q = pose[b, 3:7].astype(np.float64)
+        x, y, z, ww = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * ww), 2 * (x * z + y * ww)],
+                      [2 * (x * y + z * ww), 1 - 2 * (x * x + z * z), 2 * (y * z - x * ww)],
+                      [2 * (x * z - y * ww), 2 * (y * z + x * ww), 1 - 2 * (x * x + y * y)]])
+        e = R @ (np.array([1.0, 1.0, 0.0]) / math.sqrt(2.0))     # the long axis in world space
+        om = vel[b, 3:].astype(np.float64)
+        return i_long * e * (e @ om) + i_cross * (om - e * (e @ om))
+    l0 = ang_momentum()
+    w.step(240)
+    l1 = ang_momentum()
+    assert np.linalg.norm(l1 - l0) < 0.01 * np.linalg.norm(l0), (l0, l1)
+
+    s = scenes.Scene("l_shape", gravity=(0.0, -9.81, 0.0))
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(10.0, 0.5, 10.0))
+    b = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.5, 0.0)).can_sleep(False), ColliderBuilder.cuboid(1.0, 0.2, 0.2))
+    s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.2, 0.2, 0.8).translation((0.8, 0.0, 1.0)).density(3.0), b)
+    w = make_world(s)
+    w.step(200)
+    pose, vel = w.body_states()
+    assert abs(pose[b, 1] - 0.2) < 0.01 and np.abs(vel[b]).max() < 0.02, (pose[b], vel[b])
+    q = pose[b, 3:7]
+    assert abs(float(q[0])) < 0.01 and abs(float(q[2])) < 0.01     # still flat
+
+
+def test_compound_bodies_oracle():
+    compound_bodies(lambda s: oracle_lib.OracleWorld(s))
+
+
 # ---- capsules (parry Capsule; ColliderBuilder::capsule_{x,y,z}) ------------------------------------------------------------------
 def capsules_rest(make_world):
     """Capsules of unit mass on a slab: lying (two-point manifold, rest height = radius), standing (rest height = half height +

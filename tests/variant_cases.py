@@ -213,6 +213,36 @@ def sensors_parity_case(make_world, make_oracle, steps=200, every=20):
     assert nsens > 30, nsens
 
 
+def compound_pile():
+    """Compound bodies with general mass properties (full inertia tensor diagonalised on the host): U shapes (stress_tests/compound3.rs),
+    L shapes of two densities, rotated dumbbells, a ball-and-stick of three shape families -- dropped in a pile with spin."""
+    s = scenes.Scene("compound_pile")
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(20.0, 0.5, 20.0))
+    k = 0
+    for layer in range(3):
+        for i in range(3):
+            for j in range(2):
+                pos = (-3.0 + 3.0 * i + 0.2 * layer, 1.5 + 2.6 * layer, -1.5 + 3.0 * j + 0.1 * i)
+                b = s.bodies.insert(RigidBodyBuilder.dynamic().translation(pos).rotation((0.3 * (k % 3), 0.2 * (k % 4), 0.1 * (k % 5))).angvel((0.5 * (k % 2), 0.0, 0.3 * (k % 3))))
+                kind = k % 4
+                if kind == 0:    # U
+                    s.colliders.insert_with_parent(ColliderBuilder.cuboid(1.0, 0.15, 0.15), b)
+                    s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.15, 0.6, 0.15).translation((1.0, 0.6, 0.0)), b)
+                    s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.15, 0.6, 0.15).translation((-1.0, 0.6, 0.0)), b)
+                elif kind == 1:  # L, heavy foot
+                    s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.8, 0.15, 0.15), b)
+                    s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.15, 0.15, 0.6).translation((0.65, 0.0, 0.75)).density(3.0), b)
+                elif kind == 2:  # dumbbell on a diagonal, parts rotated
+                    s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.4, 0.2, 0.2).translation((0.6, 0.6, 0.0)).rotation((0.0, 0.0, 0.7853981633974483)), b)
+                    s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.4, 0.2, 0.2).translation((-0.6, -0.6, 0.0)).rotation((0.0, 0.0, 0.7853981633974483)), b)
+                else:            # ball + capsule + box
+                    s.colliders.insert_with_parent(ColliderBuilder.ball(0.3).translation((0.0, 0.7, 0.2)), b)
+                    s.colliders.insert_with_parent(ColliderBuilder.capsule_y(0.4, 0.12), b)
+                    s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.3, 0.1, 0.3).translation((0.1, -0.5, 0.0)).rotation((0.0, 0.4, 0.0)), b)
+                k += 1
+    return s
+
+
 def kinematic_parity_case(make_world, make_oracle, steps=150, every=15):
     """A velocity-based kinematic turntable and conveyor carrying boxes and balls, and a position-based lift driven
     along a curve with a new target every step: bit-exact against the oracle."""
