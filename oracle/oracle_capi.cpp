@@ -300,6 +300,8 @@ int64_t orc_world_debug_read(OrcWorld* o, const char* table, void* dst, int64_t 
             for (int k = 0; k < 6; ++k) put<float>(b, j.impulses[k]);
     } else if (t == "joint_color") {
         for (const Joint& j : w.joints) put<int32_t>(b, j.color);
+    } else if (t == "island_of") {   // connected component (root body) of every dynamic / kinematic body, -1 otherwise (as of the last step)
+        for (size_t i = 0; i < w.bodies.size(); ++i) put<int32_t>(b, i < w.island_of.size() ? w.island_of[i] : -1);
     } else {
         return RB_ERR_INVALID;
     }

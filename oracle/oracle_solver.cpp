@@ -475,6 +475,15 @@ static float atan2_poly(float y, float x) {   // atan2 in (-pi, pi] from the [0,
     return y < 0.0f ? -a : a;
 }
 static const float FMAX = 3.4028234663852886e38f, FINF = __builtin_inff();
+// JointConstraintHelper::recentered_angle (joint_constraint_helper.rs:468-499): the joint angle about the limited axis measured
+// from the centre of the allowed range, from the axis' imaginary part x and the real part w of the (sign-corrected) relative
+// rotation and [cos, sin] of half the centre angle; wrapped to (-pi, pi].
+static float recentered_angle(float x, float w, float c_cos, float c_sin) {
+    const float sin_half = c_cos * x - c_sin * w, cos_half = c_cos * w + c_sin * x;
+    float half = atan2_poly(sin_half, cos_half);
+    if (fabsf(half) > 1.5707964f) half = half - copysignf(3.1415927f, half);
+    return half * 2.0f;
+}
 
 // JointConstraintHelper::finalize_constraints (joint_constraint_helper.rs:676-722) on rows [a, b)
 static void finalize_rows(JointRow* out, int a, int b, V3 imsum) {
@@ -682,11 +691,7 @@ static int joint_update(const World& w, const Joint& j, float sub_dt, JointRow* 
         const int ax = i - 3;
         // recentered_angle (joint_constraint_helper.rs:468-499) + limit_angular (:503-564)
         const float c_cos = j.ang_limit_center[ax][0], c_sin = j.ang_limit_center[ax][1], half_range = j.ang_limit_half_range[ax];
-        const float x = aerr[ax], wq = ang_err.w;
-        const float sin_half = c_cos * x - c_sin * wq, cos_half = c_cos * wq + c_sin * x;
-        float half = atan2_poly(sin_half, cos_half);
-        if (fabsf(half) > 1.5707964f) half = half - copysignf(3.1415927f, half);
-        const float ang = half * 2.0f;
+        const float ang = recentered_angle(aerr[ax], ang_err.w, c_cos, c_sin);
         const bool min_enabled = ang <= -half_range, max_enabled = half_range <= ang;
         JointRow& r = out[len++];
         const V3 ang_jac = bcol[ax];
@@ -1167,6 +1172,18 @@ int kat_solver(const char* name_c, const float* in, int n_in, float* out, int n_
         }
         out[28] = c.t_impulse[0]; out[29] = c.t_impulse[1]; out[30] = c.t_impulse_acc[0]; out[31] = c.t_impulse_acc[1];
         out[32] = c.w_impulse; out[33] = c.w_impulse_acc; out[34] = c.w_r;
+        return 0;
+    }
+    if (name == "recentered_angle") {   // in: theta (rotation of frame 2 about X), limit min, limit max -> the re-centred angle
+        if (n_in < 3 || n_out < 1) return -3;   // (JointConstraintHelper::new on identity / rotation-about-X frames + AngularLimitParams::new)
+        const float theta = in[0], lo = in[1], hi = in[2];
+        Q4 q1 = qidentity(), q2 = Q4{sinf(theta * 0.5f), 0.0f, 0.0f, cosf(theta * 0.5f)};
+        const float sgn = copysignf(1.0f, qdot(q1, q2));
+        Q4 e = qmul(qconj(q1), q2);
+        const float half_range = (hi - lo) * 0.5f;
+        float c_cos = 1.0f, c_sin = 0.0f;
+        if (!(half_range >= 3.14159265358979323846f || half_range != half_range)) { const float c = (lo + hi) * 0.5f; c_cos = cosf(c * 0.5f); c_sin = sinf(c * 0.5f); }
+        out[0] = recentered_angle(e.x * sgn, e.w * sgn, c_cos, c_sin);
         return 0;
     }
     if (name == "normal_solve" || name == "tangent_solve") {

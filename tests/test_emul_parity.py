@@ -231,6 +231,11 @@ def test_compound_bodies_emulated_kernels():
             assert is_exact(d), (i, d)
 
 
+def test_island_structure_emulated_kernels():
+    from test_oracle_kat import island_structure
+    island_structure(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), lambda w: w.physics_pipeline.label_components())
+
+
 def test_dominance_groups_emulated_kernels():
     from test_oracle_kat import dominance_groups
     from variant_cases import dominance_parity_case

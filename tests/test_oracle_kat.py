@@ -1079,6 +1079,59 @@ def test_compound_bodies_oracle():
     compound_bodies(lambda s: oracle_lib.OracleWorld(s))
 
 
+# ---- island structure (crates/rapier3d/tests/persistent_islands.rs; here islands are relabelled, not maintained: DESIGN dev. 5) ----
+def island_structure(make_world, island_of):
+    """persistent_islands.rs: touching boxes share an island and distant ones do not (merge_on_touch...); a teleported top box is
+    split off in the very step its contact stops (separation_splits_immediately) and stays apart (split_on_separation); removing
+    the middle box of a touching row splits the sides (body_removal_splits_row); a detached two-box chunk leaves together."""
+    def ground():
+        s = scenes.Scene("islands", gravity=(0.0, -9.81, 0.0))
+        s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(100.0, 0.5, 100.0))
+        return s
+    box = lambda s, x, y: s.insert(RigidBodyBuilder.dynamic().translation((x, y, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    same = lambda w, a, b: island_of(w)[a] >= 0 and island_of(w)[a] == island_of(w)[b]
+    s = ground()
+    bottom, top, lone = box(s, 0.0, 0.5), box(s, 0.0, 1.5), box(s, 20.0, 0.5)
+    w = make_world(s)
+    w.step(240)
+    assert same(w, bottom, top) and not same(w, bottom, lone)
+    w.set_body_states([top], pose7=[(40.0, 0.5, 0.0, 0.0, 0.0, 0.0, 1.0)])   # set_translation(.., wake_up = true)
+    w.wake_up([top])
+    w.step(1)
+    assert not same(w, bottom, top), "the split must happen in the very step the contact stops"
+    w.step(240)
+    assert not same(w, bottom, top)
+
+    s = ground()
+    left, middle, right = box(s, 0.0, 0.5), box(s, 1.0, 0.5), box(s, 2.0, 0.5)
+    w = make_world(s)
+    w.step(240)
+    assert same(w, left, right)
+    w.remove(middle) if hasattr(w, "remove") else w.remove_bodies([middle])
+    w.step(240)
+    assert not same(w, left, right), "removing the bridging body must split the island"
+
+    s = ground()
+    a, b = box(s, 0.0, 0.5), box(s, 0.0, 1.5)       # a stack of four; the upper two are teleported away together
+    c, d = box(s, 0.0, 2.5), box(s, 0.0, 3.5)
+    w = make_world(s)
+    w.step(240)
+    assert same(w, a, d)
+    pose = w.body_states()[0]
+    moved = []
+    for h in (c, d):
+        p = pose[h].copy(); p[0] += 30.0; p[1] -= 2.0
+        moved.append(p)
+    w.set_body_states([c, d], pose7=moved)
+    w.wake_up([c, d])
+    w.step(2)
+    assert same(w, c, d) and same(w, a, b) and not same(w, a, c)
+
+
+def test_island_structure_oracle():
+    island_structure(lambda s: oracle_lib.OracleWorld(s), lambda w: w.debug_read("island_of", np.int32))
+
+
 # ---- capsules (parry Capsule; ColliderBuilder::capsule_{x,y,z}) ------------------------------------------------------------------
 def capsules_rest(make_world):
     """Capsules of unit mass on a slab: lying (two-point manifold, rest height = radius), standing (rest height = half height +

@@ -14,7 +14,7 @@ import oracle_lib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DOC = json.load(open(os.path.join(HERE, "golden", "ref_vectors.json")))
-NOUT = {"pose_drift": 1, "reduce_manifold": 5, "normal_solve": 13, "tangent_solve": 14, "generate": 39}
+NOUT = {"pose_drift": 1, "reduce_manifold": 5, "normal_solve": 13, "tangent_solve": 14, "generate": 39, "recentered_angle": 1}
 
 
 def kat_oracle(name, x):
@@ -208,3 +208,21 @@ def test_schedule_colour_buckets_emulated_kernels():
 def test_schedule_colour_buckets_cuda(built):
     from rapier_b200.world import PhysicsWorld
     _schedule_case(lambda s: PhysicsWorld(s))
+
+
+def test_recentered_angle_slope_is_one_everywhere():
+    """joint_constraint_helper.rs:804-848 (the reference's own unit test of the angular-limit measure), on the oracle's
+    restatement -- whose arctangent is the explicit polynomial the kernels share: zero at the centre of the range, +half_range at
+    the upper limit, slope one everywhere on the circle except across the wrap at the antipode of the centre."""
+    import math
+    ang = lambda theta, lo, hi: float(kat_oracle("recentered_angle", [theta, lo, hi])[0])
+    for center_deg in (-180, -135, -90, 0, 45, 135, 180):
+        lo, hi = math.radians(center_deg - 45.0), math.radians(center_deg + 45.0)
+        assert abs(ang(math.radians(center_deg), lo, hi)) < 1.0e-5, center_deg
+        assert abs(ang(math.radians(center_deg + 45.0), lo, hi) - math.radians(45.0)) < 1.0e-4, center_deg
+        for theta_deg in range(-350, 351, 7):
+            theta, eps = math.radians(theta_deg), 1.0e-3
+            a0, a1 = ang(theta - eps, lo, hi), ang(theta + eps, lo, hi)
+            if abs(a1 - a0) > 1.0:
+                continue   # the wrap discontinuity itself
+            assert abs((a1 - a0) / (2.0 * eps) - 1.0) < 1.0e-2, (center_deg, theta_deg, (a1 - a0) / (2.0 * eps))
