@@ -1149,6 +1149,11 @@ int kat_world(const char* name_c, const float* in, int n_in, float* out, int n_o
         out[0] = relative_pose_drift(base, cur, in[14]);
         return 0;
     }
+    if (name == "combine_coeff") {   // coefficient_combine_rule.rs:51-84: c1, c2, rule1, rule2
+        if (n_in < 4 || n_out < 1) return -3;
+        out[0] = combine_coeff(in[0], in[1], (int)in[2], (int)in[3]);
+        return 0;
+    }
     if (name == "reduce_manifold") {   // manifold_reduction.rs:4-84
         if (n_in < 5 || n_out < 5) return -3;
         RawManifold m{};

@@ -1132,6 +1132,25 @@ def test_island_structure_oracle():
     island_structure(lambda s: oracle_lib.OracleWorld(s), lambda w: w.debug_read("island_of", np.int32))
 
 
+# ---- the sleep metric gates on displacement (rigid_body_components.rs:1563-1590 test_sleep_gates_position_corrections) -----------
+def sleep_gates_on_displacement(make_world):
+    """update_energy tolerates a per-step displacement of 2 * threshold * dt (threshold 0.05 m/s, halved inside the test): a free
+    body creeping at 1.5 x that budget never becomes eligible, one at 0.5 x the budget or at rest falls asleep."""
+    s = scenes.Scene("creep", gravity=(0.0, 0.0, 0.0))
+    budget_speed = 2.0 * 0.05
+    fast = s.insert(RigidBodyBuilder.dynamic().linvel((budget_speed * 1.5, 0.0, 0.0)), ColliderBuilder.ball(0.5))
+    slow = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 5.0, 0.0)).linvel((budget_speed * 0.5, 0.0, 0.0)), ColliderBuilder.ball(0.5))
+    still = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 10.0, 0.0)), ColliderBuilder.ball(0.5))
+    w = make_world(s)
+    w.step(300)   # 10 x time_until_sleep
+    asleep = w.sleeping()
+    assert not asleep[fast] and asleep[slow] and asleep[still], asleep
+
+
+def test_sleep_gates_on_displacement_oracle():
+    sleep_gates_on_displacement(lambda s: oracle_lib.OracleWorld(s))
+
+
 # ---- capsules (parry Capsule; ColliderBuilder::capsule_{x,y,z}) ------------------------------------------------------------------
 def capsules_rest(make_world):
     """Capsules of unit mass on a slab: lying (two-point manifold, rest height = radius), standing (rest height = half height +

@@ -14,7 +14,7 @@ import oracle_lib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DOC = json.load(open(os.path.join(HERE, "golden", "ref_vectors.json")))
-NOUT = {"pose_drift": 1, "reduce_manifold": 5, "normal_solve": 13, "tangent_solve": 14, "generate": 39, "recentered_angle": 1}
+NOUT = {"pose_drift": 1, "reduce_manifold": 5, "normal_solve": 13, "tangent_solve": 14, "generate": 39, "recentered_angle": 1, "combine_coeff": 1}
 
 
 def kat_oracle(name, x):
@@ -226,3 +226,17 @@ def test_recentered_angle_slope_is_one_everywhere():
             if abs(a1 - a0) > 1.0:
                 continue   # the wrap discontinuity itself
             assert abs((a1 - a0) / (2.0 * eps) - 1.0) < 1.0e-2, (center_deg, theta_deg, (a1 - a0) / (2.0 * eps))
+
+
+def test_coefficient_combine_rules():
+    """coefficient_combine_rule.rs:96-130 (the reference's unit tests, literal values): the geometric mean, its clamping of
+    negative coefficients, and rule priority (the larger rule wins)."""
+    from rapier_b200 import _abi as A
+    comb = lambda c1, c2, r1, r2: float(kat_oracle("combine_coeff", [c1, c2, r1, r2])[0])
+    g, avg = A.RB_COMBINE_GEOMETRIC_MEAN, A.RB_COMBINE_AVERAGE
+    assert comb(0.25, 1.0, g, g) == 0.5
+    assert comb(0.7, 0.0, g, g) == 0.0
+    assert comb(-0.5, 0.5, g, g) == 0.0
+    assert comb(-0.5, -0.5, g, g) == 0.0
+    assert comb(0.25, 1.0, g, avg) == 0.5
+    assert comb(0.25, 1.0, avg, avg) == 0.625
