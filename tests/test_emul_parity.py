@@ -234,8 +234,9 @@ def test_compound_bodies_emulated_kernels():
 def test_island_structure_emulated_kernels():
     from test_oracle_kat import island_structure
     island_structure(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), lambda w: w.physics_pipeline.label_components())
-    from test_oracle_kat import sleep_gates_on_displacement
+    from test_oracle_kat import multi_collider_slab_sleeps, sleep_gates_on_displacement
     sleep_gates_on_displacement(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()))
+    multi_collider_slab_sleeps(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), ni=20, nj=12)
 
 
 def test_dominance_groups_emulated_kernels():

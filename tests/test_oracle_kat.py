@@ -1151,6 +1151,26 @@ def test_sleep_gates_on_displacement_oracle():
     sleep_gates_on_displacement(lambda s: oracle_lib.OracleWorld(s))
 
 
+def multi_collider_slab_sleeps(make_world, ni=50, nj=40):
+    """crates/rapier3d/tests/issue_970_multi_collider_body_perf.rs (its behavioural half): one dynamic body made of ni x nj unit boxes
+    resting just above the ground settles on it (every one of its manifolds against the ground shares the two bodies: 128 colours, the
+    rest in the overflow colour) and falls asleep within 400 steps."""
+    s = scenes.Scene("slab", gravity=(0.0, -9.81, 0.0))
+    s.colliders.insert(ColliderBuilder.cuboid(100.0, 0.5, 100.0))
+    b = s.bodies.insert(RigidBodyBuilder.dynamic().translation((0.0, 1.05, 0.0)))
+    for i in range(ni):
+        for j in range(nj):
+            s.colliders.insert_with_parent(ColliderBuilder.cuboid(0.5, 0.5, 0.5).translation((i - ni / 2.0, 0.0, j - nj / 2.0)), b)
+    w = make_world(s)
+    w.step(400)
+    pose, _ = w.body_states()
+    assert w.sleeping()[b] and abs(pose[b, 1] - 1.0) < 0.01, pose[b]
+
+
+def test_multi_collider_slab_oracle():
+    multi_collider_slab_sleeps(lambda s: oracle_lib.OracleWorld(s, threads=8))
+
+
 # ---- capsules (parry Capsule; ColliderBuilder::capsule_{x,y,z}) ------------------------------------------------------------------
 def capsules_rest(make_world):
     """Capsules of unit mass on a slab: lying (two-point manifold, rest height = radius), standing (rest height = half height +
