@@ -32,6 +32,8 @@ int32_t orc_world_add_hull(OrcWorld* w, int32_t num_vertices, const float* verti
                            const int32_t* face_sizes, const int32_t* face_indices);   /* rb_world_add_hull */
 int orc_world_insert(OrcWorld* w, int32_t nb, const RbBodyDesc* bodies, int32_t nc, const RbColliderDesc* colliders);
 int orc_world_remove_bodies(OrcWorld* w, int32_t n, const int32_t* indices);
+int orc_world_insert_joints(OrcWorld* w, int32_t n, const RbJointDesc* joints);      /* rb_world_insert_joints */
+int orc_world_remove_joints(OrcWorld* w, int32_t n, const int32_t* indices);        /* rb_world_remove_joints */
 int orc_world_set_body_states(OrcWorld* w, int32_t n, const int32_t* indices, const float* pose7,
                               const float* vel6);
 int orc_world_step(OrcWorld* w, const float gravity[3], int32_t nsteps);

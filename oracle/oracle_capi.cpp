@@ -10,6 +10,8 @@ void step_once(World& w, V3 gravity);
 int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDesc* cd, int nj, const RbJointDesc* jd);
 int insert(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDesc* cd);
 int remove_bodies(World& w, int n, const int* indices);
+int insert_joints(World& w, int n, const RbJointDesc* jd);
+int remove_joints(World& w, int n, const int* indices);
 void update_world_mass_properties(Body& b);
 void refresh_collider(World& w, Collider& c);
 void set_threads(int n);
@@ -126,6 +128,14 @@ int orc_world_insert(OrcWorld* w, int32_t nb, const RbBodyDesc* bodies, int32_t 
 int orc_world_remove_bodies(OrcWorld* w, int32_t n, const int32_t* indices) {
     if (!w || n < 0) return RB_ERR_INVALID;
     return remove_bodies(w->w, n, indices);
+}
+int orc_world_insert_joints(OrcWorld* w, int32_t n, const RbJointDesc* joints) {
+    if (!w || n < 0 || (n && !joints)) return RB_ERR_INVALID;
+    return insert_joints(w->w, n, joints);
+}
+int orc_world_remove_joints(OrcWorld* w, int32_t n, const int32_t* indices) {
+    if (!w || n < 0 || (n && !indices)) return RB_ERR_INVALID;
+    return remove_joints(w->w, n, indices);
 }
 int orc_world_set_body_states(OrcWorld* o, int32_t n, const int32_t* indices, const float* pose7, const float* vel6) {
     if (!o) return RB_ERR_INVALID;

@@ -186,6 +186,7 @@ struct Joint {
     RbJointMotor motors[6];
     float ang_limit_center[3][2], ang_limit_half_range[3];   // AngularLimitParams (joint_constraint_helper.rs:34-73)
     float limit_impulses[6], motor_impulses[6];
+    bool removed;                      // ImpulseJointSet::remove: the slot stays, the joint is neither solved nor an island edge
 };
 
 struct JointRow {  // JointConstraint<Real,1> (joint_velocity_constraint.rs:68-93)

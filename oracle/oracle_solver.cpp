@@ -942,7 +942,7 @@ void solve_island(World& w, V3 gravity) {
         Joint& j = w.joints[i];
         const Body& b1 = w.bodies[j.body1];
         const Body& b2 = w.bodies[j.body2];
-        const bool active = b1.is_awake() || b2.is_awake();   // joints of a sleeping island are not solved
+        const bool active = !j.removed && (b1.is_awake() || b2.is_awake());   // joints of a sleeping island are not solved
         jcolors[i] = active ? j.color : -1;
         j.sid1 = b1.is_awake() ? (uint32_t)j.body1 : NO_BODY;
         j.sid2 = b2.is_awake() ? (uint32_t)j.body2 : NO_BODY;

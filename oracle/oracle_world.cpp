@@ -811,7 +811,7 @@ static void label_islands(World& w) {
     for (const Pair& p : w.pairs)
         if (p.nsc > 0 && p.b1 >= 0 && p.b2 >= 0 && w.bodies[p.b1].is_dynamic() && w.bodies[p.b2].is_dynamic()) unite(p.b1, p.b2);
     for (const Joint& j : w.joints)
-        if (w.bodies[j.body1].is_dynamic() && w.bodies[j.body2].is_dynamic()) unite(j.body1, j.body2);
+        if (!j.removed && w.bodies[j.body1].is_dynamic() && w.bodies[j.body2].is_dynamic()) unite(j.body1, j.body2);
     w.island_of.assign(nb, -1);
     for (int i = 0; i < nb; ++i)
         if (w.bodies[i].is_dynamic()) w.island_of[i] = dsu_find(parent, i);
@@ -941,6 +941,97 @@ void step_once(World& w, V3 gravity) {
 static inline V3 f3(const float* p) { return V3{p[0], p[1], p[2]}; }
 static inline Q4 f4(const float* p) { return Q4{p[0], p[1], p[2], p[3]}; }
 
+// One joint of the ImpulseJointSet from its descriptor (generic_joint.rs:142-300; AngularLimitParams::new,
+// joint_constraint_helper.rs:44-73); impulses start at zero.
+static int fill_joint(World& w, Joint& j, const RbJointDesc& d) {
+    const int nb = (int)w.bodies.size();
+    if (d.body1 < 0 || d.body1 >= nb || d.body2 < 0 || d.body2 >= nb) return RB_ERR_INVALID;
+    j.removed = false;
+    j.body1 = d.body1;
+    j.body2 = d.body2;
+    j.local_frame1 = Pose{f4(d.local_frame1_q), f3(d.local_frame1_t)};
+    j.local_frame2 = Pose{f4(d.local_frame2_q), f3(d.local_frame2_t)};
+    j.locked_axes = d.locked_axes;
+    j.contacts_enabled = d.contacts_enabled;
+    j.natural_frequency = d.natural_frequency;
+    j.damping_ratio = d.damping_ratio;
+    j.limit_axes = d.limit_axes; j.motor_axes = d.motor_axes; j.coupled_axes = d.coupled_axes & 63u;
+    for (int k = 0; k < 6; ++k) {
+        j.impulses[k] = 0.0f; j.limit_impulses[k] = 0.0f; j.motor_impulses[k] = 0.0f;
+        j.limits[k][0] = d.limits[k][0]; j.limits[k][1] = d.limits[k][1];
+        j.motors[k] = d.motors[k];
+    }
+    for (int k = 0; k < 3; ++k) {   // AngularLimitParams::new (joint_constraint_helper.rs:44-73)
+        const float lo = d.limits[3 + k][0], hi = d.limits[3 + k][1];
+        const float half_range = (hi - lo) * 0.5f;
+        if (half_range >= 3.14159265358979323846f || half_range != half_range) {
+            j.ang_limit_center[k][0] = 1.0f; j.ang_limit_center[k][1] = 0.0f; j.ang_limit_half_range[k] = 10.0f;
+        } else {
+            const float center = (lo + hi) * 0.5f;
+            j.ang_limit_center[k][0] = cosf(center * 0.5f); j.ang_limit_center[k][1] = sinf(center * 0.5f);
+            j.ang_limit_half_range[k] = half_range;
+        }
+    }
+    return RB_OK;
+}
+
+// Everything derived from the joint set as a whole, recomputed whenever it changes (scene upload, insert_joints,
+// remove_joints -- as the library's upload_joints does): the body pairs whose contacts a joint disables, and the greedy first-fit
+// colouring in joint order (interaction_groups.rs:59-165: dyn-dyn from colour 0 up (< 120), dyn-fixed from 127 down).
+static void refresh_joint_set(World& w) {
+    const int nb = (int)w.bodies.size();
+    w.nocontact_body_pairs.clear();
+    for (const Joint& j : w.joints) {
+        if (j.removed || j.contacts_enabled) continue;
+        uint32_t lo = (uint32_t)std::min(j.body1, j.body2), hi = (uint32_t)std::max(j.body1, j.body2);
+        w.nocontact_body_pairs.push_back(((uint64_t)lo << 32) | hi);
+    }
+    std::sort(w.nocontact_body_pairs.begin(), w.nocontact_body_pairs.end());
+    std::vector<Mask128> jm(nb);
+    for (Joint& j : w.joints) {
+        if (j.removed) { j.color = -1; continue; }
+        bool d1 = w.bodies[j.body1].is_dynamic(), d2 = w.bodies[j.body2].is_dynamic();
+        j.sid1 = d1 ? (uint32_t)j.body1 : NO_BODY;
+        j.sid2 = d2 ? (uint32_t)j.body2 : NO_BODY;
+        j.color = 128;
+        if (d1 && d2) {
+            for (int c = 0; c < DYNAMIC_COLOR_COUNT; ++c)
+                if (!jm[j.body1].test(c) && !jm[j.body2].test(c)) { j.color = c; break; }
+            if (j.color < 128) { jm[j.body1].set(j.color); jm[j.body2].set(j.color); }
+        } else if (d1 || d2) {
+            int b = d1 ? j.body1 : j.body2;
+            for (int c = 127; c >= 0; --c)
+                if (!jm[b].test(c)) { j.color = c; break; }
+            if (j.color < 128) jm[b].set(j.color);
+        } else {
+            j.color = -1;  // both fixed: never selected (impulse_joint_set.rs:548-553)
+        }
+    }
+    w.bp_dirty = true;        // (the pair filter changed)
+    w.islands_dirty = true;
+}
+
+// Mirrors of rb_world_insert_joints / rb_world_remove_joints (ImpulseJointSet::insert / remove after the upload).
+int insert_joints(World& w, int n, const RbJointDesc* jd) {
+    const size_t n0 = w.joints.size();
+    w.joints.resize(n0 + n, Joint{});
+    for (int i = 0; i < n; ++i) {
+        int rc = fill_joint(w, w.joints[n0 + i], jd[i]);
+        if (rc != RB_OK) { w.joints.resize(n0); return rc; }
+    }
+    refresh_joint_set(w);
+    w.counters.num_joints = (int)w.joints.size();
+    return RB_OK;
+}
+int remove_joints(World& w, int n, const int* indices) {
+    for (int k = 0; k < n; ++k) {
+        if (indices[k] < 0 || indices[k] >= (int)w.joints.size()) return RB_ERR_INVALID;
+        w.joints[indices[k]].removed = true;
+    }
+    refresh_joint_set(w);
+    return RB_OK;
+}
+
 int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDesc* cd, int nj,
               const RbJointDesc* jd) {
     w.bodies.assign(nb, Body{});
@@ -988,7 +1079,6 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
         c.restitution_rule = d.restitution_combine_rule;
         c.contact_skin = d.contact_skin;
         c.active_events = d.active_events;
-    c.sensor = d.sensor;
         c.sensor = d.sensor;
     c.force_event_threshold = d.contact_force_event_threshold;
     c.memberships = d.collision_memberships;
@@ -999,63 +1089,11 @@ int set_scene(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDe
     if (rc != RB_OK) return rc;
     for (Body& b : w.bodies) update_world_mass_properties(b);
     for (Collider& c : w.colliders) refresh_collider(w, c);
-    w.nocontact_body_pairs.clear();
     for (int i = 0; i < nj; ++i) {
-        Joint& j = w.joints[i];
-        const RbJointDesc& d = jd[i];
-        if (d.body1 < 0 || d.body1 >= nb || d.body2 < 0 || d.body2 >= nb) return RB_ERR_INVALID;
-        j.body1 = d.body1;
-        j.body2 = d.body2;
-        j.local_frame1 = Pose{f4(d.local_frame1_q), f3(d.local_frame1_t)};
-        j.local_frame2 = Pose{f4(d.local_frame2_q), f3(d.local_frame2_t)};
-        j.locked_axes = d.locked_axes;
-        j.contacts_enabled = d.contacts_enabled;
-        j.natural_frequency = d.natural_frequency;
-        j.damping_ratio = d.damping_ratio;
-        j.limit_axes = d.limit_axes; j.motor_axes = d.motor_axes; j.coupled_axes = d.coupled_axes & 63u;
-        for (int k = 0; k < 6; ++k) {
-            j.impulses[k] = 0.0f; j.limit_impulses[k] = 0.0f; j.motor_impulses[k] = 0.0f;
-            j.limits[k][0] = d.limits[k][0]; j.limits[k][1] = d.limits[k][1];
-            j.motors[k] = d.motors[k];
-        }
-        for (int k = 0; k < 3; ++k) {   // AngularLimitParams::new (joint_constraint_helper.rs:44-73)
-            const float lo = d.limits[3 + k][0], hi = d.limits[3 + k][1];
-            const float half_range = (hi - lo) * 0.5f;
-            if (half_range >= 3.14159265358979323846f || half_range != half_range) {
-                j.ang_limit_center[k][0] = 1.0f; j.ang_limit_center[k][1] = 0.0f; j.ang_limit_half_range[k] = 10.0f;
-            } else {
-                const float center = (lo + hi) * 0.5f;
-                j.ang_limit_center[k][0] = cosf(center * 0.5f); j.ang_limit_center[k][1] = sinf(center * 0.5f);
-                j.ang_limit_half_range[k] = half_range;
-            }
-        }
-        if (!d.contacts_enabled) {
-            uint32_t lo = (uint32_t)std::min(d.body1, d.body2), hi = (uint32_t)std::max(d.body1, d.body2);
-            w.nocontact_body_pairs.push_back(((uint64_t)lo << 32) | hi);
-        }
+        int rcj = fill_joint(w, w.joints[i], jd[i]);
+        if (rcj != RB_OK) return rcj;
     }
-    std::sort(w.nocontact_body_pairs.begin(), w.nocontact_body_pairs.end());
-    // Joint colouring: greedy first fit in joint order (interaction_groups.rs:59-165), dyn-dyn from
-    // colour 0 up (< 120), dyn-fixed from 127 down.
-    std::vector<Mask128> jm(nb);
-    for (Joint& j : w.joints) {
-        bool d1 = w.bodies[j.body1].is_dynamic(), d2 = w.bodies[j.body2].is_dynamic();
-        j.sid1 = d1 ? (uint32_t)j.body1 : NO_BODY;
-        j.sid2 = d2 ? (uint32_t)j.body2 : NO_BODY;
-        j.color = 128;
-        if (d1 && d2) {
-            for (int c = 0; c < DYNAMIC_COLOR_COUNT; ++c)
-                if (!jm[j.body1].test(c) && !jm[j.body2].test(c)) { j.color = c; break; }
-            if (j.color < 128) { jm[j.body1].set(j.color); jm[j.body2].set(j.color); }
-        } else if (d1 || d2) {
-            int b = d1 ? j.body1 : j.body2;
-            for (int c = 127; c >= 0; --c)
-                if (!jm[b].test(c)) { j.color = c; break; }
-            if (j.color < 128) jm[b].set(j.color);
-        } else {
-            j.color = -1;  // both fixed: never selected (impulse_joint_set.rs:548-553)
-        }
-    }
+    refresh_joint_set(w);
     w.counters = RbCounters{};
     w.counters.num_bodies = nb;
     w.counters.num_colliders = nc;
@@ -1095,6 +1133,7 @@ static void fill_collider(Collider& c, const RbColliderDesc& d) {
     c.restitution_rule = d.restitution_combine_rule;
     c.contact_skin = d.contact_skin;
     c.active_events = d.active_events;
+    c.sensor = d.sensor;
     c.force_event_threshold = d.contact_force_event_threshold;
     c.memberships = d.collision_memberships;
     c.filter = d.collision_filter;

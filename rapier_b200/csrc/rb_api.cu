@@ -451,6 +451,8 @@ struct RbWorld {
     std::vector<rbhull::Hull> hulls;   // convex polyhedra (rb_world_add_hull); hull 0 = the unit cube
     int hulls_uploaded = 0;            // how many of them the device tables hold
     bool force_events = false;   // some collider has RB_EVENT_CONTACT_FORCE: run k_force_events after every step
+    std::vector<unsigned char> joint_removed;   // tombstones of rb_world_remove_joints (slots stay allocated)
+    int reserve_joints = 0, reserve_generic = 0;   // rb_world_reserve_joints
     std::vector<int> extra_keys; // distinct additional_solver_iterations of the bodies, descending (substep solve-groups); {0} = none
     int steps_since_scene = 0;   // the launch-shape hint of a new scene is awaited once (see rb_world_step)
     int coop_shape = -1;   // RB_COOP_SHAPE debugging override: 0 small, 1 big, -1 automatic
@@ -1179,6 +1181,105 @@ int rb_world_set_params(RbWorld* W, const RbIntegrationParameters* params) {
     return RB_OK;
 }
 
+// ImpulseJointSet -> device: static joint data, greedy colouring in joint order (interaction_groups.rs:59-165), stage order
+// (joints.rs:318-392), the body pairs whose contacts a joint disables.  Runs at scene upload and again whenever joints are
+// inserted or removed (rb_world_insert_joints / rb_world_remove_joints): everything is recomputed from the host's joint list,
+// the warm-start impulses of the surviving joints stay where they are.
+static int upload_joints(RbWorld* W) {
+    World& w = W->w;
+    const int NJ = w.joint_cap, NB = W->body_cap, nj = w.nj;
+    const RbJointDesc* joints = W->joints.data();
+    const RbBodyDesc* bodies = W->bodies.data();
+    W->joint_removed.resize(W->joints.size(), 0);
+        std::vector<int4> info(NJ, make_int4(-1, -1, 0, -1));
+        std::vector<float4> f1t(NJ), f1q(NJ), f2t(NJ), f2q(NJ);
+        std::vector<float2> soft(NJ);
+        std::vector<unsigned long long> nocontact;
+        struct M128 { unsigned m[4] = {0, 0, 0, 0}; bool test(int c) const { return (m[c >> 5] >> (c & 31)) & 1u; } void set(int c) { m[c >> 5] |= 1u << (c & 31); } };
+        std::vector<M128> jm(NB);
+        std::vector<int> ccount(NUM_COLORS, 0);
+        for (int i = 0; i < nj; ++i) {
+            const RbJointDesc& j = joints[i];
+            if (W->joint_removed[i]) continue;   // a removed joint keeps its slot: bodies -1 (never selected, no island edge), no colour
+            bool d1 = type_moves(bodies[j.body1].body_type), d2 = type_moves(bodies[j.body2].body_type);   // (kinematic bodies conflict like dynamic ones)
+            int color = -1;
+            if (d1 && d2) {
+                color = 128;
+                for (int c = 0; c < DYN_COLOR_COUNT; ++c)
+                    if (!jm[j.body1].test(c) && !jm[j.body2].test(c)) { color = c; break; }
+                if (color < 128) { jm[j.body1].set(color); jm[j.body2].set(color); }
+            } else if (d1 || d2) {
+                int b = d1 ? j.body1 : j.body2;
+                color = 128;
+                for (int c = 127; c >= 0; --c)
+                    if (!jm[b].test(c)) { color = c; break; }
+                if (color < 128) jm[b].set(color);
+            }
+            if (color >= 0) ccount[color]++;
+            info[i] = make_int4(j.body1, j.body2, (int)j.locked_axes, color);
+            f1t[i] = make_float4(j.local_frame1_t[0], j.local_frame1_t[1], j.local_frame1_t[2], 0.f);
+            f1q[i] = make_float4(j.local_frame1_q[0], j.local_frame1_q[1], j.local_frame1_q[2], j.local_frame1_q[3]);
+            f2t[i] = make_float4(j.local_frame2_t[0], j.local_frame2_t[1], j.local_frame2_t[2], 0.f);
+            f2q[i] = make_float4(j.local_frame2_q[0], j.local_frame2_q[1], j.local_frame2_q[2], j.local_frame2_q[3]);
+            soft[i] = make_float2(j.natural_frequency, j.damping_ratio);
+            if (!j.contacts_enabled) {
+                unsigned lo = (unsigned)std::min(j.body1, j.body2), hi = (unsigned)std::max(j.body1, j.body2);
+                nocontact.push_back(((unsigned long long)lo << 32) | hi);
+            }
+        }
+        std::sort(nocontact.begin(), nocontact.end());
+        nocontact.erase(std::unique(nocontact.begin(), nocontact.end()), nocontact.end());
+        std::vector<int> jpos(NUM_COLORS + 1, -1);
+        int pos = 0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int c = 0; c < 128; ++c) {
+                if (ccount[c] == 0 || (ccount[c] >= BIG_JCOLOR_MIN) != (pass == 0)) continue;
+                jpos[c] = pos++;
+            }
+        if (ccount[128] > 0) jpos[128] = pos++;
+        W->njused = pos;
+        CK(h2d(w.j_info, info.data(), NJ * sizeof(int4)));
+        CK(h2d(w.j_f1_t, f1t.data(), NJ * sizeof(float4)));
+        CK(h2d(w.j_f1_q, f1q.data(), NJ * sizeof(float4)));
+        CK(h2d(w.j_f2_t, f2t.data(), NJ * sizeof(float4)));
+        CK(h2d(w.j_f2_q, f2q.data(), NJ * sizeof(float4)));
+        CK(h2d(w.j_soft, soft.data(), NJ * sizeof(float2)));
+        if (w.generic_joints) {
+            std::vector<uint2> axes(NJ);
+            std::vector<float2> lim((size_t)NJ * 6), mb((size_t)NJ * 6);
+            std::vector<float4> ma((size_t)NJ * 6), al((size_t)NJ * 3);
+            for (int i = 0; i < nj; ++i) {
+                const RbJointDesc& j = joints[i];
+                axes[i] = make_uint2((j.limit_axes & 63u) | ((j.coupled_axes & 63u) << 8), j.motor_axes);
+                for (int k = 0; k < 6; ++k) {
+                    lim[(size_t)i * 6 + k] = make_float2(j.limits[k][0], j.limits[k][1]);
+                    ma[(size_t)i * 6 + k] = make_float4(j.motors[k].target_vel, j.motors[k].target_pos, j.motors[k].stiffness, j.motors[k].damping);
+                    float model_bits;
+                    memcpy(&model_bits, &j.motors[k].model, 4);
+                    mb[(size_t)i * 6 + k] = make_float2(j.motors[k].max_force, model_bits);
+                }
+                for (int k = 0; k < 3; ++k) {   // AngularLimitParams::new (joint_constraint_helper.rs:44-73)
+                    const float lo = j.limits[3 + k][0], hi = j.limits[3 + k][1];
+                    const float half_range = (hi - lo) * 0.5f;
+                    if (half_range >= 3.14159265358979323846f || half_range != half_range) al[(size_t)i * 3 + k] = make_float4(1.0f, 0.0f, 10.0f, 0.0f);
+                    else {
+                        const float center = (lo + hi) * 0.5f;
+                        al[(size_t)i * 3 + k] = make_float4(cosf(center * 0.5f), sinf(center * 0.5f), half_range, 0.0f);
+                    }
+                }
+            }
+            CK(h2d(w.j_axes, axes.data(), NJ * sizeof(uint2)));
+            CK(h2d(w.j_limits, lim.data(), lim.size() * sizeof(float2)));
+            CK(h2d(w.j_motor_a, ma.data(), ma.size() * sizeof(float4)));
+            CK(h2d(w.j_motor_b, mb.data(), mb.size() * sizeof(float2)));
+            CK(h2d(w.j_anglim, al.data(), al.size() * sizeof(float4)));
+        }
+        CK(h2d(w.jcolor_pos, jpos.data(), (NUM_COLORS + 1) * sizeof(int)));
+        w.n_nocontact = (int)nocontact.size();
+        CK(h2d(w.nocontact_keys, nocontact.data(), nocontact.size() * sizeof(unsigned long long)));
+    return RB_OK;
+}
+
 int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t nc, const RbColliderDesc* colliders,
                        int32_t nj, const RbJointDesc* joints) {
     if (!W || nb < 0 || nc < 0 || nj < 0 || (nb && !bodies) || (nc && !colliders) || (nj && !joints)) {
@@ -1230,10 +1331,10 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
     ndyn_col += NC - std::max(nc, 1);
     w.pair_cap = next_pow2_host(std::max(4096, 16 * ndyn_col)) + 160;   // (+160: row strides that are no power of two spread the rows of a record over the L2 slices)
     w.cons_cap = w.pair_cap;
-    w.joint_cap = std::max(nj, 1);
+    w.joint_cap = std::max(std::max(nj, W->reserve_joints), 1);
     w.item_cap = 4 + (NB + w.pair_cap + nj) / ITEM_TARGET;
     const int NJ = w.joint_cap;
-    w.generic_joints = (nj > 0 && W->params.warmstart_joints) ? 1 : 0;   // joint warm starting: generic path too
+    w.generic_joints = ((nj > 0 && W->params.warmstart_joints) || W->reserve_generic) ? 1 : 0;   // joint warm starting: generic path too
     for (int i = 0; i < nj; ++i) {   // any limit or motor on a free axis: the generic joint path (12 row slots per joint)
         const unsigned free_axes = ~joints[i].locked_axes & 63u;
         if ((joints[i].limit_axes | joints[i].motor_axes) & free_axes) w.generic_joints = 1;   // (coupled axes only act through a limit or a motor)
@@ -1316,95 +1417,11 @@ int rb_world_set_scene(RbWorld* W, int32_t nb, const RbBodyDesc* bodies, int32_t
         rc = upload_colliders(W, 0, nc);
         if (rc != RB_OK) return rc;
     }
-    // ---- joints: static data, greedy colouring (interaction_groups.rs:59-165), stage order (joints.rs:318-392) ----
-    {
-        std::vector<int4> info(NJ, make_int4(0, 0, 0, -1));
-        std::vector<float4> f1t(NJ), f1q(NJ), f2t(NJ), f2q(NJ);
-        std::vector<float2> soft(NJ);
-        std::vector<unsigned long long> nocontact;
-        struct M128 { unsigned m[4] = {0, 0, 0, 0}; bool test(int c) const { return (m[c >> 5] >> (c & 31)) & 1u; } void set(int c) { m[c >> 5] |= 1u << (c & 31); } };
-        std::vector<M128> jm(NB);
-        std::vector<int> ccount(NUM_COLORS, 0);
-        for (int i = 0; i < nj; ++i) {
-            const RbJointDesc& j = joints[i];
-            bool d1 = type_moves(bodies[j.body1].body_type), d2 = type_moves(bodies[j.body2].body_type);   // (kinematic bodies conflict like dynamic ones)
-            int color = -1;
-            if (d1 && d2) {
-                color = 128;
-                for (int c = 0; c < DYN_COLOR_COUNT; ++c)
-                    if (!jm[j.body1].test(c) && !jm[j.body2].test(c)) { color = c; break; }
-                if (color < 128) { jm[j.body1].set(color); jm[j.body2].set(color); }
-            } else if (d1 || d2) {
-                int b = d1 ? j.body1 : j.body2;
-                color = 128;
-                for (int c = 127; c >= 0; --c)
-                    if (!jm[b].test(c)) { color = c; break; }
-                if (color < 128) jm[b].set(color);
-            }
-            if (color >= 0) ccount[color]++;
-            info[i] = make_int4(j.body1, j.body2, (int)j.locked_axes, color);
-            f1t[i] = make_float4(j.local_frame1_t[0], j.local_frame1_t[1], j.local_frame1_t[2], 0.f);
-            f1q[i] = make_float4(j.local_frame1_q[0], j.local_frame1_q[1], j.local_frame1_q[2], j.local_frame1_q[3]);
-            f2t[i] = make_float4(j.local_frame2_t[0], j.local_frame2_t[1], j.local_frame2_t[2], 0.f);
-            f2q[i] = make_float4(j.local_frame2_q[0], j.local_frame2_q[1], j.local_frame2_q[2], j.local_frame2_q[3]);
-            soft[i] = make_float2(j.natural_frequency, j.damping_ratio);
-            if (!j.contacts_enabled) {
-                unsigned lo = (unsigned)std::min(j.body1, j.body2), hi = (unsigned)std::max(j.body1, j.body2);
-                nocontact.push_back(((unsigned long long)lo << 32) | hi);
-            }
-        }
-        std::sort(nocontact.begin(), nocontact.end());
-        nocontact.erase(std::unique(nocontact.begin(), nocontact.end()), nocontact.end());
-        std::vector<int> jpos(NUM_COLORS + 1, -1);
-        int pos = 0;
-        for (int pass = 0; pass < 2; ++pass)
-            for (int c = 0; c < 128; ++c) {
-                if (ccount[c] == 0 || (ccount[c] >= BIG_JCOLOR_MIN) != (pass == 0)) continue;
-                jpos[c] = pos++;
-            }
-        if (ccount[128] > 0) jpos[128] = pos++;
-        W->njused = pos;
-        CK(h2d(w.j_info, info.data(), NJ * sizeof(int4)));
-        CK(h2d(w.j_f1_t, f1t.data(), NJ * sizeof(float4)));
-        CK(h2d(w.j_f1_q, f1q.data(), NJ * sizeof(float4)));
-        CK(h2d(w.j_f2_t, f2t.data(), NJ * sizeof(float4)));
-        CK(h2d(w.j_f2_q, f2q.data(), NJ * sizeof(float4)));
-        CK(h2d(w.j_soft, soft.data(), NJ * sizeof(float2)));
-        if (w.generic_joints) {
-            std::vector<uint2> axes(NJ);
-            std::vector<float2> lim((size_t)NJ * 6), mb((size_t)NJ * 6);
-            std::vector<float4> ma((size_t)NJ * 6), al((size_t)NJ * 3);
-            for (int i = 0; i < nj; ++i) {
-                const RbJointDesc& j = joints[i];
-                axes[i] = make_uint2((j.limit_axes & 63u) | ((j.coupled_axes & 63u) << 8), j.motor_axes);
-                for (int k = 0; k < 6; ++k) {
-                    lim[(size_t)i * 6 + k] = make_float2(j.limits[k][0], j.limits[k][1]);
-                    ma[(size_t)i * 6 + k] = make_float4(j.motors[k].target_vel, j.motors[k].target_pos, j.motors[k].stiffness, j.motors[k].damping);
-                    float model_bits;
-                    memcpy(&model_bits, &j.motors[k].model, 4);
-                    mb[(size_t)i * 6 + k] = make_float2(j.motors[k].max_force, model_bits);
-                }
-                for (int k = 0; k < 3; ++k) {   // AngularLimitParams::new (joint_constraint_helper.rs:44-73)
-                    const float lo = j.limits[3 + k][0], hi = j.limits[3 + k][1];
-                    const float half_range = (hi - lo) * 0.5f;
-                    if (half_range >= 3.14159265358979323846f || half_range != half_range) al[(size_t)i * 3 + k] = make_float4(1.0f, 0.0f, 10.0f, 0.0f);
-                    else {
-                        const float center = (lo + hi) * 0.5f;
-                        al[(size_t)i * 3 + k] = make_float4(cosf(center * 0.5f), sinf(center * 0.5f), half_range, 0.0f);
-                    }
-                }
-            }
-            CK(h2d(w.j_axes, axes.data(), NJ * sizeof(uint2)));
-            CK(h2d(w.j_limits, lim.data(), lim.size() * sizeof(float2)));
-            CK(h2d(w.j_motor_a, ma.data(), ma.size() * sizeof(float4)));
-            CK(h2d(w.j_motor_b, mb.data(), mb.size() * sizeof(float2)));
-            CK(h2d(w.j_anglim, al.data(), al.size() * sizeof(float4)));
-        }
-        CK(h2d(w.jcolor_pos, jpos.data(), (NUM_COLORS + 1) * sizeof(int)));
-        w.n_nocontact = (int)nocontact.size();
-        ALLOC(w.nocontact_keys, std::max<size_t>(nocontact.size(), 1));
-        CK(h2d(w.nocontact_keys, nocontact.data(), nocontact.size() * sizeof(unsigned long long)));
-    }
+    // ---- joints ----
+    ALLOC(w.nocontact_keys, (size_t)NJ);
+    W->joint_removed.assign(W->joints.size(), 0);
+    rc = upload_joints(W);
+    if (rc != RB_OK) return rc;
     {
         State s;
         memset(&s, 0, sizeof(s));
@@ -1444,6 +1461,76 @@ int rb_world_reserve(RbWorld* W, int32_t max_bodies, int32_t max_colliders) {
     W->reserve_bodies = max_bodies;
     W->reserve_colliders = max_colliders;
     return RB_OK;
+}
+
+int rb_world_reserve_joints(RbWorld* W, int32_t max_joints, int32_t generic) {
+    if (!W || max_joints < 0) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    W->reserve_joints = max_joints;
+    W->reserve_generic = generic ? 1 : 0;
+    return RB_OK;
+}
+
+static int validate_joint(const RbJointDesc& j, int nb, int index) {
+    if (j.body1 < 0 || j.body1 >= nb || j.body2 < 0 || j.body2 >= nb || (j.locked_axes & ~63u)) {
+        set_err("joint with bad body index or axes%s", "");
+        return RB_ERR_INVALID;
+    }
+    const unsigned ac = (j.coupled_axes >> 3) & 7u;   // limit_angular_coupled asserts exactly two coupled angular axes (joint_constraint_helper.rs:737-739)
+    if ((j.coupled_axes & ~63u) || (ac != 0 && ac != 3u && ac != 5u && ac != 6u)) {
+        set_err("joint %s%d: coupled_axes must couple exactly two angular axes (or none)", "", index);
+        return RB_ERR_INVALID;
+    }
+    return RB_OK;
+}
+
+// The joint set changed: colours, stage order and the contact-disabling pairs were recomputed (upload_joints); the islands and
+// the schedule follow at the next step, the broad phase re-filters its pairs.
+static int joints_changed(RbWorld* W) {
+    int one = 1;
+    CK(h2d(&W->w.st->bp_dirty, &one, sizeof(int)));
+    CK(h2d(&W->w.st->sched_dirty, &one, sizeof(int)));
+    CK(h2d(&W->w.st->njused_colors, &W->njused, sizeof(int)));
+    return RB_OK;
+}
+
+// ImpulseJointSet::insert after the world has been uploaded (impulse_joint_set.rs; user_changes.rs): appended joints keep every
+// existing index.  Capacity comes from rb_world_reserve_joints (before rb_world_set_scene); joints with limits, motors or coupled
+// axes -- and any joint under warmstart_joints -- need the generic joint path, which a world without such joints only has when
+// it was reserved with generic = 1.
+int rb_world_insert_joints(RbWorld* W, int32_t n, const RbJointDesc* joints, int32_t* first_joint) {
+    if (!W || n < 0 || (n && !joints) || !W->w.st) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    const int nj0 = W->w.nj;
+    if (nj0 + n > W->w.joint_cap) { set_err("rb_world_insert_joints exceeds the reserved capacity (rb_world_reserve_joints before rb_world_set_scene)%s", ""); return RB_ERR_CAPACITY; }
+    for (int i = 0; i < n; ++i) {
+        int rc = validate_joint(joints[i], W->w.nb, nj0 + i);
+        if (rc != RB_OK) return rc;
+        const unsigned free_axes = ~joints[i].locked_axes & 63u;
+        if ((((joints[i].limit_axes | joints[i].motor_axes) & free_axes) || W->params.warmstart_joints) && !W->w.generic_joints) {
+            set_err("this joint needs the generic joint path: reserve it with rb_world_reserve_joints(.., generic = 1)%s", "");
+            return RB_ERR_INVALID;
+        }
+    }
+    int rc = sync_world(W);
+    if (rc != RB_OK) return rc;
+    W->joints.insert(W->joints.end(), joints, joints + n);
+    W->w.nj = nj0 + n;
+    if ((rc = upload_joints(W)) != RB_OK) return rc;
+    if (first_joint) *first_joint = nj0;
+    return joints_changed(W);
+}
+
+// ImpulseJointSet::remove: the slot stays allocated (indices of the other joints are unchanged), the joint is neither solved
+// nor an island edge any more, and contacts it disabled come back.
+int rb_world_remove_joints(RbWorld* W, int32_t n, const int32_t* indices) {
+    if (!W || n < 0 || (n && !indices) || !W->w.st) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    for (int k = 0; k < n; ++k)
+        if (indices[k] < 0 || indices[k] >= W->w.nj) { set_err("joint index out of range%s", ""); return RB_ERR_INVALID; }
+    int rc = sync_world(W);
+    if (rc != RB_OK) return rc;
+    W->joint_removed.resize(W->joints.size(), 0);
+    for (int k = 0; k < n; ++k) W->joint_removed[indices[k]] = 1;
+    if ((rc = upload_joints(W)) != RB_OK) return rc;
+    return joints_changed(W);
 }
 
 // Registers a convex polyhedron (closed convex mesh: vertices + polygonal faces) that RB_SHAPE_CONVEX colliders refer to

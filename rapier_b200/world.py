@@ -83,6 +83,21 @@ class PhysicsPipeline:
         idx = np.ascontiguousarray(indices, np.int32)
         self._check(self.L.rb_world_remove_bodies(self.h, len(idx), idx.ctypes.data))
 
+    def reserve_joints(self, max_joints, generic=False):
+        """Room for later insert_joints() calls (applied by the next upload); generic: also the limits / motors / coupled-axes path."""
+        self._check(self.L.rb_world_reserve_joints(self.h, max_joints, 1 if generic else 0))
+
+    def insert_joints(self, joint_descs):
+        """ImpulseJointSet::insert after the upload: appended, every existing index kept.  Returns the first new index."""
+        j = as_array(joint_descs, A.RbJointDesc)
+        first = C.c_int32(-1)
+        self._check(self.L.rb_world_insert_joints(self.h, len(joint_descs), j, C.byref(first)))
+        return first.value
+
+    def remove_joints(self, indices):
+        idx = np.ascontiguousarray(indices, np.int32)
+        self._check(self.L.rb_world_remove_joints(self.h, len(idx), idx.ctypes.data))
+
     def set_params(self, params):
         self.params = params
         self._check(self.L.rb_world_set_params(self.h, C.byref(params)))
@@ -274,8 +289,24 @@ class PhysicsWorld:
         self.physics_pipeline.remove_bodies([body_handle])
 
     def insert_impulse_joint(self, body1, body2, joint_builder):
-        self._dirty = True
-        return self.impulse_joints.insert(body1, body2, joint_builder)
+        """ImpulseJointSet::insert.  After the first step the joint is appended on the device (rb_world_insert_joints; capacity
+        from reserve_joints) without touching any other state."""
+        h = self.impulse_joints.insert(body1, body2, joint_builder)
+        nb0, nc0, nj0 = self._uploaded
+        if nb0 + nc0 > 0 and not self._dirty:
+            self.physics_pipeline.insert_joints(self.impulse_joints.descs[nj0:])
+            self._uploaded = (nb0, nc0, len(self.impulse_joints))
+        else:
+            self._dirty = True
+        return h
+
+    def remove_impulse_joint(self, joint_handle):
+        """ImpulseJointSet::remove (the handle's slot stays allocated)."""
+        self._flush()
+        self.physics_pipeline.remove_joints([joint_handle])
+
+    def reserve_joints(self, max_joints, generic=False):
+        self.physics_pipeline.reserve_joints(max_joints, generic)
 
     def _flush(self):
         if self._dirty:

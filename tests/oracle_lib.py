@@ -65,6 +65,8 @@ def lib(fast=False):
                                            C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_world_insert.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_world_remove_bodies.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_world_insert_joints.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_world_remove_joints.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_world_get_quarantine.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.orc_world_get_sleeping.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_world_wake_up.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
@@ -125,6 +127,17 @@ class OracleWorld:
         rc = self.L.orc_world_insert(self.h, len(body_descs), b, len(collider_descs), c)
         assert rc == 0, rc
         self.nb += len(body_descs)
+
+    def insert_joints(self, joint_descs):
+        """Mirror of PhysicsPipeline.insert_joints (appended joints)."""
+        j = as_array(joint_descs, A.RbJointDesc)
+        rc = self.L.orc_world_insert_joints(self.h, len(joint_descs), j)
+        assert rc == 0, rc
+
+    def remove_joints(self, indices):
+        idx = np.ascontiguousarray(indices, np.int32)
+        rc = self.L.orc_world_remove_joints(self.h, len(idx), idx.ctypes.data)
+        assert rc == 0, rc
 
     def quarantine(self):
         n = self.L.orc_world_get_quarantine(self.h, None, 0)

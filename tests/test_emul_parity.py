@@ -239,6 +239,69 @@ def test_island_structure_emulated_kernels():
     multi_collider_slab_sleeps(lambda s: PhysicsWorld(s, _lib=emul_lib.lib()), ni=20, nj=12)
 
 
+def test_joint_insertion_and_removal_emulated_kernels():
+    """ImpulseJointSet::insert / remove after the world has been stepped (rb_world_insert_joints / rb_world_remove_joints).
+    persistent_islands.rs joint_links_and_split_after_removal: a rope joint between two distant resting boxes merges their
+    islands in the next step, removing it splits them again.  Then a run with joints of every path coming and going -- a
+    spherical chain link, a spring, a revolute joint with a limit and contacts disabled between overlapping boxes -- bit-exact
+    against the oracle at every checkpoint, warm-start data of everything else untouched."""
+    from parity_util import compare_worlds, is_exact
+    from rapier_b200.sets import ColliderBuilder, RevoluteJointBuilder, RigidBodyBuilder, RopeJointBuilder, SphericalJointBuilder, SpringJointBuilder
+    s = scenes.Scene("joint_islands", gravity=(0.0, -9.81, 0.0))
+    s.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(100.0, 0.5, 100.0))
+    a = s.insert(RigidBodyBuilder.dynamic().translation((0.0, 0.5, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    b = s.insert(RigidBodyBuilder.dynamic().translation((20.0, 0.5, 0.0)), ColliderBuilder.cuboid(0.5, 0.5, 0.5))
+    for make in (lambda: PhysicsWorld(s, _lib=emul_lib.lib()), lambda: oracle_lib.OracleWorld(s)):
+        w = make()
+        island = (lambda: w.physics_pipeline.label_components()) if isinstance(w, PhysicsWorld) else (lambda: w.debug_read("island_of", np.int32))
+        if isinstance(w, PhysicsWorld):
+            w.reserve_joints(4, generic=True)
+        w.step(240)
+        assert island()[a] != island()[b]
+        rope = RopeJointBuilder(30.0).build_desc(a, b)
+        (w.physics_pipeline if isinstance(w, PhysicsWorld) else w).insert_joints([rope])
+        w.step(1)
+        assert island()[a] == island()[b], "a joint must merge islands"
+        (w.physics_pipeline if isinstance(w, PhysicsWorld) else w).remove_joints([0])
+        w.step(240)
+        assert island()[a] != island()[b], "removing the joint must split them again"
+
+    s = scenes.box_pile(3, 3, 3)
+    nb = len(s.bodies)
+    w = PhysicsWorld(s, _lib=emul_lib.lib())
+    w.reserve_joints(8, generic=True)
+    o = oracle_lib.OracleWorld(s)
+    nj0 = len(s.joints)
+    dyn = [i for i, d in enumerate(s.bodies.descs) if d.body_type == 0]
+    plan = {
+        10: ("insert", SphericalJointBuilder().local_anchor1((0.4, 0.0, 0.0)).local_anchor2((-0.4, 0.0, 0.0)).build_desc(dyn[0], dyn[1])),
+        25: ("insert", SpringJointBuilder(0.8, 150.0, 6.0).build_desc(dyn[2], dyn[5])),
+        40: ("insert", RevoluteJointBuilder((0.0, 1.0, 0.0)).local_anchor1((0.0, 0.5, 0.0)).local_anchor2((0.0, -0.5, 0.0)).limits(4, -0.4, 0.6).contacts_enabled(False).build_desc(dyn[3], dyn[4])),
+        70: ("remove", [nj0]),
+        90: ("remove", [nj0 + 2]),
+        100: ("insert", RopeJointBuilder(1.5).build_desc(dyn[0], dyn[7])),
+    }
+    for i in range(140):
+        if i in plan:
+            kind, arg = plan[i]
+            if kind == "insert":
+                w.physics_pipeline.insert_joints([arg]); o.insert_joints([arg])
+            else:
+                w.physics_pipeline.remove_joints(arg); o.remove_joints(arg)
+        w.step(); o.step()
+        if i % 10 == 9 or i in plan or i - 1 in plan:
+            d = compare_worlds(w, o)
+            assert is_exact(d), (i, d)
+            ji_w, ji_o = w.debug_read("joint_impulses", np.float32), o.debug_read("joint_impulses", np.float32)
+            assert (ji_w.view(np.uint32) == ji_o.view(np.uint32)).all(), i
+    # capacity and path errors are reported, not silently ignored
+    from rapier_b200.world import RapierError
+    w2 = PhysicsWorld(s, _lib=emul_lib.lib())
+    w2.step(1)
+    with pytest.raises(RapierError):
+        w2.physics_pipeline.insert_joints([plan[10][1]] * 64)
+
+
 def test_dominance_groups_emulated_kernels():
     from test_oracle_kat import dominance_groups
     from variant_cases import dominance_parity_case
