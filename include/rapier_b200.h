@@ -279,6 +279,10 @@ int rb_world_remove_bodies(RbWorld* w, int32_t n, const int32_t* body_indices);
 int rb_world_reserve_joints(RbWorld* w, int32_t max_joints, int32_t generic);
 int rb_world_insert_joints(RbWorld* w, int32_t n, const RbJointDesc* joints, int32_t* first_joint);
 int rb_world_remove_joints(RbWorld* w, int32_t n, const int32_t* joint_indices);
+/* ImpulseJointSet::get_mut(handle, wake_up) + edits: the listed joints take the new descriptors in place (motor targets, limits,
+ * frames, softness ...).  Bodies must stay the same; warm-start impulses are kept; wake_up != 0 wakes the attached bodies'
+ * islands (crates/rapier3d/tests/issue_692_joint_get_mut_wakes_bodies.rs). */
+int rb_world_update_joints(RbWorld* w, int32_t n, const int32_t* joint_indices, const RbJointDesc* joints, int32_t wake_up);
 
 /* ---- convex polyhedra (ColliderBuilder::{convex_hull, convex_mesh, round_convex_hull}, src/geometry/collider.rs:1039-1090;
  *      parry ConvexPolyhedron) ----

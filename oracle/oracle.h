@@ -34,6 +34,7 @@ int orc_world_insert(OrcWorld* w, int32_t nb, const RbBodyDesc* bodies, int32_t 
 int orc_world_remove_bodies(OrcWorld* w, int32_t n, const int32_t* indices);
 int orc_world_insert_joints(OrcWorld* w, int32_t n, const RbJointDesc* joints);      /* rb_world_insert_joints */
 int orc_world_remove_joints(OrcWorld* w, int32_t n, const int32_t* indices);        /* rb_world_remove_joints */
+int orc_world_update_joints(OrcWorld* w, int32_t n, const int32_t* indices, const RbJointDesc* joints, int32_t wake_up);   /* rb_world_update_joints */
 int orc_world_set_body_states(OrcWorld* w, int32_t n, const int32_t* indices, const float* pose7,
                               const float* vel6);
 int orc_world_step(OrcWorld* w, const float gravity[3], int32_t nsteps);

@@ -12,6 +12,7 @@ int insert(World& w, int nb, const RbBodyDesc* bd, int nc, const RbColliderDesc*
 int remove_bodies(World& w, int n, const int* indices);
 int insert_joints(World& w, int n, const RbJointDesc* jd);
 int remove_joints(World& w, int n, const int* indices);
+int update_joints(World& w, int n, const int* indices, const RbJointDesc* jd, int wake_up);
 void update_world_mass_properties(Body& b);
 void refresh_collider(World& w, Collider& c);
 void set_threads(int n);
@@ -132,6 +133,10 @@ int orc_world_remove_bodies(OrcWorld* w, int32_t n, const int32_t* indices) {
 int orc_world_insert_joints(OrcWorld* w, int32_t n, const RbJointDesc* joints) {
     if (!w || n < 0 || (n && !joints)) return RB_ERR_INVALID;
     return insert_joints(w->w, n, joints);
+}
+int orc_world_update_joints(OrcWorld* w, int32_t n, const int32_t* indices, const RbJointDesc* joints, int32_t wake_up) {
+    if (!w || n < 0 || (n && (!indices || !joints))) return RB_ERR_INVALID;
+    return update_joints(w->w, n, indices, joints, wake_up);
 }
 int orc_world_remove_joints(OrcWorld* w, int32_t n, const int32_t* indices) {
     if (!w || n < 0 || (n && !indices)) return RB_ERR_INVALID;

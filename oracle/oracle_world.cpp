@@ -1023,6 +1023,23 @@ int insert_joints(World& w, int n, const RbJointDesc* jd) {
     w.counters.num_joints = (int)w.joints.size();
     return RB_OK;
 }
+static void wake_island_of(World& w, int body);
+int update_joints(World& w, int n, const int* indices, const RbJointDesc* jd, int wake_up) {   // rb_world_update_joints
+    for (int k = 0; k < n; ++k) {
+        if (indices[k] < 0 || indices[k] >= (int)w.joints.size() || w.joints[indices[k]].removed) return RB_ERR_INVALID;
+        Joint& j = w.joints[indices[k]];
+        if (jd[k].body1 != j.body1 || jd[k].body2 != j.body2) return RB_ERR_INVALID;
+        float imp[3][6];
+        for (int a = 0; a < 6; ++a) { imp[0][a] = j.impulses[a]; imp[1][a] = j.limit_impulses[a]; imp[2][a] = j.motor_impulses[a]; }
+        int rc = fill_joint(w, j, jd[k]);
+        if (rc != RB_OK) return rc;
+        for (int a = 0; a < 6; ++a) { j.impulses[a] = imp[0][a]; j.limit_impulses[a] = imp[1][a]; j.motor_impulses[a] = imp[2][a]; }
+    }
+    refresh_joint_set(w);
+    if (wake_up)
+        for (int k = 0; k < n; ++k) { wake_island_of(w, jd[k].body1); wake_island_of(w, jd[k].body2); }
+    return RB_OK;
+}
 int remove_joints(World& w, int n, const int* indices) {
     for (int k = 0; k < n; ++k) {
         if (indices[k] < 0 || indices[k] >= (int)w.joints.size()) return RB_ERR_INVALID;

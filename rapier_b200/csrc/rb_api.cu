@@ -1682,6 +1682,41 @@ int rb_world_wake_up(RbWorld* W, int32_t n, const int32_t* indices) {
     return wake_impl(W, indices, n);
 }
 
+// ImpulseJointSet::get_mut(handle, wake_up) followed by edits of the joint (motor targets, limits, frames, softness ...): the
+// listed joints take the new descriptors in place.  Their bodies must stay the same (otherwise remove + insert); impulses carried
+// for warm starting are kept; with wake_up the islands of the attached bodies are woken (issue_692_joint_get_mut_wakes_bodies.rs).
+int rb_world_update_joints(RbWorld* W, int32_t n, const int32_t* indices, const RbJointDesc* joints, int32_t wake_up) {
+    if (!W || n < 0 || (n && (!indices || !joints)) || !W->w.st) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
+    W->joint_removed.resize(W->joints.size(), 0);
+    for (int k = 0; k < n; ++k) {
+        const int i = indices[k];
+        if (i < 0 || i >= W->w.nj || W->joint_removed[i]) { set_err("joint index out of range (or removed)%s", ""); return RB_ERR_INVALID; }
+        int rc = validate_joint(joints[k], W->w.nb, i);
+        if (rc != RB_OK) return rc;
+        if (joints[k].body1 != W->joints[i].body1 || joints[k].body2 != W->joints[i].body2) {
+            set_err("rb_world_update_joints cannot move a joint to other bodies: remove it and insert a new one%s", "");
+            return RB_ERR_INVALID;
+        }
+        const unsigned free_axes = ~joints[k].locked_axes & 63u;
+        if (((joints[k].limit_axes | joints[k].motor_axes) & free_axes) && !W->w.generic_joints) {
+            set_err("this joint needs the generic joint path: reserve it with rb_world_reserve_joints(.., generic = 1)%s", "");
+            return RB_ERR_INVALID;
+        }
+    }
+    int rc = sync_world(W);
+    if (rc != RB_OK) return rc;
+    std::vector<int32_t> wake;
+    for (int k = 0; k < n; ++k) {
+        W->joints[indices[k]] = joints[k];
+        wake.push_back(joints[k].body1);
+        wake.push_back(joints[k].body2);
+    }
+    if ((rc = upload_joints(W)) != RB_OK) return rc;
+    if ((rc = joints_changed(W)) != RB_OK) return rc;
+    if (wake_up && !wake.empty()) return wake_impl(W, wake.data(), (int)wake.size());
+    return RB_OK;
+}
+
 int rb_world_set_body_states(RbWorld* W, int32_t n, const int32_t* indices, const float* pose7, const float* vel6) {
     if (!W || n < 0 || (n && !indices)) { set_err("invalid arguments%s", ""); return RB_ERR_INVALID; }
     int rc = sync_world(W);

@@ -98,6 +98,12 @@ class PhysicsPipeline:
         idx = np.ascontiguousarray(indices, np.int32)
         self._check(self.L.rb_world_remove_joints(self.h, len(idx), idx.ctypes.data))
 
+    def update_joints(self, indices, joint_descs, wake_up=True):
+        """ImpulseJointSet::get_mut(handle, wake_up) + edits: new descriptors in place (same bodies), impulses kept."""
+        idx = np.ascontiguousarray(indices, np.int32)
+        j = as_array(joint_descs, A.RbJointDesc)
+        self._check(self.L.rb_world_update_joints(self.h, len(idx), idx.ctypes.data, j, 1 if wake_up else 0))
+
     def set_params(self, params):
         self.params = params
         self._check(self.L.rb_world_set_params(self.h, C.byref(params)))

@@ -67,6 +67,7 @@ def lib(fast=False):
         L.orc_world_remove_bodies.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_world_insert_joints.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_world_remove_joints.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_world_update_joints.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
         L.orc_world_get_quarantine.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.orc_world_get_sleeping.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_world_wake_up.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
@@ -137,6 +138,12 @@ class OracleWorld:
     def remove_joints(self, indices):
         idx = np.ascontiguousarray(indices, np.int32)
         rc = self.L.orc_world_remove_joints(self.h, len(idx), idx.ctypes.data)
+        assert rc == 0, rc
+
+    def update_joints(self, indices, joint_descs, wake_up=True):
+        idx = np.ascontiguousarray(indices, np.int32)
+        j = as_array(joint_descs, A.RbJointDesc)
+        rc = self.L.orc_world_update_joints(self.h, len(idx), idx.ctypes.data, j, 1 if wake_up else 0)
         assert rc == 0, rc
 
     def quarantine(self):

@@ -2,6 +2,7 @@
 (tests/emul, -DRB_EMULATE, one thread playing every CUDA thread) against the CPU oracle.  These do
 not exercise the product library; the `-m gpu` tests do that on the B200."""
 import numpy as np
+from rapier_b200 import _abi as A
 import pytest
 
 import emul_lib
@@ -300,6 +301,65 @@ def test_joint_insertion_and_removal_emulated_kernels():
     w2.step(1)
     with pytest.raises(RapierError):
         w2.physics_pipeline.insert_joints([plan[10][1]] * 64)
+
+
+def test_joint_update_emulated_kernels():
+    """rb_world_update_joints = ImpulseJointSet::get_mut(handle, wake_up) + edits.  issue_692_joint_get_mut_wakes_bodies.rs: a
+    revolute joint between a kinematic body and a ball that has fallen asleep gets a velocity motor: the ball is awake after the
+    next step and starts turning.  Then motor targets and limits of a jointed pile are changed every few steps, bit-exact against
+    the oracle (warm-start impulses carried across the updates)."""
+    from parity_util import compare_worlds, is_exact
+    from rapier_b200.sets import ColliderBuilder, RevoluteJointBuilder, RigidBodyBuilder
+    from variant_cases import joint_limits_scene
+    s = scenes.Scene("issue_692", gravity=(0.0, -9.81, 0.0))
+    kin = s.bodies.insert(RigidBodyBuilder.kinematic_position_based())
+    dyn = s.insert(RigidBodyBuilder.dynamic().translation((0.0, -2.0, 0.0)), ColliderBuilder.ball(0.5))
+    jb = lambda: RevoluteJointBuilder((1.0, 0.0, 0.0)).local_anchor1((0.0, 0.0, 0.0)).local_anchor2((0.0, 2.0, 0.0))
+    s.joints.insert(kin, dyn, jb())
+    for oracle in (False, True):
+        if oracle:
+            w = oracle_lib.OracleWorld(s); api = w
+        else:
+            w = PhysicsWorld(s, _lib=emul_lib.lib()); w.reserve_joints(0, generic=True); api = w.physics_pipeline
+        steps = 0
+        while not w.sleeping()[dyn]:
+            w.step(); steps += 1
+            assert steps < 2000
+        api.update_joints([0], [jb().motor_velocity(3, 2.0, 100.0).build_desc(kin, dyn)], wake_up=True)
+        w.step()
+        assert not w.sleeping()[dyn]
+        moved = False
+        for _ in range(50):
+            w.step()
+            moved = moved or float(np.linalg.norm(w.body_states()[1][dyn, 3:])) > 0.1
+        assert moved
+
+    s = joint_limits_scene()
+    p = A.RbIntegrationParameters.default()
+    p.warmstart_joints = 1
+    w, o = PhysicsWorld(s, integration_parameters=p, _lib=emul_lib.lib()), oracle_lib.OracleWorld(s, params=p)
+    import copy
+    descs = [copy.deepcopy(d) for d in s.joints.descs]
+    motorised = [i for i, d in enumerate(descs) if d.motor_axes]
+    limited = [i for i, d in enumerate(descs) if d.limit_axes]
+    for i in range(120):
+        if i % 9 == 4:
+            j = motorised[(i // 9) % len(motorised)]
+            ax = [a for a in range(6) if descs[j].motor_axes & (1 << a)][0]
+            descs[j].motors[ax].target_vel = 1.5 - 0.5 * (i % 7)
+            descs[j].motors[ax].target_pos = 0.1 * (i % 5)
+            w.physics_pipeline.update_joints([j], [descs[j]]); o.update_joints([j], [descs[j]])
+        if i % 14 == 7:
+            j = limited[(i // 14) % len(limited)]
+            ax = [a for a in range(6) if descs[j].limit_axes & (1 << a)][0]
+            descs[j].limits[ax][1] = descs[j].limits[ax][1] + 0.05
+            w.physics_pipeline.update_joints([j], [descs[j]], wake_up=False); o.update_joints([j], [descs[j]], wake_up=False)
+        w.step(); o.step()
+        if i % 10 == 9 or i % 9 == 4:
+            d = compare_worlds(w, o)
+            assert is_exact(d), (i, d)
+            ji_w, ji_o = w.debug_read("joint_impulses", np.float32), o.debug_read("joint_impulses", np.float32)
+            assert (ji_w.view(np.uint32) == ji_o.view(np.uint32)).all(), i
 
 
 def test_dominance_groups_emulated_kernels():
