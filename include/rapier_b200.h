@@ -271,9 +271,11 @@ int rb_world_insert(RbWorld* w, int32_t num_bodies, const RbBodyDesc* bodies, in
                     const RbColliderDesc* colliders, int32_t* first_body_index, int32_t* first_collider_index);
 int rb_world_remove_bodies(RbWorld* w, int32_t n, const int32_t* body_indices);
 /* ImpulseJointSet::insert / remove after the upload (src/dynamics/joint/impulse_joint/impulse_joint_set.rs; ABI 6).
- * rb_world_reserve_joints: room for later insertions, applied by the NEXT rb_world_set_scene; generic != 0 also reserves the
+ * rb_world_reserve_joints: the TOTAL number of joint slots (scene + later insertions, like rb_world_reserve), applied by the NEXT
+ * rb_world_set_scene; generic != 0 also reserves the
  * generic joint path (limits / motors / coupled axes / warmstart_joints) for a scene that has no such joint yet.
- * rb_world_insert_joints: appended joints keep every existing index; *first_joint receives the index of the first new one.
+ * rb_world_insert_joints: appended joints keep every existing index; *first_joint receives the index of the first new one;
+ * the islands of the attached bodies are woken (insert(.., wake_up = true)).
  * rb_world_remove_joints: the slots stay allocated; the joints are no longer solved, no longer island edges, and the
  * contacts they disabled come back.  Both recompute the joint colours and the stage order from the whole joint set. */
 int rb_world_reserve_joints(RbWorld* w, int32_t max_joints, int32_t generic);

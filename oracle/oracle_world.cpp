@@ -1012,6 +1012,7 @@ static void refresh_joint_set(World& w) {
 }
 
 // Mirrors of rb_world_insert_joints / rb_world_remove_joints (ImpulseJointSet::insert / remove after the upload).
+static void wake_island_of(World& w, int body);
 int insert_joints(World& w, int n, const RbJointDesc* jd) {
     const size_t n0 = w.joints.size();
     w.joints.resize(n0 + n, Joint{});
@@ -1021,6 +1022,7 @@ int insert_joints(World& w, int n, const RbJointDesc* jd) {
     }
     refresh_joint_set(w);
     w.counters.num_joints = (int)w.joints.size();
+    for (int i = 0; i < n; ++i) { wake_island_of(w, jd[i].body1); wake_island_of(w, jd[i].body2); }   // insert(.., wake_up = true)
     return RB_OK;
 }
 static void wake_island_of(World& w, int body);

@@ -1516,7 +1516,12 @@ int rb_world_insert_joints(RbWorld* W, int32_t n, const RbJointDesc* joints, int
     W->w.nj = nj0 + n;
     if ((rc = upload_joints(W)) != RB_OK) return rc;
     if (first_joint) *first_joint = nj0;
-    return joints_changed(W);
+    if ((rc = joints_changed(W)) != RB_OK) return rc;
+    // insert(.., wake_up = true): the attached bodies' islands are woken -- an island is awake or asleep as a whole here, and a
+    // joint between a sleeping and an awake body would otherwise merge the two states into one island
+    std::vector<int32_t> wake;
+    for (int i = 0; i < n; ++i) { wake.push_back(joints[i].body1); wake.push_back(joints[i].body2); }
+    return wake.empty() ? RB_OK : wake_impl(W, wake.data(), (int)wake.size());
 }
 
 // ImpulseJointSet::remove: the slot stays allocated (indices of the other joints are unchanged), the joint is neither solved
