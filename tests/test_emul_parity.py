@@ -362,6 +362,38 @@ def test_joint_update_emulated_kernels():
             assert (ji_w.view(np.uint32) == ji_o.view(np.uint32)).all(), i
 
 
+def test_physics_world_facade_joint_edits_emulated():
+    """PhysicsWorld.insert_impulse_joint / remove_impulse_joint after the first step go through rb_world_insert_joints /
+    rb_world_remove_joints (state of everything else untouched); without reserved capacity the insertion is refused loudly."""
+    from rapier_b200.sets import ColliderBuilder, RigidBodyBuilder, RopeJointBuilder
+    from rapier_b200.world import RapierError
+    def world(reserve):
+        w = PhysicsWorld(_lib=emul_lib.lib())
+        w.insert(RigidBodyBuilder.fixed().translation((0.0, -0.5, 0.0)), ColliderBuilder.cuboid(20.0, 0.5, 20.0))
+        a = w.insert(RigidBodyBuilder.dynamic().translation((0.0, 3.0, 0.0)).can_sleep(False), ColliderBuilder.ball(0.3))
+        b = w.insert(RigidBodyBuilder.dynamic().translation((1.0, 3.0, 0.0)).can_sleep(False), ColliderBuilder.ball(0.3))
+        if reserve:
+            w.reserve_joints(2, generic=True)
+        w.step(5)
+        return w, a, b
+    w, a, b = world(True)
+    before = w.body_states()[0][a].copy()
+    j = w.insert_impulse_joint(a, b, RopeJointBuilder(1.2))
+    assert (w.body_states()[0][a].view(np.uint32) == before.view(np.uint32)).all()      # nothing was re-uploaded
+    w.set_body_states([b], vel6=[(3.0, 0.0, 0.0, 0.0, 0.0, 0.0)])
+    w.step(60)
+    pose = w.body_states()[0]
+    assert np.linalg.norm(pose[a, :3] - pose[b, :3]) < 1.2 + 0.05                        # the rope holds
+    w.remove_impulse_joint(j)
+    w.set_body_states([b], vel6=[(4.0, 0.0, 0.0, 0.0, 0.0, 0.0)])
+    w.step(60)
+    pose = w.body_states()[0]
+    assert np.linalg.norm(pose[a, :3] - pose[b, :3]) > 1.5                               # and no longer does once removed
+    w, a, b = world(False)
+    with pytest.raises(RapierError):
+        w.insert_impulse_joint(a, b, RopeJointBuilder(1.2))
+
+
 def test_dominance_groups_emulated_kernels():
     from test_oracle_kat import dominance_groups
     from variant_cases import dominance_parity_case
